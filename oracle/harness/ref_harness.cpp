@@ -1,0 +1,369 @@
+/*
+ * ref_harness.cpp -- parity/timing harness around the UNMODIFIED reference
+ * (ngcurrier/ProteusCFD, /root/reference/ucs).  TEST INFRASTRUCTURE ONLY.
+ *
+ * This TU contains no solver arithmetic of its own: it builds a
+ * SolutionSpace<Real> exactly like ucs/main.cpp:167-223 does, injects a smooth
+ * analytic state, then calls the reference's own phase entry
+ * points in the order of SolutionSpace::NewtonIterate
+ * (ucs/solutionSpace.tcc:640-865) and dumps every intermediate array as a raw
+ * little-endian binary so the CUDA path can be compared with it.
+ *
+ *   ref_harness <case> <outdir> dump          one pass, dump everything
+ *   ref_harness <case> <outdir> time <reps>   time each phase, print one JSON line
+ *
+ * Compiled by oracle/Makefile from the sources where they lie in
+ * /root/reference; output goes to oracle/_ref/ only.
+ */
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <limits>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+#include <sys/stat.h>
+#include <sys/time.h>
+#include <mpi.h>
+
+// the reference keeps its halo maps private (ucs/parallel.h:109-121); the
+// harness only reads them.
+#define private public
+#define protected public
+#include "general.h"
+#include "exceptions.h"
+#include "bc.h"
+#include "mesh.h"
+#include "param.h"
+#include "eqnset.h"
+#include "create_functions.h"
+#include "parallel.h"
+#include "timer.h"
+#include "customics.h"
+#include "derivatives.h"
+#include "portFileio.h"
+#include "move.h"
+#include "composite.h"
+#include "solutionSpaceBase.h"
+#include "solutionSpace.h"
+#include "dataInfo.h"
+#include "solve.h"
+#include "solutionOrdering.h"
+#include "fluid_structure.h"
+#include "temporalControl.h"
+#include "pythonInterface.h"
+#include "timestep.h"
+#include "residual.h"
+#include "jacobian.h"
+#include "gradient.h"
+#include "limiters.h"
+#undef private
+#undef protected
+
+static std::string g_out;
+static int g_rank = 0;
+
+static double Now()
+{
+  timeval tv; gettimeofday(&tv, NULL);
+  return tv.tv_sec + 1e-6*tv.tv_usec;
+}
+
+template <class T>
+static void Dump(const std::string& name, const T* data, size_t n)
+{
+  std::ostringstream fn;
+  fn << g_out << "/" << name << "." << g_rank << ".bin";
+  FILE* f = fopen(fn.str().c_str(), "wb");
+  if(!f){ perror(fn.str().c_str()); exit(2); }
+  if(n) fwrite(data, sizeof(T), n, f);
+  fclose(f);
+}
+
+// smooth non-uniform state of SURVEY.md 8d, in the reference's own
+// non-dimensionalisation (rho_inf = 1, c_inf = 1, p_inf = 1/gamma)
+static void InjectState(SolutionSpace<Real>* space)
+{
+  Mesh<Real>* m = space->m;
+  EqnSet<Real>* eqnset = space->eqnset;
+  Param<Real>* param = space->param;
+  Int neqn = eqnset->neqn;
+  Int nvars = neqn + eqnset->nauxvars;
+  Int nnode = m->GetNumNodes();
+  const Real twopi = 2.0*3.14159265358979323846;
+  Real gamma = param->gamma;
+  Real mach = param->GetVelocity(space->iter);
+  for(Int i = 0; i < nnode; i++){
+    Real x = m->xyz[3*i + 0], y = m->xyz[3*i + 1], z = m->xyz[3*i + 2];
+    Real rho = 1.0 + 0.1*sin(twopi*x)*cos(twopi*y);
+    Real u = mach*param->flowdir[0] + 0.05*sin(twopi*y);
+    Real v = mach*param->flowdir[1] + 0.05*sin(twopi*z);
+    Real w = mach*param->flowdir[2] + 0.05*sin(twopi*x);
+    Real p = 1.0/gamma*(1.0 + 0.1*cos(twopi*z));
+    Real* q = &space->q[i*nvars];
+    q[0] = rho;
+    q[1] = rho*u;
+    q[2] = rho*v;
+    q[3] = rho*w;
+    q[4] = p/(gamma - 1.0) + 0.5*rho*(u*u + v*v + w*w);
+    eqnset->ComputeAuxiliaryVariables(q);
+  }
+}
+
+static void DumpMesh(SolutionSpace<Real>* space)
+{
+  Mesh<Real>* m = space->m;
+  PObj<Real>* p = space->p;
+  Int nnode = m->GetNumNodes(), gnode = m->GetNumParallelNodes(), nbnode = m->GetNumBoundaryNodes();
+  Int nedge = m->GetNumEdges(), nbedge = m->GetNumBoundaryEdges(), ngedge = m->GetNumParallelEdges();
+  Int nb = nbedge + ngedge;
+
+  std::vector<Int> en(2*(size_t)nedge);
+  std::vector<Real> ea(4*(size_t)nedge);
+  for(Int e = 0; e < nedge; e++){
+    en[2*e] = m->edges[e].n[0]; en[2*e+1] = m->edges[e].n[1];
+    for(Int k = 0; k < 4; k++) ea[4*e+k] = m->edges[e].a[k];
+  }
+  Dump("edges_n", en.data(), en.size());
+  Dump("edges_a", ea.data(), ea.size());
+  std::vector<Int> bn(2*(size_t)nb), bf(nb), bt(nb);
+  std::vector<Real> ba(4*(size_t)nb);
+  for(Int e = 0; e < nb; e++){
+    bn[2*e] = m->bedges[e].n[0]; bn[2*e+1] = m->bedges[e].n[1];
+    for(Int k = 0; k < 4; k++) ba[4*e+k] = m->bedges[e].a[k];
+    bf[e] = m->bedges[e].factag;
+    bt[e] = space->bc->GetBCType(m->bedges[e].factag);
+  }
+  Dump("bedges_n", bn.data(), bn.size());
+  Dump("bedges_a", ba.data(), ba.size());
+  Dump("bedges_factag", bf.data(), bf.size());
+  Dump("bedges_bctype", bt.data(), bt.size());
+  Dump("xyz", m->xyz, 3*(size_t)(nnode+gnode));
+  Dump("vol", m->vol, (size_t)nnode);
+  Dump("ipsp", m->ipsp, (size_t)nnode+1);
+  Dump("psp", m->psp, (size_t)m->ipsp[nnode]);
+  Dump("lsq_s", m->s, 6*(size_t)(nnode+gnode));
+  Dump("lsq_sw", m->sw, 6*(size_t)(nnode+gnode));
+  Dump("gNodeOwner", m->gNodeOwner, (size_t)gnode);
+  Dump("gNodeLocalId", m->gNodeLocalId, (size_t)gnode);
+  Int np = p->GetNp();
+  Dump("commCountsSend", p->commCountsSend, (size_t)np);
+  Dump("commCountsRecv", p->commCountsRecv, (size_t)np);
+  Dump("commOffsetsRecv", p->commOffsetsRecv, (size_t)np);
+  {
+    std::vector<Int> pack;
+    for(Int r = 0; r < np; r++){
+      for(Int j = 0; j < p->commCountsSend[r]; j++) pack.push_back(p->nodePackingList[r][j]);
+    }
+    Dump("nodePackingList", pack.data(), pack.size());
+  }
+  EqnSet<Real>* eqnset = space->eqnset;
+  Int nvars = eqnset->neqn + eqnset->nauxvars;
+  Dump("qinf", eqnset->Qinf, (size_t)nvars);
+  Dump("beta", space->GetFieldData("beta", FIELDS::STATE_NONE), (size_t)(nnode+gnode));
+
+  Param<Real>* param = space->param;
+  std::ostringstream fn;
+  fn << g_out << "/meta." << g_rank << ".txt";
+  std::ofstream f(fn.str().c_str());
+  f << std::setprecision(17);
+  f << "rank " << p->GetRank() << "\nnp " << np << "\n";
+  f << "nnode " << nnode << "\ngnode " << gnode << "\nnbnode " << nbnode << "\n";
+  f << "nedge " << nedge << "\nnbedge " << nbedge << "\nngedge " << ngedge << "\n";
+  f << "neqn " << eqnset->neqn << "\nnvars " << nvars << "\nnterms " << space->grad->GetNterms() << "\n";
+  f << "gamma " << param->gamma << "\nchi " << param->chi << "\nsorder " << param->sorder << "\n";
+  f << "limiter " << param->limiter << "\nflux_id " << param->flux_id << "\nnSgs " << param->nSgs << "\n";
+  f << "cfl " << param->GetCFL() << "\nvelocity " << param->GetVelocity(space->iter) << "\n";
+  f << "viscous " << param->viscous << "\nRe " << param->Re << "\nPr " << param->Pr << "\nPrT " << param->PrT << "\n";
+  f << "useLocalTimeStepping " << param->useLocalTimeStepping << "\ndt " << param->dt << "\n";
+  f << "torder " << param->torder << "\nfieldJacType " << param->fieldJacType << "\n";
+  f << "boundaryJacType " << param->boundaryJacType << "\nboundaryJacEval " << param->boundaryJacEval << "\n";
+  f << "no_cvbc " << param->no_cvbc << "\nsymmetry2D " << param->symmetry2D << "\n";
+  f << "eqnset_id " << param->eqnset_id << "\ngradType " << param->gradType << "\n";
+  f << "iter " << space->iter << "\nnFirstOrderSteps " << param->nFirstOrderSteps << "\n";
+  f.close();
+}
+
+int main(int argc, char* argv[])
+{
+  MPI_Init(&argc, &argv);
+  if(argc < 4){
+    std::cerr << "usage: " << argv[0] << " <case> <outdir> dump|time [reps]" << std::endl;
+    return 1;
+  }
+  std::string casestring = argv[1];
+  g_out = argv[2];
+  std::string mode = argv[3];
+  Int reps = (argc > 4) ? atoi(argv[4]) : 1;
+  mkdir(g_out.c_str(), 0777);
+
+  std::vector<Param<Real>*> paramList;
+  SolutionOrdering<Real> operations;
+  TemporalControl<Real> temporalControl;
+
+  PObj<Real> pobj;
+  g_rank = pobj.GetRank();
+
+  size_t pos = casestring.rfind('/');
+  std::string pathname;
+  if(pos != std::string::npos){
+    pathname = casestring.substr(0, pos+1);
+    casestring = casestring.substr(pos);
+  }
+  else{
+    pathname = "./";
+  }
+  Abort.rootDirectory = pathname;
+
+  // quiet the chatter of all ranks but keep stderr of rank 0
+  {
+    std::ostringstream lo;
+    lo << g_out << "/log." << g_rank << ".txt";
+    freopen(lo.str().c_str(), "w", stdout);
+    if(g_rank != 0) freopen("/dev/null", "w", stderr);
+  }
+
+  HDF_TurnOffErrorHandling();
+  if(ReadParamFile(paramList, casestring, pathname)){ Abort << "Error in param read"; return -1; }
+  if(operations.Read(casestring, pathname)){ Abort << "Error in solution ordering read"; return -1; }
+  if(temporalControl.Read(casestring, pathname)){ Abort << "Error in temporal control read"; return -1; }
+  for(UInt i = 0; i < paramList.size(); ++i) paramList[i]->mode = 0;
+
+  std::vector<SolutionSpaceBase<Real>*> solSpaces = CreateSolutionSpaces(paramList, pobj, temporalControl);
+  SolutionSpace<Real>* space = dynamic_cast<SolutionSpace<Real>*>(solSpaces[0]);
+  Mesh<Real>* m = space->m;
+  EqnSet<Real>* eqnset = space->eqnset;
+  Param<Real>* param = space->param;
+  PObj<Real>* p = space->p;
+  Int neqn = eqnset->neqn;
+  Int nvars = neqn + eqnset->nauxvars;
+  Int nnode = m->GetNumNodes(), gnode = m->GetNumParallelNodes(), nbnode = m->GetNumBoundaryNodes();
+  Int nterms = space->grad->GetNterms();
+
+  // same bookkeeping as SolutionSpace::PreIterate (solutionSpace.tcc:510-545)
+  space->iter = param->nFirstOrderSteps + 1;
+  param->UpdateCFL(space->iter, 9999.0);
+
+  InjectState(space);
+  // NewtonIterate head (solutionSpace.tcc:662-665)
+  UpdateBCs(space);
+  p->UpdateGeneralVectors(space->q, nvars);
+  // phantom nodes were written from a uniform IC before injection; run the BC
+  // update once more so phantom states are a fixed function of the injected q
+  UpdateBCs(space);
+  p->UpdateGeneralVectors(space->q, nvars);
+
+  if(mode == "dump"){
+    DumpMesh(space);
+    Dump("q0", space->q, (size_t)(nnode+gnode+nbnode)*nvars);
+
+    Real dtmin = ComputeTimesteps(space);
+    Dump("timestep", space->GetFieldData("timestep", FIELDS::STATE_NONE), (size_t)nnode);
+    Dump("dtmin", &dtmin, 1);
+
+    space->grad->Compute();
+    Dump("qgrad", space->qgrad, (size_t)(nnode+gnode)*nterms*3);
+
+    if(param->limiter){
+      space->limiter->Compute(space);
+    }
+    Dump("limiter", space->limiter->l, (size_t)(nnode+gnode)*neqn);
+
+    std::vector<Real> res = ComputeResiduals(space);
+    Dump("b", space->crs->b, (size_t)nnode*neqn);
+    Dump("resnorm", res.data(), res.size());
+
+    if(param->nSgs > 0){
+      ComputeJacobians(space);
+      CRSMatrix<Real>* A = space->crs->A;
+      Dump("ia", A->ia, (size_t)nnode+1);
+      Dump("ja", A->ja, (size_t)A->nblocks);
+      Dump("iau", A->iau, (size_t)nnode);
+      Dump("A", A->M, (size_t)A->nblocks*neqn*neqn);
+      A->PrepareSGS();
+      Dump("A_lu", A->M, (size_t)A->nblocks*neqn*neqn);
+      Dump("pv", A->pv, (size_t)nnode*neqn);
+      space->crs->BlankX();
+      Real ddq = space->crs->SGS(param->nSgs, NULL, NULL, NULL);
+      Dump("x", space->crs->x, (size_t)(nnode+gnode)*neqn);
+      Dump("sgs_ddq", &ddq, 1);
+      for(Int j = 0; j < nnode; j++){
+	eqnset->ApplyDQ(&space->crs->x[j*neqn], &space->q[j*nvars], &m->xyz[j*3]);
+      }
+    }
+    else{
+      ExplicitSolve(*space);
+      Dump("x", space->crs->x, (size_t)nnode*neqn);
+    }
+    p->UpdateGeneralVectors(space->q, nvars);
+    Dump("q1", space->q, (size_t)(nnode+gnode+nbnode)*nvars);
+  }
+  else if(mode == "time"){
+    // CPU baseline: wall time of each reference phase (the same regions the
+    // reference's own GradientTimer/ResidualTimer/JacobianAssembleTimer/
+    // LinearSolveTimer bracket, solutionSpace.tcc:593-759), max over ranks.
+    double tTs = 0, tGrad = 0, tLim = 0, tRes = 0, tJac = 0, tLU = 0, tSGS = 0, tUpd = 0;
+    Real* qsave = new Real[(size_t)(nnode+gnode+nbnode)*nvars];
+    memcpy(qsave, space->q, sizeof(Real)*(size_t)(nnode+gnode+nbnode)*nvars);
+    for(Int r = 0; r < reps; r++){
+      double t0;
+      MPI_Barrier(MPI_COMM_WORLD);
+      t0 = Now(); ComputeTimesteps(space); tTs += Now() - t0;
+      t0 = Now(); UpdateBCs(space); p->UpdateGeneralVectors(space->q, nvars); tUpd += Now() - t0;
+      t0 = Now(); space->grad->Compute(); tGrad += Now() - t0;
+      t0 = Now(); if(param->limiter) space->limiter->Compute(space); tLim += Now() - t0;
+      t0 = Now(); ComputeResiduals(space); tRes += Now() - t0;
+      if(param->nSgs > 0){
+	t0 = Now(); ComputeJacobians(space); tJac += Now() - t0;
+	t0 = Now(); space->crs->A->PrepareSGS(); tLU += Now() - t0;
+	space->crs->BlankX();
+	t0 = Now(); space->crs->SGS(param->nSgs, NULL, NULL, NULL); tSGS += Now() - t0;
+	t0 = Now();
+	for(Int j = 0; j < nnode; j++){
+	  eqnset->ApplyDQ(&space->crs->x[j*neqn], &space->q[j*nvars], &m->xyz[j*3]);
+	}
+	tUpd += Now() - t0;
+      }
+      else{
+	t0 = Now(); ExplicitSolve(*space); tUpd += Now() - t0;
+      }
+      // keep every repetition on the same state
+      memcpy(space->q, qsave, sizeof(Real)*(size_t)(nnode+gnode+nbnode)*nvars);
+    }
+    delete [] qsave;
+    double t[8] = {tTs, tGrad, tLim, tRes, tJac, tLU, tSGS, tUpd};
+    MPI_Allreduce(MPI_IN_PLACE, t, 8, MPI_DOUBLE, MPI_MAX, MPI_COMM_WORLD);
+    Int counts[3] = {nnode, m->GetNumEdges(), m->GetNumParallelEdges()};
+    MPI_Allreduce(MPI_IN_PLACE, counts, 3, MPI_INT, MPI_SUM, MPI_COMM_WORLD);
+    if(g_rank == 0){
+      std::ostringstream fn;
+      fn << g_out << "/timing.json";
+      std::ofstream f(fn.str().c_str());
+      f << std::setprecision(9);
+      // every cut edge is a half-edge on both ranks: count it once
+      f << "{\"np\": " << p->GetNp() << ", \"reps\": " << reps
+	<< ", \"nnode\": " << counts[0] << ", \"nedge\": " << counts[1] + counts[2]/2
+	<< ", \"nsgs\": " << param->nSgs
+	<< ", \"t_timestep\": " << t[0]/reps << ", \"t_gradient\": " << t[1]/reps
+	<< ", \"t_limiter\": " << t[2]/reps << ", \"t_residual\": " << t[3]/reps
+	<< ", \"t_jacobian\": " << t[4]/reps << ", \"t_lu\": " << t[5]/reps
+	<< ", \"t_sgs\": " << t[6]/reps << ", \"t_update\": " << t[7]/reps << "}" << std::endl;
+    }
+  }
+  else{
+    std::cerr << "unknown mode " << mode << std::endl;
+  }
+
+  fflush(stdout);
+  MPI_Finalize();
+  // the reference's destructors close HDF5 files etc.; nothing there matters for the dumps
+  _exit(0);
+}

@@ -1,0 +1,110 @@
+"""Synthetic Kuhn 6-tet box meshes (the benchmark/parity input).
+
+`kuhn_box(n)` returns node coordinates, tetrahedra and tagged boundary
+triangles of an n x n x n hex box split into 6 tets per hex (Kuhn/Freudenthal
+triangulation), optionally with jittered interior nodes.  `write_ugrid`
+writes the AFLR3 ASCII layout that the reference's `udecomp` reads
+(ucs/mesh.tcc:6740-6920, ReadUGRID_Ascii) so the same mesh can be fed to the
+reference oracle.
+"""
+import itertools
+
+import numpy as np
+
+# the six axis permutations = six monotone paths (0,0,0)->(1,1,1)
+_PERMS = list(itertools.permutations(range(3)))
+
+
+def kuhn_box(n, lengths=(1.0, 1.0, 1.0), jitter=0.0, seed=1234, ramp_deg=0.0, ramp_x0=0.3):
+    """Return (xyz[nn,3] f64, tets[nt,4] i32, tris[nf,3] i32, tags[nf] i32).
+
+    Node id = i + (n+1)*(j + (n+1)*k).  Boundary tags: x-min 1, x-max 2,
+    y-min 3, y-max 4, z-min 5, z-max 6.  Triangles are wound so the
+    right-hand normal points INTO the domain and tets so that nodes 0-1-2 see
+    node 3 on their right-hand side (UGRID convention).
+    `ramp_deg` shears the floor (y-min) up by that angle for x > ramp_x0,
+    blending to zero at y-max: the 15-degree supersonic ramp of BASELINE.json.
+    """
+    np1 = n + 1
+    g = np.arange(np1, dtype=np.float64) / n
+    k, j, i = np.meshgrid(g, g, g, indexing="ij")
+    xyz = np.stack([i.ravel(), j.ravel(), k.ravel()], axis=1)
+    if jitter > 0.0:
+        rng = np.random.default_rng(seed)
+        d = rng.uniform(-jitter / n, jitter / n, size=xyz.shape)
+        interior = np.all((xyz > 1e-12) & (xyz < 1 - 1e-12), axis=1)
+        xyz[interior] += d[interior]
+    if ramp_deg != 0.0:
+        t = np.tan(np.deg2rad(ramp_deg))
+        lift = np.maximum(xyz[:, 0] - ramp_x0, 0.0) * t
+        xyz[:, 1] = xyz[:, 1] + lift * (1.0 - xyz[:, 1])
+    xyz = xyz * np.asarray(lengths, dtype=np.float64)
+
+    ci, cj, ck = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    # hex order: k slowest, i fastest (same as nodes)
+    ci, cj, ck = (a.transpose(2, 1, 0).ravel() for a in (ci, cj, ck))
+
+    def nid(a, b, c):
+        return (a + np1 * (b + np1 * c)).astype(np.int64)
+
+    tets = []
+    for perm in _PERMS:
+        off = np.zeros(3, dtype=np.int64)
+        verts = [nid(ci, cj, ck)]
+        for ax in perm:
+            off = off.copy()
+            off[ax] += 1
+            verts.append(nid(ci + off[0], cj + off[1], ck + off[2]))
+        t = np.stack(verts, axis=1)
+        # parity of the permutation decides orientation; swap to make it positive
+        inv = sum(1 for a in range(3) for b in range(a + 1, 3) if perm[a] > perm[b])
+        if inv % 2 == 1:
+            t = t[:, [0, 2, 1, 3]]
+        tets.append(t)
+    # interleave so the 6 tets of a hex are consecutive
+    tets = np.stack(tets, axis=1).reshape(-1, 4)
+
+    # boundary triangles: tet faces whose 3 nodes lie on one box plane
+    faces = np.concatenate([tets[:, [1, 2, 3]], tets[:, [0, 3, 2]], tets[:, [0, 1, 3]], tets[:, [0, 2, 1]]])
+    opp = np.concatenate([tets[:, 0], tets[:, 1], tets[:, 2], tets[:, 3]])
+    ijk = np.stack([faces % np1, (faces // np1) % np1, faces // (np1 * np1)], axis=2)  # [nf,3,3]
+    tris, tags = [], []
+    tag = 0
+    for ax in range(3):
+        for val in (0, n):
+            tag += 1
+            m = np.all(ijk[:, :, ax] == val, axis=1)
+            tris.append(faces[m])
+            tags.append(np.full(int(m.sum()), tag, dtype=np.int32))
+            opp_sel = opp[m]
+            _ = opp_sel
+    tris = np.concatenate(tris)
+    tags = np.concatenate(tags)
+    # orient: right-hand normal must point into the domain (towards the box centre side)
+    p0, p1, p2 = xyz[tris[:, 0]], xyz[tris[:, 1]], xyz[tris[:, 2]]
+    nrm = np.cross(p1 - p0, p2 - p0)
+    centre = xyz.mean(axis=0)
+    inward = np.einsum("ij,ij->i", nrm, centre - (p0 + p1 + p2) / 3.0) > 0
+    tris[~inward] = tris[~inward][:, [0, 2, 1]]
+    vol = np.einsum("ij,ij->i", np.cross(xyz[tets[:, 1]] - xyz[tets[:, 0]], xyz[tets[:, 2]] - xyz[tets[:, 0]]),
+                    xyz[tets[:, 3]] - xyz[tets[:, 0]])
+    assert np.all(vol > 0), "negative tet volume (jitter too large?)"
+    return xyz, tets.astype(np.int32), tris.astype(np.int32), tags
+
+
+def write_ugrid(path, xyz, tets, tris, tags):
+    """AFLR3 ASCII .ugrid (1-based), 17 significant digits so doubles round-trip."""
+    with open(path, "w") as f:
+        f.write(f"{len(xyz)} {len(tris)} 0 {len(tets)} 0 0 0\n")
+        np.savetxt(f, xyz, fmt="%.17g")
+        np.savetxt(f, tris + 1, fmt="%d")
+        np.savetxt(f, tags, fmt="%d")
+        np.savetxt(f, tets + 1, fmt="%d")
+
+
+def renumber(xyz, tets, tris, new_of_old):
+    """Apply a node permutation (new id of each old node)."""
+    new_of_old = np.asarray(new_of_old)
+    old_of_new = np.empty_like(new_of_old)
+    old_of_new[new_of_old] = np.arange(len(new_of_old))
+    return xyz[old_of_new], new_of_old[tets].astype(np.int32), new_of_old[tris].astype(np.int32)
