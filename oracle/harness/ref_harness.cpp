@@ -253,11 +253,22 @@ int main(int argc, char* argv[])
   param->UpdateCFL(space->iter, 9999.0);
 
   InjectState(space);
+  // a steady run has q^n == q^{n+1} at the first Newton iteration of a step
+  // (fields.EvolveInTime, solutionSpace.tcc:582-592): make TemporalResidual
+  // (residual.tcc:125-179) see a zero time difference
+  memcpy(space->qold, space->q, sizeof(Real)*(size_t)nnode*nvars);
+  memcpy(space->qoldm1, space->q, sizeof(Real)*(size_t)nnode*nvars);
+  for(Int i = 0; i < nnode; i++){
+    eqnset->NativeToConservative(&space->qold[i*nvars]);
+    eqnset->NativeToConservative(&space->qoldm1[i*nvars]);
+  }
   // NewtonIterate head (solutionSpace.tcc:662-665)
   UpdateBCs(space);
   p->UpdateGeneralVectors(space->q, nvars);
-  // phantom nodes were written from a uniform IC before injection; run the BC
-  // update once more so phantom states are a fixed function of the injected q
+  // the BC update is an iterated map on the phantom states (10 sub-iterations
+  // per call, compressible.tcc:1258,1383): dump the state before and after one
+  // more call so the parity tests can replay exactly one UpdateBCs
+  if(mode == "dump") Dump("q_pre", space->q, (size_t)(nnode+gnode+nbnode)*nvars);
   UpdateBCs(space);
   p->UpdateGeneralVectors(space->q, nvars);
 

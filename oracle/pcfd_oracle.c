@@ -1,0 +1,1012 @@
+/*
+ * pcfd_oracle.c -- plain-C CPU restatement of ProteusCFD's edge-based FV hot
+ * path (perfect-gas compressible eqnset).  TEST INFRASTRUCTURE ONLY -- see
+ * pcfd_oracle.h.  Every function cites the reference lines it restates
+ * (paths relative to /root/reference/ucs).  The loops are deliberately the
+ * reference's sequential edge loops so that summation order, and therefore
+ * every rounding, is the reference's.
+ */
+#include "pcfd_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define NEQN ORC_NEQN
+#define NVARS ORC_NVARS
+#define NTERMS ORC_NTERMS
+
+static const int GRADLOC[NTERMS] = {0, 1, 2, 3, 4, 5, 7, 8, 9};   /* compressible.tcc:1009-1027 */
+
+/* macros.h:32-42 */
+static double MAXD(double x, double y){ return (x > y) ? x : y; }
+static double MIND(double x, double y){ return (x < y) ? x : y; }
+
+/* ---------------------------------------------------------------- eqnset */
+
+/* compressible.tcc:1088-1101 */
+static double compute_pressure(const double* Q, double gamma)
+{
+  double r = Q[0];
+  double u = Q[1]/r, v = Q[2]/r, w = Q[3]/r;
+  double E = Q[4];
+  double v2h = 0.5*(u*u + v*v + w*w);
+  double gm1 = gamma - 1.0;
+  return gm1*(E - r*v2h);
+}
+
+/* compressible.tcc:1230-1243 */
+static void compute_aux(double* Q, double gamma)
+{
+  double gm1 = gamma - 1.0;
+  double u = Q[1]/Q[0], v = Q[2]/Q[0], w = Q[3]/Q[0];
+  double V2 = u*u + v*v + w*w;
+  double P = gm1*(Q[4] - 0.5*Q[0]*V2);
+  Q[6] = P;
+  Q[5] = gamma*compute_pressure(Q, gamma)/Q[0];   /* ComputeTemperature :1104-1110 */
+  Q[7] = u; Q[8] = v; Q[9] = w;
+}
+
+/* compressible.tcc:996-1007 */
+static double get_theta(const double* Q, const double* avec, double vdotn)
+{
+  double u = Q[1]/Q[0], v = Q[2]/Q[0], w = Q[3]/Q[0];
+  return u*avec[0] + v*avec[1] + w*avec[2] + vdotn;
+}
+
+/* eqnset.h:231-238 */
+static double extrapolate_correction(double chi, double dQedge, const double* gradQ, const double* dx)
+{
+  return 0.5*chi*dQedge + (1.0 - chi)*(gradQ[0]*dx[0] + gradQ[1]*dx[1] + gradQ[2]*dx[2]);
+}
+
+/* compressible.tcc:1039-1052 */
+static void extrapolate_variables(double chi, double* Qho, const double* q, const double* dQedge,
+				  const double* gradQ, const double* dx, const double* limiter)
+{
+  int i;
+  for(i = 0; i < 5; i++){
+    Qho[i] = q[i] + extrapolate_correction(chi, dQedge[i], &gradQ[i*3], dx)*limiter[i];
+  }
+}
+
+/* compressible.tcc:1056-1079 */
+static int bad_extrapolation(const double* Q, double gamma)
+{
+  double r = Q[0];
+  double u = Q[1]/r, v = Q[2]/r, w = Q[3]/r;
+  double E = Q[4];
+  double v2h = 0.5*(u*u + v*v + w*w);
+  double gm1 = gamma - 1.0;
+  double p = gm1*(E - r*v2h);
+  if(p < 1.0e-10) return 1;
+  if(r < 0.0) return 1;
+  if(E < 1.0e-10) return 1;
+  return 0;
+}
+
+/* compressible.tcc:534-578 */
+static void roe_variables(const double* QL, const double* QR, double gamma, double* Qroe)
+{
+  double gm1 = gamma - 1.0;
+  double rhoL = QL[0], rhoR = QR[0];
+  double uL = QL[1]/QL[0], uR = QR[1]/QR[0];
+  double vL = QL[2]/QL[0], vR = QR[2]/QR[0];
+  double wL = QL[3]/QL[0], wR = QR[3]/QR[0];
+  double EL = QL[4], ER = QR[4];
+  double v2L = uL*uL + vL*vL + wL*wL;
+  double v2R = uR*uR + vR*vR + wR*wR;
+  double PL = gm1*(EL - 0.5*rhoL*v2L);
+  double PR = gm1*(ER - 0.5*rhoR*v2R);
+  double hL = (EL + PL)/rhoL;
+  double hR = (ER + PR)/rhoR;
+  double rho = sqrt(rhoL*rhoR);
+  double sigma = rho/(rhoL + rho);
+  double u = uL + sigma*(uR - uL);
+  double v = vL + sigma*(vR - vL);
+  double w = wL + sigma*(wR - wL);
+  double h = hL + sigma*(hR - hL);
+  double v2h = 0.5*(u*u + v*v + w*w);
+  Qroe[0] = rho;
+  Qroe[1] = rho*u;
+  Qroe[2] = rho*v;
+  Qroe[3] = rho*w;
+  Qroe[4] = rho/gamma*(h + gm1*v2h);
+}
+
+/* compressible.tcc:581-684 */
+static void eigensystem(const double* Q, const double* avec, double vdotn, double gamma,
+			double* eigenvalues, double* T, double* Tinv)
+{
+  double nx = avec[0], ny = avec[1], nz = avec[2];
+  double rho = Q[0], ru = Q[1], rv = Q[2], rw = Q[3], rE = Q[4];
+  double u = ru/rho, v = rv/rho, w = rw/rho;
+  double gm1 = gamma - 1.0;
+  double thetaf = u*nx + v*ny + w*nz;
+  double theta = thetaf + vdotn;
+  double v2h = 0.5*(u*u + v*v + w*w);
+  double P = gm1*(rE - rho*v2h);
+  double c2 = gamma*P/rho;
+  double c = sqrt(c2);
+
+  T[0] = nx;
+  T[5] = u*nx;
+  T[10] = v*nx + rho*nz;
+  T[15] = w*nx - rho*ny;
+  T[20] = v2h*nx + rho*(v*nz - w*ny);
+
+  T[1] = ny;
+  T[6] = u*ny - rho*nz;
+  T[11] = v*ny;
+  T[16] = w*ny + rho*nx;
+  T[21] = v2h*ny + rho*(w*nx - u*nz);
+
+  T[2] = nz;
+  T[7] = u*nz + rho*ny;
+  T[12] = v*nz - rho*nx;
+  T[17] = w*nz;
+  T[22] = v2h*nz + rho*(u*ny - v*nx);
+
+  T[3] = rho/c;
+  T[8] = rho*(u/c + nx);
+  T[13] = rho*(v/c + ny);
+  T[18] = rho*(w/c + nz);
+  T[23] = rho*(v2h/c + thetaf + c/gm1);
+
+  T[4] = rho/c;
+  T[9] = rho*(u/c - nx);
+  T[14] = rho*(v/c - ny);
+  T[19] = rho*(w/c - nz);
+  T[24] = rho*(v2h/c - thetaf + c/gm1);
+
+  Tinv[0]  = nx - nz*v/rho + ny*w/rho - nx/c2*v2h*gm1;
+  Tinv[1]  = nx/c2*u*gm1;
+  Tinv[2]  = nz/rho + nx/c2*v*gm1;
+  Tinv[3]  = -ny/rho + nx/c2*w*gm1;
+  Tinv[4]  = -nx/c2*  gm1;
+
+  Tinv[5]  = ny + nz*u/rho - nx*w/rho - ny/c2*v2h*gm1;
+  Tinv[6]  = -nz/rho + ny/c2*u*gm1;
+  Tinv[7]  = ny/c2*v*gm1;
+  Tinv[8]  = nx/rho + ny/c2*w*gm1;
+  Tinv[9]  = -ny/c2*gm1;
+
+  Tinv[10] = nz - ny*u/rho + nx*v/rho - nz/c2*v2h*gm1;
+  Tinv[11] = ny/rho + nz/c2*u*gm1;
+  Tinv[12] = -nx/rho + nz/c2*v*gm1;
+  Tinv[13] = nz/c2*w*gm1;
+  Tinv[14] = -nz/c2*  gm1;
+
+  Tinv[15] = -0.5/rho*(thetaf - gm1*v2h/c);
+  Tinv[16] = 0.5/rho*(nx - gm1*u/c);
+  Tinv[17] = 0.5/rho*(ny - gm1*v/c);
+  Tinv[18] = 0.5/rho*(nz - gm1*w/c);
+  Tinv[19] = 0.5/rho*(gm1 /c);
+
+  Tinv[20] = 0.5/rho*(thetaf + gm1*v2h/c);
+  Tinv[21] = -0.5/rho*(nx + gm1*u/c);
+  Tinv[22] = -0.5/rho*(ny + gm1*v/c);
+  Tinv[23] = -0.5/rho*(nz + gm1*w/c);
+  Tinv[24] = +0.5/rho*(gm1 /c);
+
+  eigenvalues[0] = theta;
+  eigenvalues[1] = theta;
+  eigenvalues[2] = theta;
+  eigenvalues[3] = theta + c;
+  eigenvalues[4] = theta - c;
+}
+
+/* compressible.tcc:687-710 */
+static void phys_flux(const double* Q, const double* avec, double vdotn, double gamma, double* flux)
+{
+  double rho = Q[0], ru = Q[1], rv = Q[2], rw = Q[3], rEt = Q[4];
+  double u = ru/rho, v = rv/rho, w = rw/rho;
+  double v2h = 0.5*(u*u + v*v + w*w);
+  double gm1 = gamma - 1.0;
+  double P = gm1*(rEt - rho*v2h);
+  double ht = (rEt + P)/rho;
+  double rhotheta = rho*(avec[0]*u + avec[1]*v + avec[2]*w + vdotn);
+  flux[0] = rhotheta;
+  flux[1] = (u*rhotheta + P*avec[0]);
+  flux[2] = (v*rhotheta + P*avec[1]);
+  flux[3] = (w*rhotheta + P*avec[2]);
+  flux[4] = (ht*rhotheta - vdotn*P);
+}
+
+/* matrix.h:63-74 */
+static void matvec(const double* a, const double* v, double* vout, int n)
+{
+  int i, j;
+  for(i = 0; i < n; i++){
+    vout[i] = a[i*n + 0]*v[0];
+    for(j = 1; j < n; j++) vout[i] += a[i*n + j]*v[j];
+  }
+}
+
+/* compressible.tcc:93-230 (Roe FDS + Harten-Hyman entropy fix #2); the NaN
+   kneecap of EqnSet::NumericalFlux (eqnset.tcc:73-88) is applied by callers */
+void orc_roe_flux(const double* QL, const double* QR, const double* avec, double vdotn, double gamma,
+		  double* flux)
+{
+  int i;
+  double Qroe[5], T[25], Tinv[25], eigenvalues[5], fluxL[5], fluxR[5], dQ[5], dv[5], dr[5];
+  double area = avec[3];
+  double gm1, thetaR, thetaL, eigL, eigR, eps, cR, cL, eig;
+
+  roe_variables(QL, QR, gamma, Qroe);
+  eigensystem(Qroe, avec, vdotn, gamma, eigenvalues, T, Tinv);
+
+  gm1 = gamma - 1.0;
+  {
+    const double rhoL = QL[0];
+    const double uL = QL[1]/rhoL, vL = QL[2]/rhoL, wL = QL[3]/rhoL;
+    const double EL = QL[4];
+    const double vmag2L = uL*uL + vL*vL + wL*wL;
+    const double PL = gm1*(EL - 0.5*rhoL*vmag2L);
+    const double rhoR = QR[0];
+    const double uR = QR[1]/rhoR, vR = QR[2]/rhoR, wR = QR[3]/rhoR;
+    const double ER = QR[4];
+    const double vmag2R = uR*uR + vR*vR + wR*wR;
+    const double PR = gm1*(ER - 0.5*rhoR*vmag2R);
+    thetaL = uL*avec[0] + vL*avec[1] + wL*avec[2] + vdotn;
+    thetaR = uR*avec[0] + vR*avec[1] + wR*avec[2] + vdotn;
+    cR = sqrt(gamma*PR/rhoR);
+    cL = sqrt(gamma*PL/rhoL);
+  }
+
+  eigL = thetaL; eigR = thetaR; eig = eigenvalues[0];
+  eps = MAXD((eig - eigL), (eigR - eig));
+  eps = MAXD(0.0, eps);
+  if(fabs(eigenvalues[0]) < eps){
+    eigenvalues[0] = 0.5*(eigenvalues[0]*eigenvalues[0]/eps + eps);
+    eigenvalues[1] = eigenvalues[0];
+    eigenvalues[2] = eigenvalues[0];
+  }
+  else{
+    eigenvalues[0] = eigenvalues[1] = eigenvalues[2] = fabs(eigenvalues[0]);
+  }
+
+  eigL = thetaL + cL; eigR = thetaR + cR; eig = eigenvalues[3];
+  eps = MAXD((eig - eigL), (eigR - eig));
+  eps = MAXD(0.0, eps);
+  if(fabs(eigenvalues[3]) < eps) eigenvalues[3] = 0.5*(eigenvalues[3]*eigenvalues[3]/eps + eps);
+  else eigenvalues[3] = fabs(eigenvalues[3]);
+
+  eigL = thetaL - cL; eigR = thetaR - cR; eig = eigenvalues[4];
+  eps = MAXD((eig - eigL), (eigR - eig));
+  eps = MAXD(0.0, eps);
+  if(fabs(eigenvalues[4]) < eps) eigenvalues[4] = 0.5*(eigenvalues[4]*eigenvalues[4]/eps + eps);
+  else eigenvalues[4] = fabs(eigenvalues[4]);
+
+  for(i = 0; i < 5; i++) dQ[i] = QR[i] - QL[i];
+  matvec(Tinv, dQ, dv, 5);
+  for(i = 0; i < 5; i++) dv[i] *= fabs(eigenvalues[i]);
+  matvec(T, dv, dr, 5);
+  phys_flux(QL, avec, vdotn, gamma, fluxL);
+  phys_flux(QR, avec, vdotn, gamma, fluxR);
+  for(i = 0; i < 5; i++) flux[i] = 0.5*area*(fluxL[i] + fluxR[i] - dr[i]);
+}
+
+/* eqnset.tcc:55-90: Roe + NaN kneecap */
+static void numerical_flux(const double* QL, const double* QR, const double* avec, double vdotn,
+			   double gamma, double* flux)
+{
+  int i;
+  orc_roe_flux(QL, QR, avec, vdotn, gamma, flux);
+  for(i = 0; i < NEQN; i++) if(isnan(flux[i])) flux[i] = 0.0;
+}
+
+/* compressible.tcc:799-821 */
+static double max_eigenvalue(const double* Q, const double* avec, double vdotn, double gamma)
+{
+  double gm1 = gamma - 1.0;
+  double rho = Q[0];
+  double u = Q[1]/rho, v = Q[2]/rho, w = Q[3]/rho;
+  double rEt = Q[4];
+  double v2h = 0.5*(u*u + v*v + w*w);
+  double P = gm1*(rEt - rho*v2h);
+  double c2 = gamma*P/rho;
+  double c = sqrt(c2);
+  double theta = get_theta(Q, avec, vdotn);
+  double eig4 = theta + c, eig5 = theta - c;
+  return MAXD(fabs(eig4), fabs(eig5));
+}
+
+/* ------------------------------------------------------------ gradients */
+
+static int is_ghost(const orc_case* c, int n){ return n >= c->nnode && n < c->nnode + c->gnode; }
+
+/* gradient.tcc:115-138 with kernels :381-542 */
+void orc_lsq_coefficients(const orc_case* c, double* s, double* sw)
+{
+  int e, k, pass;
+  int nb = c->nbedge + c->ngedge;
+  for(k = 0; k < (c->nnode + c->gnode)*6; k++) s[k] = sw[k] = 0.0;
+  for(pass = 0; pass < 2; pass++){
+    double* S = pass ? sw : s;
+    for(e = 0; e < c->nedge + nb; e++){
+      int interior = e < c->nedge;
+      int l = interior ? c->edges_n[2*e] : c->bedges_n[2*(e - c->nedge)];
+      int r = interior ? c->edges_n[2*e+1] : c->bedges_n[2*(e - c->nedge)+1];
+      double dx[3], t[6], ds2 = 1.0;
+      if(!interior && !is_ghost(c, r)) continue;
+      dx[0] = c->xyz[3*l] - c->xyz[3*r];
+      dx[1] = c->xyz[3*l+1] - c->xyz[3*r+1];
+      dx[2] = c->xyz[3*l+2] - c->xyz[3*r+2];
+      if(pass == 0){
+	t[0] = dx[0]*dx[0]; t[1] = dx[0]*dx[1]; t[2] = dx[0]*dx[2];
+	t[3] = dx[1]*dx[1]; t[4] = dx[1]*dx[2]; t[5] = dx[2]*dx[2];
+      }
+      else{
+	ds2 = 1.0/(dx[0]*dx[0] + dx[1]*dx[1] + dx[2]*dx[2]);
+	t[0] = dx[0]*dx[0]*ds2; t[1] = dx[0]*dx[1]*ds2; t[2] = dx[0]*dx[2]*ds2;
+	t[3] = dx[1]*dx[1]*ds2; t[4] = dx[1]*dx[2]*ds2; t[5] = dx[2]*dx[2]*ds2;
+      }
+      /* DriverScatter (driver.tcc:294-303): right first, then left */
+      if(interior){
+	double tr[6];
+	double mx = -dx[0], my = -dx[1], mz = -dx[2];
+	if(pass == 0){
+	  tr[0] = t[0]; tr[1] = mx*my; tr[2] = mx*mz; tr[3] = t[3]; tr[4] = my*mz; tr[5] = t[5];
+	}
+	else{
+	  tr[0] = t[0]; tr[1] = (mx*my)*ds2; tr[2] = (mx*mz)*ds2; tr[3] = t[3]; tr[4] = (my*mz)*ds2; tr[5] = t[5];
+	}
+	for(k = 0; k < 6; k++) S[6*r + k] += tr[k];
+      }
+      for(k = 0; k < 6; k++) S[6*l + k] += t[k];
+    }
+  }
+}
+
+/* gradient.tcc:141-168 */
+static void lsq_weights(const double* s, const double* dxbar, double* we)
+{
+  double s11 = s[0], s12 = s[1], s13 = s[2], s22 = s[3], s23 = s[4], s33 = s[5];
+  double r11 = s11, r12 = s12, r13 = s13;
+  double r12_r11 = (r11 == 0.0) ? 0.0 : r12/r11;
+  double r22 = s22 - r12*r12_r11;
+  double r23 = s23 - r12_r11*r13;
+  double r13_r11 = (r11 == 0.0) ? 0.0 : r13/r11;
+  double r23_r22 = (r22 == 0.0) ? 0.0 : r23/r22;
+  double r33 = s33 - r13*r13_r11 - r23*r23_r22;
+  double dykdx = (dxbar[1] - (r12_r11)*dxbar[0]);
+  we[2] = (r33 == 0.0) ? 0.0 : (dxbar[2] - r13_r11*dxbar[0] - r23_r22*dykdx)/r33;
+  we[1] = (r22 == 0.0) ? 0.0 : (dykdx - r23*we[2])/r22;
+  we[0] = (r11 == 0.0) ? 0.0 : (dxbar[0] - r12*we[1] - r13*we[2])/r11;
+}
+
+/* gradient.tcc:57-112 (type 0, weighted), kernels :251-378, symmetry fix :545-565 */
+void orc_gradient(const orc_case* c, const double* q, const double* sw, double* qgrad)
+{
+  int e, i, j, k;
+  int nb = c->nbedge + c->ngedge;
+  int ntot = (c->nnode + c->gnode)*NTERMS*3;
+  for(k = 0; k < ntot; k++) qgrad[k] = 0.0;
+  for(e = 0; e < c->nedge + nb; e++){
+    int interior = e < c->nedge;
+    int l = interior ? c->edges_n[2*e] : c->bedges_n[2*(e - c->nedge)];
+    int r = interior ? c->edges_n[2*e+1] : c->bedges_n[2*(e - c->nedge)+1];
+    double dx[3], weL[3], weR[3], dx2, weight, dq;
+    const double *qL, *qR;
+    if(!interior && !is_ghost(c, r)) continue;
+    dx[0] = c->xyz[3*l] - c->xyz[3*r];
+    dx[1] = c->xyz[3*l+1] - c->xyz[3*r+1];
+    dx[2] = c->xyz[3*l+2] - c->xyz[3*r+2];
+    qL = &q[l*NVARS]; qR = &q[r*NVARS];
+    dx2 = dx[0]*dx[0] + dx[1]*dx[1] + dx[2]*dx[2];
+    weight = 1.0/sqrt(dx2);
+    dx[0] *= weight; dx[1] *= weight; dx[2] *= weight;
+    lsq_weights(&sw[6*l], dx, weL);
+    if(interior){
+      dx[0] = -dx[0]; dx[1] = -dx[1]; dx[2] = -dx[2];
+      lsq_weights(&sw[6*r], dx, weR);
+      for(i = 0; i < NTERMS; i++){
+	dq = weight*(qR[GRADLOC[i]] - qL[GRADLOC[i]]);
+	for(j = 0; j < 3; j++) qgrad[r*NTERMS*3 + 3*i + j] += +weR[j]*dq;
+      }
+    }
+    for(i = 0; i < NTERMS; i++){
+      dq = weight*(qR[GRADLOC[i]] - qL[GRADLOC[i]]);
+      for(j = 0; j < 3; j++) qgrad[l*NTERMS*3 + 3*i + j] += -weL[j]*dq;
+    }
+  }
+  for(e = 0; e < nb; e++){
+    if(c->bedges_bctype[e] == ORC_BC_SYMMETRY){
+      int l = c->bedges_n[2*e];
+      const double* avec = &c->bedges_a[4*e];
+      double* g = &qgrad[l*NTERMS*3];
+      for(i = 0; i < NTERMS; i++){
+	double dot = g[i*3]*avec[0] + g[i*3+1]*avec[1] + g[i*3+2]*avec[2];
+	for(j = 0; j < 3; j++) g[i*3 + j] -= dot*avec[j];
+      }
+    }
+  }
+}
+
+/* ------------------------------------------------------------- limiters */
+
+static double limiter_fn(int type, double temp)
+{
+  if(type == 1){             /* Barth, limiters.tcc:263-266 */
+    temp = MAXD(0.0, temp);
+    temp = MIND(1.0, temp);
+    return temp;
+  }
+  return (temp*temp + 2.0*temp)/(temp*temp + temp + 2.0);   /* Venkat :440 */
+}
+
+static void limit_side(const orc_case* c, const double* q, const double* qgrad, const double* qmin,
+		       const double* qmax, double* lim, int me, int other, int boundary_variant)
+{
+  /* limiters.tcc:224-268 (Barth) / :399-441 (Venkat) / B-variants :304-357, :476-522 */
+  int j;
+  double QL[5], dQ[5], dx[3], ones[5] = {1.0, 1.0, 1.0, 1.0, 1.0};
+  const double* qL = &q[me*NVARS];
+  const double* qR = &q[other*NVARS];
+  for(j = 0; j < 5; j++) dQ[j] = qR[j] - qL[j];
+  dx[0] = 0.5*(c->xyz[3*other] - c->xyz[3*me]);
+  dx[1] = 0.5*(c->xyz[3*other+1] - c->xyz[3*me+1]);
+  dx[2] = 0.5*(c->xyz[3*other+2] - c->xyz[3*me+2]);
+  extrapolate_variables(c->chi, QL, qL, dQ, &qgrad[me*NTERMS*3], dx, ones);
+  (void)boundary_variant;
+  for(j = 0; j < 5; j++){
+    double temp = 1.0;
+    if(QL[j] > qL[j]) temp = (qmax[me*5 + j] - qL[j])/(QL[j] - qL[j]);
+    else if(QL[j] < qL[j]) temp = (qmin[me*5 + j] - qL[j])/(QL[j] - qL[j]);
+    temp = limiter_fn(c->limiter, temp);
+    lim[me*5 + j] = MIND(lim[me*5 + j], temp);
+  }
+}
+
+/* Right-side extrapolation in the reference negates dx and dQ of the left
+   side (limiters.tcc:243-253); -(a-b) == (b-a) and -(0.5*d) == 0.5*(-d)
+   exactly in IEEE arithmetic, so limit_side(me=r, other=l) is bit-identical. */
+
+/* limiters.tcc:53-132 */
+void orc_limiter(const orc_case* c, const double* q, const double* qgrad, double* lim)
+{
+  int e, i, j;
+  int nnode = c->nnode;
+  int nb = c->nbedge + c->ngedge;
+  double* qmin = (double*)calloc((size_t)nnode*5, sizeof(double));   /* zero-initialised: :62-63 */
+  double* qmax = (double*)calloc((size_t)nnode*5, sizeof(double));
+  for(i = 0; i < (nnode + c->gnode)*5; i++) lim[i] = 1.0;
+
+  /* min/max pass :135-191 */
+  for(e = 0; e < c->nedge; e++){
+    int l = c->edges_n[2*e], r = c->edges_n[2*e+1];
+    for(j = 0; j < 5; j++){
+      qmax[l*5+j] = MAXD(qmax[l*5+j], q[r*NVARS+j]);
+      qmin[l*5+j] = MIND(qmin[l*5+j], q[r*NVARS+j]);
+    }
+    for(j = 0; j < 5; j++){
+      qmax[r*5+j] = MAXD(qmax[r*5+j], q[l*NVARS+j]);
+      qmin[r*5+j] = MIND(qmin[r*5+j], q[l*NVARS+j]);
+    }
+  }
+  for(e = 0; e < nb; e++){
+    int l = c->bedges_n[2*e], r = c->bedges_n[2*e+1];
+    if(!is_ghost(c, r)) continue;
+    for(j = 0; j < 5; j++){
+      qmax[l*5+j] = MAXD(qmax[l*5+j], q[r*NVARS+j]);
+      qmin[l*5+j] = MIND(qmin[l*5+j], q[r*NVARS+j]);
+    }
+  }
+
+  if(c->limiter == 1 || c->limiter == 2){
+    for(e = 0; e < c->nedge; e++){
+      int l = c->edges_n[2*e], r = c->edges_n[2*e+1];
+      limit_side(c, q, qgrad, qmin, qmax, lim, l, r, 0);
+      limit_side(c, q, qgrad, qmin, qmax, lim, r, l, 0);
+    }
+    for(e = 0; e < nb; e++){
+      int l = c->bedges_n[2*e], r = c->bedges_n[2*e+1];
+      if(!is_ghost(c, r)) continue;
+      limit_side(c, q, qgrad, qmin, qmax, lim, l, r, 1);
+    }
+  }
+
+  if(c->limiter != 0){
+    /* pressure clip :737-815 -- sequential: later edges see earlier clips */
+    for(e = 0; e < c->nedge; e++){
+      int l = c->edges_n[2*e], r = c->edges_n[2*e+1];
+      double QL[NVARS], QR[NVARS], Qroe[NVARS], dQ[5], dx[3];
+      const double* qL = &q[l*NVARS];
+      const double* qR = &q[r*NVARS];
+      dx[0] = 0.5*(c->xyz[3*r] - c->xyz[3*l]);
+      dx[1] = 0.5*(c->xyz[3*r+1] - c->xyz[3*l+1]);
+      dx[2] = 0.5*(c->xyz[3*r+2] - c->xyz[3*l+2]);
+      for(j = 0; j < 5; j++) dQ[j] = qR[j] - qL[j];
+      extrapolate_variables(c->chi, QL, qL, dQ, &qgrad[l*NTERMS*3], dx, &lim[l*5]);
+      if(bad_extrapolation(QL, c->gamma)) for(i = 0; i < 5; i++) lim[l*5+i] = 0.0;
+      dx[0] = -dx[0]; dx[1] = -dx[1]; dx[2] = -dx[2];
+      for(j = 0; j < 5; j++) dQ[j] = -dQ[j];
+      extrapolate_variables(c->chi, QR, qR, dQ, &qgrad[r*NTERMS*3], dx, &lim[r*5]);
+      if(bad_extrapolation(QR, c->gamma)) for(i = 0; i < 5; i++) lim[r*5+i] = 0.0;
+      roe_variables(QL, QR, c->gamma, Qroe);
+      if(bad_extrapolation(Qroe, c->gamma)) for(i = 0; i < 5; i++) lim[l*5+i] = lim[r*5+i] = 0.0;
+    }
+    for(i = 0; i < (nnode + c->gnode)*5; i++) if(lim[i] < 0.0) lim[i] = 0.0;
+  }
+  free(qmin); free(qmax);
+}
+
+/* ------------------------------------------------- boundary conditions */
+
+/* compressible.tcc:1246-1372 (static mesh: vdotn = 0) */
+static void farfield_bc(const orc_case* c, const double* QL, double* QR, const double* Qinf,
+			const double* avec, double vdotn)
+{
+  int i, subit;
+  double gamma = c->gamma;
+  double tempspace[5];
+  for(subit = 0; subit < 10; subit++){
+    double u = vdotn*avec[0], v = vdotn*avec[1], w = vdotn*avec[2];
+    double theta, rhob, ub, vb, wb, pb, rhoi, ui, vi, wi, pi, rhoinf, uinf, vinf, winf, pinf;
+    double pavg, rhoavg, c2avg, cavg, nx, ny, nz;
+    for(i = 0; i < 5; i++) tempspace[i] = (QL[i] + QR[i])/2.0;
+    theta = get_theta(tempspace, avec, vdotn);
+    rhob = QR[0]; ub = QR[1]/QR[0]; vb = QR[2]/QR[0]; wb = QR[3]/QR[0];
+    rhoi = QL[0];
+    ui = QL[1]/QL[0] + u; vi = QL[2]/QL[0] + v; wi = QL[3]/QL[0] + w;
+    pi = QL[6];
+    rhoinf = Qinf[0];
+    uinf = Qinf[1]/Qinf[0] + u; vinf = Qinf[2]/Qinf[0] + v; winf = Qinf[3]/Qinf[0] + w;
+    pinf = Qinf[6];
+    pavg = compute_pressure(tempspace, gamma);
+    rhoavg = tempspace[0];
+    c2avg = gamma*(pavg/rhoavg);
+    cavg = sqrt(c2avg);
+    nx = avec[0]; ny = avec[1]; nz = avec[2];
+    (void)rhob; (void)ub; (void)vb; (void)wb;
+    if(theta == 0.0){
+      return;
+    }
+    else if(theta > 0.0 && fabs(theta/cavg) >= 1.0){
+      for(i = 0; i < 5; i++) QR[i] = QL[i];
+    }
+    else if(theta < 0.0 && fabs(theta/cavg) >= 1.0){
+      for(i = 0; i < 5; i++) QR[i] = Qinf[i];
+    }
+    else if(theta > 0.0 && fabs(theta/cavg) < 1.0){
+      double temp;
+      pb = pinf;
+      rhob = rhoi + (pb - pi)/c2avg;
+      temp = (pb - pi)/(rhoavg*cavg);
+      ub = ui - nx*temp; vb = vi - ny*temp; wb = wi - nz*temp;
+      QR[0] = rhob; QR[1] = rhob*ub; QR[2] = rhob*vb; QR[3] = rhob*wb;
+      QR[4] = pb/(gamma - 1.0) + 0.5*rhob*(ub*ub + vb*vb + wb*wb);
+    }
+    else if(theta < 0.0 && fabs(theta/cavg) < 1.0){
+      double temp;
+      pb = 0.5*(pinf + pi + rhoavg*cavg*(nx*(uinf - ui) + ny*(vinf - vi) + nz*(winf - wi)));
+      rhob = rhoinf + (pb - pinf)/c2avg;
+      temp = (pb - pinf)/(rhoavg*cavg);
+      ub = uinf + nx*temp; vb = vinf + ny*temp; wb = winf + nz*temp;
+      QR[0] = rhob; QR[1] = rhob*ub; QR[2] = rhob*vb; QR[3] = rhob*wb;
+      QR[4] = pb/(gamma - 1.0) + 0.5*rhob*(ub*ub + vb*vb + wb*wb);
+    }
+    else{
+      return;
+    }
+  }
+}
+
+/* compressible.tcc:1374-1472 */
+static void inviscid_wall_bc(const orc_case* c, const double* QL, double* QR, const double* avec, double vdotn)
+{
+  int i, subit;
+  double gamma = c->gamma;
+  double tempspace[5], QLmod[5];
+  for(subit = 0; subit < 10; subit++){
+    double u, v, w, ru, rv, rw, rhoi, rhob, ub, vb, wb, pb, ui, vi, wi, pi, rhoavg, pavg, c2avg, cavg;
+    memcpy(QLmod, QL, sizeof(double)*5);
+    rhoi = QLmod[0];
+    u = vdotn*avec[0]; v = vdotn*avec[1]; w = vdotn*avec[2];
+    ru = u*rhoi; rv = v*rhoi; rw = w*rhoi;
+    QLmod[1] += ru; QLmod[2] += rv; QLmod[3] += rw;
+    for(i = 0; i < 5; i++) tempspace[i] = (QL[i] + QR[i])/2.0;
+    rhoi = QL[0];
+    ui = QL[1]/QL[0] + ru; vi = QL[2]/QL[0] + rv; wi = QL[3]/QL[0] + rw;
+    pi = QL[6];
+    rhoavg = tempspace[0];
+    tempspace[1] += rhoavg*u; tempspace[2] += rhoavg*v; tempspace[3] += rhoavg*w;
+    pavg = compute_pressure(tempspace, gamma);
+    c2avg = gamma*(pavg/rhoavg);
+    cavg = sqrt(c2avg);
+    if(!c->no_cvbc){
+      double nx = avec[0], ny = avec[1], nz = avec[2], temp;
+      pb = pi + rhoavg*cavg*(get_theta(QL, avec, vdotn));
+      rhob = rhoi + (pb - pi)/c2avg;
+      temp = (pb - pi)/(rhoavg*cavg);
+      ub = ui - nx*temp; vb = vi - ny*temp; wb = wi - nz*temp;
+      QR[0] = rhob; QR[1] = rhob*ub; QR[2] = rhob*vb; QR[3] = rhob*wb;
+      QR[4] = pb/(gamma - 1.0) + 0.5*rhob*(ub*ub + vb*vb + wb*wb);
+    }
+    else{
+      /* MirrorVector (geometry.h): v - 2 (v.n) n */
+      double dot;
+      for(i = 0; i < 5; i++) QR[i] = QLmod[i];
+      dot = QLmod[1]*avec[0] + QLmod[2]*avec[1] + QLmod[3]*avec[2];
+      QR[1] = QLmod[1] - 2.0*dot*avec[0];
+      QR[2] = QLmod[2] - 2.0*dot*avec[1];
+      QR[3] = QLmod[3] - 2.0*dot*avec[2];
+    }
+  }
+}
+
+/* bc.tcc:1058-1120 dispatch for the BC types of the hot-path configs */
+static void boundary_variables(const orc_case* c, double* QL, double* QR, const double* avec, int bctype)
+{
+  int i;
+  double vdotn = 0.0;   /* static mesh (driver.tcc:97-113 with nv == 0) */
+  switch(bctype){
+  case ORC_BC_PARALLEL: return;
+  case ORC_BC_SONIC_INFLOW: case ORC_BC_DIRICHLET:
+    for(i = 0; i < NVARS; i++) QR[i] = QL[i] = c->qinf[i];
+    break;
+  case ORC_BC_SONIC_OUTFLOW: case ORC_BC_NEUMANN:
+    for(i = 0; i < NEQN; i++) QR[i] = QL[i];
+    break;
+  case ORC_BC_FARFIELD:
+    farfield_bc(c, QL, QR, c->qinf, avec, vdotn);
+    break;
+  case ORC_BC_IMPERMEABLE_WALL: case ORC_BC_SYMMETRY:
+    inviscid_wall_bc(c, QL, QR, avec, vdotn);
+    break;
+  default: break;
+  }
+  /* bc.tcc:1392-1396: aux vars of both sides are recomputed */
+  compute_aux(QR, c->gamma);
+  compute_aux(QL, c->gamma);
+}
+
+/* bc.tcc:1399-1457 -> BC_Kernel :723-745 over all half-edges */
+void orc_update_bcs(const orc_case* c, double* q, const double* beta)
+{
+  int e, nb = c->nbedge + c->ngedge;
+  (void)beta;
+  for(e = 0; e < nb; e++){
+    int l = c->bedges_n[2*e], r = c->bedges_n[2*e+1];
+    boundary_variables(c, &q[l*NVARS], &q[r*NVARS], &c->bedges_a[4*e], c->bedges_bctype[e]);
+  }
+}
+
+/* ------------------------------------------------------------- residual */
+
+/* residual.tcc:66-122 with Kernel_Inviscid_Flux :192-296, Bkernel :299-387 */
+void orc_residual(const orc_case* c, const double* q, const double* qgrad, const double* lim,
+		  const double* beta, double* b)
+{
+  int e, i, j;
+  int nb = c->nbedge + c->ngedge;
+  (void)beta;
+  for(i = 0; i < c->nnode*NEQN; i++) b[i] = 0.0;
+  for(e = 0; e < c->nedge; e++){
+    int l = c->edges_n[2*e], r = c->edges_n[2*e+1];
+    const double* avec = &c->edges_a[4*e];
+    const double* qL = &q[l*NVARS];
+    const double* qR = &q[r*NVARS];
+    double QL[NVARS], QR[NVARS], dQ[NVARS], dx[3], flux[NEQN];
+    memcpy(QL, qL, sizeof(double)*NVARS);
+    memcpy(QR, qR, sizeof(double)*NVARS);
+    if(c->sorder > 1){
+      dx[0] = 0.5*(c->xyz[3*r] - c->xyz[3*l]);
+      dx[1] = 0.5*(c->xyz[3*r+1] - c->xyz[3*l+1]);
+      dx[2] = 0.5*(c->xyz[3*r+2] - c->xyz[3*l+2]);
+      for(j = 0; j < NEQN; j++) dQ[j] = qR[j] - qL[j];
+      extrapolate_variables(c->chi, QL, qL, dQ, &qgrad[l*NTERMS*3], dx, &lim[l*NEQN]);
+      for(j = 0; j < NEQN; j++) dQ[j] = -dQ[j];
+      dx[0] = -dx[0]; dx[1] = -dx[1]; dx[2] = -dx[2];
+      extrapolate_variables(c->chi, QR, qR, dQ, &qgrad[r*NTERMS*3], dx, &lim[r*NEQN]);
+      compute_aux(QL, c->gamma);
+      compute_aux(QR, c->gamma);
+    }
+    numerical_flux(QL, QR, avec, 0.0, c->gamma, flux);
+    /* DriverScatter: right (+flux) first, then left (-flux) */
+    for(i = 0; i < NEQN; i++) b[r*NEQN + i] += flux[i];
+    for(i = 0; i < NEQN; i++) b[l*NEQN + i] += -flux[i];
+  }
+  for(e = 0; e < nb; e++){
+    int l = c->bedges_n[2*e], r = c->bedges_n[2*e+1];
+    const double* avec = &c->bedges_a[4*e];
+    const double* qL = &q[l*NVARS];
+    const double* qR = &q[r*NVARS];
+    double QL[NVARS], QR[NVARS], dQ[NVARS], dx[3], flux[NEQN];
+    memcpy(QL, qL, sizeof(double)*NVARS);
+    memcpy(QR, qR, sizeof(double)*NVARS);
+    if(c->sorder > 1){
+      if(is_ghost(c, r)){
+	for(j = 0; j < NEQN; j++) dQ[j] = qR[j] - qL[j];
+	dx[0] = 0.5*(c->xyz[3*r] - c->xyz[3*l]);
+	dx[1] = 0.5*(c->xyz[3*r+1] - c->xyz[3*l+1]);
+	dx[2] = 0.5*(c->xyz[3*r+2] - c->xyz[3*l+2]);
+	extrapolate_variables(c->chi, QL, qL, dQ, &qgrad[l*NTERMS*3], dx, &lim[l*NEQN]);
+	for(j = 0; j < NEQN; j++) dQ[j] = -dQ[j];
+	dx[0] = -dx[0]; dx[1] = -dx[1]; dx[2] = -dx[2];
+	extrapolate_variables(c->chi, QR, qR, dQ, &qgrad[r*NTERMS*3], dx, &lim[r*NEQN]);
+      }
+      compute_aux(QL, c->gamma);
+      compute_aux(QR, c->gamma);
+    }
+    numerical_flux(QL, QR, avec, 0.0, c->gamma, flux);   /* BoundaryFlux, eqnset.tcc:21-52 */
+    for(i = 0; i < NEQN; i++) b[l*NEQN + i] += -flux[i];
+  }
+  /* SourceTerm (compressible.tcc:1196-1208, gravity off) adds +0.0: node loop residual.tcc:109-115 */
+  for(i = 0; i < c->nnode*NEQN; i++) b[i] += 0.0;
+}
+
+/* ------------------------------------------------------------- timestep */
+
+/* timestep.tcc:7-49 (useLocalTimeStepping), kernels :80-143 */
+double orc_timestep(const orc_case* c, const double* q, const double* beta, double* dt)
+{
+  int e, i;
+  int nb = c->nbedge + c->ngedge;
+  double dtmin;
+  (void)beta;
+  for(i = 0; i < c->nnode; i++) dt[i] = 0.0;
+  for(e = 0; e < c->nedge + nb; e++){
+    int interior = e < c->nedge;
+    int l = interior ? c->edges_n[2*e] : c->bedges_n[2*(e - c->nedge)];
+    int r = interior ? c->edges_n[2*e+1] : c->bedges_n[2*(e - c->nedge)+1];
+    const double* avec = interior ? &c->edges_a[4*e] : &c->bedges_a[4*(e - c->nedge)];
+    double Q[NVARS], maxeig;
+    for(i = 0; i < NEQN; i++) Q[i] = 0.5*(q[l*NVARS + i] + q[r*NVARS + i]);
+    compute_aux(Q, c->gamma);
+    maxeig = max_eigenvalue(Q, avec, 0.0, c->gamma);
+    if(interior) dt[r] += maxeig*avec[3];
+    dt[l] += maxeig*avec[3];
+  }
+  dt[0] = c->cfl*(c->vol[0]/dt[0]);
+  dtmin = dt[0];
+  for(i = 1; i < c->nnode; i++){
+    dt[i] = c->cfl*(c->vol[i]/dt[i]);
+    dtmin = MIND(dtmin, dt[i]);
+  }
+  return dtmin;
+}
+
+/* --------------------------------------------------------------- update */
+
+/* compressible.tcc:929-993 */
+static void apply_dq(const double* dQ, double* Q, double gamma)
+{
+  double u, v, w, v2, rho, E;
+  double gm1 = gamma - 1.0;
+  double minP = 1.0e-10, minRho = 1.0e-10, minE = 1.0e-10;
+  if(Q[0] + dQ[0] < 0.0) Q[0] = minRho; else Q[0] += dQ[0];
+  if(Q[4] + dQ[4] < 0.0) Q[4] = minE; else Q[4] += dQ[4];
+  rho = Q[0];
+  u = Q[1]/rho; v = Q[2]/rho; w = Q[3]/rho;
+  E = Q[4];
+  v2 = u*u + v*v + w*w;
+  if(E < 0.5*rho*v2){
+    double v2mod = 2.0*(E - minP/gm1);
+    double frac = 0.0;
+    if(v2mod > 0.0) frac = sqrt(v2mod/v2);
+    u *= frac; v *= frac; w *= frac;
+    Q[1] = rho*u; Q[2] = rho*v; Q[3] = rho*w;
+  }
+  else{
+    Q[1] += dQ[1]; Q[2] += dQ[2]; Q[3] += dQ[3];
+  }
+  compute_aux(Q, gamma);
+}
+
+void orc_apply_dq(const orc_case* c, double* q, const double* x)
+{
+  int i;
+  for(i = 0; i < c->nnode; i++) apply_dq(&x[i*NEQN], &q[i*NVARS], c->gamma);
+}
+
+/* solve.tcc:71-98 (conservative-variable branch) */
+void orc_explicit_solve(const orc_case* c, double* q, const double* b, const double* dt, double* x)
+{
+  int i, j;
+  for(i = 0; i < c->nnode; i++){
+    for(j = 0; j < NEQN; j++) x[i*NEQN + j] = b[i*NEQN + j]*dt[i]/c->vol[i];
+    apply_dq(&x[i*NEQN], &q[i*NVARS], c->gamma);
+  }
+}
+
+/* ---------------------------------------------------- block-CRS + solve */
+
+/* crsmatrix.tcc:48-97 */
+void orc_crs_init(const orc_case* c, int* ia, int* ja, int* iau)
+{
+  int i, indx, count;
+  ia[0] = 0;
+  for(i = 0; i < c->nnode; i++) ia[i+1] = ia[i] + (c->ipsp[i+1] - c->ipsp[i]) + 1;
+  for(i = 0; i < c->nnode; i++){
+    count = ia[i];
+    iau[i] = count;
+    ja[count++] = i;
+    for(indx = c->ipsp[i]; indx < c->ipsp[i+1]; indx++) ja[count++] = c->psp[indx];
+  }
+}
+
+/* crsmatrix.tcc:740-781 (linear search; diagonal is first) */
+static double* get_block(const int* ia, const int* ja, double* A, int row, int col)
+{
+  int k;
+  for(k = ia[row]; k < ia[row+1]; k++) if(ja[k] == col) return &A[(size_t)k*NEQN*NEQN];
+  return NULL;
+}
+
+/* jacobian.tcc:130-250: blank, Driver(NumJac), Bdriver(BNumJac), Driver(Diag), temporal */
+void orc_jacobian(const orc_case* c, double* q, const double* beta, const double* dt,
+		  const int* ia, const int* ja, const int* iau, double* A)
+{
+  int e, i, j, k;
+  int nb = c->nbedge + c->ngedge;
+  const double h = 1.0e-8;
+  double gamma = c->gamma;
+  (void)beta; (void)iau;
+  for(k = 0; k < ia[c->nnode]*NEQN*NEQN; k++) A[k] = 0.0;
+
+  /* Kernel_NumJac :254-304 */
+  for(e = 0; e < c->nedge; e++){
+    int l = c->edges_n[2*e], r = c->edges_n[2*e+1];
+    const double* avec = &c->edges_a[4*e];
+    const double* QL = &q[l*NVARS];
+    const double* QR = &q[r*NVARS];
+    double QPL[NVARS], QPR[NVARS], fluxS[NEQN], fluxL[NEQN], fluxR[NEQN], tempL[25], tempR[25];
+    double *pR, *pL;
+    numerical_flux(QL, QR, avec, 0.0, gamma, fluxS);
+    for(i = 0; i < NEQN; i++){
+      memcpy(QPL, QL, sizeof(double)*NVARS);
+      memcpy(QPR, QR, sizeof(double)*NVARS);
+      QPL[i] += h; QPR[i] += h;
+      compute_aux(QPL, gamma); compute_aux(QPR, gamma);
+      numerical_flux(QPL, QR, avec, 0.0, gamma, fluxL);
+      numerical_flux(QL, QPR, avec, 0.0, gamma, fluxR);
+      for(j = 0; j < NEQN; j++) tempL[j*NEQN + i] = (fluxS[j] - fluxL[j])/h;
+      for(j = 0; j < NEQN; j++) tempR[j*NEQN + i] = (fluxR[j] - fluxS[j])/h;
+    }
+    pR = get_block(ia, ja, A, l, r);
+    pL = get_block(ia, ja, A, r, l);
+    for(k = 0; k < 25; k++) pR[k] += tempR[k];
+    for(k = 0; k < 25; k++) pL[k] += tempL[k];
+  }
+
+  /* Bkernel_NumJac :459-544 */
+  for(e = 0; e < nb; e++){
+    int l = c->bedges_n[2*e], r = c->bedges_n[2*e+1];
+    const double* avec = &c->bedges_a[4*e];
+    double* QL = &q[l*NVARS];
+    double* QR = &q[r*NVARS];
+    int bctype = c->bedges_bctype[e];
+    double QPL[NVARS], QPR[NVARS], fluxS[NEQN], fluxL[NEQN], fluxR[NEQN], tempL[25], tempR[25];
+    double *pL;
+    boundary_variables(c, QL, QR, avec, bctype);
+    numerical_flux(QL, QR, avec, 0.0, gamma, fluxS);
+    for(i = 0; i < NEQN; i++){
+      memcpy(QPL, QL, sizeof(double)*NVARS);
+      memcpy(QPR, QR, sizeof(double)*NVARS);
+      QPL[i] += h; QPR[i] += h;
+      compute_aux(QPL, gamma); compute_aux(QPR, gamma);
+      numerical_flux(QL, QPR, avec, 0.0, gamma, fluxR);
+      if(!is_ghost(c, r)){     /* boundaryJacEval == 0 */
+	memcpy(QPR, QR, sizeof(double)*NVARS);
+	compute_aux(QPR, gamma);
+	boundary_variables(c, QPL, QPR, avec, bctype);
+	numerical_flux(QPL, QPR, avec, 0.0, gamma, fluxL);
+      }
+      else{
+	numerical_flux(QPL, QR, avec, 0.0, gamma, fluxL);
+      }
+      for(j = 0; j < NEQN; j++){
+	tempL[j*NEQN + i] = (fluxL[j] - fluxS[j])/h;
+	tempR[j*NEQN + i] = (fluxR[j] - fluxS[j])/h;
+      }
+    }
+    if(is_ghost(c, r)){
+      double* pR = get_block(ia, ja, A, l, r);
+      for(k = 0; k < 25; k++) pR[k] += tempR[k];
+    }
+    pL = get_block(ia, ja, A, l, l);
+    for(k = 0; k < 25; k++) pL[k] += tempL[k];
+  }
+
+  /* Kernel_Diag_NumJac :434-456; scatter right first, then left */
+  for(e = 0; e < c->nedge; e++){
+    int l = c->edges_n[2*e], r = c->edges_n[2*e+1];
+    double* dL = get_block(ia, ja, A, l, l);
+    double* dR = get_block(ia, ja, A, r, r);
+    const double* jacL = get_block(ia, ja, A, r, l);
+    const double* jacR = get_block(ia, ja, A, l, r);
+    for(k = 0; k < 25; k++) dR[k] += -jacR[k];
+    for(k = 0; k < 25; k++) dL[k] += -jacL[k];
+  }
+
+  /* source-term Jacobian (eqnset.tcc:163-187) is identically zero without gravity:
+     jac[j] -= 0.0 (jacobian.tcc:199-208) */
+
+  /* ContributeTemporalTerms :214-250 -> eqnset.tcc:195-208 (steady: param->dt < 0, cnp1 = 1) */
+  for(i = 0; i < c->nnode; i++){
+    double* d = get_block(ia, ja, A, i, i);
+    for(k = 0; k < NEQN; k++) d[k*NEQN + k] += 1.0*c->vol[i]/dt[i];
+  }
+}
+
+/* matrix.h:110-190 */
+static int lu(double* a, int* p, int n)
+{
+  int i, j, k, row = 0, temp, condBad = 0;
+  double large;
+  const double smallnum = 1.0e-15;
+  for(i = 0; i < n; i++) p[i] = i;
+  for(i = 0; i < n; i++){
+    large = 0.0;
+    for(j = i; j < n; j++){
+      if(fabs(a[p[j]*n + i]) > fabs(large)){ large = a[p[j]*n + i]; row = j; }
+    }
+    if(large == 0.0) condBad++;
+    else if(fabs(large) < smallnum) condBad++;
+    temp = p[i]; p[i] = p[row]; p[row] = temp;
+    large = 1.0/large;
+    for(j = i+1; j < n; j++) a[p[j]*n + i] *= large;
+    for(j = i+1; j < n; j++){
+      for(k = i+1; k < n; k++) a[p[j]*n + k] -= a[p[j]*n + i]*a[p[i]*n + k];
+    }
+  }
+  return condBad > 0;
+}
+
+/* matrix.h:237-264 */
+static void lu_solve(const double* a, double* b, const int* p, double* x, int n)
+{
+  int i, j;
+  double sum;
+  for(i = 0; i < n; i++){
+    sum = 0.0;
+    for(j = 0; j < i; j++) sum += a[p[i]*n + j]*x[j];
+    x[i] = b[p[i]] - sum;
+  }
+  for(i = n-1; i >= 0; i--){
+    sum = 0.0;
+    for(j = n-1; j > i; j--) sum += a[p[i]*n + j]*b[j];
+    b[i] = (x[i] - sum)/a[p[i]*n + i];
+  }
+}
+
+/* crsmatrix.tcc:840-876 */
+void orc_prepare_sgs(const orc_case* c, const int* iau, double* A, int* pv)
+{
+  int i;
+  for(i = 0; i < c->nnode; i++) lu(&A[(size_t)iau[i]*NEQN*NEQN], &pv[i*NEQN], NEQN);
+}
+
+/* crs.tcc:62-173 on one rank (halo update is a no-op); norm = parallel.h:160-181 */
+double orc_sgs(const orc_case* c, int nsgs, const int* ia, const int* ja, const int* iau,
+	       const double* A, const int* pv, const double* b, double* x)
+{
+  int isgs, i, k, indx, dir;
+  double rhs[NEQN], vout[NEQN], temp[NEQN];
+  double xOld = 0.0, xNorm = 0.0;
+  int n = c->nnode;
+  for(isgs = 0; isgs < nsgs; isgs++){
+    for(dir = 0; dir < 2; dir++){
+      for(k = 0; k < n; k++){
+	i = dir ? (n - 1 - k) : k;
+	memcpy(rhs, &b[i*NEQN], sizeof(rhs));
+	for(indx = ia[i]+1; indx < ia[i+1]; indx++){
+	  int j, node2 = ja[indx];
+	  matvec(&A[(size_t)indx*25], &x[node2*NEQN], vout, NEQN);
+	  for(j = 0; j < NEQN; j++) rhs[j] -= vout[j];
+	}
+	lu_solve(&A[(size_t)iau[i]*25], rhs, &pv[i*NEQN], temp, NEQN);
+	memcpy(&x[i*NEQN], rhs, sizeof(rhs));
+      }
+    }
+    xOld = xNorm;
+    {
+      double s = 0.0;
+      for(i = 0; i < n*NEQN; i++) s += x[i]*x[i];
+      xNorm = sqrt(s)/(double)(n*NEQN);
+    }
+  }
+  return fabs(xOld - xNorm);
+}

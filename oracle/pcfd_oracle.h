@@ -1,0 +1,90 @@
+/*
+ * pcfd_oracle.h -- plain-C CPU restatement of ProteusCFD's edge-based
+ * finite-volume hot path.  TEST INFRASTRUCTURE ONLY: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline leg may use it; the
+ * product (proteuscfd_b200/) never links, imports or calls it.
+ *
+ * Parity status: PINNED.  tests/test_oracle.py checks every function here
+ * against tests/golden/ npz files, which tools/make_golden.py produced by running
+ * the unmodified reference (oracle/_ref/ref_harness) -- including the
+ * reference's own unit-test fixture cube_LowFi.0.h5.
+ *
+ * Array layouts are exactly the reference's (AoS, ucs/solutionSpace.h:94-113):
+ *   q     [(nnode+gnode+nbnode) * nvars]   nvars = 10  [rho,ru,rv,rw,rE | T,P,u,v,w]
+ *   qgrad [(nnode+gnode) * nterms*3]       nterms = 9  (vars 0,1,2,3,4,5,7,8,9)
+ *   lim   [(nnode+gnode) * neqn]           neqn = 5
+ *   b     [nnode * neqn],  x [(nnode+gnode) * neqn]
+ *   A     block-CRS, diagonal block first in each row (ucs/crsmatrix.tcc:48-97)
+ */
+#ifndef PCFD_ORACLE_H
+#define PCFD_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_NEQN 5
+#define ORC_NVARS 10
+#define ORC_NTERMS 9
+
+/* ucs/bc_defines.h:4-30 */
+enum { ORC_BC_PARALLEL = 0, ORC_BC_DIRICHLET = 1, ORC_BC_NEUMANN = 2, ORC_BC_IMPERMEABLE_WALL = 3,
+       ORC_BC_NOSLIP = 4, ORC_BC_FARFIELD_VISCOUS = 5, ORC_BC_FARFIELD = 6, ORC_BC_SONIC_INFLOW = 7,
+       ORC_BC_SONIC_OUTFLOW = 8, ORC_BC_SYMMETRY = 9 };
+
+typedef struct {
+  int nnode, gnode, nbnode;
+  int nedge, nbedge, ngedge;
+  const int* edges_n;        /* [2*nedge]            uns_base.h:12-22 */
+  const double* edges_a;     /* [4*nedge]  unit normal + area */
+  const int* bedges_n;       /* [2*(nbedge+ngedge)]  uns_base.h:28-37 */
+  const double* bedges_a;    /* [4*(nbedge+ngedge)] */
+  const int* bedges_bctype;  /* [nbedge+ngedge]      bc->GetBCType(factag) */
+  const double* xyz;         /* [3*(nnode+gnode)] */
+  const double* vol;         /* [nnode] */
+  const int* ipsp;           /* [nnode+1] */
+  const int* psp;            /* [ipsp[nnode]] */
+  double gamma, chi, cfl;
+  int limiter;               /* 0 none, 1 Barth, 2 Venkatakrishnan */
+  int sorder;                /* 1 or 2 */
+  int no_cvbc;
+  double qinf[ORC_NVARS];
+} orc_case;
+
+/* gradient.tcc:115-138, 381-542 : s and sw, each [(nnode+gnode)*6] */
+void orc_lsq_coefficients(const orc_case* c, double* s, double* sw);
+/* gradient.tcc:57-112, 251-378, 545-565 */
+void orc_gradient(const orc_case* c, const double* q, const double* sw, double* qgrad);
+/* limiters.tcc:53-132 (+ kernels) */
+void orc_limiter(const orc_case* c, const double* q, const double* qgrad, double* lim);
+/* bc.tcc:1399-1457, 1058-1120; compressible.tcc:1246-1475 */
+void orc_update_bcs(const orc_case* c, double* q, const double* beta);
+/* residual.tcc:66-122, 192-387 ; returns nothing, b is overwritten */
+void orc_residual(const orc_case* c, const double* q, const double* qgrad, const double* lim,
+		  const double* beta, double* b);
+/* timestep.tcc:7-143 (local time stepping branch); returns dtmin */
+double orc_timestep(const orc_case* c, const double* q, const double* beta, double* dt);
+/* solve.tcc:71-98 + compressible.tcc:929-993 */
+void orc_explicit_solve(const orc_case* c, double* q, const double* b, const double* dt, double* x);
+void orc_apply_dq(const orc_case* c, double* q, const double* x);
+
+/* crsmatrix.tcc:48-97 : ia[nnode+1], ja[ia[nnode]], iau[nnode] */
+void orc_crs_init(const orc_case* c, int* ia, int* ja, int* iau);
+/* jacobian.tcc:13-18, 130-250, 254-304, 437-544 (one-sided FD, h = 1e-8).
+   q is written (phantom nodes) exactly as the reference does. */
+void orc_jacobian(const orc_case* c, double* q, const double* beta, const double* dt,
+		  const int* ia, const int* ja, const int* iau, double* A);
+/* crsmatrix.tcc:840-876 + matrix.h:110-190 */
+void orc_prepare_sgs(const orc_case* c, const int* iau, double* A, int* pv);
+/* crs.tcc:62-173 (single rank); returns |xOld - xNorm| */
+double orc_sgs(const orc_case* c, int nsgs, const int* ia, const int* ja, const int* iau,
+	       const double* A, const int* pv, const double* b, double* x);
+
+/* compressible.tcc:93-230 -- exposed for unit tests */
+void orc_roe_flux(const double* QL, const double* QR, const double* avec, double vdotn, double gamma,
+		  double* flux);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,132 @@
+"""ctypes wrapper around oracle/libpcfd_oracle.so (the plain-C restatement).
+
+TEST INFRASTRUCTURE: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline leg only.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+NEQN, NVARS, NTERMS = 5, 10, 9
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+class OrcCase(C.Structure):
+    _fields_ = [("nnode", C.c_int), ("gnode", C.c_int), ("nbnode", C.c_int),
+                ("nedge", C.c_int), ("nbedge", C.c_int), ("ngedge", C.c_int),
+                ("edges_n", _ip), ("edges_a", _dp), ("bedges_n", _ip), ("bedges_a", _dp),
+                ("bedges_bctype", _ip), ("xyz", _dp), ("vol", _dp), ("ipsp", _ip), ("psp", _ip),
+                ("gamma", C.c_double), ("chi", C.c_double), ("cfl", C.c_double),
+                ("limiter", C.c_int), ("sorder", C.c_int), ("no_cvbc", C.c_int),
+                ("qinf", C.c_double * NVARS)]
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+def load_golden(name):
+    d = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    meta = dict(zip([str(k) for k in d.pop("meta_keys")], d.pop("meta_vals")))
+    return d, meta
+
+
+class Oracle:
+    """One mesh + parameter set bound to the C oracle."""
+
+    def __init__(self, lib, g, meta):
+        self.lib = lib
+        self.keep = {k: np.ascontiguousarray(v) for k, v in g.items()}
+        k = self.keep
+        c = OrcCase()
+        for f in ("nnode", "gnode", "nbnode", "nedge", "nbedge", "ngedge", "limiter", "sorder", "no_cvbc"):
+            setattr(c, f, int(meta[f]))
+        c.gamma, c.chi, c.cfl = meta["gamma"], meta["chi"], meta["cfl"]
+        c.edges_n, c.edges_a = _i(k["edges_n"]), _d(k["edges_a"])
+        c.bedges_n, c.bedges_a, c.bedges_bctype = _i(k["bedges_n"]), _d(k["bedges_a"]), _i(k["bedges_bctype"])
+        c.xyz, c.vol, c.ipsp, c.psp = _d(k["xyz"]), _d(k["vol"]), _i(k["ipsp"]), _i(k["psp"])
+        for j in range(NVARS):
+            c.qinf[j] = k["qinf"][j]
+        self.c = c
+        self.nn = c.nnode + c.gnode
+        self.nnode = c.nnode
+        self.nblocks = int(k["ipsp"][c.nnode]) + c.nnode
+
+    def lsq(self):
+        s, sw = np.zeros(self.nn * 6), np.zeros(self.nn * 6)
+        self.lib.orc_lsq_coefficients(C.byref(self.c), _d(s), _d(sw))
+        return s, sw
+
+    def gradient(self, q, sw):
+        g = np.zeros(self.nn * NTERMS * 3)
+        self.lib.orc_gradient(C.byref(self.c), _d(q), _d(sw), _d(g))
+        return g
+
+    def limiter(self, q, grad):
+        lim = np.zeros(self.nn * NEQN)
+        self.lib.orc_limiter(C.byref(self.c), _d(q), _d(grad), _d(lim))
+        return lim
+
+    def update_bcs(self, q, beta):
+        self.lib.orc_update_bcs(C.byref(self.c), _d(q), _d(beta))
+
+    def residual(self, q, grad, lim, beta):
+        b = np.zeros(self.nnode * NEQN)
+        self.lib.orc_residual(C.byref(self.c), _d(q), _d(grad), _d(lim), _d(beta), _d(b))
+        return b
+
+    def timestep(self, q, beta):
+        dt = np.zeros(self.nnode)
+        self.lib.orc_timestep.restype = C.c_double
+        dtmin = self.lib.orc_timestep(C.byref(self.c), _d(q), _d(beta), _d(dt))
+        return dt, dtmin
+
+    def explicit_solve(self, q, b, dt):
+        x = np.zeros(self.nnode * NEQN)
+        self.lib.orc_explicit_solve(C.byref(self.c), _d(q), _d(b), _d(dt), _d(x))
+        return x
+
+    def apply_dq(self, q, x):
+        self.lib.orc_apply_dq(C.byref(self.c), _d(q), _d(x))
+
+    def crs_init(self):
+        ia = np.zeros(self.nnode + 1, dtype=np.int32)
+        ja = np.zeros(self.nblocks, dtype=np.int32)
+        iau = np.zeros(self.nnode, dtype=np.int32)
+        self.lib.orc_crs_init(C.byref(self.c), _i(ia), _i(ja), _i(iau))
+        return ia, ja, iau
+
+    def jacobian(self, q, beta, dt, ia, ja, iau):
+        A = np.zeros(self.nblocks * 25)
+        self.lib.orc_jacobian(C.byref(self.c), _d(q), _d(beta), _d(dt), _i(ia), _i(ja), _i(iau), _d(A))
+        return A
+
+    def prepare_sgs(self, iau, A):
+        pv = np.zeros(self.nnode * NEQN, dtype=np.int32)
+        self.lib.orc_prepare_sgs(C.byref(self.c), _i(iau), _d(A), _i(pv))
+        return pv
+
+    def sgs(self, nsgs, ia, ja, iau, A, pv, b):
+        x = np.zeros(self.nn * NEQN)
+        self.lib.orc_sgs.restype = C.c_double
+        d = self.lib.orc_sgs(C.byref(self.c), nsgs, _i(ia), _i(ja), _i(iau), _d(A), _i(pv), _d(b), _d(x))
+        return x, d
+
+
+def load_oracle():
+    so = os.path.join(ORACLE_DIR, "libpcfd_oracle.so")
+    src = os.path.join(ORACLE_DIR, "pcfd_oracle.c")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "oracle"], stdout=subprocess.DEVNULL)
+    return C.CDLL(so)

@@ -1,0 +1,100 @@
+"""The C oracle (oracle/pcfd_oracle.c) against fixtures produced by the reference itself.
+
+tests/golden/*.npz were written by tools/make_golden.py from runs of the
+unmodified reference (oracle/_ref/ref_harness).  The oracle restates the
+reference's loops in the reference's order and is compiled without FMA
+contraction like the reference, so the bar here is BIT-EXACT equality.
+"""
+import numpy as np
+import pytest
+
+from tests.oracle_lib import Oracle, load_golden
+
+ALL = ["box8_explicit_venkat", "box8_explicit_barth", "box6_implicit_sgs", "box6c_implicit_sgs",
+       "ramp15_implicit", "cube_LowFi"]
+IMPLICIT = ["box6_implicit_sgs", "box6c_implicit_sgs", "ramp15_implicit", "cube_LowFi"]
+EXPLICIT = ["box8_explicit_venkat", "box8_explicit_barth"]
+
+
+def exact(a, b, what):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, what
+    bad = ~((a == b) | (np.isnan(a) & np.isnan(b)))
+    if bad.any():
+        i = int(np.argmax(bad))
+        scale = np.abs(b).max()
+        raise AssertionError(f"{what}: {int(bad.sum())}/{a.size} differ; first at {i}: {a.flat[i]!r} vs "
+                             f"{b.flat[i]!r}; max |diff|/max|ref| = {np.abs(a - b).max() / scale:.3e}")
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_lsq_coefficients(oracle, name):
+    g, meta = load_golden(name)
+    o = Oracle(oracle, g, meta)
+    s, sw = o.lsq()
+    exact(s, g["lsq_s"], "s")
+    exact(sw, g["lsq_sw"], "sw")
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_update_bcs(oracle, name):
+    # q_pre -> (one UpdateBCs, bc.tcc:1399-1457) -> q0 in the reference run
+    g, meta = load_golden(name)
+    o = Oracle(oracle, g, meta)
+    q = g["q_pre"].copy()
+    o.update_bcs(q, g["beta"])
+    exact(q, g["q0"], "q after BC update")
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_gradient_limiter_residual_timestep(oracle, name):
+    g, meta = load_golden(name)
+    o = Oracle(oracle, g, meta)
+    q = g["q0"].copy()
+    grad = o.gradient(q, g["lsq_sw"])
+    exact(grad, g["qgrad"], "qgrad")
+    lim = o.limiter(q, grad)
+    exact(lim, g["limiter"], "limiter")
+    b = o.residual(q, grad, lim, g["beta"])
+    exact(b, g["b"], "b")
+    dt, dtmin = o.timestep(q, g["beta"])
+    exact(dt, g["timestep"], "timestep")
+    assert dtmin == g["dtmin"][0]
+
+
+@pytest.mark.parametrize("name", EXPLICIT)
+def test_explicit_update(oracle, name):
+    g, meta = load_golden(name)
+    o = Oracle(oracle, g, meta)
+    q = g["q0"].copy()
+    x = o.explicit_solve(q, g["b"], g["timestep"])
+    exact(x, g["x"], "x")
+    exact(q, g["q1"], "q1")
+
+
+@pytest.mark.parametrize("name", IMPLICIT)
+def test_jacobian_lu_sgs(oracle, name):
+    g, meta = load_golden(name)
+    o = Oracle(oracle, g, meta)
+    ia, ja, iau = o.crs_init()
+    exact(ia, g["ia"], "ia")
+    exact(ja, g["ja"], "ja")
+    exact(iau, g["iau"], "iau")
+    q = g["q0"].copy()
+    A = o.jacobian(q, g["beta"], g["timestep"], ia, ja, iau)
+    exact(A, g["A"], "A")
+    pv = o.prepare_sgs(iau, A)
+    exact(A, g["A_lu"], "A_lu")
+    exact(pv, g["pv"], "pv")
+    x, ddq = o.sgs(int(meta["nSgs"]), ia, ja, iau, A, pv, g["b"])
+    exact(x, g["x"], "x")
+    assert ddq == g["sgs_ddq"][0]
+    o.apply_dq(q, x)
+    exact(q, g["q1"], "q1")
+
+
+def test_resnorm_matches_reference_definition():
+    # ParallelL2Norm (ucs/parallel.h:160-181): sqrt(sum x^2)/N
+    g, meta = load_golden("box8_explicit_venkat")
+    b = g["b"]
+    assert np.isclose(np.sqrt(np.sum(b * b)) / b.size, g["resnorm"][0], rtol=1e-13)

@@ -1,0 +1,177 @@
+#!/usr/bin/env python
+"""Generate the golden parity fixtures under tests/golden/ by RUNNING THE REFERENCE.
+
+Needs /root/reference and the binaries built by `make -C oracle ref`
+(oracle/_ref/udecomp_ref, oracle/_ref/ref_harness).  For each case it writes a
+synthetic mesh (or copies one of the reference's own unit-test fixtures),
+partitions it with the reference's udecomp, runs the reference harness (which
+calls the reference's own Gradient::Compute / Limiter::Compute /
+ComputeResiduals / ComputeJacobians / CRS::SGS ...) and packs every dumped
+array into tests/golden/<case>.npz.  The fixtures are small and committed; this
+script is how they were made.
+
+    python tools/make_golden.py [case ...]
+"""
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from proteuscfd_b200.boxmesh import kuhn_box, renumber, write_ugrid  # noqa: E402
+from proteuscfd_b200.ordering import greedy_color_order  # noqa: E402
+
+REFBIN = os.path.join(ROOT, "oracle", "_ref")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+REFERENCE = "/root/reference"
+
+PARAM_TMPL = """<<<BEGIN TEMPORAL CONTROL>>>
+numTimeSteps = 1
+newtonIterations = 1
+<<<END TEMPORAL CONTROL>>>
+
+<<<BEGIN SOLUTION ORDERING>>>
+Iterate {name}
+<<<END SOLUTION ORDERING>>>
+
+<<<BEGIN SPACE {name}>>>
+equationSet = {eqnset}
+fluxType = roeFlux
+spatialOrder = {sorder}
+limiter = {limiter}
+numberSGS = {nsgs}
+reorderMesh = 0
+refPressure = 101325
+velocity = {mach}
+CFL = {cfl}
+flowDirection = [{fx}, {fy}, {fz}]
+jacobianFieldType = {jactype}
+jacobianBoundaryType = {jactype}
+<<<END SPACE>>>
+"""
+
+INT_ARRAYS = {"edges_n", "bedges_n", "bedges_factag", "bedges_bctype", "ipsp", "psp", "gNodeOwner",
+              "gNodeLocalId", "commCountsSend", "commCountsRecv", "commOffsetsRecv", "nodePackingList",
+              "ia", "ja", "iau", "pv"}
+
+BOX_BC = """surface #1 = farField "xmin"
+surface #2 = farField "xmax"
+surface #3 = symmetry "ymin"
+surface #4 = impermeableWall "ymax"
+surface #5 = farField "zmin"
+surface #6 = farField "zmax"
+"""
+
+# docs/master.bc:5-10 layout of the 15-degree ramp: symmetry side walls,
+# farField inflow/outlet/top, impermeableWall ramp floor
+RAMP_BC = """surface #1 = farField "inflow"
+surface #2 = farField "outlet"
+surface #3 = impermeableWall "ramp"
+surface #4 = farField "top"
+surface #5 = symmetry "wall0"
+surface #6 = symmetry "wall1"
+"""
+
+
+def run(cmd, cwd, env=None):
+    e = dict(os.environ)
+    e["HOME"] = cwd
+    if env:
+        e.update(env)
+    r = subprocess.run(cmd, cwd=cwd, env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        print(r.stdout[-4000:])
+        raise RuntimeError(f"{cmd} failed with {r.returncode}")
+    return r.stdout
+
+
+def collect(outdir, rank):
+    d = {}
+    meta = {}
+    with open(os.path.join(outdir, f"meta.{rank}.txt")) as f:
+        for line in f:
+            k, v = line.split()
+            meta[k] = float(v)
+    for fn in sorted(os.listdir(outdir)):
+        if not fn.endswith(f".{rank}.bin"):
+            continue
+        name = fn[: -len(f".{rank}.bin")]
+        dt = np.int32 if name in INT_ARRAYS else np.float64
+        d[name] = np.fromfile(os.path.join(outdir, fn), dtype=dt)
+    d["meta_keys"] = np.array(sorted(meta.keys()))
+    d["meta_vals"] = np.array([meta[k] for k in sorted(meta.keys())], dtype=np.float64)
+    return d
+
+
+def make_case(name, mesh=None, h5=None, bc=BOX_BC, np_ranks=1, part=None, **kw):
+    opts = dict(eqnset="compressibleEuler", sorder=2, limiter=2, nsgs=0, mach=0.5, cfl=0.5,
+                fx=1.0, fy=0.0, fz=0.0, jactype=0)
+    opts.update(kw)
+    work = tempfile.mkdtemp(prefix="pcfd_golden_")
+    try:
+        with open(os.path.join(work, f"{name}.param"), "w") as f:
+            f.write(PARAM_TMPL.format(name=name, **opts))
+        with open(os.path.join(work, f"{name}.bc"), "w") as f:
+            f.write(bc)
+        if h5 is not None:
+            shutil.copy(h5, os.path.join(work, f"{name}.0.h5"))
+        else:
+            xyz, tets, tris, tags = mesh
+            write_ugrid(os.path.join(work, f"{name}.ugrid"), xyz, tets, tris, tags)
+            env = {}
+            if np_ranks > 1:
+                np.savetxt(os.path.join(work, "part.txt"), part, fmt="%d")
+                env["PCFD_PARTITION_FILE"] = os.path.join(work, "part.txt")
+            run([os.path.join(REFBIN, "udecomp_ref"), f"{name}.ugrid", str(np_ranks)], work, env)
+        run([os.path.join(REFBIN, "ref_harness"), os.path.join(work, name), os.path.join(work, "out"), "dump"],
+            work, {"PCFD_MPI_NP": str(np_ranks)})
+        os.makedirs(GOLDEN, exist_ok=True)
+        for r in range(np_ranks):
+            d = collect(os.path.join(work, "out"), r)
+            suffix = "" if np_ranks == 1 else f"_r{r}of{np_ranks}"
+            path = os.path.join(GOLDEN, f"{name}{suffix}.npz")
+            np.savez_compressed(path, **d)
+            print(f"wrote {path}: {os.path.getsize(path)/1024:.0f} KiB, nnode={int(d['vol'].size)}")
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+def colored_box(n, **kw):
+    """Box whose node numbering is colour-sorted (multicolour SGS == sequential SGS)."""
+    xyz, tets, tris, tags = kuhn_box(n, **kw)
+    new_of_old, _ = greedy_color_order(len(xyz), tets)
+    xyz, tets, tris = renumber(xyz, tets, tris, new_of_old)
+    return xyz, tets, tris, tags
+
+
+CASES = {
+    # config[1] in miniature: explicit Euler, Roe, 2nd order, Venkatakrishnan limiter
+    "box8_explicit_venkat": lambda: make_case("box8_explicit_venkat", mesh=kuhn_box(8, jitter=0.15)),
+    # Barth limiter on the same mesh
+    "box8_explicit_barth": lambda: make_case("box8_explicit_barth", mesh=kuhn_box(8, jitter=0.15), limiter=1),
+    # implicit: FD Jacobian, LU, 3 SGS sweeps on natural (lexicographic) numbering
+    "box6_implicit_sgs": lambda: make_case("box6_implicit_sgs", mesh=kuhn_box(6, jitter=0.15), nsgs=3, cfl=5.0),
+    # implicit on a colour-sorted numbering (the multicolour schedule used at scale)
+    "box6c_implicit_sgs": lambda: make_case("box6c_implicit_sgs", mesh=colored_box(6, jitter=0.15), nsgs=3, cfl=5.0),
+    # config[0]: 15-degree ramp, supersonic inviscid Euler, 1 partition, Roe + LSQ, 5 SGS
+    "ramp15_implicit": lambda: make_case("ramp15_implicit", mesh=kuhn_box(8, ramp_deg=15.0, jitter=0.1), bc=RAMP_BC,
+                                         mach=2.0, nsgs=5, cfl=5.0),
+    # the reference's own unit-test fixture (unitTest/gradientTest.h:20-232): prism cube, 216 nodes
+    "cube_LowFi": lambda: make_case(
+        "cube_LowFi", h5=os.path.join(REFERENCE, "unitTest/meshResources/cubeStructuredSeries/cube_LowFi.0.h5"),
+        bc="".join(f"surface #{i} = farField\n" for i in range(1, 27)), nsgs=2, cfl=5.0),
+}
+
+
+def main():
+    names = sys.argv[1:] or list(CASES)
+    for n in names:
+        CASES[n]()
+
+
+if __name__ == "__main__":
+    main()
