@@ -1,0 +1,150 @@
+/*
+ * pcfd.h -- C ABI of libpcfd_b200.so: the B200 (sm_100a) implementation of
+ * ProteusCFD's edge-based finite-volume hot path.
+ *
+ * The reference has no FFI: its "plugin surface" is in-process C++ (SURVEY.md
+ * 8b).  Each entry point below replaces the body of one reference phase
+ * function; the citation gives the reference call site (paths relative to
+ * /root/reference/ucs).  INTEGRATION.md shows the C++ shim a ucs.x maintainer
+ * adds at those call sites.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on error; the message is
+ *    available from pcfd_last_error().  Nothing throws across this boundary.
+ *  - the caller owns all host buffers; the library owns all device memory.
+ *  - host arrays use exactly the reference's layouts (AoS, row-major):
+ *      q     [(nnode+gnode+nbnode) * nvars]   (solutionSpace.h:94-113)
+ *      qgrad [(nnode+gnode) * nterms*3]
+ *      lim   [(nnode+gnode) * neqn]           (limiters.h: Limiter::l)
+ *      b     [nnode*neqn], x [(nnode+gnode)*neqn]   (crs.h: CRS::b, CRS::x)
+ *      A     [nblocks*neqn*neqn], diagonal block first in each row (crsmatrix.tcc:48-97)
+ *  - one context per GPU; calls on one context are serialised by the caller.
+ *  - there is NO CPU fallback: pcfd_create fails if no sm_100-class device is
+ *    usable.
+ */
+#ifndef PCFD_H
+#define PCFD_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCFD_ABI_VERSION 1
+
+/* eqnset ids follow eqnset_defines.h / create_functions.h:17-45 */
+enum { PCFD_EQNSET_COMPRESSIBLE_EULER = 2 };
+
+/* BC types: bc_defines.h:4-30 (the value bc->GetBCType(factag) returns) */
+enum { PCFD_BC_PARALLEL = 0, PCFD_BC_DIRICHLET = 1, PCFD_BC_NEUMANN = 2, PCFD_BC_IMPERMEABLE_WALL = 3,
+       PCFD_BC_NOSLIP = 4, PCFD_BC_FARFIELD_VISCOUS = 5, PCFD_BC_FARFIELD = 6, PCFD_BC_SONIC_INFLOW = 7,
+       PCFD_BC_SONIC_OUTFLOW = 8, PCFD_BC_SYMMETRY = 9 };
+
+/* fields that can be moved across the boundary with pcfd_set_field/pcfd_get_field */
+enum {
+  PCFD_F_Q = 0,        /* SolutionSpace::q        (nnode+gnode+nbnode)*nvars */
+  PCFD_F_QGRAD = 1,    /* SolutionSpace::qgrad    (nnode+gnode)*nterms*3 */
+  PCFD_F_LIMITER = 2,  /* Limiter::l              (nnode+gnode)*neqn */
+  PCFD_F_B = 3,        /* CRS::b                  nnode*neqn */
+  PCFD_F_X = 4,        /* CRS::x                  (nnode+gnode)*neqn */
+  PCFD_F_TIMESTEP = 5, /* field "timestep"        nnode */
+  PCFD_F_BETA = 6,     /* field "beta"            nnode+gnode+nbnode (unused by the perfect-gas eqnset) */
+  PCFD_F_LSQ_S = 7,    /* Mesh::s                 (nnode+gnode)*6 */
+  PCFD_F_LSQ_SW = 8,   /* Mesh::sw                (nnode+gnode)*6 */
+  PCFD_F_A = 9,        /* CRSMatrix::M            nblocks*neqn*neqn */
+  PCFD_F_COUNT = 10
+};
+
+/* Mesh::edges / bedges / xyz / vol / ipsp / psp as flat arrays (uns_base.h:12-37, mesh.h:199-254) */
+typedef struct {
+  int nnode, gnode, nbnode;
+  int nedge, nbedge, ngedge;
+  const int* edges_n;        /* [2*nedge]   Edges::n           */
+  const double* edges_a;     /* [4*nedge]   Edges::a (unit normal, area) */
+  const int* bedges_n;       /* [2*(nbedge+ngedge)]  HalfEdges::n */
+  const double* bedges_a;    /* [4*(nbedge+ngedge)]  HalfEdges::a */
+  const int* bedges_bctype;  /* [nbedge+ngedge]  bc->GetBCType(HalfEdges::factag) */
+  const double* xyz;         /* [3*(nnode+gnode)] */
+  const double* vol;         /* [nnode] */
+  const int* ipsp;           /* [nnode+1] */
+  const int* psp;            /* [ipsp[nnode]]  order preserved: it fixes the CRS column order */
+} pcfd_mesh_desc;
+
+/* the Param<Type> fields the hot path reads (param.tcc:84-229) */
+typedef struct {
+  int eqnset;                /* PCFD_EQNSET_* */
+  int sorder;                /* spatialOrder 1|2 */
+  int limiter;               /* 0 none, 1 Barth, 2 Venkatakrishnan */
+  int no_cvbc;
+  double gamma, chi, cfl;
+  double qinf[10];           /* free-stream state incl. aux vars (bc.tcc: Qinf) */
+} pcfd_params;
+
+typedef struct pcfd_ctx pcfd_ctx;
+
+int pcfd_abi_version(void);
+/* message of the last failed call on ctx (ctx may be NULL for pcfd_create failures) */
+const char* pcfd_last_error(const pcfd_ctx* ctx);
+
+/* SolutionSpace ctor + Init (solutionSpace.tcc:26-114, 148-376): uploads the mesh,
+   builds the node->edge gather lists, the block-CRS pattern (CRSMatrix::Init,
+   crsmatrix.tcc:48-97) and the SGS level schedule. */
+int pcfd_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int device, pcfd_ctx** out);
+int pcfd_destroy(pcfd_ctx* ctx);
+/* run all subsequent work of ctx on an existing cudaStream_t (NULL = the context's own stream) */
+int pcfd_set_stream(pcfd_ctx* ctx, void* cuda_stream);
+int pcfd_synchronize(pcfd_ctx* ctx);
+int pcfd_set_cfl(pcfd_ctx* ctx, double cfl);           /* Param::UpdateCFL (solutionSpace.tcc:629) */
+
+size_t pcfd_field_size(const pcfd_ctx* ctx, int field); /* number of doubles */
+int pcfd_set_field(pcfd_ctx* ctx, int field, const double* host, size_t n);
+int pcfd_get_field(pcfd_ctx* ctx, int field, double* host, size_t n);
+void* pcfd_field_device_ptr(pcfd_ctx* ctx, int field);  /* device-resident access (same layout) */
+/* CRSMatrix::{ia,ja,iau,pv}; any pointer may be NULL */
+int pcfd_crs_sizes(const pcfd_ctx* ctx, int* nrows, int* nblocks);
+int pcfd_get_crs(pcfd_ctx* ctx, int* ia, int* ja, int* iau, int* pv);
+
+/* Gradient::ComputeNodeLSQCoefficients (gradient.tcc:115-138) -> Mesh::s, Mesh::sw */
+int pcfd_lsq_coefficients(pcfd_ctx* ctx);
+/* UpdateBCs (bc.tcc:1399-1457): phantom-node states of q */
+int pcfd_update_bcs(pcfd_ctx* ctx);
+/* Gradient::Compute (gradient.tcc:57-112), weighted LSQ */
+int pcfd_gradient(pcfd_ctx* ctx);
+/* Limiter::Compute (limiters.tcc:53-132) */
+int pcfd_limiter(pcfd_ctx* ctx);
+/* ComputeResiduals -> SpatialResidual (residual.tcc:13-122); resnorm (may be NULL) receives
+   [ParallelL2Norm(b), StridedParallelL2Norm(b, eq) for eq < neqn] of this rank's nodes
+   as sum-of-squares (the caller finishes sqrt(sum)/N across ranks, parallel.h:160-219) */
+int pcfd_residual(pcfd_ctx* ctx, double* sumsq);
+/* ComputeTimesteps (timestep.tcc:7-77), local time stepping; dtmin may be NULL */
+int pcfd_timestep(pcfd_ctx* ctx, double* dtmin);
+/* ExplicitSolve (solve.tcc:71-140): x = b*dt/vol, q <- ApplyDQ(x) */
+int pcfd_explicit_solve(pcfd_ctx* ctx);
+/* ComputeJacobians (jacobian.tcc:13-18, 130-250), one-sided FD field + boundary Jacobians */
+int pcfd_jacobian(pcfd_ctx* ctx);
+/* CRSMatrix::PrepareSGS (crsmatrix.tcc:840-876) */
+int pcfd_prepare_sgs(pcfd_ctx* ctx);
+/* CRS::BlankX (crs.tcc:448-460) */
+int pcfd_blank_x(pcfd_ctx* ctx);
+/* CRS::SGS (crs.tcc:62-173); ddq (may be NULL) receives |xOld - xNorm| */
+int pcfd_sgs(pcfd_ctx* ctx, int nsgs, double* ddq);
+/* loop over nnode of EqnSet::ApplyDQ (solutionSpace.tcc:802-804) */
+int pcfd_apply_dq(pcfd_ctx* ctx);
+
+/* One explicit iteration as SolutionSpace::NewtonIterate runs it with nSgs == 0
+   (solutionSpace.tcc:640-904): UpdateBCs, Gradient, Limiter, ComputeResiduals,
+   ExplicitSolve.  ComputeTimesteps is run first when refresh_dt != 0. */
+int pcfd_explicit_iterate(pcfd_ctx* ctx, int refresh_dt, double* sumsq);
+/* One implicit iteration (nSgs > 0): [ComputeJacobians + ComputeTimesteps when
+   refresh_jac != 0], UpdateBCs, Gradient, Limiter, ComputeResiduals, PrepareSGS,
+   BlankX, SGS(nsgs), ApplyDQ. */
+int pcfd_implicit_iterate(pcfd_ctx* ctx, int refresh_jac, int nsgs, double* sumsq, double* ddq);
+
+/* number of CUDA kernels this context has launched since creation */
+long long pcfd_launch_count(const pcfd_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

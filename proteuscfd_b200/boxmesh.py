@@ -5,7 +5,7 @@ triangles of an n x n x n hex box split into 6 tets per hex (Kuhn/Freudenthal
 triangulation), optionally with jittered interior nodes.  `write_ugrid`
 writes the AFLR3 ASCII layout that the reference's `udecomp` reads
 (ucs/mesh.tcc:6740-6920, ReadUGRID_Ascii) so the same mesh can be fed to the
-reference oracle.
+reference build used for parity fixtures.
 """
 import itertools
 

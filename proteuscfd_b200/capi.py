@@ -1,0 +1,243 @@
+"""ctypes binding of libpcfd_b200.so (include/pcfd.h) -- the only compute path.
+
+There is deliberately no fallback: if the CUDA library is missing or no B200 is
+visible, loading / `pcfd_create` raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpcfd_b200.so")
+
+NEQN, NVARS, NTERMS = 5, 10, 9
+EQNSET_COMPRESSIBLE_EULER = 2
+
+BC_PARALLEL, BC_DIRICHLET, BC_NEUMANN, BC_IMPERMEABLE_WALL, BC_NOSLIP = 0, 1, 2, 3, 4
+BC_FARFIELD_VISCOUS, BC_FARFIELD, BC_SONIC_INFLOW, BC_SONIC_OUTFLOW, BC_SYMMETRY = 5, 6, 7, 8, 9
+
+F_Q, F_QGRAD, F_LIMITER, F_B, F_X, F_TIMESTEP, F_BETA, F_LSQ_S, F_LSQ_SW, F_A = range(10)
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+# every symbol include/pcfd.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "pcfd_abi_version", "pcfd_last_error", "pcfd_create", "pcfd_destroy", "pcfd_set_stream", "pcfd_synchronize",
+    "pcfd_set_cfl", "pcfd_field_size", "pcfd_set_field", "pcfd_get_field", "pcfd_field_device_ptr", "pcfd_crs_sizes",
+    "pcfd_get_crs", "pcfd_lsq_coefficients", "pcfd_update_bcs", "pcfd_gradient", "pcfd_limiter", "pcfd_residual",
+    "pcfd_timestep", "pcfd_explicit_solve", "pcfd_jacobian", "pcfd_prepare_sgs", "pcfd_blank_x", "pcfd_sgs",
+    "pcfd_apply_dq", "pcfd_explicit_iterate", "pcfd_implicit_iterate", "pcfd_launch_count",
+]
+
+
+class MeshDesc(C.Structure):
+    _fields_ = [("nnode", C.c_int), ("gnode", C.c_int), ("nbnode", C.c_int),
+                ("nedge", C.c_int), ("nbedge", C.c_int), ("ngedge", C.c_int),
+                ("edges_n", _ip), ("edges_a", _dp), ("bedges_n", _ip), ("bedges_a", _dp), ("bedges_bctype", _ip),
+                ("xyz", _dp), ("vol", _dp), ("ipsp", _ip), ("psp", _ip)]
+
+
+class Params(C.Structure):
+    _fields_ = [("eqnset", C.c_int), ("sorder", C.c_int), ("limiter", C.c_int), ("no_cvbc", C.c_int),
+                ("gamma", C.c_double), ("chi", C.c_double), ("cfl", C.c_double), ("qinf", C.c_double * NVARS)]
+
+
+_lib = None
+
+
+def load_library(path=LIB_PATH):
+    """dlopen the CUDA library; raise (never fall back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+    lib = C.CDLL(path)
+    lib.pcfd_last_error.restype = C.c_char_p
+    lib.pcfd_last_error.argtypes = [C.c_void_p]
+    lib.pcfd_create.argtypes = [C.POINTER(MeshDesc), C.POINTER(Params), C.c_int, C.POINTER(C.c_void_p)]
+    lib.pcfd_field_size.restype = C.c_size_t
+    lib.pcfd_field_size.argtypes = [C.c_void_p, C.c_int]
+    lib.pcfd_set_field.argtypes = [C.c_void_p, C.c_int, _dp, C.c_size_t]
+    lib.pcfd_get_field.argtypes = [C.c_void_p, C.c_int, _dp, C.c_size_t]
+    lib.pcfd_field_device_ptr.restype = C.c_void_p
+    lib.pcfd_field_device_ptr.argtypes = [C.c_void_p, C.c_int]
+    lib.pcfd_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.pcfd_set_cfl.argtypes = [C.c_void_p, C.c_double]
+    lib.pcfd_crs_sizes.argtypes = [C.c_void_p, _ip, _ip]
+    lib.pcfd_get_crs.argtypes = [C.c_void_p, _ip, _ip, _ip, _ip]
+    lib.pcfd_residual.argtypes = [C.c_void_p, _dp]
+    lib.pcfd_timestep.argtypes = [C.c_void_p, _dp]
+    lib.pcfd_sgs.argtypes = [C.c_void_p, C.c_int, _dp]
+    lib.pcfd_explicit_iterate.argtypes = [C.c_void_p, C.c_int, _dp]
+    lib.pcfd_implicit_iterate.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp]
+    lib.pcfd_launch_count.restype = C.c_longlong
+    lib.pcfd_launch_count.argtypes = [C.c_void_p]
+    for name in ("pcfd_destroy", "pcfd_synchronize", "pcfd_lsq_coefficients", "pcfd_update_bcs", "pcfd_gradient",
+                 "pcfd_limiter", "pcfd_explicit_solve", "pcfd_jacobian", "pcfd_prepare_sgs", "pcfd_blank_x",
+                 "pcfd_apply_dq"):
+        getattr(lib, name).argtypes = [C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+class PcfdError(RuntimeError):
+    pass
+
+
+class Context:
+    """One hot-path context on one GPU (thin, 1:1 with the C ABI)."""
+
+    def __init__(self, mesh, params, device=0):
+        """mesh: dict with the pcfd_mesh_desc arrays (+ counts); params: dict with the pcfd_params fields."""
+        self.lib = load_library()
+        self._keep = {}
+        md = MeshDesc()
+        for k in ("nnode", "gnode", "nbnode", "nedge", "nbedge", "ngedge"):
+            setattr(md, k, int(mesh[k]))
+        for k, ctype in (("edges_n", np.int32), ("edges_a", np.float64), ("bedges_n", np.int32),
+                         ("bedges_a", np.float64), ("bedges_bctype", np.int32), ("xyz", np.float64),
+                         ("vol", np.float64), ("ipsp", np.int32), ("psp", np.int32)):
+            a = np.ascontiguousarray(np.asarray(mesh[k]).reshape(-1), dtype=ctype)
+            self._keep[k] = a
+            setattr(md, k, _i(a) if ctype == np.int32 else _d(a))
+        pr = Params()
+        pr.eqnset = int(params.get("eqnset", EQNSET_COMPRESSIBLE_EULER))
+        pr.sorder, pr.limiter, pr.no_cvbc = int(params["sorder"]), int(params["limiter"]), int(params.get("no_cvbc", 0))
+        pr.gamma, pr.chi, pr.cfl = float(params["gamma"]), float(params.get("chi", 0.0)), float(params["cfl"])
+        for j in range(NVARS):
+            pr.qinf[j] = float(params["qinf"][j])
+        self.nnode, self.gnode, self.nbnode = md.nnode, md.gnode, md.nbnode
+        self.nedge, self.nbedge, self.ngedge = md.nedge, md.nbedge, md.ngedge
+        h = C.c_void_p()
+        if self.lib.pcfd_create(C.byref(md), C.byref(pr), int(device), C.byref(h)) != 0:
+            raise PcfdError(self.lib.pcfd_last_error(None).decode())
+        self.h = h
+        self._keep.clear()   # the library has copied everything it needs
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pcfd_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise PcfdError(self.lib.pcfd_last_error(self.h).decode())
+
+    # -- data movement
+    def field_size(self, field):
+        return int(self.lib.pcfd_field_size(self.h, field))
+
+    def set_field(self, field, host):
+        host = np.ascontiguousarray(host, dtype=np.float64).reshape(-1)
+        self._ck(self.lib.pcfd_set_field(self.h, field, _d(host), host.size))
+
+    def get_field(self, field, out=None):
+        if out is None:
+            out = np.empty(self.field_size(field), dtype=np.float64)
+        self._ck(self.lib.pcfd_get_field(self.h, field, _d(out), out.size))
+        return out
+
+    def device_ptr(self, field):
+        return self.lib.pcfd_field_device_ptr(self.h, field)
+
+    def get_crs(self):
+        nrows, nblocks = C.c_int(), C.c_int()
+        self._ck(self.lib.pcfd_crs_sizes(self.h, C.byref(nrows), C.byref(nblocks)))
+        ia = np.empty(nrows.value + 1, np.int32)
+        ja = np.empty(nblocks.value, np.int32)
+        iau = np.empty(nrows.value, np.int32)
+        pv = np.empty(nrows.value * NEQN, np.int32)
+        self._ck(self.lib.pcfd_get_crs(self.h, _i(ia), _i(ja), _i(iau), _i(pv)))
+        return ia, ja, iau, pv
+
+    def set_stream(self, cuda_stream):
+        self._ck(self.lib.pcfd_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._ck(self.lib.pcfd_synchronize(self.h))
+
+    def set_cfl(self, cfl):
+        self._ck(self.lib.pcfd_set_cfl(self.h, float(cfl)))
+
+    def launch_count(self):
+        return int(self.lib.pcfd_launch_count(self.h))
+
+    # -- phases (names follow the reference functions they replace)
+    def lsq_coefficients(self):
+        self._ck(self.lib.pcfd_lsq_coefficients(self.h))
+
+    def update_bcs(self):
+        self._ck(self.lib.pcfd_update_bcs(self.h))
+
+    def gradient(self):
+        self._ck(self.lib.pcfd_gradient(self.h))
+
+    def limiter(self):
+        self._ck(self.lib.pcfd_limiter(self.h))
+
+    def residual(self, want_norms=False):
+        if not want_norms:
+            self._ck(self.lib.pcfd_residual(self.h, None))
+            return None
+        s = np.zeros(1 + NEQN)
+        self._ck(self.lib.pcfd_residual(self.h, _d(s)))
+        return s
+
+    def timestep(self, want_min=True):
+        if not want_min:
+            self._ck(self.lib.pcfd_timestep(self.h, None))
+            return None
+        d = C.c_double()
+        self._ck(self.lib.pcfd_timestep(self.h, C.byref(d)))
+        return d.value
+
+    def explicit_solve(self):
+        self._ck(self.lib.pcfd_explicit_solve(self.h))
+
+    def jacobian(self):
+        self._ck(self.lib.pcfd_jacobian(self.h))
+
+    def prepare_sgs(self):
+        self._ck(self.lib.pcfd_prepare_sgs(self.h))
+
+    def blank_x(self):
+        self._ck(self.lib.pcfd_blank_x(self.h))
+
+    def sgs(self, nsgs, want_ddq=True):
+        if not want_ddq:
+            self._ck(self.lib.pcfd_sgs(self.h, int(nsgs), None))
+            return None
+        d = C.c_double()
+        self._ck(self.lib.pcfd_sgs(self.h, int(nsgs), C.byref(d)))
+        return d.value
+
+    def apply_dq(self):
+        self._ck(self.lib.pcfd_apply_dq(self.h))
+
+    def explicit_iterate(self, refresh_dt=True, want_norms=False):
+        s = np.zeros(1 + NEQN) if want_norms else None
+        self._ck(self.lib.pcfd_explicit_iterate(self.h, int(refresh_dt), _d(s) if want_norms else None))
+        return s
+
+    def implicit_iterate(self, nsgs, refresh_jac=True, want_norms=False):
+        s = np.zeros(1 + NEQN) if want_norms else None
+        self._ck(self.lib.pcfd_implicit_iterate(self.h, int(refresh_jac), int(nsgs), _d(s) if want_norms else None, None))
+        return s
