@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""bench.py -- the hot-path benchmark (contract: see the task statement, section 4).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--n 118]
+
+Workload (BASELINE.json configs[1]): inviscid Euler on a synthetic ~10 M-cell
+tetrahedralised box (Kuhn box, n = 118 hexes per side: 9.86 M tets, 1.69 M nodes,
+11.7 M edges), second-order Roe + weighted-LSQ gradient + Venkatakrishnan limiter,
+explicit update.  One "step" = one explicit iteration exactly as
+SolutionSpace::NewtonIterate runs it with numberSGS = 0 (ucs/solutionSpace.tcc:640-904):
+ComputeTimesteps, UpdateBCs, Gradient::Compute, Limiter::Compute, ComputeResiduals,
+ExplicitSolve.  `value` = interior edges x steps / time: million edges per second
+through the WHOLE iteration; per-phase figures (residual-only Medges/s, SGS sweeps/s)
+ride along under "phases" / "sgs".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "explicit_iteration_throughput (UpdateBCs+LSQ gradient+Venkat limiter+Roe residual+timestep+update)"
+UNIT = "Medges/s"
+NEQN, NVARS, NTERMS = 5, 10, 9
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# SURVEY.md 8d algorithmic (compulsory) bytes per pass, 5-equation Euler
+def pass_bytes(ne, nn, nblocks=0):
+    neqn, nterms = NEQN, NTERMS
+    return {
+        "gradient": 8 * ne + nn * (24 + 8 * nterms + 48 + 24 * nterms),
+        "limiter": (8 * ne + nn * (8 * neqn + 16 * neqn)) + (8 * ne + nn * (8 * neqn + 24 * neqn + 24 + 16 * neqn) + nn * 8 * neqn)
+                   + (8 * ne + nn * (8 * neqn + 24 * neqn + 24 + 8 * neqn) + nn * 8 * neqn),
+        "residual": 40 * ne + nn * (8 * neqn + 24 * neqn + 8 * neqn + 24 + 8) + nn * 8 * neqn,
+        "timestep": 40 * ne + nn * (8 * neqn + 8) + nn * 8,
+        "sgs_sweep": 2 * (nblocks * 8 * neqn * neqn + 4 * nblocks + 4 * (nn + 1) + 4 * neqn * nn + 8 * neqn * (nn + 2 * nn)),
+    }
+
+
+# which kernels make up which reference pass
+PASS_KERNELS = {
+    "timestep": ["k_timestep"],
+    "update_bcs": ["k_update_bcs"],
+    "gradient": ["k_gradient"],
+    "limiter": ["k_limiter", "k_fill_int", "k_clip_edges", "k_clip_nodes", "k_limiter_final"],
+    "residual": ["k_flux_edges", "k_flux_bedges", "k_residual_gather"],
+    "update": ["k_explicit"],
+}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons while the timed region runs (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def reference_arm(args, rank):
+    """--impl reference: the reference's own CPU implementation (oracle/_ref, built from /root/reference by
+    oracle/Makefile) on all host cores, on a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    from oracle import ref_bench
+    cores = os.cpu_count() or 1
+    ranks = 1
+    while ranks * 2 <= min(cores, 64):
+        ranks *= 2
+    n = args.ref_n
+    if not ref_bench.available():
+        # the C port of the same loops (oracle/pcfd_oracle.c), single core
+        v, sample, ms = port_baseline(min(n, 40), max(1, args.steps))
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": sample},
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+    case = ref_bench.ReferenceCase(n, ranks, limiter=2, nsgs=0, cfl=0.5)
+    try:
+        if args.warmup > 0:
+            case.time(min(args.warmup, 1))
+        t = case.time(max(1, args.steps))
+    finally:
+        case.close()
+    per_it = t["t_timestep"] + t["t_update"] + t["t_gradient"] + t["t_limiter"] + t["t_residual"]
+    v = t["nedge"] / per_it / 1e6
+    sample = (f"Kuhn box n={n} ({6 * n ** 3} tets, {t['nnode']} nodes, {t['nedge']} edges), {ranks} reference ranks "
+              f"(process-based MPI shim, block partitions cut by the reference's udecomp), {max(1, args.steps)} iterations")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": per_it * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "inviscid Euler, Roe 2nd order + LSQ + Venkatakrishnan, explicit; " + sample},
+            "phases": {"residual_Medges_s": t["nedge"] / t["t_residual"] / 1e6,
+                       "gradient_limiter_Medges_s": t["nedge"] / (t["t_gradient"] + t["t_limiter"]) / 1e6,
+                       "seconds": {k: t[k] for k in t if k.startswith("t_")}},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": ranks, "kind": "reference", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def port_baseline(n, iters):
+    """Single-core C port (oracle/pcfd_oracle.c) of one explicit iteration on an n-box."""
+    from proteuscfd_b200.cases import box_case
+    from tests.oracle_lib import load_oracle
+    from tests.oracle_lib import oracle_for
+    mesh, params, q = box_case(n)
+    o = oracle_for(load_oracle(), mesh, params)
+    _, sw = o.lsq()
+    beta = np.zeros(1)
+    t0 = time.time()
+    for _ in range(iters):
+        dt, _ = o.timestep(q, beta)
+        o.update_bcs(q, beta)
+        grad = o.gradient(q, sw)
+        lim = o.limiter(q, grad)
+        b = o.residual(q, grad, lim, beta)
+        o.explicit_solve(q, b, dt)
+    el = (time.time() - t0) / iters
+    sample = f"Kuhn box n={n} ({mesh['nnode']} nodes, {mesh['nedge']} edges), C port of the reference loops, 1 core, {iters} iterations"
+    return mesh["nedge"] / el / 1e6, sample, el * 1e3
+
+
+def cpu_baseline(args):
+    """Bounded reference-CPU sample for the default line (rank 0, N = 1): ~10-30 s of CPU work."""
+    from oracle import ref_bench
+    if ref_bench.available():
+        cores = os.cpu_count() or 1
+        ranks = 1
+        while ranks * 2 <= min(cores, 64):
+            ranks *= 2
+        n = args.ref_n
+        case = ref_bench.ReferenceCase(n, ranks, limiter=2, nsgs=0, cfl=0.5)
+        try:
+            t = case.time(3)
+        finally:
+            case.close()
+        per_it = t["t_timestep"] + t["t_update"] + t["t_gradient"] + t["t_limiter"] + t["t_residual"]
+        sample = (f"Kuhn box n={n} ({t['nnode']} nodes, {t['nedge']} edges), unmodified reference (oracle/_ref/ref_harness), "
+                  f"{ranks} ranks, 3 iterations")
+        return {"value": t["nedge"] / per_it / 1e6, "unit": UNIT, "cores": ranks, "kind": "reference", "sample": sample,
+                "residual_Medges_s": t["nedge"] / t["t_residual"] / 1e6}
+    v, sample, _ = port_baseline(40, 3)
+    return {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=118, help="hexes per box side (118 -> ~10 M tets)")
+    ap.add_argument("--ref-n", type=int, default=48, help="box side of the bounded CPU reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sgs", action="store_true")
+    ap.add_argument("--sgs-n", type=int, default=0, help="box side for the SGS sub-benchmark (0: same as --n)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from proteuscfd_b200 import capi
+    from proteuscfd_b200.cases import box_case
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    W = max(3, args.warmup)
+    K = max(1, args.steps)
+    t_setup = time.time()
+    # weak scaling: every rank owns one box of the named size (independent partitions; the halo
+    # exchange of a cut mesh is the next row of SURVEY.md 8e and is not in this line yet)
+    mesh, params, q0 = box_case(args.n, device=f"cuda:{local_rank}", seed=1234 + rank)
+    ctx = capi.Context(mesh, params, device=local_rank)
+    # a real (non-default) torch stream: the library launches on it and torch.cuda.Event times it
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    ctx.set_stream(stream.cuda_stream)
+    ctx.lsq_coefficients()
+    ctx.set_field(capi.F_Q, q0)
+    ne, nn = ctx.nedge, ctx.nnode
+    t_setup = time.time() - t_setup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- device-resident timing
+    for _ in range(W):
+        ctx.explicit_iterate(refresh_dt=True)
+    ctx.profile(on=True, reset=True)
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(K):
+        ctx.explicit_iterate(refresh_dt=True)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - launches0
+    ctx.profile(on=False)
+    table = ctx.profile_table()
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / K
+    value = world * ne / (ms_step * 1e-3) / 1e6
+
+    # ---------------------------------------------------------------- end to end through the C ABI with HOST buffers
+    nq = ctx.field_size(capi.F_Q)
+    hq = torch.empty(nq, dtype=torch.float64).pin_memory()
+    hq.numpy()[:] = ctx.get_field(capi.F_Q)
+    hq_np = hq.numpy()
+    for _ in range(2):
+        ctx.set_field(capi.F_Q, hq_np)
+        ctx.explicit_iterate(refresh_dt=True)
+        ctx.get_field(capi.F_Q, out=hq_np)
+    Ke = max(3, K // 2)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(Ke):
+        ctx.set_field(capi.F_Q, hq_np)          # H2D of the step's input state (pinned)
+        ctx.explicit_iterate(refresh_dt=True)
+        ctx.get_field(capi.F_Q, out=hq_np)      # D2H of the updated state
+    e1.record(stream)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1) / Ke
+    if world > 1:
+        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * ne / (e2e_ms * 1e-3) / 1e6
+
+    # ---------------------------------------------------------------- per-pass roofline from the live kernel timings
+    peak, peak_src = measured_peaks()
+    pb = pass_bytes(ne, nn)
+    kern = {k: {"ms_avg": v[0] / max(v[1], 1), "launches_per_step": v[1] / K, "ms_per_step": v[0] / K} for k, v in table.items()}
+    passes = {}
+    for pname, ks in PASS_KERNELS.items():
+        ms = sum(kern[k]["ms_per_step"] for k in ks if k in kern)
+        if ms <= 0:
+            continue
+        d = {"ms_per_step": ms, "share": ms / ms_step}
+        if pname in pb:
+            d["algorithmic_bytes"] = pb[pname]
+            d["GBps"] = pb[pname] / (ms * 1e-3) / 1e9
+            d["frac_hbm"] = d["GBps"] / peak
+        passes[pname] = d
+    dominant = max((p for p in passes if "GBps" in passes[p]), key=lambda p: passes[p]["ms_per_step"])
+    roofline = {"bound": "hbm", "kernel": "+".join(k for k in PASS_KERNELS[dominant] if k in kern), "pass": dominant,
+                "achieved": passes[dominant]["GBps"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": passes[dominant]["frac_hbm"], "traffic": None,
+                "bytes_per_launch": passes[dominant]["algorithmic_bytes"], "ms_per_launch": passes[dominant]["ms_per_step"],
+                "note": "algorithmic bytes = SURVEY.md 8d compulsory bytes of the pass; the Roe flux is FP64-pipe-bound "
+                        "(see profiles/), so frac is reported for completeness, not as the limiter"}
+    step_bytes = sum(pb[p] for p in ("gradient", "limiter", "residual", "timestep"))
+    phases = {"residual_Medges_s": ne / (passes["residual"]["ms_per_step"] * 1e-3) / 1e6 if "residual" in passes else None,
+              "gradient_limiter_Medges_s": ne / ((passes["gradient"]["ms_per_step"] + passes["limiter"]["ms_per_step"]) * 1e-3) / 1e6,
+              "iteration_frac_hbm": step_bytes / (ms_step * 1e-3) / 1e9 / peak,
+              "passes": passes, "kernels": kern}
+
+    # ---------------------------------------------------------------- SGS sweeps/s (second half of the metric)
+    sgs = None
+    if not args.no_sgs and rank == 0 and world == 1:
+        sgs = sgs_bench(args, ctx, mesh, params, q0, peak, torch, stream, local_rank)
+
+    base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            base = cpu_baseline(args)
+        except Exception as e:   # never lose the GPU line to a baseline hiccup
+            base = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": f"failed: {e}"[:300]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[1]: inviscid Euler, synthetic Kuhn box n={args.n} ({6 * args.n ** 3} tets, "
+                                   f"{nn} nodes, {ne} edges) per GPU, Roe 2nd order + weighted LSQ + Venkatakrishnan, "
+                                   "explicit single-stage update (the reference has no multistage RK)",
+                       "parallelism": "1 box per GPU, no data-path collective (independent partitions)",
+                       "cache": "inputs larger than L2 (q 135 MB, qgrad 364 MB, edges 470 MB per pass); no flush needed",
+                       "setup_s": t_setup},
+            "roofline": roofline, "cpu_baseline": base,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": nq * 8,
+                    "d2h_bytes_per_step": nq * 8, "what": "pcfd_set_field(q) from pinned host memory + pcfd_explicit_iterate + "
+                                                          "pcfd_get_field(q) per step"},
+            "gpu_launches": int(launches), "clocks": clocks, "phases": phases, "sgs": sgs,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def sgs_bench(args, ctx, mesh, params, q0, peak, torch, stream, local_rank):
+    """SGS sweeps/s on the implicit version of the same case (5x5 blocks, colour-sorted numbering)."""
+    from proteuscfd_b200 import capi
+    from proteuscfd_b200.cases import box_case
+    n = args.sgs_n or args.n
+    ctx.close()
+    torch.cuda.empty_cache()
+    mesh, params, q = box_case(n, cfl=5.0, colored=True, device=f"cuda:{local_rank}")
+    c = capi.Context(mesh, params, device=local_rank)
+    c.set_stream(stream.cuda_stream)
+    c.lsq_coefficients()
+    c.set_field(capi.F_Q, q)
+    c.profile(on=True, reset=True)
+    c.implicit_iterate(2, refresh_jac=True)       # builds A, LU, 2 sweeps (warm-up)
+    c.blank_x()
+    c.sgs(2, want_ddq=False)
+    torch.cuda.synchronize()
+    tab0 = c.profile_table()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nsw = 10
+    e0.record(stream)
+    c.sgs(nsw, want_ddq=False)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / nsw
+    tab = c.profile_table()
+    _, nblocks = c.get_crs()[1].size, c.get_crs()[1].size
+    bytes_sweep = pass_bytes(c.nedge, c.nnode, nblocks)["sgs_sweep"]
+    out = {"sweeps_per_s": 1e3 / ms, "ms_per_sweep": ms, "nodes": c.nnode, "blocks": int(nblocks), "block": "5x5",
+           "levels_fwd_bwd": "colour-sorted numbering: one launch per colour per direction",
+           "algorithmic_bytes_per_sweep": bytes_sweep, "GBps": bytes_sweep / (ms * 1e-3) / 1e9,
+           "frac_hbm": bytes_sweep / (ms * 1e-3) / 1e9 / peak,
+           "jacobian_ms": {k: tab0[k][0] / tab0[k][1] for k in ("k_jac_edges", "k_jac_bnodes", "k_jac_diag", "k_lu_diag") if k in tab0},
+           "launches_per_sweep": (tab["k_sgs_level"][1] - tab0["k_sgs_level"][1]) / nsw}
+    c.close()
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -144,6 +144,15 @@ int pcfd_implicit_iterate(pcfd_ctx* ctx, int refresh_jac, int nsgs, double* sums
 /* number of CUDA kernels this context has launched since creation */
 long long pcfd_launch_count(const pcfd_ctx* ctx);
 
+/* Per-kernel device timing (CUDA events on the launch stream around every kernel), the
+   GPU-side counterpart of the reference's TimerList (timer.h:29-89; solutionSpace.tcc:34-43).
+   enable(1) starts recording, count() drains pending events and returns the number of
+   distinct kernels seen, get(i) returns the i-th kernel's name, summed milliseconds and launches. */
+int pcfd_profile_enable(pcfd_ctx* ctx, int on);
+int pcfd_profile_reset(pcfd_ctx* ctx);
+int pcfd_profile_count(pcfd_ctx* ctx);
+int pcfd_profile_get(pcfd_ctx* ctx, int i, const char** name, double* total_ms, long long* launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,7 @@ SYMBOLS = [
     "pcfd_get_crs", "pcfd_lsq_coefficients", "pcfd_update_bcs", "pcfd_gradient", "pcfd_limiter", "pcfd_residual",
     "pcfd_timestep", "pcfd_explicit_solve", "pcfd_jacobian", "pcfd_prepare_sgs", "pcfd_blank_x", "pcfd_sgs",
     "pcfd_apply_dq", "pcfd_explicit_iterate", "pcfd_implicit_iterate", "pcfd_launch_count",
+    "pcfd_profile_enable", "pcfd_profile_reset", "pcfd_profile_count", "pcfd_profile_get",
 ]
 
 
@@ -76,6 +77,10 @@ def load_library(path=LIB_PATH):
     lib.pcfd_implicit_iterate.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp]
     lib.pcfd_launch_count.restype = C.c_longlong
     lib.pcfd_launch_count.argtypes = [C.c_void_p]
+    lib.pcfd_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    lib.pcfd_profile_reset.argtypes = [C.c_void_p]
+    lib.pcfd_profile_count.argtypes = [C.c_void_p]
+    lib.pcfd_profile_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), _dp, C.POINTER(C.c_longlong)]
     for name in ("pcfd_destroy", "pcfd_synchronize", "pcfd_lsq_coefficients", "pcfd_update_bcs", "pcfd_gradient",
                  "pcfd_limiter", "pcfd_explicit_solve", "pcfd_jacobian", "pcfd_prepare_sgs", "pcfd_blank_x",
                  "pcfd_apply_dq"):
@@ -179,6 +184,20 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.pcfd_launch_count(self.h))
+
+    def profile(self, on=True, reset=False):
+        if reset:
+            self._ck(self.lib.pcfd_profile_reset(self.h))
+        self._ck(self.lib.pcfd_profile_enable(self.h, int(on)))
+
+    def profile_table(self):
+        """{kernel name: (total ms, launches)} accumulated since the last reset."""
+        out = {}
+        for i in range(self.lib.pcfd_profile_count(self.h)):
+            name, ms, n = C.c_char_p(), C.c_double(), C.c_longlong()
+            self._ck(self.lib.pcfd_profile_get(self.h, i, C.byref(name), C.byref(ms), C.byref(n)))
+            out[name.value.decode()] = (ms.value, n.value)
+        return out
 
     # -- phases (names follow the reference functions they replace)
     def lsq_coefficients(self):

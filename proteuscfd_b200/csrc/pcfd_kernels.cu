@@ -813,6 +813,13 @@ struct pcfd_ctx {
   std::vector<void*> allocs;
   std::string err;
   long long launches = 0;
+  // optional per-kernel timing with CUDA events on the launch stream (pcfd_profile_*)
+  bool prof = false;
+  struct ProfRec { const char* name; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof_pending;
+  std::vector<cudaEvent_t> prof_pool;
+  struct ProfAcc { std::string name; double ms = 0; long long n = 0; };
+  std::vector<ProfAcc> prof_acc;
 };
 
 namespace {
@@ -829,12 +836,48 @@ int fail(pcfd_ctx* c, const std::string& msg) {
     cudaError_t e_ = (call);                                                                           \
     if (e_ != cudaSuccess) return fail(c, std::string(#call) + ": " + cudaGetErrorString(e_));         \
   } while (0)
+#define PROF(name)                                                                                     \
+  do {                                                                                                 \
+    if (c->prof) prof_begin(c, name);                                                                  \
+  } while (0)
 #define LAUNCH_CHECK()                                                                                 \
   do {                                                                                                 \
     c->launches++;                                                                                     \
+    if (c->prof) prof_end(c);                                                                          \
     cudaError_t e_ = cudaGetLastError();                                                               \
     if (e_ != cudaSuccess) return fail(c, std::string("kernel launch: ") + cudaGetErrorString(e_));    \
   } while (0)
+
+cudaEvent_t prof_event(pcfd_ctx* c) {
+  if (!c->prof_pool.empty()) { cudaEvent_t e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+void prof_begin(pcfd_ctx* c, const char* name) {
+  pcfd_ctx::ProfRec r{name, prof_event(c), prof_event(c)};
+  cudaEventRecord(r.a, c->stream);
+  c->prof_pending.push_back(r);
+}
+void prof_end(pcfd_ctx* c) {
+  if (!c->prof_pending.empty()) cudaEventRecord(c->prof_pending.back().b, c->stream);
+}
+void prof_drain(pcfd_ctx* c) {
+  cudaStreamSynchronize(c->stream);
+  for (auto& r : c->prof_pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      pcfd_ctx::ProfAcc* acc = nullptr;
+      for (auto& a : c->prof_acc) if (a.name == r.name) acc = &a;
+      if (!acc) { c->prof_acc.push_back({r.name, 0.0, 0}); acc = &c->prof_acc.back(); }
+      acc->ms += ms;
+      acc->n++;
+    }
+    c->prof_pool.push_back(r.a);
+    c->prof_pool.push_back(r.b);
+  }
+  c->prof_pending.clear();
+}
 
 template <class T>
 int dev_alloc(pcfd_ctx* c, T** p, size_t n) {
@@ -1067,6 +1110,34 @@ int pcfd_set_cfl(pcfd_ctx* c, double cfl) {
 }
 long long pcfd_launch_count(const pcfd_ctx* c) { return c ? c->launches : 0; }
 
+int pcfd_profile_enable(pcfd_ctx* c, int on) {
+  if (!c) return 1;
+  cudaSetDevice(c->device);
+  if (!on && c->prof) prof_drain(c);
+  c->prof = on != 0;
+  return 0;
+}
+int pcfd_profile_reset(pcfd_ctx* c) {
+  if (!c) return 1;
+  cudaSetDevice(c->device);
+  prof_drain(c);
+  c->prof_acc.clear();
+  return 0;
+}
+int pcfd_profile_count(pcfd_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  prof_drain(c);
+  return (int)c->prof_acc.size();
+}
+int pcfd_profile_get(pcfd_ctx* c, int i, const char** name, double* total_ms, long long* launches) {
+  if (!c || i < 0 || i >= (int)c->prof_acc.size()) return 1;
+  if (name) *name = c->prof_acc[i].name.c_str();
+  if (total_ms) *total_ms = c->prof_acc[i].ms;
+  if (launches) *launches = c->prof_acc[i].n;
+  return 0;
+}
+
 static int ensure_matrix(pcfd_ctx* c) {
   if (c->f[PCFD_F_A]) return 0;
   c->fsize[PCFD_F_A] = (size_t)c->nblocks * NEQN2;
@@ -1125,6 +1196,7 @@ int pcfd_get_crs(pcfd_ctx* c, int* ia, int* ja, int* iau, int* pv) {
 int pcfd_lsq_coefficients(pcfd_ctx* c) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
+  PROF("k_lsq_coeff");
   k_lsq_coeff<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->f[PCFD_F_LSQ_S], c->f[PCFD_F_LSQ_SW]);
   LAUNCH_CHECK();
   return 0;
@@ -1134,6 +1206,7 @@ int pcfd_update_bcs(pcfd_ctx* c) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
   if (c->nbn == 0) return 0;
+  PROF("k_update_bcs");
   k_update_bcs<<<nblk(c->nbn, 128), 128, 0, c->stream>>>(c->dm, c->bp, c->bnodes, c->nbn, c->f[PCFD_F_Q]);
   LAUNCH_CHECK();
   return 0;
@@ -1142,6 +1215,7 @@ int pcfd_update_bcs(pcfd_ctx* c) {
 int pcfd_gradient(pcfd_ctx* c) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
+  PROF("k_gradient");
   k_gradient<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->f[PCFD_F_Q], c->f[PCFD_F_LSQ_SW], c->f[PCFD_F_QGRAD]);
   LAUNCH_CHECK();
   return 0;
@@ -1152,17 +1226,20 @@ int pcfd_limiter(pcfd_ctx* c) {
   CK(cudaSetDevice(c->device));
   const int type = c->prm.limiter;
   double* lim = c->f[PCFD_F_LIMITER];
+  PROF("k_limiter");
   k_limiter<<<nblk(c->nn, 128), 128, 0, c->stream>>>(c->dm, type, c->prm.chi, c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD], lim);
   LAUNCH_CHECK();
   if (type == 0) return 0;
   // pressure clip: iterate (edges -> flags, nodes -> first clipping edge) to the fixed point
   int cur = 0;
   bool clipped = false;
+  PROF("k_fill_int");
   k_fill_int<<<nblk(c->nnode, 256), 256, 0, c->stream>>>(c->tclip[0], c->nnode, INT_MAX);
   LAUNCH_CHECK();
   for (int it = 0; it < c->nedge + 2; it++) {
     int hflags[2] = {0, 0};
     CK(cudaMemsetAsync(c->dflags, 0, 2 * sizeof(int), c->stream));
+    PROF("k_clip_edges");
     k_clip_edges<<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, c->prm.chi, c->prm.gamma, c->f[PCFD_F_Q],
                                                              c->f[PCFD_F_QGRAD], lim, c->tclip[cur], c->clipflag,
                                                              c->dflags);
@@ -1173,6 +1250,7 @@ int pcfd_limiter(pcfd_ctx* c) {
       if (!hflags[0]) break;   // no edge clips anything: the common case
       clipped = true;
     }
+    PROF("k_clip_nodes");
     k_clip_nodes<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->clipflag, c->tclip[cur], c->tclip[cur ^ 1],
                                                              c->dflags + 1);
     LAUNCH_CHECK();
@@ -1181,6 +1259,7 @@ int pcfd_limiter(pcfd_ctx* c) {
     CK(cudaStreamSynchronize(c->stream));
     if (!hflags[1]) break;     // tclip reproduced itself: fixed point
   }
+  PROF("k_limiter_final");
   k_limiter_final<<<nblk((long long)c->nn * 5, 256), 256, 0, c->stream>>>(c->nn, c->nnode, clipped ? c->tclip[cur] : nullptr,
                                                                          lim);
   LAUNCH_CHECK();
@@ -1189,25 +1268,30 @@ int pcfd_limiter(pcfd_ctx* c) {
 
 static int run_flux(pcfd_ctx* c) {
   if (c->nedge) {
+    PROF("k_flux_edges");
     k_flux_edges<<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, c->prm.sorder, c->prm.chi, c->prm.gamma,
                                                              c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD], c->f[PCFD_F_LIMITER],
                                                              c->flux);
     LAUNCH_CHECK();
   }
   if (c->nb) {
+    PROF("k_flux_bedges");
     k_flux_bedges<<<nblk(c->nb, 128), 128, 0, c->stream>>>(c->dm, c->prm.sorder, c->prm.chi, c->prm.gamma,
                                                            c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD], c->f[PCFD_F_LIMITER],
                                                            c->bflux);
     LAUNCH_CHECK();
   }
+  PROF("k_residual_gather");
   k_residual_gather<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->flux, c->bflux, c->f[PCFD_F_B]);
   LAUNCH_CHECK();
   return 0;
 }
 
 static int run_sumsq(pcfd_ctx* c, const double* v, int nrows, double* host_out) {
+  PROF("k_sumsq_partial");
   k_sumsq_partial<256, NEQN><<<RED_BLOCKS, 256, 0, c->stream>>>(v, nrows, c->red);
   LAUNCH_CHECK();
+  PROF("k_sumsq_final");
   k_sumsq_final<256, NEQN><<<1, 256, 0, c->stream>>>(c->red, RED_BLOCKS, c->redout);
   LAUNCH_CHECK();
   if (host_out) {
@@ -1228,12 +1312,15 @@ int pcfd_residual(pcfd_ctx* c, double* sumsq) {
 int pcfd_timestep(pcfd_ctx* c, double* dtmin) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
+  PROF("k_timestep");
   k_timestep<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->prm.gamma, c->prm.cfl, c->f[PCFD_F_Q],
                                                          c->f[PCFD_F_TIMESTEP]);
   LAUNCH_CHECK();
   if (dtmin) {
+    PROF("k_min_partial");
     k_min_partial<256><<<RED_BLOCKS, 256, 0, c->stream>>>(c->f[PCFD_F_TIMESTEP], c->nnode, c->red);
     LAUNCH_CHECK();
+    PROF("k_min_final");
     k_min_final<256><<<1, 256, 0, c->stream>>>(c->red, RED_BLOCKS, c->redout + 8);
     LAUNCH_CHECK();
     CK(cudaMemcpyAsync(dtmin, c->redout + 8, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -1245,6 +1332,7 @@ int pcfd_timestep(pcfd_ctx* c, double* dtmin) {
 int pcfd_explicit_solve(pcfd_ctx* c) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
+  PROF("k_explicit");
   k_explicit<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->nnode, c->prm.gamma, c->f[PCFD_F_B], c->f[PCFD_F_TIMESTEP],
                                                          c->vol, c->f[PCFD_F_X], c->f[PCFD_F_Q]);
   LAUNCH_CHECK();
@@ -1254,6 +1342,7 @@ int pcfd_explicit_solve(pcfd_ctx* c) {
 int pcfd_apply_dq(pcfd_ctx* c) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
+  PROF("k_apply_dq");
   k_apply_dq<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->nnode, c->prm.gamma, c->f[PCFD_F_X], c->f[PCFD_F_Q]);
   LAUNCH_CHECK();
   return 0;
@@ -1267,13 +1356,16 @@ int pcfd_jacobian(pcfd_ctx* c) {
   CK(cudaMemsetAsync(A, 0, c->fsize[PCFD_F_A] * sizeof(double), c->stream));   // CRSMatrix::Blank
   c->ludiag = false;
   if (c->nedge) {
+    PROF("k_jac_edges");
     k_jac_edges<<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, c->prm.gamma, c->f[PCFD_F_Q], c->posLR, c->posRL, A);
     LAUNCH_CHECK();
   }
   if (c->nbn) {
+    PROF("k_jac_bnodes");
     k_jac_bnodes<<<nblk(c->nbn, 64), 64, 0, c->stream>>>(c->dm, c->bp, c->bnodes, c->nbn, c->f[PCFD_F_Q], c->iau, c->bpos, A);
     LAUNCH_CHECK();
   }
+  PROF("k_jac_diag");
   k_jac_diag<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->iau, c->posLR, c->posRL, c->f[PCFD_F_TIMESTEP], A);
   LAUNCH_CHECK();
   return 0;
@@ -1284,6 +1376,7 @@ int pcfd_prepare_sgs(pcfd_ctx* c) {
   CK(cudaSetDevice(c->device));
   if (ensure_matrix(c)) return 1;
   if (c->ludiag) return 0;   // CRSMatrix::ludiag (crsmatrix.tcc:844)
+  PROF("k_lu_diag");
   k_lu_diag<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->nnode, c->iau, c->f[PCFD_F_A], c->pv);
   LAUNCH_CHECK();
   c->ludiag = true;
@@ -1311,6 +1404,7 @@ int pcfd_sgs(pcfd_ctx* c, int nsgs, double* ddq) {
       for (size_t l = 0; l + 1 < off.size(); l++) {
         const int nr = off[l + 1] - off[l];
         const int warps = (nr + RPW - 1) / RPW;
+        PROF("k_sgs_level");
         k_sgs_level<<<nblk((long long)warps * 32, 128), 128, 0, c->stream>>>(rows + off[l], nr, c->ia, c->ja, c->iau, A,
                                                                              c->pv, c->f[PCFD_F_B], x);
         LAUNCH_CHECK();
@@ -1318,8 +1412,10 @@ int pcfd_sgs(pcfd_ctx* c, int nsgs, double* ddq) {
     }
     // xNorm of the last two sweeps only (crs.tcc:149-172 uses nothing else)
     if (ddq && s >= nsgs - 2) {
+      PROF("k_sumsq_partial");
       k_sumsq_partial<256, NEQN><<<RED_BLOCKS, 256, 0, c->stream>>>(x, c->nnode, c->red);
       LAUNCH_CHECK();
+      PROF("k_sumsq_final");
       k_sumsq_final<256, NEQN><<<1, 256, 0, c->stream>>>(c->red, RED_BLOCKS, c->redout + ((s == nsgs - 1) ? 0 : 8));
       LAUNCH_CHECK();
     }

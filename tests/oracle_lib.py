@@ -124,6 +124,17 @@ class Oracle:
         return x, d
 
 
+def oracle_for(lib, mesh, params):
+    """Bind the C oracle to a mesh/params pair in the C-ABI dict form (proteuscfd_b200.cases)."""
+    g = {k: np.asarray(mesh[k]) for k in ("edges_n", "edges_a", "bedges_n", "bedges_a", "bedges_bctype", "xyz", "vol",
+                                          "ipsp", "psp")}
+    g["qinf"] = np.asarray(params["qinf"])
+    meta = {k: mesh[k] for k in ("nnode", "gnode", "nbnode", "nedge", "nbedge", "ngedge")}
+    meta.update(limiter=params["limiter"], sorder=params["sorder"], no_cvbc=params["no_cvbc"], gamma=params["gamma"],
+                chi=params["chi"], cfl=params["cfl"])
+    return Oracle(lib, g, meta)
+
+
 def load_oracle():
     so = os.path.join(ORACLE_DIR, "libpcfd_oracle.so")
     src = os.path.join(ORACLE_DIR, "pcfd_oracle.c")

@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""Small driver for ncu: one explicit and one implicit iteration of the hot path at bench size,
+bracketed by cudaProfilerStart/Stop so `ncu --profile-from-start off` sees only those launches.
+
+    ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/prof \
+        python tools/profile_run.py --n 118
+"""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=118)
+    ap.add_argument("--nsgs", type=int, default=1)
+    ap.add_argument("--explicit-only", action="store_true")
+    args = ap.parse_args()
+    import torch
+    from proteuscfd_b200 import capi
+    from proteuscfd_b200.cases import box_case
+    mesh, params, q = box_case(args.n, colored=True, device="cuda:0")
+    ctx = capi.Context(mesh, params, device=0)
+    ctx.lsq_coefficients()
+    ctx.set_field(capi.F_Q, q)
+    ctx.explicit_iterate(refresh_dt=True)      # warm-up
+    ctx.synchronize()
+    torch.cuda.profiler.start()
+    ctx.explicit_iterate(refresh_dt=True)
+    if not args.explicit_only:
+        ctx.set_cfl(5.0)
+        ctx.implicit_iterate(args.nsgs, refresh_jac=True)
+    ctx.synchronize()
+    torch.cuda.profiler.stop()
+    print("profiled launches done; total launches", ctx.launch_count())
+
+
+if __name__ == "__main__":
+    main()
