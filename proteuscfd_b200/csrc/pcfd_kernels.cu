@@ -25,6 +25,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -568,6 +569,33 @@ __global__ void __launch_bounds__(128) k_update_bcs(DevMesh m, eq::BcParams bp, 
   if (touched) store_q10(q, n, QL);
 }
 
+// The same update with one thread per half-edge, for left nodes that own no Dirichlet-type
+// half-edge (those rewrite QL itself and stay on the sequential kernel above).  The only
+// coupling between two half-edges of a node is then ComputeAuxiliaryVariables(QL) at the end
+// of each call (bc.tcc:1392-1396): the first half-edge sees the stored aux values, every later
+// one sees them recomputed from QL[0..4] -- which a thread reproduces locally.
+__global__ void __launch_bounds__(128) k_update_bcs_edges(DevMesh m, eq::BcParams bp, const int* __restrict__ list, int n,
+                                                           const unsigned char* __restrict__ bfirst, double* q) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int be = list[t];
+  const int2 lr = m.ben[be];
+  const bool first = bfirst[be] != 0;
+  double QL[NVARS], QR[NVARS], av[4];
+  load_q10(q, lr.x, QL);
+  load_q10(q, lr.y, QR);
+  load_avec(m.bea, be, av);
+  if (!first) eq::aux(QL, bp.gamma);
+  eq::boundary_variables(bp, QL, QR, av, m.bctype[be]);
+  store_q10(q, lr.y, QR);
+  if (first) {   // only aux of QL can have changed
+    double2* pq = reinterpret_cast<double2*>(q + (size_t)lr.x * NVARS);
+    q[(size_t)lr.x * NVARS + 5] = QL[5];
+    pq[3] = make_double2(QL[6], QL[7]);
+    pq[4] = make_double2(QL[8], QL[9]);
+  }
+}
+
 // ====================================================================== Jacobian
 // Kernel_NumJac (jacobian.tcc:254-304): one-sided finite differences, h = 1e-8, of the
 // FIRST-ORDER flux; writes A(l,r) = dF/dqR and A(r,l) = -dF/dqL into their slots.
@@ -604,60 +632,89 @@ __global__ void __launch_bounds__(128) k_jac_edges(DevMesh m, double gamma, cons
   }
 }
 
-// Bkernel_NumJac (jacobian.tcc:459-544), boundaryJacEval == 0: per boundary node, in
-// half-edge order.  Writes the phantom-node state like the reference does, accumulates
-// dF/dqL into the node's diagonal block and, for ghost half-edges, dF/dqR into A(l,ghost).
-__global__ void __launch_bounds__(64) k_jac_bnodes(DevMesh m, eq::BcParams bp, const int* __restrict__ bnodes, int nb,
-                                                    double* __restrict__ q, const int* __restrict__ iau,
-                                                    const int* __restrict__ bpos, double* __restrict__ A) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nb) return;
+// Bkernel_NumJac (jacobian.tcc:459-544), boundaryJacEval == 0, for ONE half-edge: updates the
+// phantom state like the reference does, writes dF/dqL to bdiag[be] (summed into the node's
+// diagonal block, in half-edge order, by k_jac_diag) and, for ghost half-edges, dF/dqR to A(l,ghost).
+__device__ __forceinline__ void jac_half_edge(const DevMesh& m, const eq::BcParams& bp, int be, double* QL, double* q,
+                                              const int* __restrict__ bpos, double* __restrict__ bdiag,
+                                              double* __restrict__ A) {
   const double h = 1.0e-8;
   const double gamma = bp.gamma;
+  const int type = m.bctype[be];
+  const int r = m.ben[be].y;
+  const bool ghost = is_ghost(m, r);
+  double QR[NVARS], av[4], fS[5];
+  load_q10(q, r, QR);
+  load_avec(m.bea, be, av);
+  eq::boundary_variables(bp, QL, QR, av, type);
+  if (type != PCFD_BC_PARALLEL) store_q10(q, r, QR);
+  eq::numerical_flux(QL, QR, av, 0.0, gamma, fS);
+  double* pR = ghost ? A + (size_t)bpos[be] * NEQN2 : nullptr;
+  double* bd = bdiag + (size_t)be * NEQN2;
+#pragma unroll 1
+  for (int i = 0; i < 5; i++) {
+    double QPL[NVARS], QPR[NVARS], fL[5], fR[5];
+#pragma unroll
+    for (int j = 0; j < NVARS; j++) { QPL[j] = QL[j]; QPR[j] = QR[j]; }
+    QPL[i] += h;
+    QPR[i] += h;
+    eq::aux(QPL, gamma);
+    eq::aux(QPR, gamma);
+    if (ghost) {
+      eq::numerical_flux(QL, QPR, av, 0.0, gamma, fR);
+      eq::numerical_flux(QPL, QR, av, 0.0, gamma, fL);
+#pragma unroll
+      for (int j = 0; j < 5; j++) pR[j * 5 + i] = 0.0 + (fR[j] - fS[j]) / h;
+    } else {
+#pragma unroll
+      for (int j = 0; j < NVARS; j++) QPR[j] = QR[j];
+      eq::aux(QPR, gamma);
+      eq::boundary_variables(bp, QPL, QPR, av, type);
+      eq::numerical_flux(QPL, QPR, av, 0.0, gamma, fL);
+    }
+#pragma unroll
+    for (int j = 0; j < 5; j++) bd[j * 5 + i] = (fL[j] - fS[j]) / h;
+  }
+}
+
+// nodes that own a Dirichlet-type half-edge: sequential over the node's half-edges
+__global__ void __launch_bounds__(64) k_jac_bnodes(DevMesh m, eq::BcParams bp, const int* __restrict__ bnodes, int nb,
+                                                    double* q, const int* __restrict__ bpos, double* __restrict__ bdiag,
+                                                    double* __restrict__ A) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nb) return;
   const int n = bnodes[t];
-  double* dg = A + (size_t)iau[n] * NEQN2;
   double QL[NVARS];
   load_q10(q, n, QL);
   for (int k = m.adjp[n]; k < m.adjp[n + 1]; k++) {
     const int2 a = m.adj[k];
     if (a.y < m.nedge) continue;
-    const int be = a.y - m.nedge;
-    const int type = m.bctype[be];
-    const int r = a.x & 0x7fffffff;
-    const bool ghost = is_ghost(m, r);
-    double QR[NVARS], av[4], fS[5];
-    load_q10(q, r, QR);
-    load_avec(m.bea, be, av);
-    eq::boundary_variables(bp, QL, QR, av, type);
-    if (type != PCFD_BC_PARALLEL) store_q10(q, r, QR);
-    eq::numerical_flux(QL, QR, av, 0.0, gamma, fS);
-    double* pR = ghost ? A + (size_t)bpos[be] * NEQN2 : nullptr;
-#pragma unroll 1
-    for (int i = 0; i < 5; i++) {
-      double QPL[NVARS], QPR[NVARS], fL[5], fR[5];
-#pragma unroll
-      for (int j = 0; j < NVARS; j++) { QPL[j] = QL[j]; QPR[j] = QR[j]; }
-      QPL[i] += h;
-      QPR[i] += h;
-      eq::aux(QPL, gamma);
-      eq::aux(QPR, gamma);
-      if (ghost) {
-        eq::numerical_flux(QL, QPR, av, 0.0, gamma, fR);
-        eq::numerical_flux(QPL, QR, av, 0.0, gamma, fL);
-#pragma unroll
-        for (int j = 0; j < 5; j++) pR[j * 5 + i] = 0.0 + (fR[j] - fS[j]) / h;
-      } else {
-#pragma unroll
-        for (int j = 0; j < NVARS; j++) QPR[j] = QR[j];
-        eq::aux(QPR, gamma);
-        eq::boundary_variables(bp, QPL, QPR, av, type);
-        eq::numerical_flux(QPL, QPR, av, 0.0, gamma, fL);
-      }
-#pragma unroll
-      for (int j = 0; j < 5; j++) dg[j * 5 + i] += (fL[j] - fS[j]) / h;
-    }
+    jac_half_edge(m, bp, a.y - m.nedge, QL, q, bpos, bdiag, A);
   }
   store_q10(q, n, QL);
+}
+
+// all other half-edges, one thread each (see k_update_bcs_edges for why this is the same sequence)
+__global__ void __launch_bounds__(64) k_jac_bedges(DevMesh m, eq::BcParams bp, const int* __restrict__ list, int n,
+                                                    const unsigned char* __restrict__ bfirst, double* q,
+                                                    const int* __restrict__ bpos, double* __restrict__ bdiag,
+                                                    double* __restrict__ A) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int be = list[t];
+  const int l = m.ben[be].x;
+  const int type = m.bctype[be];
+  const bool first = bfirst[be] != 0;
+  double QL[NVARS];
+  load_q10(q, l, QL);
+  if (!first && type != PCFD_BC_PARALLEL) eq::aux(QL, bp.gamma);
+  jac_half_edge(m, bp, be, QL, q, bpos, bdiag, A);
+  if (first && type != PCFD_BC_PARALLEL) {
+    double2* pq = reinterpret_cast<double2*>(q + (size_t)l * NVARS);
+    q[(size_t)l * NVARS + 5] = QL[5];
+    pq[3] = make_double2(QL[6], QL[7]);
+    pq[4] = make_double2(QL[8], QL[9]);
+  }
 }
 
 // Kernel_Diag_NumJac (jacobian.tcc:434-456) + ContributeTemporalTerms (:214-250 ->
@@ -665,14 +722,23 @@ __global__ void __launch_bounds__(64) k_jac_bnodes(DevMesh m, eq::BcParams bp, c
 // += vol/dt on its diagonal.
 __global__ void __launch_bounds__(128) k_jac_diag(DevMesh m, const int* __restrict__ iau, const int* __restrict__ posLR,
                                                    const int* __restrict__ posRL, const double* __restrict__ dt,
-                                                   double* __restrict__ A) {
+                                                   const double* __restrict__ bdiag, double* A) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= m.nnode) return;
   double* dg = A + (size_t)iau[n] * NEQN2;
   double d[NEQN2];
 #pragma unroll
-  for (int k = 0; k < NEQN2; k++) d[k] = dg[k];
-  for (int k = m.adjp[n]; k < m.adjp[n + 1]; k++) {
+  for (int k = 0; k < NEQN2; k++) d[k] = 0.0;
+  const int kbeg = m.adjp[n], kend = m.adjp[n + 1];
+  // Bdriver runs before the diagonal pass: half-edge terms first, in half-edge order
+  for (int k = kbeg; k < kend; k++) {
+    const int2 a = m.adj[k];
+    if (a.y < m.nedge) continue;
+    const double* src = bdiag + (size_t)(a.y - m.nedge) * NEQN2;
+#pragma unroll
+    for (int kk = 0; kk < NEQN2; kk++) d[kk] += __ldg(src + kk);
+  }
+  for (int k = kbeg; k < kend; k++) {
     const int2 a = m.adj[k];
     if (a.y >= m.nedge) break;
     // this node is the right node: the other row's block for column n is A(l,r) at posLR
@@ -724,10 +790,11 @@ __global__ void __launch_bounds__(128) k_lu_diag(int nnode, const int* __restric
 // owns block-row i, accumulates rhs[i] -= (M_k x_k)[i] block after block in ja order
 // (MatVecMult, matrix.h:63-74), the lanes exchange rhs by shuffle and each runs the
 // permuted LuSolve (matrix.h:237-264) redundantly; lane i stores x[i].
+template <int U>
 __global__ void __launch_bounds__(128) k_sgs_level(const int* __restrict__ rows, int nrows, const int* __restrict__ ia,
                                                     const int* __restrict__ ja, const int* __restrict__ iau,
                                                     const double* __restrict__ A, const int* __restrict__ pv,
-                                                    const double* __restrict__ b, double* __restrict__ x) {
+                                                    const double* __restrict__ b, double* x) {
   constexpr int RPW = 32 / NEQN;   // rows per warp
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -738,24 +805,48 @@ __global__ void __launch_bounds__(128) k_sgs_level(const int* __restrict__ rows,
   const unsigned mask = __ballot_sync(0xffffffffu, active);
   if (!active) return;
   const int row = rows[slot];
-  double rhs = b[(size_t)row * NEQN + i];
-  const int k0 = ia[row], k1 = ia[row + 1];
-  for (int k = k0 + 1; k < k1; k++) {
-    const double* a = A + (size_t)k * NEQN2 + i * NEQN;
-    const double* xv = x + (size_t)ja[k] * NEQN;
-    double v = a[0] * xv[0];
+  const int k0 = __ldg(ia + row), k1 = __ldg(ia + row + 1);
+  int p[NEQN];
 #pragma unroll
-    for (int j = 1; j < NEQN; j++) v += a[j] * xv[j];
+  for (int j = 0; j < NEQN; j++) p[j] = __ldg(pv + (size_t)row * NEQN + j);
+  double rhs = __ldg(b + (size_t)row * NEQN + i);
+  int k = k0 + 1;
+  // U blocks at a time: all the (streaming, read-once) matrix loads and the x gathers of the
+  // group are issued before the first use, the arithmetic stays in ja order
+  for (; k + U <= k1; k += U) {
+    int col[U];
+    double a[U][NEQN], xv[U][NEQN];
+#pragma unroll
+    for (int u = 0; u < U; u++) col[u] = __ldg(ja + k + u);
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+      for (int j = 0; j < NEQN; j++) a[u][j] = __ldcs(A + (size_t)(k + u) * NEQN2 + i * NEQN + j);
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+      for (int j = 0; j < NEQN; j++) xv[u][j] = x[(size_t)col[u] * NEQN + j];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      double v = a[u][0] * xv[u][0];
+#pragma unroll
+      for (int j = 1; j < NEQN; j++) v += a[u][j] * xv[u][j];
+      rhs -= v;
+    }
+  }
+  for (; k < k1; k++) {
+    const double* a = A + (size_t)k * NEQN2 + i * NEQN;
+    const double* xv = x + (size_t)__ldg(ja + k) * NEQN;
+    double v = __ldcs(a) * xv[0];
+#pragma unroll
+    for (int j = 1; j < NEQN; j++) v += __ldcs(a + j) * xv[j];
     rhs -= v;
   }
   // gather the full right-hand side of this row into every lane of the group
   double bb[NEQN], xx[NEQN];
 #pragma unroll
   for (int j = 0; j < NEQN; j++) bb[j] = __shfl_sync(mask, rhs, grp * NEQN + j);
-  const double* d = A + (size_t)iau[row] * NEQN2;
-  int p[NEQN];
-#pragma unroll
-  for (int j = 0; j < NEQN; j++) p[j] = pv[(size_t)row * NEQN + j];
+  const double* d = A + (size_t)__ldg(iau + row) * NEQN2;
   // forward: x_r = b[p_r] - sum_{j<r} a[p_r][j] x_j
 #pragma unroll
   for (int r = 0; r < NEQN; r++) {
@@ -801,8 +892,13 @@ struct pcfd_ctx {
   size_t fsize[PCFD_F_COUNT] = {};
   int2 *en = nullptr, *ben = nullptr, *adj = nullptr;
   double *ea = nullptr, *bea = nullptr, *xyz = nullptr, *vol = nullptr;
-  int *bctype = nullptr, *adjp = nullptr, *bnodes = nullptr;
-  int nbn = 0;
+  int *bctype = nullptr, *adjp = nullptr;
+  // half-edge work lists: nodes owning a Dirichlet-type half-edge are walked sequentially (bnodes),
+  // every other half-edge gets its own thread (blist: BC half-edges first, then ghost half-edges)
+  int *bnodes = nullptr, *blist = nullptr;
+  unsigned char* bfirst = nullptr;
+  int nbn = 0, nblist = 0, nblist_bc = 0;
+  double* bdiag = nullptr;
   double *flux = nullptr, *bflux = nullptr, *red = nullptr, *redout = nullptr;
   unsigned char* clipflag = nullptr;
   int *tclip[2] = {nullptr, nullptr}, *dflags = nullptr;
@@ -810,6 +906,7 @@ struct pcfd_ctx {
   int *rows_f = nullptr, *rows_b = nullptr;
   std::vector<int> lev_f, lev_b;   // level offsets into rows_f / rows_b
   bool ludiag = false;
+  int sgs_unroll = 4;      // blocks in flight per lane in k_sgs_level (PCFD_SGS_UNROLL overrides, for tuning)
   std::vector<void*> allocs;
   std::string err;
   long long launches = 0;
@@ -957,6 +1054,7 @@ int pcfd_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int devic
   c = new pcfd_ctx();
   struct Guard { pcfd_ctx* c; bool ok = false; ~Guard() { if (!ok) { g_create_err = c->err; pcfd_destroy(c); } } } guard{c};
   c->device = device;
+  if (const char* e = getenv("PCFD_SGS_UNROLL")) c->sgs_unroll = atoi(e);
   CK(cudaSetDevice(device));
   CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
@@ -997,11 +1095,27 @@ int pcfd_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int devic
       adj[cur[l]++] = make_int2(r, nedge + e);
     }
   }
-  std::vector<int> bnodes;
+  std::vector<int> bnodes, blist;
+  std::vector<unsigned char> bfirst(std::max(nb, 1), 0);
   {
-    std::vector<char> has(nnode, 0);
-    for (int e = 0; e < nb; e++) has[mesh->bedges_n[2 * e]] = 1;
-    for (int i = 0; i < nnode; i++) if (has[i]) bnodes.push_back(i);
+    std::vector<char> seq(nnode, 0), seen(nnode, 0);
+    for (int e = 0; e < nb; e++) {
+      const int t = mesh->bedges_bctype[e];
+      if (t == PCFD_BC_DIRICHLET || t == PCFD_BC_SONIC_INFLOW) seq[mesh->bedges_n[2 * e]] = 1;
+    }
+    for (int i = 0; i < nnode; i++) if (seq[i]) bnodes.push_back(i);
+    for (int e = 0; e < nb; e++) {      // BC half-edges (everything that is not a parallel boundary)
+      const int l = mesh->bedges_n[2 * e];
+      if (mesh->bedges_bctype[e] == PCFD_BC_PARALLEL) continue;
+      if (!seen[l]) { seen[l] = 1; bfirst[e] = 1; }
+      if (!seq[l]) blist.push_back(e);
+    }
+    c->nblist_bc = (int)blist.size();
+    for (int e = 0; e < nb; e++) {      // ghost half-edges
+      if (mesh->bedges_bctype[e] != PCFD_BC_PARALLEL) continue;
+      if (!seq[mesh->bedges_n[2 * e]]) blist.push_back(e);
+    }
+    c->nblist = (int)blist.size();
   }
   c->nbn = (int)bnodes.size();
 
@@ -1047,6 +1161,8 @@ int pcfd_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int devic
   if (dev_upload(c, &c->adjp, adjp.data(), adjp.size())) return 1;
   if (dev_upload(c, &c->adj, adj.data(), adj.size())) return 1;
   if (dev_upload(c, &c->bnodes, bnodes.data(), bnodes.size())) return 1;
+  if (dev_upload(c, &c->blist, blist.data(), blist.size())) return 1;
+  if (dev_upload(c, &c->bfirst, bfirst.data(), bfirst.size())) return 1;
   if (dev_upload(c, &c->ia, ia.data(), ia.size())) return 1;
   if (dev_upload(c, &c->ja, ja.data(), ja.size())) return 1;
   if (dev_upload(c, &c->iau, iau.data(), iau.size())) return 1;
@@ -1142,6 +1258,7 @@ static int ensure_matrix(pcfd_ctx* c) {
   if (c->f[PCFD_F_A]) return 0;
   c->fsize[PCFD_F_A] = (size_t)c->nblocks * NEQN2;
   if (dev_alloc(c, &c->f[PCFD_F_A], c->fsize[PCFD_F_A])) return 1;
+  if (dev_alloc(c, &c->bdiag, (size_t)c->nb * NEQN2)) return 1;
   CK(cudaMemsetAsync(c->f[PCFD_F_A], 0, c->fsize[PCFD_F_A] * sizeof(double), c->stream));
   return 0;
 }
@@ -1205,10 +1322,17 @@ int pcfd_lsq_coefficients(pcfd_ctx* c) {
 int pcfd_update_bcs(pcfd_ctx* c) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
-  if (c->nbn == 0) return 0;
-  PROF("k_update_bcs");
-  k_update_bcs<<<nblk(c->nbn, 128), 128, 0, c->stream>>>(c->dm, c->bp, c->bnodes, c->nbn, c->f[PCFD_F_Q]);
-  LAUNCH_CHECK();
+  if (c->nbn) {
+    PROF("k_update_bcs");
+    k_update_bcs<<<nblk(c->nbn, 128), 128, 0, c->stream>>>(c->dm, c->bp, c->bnodes, c->nbn, c->f[PCFD_F_Q]);
+    LAUNCH_CHECK();
+  }
+  if (c->nblist_bc) {
+    PROF("k_update_bcs_edges");
+    k_update_bcs_edges<<<nblk(c->nblist_bc, 128), 128, 0, c->stream>>>(c->dm, c->bp, c->blist, c->nblist_bc, c->bfirst,
+                                                                       c->f[PCFD_F_Q]);
+    LAUNCH_CHECK();
+  }
   return 0;
 }
 
@@ -1362,11 +1486,18 @@ int pcfd_jacobian(pcfd_ctx* c) {
   }
   if (c->nbn) {
     PROF("k_jac_bnodes");
-    k_jac_bnodes<<<nblk(c->nbn, 64), 64, 0, c->stream>>>(c->dm, c->bp, c->bnodes, c->nbn, c->f[PCFD_F_Q], c->iau, c->bpos, A);
+    k_jac_bnodes<<<nblk(c->nbn, 64), 64, 0, c->stream>>>(c->dm, c->bp, c->bnodes, c->nbn, c->f[PCFD_F_Q], c->bpos, c->bdiag, A);
+    LAUNCH_CHECK();
+  }
+  if (c->nblist) {
+    PROF("k_jac_bedges");
+    k_jac_bedges<<<nblk(c->nblist, 64), 64, 0, c->stream>>>(c->dm, c->bp, c->blist, c->nblist, c->bfirst, c->f[PCFD_F_Q],
+                                                            c->bpos, c->bdiag, A);
     LAUNCH_CHECK();
   }
   PROF("k_jac_diag");
-  k_jac_diag<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->iau, c->posLR, c->posRL, c->f[PCFD_F_TIMESTEP], A);
+  k_jac_diag<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->iau, c->posLR, c->posRL, c->f[PCFD_F_TIMESTEP],
+                                                         c->bdiag, A);
   LAUNCH_CHECK();
   return 0;
 }
@@ -1405,8 +1536,13 @@ int pcfd_sgs(pcfd_ctx* c, int nsgs, double* ddq) {
         const int nr = off[l + 1] - off[l];
         const int warps = (nr + RPW - 1) / RPW;
         PROF("k_sgs_level");
-        k_sgs_level<<<nblk((long long)warps * 32, 128), 128, 0, c->stream>>>(rows + off[l], nr, c->ia, c->ja, c->iau, A,
-                                                                             c->pv, c->f[PCFD_F_B], x);
+        const int nb_ = nblk((long long)warps * 32, 128);
+        switch (c->sgs_unroll) {
+          case 1: k_sgs_level<1><<<nb_, 128, 0, c->stream>>>(rows + off[l], nr, c->ia, c->ja, c->iau, A, c->pv, c->f[PCFD_F_B], x); break;
+          case 2: k_sgs_level<2><<<nb_, 128, 0, c->stream>>>(rows + off[l], nr, c->ia, c->ja, c->iau, A, c->pv, c->f[PCFD_F_B], x); break;
+          case 7: k_sgs_level<7><<<nb_, 128, 0, c->stream>>>(rows + off[l], nr, c->ia, c->ja, c->iau, A, c->pv, c->f[PCFD_F_B], x); break;
+          default: k_sgs_level<4><<<nb_, 128, 0, c->stream>>>(rows + off[l], nr, c->ia, c->ja, c->iau, A, c->pv, c->f[PCFD_F_B], x); break;
+        }
         LAUNCH_CHECK();
       }
     }

@@ -157,6 +157,29 @@ def test_ramp_explicit_vs_oracle(oracle):
     run_both_explicit(oracle, mesh, params, q)
 
 
+def test_dirichlet_type_bcs_vs_oracle(oracle):
+    """Dirichlet / sonic-inflow half-edges overwrite the LEFT node state (bc.tcc:1058-1120), so the nodes that own
+    one are walked sequentially; mixed with far-field half-edges at the same nodes (box edges and corners)."""
+    from proteuscfd_b200 import capi
+    from proteuscfd_b200.cases import box_case
+    bc = {1: capi.BC_SONIC_INFLOW, 2: capi.BC_SONIC_OUTFLOW, 3: capi.BC_SYMMETRY, 4: capi.BC_DIRICHLET,
+          5: capi.BC_FARFIELD, 6: capi.BC_NEUMANN}
+    mesh, params, q = box_case(10, bc=bc, cfl=5.0)
+    run_both_explicit(oracle, mesh, params, q)
+    # and through the boundary Jacobian
+    o = oracle_for(oracle, mesh, params)
+    ctx = capi.Context(mesh, params)
+    ia, ja, iau = o.crs_init()
+    ctx.set_field(capi.F_Q, q)
+    qo = q.copy()
+    dt, _ = o.timestep(qo, np.zeros(1))
+    A = o.jacobian(qo, np.zeros(1), dt, ia, ja, iau)
+    ctx.timestep(want_min=False)
+    ctx.jacobian()
+    exact(ctx.get_field(capi.F_A), A, "A")
+    exact(ctx.get_field(capi.F_Q), qo, "q after the boundary Jacobian")
+
+
 def test_pressure_clip_sequential_semantics(oracle):
     """A rough state makes Kernel_PressureClip (limiters.tcc:737-815) fire on many edges, including
     chains where a later edge sees an earlier clip; the fixed-point iteration must reproduce the

@@ -18,11 +18,12 @@ def main():
     ap.add_argument("--n", type=int, default=118)
     ap.add_argument("--nsgs", type=int, default=1)
     ap.add_argument("--explicit-only", action="store_true")
+    ap.add_argument("--natural", action="store_true", help="lexicographic node numbering (the explicit bench case)")
     args = ap.parse_args()
     import torch
     from proteuscfd_b200 import capi
     from proteuscfd_b200.cases import box_case
-    mesh, params, q = box_case(args.n, colored=True, device="cuda:0")
+    mesh, params, q = box_case(args.n, colored=not args.natural, device="cuda:0")
     ctx = capi.Context(mesh, params, device=0)
     ctx.lsq_coefficients()
     ctx.set_field(capi.F_Q, q)

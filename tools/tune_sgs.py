@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""Time CRS::SGS sweeps for the tuning variants of k_sgs_level (PCFD_SGS_UNROLL) at bench size."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 118
+    import torch
+    from proteuscfd_b200 import capi
+    from proteuscfd_b200.cases import box_case
+    mesh, params, q = box_case(n, cfl=5.0, colored=True, device="cuda:0")
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    for u in (1, 2, 4, 7):
+        os.environ["PCFD_SGS_UNROLL"] = str(u)
+        c = capi.Context(mesh, params, device=0)
+        c.set_stream(stream.cuda_stream)
+        c.lsq_coefficients()
+        c.set_field(capi.F_Q, q)
+        c.implicit_iterate(2, refresh_jac=True)
+        c.blank_x()
+        c.sgs(2, want_ddq=False)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        c.sgs(10, want_ddq=False)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        print(f"PCFD_SGS_UNROLL={u}: {e0.elapsed_time(e1) / 10:.4f} ms/sweep", flush=True)
+        c.close()
+
+
+if __name__ == "__main__":
+    main()
