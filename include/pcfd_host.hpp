@@ -1,0 +1,159 @@
+// pcfd_host.hpp -- header-only C++ host shim between ProteusCFD's in-process seams and the
+// C ABI of libpcfd_b200.so (include/pcfd.h).
+//
+// pcfd::DropIn<Space> is instantiated with the reference's own SolutionSpace<Real>
+// (ucs/solutionSpace.h:94-113).  Each public method is named after, and replaces the body
+// of, one reference phase call in SolutionSpace::NewtonIterate / PreTimeAdvance
+// (ucs/solutionSpace.tcc:573-904); results land in the reference's own arrays
+// (space->qgrad, space->limiter->l, space->crs->b/x, space->crs->A->M/pv, field "timestep",
+// space->q), so the rest of ucs.x (norms, output, forces, restart) is untouched.
+//
+// The template is duck-typed: it only needs the public members it names, so it also
+// compiles against a mock (tests/cpp/mock_space.hpp).  C++11, like the reference
+// (make.opts:44).  Error behaviour follows the reference: a failed call is fatal
+// (`Abort << ...`, ucs/exceptions.h:30-49); here the handler is pluggable and defaults to
+// printing pcfd_last_error and calling std::abort().
+#ifndef PCFD_HOST_HPP
+#define PCFD_HOST_HPP
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "pcfd.h"
+
+namespace pcfd {
+
+typedef void (*ErrorHandler)(const char* where, const char* message);
+
+inline void DefaultErrorHandler(const char* where, const char* message) {
+  std::fprintf(stderr, "pcfd: %s failed: %s\n", where, message);
+  std::abort();
+}
+
+template <class Space>
+class DropIn {
+ public:
+  // SolutionSpace ctor + Init (solutionSpace.tcc:26-114, 148-376) have already built the mesh,
+  // metrics, eqnset and CRS; flatten what the hot path reads and create the device context.
+  explicit DropIn(Space* space, int device = 0, ErrorHandler onError = DefaultErrorHandler)
+      : s_(space), ctx_(NULL), onError_(onError) {
+    nnode_ = s_->m->GetNumNodes();
+    gnode_ = s_->m->GetNumParallelNodes();
+    nbnode_ = s_->m->GetNumBoundaryNodes();
+    nedge_ = s_->m->GetNumEdges();
+    nbedge_ = s_->m->GetNumBoundaryEdges();
+    ngedge_ = s_->m->GetNumParallelEdges();
+    neqn_ = s_->eqnset->neqn;
+    nvars_ = neqn_ + s_->eqnset->nauxvars;
+    nterms_ = s_->grad->GetNterms();
+    const int nb = nbedge_ + ngedge_;
+
+    std::vector<int> en(2 * (size_t)nedge_), bn(2 * (size_t)nb), bt((size_t)nb);
+    std::vector<double> ea(4 * (size_t)nedge_), ba(4 * (size_t)nb);
+    for (int e = 0; e < nedge_; e++) {          // Edges<Type>, uns_base.h:12-22
+      en[2 * e] = s_->m->edges[e].n[0];
+      en[2 * e + 1] = s_->m->edges[e].n[1];
+      for (int k = 0; k < 4; k++) ea[4 * (size_t)e + k] = s_->m->edges[e].a[k];
+    }
+    for (int e = 0; e < nb; e++) {              // HalfEdges<Type>, uns_base.h:28-37
+      bn[2 * e] = s_->m->bedges[e].n[0];
+      bn[2 * e + 1] = s_->m->bedges[e].n[1];
+      for (int k = 0; k < 4; k++) ba[4 * (size_t)e + k] = s_->m->bedges[e].a[k];
+      bt[e] = s_->bc->GetBCType(s_->m->bedges[e].factag);   // bc.tcc:70-74
+    }
+    pcfd_mesh_desc md;
+    md.nnode = nnode_; md.gnode = gnode_; md.nbnode = nbnode_;
+    md.nedge = nedge_; md.nbedge = nbedge_; md.ngedge = ngedge_;
+    md.edges_n = en.data(); md.edges_a = ea.data();
+    md.bedges_n = bn.data(); md.bedges_a = ba.data(); md.bedges_bctype = bt.data();
+    md.xyz = s_->m->xyz; md.vol = s_->m->vol; md.ipsp = s_->m->ipsp; md.psp = s_->m->psp;
+
+    pcfd_params pr;
+    pr.eqnset = s_->param->eqnset_id;
+    pr.sorder = s_->param->sorder;
+    pr.limiter = s_->param->limiter;
+    pr.no_cvbc = s_->param->no_cvbc;
+    pr.gamma = s_->param->gamma;
+    pr.chi = s_->param->chi;
+    pr.cfl = s_->param->GetCFL();
+    for (int k = 0; k < 10; k++) pr.qinf[k] = (k < nvars_) ? s_->eqnset->Qinf[k] : 0.0;
+
+    if (pcfd_create(&md, &pr, device, &ctx_) != 0) onError_("pcfd_create", pcfd_last_error(NULL));
+    // Mesh::s / Mesh::sw were filled by ComputeNodeLSQCoefficients during Init: reuse them
+    Check(pcfd_set_field(ctx_, PCFD_F_LSQ_S, s_->m->s, 6 * (size_t)(nnode_ + gnode_)), "set s");
+    Check(pcfd_set_field(ctx_, PCFD_F_LSQ_SW, s_->m->sw, 6 * (size_t)(nnode_ + gnode_)), "set sw");
+  }
+  ~DropIn() { pcfd_destroy(ctx_); }
+
+  pcfd_ctx* Context() { return ctx_; }
+
+  // ---- state in / out, in the reference's own arrays
+  void PushQ() { Check(pcfd_set_field(ctx_, PCFD_F_Q, s_->q, NQ()), "PushQ"); }
+  void PullQ() { Check(pcfd_get_field(ctx_, PCFD_F_Q, s_->q, NQ()), "PullQ"); }
+  void PushB() { Check(pcfd_set_field(ctx_, PCFD_F_B, s_->crs->b, (size_t)nnode_ * neqn_), "PushB"); }
+  void PullB() { Check(pcfd_get_field(ctx_, PCFD_F_B, s_->crs->b, (size_t)nnode_ * neqn_), "PullB"); }
+  void PullX() { Check(pcfd_get_field(ctx_, PCFD_F_X, s_->crs->x, (size_t)(nnode_ + gnode_) * neqn_), "PullX"); }
+  void PullGradient() {
+    Check(pcfd_get_field(ctx_, PCFD_F_QGRAD, s_->qgrad, (size_t)(nnode_ + gnode_) * nterms_ * 3), "PullGradient");
+  }
+  void PullLimiter() {
+    Check(pcfd_get_field(ctx_, PCFD_F_LIMITER, s_->limiter->l, (size_t)(nnode_ + gnode_) * neqn_), "PullLimiter");
+  }
+  void PullTimestep(double* dt) { Check(pcfd_get_field(ctx_, PCFD_F_TIMESTEP, dt, (size_t)nnode_), "PullTimestep"); }
+  void PullMatrix() {   // CRSMatrix::M and ::pv
+    Check(pcfd_get_field(ctx_, PCFD_F_A, s_->crs->A->M, (size_t)s_->crs->A->nblocks * neqn_ * neqn_), "PullMatrix");
+    Check(pcfd_get_crs(ctx_, NULL, NULL, NULL, s_->crs->A->pv), "PullMatrix pv");
+  }
+
+  // ---- phase replacements (same order and meaning as the reference calls they stand for)
+  void ComputeNodeLSQCoefficients() { Check(pcfd_lsq_coefficients(ctx_), "ComputeNodeLSQCoefficients"); }  // gradient.tcc:115
+  void UpdateBCs() { Check(pcfd_update_bcs(ctx_), "UpdateBCs"); }                                          // bc.tcc:1399
+  void GradientCompute() { Check(pcfd_gradient(ctx_), "Gradient::Compute"); }                              // gradient.tcc:57
+  void LimiterCompute() { Check(pcfd_limiter(ctx_), "Limiter::Compute"); }                                 // limiters.tcc:53
+  // residual.tcc:13-63: returns [resGlobal, res_0 .. res_{neqn-1}] with the reference's norm sqrt(sum)/N
+  // (parallel.h:160-219); single rank here -- with several ranks the caller all-reduces the sums first
+  std::vector<double> ComputeResiduals() {
+    double ss[1 + 16];
+    Check(pcfd_residual(ctx_, ss), "ComputeResiduals");
+    std::vector<double> res(1 + neqn_);
+    res[0] = std::sqrt(ss[0]) / ((double)nnode_ * neqn_);
+    for (int k = 0; k < neqn_; k++) res[1 + k] = std::sqrt(ss[1 + k]) / (double)nnode_;
+    return res;
+  }
+  double ComputeTimesteps() {                                                                              // timestep.tcc:7
+    double dtmin = 0.0;
+    Check(pcfd_set_cfl(ctx_, s_->param->GetCFL()), "set CFL");
+    Check(pcfd_timestep(ctx_, &dtmin), "ComputeTimesteps");
+    return dtmin;
+  }
+  void ComputeJacobians() { Check(pcfd_jacobian(ctx_), "ComputeJacobians"); }                              // jacobian.tcc:13
+  void PrepareSGS() { Check(pcfd_prepare_sgs(ctx_), "CRSMatrix::PrepareSGS"); }                            // crsmatrix.tcc:840
+  void BlankX() { Check(pcfd_blank_x(ctx_), "CRS::BlankX"); }                                              // crs.tcc:448
+  double SGS(int nSgs) {                                                                                   // crs.tcc:62
+    double ddq = 0.0;
+    Check(pcfd_sgs(ctx_, nSgs, &ddq), "CRS::SGS");
+    return ddq;
+  }
+  void ExplicitSolve() { Check(pcfd_explicit_solve(ctx_), "ExplicitSolve"); }                              // solve.tcc:71
+  void ApplyDQ() { Check(pcfd_apply_dq(ctx_), "ApplyDQ"); }                                                // solutionSpace.tcc:802
+
+ private:
+  size_t NQ() const { return (size_t)(nnode_ + gnode_ + nbnode_) * nvars_; }
+  void Check(int rc, const char* where) {
+    if (rc != 0) onError_(where, pcfd_last_error(ctx_));
+  }
+  DropIn(const DropIn&);
+  DropIn& operator=(const DropIn&);
+
+  Space* s_;
+  pcfd_ctx* ctx_;
+  ErrorHandler onError_;
+  int nnode_, gnode_, nbnode_, nedge_, nbedge_, ngedge_, neqn_, nvars_, nterms_;
+};
+
+}  // namespace pcfd
+
+#endif

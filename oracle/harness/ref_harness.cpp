@@ -68,6 +68,12 @@
 #undef private
 #undef protected
 
+#ifdef PCFD_DROPIN
+// the same harness with every phase call swapped for the B200 drop-in shim: this is what
+// INTEGRATION.md tells a ucs.x maintainer to do, compiled against the real reference headers
+#include "pcfd_host.hpp"
+#endif
+
 static std::string g_out;
 static int g_rank = 0;
 
@@ -272,6 +278,62 @@ int main(int argc, char* argv[])
   UpdateBCs(space);
   p->UpdateGeneralVectors(space->q, nvars);
 
+#ifdef PCFD_DROPIN
+  if(mode == "dump"){
+    DumpMesh(space);
+    Dump("q0", space->q, (size_t)(nnode+gnode+nbnode)*nvars);
+    pcfd::DropIn<SolutionSpace<Real> > gpu(space, 0);
+    gpu.PushQ();
+
+    Real dtmin = gpu.ComputeTimesteps();
+    gpu.PullTimestep(space->GetFieldData("timestep", FIELDS::STATE_NONE));
+    Dump("timestep", space->GetFieldData("timestep", FIELDS::STATE_NONE), (size_t)nnode);
+    Dump("dtmin", &dtmin, 1);
+
+    gpu.GradientCompute();
+    gpu.PullGradient();
+    Dump("qgrad", space->qgrad, (size_t)(nnode+gnode)*nterms*3);
+
+    if(param->limiter){
+      gpu.LimiterCompute();
+      gpu.PullLimiter();
+    }
+    Dump("limiter", space->limiter->l, (size_t)(nnode+gnode)*neqn);
+
+    std::vector<Real> res = gpu.ComputeResiduals();
+    gpu.PullB();
+    Dump("b", space->crs->b, (size_t)nnode*neqn);
+    Dump("resnorm", res.data(), res.size());
+
+    if(param->nSgs > 0){
+      gpu.ComputeJacobians();
+      gpu.PullMatrix();
+      CRSMatrix<Real>* A = space->crs->A;
+      Dump("ia", A->ia, (size_t)nnode+1);
+      Dump("ja", A->ja, (size_t)A->nblocks);
+      Dump("iau", A->iau, (size_t)nnode);
+      Dump("A", A->M, (size_t)A->nblocks*neqn*neqn);
+      gpu.PrepareSGS();
+      gpu.PullMatrix();
+      Dump("A_lu", A->M, (size_t)A->nblocks*neqn*neqn);
+      Dump("pv", A->pv, (size_t)nnode*neqn);
+      gpu.BlankX();
+      Real ddq = gpu.SGS(param->nSgs);
+      gpu.PullX();
+      Dump("x", space->crs->x, (size_t)(nnode+gnode)*neqn);
+      Dump("sgs_ddq", &ddq, 1);
+      gpu.ApplyDQ();
+    }
+    else{
+      gpu.ExplicitSolve();
+      gpu.PullX();
+      Dump("x", space->crs->x, (size_t)nnode*neqn);
+    }
+    gpu.PullQ();
+    p->UpdateGeneralVectors(space->q, nvars);
+    Dump("q1", space->q, (size_t)(nnode+gnode+nbnode)*nvars);
+  }
+#else
   if(mode == "dump"){
     DumpMesh(space);
     Dump("q0", space->q, (size_t)(nnode+gnode+nbnode)*nvars);
@@ -317,6 +379,7 @@ int main(int argc, char* argv[])
     p->UpdateGeneralVectors(space->q, nvars);
     Dump("q1", space->q, (size_t)(nnode+gnode+nbnode)*nvars);
   }
+#endif
   else if(mode == "time"){
     // CPU baseline: wall time of each reference phase (the same regions the
     // reference's own GradientTimer/ResidualTimer/JacobianAssembleTimer/

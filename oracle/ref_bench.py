@@ -54,8 +54,9 @@ surface #6 = farField "zmax"
 """
 
 
-def available():
-    return all(os.access(os.path.join(REFBIN, b), os.X_OK) for b in ("ref_harness", "udecomp_ref"))
+def available(dropin=False):
+    bins = ("ref_harness", "udecomp_ref") + (("ref_harness_gpu",) if dropin else ())
+    return all(os.access(os.path.join(REFBIN, b), os.X_OK) for b in bins)
 
 
 def _run(cmd, cwd, env=None, timeout=None):
@@ -122,6 +123,26 @@ class ReferenceCase:
              self.work, {"PCFD_MPI_NP": str(self.ranks)}, timeout=timeout)
         with open(os.path.join(out, "timing.json")) as f:
             return json.load(f)
+
+    INT_ARRAYS = {"edges_n", "bedges_n", "bedges_factag", "bedges_bctype", "ipsp", "psp", "gNodeOwner", "gNodeLocalId",
+                  "commCountsSend", "commCountsRecv", "commOffsetsRecv", "nodePackingList", "ia", "ja", "iau", "pv"}
+
+    def dump(self, dropin=False, timeout=600):
+        """One pass with every intermediate array dumped; dropin=True runs oracle/_ref/ref_harness_gpu, the same
+        harness with the phase calls replaced by include/pcfd_host.hpp (needs a B200).  Returns {rank: {name: array}}."""
+        binary = "ref_harness_gpu" if dropin else "ref_harness"
+        out = os.path.join(self.work, "out_gpu" if dropin else "out_cpu")
+        _run([os.path.join(REFBIN, binary), os.path.join(self.work, self.name), out, "dump"], self.work,
+             {"PCFD_MPI_NP": str(self.ranks)}, timeout=timeout)
+        res = {}
+        for r in range(self.ranks):
+            d = {}
+            for fn in sorted(os.listdir(out)):
+                if fn.endswith(f".{r}.bin"):
+                    name = fn[: -len(f".{r}.bin")]
+                    d[name] = np.fromfile(os.path.join(out, fn), dtype=np.int32 if name in self.INT_ARRAYS else np.float64)
+            res[r] = d
+        return res
 
     def close(self):
         shutil.rmtree(self.work, ignore_errors=True)

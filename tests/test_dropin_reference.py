@@ -1,0 +1,37 @@
+"""The drop-in, end to end: the UNMODIFIED reference (SolutionSpace set-up, mesh metrics, BC tables, CRS -- all the
+reference's own code, oracle/_ref/ref_harness_gpu) with its phase calls replaced by include/pcfd_host.hpp, against the
+same harness running the reference's own CPU phases.  Every dumped array must be bit-identical."""
+import numpy as np
+import pytest
+
+from tests.test_oracle import exact
+
+pytestmark = pytest.mark.gpu
+
+FLOAT_TOL = {"resnorm": 1e-13, "sgs_ddq": None}   # parallel-sum monitors
+
+
+@pytest.mark.parametrize("kind", ["explicit_venkat", "implicit_sgs_colored"])
+def test_reference_with_dropin_matches_reference(kind):
+    from oracle import ref_bench
+    if not ref_bench.available(dropin=True):
+        pytest.skip("oracle/_ref binaries not built (needs /root/reference at build time)")
+    if kind == "explicit_venkat":
+        case = ref_bench.ReferenceCase(10, 1, limiter=2, nsgs=0, cfl=0.5)
+    else:
+        case = ref_bench.ReferenceCase(8, 1, limiter=2, nsgs=3, cfl=5.0, colored=True)
+    try:
+        cpu = case.dump(dropin=False)[0]
+        gpu = case.dump(dropin=True)[0]
+    finally:
+        case.close()
+    assert set(cpu) == set(gpu)
+    assert {"qgrad", "limiter", "b", "x", "q1", "timestep"} <= set(cpu)
+    for name in sorted(cpu):
+        if name == "resnorm":
+            assert np.allclose(gpu[name], cpu[name], rtol=1e-13, atol=0), name
+        elif name == "sgs_ddq":
+            xn = np.sqrt(np.sum(cpu["x"] ** 2)) / max(cpu["b"].size, 1)
+            assert abs(gpu[name][0] - cpu[name][0]) <= 1e-12 * xn
+        else:
+            exact(gpu[name], cpu[name], name)
