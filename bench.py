@@ -214,6 +214,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=118, help="hexes per box side (118 -> ~10 M tets)")
     ap.add_argument("--ref-n", type=int, default=48, help="box side of the bounded CPU reference sample")
+    ap.add_argument("--halo", default="put", choices=["put", "nccl"],
+                    help="N>1 halo exchange: direct puts into peer ghost segments over NVLink (CUDA IPC) or NCCL send/recv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sgs", action="store_true")
     ap.add_argument("--sgs-n", type=int, default=0, help="box side for the SGS sub-benchmark (0: same as --n)")
@@ -240,18 +242,41 @@ def main():
     W = max(3, args.warmup)
     K = max(1, args.steps)
     t_setup = time.time()
-    # weak scaling: every rank owns one box of the named size (independent partitions; the halo
-    # exchange of a cut mesh is the next row of SURVEY.md 8e and is not in this line yet)
-    mesh, params, q0 = box_case(args.n, device=f"cuda:{local_rank}", seed=1234 + rank)
+    # weak scaling: the domain grows with N (a box of n x n x (n*N) hexes cut into N z-slabs, one per GPU, in the
+    # layout udecomp writes); cut edges are ghost half-edges and node states cross ranks through the halo exchange
+    # at the reference's four places per iteration (q, qgrad, limiter, q)
+    if world > 1:
+        from proteuscfd_b200.cases import slab_case
+        from proteuscfd_b200.parallel import DistributedHotPath, NcclExchange, PObj, PutExchange, TorchGroup
+        mesh, params, q0 = slab_case(args.n, rank, world, device=f"cuda:{local_rank}")
+    else:
+        mesh, params, q0 = box_case(args.n, device=f"cuda:{local_rank}")
     ctx = capi.Context(mesh, params, device=local_rank)
     # a real (non-default) torch stream: the library launches on it and torch.cuda.Event times it
     stream = torch.cuda.Stream(device=local_rank)
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
-    ctx.lsq_coefficients()
-    ctx.set_field(capi.F_Q, q0)
     ne, nn = ctx.nedge, ctx.nnode
+    ne_global = ne
+    if world > 1:
+        group = TorchGroup(dist)
+        pobj = PObj(rank, world).BuildCommMaps(mesh["gNodeOwner"], mesh["gNodeLocalId"], group)
+        dev = torch.device("cuda", local_rank)
+        xch = PutExchange(ctx, pobj, dist, torch, dev, group) if args.halo == "put" else NcclExchange(ctx, pobj, dist, torch, dev)
+        hp = DistributedHotPath(ctx, xch)
+        hp.setup()
+        ctx.set_field(capi.F_Q, q0)
+        step = lambda: hp.explicit_iterate(refresh_dt=True)
+        t = torch.tensor([2 * ctx.nedge + ctx.ngedge], device="cuda", dtype=torch.int64)   # a cut edge lives on two ranks
+        dist.all_reduce(t)
+        ne_global = int(t.item()) // 2
+        halo_rows = int(pobj.commCountsSend.sum())
+    else:
+        ctx.lsq_coefficients()
+        ctx.set_field(capi.F_Q, q0)
+        step = lambda: ctx.explicit_iterate(refresh_dt=True)
+        halo_rows = 0
     t_setup = time.time() - t_setup
 
     def barrier():
@@ -261,7 +286,7 @@ def main():
 
     # ---------------------------------------------------------------- device-resident timing
     for _ in range(W):
-        ctx.explicit_iterate(refresh_dt=True)
+        step()
     ctx.profile(on=True, reset=True)
     launches0 = ctx.launch_count()
     sampler = ClockSampler(local_rank)
@@ -271,7 +296,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(K):
-        ctx.explicit_iterate(refresh_dt=True)
+        step()
     e1.record(stream)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -284,7 +309,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_step = ms_total / K
-    value = world * ne / (ms_step * 1e-3) / 1e6
+    value = ne_global / (ms_step * 1e-3) / 1e6
 
     # ---------------------------------------------------------------- end to end through the C ABI with HOST buffers
     nq = ctx.field_size(capi.F_Q)
@@ -293,7 +318,7 @@ def main():
     hq_np = hq.numpy()
     for _ in range(2):
         ctx.set_field(capi.F_Q, hq_np)
-        ctx.explicit_iterate(refresh_dt=True)
+        step()
         ctx.get_field(capi.F_Q, out=hq_np)
     Ke = max(3, K // 2)
     barrier()
@@ -301,7 +326,7 @@ def main():
     e0.record(stream)
     for _ in range(Ke):
         ctx.set_field(capi.F_Q, hq_np)          # H2D of the step's input state (pinned)
-        ctx.explicit_iterate(refresh_dt=True)
+        step()
         ctx.get_field(capi.F_Q, out=hq_np)      # D2H of the updated state
     e1.record(stream)
     barrier()
@@ -310,7 +335,7 @@ def main():
         t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
-    e2e_value = world * ne / (e2e_ms * 1e-3) / 1e6
+    e2e_value = ne_global / (e2e_ms * 1e-3) / 1e6
 
     # ---------------------------------------------------------------- per-pass roofline from the live kernel timings
     peak, peak_src = measured_peaks()
@@ -360,14 +385,17 @@ def main():
             "config": {"workload": f"BASELINE configs[1]: inviscid Euler, synthetic Kuhn box n={args.n} ({6 * args.n ** 3} tets, "
                                    f"{nn} nodes, {ne} edges) per GPU, Roe 2nd order + weighted LSQ + Venkatakrishnan, "
                                    "explicit single-stage update (the reference has no multistage RK)",
-                       "parallelism": "1 box per GPU, no data-path collective (independent partitions)",
+                       "parallelism": ("single partition" if world == 1 else
+                                       f"{world} z-slab partitions of an n x n x {args.n * world} box, one per GPU; halo exchange "
+                                       f"'{args.halo}' of q, qgrad, limiter, q per iteration ({halo_rows} rows/rank/exchange); "
+                                       f"{ne_global} edges in total"),
                        "cache": "inputs larger than L2 (q 135 MB, qgrad 364 MB, edges 470 MB per pass); no flush needed",
                        "setup_s": t_setup},
             "roofline": roofline, "cpu_baseline": base,
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": nq * 8,
-                    "d2h_bytes_per_step": nq * 8, "what": "pcfd_set_field(q) from pinned host memory + pcfd_explicit_iterate + "
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": nq * 8 * world,
+                    "d2h_bytes_per_step": nq * 8 * world, "what": "pcfd_set_field(q) from pinned host memory + pcfd_explicit_iterate + "
                                                           "pcfd_get_field(q) per step"},
-            "gpu_launches": int(launches), "clocks": clocks, "phases": phases, "sgs": sgs,
+            "gpu_launches": int(launches) * world, "clocks": clocks, "phases": phases, "sgs": sgs,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -141,6 +141,26 @@ int pcfd_explicit_iterate(pcfd_ctx* ctx, int refresh_dt, double* sumsq);
    BlankX, SGS(nsgs), ApplyDQ. */
 int pcfd_implicit_iterate(pcfd_ctx* ctx, int refresh_jac, int nsgs, double* sumsq, double* ddq);
 
+/* ---- halo exchange: PObj (parallel.tcc).  The send lists are persistent (the reference re-sends the index
+   lists on every call, parallel.tcc:809-827).  send_list = PObj::nodePackingList concatenated in peer order
+   (local ids peer p wants, in p's ghost order); recv_counts = PObj::commCountsRecv; the rows received from
+   peer p land at ghost rows [commOffsetsRecv[p], +recv_counts[p]) (parallel.tcc:848-864). */
+int pcfd_halo_configure(pcfd_ctx* ctx, int rank, int nranks, const int* send_counts, const int* send_list,
+                        const int* recv_counts);
+int pcfd_halo_width(const pcfd_ctx* ctx, int field);      /* doubles per node of a field (0: not exchangeable) */
+int pcfd_halo_send_total(const pcfd_ctx* ctx);            /* rows this rank sends per exchange, all peers */
+/* gather the rows owed to `peer` (peer < 0: all peers in rank order) into device memory dst; dst may be a
+   local staging buffer or a peer GPU's ghost segment mapped with CUDA IPC (direct put over NVLink) */
+int pcfd_halo_pack(pcfd_ctx* ctx, int field, int peer, void* dst);
+/* device address of the ghost rows filled by `peer` (peer < 0: start of the ghost segment) */
+void* pcfd_halo_recv_ptr(pcfd_ctx* ctx, int field, int peer);
+
+/* CUDA-IPC mapping of a field for the direct-put exchange between one-process-per-GPU ranks: export a 64-byte
+   handle here, open it in the peer process, and pass (opened base + ghost offset) as dst of pcfd_halo_pack. */
+int pcfd_ipc_export(pcfd_ctx* ctx, int field, void* handle64);
+int pcfd_ipc_open(pcfd_ctx* ctx, const void* handle64, void** devptr);
+int pcfd_ipc_close(pcfd_ctx* ctx, void* devptr);
+
 /* number of CUDA kernels this context has launched since creation */
 long long pcfd_launch_count(const pcfd_ctx* ctx);
 

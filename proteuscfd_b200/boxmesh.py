@@ -108,3 +108,80 @@ def renumber(xyz, tets, tris, new_of_old):
     old_of_new = np.empty_like(new_of_old)
     old_of_new[new_of_old] = np.arange(len(new_of_old))
     return xyz[old_of_new], new_of_old[tets].astype(np.int32), new_of_old[tris].astype(np.int32)
+
+
+def _hash_uniform(gid, seed, salt):
+    """Counter-based uniform [0,1) per global node id (splitmix64), so every rank jitters a shared node identically."""
+    with np.errstate(over="ignore"):
+        x = (gid.astype(np.uint64) + np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15)
+             + np.uint64(salt) * np.uint64(0xD1B54A32D192ED03))
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        x = x ^ (x >> np.uint64(31))
+    return (x >> np.uint64(11)).astype(np.float64) / float(1 << 53)
+
+
+def kuhn_slab(n, k_lo, k_hi, nz_total, jitter=0.0, seed=1234):
+    """Planes k_lo..k_hi (inclusive, global indices) of the Kuhn box with n x n x nz_total hexes of size 1/n.
+
+    Returns (xyz, tets, tris, tags, gid): local node id = i + (n+1)*(j + (n+1)*(k - k_lo)), gid = the global id
+    i + (n+1)*(j + (n+1)*k).  Only faces of the GLOBAL box are boundary triangles (tags as kuhn_box); the cut planes
+    k_lo / k_hi carry none.  Jitter is a hash of the global id, identical on every rank that holds the node.
+    """
+    np1 = n + 1
+    nzl = k_hi - k_lo
+    ii = np.arange(np1, dtype=np.int64)
+    kk = np.arange(k_lo, k_hi + 1, dtype=np.int64)
+    K, J, I = np.meshgrid(kk, ii, ii, indexing="ij")
+    I, J, K = I.ravel(), J.ravel(), K.ravel()
+    gid = I + np1 * (J + np1 * K)
+    xyz = np.stack([I, J, K], axis=1).astype(np.float64) / n
+    if jitter > 0.0:
+        interior = (I > 0) & (I < n) & (J > 0) & (J < n) & (K > 0) & (K < nz_total)
+        d = np.stack([_hash_uniform(gid, seed, s) for s in (1, 2, 3)], axis=1)
+        d = (2.0 * d - 1.0) * (jitter / n)
+        xyz[interior] += d[interior]
+    ci, cj, ck = np.meshgrid(np.arange(n), np.arange(n), np.arange(nzl), indexing="ij")
+    ci, cj, ck = (a.transpose(2, 1, 0).ravel() for a in (ci, cj, ck))
+
+    def nid(a, b, c):
+        return (a + np1 * (b + np1 * c)).astype(np.int64)
+
+    tets = []
+    for perm in _PERMS:
+        off = np.zeros(3, dtype=np.int64)
+        verts = [nid(ci, cj, ck)]
+        for ax in perm:
+            off = off.copy()
+            off[ax] += 1
+            verts.append(nid(ci + off[0], cj + off[1], ck + off[2]))
+        t = np.stack(verts, axis=1)
+        inv = sum(1 for a in range(3) for b in range(a + 1, 3) if perm[a] > perm[b])
+        if inv % 2 == 1:
+            t = t[:, [0, 2, 1, 3]]
+        tets.append(t)
+    tets = np.stack(tets, axis=1).reshape(-1, 4)
+    vol = np.einsum("ij,ij->i", np.cross(xyz[tets[:, 1]] - xyz[tets[:, 0]], xyz[tets[:, 2]] - xyz[tets[:, 0]]),
+                    xyz[tets[:, 3]] - xyz[tets[:, 0]])
+    assert np.all(vol > 0), "negative tet volume"
+
+    faces = np.concatenate([tets[:, [1, 2, 3]], tets[:, [0, 3, 2]], tets[:, [0, 1, 3]], tets[:, [0, 2, 1]]])
+    opp = np.concatenate([tets[:, 0], tets[:, 1], tets[:, 2], tets[:, 3]])
+    coords = (I, J, K)
+    limits = ((0, n), (0, n), (0, nz_total))
+    tris, tags = [], []
+    tag = 0
+    for ax in range(3):
+        for val in limits[ax]:
+            tag += 1
+            m = np.all(coords[ax][faces] == val, axis=1)
+            f = faces[m]
+            if len(f):
+                # wind so the right-hand normal points into the domain: towards the opposite tet vertex
+                p0, p1, p2 = xyz[f[:, 0]], xyz[f[:, 1]], xyz[f[:, 2]]
+                nrm = np.cross(p1 - p0, p2 - p0)
+                inward = np.einsum("ij,ij->i", nrm, xyz[opp[m]] - p0) > 0
+                f[~inward] = f[~inward][:, [0, 2, 1]]
+            tris.append(f)
+            tags.append(np.full(len(f), tag, dtype=np.int32))
+    return xyz, tets.astype(np.int32), np.concatenate(tris).astype(np.int32), np.concatenate(tags), gid

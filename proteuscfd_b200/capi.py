@@ -30,6 +30,8 @@ SYMBOLS = [
     "pcfd_timestep", "pcfd_explicit_solve", "pcfd_jacobian", "pcfd_prepare_sgs", "pcfd_blank_x", "pcfd_sgs",
     "pcfd_apply_dq", "pcfd_explicit_iterate", "pcfd_implicit_iterate", "pcfd_launch_count",
     "pcfd_profile_enable", "pcfd_profile_reset", "pcfd_profile_count", "pcfd_profile_get",
+    "pcfd_ipc_export", "pcfd_ipc_open", "pcfd_ipc_close",
+    "pcfd_halo_configure", "pcfd_halo_width", "pcfd_halo_send_total", "pcfd_halo_pack", "pcfd_halo_recv_ptr",
 ]
 
 
@@ -81,6 +83,15 @@ def load_library(path=LIB_PATH):
     lib.pcfd_profile_reset.argtypes = [C.c_void_p]
     lib.pcfd_profile_count.argtypes = [C.c_void_p]
     lib.pcfd_profile_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), _dp, C.POINTER(C.c_longlong)]
+    lib.pcfd_ipc_export.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.pcfd_ipc_open.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.pcfd_ipc_close.argtypes = [C.c_void_p, C.c_void_p]
+    lib.pcfd_halo_configure.argtypes = [C.c_void_p, C.c_int, C.c_int, _ip, _ip, _ip]
+    lib.pcfd_halo_width.argtypes = [C.c_void_p, C.c_int]
+    lib.pcfd_halo_send_total.argtypes = [C.c_void_p]
+    lib.pcfd_halo_pack.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.pcfd_halo_recv_ptr.restype = C.c_void_p
+    lib.pcfd_halo_recv_ptr.argtypes = [C.c_void_p, C.c_int, C.c_int]
     for name in ("pcfd_destroy", "pcfd_synchronize", "pcfd_lsq_coefficients", "pcfd_update_bcs", "pcfd_gradient",
                  "pcfd_limiter", "pcfd_explicit_solve", "pcfd_jacobian", "pcfd_prepare_sgs", "pcfd_blank_x",
                  "pcfd_apply_dq"):
@@ -184,6 +195,37 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.pcfd_launch_count(self.h))
+
+    # -- halo (PObj)
+    def halo_configure(self, rank, nranks, send_counts, send_list, recv_counts):
+        sc = np.ascontiguousarray(send_counts, dtype=np.int32)
+        sl = np.ascontiguousarray(send_list, dtype=np.int32)
+        rc = np.ascontiguousarray(recv_counts, dtype=np.int32)
+        if sl.size == 0:
+            sl = np.zeros(1, np.int32)
+        self._ck(self.lib.pcfd_halo_configure(self.h, int(rank), int(nranks), _i(sc), _i(sl), _i(rc)))
+
+    def halo_width(self, field):
+        return int(self.lib.pcfd_halo_width(self.h, field))
+
+    def halo_pack(self, field, dst_ptr, peer=-1):
+        self._ck(self.lib.pcfd_halo_pack(self.h, field, int(peer), C.c_void_p(dst_ptr)))
+
+    def halo_recv_ptr(self, field, peer=-1):
+        return self.lib.pcfd_halo_recv_ptr(self.h, field, int(peer))
+
+    def ipc_export(self, field):
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.pcfd_ipc_export(self.h, field, buf))
+        return buf.raw
+
+    def ipc_open(self, handle):
+        p = C.c_void_p()
+        self._ck(self.lib.pcfd_ipc_open(self.h, C.c_char_p(handle), C.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr):
+        self._ck(self.lib.pcfd_ipc_close(self.h, C.c_void_p(ptr)))
 
     def profile(self, on=True, reset=False):
         if reset:

@@ -81,3 +81,118 @@ def box_case(n, jitter=0.15, mach=0.5, gamma=1.4, cfl=0.5, limiter=2, sorder=2, 
     # UpdateBCs overwrites them before first use)
     q[nn:] = q[mesh["bedges_n"].reshape(-1, 2)[:, 0]]
     return mesh, params, q.reshape(-1)
+
+
+# ------------------------------------------------------------------------------------------ partitioned boxes
+def _slab_ranges(n, nranks):
+    """Owned planes of every rank for a box of n x n x (n*nranks) hexes: rank r owns k in [r*n, (r+1)*n), the last
+    rank also the closing plane."""
+    nz = n * nranks
+    return [(r * n, (r + 1) * n - 1 if r < nranks - 1 else nz) for r in range(nranks)], nz
+
+
+def _owned_order(n, k0, k1, colored):
+    """Local id of every owned node (planes k0..k1, ascending global id, optionally colour-sorted)."""
+    np1 = n + 1
+    cnt = (k1 - k0 + 1) * np1 * np1
+    if not colored:
+        return np.arange(cnt, dtype=np.int64)
+    loc = np.arange(cnt, dtype=np.int64)
+    i, j, k = loc % np1, (loc // np1) % np1, loc // (np1 * np1) + k0
+    color = (i + 2 * j + 4 * k) % 8
+    old_of_new = np.argsort(color, kind="stable")
+    new_of_old = np.empty_like(old_of_new)
+    new_of_old[old_of_new] = np.arange(cnt)
+    return new_of_old
+
+
+def slab_case(n, rank, nranks, jitter=0.15, mach=0.5, gamma=1.4, cfl=0.5, limiter=2, sorder=2, colored=False,
+              device="cpu", seed=1234):
+    """Partition `rank` of a box of n x n x (n*nranks) hexes cut into z-slabs, in the layout udecomp writes
+    (ucs/decomp.cpp:122-273): owned nodes first, ghost nodes grouped by owning rank, cut edges as ghost half-edges
+    carrying the full dual face, `gNodeOwner` / `gNodeLocalId` for the halo maps.  Every rank builds only its own
+    slab plus one ghost plane per side; shared nodes get identical coordinates (hash jitter)."""
+    from .boxmesh import kuhn_slab
+    ranges, nz = _slab_ranges(n, nranks)
+    k0, k1 = ranges[rank]
+    k_lo, k_hi = max(k0 - 1, 0), min(k1 + 1, nz)
+    np1 = n + 1
+    xyz, tets, tris, tags, gid = kuhn_slab(n, k_lo, k_hi, nz, jitter=jitter, seed=seed)
+    full = median_dual(xyz, tets, tris, tags, device=device)
+    K = gid // (np1 * np1)
+    owned = (K >= k0) & (K <= k1)
+    nnode = int(owned.sum())
+    # new local ids: owned (ascending gid or colour-sorted), then ghosts by (owner, gid)
+    new = np.full(len(gid), -1, dtype=np.int64)
+    new[owned] = _owned_order(n, k0, k1, colored)
+    owner = np.where(K < k0, rank - 1, rank + 1)
+    gsel = np.nonzero(~owned)[0]
+    gsel = gsel[np.lexsort((gid[gsel], owner[gsel]))]
+    gnode = len(gsel)
+    new[gsel] = nnode + np.arange(gnode)
+    g_owner = owner[gsel].astype(np.int32)
+    g_local = np.zeros(gnode, dtype=np.int32)
+    for peer in np.unique(g_owner):
+        pk0, pk1 = ranges[peer]
+        order = _owned_order(n, pk0, pk1, colored)
+        sel = g_owner == peer
+        g_local[sel] = order[gid[gsel[sel]] - pk0 * np1 * np1]
+
+    en = full["edges_n"].reshape(-1, 2).astype(np.int64)
+    ea = full["edges_a"].reshape(-1, 4).copy()
+    a, b = new[en[:, 0]], new[en[:, 1]]
+    oa, ob = owned[en[:, 0]], owned[en[:, 1]]
+    # interior edges: both ends owned; orient n0 < n1 in the new numbering
+    m = oa & ob
+    ia_, ib_, iav = a[m], b[m], ea[m]
+    sw = ia_ > ib_
+    ia_, ib_ = np.where(sw, ib_, ia_), np.where(sw, ia_, ib_)
+    iav[sw, :3] *= -1.0
+    o = np.lexsort((ib_, ia_))
+    edges_n = np.stack([ia_[o], ib_[o]], axis=1)
+    edges_a = iav[o]
+    # ghost half-edges: owned -> ghost, normal pointing away from the owned node
+    m = oa ^ ob
+    ga, gb, gav = a[m], b[m], ea[m]
+    sw = ~oa[m]
+    ga, gb = np.where(sw, gb, ga), np.where(sw, ga, gb)
+    gav[sw, :3] *= -1.0
+    o = np.lexsort((gb, ga))
+    gh_n = np.stack([ga[o], gb[o]], axis=1)
+    gh_a = gav[o]
+    # BC half-edges of owned nodes, phantom nodes numbered behind the ghosts
+    bn = full["bedges_n"].reshape(-1, 2).astype(np.int64)
+    keep = owned[bn[:, 0]]
+    bleft = new[bn[keep, 0]]
+    nbedge = int(keep.sum())
+    b_n = np.stack([bleft, nnode + gnode + np.arange(nbedge)], axis=1)
+    b_a = full["bedges_a"].reshape(-1, 4)[keep]
+    factag = full["bedges_factag"][keep]
+    # psp of owned nodes (neighbours may be ghosts), ascending
+    pa = np.concatenate([edges_n[:, 0], edges_n[:, 1], gh_n[:, 0]])
+    pb = np.concatenate([edges_n[:, 1], edges_n[:, 0], gh_n[:, 1]])
+    o = np.lexsort((pb, pa))
+    psp = pb[o]
+    ipsp = np.zeros(nnode + 1, dtype=np.int64)
+    ipsp[1:] = np.cumsum(np.bincount(pa, minlength=nnode))
+    inv = np.empty(nnode + gnode, dtype=np.int64)
+    inv[new[new >= 0]] = np.nonzero(new >= 0)[0]
+    lut = np.zeros(max(BOX_BC) + 1, dtype=np.int32)
+    for t, bc in BOX_BC.items():
+        lut[t] = bc
+    mesh = dict(
+        nnode=nnode, gnode=gnode, nbnode=nbedge, nedge=len(edges_n), nbedge=nbedge, ngedge=len(gh_n),
+        edges_n=edges_n.astype(np.int32).reshape(-1), edges_a=np.ascontiguousarray(edges_a).reshape(-1),
+        bedges_n=np.concatenate([b_n, gh_n]).astype(np.int32).reshape(-1),
+        bedges_a=np.ascontiguousarray(np.concatenate([b_a, gh_a])).reshape(-1),
+        bedges_bctype=np.concatenate([lut[factag], np.zeros(len(gh_n), dtype=np.int32)]).astype(np.int32),
+        xyz=np.ascontiguousarray(full["xyz"].reshape(-1, 3)[inv]).reshape(-1),
+        vol=np.ascontiguousarray(full["vol"][inv[:nnode]]), ipsp=ipsp.astype(np.int32), psp=psp.astype(np.int32),
+        gNodeOwner=g_owner, gNodeLocalId=g_local, gid=gid[inv])
+    qinf = freestream(mach, gamma)
+    params = dict(eqnset=capi.EQNSET_COMPRESSIBLE_EULER, sorder=sorder, limiter=limiter, no_cvbc=0, gamma=gamma,
+                  chi=0.0, cfl=cfl, qinf=qinf)
+    q = np.zeros((nnode + gnode + nbedge, 10))
+    q[: nnode + gnode] = smooth_state(mesh["xyz"].reshape(-1, 3), mach, gamma)
+    q[nnode + gnode:] = q[b_n[:, 0]]
+    return mesh, params, q.reshape(-1)

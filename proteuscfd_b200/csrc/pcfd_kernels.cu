@@ -872,6 +872,17 @@ __global__ void __launch_bounds__(128) k_sgs_level(const int* __restrict__ rows,
   x[(size_t)row * NEQN + i] = out;
 }
 
+// PObj::UpdateGeneralVectors pack loop (parallel.tcc:829-846) with persistent send lists: row j of the
+// send buffer is node list[j] of field v (width n doubles).  dst may be local staging memory or, for the
+// direct-put exchange, a peer GPU's ghost segment mapped through CUDA IPC.
+__global__ void k_halo_pack(const int* __restrict__ list, int count, int n, const double* __restrict__ v,
+                            double* __restrict__ dst) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)count * n) return;
+  const int j = (int)(t / n), cidx = (int)(t - (long long)j * n);
+  dst[t] = v[(size_t)list[j] * n + cidx];
+}
+
 __global__ void k_fill_int(int* p, int n, int v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -905,6 +916,11 @@ struct pcfd_ctx {
   int *ia = nullptr, *ja = nullptr, *iau = nullptr, *pv = nullptr, *posLR = nullptr, *posRL = nullptr, *bpos = nullptr;
   int *rows_f = nullptr, *rows_b = nullptr;
   std::vector<int> lev_f, lev_b;   // level offsets into rows_f / rows_b
+  // halo maps (PObj::BuildCommMaps, parallel.tcc:461-554): what this rank sends to / receives from each peer
+  int rank = 0, nranks = 1;
+  std::vector<int> send_counts, send_offsets, recv_counts, recv_offsets;
+  int* send_list = nullptr;
+  int send_total = 0;
   bool ludiag = false;
   int sgs_unroll = 4;      // blocks in flight per lane in k_sgs_level (PCFD_SGS_UNROLL overrides, for tuning)
   std::vector<void*> allocs;
@@ -1565,6 +1581,99 @@ int pcfd_sgs(pcfd_ctx* c, int nsgs, double* ddq) {
     const double xOld = (nsgs >= 2) ? sqrt(h[8]) / N : 0.0;
     *ddq = fabs(xOld - xNorm);
   }
+  return 0;
+}
+
+static int field_width(int field) {
+  switch (field) {
+    case PCFD_F_Q: return NVARS;
+    case PCFD_F_QGRAD: return NTERMS * 3;
+    case PCFD_F_LIMITER: case PCFD_F_X: return NEQN;
+    case PCFD_F_LSQ_S: case PCFD_F_LSQ_SW: return 6;
+    case PCFD_F_BETA: return 1;
+    default: return 0;
+  }
+}
+
+int pcfd_halo_configure(pcfd_ctx* c, int rank, int nranks, const int* send_counts, const int* send_list,
+                        const int* recv_counts) {
+  if (!c) return 1;
+  if (nranks < 1 || rank < 0 || rank >= nranks || !send_counts || !recv_counts) return fail(c, "pcfd_halo_configure: bad argument");
+  CK(cudaSetDevice(c->device));
+  c->rank = rank;
+  c->nranks = nranks;
+  c->send_counts.assign(send_counts, send_counts + nranks);
+  c->recv_counts.assign(recv_counts, recv_counts + nranks);
+  c->send_offsets.assign(nranks + 1, 0);
+  c->recv_offsets.assign(nranks + 1, 0);
+  for (int p = 0; p < nranks; p++) {
+    if (send_counts[p] < 0 || recv_counts[p] < 0) return fail(c, "pcfd_halo_configure: negative count");
+    c->send_offsets[p + 1] = c->send_offsets[p] + send_counts[p];
+    c->recv_offsets[p + 1] = c->recv_offsets[p] + recv_counts[p];
+  }
+  if (c->recv_offsets[nranks] != c->gnode) return fail(c, "pcfd_halo_configure: receive counts do not add up to gnode");
+  c->send_total = c->send_offsets[nranks];
+  for (int j = 0; j < c->send_total; j++)
+    if (!send_list || send_list[j] < 0 || send_list[j] >= c->nnode) return fail(c, "pcfd_halo_configure: send list entry is not a local node");
+  if (dev_upload(c, &c->send_list, send_list, (size_t)c->send_total)) return 1;
+  return 0;
+}
+
+int pcfd_halo_width(const pcfd_ctx* c, int field) { return c ? field_width(field) : 0; }
+int pcfd_halo_send_total(const pcfd_ctx* c) { return c ? c->send_total : 0; }
+
+/* pack the rows this rank owes peer `peer` (peer < 0: all peers, in rank order) into dst (device memory,
+   count*width doubles) */
+int pcfd_halo_pack(pcfd_ctx* c, int field, int peer, void* dst) {
+  if (!c) return 1;
+  const int n = field_width(field);
+  if (n == 0 || !dst || peer >= c->nranks) return fail(c, "pcfd_halo_pack: bad argument");
+  if (c->send_offsets.empty()) return fail(c, "pcfd_halo_pack: pcfd_halo_configure has not been called");
+  CK(cudaSetDevice(c->device));
+  const int off = peer < 0 ? 0 : c->send_offsets[peer];
+  const int cnt = peer < 0 ? c->send_total : c->send_counts[peer];
+  if (cnt == 0) return 0;
+  PROF("k_halo_pack");
+  k_halo_pack<<<nblk((long long)cnt * n, 256), 256, 0, c->stream>>>(c->send_list + off, cnt, n, c->f[field],
+                                                                   static_cast<double*>(dst));
+  LAUNCH_CHECK();
+  return 0;
+}
+
+/* device address where the rows received from `peer` (peer < 0: from all peers) land: the ghost segment of the
+   field is contiguous per owner (decomp.cpp:245-273), so receives go straight into it, no unpack */
+void* pcfd_halo_recv_ptr(pcfd_ctx* c, int field, int peer) {
+  if (!c) return nullptr;
+  const int n = field_width(field);
+  if (n == 0 || peer >= c->nranks || c->recv_offsets.empty()) return nullptr;
+  const int off = peer < 0 ? 0 : c->recv_offsets[peer];
+  return c->f[field] + ((size_t)c->nnode + off) * n;
+}
+
+/* CUDA IPC: let a peer process map this context's field so that its k_halo_pack can store straight into our
+   ghost segment (one process per GPU; NVLink P2P).  handle is CUDA_IPC_HANDLE_SIZE (64) bytes. */
+int pcfd_ipc_export(pcfd_ctx* c, int field, void* handle) {
+  if (!c) return 1;
+  if (field < 0 || field >= PCFD_F_COUNT || !handle || !c->f[field]) return fail(c, "pcfd_ipc_export: bad argument");
+  CK(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, c->f[field]));
+  memcpy(handle, &h, sizeof(h));
+  return 0;
+}
+int pcfd_ipc_open(pcfd_ctx* c, const void* handle, void** devptr) {
+  if (!c) return 1;
+  if (!handle || !devptr) return fail(c, "pcfd_ipc_open: bad argument");
+  CK(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  CK(cudaIpcOpenMemHandle(devptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+int pcfd_ipc_close(pcfd_ctx* c, void* devptr) {
+  if (!c) return 1;
+  CK(cudaSetDevice(c->device));
+  CK(cudaIpcCloseMemHandle(devptr));
   return 0;
 }
 

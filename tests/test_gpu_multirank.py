@@ -1,0 +1,210 @@
+"""Multi-rank numerics on the GPU against fixtures written by MULTI-RANK runs of the reference (2 and 3 ranks over the
+process-based MPI shim).  All ranks' contexts live on one GPU and exchange halos by direct puts into each other's
+ghost segments (LoopbackExchange: the same k_halo_pack-into-peer-memory path the IPC exchange uses).  Bit-exact,
+ghost rows included."""
+import numpy as np
+import pytest
+
+from tests.oracle_lib import load_golden
+from tests.test_oracle import exact
+from tests.test_parallel_maps import CASES, load_ranks
+
+pytestmark = pytest.mark.gpu
+
+
+def make_ranks(name):
+    from proteuscfd_b200 import capi
+    from proteuscfd_b200.parallel import LoopbackExchange, build_local_group_maps
+    ranks = load_ranks(name)
+    ctxs = []
+    for g, meta in ranks:
+        mesh = {k: g[k] for k in ("edges_n", "edges_a", "bedges_n", "bedges_a", "bedges_bctype", "xyz", "vol", "ipsp", "psp")}
+        for k in ("nnode", "gnode", "nbnode", "nedge", "nbedge", "ngedge"):
+            mesh[k] = int(meta[k])
+        params = dict(sorder=int(meta["sorder"]), limiter=int(meta["limiter"]), no_cvbc=int(meta["no_cvbc"]),
+                      gamma=meta["gamma"], chi=meta["chi"], cfl=meta["cfl"], qinf=g["qinf"])
+        ctxs.append(capi.Context(mesh, params))
+    pobjs = build_local_group_maps([(g["gNodeOwner"], g["gNodeLocalId"]) for g, _ in ranks])
+    return ranks, ctxs, LoopbackExchange(ctxs, pobjs)
+
+
+def each(ctxs, fn):
+    for c in ctxs:
+        fn(c)
+
+
+def check(ranks, ctxs, field, key, what=None):
+    for r, ((g, _), c) in enumerate(zip(ranks, ctxs)):
+        got = c.get_field(field)
+        exact(got[: g[key].size], g[key], f"{what or key} rank {r}")
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_multirank_iteration_matches_reference(name):
+    from proteuscfd_b200 import capi
+    ranks, ctxs, x = make_ranks(name)
+    nsgs = int(ranks[0][1]["nSgs"])
+    # ComputeNodeLSQCoefficients + halos of s, sw (gradient.tcc:115-138)
+    each(ctxs, lambda c: c.lsq_coefficients())
+    x.update(capi.F_LSQ_S)
+    x.update(capi.F_LSQ_SW)
+    check(ranks, ctxs, capi.F_LSQ_S, "lsq_s")
+    check(ranks, ctxs, capi.F_LSQ_SW, "lsq_sw")
+    # NewtonIterate head: UpdateBCs + halo(q)
+    for (g, _), c in zip(ranks, ctxs):
+        c.set_field(capi.F_Q, g["q_pre"])
+    each(ctxs, lambda c: c.update_bcs())
+    x.update(capi.F_Q)
+    check(ranks, ctxs, capi.F_Q, "q0")
+    for (g, _), c in zip(ranks, ctxs):
+        assert c.timestep() == float(g["dtmin"][0])      # ComputeTimesteps returns the rank-local minimum
+    check(ranks, ctxs, capi.F_TIMESTEP, "timestep")
+    each(ctxs, lambda c: c.gradient())
+    x.update(capi.F_QGRAD)
+    check(ranks, ctxs, capi.F_QGRAD, "qgrad")
+    each(ctxs, lambda c: c.limiter())
+    x.update(capi.F_LIMITER)
+    check(ranks, ctxs, capi.F_LIMITER, "limiter")
+    sums = [c.residual(want_norms=True) for c in ctxs]
+    check(ranks, ctxs, capi.F_B, "b")
+    # ParallelL2Norm across ranks (parallel.h:160-181): sqrt(sum over ranks)/N_global
+    ntot = sum(int(m["nnode"]) for _, m in ranks) * 5
+    res = np.sqrt(sum(s[0] for s in sums)) / ntot
+    assert np.isclose(res, ranks[0][0]["resnorm"][0], rtol=1e-13)
+    if nsgs > 0:
+        each(ctxs, lambda c: c.jacobian())
+        check(ranks, ctxs, capi.F_A, "A")
+        each(ctxs, lambda c: c.prepare_sgs())
+        check(ranks, ctxs, capi.F_A, "A_lu")
+        for (g, _), c in zip(ranks, ctxs):
+            exact(c.get_crs()[3], g["pv"], "pv")
+        each(ctxs, lambda c: c.blank_x())
+        x.update(capi.F_X)                       # crs.tcc:88
+        for _ in range(nsgs):                    # block-Jacobi across ranks: ghosts frozen during a sweep
+            each(ctxs, lambda c: c.sgs(1, want_ddq=False))
+            x.update(capi.F_X)                   # crs.tcc:146
+        check(ranks, ctxs, capi.F_X, "x")
+        each(ctxs, lambda c: c.apply_dq())
+    else:
+        each(ctxs, lambda c: c.explicit_solve())
+        check(ranks, ctxs, capi.F_X, "x")
+    x.update(capi.F_Q)
+    check(ranks, ctxs, capi.F_Q, "q1")
+
+
+@pytest.mark.parametrize("colored,implicit", [(False, False), (True, True)])
+def test_slab_partitions_vs_oracle(oracle, colored, implicit):
+    """Partitions generated in memory (cases.slab_case, the bench's multi-GPU input): three ranks on one GPU with
+    direct-put halos against the C oracle run per rank with a numpy halo exchange through the same maps."""
+    from proteuscfd_b200 import capi
+    from proteuscfd_b200.cases import slab_case
+    from proteuscfd_b200.parallel import LoopbackExchange, build_local_group_maps
+    from tests.oracle_lib import oracle_for
+    nr = 3
+    parts = [slab_case(7, r, nr, colored=colored, cfl=5.0 if implicit else 0.5) for r in range(nr)]
+    pobjs = build_local_group_maps([(m["gNodeOwner"], m["gNodeLocalId"]) for m, _, _ in parts])
+    orcs = [oracle_for(oracle, m, p) for m, p, _ in parts]
+    ctxs = [capi.Context(m, p) for m, p, _ in parts]
+    x = LoopbackExchange(ctxs, build_local_group_maps([(m["gNodeOwner"], m["gNodeLocalId"]) for m, _, _ in parts]))
+    nn = [m["nnode"] for m, _, _ in parts]
+
+    def halo(arrs, w):
+        packed = [pobjs[r].pack_numpy(arrs[r], w) for r in range(nr)]
+        for r in range(nr):
+            pobjs[r].unpack_numpy(arrs[r], w, nn[r], [packed[p][r] for p in range(nr)])
+
+    beta = np.zeros(1)
+    qs = [q.copy() for _, _, q in parts]
+    sws = []
+    ss = []
+    for o in orcs:
+        s_, sw_ = o.lsq()
+        ss.append(s_); sws.append(sw_)
+    halo(sws, 6)
+    each(ctxs, lambda c: c.lsq_coefficients())
+    x.update(capi.F_LSQ_SW)
+    for r in range(nr):
+        ctxs[r].set_field(capi.F_Q, qs[r])
+        exact(ctxs[r].get_field(capi.F_LSQ_SW), sws[r], f"sw rank {r}")
+    for it in range(2):
+        dts = [orcs[r].timestep(qs[r], beta)[0] for r in range(nr)]
+        if implicit:
+            crs = [o.crs_init() for o in orcs]
+            As = [orcs[r].jacobian(qs[r], beta, dts[r], *crs[r]) for r in range(nr)]
+        for r in range(nr):
+            orcs[r].update_bcs(qs[r], beta)
+        halo(qs, 10)
+        grads = [orcs[r].gradient(qs[r], sws[r]) for r in range(nr)]
+        halo(grads, 27)
+        lims = [orcs[r].limiter(qs[r], grads[r]) for r in range(nr)]
+        halo(lims, 5)
+        bs = [orcs[r].residual(qs[r], grads[r], lims[r], beta) for r in range(nr)]
+        each(ctxs, lambda c: c.timestep(want_min=False))
+        if implicit:
+            each(ctxs, lambda c: c.jacobian())
+        each(ctxs, lambda c: c.update_bcs())
+        x.update(capi.F_Q)
+        each(ctxs, lambda c: c.gradient())
+        x.update(capi.F_QGRAD)
+        each(ctxs, lambda c: c.limiter())
+        x.update(capi.F_LIMITER)
+        each(ctxs, lambda c: c.residual())
+        for r in range(nr):
+            exact(ctxs[r].get_field(capi.F_QGRAD), grads[r], f"qgrad rank {r} it {it}")
+            exact(ctxs[r].get_field(capi.F_LIMITER), lims[r], f"limiter rank {r} it {it}")
+            exact(ctxs[r].get_field(capi.F_B), bs[r], f"b rank {r} it {it}")
+        if implicit:
+            xs = []
+            for r in range(nr):
+                exact(ctxs[r].get_field(capi.F_A), As[r], f"A rank {r}")
+                pv = orcs[r].prepare_sgs(crs[r][2], As[r])
+                xs.append((pv, np.zeros((nn[r] + parts[r][0]["gnode"]) * 5)))
+            each(ctxs, lambda c: c.prepare_sgs())
+            each(ctxs, lambda c: c.blank_x())
+            x.update(capi.F_X)
+            for sweep in range(3):
+                for r in range(nr):
+                    # one sweep of the oracle continuing from the current x (ghost values frozen)
+                    xr = xs[r][1]
+                    orcs[r].lib.orc_sgs.restype = __import__("ctypes").c_double
+                    from tests.oracle_lib import _d, _i
+                    import ctypes as C
+                    orcs[r].lib.orc_sgs(C.byref(orcs[r].c), 1, _i(crs[r][0]), _i(crs[r][1]), _i(crs[r][2]), _d(As[r]),
+                                        _i(xs[r][0]), _d(bs[r]), _d(xr))
+                halo([xx[1] for xx in xs], 5)
+                each(ctxs, lambda c: c.sgs(1, want_ddq=False))
+                x.update(capi.F_X)
+            for r in range(nr):
+                exact(ctxs[r].get_field(capi.F_X), xs[r][1], f"x rank {r} it {it}")
+                orcs[r].apply_dq(qs[r], xs[r][1])
+            each(ctxs, lambda c: c.apply_dq())
+        else:
+            for r in range(nr):
+                orcs[r].explicit_solve(qs[r], bs[r], dts[r])
+            each(ctxs, lambda c: c.explicit_solve())
+        halo(qs, 10)
+        x.update(capi.F_Q)
+        for r in range(nr):
+            exact(ctxs[r].get_field(capi.F_Q), qs[r], f"q rank {r} it {it}")
+
+
+def test_nccl_two_process_exchange():
+    """The real thing: one process per GPU, NCCL send/recv into the ghost segments and the direct-put exchange,
+    launched with torchrun when the box has >= 2 GPUs (gpurun --gpus 2)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29713", os.path.join(root, "tests", "nccl_worker.py"),
+                        "box8_2rank_explicit"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("RANK_OK") == 2, r.stdout[-3000:]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29714", os.path.join(root, "tests", "nccl_worker.py"),
+                        "box8_2rank_explicit", "put"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("RANK_OK") == 2, r.stdout[-3000:]

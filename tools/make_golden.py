@@ -140,6 +140,12 @@ def make_case(name, mesh=None, h5=None, bc=BOX_BC, np_ranks=1, part=None, **kw):
         shutil.rmtree(work, ignore_errors=True)
 
 
+def slab_part(xyz, ranks, axis=2):
+    """Partition id per node: equal slabs along one axis."""
+    x = np.clip(xyz[:, axis], 0.0, 1.0 - 1e-12)
+    return (x * ranks).astype(np.int64)
+
+
 def colored_box(n, **kw):
     """Box whose node numbering is colour-sorted (multicolour SGS == sequential SGS)."""
     xyz, tets, tris, tags = kuhn_box(n, **kw)
@@ -160,6 +166,11 @@ CASES = {
     # config[0]: 15-degree ramp, supersonic inviscid Euler, 1 partition, Roe + LSQ, 5 SGS
     "ramp15_implicit": lambda: make_case("ramp15_implicit", mesh=kuhn_box(8, ramp_deg=15.0, jitter=0.1), bc=RAMP_BC,
                                          mach=2.0, nsgs=5, cfl=5.0),
+    # two reference ranks (process-based MPI shim): halo maps + multi-rank numerics, explicit and implicit
+    "box8_2rank_explicit": lambda: make_case("box8_2rank_explicit", mesh=kuhn_box(8, jitter=0.15), np_ranks=2,
+                                             part=slab_part(kuhn_box(8, jitter=0.15)[0], 2)),
+    "box9_3rank_implicit": lambda: make_case("box9_3rank_implicit", mesh=kuhn_box(9, jitter=0.15), np_ranks=3,
+                                             part=slab_part(kuhn_box(9, jitter=0.15)[0], 3, axis=0), nsgs=3, cfl=5.0),
     # the reference's own unit-test fixture (unitTest/gradientTest.h:20-232): prism cube, 216 nodes
     "cube_LowFi": lambda: make_case(
         "cube_LowFi", h5=os.path.join(REFERENCE, "unitTest/meshResources/cubeStructuredSeries/cube_LowFi.0.h5"),
