@@ -151,6 +151,14 @@ static void DumpMesh(SolutionSpace<Real>* space)
   Dump("bedges_n", bn.data(), bn.size());
   Dump("bedges_a", ba.data(), ba.size());
   Dump("bedges_factag", bf.data(), bf.size());
+  {
+    // non-dimensional wall temperature of each BC half-edge's surface, as bc.tcc:1283-1286 forms it
+    std::vector<Real> tw(nbedge);
+    for(Int e = 0; e < nbedge; e++){
+      tw[e] = space->bc->GetBCObj(m->bedges[e].factag)->twall / space->param->ref_temperature;
+    }
+    Dump("bedges_twall", tw.data(), tw.size());
+  }
   Dump("bedges_bctype", bt.data(), bt.size());
   Dump("xyz", m->xyz, 3*(size_t)(nnode+gnode));
   Dump("vol", m->vol, (size_t)nnode);
@@ -194,6 +202,7 @@ static void DumpMesh(SolutionSpace<Real>* space)
   f << "boundaryJacType " << param->boundaryJacType << "\nboundaryJacEval " << param->boundaryJacEval << "\n";
   f << "no_cvbc " << param->no_cvbc << "\nsymmetry2D " << param->symmetry2D << "\n";
   f << "eqnset_id " << param->eqnset_id << "\ngradType " << param->gradType << "\n";
+  f << "ref_temperature " << param->ref_temperature << "\nenableVNN " << param->enableVNN << "\nVNN " << param->VNN << "\n";
   f << "iter " << space->iter << "\nnFirstOrderSteps " << param->nFirstOrderSteps << "\n";
   f.close();
 }

@@ -312,6 +312,187 @@ static double max_eigenvalue(const double* Q, const double* avec, double vdotn, 
   return MAXD(fabs(eig4), fabs(eig5));
 }
 
+/* ------------------------------------------------------- viscous terms */
+
+/* eqnset.h:251-268 Sutherland's law, non-dimensional; T = Q[5] (compressible.tcc:1162-1165) */
+static double compute_viscosity(const orc_case* c, const double* Q)
+{
+  double T = Q[5];
+  double S = 110.4/c->tref;
+  return (1.0 + S)*pow(T, 1.5)/(T + S);
+}
+
+/* compressible.tcc:713-795.  grad rows: 5 = T, 6..8 = u, v, w (GetGradientsLocation :1009-1027) */
+void orc_viscous_flux(const orc_case* c, const double* Q, const double* grad, const double* avec, double mut,
+		      double* flux)
+{
+  const double *gT = &grad[15], *gu = &grad[18], *gv = &grad[21], *gw = &grad[24];
+  double rho = Q[0];
+  double u = Q[1]/rho, v = Q[2]/rho, w = Q[3]/rho;
+  double mu = compute_viscosity(c, Q);
+  double tmut = (mu + mut);
+  double fact = -2.0/3.0*(gu[0] + gv[1] + gw[2]);
+  double tauxx = 2.0*gu[0] + fact, tauyy = 2.0*gv[1] + fact, tauzz = 2.0*gw[2] + fact;
+  double tauxy = gu[1] + gv[0], tauxz = gu[2] + gw[0], tauyz = gv[2] + gw[1];
+  double ReTilde = c->Re/c->mach;
+  double RK = avec[3]/ReTilde;
+  double RKT = RK*tmut;
+  double cp = 1.0/(c->gamma - 1.0);
+  double k = mu/c->Pr*cp;
+  double kT = mut/c->PrT*cp;
+  double c1 = -(k + kT);
+  double Tn = gT[0]*avec[0] + gT[1]*avec[1] + gT[2]*avec[2];
+  double tauxn = tauxx*avec[0] + tauxy*avec[1] + tauxz*avec[2];
+  double tauyn = tauxy*avec[0] + tauyy*avec[1] + tauyz*avec[2];
+  double tauzn = tauxz*avec[0] + tauyz*avec[1] + tauzz*avec[2];
+  flux[0] = 0.0;
+  flux[1] = -RKT*(tauxn);
+  flux[2] = -RKT*(tauyn);
+  flux[3] = -RKT*(tauzn);
+  flux[4] = -RKT*(tauxn*u + tauyn*v + tauzn*w) + RK*c1*Tn;
+}
+
+/* one side of compressible.tcc:1633-1893: D = -/+ dx/(rho_side*s2), (us,vs,ws,Ps,rhos) the side's own
+   state, (u,v,w) the edge-averaged velocity */
+static void viscous_jac_side(const double* D, double rhos, double us, double vs, double ws, double Ps,
+			     double u, double v, double w, const double* avec, double RK, double RKT,
+			     double c1, double gamma, double* a)
+{
+  double c43 = 4.0/3.0, mc23 = -2.0/3.0;
+  double gm1 = (gamma - 1.0);
+  double dux = -u*D[0], duy = -u*D[1], duz = -u*D[2];
+  double dvx = -v*D[0], dvy = -v*D[1], dvz = -v*D[2];
+  double dwx = -w*D[0], dwy = -w*D[1], dwz = -w*D[2];
+  double dfact = -2.0/3.0*(dux + dvy + dwz);
+  double dtauxx = (2.0*dux + dfact), dtauyy = (2.0*dvy + dfact), dtauzz = (2.0*dwz + dfact);
+  double dtauxy = duy + dvx, dtauxz = duz + dwx, dtauyz = dvz + dwy;
+  double dtauxn = dtauxx*avec[0] + dtauxy*avec[1] + dtauxz*avec[2];
+  double dtauyn = dtauxy*avec[0] + dtauyy*avec[1] + dtauyz*avec[2];
+  double dtauzn = dtauxz*avec[0] + dtauyz*avec[1] + dtauzz*avec[2];
+  double dR2_drhou = (c43*D[0]*avec[0] + D[1]*avec[1] + D[2]*avec[2]);
+  double dR2_drhov = (mc23*D[1]*avec[0] + D[0]*avec[1]);
+  double dR2_drhow = (mc23*D[2]*avec[0] + D[0]*avec[2]);
+  double dR3_drhou = (mc23*D[0]*avec[1] + D[1]*avec[0]);
+  double dR3_drhov = (D[0]*avec[0] + c43*D[1]*avec[1] + D[2]*avec[2]);
+  double dR3_drhow = (mc23*D[2]*avec[1] + D[1]*avec[2]);
+  double dR4_drhou = (mc23*D[0]*avec[2] + D[2]*avec[0]);
+  double dR4_drhov = (mc23*D[1]*avec[2] + D[2]*avec[1]);
+  double dR4_drhow = (D[0]*avec[0] + D[1]*avec[1] + c43*D[2]*avec[2]);
+  double v2 = (us*us + vs*vs + ws*ws);
+  double dT_dP = gamma/rhos;
+  double dP_dr = +gm1*0.5*v2, dP_dru = -gm1*us, dP_drv = -gm1*vs, dP_drw = -gm1*ws, dP_dret = +gm1;
+  double Tn = (D[0]*avec[0] + D[1]*avec[1] + D[2]*avec[2])*dT_dP*c1;
+  int i;
+  for(i = 0; i < 5; i++) a[i] = 0.0;
+  a[5] = -RKT*(dtauxn); a[6] = -RKT*dR2_drhou; a[7] = -RKT*dR2_drhov; a[8] = -RKT*dR2_drhow; a[9] = 0.0;
+  a[10] = -RKT*(dtauyn); a[11] = -RKT*dR3_drhou; a[12] = -RKT*dR3_drhov; a[13] = -RKT*dR3_drhow; a[14] = 0.0;
+  a[15] = -RKT*(dtauzn); a[16] = -RKT*dR4_drhou; a[17] = -RKT*dR4_drhov; a[18] = -RKT*dR4_drhow; a[19] = 0.0;
+  a[20] = -RKT*(dtauxn*u + dtauyn*v + dtauzn*w) + RK*Tn*(dP_dr - Ps/rhos);
+  a[21] = -RKT*(dR2_drhou*u + dR3_drhou*v + dR4_drhou*w) + RK*Tn*dP_dru;
+  a[22] = -RKT*(dR2_drhov*u + dR3_drhov*v + dR4_drhov*w) + RK*Tn*dP_drv;
+  a[23] = -RKT*(dR2_drhow*u + dR3_drhow*v + dR4_drhow*w) + RK*Tn*dP_drw;
+  a[24] = RK*Tn*dP_dret;
+}
+
+/* compressible.tcc:1633-1893 ViscousJacobian: aL (sign already flipped for the left scatter) and aR */
+void orc_viscous_jacobian(const orc_case* c, const double* QL, const double* QR, const double* dx, double s2,
+			  const double* avec, double mut, double* aL, double* aR)
+{
+  int i;
+  double Qavg[NVARS], DxL[3], DxR[3];
+  double mu, tmut, ReTilde, RK, RKT, cp, k, kT, c1;
+  double rhoL = QL[0], uL = QL[1]/rhoL, vL = QL[2]/rhoL, wL = QL[3]/rhoL, PL = QL[6];
+  double rhoR = QR[0], uR = QR[1]/rhoR, vR = QR[2]/rhoR, wR = QR[3]/rhoR, PR = QR[6];
+  double u = 0.5*(uL + uR), v = 0.5*(vL + vR), w = 0.5*(wL + wR);
+  for(i = 0; i < NEQN; i++) Qavg[i] = 0.5*(QL[i] + QR[i]);
+  compute_aux(Qavg, c->gamma);
+  mu = compute_viscosity(c, Qavg);
+  tmut = (mu + mut);
+  ReTilde = c->Re/c->mach;
+  RK = avec[3]/ReTilde;
+  RKT = RK*tmut;
+  for(i = 0; i < 3; i++){
+    DxL[i] = -dx[i]/(rhoL*s2);
+    DxR[i] = dx[i]/(rhoR*s2);
+  }
+  cp = 1.0/(c->gamma - 1.0);
+  k = mu/c->Pr*cp;
+  kT = mut/c->PrT*cp;
+  c1 = -(k + kT);
+  viscous_jac_side(DxR, rhoR, uR, vR, wR, PR, u, v, w, avec, RK, RKT, c1, c->gamma, aR);
+  viscous_jac_side(DxL, rhoL, uL, vL, wL, PL, u, v, w, avec, RK, RKT, c1, c->gamma, aL);
+  for(i = 0; i < NEQN*NEQN; i++) aL[i] = -aL[i];
+}
+
+/* face gradient of Kernel_Viscous_Flux (residual.tcc:432-455): average + directional correction */
+static void face_gradient(const orc_case* c, const double* qL, const double* qR, const double* gradL,
+			  const double* gradR, const double* xL, const double* xR, double* grad)
+{
+  int i, j;
+  for(i = 0; i < NTERMS*3; i++) grad[i] = 0.5*(gradL[i] + gradR[i]);
+  if(c->sorder > 1){
+    double dx[3], s2 = 0.0;
+    for(i = 0; i < 3; i++){
+      dx[i] = (xR[i] - xL[i]);
+      s2 += dx[i]*dx[i];
+    }
+    for(j = 0; j < NTERMS; j++){
+      double qdots = dx[0]*grad[j*3] + dx[1]*grad[j*3+1] + dx[2]*grad[j*3+2];
+      int loc = GRADLOC[j];
+      double dq = (qR[loc] - qL[loc] - qdots)/s2;
+      for(i = 0; i < 3; i++) grad[j*3 + i] += dq*dx[i];
+    }
+  }
+}
+
+/* the "most normal node off the wall" search repeated in bc.tcc:773-800, 925-951, 1182-1206 */
+int orc_normal_node(const orc_case* c, int e)
+{
+  int left = c->bedges_n[2*e];
+  const double* avec = &c->bedges_a[4*e];
+  const double* wallx = &c->xyz[3*left];
+  int indx, i, normalNode = -1;
+  double dotmax = 0.0;
+  for(indx = c->ipsp[left]; indx < c->ipsp[left+1]; indx++){
+    int pt = c->psp[indx];
+    const double* ptx = &c->xyz[3*pt];
+    double dx[3], mag, dot = 0.0;
+    for(i = 0; i < 3; i++) dx[i] = ptx[i] - wallx[i];
+    mag = sqrt(dx[0]*dx[0] + dx[1]*dx[1] + dx[2]*dx[2]);
+    for(i = 0; i < 3; i++) dx[i] = dx[i]/mag;
+    for(i = 0; i < 3; i++) dot -= dx[i]*avec[i];
+    if(dot >= dotmax){ normalNode = pt; dotmax = dot; }
+  }
+  return normalNode;
+}
+
+static double wall_temperature(const orc_case* c, int e)
+{
+  return c->bedges_twall ? c->bedges_twall[e] : 1.0/c->tref;
+}
+
+/* compressible.tcc:1544-1574 GetViscousWallBoundaryVariables, static wall (vel = 0 after
+   bc.tcc:1207-1254 with movement == 0, bleedSteps == 0, velw == 0) */
+static void viscous_wall_bc(const orc_case* c, double* QL, double* QR, const double* vel, const double* normalQ,
+			    double Twall)
+{
+  if(Twall < 0.0){
+    QR[0] = QL[0] = normalQ[0];
+    QR[4] = QL[4] = normalQ[4];
+  }
+  else{
+    double v2 = vel[0]*vel[0] + vel[1]*vel[1] + vel[2]*vel[2];
+    double gamma = c->gamma;
+    double gm1 = gamma - 1.0;
+    double rhoEt = (Twall*QL[0]/(gamma*gm1) + 0.5*QR[0]*v2);
+    QR[0] = QL[0];
+    QR[4] = QL[4] = rhoEt;
+  }
+  QR[1] = QL[1] = QL[0]*vel[0];
+  QR[2] = QL[2] = QL[0]*vel[1];
+  QR[3] = QL[3] = QL[0]*vel[2];
+}
+
 /* ------------------------------------------------------------ gradients */
 
 static int is_ghost(const orc_case* c, int n){ return n >= c->nnode && n < c->nnode + c->gnode; }
@@ -637,7 +818,8 @@ static void inviscid_wall_bc(const orc_case* c, const double* QL, double* QR, co
 }
 
 /* bc.tcc:1058-1120 dispatch for the BC types of the hot-path configs */
-static void boundary_variables(const orc_case* c, double* QL, double* QR, const double* avec, int bctype)
+static void boundary_variables(const orc_case* c, double* QL, double* QR, const double* avec, int bctype,
+			       int e, const double* q)
 {
   int i;
   double vdotn = 0.0;   /* static mesh (driver.tcc:97-113 with nv == 0) */
@@ -655,6 +837,14 @@ static void boundary_variables(const orc_case* c, double* QL, double* QR, const 
   case ORC_BC_IMPERMEABLE_WALL: case ORC_BC_SYMMETRY:
     inviscid_wall_bc(c, QL, QR, avec, vdotn);
     break;
+  case ORC_BC_NOSLIP: {   /* bc.tcc:1182-1291 */
+    double vel[3] = {0.0, 0.0, 0.0}, nQ[NVARS];
+    int normalNode = orc_normal_node(c, e);
+    vel[0] += 0.0; vel[1] += 0.0; vel[2] += 0.0;   /* velw */
+    for(i = 0; i < NVARS; i++) nQ[i] = q[normalNode*NVARS + i];
+    viscous_wall_bc(c, QL, QR, vel, nQ, wall_temperature(c, e));
+    break;
+  }
   default: break;
   }
   /* bc.tcc:1392-1396: aux vars of both sides are recomputed */
@@ -669,7 +859,7 @@ void orc_update_bcs(const orc_case* c, double* q, const double* beta)
   (void)beta;
   for(e = 0; e < nb; e++){
     int l = c->bedges_n[2*e], r = c->bedges_n[2*e+1];
-    boundary_variables(c, &q[l*NVARS], &q[r*NVARS], &c->bedges_a[4*e], c->bedges_bctype[e]);
+    boundary_variables(c, &q[l*NVARS], &q[r*NVARS], &c->bedges_a[4*e], c->bedges_bctype[e], e, q);
   }
 }
 
@@ -733,8 +923,52 @@ void orc_residual(const orc_case* c, const double* q, const double* qgrad, const
     numerical_flux(QL, QR, avec, 0.0, c->gamma, flux);   /* BoundaryFlux, eqnset.tcc:21-52 */
     for(i = 0; i < NEQN; i++) b[l*NEQN + i] += -flux[i];
   }
+  if(c->viscous){
+    /* Kernel_Viscous_Flux residual.tcc:388-466 */
+    for(e = 0; e < c->nedge; e++){
+      int l = c->edges_n[2*e], r = c->edges_n[2*e+1];
+      const double* qL = &q[l*NVARS];
+      const double* qR = &q[r*NVARS];
+      double Qavg[NVARS], grad[NTERMS*3], flux[NEQN], tmut;
+      for(i = 0; i < NEQN; i++) Qavg[i] = (qL[i] + qR[i])/2.0;
+      compute_aux(Qavg, c->gamma);
+      tmut = c->mut ? 0.5*(c->mut[l] + c->mut[r]) : 0.0;
+      face_gradient(c, qL, qR, &qgrad[l*NTERMS*3], &qgrad[r*NTERMS*3], &c->xyz[3*l], &c->xyz[3*r], grad);
+      orc_viscous_flux(c, Qavg, grad, &c->edges_a[4*e], tmut, flux);
+      for(i = 0; i < NEQN; i++) b[r*NEQN + i] += flux[i];
+      for(i = 0; i < NEQN; i++) b[l*NEQN + i] += -flux[i];
+    }
+    /* Bkernel_Viscous_Flux residual.tcc:468-562 */
+    for(e = 0; e < nb; e++){
+      int l = c->bedges_n[2*e], r = c->bedges_n[2*e+1];
+      const double* qL = &q[l*NVARS];
+      const double* qR = &q[r*NVARS];
+      double Qavg[NVARS], grad[NTERMS*3], flux[NEQN], tmut;
+      for(i = 0; i < NEQN; i++) Qavg[i] = 0.5*(qL[i] + qR[i]);
+      compute_aux(Qavg, c->gamma);
+      if(is_ghost(c, r)){
+	tmut = c->mut ? (c->mut[l] + c->mut[r])/2.0 : 0.0;
+	face_gradient(c, qL, qR, &qgrad[l*NTERMS*3], &qgrad[r*NTERMS*3], &c->xyz[3*l], &c->xyz[3*r], grad);
+      }
+      else{
+	tmut = c->mut ? c->mut[l] : 0.0;
+	memcpy(grad, &qgrad[l*NTERMS*3], sizeof(double)*3*NTERMS);
+      }
+      orc_viscous_flux(c, Qavg, grad, &c->bedges_a[4*e], tmut, flux);
+      for(i = 0; i < NEQN; i++) b[l*NEQN + i] += -flux[i];
+    }
+  }
   /* SourceTerm (compressible.tcc:1196-1208, gravity off) adds +0.0: node loop residual.tcc:109-115 */
   for(i = 0; i < c->nnode*NEQN; i++) b[i] += 0.0;
+  /* Bkernel_BC_Res_Modify (residual.tcc:40-43, bc.tcc:905-1056) -> ModifyViscousWallResidual
+     (compressible.tcc:1611-1631) */
+  for(e = 0; e < nb; e++){
+    if(c->bedges_bctype[e] == ORC_BC_NOSLIP){
+      double* res = &b[c->bedges_n[2*e]*NEQN];
+      res[1] = 0.0; res[2] = 0.0; res[3] = 0.0; res[4] = 0.0;
+      if(wall_temperature(c, e) < 0.0) res[0] = 0.0;
+    }
+  }
 }
 
 /* ------------------------------------------------------------- timestep */
@@ -763,6 +997,8 @@ double orc_timestep(const orc_case* c, const double* q, const double* beta, doub
   dtmin = dt[0];
   for(i = 1; i < c->nnode; i++){
     dt[i] = c->cfl*(c->vol[i]/dt[i]);
+    /* timestep.tcc:37-41: the Von Neumann limit is applied from node 1 on */
+    if(c->enable_vnn) dt[i] = MIND(dt[i], c->vnn*pow(c->vol[i], 2.0/3.0));
     dtmin = MIND(dtmin, dt[i]);
   }
   return dtmin;
@@ -880,7 +1116,7 @@ void orc_jacobian(const orc_case* c, double* q, const double* beta, const double
     int bctype = c->bedges_bctype[e];
     double QPL[NVARS], QPR[NVARS], fluxS[NEQN], fluxL[NEQN], fluxR[NEQN], tempL[25], tempR[25];
     double *pL;
-    boundary_variables(c, QL, QR, avec, bctype);
+    boundary_variables(c, QL, QR, avec, bctype, e, q);
     numerical_flux(QL, QR, avec, 0.0, gamma, fluxS);
     for(i = 0; i < NEQN; i++){
       memcpy(QPL, QL, sizeof(double)*NVARS);
@@ -891,7 +1127,7 @@ void orc_jacobian(const orc_case* c, double* q, const double* beta, const double
       if(!is_ghost(c, r)){     /* boundaryJacEval == 0 */
 	memcpy(QPR, QR, sizeof(double)*NVARS);
 	compute_aux(QPR, gamma);
-	boundary_variables(c, QPL, QPR, avec, bctype);
+	boundary_variables(c, QPL, QPR, avec, bctype, e, q);
 	numerical_flux(QPL, QPR, avec, 0.0, gamma, fluxL);
       }
       else{
@@ -908,6 +1144,25 @@ void orc_jacobian(const orc_case* c, double* q, const double* beta, const double
     }
     pL = get_block(ia, ja, A, l, l);
     for(k = 0; k < 25; k++) pL[k] += tempL[k];
+  }
+
+  /* Kernel_Viscous_Jac :768-800 (Bkernel_Viscous_Jac :802-848 always ends with size = 0: no-op) */
+  if(c->viscous){
+    for(e = 0; e < c->nedge; e++){
+      int l = c->edges_n[2*e], r = c->edges_n[2*e+1];
+      double tmut = c->mut ? (c->mut[l] + c->mut[r])/2.0 : 0.0;
+      double dx[3], s2 = 0.0, tempL[25], tempR[25];
+      double *pL, *pR;
+      for(i = 0; i < 3; i++){
+	dx[i] = (c->xyz[3*r+i] - c->xyz[3*l+i]);
+	s2 += dx[i]*dx[i];
+      }
+      orc_viscous_jacobian(c, &q[l*NVARS], &q[r*NVARS], dx, s2, &c->edges_a[4*e], tmut, tempL, tempR);
+      pL = get_block(ia, ja, A, r, l);
+      pR = get_block(ia, ja, A, l, r);
+      for(k = 0; k < 25; k++) pR[k] += tempR[k];
+      for(k = 0; k < 25; k++) pL[k] += tempL[k];
+    }
   }
 
   /* Kernel_Diag_NumJac :434-456; scatter right first, then left */
@@ -928,6 +1183,34 @@ void orc_jacobian(const orc_case* c, double* q, const double* beta, const double
   for(i = 0; i < c->nnode; i++){
     double* d = get_block(ia, ja, A, i, i);
     for(k = 0; k < NEQN; k++) d[k*NEQN + k] += 1.0*c->vol[i]/dt[i];
+  }
+
+  /* Bkernel_BC_Jac_Modify (jacobian.tcc:247-249, bc.tcc:747-903) -> ModifyViscousWallJacobian
+     (compressible.tcc:1576-1609) with CRSMatrix::BlankSubRow (crsmatrix.tcc:524-541) */
+  for(e = 0; e < nb; e++){
+    if(c->bedges_bctype[e] == ORC_BC_NOSLIP){
+      int cv = c->bedges_n[2*e];
+      double Twall = wall_temperature(c, e);
+      double* diag = get_block(ia, ja, A, cv, cv);
+      int rows[5], nrows = 0, rr;
+      rows[nrows++] = 1; rows[nrows++] = 2; rows[nrows++] = 3;
+      if(Twall < 0.0){ rows[nrows++] = 0; rows[nrows++] = 4; }
+      else rows[nrows++] = 4;
+      for(rr = 0; rr < nrows; rr++){
+	int sub = rows[rr];
+	for(k = ia[cv]; k < ia[cv+1]; k++) for(j = 0; j < NEQN; j++) A[(size_t)k*25 + sub*NEQN + j] = 0.0;
+	diag[sub*NEQN + sub] = 1.0;
+      }
+      if(Twall < 0.0){
+	double* off = get_block(ia, ja, A, cv, orc_normal_node(c, e));
+	off[0*NEQN + 0] = -1.0;
+	off[4*NEQN + 4] = -1.0;
+      }
+      else{
+	double v2 = 0.0;   /* static wall */
+	diag[4*NEQN + 0] = -(Twall/(gamma*(gamma - 1.0)) + 0.5*v2);
+      }
+    }
   }
 }
 

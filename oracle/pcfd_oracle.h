@@ -49,6 +49,13 @@ typedef struct {
   int sorder;                /* 1 or 2 */
   int no_cvbc;
   double qinf[ORC_NVARS];
+  /* viscous terms -- compressibleNS (param.h: viscous, Re, Pr, PrT, ref_temperature, velocity;
+     timestep.tcc:37-41 enableVNN / VNN) */
+  int viscous, enable_vnn;
+  double Re, Pr, PrT, tref, mach, vnn;
+  const double* bedges_twall;  /* [nbedge] bcobj->twall / ref_temperature of the half-edge's surface
+                                  (read for NoSlip only; < 0: adiabatic).  NULL: 1/tref (bcobj.tcc:31) */
+  const double* mut;           /* field "mut" [nnode+gnode+nbnode]; NULL: zero (laminar) */
 } orc_case;
 
 /* gradient.tcc:115-138, 381-542 : s and sw, each [(nnode+gnode)*6] */
@@ -79,6 +86,15 @@ void orc_prepare_sgs(const orc_case* c, const int* iau, double* A, int* pv);
 /* crs.tcc:62-173 (single rank); returns |xOld - xNorm| */
 double orc_sgs(const orc_case* c, int nsgs, const int* ia, const int* ja, const int* iau,
 	       const double* A, const int* pv, const double* b, double* x);
+
+/* compressible.tcc:713-795 ViscousFlux and :1633-1893 ViscousJacobian -- exposed for unit tests.
+   Q, QL, QR are full nvars states (aux vars valid). */
+void orc_viscous_flux(const orc_case* c, const double* Q, const double* grad, const double* avec, double mut,
+		      double* flux);
+void orc_viscous_jacobian(const orc_case* c, const double* QL, const double* QR, const double* dx, double s2,
+			  const double* avec, double mut, double* aL, double* aR);
+/* most-normal neighbour of a wall node (bc.tcc:1182-1206) for half-edge e */
+int orc_normal_node(const orc_case* c, int e);
 
 /* compressible.tcc:93-230 -- exposed for unit tests */
 void orc_roe_flux(const double* QL, const double* QR, const double* avec, double vdotn, double gamma,

@@ -25,7 +25,10 @@ class OrcCase(C.Structure):
                 ("bedges_bctype", _ip), ("xyz", _dp), ("vol", _dp), ("ipsp", _ip), ("psp", _ip),
                 ("gamma", C.c_double), ("chi", C.c_double), ("cfl", C.c_double),
                 ("limiter", C.c_int), ("sorder", C.c_int), ("no_cvbc", C.c_int),
-                ("qinf", C.c_double * NVARS)]
+                ("qinf", C.c_double * NVARS),
+                ("viscous", C.c_int), ("enable_vnn", C.c_int),
+                ("Re", C.c_double), ("Pr", C.c_double), ("PrT", C.c_double), ("tref", C.c_double),
+                ("mach", C.c_double), ("vnn", C.c_double), ("bedges_twall", _dp), ("mut", _dp)]
 
 
 def _d(a):
@@ -58,6 +61,12 @@ class Oracle:
         c.xyz, c.vol, c.ipsp, c.psp = _d(k["xyz"]), _d(k["vol"]), _i(k["ipsp"]), _i(k["psp"])
         for j in range(NVARS):
             c.qinf[j] = k["qinf"][j]
+        # viscous terms (compressibleNS); absent keys mean an inviscid case
+        c.viscous, c.enable_vnn = int(meta.get("viscous", 0)), int(meta.get("enableVNN", 0))
+        c.Re, c.Pr, c.PrT = meta.get("Re", 1.0), meta.get("Pr", 0.72), meta.get("PrT", 0.85)
+        c.tref, c.mach, c.vnn = meta.get("ref_temperature", 300.0), meta.get("velocity", 0.0), meta.get("VNN", 20.0)
+        c.bedges_twall = _d(k["bedges_twall"]) if "bedges_twall" in k and k["bedges_twall"].size else None
+        c.mut = _d(k["mut"]) if "mut" in k else None
         self.c = c
         self.nn = c.nnode + c.gnode
         self.nnode = c.nnode
@@ -129,9 +138,14 @@ def oracle_for(lib, mesh, params):
     g = {k: np.asarray(mesh[k]) for k in ("edges_n", "edges_a", "bedges_n", "bedges_a", "bedges_bctype", "xyz", "vol",
                                           "ipsp", "psp")}
     g["qinf"] = np.asarray(params["qinf"])
+    if mesh.get("bedges_twall") is not None:
+        g["bedges_twall"] = np.asarray(mesh["bedges_twall"], dtype=np.float64)
     meta = {k: mesh[k] for k in ("nnode", "gnode", "nbnode", "nedge", "nbedge", "ngedge")}
     meta.update(limiter=params["limiter"], sorder=params["sorder"], no_cvbc=params["no_cvbc"], gamma=params["gamma"],
                 chi=params["chi"], cfl=params["cfl"])
+    if params.get("viscous"):
+        meta.update(viscous=1, Re=params["Re"], Pr=params["Pr"], PrT=params["PrT"], ref_temperature=params["tref"],
+                    velocity=params["mach"], enableVNN=params.get("enable_vnn", 0), VNN=params.get("vnn", 20.0))
     return Oracle(lib, g, meta)
 
 

@@ -11,8 +11,9 @@ import pytest
 from tests.oracle_lib import Oracle, load_golden
 
 ALL = ["box8_explicit_venkat", "box8_explicit_barth", "box6_implicit_sgs", "box6c_implicit_sgs",
-       "ramp15_implicit", "cube_LowFi"]
-IMPLICIT = ["box6_implicit_sgs", "box6c_implicit_sgs", "ramp15_implicit", "cube_LowFi"]
+       "ramp15_implicit", "cube_LowFi", "box6_ns_implicit", "box6_ns_adiabatic"]
+IMPLICIT = ["box6_implicit_sgs", "box6c_implicit_sgs", "ramp15_implicit", "cube_LowFi", "box6_ns_implicit",
+            "box6_ns_adiabatic"]
 EXPLICIT = ["box8_explicit_venkat", "box8_explicit_barth"]
 
 

@@ -51,6 +51,8 @@ CFL = {cfl}
 flowDirection = [{fx}, {fy}, {fz}]
 jacobianFieldType = {jactype}
 jacobianBoundaryType = {jactype}
+refViscosity = {refvisc}
+enableVNN = {vnn}
 <<<END SPACE>>>
 """
 
@@ -74,6 +76,17 @@ surface #3 = impermeableWall "ramp"
 surface #4 = farField "top"
 surface #5 = symmetry "wall0"
 surface #6 = symmetry "wall1"
+"""
+
+
+# laminar Navier-Stokes box: no-slip floor (isothermal or adiabatic through twall), far field elsewhere
+def ns_bc(twall):
+    return f"""surface #1 = farField "xmin"
+surface #2 = farField "xmax"
+surface #3 = symmetry "ymin"
+surface #4 = symmetry "ymax"
+surface #5 = noSlip "floor" twall = [{twall}]
+surface #6 = farField "zmax"
 """
 
 
@@ -109,7 +122,7 @@ def collect(outdir, rank):
 
 def make_case(name, mesh=None, h5=None, bc=BOX_BC, np_ranks=1, part=None, **kw):
     opts = dict(eqnset="compressibleEuler", sorder=2, limiter=2, nsgs=0, mach=0.5, cfl=0.5,
-                fx=1.0, fy=0.0, fz=0.0, jactype=0)
+                fx=1.0, fy=0.0, fz=0.0, jactype=0, refvisc=1.0, vnn=0)
     opts.update(kw)
     work = tempfile.mkdtemp(prefix="pcfd_golden_")
     try:
@@ -171,6 +184,13 @@ CASES = {
                                              part=slab_part(kuhn_box(8, jitter=0.15)[0], 2)),
     "box9_3rank_implicit": lambda: make_case("box9_3rank_implicit", mesh=kuhn_box(9, jitter=0.15), np_ranks=3,
                                              part=slab_part(kuhn_box(9, jitter=0.15)[0], 3, axis=0), nsgs=3, cfl=5.0),
+    # config[2] in miniature: laminar Navier-Stokes (compressibleNS), viscous flux + analytic viscous Jacobian,
+    # isothermal no-slip wall, implicit; Re = 146 / refViscosity
+    "box6_ns_implicit": lambda: make_case("box6_ns_implicit", mesh=kuhn_box(6, jitter=0.15), bc=ns_bc(330.0),
+                                          eqnset="compressibleNS", nsgs=3, cfl=5.0, refvisc=0.5),
+    # adiabatic wall, explicit, Von Neumann time-step limit on
+    "box6_ns_adiabatic": lambda: make_case("box6_ns_adiabatic", mesh=kuhn_box(6, jitter=0.15), bc=ns_bc(-1.0),
+                                           eqnset="compressibleNS", nsgs=2, cfl=5.0, refvisc=0.25, vnn=1),
     # the reference's own unit-test fixture (unitTest/gradientTest.h:20-232): prism cube, 216 nodes
     "cube_LowFi": lambda: make_case(
         "cube_LowFi", h5=os.path.join(REFERENCE, "unitTest/meshResources/cubeStructuredSeries/cube_LowFi.0.h5"),
