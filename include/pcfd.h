@@ -31,10 +31,10 @@
 extern "C" {
 #endif
 
-#define PCFD_ABI_VERSION 1
+#define PCFD_ABI_VERSION 2
 
 /* eqnset ids follow eqnset_defines.h / create_functions.h:17-45 */
-enum { PCFD_EQNSET_COMPRESSIBLE_EULER = 2 };
+enum { PCFD_EQNSET_COMPRESSIBLE_EULER = 2, PCFD_EQNSET_COMPRESSIBLE_NS = 3 };
 
 /* BC types: bc_defines.h:4-30 (the value bc->GetBCType(factag) returns) */
 enum { PCFD_BC_PARALLEL = 0, PCFD_BC_DIRICHLET = 1, PCFD_BC_NEUMANN = 2, PCFD_BC_IMPERMEABLE_WALL = 3,
@@ -53,7 +53,8 @@ enum {
   PCFD_F_LSQ_S = 7,    /* Mesh::s                 (nnode+gnode)*6 */
   PCFD_F_LSQ_SW = 8,   /* Mesh::sw                (nnode+gnode)*6 */
   PCFD_F_A = 9,        /* CRSMatrix::M            nblocks*neqn*neqn */
-  PCFD_F_COUNT = 10
+  PCFD_F_MUT = 10,     /* field "mut" (eddy viscosity) nnode+gnode+nbnode; zero for laminar flow */
+  PCFD_F_COUNT = 11
 };
 
 /* Mesh::edges / bedges / xyz / vol / ipsp / psp as flat arrays (uns_base.h:12-37, mesh.h:199-254) */
@@ -69,6 +70,8 @@ typedef struct {
   const double* vol;         /* [nnode] */
   const int* ipsp;           /* [nnode+1] */
   const int* psp;            /* [ipsp[nnode]]  order preserved: it fixes the CRS column order */
+  const double* bedges_twall;/* [nbedge] bcobj->twall / Param::ref_temperature of the half-edge's surface (bc.tcc:1283-1286),
+                                read for NoSlip half-edges only; < 0: adiabatic wall.  NULL: 1/tref (bcobj.tcc:31) */
 } pcfd_mesh_desc;
 
 /* the Param<Type> fields the hot path reads (param.tcc:84-229) */
@@ -79,6 +82,12 @@ typedef struct {
   int no_cvbc;
   double gamma, chi, cfl;
   double qinf[10];           /* free-stream state incl. aux vars (bc.tcc: Qinf) */
+  /* viscous terms, read when eqnset == PCFD_EQNSET_COMPRESSIBLE_NS (param.tcc:401-404 sets Param::viscous) */
+  int enable_vnn;            /* Param::enableVNN: Von Neumann time-step limit (timestep.tcc:37-41) */
+  double vnn;                /* Param::VNN */
+  double Re, Pr, PrT;        /* Param::Re (compressible.tcc:85-89), prandtlNumber, turbulent Prandtl number */
+  double tref;               /* Param::ref_temperature [K] (Sutherland constant 110.4/tref, eqnset.h:259) */
+  double mach;               /* Param::GetVelocity(iter): Re is rescaled by it (compressible.tcc:753-755) */
 } pcfd_params;
 
 typedef struct pcfd_ctx pcfd_ctx;

@@ -52,7 +52,7 @@ class DropIn {
     const int nb = nbedge_ + ngedge_;
 
     std::vector<int> en(2 * (size_t)nedge_), bn(2 * (size_t)nb), bt((size_t)nb);
-    std::vector<double> ea(4 * (size_t)nedge_), ba(4 * (size_t)nb);
+    std::vector<double> ea(4 * (size_t)nedge_), ba(4 * (size_t)nb), tw((size_t)(nbedge_ > 0 ? nbedge_ : 1));
     for (int e = 0; e < nedge_; e++) {          // Edges<Type>, uns_base.h:12-22
       en[2 * e] = s_->m->edges[e].n[0];
       en[2 * e + 1] = s_->m->edges[e].n[1];
@@ -63,6 +63,8 @@ class DropIn {
       bn[2 * e + 1] = s_->m->bedges[e].n[1];
       for (int k = 0; k < 4; k++) ba[4 * (size_t)e + k] = s_->m->bedges[e].a[k];
       bt[e] = s_->bc->GetBCType(s_->m->bedges[e].factag);   // bc.tcc:70-74
+      // wall temperature as bc.tcc:1283-1286 non-dimensionalises it (read for NoSlip surfaces only)
+      if (e < nbedge_) tw[e] = s_->bc->GetBCObj(s_->m->bedges[e].factag)->twall / s_->param->ref_temperature;
     }
     pcfd_mesh_desc md;
     md.nnode = nnode_; md.gnode = gnode_; md.nbnode = nbnode_;
@@ -70,6 +72,7 @@ class DropIn {
     md.edges_n = en.data(); md.edges_a = ea.data();
     md.bedges_n = bn.data(); md.bedges_a = ba.data(); md.bedges_bctype = bt.data();
     md.xyz = s_->m->xyz; md.vol = s_->m->vol; md.ipsp = s_->m->ipsp; md.psp = s_->m->psp;
+    md.bedges_twall = tw.data();
 
     pcfd_params pr;
     pr.eqnset = s_->param->eqnset_id;
@@ -80,6 +83,11 @@ class DropIn {
     pr.chi = s_->param->chi;
     pr.cfl = s_->param->GetCFL();
     for (int k = 0; k < 10; k++) pr.qinf[k] = (k < nvars_) ? s_->eqnset->Qinf[k] : 0.0;
+    pr.enable_vnn = s_->param->enableVNN ? 1 : 0;
+    pr.vnn = s_->param->VNN;
+    pr.Re = s_->param->Re; pr.Pr = s_->param->Pr; pr.PrT = s_->param->PrT;
+    pr.tref = s_->param->ref_temperature;
+    pr.mach = s_->param->GetVelocity(s_->iter);
 
     if (pcfd_create(&md, &pr, device, &ctx_) != 0) onError_("pcfd_create", pcfd_last_error(NULL));
     // Mesh::s / Mesh::sw were filled by ComputeNodeLSQCoefficients during Init: reuse them

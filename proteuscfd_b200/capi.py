@@ -13,11 +13,12 @@ LIB_PATH = os.path.join(_HERE, "libpcfd_b200.so")
 
 NEQN, NVARS, NTERMS = 5, 10, 9
 EQNSET_COMPRESSIBLE_EULER = 2
+EQNSET_COMPRESSIBLE_NS = 3
 
 BC_PARALLEL, BC_DIRICHLET, BC_NEUMANN, BC_IMPERMEABLE_WALL, BC_NOSLIP = 0, 1, 2, 3, 4
 BC_FARFIELD_VISCOUS, BC_FARFIELD, BC_SONIC_INFLOW, BC_SONIC_OUTFLOW, BC_SYMMETRY = 5, 6, 7, 8, 9
 
-F_Q, F_QGRAD, F_LIMITER, F_B, F_X, F_TIMESTEP, F_BETA, F_LSQ_S, F_LSQ_SW, F_A = range(10)
+F_Q, F_QGRAD, F_LIMITER, F_B, F_X, F_TIMESTEP, F_BETA, F_LSQ_S, F_LSQ_SW, F_A, F_MUT = range(11)
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -39,12 +40,14 @@ class MeshDesc(C.Structure):
     _fields_ = [("nnode", C.c_int), ("gnode", C.c_int), ("nbnode", C.c_int),
                 ("nedge", C.c_int), ("nbedge", C.c_int), ("ngedge", C.c_int),
                 ("edges_n", _ip), ("edges_a", _dp), ("bedges_n", _ip), ("bedges_a", _dp), ("bedges_bctype", _ip),
-                ("xyz", _dp), ("vol", _dp), ("ipsp", _ip), ("psp", _ip)]
+                ("xyz", _dp), ("vol", _dp), ("ipsp", _ip), ("psp", _ip), ("bedges_twall", _dp)]
 
 
 class Params(C.Structure):
     _fields_ = [("eqnset", C.c_int), ("sorder", C.c_int), ("limiter", C.c_int), ("no_cvbc", C.c_int),
-                ("gamma", C.c_double), ("chi", C.c_double), ("cfl", C.c_double), ("qinf", C.c_double * NVARS)]
+                ("gamma", C.c_double), ("chi", C.c_double), ("cfl", C.c_double), ("qinf", C.c_double * NVARS),
+                ("enable_vnn", C.c_int), ("vnn", C.c_double), ("Re", C.c_double), ("Pr", C.c_double),
+                ("PrT", C.c_double), ("tref", C.c_double), ("mach", C.c_double)]
 
 
 _lib = None
@@ -128,12 +131,21 @@ class Context:
             a = np.ascontiguousarray(np.asarray(mesh[k]).reshape(-1), dtype=ctype)
             self._keep[k] = a
             setattr(md, k, _i(a) if ctype == np.int32 else _d(a))
+        if mesh.get("bedges_twall") is not None:
+            a = np.ascontiguousarray(np.asarray(mesh["bedges_twall"]).reshape(-1), dtype=np.float64)
+            if a.size != md.nbedge:
+                raise ValueError("bedges_twall must hold one value per BC half-edge")
+            self._keep["bedges_twall"] = a
+            md.bedges_twall = _d(a)
         pr = Params()
         pr.eqnset = int(params.get("eqnset", EQNSET_COMPRESSIBLE_EULER))
         pr.sorder, pr.limiter, pr.no_cvbc = int(params["sorder"]), int(params["limiter"]), int(params.get("no_cvbc", 0))
         pr.gamma, pr.chi, pr.cfl = float(params["gamma"]), float(params.get("chi", 0.0)), float(params["cfl"])
         for j in range(NVARS):
             pr.qinf[j] = float(params["qinf"][j])
+        pr.enable_vnn, pr.vnn = int(params.get("enable_vnn", 0)), float(params.get("vnn", 20.0))
+        pr.Re, pr.Pr, pr.PrT = float(params.get("Re", 0.0)), float(params.get("Pr", 0.72)), float(params.get("PrT", 0.85))
+        pr.tref, pr.mach = float(params.get("tref", 0.0)), float(params.get("mach", 0.0))
         self.nnode, self.gnode, self.nbnode = md.nnode, md.gnode, md.nbnode
         self.nedge, self.nbedge, self.ngedge = md.nedge, md.nbedge, md.ngedge
         h = C.c_void_p()

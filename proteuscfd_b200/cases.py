@@ -15,6 +15,9 @@ from .ordering import color_order, kuhn_box_colors
 BOX_BC = {1: capi.BC_FARFIELD, 2: capi.BC_FARFIELD, 3: capi.BC_SYMMETRY, 4: capi.BC_IMPERMEABLE_WALL,
           5: capi.BC_FARFIELD, 6: capi.BC_FARFIELD}
 # docs/master.bc:5-10 layout of the 15-degree ramp
+# laminar Navier-Stokes box (tools/make_golden.py ns_bc): no-slip floor (zmin), symmetry side walls
+NS_BC = {1: capi.BC_FARFIELD, 2: capi.BC_FARFIELD, 3: capi.BC_SYMMETRY, 4: capi.BC_SYMMETRY,
+         5: capi.BC_NOSLIP, 6: capi.BC_FARFIELD}
 RAMP_BC = {1: capi.BC_FARFIELD, 2: capi.BC_FARFIELD, 3: capi.BC_IMPERMEABLE_WALL, 4: capi.BC_FARFIELD,
            5: capi.BC_SYMMETRY, 6: capi.BC_SYMMETRY}
 
@@ -59,14 +62,16 @@ def smooth_state(xyz, mach, gamma, amp=1.0):
 
 
 def box_case(n, jitter=0.15, mach=0.5, gamma=1.4, cfl=0.5, limiter=2, sorder=2, colored=False, ramp_deg=0.0,
-             bc=None, device="cpu", amp=1.0, seed=1234):
-    """Return (mesh dict, params dict, q [(nnode+nbnode)*10]) for an n^3-hex Kuhn box."""
+             bc=None, device="cpu", amp=1.0, seed=1234, viscous=False, reynolds=400.0, twall=1.1, tref=300.0,
+             enable_vnn=0):
+    """Return (mesh dict, params dict, q [(nnode+nbnode)*10]) for an n^3-hex Kuhn box.  viscous=True selects the
+    compressibleNS eqnset with a no-slip floor (wall temperature `twall`, non-dimensional; < 0: adiabatic)."""
     xyz, tets, tris, tags = kuhn_box(n, jitter=jitter, seed=seed, ramp_deg=ramp_deg)
     if colored:
         # colour-sorted numbering: sequential SGS == multicolour SGS (ordering.py)
         xyz, tets, tris = renumber(xyz, tets, tris, color_order(kuhn_box_colors(n)))
     mesh = median_dual(xyz, tets, tris, tags, device=device)
-    table = bc or (RAMP_BC if ramp_deg else BOX_BC)
+    table = bc or (RAMP_BC if ramp_deg else (NS_BC if viscous else BOX_BC))
     lut = np.zeros(max(table) + 1, dtype=np.int32)
     for t, b in table.items():
         lut[t] = b
@@ -74,6 +79,10 @@ def box_case(n, jitter=0.15, mach=0.5, gamma=1.4, cfl=0.5, limiter=2, sorder=2, 
     qinf = freestream(mach, gamma)
     params = dict(eqnset=capi.EQNSET_COMPRESSIBLE_EULER, sorder=sorder, limiter=limiter, no_cvbc=0, gamma=gamma,
                   chi=0.0, cfl=cfl, qinf=qinf)
+    if viscous:
+        params.update(eqnset=capi.EQNSET_COMPRESSIBLE_NS, viscous=1, Re=reynolds, Pr=0.72, PrT=0.85, tref=tref, mach=mach,
+                      enable_vnn=enable_vnn, vnn=20.0)
+        mesh["bedges_twall"] = np.where(mesh["bedges_bctype"] == capi.BC_NOSLIP, twall, 1.0 / tref)
     nn, nb = mesh["nnode"], mesh["nbnode"]
     q = np.zeros((nn + nb, 10))
     q[:nn] = smooth_state(mesh["xyz"].reshape(-1, 3), mach, gamma, amp)

@@ -246,6 +246,135 @@ __device__ __forceinline__ void apply_dq(const double* dQ, double* Q, double gam
   aux(Q, gamma);
 }
 
+// ------------------------------------------------------------------ viscous terms
+
+struct ViscParams {
+  double gamma, Re, Pr, PrT, tref, mach;
+};
+
+// T^1.5 for Sutherland's law.  The reference calls libm pow(T, 1.5) (eqnset.h:264); glibc's pow is
+// accurate to ~0.52 ulp, not reproducible bit for bit without its tables.  T*sqrt(T) is evaluated
+// here in double-double and rounded once, i.e. to within 0.5 ulp (+2^-100) of the exact value: it
+// equals glibc's result except where glibc itself misses the correctly rounded value (then 1 ulp).
+__device__ __forceinline__ double pow15(double T) {
+  const double s = sqrt(T);
+  const double e = __fma_rn(-s, s, T);   // T - s*s, exact
+  const double sl = e / (2.0 * s);       // sqrt(T) = s + sl
+  const double p = T * s;
+  const double pe = __fma_rn(T, s, -p);  // T*s - p, exact
+  return p + (pe + T * sl);
+}
+
+// eqnset.h:251-268 ComputeViscosity (Sutherland, non-dimensional); T = Q[5]
+__device__ __forceinline__ double viscosity(const ViscParams& vp, double T) {
+  const double S = 110.4 / vp.tref;
+  return (1.0 + S) * pow15(T) / (T + S);
+}
+
+// compressible.tcc:713-795 ViscousFlux.  Q[0..3] and T of the edge-averaged state; g = gradient rows
+// [T, u, v, w] (terms 5..8 of qgrad, 12 doubles); flux[0] is identically 0 and not returned.
+__device__ __forceinline__ void viscous_flux(const ViscParams& vp, const double* Q, double T, const double* g,
+                                             const double* n, double mut, double* f14) {
+  const double* gT = g;
+  const double* gu = g + 3;
+  const double* gv = g + 6;
+  const double* gw = g + 9;
+  const double rho = Q[0];
+  const double u = Q[1] / rho, v = Q[2] / rho, w = Q[3] / rho;
+  const double mu = viscosity(vp, T);
+  const double tmut = (mu + mut);
+  const double fact = -2.0 / 3.0 * (gu[0] + gv[1] + gw[2]);
+  const double tauxx = 2.0 * gu[0] + fact, tauyy = 2.0 * gv[1] + fact, tauzz = 2.0 * gw[2] + fact;
+  const double tauxy = gu[1] + gv[0], tauxz = gu[2] + gw[0], tauyz = gv[2] + gw[1];
+  const double ReTilde = vp.Re / vp.mach;
+  const double RK = n[3] / ReTilde;
+  const double RKT = RK * tmut;
+  const double cp = 1.0 / (vp.gamma - 1.0);
+  const double k = mu / vp.Pr * cp;
+  const double kT = mut / vp.PrT * cp;
+  const double c1 = -(k + kT);
+  const double Tn = gT[0] * n[0] + gT[1] * n[1] + gT[2] * n[2];
+  const double tauxn = tauxx * n[0] + tauxy * n[1] + tauxz * n[2];
+  const double tauyn = tauxy * n[0] + tauyy * n[1] + tauyz * n[2];
+  const double tauzn = tauxz * n[0] + tauyz * n[1] + tauzz * n[2];
+  f14[0] = -RKT * (tauxn);
+  f14[1] = -RKT * (tauyn);
+  f14[2] = -RKT * (tauzn);
+  f14[3] = -RKT * (tauxn * u + tauyn * v + tauzn * w) + RK * c1 * Tn;
+}
+
+// one side of ViscousJacobian (compressible.tcc:1633-1893): D = -/+ dx/(rho_side*s2); (rs,us,vs,ws,Ps)
+// the side's own state, (u,v,w) the edge-averaged velocity.  Adds sign*a to the 5x5 block at dst.
+__device__ __forceinline__ void viscous_jac_side(const double* D, double rs, double us, double vs, double ws, double Ps,
+                                                 double u, double v, double w, const double* n, double RK, double RKT,
+                                                 double c1, double gamma, bool negate, double* dst) {
+  const double c43 = 4.0 / 3.0, mc23 = -2.0 / 3.0;
+  const double gm1 = (gamma - 1.0);
+  const double dux = -u * D[0], duy = -u * D[1], duz = -u * D[2];
+  const double dvx = -v * D[0], dvy = -v * D[1], dvz = -v * D[2];
+  const double dwx = -w * D[0], dwy = -w * D[1], dwz = -w * D[2];
+  const double dfact = -2.0 / 3.0 * (dux + dvy + dwz);
+  const double dtauxx = (2.0 * dux + dfact), dtauyy = (2.0 * dvy + dfact), dtauzz = (2.0 * dwz + dfact);
+  const double dtauxy = duy + dvx, dtauxz = duz + dwx, dtauyz = dvz + dwy;
+  const double dtauxn = dtauxx * n[0] + dtauxy * n[1] + dtauxz * n[2];
+  const double dtauyn = dtauxy * n[0] + dtauyy * n[1] + dtauyz * n[2];
+  const double dtauzn = dtauxz * n[0] + dtauyz * n[1] + dtauzz * n[2];
+  const double dR2u = (c43 * D[0] * n[0] + D[1] * n[1] + D[2] * n[2]);
+  const double dR2v = (mc23 * D[1] * n[0] + D[0] * n[1]);
+  const double dR2w = (mc23 * D[2] * n[0] + D[0] * n[2]);
+  const double dR3u = (mc23 * D[0] * n[1] + D[1] * n[0]);
+  const double dR3v = (D[0] * n[0] + c43 * D[1] * n[1] + D[2] * n[2]);
+  const double dR3w = (mc23 * D[2] * n[1] + D[1] * n[2]);
+  const double dR4u = (mc23 * D[0] * n[2] + D[2] * n[0]);
+  const double dR4v = (mc23 * D[1] * n[2] + D[2] * n[1]);
+  const double dR4w = (D[0] * n[0] + D[1] * n[1] + c43 * D[2] * n[2]);
+  const double v2 = (us * us + vs * vs + ws * ws);
+  const double dT_dP = gamma / rs;
+  const double dP_dr = +gm1 * 0.5 * v2, dP_dru = -gm1 * us, dP_drv = -gm1 * vs, dP_drw = -gm1 * ws, dP_dret = +gm1;
+  const double Tn = (D[0] * n[0] + D[1] * n[1] + D[2] * n[2]) * dT_dP * c1;
+  double a[20];   // rows 1..4 (row 0 is zero)
+  a[0] = -RKT * (dtauxn); a[1] = -RKT * dR2u; a[2] = -RKT * dR2v; a[3] = -RKT * dR2w; a[4] = 0.0;
+  a[5] = -RKT * (dtauyn); a[6] = -RKT * dR3u; a[7] = -RKT * dR3v; a[8] = -RKT * dR3w; a[9] = 0.0;
+  a[10] = -RKT * (dtauzn); a[11] = -RKT * dR4u; a[12] = -RKT * dR4v; a[13] = -RKT * dR4w; a[14] = 0.0;
+  a[15] = -RKT * (dtauxn * u + dtauyn * v + dtauzn * w) + RK * Tn * (dP_dr - Ps / rs);
+  a[16] = -RKT * (dR2u * u + dR3u * v + dR4u * w) + RK * Tn * dP_dru;
+  a[17] = -RKT * (dR2v * u + dR3v * v + dR4v * w) + RK * Tn * dP_drv;
+  a[18] = -RKT * (dR2w * u + dR3w * v + dR4w * w) + RK * Tn * dP_drw;
+  a[19] = RK * Tn * dP_dret;
+  // row 0 receives +/-0.0, which leaves every value (up to the sign of a zero) unchanged
+#pragma unroll
+  for (int k = 0; k < 20; k++) dst[5 + k] += negate ? -a[k] : a[k];
+}
+
+// Kernel_Viscous_Jac (jacobian.tcc:768-800) for one edge: A(l,r) += aR, A(r,l) += aL (aL sign-flipped)
+__device__ __forceinline__ void viscous_jacobian(const ViscParams& vp, const double* QL, const double* QR, const double* dx,
+                                                 double s2, const double* n, double mut, double* pRL, double* pLR) {
+  double Qavg[5];
+#pragma unroll
+  for (int i = 0; i < 5; i++) Qavg[i] = 0.5 * (QL[i] + QR[i]);
+  const double Tavg = vp.gamma * pressure(Qavg, vp.gamma) / Qavg[0];   // aux(): Q[5]
+  const double mu = viscosity(vp, Tavg);
+  const double tmut = (mu + mut);
+  const double ReTilde = vp.Re / vp.mach;
+  const double RK = n[3] / ReTilde;
+  const double RKT = RK * tmut;
+  const double rhoL = QL[0], uL = QL[1] / rhoL, vL = QL[2] / rhoL, wL = QL[3] / rhoL, PL = QL[6];
+  const double rhoR = QR[0], uR = QR[1] / rhoR, vR = QR[2] / rhoR, wR = QR[3] / rhoR, PR = QR[6];
+  const double u = 0.5 * (uL + uR), v = 0.5 * (vL + vR), w = 0.5 * (wL + wR);
+  double DxL[3], DxR[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    DxL[i] = -dx[i] / (rhoL * s2);
+    DxR[i] = dx[i] / (rhoR * s2);
+  }
+  const double cp = 1.0 / (vp.gamma - 1.0);
+  const double k = mu / vp.Pr * cp;
+  const double kT = mut / vp.PrT * cp;
+  const double c1 = -(k + kT);
+  viscous_jac_side(DxR, rhoR, uR, vR, wR, PR, u, v, w, n, RK, RKT, c1, vp.gamma, false, pLR);
+  viscous_jac_side(DxL, rhoL, uL, vL, wL, PL, u, v, w, n, RK, RKT, c1, vp.gamma, true, pRL);
+}
+
 // ---------------------------------------------------------------- boundary states
 
 struct BcParams {
@@ -253,6 +382,25 @@ struct BcParams {
   int no_cvbc;
   double qinf[PCFD_NVARS];
 };
+
+// compressible.tcc:1544-1574 GetViscousWallBoundaryVariables on a static wall (vel = 0: bc.tcc:1207-1254
+// with movement == 0, bleedSteps == 0, velw == 0); normalQ = state of the most-normal neighbour
+__device__ __forceinline__ void viscous_wall_bc(double gamma, double* QL, double* QR, const double* normalQ, double Twall) {
+  const double vel[3] = {0.0, 0.0, 0.0};
+  if (Twall < 0.0) {
+    QR[0] = QL[0] = normalQ[0];
+    QR[4] = QL[4] = normalQ[4];
+  } else {
+    const double v2 = vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2];
+    const double gm1 = gamma - 1.0;
+    const double rhoEt = (Twall * QL[0] / (gamma * gm1) + 0.5 * QR[0] * v2);
+    QR[0] = QL[0];
+    QR[4] = QL[4] = rhoEt;
+  }
+  QR[1] = QL[1] = QL[0] * vel[0];
+  QR[2] = QL[2] = QL[0] * vel[1];
+  QR[3] = QL[3] = QL[0] * vel[2];
+}
 
 // compressible.tcc:1246-1372 characteristic far field (static mesh, 10 sub-iterations)
 __device__ __forceinline__ void farfield_bc(const BcParams& p, const double* QL, double* QR, const double* n, double vdotn) {
@@ -347,7 +495,8 @@ __device__ __forceinline__ void inviscid_wall_bc(const BcParams& p, const double
 
 // bc.tcc:1058-1120 + :1392-1396 CalculateBoundaryVariables for the BC types of the
 // hot-path configs; QL and QR are full nvars states.
-__device__ __forceinline__ void boundary_variables(const BcParams& p, double* QL, double* QR, const double* n, int bctype) {
+__device__ __forceinline__ void boundary_variables(const BcParams& p, double* QL, double* QR, const double* n, int bctype,
+                                                   const double* normalQ = nullptr, double twall = 0.0) {
   const double vdotn = 0.0;   // static mesh: driver.tcc:97-113 with Mesh::nv == 0
   switch (bctype) {
     case PCFD_BC_PARALLEL:
@@ -368,6 +517,9 @@ __device__ __forceinline__ void boundary_variables(const BcParams& p, double* QL
     case PCFD_BC_IMPERMEABLE_WALL:
     case PCFD_BC_SYMMETRY:
       inviscid_wall_bc(p, QL, QR, n, vdotn);
+      break;
+    case PCFD_BC_NOSLIP:   // bc.tcc:1182-1291
+      viscous_wall_bc(p.gamma, QL, QR, normalQ, twall);
       break;
     default:
       break;

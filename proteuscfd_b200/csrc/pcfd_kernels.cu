@@ -53,6 +53,8 @@ struct DevMesh {
   const double* vol;     // [nnode]
   const int* adjp;       // [nnode+1]
   const int2* adj;       // (.x = other node | role<<31 (1 = this node is the RIGHT node), .y = edge id; >= nedge: half-edge)
+  const int* bnormal;    // [nbedge] most-normal neighbour of the wall node (NoSlip half-edges, else -1)
+  const double* btwall;  // [nbedge] non-dimensional wall temperature of the half-edge's surface (< 0: adiabatic)
 };
 
 __device__ __forceinline__ bool is_ghost(const DevMesh& m, int n) { return n >= m.nnode && n < m.nnode + m.gnode; }
@@ -405,12 +407,22 @@ __global__ void __launch_bounds__(128) k_flux_bedges(DevMesh m, int sorder, doub
 // DriverScatter (driver.tcc:274-306) turned into an ordered gather: b[n] accumulates
 // +flux (n is the right node) / -flux (left node) in edge order, half-edges last,
 // then the (zero) source term of residual.tcc:109-115.
+// With VISC the viscous edge fluxes (Kernel_Viscous_Flux / Bkernel_Viscous_Flux, residual.tcc:388-562) follow in
+// a second pass over the same list -- the reference runs its viscous Driver/Bdriver after the inviscid pair --
+// and Bkernel_BC_Res_Modify (bc.tcc:905-1056 -> ModifyViscousWallResidual, compressible.tcc:1611-1631) zeroes the
+// hard-set rows of no-slip wall nodes (wallflag: bit 0 = owns a NoSlip half-edge, bit 1 = an adiabatic one).
+template <bool VISC>
 __global__ void __launch_bounds__(128) k_residual_gather(DevMesh m, const double* __restrict__ flux,
-                                                          const double* __restrict__ bflux, double* __restrict__ b) {
+                                                          const double* __restrict__ bflux,
+                                                          const double* __restrict__ vflux,
+                                                          const double* __restrict__ bvflux,
+                                                          const unsigned char* __restrict__ wallflag,
+                                                          double* __restrict__ b) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= m.nnode) return;
   double acc[5] = {0, 0, 0, 0, 0};
-  for (int k = m.adjp[n]; k < m.adjp[n + 1]; k++) {
+  const int k0 = m.adjp[n], k1 = m.adjp[n + 1];
+  for (int k = k0; k < k1; k++) {
     const int2 a = m.adj[k];
     const bool right = a.x < 0;
     const double* f = (a.y < m.nedge) ? flux + (size_t)a.y * 5 : bflux + (size_t)(a.y - m.nedge) * 5;
@@ -419,14 +431,117 @@ __global__ void __launch_bounds__(128) k_residual_gather(DevMesh m, const double
 #pragma unroll
     for (int j = 0; j < 5; j++) acc[j] += right ? fv[j] : -fv[j];
   }
+  if (VISC) {
+    for (int k = k0; k < k1; k++) {
+      const int2 a = m.adj[k];
+      const bool right = a.x < 0;
+      const double2* f = reinterpret_cast<const double2*>((a.y < m.nedge) ? vflux + (size_t)a.y * 4
+                                                                           : bvflux + (size_t)(a.y - m.nedge) * 4);
+      const double2 f01 = __ldg(f), f23 = __ldg(f + 1);
+      acc[1] += right ? f01.x : -f01.x;
+      acc[2] += right ? f01.y : -f01.y;
+      acc[3] += right ? f23.x : -f23.x;
+      acc[4] += right ? f23.y : -f23.y;
+    }
+  }
 #pragma unroll
-  for (int j = 0; j < 5; j++) b[(size_t)n * 5 + j] = acc[j] + 0.0;
+  for (int j = 0; j < 5; j++) acc[j] = acc[j] + 0.0;
+  if (VISC) {
+    const unsigned char wf = wallflag[n];
+    if (wf & 1) { acc[1] = acc[2] = acc[3] = acc[4] = 0.0; }
+    if (wf & 2) acc[0] = 0.0;
+  }
+#pragma unroll
+  for (int j = 0; j < 5; j++) b[(size_t)n * 5 + j] = acc[j];
+}
+
+// Kernel_Viscous_Flux (residual.tcc:388-466): face gradient = average of the two nodal gradients plus the
+// directional correction (dq - g.dx)/|dx|^2 dx, then CompressibleEqnSet::ViscousFlux.  Only the gradient rows the
+// flux reads (T, u, v, w = terms 5..8) are formed.  One thread per edge; vflux[e] = flux[1..4] (flux[0] == 0).
+__device__ __forceinline__ void face_gradient_Tuvw(const DevMesh& m, int sorder, const double* __restrict__ q,
+                                                   const double* __restrict__ qgrad, int l, int r, double* g) {
+  const double* gl = qgrad + (size_t)l * NTERMS * 3 + 15;
+  const double* gr = qgrad + (size_t)r * NTERMS * 3 + 15;
+#pragma unroll
+  for (int i = 0; i < 12; i++) g[i] = 0.5 * (__ldg(gl + i) + __ldg(gr + i));
+  if (sorder > 1) {
+    double dx[3], s2 = 0.0;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      dx[d] = (__ldg(m.xyz + 3 * r + d) - __ldg(m.xyz + 3 * l + d));
+      s2 += dx[d] * dx[d];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int loc = (j == 0) ? 5 : 6 + j;   // c_gradloc[5..8] = 5, 7, 8, 9
+      const double qdots = dx[0] * g[j * 3] + dx[1] * g[j * 3 + 1] + dx[2] * g[j * 3 + 2];
+      const double dq = (__ldg(q + (size_t)r * NVARS + loc) - __ldg(q + (size_t)l * NVARS + loc) - qdots) / s2;
+#pragma unroll
+      for (int d = 0; d < 3; d++) g[j * 3 + d] += dq * dx[d];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_vflux_edges(DevMesh m, int sorder, eq::ViscParams vp,
+                                                      const double* __restrict__ q, const double* __restrict__ qgrad,
+                                                      const double* __restrict__ mut, double* __restrict__ vflux) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m.nedge) return;
+  const int2 lr = m.en[e];
+  const int l = lr.x, r = lr.y;
+  double av[4], qL[5], qR[5], Qavg[5], g[12], f[4];
+  load_avec(m.ea, e, av);
+  load_q5(q, l, qL);
+  load_q5(q, r, qR);
+#pragma unroll
+  for (int i = 0; i < 5; i++) Qavg[i] = (qL[i] + qR[i]) / 2.0;
+  const double T = vp.gamma * eq::pressure(Qavg, vp.gamma) / Qavg[0];
+  const double tmut = 0.5 * (__ldg(mut + l) + __ldg(mut + r));
+  face_gradient_Tuvw(m, sorder, q, qgrad, l, r, g);
+  eq::viscous_flux(vp, Qavg, T, g, av, tmut, f);
+  double2* out = reinterpret_cast<double2*>(vflux + (size_t)e * 4);
+  out[0] = make_double2(f[0], f[1]);
+  out[1] = make_double2(f[2], f[3]);
+}
+
+// Bkernel_Viscous_Flux (residual.tcc:468-562): ghost half-edges like interior edges, boundary half-edges with
+// the wall node's own gradient and mut
+__global__ void __launch_bounds__(128) k_vflux_bedges(DevMesh m, int sorder, eq::ViscParams vp,
+                                                       const double* __restrict__ q, const double* __restrict__ qgrad,
+                                                       const double* __restrict__ mut, double* __restrict__ bvflux) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m.nbedge + m.ngedge) return;
+  const int2 lr = m.ben[e];
+  const int l = lr.x, r = lr.y;
+  double av[4], qL[5], qR[5], Qavg[5], g[12], f[4];
+  load_avec(m.bea, e, av);
+  load_q5(q, l, qL);
+  load_q5(q, r, qR);
+#pragma unroll
+  for (int i = 0; i < 5; i++) Qavg[i] = 0.5 * (qL[i] + qR[i]);
+  const double T = vp.gamma * eq::pressure(Qavg, vp.gamma) / Qavg[0];
+  double tmut;
+  if (is_ghost(m, r)) {
+    tmut = (__ldg(mut + l) + __ldg(mut + r)) / 2.0;
+    face_gradient_Tuvw(m, sorder, q, qgrad, l, r, g);
+  } else {
+    tmut = __ldg(mut + l);
+    const double* gl = qgrad + (size_t)l * NTERMS * 3 + 15;
+#pragma unroll
+    for (int i = 0; i < 12; i++) g[i] = __ldg(gl + i);
+  }
+  eq::viscous_flux(vp, Qavg, T, g, av, tmut, f);
+  double2* out = reinterpret_cast<double2*>(bvflux + (size_t)e * 4);
+  out[0] = make_double2(f[0], f[1]);
+  out[1] = make_double2(f[2], f[3]);
 }
 
 // ====================================================================== timestep
 // ComputeTimesteps (timestep.tcc:7-49) + Kernel_Timestep/Bkernel_Timestep (:80-143)
+// vnn23 (may be null) = VNN * pow(vol, 2/3), the Von Neumann limit of timestep.tcc:37-41, formed once on the host
+// with the same libm pow as the reference; the reference applies it from node 1 on.
 __global__ void __launch_bounds__(128) k_timestep(DevMesh m, double gamma, double cfl, const double* __restrict__ q,
-                                                   double* __restrict__ dt) {
+                                                   const double* __restrict__ vnn23, double* __restrict__ dt) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= m.nnode) return;
   double qn[5];
@@ -445,7 +560,9 @@ __global__ void __launch_bounds__(128) k_timestep(DevMesh m, double gamma, doubl
     const double maxeig = eq::max_eigenvalue(Q, av, 0.0, gamma);
     acc += maxeig * av[3];
   }
-  dt[n] = cfl * (m.vol[n] / acc);
+  double d = cfl * (m.vol[n] / acc);
+  if (vnn23 != nullptr && n >= 1) d = eq::mind(d, vnn23[n]);
+  dt[n] = d;
 }
 
 // deterministic min / sum-of-squares reductions (fixed grid, fixed tree)
@@ -559,10 +676,12 @@ __global__ void __launch_bounds__(128) k_update_bcs(DevMesh m, eq::BcParams bp, 
     const int type = m.bctype[be];
     if (type == PCFD_BC_PARALLEL) continue;
     const int r = a.x & 0x7fffffff;
-    double QR[NVARS], av[4];
+    double QR[NVARS], av[4], nQ[NVARS];
     load_q10(q, r, QR);
     load_avec(m.bea, be, av);
-    eq::boundary_variables(bp, QL, QR, av, type);
+    double tw = 0.0;
+    if (type == PCFD_BC_NOSLIP) { load_q10(q, m.bnormal[be], nQ); tw = m.btwall[be]; }
+    eq::boundary_variables(bp, QL, QR, av, type, nQ, tw);
     store_q10(q, r, QR);
     touched = true;
   }
@@ -632,6 +751,66 @@ __global__ void __launch_bounds__(128) k_jac_edges(DevMesh m, double gamma, cons
   }
 }
 
+// Kernel_Viscous_Jac (jacobian.tcc:768-800): analytic viscous blocks added onto the two off-diagonal blocks of
+// the edge.  A separate pass AFTER the boundary Jacobian kernels, as in the reference (jacobian.tcc:183-193):
+// Bkernel_NumJac updates the wall-node and phantom states this kernel reads.
+__global__ void __launch_bounds__(128) k_vjac_edges(DevMesh m, eq::ViscParams vp, const double* __restrict__ q,
+                                                     const double* __restrict__ mut, const int* __restrict__ posLR,
+                                                     const int* __restrict__ posRL, double* A) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m.nedge) return;
+  const int2 lr = m.en[e];
+  double av[4], qL[NVARS], qR[NVARS], dx[3], s2 = 0.0;
+  load_avec(m.ea, e, av);
+  load_q10(q, lr.x, qL);
+  load_q10(q, lr.y, qR);
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    dx[d] = (__ldg(m.xyz + 3 * lr.y + d) - __ldg(m.xyz + 3 * lr.x + d));
+    s2 += dx[d] * dx[d];
+  }
+  const double tmut = (__ldg(mut + lr.x) + __ldg(mut + lr.y)) / 2.0;
+  eq::viscous_jacobian(vp, qL, qR, dx, s2, av, tmut, A + (size_t)posRL[e] * NEQN2, A + (size_t)posLR[e] * NEQN2);
+}
+
+// Bkernel_BC_Jac_Modify (jacobian.tcc:247-249, bc.tcc:747-903) -> ModifyViscousWallJacobian
+// (compressible.tcc:1576-1609) with CRSMatrix::BlankSubRow (crsmatrix.tcc:524-541).  One thread per wall node,
+// its NoSlip half-edges in half-edge order (the reference re-applies the modification per half-edge).
+__global__ void k_jac_wall(DevMesh m, double gamma, const int* __restrict__ wnodes, int nw, const int* __restrict__ ia,
+                           const int* __restrict__ ja, const int* __restrict__ iau, double* A) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nw) return;
+  const int n = wnodes[t];
+  const int r0 = ia[n], r1 = ia[n + 1];
+  double* diag = A + (size_t)iau[n] * NEQN2;
+  for (int k = m.adjp[n]; k < m.adjp[n + 1]; k++) {
+    const int2 a = m.adj[k];
+    if (a.y < m.nedge) continue;
+    const int be = a.y - m.nedge;
+    if (m.bctype[be] != PCFD_BC_NOSLIP) continue;
+    const double Twall = m.btwall[be];
+    const bool adiabatic = Twall < 0.0;
+    for (int sub = 0; sub < NEQN; sub++) {
+      if (sub == 0 && !adiabatic) continue;
+      for (int kk = r0; kk < r1; kk++)
+        for (int j = 0; j < NEQN; j++) A[(size_t)kk * NEQN2 + sub * NEQN + j] = 0.0;
+      diag[sub * NEQN + sub] = 1.0;
+    }
+    if (adiabatic) {
+      const int nn_ = m.bnormal[be];
+      for (int kk = r0; kk < r1; kk++)
+        if (ja[kk] == nn_) {
+          A[(size_t)kk * NEQN2 + 0] = -1.0;
+          A[(size_t)kk * NEQN2 + 4 * NEQN + 4] = -1.0;
+          break;
+        }
+    } else {
+      const double v2 = 0.0;   // static wall
+      diag[4 * NEQN + 0] = -(Twall / (gamma * (gamma - 1.0)) + 0.5 * v2);
+    }
+  }
+}
+
 // Bkernel_NumJac (jacobian.tcc:459-544), boundaryJacEval == 0, for ONE half-edge: updates the
 // phantom state like the reference does, writes dF/dqL to bdiag[be] (summed into the node's
 // diagonal block, in half-edge order, by k_jac_diag) and, for ghost half-edges, dF/dqR to A(l,ghost).
@@ -643,10 +822,12 @@ __device__ __forceinline__ void jac_half_edge(const DevMesh& m, const eq::BcPara
   const int type = m.bctype[be];
   const int r = m.ben[be].y;
   const bool ghost = is_ghost(m, r);
-  double QR[NVARS], av[4], fS[5];
+  double QR[NVARS], av[4], fS[5], nQ[NVARS];
+  double tw = 0.0;
   load_q10(q, r, QR);
   load_avec(m.bea, be, av);
-  eq::boundary_variables(bp, QL, QR, av, type);
+  if (type == PCFD_BC_NOSLIP) { load_q10(q, m.bnormal[be], nQ); tw = m.btwall[be]; }
+  eq::boundary_variables(bp, QL, QR, av, type, nQ, tw);
   if (type != PCFD_BC_PARALLEL) store_q10(q, r, QR);
   eq::numerical_flux(QL, QR, av, 0.0, gamma, fS);
   double* pR = ghost ? A + (size_t)bpos[be] * NEQN2 : nullptr;
@@ -669,7 +850,7 @@ __device__ __forceinline__ void jac_half_edge(const DevMesh& m, const eq::BcPara
 #pragma unroll
       for (int j = 0; j < NVARS; j++) QPR[j] = QR[j];
       eq::aux(QPR, gamma);
-      eq::boundary_variables(bp, QPL, QPR, av, type);
+      eq::boundary_variables(bp, QPL, QPR, av, type, nQ, tw);
       eq::numerical_flux(QPL, QPR, av, 0.0, gamma, fL);
     }
 #pragma unroll
@@ -911,6 +1092,13 @@ struct pcfd_ctx {
   int nbn = 0, nblist = 0, nblist_bc = 0;
   double* bdiag = nullptr;
   double *flux = nullptr, *bflux = nullptr, *red = nullptr, *redout = nullptr;
+  // viscous terms (compressibleNS): per-edge viscous flux slots, wall-node bookkeeping, VNN time-step limit
+  bool viscous = false;
+  eq::ViscParams vp{};
+  double *vflux = nullptr, *bvflux = nullptr, *btwall = nullptr, *vnn23 = nullptr;
+  int *bnormal = nullptr, *wnodes = nullptr;
+  unsigned char* wallflag = nullptr;
+  int nwall = 0;
   unsigned char* clipflag = nullptr;
   int *tclip[2] = {nullptr, nullptr}, *dflags = nullptr;
   int *ia = nullptr, *ja = nullptr, *iau = nullptr, *pv = nullptr, *posLR = nullptr, *posRL = nullptr, *bpos = nullptr;
@@ -1058,7 +1246,12 @@ int pcfd_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int devic
   pcfd_ctx* c = nullptr;
   if (!mesh || !params || !out) return fail(c, "pcfd_create: null argument");
   *out = nullptr;
-  if (params->eqnset != PCFD_EQNSET_COMPRESSIBLE_EULER) return fail(c, "pcfd_create: unsupported eqnset id");
+  if (params->eqnset != PCFD_EQNSET_COMPRESSIBLE_EULER && params->eqnset != PCFD_EQNSET_COMPRESSIBLE_NS)
+    return fail(c, "pcfd_create: unsupported eqnset id");
+  // param.tcc:401-404: the NS eqnset ids switch the viscous terms on
+  const bool viscous = params->eqnset == PCFD_EQNSET_COMPRESSIBLE_NS;
+  if (viscous && !(params->Re > 0.0 && params->Pr > 0.0 && params->PrT > 0.0 && params->tref > 0.0 && params->mach > 0.0))
+    return fail(c, "pcfd_create: compressibleNS needs positive Re, Pr, PrT, tref and mach");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(c, "pcfd_create: no CUDA device (this library has no CPU fallback)");
@@ -1117,7 +1310,7 @@ int pcfd_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int devic
     std::vector<char> seq(nnode, 0), seen(nnode, 0);
     for (int e = 0; e < nb; e++) {
       const int t = mesh->bedges_bctype[e];
-      if (t == PCFD_BC_DIRICHLET || t == PCFD_BC_SONIC_INFLOW) seq[mesh->bedges_n[2 * e]] = 1;
+      if (t == PCFD_BC_DIRICHLET || t == PCFD_BC_SONIC_INFLOW || t == PCFD_BC_NOSLIP) seq[mesh->bedges_n[2 * e]] = 1;
     }
     for (int i = 0; i < nnode; i++) if (seq[i]) bnodes.push_back(i);
     for (int e = 0; e < nb; e++) {      // BC half-edges (everything that is not a parallel boundary)
@@ -1134,6 +1327,50 @@ int pcfd_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int devic
     c->nblist = (int)blist.size();
   }
   c->nbn = (int)bnodes.size();
+
+  // ---- no-slip walls: the "most normal node off the wall" search of bc.tcc:1182-1206 is pure geometry, so it is
+  // done once here (same arithmetic); wall temperature per half-edge; per-node flags for the residual hook
+  std::vector<int> bnormal(std::max(c->nbedge, 1), -1), wnodes;
+  std::vector<double> btwall(std::max(c->nbedge, 1), 1.0 / (params->tref > 0.0 ? params->tref : 1.0));
+  std::vector<unsigned char> wallflag(nnode, 0);
+  for (int e = 0; e < c->nbedge; e++) {
+    if (mesh->bedges_twall) btwall[e] = mesh->bedges_twall[e];
+    if (mesh->bedges_bctype[e] != PCFD_BC_NOSLIP) continue;
+    const int left = mesh->bedges_n[2 * e];
+    const double* av = mesh->bedges_a + 4 * (size_t)e;
+    const double* wx = mesh->xyz + 3 * (size_t)left;
+    double dotmax = 0.0;
+    int nn_ = -1;
+    for (int p = mesh->ipsp[left]; p < mesh->ipsp[left + 1]; p++) {
+      const int pt = mesh->psp[p];
+      const double* px = mesh->xyz + 3 * (size_t)pt;
+      double dx[3] = {px[0] - wx[0], px[1] - wx[1], px[2] - wx[2]};
+      const double mag = std::sqrt(dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2]);
+      double dot = 0.0;
+      for (int i = 0; i < 3; i++) { dx[i] = dx[i] / mag; dot -= dx[i] * av[i]; }
+      if (dot >= dotmax) { nn_ = pt; dotmax = dot; }
+    }
+    if (nn_ < 0) return fail(c, "pcfd_create: no-slip wall node without a neighbour off the wall");
+    bnormal[e] = nn_;
+    if (!wallflag[left]) wnodes.push_back(left);
+    wallflag[left] |= 1;
+    if (btwall[e] < 0.0) wallflag[left] |= 2;
+  }
+  std::sort(wnodes.begin(), wnodes.end());
+  for (int e = 0; e < c->nbedge; e++) {
+    // an adiabatic wall copies rho and rho*E from the normal node (compressible.tcc:1548-1554): in the
+    // reference's sequential BC loop that is order-dependent only if the normal node is itself hard-set
+    if (bnormal[e] >= 0 && btwall[e] < 0.0 && bnormal[e] < nnode && wallflag[bnormal[e]])
+      return fail(c, "pcfd_create: adiabatic no-slip wall whose most-normal neighbour is itself a wall node is not supported");
+  }
+  c->nwall = (int)wnodes.size();
+  c->viscous = viscous;
+  c->vp = eq::ViscParams{params->gamma, params->Re, params->Pr, params->PrT, params->tref, params->mach};
+  std::vector<double> vnn23;
+  if (params->enable_vnn) {   // timestep.tcc:37-41
+    vnn23.resize(nnode);
+    for (int i = 0; i < nnode; i++) vnn23[i] = params->vnn * std::pow(mesh->vol[i], 2.0 / 3.0);
+  }
 
   // ---- block-CRS pattern: CRSMatrix::Init (crsmatrix.tcc:48-97), diagonal first, then psp order
   std::vector<int> ia(nnode + 1), iau(nnode);
@@ -1179,6 +1416,11 @@ int pcfd_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int devic
   if (dev_upload(c, &c->bnodes, bnodes.data(), bnodes.size())) return 1;
   if (dev_upload(c, &c->blist, blist.data(), blist.size())) return 1;
   if (dev_upload(c, &c->bfirst, bfirst.data(), bfirst.size())) return 1;
+  if (dev_upload(c, &c->bnormal, bnormal.data(), bnormal.size())) return 1;
+  if (dev_upload(c, &c->btwall, btwall.data(), btwall.size())) return 1;
+  if (dev_upload(c, &c->wallflag, wallflag.data(), wallflag.size())) return 1;
+  if (dev_upload(c, &c->wnodes, wnodes.data(), wnodes.size())) return 1;
+  if (!vnn23.empty() && dev_upload(c, &c->vnn23, vnn23.data(), vnn23.size())) return 1;
   if (dev_upload(c, &c->ia, ia.data(), ia.size())) return 1;
   if (dev_upload(c, &c->ja, ja.data(), ja.size())) return 1;
   if (dev_upload(c, &c->iau, iau.data(), iau.size())) return 1;
@@ -1198,6 +1440,7 @@ int pcfd_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int devic
   c->fsize[PCFD_F_BETA] = (size_t)c->ntot;
   c->fsize[PCFD_F_LSQ_S] = (size_t)c->nn * 6;
   c->fsize[PCFD_F_LSQ_SW] = (size_t)c->nn * 6;
+  c->fsize[PCFD_F_MUT] = (size_t)c->ntot;
   c->fsize[PCFD_F_A] = 0;   // allocated on first use (implicit runs only)
   for (int k = 0; k < PCFD_F_COUNT; k++) {
     if (k == PCFD_F_A) continue;
@@ -1206,6 +1449,10 @@ int pcfd_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int devic
   }
   if (dev_alloc(c, &c->flux, (size_t)nedge * 5)) return 1;
   if (dev_alloc(c, &c->bflux, (size_t)nb * 5)) return 1;
+  if (viscous) {
+    if (dev_alloc(c, &c->vflux, (size_t)nedge * 4)) return 1;
+    if (dev_alloc(c, &c->bvflux, (size_t)nb * 4)) return 1;
+  }
   if (dev_alloc(c, &c->red, (size_t)RED_BLOCKS * 8)) return 1;
   if (dev_alloc(c, &c->redout, 16)) return 1;
   if (dev_alloc(c, &c->clipflag, (size_t)nedge)) return 1;
@@ -1214,7 +1461,7 @@ int pcfd_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int devic
   if (dev_alloc(c, &c->dflags, 4)) return 1;
 
   c->dm = DevMesh{c->nnode, c->gnode, c->nbnode, c->nedge, c->nbedge, c->ngedge, c->en, c->ea, c->ben, c->bea,
-                  c->bctype, c->xyz, c->vol, c->adjp, c->adj};
+                  c->bctype, c->xyz, c->vol, c->adjp, c->adj, c->bnormal, c->btwall};
   c->bp.gamma = params->gamma;
   c->bp.no_cvbc = params->no_cvbc;
   for (int i = 0; i < NVARS; i++) c->bp.qinf[i] = params->qinf[i];
@@ -1421,8 +1668,28 @@ static int run_flux(pcfd_ctx* c) {
                                                            c->bflux);
     LAUNCH_CHECK();
   }
+  if (c->viscous) {
+    if (c->nedge) {
+      PROF("k_vflux_edges");
+      k_vflux_edges<<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, c->prm.sorder, c->vp, c->f[PCFD_F_Q],
+                                                                c->f[PCFD_F_QGRAD], c->f[PCFD_F_MUT], c->vflux);
+      LAUNCH_CHECK();
+    }
+    if (c->nb) {
+      PROF("k_vflux_bedges");
+      k_vflux_bedges<<<nblk(c->nb, 128), 128, 0, c->stream>>>(c->dm, c->prm.sorder, c->vp, c->f[PCFD_F_Q],
+                                                              c->f[PCFD_F_QGRAD], c->f[PCFD_F_MUT], c->bvflux);
+      LAUNCH_CHECK();
+    }
+    PROF("k_residual_gather");
+    k_residual_gather<true><<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->flux, c->bflux, c->vflux, c->bvflux,
+                                                                        c->wallflag, c->f[PCFD_F_B]);
+    LAUNCH_CHECK();
+    return 0;
+  }
   PROF("k_residual_gather");
-  k_residual_gather<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->flux, c->bflux, c->f[PCFD_F_B]);
+  k_residual_gather<false><<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->flux, c->bflux, nullptr, nullptr, nullptr,
+                                                                       c->f[PCFD_F_B]);
   LAUNCH_CHECK();
   return 0;
 }
@@ -1453,7 +1720,7 @@ int pcfd_timestep(pcfd_ctx* c, double* dtmin) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
   PROF("k_timestep");
-  k_timestep<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->prm.gamma, c->prm.cfl, c->f[PCFD_F_Q],
+  k_timestep<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->prm.gamma, c->prm.cfl, c->f[PCFD_F_Q], c->vnn23,
                                                          c->f[PCFD_F_TIMESTEP]);
   LAUNCH_CHECK();
   if (dtmin) {
@@ -1511,10 +1778,21 @@ int pcfd_jacobian(pcfd_ctx* c) {
                                                             c->bpos, c->bdiag, A);
     LAUNCH_CHECK();
   }
+  if (c->viscous && c->nedge) {
+    PROF("k_vjac_edges");
+    k_vjac_edges<<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, c->vp, c->f[PCFD_F_Q], c->f[PCFD_F_MUT], c->posLR,
+                                                             c->posRL, A);
+    LAUNCH_CHECK();
+  }
   PROF("k_jac_diag");
   k_jac_diag<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->iau, c->posLR, c->posRL, c->f[PCFD_F_TIMESTEP],
                                                          c->bdiag, A);
   LAUNCH_CHECK();
+  if (c->nwall) {
+    PROF("k_jac_wall");
+    k_jac_wall<<<nblk(c->nwall, 64), 64, 0, c->stream>>>(c->dm, c->prm.gamma, c->wnodes, c->nwall, c->ia, c->ja, c->iau, A);
+    LAUNCH_CHECK();
+  }
   return 0;
 }
 
@@ -1590,7 +1868,7 @@ static int field_width(int field) {
     case PCFD_F_QGRAD: return NTERMS * 3;
     case PCFD_F_LIMITER: case PCFD_F_X: return NEQN;
     case PCFD_F_LSQ_S: case PCFD_F_LSQ_SW: return 6;
-    case PCFD_F_BETA: return 1;
+    case PCFD_F_BETA: case PCFD_F_MUT: return 1;
     default: return 0;
   }
 }

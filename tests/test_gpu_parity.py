@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from tests.oracle_lib import Oracle, load_golden, oracle_for
-from tests.test_oracle import ALL, EXPLICIT, IMPLICIT, exact
+from tests.test_oracle import EXPLICIT, INVISCID as ALL, INVISCID_IMPLICIT as IMPLICIT, exact
 
 pytestmark = pytest.mark.gpu
 
@@ -23,6 +23,11 @@ def golden_ctx(name):
         mesh[k] = int(meta[k])
     params = dict(sorder=int(meta["sorder"]), limiter=int(meta["limiter"]), no_cvbc=int(meta["no_cvbc"]),
                   gamma=meta["gamma"], chi=meta["chi"], cfl=meta["cfl"], qinf=g["qinf"])
+    if int(meta.get("viscous", 0)):
+        mesh["bedges_twall"] = g["bedges_twall"]
+        params.update(eqnset=capi.EQNSET_COMPRESSIBLE_NS, Re=meta["Re"], Pr=meta["Pr"], PrT=meta["PrT"],
+                      tref=meta["ref_temperature"], mach=meta["velocity"], enable_vnn=int(meta["enableVNN"]),
+                      vnn=meta["VNN"])
     return capi.Context(mesh, params), g, meta
 
 

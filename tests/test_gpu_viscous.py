@@ -1,0 +1,116 @@
+"""Laminar Navier-Stokes (compressibleNS) on the GPU against fixtures written by the reference itself
+(tests/golden/box6_ns_*.npz, tools/make_golden.py) and against the C oracle on a larger box.
+
+Everything that does not touch Sutherland's law is held BIT-EXACT (BC states incl. the hard-set no-slip
+wall, gradient, limiter, time step incl. the VNN limit, CRS pattern).  The viscous flux and the analytic
+viscous Jacobian contain mu = (1+S) T^1.5/(T+S); the reference evaluates T^1.5 with glibc pow (0.52 ulp,
+not reproducible on a GPU bit for bit), the device with a double-double T*sqrt(T) (0.5 ulp).  The two can
+differ by 1 ulp of mu on a few edges, so b, A, x and q carry the north-star tolerance: 1e-12 relative per
+node, |gpu - ref| <= 1e-12 * max(|ref|, max |ref| over the node's block/row).
+"""
+import numpy as np
+import pytest
+
+from tests.oracle_lib import oracle_for
+from tests.test_gpu_parity import golden_ctx
+from tests.test_oracle import NS, exact
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+def close_per_node(a, b, width, what):
+    a, b = np.asarray(a).reshape(-1, width), np.asarray(b).reshape(-1, width)
+    assert a.shape == b.shape, what
+    scale = np.maximum(np.abs(b), np.abs(b).max(axis=1, keepdims=True))
+    err = np.abs(a - b)
+    bad = err > RTOL * scale
+    if bad.any():
+        i = np.unravel_index(int(np.argmax(err / np.maximum(scale, 1e-300))), a.shape)
+        raise AssertionError(f"{what}: {int(bad.sum())}/{a.size} outside {RTOL:g} relative per node; worst at {i}: "
+                             f"{a[i]!r} vs {b[i]!r}")
+    return float((a == b).mean())
+
+
+@pytest.mark.parametrize("name", NS)
+def test_ns_bcs_gradient_limiter_timestep_bit_exact(name):
+    from proteuscfd_b200 import capi
+    ctx, g, _ = golden_ctx(name)
+    ctx.lsq_coefficients()
+    ctx.set_field(capi.F_Q, g["q_pre"])
+    ctx.update_bcs()
+    exact(ctx.get_field(capi.F_Q), g["q0"], "q after UpdateBCs (no-slip wall hard-set)")
+    ctx.set_field(capi.F_Q, g["q0"])
+    ctx.gradient()
+    exact(ctx.get_field(capi.F_QGRAD), g["qgrad"], "qgrad")
+    ctx.limiter()
+    exact(ctx.get_field(capi.F_LIMITER), g["limiter"], "limiter")
+    dtmin = ctx.timestep()
+    exact(ctx.get_field(capi.F_TIMESTEP), g["timestep"], "timestep (VNN limit)")
+    assert dtmin == g["dtmin"][0]
+
+
+@pytest.mark.parametrize("name", NS)
+def test_ns_residual(name):
+    from proteuscfd_b200 import capi
+    ctx, g, _ = golden_ctx(name)
+    ctx.set_field(capi.F_Q, g["q0"])
+    ctx.set_field(capi.F_QGRAD, g["qgrad"])
+    ctx.set_field(capi.F_LIMITER, g["limiter"])
+    s = ctx.residual(want_norms=True)
+    b = ctx.get_field(capi.F_B)
+    frac = close_per_node(b, g["b"], 5, "b")
+    assert frac > 0.5, f"only {frac:.2%} of b is bit-identical: more than Sutherland rounding is off"
+    assert np.isclose(np.sqrt(s[0]) / b.size, g["resnorm"][0], rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", NS)
+def test_ns_jacobian_lu_sgs(name):
+    from proteuscfd_b200 import capi
+    ctx, g, meta = golden_ctx(name)
+    ia, ja, iau, _ = ctx.get_crs()
+    exact(ia, g["ia"], "ia")
+    exact(ja, g["ja"], "ja")
+    ctx.set_field(capi.F_Q, g["q0"])
+    ctx.set_field(capi.F_TIMESTEP, g["timestep"])
+    ctx.jacobian()
+    close_per_node(ctx.get_field(capi.F_A), g["A"], 25, "A")
+    ctx.prepare_sgs()
+    close_per_node(ctx.get_field(capi.F_A), g["A_lu"], 25, "A_lu")
+    exact(ctx.get_crs()[3], g["pv"], "pv")
+    ctx.set_field(capi.F_B, g["b"])
+    ctx.blank_x()
+    ctx.sgs(int(meta["nSgs"]))
+    close_per_node(ctx.get_field(capi.F_X), g["x"], 5, "x")
+    ctx.apply_dq()
+    close_per_node(ctx.get_field(capi.F_Q), g["q1"], 10, "q1")
+
+
+def test_ns_implicit_iterations_vs_oracle(oracle):
+    """Two full implicit laminar iterations on a 12^3 box with an isothermal no-slip floor, GPU vs C oracle."""
+    from proteuscfd_b200 import capi
+    from proteuscfd_b200.cases import box_case
+    mesh, params, q = box_case(12, cfl=5.0, colored=True, viscous=True)
+    o = oracle_for(oracle, mesh, params)
+    ctx = capi.Context(mesh, params)
+    ctx.lsq_coefficients()
+    ctx.set_field(capi.F_Q, q)
+    qo = q.copy()
+    beta = np.zeros(1)
+    _, sw = o.lsq()
+    ia, ja, iau = o.crs_init()
+    for it in range(2):
+        dt, _ = o.timestep(qo, beta)
+        A = o.jacobian(qo, beta, dt, ia, ja, iau)
+        o.update_bcs(qo, beta)
+        grad = o.gradient(qo, sw)
+        lim = o.limiter(qo, grad)
+        b = o.residual(qo, grad, lim, beta)
+        pv = o.prepare_sgs(iau, A)
+        x, _ = o.sgs(3, ia, ja, iau, A, pv, b)
+        o.apply_dq(qo, x)
+        ctx.implicit_iterate(3, refresh_jac=True)
+        close_per_node(ctx.get_field(capi.F_B), b, 5, f"b it{it}")
+        close_per_node(ctx.get_field(capi.F_X), x, 5, f"x it{it}")
+        close_per_node(ctx.get_field(capi.F_Q), qo, 10, f"q it{it}")
