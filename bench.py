@@ -435,7 +435,8 @@ def sgs_bench(args, ctx, mesh, params, q0, peak, torch, stream, local_rank):
            "algorithmic_bytes_per_sweep": bytes_sweep, "GBps": bytes_sweep / (ms * 1e-3) / 1e9,
            "frac_hbm": bytes_sweep / (ms * 1e-3) / 1e9 / peak,
            "jacobian_ms": {k: tab0[k][0] / tab0[k][1] for k in ("k_jac_edges", "k_jac_bnodes", "k_jac_diag", "k_lu_diag") if k in tab0},
-           "launches_per_sweep": (tab["k_sgs_level"][1] - tab0["k_sgs_level"][1]) / nsw}
+           "kernel": "k_sgs_tile (cp.async.bulk + mbarrier streamed tiles)" if "k_sgs_tile" in tab else "k_sgs_level",
+           "launches_per_sweep": sum(tab[k][1] - tab0.get(k, (0, 0))[1] for k in ("k_sgs_level", "k_sgs_tile") if k in tab) / nsw}
     c.close()
     return out
 

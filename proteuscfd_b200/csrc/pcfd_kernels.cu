@@ -1053,6 +1053,371 @@ __global__ void __launch_bounds__(128) k_sgs_level(const int* __restrict__ rows,
   x[(size_t)row * NEQN + i] = out;
 }
 
+// ---- the same level with the matrix STREAMED through shared memory by bulk async copies (TMA engine,
+// cp.async.bulk + mbarrier) instead of per-lane 8-byte loads.  When the rows of a level are consecutive in
+// memory (always the case for a colour-sorted numbering) the blocks of a tile of rows form ONE contiguous byte
+// range of A (and of ja): one elected thread issues two bulk copies for the whole tile, the lanes fetch their
+// row's b / pv meanwhile and then run the identical ja-ordered arithmetic out of shared memory.  Several CTAs
+// per SM keep ~200 KB of matrix in flight per SM, which is what the HBM stream needs; x stays a gather (L2).
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+__device__ __forceinline__ unsigned long long policy_evict_first() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, unsigned bytes, unsigned long long* bar,
+                                              unsigned long long pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
+
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
+// rows of the tile: row0 + step*slot (step = +1 forward, -1 backward).  Work split inside a row's 5-lane group:
+// lane t takes the off-diagonal blocks u = t, t+5, t+10, ... WHOLE: while the bulk copy of the tile's matrix bytes
+// is in flight (L2 evict-first: the matrix is read once per sweep and must not push x out of L2) it fetches the
+// column index and the 5-vector x[col] of its blocks (one dependent hop for the whole row), then forms
+// v_u = M_u x_u (MatVecMult order, matrix.h:63-74) out of shared memory and parks it on top of block u.  After a
+// group-level sync lane i accumulates rhs[i] -= v_u[i] for u = 0, 1, 2, ... -- the reference's ja order -- and the
+// group runs the permuted LuSolve as in k_sgs_level.
+// LPR = lanes per row (5, 10 or 16): more lanes per row = fewer rows (less shared memory) per warp, hence more
+// warps per SM to hide the latency of the serial part (ordered accumulation + LuSolve, done by lanes 0..4).
+template <int WARPS, int LPR>
+__global__ void __launch_bounds__(WARPS * 32) k_sgs_tile(int row0, int step, int nrows, const int* __restrict__ ia,
+                                                          const int* __restrict__ ja, const double* __restrict__ A,
+                                                          const int* __restrict__ pv, const double* __restrict__ b,
+                                                          double* x, int pf_dist) {
+  constexpr int RPW = 32 / LPR;
+  constexpr int RT = WARPS * RPW;   // rows per tile
+  constexpr int R = (16 + LPR - 1) / LPR;   // rounds held in registers: up to R*LPR neighbour blocks before looping
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem);
+  unsigned char* sA = smem + 16;
+  const int s0 = blockIdx.x * RT;
+  const int s1 = min(s0 + RT, nrows);
+  const int rfirst = row0 + step * s0, rlast = row0 + step * (s1 - 1);
+  const int rlo = min(rfirst, rlast), rhi = max(rfirst, rlast);
+  const int kb0 = __ldg(ia + rlo);
+  const unsigned offA = (kb0 & 1) * 8u;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    const int kb1 = __ldg(ia + rhi + 1);
+    const unsigned bytesA = ((unsigned)(kb1 - kb0) * (NEQN2 * 8u) + offA + 15u) & ~15u;
+    mbar_expect_tx(bar, bytesA);
+    bulk_g2s_hint(sA, reinterpret_cast<const unsigned char*>(A) + (size_t)kb0 * (NEQN2 * 8) - offA, bytesA, bar,
+                  policy_evict_first());
+  }
+  if (threadIdx.x == 1 && pf_dist > 0) {
+    // pull the matrix / ja / b / pv bytes of the tile that a CTA pf_dist tiles later will need from HBM into L2
+    // now, so that its bulk copy and its ja -> x dependent loads are L2 hits (the HBM stream then runs pf_dist
+    // tiles ahead of the compute instead of being exposed in every CTA's lifetime)
+    const int f0 = (blockIdx.x + pf_dist) * RT;
+    if (f0 < nrows) {
+      const int f1 = min(f0 + RT, nrows);
+      const int qfirst = row0 + step * f0, qlast = row0 + step * (f1 - 1);
+      const int qlo = min(qfirst, qlast), qhi = max(qfirst, qlast);
+      const int pb0 = __ldg(ia + qlo), pb1 = __ldg(ia + qhi + 1);
+      const unsigned oA = (pb0 & 1) * 8u, oJ = (pb0 & 3) * 4u;
+      bulk_prefetch_l2(reinterpret_cast<const unsigned char*>(A) + (size_t)pb0 * (NEQN2 * 8) - oA,
+                       ((unsigned)(pb1 - pb0) * (NEQN2 * 8u) + oA + 15u) & ~15u);
+      bulk_prefetch_l2(reinterpret_cast<const unsigned char*>(ja) + (size_t)pb0 * 4 - oJ,
+                       ((unsigned)(pb1 - pb0) * 4u + oJ + 15u) & ~15u);
+      const unsigned oB = (qlo & 1) * 8u, oP = ((unsigned)qlo * 20u) & 15u;
+      bulk_prefetch_l2(reinterpret_cast<const unsigned char*>(b) + (size_t)qlo * (NEQN * 8) - oB,
+                       ((unsigned)(qhi - qlo + 1) * (NEQN * 8u) + oB + 15u) & ~15u);
+      bulk_prefetch_l2(reinterpret_cast<const unsigned char*>(pv) + (size_t)qlo * (NEQN * 4) - oP,
+                       ((unsigned)(qhi - qlo + 1) * (NEQN * 4u) + oP + 15u) & ~15u);
+    }
+  }
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int grp = lane / LPR;
+  const int t = lane - grp * LPR;
+  const int slot = s0 + warp * RPW + grp;
+  const bool active = (grp < RPW) && (slot < s1);
+  const unsigned gmask = (LPR == 16 ? 0xffffu : ((1u << LPR) - 1u)) << (grp * LPR);   // the row's own lanes
+  int row = 0, k0 = 0, nb = 0;
+  int p[NEQN];
+  double rhs = 0.0;
+  double xr[R][NEQN];
+  if (active) {
+    row = row0 + step * slot;
+    k0 = __ldg(ia + row);
+    nb = __ldg(ia + row + 1) - k0 - 1;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const int u = r * LPR + t;
+      if (u < nb) {
+        const double* xc = x + (size_t)__ldg(ja + k0 + 1 + u) * NEQN;
+#pragma unroll
+        for (int j = 0; j < NEQN; j++) xr[r][j] = xc[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NEQN; j++) p[j] = __ldg(pv + (size_t)row * NEQN + j);
+    if (t < NEQN) rhs = __ldg(b + (size_t)row * NEQN + t);
+  }
+  __syncthreads();        // mbarrier initialised before anyone waits on it
+  mbar_wait(bar, 0);
+  if (!active) return;
+  double* tA = reinterpret_cast<double*>(sA + offA) - (size_t)kb0 * NEQN2;   // tA[k*25 + ..], k in the tile
+  for (int base = 0;;) {
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const int u = base + r * LPR + t;
+      if (u < nb) {
+        double* m = tA + (size_t)(k0 + 1 + u) * NEQN2;
+        double v[NEQN];
+#pragma unroll
+        for (int ii = 0; ii < NEQN; ii++) {
+          double acc = m[ii * NEQN] * xr[r][0];
+#pragma unroll
+          for (int j = 1; j < NEQN; j++) acc += m[ii * NEQN + j] * xr[r][j];
+          v[ii] = acc;
+        }
+#pragma unroll
+        for (int ii = 0; ii < NEQN; ii++) m[ii] = v[ii];   // only this lane ever reads block u's matrix entries
+      }
+    }
+    base += R * LPR;
+    if (base >= nb) break;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const int u = base + r * LPR + t;
+      if (u < nb) {
+        const double* xc = x + (size_t)__ldg(ja + k0 + 1 + u) * NEQN;
+#pragma unroll
+        for (int j = 0; j < NEQN; j++) xr[r][j] = xc[j];
+      }
+    }
+  }
+  __syncwarp(gmask);
+  if (t < NEQN) {
+    const double* vv = tA + (size_t)(k0 + 1) * NEQN2 + t;
+    for (int u = 0; u < nb; u++) rhs -= vv[(size_t)u * NEQN2];
+  }
+  double bb[NEQN], xx[NEQN];
+#pragma unroll
+  for (int j = 0; j < NEQN; j++) bb[j] = __shfl_sync(gmask, rhs, grp * LPR + j);
+  if (t >= NEQN) return;
+  const double* d = tA + (size_t)k0 * NEQN2;   // the diagonal block is the first of the row (iau == ia)
+#pragma unroll
+  for (int r = 0; r < NEQN; r++) {
+    double sum = 0.0;
+#pragma unroll
+    for (int j = 0; j < r; j++) sum += d[p[r] * NEQN + j] * xx[j];
+    double bp = bb[0];
+#pragma unroll
+    for (int j = 1; j < NEQN; j++) bp = (p[r] == j) ? bb[j] : bp;
+    xx[r] = bp - sum;
+  }
+#pragma unroll
+  for (int r = NEQN - 1; r >= 0; r--) {
+    double sum = 0.0;
+#pragma unroll
+    for (int j = NEQN - 1; j > r; j--) sum += d[p[r] * NEQN + j] * bb[j];
+    bb[r] = (xx[r] - sum) / d[p[r] * NEQN + r];
+  }
+  double out = bb[0];
+#pragma unroll
+  for (int j = 1; j < NEQN; j++) out = (t == j) ? bb[j] : out;
+  x[(size_t)row * NEQN + t] = out;
+}
+
+// ---- persistent variant: one warp per CTA walks tiles blockIdx.x, +gridDim.x, ... of the level through an
+// S-stage ring of shared-memory buffers.  Lane 0 is the producer: it keeps S-1 bulk copies (cp.async.bulk, one
+// mbarrier per stage, complete_tx bytes) in flight ahead of the tile being computed, so the shared memory of every
+// resident CTA is in flight nearly all the time and the ia -> copy dependency is off the critical path; the x / ja /
+// b / pv fetches of tile k+1 are issued before tile k is computed.  Arithmetic and its order are those of k_sgs_tile.
+template <int LPR>
+struct SgsRowState {
+  static constexpr int R = (16 + LPR - 1) / LPR;
+  int row, k0, nb, kb0;
+  int p[NEQN];
+  double rhs;
+  double xr[R][NEQN];
+  bool active;
+};
+
+template <int LPR, int S>
+__global__ void __launch_bounds__(32) k_sgs_ring(int row0, int step, int nrows, const int* __restrict__ ia,
+                                                  const int* __restrict__ ja, const double* __restrict__ A,
+                                                  const int* __restrict__ pv, const double* __restrict__ b, double* x,
+                                                  int stage_bytes) {
+  constexpr int RPW = 32 / LPR;
+  constexpr int R = SgsRowState<LPR>::R;
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem);
+  unsigned char* stage0 = smem + ((S * 8 + 15) & ~15);
+  const int lane = threadIdx.x;
+  const int grp = lane / LPR;
+  const int t = lane - grp * LPR;
+  const unsigned gmask = (LPR == 16 ? 0xffffu : ((1u << LPR) - 1u)) << ((grp * LPR) & 31);
+  const int ntiles = (nrows + RPW - 1) / RPW;
+  const int G = gridDim.x;
+  const int K = (ntiles - (int)blockIdx.x + G - 1) / G;   // tiles of this CTA
+  if (lane == 0) {
+#pragma unroll
+    for (int st = 0; st < S; st++) mbar_init(bars + st, 1);
+  }
+  __syncwarp();
+  const unsigned long long pol = policy_evict_first();
+
+  auto issue = [&](int k) {   // producer (lane 0): bulk copy of tile k into stage k % S
+    const int s0 = ((int)blockIdx.x + k * G) * RPW;
+    const int s1 = min(s0 + RPW, nrows);
+    const int rfirst = row0 + step * s0, rlast = row0 + step * (s1 - 1);
+    const int kb0 = __ldg(ia + min(rfirst, rlast)), kb1 = __ldg(ia + max(rfirst, rlast) + 1);
+    const unsigned offA = (kb0 & 1) * 8u;
+    const unsigned bytes = ((unsigned)(kb1 - kb0) * (NEQN2 * 8u) + offA + 15u) & ~15u;
+    const int st = k % S;
+    mbar_expect_tx(bars + st, bytes);
+    bulk_g2s_hint(stage0 + (size_t)st * stage_bytes, reinterpret_cast<const unsigned char*>(A) + (size_t)kb0 * (NEQN2 * 8) - offA,
+                  bytes, bars + st, pol);
+  };
+  auto fetch = [&](int k, SgsRowState<LPR>& rs) {   // every lane: row metadata + x gather of tile k
+    const int s0 = ((int)blockIdx.x + k * G) * RPW;
+    const int s1 = min(s0 + RPW, nrows);
+    const int rfirst = row0 + step * s0, rlast = row0 + step * (s1 - 1);
+    rs.kb0 = __ldg(ia + min(rfirst, rlast));
+    const int slot = s0 + grp;
+    rs.active = (grp < RPW) && (slot < s1);
+    rs.row = 0; rs.k0 = 0; rs.nb = 0; rs.rhs = 0.0;
+    if (rs.active) {
+      rs.row = row0 + step * slot;
+      rs.k0 = __ldg(ia + rs.row);
+      rs.nb = __ldg(ia + rs.row + 1) - rs.k0 - 1;
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        const int u = r * LPR + t;
+        if (u < rs.nb) {
+          const double* xc = x + (size_t)__ldg(ja + rs.k0 + 1 + u) * NEQN;
+#pragma unroll
+          for (int j = 0; j < NEQN; j++) rs.xr[r][j] = xc[j];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NEQN; j++) rs.p[j] = __ldg(pv + (size_t)rs.row * NEQN + j);
+      if (t < NEQN) rs.rhs = __ldg(b + (size_t)rs.row * NEQN + t);
+    }
+  };
+
+  if (lane == 0) {
+    for (int k = 0; k < S - 1 && k < K; k++) issue(k);
+  }
+  SgsRowState<LPR> cur, nxt;
+  if (K > 0) fetch(0, cur);
+  for (int k = 0; k < K; k++) {
+    if (lane == 0 && k + S - 1 < K) issue(k + S - 1);   // stage (k-1) % S was released at the end of iteration k-1
+    if (k + 1 < K) fetch(k + 1, nxt);
+    const int st = k % S;
+    mbar_wait(bars + st, (unsigned)((k / S) & 1));
+    if (cur.active) {
+      const unsigned offA = (cur.kb0 & 1) * 8u;
+      double* tA = reinterpret_cast<double*>(stage0 + (size_t)st * stage_bytes + offA) - (size_t)cur.kb0 * NEQN2;
+      const int k0 = cur.k0, nb = cur.nb;
+      for (int base = 0;;) {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          const int u = base + r * LPR + t;
+          if (u < nb) {
+            double* m = tA + (size_t)(k0 + 1 + u) * NEQN2;
+            double v[NEQN];
+#pragma unroll
+            for (int ii = 0; ii < NEQN; ii++) {
+              double acc = m[ii * NEQN] * cur.xr[r][0];
+#pragma unroll
+              for (int j = 1; j < NEQN; j++) acc += m[ii * NEQN + j] * cur.xr[r][j];
+              v[ii] = acc;
+            }
+#pragma unroll
+            for (int ii = 0; ii < NEQN; ii++) m[ii] = v[ii];
+          }
+        }
+        base += R * LPR;
+        if (base >= nb) break;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          const int u = base + r * LPR + t;
+          if (u < nb) {
+            const double* xc = x + (size_t)__ldg(ja + k0 + 1 + u) * NEQN;
+#pragma unroll
+            for (int j = 0; j < NEQN; j++) cur.xr[r][j] = xc[j];
+          }
+        }
+      }
+      __syncwarp(gmask);
+      double rhs = cur.rhs;
+      if (t < NEQN) {
+        const double* vv = tA + (size_t)(k0 + 1) * NEQN2 + t;
+        for (int u = 0; u < nb; u++) rhs -= vv[(size_t)u * NEQN2];
+      }
+      double bb[NEQN], xx[NEQN];
+#pragma unroll
+      for (int j = 0; j < NEQN; j++) bb[j] = __shfl_sync(gmask, rhs, grp * LPR + j);
+      if (t < NEQN) {
+        const double* d = tA + (size_t)k0 * NEQN2;
+#pragma unroll
+        for (int r = 0; r < NEQN; r++) {
+          double sum = 0.0;
+#pragma unroll
+          for (int j = 0; j < r; j++) sum += d[cur.p[r] * NEQN + j] * xx[j];
+          double bp = bb[0];
+#pragma unroll
+          for (int j = 1; j < NEQN; j++) bp = (cur.p[r] == j) ? bb[j] : bp;
+          xx[r] = bp - sum;
+        }
+#pragma unroll
+        for (int r = NEQN - 1; r >= 0; r--) {
+          double sum = 0.0;
+#pragma unroll
+          for (int j = NEQN - 1; j > r; j--) sum += d[cur.p[r] * NEQN + j] * bb[j];
+          bb[r] = (xx[r] - sum) / d[cur.p[r] * NEQN + r];
+        }
+        double out = bb[0];
+#pragma unroll
+        for (int j = 1; j < NEQN; j++) out = (t == j) ? bb[j] : out;
+        x[(size_t)cur.row * NEQN + t] = out;
+      }
+    }
+    // release the stage: generic-proxy accesses (reads and the parked v_u writes) before the next async-proxy write
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    cur = nxt;
+  }
+}
+
 // PObj::UpdateGeneralVectors pack loop (parallel.tcc:829-846) with persistent send lists: row j of the
 // send buffer is node list[j] of field v (width n doubles).  dst may be local staging memory or, for the
 // direct-put exchange, a peer GPU's ghost segment mapped through CUDA IPC.
@@ -1111,6 +1476,12 @@ struct pcfd_ctx {
   int send_total = 0;
   bool ludiag = false;
   int sgs_unroll = 4;      // blocks in flight per lane in k_sgs_level (PCFD_SGS_UNROLL overrides, for tuning)
+  // bulk-copy (TMA) streaming variant: per level, shared-memory bytes for the matrix part of a tile (0: the rows of
+  // the level are not consecutive in memory -> per-lane-load kernel); PCFD_SGS_TILE_WARPS = 0 disables it
+  int sgs_tile_warps = 4, sgs_tile_lpr = 16;   // PCFD_SGS_TILE_WARPS / PCFD_SGS_TILE_LPR (lanes per row: 5, 10, 16)
+  int sgs_pf_dist = -1;    // PCFD_SGS_PREFETCH_TILES (-1: automatic, 0: off)
+  int sgs_ring_stages = 0, sgs_ring_ctas_per_sm = 0, ring_cap_blocks = 0, num_sms = 148;
+  std::vector<int> tile_cap_f, tile_cap_b, lev_first_f, lev_first_b, lev_step_f, lev_step_b;
   std::vector<void*> allocs;
   std::string err;
   long long launches = 0;
@@ -1224,6 +1595,28 @@ void build_levels(int n, const int* ia, const int* ja, bool forward, std::vector
   }
 }
 
+// Alternative schedule for numberings that are already colour-sorted: cut 0..n-1 into maximal CONTIGUOUS index
+// ranges that contain no two coupled rows.  Sweeping the ranges in order (rows of a range in parallel) is the
+// sequential Gauss-Seidel sweep exactly, forward and -- with the ranges reversed -- backward, and every range is one
+// contiguous slab of A, which is what the bulk-copy kernel streams.  Returns the range offsets.
+std::vector<int> contiguous_ranges(int n, const int* ia, const int* ja) {
+  std::vector<int> dep(n, -1), off;
+  int start = 0;
+  off.push_back(0);
+  for (int i = 0; i < n; i++) {
+    bool conflict = dep[i] >= start;
+    for (int k = ia[i] + 1; k < ia[i + 1]; k++) {
+      const int j = ja[k];
+      if (j >= n) continue;
+      if (j < i) conflict = conflict || j >= start;
+      else dep[j] = std::max(dep[j], i);
+    }
+    if (conflict) { off.push_back(i); start = i; }
+  }
+  off.push_back(n);
+  return off;
+}
+
 }  // namespace
 
 // ======================================================================= C ABI
@@ -1264,6 +1657,15 @@ int pcfd_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int devic
   struct Guard { pcfd_ctx* c; bool ok = false; ~Guard() { if (!ok) { g_create_err = c->err; pcfd_destroy(c); } } } guard{c};
   c->device = device;
   if (const char* e = getenv("PCFD_SGS_UNROLL")) c->sgs_unroll = atoi(e);
+  if (const char* e = getenv("PCFD_SGS_TILE_WARPS")) c->sgs_tile_warps = atoi(e);
+  if (c->sgs_tile_warps != 0 && c->sgs_tile_warps != 1 && c->sgs_tile_warps != 2 && c->sgs_tile_warps != 4) c->sgs_tile_warps = 4;
+  if (const char* e = getenv("PCFD_SGS_PREFETCH_TILES")) c->sgs_pf_dist = atoi(e);
+  if (const char* e = getenv("PCFD_SGS_RING_STAGES")) c->sgs_ring_stages = atoi(e);
+  if (const char* e = getenv("PCFD_SGS_RING_CTAS")) c->sgs_ring_ctas_per_sm = atoi(e);
+  if (c->sgs_ring_stages > 0) c->sgs_tile_warps = 1;   // ring tiles are one warp's rows
+  c->num_sms = prop.multiProcessorCount;
+  if (const char* e = getenv("PCFD_SGS_TILE_LPR")) c->sgs_tile_lpr = atoi(e);
+  if (c->sgs_tile_lpr != 5 && c->sgs_tile_lpr != 10 && c->sgs_tile_lpr != 16) c->sgs_tile_lpr = 16;
   CK(cudaSetDevice(device));
   CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
@@ -1400,8 +1802,53 @@ int pcfd_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int devic
     if (bpos[e] < 0) return fail(c, "pcfd_create: ghost half-edge without a matching psp entry");
   }
   std::vector<int> rows_f, rows_b;
-  build_levels(nnode, ia.data(), ja.data(), true, rows_f, c->lev_f);
-  build_levels(nnode, ia.data(), ja.data(), false, rows_b, c->lev_b);
+  {
+    const std::vector<int> rng = contiguous_ranges(nnode, ia.data(), ja.data());
+    const int nr = (int)rng.size() - 1;
+    if (nr <= 64 && nnode / nr >= 1024 && !getenv("PCFD_SGS_LEVEL_SCHEDULE")) {
+      // colour-sorted numbering: the ranges are the colours
+      c->lev_f = rng;
+      rows_f.resize(nnode);
+      rows_b.resize(nnode);
+      for (int i = 0; i < nnode; i++) { rows_f[i] = i; rows_b[i] = nnode - 1 - i; }
+      c->lev_b.assign(nr + 1, 0);
+      for (int l = 0; l <= nr; l++) c->lev_b[l] = nnode - rng[nr - l];
+    } else {
+      build_levels(nnode, ia.data(), ja.data(), true, rows_f, c->lev_f);
+      build_levels(nnode, ia.data(), ja.data(), false, rows_b, c->lev_b);
+    }
+  }
+  // per level: can a tile of rows be fetched as one contiguous byte range (rows consecutive in memory), and how
+  // many blocks does the largest tile hold
+  auto tile_caps = [&](const std::vector<int>& rows, const std::vector<int>& off, std::vector<int>& cap,
+                       std::vector<int>& first, std::vector<int>& stepv) {
+    cap.assign(off.size() - 1, 0);
+    first.assign(off.size() - 1, 0);
+    stepv.assign(off.size() - 1, 1);
+    for (size_t l = 0; l + 1 < off.size(); l++) {
+      first[l] = rows[off[l]];
+      stepv[l] = (off[l + 1] - off[l] > 1 && rows[off[l] + 1] < rows[off[l]]) ? -1 : 1;
+    }
+    if (c->sgs_tile_warps == 0) return;
+    const int RT = c->sgs_tile_warps * (32 / c->sgs_tile_lpr);
+    for (size_t l = 0; l + 1 < off.size(); l++) {
+      bool consecutive = true;
+      for (int s = off[l]; s + 1 < off[l + 1] && consecutive; s++) consecutive = rows[s + 1] - rows[s] == stepv[l];
+      if (!consecutive) continue;
+      int mx = 0;
+      for (int s0 = off[l]; s0 < off[l + 1]; s0 += RT) {
+        const int s1 = std::min(s0 + RT, off[l + 1]);
+        const int rlo = std::min(rows[s0], rows[s1 - 1]), rhi = std::max(rows[s0], rows[s1 - 1]);
+        if (rhi - rlo + 1 != s1 - s0) { mx = 0; consecutive = false; break; }
+        mx = std::max(mx, ia[rhi + 1] - ia[rlo]);
+      }
+      if (consecutive && (size_t)mx * (NEQN2 * 8 + 4) + 64 <= 100 * 1024) cap[l] = mx;
+    }
+  };
+  tile_caps(rows_f, c->lev_f, c->tile_cap_f, c->lev_first_f, c->lev_step_f);
+  tile_caps(rows_b, c->lev_b, c->tile_cap_b, c->lev_first_b, c->lev_step_b);
+  for (int v : c->tile_cap_f) c->ring_cap_blocks = std::max(c->ring_cap_blocks, v);
+  for (int v : c->tile_cap_b) c->ring_cap_blocks = std::max(c->ring_cap_blocks, v);
 
   // ---- upload
   if (dev_upload(c, &c->en, reinterpret_cast<const int2*>(mesh->edges_n), (size_t)nedge)) return 1;
@@ -1422,14 +1869,18 @@ int pcfd_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int devic
   if (dev_upload(c, &c->wnodes, wnodes.data(), wnodes.size())) return 1;
   if (!vnn23.empty() && dev_upload(c, &c->vnn23, vnn23.data(), vnn23.size())) return 1;
   if (dev_upload(c, &c->ia, ia.data(), ia.size())) return 1;
-  if (dev_upload(c, &c->ja, ja.data(), ja.size())) return 1;
+  {   // 16 bytes of slack behind ja (and A): the bulk copies of k_sgs_tile round their byte ranges to 16
+    std::vector<int> japad(ja);
+    japad.resize(ja.size() + 4, 0);
+    if (dev_upload(c, &c->ja, japad.data(), japad.size())) return 1;
+  }
   if (dev_upload(c, &c->iau, iau.data(), iau.size())) return 1;
   if (dev_upload(c, &c->posLR, posLR.data(), posLR.size())) return 1;
   if (dev_upload(c, &c->posRL, posRL.data(), posRL.size())) return 1;
   if (dev_upload(c, &c->bpos, bpos.data(), bpos.size())) return 1;
   if (dev_upload(c, &c->rows_f, rows_f.data(), rows_f.size())) return 1;
   if (dev_upload(c, &c->rows_b, rows_b.data(), rows_b.size())) return 1;
-  if (dev_alloc(c, &c->pv, (size_t)nnode * NEQN)) return 1;
+  if (dev_alloc(c, &c->pv, (size_t)nnode * NEQN + 8)) return 1;
 
   c->fsize[PCFD_F_Q] = (size_t)c->ntot * NVARS;
   c->fsize[PCFD_F_QGRAD] = (size_t)c->nn * NTERMS * 3;
@@ -1444,7 +1895,7 @@ int pcfd_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int devic
   c->fsize[PCFD_F_A] = 0;   // allocated on first use (implicit runs only)
   for (int k = 0; k < PCFD_F_COUNT; k++) {
     if (k == PCFD_F_A) continue;
-    if (dev_alloc(c, &c->f[k], c->fsize[k])) return 1;
+    if (dev_alloc(c, &c->f[k], c->fsize[k] + 4)) return 1;   // slack: 16-byte rounded bulk prefetches
     CK(cudaMemset(c->f[k], 0, std::max<size_t>(c->fsize[k], 1) * sizeof(double)));
   }
   if (dev_alloc(c, &c->flux, (size_t)nedge * 5)) return 1;
@@ -1520,7 +1971,7 @@ int pcfd_profile_get(pcfd_ctx* c, int i, const char** name, double* total_ms, lo
 static int ensure_matrix(pcfd_ctx* c) {
   if (c->f[PCFD_F_A]) return 0;
   c->fsize[PCFD_F_A] = (size_t)c->nblocks * NEQN2;
-  if (dev_alloc(c, &c->f[PCFD_F_A], c->fsize[PCFD_F_A])) return 1;
+  if (dev_alloc(c, &c->f[PCFD_F_A], c->fsize[PCFD_F_A] + 2)) return 1;
   if (dev_alloc(c, &c->bdiag, (size_t)c->nb * NEQN2)) return 1;
   CK(cudaMemsetAsync(c->f[PCFD_F_A], 0, c->fsize[PCFD_F_A] * sizeof(double), c->stream));
   return 0;
@@ -1829,6 +2280,68 @@ int pcfd_sgs(pcfd_ctx* c, int nsgs, double* ddq) {
       for (size_t l = 0; l + 1 < off.size(); l++) {
         const int nr = off[l + 1] - off[l];
         const int warps = (nr + RPW - 1) / RPW;
+        const int cap = (dir ? c->tile_cap_b : c->tile_cap_f)[l];
+        if (cap > 0) {
+          // bulk-copy streaming variant: one CTA per tile of tile_warps*6 consecutive rows
+          if (c->sgs_ring_stages > 0) {
+            const int LPRr = c->sgs_tile_lpr, St = c->sgs_ring_stages;
+            const int RPWr = 32 / LPRr;
+            const int stage_bytes = (c->ring_cap_blocks * NEQN2 * 8 + 8 + 15) & ~15;
+            const size_t shm = ((St * 8 + 15) & ~15) + (size_t)St * stage_bytes;
+            const int tiles = (nr + RPWr - 1) / RPWr;
+            int per_sm = (int)std::min<size_t>(32, (size_t)(220 * 1024) / (shm + 1024));
+            if (c->sgs_ring_ctas_per_sm > 0) per_sm = std::min(per_sm, c->sgs_ring_ctas_per_sm);
+            const int grid = std::max(1, std::min(tiles, c->num_sms * std::max(per_sm, 1)));
+            const int row0 = dir ? c->lev_first_b[l] : c->lev_first_f[l];
+            const int step = dir ? c->lev_step_b[l] : c->lev_step_f[l];
+            PROF("k_sgs_ring");
+#define PCFD_RING_LAUNCH(LL, SS)                                                                                     \
+  do {                                                                                                               \
+    static size_t set_##LL##_##SS = 0;                                                                               \
+    if (shm > set_##LL##_##SS) {                                                                                     \
+      CK(cudaFuncSetAttribute(k_sgs_ring<LL, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));           \
+      set_##LL##_##SS = shm;                                                                                         \
+    }                                                                                                                \
+    k_sgs_ring<LL, SS><<<grid, 32, shm, c->stream>>>(row0, step, nr, c->ia, c->ja, A, c->pv, c->f[PCFD_F_B], x,      \
+                                                     stage_bytes);                                                   \
+  } while (0)
+#define PCFD_RING_LPR(SS)                                                                                            \
+  do {                                                                                                               \
+    if (LPRr == 5) PCFD_RING_LAUNCH(5, SS); else if (LPRr == 10) PCFD_RING_LAUNCH(10, SS); else PCFD_RING_LAUNCH(16, SS); \
+  } while (0)
+            if (St == 2) PCFD_RING_LPR(2); else if (St == 3) PCFD_RING_LPR(3); else if (St == 6) PCFD_RING_LPR(6); else PCFD_RING_LPR(4);
+#undef PCFD_RING_LPR
+#undef PCFD_RING_LAUNCH
+            LAUNCH_CHECK();
+            continue;
+          }
+          const int W = c->sgs_tile_warps, LPR = c->sgs_tile_lpr;
+          const int RT = W * (32 / LPR);
+          const int capA = (cap * NEQN2 * 8 + 8 + 15) & ~15;
+          const size_t shm = 16 + (size_t)capA;
+          const int tiles = (nr + RT - 1) / RT;
+          // L2 prefetch distance in tiles: ~24 MB of matrix ahead of the compute front (measured best on B200; much
+          // further and the prefetched lines are evicted before use)
+          const int pf = c->sgs_pf_dist >= 0 ? c->sgs_pf_dist : (int)((size_t)(24 << 20) / shm);
+          const int row0 = dir ? c->lev_first_b[l] : c->lev_first_f[l];
+          const int step = dir ? c->lev_step_b[l] : c->lev_step_f[l];
+          PROF("k_sgs_tile");
+#define PCFD_TILE_LAUNCH(WW, LL)                                                                                      \
+  do {                                                                                                                \
+    static size_t set_##WW##_##LL = 0;                                                                                \
+    if (shm > set_##WW##_##LL) {                                                                                      \
+      CK(cudaFuncSetAttribute(k_sgs_tile<WW, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));            \
+      set_##WW##_##LL = shm;                                                                                          \
+    }                                                                                                                 \
+    k_sgs_tile<WW, LL><<<tiles, WW * 32, shm, c->stream>>>(row0, step, nr, c->ia, c->ja, A, c->pv, c->f[PCFD_F_B], x, pf); \
+  } while (0)
+          if (LPR == 5) { if (W == 1) PCFD_TILE_LAUNCH(1, 5); else if (W == 4) PCFD_TILE_LAUNCH(4, 5); else PCFD_TILE_LAUNCH(2, 5); }
+          else if (LPR == 10) { if (W == 1) PCFD_TILE_LAUNCH(1, 10); else if (W == 4) PCFD_TILE_LAUNCH(4, 10); else PCFD_TILE_LAUNCH(2, 10); }
+          else { if (W == 1) PCFD_TILE_LAUNCH(1, 16); else if (W == 4) PCFD_TILE_LAUNCH(4, 16); else PCFD_TILE_LAUNCH(2, 16); }
+#undef PCFD_TILE_LAUNCH
+          LAUNCH_CHECK();
+          continue;
+        }
         PROF("k_sgs_level");
         const int nb_ = nblk((long long)warps * 32, 128);
         switch (c->sgs_unroll) {

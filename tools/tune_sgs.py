@@ -15,8 +15,13 @@ def main():
     mesh, params, q = box_case(n, cfl=5.0, colored=True, device="cuda:0")
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    for u in (1, 2, 4, 7):
-        os.environ["PCFD_SGS_UNROLL"] = str(u)
+    variants = [(0, 5, 0)] + [(w, lpr, pf) for (w, lpr) in ((1, 5), (2, 10), (4, 16), (1, 16)) for pf in (0, -1, 1000, 4000, 16000)]
+    xref = None
+    for w, lpr, pf in variants:
+        os.environ["PCFD_SGS_TILE_WARPS"] = str(w)
+        os.environ["PCFD_SGS_TILE_LPR"] = str(lpr)
+        os.environ["PCFD_SGS_PREFETCH_TILES"] = str(pf)
+        var, u = "tile warps / lanes per row / L2 prefetch distance", (w, lpr, pf)
         c = capi.Context(mesh, params, device=0)
         c.set_stream(stream.cuda_stream)
         c.lsq_coefficients()
@@ -30,7 +35,11 @@ def main():
         c.sgs(10, want_ddq=False)
         e1.record(stream)
         torch.cuda.synchronize()
-        print(f"PCFD_SGS_UNROLL={u}: {e0.elapsed_time(e1) / 10:.4f} ms/sweep", flush=True)
+        x = c.get_field(capi.F_X)
+        if xref is None:
+            xref = x
+        same = bool((x == xref).all())
+        print(f"{var}={u}: {e0.elapsed_time(e1) / 10:.4f} ms/sweep, x bit-identical to the first variant: {same}", flush=True)
         c.close()
 
 
