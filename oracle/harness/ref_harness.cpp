@@ -183,6 +183,10 @@ static void DumpMesh(SolutionSpace<Real>* space)
   Int nvars = eqnset->neqn + eqnset->nauxvars;
   Dump("qinf", eqnset->Qinf, (size_t)nvars);
   Dump("beta", space->GetFieldData("beta", FIELDS::STATE_NONE), (size_t)(nnode+gnode));
+  if(space->param->viscous){
+    // eddy viscosity seen by the flow's viscous flux / Jacobian (zero unless a turbulence model initialised it)
+    Dump("mut", space->GetFieldData("mut", FIELDS::STATE_NONE), (size_t)(nnode+gnode));
+  }
 
   Param<Real>* param = space->param;
   std::ostringstream fn;
@@ -203,8 +207,46 @@ static void DumpMesh(SolutionSpace<Real>* space)
   f << "no_cvbc " << param->no_cvbc << "\nsymmetry2D " << param->symmetry2D << "\n";
   f << "eqnset_id " << param->eqnset_id << "\ngradType " << param->gradType << "\n";
   f << "ref_temperature " << param->ref_temperature << "\nenableVNN " << param->enableVNN << "\nVNN " << param->VNN << "\n";
+  f << "turbModel " << param->turbModel << "\nturbModelSorder " << param->turbModelSorder << "\n";
   f << "iter " << space->iter << "\nnFirstOrderSteps " << param->nFirstOrderSteps << "\n";
   f.close();
+}
+
+
+// Spalart-Allmaras (turbulenceModel = 1): inject a smooth positive nu~ field and run the reference's own
+// TurbulenceModel::Compute (turb.tcc:163-339) on the state the flow iteration left behind
+static void DumpTurbulence(SolutionSpace<Real>* space)
+{
+  Mesh<Real>* m = space->m;
+  Param<Real>* param = space->param;
+  if(!param->viscous || param->turbModel != 1) return;
+  TurbulenceModel<Real>* turb = space->turb;
+  Int nnode = m->GetNumNodes(), gnode = m->GetNumParallelNodes(), nbnode = m->GetNumBoundaryNodes();
+  Int nb = m->GetNumBoundaryEdges() + m->GetNumParallelEdges();
+  const Real twopi = 2.0*3.14159265358979323846;
+  for(Int i = 0; i < nnode; i++){
+    Real x = m->xyz[3*i + 0], y = m->xyz[3*i + 1], z = m->xyz[3*i + 2];
+    turb->tvar[i] = turb->tvarinf[0]*(1.0 + 0.3*sin(twopi*x)*cos(twopi*z) + 0.2*sin(twopi*y));
+  }
+  space->p->UpdateGeneralVectors(turb->tvar, 1);
+  for(Int e = 0; e < nb; e++){
+    if(!m->IsGhostNode(m->bedges[e].n[1])) turb->tvar[m->bedges[e].n[1]] = turb->tvar[m->bedges[e].n[0]];
+  }
+  memcpy(turb->tvarold, turb->tvar, sizeof(Real)*(size_t)(nnode+gnode+nbnode));
+  memcpy(turb->tvaroldm1, turb->tvar, sizeof(Real)*(size_t)(nnode+gnode+nbnode));
+  Dump("turb_tvar0", turb->tvar, (size_t)(nnode+gnode+nbnode));
+  Dump("turb_q", space->q, (size_t)(nnode+gnode+nbnode)*(space->eqnset->neqn + space->eqnset->nauxvars));
+  Dump("turb_qgrad", space->qgrad, (size_t)(nnode+gnode)*space->grad->GetNterms()*3);
+  Dump("turb_dt", space->GetFieldData("timestep", FIELDS::STATE_NONE), (size_t)nnode);
+  Dump("wallDistance", space->GetFieldData("wallDistance", FIELDS::STATE_NONE), (size_t)(nnode+gnode));
+  Real res = turb->Compute();
+  Dump("turb_res", &res, 1);
+  Dump("turb_tgrad", turb->tgrad, (size_t)(nnode+gnode)*3);
+  Dump("turb_b", turb->crs.b, (size_t)nnode);
+  Dump("turb_x", turb->crs.x, (size_t)(nnode+gnode));
+  Dump("turb_A", turb->crs.A->M, (size_t)turb->crs.A->nblocks);
+  Dump("turb_tvar1", turb->tvar, (size_t)(nnode+gnode+nbnode));
+  Dump("turb_mut", space->GetFieldData("mut", FIELDS::STATE_NONE), (size_t)(nnode+gnode));
 }
 
 int main(int argc, char* argv[])
@@ -387,6 +429,7 @@ int main(int argc, char* argv[])
     }
     p->UpdateGeneralVectors(space->q, nvars);
     Dump("q1", space->q, (size_t)(nnode+gnode+nbnode)*nvars);
+    DumpTurbulence(space);
   }
 #endif
   else if(mode == "time"){

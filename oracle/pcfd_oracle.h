@@ -96,6 +96,16 @@ void orc_viscous_jacobian(const orc_case* c, const double* QL, const double* QR,
 /* most-normal neighbour of a wall node (bc.tcc:1182-1206) for half-edge e */
 int orc_normal_node(const orc_case* c, int e);
 
+/* Spalart-Allmaras one-equation model, one TurbulenceModel::Compute (turb.tcc:163-339 with spalart.tcc:141-361),
+   turbulenceSpatialOrder = 1 (the reference's order-2 path calls the 5-equation ExtrapolateVariables on
+   1-variable arrays, limiters.tcc:412 -- out-of-bounds, not reproducible).  In/out tvar [(nnode+gnode+nbnode)];
+   q, qgrad, dt as left by the flow iteration; s = unweighted LSQ sums (Mesh::s); dist = field "wallDistance".
+   Out: tgrad [(nnode+gnode)*3], b [nnode], A [nblocks] (diagonal entries inverted by PrepareSGS,
+   crsmatrix.tcc:852-858), x [nnode+gnode], mut [nnode+gnode].  Returns ParallelL2Norm(b). */
+double orc_turb_sa(const orc_case* c, int nsgs, const double* q, const double* qgrad, const double* s,
+		   const double* dist, const double* dt, const int* ia, const int* ja, const int* iau,
+		   double* tvar, double* tgrad, double* b, double* A, double* x, double* mut);
+
 /* compressible.tcc:93-230 -- exposed for unit tests */
 void orc_roe_flux(const double* QL, const double* QR, const double* avec, double vdotn, double gamma,
 		  double* flux);

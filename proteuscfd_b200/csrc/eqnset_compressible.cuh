@@ -97,7 +97,8 @@ __device__ __forceinline__ void roe_variables(const double* QL, const double* QR
 }
 
 // compressible.tcc:687-710 Flux
-__device__ __forceinline__ void phys_flux(const double* Q, const double* n, double vdotn, double gamma, double* f) {
+__device__ __forceinline__ void phys_flux(const double* Q, const double* n, double vdotn, double gamma, double* f,
+                                          double* Pout = nullptr) {
   const double rho = Q[0];
   const double u = Q[1] / rho, v = Q[2] / rho, w = Q[3] / rho;
   const double rEt = Q[4];
@@ -110,6 +111,7 @@ __device__ __forceinline__ void phys_flux(const double* Q, const double* n, doub
   f[2] = (v * rhotheta + P * n[1]);
   f[3] = (w * rhotheta + P * n[2]);
   f[4] = (ht * rhotheta - vdotn * P);
+  if (Pout) *Pout = P;   // == ComputePressure(Q): the quantity BadExtrapolation tests
 }
 
 // Harten-Hyman entropy fix #2 on one wave (compressible.tcc:150-196)
@@ -132,8 +134,11 @@ __device__ __forceinline__ double row5(double a0, double a1, double a2, double a
 
 // compressible.tcc:93-230 RoeFlux, with Eigensystem (:581-684) evaluated row by row
 // instead of through stored 5x5 T / Tinv arrays; n[0..2] unit normal, n[3] area.
+// `bad` (optional) receives BadExtrapolation(QL) || BadExtrapolation(QR) || BadExtrapolation(Qroe)
+// (compressible.tcc:1056-1079, the test of Kernel_PressureClip, limiters.tcc:777-813) from the pressures this
+// routine forms anyway: the same expressions, so the same bits, at no extra divisions.
 __device__ __forceinline__ void roe_flux(const double* QL, const double* QR, const double* n, double vdotn,
-                                         double gamma, double* flux) {
+                                         double gamma, double* flux, bool* bad = nullptr) {
   double Qroe[5];
   roe_variables(QL, QR, gamma, Qroe);
   const double gm1 = gamma - 1.0;
@@ -197,17 +202,20 @@ __device__ __forceinline__ void roe_flux(const double* QL, const double* QR, con
   dr[4] = row5(v2h * nx + rho * (v * nz - w * ny), v2h * ny + rho * (w * nx - u * nz), v2h * nz + rho * (u * ny - v * nx),
                rho * (v2h / c + thetaf + c / gm1), rho * (v2h / c - thetaf + c / gm1), dv);
 
-  double fL[5], fR[5];
-  phys_flux(QL, n, vdotn, gamma, fL);
-  phys_flux(QR, n, vdotn, gamma, fR);
+  double fL[5], fR[5], pL, pR;
+  phys_flux(QL, n, vdotn, gamma, fL, &pL);
+  phys_flux(QR, n, vdotn, gamma, fR, &pR);
 #pragma unroll
   for (int i = 0; i < 5; i++) flux[i] = 0.5 * area * (fL[i] + fR[i] - dr[i]);
+  if (bad)
+    *bad = (pL < 1.0e-10) || (QL[0] < 0.0) || (QL[4] < 1.0e-10) || (pR < 1.0e-10) || (QR[0] < 0.0) || (QR[4] < 1.0e-10) ||
+           (P < 1.0e-10) || (rho < 0.0) || (Qroe[4] < 1.0e-10);
 }
 
 // EqnSet::NumericalFlux (eqnset.tcc:55-90): Roe + the NaN kneecap
 __device__ __forceinline__ void numerical_flux(const double* QL, const double* QR, const double* n, double vdotn,
-                                               double gamma, double* flux) {
-  roe_flux(QL, QR, n, vdotn, gamma, flux);
+                                               double gamma, double* flux, bool* bad = nullptr) {
+  roe_flux(QL, QR, n, vdotn, gamma, flux, bad);
 #pragma unroll
   for (int i = 0; i < 5; i++)
     if (isnan(flux[i])) flux[i] = 0.0;

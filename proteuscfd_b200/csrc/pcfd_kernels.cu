@@ -212,53 +212,50 @@ __device__ __forceinline__ double limiter_fn(int type, double t) {
 
 // Limiter::Compute passes 1+2 (limiters.tcc:53-110): neighbour min/max (from ZERO,
 // :62-63) and Barth / Venkatakrishnan limiting, both as gathers over the node's edges.
-// Writes the UNCLAMPED limiter; pressure clip and clamp follow.
-__global__ void __launch_bounds__(128) k_limiter(DevMesh m, int type, double chi, const double* __restrict__ q,
+// Writes the UNCLAMPED limiter; pressure clip and clamp follow.  FIVE threads per node, one equation each: the
+// limiter of a variable depends on that variable's data only.
+__global__ void __launch_bounds__(160) k_limiter(DevMesh m, int type, double chi, const double* __restrict__ q,
                                                   const double* __restrict__ qgrad, double* __restrict__ lim) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = tid / 5;
   if (n >= m.nnode + m.gnode) return;
-  double l[5] = {1.0, 1.0, 1.0, 1.0, 1.0};
+  const int j = tid - n * 5;
+  double l = 1.0;
   if (n < m.nnode && (type == 1 || type == 2)) {
-    double qmin[5] = {0, 0, 0, 0, 0}, qmax[5] = {0, 0, 0, 0, 0};
+    double qmin = 0.0, qmax = 0.0;
     const int k0 = m.adjp[n], k1 = m.adjp[n + 1];
     for (int k = k0; k < k1; k++) {
       const int2 a = m.adj[k];
       const int o = a.x & 0x7fffffff;
       if (a.y >= m.nedge && !is_ghost(m, o)) continue;
-      double qo[5];
-      load_q5(q, o, qo);
-#pragma unroll
-      for (int j = 0; j < 5; j++) { qmax[j] = eq::maxd(qmax[j], qo[j]); qmin[j] = eq::mind(qmin[j], qo[j]); }
+      const double qo = __ldg(q + (size_t)o * NVARS + j);
+      qmax = eq::maxd(qmax, qo);
+      qmin = eq::mind(qmin, qo);
     }
-    double qn[5], gr[15];
-    load_q5(q, n, qn);
-#pragma unroll
-    for (int j = 0; j < 15; j++) gr[j] = qgrad[(size_t)n * NTERMS * 3 + j];
+    const double qn = __ldg(q + (size_t)n * NVARS + j);
+    const double* gp = qgrad + (size_t)n * NTERMS * 3 + j * 3;
+    const double g0 = gp[0], g1 = gp[1], g2 = gp[2];
     const double xn[3] = {m.xyz[3 * n], m.xyz[3 * n + 1], m.xyz[3 * n + 2]};
-    const double ones[5] = {1.0, 1.0, 1.0, 1.0, 1.0};
     for (int k = k0; k < k1; k++) {
       const int2 a = m.adj[k];
       const int o = a.x & 0x7fffffff;
       if (a.y >= m.nedge && !is_ghost(m, o)) continue;
-      double qo[5], dQ[5], dx[3], QH[5];
-      load_q5(q, o, qo);
-#pragma unroll
-      for (int j = 0; j < 5; j++) dQ[j] = qo[j] - qn[j];
+      const double qo = __ldg(q + (size_t)o * NVARS + j);
+      const double dQ = qo - qn;
+      double dx[3];
 #pragma unroll
       for (int d = 0; d < 3; d++) dx[d] = 0.5 * (__ldg(m.xyz + 3 * o + d) - xn[d]);
-      eq::extrapolate(chi, QH, qn, dQ, gr, dx, ones);
-#pragma unroll
-      for (int j = 0; j < 5; j++) {
-        double t = 1.0;
-        if (QH[j] > qn[j]) t = (qmax[j] - qn[j]) / (QH[j] - qn[j]);
-        else if (QH[j] < qn[j]) t = (qmin[j] - qn[j]) / (QH[j] - qn[j]);
-        t = limiter_fn(type, t);
-        l[j] = eq::mind(l[j], t);
-      }
+      // eq::extrapolate with a unit limiter
+      const double corr = 0.5 * chi * dQ + (1.0 - chi) * (g0 * dx[0] + g1 * dx[1] + g2 * dx[2]);
+      const double QH = qn + corr * 1.0;
+      double t = 1.0;
+      if (QH > qn) t = (qmax - qn) / (QH - qn);
+      else if (QH < qn) t = (qmin - qn) / (QH - qn);
+      t = limiter_fn(type, t);
+      l = eq::mind(l, t);
     }
   }
-#pragma unroll
-  for (int j = 0; j < 5; j++) lim[(size_t)n * 5 + j] = l[j];
+  lim[(size_t)n * 5 + j] = l;
 }
 
 // Kernel_PressureClip (limiters.tcc:737-815) is sequential in the reference: an edge
@@ -332,10 +329,17 @@ __global__ void k_limiter_final(int ntot, int nnode, const int* __restrict__ tcl
 }
 
 // ====================================================================== residual
-// Kernel_Inviscid_Flux (residual.tcc:192-296): MUSCL reconstruction + Roe flux, once per edge
+// Kernel_Inviscid_Flux (residual.tcc:192-296): MUSCL reconstruction + Roe flux, once per edge.
+// DET = true is the fused fast path of the composite iterations: `lim` then holds the RAW limiter of k_limiter (before
+// Kernel_PressureClip and the clamp of negatives, limiters.tcc:105-125).  The flux uses the clamped value, and the
+// pressure-clip test (k_clip_edges) is evaluated on the way with the raw one -- same reconstruction, same Roe state,
+// almost no extra work.  If no edge anywhere raises *any, clip(lim) == lim and this flux is final; otherwise the
+// caller discards it and takes the ordered clip path.
+template <bool DET>
 __global__ void __launch_bounds__(128) k_flux_edges(DevMesh m, int sorder, double chi, double gamma,
                                                      const double* __restrict__ q, const double* __restrict__ qgrad,
-                                                     const double* __restrict__ lim, double* __restrict__ flux) {
+                                                     const double* __restrict__ lim, double* __restrict__ flux,
+                                                     int* __restrict__ any) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= m.nedge) return;
   const int2 lr = m.en[e];
@@ -344,26 +348,55 @@ __global__ void __launch_bounds__(128) k_flux_edges(DevMesh m, int sorder, doubl
   load_avec(m.ea, e, av);
   load_q5(q, l, QL);
   load_q5(q, r, QR);
+  bool neg = false;
   if (sorder > 1) {
-    double dQ[5], dx[3], gr[15], lm[5], qL[5], qR[5];
+    double dQ[5], dx[3], gr[15], lmL[5], lmR[5], qL[5], qR[5];
 #pragma unroll
     for (int j = 0; j < 5; j++) { qL[j] = QL[j]; qR[j] = QR[j]; dQ[j] = qR[j] - qL[j]; }
 #pragma unroll
     for (int d = 0; d < 3; d++) dx[d] = 0.5 * (__ldg(m.xyz + 3 * r + d) - __ldg(m.xyz + 3 * l + d));
+    load5(lim + (size_t)l * 5, lmL);
+    load5(lim + (size_t)r * 5, lmR);
+    if (DET) {
+      double cL[5], cR[5];
+#pragma unroll
+      for (int j = 0; j < 5; j++) {
+        neg = neg || (lmL[j] < 0.0) || (lmR[j] < 0.0);
+        cL[j] = (lmL[j] < 0.0) ? 0.0 : lmL[j];
+        cR[j] = (lmR[j] < 0.0) ? 0.0 : lmR[j];
+      }
+      if (neg) {   // rare: the clip test sees the unclamped limiter, the flux the clamped one
+        double TL[5], TR[5], Troe[5], mdQ[5], mdx[3];
+#pragma unroll
+        for (int j = 0; j < 15; j++) gr[j] = __ldg(qgrad + (size_t)l * NTERMS * 3 + j);
+        eq::extrapolate(chi, TL, qL, dQ, gr, dx, lmL);
+#pragma unroll
+        for (int j = 0; j < 5; j++) mdQ[j] = -dQ[j];
+#pragma unroll
+        for (int d = 0; d < 3; d++) mdx[d] = -dx[d];
+#pragma unroll
+        for (int j = 0; j < 15; j++) gr[j] = __ldg(qgrad + (size_t)r * NTERMS * 3 + j);
+        eq::extrapolate(chi, TR, qR, mdQ, gr, mdx, lmR);
+        eq::roe_variables(TL, TR, gamma, Troe);
+        if (eq::bad_extrapolation(TL, gamma) || eq::bad_extrapolation(TR, gamma) || eq::bad_extrapolation(Troe, gamma)) *any = 1;
+      }
+#pragma unroll
+      for (int j = 0; j < 5; j++) { lmL[j] = cL[j]; lmR[j] = cR[j]; }
+    }
 #pragma unroll
     for (int j = 0; j < 15; j++) gr[j] = __ldg(qgrad + (size_t)l * NTERMS * 3 + j);
-    load5(lim + (size_t)l * 5, lm);
-    eq::extrapolate(chi, QL, qL, dQ, gr, dx, lm);
+    eq::extrapolate(chi, QL, qL, dQ, gr, dx, lmL);
 #pragma unroll
     for (int j = 0; j < 5; j++) dQ[j] = -dQ[j];
 #pragma unroll
     for (int d = 0; d < 3; d++) dx[d] = -dx[d];
 #pragma unroll
     for (int j = 0; j < 15; j++) gr[j] = __ldg(qgrad + (size_t)r * NTERMS * 3 + j);
-    load5(lim + (size_t)r * 5, lm);
-    eq::extrapolate(chi, QR, qR, dQ, gr, dx, lm);
+    eq::extrapolate(chi, QR, qR, dQ, gr, dx, lmR);
   }
-  eq::numerical_flux(QL, QR, av, 0.0, gamma, f);
+  bool bad = false;
+  eq::numerical_flux(QL, QR, av, 0.0, gamma, f, DET ? &bad : nullptr);
+  if (DET && bad && !neg && sorder > 1) *any = 1;   // with a clamped component the raw-limiter test above decides
 #pragma unroll
   for (int j = 0; j < 5; j++) flux[(size_t)e * 5 + j] = f[j];
 }
@@ -1466,6 +1499,10 @@ struct pcfd_ctx {
   int nwall = 0;
   unsigned char* clipflag = nullptr;
   int *tclip[2] = {nullptr, nullptr}, *dflags = nullptr;
+  int* hflag = nullptr;            // pinned host copy of the fused clip flag
+  cudaEvent_t ev_flag = nullptr;
+  bool fused_clip = true;          // PCFD_FUSED_CLIP=0 keeps the separate clip pass in the composite iterations
+  long long clip_fallbacks = 0;
   int *ia = nullptr, *ja = nullptr, *iau = nullptr, *pv = nullptr, *posLR = nullptr, *posRL = nullptr, *bpos = nullptr;
   int *rows_f = nullptr, *rows_b = nullptr;
   std::vector<int> lev_f, lev_b;   // level offsets into rows_f / rows_b
@@ -1631,6 +1668,8 @@ int pcfd_destroy(pcfd_ctx* c) {
   cudaSetDevice(c->device);
   for (void* p : c->allocs) cudaFree(p);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->hflag) cudaFreeHost(c->hflag);
+  if (c->ev_flag) cudaEventDestroy(c->ev_flag);
   delete c;
   return 0;
 }
@@ -1910,6 +1949,9 @@ int pcfd_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int devic
   if (dev_alloc(c, &c->tclip[0], (size_t)nnode)) return 1;
   if (dev_alloc(c, &c->tclip[1], (size_t)nnode)) return 1;
   if (dev_alloc(c, &c->dflags, 4)) return 1;
+  CK(cudaMallocHost(reinterpret_cast<void**>(&c->hflag), sizeof(int)));
+  CK(cudaEventCreateWithFlags(&c->ev_flag, cudaEventDisableTiming));
+  if (const char* e = getenv("PCFD_FUSED_CLIP")) c->fused_clip = atoi(e) != 0;
 
   c->dm = DevMesh{c->nnode, c->gnode, c->nbnode, c->nedge, c->nbedge, c->ngedge, c->en, c->ea, c->ben, c->bea,
                   c->bctype, c->xyz, c->vol, c->adjp, c->adj, c->bnormal, c->btwall};
@@ -2059,13 +2101,17 @@ int pcfd_gradient(pcfd_ctx* c) {
   return 0;
 }
 
+static int run_limiter_final(pcfd_ctx* c, const int* tclip);
+static int run_flux(pcfd_ctx* c, bool fused = false, bool* clip_hit = nullptr);
+static int run_sumsq(pcfd_ctx* c, const double* v, int nrows, double* host_out);
+
 int pcfd_limiter(pcfd_ctx* c) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
   const int type = c->prm.limiter;
   double* lim = c->f[PCFD_F_LIMITER];
   PROF("k_limiter");
-  k_limiter<<<nblk(c->nn, 128), 128, 0, c->stream>>>(c->dm, type, c->prm.chi, c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD], lim);
+  k_limiter<<<nblk((long long)c->nn * 5, 160), 160, 0, c->stream>>>(c->dm, type, c->prm.chi, c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD], lim);
   LAUNCH_CHECK();
   if (type == 0) return 0;
   // pressure clip: iterate (edges -> flags, nodes -> first clipping edge) to the fixed point
@@ -2097,20 +2143,62 @@ int pcfd_limiter(pcfd_ctx* c) {
     CK(cudaStreamSynchronize(c->stream));
     if (!hflags[1]) break;     // tclip reproduced itself: fixed point
   }
+  return run_limiter_final(c, clipped ? c->tclip[cur] : nullptr);
+}
+
+// Gradient -> Limiter -> ComputeResiduals of the composite iterations.  With a limiter on, the pressure-clip test
+// rides along in the edge-flux kernel (k_flux_edges<true>); only when some edge actually clips (rare: the limiter
+// exists to prevent exactly that) are the ordered clip passes and the flux redone.
+static int gradient_limiter_residual(pcfd_ctx* c, double* sumsq) {
+  if (c->prm.sorder > 1) {
+    if (pcfd_gradient(c)) return 1;
+    const int type = c->prm.limiter;
+    if (type != 0 && c->fused_clip) {
+      PROF("k_limiter");
+      k_limiter<<<nblk((long long)c->nn * 5, 160), 160, 0, c->stream>>>(c->dm, type, c->prm.chi, c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD],
+                                                         c->f[PCFD_F_LIMITER]);
+      LAUNCH_CHECK();
+      bool hit = false;
+      if (run_flux(c, true, &hit)) return 1;
+      if (!hit) {
+        if (sumsq) return run_sumsq(c, c->f[PCFD_F_B], c->nnode, sumsq);
+        return 0;
+      }
+      c->clip_fallbacks++;
+    }
+    if (pcfd_limiter(c)) return 1;
+  }
+  return pcfd_residual(c, sumsq);
+}
+
+static int run_limiter_final(pcfd_ctx* c, const int* tclip) {
   PROF("k_limiter_final");
-  k_limiter_final<<<nblk((long long)c->nn * 5, 256), 256, 0, c->stream>>>(c->nn, c->nnode, clipped ? c->tclip[cur] : nullptr,
-                                                                         lim);
+  k_limiter_final<<<nblk((long long)c->nn * 5, 256), 256, 0, c->stream>>>(c->nn, c->nnode, tclip, c->f[PCFD_F_LIMITER]);
   LAUNCH_CHECK();
   return 0;
 }
 
-static int run_flux(pcfd_ctx* c) {
+// fused = true: lim holds the raw limiter; the edge kernel clamps on the fly and raises dflags[2] if the pressure
+// clip would act anywhere, k_limiter_final then clamps in place, and *clip_hit reports the flag (one event wait that
+// overlaps with the kernels queued behind it)
+static int run_flux(pcfd_ctx* c, bool fused, bool* clip_hit) {
+  if (fused) CK(cudaMemsetAsync(c->dflags + 2, 0, sizeof(int), c->stream));
   if (c->nedge) {
     PROF("k_flux_edges");
-    k_flux_edges<<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, c->prm.sorder, c->prm.chi, c->prm.gamma,
-                                                             c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD], c->f[PCFD_F_LIMITER],
-                                                             c->flux);
+    if (fused)
+      k_flux_edges<true><<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, c->prm.sorder, c->prm.chi, c->prm.gamma,
+                                                                     c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD],
+                                                                     c->f[PCFD_F_LIMITER], c->flux, c->dflags + 2);
+    else
+      k_flux_edges<false><<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, c->prm.sorder, c->prm.chi, c->prm.gamma,
+                                                                      c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD],
+                                                                      c->f[PCFD_F_LIMITER], c->flux, nullptr);
     LAUNCH_CHECK();
+  }
+  if (fused) {
+    CK(cudaMemcpyAsync(c->hflag, c->dflags + 2, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaEventRecord(c->ev_flag, c->stream));
+    if (run_limiter_final(c, nullptr)) return 1;
   }
   if (c->nb) {
     PROF("k_flux_bedges");
@@ -2136,12 +2224,20 @@ static int run_flux(pcfd_ctx* c) {
     k_residual_gather<true><<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->flux, c->bflux, c->vflux, c->bvflux,
                                                                         c->wallflag, c->f[PCFD_F_B]);
     LAUNCH_CHECK();
+    if (fused) {
+      CK(cudaEventSynchronize(c->ev_flag));
+      *clip_hit = *c->hflag != 0;
+    }
     return 0;
   }
   PROF("k_residual_gather");
   k_residual_gather<false><<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->flux, c->bflux, nullptr, nullptr, nullptr,
                                                                        c->f[PCFD_F_B]);
   LAUNCH_CHECK();
+  if (fused) {
+    CK(cudaEventSynchronize(c->ev_flag));
+    *clip_hit = *c->hflag != 0;
+  }
   return 0;
 }
 
@@ -2472,11 +2568,7 @@ int pcfd_explicit_iterate(pcfd_ctx* c, int refresh_dt, double* sumsq) {
   if (!c) return 1;
   if (refresh_dt && pcfd_timestep(c, nullptr)) return 1;
   if (pcfd_update_bcs(c)) return 1;
-  if (c->prm.sorder > 1) {
-    if (pcfd_gradient(c)) return 1;
-    if (pcfd_limiter(c)) return 1;
-  }
-  if (pcfd_residual(c, sumsq)) return 1;
+  if (gradient_limiter_residual(c, sumsq)) return 1;
   return pcfd_explicit_solve(c);
 }
 
@@ -2487,11 +2579,7 @@ int pcfd_implicit_iterate(pcfd_ctx* c, int refresh_jac, int nsgs, double* sumsq,
     if (pcfd_jacobian(c)) return 1;
   }
   if (pcfd_update_bcs(c)) return 1;
-  if (c->prm.sorder > 1) {
-    if (pcfd_gradient(c)) return 1;
-    if (pcfd_limiter(c)) return 1;
-  }
-  if (pcfd_residual(c, sumsq)) return 1;
+  if (gradient_limiter_residual(c, sumsq)) return 1;
   if (pcfd_prepare_sgs(c)) return 1;
   if (pcfd_blank_x(c)) return 1;
   if (pcfd_sgs(c, nsgs, ddq)) return 1;

@@ -133,6 +133,17 @@ class Oracle:
         return x, d
 
 
+    def turb_sa(self, nsgs, q, qgrad, s, dist, dt, ia, ja, iau, tvar):
+        """One TurbulenceModel::Compute of the Spalart-Allmaras model; tvar is updated in place."""
+        out = dict(tgrad=np.zeros(self.nn * 3), b=np.zeros(self.nnode), A=np.zeros(self.nblocks), x=np.zeros(self.nn),
+                   mut=np.zeros(self.nn))
+        self.lib.orc_turb_sa.restype = C.c_double
+        out["res"] = self.lib.orc_turb_sa(C.byref(self.c), int(nsgs), _d(q), _d(qgrad), _d(s), _d(dist), _d(dt), _i(ia), _i(ja),
+                                          _i(iau), _d(tvar), _d(out["tgrad"]), _d(out["b"]), _d(out["A"]), _d(out["x"]),
+                                          _d(out["mut"]))
+        return out
+
+
 def oracle_for(lib, mesh, params):
     """Bind the C oracle to a mesh/params pair in the C-ABI dict form (proteuscfd_b200.cases)."""
     g = {k: np.asarray(mesh[k]) for k in ("edges_n", "edges_a", "bedges_n", "bedges_a", "bedges_bctype", "xyz", "vol",

@@ -13,7 +13,7 @@ from tests.oracle_lib import Oracle, load_golden
 INVISCID = ["box8_explicit_venkat", "box8_explicit_barth", "box6_implicit_sgs", "box6c_implicit_sgs",
             "ramp15_implicit", "cube_LowFi"]
 # laminar Navier-Stokes (compressibleNS): viscous flux + analytic viscous Jacobian + no-slip wall hooks
-NS = ["box6_ns_implicit", "box6_ns_adiabatic"]
+NS = ["box6_ns_implicit", "box6_ns_adiabatic", "box6_sa_implicit"]
 ALL = INVISCID + NS
 INVISCID_IMPLICIT = ["box6_implicit_sgs", "box6c_implicit_sgs", "ramp15_implicit", "cube_LowFi"]
 IMPLICIT = INVISCID_IMPLICIT + NS
@@ -95,6 +95,22 @@ def test_jacobian_lu_sgs(oracle, name):
     assert ddq == g["sgs_ddq"][0]
     o.apply_dq(q, x)
     exact(q, g["q1"], "q1")
+
+
+def test_spalart_allmaras_compute(oracle):
+    """One TurbulenceModel::Compute (turb.tcc:163-339) of the SA model on the reference's own state: BCs, unweighted
+    LSQ gradient, first-order convection + diffusion with inline Jacobians, source (exp / pow), scalar SGS, update,
+    eddy viscosity.  The oracle calls the same libm, so this too is bit-exact."""
+    g, meta = load_golden("box6_sa_implicit")
+    o = Oracle(oracle, g, meta)
+    ia, ja, iau = o.crs_init()
+    tvar = g["turb_tvar0"].copy()
+    out = o.turb_sa(int(meta["nSgs"]), g["turb_q"], g["turb_qgrad"], g["lsq_s"], g["wallDistance"], g["turb_dt"], ia, ja,
+                    iau, tvar)
+    for k in ("tgrad", "b", "A", "x", "mut"):
+        exact(out[k], g["turb_" + k], "turb " + k)
+    exact(tvar, g["turb_tvar1"], "tvar after the update")
+    assert out["res"] == g["turb_res"][0]
 
 
 def test_resnorm_matches_reference_definition():

@@ -53,6 +53,8 @@ jacobianFieldType = {jactype}
 jacobianBoundaryType = {jactype}
 refViscosity = {refvisc}
 enableVNN = {vnn}
+turbulenceModel = {turb}
+turbulenceSpatialOrder = 1
 <<<END SPACE>>>
 """
 
@@ -122,7 +124,7 @@ def collect(outdir, rank):
 
 def make_case(name, mesh=None, h5=None, bc=BOX_BC, np_ranks=1, part=None, **kw):
     opts = dict(eqnset="compressibleEuler", sorder=2, limiter=2, nsgs=0, mach=0.5, cfl=0.5,
-                fx=1.0, fy=0.0, fz=0.0, jactype=0, refvisc=1.0, vnn=0)
+                fx=1.0, fy=0.0, fz=0.0, jactype=0, refvisc=1.0, vnn=0, turb=0)
     opts.update(kw)
     work = tempfile.mkdtemp(prefix="pcfd_golden_")
     try:
@@ -191,6 +193,10 @@ CASES = {
     # adiabatic wall, explicit, Von Neumann time-step limit on
     "box6_ns_adiabatic": lambda: make_case("box6_ns_adiabatic", mesh=kuhn_box(6, jitter=0.15), bc=ns_bc(-1.0),
                                            eqnset="compressibleNS", nsgs=2, cfl=5.0, refvisc=0.25, vnn=1),
+    # config[3] in miniature: RANS, Spalart-Allmaras one-equation model (segregated scalar system, first-order
+    # convection), no-slip floor; Re = 146 / refViscosity
+    "box6_sa_implicit": lambda: make_case("box6_sa_implicit", mesh=kuhn_box(6, jitter=0.15), bc=ns_bc(330.0),
+                                          eqnset="compressibleNS", nsgs=3, cfl=5.0, refvisc=0.01, turb=1),
     # the reference's own unit-test fixture (unitTest/gradientTest.h:20-232): prism cube, 216 nodes
     "cube_LowFi": lambda: make_case(
         "cube_LowFi", h5=os.path.join(REFERENCE, "unitTest/meshResources/cubeStructuredSeries/cube_LowFi.0.h5"),
