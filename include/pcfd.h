@@ -54,7 +54,15 @@ enum {
   PCFD_F_LSQ_SW = 8,   /* Mesh::sw                (nnode+gnode)*6 */
   PCFD_F_A = 9,        /* CRSMatrix::M            nblocks*neqn*neqn */
   PCFD_F_MUT = 10,     /* field "mut" (eddy viscosity) nnode+gnode+nbnode; zero for laminar flow */
-  PCFD_F_COUNT = 11
+  /* Spalart-Allmaras model (turb.h:24-30): TurbulenceModel::tvar, ::tgrad, field "wallDistance", and the scalar
+     system TurbulenceModel::crs (b, x, A->M with one double per block on the flow's CRS pattern) */
+  PCFD_F_TVAR = 11,      /* nnode+gnode+nbnode */
+  PCFD_F_TGRAD = 12,     /* (nnode+gnode)*3 */
+  PCFD_F_WALLDIST = 13,  /* nnode+gnode */
+  PCFD_F_TURB_B = 14,    /* nnode */
+  PCFD_F_TURB_X = 15,    /* nnode+gnode */
+  PCFD_F_TURB_A = 16,    /* nblocks */
+  PCFD_F_COUNT = 17
 };
 
 /* Mesh::edges / bedges / xyz / vol / ipsp / psp as flat arrays (uns_base.h:12-37, mesh.h:199-254) */
@@ -88,6 +96,7 @@ typedef struct {
   double Re, Pr, PrT;        /* Param::Re (compressible.tcc:85-89), prandtlNumber, turbulent Prandtl number */
   double tref;               /* Param::ref_temperature [K] (Sutherland constant 110.4/tref, eqnset.h:259) */
   double mach;               /* Param::GetVelocity(iter): Re is rescaled by it (compressible.tcc:753-755) */
+  int turb_model;            /* Param::turbModel: 0 laminar, 1 Spalart-Allmaras (turb.h:91-107) */
 } pcfd_params;
 
 typedef struct pcfd_ctx pcfd_ctx;
@@ -147,8 +156,15 @@ int pcfd_apply_dq(pcfd_ctx* ctx);
 int pcfd_explicit_iterate(pcfd_ctx* ctx, int refresh_dt, double* sumsq);
 /* One implicit iteration (nSgs > 0): [ComputeJacobians + ComputeTimesteps when
    refresh_jac != 0], UpdateBCs, Gradient, Limiter, ComputeResiduals, PrepareSGS,
-   BlankX, SGS(nsgs), ApplyDQ. */
+   BlankX, SGS(nsgs), ApplyDQ, and -- with a turbulence model -- TurbulenceModel::Compute
+   (solutionSpace.tcc:862-866). */
 int pcfd_implicit_iterate(pcfd_ctx* ctx, int refresh_jac, int nsgs, double* sumsq, double* ddq);
+
+/* TurbulenceModel::Compute (turb.tcc:163-339) for the Spalart-Allmaras model (spalart.tcc), turbulenceSpatialOrder = 1:
+   BCs, unweighted LSQ gradient of nu~, convective + diffusive + source terms with their Jacobians, nsgs scalar SGS
+   sweeps (nsgs == 0: explicit update), nu~ update with the clip at zero, eddy viscosity into field "mut".
+   Reads q, qgrad and timestep as the flow iteration left them.  sumsq (may be NULL) receives sum(b^2). */
+int pcfd_turb_compute(pcfd_ctx* ctx, int nsgs, double* sumsq);
 
 /* ---- halo exchange: PObj (parallel.tcc).  The send lists are persistent (the reference re-sends the index
    lists on every call, parallel.tcc:809-827).  send_list = PObj::nodePackingList concatenated in peer order

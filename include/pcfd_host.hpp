@@ -88,6 +88,7 @@ class DropIn {
     pr.Re = s_->param->Re; pr.Pr = s_->param->Pr; pr.PrT = s_->param->PrT;
     pr.tref = s_->param->ref_temperature;
     pr.mach = s_->param->GetVelocity(s_->iter);
+    pr.turb_model = s_->param->viscous ? s_->param->turbModel : 0;
 
     if (pcfd_create(&md, &pr, device, &ctx_) != 0) onError_("pcfd_create", pcfd_last_error(NULL));
     // Mesh::s / Mesh::sw were filled by ComputeNodeLSQCoefficients during Init: reuse them
@@ -144,6 +145,25 @@ class DropIn {
     double ddq = 0.0;
     Check(pcfd_sgs(ctx_, nSgs, &ddq), "CRS::SGS");
     return ddq;
+  }
+  // TurbulenceModel::Compute (turb.tcc:163-339), Spalart-Allmaras: state in / out through the reference's own
+  // TurbulenceModel::tvar, field "wallDistance" and field "mut"; returns the reference's residual norm sqrt(sum)/N
+  void PushTurbulence() {
+    Check(pcfd_set_field(ctx_, PCFD_F_TVAR, s_->turb->tvar, (size_t)(nnode_ + gnode_ + nbnode_)), "push tvar");
+    Check(pcfd_set_field(ctx_, PCFD_F_WALLDIST, s_->GetFieldData("wallDistance", FIELDS::STATE_NONE),
+                         (size_t)(nnode_ + gnode_)), "push wallDistance");
+  }
+  double TurbulenceCompute(int nSgs) {
+    double ss = 0.0;
+    Check(pcfd_turb_compute(ctx_, nSgs, &ss), "TurbulenceModel::Compute");
+    return std::sqrt(ss) / (double)nnode_;
+  }
+  void PullTurbulence() {
+    Check(pcfd_get_field(ctx_, PCFD_F_TVAR, s_->turb->tvar, (size_t)(nnode_ + gnode_ + nbnode_)), "pull tvar");
+    std::vector<double> mut((size_t)(nnode_ + gnode_ + nbnode_));
+    Check(pcfd_get_field(ctx_, PCFD_F_MUT, mut.data(), mut.size()), "pull mut");
+    double* dst = s_->GetFieldData("mut", FIELDS::STATE_NONE);
+    for (int i = 0; i < nnode_ + gnode_; i++) dst[i] = mut[i];
   }
   void ExplicitSolve() { Check(pcfd_explicit_solve(ctx_), "ExplicitSolve"); }                              // solve.tcc:71
   void ApplyDQ() { Check(pcfd_apply_dq(ctx_), "ApplyDQ"); }                                                // solutionSpace.tcc:802

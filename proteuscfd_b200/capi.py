@@ -19,6 +19,7 @@ BC_PARALLEL, BC_DIRICHLET, BC_NEUMANN, BC_IMPERMEABLE_WALL, BC_NOSLIP = 0, 1, 2,
 BC_FARFIELD_VISCOUS, BC_FARFIELD, BC_SONIC_INFLOW, BC_SONIC_OUTFLOW, BC_SYMMETRY = 5, 6, 7, 8, 9
 
 F_Q, F_QGRAD, F_LIMITER, F_B, F_X, F_TIMESTEP, F_BETA, F_LSQ_S, F_LSQ_SW, F_A, F_MUT = range(11)
+F_TVAR, F_TGRAD, F_WALLDIST, F_TURB_B, F_TURB_X, F_TURB_A = range(11, 17)
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -32,7 +33,7 @@ SYMBOLS = [
     "pcfd_apply_dq", "pcfd_explicit_iterate", "pcfd_implicit_iterate", "pcfd_launch_count",
     "pcfd_profile_enable", "pcfd_profile_reset", "pcfd_profile_count", "pcfd_profile_get",
     "pcfd_ipc_export", "pcfd_ipc_open", "pcfd_ipc_close",
-    "pcfd_halo_configure", "pcfd_halo_width", "pcfd_halo_send_total", "pcfd_halo_pack", "pcfd_halo_recv_ptr",
+    "pcfd_turb_compute", "pcfd_halo_configure", "pcfd_halo_width", "pcfd_halo_send_total", "pcfd_halo_pack", "pcfd_halo_recv_ptr",
 ]
 
 
@@ -47,7 +48,7 @@ class Params(C.Structure):
     _fields_ = [("eqnset", C.c_int), ("sorder", C.c_int), ("limiter", C.c_int), ("no_cvbc", C.c_int),
                 ("gamma", C.c_double), ("chi", C.c_double), ("cfl", C.c_double), ("qinf", C.c_double * NVARS),
                 ("enable_vnn", C.c_int), ("vnn", C.c_double), ("Re", C.c_double), ("Pr", C.c_double),
-                ("PrT", C.c_double), ("tref", C.c_double), ("mach", C.c_double)]
+                ("PrT", C.c_double), ("tref", C.c_double), ("mach", C.c_double), ("turb_model", C.c_int)]
 
 
 _lib = None
@@ -78,6 +79,7 @@ def load_library(path=LIB_PATH):
     lib.pcfd_residual.argtypes = [C.c_void_p, _dp]
     lib.pcfd_timestep.argtypes = [C.c_void_p, _dp]
     lib.pcfd_sgs.argtypes = [C.c_void_p, C.c_int, _dp]
+    lib.pcfd_turb_compute.argtypes = [C.c_void_p, C.c_int, _dp]
     lib.pcfd_explicit_iterate.argtypes = [C.c_void_p, C.c_int, _dp]
     lib.pcfd_implicit_iterate.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp]
     lib.pcfd_launch_count.restype = C.c_longlong
@@ -146,6 +148,7 @@ class Context:
         pr.enable_vnn, pr.vnn = int(params.get("enable_vnn", 0)), float(params.get("vnn", 20.0))
         pr.Re, pr.Pr, pr.PrT = float(params.get("Re", 0.0)), float(params.get("Pr", 0.72)), float(params.get("PrT", 0.85))
         pr.tref, pr.mach = float(params.get("tref", 0.0)), float(params.get("mach", 0.0))
+        pr.turb_model = int(params.get("turb_model", 0))
         self.nnode, self.gnode, self.nbnode = md.nnode, md.gnode, md.nbnode
         self.nedge, self.nbedge, self.ngedge = md.nedge, md.nbedge, md.ngedge
         h = C.c_void_p()
@@ -300,6 +303,15 @@ class Context:
             return None
         d = C.c_double()
         self._ck(self.lib.pcfd_sgs(self.h, int(nsgs), C.byref(d)))
+        return d.value
+
+    def turb_compute(self, nsgs, want_norm=False):
+        """TurbulenceModel::Compute (Spalart-Allmaras); returns sum(b^2) of the turbulence residual when asked."""
+        if not want_norm:
+            self._ck(self.lib.pcfd_turb_compute(self.h, int(nsgs), None))
+            return None
+        d = C.c_double()
+        self._ck(self.lib.pcfd_turb_compute(self.h, int(nsgs), C.byref(d)))
         return d.value
 
     def apply_dq(self):

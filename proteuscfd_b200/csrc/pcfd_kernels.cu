@@ -1462,6 +1462,356 @@ __global__ void k_halo_pack(const int* __restrict__ list, int count, int n, cons
   dst[t] = v[(size_t)list[j] * n + cidx];
 }
 
+// ====================================================== Spalart-Allmaras turbulence model
+// TurbulenceModel::Compute (turb.tcc:163-339) with Spalart (spalart.tcc:141-361): a segregated SCALAR system on the
+// flow's CRS pattern (one double per block), first-order convection (turbulenceSpatialOrder = 1).  Same pattern as
+// the flow: per-edge quantities once per edge into private slots, then ordered gathers per node.
+namespace sa {
+constexpr double kTinf = 1.341946;   // spalart.tcc:79
+constexpr double sigma = 2.0 / 3.0, cb1 = 0.1355, cb2 = 0.622, kappa = 0.41, cw2 = 0.3, cw3 = 2.0, cv1 = 7.1;
+constexpr double ct3 = 1.2, ct4 = 0.5;
+
+// spalart.tcc:303-340 Diffusive
+__device__ __forceinline__ void diffusive(double Re, double nu, const double* tg, double nutL, double nutR, const double* av,
+                                          double dgrad, double* resL, double* resR, double* jacL, double* jacR) {
+  const double nut = 0.5 * (nutL + nutR);
+  const double gdot = tg[0] * av[0] + tg[1] * av[1] + tg[2] * av[2];
+  const double area = av[3];
+  const double Reinv = 1.0 / Re;
+  const double c1 = (1.0 + cb2) * nut + nu;
+  double rl = c1 * gdot - cb2 * nutL * gdot;
+  rl *= 1.0 / sigma * area * Reinv;
+  double rr = c1 * gdot - cb2 * nutR * gdot;
+  rr *= 1.0 / sigma * area * Reinv;
+  double jl = c1 * dgrad - cb2 * nutL * dgrad;
+  jl *= 1.0 / sigma * area * Reinv;
+  double jr = c1 * dgrad - cb2 * nutR * dgrad;
+  jr *= 1.0 / sigma * area * Reinv;
+  *resL = rl; *resR = rr; *jacL = jl; *jacR = jr;
+}
+
+// spalart.tcc:206-300 Source.  exp / pow are CUDA libm (<= 2 ulp), the reference's are glibc: parity to rounding.
+__device__ __forceinline__ void source(double Re, double nu, double d, const double* vgrad, double nut, double vol,
+                                       double* res, double* jac) {
+  const double cw1 = cb1 / (kappa * kappa) + (1.0 + cb2) / sigma;
+  const double cw36 = cw3 * cw3 * cw3 * cw3 * cw3 * cw3;
+  const double cv13 = cv1 * cv1 * cv1;
+  double chi = nut / nu;
+  if (nu == 0.0) chi = 0.0;
+  const double chi2 = chi * chi;
+  const double chi3 = chi2 * chi;
+  const double ft2 = ct3 * exp(-ct4 * chi2);
+  const double d2 = d * d;
+  const double uy = vgrad[1], uz = vgrad[2], vx = vgrad[3], vz = vgrad[5], wx = vgrad[6], wy = vgrad[7];
+  const double o0 = wy - vz, o1 = uz - wx, o2 = vx - uy;
+  const double Reinv = 1.0 / Re;
+  const double fv1 = chi3 / (chi3 + cv13);
+  const double fv2 = 1.0 - chi / (1.0 + chi * fv1);
+  const double magw = sqrt(o0 * o0 + o1 * o1 + o2 * o2);
+  double sv = magw + (nut / (kappa * kappa * d2)) * fv2 * Reinv;
+  sv = eq::maxd(eq::maxd(sv, 0.3 * magw), 1.0e-12);
+  const double r = eq::mind(10.0, nut / (sv * kappa * kappa * d2) * Reinv);
+  double r6 = r * r * r;
+  r6 = r6 * r6;
+  const double g = r + cw2 * (r6 - r);
+  double g6 = g * g * g;
+  g6 = g6 * g6;
+  const double fw = g * pow(((1.0 + cw36) / (g6 + cw36)), 1.0 / 6.0);
+  const double pi = cb1 * (1.0 - ft2) * sv;
+  const double prod = pi * nut;
+  const double di = (cw1 * fw - cb1 * ft2 / (kappa * kappa)) * Reinv * (nut / (d2));
+  const double dest = di * nut;
+  const double dsdnut = fv2 * Reinv / (kappa * kappa * d2);
+  const double dPdnut = pi * nut * dsdnut / sv;
+  const double dDdnut = di;
+  *res = (prod - dest) * vol;
+  *jac = (eq::maxd(0.0, -(pi - di)) + eq::maxd(0.0, -(dPdnut - dDdnut))) * vol;
+}
+
+// spalart.tcc:343-359 ComputeEddyViscosity
+__device__ __forceinline__ double eddy_viscosity(double rho, double nu, double nut) {
+  const double cv13 = cv1 * cv1 * cv1;
+  const double chi = nut / nu;
+  if (nut <= 0.0) return 0.0;
+  const double chi3 = chi * chi * chi;
+  const double fv1 = chi3 / (chi3 + cv13);
+  return rho * nut * fv1;
+}
+}  // namespace sa
+
+// Spalart::BC_Kernel (spalart.tcc:141-170): one thread per node owning BC half-edges, in half-edge order (a
+// no-slip half-edge zeroes the node's own value, which a later symmetry half-edge of the same node copies)
+__global__ void k_turb_bcs(DevMesh m, const int* __restrict__ nodes, int nn_, double* tvar) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nn_) return;
+  const int n = nodes[t];
+  double tl = tvar[n];
+  for (int k = m.adjp[n]; k < m.adjp[n + 1]; k++) {
+    const int2 a = m.adj[k];
+    if (a.y < m.nedge) continue;
+    const int type = m.bctype[a.y - m.nedge];
+    const int r = a.x & 0x7fffffff;
+    if (type == PCFD_BC_PARALLEL) continue;
+    if (type == PCFD_BC_NOSLIP) { tvar[r] = 0.0; tl = 0.0; }
+    else if (type == PCFD_BC_SYMMETRY || type == PCFD_BC_IMPERMEABLE_WALL) tvar[r] = tl;
+    else tvar[r] = sa::kTinf;
+  }
+  tvar[n] = tl;
+}
+
+// unweighted LSQ gradient of the turbulence variable (turb.tcc:186-190 -> gradient.tcc:251-378 with Mesh::s,
+// weight = 1) + symmetry fix (:545-565)
+__global__ void __launch_bounds__(128) k_turb_gradient(DevMesh m, const double* __restrict__ tvar, const double* __restrict__ s,
+                                                        double* __restrict__ tgrad) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= m.nnode) return;
+  double g[3] = {0.0, 0.0, 0.0}, sn[6];
+#pragma unroll
+  for (int k = 0; k < 6; k++) sn[k] = s[6 * (size_t)n + k];
+  const double tn = tvar[n];
+  const double xn[3] = {m.xyz[3 * n], m.xyz[3 * n + 1], m.xyz[3 * n + 2]};
+  const int kbeg = m.adjp[n], kend = m.adjp[n + 1];
+  for (int k = kbeg; k < kend; k++) {
+    const int2 a = m.adj[k];
+    const int o = a.x & 0x7fffffff;
+    const bool right = a.x < 0;
+    if (a.y >= m.nedge && !is_ghost(m, o)) continue;
+    const double to = __ldg(tvar + o);
+    double dx[3], we[3];   // x_left - x_right, negated for the right node
+#pragma unroll
+    for (int d = 0; d < 3; d++) dx[d] = right ? (__ldg(m.xyz + 3 * o + d) - xn[d]) : (xn[d] - __ldg(m.xyz + 3 * o + d));
+    if (right) { dx[0] = -dx[0]; dx[1] = -dx[1]; dx[2] = -dx[2]; }
+    lsq_weights(sn, dx, we);
+    const double dq = right ? 1.0 * (tn - to) : 1.0 * (to - tn);
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      if (right) g[j] += +we[j] * dq;
+      else g[j] += -we[j] * dq;
+    }
+  }
+  for (int k = kbeg; k < kend; k++) {
+    const int2 a = m.adj[k];
+    if (a.y < m.nedge) continue;
+    const int be = a.y - m.nedge;
+    if (m.bctype[be] != PCFD_BC_SYMMETRY) continue;
+    double av[4];
+    load_avec(m.bea, be, av);
+    const double dot = g[0] * av[0] + g[1] * av[1] + g[2] * av[2];
+#pragma unroll
+    for (int j = 0; j < 3; j++) g[j] -= dot * av[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 3; j++) tgrad[(size_t)n * 3 + j] = g[j];
+}
+
+// Kernel_Convective (turb.tcc:342-449) + Kernel_Diffusive (:563-650) for one interior edge.  slots[e] =
+// {convective flux, diffusive resL, diffusive resR}; the two off-diagonal entries are final after this kernel.
+__global__ void __launch_bounds__(128) k_turb_edges(DevMesh m, eq::ViscParams vp, const double* __restrict__ q,
+                                                     const double* __restrict__ tvar, const double* __restrict__ tgrad,
+                                                     const int* __restrict__ posLR, const int* __restrict__ posRL,
+                                                     double* __restrict__ slots, double* __restrict__ A) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m.nedge) return;
+  const int2 lr = m.en[e];
+  const int l = lr.x, r = lr.y;
+  double av[4], qL[5], qR[5], qa[5];
+  load_avec(m.ea, e, av);
+  load_q5(q, l, qL);
+  load_q5(q, r, qR);
+#pragma unroll
+  for (int i = 0; i < 5; i++) qa[i] = 0.5 * (qL[i] + qR[i]);
+  const double tL = __ldg(tvar + l), tR = __ldg(tvar + r);
+  const double theta = eq::theta(qa, av, 0.0);
+  const double ta = theta * av[3];
+  double aRL = 0.0, aLR = 0.0, conv;   // A(r,l), A(l,r)
+  if (theta > 0.0) { aRL -= ta; conv = ta * tL; }
+  else { aLR += ta; conv = ta * tR; }
+  double de[3], ds2 = 0.0, tg[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    de[d] = __ldg(m.xyz + 3 * r + d) - __ldg(m.xyz + 3 * l + d);
+    ds2 += de[d] * de[d];
+  }
+  const double dsum = de[0] * av[0] + de[1] * av[1] + de[2] * av[2];
+  const double dgrad = dsum / ds2;
+  const double T = vp.gamma * eq::pressure(qa, vp.gamma) / qa[0];
+  const double nu = eq::viscosity(vp, T) / qa[0];
+#pragma unroll
+  for (int d = 0; d < 3; d++) tg[d] = 0.5 * (__ldg(tgrad + (size_t)l * 3 + d) + __ldg(tgrad + (size_t)r * 3 + d));
+  double resL, resR, jacL, jacR;
+  sa::diffusive(vp.Re / vp.mach, nu, tg, tL, tR, av, dgrad, &resL, &resR, &jacL, &jacR);
+  aRL -= jacL;
+  aLR -= jacR;
+  A[posRL[e]] = aRL;
+  A[posLR[e]] = aLR;
+  slots[(size_t)e * 3] = conv;
+  slots[(size_t)e * 3 + 1] = resL;
+  slots[(size_t)e * 3 + 2] = resR;
+}
+
+// Bkernel_Convective (turb.tcc:451-561) + Bkernel_Diffusive (:653-755) for one half-edge.  bslots[be] =
+// {convective flux, diffusive resL, convective diagonal term, diffusive diagonal term}
+__global__ void __launch_bounds__(128) k_turb_bedges(DevMesh m, eq::ViscParams vp, const double* __restrict__ q,
+                                                      const double* __restrict__ tvar, const double* __restrict__ tgrad,
+                                                      const int* __restrict__ bpos, double* __restrict__ bslots,
+                                                      double* __restrict__ A) {
+  const int be = blockIdx.x * blockDim.x + threadIdx.x;
+  if (be >= m.nbedge + m.ngedge) return;
+  const int2 lr = m.ben[be];
+  const int l = lr.x, r = lr.y;
+  const bool ghost = is_ghost(m, r);
+  double av[4], qL[5], qR[5], qa[5];
+  load_avec(m.bea, be, av);
+  load_q5(q, l, qL);
+  load_q5(q, r, qR);
+#pragma unroll
+  for (int i = 0; i < 5; i++) qa[i] = 0.5 * (qL[i] + qR[i]);
+  const double tL = tvar[l], tR = tvar[r];
+  const double theta = eq::theta(qa, av, 0.0);
+  const double ta = theta * av[3];
+  double conv, dconv = 0.0, aLR = 0.0;
+  if (theta > 0.0) { dconv = ta; conv = ta * tL; }
+  else { if (ghost) aLR += ta; conv = ta * tR; }
+  const double T = vp.gamma * eq::pressure(qa, vp.gamma) / qa[0];
+  const double nu = eq::viscosity(vp, T) / qa[0];
+  double tg[3], dgrad = 0.0;   // the reference leaves dgrad unset on physical boundaries (turb.tcc:669, 731)
+  if (ghost) {
+    double de[3], ds2 = 0.0;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      de[d] = (m.xyz[3 * r + d] - m.xyz[3 * l + d]);
+      ds2 += de[d] * de[d];
+    }
+    const double dsum = de[0] * av[0] + de[1] * av[1] + de[2] * av[2];
+    dgrad = dsum / ds2;
+#pragma unroll
+    for (int d = 0; d < 3; d++) tg[d] = 0.5 * (tgrad[(size_t)l * 3 + d] + tgrad[(size_t)r * 3 + d]);
+    const double qdots = de[0] * tg[0] + de[1] * tg[1] + de[2] * tg[2];
+    const double dq = (tR - tL - qdots) / ds2;
+#pragma unroll
+    for (int d = 0; d < 3; d++) tg[d] += dq * de[d];
+  } else {
+#pragma unroll
+    for (int d = 0; d < 3; d++) tg[d] = tgrad[(size_t)l * 3 + d];
+  }
+  double resL, resR, jacL, jacR;
+  sa::diffusive(vp.Re / vp.mach, nu, tg, tL, tR, av, dgrad, &resL, &resR, &jacL, &jacR);
+  double ddiff = 0.0;
+  if (ghost) { aLR -= jacR; A[bpos[be]] = aLR; }
+  else ddiff = jacL;
+  bslots[(size_t)be * 4] = conv;
+  bslots[(size_t)be * 4 + 1] = resL;
+  bslots[(size_t)be * 4 + 2] = dconv;
+  bslots[(size_t)be * 4 + 3] = ddiff;
+}
+
+// per node, in the reference's order: convective edges, convective half-edges, diffusive edges, diffusive half-edges,
+// source (turb.tcc:207-233), Kernel_Diag_NumJac (:241-243), temporal term (:246-252)
+__global__ void __launch_bounds__(128) k_turb_node(DevMesh m, eq::ViscParams vp, const double* __restrict__ q,
+                                                    const double* __restrict__ qgrad, const double* __restrict__ tvar,
+                                                    const double* __restrict__ dist, const double* __restrict__ dt,
+                                                    const double* __restrict__ slots, const double* __restrict__ bslots,
+                                                    const int* __restrict__ iau, const int* __restrict__ posLR,
+                                                    const int* __restrict__ posRL, double* __restrict__ b, double* A) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= m.nnode) return;
+  const int k0 = m.adjp[n], k1 = m.adjp[n + 1];
+  double res = 0.0, diag = 0.0;
+  for (int k = k0; k < k1; k++) {   // Convective: Driver, then Bdriver
+    const int2 a = m.adj[k];
+    if (a.y < m.nedge) {
+      const double f = __ldg(slots + (size_t)a.y * 3);
+      res += (a.x < 0) ? f : -f;
+    } else {
+      const double* bs = bslots + (size_t)(a.y - m.nedge) * 4;
+      res += -__ldg(bs);
+      diag += __ldg(bs + 2);
+    }
+  }
+  for (int k = k0; k < k1; k++) {   // DiffusiveDriver
+    const int2 a = m.adj[k];
+    if (a.y < m.nedge) {
+      if (a.x < 0) res -= __ldg(slots + (size_t)a.y * 3 + 2);
+      else res += __ldg(slots + (size_t)a.y * 3 + 1);
+    } else {
+      const double* bs = bslots + (size_t)(a.y - m.nedge) * 4;
+      res += __ldg(bs + 1);
+      diag += __ldg(bs + 3);
+    }
+  }
+  const double d = dist[n];
+  if (!(d < 1.0e-16)) {
+    double Q[NVARS];
+    load_q10(q, n, Q);
+    const double nu = eq::viscosity(vp, Q[5]) / Q[0];
+    double vg[9], tres, tjac;
+#pragma unroll
+    for (int i = 0; i < 9; i++) vg[i] = __ldg(qgrad + (size_t)n * NTERMS * 3 + 3 + i);   // GetVelocityGradLocation()*3
+    sa::source(vp.Re / vp.mach, nu, d, vg, tvar[n], m.vol[n], &tres, &tjac);
+    res += tres;
+    diag += tjac;
+  }
+  for (int k = k0; k < k1; k++) {   // Kernel_Diag_NumJac
+    const int2 a = m.adj[k];
+    if (a.y >= m.nedge) break;
+    const int pos = (a.x < 0) ? posLR[a.y] : posRL[a.y];
+    diag += -A[pos];
+  }
+  diag += 1.0 * m.vol[n] / dt[n];
+  b[n] = res;
+  A[iau[n]] = diag;
+}
+
+// Spalart::BC_Jac_Kernel (spalart.tcc:173-203) on no-slip nodes, then CRSMatrix::PrepareSGS for neqn == 1
+// (crsmatrix.tcc:852-858: the diagonal is replaced by its inverse)
+__global__ void k_turb_wall(const int* __restrict__ wnodes, int nw, const int* __restrict__ ia, const int* __restrict__ iau,
+                            double* b, double* x, double* A) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nw) return;
+  const int n = wnodes[t];
+  b[n] = 0.0;
+  x[n] = 0.0;
+  for (int k = ia[n]; k < ia[n + 1]; k++) A[k] = 0.0;
+  A[iau[n]] = 1.0;
+}
+__global__ void k_turb_invdiag(int nnode, const int* __restrict__ iau, double* A) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < nnode) A[iau[n]] = 1.0 / A[iau[n]];
+}
+
+// one level of CRS::SGS for neqn == 1 (crs.tcc:109-113): x = Dinv * (b - sum A_k x_k), ja order
+__global__ void __launch_bounds__(128) k_sgs_scalar_level(const int* __restrict__ rows, int nrows, const int* __restrict__ ia,
+                                                           const int* __restrict__ ja, const double* __restrict__ A,
+                                                           const double* __restrict__ b, double* x) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nrows) return;
+  const int row = rows[t];
+  const int k0 = ia[row], k1 = ia[row + 1];
+  double rhs = b[row];
+  for (int k = k0 + 1; k < k1; k++) {
+    const double vout = __ldcs(A + k) * x[__ldg(ja + k)];
+    rhs -= vout;
+  }
+  x[row] = A[k0] * rhs;
+}
+
+// tvar += x with the clip at zero (turb.tcc:306-320), then mut = rho nu~ fv1 for local and ghost nodes (:324-336)
+__global__ void k_turb_update(int nnode, const double* __restrict__ x, double* tvar) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nnode) return;
+  double t = tvar[n] + x[n];
+  if (t < 0.0) t = 0.0;
+  tvar[n] = t;
+}
+__global__ void k_turb_mut(int nn_, eq::ViscParams vp, const double* __restrict__ q, const double* __restrict__ tvar,
+                           double* __restrict__ mut) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nn_) return;
+  const double rho = q[(size_t)n * NVARS], T = q[(size_t)n * NVARS + 5];
+  const double nu = eq::viscosity(vp, T) / rho;
+  mut[n] = sa::eddy_viscosity(rho, nu, tvar[n]);
+}
+
 __global__ void k_fill_int(int* p, int n, int v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -1494,7 +1844,9 @@ struct pcfd_ctx {
   bool viscous = false;
   eq::ViscParams vp{};
   double *vflux = nullptr, *bvflux = nullptr, *btwall = nullptr, *vnn23 = nullptr;
-  int *bnormal = nullptr, *wnodes = nullptr;
+  int *bnormal = nullptr, *wnodes = nullptr, *tbnodes = nullptr;
+  int ntbnodes = 0;
+  double *tslots = nullptr, *tbslots = nullptr;   // Spalart-Allmaras per-edge / per-half-edge slots
   unsigned char* wallflag = nullptr;
   int nwall = 0;
   unsigned char* clipflag = nullptr;
@@ -1805,6 +2157,16 @@ int pcfd_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int devic
       return fail(c, "pcfd_create: adiabatic no-slip wall whose most-normal neighbour is itself a wall node is not supported");
   }
   c->nwall = (int)wnodes.size();
+  std::vector<int> tbnodes;   // nodes owning at least one BC (non-parallel) half-edge: Spalart::BC_Kernel walks them
+  {
+    std::vector<char> has(nnode, 0);
+    for (int e = 0; e < nb; e++)
+      if (mesh->bedges_bctype[e] != PCFD_BC_PARALLEL) has[mesh->bedges_n[2 * e]] = 1;
+    for (int i = 0; i < nnode; i++) if (has[i]) tbnodes.push_back(i);
+  }
+  c->ntbnodes = (int)tbnodes.size();
+  if (params->turb_model != 0 && params->turb_model != 1) return fail(c, "pcfd_create: unknown turbulence model");
+  if (params->turb_model == 1 && !viscous) return fail(c, "pcfd_create: Spalart-Allmaras needs the compressibleNS eqnset");
   c->viscous = viscous;
   c->vp = eq::ViscParams{params->gamma, params->Re, params->Pr, params->PrT, params->tref, params->mach};
   std::vector<double> vnn23;
@@ -1906,6 +2268,7 @@ int pcfd_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int devic
   if (dev_upload(c, &c->btwall, btwall.data(), btwall.size())) return 1;
   if (dev_upload(c, &c->wallflag, wallflag.data(), wallflag.size())) return 1;
   if (dev_upload(c, &c->wnodes, wnodes.data(), wnodes.size())) return 1;
+  if (dev_upload(c, &c->tbnodes, tbnodes.data(), tbnodes.size())) return 1;
   if (!vnn23.empty() && dev_upload(c, &c->vnn23, vnn23.data(), vnn23.size())) return 1;
   if (dev_upload(c, &c->ia, ia.data(), ia.size())) return 1;
   {   // 16 bytes of slack behind ja (and A): the bulk copies of k_sgs_tile round their byte ranges to 16
@@ -1931,6 +2294,13 @@ int pcfd_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int devic
   c->fsize[PCFD_F_LSQ_S] = (size_t)c->nn * 6;
   c->fsize[PCFD_F_LSQ_SW] = (size_t)c->nn * 6;
   c->fsize[PCFD_F_MUT] = (size_t)c->ntot;
+  const bool sa_on = params->turb_model == 1;
+  c->fsize[PCFD_F_TVAR] = sa_on ? (size_t)c->ntot : 0;
+  c->fsize[PCFD_F_TGRAD] = sa_on ? (size_t)c->nn * 3 : 0;
+  c->fsize[PCFD_F_WALLDIST] = sa_on ? (size_t)c->nn : 0;
+  c->fsize[PCFD_F_TURB_B] = sa_on ? (size_t)nnode : 0;
+  c->fsize[PCFD_F_TURB_X] = sa_on ? (size_t)c->nn : 0;
+  c->fsize[PCFD_F_TURB_A] = sa_on ? (size_t)c->nblocks : 0;
   c->fsize[PCFD_F_A] = 0;   // allocated on first use (implicit runs only)
   for (int k = 0; k < PCFD_F_COUNT; k++) {
     if (k == PCFD_F_A) continue;
@@ -1939,6 +2309,10 @@ int pcfd_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int devic
   }
   if (dev_alloc(c, &c->flux, (size_t)nedge * 5)) return 1;
   if (dev_alloc(c, &c->bflux, (size_t)nb * 5)) return 1;
+  if (sa_on) {
+    if (dev_alloc(c, &c->tslots, (size_t)nedge * 3)) return 1;
+    if (dev_alloc(c, &c->tbslots, (size_t)nb * 4)) return 1;
+  }
   if (viscous) {
     if (dev_alloc(c, &c->vflux, (size_t)nedge * 4)) return 1;
     if (dev_alloc(c, &c->bvflux, (size_t)nb * 4)) return 1;
@@ -2477,7 +2851,8 @@ static int field_width(int field) {
     case PCFD_F_QGRAD: return NTERMS * 3;
     case PCFD_F_LIMITER: case PCFD_F_X: return NEQN;
     case PCFD_F_LSQ_S: case PCFD_F_LSQ_SW: return 6;
-    case PCFD_F_BETA: case PCFD_F_MUT: return 1;
+    case PCFD_F_BETA: case PCFD_F_MUT: case PCFD_F_TVAR: case PCFD_F_TURB_X: case PCFD_F_WALLDIST: return 1;
+    case PCFD_F_TGRAD: return 3;
     default: return 0;
   }
 }
@@ -2564,6 +2939,82 @@ int pcfd_ipc_close(pcfd_ctx* c, void* devptr) {
   return 0;
 }
 
+int pcfd_turb_compute(pcfd_ctx* c, int nsgs, double* sumsq) {
+  if (!c) return 1;
+  if (c->prm.turb_model != 1) return fail(c, "pcfd_turb_compute: the context was created without a turbulence model");
+  CK(cudaSetDevice(c->device));
+  double *tvar = c->f[PCFD_F_TVAR], *tgrad = c->f[PCFD_F_TGRAD], *tb = c->f[PCFD_F_TURB_B], *tx = c->f[PCFD_F_TURB_X],
+         *tA = c->f[PCFD_F_TURB_A];
+  // crs.BlankSystem (crs.tcc:417-425); every interior off-diagonal and every diagonal entry is overwritten below
+  CK(cudaMemsetAsync(tA, 0, c->fsize[PCFD_F_TURB_A] * sizeof(double), c->stream));
+  CK(cudaMemsetAsync(tx, 0, c->fsize[PCFD_F_TURB_X] * sizeof(double), c->stream));
+  if (c->ntbnodes) {
+    PROF("k_turb_bcs");
+    k_turb_bcs<<<nblk(c->ntbnodes, 128), 128, 0, c->stream>>>(c->dm, c->tbnodes, c->ntbnodes, tvar);
+    LAUNCH_CHECK();
+  }
+  PROF("k_turb_gradient");
+  k_turb_gradient<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, tvar, c->f[PCFD_F_LSQ_S], tgrad);
+  LAUNCH_CHECK();
+  if (c->nedge) {
+    PROF("k_turb_edges");
+    k_turb_edges<<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, c->vp, c->f[PCFD_F_Q], tvar, tgrad, c->posLR, c->posRL,
+                                                             c->tslots, tA);
+    LAUNCH_CHECK();
+  }
+  if (c->nb) {
+    PROF("k_turb_bedges");
+    k_turb_bedges<<<nblk(c->nb, 128), 128, 0, c->stream>>>(c->dm, c->vp, c->f[PCFD_F_Q], tvar, tgrad, c->bpos, c->tbslots, tA);
+    LAUNCH_CHECK();
+  }
+  PROF("k_turb_node");
+  k_turb_node<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->vp, c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD], tvar,
+                                                          c->f[PCFD_F_WALLDIST], c->f[PCFD_F_TIMESTEP], c->tslots,
+                                                          c->tbslots, c->iau, c->posLR, c->posRL, tb, tA);
+  LAUNCH_CHECK();
+  if (c->nwall) {
+    PROF("k_turb_wall");
+    k_turb_wall<<<nblk(c->nwall, 128), 128, 0, c->stream>>>(c->wnodes, c->nwall, c->ia, c->iau, tb, tx, tA);
+    LAUNCH_CHECK();
+  }
+  if (sumsq) {
+    PROF("k_sumsq_partial");
+    k_sumsq_partial<256, 1><<<RED_BLOCKS, 256, 0, c->stream>>>(tb, c->nnode, c->red);
+    LAUNCH_CHECK();
+    PROF("k_sumsq_final");
+    k_sumsq_final<256, 1><<<1, 256, 0, c->stream>>>(c->red, RED_BLOCKS, c->redout);
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(sumsq, c->redout, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (nsgs > 0) {
+    PROF("k_turb_invdiag");
+    k_turb_invdiag<<<nblk(c->nnode, 256), 256, 0, c->stream>>>(c->nnode, c->iau, tA);
+    LAUNCH_CHECK();
+    for (int s = 0; s < nsgs; s++) {
+      for (int dir = 0; dir < 2; dir++) {
+        const std::vector<int>& off = dir ? c->lev_b : c->lev_f;
+        const int* rows = dir ? c->rows_b : c->rows_f;
+        for (size_t l = 0; l + 1 < off.size(); l++) {
+          const int nr = off[l + 1] - off[l];
+          PROF("k_sgs_scalar_level");
+          k_sgs_scalar_level<<<nblk(nr, 128), 128, 0, c->stream>>>(rows + off[l], nr, c->ia, c->ja, tA, tb, tx);
+          LAUNCH_CHECK();
+        }
+      }
+    }
+  } else {
+    return fail(c, "pcfd_turb_compute: nsgs == 0 (explicit turbulence update) is not implemented");
+  }
+  PROF("k_turb_update");
+  k_turb_update<<<nblk(c->nnode, 256), 256, 0, c->stream>>>(c->nnode, tx, tvar);
+  LAUNCH_CHECK();
+  PROF("k_turb_mut");
+  k_turb_mut<<<nblk(c->nn, 256), 256, 0, c->stream>>>(c->nn, c->vp, c->f[PCFD_F_Q], tvar, c->f[PCFD_F_MUT]);
+  LAUNCH_CHECK();
+  if (sumsq) CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 int pcfd_explicit_iterate(pcfd_ctx* c, int refresh_dt, double* sumsq) {
   if (!c) return 1;
   if (refresh_dt && pcfd_timestep(c, nullptr)) return 1;
@@ -2583,7 +3034,10 @@ int pcfd_implicit_iterate(pcfd_ctx* c, int refresh_jac, int nsgs, double* sumsq,
   if (pcfd_prepare_sgs(c)) return 1;
   if (pcfd_blank_x(c)) return 1;
   if (pcfd_sgs(c, nsgs, ddq)) return 1;
-  return pcfd_apply_dq(c);
+  if (pcfd_apply_dq(c)) return 1;
+  // NewtonIterate updates the turbulence model after the flow update (solutionSpace.tcc:862-866)
+  if (c->prm.turb_model == 1) return pcfd_turb_compute(c, nsgs, nullptr);
+  return 0;
 }
 
 }  // extern "C"

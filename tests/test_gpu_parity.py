@@ -27,8 +27,13 @@ def golden_ctx(name):
         mesh["bedges_twall"] = g["bedges_twall"]
         params.update(eqnset=capi.EQNSET_COMPRESSIBLE_NS, Re=meta["Re"], Pr=meta["Pr"], PrT=meta["PrT"],
                       tref=meta["ref_temperature"], mach=meta["velocity"], enable_vnn=int(meta["enableVNN"]),
-                      vnn=meta["VNN"])
-    return capi.Context(mesh, params), g, meta
+                      vnn=meta["VNN"], turb_model=int(meta.get("turbModel", 0)))
+    ctx = capi.Context(mesh, params)
+    if "mut" in g:   # eddy viscosity the flow's viscous terms saw in the reference run
+        mut = np.zeros(ctx.field_size(capi.F_MUT))
+        mut[: g["mut"].size] = g["mut"]
+        ctx.set_field(capi.F_MUT, mut)
+    return ctx, g, meta
 
 
 @pytest.mark.parametrize("name", ALL)

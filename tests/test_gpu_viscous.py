@@ -114,3 +114,26 @@ def test_ns_implicit_iterations_vs_oracle(oracle):
         close_per_node(ctx.get_field(capi.F_B), b, 5, f"b it{it}")
         close_per_node(ctx.get_field(capi.F_X), x, 5, f"x it{it}")
         close_per_node(ctx.get_field(capi.F_Q), qo, 10, f"q it{it}")
+
+
+def test_spalart_allmaras_compute_vs_reference():
+    """pcfd_turb_compute against the reference's own TurbulenceModel::Compute (tests/golden/box6_sa_implicit.npz).
+    BCs, the unweighted LSQ gradient and the matrix pattern are bit-exact; everything downstream of Sutherland's law
+    and of the source term's exp / pow (CUDA libm vs glibc) carries the 1e-12 per-node tolerance."""
+    from proteuscfd_b200 import capi
+    ctx, g, meta = golden_ctx("box6_sa_implicit")
+    ctx.set_field(capi.F_Q, g["turb_q"])
+    ctx.set_field(capi.F_QGRAD, g["turb_qgrad"])
+    ctx.set_field(capi.F_TIMESTEP, g["turb_dt"])
+    ctx.set_field(capi.F_LSQ_S, g["lsq_s"])
+    ctx.set_field(capi.F_WALLDIST, g["wallDistance"])
+    ctx.set_field(capi.F_TVAR, g["turb_tvar0"])
+    ss = ctx.turb_compute(int(meta["nSgs"]), want_norm=True)
+    exact(ctx.get_field(capi.F_TGRAD), g["turb_tgrad"], "tgrad")
+    close_per_node(ctx.get_field(capi.F_TURB_B), g["turb_b"], 1, "turbulence residual b")
+    close_per_node(ctx.get_field(capi.F_TURB_A), g["turb_A"], 1, "turbulence matrix (inverted diagonal)")
+    close_per_node(ctx.get_field(capi.F_TURB_X), g["turb_x"], 1, "turbulence update x")
+    close_per_node(ctx.get_field(capi.F_TVAR), g["turb_tvar1"], 1, "nu~ after the update")
+    nn = g["turb_mut"].size
+    close_per_node(ctx.get_field(capi.F_MUT)[:nn], g["turb_mut"], 1, "eddy viscosity")
+    assert np.isclose(np.sqrt(ss) / ctx.nnode, g["turb_res"][0], rtol=1e-12)
