@@ -198,6 +198,51 @@ int pcfd_profile_reset(pcfd_ctx* ctx);
 int pcfd_profile_count(pcfd_ctx* ctx);
 int pcfd_profile_get(pcfd_ctx* ctx, int i, const char** name, double* total_ms, long long* launches);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Finite-rate chemistry source term of the reacting eqnset (compressibleFR): ChemModel / Reaction / Species
+ * (chem.h:32-120, reaction.h:40-100, species.h:20-60).  Independent of pcfd_ctx (which carries the 5-equation
+ * perfect-gas system): a model handle plus node-parallel entry points.
+ */
+#define PCFD_CHEM_MAX_SPECIES 16
+#define PCFD_CHEM_MAX_REACTIONS 32
+
+/* the tables the reference builds from <case>.rxn and chemdb.hdf5, as flat arrays */
+typedef struct {
+  int nspecies, nreactions;
+  double mw[PCFD_CHEM_MAX_SPECIES];               /* Species::MW after GetDBInfo's /1000 (species.tcc:160-166) */
+  double nasa7[PCFD_CHEM_MAX_SPECIES][2][7];      /* Species::thermo_coeff[0] (T <= 1000 K) and [1] (T > 1000 K) */
+  int rxn_type[PCFD_CHEM_MAX_REACTIONS];          /* 0 Arrhenius, 1 ModArrhenius, 2 GuptaModArrhenius, 3 Power */
+  int third_body[PCFD_CHEM_MAX_REACTIONS];        /* Reaction::thirdBodiesPresent */
+  int backward_given[PCFD_CHEM_MAX_REACTIONS];    /* Reaction::backwardRateGiven (+ rxn_type_b, Ab, EAb, nb) */
+  int rxn_type_b[PCFD_CHEM_MAX_REACTIONS];
+  int nsp[PCFD_CHEM_MAX_REACTIONS];               /* species taking part (third-body-only ones included), local order */
+  int species[PCFD_CHEM_MAX_REACTIONS][PCFD_CHEM_MAX_SPECIES];   /* Reaction::globalIndx */
+  double A[PCFD_CHEM_MAX_REACTIONS], EA[PCFD_CHEM_MAX_REACTIONS], n[PCFD_CHEM_MAX_REACTIONS];
+  double Ab[PCFD_CHEM_MAX_REACTIONS], EAb[PCFD_CHEM_MAX_REACTIONS], nb[PCFD_CHEM_MAX_REACTIONS];
+  double nup[PCFD_CHEM_MAX_REACTIONS][PCFD_CHEM_MAX_SPECIES];    /* Reaction::Nup, Nupp, TBEff by local index */
+  double nupp[PCFD_CHEM_MAX_REACTIONS][PCFD_CHEM_MAX_SPECIES];
+  double tbeff[PCFD_CHEM_MAX_REACTIONS][PCFD_CHEM_MAX_SPECIES];
+} pcfd_chem_model;
+
+typedef struct pcfd_chem pcfd_chem;
+
+int pcfd_chem_create(const pcfd_chem_model* model, int device, pcfd_chem** out);
+int pcfd_chem_destroy(pcfd_chem* chem);
+const char* pcfd_chem_last_error(const pcfd_chem* chem);   /* chem may be NULL for pcfd_chem_create failures */
+/* ChemModel::GetMassProductionRates (chem.tcc:575-583) -> Reaction::GetMassProductionRate (reaction.tcc:763-856)
+   for n states.  HOST buffers: rhoi [n*nspecies] kg/m^3, T [n] K; wdot [n*nspecies] kg/(m^3 s). */
+int pcfd_chem_mass_production(pcfd_chem* chem, int n, const double* rhoi, const double* T, double* wdot);
+/* CompressibleFREqnSet::SourceTerm (compressibleFR.tcc:1276-1316; rxnOn, gravity off) for n nodes.  Q rows of
+   `stride` doubles in the eqnset's non-dimensional variables [rho_0..rho_{ns-1}, u, v, w, T, ...]; source rows of
+   nspecies+4 doubles (species rows = vol*wdot_i/(ref_density/ref_time), momentum and energy rows 0).
+   DEVICE pointers, launched on `cuda_stream` (NULL: the default stream) -- the residency entry point. */
+int pcfd_chem_source_term_device(pcfd_chem* chem, int n, int stride, const void* d_Q, const void* d_vol,
+                                 double ref_density, double ref_time, double ref_temperature, void* d_source,
+                                 void* cuda_stream);
+/* the same with HOST buffers (copies in and out) */
+int pcfd_chem_source_term(pcfd_chem* chem, int n, int stride, const double* Q, const double* vol, double ref_density,
+                          double ref_time, double ref_temperature, double* source);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1599,3 +1599,139 @@ double orc_turb_sa(const orc_case* c, int nsgs, const double* q, const double* q
   }
   return resid;
 }
+
+/* ------------------------------------------------ finite-rate chemistry */
+
+#define CHEM_UNIV_R 8.31447215   /* chem_constants.h:5 */
+
+/* macros.h:24-30 */
+static int is_whole_number(double x)
+{
+  int up = (int)(x + 0.5);
+  int flat = (int)x;
+  return up == flat;
+}
+
+/* std::pow(Type, Int) (reaction.tcc:814-826): the int exponent is promoted to double */
+static double pow_stoich(double x, double nu)
+{
+  if(is_whole_number(nu)) return pow(x, (double)(int)nu);
+  return pow(x, nu);
+}
+
+/* reaction.tcc:607-624 with :705-760 */
+static double rate_constant(int type, double A, double EA, double n, double T)
+{
+  switch(type){
+  case 0: return A*exp(-EA/(CHEM_UNIV_R*T));
+  case 1: return A*pow(T, n)*exp(-EA/(CHEM_UNIV_R*T));
+  case 2: return A*pow(T, n)*exp(-EA/T);
+  case 3: return A*pow(T, n);
+  default: return -999;
+  }
+}
+
+/* species.tcc:96-138 */
+static const double* thermo_coeff(const orc_chem_model* m, int sp, double T)
+{
+  if(T < 200.0) return m->nasa7[sp][0];
+  if(T > 6000.0) return m->nasa7[sp][1];
+  return (T > 1000.0) ? m->nasa7[sp][1] : m->nasa7[sp][0];
+}
+
+/* reaction.tcc:626-680 */
+static double equilibrium_constant(const orc_chem_model* m, int j, double T)
+{
+  int i;
+  double nu = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0, d4 = 0.0, d5 = 0.0, d6 = 0.0, d7 = 0.0, Kp, Kc;
+  for(i = 0; i < m->nsp[j]; i++){
+    const double* a = thermo_coeff(m, m->species[j][i], T);
+    double dnu = m->nupp[j][i] - m->nup[j][i];
+    nu += dnu;
+    d1 += dnu*a[0]; d2 += dnu*a[1]; d3 += dnu*a[2]; d4 += dnu*a[3];
+    d5 += dnu*a[4]; d6 += dnu*a[5]; d7 += dnu*a[6];
+  }
+  Kp = exp(d1*(log(T) - 1.0) + T*(d2/2.0 + T*(d3/6.0 + T*(d4/12.0 + d5/20.0*T))) - d6/T + d7);
+  Kc = Kp;
+  if(!(fabs(nu) < 1.0e-15)){
+    double Pref = 101325.0;
+    if(is_whole_number(nu)) Kc *= pow(Pref/(CHEM_UNIV_R*T), (double)(int)nu);
+    else Kc *= pow(Pref/(CHEM_UNIV_R*T), nu);
+  }
+  return Kc;
+}
+
+static double backward_rate(const orc_chem_model* m, int j, double T)
+{
+  if(m->backward_given[j]) return rate_constant(m->rxn_type_b[j], m->Ab[j], m->EAb[j], m->nb[j], T);
+  return rate_constant(m->rxn_type[j], m->A[j], m->EA[j], m->n[j], T)/equilibrium_constant(m, j, T);
+}
+
+/* Reaction::GetMassProductionRate (reaction.tcc:763-856) of reaction j for global species sp */
+static double reaction_wdot(const orc_chem_model* m, int j, const double* rhoi, double T, int sp, double* scale)
+{
+  int k, kk = -1, ns = m->nspecies;
+  double nu_ir = 0.0, X[ORC_CHEM_MAX_SPECIES], Kf, Kb, prod_form = 1.0, prod_dest = 1.0, Mconc, net, wdot;
+  for(k = 0; k < m->nsp[j]; k++) if(m->species[j][k] == sp){ kk = k; break; }
+  if(kk != -1) nu_ir = m->nupp[j][kk] - m->nup[j][kk];
+  *scale = 0.0;
+  if(fabs(nu_ir - 0.0) <= fabs(nu_ir)*1.0e-15) return 0.0;   /* AlmostEqualRelative, macros.h:71-84 */
+  for(k = 0; k < ns; k++) X[k] = rhoi[k]/m->mw[k];
+  Kf = rate_constant(m->rxn_type[j], m->A[j], m->EA[j], m->n[j], T);
+  Kb = backward_rate(m, j, T);
+  for(k = 0; k < m->nsp[j]; k++){
+    double x = X[m->species[j][k]];
+    prod_form *= pow_stoich(x, m->nup[j][k]);
+    prod_dest *= pow_stoich(x, m->nupp[j][k]);
+  }
+  Mconc = 1.0;
+  if(m->third_body[j]){
+    Mconc = 0.0;
+    for(k = 0; k < ns; k++) Mconc += X[k];
+    for(k = 0; k < m->nsp[j]; k++) Mconc += (m->tbeff[j][k] - 1.0)*X[m->species[j][k]];
+  }
+  net = Kf*prod_form - Kb*prod_dest;
+  wdot = nu_ir*Mconc*net;
+  wdot *= m->mw[sp];
+  *scale = fabs(nu_ir)*fabs(Mconc)*(fabs(Kf*prod_form) + fabs(Kb*prod_dest))*m->mw[sp];
+  return wdot;
+}
+
+void orc_chem_mass_production(const orc_chem_model* m, int n, const double* rhoi, const double* T, double* wdot,
+			      double* wscale, double* kf, double* kb)
+{
+  int s, i, j, ns = m->nspecies, nr = m->nreactions;
+  for(s = 0; s < n; s++){
+    for(i = 0; i < ns; i++){
+      double w = 0.0, sc = 0.0, scj;
+      for(j = 0; j < nr; j++){
+	w += reaction_wdot(m, j, &rhoi[(size_t)s*ns], T[s], i, &scj);
+	sc += scj;
+      }
+      wdot[(size_t)s*ns + i] = w;
+      if(wscale) wscale[(size_t)s*ns + i] = sc;
+    }
+    for(j = 0; j < nr; j++){
+      if(kf) kf[(size_t)s*nr + j] = rate_constant(m->rxn_type[j], m->A[j], m->EA[j], m->n[j], T[s]);
+      if(kb) kb[(size_t)s*nr + j] = backward_rate(m, j, T[s]);
+    }
+  }
+}
+
+void orc_chem_source_term(const orc_chem_model* m, int n, int stride, const double* Q, const double* vol,
+			  double ref_density, double ref_time, double ref_temperature, double* source)
+{
+  int s, i, ns = m->nspecies, neqn = m->nspecies + 4;
+  for(s = 0; s < n; s++){
+    const double* q = &Q[(size_t)s*stride];
+    double rhoi[ORC_CHEM_MAX_SPECIES], wdot[ORC_CHEM_MAX_SPECIES];
+    double T = q[ns+3]*ref_temperature;
+    for(i = 0; i < neqn; i++) source[(size_t)s*neqn + i] = 0.0;
+    for(i = 0; i < ns; i++) rhoi[i] = q[i]*ref_density;
+    orc_chem_mass_production(m, 1, rhoi, &T, wdot, NULL, NULL, NULL);
+    for(i = 0; i < ns; i++){
+      wdot[i] /= (ref_density/ref_time);
+      source[(size_t)s*neqn + i] = vol[s]*wdot[i];
+    }
+  }
+}

@@ -110,6 +110,34 @@ double orc_turb_sa(const orc_case* c, int nsgs, const double* q, const double* q
 void orc_roe_flux(const double* QL, const double* QR, const double* avec, double vdotn, double gamma,
 		  double* flux);
 
+/* ---- finite-rate chemistry (compressibleFR source term).  Tables as the reference's ChemModel holds them
+   (same layout as pcfd_chem_model in include/pcfd.h; kept separate so the oracle includes nothing of the product). */
+#define ORC_CHEM_MAX_SPECIES 16
+#define ORC_CHEM_MAX_REACTIONS 32
+typedef struct {
+  int nspecies, nreactions;
+  double mw[ORC_CHEM_MAX_SPECIES];
+  double nasa7[ORC_CHEM_MAX_SPECIES][2][7];
+  int rxn_type[ORC_CHEM_MAX_REACTIONS], third_body[ORC_CHEM_MAX_REACTIONS], backward_given[ORC_CHEM_MAX_REACTIONS];
+  int rxn_type_b[ORC_CHEM_MAX_REACTIONS], nsp[ORC_CHEM_MAX_REACTIONS];
+  int species[ORC_CHEM_MAX_REACTIONS][ORC_CHEM_MAX_SPECIES];
+  double A[ORC_CHEM_MAX_REACTIONS], EA[ORC_CHEM_MAX_REACTIONS], n[ORC_CHEM_MAX_REACTIONS];
+  double Ab[ORC_CHEM_MAX_REACTIONS], EAb[ORC_CHEM_MAX_REACTIONS], nb[ORC_CHEM_MAX_REACTIONS];
+  double nup[ORC_CHEM_MAX_REACTIONS][ORC_CHEM_MAX_SPECIES];
+  double nupp[ORC_CHEM_MAX_REACTIONS][ORC_CHEM_MAX_SPECIES];
+  double tbeff[ORC_CHEM_MAX_REACTIONS][ORC_CHEM_MAX_SPECIES];
+} orc_chem_model;
+
+/* ChemModel::GetMassProductionRates (chem.tcc:575-583; reaction.tcc:607-856; species.tcc:96-138) for n states:
+   rhoi [n*ns] kg/m^3, T [n] K -> wdot [n*ns] kg/(m^3 s).  wscale (may be NULL) [n*ns] receives
+   MW_i sum_r |nu_ir| Gamma_r (|k_f prod_f| + |k_b prod_b|): the magnitude the net rates cancel from, i.e. the
+   scale against which a rounding-level comparison of wdot is meaningful.  kf, kb (may be NULL) [n*nr]. */
+void orc_chem_mass_production(const orc_chem_model* m, int n, const double* rhoi, const double* T, double* wdot,
+			      double* wscale, double* kf, double* kb);
+/* CompressibleFREqnSet::SourceTerm (compressibleFR.tcc:1276-1316), rxnOn, gravity off */
+void orc_chem_source_term(const orc_chem_model* m, int n, int stride, const double* Q, const double* vol,
+			  double ref_density, double ref_time, double ref_temperature, double* source);
+
 #ifdef __cplusplus
 }
 #endif

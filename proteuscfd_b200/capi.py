@@ -33,7 +33,9 @@ SYMBOLS = [
     "pcfd_apply_dq", "pcfd_explicit_iterate", "pcfd_implicit_iterate", "pcfd_launch_count",
     "pcfd_profile_enable", "pcfd_profile_reset", "pcfd_profile_count", "pcfd_profile_get",
     "pcfd_ipc_export", "pcfd_ipc_open", "pcfd_ipc_close",
-    "pcfd_turb_compute", "pcfd_halo_configure", "pcfd_halo_width", "pcfd_halo_send_total", "pcfd_halo_pack", "pcfd_halo_recv_ptr",
+    "pcfd_turb_compute", "pcfd_halo_configure",
+    "pcfd_chem_create", "pcfd_chem_destroy", "pcfd_chem_last_error", "pcfd_chem_mass_production",
+    "pcfd_chem_source_term", "pcfd_chem_source_term_device", "pcfd_halo_width", "pcfd_halo_send_total", "pcfd_halo_pack", "pcfd_halo_recv_ptr",
 ]
 
 
@@ -49,6 +51,46 @@ class Params(C.Structure):
                 ("gamma", C.c_double), ("chi", C.c_double), ("cfl", C.c_double), ("qinf", C.c_double * NVARS),
                 ("enable_vnn", C.c_int), ("vnn", C.c_double), ("Re", C.c_double), ("Pr", C.c_double),
                 ("PrT", C.c_double), ("tref", C.c_double), ("mach", C.c_double), ("turb_model", C.c_int)]
+
+
+CHEM_MAX_SPECIES, CHEM_MAX_REACTIONS = 16, 32
+
+
+class ChemModelDesc(C.Structure):
+    """pcfd_chem_model (include/pcfd.h)."""
+    _S, _R = CHEM_MAX_SPECIES, CHEM_MAX_REACTIONS
+    _fields_ = [("nspecies", C.c_int), ("nreactions", C.c_int),
+                ("mw", C.c_double * _S), ("nasa7", C.c_double * 7 * 2 * _S),
+                ("rxn_type", C.c_int * _R), ("third_body", C.c_int * _R), ("backward_given", C.c_int * _R),
+                ("rxn_type_b", C.c_int * _R), ("nsp", C.c_int * _R), ("species", C.c_int * _S * _R),
+                ("A", C.c_double * _R), ("EA", C.c_double * _R), ("n", C.c_double * _R),
+                ("Ab", C.c_double * _R), ("EAb", C.c_double * _R), ("nb", C.c_double * _R),
+                ("nup", C.c_double * _S * _R), ("nupp", C.c_double * _S * _R), ("tbeff", C.c_double * _S * _R)]
+
+
+def fill_chem_model(md, t):
+    """Fill a pcfd_chem_model-shaped ctypes struct from the flat tables of a fixture / a reference ChemModel:
+    t = dict(dims=[ns, nr], species_mw, species_nasa7 [ns*14], rxn_A_EA_n [nr*3], rxn_flags [nr*4: type, third body,
+    backward given, nsp], rxn_species [nr*ns local->global], rxn_nup, rxn_nupp, rxn_tbeff [nr*ns by local index])."""
+    ns, nr = int(t["dims"][0]), int(t["dims"][1])
+    md.nspecies, md.nreactions = ns, nr
+    coeff = np.asarray(t["species_nasa7"]).reshape(ns, 2, 7)
+    for i in range(ns):
+        md.mw[i] = float(t["species_mw"][i])
+        for r in range(2):
+            for k in range(7):
+                md.nasa7[i][r][k] = float(coeff[i, r, k])
+    rk = np.asarray(t["rxn_A_EA_n"]).reshape(nr, 3)
+    fl = np.asarray(t["rxn_flags"]).reshape(nr, 4)
+    sp = np.asarray(t["rxn_species"]).reshape(nr, ns)
+    nup, nupp, tb = (np.asarray(t[k]).reshape(nr, ns) for k in ("rxn_nup", "rxn_nupp", "rxn_tbeff"))
+    for j in range(nr):
+        md.rxn_type[j], md.third_body[j], md.backward_given[j], md.nsp[j] = (int(v) for v in fl[j])
+        md.A[j], md.EA[j], md.n[j] = (float(v) for v in rk[j])
+        for k in range(int(fl[j, 3])):
+            md.species[j][k] = int(sp[j, k])
+            md.nup[j][k], md.nupp[j][k], md.tbeff[j][k] = float(nup[j, k]), float(nupp[j, k]), float(tb[j, k])
+    return md
 
 
 _lib = None
@@ -80,6 +122,14 @@ def load_library(path=LIB_PATH):
     lib.pcfd_timestep.argtypes = [C.c_void_p, _dp]
     lib.pcfd_sgs.argtypes = [C.c_void_p, C.c_int, _dp]
     lib.pcfd_turb_compute.argtypes = [C.c_void_p, C.c_int, _dp]
+    lib.pcfd_chem_create.argtypes = [C.POINTER(ChemModelDesc), C.c_int, C.POINTER(C.c_void_p)]
+    lib.pcfd_chem_destroy.argtypes = [C.c_void_p]
+    lib.pcfd_chem_last_error.restype = C.c_char_p
+    lib.pcfd_chem_last_error.argtypes = [C.c_void_p]
+    lib.pcfd_chem_mass_production.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
+    lib.pcfd_chem_source_term.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, C.c_double, C.c_double, C.c_double, _dp]
+    lib.pcfd_chem_source_term_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double,
+                                                 C.c_double, C.c_double, C.c_void_p, C.c_void_p]
     lib.pcfd_explicit_iterate.argtypes = [C.c_void_p, C.c_int, _dp]
     lib.pcfd_implicit_iterate.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp]
     lib.pcfd_launch_count.restype = C.c_longlong
@@ -326,3 +376,53 @@ class Context:
         s = np.zeros(1 + NEQN) if want_norms else None
         self._ck(self.lib.pcfd_implicit_iterate(self.h, int(refresh_jac), int(nsgs), _d(s) if want_norms else None, None))
         return s
+
+
+class Chem:
+    """Finite-rate chemistry handle (pcfd_chem): the compressibleFR source term."""
+
+    def __init__(self, tables, device=0):
+        self.lib = load_library()
+        md = fill_chem_model(ChemModelDesc(), tables)
+        self.ns, self.nr = md.nspecies, md.nreactions
+        h = C.c_void_p()
+        if self.lib.pcfd_chem_create(C.byref(md), int(device), C.byref(h)) != 0:
+            raise PcfdError(self.lib.pcfd_chem_last_error(None).decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pcfd_chem_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise PcfdError(self.lib.pcfd_chem_last_error(self.h).decode())
+
+    def mass_production(self, rhoi, T):
+        """ChemModel::GetMassProductionRates: rhoi [n, ns] kg/m^3, T [n] K -> wdot [n, ns] kg/(m^3 s)."""
+        rhoi = np.ascontiguousarray(rhoi, dtype=np.float64).reshape(-1, self.ns)
+        T = np.ascontiguousarray(T, dtype=np.float64).reshape(-1)
+        w = np.empty_like(rhoi)
+        self._ck(self.lib.pcfd_chem_mass_production(self.h, len(T), _d(rhoi), _d(T), _d(w)))
+        return w
+
+    def source_term(self, Q, vol, ref_density, ref_time, ref_temperature):
+        """CompressibleFREqnSet::SourceTerm on host arrays: Q [n, stride], vol [n] -> source [n, ns + 4]."""
+        Q = np.ascontiguousarray(Q, dtype=np.float64)
+        vol = np.ascontiguousarray(vol, dtype=np.float64).reshape(-1)
+        src = np.empty((len(vol), self.ns + 4))
+        self._ck(self.lib.pcfd_chem_source_term(self.h, len(vol), Q.shape[1], _d(Q), _d(vol), float(ref_density),
+                                                float(ref_time), float(ref_temperature), _d(src)))
+        return src
+
+    def source_term_device(self, n, stride, d_Q, d_vol, ref_density, ref_time, ref_temperature, d_source, stream=0):
+        self._ck(self.lib.pcfd_chem_source_term_device(self.h, int(n), int(stride), C.c_void_p(d_Q), C.c_void_p(d_vol),
+                                                       float(ref_density), float(ref_time), float(ref_temperature),
+                                                       C.c_void_p(d_source), C.c_void_p(stream)))

@@ -166,3 +166,42 @@ def load_oracle():
     if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "oracle"], stdout=subprocess.DEVNULL)
     return C.CDLL(so)
+
+
+class OrcChemModel(C.Structure):
+    """orc_chem_model (oracle/pcfd_oracle.h) -- same layout as the product's pcfd_chem_model."""
+    _S, _R = 16, 32
+    _fields_ = [("nspecies", C.c_int), ("nreactions", C.c_int),
+                ("mw", C.c_double * _S), ("nasa7", C.c_double * 7 * 2 * _S),
+                ("rxn_type", C.c_int * _R), ("third_body", C.c_int * _R), ("backward_given", C.c_int * _R),
+                ("rxn_type_b", C.c_int * _R), ("nsp", C.c_int * _R), ("species", C.c_int * _S * _R),
+                ("A", C.c_double * _R), ("EA", C.c_double * _R), ("n", C.c_double * _R),
+                ("Ab", C.c_double * _R), ("EAb", C.c_double * _R), ("nb", C.c_double * _R),
+                ("nup", C.c_double * _S * _R), ("nupp", C.c_double * _S * _R), ("tbeff", C.c_double * _S * _R)]
+
+
+class ChemOracle:
+    def __init__(self, lib, tables):
+        from proteuscfd_b200.capi import fill_chem_model   # a pure-Python table filler, no compute
+        self.lib = lib
+        self.m = fill_chem_model(OrcChemModel(), tables)
+        self.ns, self.nr = self.m.nspecies, self.m.nreactions
+
+    def mass_production(self, rhoi, T):
+        rhoi = np.ascontiguousarray(rhoi, dtype=np.float64).reshape(-1, self.ns)
+        T = np.ascontiguousarray(T, dtype=np.float64).reshape(-1)
+        n = len(T)
+        w, sc = np.empty_like(rhoi), np.empty_like(rhoi)
+        kf, kb = np.empty((n, self.nr)), np.empty((n, self.nr))
+        self.lib.orc_chem_mass_production(C.byref(self.m), n, _d(rhoi), _d(T), _d(w), _d(sc), _d(kf), _d(kb))
+        return w, sc, kf, kb
+
+    def source_term(self, Q, vol, ref_density, ref_time, ref_temperature):
+        Q = np.ascontiguousarray(Q, dtype=np.float64)
+        vol = np.ascontiguousarray(vol, dtype=np.float64).reshape(-1)
+        src = np.empty((len(vol), self.ns + 4))
+        self.lib.orc_chem_source_term.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, C.c_double, C.c_double,
+                                                  C.c_double, _dp]
+        self.lib.orc_chem_source_term(C.byref(self.m), len(vol), Q.shape[1], _d(Q), _d(vol), ref_density, ref_time,
+                                      ref_temperature, _d(src))
+        return src
