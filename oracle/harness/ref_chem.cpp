@@ -157,5 +157,6 @@ int main(int argc, char* argv[])
   }
   fflush(stdout);
   MPI_Finalize();
+  H5close();   // the model keeps the database open; flush it so that <outdir>/chemdb.hdf5 is a valid file for ref_harness
   _exit(0);
 }

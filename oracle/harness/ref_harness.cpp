@@ -107,6 +107,25 @@ static void InjectState(SolutionSpace<Real>* space)
   const Real twopi = 2.0*3.14159265358979323846;
   Real gamma = param->gamma;
   Real mach = param->GetVelocity(space->iter);
+  if(param->eqnset_id == CompressibleEulerFR || param->eqnset_id == CompressibleNSFR){
+    // reacting eqnset: native variables [rho_i..., u, v, w, T] (compressibleFR.tcc:14-31); species densities,
+    // velocity and temperature perturbed around the free stream so that every reaction is active
+    CompressibleFREqnSet<Real>* fr = dynamic_cast<CompressibleFREqnSet<Real>*>(eqnset);
+    Int ns = fr->nspecies;
+    for(Int i = 0; i < nnode; i++){
+      Real x = m->xyz[3*i + 0], y = m->xyz[3*i + 1], z = m->xyz[3*i + 2];
+      Real* q = &space->q[i*nvars];
+      for(Int k = 0; k < ns; k++){
+	q[k] = eqnset->Qinf[k]*(1.0 + 0.1*sin(twopi*x)*cos(twopi*y))*(1.0 + 0.05*sin(twopi*(z + 0.17*k)));
+      }
+      q[ns+0] = mach*param->flowdir[0] + 0.05*sin(twopi*y);
+      q[ns+1] = mach*param->flowdir[1] + 0.05*sin(twopi*z);
+      q[ns+2] = mach*param->flowdir[2] + 0.05*sin(twopi*x);
+      q[ns+3] = eqnset->Qinf[ns+3]*(1.0 + 0.1*cos(twopi*z));
+      eqnset->ComputeAuxiliaryVariables(q);
+    }
+    return;
+  }
   for(Int i = 0; i < nnode; i++){
     Real x = m->xyz[3*i + 0], y = m->xyz[3*i + 1], z = m->xyz[3*i + 2];
     Real rho = 1.0 + 0.1*sin(twopi*x)*cos(twopi*y);
