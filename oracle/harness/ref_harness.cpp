@@ -65,6 +65,10 @@
 #include "jacobian.h"
 #include "gradient.h"
 #include "limiters.h"
+#include "compressibleFR.h"
+#include "chem.h"
+#include "reaction.h"
+#include "species.h"
 #undef private
 #undef protected
 
@@ -228,7 +232,55 @@ static void DumpMesh(SolutionSpace<Real>* space)
   f << "ref_temperature " << param->ref_temperature << "\nenableVNN " << param->enableVNN << "\nVNN " << param->VNN << "\n";
   f << "turbModel " << param->turbModel << "\nturbModelSorder " << param->turbModelSorder << "\n";
   f << "iter " << space->iter << "\nnFirstOrderSteps " << param->nFirstOrderSteps << "\n";
+  f << "ref_density " << param->ref_density << "\nref_velocity " << param->ref_velocity << "\n";
+  f << "ref_pressure " << param->ref_pressure << "\nref_time " << param->ref_time << "\n";
+  f << "ref_length " << param->ref_length << "\nref_specific_enthalpy " << param->ref_specific_enthalpy << "\n";
+  f << "rxnOn " << param->rxnOn << "\ngravity_on " << param->gravity_on << "\n";
+  if(param->eqnset_id == CompressibleEulerFR || param->eqnset_id == CompressibleNSFR){
+    CompressibleFREqnSet<Real>* fr = dynamic_cast<CompressibleFREqnSet<Real>*>(eqnset);
+    f << "nspecies " << fr->nspecies << "\nPref " << fr->Pref << "\n";
+  }
   f.close();
+  if(param->eqnset_id == CompressibleEulerFR || param->eqnset_id == CompressibleNSFR){
+    // the chemistry tables exactly as the reference's ChemModel holds them (same layout as ref_chem.cpp)
+    CompressibleFREqnSet<Real>* fr = dynamic_cast<CompressibleFREqnSet<Real>*>(eqnset);
+    ChemModel<Real>& chem = *fr->chem;
+    Int ns = chem.nspecies, nr = chem.nreactions;
+    std::vector<Real> mw(ns), coeff(ns*14), Rs(ns);
+    for(Int i = 0; i < ns; i++){
+      mw[i] = chem.species[i].MW;
+      Rs[i] = chem.species[i].R;
+      for(Int k = 0; k < 7; k++){
+	coeff[i*14 + k] = chem.species[i].thermo_coeff[0][k];
+	coeff[i*14 + 7 + k] = chem.species[i].thermo_coeff[1][k];
+      }
+    }
+    Dump("species_mw", mw.data(), mw.size());
+    Dump("species_R", Rs.data(), Rs.size());
+    Dump("species_nasa7", coeff.data(), coeff.size());
+    std::vector<Real> rk(nr*3), nup(nr*ns, 0.0), nupp(nr*ns, 0.0), tbeff(nr*ns, 1.0);
+    std::vector<Int> flags(nr*4), order(nr*ns, -1);
+    for(Int j = 0; j < nr; j++){
+      Reaction<Real>& r = chem.reactions[j];
+      rk[j*3] = r.A; rk[j*3+1] = r.EA; rk[j*3+2] = r.n;
+      flags[j*4] = r.rxnType; flags[j*4+1] = r.thirdBodiesPresent; flags[j*4+2] = r.backwardRateGiven;
+      flags[j*4+3] = r.GetNspecies();
+      for(Int k = 0; k < r.GetNspecies(); k++){
+	order[j*ns + k] = r.globalIndx[k];
+	nup[j*ns + k] = r.Nup[k];
+	nupp[j*ns + k] = r.Nupp[k];
+	if(r.thirdBodiesPresent && (size_t)k < r.TBEff.size()) tbeff[j*ns + k] = r.TBEff[k];
+      }
+    }
+    Dump("rxn_A_EA_n", rk.data(), rk.size());
+    Dump("rxn_flags", flags.data(), flags.size());
+    Dump("rxn_species", order.data(), order.size());
+    Dump("rxn_nup", nup.data(), nup.size());
+    Dump("rxn_nupp", nupp.data(), nupp.size());
+    Dump("rxn_tbeff", tbeff.data(), tbeff.size());
+    Int dims[2] = {ns, nr};
+    Dump("chem_dims", dims, 2);
+  }
 }
 
 
@@ -445,6 +497,13 @@ int main(int argc, char* argv[])
     else{
       ExplicitSolve(*space);
       Dump("x", space->crs->x, (size_t)nnode*neqn);
+      if(!eqnset->varsConservative){
+	// ExplicitSolve leaves q untouched for native-variable eqnsets (solve.tcc:112-130); the update is applied by
+	// the node loop of NewtonIterate (solutionSpace.tcc:797-812)
+	for(Int j = 0; j < nnode; j++){
+	  eqnset->ApplyDQ(&space->crs->x[j*neqn], &space->q[j*nvars], &m->xyz[j*3]);
+	}
+      }
     }
     p->UpdateGeneralVectors(space->q, nvars);
     Dump("q1", space->q, (size_t)(nnode+gnode+nbnode)*nvars);

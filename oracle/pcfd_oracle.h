@@ -138,6 +138,38 @@ void orc_chem_mass_production(const orc_chem_model* m, int n, const double* rhoi
 void orc_chem_source_term(const orc_chem_model* m, int n, int stride, const double* Q, const double* vol,
 			  double ref_density, double ref_time, double ref_temperature, double* source);
 
+/* ---- reacting eqnset (CompressibleFREqnSet, compressibleFR.tcc), oracle/pcfd_oracle_fr.c.  The mesh, chi, cfl,
+   limiter, sorder, no_cvbc and the VNN fields of orc_case are used; gamma and qinf[10] are not.  ns = nspecies:
+   neqn = ns+4, nvars = 3ns+6 [rho_i | u v w | T | P | rho | cv_i | mol_i], nterms = 2ns+4. */
+typedef struct {
+  const orc_chem_model* chem;
+  double ref_density, ref_velocity, ref_temperature, ref_pressure, ref_time, ref_specific_enthalpy;  /* param.tcc:352-398 */
+  double Pref;             /* CompressibleFREqnSet::Pref = GetPressure(Qinf) (compressibleFR.tcc:1515) */
+  double dt_param;         /* Param::dt (negative: steady) */
+  int use_local_dt;        /* Param::useLocalTimeStepping */
+  int rxn_on;              /* Param::rxnOn */
+  double qinf[3*ORC_CHEM_MAX_SPECIES + 6];
+} orc_fr_params;
+
+void orc_fr_update_bcs(const orc_case* c, const orc_fr_params* p, double* q, const double* beta);
+void orc_fr_gradient(const orc_case* c, const orc_fr_params* p, const double* q, const double* sw, double* qgrad);
+void orc_fr_limiter(const orc_case* c, const orc_fr_params* p, const double* q, const double* qgrad, double* lim);
+void orc_fr_residual(const orc_case* c, const orc_fr_params* p, const double* q, const double* qgrad,
+		     const double* lim, const double* beta, double* b);
+double orc_fr_timestep(const orc_case* c, const orc_fr_params* p, const double* q, const double* beta, double* dt);
+/* returns the number of nodes whose ConservativeToNative Newton iteration did not converge (the reference aborts) */
+int orc_fr_explicit_solve(const orc_case* c, const orc_fr_params* p, double* q, const double* b, const double* dt,
+			  double* x);
+void orc_fr_apply_dq(const orc_case* c, const orc_fr_params* p, double* q, const double* x);
+void orc_fr_jacobian(const orc_case* c, const orc_fr_params* p, double* q, const double* beta, const double* dt,
+		     const int* ia, const int* ja, const int* iau, double* A);
+void orc_fr_prepare_sgs(const orc_case* c, const orc_fr_params* p, const int* iau, double* A, int* pv);
+double orc_fr_sgs(const orc_case* c, const orc_fr_params* p, int nsgs, const int* ia, const int* ja, const int* iau,
+		  const double* A, const int* pv, const double* b, double* x);
+void orc_fr_compute_aux(const orc_fr_params* p, double* Q);
+void orc_fr_hllc_flux(const orc_fr_params* p, const double* QL, const double* QR, const double* avec, double vdotn,
+		      double beta, double* flux);
+
 #ifdef __cplusplus
 }
 #endif

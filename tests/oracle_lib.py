@@ -162,8 +162,8 @@ def oracle_for(lib, mesh, params):
 
 def load_oracle():
     so = os.path.join(ORACLE_DIR, "libpcfd_oracle.so")
-    src = os.path.join(ORACLE_DIR, "pcfd_oracle.c")
-    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("pcfd_oracle.c", "pcfd_oracle_fr.c", "pcfd_oracle.h")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "oracle"], stdout=subprocess.DEVNULL)
     return C.CDLL(so)
 
@@ -205,3 +205,92 @@ class ChemOracle:
         self.lib.orc_chem_source_term(C.byref(self.m), len(vol), Q.shape[1], _d(Q), _d(vol), ref_density, ref_time,
                                       ref_temperature, _d(src))
         return src
+
+
+class OrcFrParams(C.Structure):
+    """orc_fr_params (oracle/pcfd_oracle.h)."""
+    _fields_ = [("chem", C.POINTER(OrcChemModel)),
+                ("ref_density", C.c_double), ("ref_velocity", C.c_double), ("ref_temperature", C.c_double),
+                ("ref_pressure", C.c_double), ("ref_time", C.c_double), ("ref_specific_enthalpy", C.c_double),
+                ("Pref", C.c_double), ("dt_param", C.c_double), ("use_local_dt", C.c_int), ("rxn_on", C.c_int),
+                ("qinf", C.c_double * (3 * 16 + 6))]
+
+
+def chem_tables(g):
+    """The chemistry tables of an FR fixture in fill_chem_model's form."""
+    t = {k: g[k] for k in ("species_mw", "species_nasa7", "rxn_A_EA_n", "rxn_flags", "rxn_species", "rxn_nup", "rxn_nupp",
+                           "rxn_tbeff")}
+    t["dims"] = g["chem_dims"]
+    return t
+
+
+class FrOracle(Oracle):
+    """The reacting eqnset (oracle/pcfd_oracle_fr.c) on one mesh + parameter set."""
+
+    def __init__(self, lib, g, meta):
+        g = dict(g)
+        qinf = np.asarray(g["qinf"], dtype=np.float64)
+        g["qinf"] = np.zeros(NVARS)     # orc_case.qinf belongs to the perfect-gas eqnset
+        super().__init__(lib, g, meta)
+        from proteuscfd_b200.capi import fill_chem_model
+        self.chem = fill_chem_model(OrcChemModel(), chem_tables(g))
+        self.ns = self.chem.nspecies
+        self.neqn, self.nvars, self.nterms = self.ns + 4, 3 * self.ns + 6, 2 * self.ns + 4
+        p = OrcFrParams()
+        p.chem = C.pointer(self.chem)
+        for f in ("ref_density", "ref_velocity", "ref_temperature", "ref_pressure", "ref_time", "ref_specific_enthalpy",
+                  "Pref"):
+            setattr(p, f, float(meta[f]))
+        p.dt_param, p.use_local_dt, p.rxn_on = float(meta["dt"]), int(meta["useLocalTimeStepping"]), int(meta["rxnOn"])
+        for j in range(self.nvars):
+            p.qinf[j] = qinf[j]
+        self.p = p
+        lib.orc_fr_timestep.restype = C.c_double
+        lib.orc_fr_sgs.restype = C.c_double
+
+    def gradient(self, q, sw):
+        g = np.zeros(self.nn * self.nterms * 3)
+        self.lib.orc_fr_gradient(C.byref(self.c), C.byref(self.p), _d(q), _d(sw), _d(g))
+        return g
+
+    def limiter(self, q, grad):
+        lim = np.zeros(self.nn * self.neqn)
+        self.lib.orc_fr_limiter(C.byref(self.c), C.byref(self.p), _d(q), _d(grad), _d(lim))
+        return lim
+
+    def update_bcs(self, q, beta):
+        self.lib.orc_fr_update_bcs(C.byref(self.c), C.byref(self.p), _d(q), _d(beta))
+
+    def residual(self, q, grad, lim, beta):
+        b = np.zeros(self.nnode * self.neqn)
+        self.lib.orc_fr_residual(C.byref(self.c), C.byref(self.p), _d(q), _d(grad), _d(lim), _d(beta), _d(b))
+        return b
+
+    def timestep(self, q, beta):
+        dt = np.zeros(self.nnode)
+        dtmin = self.lib.orc_fr_timestep(C.byref(self.c), C.byref(self.p), _d(q), _d(beta), _d(dt))
+        return dt, dtmin
+
+    def explicit_solve(self, q, b, dt):
+        x = np.zeros(self.nnode * self.neqn)
+        bad = self.lib.orc_fr_explicit_solve(C.byref(self.c), C.byref(self.p), _d(q), _d(b), _d(dt), _d(x))
+        assert bad == 0, "ConservativeToNative did not converge"
+        return x
+
+    def apply_dq(self, q, x):
+        self.lib.orc_fr_apply_dq(C.byref(self.c), C.byref(self.p), _d(q), _d(x))
+
+    def jacobian(self, q, beta, dt, ia, ja, iau):
+        A = np.zeros(self.nblocks * self.neqn * self.neqn)
+        self.lib.orc_fr_jacobian(C.byref(self.c), C.byref(self.p), _d(q), _d(beta), _d(dt), _i(ia), _i(ja), _i(iau), _d(A))
+        return A
+
+    def prepare_sgs(self, iau, A):
+        pv = np.zeros(self.nnode * self.neqn, dtype=np.int32)
+        self.lib.orc_fr_prepare_sgs(C.byref(self.c), C.byref(self.p), _i(iau), _d(A), _i(pv))
+        return pv
+
+    def sgs(self, nsgs, ia, ja, iau, A, pv, b):
+        x = np.zeros(self.nn * self.neqn)
+        d = self.lib.orc_fr_sgs(C.byref(self.c), C.byref(self.p), nsgs, _i(ia), _i(ja), _i(iau), _d(A), _i(pv), _d(b), _d(x))
+        return x, d

@@ -1,0 +1,78 @@
+"""The reacting-eqnset oracle (oracle/pcfd_oracle_fr.c) against fixtures produced by the reference itself.
+
+tests/golden/box5_fr_explicit.npz and box4_fr_implicit.npz were written by tools/make_golden.py from runs of the
+unmodified reference (oracle/_ref/ref_harness, equationSet = compressibleEulerFR on the reference's own
+chemModels/5speciesAir.rxn).  Same loops, same order, same libm, no FMA contraction: the bar is BIT-EXACT equality.
+"""
+import numpy as np
+import pytest
+
+from tests.oracle_lib import FrOracle, load_golden
+from tests.test_oracle import exact
+
+FR = ["box5_fr_explicit", "box4_fr_implicit"]
+
+
+@pytest.mark.parametrize("name", FR)
+def test_fr_fixture_is_the_reacting_eqnset(name):
+    g, meta = load_golden(name)
+    assert int(meta["nspecies"]) == 5 and int(meta["neqn"]) == 9 and int(meta["nvars"]) == 21 and int(meta["nterms"]) == 14
+    assert int(meta["rxnOn"]) == 1 and g["beta"][0] == 0.25       # preconditioned: beta = Mach^2 (solutionSpace.tcc:238-243)
+    assert np.array_equal(g["species_R"], 8.31447215 / g["species_mw"])
+
+
+@pytest.mark.parametrize("name", FR)
+def test_fr_update_bcs(oracle, name):
+    # far field (characteristic, 9x9 eigensystem + Newton on T), slip wall / symmetry (9x9 LU), 10 sub-iterations
+    g, meta = load_golden(name)
+    o = FrOracle(oracle, g, meta)
+    q = g["q_pre"].copy()
+    o.update_bcs(q, g["beta"])
+    exact(q, g["q0"], "q after BC update")
+
+
+@pytest.mark.parametrize("name", FR)
+def test_fr_gradient_limiter_residual_timestep(oracle, name):
+    g, meta = load_golden(name)
+    o = FrOracle(oracle, g, meta)
+    q = g["q0"].copy()
+    grad = o.gradient(q, g["lsq_sw"])
+    exact(grad, g["qgrad"], "qgrad")
+    lim = o.limiter(q, grad)
+    exact(lim, g["limiter"], "limiter")
+    b = o.residual(q, grad, lim, g["beta"])
+    exact(b, g["b"], "b")
+    dt, dtmin = o.timestep(q, g["beta"])
+    exact(dt, g["timestep"], "timestep")
+    assert dtmin == g["dtmin"][0]
+
+
+def test_fr_explicit_update(oracle):
+    # native -> conservative, update, Newton back to temperature (solve.tcc:112-130), then ApplyDQ
+    g, meta = load_golden("box5_fr_explicit")
+    o = FrOracle(oracle, g, meta)
+    q = g["q0"].copy()
+    x = o.explicit_solve(q, g["b"], g["timestep"])
+    exact(x, g["x"], "x")
+    exact(q, g["q0"], "q untouched by ExplicitSolve")
+    o.apply_dq(q, x)
+    exact(q, g["q1"], "q1")
+
+
+def test_fr_jacobian_lu_sgs(oracle):
+    g, meta = load_golden("box4_fr_implicit")
+    o = FrOracle(oracle, g, meta)
+    ia, ja, iau = o.crs_init()
+    exact(ia, g["ia"], "ia")
+    exact(ja, g["ja"], "ja")
+    q = g["q0"].copy()
+    A = o.jacobian(q, g["beta"], g["timestep"], ia, ja, iau)
+    exact(A, g["A"], "A")
+    pv = o.prepare_sgs(iau, A)
+    exact(A, g["A_lu"], "A_lu")
+    exact(pv, g["pv"], "pv")
+    x, ddq = o.sgs(int(meta["nSgs"]), ia, ja, iau, A, pv, g["b"])
+    exact(x, g["x"], "x")
+    assert ddq == g["sgs_ddq"][0]
+    o.apply_dq(q, x)
+    exact(q, g["q1"], "q1")

@@ -55,10 +55,19 @@ refViscosity = {refvisc}
 enableVNN = {vnn}
 turbulenceModel = {turb}
 turbulenceSpatialOrder = 1
-<<<END SPACE>>>
+{extra}<<<END SPACE>>>
 """
 
-INT_ARRAYS = {"edges_n", "bedges_n", "bedges_factag", "bedges_bctype", "ipsp", "psp", "gNodeOwner",
+# reacting eqnset (compressibleEulerFR): 5-species air (chemModels/5speciesAir.rxn), free stream at 3000 K so that all
+# six reactions are active; mass fractions in the MODEL's species order [O2, O, N, N2, NO]
+FR_EXTRA = """initialPressure = {pres}
+initialTemperature = {temp}
+chemicalDatabase = chemdb.hdf5
+massFractions = [0.20, 0.02, 0.01, 0.75, 0.02]
+reactionsOn = {rxn}
+"""
+
+INT_ARRAYS = {"rxn_flags", "rxn_species", "chem_dims", "edges_n", "bedges_n", "bedges_factag", "bedges_bctype", "ipsp", "psp", "gNodeOwner",
               "gNodeLocalId", "commCountsSend", "commCountsRecv", "commOffsetsRecv", "nodePackingList",
               "ia", "ja", "iau", "pv"}
 
@@ -124,10 +133,12 @@ def collect(outdir, rank):
 
 def make_case(name, mesh=None, h5=None, bc=BOX_BC, np_ranks=1, part=None, **kw):
     opts = dict(eqnset="compressibleEuler", sorder=2, limiter=2, nsgs=0, mach=0.5, cfl=0.5,
-                fx=1.0, fy=0.0, fz=0.0, jactype=0, refvisc=1.0, vnn=0, turb=0)
+                fx=1.0, fy=0.0, fz=0.0, jactype=0, refvisc=1.0, vnn=0, turb=0, extra="")
     opts.update(kw)
     work = tempfile.mkdtemp(prefix="pcfd_golden_")
     try:
+        if opts["eqnset"].endswith("FR"):
+            fr_inputs(work, name)
         with open(os.path.join(work, f"{name}.param"), "w") as f:
             f.write(PARAM_TMPL.format(name=name, **opts))
         with open(os.path.join(work, f"{name}.bc"), "w") as f:
@@ -152,7 +163,24 @@ def make_case(name, mesh=None, h5=None, bc=BOX_BC, np_ranks=1, part=None, **kw):
             np.savez_compressed(path, **d)
             print(f"wrote {path}: {os.path.getsize(path)/1024:.0f} KiB, nnode={int(d['vol'].size)}")
     finally:
-        shutil.rmtree(work, ignore_errors=True)
+        if not os.environ.get('PCFD_KEEP'): shutil.rmtree(work, ignore_errors=True)
+        else: print('kept', work)
+
+
+def fr_inputs(work, name):
+    """<case>.rxn (the reference's own 5speciesAir model) and chemdb.hdf5 (written by oracle/_ref/ref_chem through the
+    reference's HDF layer from the NASA-7 records of the reference's chemdata/BURCAT_FIXED.THR)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_chem_golden as mc
+    with open(os.path.join(work, "species.txt"), "w") as f:
+        for s, mw, hf, low, high in mc.species_table():
+            f.write(f"{s} {mw!r} {hf!r} " + " ".join(repr(v) for v in low) + " " + " ".join(repr(v) for v in high) + "\n")
+    np.zeros(0).tofile(os.path.join(work, "states.bin"))
+    run([os.path.join(REFBIN, "ref_chem"), os.path.join(REFERENCE, "chemModels", "5speciesAir"),
+         os.path.join(work, "species.txt"), os.path.join(work, "states.bin"), os.path.join(work, "chemout")], work)
+    shutil.copy(os.path.join(work, "chemout", "chemdb.hdf5"), os.path.join(work, "chemdb.hdf5"))
+    shutil.copy(os.path.join(REFERENCE, "chemModels", "5speciesAir.rxn"), os.path.join(work, f"{name}.rxn"))
+    os.chmod(os.path.join(work, f"{name}.rxn"), 0o644)
 
 
 def slab_part(xyz, ranks, axis=2):
@@ -197,6 +225,13 @@ CASES = {
     # convection), no-slip floor; Re = 146 / refViscosity
     "box6_sa_implicit": lambda: make_case("box6_sa_implicit", mesh=kuhn_box(6, jitter=0.15), bc=ns_bc(330.0),
                                           eqnset="compressibleNS", nsgs=3, cfl=5.0, refvisc=0.01, turb=1),
+    # config[4] in miniature: reacting 5-species air (compressibleEulerFR), HLLC flux with preconditioned wave speeds,
+    # finite-rate source term; explicit (native <-> conservative Newton solve) and implicit (9x9 blocks, FD flux and
+    # source Jacobians, dense temporal terms, 3 SGS sweeps)
+    "box5_fr_explicit": lambda: make_case("box5_fr_explicit", mesh=kuhn_box(5, jitter=0.15), eqnset="compressibleEulerFR",
+                                          cfl=0.05, extra=FR_EXTRA.format(temp=2500, pres=2000, rxn=1)),
+    "box4_fr_implicit": lambda: make_case("box4_fr_implicit", mesh=kuhn_box(4, jitter=0.15), eqnset="compressibleEulerFR",
+                                          nsgs=3, cfl=5.0, extra=FR_EXTRA.format(temp=3000, pres=101325, rxn=1)),
     # the reference's own unit-test fixture (unitTest/gradientTest.h:20-232): prism cube, 216 nodes
     "cube_LowFi": lambda: make_case(
         "cube_LowFi", h5=os.path.join(REFERENCE, "unitTest/meshResources/cubeStructuredSeries/cube_LowFi.0.h5"),
