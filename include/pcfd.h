@@ -31,10 +31,10 @@
 extern "C" {
 #endif
 
-#define PCFD_ABI_VERSION 2
+#define PCFD_ABI_VERSION 3
 
 /* eqnset ids follow eqnset_defines.h / create_functions.h:17-45 */
-enum { PCFD_EQNSET_COMPRESSIBLE_EULER = 2, PCFD_EQNSET_COMPRESSIBLE_NS = 3 };
+enum { PCFD_EQNSET_COMPRESSIBLE_EULER_FR = 0, PCFD_EQNSET_COMPRESSIBLE_EULER = 2, PCFD_EQNSET_COMPRESSIBLE_NS = 3 };
 
 /* BC types: bc_defines.h:4-30 (the value bc->GetBCType(factag) returns) */
 enum { PCFD_BC_PARALLEL = 0, PCFD_BC_DIRICHLET = 1, PCFD_BC_NEUMANN = 2, PCFD_BC_IMPERMEABLE_WALL = 3,
@@ -242,6 +242,35 @@ int pcfd_chem_source_term_device(pcfd_chem* chem, int n, int stride, const void*
 /* the same with HOST buffers (copies in and out) */
 int pcfd_chem_source_term(pcfd_chem* chem, int n, int stride, const double* Q, const double* vol, double ref_density,
                           double ref_time, double ref_temperature, double* source);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * The reacting eqnset on the full hot path: CompressibleFREqnSet (compressibleFR.h/.tcc), equationSet =
+ * compressibleEulerFR.  Native variables [rho_1..rho_ns, u, v, w, T]; with ns species
+ *    neqn = ns+4, nvars = 3ns+6 [rho_i | u v w | T | P | rho | cv_i | mol_i], nterms = 2ns+4
+ * (compressibleFR.tcc:14-31, 43-44, 693-711), so q / qgrad / limiter / b / x / A rows have these widths and A holds
+ * (ns+4)x(ns+4) blocks.  HLLC flux with preconditioned wave speeds (:301-548), NASA-7 thermodynamics, characteristic
+ * far-field and slip-wall BCs (:940-1134), finite-rate source term (:1276-1316) and its finite-difference Jacobian
+ * (eqnset.tcc:163-187), dense temporal terms (:1319-1463), native <-> conservative explicit update (solve.tcc:112-130).
+ * Every pcfd_* phase entry point above works on such a context; pcfd_turb_compute does not.
+ */
+typedef struct {
+  pcfd_chem_model chem;      /* ChemModel tables (species order = the model's) */
+  /* Param reference values (param.tcc:352-398) */
+  double ref_density, ref_velocity, ref_temperature, ref_pressure, ref_time, ref_specific_enthalpy;
+  double pref;               /* CompressibleFREqnSet::Pref = GetPressure(Qinf) (compressibleFR.tcc:1515) */
+  double dt;                 /* Param::dt (negative: steady); enters ContributeTemporalTerms (:1326-1331) */
+  int use_local_dt;          /* Param::useLocalTimeStepping */
+  int rxn_on;                /* Param::rxnOn */
+  double qinf[3 * PCFD_CHEM_MAX_SPECIES + 6];   /* EqnSet::Qinf, all nvars entries */
+} pcfd_fr_params;
+
+/* params->eqnset must be PCFD_EQNSET_COMPRESSIBLE_EULER_FR; sorder, limiter, chi, cfl, no_cvbc, enable_vnn / vnn are
+   read from params, gamma / qinf / the viscous fields are not.  The preconditioning field "beta"
+   (solutionSpace.tcc:235-247) is set with pcfd_set_field(PCFD_F_BETA). */
+int pcfd_create_fr(const pcfd_mesh_desc* mesh, const pcfd_params* params, const pcfd_fr_params* fr, int device,
+                   pcfd_ctx** out);
+/* system widths of a context: 5 / 10 / 9 for the perfect-gas eqnsets */
+int pcfd_widths(const pcfd_ctx* ctx, int* neqn, int* nvars, int* nterms);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpcfd_b200.so")
 
 NEQN, NVARS, NTERMS = 5, 10, 9
+EQNSET_COMPRESSIBLE_EULER_FR = 0
 EQNSET_COMPRESSIBLE_EULER = 2
 EQNSET_COMPRESSIBLE_NS = 3
 
@@ -35,6 +36,7 @@ SYMBOLS = [
     "pcfd_ipc_export", "pcfd_ipc_open", "pcfd_ipc_close",
     "pcfd_turb_compute", "pcfd_halo_configure",
     "pcfd_chem_create", "pcfd_chem_destroy", "pcfd_chem_last_error", "pcfd_chem_mass_production",
+    "pcfd_create_fr", "pcfd_widths",
     "pcfd_chem_source_term", "pcfd_chem_source_term_device", "pcfd_halo_width", "pcfd_halo_send_total", "pcfd_halo_pack", "pcfd_halo_recv_ptr",
 ]
 
@@ -66,6 +68,15 @@ class ChemModelDesc(C.Structure):
                 ("A", C.c_double * _R), ("EA", C.c_double * _R), ("n", C.c_double * _R),
                 ("Ab", C.c_double * _R), ("EAb", C.c_double * _R), ("nb", C.c_double * _R),
                 ("nup", C.c_double * _S * _R), ("nupp", C.c_double * _S * _R), ("tbeff", C.c_double * _S * _R)]
+
+
+class FrParams(C.Structure):
+    """pcfd_fr_params (include/pcfd.h): the reacting eqnset's chemistry tables, reference values and free stream."""
+    _fields_ = [("chem", ChemModelDesc),
+                ("ref_density", C.c_double), ("ref_velocity", C.c_double), ("ref_temperature", C.c_double),
+                ("ref_pressure", C.c_double), ("ref_time", C.c_double), ("ref_specific_enthalpy", C.c_double),
+                ("pref", C.c_double), ("dt", C.c_double), ("use_local_dt", C.c_int), ("rxn_on", C.c_int),
+                ("qinf", C.c_double * (3 * CHEM_MAX_SPECIES + 6))]
 
 
 def fill_chem_model(md, t):
@@ -130,6 +141,9 @@ def load_library(path=LIB_PATH):
     lib.pcfd_chem_source_term.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, C.c_double, C.c_double, C.c_double, _dp]
     lib.pcfd_chem_source_term_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double,
                                                  C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+    lib.pcfd_create_fr.argtypes = [C.POINTER(MeshDesc), C.POINTER(Params), C.POINTER(FrParams), C.c_int,
+                                   C.POINTER(C.c_void_p)]
+    lib.pcfd_widths.argtypes = [C.c_void_p, _ip, _ip, _ip]
     lib.pcfd_explicit_iterate.argtypes = [C.c_void_p, C.c_int, _dp]
     lib.pcfd_implicit_iterate.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp]
     lib.pcfd_launch_count.restype = C.c_longlong
@@ -193,8 +207,10 @@ class Context:
         pr.eqnset = int(params.get("eqnset", EQNSET_COMPRESSIBLE_EULER))
         pr.sorder, pr.limiter, pr.no_cvbc = int(params["sorder"]), int(params["limiter"]), int(params.get("no_cvbc", 0))
         pr.gamma, pr.chi, pr.cfl = float(params["gamma"]), float(params.get("chi", 0.0)), float(params["cfl"])
-        for j in range(NVARS):
-            pr.qinf[j] = float(params["qinf"][j])
+        fr = params.get("fr")      # reacting eqnset: dict(chem tables, reference values, qinf [nvars], ...)
+        if fr is None:
+            for j in range(NVARS):
+                pr.qinf[j] = float(params["qinf"][j])
         pr.enable_vnn, pr.vnn = int(params.get("enable_vnn", 0)), float(params.get("vnn", 20.0))
         pr.Re, pr.Pr, pr.PrT = float(params.get("Re", 0.0)), float(params.get("Pr", 0.72)), float(params.get("PrT", 0.85))
         pr.tref, pr.mach = float(params.get("tref", 0.0)), float(params.get("mach", 0.0))
@@ -202,9 +218,25 @@ class Context:
         self.nnode, self.gnode, self.nbnode = md.nnode, md.gnode, md.nbnode
         self.nedge, self.nbedge, self.ngedge = md.nedge, md.nbedge, md.ngedge
         h = C.c_void_p()
-        if self.lib.pcfd_create(C.byref(md), C.byref(pr), int(device), C.byref(h)) != 0:
+        if fr is not None:
+            fp = FrParams()
+            fill_chem_model(fp.chem, fr["chem"])
+            for k in ("ref_density", "ref_velocity", "ref_temperature", "ref_pressure", "ref_time", "ref_specific_enthalpy",
+                      "pref", "dt"):
+                setattr(fp, k, float(fr[k]))
+            fp.use_local_dt, fp.rxn_on = int(fr.get("use_local_dt", 1)), int(fr.get("rxn_on", 1))
+            for j, v in enumerate(np.asarray(fr["qinf"], dtype=np.float64).reshape(-1)):
+                fp.qinf[j] = float(v)
+            pr.eqnset = EQNSET_COMPRESSIBLE_EULER_FR
+            rc = self.lib.pcfd_create_fr(C.byref(md), C.byref(pr), C.byref(fp), int(device), C.byref(h))
+        else:
+            rc = self.lib.pcfd_create(C.byref(md), C.byref(pr), int(device), C.byref(h))
+        if rc != 0:
             raise PcfdError(self.lib.pcfd_last_error(None).decode())
         self.h = h
+        ne, nv, nt = C.c_int(), C.c_int(), C.c_int()
+        self.lib.pcfd_widths(self.h, C.byref(ne), C.byref(nv), C.byref(nt))
+        self.neqn, self.nvars, self.nterms = ne.value, nv.value, nt.value
         self._keep.clear()   # the library has copied everything it needs
 
     def close(self):
@@ -245,7 +277,7 @@ class Context:
         ia = np.empty(nrows.value + 1, np.int32)
         ja = np.empty(nblocks.value, np.int32)
         iau = np.empty(nrows.value, np.int32)
-        pv = np.empty(nrows.value * NEQN, np.int32)
+        pv = np.empty(nrows.value * self.neqn, np.int32)
         self._ck(self.lib.pcfd_get_crs(self.h, _i(ia), _i(ja), _i(iau), _i(pv)))
         return ia, ja, iau, pv
 
@@ -323,7 +355,7 @@ class Context:
         if not want_norms:
             self._ck(self.lib.pcfd_residual(self.h, None))
             return None
-        s = np.zeros(1 + NEQN)
+        s = np.zeros(1 + self.neqn)
         self._ck(self.lib.pcfd_residual(self.h, _d(s)))
         return s
 
@@ -368,12 +400,12 @@ class Context:
         self._ck(self.lib.pcfd_apply_dq(self.h))
 
     def explicit_iterate(self, refresh_dt=True, want_norms=False):
-        s = np.zeros(1 + NEQN) if want_norms else None
+        s = np.zeros(1 + self.neqn) if want_norms else None
         self._ck(self.lib.pcfd_explicit_iterate(self.h, int(refresh_dt), _d(s) if want_norms else None))
         return s
 
     def implicit_iterate(self, nsgs, refresh_jac=True, want_norms=False):
-        s = np.zeros(1 + NEQN) if want_norms else None
+        s = np.zeros(1 + self.neqn) if want_norms else None
         self._ck(self.lib.pcfd_implicit_iterate(self.h, int(refresh_jac), int(nsgs), _d(s) if want_norms else None, None))
         return s
 

@@ -1,0 +1,711 @@
+// eqnset_fr.cuh -- device-side physics of the reacting eqnset (CompressibleFREqnSet, ucs/compressibleFR.tcc) for
+// sm_100a, FP64.  NS = number of species is a template parameter: NEQ = NS+4 equations, NV = 3NS+6 variables per node
+// [rho_i | u v w | T | P | rho | cv_i | mol_i] (compressibleFR.tcc:14-31), NT = 2NS+4 gradient terms (:693-711).
+//
+// Parity contract (same as eqnset_compressible.cuh): every expression keeps the reference's operand order and the
+// library is built with --fmad=false, so +, -, *, /, sqrt round exactly as the reference's x86-64 build does.  The
+// chemistry source term (chem_device.cuh) calls exp / log / pow, which are CUDA libm here and glibc there: those rows
+// agree to rounding (1e-12 of the rate scale), everything else is bit-identical.
+#pragma once
+
+#include "chem_device.cuh"
+
+namespace fr {
+
+template <int NS>
+struct Params {
+  const pcfd_chem_model* chem;   // device copy of the reaction tables (source term)
+  double Rs[NS];                 // Species::R = UNIV_R / MW (species.tcc:315)
+  double mw[NS];
+  double nasa[NS][2][7];         // Species::thermo_coeff
+  double ref_density, ref_velocity, ref_temperature, ref_pressure, ref_time, ref_specific_enthalpy;
+  double Pref, dt;
+  double chi, cfl;
+  int use_local_dt, rxn_on, no_cvbc, sorder, limiter;
+  double qinf[3 * NS + 6];
+};
+
+__device__ __forceinline__ double maxd(double x, double y) { return (x > y) ? x : y; }
+__device__ __forceinline__ double mind(double x, double y) { return (x < y) ? x : y; }
+
+// Species::GetThermoCoeff (species.tcc:96-138): the pinned temperature is local to that function
+__device__ __forceinline__ int thermo_range(double T) {
+  if (T < 200.0) return 0;
+  if (T > 6000.0) return 1;
+  return (T > 1000.0) ? 1 : 0;
+}
+// Species::GetCp (species.tcc:43-53); GetdHdT (:337-349) is the same polynomial
+template <int NS>
+__device__ __forceinline__ double sp_cp(const Params<NS>& p, int i, int rng, double T) {
+  const double* a = p.nasa[i][rng];
+  const double cp_R = a[0] + T * (a[1] + T * (a[2] + T * (a[3] + T * a[4])));
+  return cp_R * p.Rs[i];
+}
+// Species::GetH (species.tcc:55-71), href == 0
+template <int NS>
+__device__ __forceinline__ double sp_h(const Params<NS>& p, int i, int rng, double T) {
+  const double* a = p.nasa[i][rng];
+  const double h_R = a[5] + T * (a[0] + T * (a[1] / 2.0 + T * (a[2] / 3.0 + T * (a[3] / 4.0 + T * a[4] / 5.0))));
+  return h_R * p.Rs[i];
+}
+// ChemModel::GetP (chem.tcc:989-999), IdealGasEOS::GetP (EOS.tcc:36-40)
+template <int NS>
+__device__ __forceinline__ double chem_P(const Params<NS>& p, const double* rhoiDim, double T) {
+  double P = 0.0;
+#pragma unroll
+  for (int i = 0; i < NS; i++) P += rhoiDim[i] * p.Rs[i] * T;
+  return P;
+}
+// ChemModel::GetSpecificEnthalpy (chem.tcc:586-595)
+template <int NS>
+__device__ __forceinline__ double chem_h(const Params<NS>& p, const double* X, double T) {
+  const int rng = thermo_range(T);
+  double h = 0.0;
+#pragma unroll
+  for (int i = 0; i < NS; i++) h += sp_h(p, i, rng, T) * X[i];
+  return h;
+}
+
+// ComputeAuxiliaryVariables (compressibleFR.tcc:755-814): P and rho only -- what the fluxes read
+template <int NS>
+__device__ __forceinline__ void aux_pr(const Params<NS>& p, double* Q) {
+  double rho = 0.0, rhoiDim[NS];
+#pragma unroll
+  for (int i = 0; i < NS; i++) { rho += Q[i]; rhoiDim[i] = Q[i] * p.ref_density; }
+  const double TDim = Q[NS + 3] * p.ref_temperature;
+  Q[NS + 4] = chem_P(p, rhoiDim, TDim) / p.ref_pressure;
+  Q[NS + 5] = rho;
+}
+// ... and the stored ones as well (cv_i, molar concentrations)
+template <int NS>
+__device__ __forceinline__ void aux(const Params<NS>& p, double* Q) {
+  aux_pr(p, Q);
+  const double TDim = Q[NS + 3] * p.ref_temperature;
+  const double s_ref = (p.ref_velocity * p.ref_velocity / p.ref_temperature);
+  const int rng = thermo_range(TDim);
+#pragma unroll
+  for (int i = 0; i < NS; i++) {
+    const double cpiDim = sp_cp(p, i, rng, TDim);
+    Q[NS + 6 + i] = (cpiDim - p.Rs[i]) / s_ref;           // IdealGasEOS::GetCv (EOS.tcc:79-91)
+  }
+#pragma unroll
+  for (int i = 0; i < NS; i++) Q[NS + NS + 6 + i] = Q[i] / p.mw[i] / 1000.0;   // MassToMole (chem.tcc:980-986)
+}
+
+// GetFluidProperties (compressibleFR.tcc:1523-1570) -> ChemModel::GetFluidProperties (chem.tcc:545-572): mixture gas
+// constant and speed of sound squared (non-dimensional); cv, cp, P, rho of that call are never read by the path
+template <int NS>
+__device__ __forceinline__ void fluid_props(const Params<NS>& p, const double* rhoi, double T, double& R, double& c2) {
+  const double s_ref = (p.ref_velocity * p.ref_velocity / p.ref_temperature);
+  double rhoiDim[NS];
+#pragma unroll
+  for (int i = 0; i < NS; i++) rhoiDim[i] = rhoi[i] * p.ref_density;
+  const double Tdim = T * p.ref_temperature;
+  double RDim = 0.0, rhoDim = 0.0, cpDim = 0.0, cvDim = 0.0;
+#pragma unroll
+  for (int i = 0; i < NS; i++) rhoDim += rhoiDim[i];
+#pragma unroll
+  for (int i = 0; i < NS; i++) RDim += rhoiDim[i] * p.Rs[i];
+  RDim /= rhoDim;
+  const int rng = thermo_range(Tdim);
+#pragma unroll
+  for (int i = 0; i < NS; i++) {
+    const double X = rhoiDim[i] / rhoDim;
+    const double cpi = sp_cp(p, i, rng, Tdim);
+    cpDim += cpi * X;
+    cvDim += X * (cpi - p.Rs[i]);
+  }
+  const double g = cpDim / cvDim;
+  const double c2Dim = g * RDim * Tdim;
+  R = RDim / s_ref;
+  c2 = c2Dim / (p.ref_velocity * p.ref_velocity);
+}
+
+// GetTotalEnthalpy (compressibleFR.tcc:1249-1273)
+template <int NS>
+__device__ __forceinline__ double total_enthalpy(const Params<NS>& p, const double* Q) {
+  double X[NS];
+  const double T = Q[NS + 3], rho = Q[NS + 5], u = Q[NS], v = Q[NS + 1], w = Q[NS + 2];
+  const double v2 = u * u + v * v + w * w;
+#pragma unroll
+  for (int i = 0; i < NS; i++) X[i] = Q[i] / rho;
+  const double h = chem_h(p, X, T * p.ref_temperature) / p.ref_specific_enthalpy;
+  return h * rho + 0.5 * rho * v2;
+}
+// GetTotalEnergy (compressibleFR.tcc:1219-1246)
+template <int NS>
+__device__ __forceinline__ double total_energy(const Params<NS>& p, const double* Q) {
+  double X[NS];
+  const double T = Q[NS + 3], P = Q[NS + 4], rho = Q[NS + 5], u = Q[NS], v = Q[NS + 1], w = Q[NS + 2];
+  const double v2 = u * u + v * v + w * w;
+#pragma unroll
+  for (int i = 0; i < NS; i++) X[i] = Q[i] / rho;
+  const double h = chem_h(p, X, T * p.ref_temperature) / p.ref_specific_enthalpy;
+  const double E = h * rho - P;
+  return E + 0.5 * rho * v2;
+}
+// GetTheta (compressibleFR.tcc:1640-1644)
+template <int NS>
+__device__ __forceinline__ double theta_of(const double* Q, const double* n, double vdotn) {
+  return (Q[NS] * n[0] + Q[NS + 1] * n[1] + Q[NS + 2] * n[2] + vdotn);
+}
+
+// HLLCFlux (compressibleFR.tcc:301-548; RoeFlux :293-298 forwards here).  QL / QR need entries [0, NS+6).  The
+// Roe-averaged state only feeds GetFluidProperties (rho_i, T), so its auxiliary variables are not formed.  The NaN
+// kneecap of EqnSet::NumericalFlux (eqnset.tcc:73-88) is applied here.
+template <int NS>
+__device__ __forceinline__ void numerical_flux(const Params<NS>& p, const double* QL, const double* QR, const double* av,
+                                               double vdotn, double beta, double* flux) {
+  const double uL = QL[NS], vL = QL[NS + 1], wL = QL[NS + 2], TL = QL[NS + 3], pL = QL[NS + 4];
+  const double pgL = pL - p.Pref, rhoL = QL[NS + 5];
+  double RL, c2L, RR, c2R, Rm, c2;
+  fluid_props(p, QL, TL, RL, c2L);
+  const double HTL = total_enthalpy(p, QL);
+  const double ETL = HTL - pL;
+  const double thetaL = theta_of<NS>(QL, av, vdotn);
+  const double uR = QR[NS], vR = QR[NS + 1], wR = QR[NS + 2], TR = QR[NS + 3], pR = QR[NS + 4];
+  const double pgR = pR - p.Pref, rhoR = QR[NS + 5];
+  fluid_props(p, QR, TR, RR, c2R);
+  const double HTR = total_enthalpy(p, QR);
+  const double ETR = HTR - pR;
+  const double thetaR = theta_of<NS>(QR, av, vdotn);
+
+  const double rho = sqrt(rhoL * rhoR);
+  const double sigma = rho / (rhoL + rho);
+  double roeQ[NS + 4];
+#pragma unroll
+  for (int i = 0; i < NS; i++) roeQ[i] = QL[i] + sigma * (QR[i] - QL[i]);
+  roeQ[NS + 0] = uL + sigma * (uR - uL);
+  roeQ[NS + 1] = vL + sigma * (vR - vL);
+  roeQ[NS + 2] = wL + sigma * (wR - wL);
+  roeQ[NS + 3] = TL + sigma * (TR - TL);
+  double theta = theta_of<NS>(roeQ, av, vdotn);
+  fluid_props(p, roeQ, roeQ[NS + 3], Rm, c2);
+
+  const double oneMBeta = 1.0 - beta;
+  const double thetaPrime = theta * (1.0 + beta) * 0.5;
+  const double cPrime = 0.5 * sqrt(theta * theta * (oneMBeta * oneMBeta) + 4.0 * beta * c2);
+  const double thetaLPrime = thetaL * (1.0 + beta) * 0.5;
+  const double thetaRPrime = thetaR * (1.0 + beta) * 0.5;
+  const double cLPrime = 0.5 * sqrt(thetaL * thetaL * (oneMBeta * oneMBeta) + 4.0 * beta * c2L);
+  const double cRPrime = 0.5 * sqrt(thetaR * thetaR * (oneMBeta * oneMBeta) + 4.0 * beta * c2R);
+  const double eig5L = thetaLPrime - cLPrime;
+  const double eig4R = thetaRPrime + cRPrime;
+  const double eig4 = thetaPrime + cPrime;
+  const double eig5 = thetaPrime - cPrime;
+  const double SL = mind(eig5L, eig5);
+  const double SR = maxd(eig4R, eig4);
+  double SM = (pgR - pgL + rhoL * thetaL * (SL - thetaL) - rhoR * thetaR * (SR - thetaR)) /
+              (rhoL * (SL - thetaL) - rhoR * (SR - thetaR));
+
+  double Qf[NS + 4], pStar = 0.0;
+  if (SL >= 0.0) {
+#pragma unroll
+    for (int i = 0; i < NS; i++) Qf[i] = QL[i];
+    Qf[NS] = rhoL * uL; Qf[NS + 1] = rhoL * vL; Qf[NS + 2] = rhoL * wL; Qf[NS + 3] = ETL;
+    pStar = pgL;
+    SM = thetaL;
+  } else if (SR <= 0.0) {
+#pragma unroll
+    for (int i = 0; i < NS; i++) Qf[i] = QR[i];
+    Qf[NS] = rhoR * uR; Qf[NS + 1] = rhoR * vR; Qf[NS + 2] = rhoR * wR; Qf[NS + 3] = ETR;
+    pStar = pgR;
+    SM = thetaR;
+  } else if ((SL <= 0.0) && (SM >= 0.0)) {
+    pStar = pgL + rhoL * (thetaL - SL) * (thetaL - SM);
+    const double omega = 1.0 / (SL - SM);
+    const double const1 = SL - thetaL;
+    const double const2 = pStar - pgL;
+#pragma unroll
+    for (int i = 0; i < NS; i++) Qf[i] = omega * const1 * QL[i];
+    Qf[NS] = omega * (const1 * rhoL * uL + const2 * av[0]);
+    Qf[NS + 1] = omega * (const1 * rhoL * vL + const2 * av[1]);
+    Qf[NS + 2] = omega * (const1 * rhoL * wL + const2 * av[2]);
+    Qf[NS + 3] = omega * (const1 * ETL - pgL * thetaL + (pStar * SM)) + p.Pref * (SM - thetaL) * omega;
+  } else if ((SM <= 0.0) && (SR >= 0.0)) {
+    pStar = pgR + rhoR * (thetaR - SR) * (thetaR - SM);
+    const double omega = 1.0 / (SR - SM);
+    const double const1 = SR - thetaR;
+    const double const2 = pStar - pgR;
+#pragma unroll
+    for (int i = 0; i < NS; i++) Qf[i] = omega * const1 * QR[i];
+    Qf[NS] = omega * (const1 * rhoR * uR + const2 * av[0]);
+    Qf[NS + 1] = omega * (const1 * rhoR * vR + const2 * av[1]);
+    Qf[NS + 2] = omega * (const1 * rhoR * wR + const2 * av[2]);
+    Qf[NS + 3] = omega * (const1 * ETR - pgR * thetaR + (pStar * SM)) + p.Pref * (SM - thetaR) * omega;
+  } else {   // NaN wave speeds ("HLLC: Should never be here"): every component ends up kneecapped
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+    for (int i = 0; i < NS + 4; i++) Qf[i] = qnan;
+  }
+  const double area = av[3];
+  const double Et = Qf[NS + 3];
+  theta = SM;
+  const double thetabar = theta - vdotn;
+#pragma unroll
+  for (int i = 0; i < NS; i++) flux[i] = area * Qf[i] * theta;
+  flux[NS] = area * (Qf[NS] * theta + pStar * av[0]);
+  flux[NS + 1] = area * (Qf[NS + 1] * theta + pStar * av[1]);
+  flux[NS + 2] = area * (Qf[NS + 2] * theta + pStar * av[2]);
+  flux[NS + 3] = area * (Et * theta + pStar * thetabar) + p.Pref * thetabar * area;
+#pragma unroll
+  for (int i = 0; i < NS + 4; i++) if (isnan(flux[i])) flux[i] = 0.0;
+}
+
+// MaxEigenvalue (compressibleFR.tcc:1603-1637)
+template <int NS>
+__device__ __forceinline__ double max_eigenvalue(const Params<NS>& p, const double* Q, const double* av, double vdotn,
+                                                 double beta) {
+  double R, c2;
+  fluid_props(p, Q, Q[NS + 3], R, c2);
+  const double theta = theta_of<NS>(Q, av, vdotn);
+  const double oneMBeta = 1.0 - beta;
+  const double thetaPrime = theta * (1.0 + beta) * 0.5;
+  const double cPrime = 0.5 * sqrt(theta * theta * (oneMBeta * oneMBeta) + 4.0 * beta * c2);
+  const double eig4 = thetaPrime + cPrime;
+  const double eig5 = thetaPrime - cPrime;
+  return maxd(fabs(eig4), fabs(eig5));
+}
+
+// ExtrapolateVariables (compressibleFR.tcc:734-752) with ExtrapolateCorrection (eqnset.h:231-238); g = first NEQ
+// gradient rows of the node
+template <int NS>
+__device__ __forceinline__ void extrapolate(double chi, double* Qho, const double* Q, const double* dQedge,
+                                            const double* g, const double* dx, const double* lim) {
+#pragma unroll
+  for (int i = 0; i < NS + 4; i++) {
+    const double corr = (0.5 * chi * dQedge[i] + (1.0 - chi) * (g[i * 3] * dx[0] + g[i * 3 + 1] * dx[1] + g[i * 3 + 2] * dx[2]));
+    Qho[i] = Q[i] + corr * lim[i];
+  }
+}
+
+// BadExtrapolation (compressibleFR.tcc:714-731); Q carries valid P and rho
+template <int NS>
+__device__ __forceinline__ bool bad_extrapolation(const Params<NS>& p, const double* Q) {
+#pragma unroll
+  for (int i = 0; i < NS; i++) if (Q[i] < 0.0) return true;
+  if (total_energy(p, Q) <= 0.0) return true;
+  if (Q[NS + 4] < 1.0e-10) return true;
+  if (Q[NS + 3] < 1.0e-10) return true;
+  return false;
+}
+
+// ---------------------------------------------------------------- small dense algebra (matrix.h)
+// MatVecMult (matrix.h:63-74)
+template <int N>
+__device__ __forceinline__ void matvec(const double* a, const double* v, double* out) {
+  for (int i = 0; i < N; i++) {
+    double s = a[i * N + 0] * v[0];
+    for (int j = 1; j < N; j++) s += a[i * N + j] * v[j];
+    out[i] = s;
+  }
+}
+// LU (matrix.h:110-190): partial pivoting through the permutation p, rows not swapped
+template <int N>
+__device__ __forceinline__ void lu(double* a, int* p) {
+  for (int i = 0; i < N; i++) p[i] = i;
+  int row = 0;
+  for (int i = 0; i < N; i++) {
+    double large = 0.0;
+    for (int j = i; j < N; j++) {
+      if (fabs(a[p[j] * N + i]) > fabs(large)) { large = a[p[j] * N + i]; row = j; }
+    }
+    const int t = p[i]; p[i] = p[row]; p[row] = t;
+    large = 1.0 / large;
+    for (int j = i + 1; j < N; j++) a[p[j] * N + i] *= large;
+    for (int j = i + 1; j < N; j++) {
+      for (int k = i + 1; k < N; k++) a[p[j] * N + k] -= a[p[j] * N + i] * a[p[i] * N + k];
+    }
+  }
+}
+// LuSolve (matrix.h:237-264): the solution overwrites b, x is scratch
+template <int N>
+__device__ __forceinline__ void lu_solve(const double* a, double* b, const int* p, double* x) {
+  for (int i = 0; i < N; i++) {
+    double sum = 0.0;
+    for (int j = 0; j < i; j++) sum += a[p[i] * N + j] * x[j];
+    x[i] = b[p[i]] - sum;
+  }
+  for (int i = N - 1; i >= 0; i--) {
+    double sum = 0.0;
+    for (int j = N - 1; j > i; j--) sum += a[p[i] * N + j] * b[j];
+    b[i] = (x[i] - sum) / a[p[i] * N + i];
+  }
+}
+
+// ---------------------------------------------------------------- boundary conditions
+// PerpVectors (geometry.h:101-129)
+__device__ __forceinline__ void perp_vectors(const double* n, double* v1, double* v2) {
+  double dot;
+  v1[0] = v1[1] = v1[2] = 0.0;
+  if (fabs(dot = n[0]) < 0.95) v1[0] = 1.0;
+  else if (fabs(dot = n[1]) < 0.95) v1[1] = 1.0;
+  else { dot = n[2]; v1[2] = 1.0; }
+  v1[0] -= dot * n[0];
+  v1[1] -= dot * n[1];
+  v1[2] -= dot * n[2];
+  double mag = sqrt(v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2]);
+  v1[0] = v1[0] / mag; v1[1] = v1[1] / mag; v1[2] = v1[2] / mag;
+  v2[0] = n[1] * v1[2] - v1[1] * n[2];
+  v2[1] = n[2] * v1[0] - v1[2] * n[0];
+  v2[2] = n[0] * v1[1] - v1[0] * n[1];
+  mag = sqrt(v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2]);
+  v2[0] = v2[0] / mag; v2[1] = v2[1] / mag; v2[2] = v2[2] / mag;
+}
+
+// Eigensystem (compressibleFR.tcc:150-290); the per-species c2i are overwritten by the bulk c2 there (:176-180)
+template <int NS>
+__device__ void eigensystem(const Params<NS>& p, const double* Q, const double* av, double vdotn, double* eig, double* T,
+                            double* Tinv, double beta) {
+  constexpr int N = NS + 4;
+  const double nx = av[0], ny = av[1], nz = av[2];
+  const double bm1 = beta - 1.0, bp1 = beta + 1.0, oneMBeta = 1.0 - beta;
+  const double theta = theta_of<NS>(Q, av, vdotn);
+  const double rho = Q[NS + 5];
+  double R, c2, l[3], m[3];
+  fluid_props(p, Q, Q[NS + 3], R, c2);
+  const double thetaPrime = 0.5 * bp1 * theta;
+  const double cPrime = 0.5 * sqrt(theta * theta * (oneMBeta * oneMBeta) + 4.0 * beta * c2);
+  perp_vectors(av, l, m);
+  const double lx = l[0], ly = l[1], lz = l[2], mx = m[0], my = m[1], mz = m[2];
+  constexpr int uloc = NS, vloc = NS + 1, wloc = NS + 2, tloc = NS + 3;
+  for (int i = 0; i < NS + 2; i++) eig[i] = theta;
+  eig[wloc] = thetaPrime + cPrime;
+  eig[tloc] = thetaPrime - cPrime;
+  const double betam = oneMBeta * 0.5;
+  const double Xp = theta * betam + cPrime;
+  const double Xm = theta * betam - cPrime;
+  for (int i = 0; i < N * N; i++) T[i] = 0.0;
+  for (int i = 0; i < NS; i++) {
+    T[N * i + i] = 1.0;
+    T[N * i + wloc] = -(Q[i] * (c2 + bm1 * c2 - theta * bm1 * Xm)) / (c2 * Xm);
+    T[N * i + tloc] = (Q[i] * (c2 + bm1 * c2 - theta * bm1 * Xp)) / (c2 * Xp);
+  }
+  T[N * (NS + 0) + (NS + 0)] = lx; T[N * (NS + 0) + (NS + 1)] = mx; T[N * (NS + 0) + (NS + 2)] = nx; T[N * (NS + 0) + (NS + 3)] = -nx;
+  T[N * (NS + 1) + (NS + 0)] = ly; T[N * (NS + 1) + (NS + 1)] = my; T[N * (NS + 1) + (NS + 2)] = ny; T[N * (NS + 1) + (NS + 3)] = -ny;
+  T[N * (NS + 2) + (NS + 0)] = lz; T[N * (NS + 2) + (NS + 1)] = mz; T[N * (NS + 2) + (NS + 2)] = nz; T[N * (NS + 2) + (NS + 3)] = -nz;
+  T[N * (NS + 3) + wloc] = -rho * Xm;
+  T[N * (NS + 3) + tloc] = rho * Xp;
+  for (int i = 0; i < N * N; i++) Tinv[i] = 0.0;
+  for (int i = 0; i < NS; i++) {
+    const double KK = -Q[i] * (c2 * (Xm + Xp) - bm1 * Xm * Xp * theta + bm1 * c2 * (Xm + Xp));
+    Tinv[i * N + i] = 1.0;
+    Tinv[i * N + uloc] = -((ly * mz - lz * my) * KK) / (c2 * Xm * Xp);
+    Tinv[i * N + vloc] = ((lx * mz - lz * mx) * KK) / (c2 * Xm * Xp);
+    Tinv[i * N + wloc] = -((lx * my - ly * mx) * KK) / (c2 * Xm * Xp);
+    Tinv[i * N + tloc] = (Q[i] * (c2 + bm1 * c2)) / (rho * c2 * Xm * Xp);
+  }
+  Tinv[N * uloc + uloc] = my * nz - mz * ny;
+  Tinv[N * uloc + vloc] = -(mx * nz - mz * nx);
+  Tinv[N * uloc + wloc] = mx * ny - my * nx;
+  Tinv[N * uloc + tloc] = 0.0;
+  Tinv[N * vloc + uloc] = -(ly * nz - lz * ny);
+  Tinv[N * vloc + vloc] = lx * nz - lz * nx;
+  Tinv[N * vloc + wloc] = -(lx * ny - ly * nx);
+  Tinv[N * vloc + tloc] = 0.0;
+  Tinv[N * wloc + uloc] = ((Xp) * (ly * mz - lz * my)) / (2.0 * cPrime);
+  Tinv[N * wloc + vloc] = -((Xp) * (lx * mz - lz * mx)) / (2.0 * cPrime);
+  Tinv[N * wloc + wloc] = ((Xp) * (lx * my - ly * mx)) / (2.0 * cPrime);
+  Tinv[N * wloc + tloc] = 1.0 / (2.0 * rho * cPrime);
+  Tinv[N * tloc + uloc] = ((Xm) * (ly * mz - lz * my)) / (2.0 * cPrime);
+  Tinv[N * tloc + vloc] = -((Xm) * (lx * mz - lz * mx)) / (2.0 * cPrime);
+  Tinv[N * tloc + wloc] = ((Xm) * (lx * my - ly * mx)) / (2.0 * cPrime);
+  Tinv[N * tloc + tloc] = 1.0 / (2.0 * rho * cPrime);
+}
+
+// NewtonFindTGivenP (compressibleFR.tcc:2343-2378)
+template <int NS>
+__device__ double newton_T_given_P(const Params<NS>& p, const double* rhoi, double Pgoal, double Tinit) {
+  double TDim = Tinit * p.ref_temperature;
+  const double PgoalDim = Pgoal * p.ref_pressure;
+  double rhoiDim[NS];
+  for (int i = 0; i < NS; i++) rhoiDim[i] = rhoi[i] * p.ref_density;
+  for (int j = 0; j < 28; j++) {
+    const double TpDim = TDim + 1.0e-8;
+    const double PDim = chem_P(p, rhoiDim, TDim);
+    const double PpDim = chem_P(p, rhoiDim, TpDim);
+    const double zpoint = PgoalDim - PDim;
+    const double zpointp = PgoalDim - PpDim;
+    const double dzdT = (zpointp - zpoint) / (TpDim - TDim);
+    const double dT = -zpoint / dzdT;
+    if (fabs(dT / p.ref_temperature) < 1.0e-15) break;
+    else TDim += dT;
+  }
+  return TDim / p.ref_temperature;
+}
+
+constexpr int N_SUBIT = 10;   // compressibleFR.tcc:32
+
+// GetFarfieldBoundaryVariables (compressibleFR.tcc:940-1039)
+template <int NS>
+__device__ void farfield_bc(const Params<NS>& p, const double* QL, double* QR, const double* av, double vdotn, double beta) {
+  constexpr int N = NS + 4, NV = 3 * NS + 6;
+  double qavg[NS + 6], eig[N], Tinv[N * N], T[N * N], rhs[N], ql[N], qinf[N];
+  for (int subit = 0; subit < N_SUBIT; subit++) {
+    for (int i = 0; i < N; i++) qavg[i] = 0.5 * (QL[i] + QR[i]);
+    aux_pr(p, qavg);
+    eigensystem(p, qavg, av, vdotn, eig, T, Tinv, beta);
+    if (p.no_cvbc) {
+      if (eig[0] >= 0.0) { for (int i = 0; i < NV; i++) QR[i] = QL[i]; }
+      else { for (int i = 0; i < NV; i++) QR[i] = p.qinf[i]; }
+    } else {
+      for (int i = 0; i < N; i++) { ql[i] = QL[i]; qinf[i] = p.qinf[i]; }
+      const double Tguess = ql[N - 1];
+      ql[N - 1] = QL[NS + 4];
+      qinf[N - 1] = p.qinf[NS + 4];
+      for (int i = 0; i < N; i++) {
+        double s = 0.0;
+        for (int j = 0; j < N; j++) s += Tinv[i * N + j] * (eig[i] >= 0.0 ? ql[j] : qinf[j]);
+        rhs[i] = s;
+      }
+      matvec<N>(T, rhs, QR);
+      for (int i = 0; i < NS; i++) if (QR[i] < 0.0) QR[i] = 0.0;
+      const double pgoal = QR[N - 1];
+      QR[N - 1] = newton_T_given_P(p, QR, pgoal, Tguess);
+    }
+  }
+}
+
+// GetInviscidWallBoundaryVariables (compressibleFR.tcc:1042-1134)
+template <int NS>
+__device__ void inviscid_wall_bc(const Params<NS>& p, const double* QL, double* QR, const double* av, double vdotn,
+                                 double beta) {
+  constexpr int N = NS + 4, NV = 3 * NS + 6;
+  if (!p.no_cvbc) {
+    double qavg[NS + 6], eig[N], Tinv[N * N], T[N * N], rhs[N], scr[N], ql[N];
+    int pv[N];
+    for (int subit = 0; subit < N_SUBIT; subit++) {
+      for (int i = 0; i < N; i++) qavg[i] = 0.5 * (QL[i] + QR[i]);
+      aux_pr(p, qavg);
+      eigensystem(p, qavg, av, vdotn, eig, T, Tinv, beta);
+      for (int i = 0; i < N; i++) ql[i] = QL[i];
+      const double Tguess = ql[N - 1];
+      ql[N - 1] = QL[NS + 4];
+      for (int i = 0; i < N; i++) {
+        double s = 0.0;
+        for (int j = 0; j < N; j++) s += Tinv[i * N + j] * ql[j];
+        rhs[i] = s;
+      }
+      for (int i = 0; i < NS; i++) Tinv[(N - 1) * N + i] = 0.0;
+      Tinv[(N - 1) * N + NS] = av[0];
+      Tinv[(N - 1) * N + NS + 1] = av[1];
+      Tinv[(N - 1) * N + NS + 2] = av[2];
+      Tinv[(N - 1) * N + NS + 3] = 0.0;
+      rhs[N - 1] = vdotn;
+      lu<N>(Tinv, pv);
+      lu_solve<N>(Tinv, rhs, pv, scr);
+      for (int i = 0; i < N; i++) QR[i] = rhs[i];
+      const double pgoal = QR[N - 1];
+      QR[N - 1] = newton_T_given_P(p, QR, pgoal, Tguess);
+    }
+  } else {
+    double QLmod[NV];
+    for (int i = 0; i < NV; i++) QLmod[i] = QL[i];
+    QLmod[NS] += vdotn * av[0];
+    QLmod[NS + 1] += vdotn * av[1];
+    QLmod[NS + 2] += vdotn * av[2];
+    for (int i = 0; i < N; i++) QR[i] = QLmod[i];
+    const double dot = 2.0 * (QLmod[NS] * av[0] + QLmod[NS + 1] * av[1] + QLmod[NS + 2] * av[2]);   // MirrorVector
+    QR[NS] = QLmod[NS] - dot * av[0];
+    QR[NS + 1] = QLmod[NS + 1] - dot * av[1];
+    QR[NS + 2] = QLmod[NS + 2] - dot * av[2];
+  }
+}
+
+// CalculateBoundaryVariables (bc.tcc:1058-1397) for the BC types of the reacting configs; QL and QR are full rows
+template <int NS>
+__device__ void boundary_variables(const Params<NS>& p, double* QL, double* QR, const double* av, int bctype, double betaL) {
+  constexpr int N = NS + 4;
+  const double vdotn = 0.0;   // static mesh
+  switch (bctype) {
+    case PCFD_BC_PARALLEL: return;
+    case PCFD_BC_SONIC_OUTFLOW: case PCFD_BC_NEUMANN:
+      for (int i = 0; i < N; i++) QR[i] = QL[i];
+      break;
+    case PCFD_BC_FARFIELD:
+      farfield_bc(p, QL, QR, av, vdotn, betaL);
+      break;
+    case PCFD_BC_IMPERMEABLE_WALL: case PCFD_BC_SYMMETRY:
+      inviscid_wall_bc(p, QL, QR, av, vdotn, betaL);
+      break;
+    default: break;
+  }
+  aux(p, QR);
+  aux(p, QL);
+}
+
+// ---------------------------------------------------------------- update
+// ApplyDQ (compressibleFR.tcc:886-937)
+template <int NS>
+__device__ __forceinline__ void apply_dq(const Params<NS>& p, const double* dQ, double* Q) {
+  for (int i = 0; i < NS; i++) {
+    const double rho = Q[i] + dQ[i];
+    if (!(rho < 0.0)) Q[i] += dQ[i];   // a negative projected density: the update is refused
+  }
+  const double projectedT = Q[NS + 3] + dQ[NS + 3];
+  if (projectedT < 0.0) Q[NS + 3] = 1.0e-10;
+  else Q[NS + 3] = projectedT;
+  Q[NS] += dQ[NS];
+  Q[NS + 1] += dQ[NS + 1];
+  Q[NS + 2] += dQ[NS + 2];
+  aux(p, Q);
+}
+
+// NativeToConservative (compressibleFR.tcc:2117-2130)
+template <int NS>
+__device__ __forceinline__ void native_to_conservative(const Params<NS>& p, double* Q) {
+  const double rho = Q[NS + 5];
+  const double Et = total_energy(p, Q);
+  Q[NS] *= rho;
+  Q[NS + 1] *= rho;
+  Q[NS + 2] *= rho;
+  Q[NS + 3] = Et;
+}
+// ConservativeToNative (compressibleFR.tcc:2133-2201); returns false if the Newton iteration did not converge
+template <int NS>
+__device__ bool conservative_to_native(const Params<NS>& p, double* Q) {
+  double rho = 0.0, Y[NS], rhoiDim[NS], R = 0.0;
+  for (int i = 0; i < NS; i++) {
+    rho += Q[i];
+    rhoiDim[i] = Q[i] * p.ref_density;
+    R += rhoiDim[i] * p.Rs[i];
+  }
+  R /= p.ref_density * rho;
+  for (int i = 0; i < NS; i++) Y[i] = Q[i] / rho;
+  const double u = Q[NS] / rho, v = Q[NS + 1] / rho, w = Q[NS + 2] / rho;
+  const double v2 = u * u + v * v + w * w;
+  const double res = Q[NS + 3] - 0.5 * v2 * rho;
+  const double P = Q[NS + 4];
+  double T = ((P * p.ref_pressure) / ((rho * p.ref_density) * R)) / p.ref_temperature;   // IdealGasEOS::GetT
+  int j = 0;
+  for (; j < 20; j++) {
+    const double Tp = T + 1.0e-8;
+    const double H = rho * (chem_h(p, Y, T * p.ref_temperature) / p.ref_specific_enthalpy);
+    const double Hp = rho * (chem_h(p, Y, Tp * p.ref_temperature) / p.ref_specific_enthalpy);
+    const double Pn = chem_P(p, rhoiDim, T * (p.ref_temperature)) / p.ref_pressure;
+    const double Pp = chem_P(p, rhoiDim, Tp * (p.ref_temperature)) / p.ref_pressure;
+    const double E = H - Pn;
+    const double Ep = Hp - Pp;
+    const double zpoint = res - E;
+    const double zpointp = res - Ep;
+    const double dzdT = (zpointp - zpoint) / (Tp - T);
+    const double dT = -zpoint / dzdT;
+    T += dT;
+    if (fabs(dT) < 1.0e-12) break;
+  }
+  Q[NS] = u; Q[NS + 1] = v; Q[NS + 2] = w;
+  Q[NS + 3] = T;
+  return j != 20;
+}
+
+// SourceTerm (compressibleFR.tcc:1276-1316), species rows only (the others are zero; gravity off)
+template <int NS>
+__device__ __forceinline__ void source_term(const Params<NS>& p, const double* Q, double vol, double* source) {
+  if (!p.rxn_on) {
+#pragma unroll
+    for (int i = 0; i < NS; i++) source[i] = 0.0;
+    return;
+  }
+  double rhoi[PCFD_CHEM_MAX_SPECIES], wdot[PCFD_CHEM_MAX_SPECIES];
+  const double T = Q[NS + 3] * p.ref_temperature;
+#pragma unroll
+  for (int i = 0; i < NS; i++) rhoi[i] = Q[i] * p.ref_density;
+  chemdev::mass_production(p.chem, rhoi, T, wdot);
+#pragma unroll
+  for (int i = 0; i < NS; i++) {
+    double w = wdot[i];
+    w /= (p.ref_density / p.ref_time);
+    source[i] = vol * w;
+  }
+}
+
+// ChemModel::dRmixdRhoi (chem.tcc:861-873)
+template <int NS>
+__device__ __forceinline__ double dRmixdRhoi(const Params<NS>& p, const double* rhoi, double rho, int i) {
+  double d = p.Rs[i] * (rho - rhoi[i]) / (rho * rho);
+  for (int j = 0; j < NS; j++) {
+    if (j == i) continue;
+    d -= p.Rs[j] * rhoi[j] / (rho * rho);
+  }
+  return d;
+}
+
+// ContributeTemporalTerms (compressibleFR.tcc:1319-1463) with ChemModel::dEtdP_dEtdRhoi (chem.tcc:829-858) and the
+// IdealGasEOS derivatives (EOS.tcc:42-76); A = the node's diagonal block, row-major N x N, accumulated in place
+template <int NS>
+__device__ void temporal_terms(const Params<NS>& p, const double* Q, double vol, double cnp1, double dtau, double* A,
+                               double beta) {
+  constexpr int N = NS + 4, uloc = NS, vloc = NS + 1, wloc = NS + 2, tloc = NS + 3;
+  double dEtdRhoi[NS], rhoiDim[NS], Yi[NS], thetaOBetai[NS];
+  double vOverDt;
+  if (p.use_local_dt) vOverDt = cnp1 * vol / p.dt + vol / dtau;
+  else vOverDt = cnp1 * vol / dtau;
+  const double rho = Q[NS + 5], T = Q[tloc], P = Q[NS + 4], u = Q[uloc], v = Q[vloc], w = Q[wloc];
+  const double rvOverDt = rho * vOverDt;
+  double v2 = u * u + v * v + w * w;
+  double R, c2;
+  fluid_props(p, Q, T, R, c2);
+  const double s_ref = (p.ref_velocity * p.ref_velocity / p.ref_temperature);
+  const double rhoDim = rho * p.ref_density;
+  const double TDim = T * p.ref_temperature;
+  const double PDim = P * p.ref_pressure;
+  (void)PDim;
+  v2 *= p.ref_velocity * p.ref_velocity;
+  for (int i = 0; i < NS; i++) {
+    rhoiDim[i] = Q[i] * p.ref_density;
+    Yi[i] = Q[i] / rho;
+  }
+  // dEtdP_dEtdRhoi
+  double dEtdP = 0.0;
+  {
+    const double hv2 = 0.5 * v2;
+    double rhomix = 0.0, Rmix = 0.0;
+    for (int i = 0; i < NS; i++) {
+      rhomix += rhoiDim[i];
+      Rmix += rhoiDim[i] * p.Rs[i];
+    }
+    Rmix /= rhomix;
+    const double dPdrhomix = (Rmix * TDim);
+    const double dPdRmix = (rhomix * TDim);
+    const int rng = thermo_range(TDim);
+    for (int i = 0; i < NS; i++)
+      dEtdRhoi[i] = hv2 + sp_h(p, i, rng, TDim) - (dPdrhomix + dPdRmix * dRmixdRhoi(p, rhoiDim, rhomix, i));
+    const double dTdP = (1.0 / (rhomix * Rmix));
+    for (int i = 0; i < NS; i++) dEtdP += rhoiDim[i] * (sp_cp(p, i, rng, TDim)) * dTdP;
+    dEtdP -= 1.0;
+  }
+  const double ref_detdrho = p.ref_specific_enthalpy * p.ref_density / p.ref_density;
+  for (int i = 0; i < NS; i++) dEtdRhoi[i] /= ref_detdrho;
+  const double ref_detdP = p.ref_specific_enthalpy * p.ref_density / p.ref_pressure;
+  dEtdP /= ref_detdP;
+  double dPdT = (rhoDim * (R * s_ref));
+  dPdT /= (p.ref_pressure / p.ref_temperature);
+  const double oneOBeta = 1.0 / beta;
+  const double oneMbeta = 1.0 - beta;
+  for (int i = 0; i < NS; i++) thetaOBetai[i] = (Yi[i] * oneMbeta / c2) * oneOBeta;
+  for (int i = 0; i < NS; i++) {
+    A[N * i + i] += vOverDt;
+    A[N * i + tloc] += thetaOBetai[i] * vOverDt * dPdT;
+  }
+  double precond = 0.0;
+  for (int j = 0; j < NS; j++) { A[N * uloc + j] += u * vOverDt; precond += thetaOBetai[j] * u; }
+  A[N * uloc + uloc] += rvOverDt;
+  A[N * uloc + tloc] += precond * vOverDt * dPdT;
+  precond = 0.0;
+  for (int j = 0; j < NS; j++) { A[N * vloc + j] += v * vOverDt; precond += thetaOBetai[j] * v; }
+  A[N * vloc + vloc] += rvOverDt;
+  A[N * vloc + tloc] += precond * vOverDt * dPdT;
+  precond = 0.0;
+  for (int j = 0; j < NS; j++) { A[N * wloc + j] += w * vOverDt; precond += thetaOBetai[j] * w; }
+  A[N * wloc + wloc] += rvOverDt;
+  A[N * wloc + tloc] += precond * vOverDt * dPdT;
+  precond = 0.0;
+  for (int j = 0; j < NS; j++) { A[N * tloc + j] += dEtdRhoi[j] * vOverDt; precond += dEtdRhoi[j] * thetaOBetai[j]; }
+  A[N * tloc + uloc] += u * rvOverDt;
+  A[N * tloc + vloc] += v * rvOverDt;
+  A[N * tloc + wloc] += w * rvOverDt;
+  precond += dEtdP * (oneOBeta);
+  A[N * tloc + tloc] += precond * vOverDt * dPdT;
+}
+
+}  // namespace fr

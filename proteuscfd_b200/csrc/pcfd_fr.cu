@@ -1,0 +1,1088 @@
+// pcfd_fr.cu -- the reacting eqnset (CompressibleFREqnSet, equationSet = compressibleEulerFR) on the hot path:
+// CUDA kernels (sm_100a, FP64) and the host side of every phase entry point for contexts made by pcfd_create_fr.
+//
+// Same design as pcfd_kernels.cu: expensive per-edge work (HLLC flux, the 19-flux finite-difference Jacobian) is done
+// once per edge by edge-parallel kernels that write private slots; every reduction onto a node is an ordered gather
+// by the threads that own the node, in the reference's edge order, so there are no atomics and the floating-point
+// summation order is the reference's.  The kernels are templates on the species count NS (NEQ = NS+4 equations per
+// node, NEQ x NEQ blocks); `fr_dispatch` instantiates the sizes the library ships with.
+//
+// What differs from the perfect-gas path because the blocks are 9x9 and the state is 21 doubles wide:
+//  * rows of a node are shared by NEQ consecutive threads wherever the work is per (node, equation): limiter,
+//    residual gather, Jacobian diagonal, SGS -- consecutive lanes then read consecutive doubles of a block row;
+//  * the FD Jacobian of an edge is spread over 2*NEQ+1 = 19 lanes, one HLLC flux each (reference state, NEQ left and
+//    NEQ right perturbations), which write the two off-diagonal blocks column by column.
+
+#include "pcfd_internal.cuh"
+#include "eqnset_fr.cuh"
+
+struct pcfd_fr_state {
+  pcfd_fr_params host{};
+  pcfd_chem_model* chem_dev = nullptr;
+  double *eig = nullptr, *beig = nullptr;   // spectral radius x area per edge / half-edge (time step)
+  double* src = nullptr;                    // source term rows (species only) per node
+  double *red = nullptr, *redout = nullptr;
+  int bad_newton = 0;
+  int* dbad = nullptr;
+};
+
+namespace {
+
+constexpr int FR_RED_BLOCKS = 296;
+
+template <int NS>
+struct W {
+  static constexpr int NEQ = NS + 4, NV = 3 * NS + 6, NT = 2 * NS + 4, N2 = NEQ * NEQ;
+};
+
+// GetGradientsLocation (compressibleFR.tcc:693-711)
+template <int NS>
+__device__ __forceinline__ int gradloc(int i) { return (i < NS + 4) ? i : (NS + NS + 6 + (i - (NS + 4))); }
+
+template <int NS, int CNT>
+__device__ __forceinline__ void load_row(const double* __restrict__ q, int n, double* v) {
+  const double* p = q + (size_t)n * W<NS>::NV;
+#pragma unroll
+  for (int i = 0; i < CNT; i++) v[i] = p[i];
+}
+
+// ============================================================ boundary conditions
+// UpdateBCs (bc.tcc:1399-1457): one thread per BC half-edge.  Two half-edges of a node interact only through
+// ComputeAuxiliaryVariables(QL) at the end of each call: the first half-edge sees the stored aux values, every later
+// one sees them recomputed -- which a thread reproduces locally (same argument as k_update_bcs_edges).
+template <int NS>
+__global__ void __launch_bounds__(64) kfr_update_bcs_edges(DevMesh m, fr::Params<NS> p, const int* __restrict__ list, int n,
+                                                            const unsigned char* __restrict__ bfirst,
+                                                            const double* __restrict__ beta, double* q) {
+  constexpr int NV = W<NS>::NV;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int be = list[t];
+  const int2 lr = m.ben[be];
+  const bool first = bfirst[be] != 0;
+  double QL[NV], QR[NV], av[4];
+  load_row<NS, NV>(q, lr.x, QL);
+  load_row<NS, NV>(q, lr.y, QR);
+  load_avec(m.bea, be, av);
+  if (!first) fr::aux(p, QL);
+  fr::boundary_variables(p, QL, QR, av, m.bctype[be], beta[lr.x]);
+  double* qr = q + (size_t)lr.y * NV;
+  for (int i = 0; i < NV; i++) qr[i] = QR[i];
+  if (first) {
+    double* ql = q + (size_t)lr.x * NV;
+    for (int i = NS + 4; i < NV; i++) ql[i] = QL[i];
+  }
+}
+
+// ====================================================================== gradient
+// Gradient::Compute (gradient.tcc:57-112, weighted LSQ kernels :251-378, symmetry fix :545-565): ordered gather
+template <int NS>
+__global__ void __launch_bounds__(128) kfr_gradient(DevMesh m, const double* __restrict__ q, const double* __restrict__ sw,
+                                                     double* __restrict__ qgrad) {
+  constexpr int NV = W<NS>::NV, NT = W<NS>::NT;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= m.nnode) return;
+  double g[NT * 3], qn[NT], swn[6];
+#pragma unroll
+  for (int k = 0; k < NT * 3; k++) g[k] = 0.0;
+#pragma unroll
+  for (int i = 0; i < NT; i++) qn[i] = q[(size_t)n * NV + gradloc<NS>(i)];
+#pragma unroll
+  for (int k = 0; k < 6; k++) swn[k] = sw[6 * (size_t)n + k];
+  const double xn[3] = {m.xyz[3 * n], m.xyz[3 * n + 1], m.xyz[3 * n + 2]};
+  const int kbeg = m.adjp[n], kend = m.adjp[n + 1];
+  for (int k = kbeg; k < kend; k++) {
+    const int2 a = m.adj[k];
+    const int o = a.x & 0x7fffffff;
+    const bool right = a.x < 0;
+    if (a.y >= m.nedge && !is_ghost(m, o)) continue;
+    const double xo[3] = {__ldg(m.xyz + 3 * o), __ldg(m.xyz + 3 * o + 1), __ldg(m.xyz + 3 * o + 2)};
+    double dx[3], we[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) dx[d] = right ? (xo[d] - xn[d]) : (xn[d] - xo[d]);
+    const double dx2 = dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2];
+    const double weight = 1.0 / sqrt(dx2);
+    dx[0] *= weight; dx[1] *= weight; dx[2] *= weight;
+    if (right) { dx[0] = -dx[0]; dx[1] = -dx[1]; dx[2] = -dx[2]; }
+    lsq_weights(swn, dx, we);
+#pragma unroll
+    for (int i = 0; i < NT; i++) {
+      const double qo = __ldg(q + (size_t)o * NV + gradloc<NS>(i));
+      const double dq = right ? weight * (qn[i] - qo) : weight * (qo - qn[i]);
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        if (right) g[3 * i + j] += +we[j] * dq;
+        else g[3 * i + j] += -we[j] * dq;
+      }
+    }
+  }
+  for (int k = kbeg; k < kend; k++) {
+    const int2 a = m.adj[k];
+    if (a.y < m.nedge) continue;
+    const int be = a.y - m.nedge;
+    if (m.bctype[be] != PCFD_BC_SYMMETRY) continue;
+    double av[4];
+    load_avec(m.bea, be, av);
+#pragma unroll
+    for (int i = 0; i < NT; i++) {
+      const double dot = g[i * 3] * av[0] + g[i * 3 + 1] * av[1] + g[i * 3 + 2] * av[2];
+#pragma unroll
+      for (int j = 0; j < 3; j++) g[i * 3 + j] -= dot * av[j];
+    }
+  }
+  double* out = qgrad + (size_t)n * NT * 3;
+#pragma unroll
+  for (int kk = 0; kk < NT * 3; kk++) out[kk] = g[kk];
+}
+
+// ======================================================================= limiter
+// Limiter::Compute passes 1+2 (limiters.tcc:53-110), NEQ threads per node (one equation each); unclamped output
+template <int NS>
+__global__ void __launch_bounds__(W<NS>::NEQ * 16) kfr_limiter(DevMesh m, int type, double chi, const double* __restrict__ q,
+                                                                const double* __restrict__ qgrad, double* __restrict__ lim) {
+  constexpr int NEQ = W<NS>::NEQ, NV = W<NS>::NV, NT = W<NS>::NT;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = tid / NEQ;
+  if (n >= m.nnode + m.gnode) return;
+  const int j = tid - n * NEQ;
+  double l = 1.0;
+  if (n < m.nnode && (type == 1 || type == 2)) {
+    double qmin = 0.0, qmax = 0.0;
+    const int k0 = m.adjp[n], k1 = m.adjp[n + 1];
+    for (int k = k0; k < k1; k++) {
+      const int2 a = m.adj[k];
+      const int o = a.x & 0x7fffffff;
+      if (a.y >= m.nedge && !is_ghost(m, o)) continue;
+      const double qo = __ldg(q + (size_t)o * NV + j);
+      qmax = fr::maxd(qmax, qo);
+      qmin = fr::mind(qmin, qo);
+    }
+    const double qn = __ldg(q + (size_t)n * NV + j);
+    const double* gp = qgrad + (size_t)n * NT * 3 + j * 3;
+    const double g0 = gp[0], g1 = gp[1], g2 = gp[2];
+    const double xn[3] = {m.xyz[3 * n], m.xyz[3 * n + 1], m.xyz[3 * n + 2]};
+    for (int k = k0; k < k1; k++) {
+      const int2 a = m.adj[k];
+      const int o = a.x & 0x7fffffff;
+      if (a.y >= m.nedge && !is_ghost(m, o)) continue;
+      const double qo = __ldg(q + (size_t)o * NV + j);
+      const double dQ = qo - qn;
+      double dx[3];
+#pragma unroll
+      for (int d = 0; d < 3; d++) dx[d] = 0.5 * (__ldg(m.xyz + 3 * o + d) - xn[d]);
+      const double corr = (0.5 * chi * dQ + (1.0 - chi) * (g0 * dx[0] + g1 * dx[1] + g2 * dx[2]));
+      const double QH = qn + corr * 1.0;
+      double t = 1.0;
+      if (QH > qn) t = (qmax - qn) / (QH - qn);
+      else if (QH < qn) t = (qmin - qn) / (QH - qn);
+      t = limiter_fn(type, t);
+      l = fr::mind(l, t);
+    }
+  }
+  lim[(size_t)n * NEQ + j] = l;
+}
+
+// Kernel_PressureClip (limiters.tcc:737-815) as the fixed point on "first edge that zeroes node n" (see
+// k_clip_edges in pcfd_kernels.cu); no Roe-state test for this eqnset (EqnSet::RoeVariables returns false)
+template <int NS>
+__global__ void __launch_bounds__(128) kfr_clip_edges(DevMesh m, fr::Params<NS> p, const double* __restrict__ q,
+                                                       const double* __restrict__ qgrad, const double* __restrict__ lim,
+                                                       const int* __restrict__ tclip, unsigned char* __restrict__ flag,
+                                                       int* __restrict__ any) {
+  constexpr int NEQ = W<NS>::NEQ, NT = W<NS>::NT;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m.nedge) return;
+  const int2 lr = m.en[e];
+  const int l = lr.x, r = lr.y;
+  double qL[NEQ], qR[NEQ], lm[NEQ], dQ[NEQ], dx[3], Qx[NS + 6], gr[NEQ * 3];
+  load_row<NS, NEQ>(q, l, qL);
+  load_row<NS, NEQ>(q, r, qR);
+  const bool zl = tclip[l] < e, zr = tclip[r] < e;
+#pragma unroll
+  for (int d = 0; d < 3; d++) dx[d] = 0.5 * (__ldg(m.xyz + 3 * r + d) - __ldg(m.xyz + 3 * l + d));
+#pragma unroll
+  for (int j = 0; j < NEQ; j++) { dQ[j] = qR[j] - qL[j]; lm[j] = zl ? 0.0 : lim[(size_t)l * NEQ + j]; }
+#pragma unroll
+  for (int j = 0; j < NEQ * 3; j++) gr[j] = __ldg(qgrad + (size_t)l * NT * 3 + j);
+  fr::extrapolate<NS>(p.chi, Qx, qL, dQ, gr, dx, lm);
+  fr::aux_pr(p, Qx);
+  const bool cl = fr::bad_extrapolation(p, Qx);
+#pragma unroll
+  for (int d = 0; d < 3; d++) dx[d] = -dx[d];
+#pragma unroll
+  for (int j = 0; j < NEQ; j++) { dQ[j] = -dQ[j]; lm[j] = zr ? 0.0 : lim[(size_t)r * NEQ + j]; }
+#pragma unroll
+  for (int j = 0; j < NEQ * 3; j++) gr[j] = __ldg(qgrad + (size_t)r * NT * 3 + j);
+  fr::extrapolate<NS>(p.chi, Qx, qR, dQ, gr, dx, lm);
+  fr::aux_pr(p, Qx);
+  const bool cr = fr::bad_extrapolation(p, Qx);
+  const unsigned char f = (cl ? 1 : 0) | (cr ? 2 : 0);
+  flag[e] = f;
+  if (f) *any = 1;
+}
+
+__global__ void kfr_clip_nodes(DevMesh m, const unsigned char* __restrict__ flag, const int* __restrict__ told,
+                               int* __restrict__ tnew, int* __restrict__ changed) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= m.nnode) return;
+  int t = INT_MAX;
+  for (int k = m.adjp[n]; k < m.adjp[n + 1]; k++) {
+    const int2 a = m.adj[k];
+    if (a.y >= m.nedge) break;
+    const unsigned char f = flag[a.y];
+    if (f & ((a.x < 0) ? 2 : 1)) { t = a.y; break; }
+  }
+  tnew[n] = t;
+  if (t != told[n]) *changed = 1;
+}
+
+__global__ void kfr_limiter_final(int ntot, int nnode, int neqn, const int* __restrict__ tclip, double* __restrict__ lim) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ntot * neqn) return;
+  const int n = i / neqn;
+  double v = lim[i];
+  if (tclip != nullptr && n < nnode && tclip[n] != INT_MAX) v = 0.0;
+  if (v < 0.0) v = 0.0;
+  lim[i] = v;
+}
+
+__global__ void kfr_fill_int(int* p, int n, int v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ====================================================================== residual
+// MUSCL reconstruction of one side pair (Kernel_Inviscid_Flux, residual.tcc:192-296): QL / QR hold [0, NS+6)
+template <int NS>
+__device__ __forceinline__ void reconstruct(const DevMesh& m, const fr::Params<NS>& p, int l, int r,
+                                            const double* __restrict__ qgrad, const double* __restrict__ lim, double* QL,
+                                            double* QR) {
+  constexpr int NEQ = W<NS>::NEQ, NT = W<NS>::NT;
+  double dQ[NEQ], dx[3], gr[NEQ * 3], lm[NEQ], qL[NEQ], qR[NEQ];
+#pragma unroll
+  for (int j = 0; j < NEQ; j++) { qL[j] = QL[j]; qR[j] = QR[j]; dQ[j] = qR[j] - qL[j]; }
+#pragma unroll
+  for (int d = 0; d < 3; d++) dx[d] = 0.5 * (__ldg(m.xyz + 3 * r + d) - __ldg(m.xyz + 3 * l + d));
+#pragma unroll
+  for (int j = 0; j < NEQ * 3; j++) gr[j] = __ldg(qgrad + (size_t)l * NT * 3 + j);
+#pragma unroll
+  for (int j = 0; j < NEQ; j++) lm[j] = __ldg(lim + (size_t)l * NEQ + j);
+  fr::extrapolate<NS>(p.chi, QL, qL, dQ, gr, dx, lm);
+#pragma unroll
+  for (int j = 0; j < NEQ; j++) dQ[j] = -dQ[j];
+#pragma unroll
+  for (int d = 0; d < 3; d++) dx[d] = -dx[d];
+#pragma unroll
+  for (int j = 0; j < NEQ * 3; j++) gr[j] = __ldg(qgrad + (size_t)r * NT * 3 + j);
+#pragma unroll
+  for (int j = 0; j < NEQ; j++) lm[j] = __ldg(lim + (size_t)r * NEQ + j);
+  fr::extrapolate<NS>(p.chi, QR, qR, dQ, gr, dx, lm);
+}
+
+template <int NS>
+__global__ void __launch_bounds__(128) kfr_flux_edges(DevMesh m, fr::Params<NS> p, const double* __restrict__ q,
+                                                       const double* __restrict__ qgrad, const double* __restrict__ lim,
+                                                       const double* __restrict__ beta, double* __restrict__ flux) {
+  constexpr int NEQ = W<NS>::NEQ;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m.nedge) return;
+  const int2 lr = m.en[e];
+  const int l = lr.x, r = lr.y;
+  double av[4], QL[NS + 6], QR[NS + 6], f[NEQ];
+  load_avec(m.ea, e, av);
+  load_row<NS, NS + 6>(q, l, QL);
+  load_row<NS, NS + 6>(q, r, QR);
+  const double avbeta = 0.5 * (beta[l] + beta[r]);
+  if (p.sorder > 1) {
+    reconstruct<NS>(m, p, l, r, qgrad, lim, QL, QR);
+    fr::aux_pr(p, QL);
+    fr::aux_pr(p, QR);
+  }
+  fr::numerical_flux(p, QL, QR, av, 0.0, avbeta, f);
+#pragma unroll
+  for (int j = 0; j < NEQ; j++) flux[(size_t)e * NEQ + j] = f[j];
+}
+
+// Bkernel_Inviscid_Flux (residual.tcc:299-387)
+template <int NS>
+__global__ void __launch_bounds__(128) kfr_flux_bedges(DevMesh m, fr::Params<NS> p, const double* __restrict__ q,
+                                                        const double* __restrict__ qgrad, const double* __restrict__ lim,
+                                                        const double* __restrict__ beta, double* __restrict__ bflux) {
+  constexpr int NEQ = W<NS>::NEQ;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m.nbedge + m.ngedge) return;
+  const int2 lr = m.ben[e];
+  const int l = lr.x, r = lr.y;
+  double av[4], QL[NS + 6], QR[NS + 6], f[NEQ];
+  load_avec(m.bea, e, av);
+  load_row<NS, NS + 6>(q, l, QL);
+  load_row<NS, NS + 6>(q, r, QR);
+  if (p.sorder > 1) {
+    if (is_ghost(m, r)) reconstruct<NS>(m, p, l, r, qgrad, lim, QL, QR);
+    fr::aux_pr(p, QL);
+    fr::aux_pr(p, QR);
+  }
+  fr::numerical_flux(p, QL, QR, av, 0.0, beta[l], f);
+#pragma unroll
+  for (int j = 0; j < NEQ; j++) bflux[(size_t)e * NEQ + j] = f[j];
+}
+
+// SourceTerm (compressibleFR.tcc:1276-1316) per node -> src[n*NS]
+template <int NS>
+__global__ void __launch_bounds__(128) kfr_source(int nnode, fr::Params<NS> p, const double* __restrict__ q,
+                                                   const double* __restrict__ vol, double* __restrict__ src) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nnode) return;
+  double Q[NS + 4], s[NS];
+  load_row<NS, NS + 4>(q, n, Q);
+  fr::source_term(p, Q, vol[n], s);
+#pragma unroll
+  for (int i = 0; i < NS; i++) src[(size_t)n * NS + i] = s[i];
+}
+
+// DriverScatter (driver.tcc:274-306) as an ordered gather, then the source term (residual.tcc:109-115); NEQ threads
+// per node, one equation each
+template <int NS>
+__global__ void __launch_bounds__(W<NS>::NEQ * 16) kfr_residual_gather(DevMesh m, const double* __restrict__ flux,
+                                                                        const double* __restrict__ bflux,
+                                                                        const double* __restrict__ src, double* __restrict__ b) {
+  constexpr int NEQ = W<NS>::NEQ;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = tid / NEQ;
+  if (n >= m.nnode) return;
+  const int j = tid - n * NEQ;
+  double acc = 0.0;
+  const int k0 = m.adjp[n], k1 = m.adjp[n + 1];
+  for (int k = k0; k < k1; k++) {
+    const int2 a = m.adj[k];
+    const double f = (a.y < m.nedge) ? __ldg(flux + (size_t)a.y * NEQ + j) : __ldg(bflux + (size_t)(a.y - m.nedge) * NEQ + j);
+    acc += (a.x < 0) ? f : -f;
+  }
+  acc += (j < NS) ? src[(size_t)n * NS + j] : 0.0;
+  b[(size_t)n * NEQ + j] = acc;
+}
+
+// ====================================================================== time step
+// Kernel_Timestep / Bkernel_Timestep (timestep.tcc:80-143): spectral radius x area of the averaged state, per edge
+template <int NS>
+__global__ void __launch_bounds__(128) kfr_eig_edges(DevMesh m, fr::Params<NS> p, const double* __restrict__ q,
+                                                      const double* __restrict__ beta, double* __restrict__ eig,
+                                                      double* __restrict__ beig) {
+  constexpr int NEQ = W<NS>::NEQ;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nb = m.nbedge + m.ngedge;
+  if (t >= m.nedge + nb) return;
+  const bool interior = t < m.nedge;
+  const int2 lr = interior ? m.en[t] : m.ben[t - m.nedge];
+  double av[4], QL[NEQ], QR[NEQ], Q[NS + 6];
+  load_avec(interior ? m.ea : m.bea, interior ? t : t - m.nedge, av);
+  load_row<NS, NEQ>(q, lr.x, QL);
+  load_row<NS, NEQ>(q, lr.y, QR);
+#pragma unroll
+  for (int i = 0; i < NEQ; i++) Q[i] = 0.5 * (QL[i] + QR[i]);
+  fr::aux_pr(p, Q);
+  const double bta = interior ? 0.5 * (beta[lr.x] + beta[lr.y]) : beta[lr.x];
+  const double me = fr::max_eigenvalue(p, Q, av, 0.0, bta);
+  if (interior) eig[t] = me * av[3];
+  else beig[t - m.nedge] = me * av[3];
+}
+
+// ComputeTimesteps (timestep.tcc:7-49): dt = CFL * vol / sum, VNN limit from node 1 on
+__global__ void __launch_bounds__(128) kfr_timestep(DevMesh m, double cfl, const double* __restrict__ eig,
+                                                     const double* __restrict__ beig, const double* __restrict__ vnn23,
+                                                     double* __restrict__ dt) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= m.nnode) return;
+  double s = 0.0;
+  for (int k = m.adjp[n]; k < m.adjp[n + 1]; k++) {
+    const int2 a = m.adj[k];
+    s += (a.y < m.nedge) ? __ldg(eig + a.y) : __ldg(beig + (a.y - m.nedge));
+  }
+  double d = cfl * (m.vol[n] / s);
+  if (vnn23 != nullptr && n > 0) d = fr::mind(d, vnn23[n]);
+  dt[n] = d;
+}
+
+__global__ void kfr_min_partial(const double* __restrict__ v, int n, double* __restrict__ part) {
+  __shared__ double sh[256];
+  double a = INFINITY;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) a = fmin(a, v[i]);
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] = fmin(sh[threadIdx.x], sh[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
+__global__ void kfr_min_final(const double* __restrict__ part, int n, double* __restrict__ out) {
+  __shared__ double sh[256];
+  double a = INFINITY;
+  for (int i = threadIdx.x; i < n; i += 256) a = fmin(a, part[i]);
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] = fmin(sh[threadIdx.x], sh[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sh[0];
+}
+
+// sum of squares per column and in total: out[0] = total, out[1 + c] = column c
+__global__ void kfr_sumsq_partial(const double* __restrict__ v, int nrows, int stride, double* __restrict__ part) {
+  __shared__ double sh[256];
+  for (int c = 0; c < stride; c++) {
+    double a = 0.0;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < nrows; i += gridDim.x * 256) { const double t = v[(size_t)i * stride + c]; a += t * t; }
+    sh[threadIdx.x] = a;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+      if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) part[(size_t)blockIdx.x * stride + c] = sh[0];
+    __syncthreads();
+  }
+}
+__global__ void kfr_sumsq_final(const double* __restrict__ part, int nparts, int stride, double* __restrict__ out) {
+  __shared__ double sh[256];
+  double total = 0.0;
+  for (int c = 0; c < stride; c++) {
+    double a = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += 256) a += part[(size_t)i * stride + c];
+    sh[threadIdx.x] = a;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+      if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[1 + c] = sh[0]; total += sh[0]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = total;
+}
+
+// ======================================================================== update
+// ExplicitSolve, native-variable branch (solve.tcc:112-130): q is left untouched, x = change of the native variables
+template <int NS>
+__global__ void __launch_bounds__(128) kfr_explicit(int nnode, fr::Params<NS> p, const double* __restrict__ b,
+                                                     const double* __restrict__ dt, const double* __restrict__ vol,
+                                                     const double* __restrict__ q, double* __restrict__ x,
+                                                     int* __restrict__ bad) {
+  constexpr int NEQ = W<NS>::NEQ;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nnode) return;
+  double Q[NS + 6], qc[NEQ];
+  load_row<NS, NS + 6>(q, n, Q);
+#pragma unroll
+  for (int j = 0; j < NEQ; j++) qc[j] = Q[j];
+  fr::native_to_conservative(p, Q);
+  const double d = dt[n], v = vol[n];
+#pragma unroll
+  for (int j = 0; j < NEQ; j++) Q[j] += b[(size_t)n * NEQ + j] * d / v;
+  if (!fr::conservative_to_native(p, Q)) atomicAdd(bad, 1);
+#pragma unroll
+  for (int j = 0; j < NEQ; j++) x[(size_t)n * NEQ + j] = Q[j] - qc[j];
+}
+
+// the ApplyDQ loop of NewtonIterate (solutionSpace.tcc:802-804)
+template <int NS>
+__global__ void __launch_bounds__(128) kfr_apply_dq(int nnode, fr::Params<NS> p, const double* __restrict__ x, double* q) {
+  constexpr int NEQ = W<NS>::NEQ, NV = W<NS>::NV;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nnode) return;
+  double Q[NV], dQ[NEQ];
+  load_row<NS, NEQ>(q, n, Q);
+#pragma unroll
+  for (int j = 0; j < NEQ; j++) dQ[j] = x[(size_t)n * NEQ + j];
+  fr::apply_dq(p, dQ, Q);
+  double* out = q + (size_t)n * NV;
+#pragma unroll
+  for (int j = 0; j < NV; j++) out[j] = Q[j];
+}
+
+// ====================================================================== Jacobian
+// Kernel_NumJac (jacobian.tcc:254-304): one-sided finite differences (h = 1e-8) of the FIRST-ORDER flux.  2*NEQ+1
+// lanes per edge, one HLLC flux each: lane 0 the reference state, lanes 1..NEQ the left perturbations (column i of
+// A(r,l) = (F_S - F_L,i)/h), lanes NEQ+1..2NEQ the right ones (column i of A(l,r) = (F_R,i - F_S)/h).
+template <int NS, int EPB>
+__global__ void __launch_bounds__((2 * W<NS>::NEQ + 1) * EPB) kfr_jac_edges(DevMesh m, fr::Params<NS> p,
+                                                                             const double* __restrict__ q,
+                                                                             const double* __restrict__ beta,
+                                                                             const int* __restrict__ posLR,
+                                                                             const int* __restrict__ posRL,
+                                                                             double* __restrict__ A) {
+  constexpr int NEQ = W<NS>::NEQ, N2 = W<NS>::N2, LPE = 2 * NEQ + 1;
+  __shared__ double fS[EPB][NEQ];
+  const int slot = threadIdx.x / LPE;
+  const int role = threadIdx.x - slot * LPE;
+  const int e = blockIdx.x * EPB + slot;
+  const bool live = e < m.nedge;
+  const double h = 1.0e-8;
+  double f[NEQ];
+  int l = 0, r = 0;
+  if (live) {
+    const int2 lr = m.en[e];
+    l = lr.x; r = lr.y;
+    double av[4], QL[NS + 6], QR[NS + 6];
+    load_avec(m.ea, e, av);
+    load_row<NS, NS + 6>(q, l, QL);
+    load_row<NS, NS + 6>(q, r, QR);
+    const double avbeta = 0.5 * (beta[l] + beta[r]);
+    if (role >= 1 && role <= NEQ) { QL[role - 1] += h; fr::aux_pr(p, QL); }
+    else if (role > NEQ) { QR[role - NEQ - 1] += h; fr::aux_pr(p, QR); }
+    fr::numerical_flux(p, QL, QR, av, 0.0, avbeta, f);
+    if (role == 0) {
+#pragma unroll
+      for (int j = 0; j < NEQ; j++) fS[slot][j] = f[j];
+    }
+  }
+  __syncthreads();
+  if (!live || role == 0) return;
+  if (role <= NEQ) {
+    double* dst = A + (size_t)posRL[e] * N2 + (role - 1);
+#pragma unroll
+    for (int j = 0; j < NEQ; j++) dst[j * NEQ] = 0.0 + (fS[slot][j] - f[j]) / h;
+  } else {
+    double* dst = A + (size_t)posLR[e] * N2 + (role - NEQ - 1);
+#pragma unroll
+    for (int j = 0; j < NEQ; j++) dst[j * NEQ] = 0.0 + (f[j] - fS[slot][j]) / h;
+  }
+}
+
+// Bkernel_NumJac (jacobian.tcc:459-544), boundaryJacEval == 0: one thread per half-edge; the boundary state is
+// recomputed for every perturbation of the interior state.  Writes q exactly as the reference does (phantom state,
+// aux of the left node), the diagonal contribution into the half-edge's bdiag slot and -- ghost half-edges -- A(l,ghost).
+template <int NS>
+__global__ void __launch_bounds__(64) kfr_jac_bedges(DevMesh m, fr::Params<NS> p, const int* __restrict__ list, int n,
+                                                      const unsigned char* __restrict__ bfirst, const double* __restrict__ beta,
+                                                      double* q, const int* __restrict__ bpos, double* __restrict__ bdiag,
+                                                      double* __restrict__ A) {
+  constexpr int NEQ = W<NS>::NEQ, NV = W<NS>::NV, N2 = W<NS>::N2;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int be = list[t];
+  const int2 lr = m.ben[be];
+  const int l = lr.x, r = lr.y;
+  const int type = m.bctype[be];
+  const bool first = bfirst[be] != 0;
+  const bool ghost = is_ghost(m, r);
+  const double h = 1.0e-8;
+  const double betaL = beta[l];
+  double QL[NV], QR[NV], av[4], fS[NEQ], fL[NEQ], fR[NEQ];
+  load_row<NS, NV>(q, l, QL);
+  load_row<NS, NV>(q, r, QR);
+  load_avec(m.bea, be, av);
+  if (!first && type != PCFD_BC_PARALLEL) fr::aux(p, QL);
+  fr::boundary_variables(p, QL, QR, av, type, betaL);
+  if (type != PCFD_BC_PARALLEL) {
+    double* qr = q + (size_t)r * NV;
+    for (int i = 0; i < NV; i++) qr[i] = QR[i];
+    if (first) {
+      double* ql = q + (size_t)l * NV;
+      for (int i = NS + 4; i < NV; i++) ql[i] = QL[i];
+    }
+  }
+  fr::numerical_flux(p, QL, QR, av, 0.0, betaL, fS);
+  double* bd = bdiag + (size_t)be * N2;
+  double* ag = ghost ? A + (size_t)bpos[be] * N2 : nullptr;
+  for (int i = 0; i < NEQ; i++) {
+    double QPL[NV], QPR[NV];
+    for (int k = 0; k < NV; k++) { QPL[k] = QL[k]; QPR[k] = QR[k]; }
+    QPL[i] += h; QPR[i] += h;
+    fr::aux(p, QPL);
+    fr::aux_pr(p, QPR);
+    fr::numerical_flux(p, QL, QPR, av, 0.0, betaL, fR);
+    if (!ghost) {
+      for (int k = 0; k < NV; k++) QPR[k] = QR[k];
+      fr::boundary_variables(p, QPL, QPR, av, type, betaL);
+      fr::numerical_flux(p, QPL, QPR, av, 0.0, betaL, fL);
+    } else {
+      fr::numerical_flux(p, QPL, QR, av, 0.0, betaL, fL);
+    }
+    for (int j = 0; j < NEQ; j++) bd[j * NEQ + i] = (fL[j] - fS[j]) / h;
+    if (ghost) for (int j = 0; j < NEQ; j++) ag[j * NEQ + i] = 0.0 + (fR[j] - fS[j]) / h;
+  }
+}
+
+// Kernel_Diag_NumJac (jacobian.tcc:434-456) after the boundary terms: NEQ threads per node, one block row each
+template <int NS>
+__global__ void __launch_bounds__(W<NS>::NEQ * 16) kfr_jac_diag(DevMesh m, const int* __restrict__ iau,
+                                                                 const int* __restrict__ posLR, const int* __restrict__ posRL,
+                                                                 const double* __restrict__ bdiag, double* A) {
+  constexpr int NEQ = W<NS>::NEQ, N2 = W<NS>::N2;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = tid / NEQ;
+  if (n >= m.nnode) return;
+  const int j = tid - n * NEQ;
+  double d[NEQ];
+#pragma unroll
+  for (int k = 0; k < NEQ; k++) d[k] = 0.0;
+  const int kbeg = m.adjp[n], kend = m.adjp[n + 1];
+  for (int k = kbeg; k < kend; k++) {
+    const int2 a = m.adj[k];
+    if (a.y < m.nedge) continue;
+    const double* src = bdiag + (size_t)(a.y - m.nedge) * N2 + j * NEQ;
+#pragma unroll
+    for (int kk = 0; kk < NEQ; kk++) d[kk] += __ldg(src + kk);
+  }
+  for (int k = kbeg; k < kend; k++) {
+    const int2 a = m.adj[k];
+    if (a.y >= m.nedge) break;
+    const int pos = (a.x < 0) ? posLR[a.y] : posRL[a.y];
+    const double* src = A + (size_t)pos * N2 + j * NEQ;
+#pragma unroll
+    for (int kk = 0; kk < NEQ; kk++) d[kk] += -src[kk];
+  }
+  double* dg = A + (size_t)iau[n] * N2 + j * NEQ;
+#pragma unroll
+  for (int k = 0; k < NEQ; k++) dg[k] = d[k];
+}
+
+// per node: the source-term Jacobian (EqnSet::SourceTermJacobian, eqnset.tcc:163-187: one-sided FD on the native
+// variables, subtracted from the diagonal block, jacobian.tcc:199-208) and ContributeTemporalTerms (:214-250)
+template <int NS>
+__global__ void __launch_bounds__(64) kfr_jac_node(DevMesh m, fr::Params<NS> p, const int* __restrict__ iau,
+                                                    const double* __restrict__ q, const double* __restrict__ dt,
+                                                    const double* __restrict__ beta, double* A) {
+  constexpr int NEQ = W<NS>::NEQ, N2 = W<NS>::N2;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= m.nnode) return;
+  const double h = 1.0e-8;
+  double Q[NS + 6], s0[NS], sP[NS];
+  load_row<NS, NS + 6>(q, n, Q);
+  double* dg = A + (size_t)iau[n] * N2;
+  const double vol = m.vol[n];
+  if (p.rxn_on) {
+    fr::source_term(p, Q, vol, s0);
+    for (int i = 0; i < NEQ; i++) {
+      double QP[NS + 4];
+#pragma unroll
+      for (int k = 0; k < NS + 4; k++) QP[k] = Q[k];
+      QP[i] += h;
+      fr::source_term(p, QP, vol, sP);
+      for (int j = 0; j < NS; j++) dg[j * NEQ + i] -= (sP[j] - s0[j]) / h;
+    }
+  }
+  fr::temporal_terms(p, Q, vol, 1.0, dt[n], dg, beta[n]);
+}
+
+// CRSMatrix::PrepareSGS (crsmatrix.tcc:840-876) -> LU (matrix.h:110-190)
+template <int NS>
+__global__ void __launch_bounds__(64) kfr_lu_diag(int nnode, const int* __restrict__ iau, double* __restrict__ A,
+                                                   int* __restrict__ pv) {
+  constexpr int NEQ = W<NS>::NEQ, N2 = W<NS>::N2;
+  const int nd = blockIdx.x * blockDim.x + threadIdx.x;
+  if (nd >= nnode) return;
+  double* g = A + (size_t)iau[nd] * N2;
+  double a[N2];
+  int pp[NEQ];
+  for (int k = 0; k < N2; k++) a[k] = g[k];
+  fr::lu<NEQ>(a, pp);
+  for (int k = 0; k < N2; k++) g[k] = a[k];
+  for (int i = 0; i < NEQ; i++) pv[(size_t)nd * NEQ + i] = pp[i];
+}
+
+// ========================================================================== SGS
+// One level of CRS::SGS (crs.tcc:90-145): NEQ lanes per row (3 rows per warp for 9x9 blocks), lane i owns block-row i,
+// accumulates rhs[i] -= (M_k x_k)[i] block after block in ja order, the lanes exchange rhs by shuffle and each runs
+// the permuted LuSolve redundantly out of the (L1-broadcast) diagonal block; lane i stores x[i].
+template <int NS, int U>
+__global__ void __launch_bounds__(128) kfr_sgs_level(const int* __restrict__ rows, int nrows, const int* __restrict__ ia,
+                                                      const int* __restrict__ ja, const int* __restrict__ iau,
+                                                      const double* __restrict__ A, const int* __restrict__ pv,
+                                                      const double* __restrict__ b, double* x) {
+  constexpr int NEQ = W<NS>::NEQ, N2 = W<NS>::N2, RPW = 32 / NEQ;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int grp = lane / NEQ;
+  const int i = lane - grp * NEQ;
+  const int slot = warp * RPW + grp;
+  const bool active = (grp < RPW) && (slot < nrows);
+  const unsigned mask = __ballot_sync(0xffffffffu, active);
+  if (!active) return;
+  const int row = rows[slot];
+  const int k0 = __ldg(ia + row), k1 = __ldg(ia + row + 1);
+  double rhs = __ldg(b + (size_t)row * NEQ + i);
+  int k = k0 + 1;
+  for (; k + U <= k1; k += U) {
+    int col[U];
+    double a[U][NEQ], xv[U][NEQ];
+#pragma unroll
+    for (int u = 0; u < U; u++) col[u] = __ldg(ja + k + u);
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+      for (int j = 0; j < NEQ; j++) a[u][j] = __ldcs(A + (size_t)(k + u) * N2 + i * NEQ + j);
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+      for (int j = 0; j < NEQ; j++) xv[u][j] = x[(size_t)col[u] * NEQ + j];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      double v = a[u][0] * xv[u][0];
+#pragma unroll
+      for (int j = 1; j < NEQ; j++) v += a[u][j] * xv[u][j];
+      rhs -= v;
+    }
+  }
+  for (; k < k1; k++) {
+    const double* a = A + (size_t)k * N2 + i * NEQ;
+    const double* xv = x + (size_t)__ldg(ja + k) * NEQ;
+    double v = __ldcs(a) * xv[0];
+#pragma unroll
+    for (int j = 1; j < NEQ; j++) v += __ldcs(a + j) * xv[j];
+    rhs -= v;
+  }
+  double bb[NEQ], xx[NEQ];
+  int pp[NEQ];
+#pragma unroll
+  for (int j = 0; j < NEQ; j++) bb[j] = __shfl_sync(mask, rhs, grp * NEQ + j);
+#pragma unroll
+  for (int j = 0; j < NEQ; j++) pp[j] = __ldg(pv + (size_t)row * NEQ + j);
+  const double* d = A + (size_t)__ldg(iau + row) * N2;
+#pragma unroll
+  for (int r = 0; r < NEQ; r++) {
+    double sum = 0.0;
+#pragma unroll
+    for (int j = 0; j < r; j++) sum += d[pp[r] * NEQ + j] * xx[j];
+    double bp = bb[0];
+#pragma unroll
+    for (int j = 1; j < NEQ; j++) bp = (pp[r] == j) ? bb[j] : bp;
+    xx[r] = bp - sum;
+  }
+#pragma unroll
+  for (int r = NEQ - 1; r >= 0; r--) {
+    double sum = 0.0;
+#pragma unroll
+    for (int j = NEQ - 1; j > r; j--) sum += d[pp[r] * NEQ + j] * bb[j];
+    bb[r] = (xx[r] - sum) / d[pp[r] * NEQ + r];
+  }
+  double out = bb[0];
+#pragma unroll
+  for (int j = 1; j < NEQ; j++) out = (i == j) ? bb[j] : out;
+  x[(size_t)row * NEQ + i] = out;
+}
+
+// ------------------------------------------------------------------ host side
+template <int NS>
+fr::Params<NS> make_params(const pcfd_ctx* c) {
+  const pcfd_fr_state* s = c->fr;
+  fr::Params<NS> p{};
+  p.chem = s->chem_dev;
+  for (int i = 0; i < NS; i++) {
+    p.mw[i] = s->host.chem.mw[i];
+    p.Rs[i] = chemdev::UNIV_R / s->host.chem.mw[i];
+    for (int r = 0; r < 2; r++)
+      for (int k = 0; k < 7; k++) p.nasa[i][r][k] = s->host.chem.nasa7[i][r][k];
+  }
+  p.ref_density = s->host.ref_density; p.ref_velocity = s->host.ref_velocity; p.ref_temperature = s->host.ref_temperature;
+  p.ref_pressure = s->host.ref_pressure; p.ref_time = s->host.ref_time; p.ref_specific_enthalpy = s->host.ref_specific_enthalpy;
+  p.Pref = s->host.pref; p.dt = s->host.dt;
+  p.chi = c->prm.chi; p.cfl = c->prm.cfl;
+  p.use_local_dt = s->host.use_local_dt; p.rxn_on = s->host.rxn_on; p.no_cvbc = c->prm.no_cvbc;
+  p.sorder = c->prm.sorder; p.limiter = c->prm.limiter;
+  for (int i = 0; i < 3 * NS + 6; i++) p.qinf[i] = s->host.qinf[i];
+  return p;
+}
+
+int fr_sumsq(pcfd_ctx* c, const double* v, int nrows, int slot, double* host_out) {
+  pcfd_fr_state* s = c->fr;
+  PROF("kfr_sumsq_partial");
+  kfr_sumsq_partial<<<FR_RED_BLOCKS, 256, 0, c->stream>>>(v, nrows, c->neqn, s->red);
+  LAUNCH_CHECK();
+  PROF("kfr_sumsq_final");
+  kfr_sumsq_final<<<1, 256, 0, c->stream>>>(s->red, FR_RED_BLOCKS, c->neqn, s->redout + slot * 32);
+  LAUNCH_CHECK();
+  if (host_out) {
+    CK(cudaMemcpyAsync(host_out, s->redout + slot * 32, (1 + c->neqn) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+
+template <int NS>
+struct Impl {
+  using Wd = W<NS>;
+
+  static int update_bcs(pcfd_ctx* c) {
+    if (!c->nblist_bc) return 0;
+    PROF("kfr_update_bcs_edges");
+    kfr_update_bcs_edges<NS><<<nblk(c->nblist_bc, 64), 64, 0, c->stream>>>(c->dm, make_params<NS>(c), c->blist, c->nblist_bc,
+                                                                          c->bfirst, c->f[PCFD_F_BETA], c->f[PCFD_F_Q]);
+    LAUNCH_CHECK();
+    return 0;
+  }
+  static int gradient(pcfd_ctx* c) {
+    PROF("kfr_gradient");
+    kfr_gradient<NS><<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->f[PCFD_F_Q], c->f[PCFD_F_LSQ_SW], c->f[PCFD_F_QGRAD]);
+    LAUNCH_CHECK();
+    return 0;
+  }
+  static int limiter(pcfd_ctx* c) {
+    constexpr int BS = Wd::NEQ * 16;
+    const int type = c->prm.limiter;
+    double* lim = c->f[PCFD_F_LIMITER];
+    const fr::Params<NS> p = make_params<NS>(c);
+    PROF("kfr_limiter");
+    kfr_limiter<NS><<<nblk((long long)c->nn * Wd::NEQ, BS), BS, 0, c->stream>>>(c->dm, type, c->prm.chi, c->f[PCFD_F_Q],
+                                                                               c->f[PCFD_F_QGRAD], lim);
+    LAUNCH_CHECK();
+    if (type == 0) return 0;
+    int cur = 0;
+    bool clipped = false;
+    PROF("kfr_fill_int");
+    kfr_fill_int<<<nblk(c->nnode, 256), 256, 0, c->stream>>>(c->tclip[0], c->nnode, INT_MAX);
+    LAUNCH_CHECK();
+    for (int it = 0; it < c->nedge + 2; it++) {
+      int hflags[2] = {0, 0};
+      CK(cudaMemsetAsync(c->dflags, 0, 2 * sizeof(int), c->stream));
+      if (c->nedge) {
+        PROF("kfr_clip_edges");
+        kfr_clip_edges<NS><<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, p, c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD], lim,
+                                                                      c->tclip[cur], c->clipflag, c->dflags);
+        LAUNCH_CHECK();
+      }
+      if (it == 0) {
+        CK(cudaMemcpyAsync(hflags, c->dflags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (!hflags[0]) break;
+        clipped = true;
+      }
+      PROF("kfr_clip_nodes");
+      kfr_clip_nodes<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->clipflag, c->tclip[cur], c->tclip[cur ^ 1],
+                                                                 c->dflags + 1);
+      LAUNCH_CHECK();
+      cur ^= 1;
+      CK(cudaMemcpyAsync(hflags, c->dflags, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      if (!hflags[1]) break;
+    }
+    PROF("kfr_limiter_final");
+    kfr_limiter_final<<<nblk((long long)c->nn * Wd::NEQ, 256), 256, 0, c->stream>>>(c->nn, c->nnode, Wd::NEQ,
+                                                                                   clipped ? c->tclip[cur] : nullptr, lim);
+    LAUNCH_CHECK();
+    return 0;
+  }
+  static int residual(pcfd_ctx* c, double* sumsq) {
+    constexpr int BS = Wd::NEQ * 16;
+    const fr::Params<NS> p = make_params<NS>(c);
+    const double* beta = c->f[PCFD_F_BETA];
+    if (c->nedge) {
+      PROF("kfr_flux_edges");
+      kfr_flux_edges<NS><<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, p, c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD],
+                                                                    c->f[PCFD_F_LIMITER], beta, c->flux);
+      LAUNCH_CHECK();
+    }
+    if (c->nb) {
+      PROF("kfr_flux_bedges");
+      kfr_flux_bedges<NS><<<nblk(c->nb, 128), 128, 0, c->stream>>>(c->dm, p, c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD],
+                                                                  c->f[PCFD_F_LIMITER], beta, c->bflux);
+      LAUNCH_CHECK();
+    }
+    PROF("kfr_source");
+    kfr_source<NS><<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->nnode, p, c->f[PCFD_F_Q], c->vol, c->fr->src);
+    LAUNCH_CHECK();
+    PROF("kfr_residual_gather");
+    kfr_residual_gather<NS><<<nblk((long long)c->nnode * Wd::NEQ, BS), BS, 0, c->stream>>>(c->dm, c->flux, c->bflux, c->fr->src,
+                                                                                          c->f[PCFD_F_B]);
+    LAUNCH_CHECK();
+    if (sumsq) return fr_sumsq(c, c->f[PCFD_F_B], c->nnode, 0, sumsq);
+    return 0;
+  }
+  static int timestep(pcfd_ctx* c, double* dtmin) {
+    pcfd_fr_state* s = c->fr;
+    PROF("kfr_eig_edges");
+    kfr_eig_edges<NS><<<nblk((long long)c->nedge + c->nb, 128), 128, 0, c->stream>>>(c->dm, make_params<NS>(c), c->f[PCFD_F_Q],
+                                                                                    c->f[PCFD_F_BETA], s->eig, s->beig);
+    LAUNCH_CHECK();
+    PROF("kfr_timestep");
+    kfr_timestep<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->prm.cfl, s->eig, s->beig, c->vnn23,
+                                                             c->f[PCFD_F_TIMESTEP]);
+    LAUNCH_CHECK();
+    if (dtmin) {
+      PROF("kfr_min_partial");
+      kfr_min_partial<<<FR_RED_BLOCKS, 256, 0, c->stream>>>(c->f[PCFD_F_TIMESTEP], c->nnode, s->red);
+      LAUNCH_CHECK();
+      PROF("kfr_min_final");
+      kfr_min_final<<<1, 256, 0, c->stream>>>(s->red, FR_RED_BLOCKS, s->redout + 96);
+      LAUNCH_CHECK();
+      CK(cudaMemcpyAsync(dtmin, s->redout + 96, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+  }
+  static int explicit_solve(pcfd_ctx* c) {
+    pcfd_fr_state* s = c->fr;
+    CK(cudaMemsetAsync(s->dbad, 0, sizeof(int), c->stream));
+    PROF("kfr_explicit");
+    kfr_explicit<NS><<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->nnode, make_params<NS>(c), c->f[PCFD_F_B],
+                                                                c->f[PCFD_F_TIMESTEP], c->vol, c->f[PCFD_F_Q], c->f[PCFD_F_X],
+                                                                s->dbad);
+    LAUNCH_CHECK();
+    // ExplicitSolve leaves q alone for this eqnset; NewtonIterate then applies the update (solutionSpace.tcc:802-804)
+    return apply_dq(c);
+  }
+  static int apply_dq(pcfd_ctx* c) {
+    PROF("kfr_apply_dq");
+    kfr_apply_dq<NS><<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->nnode, make_params<NS>(c), c->f[PCFD_F_X], c->f[PCFD_F_Q]);
+    LAUNCH_CHECK();
+    return 0;
+  }
+  static int jacobian(pcfd_ctx* c) {
+    constexpr int EPB = 8, LPE = 2 * Wd::NEQ + 1, BS = Wd::NEQ * 16;
+    const fr::Params<NS> p = make_params<NS>(c);
+    double* A = c->f[PCFD_F_A];
+    const double* beta = c->f[PCFD_F_BETA];
+    CK(cudaMemsetAsync(A, 0, c->fsize[PCFD_F_A] * sizeof(double), c->stream));
+    c->ludiag = false;
+    if (c->nedge) {
+      PROF("kfr_jac_edges");
+      kfr_jac_edges<NS, EPB><<<nblk(c->nedge, EPB), LPE * EPB, 0, c->stream>>>(c->dm, p, c->f[PCFD_F_Q], beta, c->posLR,
+                                                                              c->posRL, A);
+      LAUNCH_CHECK();
+    }
+    if (c->nblist) {
+      PROF("kfr_jac_bedges");
+      kfr_jac_bedges<NS><<<nblk(c->nblist, 64), 64, 0, c->stream>>>(c->dm, p, c->blist, c->nblist, c->bfirst, beta,
+                                                                   c->f[PCFD_F_Q], c->bpos, c->bdiag, A);
+      LAUNCH_CHECK();
+    }
+    PROF("kfr_jac_diag");
+    kfr_jac_diag<NS><<<nblk((long long)c->nnode * Wd::NEQ, BS), BS, 0, c->stream>>>(c->dm, c->iau, c->posLR, c->posRL, c->bdiag, A);
+    LAUNCH_CHECK();
+    PROF("kfr_jac_node");
+    kfr_jac_node<NS><<<nblk(c->nnode, 64), 64, 0, c->stream>>>(c->dm, p, c->iau, c->f[PCFD_F_Q], c->f[PCFD_F_TIMESTEP], beta, A);
+    LAUNCH_CHECK();
+    return 0;
+  }
+  static int prepare_sgs(pcfd_ctx* c) {
+    if (c->ludiag) return 0;
+    PROF("kfr_lu_diag");
+    kfr_lu_diag<NS><<<nblk(c->nnode, 64), 64, 0, c->stream>>>(c->nnode, c->iau, c->f[PCFD_F_A], c->pv);
+    LAUNCH_CHECK();
+    c->ludiag = true;
+    return 0;
+  }
+  static int sgs(pcfd_ctx* c, int nsgs, double* ddq) {
+    constexpr int RPW = 32 / Wd::NEQ;
+    const double* A = c->f[PCFD_F_A];
+    double* x = c->f[PCFD_F_X];
+    for (int s = 0; s < nsgs; s++) {
+      for (int dir = 0; dir < 2; dir++) {
+        const std::vector<int>& off = dir ? c->lev_b : c->lev_f;
+        const int* rows = dir ? c->rows_b : c->rows_f;
+        for (size_t l = 0; l + 1 < off.size(); l++) {
+          const int nr = off[l + 1] - off[l];
+          const int warps = (nr + RPW - 1) / RPW;
+          PROF("kfr_sgs_level");
+          kfr_sgs_level<NS, 2><<<nblk((long long)warps * 32, 128), 128, 0, c->stream>>>(rows + off[l], nr, c->ia, c->ja, c->iau, A,
+                                                                                       c->pv, c->f[PCFD_F_B], x);
+          LAUNCH_CHECK();
+        }
+      }
+      // the reference halo-updates x here (crs.tcc:147-150); its |xOld - xNorm| monitor needs the last two norms
+      if (ddq && s >= nsgs - 2) {
+        if (fr_sumsq(c, x, c->nnode, (s == nsgs - 1) ? 0 : 1, nullptr)) return 1;
+      }
+    }
+    if (ddq) {
+      double h[64];
+      CK(cudaMemcpyAsync(h, c->fr->redout, 64 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      const double N = (double)c->nnode * Wd::NEQ;
+      const double xNorm = (nsgs >= 1) ? sqrt(h[0]) / N : 0.0;
+      const double xOld = (nsgs >= 2) ? sqrt(h[32]) / N : 0.0;
+      *ddq = fabs(xOld - xNorm);
+    }
+    return 0;
+  }
+};
+
+// the species counts the library is built for
+#define FR_DISPATCH(c, call)                                                                         \
+  switch ((c)->fr->host.chem.nspecies) {                                                             \
+    case 5: return Impl<5>::call;                                                                    \
+    default: return fail(c, "reacting eqnset: this build carries kernels for 5 species only");       \
+  }
+
+}  // namespace
+
+void pcfd_fr_destroy(pcfd_ctx* c) {
+  if (!c || !c->fr) return;
+  if (c->fr->chem_dev) cudaFree(c->fr->chem_dev);
+  delete c->fr;
+  c->fr = nullptr;
+}
+int pcfd_fr_update_bcs(pcfd_ctx* c) { FR_DISPATCH(c, update_bcs(c)); }
+int pcfd_fr_gradient(pcfd_ctx* c) { FR_DISPATCH(c, gradient(c)); }
+int pcfd_fr_limiter(pcfd_ctx* c) { FR_DISPATCH(c, limiter(c)); }
+int pcfd_fr_residual(pcfd_ctx* c, double* sumsq) { FR_DISPATCH(c, residual(c, sumsq)); }
+int pcfd_fr_timestep(pcfd_ctx* c, double* dtmin) { FR_DISPATCH(c, timestep(c, dtmin)); }
+int pcfd_fr_explicit_solve(pcfd_ctx* c) { FR_DISPATCH(c, explicit_solve(c)); }
+int pcfd_fr_apply_dq(pcfd_ctx* c) { FR_DISPATCH(c, apply_dq(c)); }
+int pcfd_fr_jacobian(pcfd_ctx* c) { FR_DISPATCH(c, jacobian(c)); }
+int pcfd_fr_prepare_sgs(pcfd_ctx* c) { FR_DISPATCH(c, prepare_sgs(c)); }
+int pcfd_fr_sgs(pcfd_ctx* c, int nsgs, double* ddq) { FR_DISPATCH(c, sgs(c, nsgs, ddq)); }
+
+extern "C" {
+
+int pcfd_create_fr(const pcfd_mesh_desc* mesh, const pcfd_params* params, const pcfd_fr_params* frp, int device,
+                   pcfd_ctx** out) {
+  pcfd_ctx* c = nullptr;
+  if (!mesh || !params || !frp || !out) return fail(c, "pcfd_create_fr: null argument");
+  *out = nullptr;
+  if (params->eqnset != PCFD_EQNSET_COMPRESSIBLE_EULER_FR) return fail(c, "pcfd_create_fr: eqnset must be compressibleEulerFR");
+  const int ns = frp->chem.nspecies;
+  if (ns != 5) return fail(c, "pcfd_create_fr: this build carries kernels for 5 species only");
+  if (frp->chem.nreactions < 0 || frp->chem.nreactions > PCFD_CHEM_MAX_REACTIONS) return fail(c, "pcfd_create_fr: bad reaction count");
+  for (int j = 0; j < frp->chem.nreactions; j++) {
+    if (frp->chem.nsp[j] < 1 || frp->chem.nsp[j] > ns) return fail(c, "pcfd_create_fr: bad species count in a reaction");
+    for (int k = 0; k < frp->chem.nsp[j]; k++)
+      if (frp->chem.species[j][k] < 0 || frp->chem.species[j][k] >= ns) return fail(c, "pcfd_create_fr: reaction references an unknown species");
+  }
+  if (!(frp->ref_density > 0.0 && frp->ref_velocity > 0.0 && frp->ref_temperature > 0.0 && frp->ref_pressure > 0.0 &&
+        frp->ref_time > 0.0 && frp->ref_specific_enthalpy > 0.0))
+    return fail(c, "pcfd_create_fr: reference values must be positive");
+  const int nb = mesh->nbedge + mesh->ngedge;
+  for (int e = 0; e < nb; e++) {
+    const int t = mesh->bedges_bctype[e];
+    if (t == PCFD_BC_DIRICHLET || t == PCFD_BC_SONIC_INFLOW || t == PCFD_BC_NOSLIP || t == PCFD_BC_FARFIELD_VISCOUS)
+      return fail(c, "pcfd_create_fr: Dirichlet / sonic-inflow / no-slip / viscous far-field BCs are not available for the reacting eqnset");
+  }
+  pcfd_params prm = *params;
+  prm.turb_model = 0;
+  if (pcfd_internal_create(mesh, &prm, device, ns + 4, 3 * ns + 6, 2 * ns + 4, &c)) return 1;
+  c->prm.eqnset = PCFD_EQNSET_COMPRESSIBLE_EULER_FR;
+  pcfd_fr_state* s = new pcfd_fr_state();
+  c->fr = s;
+  s->host = *frp;
+  struct Guard { pcfd_ctx* c; bool ok = false; ~Guard() { if (!ok) { pcfd_create_err() = c->err; pcfd_destroy(c); } } } guard{c};
+  CK(cudaMalloc(reinterpret_cast<void**>(&s->chem_dev), sizeof(pcfd_chem_model)));
+  CK(cudaMemcpy(s->chem_dev, &frp->chem, sizeof(pcfd_chem_model), cudaMemcpyHostToDevice));
+  if (dev_alloc(c, &s->eig, (size_t)c->nedge)) return 1;
+  if (dev_alloc(c, &s->beig, (size_t)c->nb)) return 1;
+  if (dev_alloc(c, &s->src, (size_t)c->nnode * ns)) return 1;
+  if (dev_alloc(c, &s->red, (size_t)FR_RED_BLOCKS * 32)) return 1;
+  if (dev_alloc(c, &s->redout, 128)) return 1;
+  if (dev_alloc(c, &s->dbad, 4)) return 1;
+  // the implicit path always needs the matrix; allocate it lazily like the perfect-gas path does (pcfd_jacobian)
+  {   // beta defaults to 1 (no preconditioning) until the host sets the field
+    std::vector<double> ones(c->fsize[PCFD_F_BETA], 1.0);
+    CK(cudaMemcpy(c->f[PCFD_F_BETA], ones.data(), ones.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  CK(cudaDeviceSynchronize());
+  guard.ok = true;
+  *out = c;
+  return 0;
+}
+
+int pcfd_widths(const pcfd_ctx* c, int* neqn, int* nvars, int* nterms) {
+  if (!c) return 1;
+  if (neqn) *neqn = c->neqn;
+  if (nvars) *nvars = c->nvars;
+  if (nterms) *nterms = c->nterms;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,227 @@
+// pcfd_internal.cuh -- definitions shared by the translation units of libpcfd_b200.so (pcfd_kernels.cu: perfect-gas
+// eqnsets + the C ABI; pcfd_fr.cu: the reacting eqnset).  Not part of the public interface (include/pcfd.h is).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pcfd.h"
+#include "eqnset_compressible.cuh"
+
+std::string& pcfd_create_err();   // message of a failed pcfd_create* (pcfd_last_error(NULL))
+
+namespace {
+
+struct DevMesh {
+  int nnode, gnode, nbnode, nedge, nbedge, ngedge;
+  const int2* en;        // [nedge]   (left, right)
+  const double* ea;      // [nedge*4]
+  const int2* ben;       // [nbedge+ngedge]
+  const double* bea;     // [(nbedge+ngedge)*4]
+  const int* bctype;     // [nbedge+ngedge]
+  const double* xyz;     // [(nnode+gnode)*3]
+  const double* vol;     // [nnode]
+  const int* adjp;       // [nnode+1]
+  const int2* adj;       // (.x = other node | role<<31 (1 = this node is the RIGHT node), .y = edge id; >= nedge: half-edge)
+  const int* bnormal;    // [nbedge] most-normal neighbour of the wall node (NoSlip half-edges, else -1)
+  const double* btwall;  // [nbedge] non-dimensional wall temperature of the half-edge's surface (< 0: adiabatic)
+};
+
+__device__ __forceinline__ bool is_ghost(const DevMesh& m, int n) { return n >= m.nnode && n < m.nnode + m.gnode; }
+
+__device__ __forceinline__ void load_avec(const double* __restrict__ a, int e, double* v) {
+  const double2* p = reinterpret_cast<const double2*>(a + (size_t)e * 4);
+  const double2 x = __ldg(p), y = __ldg(p + 1);
+  v[0] = x.x; v[1] = x.y; v[2] = y.x; v[3] = y.y;
+}
+
+// gradient.tcc:141-168 ComputeLSQCoefficients
+__device__ __forceinline__ void lsq_weights(const double* s, const double* dxbar, double* we) {
+  const double r11 = s[0], r12 = s[1], r13 = s[2], s22 = s[3], s23 = s[4], s33 = s[5];
+  const double r12_r11 = (r11 == 0.0) ? 0.0 : r12 / r11;
+  const double r22 = s22 - r12 * r12_r11;
+  const double r23 = s23 - r12_r11 * r13;
+  const double r13_r11 = (r11 == 0.0) ? 0.0 : r13 / r11;
+  const double r23_r22 = (r22 == 0.0) ? 0.0 : r23 / r22;
+  const double r33 = s33 - r13 * r13_r11 - r23 * r23_r22;
+  const double dykdx = (dxbar[1] - (r12_r11)*dxbar[0]);
+  we[2] = (r33 == 0.0) ? 0.0 : (dxbar[2] - r13_r11 * dxbar[0] - r23_r22 * dykdx) / r33;
+  we[1] = (r22 == 0.0) ? 0.0 : (dykdx - r23 * we[2]) / r22;
+  we[0] = (r11 == 0.0) ? 0.0 : (dxbar[0] - r12 * we[1] - r13 * we[2]) / r11;
+}
+
+__device__ __forceinline__ double limiter_fn(int type, double t) {
+  if (type == 1) {   // Barth, limiters.tcc:263-266
+    t = eq::maxd(0.0, t);
+    t = eq::mind(1.0, t);
+    return t;
+  }
+  return (t * t + 2.0 * t) / (t * t + t + 2.0);   // Venkatakrishnan, :440
+}
+
+}  // namespace
+
+// ===================================================================== context
+struct pcfd_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr, own_stream = nullptr;
+  int nnode = 0, gnode = 0, nbnode = 0, nedge = 0, nbedge = 0, ngedge = 0;
+  int nb = 0, nn = 0, ntot = 0, nblocks = 0;
+  pcfd_params prm{};
+  // system widths: 5 / 10 / 9 for the perfect-gas eqnsets, ns+4 / 3ns+6 / 2ns+4 for the reacting one
+  int neqn = PCFD_NEQN, nvars = PCFD_NVARS, nterms = PCFD_NTERMS;
+  struct pcfd_fr_state* fr = nullptr;   // reacting eqnset (pcfd_fr.cu); null for the perfect-gas eqnsets
+  DevMesh dm{};
+  eq::BcParams bp{};
+  double* f[PCFD_F_COUNT] = {};
+  size_t fsize[PCFD_F_COUNT] = {};
+  int2 *en = nullptr, *ben = nullptr, *adj = nullptr;
+  double *ea = nullptr, *bea = nullptr, *xyz = nullptr, *vol = nullptr;
+  int *bctype = nullptr, *adjp = nullptr;
+  // half-edge work lists: nodes owning a Dirichlet-type half-edge are walked sequentially (bnodes),
+  // every other half-edge gets its own thread (blist: BC half-edges first, then ghost half-edges)
+  int *bnodes = nullptr, *blist = nullptr;
+  unsigned char* bfirst = nullptr;
+  int nbn = 0, nblist = 0, nblist_bc = 0;
+  double* bdiag = nullptr;
+  double *flux = nullptr, *bflux = nullptr, *red = nullptr, *redout = nullptr;
+  // viscous terms (compressibleNS): per-edge viscous flux slots, wall-node bookkeeping, VNN time-step limit
+  bool viscous = false;
+  eq::ViscParams vp{};
+  double *vflux = nullptr, *bvflux = nullptr, *btwall = nullptr, *vnn23 = nullptr;
+  int *bnormal = nullptr, *wnodes = nullptr, *tbnodes = nullptr;
+  int ntbnodes = 0;
+  double *tslots = nullptr, *tbslots = nullptr;   // Spalart-Allmaras per-edge / per-half-edge slots
+  unsigned char* wallflag = nullptr;
+  int nwall = 0;
+  unsigned char* clipflag = nullptr;
+  int *tclip[2] = {nullptr, nullptr}, *dflags = nullptr;
+  int* hflag = nullptr;            // pinned host copy of the fused clip flag
+  cudaEvent_t ev_flag = nullptr;
+  bool fused_clip = true;          // PCFD_FUSED_CLIP=0 keeps the separate clip pass in the composite iterations
+  long long clip_fallbacks = 0;
+  int *ia = nullptr, *ja = nullptr, *iau = nullptr, *pv = nullptr, *posLR = nullptr, *posRL = nullptr, *bpos = nullptr;
+  int *rows_f = nullptr, *rows_b = nullptr;
+  std::vector<int> lev_f, lev_b;   // level offsets into rows_f / rows_b
+  // halo maps (PObj::BuildCommMaps, parallel.tcc:461-554): what this rank sends to / receives from each peer
+  int rank = 0, nranks = 1;
+  std::vector<int> send_counts, send_offsets, recv_counts, recv_offsets;
+  int* send_list = nullptr;
+  int send_total = 0;
+  bool ludiag = false;
+  int sgs_unroll = 4;      // blocks in flight per lane in k_sgs_level (PCFD_SGS_UNROLL overrides, for tuning)
+  // bulk-copy (TMA) streaming variant: per level, shared-memory bytes for the matrix part of a tile (0: the rows of
+  // the level are not consecutive in memory -> per-lane-load kernel); PCFD_SGS_TILE_WARPS = 0 disables it
+  int sgs_tile_warps = 4, sgs_tile_lpr = 16;   // PCFD_SGS_TILE_WARPS / PCFD_SGS_TILE_LPR (lanes per row: 5, 10, 16)
+  int sgs_pf_dist = -1;    // PCFD_SGS_PREFETCH_TILES (-1: automatic, 0: off)
+  int sgs_ring_stages = 0, sgs_ring_ctas_per_sm = 0, ring_cap_blocks = 0, num_sms = 148;
+  std::vector<int> tile_cap_f, tile_cap_b, lev_first_f, lev_first_b, lev_step_f, lev_step_b;
+  std::vector<void*> allocs;
+  std::string err;
+  long long launches = 0;
+  // optional per-kernel timing with CUDA events on the launch stream (pcfd_profile_*)
+  bool prof = false;
+  struct ProfRec { const char* name; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof_pending;
+  std::vector<cudaEvent_t> prof_pool;
+  struct ProfAcc { std::string name; double ms = 0; long long n = 0; };
+  std::vector<ProfAcc> prof_acc;
+};
+
+namespace {
+
+constexpr int RED_BLOCKS = 296;   // 2 x 148 SMs
+
+int fail(pcfd_ctx* c, const std::string& msg) {
+  if (c) c->err = msg; else pcfd_create_err() = msg;
+  return 1;
+}
+#define CK(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess) return fail(c, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+  } while (0)
+#define PROF(name)                                                                                     \
+  do {                                                                                                 \
+    if (c->prof) prof_begin(c, name);                                                                  \
+  } while (0)
+#define LAUNCH_CHECK()                                                                                 \
+  do {                                                                                                 \
+    c->launches++;                                                                                     \
+    if (c->prof) prof_end(c);                                                                          \
+    cudaError_t e_ = cudaGetLastError();                                                               \
+    if (e_ != cudaSuccess) return fail(c, std::string("kernel launch: ") + cudaGetErrorString(e_));    \
+  } while (0)
+
+cudaEvent_t prof_event(pcfd_ctx* c) {
+  if (!c->prof_pool.empty()) { cudaEvent_t e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+void prof_begin(pcfd_ctx* c, const char* name) {
+  pcfd_ctx::ProfRec r{name, prof_event(c), prof_event(c)};
+  cudaEventRecord(r.a, c->stream);
+  c->prof_pending.push_back(r);
+}
+void prof_end(pcfd_ctx* c) {
+  if (!c->prof_pending.empty()) cudaEventRecord(c->prof_pending.back().b, c->stream);
+}
+void prof_drain(pcfd_ctx* c) {
+  cudaStreamSynchronize(c->stream);
+  for (auto& r : c->prof_pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      pcfd_ctx::ProfAcc* acc = nullptr;
+      for (auto& a : c->prof_acc) if (a.name == r.name) acc = &a;
+      if (!acc) { c->prof_acc.push_back({r.name, 0.0, 0}); acc = &c->prof_acc.back(); }
+      acc->ms += ms;
+      acc->n++;
+    }
+    c->prof_pool.push_back(r.a);
+    c->prof_pool.push_back(r.b);
+  }
+  c->prof_pending.clear();
+}
+
+template <class T>
+int dev_alloc(pcfd_ctx* c, T** p, size_t n) {
+  void* v = nullptr;
+  CK(cudaMalloc(&v, std::max<size_t>(n, 1) * sizeof(T)));
+  c->allocs.push_back(v);
+  *p = static_cast<T*>(v);
+  return 0;
+}
+template <class T>
+int dev_upload(pcfd_ctx* c, T** p, const T* host, size_t n) {
+  if (dev_alloc(c, p, n)) return 1;
+  if (n) CK(cudaMemcpy(*p, host, n * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+inline int nblk(long long n, int bs) { return (int)std::max<long long>(1, (n + bs - 1) / bs); }
+
+}  // namespace
+
+// ---- the reacting eqnset's side of every phase entry point (pcfd_fr.cu); the C ABI functions in pcfd_kernels.cu
+// forward to these when ctx->fr is set
+int pcfd_internal_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int device, int neqn, int nvars,
+                         int nterms, pcfd_ctx** out);
+void pcfd_fr_destroy(pcfd_ctx* c);
+int pcfd_fr_update_bcs(pcfd_ctx* c);
+int pcfd_fr_gradient(pcfd_ctx* c);
+int pcfd_fr_limiter(pcfd_ctx* c);
+int pcfd_fr_residual(pcfd_ctx* c, double* sumsq);
+int pcfd_fr_timestep(pcfd_ctx* c, double* dtmin);
+int pcfd_fr_explicit_solve(pcfd_ctx* c);
+int pcfd_fr_apply_dq(pcfd_ctx* c);
+int pcfd_fr_jacobian(pcfd_ctx* c);
+int pcfd_fr_prepare_sgs(pcfd_ctx* c);
+int pcfd_fr_sgs(pcfd_ctx* c, int nsgs, double* ddq);

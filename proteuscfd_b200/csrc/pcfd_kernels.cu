@@ -19,19 +19,7 @@
 //
 // Compile with --fmad=false (see eqnset_compressible.cuh for why).
 
-#include <cuda_runtime.h>
-
-#include <algorithm>
-#include <climits>
-#include <cmath>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <string>
-#include <vector>
-
-#include "../../include/pcfd.h"
-#include "eqnset_compressible.cuh"
+#include "pcfd_internal.cuh"
 
 #define NEQN PCFD_NEQN
 #define NVARS PCFD_NVARS
@@ -42,22 +30,6 @@ namespace {
 
 __constant__ int c_gradloc[NTERMS] = {0, 1, 2, 3, 4, 5, 7, 8, 9};   // compressible.tcc:1009-1027
 
-struct DevMesh {
-  int nnode, gnode, nbnode, nedge, nbedge, ngedge;
-  const int2* en;        // [nedge]   (left, right)
-  const double* ea;      // [nedge*4]
-  const int2* ben;       // [nbedge+ngedge]
-  const double* bea;     // [(nbedge+ngedge)*4]
-  const int* bctype;     // [nbedge+ngedge]
-  const double* xyz;     // [(nnode+gnode)*3]
-  const double* vol;     // [nnode]
-  const int* adjp;       // [nnode+1]
-  const int2* adj;       // (.x = other node | role<<31 (1 = this node is the RIGHT node), .y = edge id; >= nedge: half-edge)
-  const int* bnormal;    // [nbedge] most-normal neighbour of the wall node (NoSlip half-edges, else -1)
-  const double* btwall;  // [nbedge] non-dimensional wall temperature of the half-edge's surface (< 0: adiabatic)
-};
-
-__device__ __forceinline__ bool is_ghost(const DevMesh& m, int n) { return n >= m.nnode && n < m.nnode + m.gnode; }
 
 __device__ __forceinline__ void load5(const double* __restrict__ p, double* v) {
 #pragma unroll
@@ -79,11 +51,6 @@ __device__ __forceinline__ void store_q10(double* q, int n, const double* v) {
   double2* p = reinterpret_cast<double2*>(q + (size_t)n * NVARS);
 #pragma unroll
   for (int i = 0; i < 5; i++) p[i] = make_double2(v[2 * i], v[2 * i + 1]);
-}
-__device__ __forceinline__ void load_avec(const double* __restrict__ a, int e, double* v) {
-  const double2* p = reinterpret_cast<const double2*>(a + (size_t)e * 4);
-  const double2 x = __ldg(p), y = __ldg(p + 1);
-  v[0] = x.x; v[1] = x.y; v[2] = y.x; v[3] = y.y;
 }
 
 // ============================================================== LSQ coefficients
@@ -120,20 +87,6 @@ __global__ void k_lsq_coeff(DevMesh m, double* __restrict__ s, double* __restric
   for (int k = 0; k < 6; k++) { s[6 * (size_t)n + k] = S[k]; sw[6 * (size_t)n + k] = W[k]; }
 }
 
-// gradient.tcc:141-168 ComputeLSQCoefficients
-__device__ __forceinline__ void lsq_weights(const double* s, const double* dxbar, double* we) {
-  const double r11 = s[0], r12 = s[1], r13 = s[2], s22 = s[3], s23 = s[4], s33 = s[5];
-  const double r12_r11 = (r11 == 0.0) ? 0.0 : r12 / r11;
-  const double r22 = s22 - r12 * r12_r11;
-  const double r23 = s23 - r12_r11 * r13;
-  const double r13_r11 = (r11 == 0.0) ? 0.0 : r13 / r11;
-  const double r23_r22 = (r22 == 0.0) ? 0.0 : r23 / r22;
-  const double r33 = s33 - r13 * r13_r11 - r23 * r23_r22;
-  const double dykdx = (dxbar[1] - (r12_r11)*dxbar[0]);
-  we[2] = (r33 == 0.0) ? 0.0 : (dxbar[2] - r13_r11 * dxbar[0] - r23_r22 * dykdx) / r33;
-  we[1] = (r22 == 0.0) ? 0.0 : (dykdx - r23 * we[2]) / r22;
-  we[0] = (r11 == 0.0) ? 0.0 : (dxbar[0] - r12 * we[1] - r13 * we[2]) / r11;
-}
 
 // ====================================================================== gradient
 // Gradient::Compute (gradient.tcc:57-112), weighted LSQ kernels :251-378 and the
@@ -201,14 +154,6 @@ __global__ void __launch_bounds__(128) k_gradient(DevMesh m, const double* __res
 }
 
 // ======================================================================= limiter
-__device__ __forceinline__ double limiter_fn(int type, double t) {
-  if (type == 1) {   // Barth, limiters.tcc:263-266
-    t = eq::maxd(0.0, t);
-    t = eq::mind(1.0, t);
-    return t;
-  }
-  return (t * t + 2.0 * t) / (t * t + t + 2.0);   // Venkatakrishnan, :440
-}
 
 // Limiter::Compute passes 1+2 (limiters.tcc:53-110): neighbour min/max (from ZERO,
 // :62-63) and Barth / Venkatakrishnan limiting, both as gathers over the node's edges.
@@ -1819,142 +1764,12 @@ __global__ void k_fill_int(int* p, int n, int v) {
 
 }  // namespace
 
-// ===================================================================== context
-struct pcfd_ctx {
-  int device = 0;
-  cudaStream_t stream = nullptr, own_stream = nullptr;
-  int nnode = 0, gnode = 0, nbnode = 0, nedge = 0, nbedge = 0, ngedge = 0;
-  int nb = 0, nn = 0, ntot = 0, nblocks = 0;
-  pcfd_params prm{};
-  DevMesh dm{};
-  eq::BcParams bp{};
-  double* f[PCFD_F_COUNT] = {};
-  size_t fsize[PCFD_F_COUNT] = {};
-  int2 *en = nullptr, *ben = nullptr, *adj = nullptr;
-  double *ea = nullptr, *bea = nullptr, *xyz = nullptr, *vol = nullptr;
-  int *bctype = nullptr, *adjp = nullptr;
-  // half-edge work lists: nodes owning a Dirichlet-type half-edge are walked sequentially (bnodes),
-  // every other half-edge gets its own thread (blist: BC half-edges first, then ghost half-edges)
-  int *bnodes = nullptr, *blist = nullptr;
-  unsigned char* bfirst = nullptr;
-  int nbn = 0, nblist = 0, nblist_bc = 0;
-  double* bdiag = nullptr;
-  double *flux = nullptr, *bflux = nullptr, *red = nullptr, *redout = nullptr;
-  // viscous terms (compressibleNS): per-edge viscous flux slots, wall-node bookkeeping, VNN time-step limit
-  bool viscous = false;
-  eq::ViscParams vp{};
-  double *vflux = nullptr, *bvflux = nullptr, *btwall = nullptr, *vnn23 = nullptr;
-  int *bnormal = nullptr, *wnodes = nullptr, *tbnodes = nullptr;
-  int ntbnodes = 0;
-  double *tslots = nullptr, *tbslots = nullptr;   // Spalart-Allmaras per-edge / per-half-edge slots
-  unsigned char* wallflag = nullptr;
-  int nwall = 0;
-  unsigned char* clipflag = nullptr;
-  int *tclip[2] = {nullptr, nullptr}, *dflags = nullptr;
-  int* hflag = nullptr;            // pinned host copy of the fused clip flag
-  cudaEvent_t ev_flag = nullptr;
-  bool fused_clip = true;          // PCFD_FUSED_CLIP=0 keeps the separate clip pass in the composite iterations
-  long long clip_fallbacks = 0;
-  int *ia = nullptr, *ja = nullptr, *iau = nullptr, *pv = nullptr, *posLR = nullptr, *posRL = nullptr, *bpos = nullptr;
-  int *rows_f = nullptr, *rows_b = nullptr;
-  std::vector<int> lev_f, lev_b;   // level offsets into rows_f / rows_b
-  // halo maps (PObj::BuildCommMaps, parallel.tcc:461-554): what this rank sends to / receives from each peer
-  int rank = 0, nranks = 1;
-  std::vector<int> send_counts, send_offsets, recv_counts, recv_offsets;
-  int* send_list = nullptr;
-  int send_total = 0;
-  bool ludiag = false;
-  int sgs_unroll = 4;      // blocks in flight per lane in k_sgs_level (PCFD_SGS_UNROLL overrides, for tuning)
-  // bulk-copy (TMA) streaming variant: per level, shared-memory bytes for the matrix part of a tile (0: the rows of
-  // the level are not consecutive in memory -> per-lane-load kernel); PCFD_SGS_TILE_WARPS = 0 disables it
-  int sgs_tile_warps = 4, sgs_tile_lpr = 16;   // PCFD_SGS_TILE_WARPS / PCFD_SGS_TILE_LPR (lanes per row: 5, 10, 16)
-  int sgs_pf_dist = -1;    // PCFD_SGS_PREFETCH_TILES (-1: automatic, 0: off)
-  int sgs_ring_stages = 0, sgs_ring_ctas_per_sm = 0, ring_cap_blocks = 0, num_sms = 148;
-  std::vector<int> tile_cap_f, tile_cap_b, lev_first_f, lev_first_b, lev_step_f, lev_step_b;
-  std::vector<void*> allocs;
-  std::string err;
-  long long launches = 0;
-  // optional per-kernel timing with CUDA events on the launch stream (pcfd_profile_*)
-  bool prof = false;
-  struct ProfRec { const char* name; cudaEvent_t a, b; };
-  std::vector<ProfRec> prof_pending;
-  std::vector<cudaEvent_t> prof_pool;
-  struct ProfAcc { std::string name; double ms = 0; long long n = 0; };
-  std::vector<ProfAcc> prof_acc;
-};
-
-namespace {
-
-std::string g_create_err;
-constexpr int RED_BLOCKS = 296;   // 2 x 148 SMs
-
-int fail(pcfd_ctx* c, const std::string& msg) {
-  if (c) c->err = msg; else g_create_err = msg;
-  return 1;
-}
-#define CK(call)                                                                                       \
-  do {                                                                                                 \
-    cudaError_t e_ = (call);                                                                           \
-    if (e_ != cudaSuccess) return fail(c, std::string(#call) + ": " + cudaGetErrorString(e_));         \
-  } while (0)
-#define PROF(name)                                                                                     \
-  do {                                                                                                 \
-    if (c->prof) prof_begin(c, name);                                                                  \
-  } while (0)
-#define LAUNCH_CHECK()                                                                                 \
-  do {                                                                                                 \
-    c->launches++;                                                                                     \
-    if (c->prof) prof_end(c);                                                                          \
-    cudaError_t e_ = cudaGetLastError();                                                               \
-    if (e_ != cudaSuccess) return fail(c, std::string("kernel launch: ") + cudaGetErrorString(e_));    \
-  } while (0)
-
-cudaEvent_t prof_event(pcfd_ctx* c) {
-  if (!c->prof_pool.empty()) { cudaEvent_t e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
-  cudaEvent_t e;
-  cudaEventCreate(&e);
+std::string& pcfd_create_err() {
+  static std::string e;
   return e;
 }
-void prof_begin(pcfd_ctx* c, const char* name) {
-  pcfd_ctx::ProfRec r{name, prof_event(c), prof_event(c)};
-  cudaEventRecord(r.a, c->stream);
-  c->prof_pending.push_back(r);
-}
-void prof_end(pcfd_ctx* c) {
-  if (!c->prof_pending.empty()) cudaEventRecord(c->prof_pending.back().b, c->stream);
-}
-void prof_drain(pcfd_ctx* c) {
-  cudaStreamSynchronize(c->stream);
-  for (auto& r : c->prof_pending) {
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
-      pcfd_ctx::ProfAcc* acc = nullptr;
-      for (auto& a : c->prof_acc) if (a.name == r.name) acc = &a;
-      if (!acc) { c->prof_acc.push_back({r.name, 0.0, 0}); acc = &c->prof_acc.back(); }
-      acc->ms += ms;
-      acc->n++;
-    }
-    c->prof_pool.push_back(r.a);
-    c->prof_pool.push_back(r.b);
-  }
-  c->prof_pending.clear();
-}
 
-template <class T>
-int dev_alloc(pcfd_ctx* c, T** p, size_t n) {
-  void* v = nullptr;
-  CK(cudaMalloc(&v, std::max<size_t>(n, 1) * sizeof(T)));
-  c->allocs.push_back(v);
-  *p = static_cast<T*>(v);
-  return 0;
-}
-template <class T>
-int dev_upload(pcfd_ctx* c, T** p, const T* host, size_t n) {
-  if (dev_alloc(c, p, n)) return 1;
-  if (n) CK(cudaMemcpy(*p, host, n * sizeof(T), cudaMemcpyHostToDevice));
-  return 0;
-}
-inline int nblk(long long n, int bs) { return (int)std::max<long long>(1, (n + bs - 1) / bs); }
+namespace {
 
 // level schedule of the sequential sweep: level[i] = 1 + max(level[j]) over the
 // columns j of row i that the sweep has already updated (j < i forward, j > i backward)
@@ -2013,11 +1828,12 @@ extern "C" {
 
 int pcfd_abi_version(void) { return PCFD_ABI_VERSION; }
 
-const char* pcfd_last_error(const pcfd_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+const char* pcfd_last_error(const pcfd_ctx* ctx) { return ctx ? ctx->err.c_str() : pcfd_create_err().c_str(); }
 
 int pcfd_destroy(pcfd_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
+  if (c->fr) pcfd_fr_destroy(c);
   for (void* p : c->allocs) cudaFree(p);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->hflag) cudaFreeHost(c->hflag);
@@ -2026,12 +1842,12 @@ int pcfd_destroy(pcfd_ctx* c) {
   return 0;
 }
 
-int pcfd_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int device, pcfd_ctx** out) {
+// shared by pcfd_create (perfect gas: 5 / 10 / 9) and pcfd_create_fr (reacting: ns+4 / 3ns+6 / 2ns+4, pcfd_fr.cu)
+static int create_impl(const pcfd_mesh_desc* mesh, const pcfd_params* params, int device, int neqn, int nvars, int nterms,
+                       pcfd_ctx** out) {
   pcfd_ctx* c = nullptr;
   if (!mesh || !params || !out) return fail(c, "pcfd_create: null argument");
   *out = nullptr;
-  if (params->eqnset != PCFD_EQNSET_COMPRESSIBLE_EULER && params->eqnset != PCFD_EQNSET_COMPRESSIBLE_NS)
-    return fail(c, "pcfd_create: unsupported eqnset id");
   // param.tcc:401-404: the NS eqnset ids switch the viscous terms on
   const bool viscous = params->eqnset == PCFD_EQNSET_COMPRESSIBLE_NS;
   if (viscous && !(params->Re > 0.0 && params->Pr > 0.0 && params->PrT > 0.0 && params->tref > 0.0 && params->mach > 0.0))
@@ -2045,7 +1861,8 @@ int pcfd_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int devic
   if (prop.major != 10) return fail(c, std::string("pcfd_create: built for sm_100a only, device is ") + prop.name);
 
   c = new pcfd_ctx();
-  struct Guard { pcfd_ctx* c; bool ok = false; ~Guard() { if (!ok) { g_create_err = c->err; pcfd_destroy(c); } } } guard{c};
+  c->neqn = neqn; c->nvars = nvars; c->nterms = nterms;
+  struct Guard { pcfd_ctx* c; bool ok = false; ~Guard() { if (!ok) { pcfd_create_err() = c->err; pcfd_destroy(c); } } } guard{c};
   c->device = device;
   if (const char* e = getenv("PCFD_SGS_UNROLL")) c->sgs_unroll = atoi(e);
   if (const char* e = getenv("PCFD_SGS_TILE_WARPS")) c->sgs_tile_warps = atoi(e);
@@ -2057,6 +1874,7 @@ int pcfd_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int devic
   c->num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("PCFD_SGS_TILE_LPR")) c->sgs_tile_lpr = atoi(e);
   if (c->sgs_tile_lpr != 5 && c->sgs_tile_lpr != 10 && c->sgs_tile_lpr != 16) c->sgs_tile_lpr = 16;
+  if (neqn != NEQN) { c->sgs_tile_warps = 0; c->sgs_ring_stages = 0; }   // the bulk-copy tile kernels are 5x5 only
   CK(cudaSetDevice(device));
   CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
@@ -2282,13 +2100,13 @@ int pcfd_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int devic
   if (dev_upload(c, &c->bpos, bpos.data(), bpos.size())) return 1;
   if (dev_upload(c, &c->rows_f, rows_f.data(), rows_f.size())) return 1;
   if (dev_upload(c, &c->rows_b, rows_b.data(), rows_b.size())) return 1;
-  if (dev_alloc(c, &c->pv, (size_t)nnode * NEQN + 8)) return 1;
+  if (dev_alloc(c, &c->pv, (size_t)nnode * neqn + 8)) return 1;
 
-  c->fsize[PCFD_F_Q] = (size_t)c->ntot * NVARS;
-  c->fsize[PCFD_F_QGRAD] = (size_t)c->nn * NTERMS * 3;
-  c->fsize[PCFD_F_LIMITER] = (size_t)c->nn * NEQN;
-  c->fsize[PCFD_F_B] = (size_t)nnode * NEQN;
-  c->fsize[PCFD_F_X] = (size_t)c->nn * NEQN;
+  c->fsize[PCFD_F_Q] = (size_t)c->ntot * nvars;
+  c->fsize[PCFD_F_QGRAD] = (size_t)c->nn * nterms * 3;
+  c->fsize[PCFD_F_LIMITER] = (size_t)c->nn * neqn;
+  c->fsize[PCFD_F_B] = (size_t)nnode * neqn;
+  c->fsize[PCFD_F_X] = (size_t)c->nn * neqn;
   c->fsize[PCFD_F_TIMESTEP] = (size_t)nnode;
   c->fsize[PCFD_F_BETA] = (size_t)c->ntot;
   c->fsize[PCFD_F_LSQ_S] = (size_t)c->nn * 6;
@@ -2307,8 +2125,8 @@ int pcfd_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int devic
     if (dev_alloc(c, &c->f[k], c->fsize[k] + 4)) return 1;   // slack: 16-byte rounded bulk prefetches
     CK(cudaMemset(c->f[k], 0, std::max<size_t>(c->fsize[k], 1) * sizeof(double)));
   }
-  if (dev_alloc(c, &c->flux, (size_t)nedge * 5)) return 1;
-  if (dev_alloc(c, &c->bflux, (size_t)nb * 5)) return 1;
+  if (dev_alloc(c, &c->flux, (size_t)nedge * neqn)) return 1;
+  if (dev_alloc(c, &c->bflux, (size_t)nb * neqn)) return 1;
   if (sa_on) {
     if (dev_alloc(c, &c->tslots, (size_t)nedge * 3)) return 1;
     if (dev_alloc(c, &c->tbslots, (size_t)nb * 4)) return 1;
@@ -2336,6 +2154,14 @@ int pcfd_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int devic
   guard.ok = true;
   *out = c;
   return 0;
+}
+
+int pcfd_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int device, pcfd_ctx** out) {
+  if (params && params->eqnset != PCFD_EQNSET_COMPRESSIBLE_EULER && params->eqnset != PCFD_EQNSET_COMPRESSIBLE_NS) {
+    if (out) *out = nullptr;
+    return fail(nullptr, "pcfd_create: unsupported eqnset id (the reacting eqnset is created with pcfd_create_fr)");
+  }
+  return create_impl(mesh, params, device, NEQN, NVARS, NTERMS, out);
 }
 
 int pcfd_set_stream(pcfd_ctx* c, void* s) {
@@ -2386,16 +2212,16 @@ int pcfd_profile_get(pcfd_ctx* c, int i, const char** name, double* total_ms, lo
 
 static int ensure_matrix(pcfd_ctx* c) {
   if (c->f[PCFD_F_A]) return 0;
-  c->fsize[PCFD_F_A] = (size_t)c->nblocks * NEQN2;
+  c->fsize[PCFD_F_A] = (size_t)c->nblocks * c->neqn * c->neqn;
   if (dev_alloc(c, &c->f[PCFD_F_A], c->fsize[PCFD_F_A] + 2)) return 1;
-  if (dev_alloc(c, &c->bdiag, (size_t)c->nb * NEQN2)) return 1;
+  if (dev_alloc(c, &c->bdiag, (size_t)c->nb * c->neqn * c->neqn)) return 1;
   CK(cudaMemsetAsync(c->f[PCFD_F_A], 0, c->fsize[PCFD_F_A] * sizeof(double), c->stream));
   return 0;
 }
 
 size_t pcfd_field_size(const pcfd_ctx* c, int field) {
   if (!c || field < 0 || field >= PCFD_F_COUNT) return 0;
-  if (field == PCFD_F_A) return (size_t)c->nblocks * NEQN2;
+  if (field == PCFD_F_A) return (size_t)c->nblocks * c->neqn * c->neqn;
   return c->fsize[field];
 }
 int pcfd_set_field(pcfd_ctx* c, int field, const double* host, size_t n) {
@@ -2436,7 +2262,7 @@ int pcfd_get_crs(pcfd_ctx* c, int* ia, int* ja, int* iau, int* pv) {
   if (ia) CK(cudaMemcpy(ia, c->ia, (size_t)(c->nnode + 1) * sizeof(int), cudaMemcpyDeviceToHost));
   if (ja) CK(cudaMemcpy(ja, c->ja, (size_t)c->nblocks * sizeof(int), cudaMemcpyDeviceToHost));
   if (iau) CK(cudaMemcpy(iau, c->iau, (size_t)c->nnode * sizeof(int), cudaMemcpyDeviceToHost));
-  if (pv) CK(cudaMemcpy(pv, c->pv, (size_t)c->nnode * NEQN * sizeof(int), cudaMemcpyDeviceToHost));
+  if (pv) CK(cudaMemcpy(pv, c->pv, (size_t)c->nnode * c->neqn * sizeof(int), cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -2452,6 +2278,7 @@ int pcfd_lsq_coefficients(pcfd_ctx* c) {
 int pcfd_update_bcs(pcfd_ctx* c) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
+  if (c->fr) return pcfd_fr_update_bcs(c);
   if (c->nbn) {
     PROF("k_update_bcs");
     k_update_bcs<<<nblk(c->nbn, 128), 128, 0, c->stream>>>(c->dm, c->bp, c->bnodes, c->nbn, c->f[PCFD_F_Q]);
@@ -2469,6 +2296,7 @@ int pcfd_update_bcs(pcfd_ctx* c) {
 int pcfd_gradient(pcfd_ctx* c) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
+  if (c->fr) return pcfd_fr_gradient(c);
   PROF("k_gradient");
   k_gradient<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->f[PCFD_F_Q], c->f[PCFD_F_LSQ_SW], c->f[PCFD_F_QGRAD]);
   LAUNCH_CHECK();
@@ -2482,6 +2310,7 @@ static int run_sumsq(pcfd_ctx* c, const double* v, int nrows, double* host_out);
 int pcfd_limiter(pcfd_ctx* c) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
+  if (c->fr) return pcfd_fr_limiter(c);
   const int type = c->prm.limiter;
   double* lim = c->f[PCFD_F_LIMITER];
   PROF("k_limiter");
@@ -2524,6 +2353,10 @@ int pcfd_limiter(pcfd_ctx* c) {
 // rides along in the edge-flux kernel (k_flux_edges<true>); only when some edge actually clips (rare: the limiter
 // exists to prevent exactly that) are the ordered clip passes and the flux redone.
 static int gradient_limiter_residual(pcfd_ctx* c, double* sumsq) {
+  if (c->fr) {
+    if (c->prm.sorder > 1 && (pcfd_gradient(c) || pcfd_limiter(c))) return 1;
+    return pcfd_residual(c, sumsq);
+  }
   if (c->prm.sorder > 1) {
     if (pcfd_gradient(c)) return 1;
     const int type = c->prm.limiter;
@@ -2632,6 +2465,7 @@ static int run_sumsq(pcfd_ctx* c, const double* v, int nrows, double* host_out) 
 int pcfd_residual(pcfd_ctx* c, double* sumsq) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
+  if (c->fr) return pcfd_fr_residual(c, sumsq);
   if (run_flux(c)) return 1;
   if (sumsq) return run_sumsq(c, c->f[PCFD_F_B], c->nnode, sumsq);
   return 0;
@@ -2640,6 +2474,7 @@ int pcfd_residual(pcfd_ctx* c, double* sumsq) {
 int pcfd_timestep(pcfd_ctx* c, double* dtmin) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
+  if (c->fr) return pcfd_fr_timestep(c, dtmin);
   PROF("k_timestep");
   k_timestep<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->prm.gamma, c->prm.cfl, c->f[PCFD_F_Q], c->vnn23,
                                                          c->f[PCFD_F_TIMESTEP]);
@@ -2660,6 +2495,7 @@ int pcfd_timestep(pcfd_ctx* c, double* dtmin) {
 int pcfd_explicit_solve(pcfd_ctx* c) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
+  if (c->fr) return pcfd_fr_explicit_solve(c);
   PROF("k_explicit");
   k_explicit<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->nnode, c->prm.gamma, c->f[PCFD_F_B], c->f[PCFD_F_TIMESTEP],
                                                          c->vol, c->f[PCFD_F_X], c->f[PCFD_F_Q]);
@@ -2670,6 +2506,7 @@ int pcfd_explicit_solve(pcfd_ctx* c) {
 int pcfd_apply_dq(pcfd_ctx* c) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
+  if (c->fr) return pcfd_fr_apply_dq(c);
   PROF("k_apply_dq");
   k_apply_dq<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->nnode, c->prm.gamma, c->f[PCFD_F_X], c->f[PCFD_F_Q]);
   LAUNCH_CHECK();
@@ -2680,6 +2517,7 @@ int pcfd_jacobian(pcfd_ctx* c) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
   if (ensure_matrix(c)) return 1;
+  if (c->fr) return pcfd_fr_jacobian(c);
   double* A = c->f[PCFD_F_A];
   CK(cudaMemsetAsync(A, 0, c->fsize[PCFD_F_A] * sizeof(double), c->stream));   // CRSMatrix::Blank
   c->ludiag = false;
@@ -2721,6 +2559,7 @@ int pcfd_prepare_sgs(pcfd_ctx* c) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
   if (ensure_matrix(c)) return 1;
+  if (c->fr) return pcfd_fr_prepare_sgs(c);
   if (c->ludiag) return 0;   // CRSMatrix::ludiag (crsmatrix.tcc:844)
   PROF("k_lu_diag");
   k_lu_diag<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->nnode, c->iau, c->f[PCFD_F_A], c->pv);
@@ -2740,6 +2579,7 @@ int pcfd_sgs(pcfd_ctx* c, int nsgs, double* ddq) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
   if (ensure_matrix(c)) return 1;
+  if (c->fr) return pcfd_fr_sgs(c, nsgs, ddq);
   constexpr int RPW = 32 / NEQN;
   const double* A = c->f[PCFD_F_A];
   double* x = c->f[PCFD_F_X];
@@ -2845,11 +2685,11 @@ int pcfd_sgs(pcfd_ctx* c, int nsgs, double* ddq) {
   return 0;
 }
 
-static int field_width(int field) {
+static int field_width(const pcfd_ctx* c, int field) {
   switch (field) {
-    case PCFD_F_Q: return NVARS;
-    case PCFD_F_QGRAD: return NTERMS * 3;
-    case PCFD_F_LIMITER: case PCFD_F_X: return NEQN;
+    case PCFD_F_Q: return c->nvars;
+    case PCFD_F_QGRAD: return c->nterms * 3;
+    case PCFD_F_LIMITER: case PCFD_F_X: return c->neqn;
     case PCFD_F_LSQ_S: case PCFD_F_LSQ_SW: return 6;
     case PCFD_F_BETA: case PCFD_F_MUT: case PCFD_F_TVAR: case PCFD_F_TURB_X: case PCFD_F_WALLDIST: return 1;
     case PCFD_F_TGRAD: return 3;
@@ -2881,14 +2721,14 @@ int pcfd_halo_configure(pcfd_ctx* c, int rank, int nranks, const int* send_count
   return 0;
 }
 
-int pcfd_halo_width(const pcfd_ctx* c, int field) { return c ? field_width(field) : 0; }
+int pcfd_halo_width(const pcfd_ctx* c, int field) { return c ? field_width(c, field) : 0; }
 int pcfd_halo_send_total(const pcfd_ctx* c) { return c ? c->send_total : 0; }
 
 /* pack the rows this rank owes peer `peer` (peer < 0: all peers, in rank order) into dst (device memory,
    count*width doubles) */
 int pcfd_halo_pack(pcfd_ctx* c, int field, int peer, void* dst) {
   if (!c) return 1;
-  const int n = field_width(field);
+  const int n = field_width(c, field);
   if (n == 0 || !dst || peer >= c->nranks) return fail(c, "pcfd_halo_pack: bad argument");
   if (c->send_offsets.empty()) return fail(c, "pcfd_halo_pack: pcfd_halo_configure has not been called");
   CK(cudaSetDevice(c->device));
@@ -2906,7 +2746,7 @@ int pcfd_halo_pack(pcfd_ctx* c, int field, int peer, void* dst) {
    field is contiguous per owner (decomp.cpp:245-273), so receives go straight into it, no unpack */
 void* pcfd_halo_recv_ptr(pcfd_ctx* c, int field, int peer) {
   if (!c) return nullptr;
-  const int n = field_width(field);
+  const int n = field_width(c, field);
   if (n == 0 || peer >= c->nranks || c->recv_offsets.empty()) return nullptr;
   const int off = peer < 0 ? 0 : c->recv_offsets[peer];
   return c->f[field] + ((size_t)c->nnode + off) * n;
@@ -2941,6 +2781,7 @@ int pcfd_ipc_close(pcfd_ctx* c, void* devptr) {
 
 int pcfd_turb_compute(pcfd_ctx* c, int nsgs, double* sumsq) {
   if (!c) return 1;
+  if (c->fr) return fail(c, "pcfd_turb_compute: not available for the reacting eqnset");
   if (c->prm.turb_model != 1) return fail(c, "pcfd_turb_compute: the context was created without a turbulence model");
   CK(cudaSetDevice(c->device));
   double *tvar = c->f[PCFD_F_TVAR], *tgrad = c->f[PCFD_F_TGRAD], *tb = c->f[PCFD_F_TURB_B], *tx = c->f[PCFD_F_TURB_X],
@@ -3041,3 +2882,8 @@ int pcfd_implicit_iterate(pcfd_ctx* c, int refresh_jac, int nsgs, double* sumsq,
 }
 
 }  // extern "C"
+
+int pcfd_internal_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int device, int neqn, int nvars,
+                         int nterms, pcfd_ctx** out) {
+  return create_impl(mesh, params, device, neqn, nvars, nterms, out);
+}

@@ -1,0 +1,184 @@
+"""The reacting eqnset (compressibleEulerFR: HLLC flux, NASA-7 thermodynamics, characteristic BCs, finite-rate source
+term, 9x9 block Jacobian + SGS) on the GPU, through the C ABI, against the fixtures written by the reference itself
+(tests/golden/box5_fr_explicit.npz, box4_fr_implicit.npz) and against the C oracle on a larger seeded box.
+
+Bars, and why:
+ * BIT-EXACT: BC states, gradient, limiter, time step, the momentum and energy rows of the residual, the flux part of
+   the Jacobian, LU and SGS given the same matrix -- only +, -, *, /, sqrt, in the reference's order (--fmad=false).
+ * 1e-12 of the rate scale: the species rows of the residual.  They carry the chemistry source term, which calls
+   exp / log / pow: CUDA libm there, glibc in the reference (1-2 ulp apart), and the net production rate cancels.
+ * FD-amplified: the reference forms the source-term Jacobian by one-sided finite differences with h = 1e-8
+   (eqnset.tcc:163-187), so a 1-ulp difference of the source becomes ~1e-8 of |S|/h-sized entries in the diagonal
+   blocks.  Diagonal blocks are compared to 2e-6 of the block's largest entry, the implicit update to 1e-6 relative;
+   with reactionsOn = 0 the whole implicit iteration is bit-exact (test_fr_frozen_implicit_bit_exact).
+"""
+import numpy as np
+import pytest
+
+from tests.oracle_lib import FrOracle, chem_tables, load_golden
+from tests.test_oracle import exact
+
+pytestmark = pytest.mark.gpu
+
+NS, NEQ, NV, NT = 5, 9, 21, 14
+
+
+def fr_ctx(name, rxn_on=None):
+    from proteuscfd_b200 import capi
+    g, meta = load_golden(name)
+    mesh = {k: g[k] for k in ("edges_n", "edges_a", "bedges_n", "bedges_a", "bedges_bctype", "xyz", "vol", "ipsp", "psp")}
+    for k in ("nnode", "gnode", "nbnode", "nedge", "nbedge", "ngedge"):
+        mesh[k] = int(meta[k])
+    fr = dict(chem=chem_tables(g), ref_density=meta["ref_density"], ref_velocity=meta["ref_velocity"],
+              ref_temperature=meta["ref_temperature"], ref_pressure=meta["ref_pressure"], ref_time=meta["ref_time"],
+              ref_specific_enthalpy=meta["ref_specific_enthalpy"], pref=meta["Pref"], dt=meta["dt"],
+              use_local_dt=int(meta["useLocalTimeStepping"]), rxn_on=int(meta["rxnOn"]) if rxn_on is None else rxn_on,
+              qinf=g["qinf"])
+    params = dict(sorder=int(meta["sorder"]), limiter=int(meta["limiter"]), no_cvbc=int(meta["no_cvbc"]), gamma=0.0,
+                  chi=meta["chi"], cfl=meta["cfl"], fr=fr)
+    ctx = capi.Context(mesh, params)
+    assert (ctx.neqn, ctx.nvars, ctx.nterms) == (NEQ, NV, NT)
+    beta = np.ones(ctx.field_size(capi.F_BETA))
+    beta[: g["beta"].size] = g["beta"]
+    ctx.set_field(capi.F_BETA, beta)
+    return ctx, g, meta
+
+
+def species_rows_close(b, bref, src_scale, what):
+    """momentum / energy rows exact; species rows within 1e-12 of the production-rate scale of the node."""
+    b, bref = b.reshape(-1, NEQ), bref.reshape(-1, NEQ)
+    exact(b[:, NS:], bref[:, NS:], what + " (momentum, energy rows)")
+    err = np.abs(b[:, :NS] - bref[:, :NS])
+    assert np.all(err <= 1e-12 * src_scale + 1e-300), f"{what}: species rows off by {np.max(err / (src_scale + 1e-300)):.3e} of scale"
+
+
+def source_scale(oracle, g, meta, q, vol):
+    """vol * (rate magnitude the net production cancels from), non-dimensional, per node and species."""
+    from tests.oracle_lib import ChemOracle
+    t = chem_tables(g)
+    o = ChemOracle(oracle, t)
+    n = vol.size
+    Q = q.reshape(-1, NV)[:n]
+    _, sc, _, _ = o.mass_production(Q[:, :NS] * meta["ref_density"], Q[:, NS + 3] * meta["ref_temperature"])
+    return vol[:, None] * sc / (meta["ref_density"] / meta["ref_time"])
+
+
+@pytest.mark.parametrize("name", ["box5_fr_explicit", "box4_fr_implicit"])
+def test_fr_update_bcs(name):
+    from proteuscfd_b200 import capi
+    ctx, g, _ = fr_ctx(name)
+    ctx.set_field(capi.F_Q, g["q_pre"])
+    ctx.update_bcs()
+    exact(ctx.get_field(capi.F_Q), g["q0"], "q after UpdateBCs")
+
+
+@pytest.mark.parametrize("name", ["box5_fr_explicit", "box4_fr_implicit"])
+def test_fr_gradient_limiter_residual_timestep(oracle, name):
+    from proteuscfd_b200 import capi
+    ctx, g, meta = fr_ctx(name)
+    ctx.lsq_coefficients()
+    exact(ctx.get_field(capi.F_LSQ_SW), g["lsq_sw"], "sw")
+    ctx.set_field(capi.F_Q, g["q0"])
+    ctx.gradient()
+    exact(ctx.get_field(capi.F_QGRAD), g["qgrad"], "qgrad")
+    ctx.limiter()
+    exact(ctx.get_field(capi.F_LIMITER), g["limiter"], "limiter")
+    s = ctx.residual(want_norms=True)
+    b = ctx.get_field(capi.F_B)
+    species_rows_close(b, g["b"], source_scale(oracle, g, meta, g["q0"], g["vol"]), "b")
+    assert np.isclose(np.sqrt(s[0]) / b.size, g["resnorm"][0], rtol=1e-12)
+    dtmin = ctx.timestep()
+    exact(ctx.get_field(capi.F_TIMESTEP), g["timestep"], "timestep")
+    assert dtmin == g["dtmin"][0]
+
+
+def test_fr_explicit_update():
+    """ExplicitSolve's native -> conservative -> Newton-on-T -> native update (solve.tcc:112-130) and ApplyDQ, fed the
+    reference's own residual so that the comparison is exact."""
+    from proteuscfd_b200 import capi
+    ctx, g, _ = fr_ctx("box5_fr_explicit")
+    ctx.set_field(capi.F_Q, g["q0"])
+    ctx.set_field(capi.F_B, g["b"])
+    ctx.set_field(capi.F_TIMESTEP, g["timestep"])
+    ctx.explicit_solve()
+    exact(ctx.get_field(capi.F_X)[: g["x"].size], g["x"], "x")
+    exact(ctx.get_field(capi.F_Q), g["q1"], "q1")
+
+
+def test_fr_jacobian_lu_sgs():
+    from proteuscfd_b200 import capi
+    ctx, g, meta = fr_ctx("box4_fr_implicit")
+    ctx.set_field(capi.F_Q, g["q0"])
+    ctx.set_field(capi.F_TIMESTEP, g["timestep"])
+    ctx.jacobian()
+    ia, ja, iau, _ = ctx.get_crs()
+    exact(ia, g["ia"], "ia")
+    exact(ja, g["ja"], "ja")
+    A = ctx.get_field(capi.F_A).reshape(-1, NEQ * NEQ)
+    Aref = g["A"].reshape(-1, NEQ * NEQ)
+    offd = np.ones(len(A), bool)
+    offd[iau] = False
+    exact(A[offd], Aref[offd], "off-diagonal blocks (flux Jacobian)")
+    # diagonal blocks carry the FD source-term Jacobian: libm rounding / h (see the module docstring)
+    scale = np.abs(Aref[iau]).max(axis=1, keepdims=True)
+    assert np.all(np.abs(A[iau] - Aref[iau]) <= 2e-6 * scale)
+    # Bkernel_NumJac re-runs the (iterated) BC map on the phantom states: the reference's q1 holds them
+    nloc = int(meta["nnode"]) + int(meta["gnode"])
+    qa = ctx.get_field(capi.F_Q).reshape(-1, NV)
+    exact(qa[:nloc], g["q0"].reshape(-1, NV)[:nloc], "interior rows after the boundary Jacobian pass")
+    exact(qa[nloc:], g["q1"].reshape(-1, NV)[nloc:], "phantom rows after the boundary Jacobian pass")
+    # LU + SGS on the reference's own matrix and right-hand side: exact
+    ctx.set_field(capi.F_A, g["A"])
+    ctx.set_field(capi.F_B, g["b"])
+    ctx.prepare_sgs()
+    exact(ctx.get_field(capi.F_A), g["A_lu"], "A after LU")
+    exact(ctx.get_crs()[3], g["pv"], "pv")
+    ctx.blank_x()
+    ddq = ctx.sgs(int(meta["nSgs"]))
+    exact(ctx.get_field(capi.F_X), g["x"], "x")
+    assert np.isclose(ddq, g["sgs_ddq"][0], rtol=1e-10)
+    ctx.apply_dq()
+    exact(ctx.get_field(capi.F_Q), g["q1"], "q1")
+
+
+def test_fr_implicit_iteration_close():
+    """the whole implicit iteration from q_pre, own residual and own Jacobian: 1e-6 relative on the update."""
+    from proteuscfd_b200 import capi
+    ctx, g, meta = fr_ctx("box4_fr_implicit")
+    ctx.lsq_coefficients()
+    ctx.set_field(capi.F_Q, g["q_pre"])
+    ctx.implicit_iterate(int(meta["nSgs"]), refresh_jac=True)
+    x = ctx.get_field(capi.F_X).reshape(-1, NEQ)
+    xref = g["x"].reshape(-1, NEQ)
+    assert np.all(np.abs(x - xref) <= 1e-6 * np.abs(xref).max(axis=0))
+
+
+def test_fr_frozen_implicit_bit_exact(oracle):
+    """reactionsOn = 0 removes the only libm calls: the implicit iteration (HLLC residual, 19-flux FD Jacobian, boundary
+    Jacobian, dense temporal terms, LU, SGS, ApplyDQ) is then bit-identical to the oracle, here on a 10^3 box in the
+    reference's state."""
+    from proteuscfd_b200 import capi
+    g, meta = load_golden("box4_fr_implicit")
+    meta = dict(meta, rxnOn=0.0)
+    o = FrOracle(oracle, g, meta)
+    ctx, _, _ = fr_ctx("box4_fr_implicit", rxn_on=0)
+    q = g["q_pre"].copy()
+    beta = g["beta"]
+    sw = g["lsq_sw"]
+    ia, ja, iau = o.crs_init()
+    dt, _ = o.timestep(q, beta)
+    A = o.jacobian(q, beta, dt, ia, ja, iau)
+    o.update_bcs(q, beta)
+    grad = o.gradient(q, sw)
+    lim = o.limiter(q, grad)
+    b = o.residual(q, grad, lim, beta)
+    pv = o.prepare_sgs(iau, A)
+    x, _ = o.sgs(3, ia, ja, iau, A, pv, b)
+    o.apply_dq(q, x)
+    ctx.lsq_coefficients()
+    ctx.set_field(capi.F_Q, g["q_pre"])
+    ctx.implicit_iterate(3, refresh_jac=True)
+    exact(ctx.get_field(capi.F_B), b, "b")
+    exact(ctx.get_field(capi.F_A), A, "A (LU form)")
+    exact(ctx.get_field(capi.F_X), x, "x")
+    exact(ctx.get_field(capi.F_Q), q, "q")
