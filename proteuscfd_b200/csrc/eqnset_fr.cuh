@@ -353,9 +353,14 @@ __device__ __forceinline__ void perp_vectors(const double* n, double* v1, double
   v2[0] = v2[0] / mag; v2[1] = v2[1] / mag; v2[2] = v2[2] / mag;
 }
 
+// NOTE on __noinline__ (eigensystem, farfield_bc, inviscid_wall_bc, boundary_variables): with these inlined into the
+// boundary-Jacobian kernel, nvcc 12.9 (-O3, sm_100a) overlaid the caller's perturbed left state with a temporary of
+// the inlined wall BC (the state came back with its v-component overwritten by the BC solution; the same source built
+// for the host is clean under ASan/UBSan).  As real calls each gets its own frame; they run per boundary half-edge only.
+
 // Eigensystem (compressibleFR.tcc:150-290); the per-species c2i are overwritten by the bulk c2 there (:176-180)
 template <int NS>
-__device__ void eigensystem(const Params<NS>& p, const double* Q, const double* av, double vdotn, double* eig, double* T,
+__device__ __noinline__ void eigensystem(const Params<NS>& p, const double* Q, const double* av, double vdotn, double* eig, double* T,
                             double* Tinv, double beta) {
   constexpr int N = NS + 4;
   const double nx = av[0], ny = av[1], nz = av[2];
@@ -438,7 +443,7 @@ constexpr int N_SUBIT = 10;   // compressibleFR.tcc:32
 
 // GetFarfieldBoundaryVariables (compressibleFR.tcc:940-1039)
 template <int NS>
-__device__ void farfield_bc(const Params<NS>& p, const double* QL, double* QR, const double* av, double vdotn, double beta) {
+__device__ __noinline__ void farfield_bc(const Params<NS>& p, const double* QL, double* QR, const double* av, double vdotn, double beta) {
   constexpr int N = NS + 4, NV = 3 * NS + 6;
   double qavg[NS + 6], eig[N], Tinv[N * N], T[N * N], rhs[N], ql[N], qinf[N];
   for (int subit = 0; subit < N_SUBIT; subit++) {
@@ -468,7 +473,7 @@ __device__ void farfield_bc(const Params<NS>& p, const double* QL, double* QR, c
 
 // GetInviscidWallBoundaryVariables (compressibleFR.tcc:1042-1134)
 template <int NS>
-__device__ void inviscid_wall_bc(const Params<NS>& p, const double* QL, double* QR, const double* av, double vdotn,
+__device__ __noinline__ void inviscid_wall_bc(const Params<NS>& p, const double* QL, double* QR, const double* av, double vdotn,
                                  double beta) {
   constexpr int N = NS + 4, NV = 3 * NS + 6;
   if (!p.no_cvbc) {
@@ -514,7 +519,7 @@ __device__ void inviscid_wall_bc(const Params<NS>& p, const double* QL, double* 
 
 // CalculateBoundaryVariables (bc.tcc:1058-1397) for the BC types of the reacting configs; QL and QR are full rows
 template <int NS>
-__device__ void boundary_variables(const Params<NS>& p, double* QL, double* QR, const double* av, int bctype, double betaL) {
+__device__ __noinline__ void boundary_variables(const Params<NS>& p, double* QL, double* QR, const double* av, int bctype, double betaL) {
   constexpr int N = NS + 4;
   const double vdotn = 0.0;   // static mesh
   switch (bctype) {
