@@ -218,6 +218,8 @@ def main():
                     help="N>1 halo exchange: direct puts into peer ghost segments over NVLink (CUDA IPC) or NCCL send/recv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sgs", action="store_true")
+    ap.add_argument("--no-fr", action="store_true", help="skip the reacting-eqnset (compressibleEulerFR) sub-benchmark")
+    ap.add_argument("--fr-n", type=int, default=0, help="box side for the reacting sub-benchmark (0: same as --n)")
     ap.add_argument("--sgs-n", type=int, default=0, help="box side for the SGS sub-benchmark (0: same as --n)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -370,6 +372,14 @@ def main():
     if not args.no_sgs and rank == 0 and world == 1:
         sgs = sgs_bench(args, ctx, mesh, params, q0, peak, torch, stream, local_rank)
 
+    # ---------------------------------------------------------------- reacting eqnset (BASELINE configs[4] on one GPU)
+    frb = None
+    if not args.no_fr and rank == 0 and world == 1:
+        try:
+            frb = fr_bench(args, peak, torch, stream, local_rank)
+        except Exception as e:
+            frb = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -395,7 +405,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": nq * 8 * world,
                     "d2h_bytes_per_step": nq * 8 * world, "what": "pcfd_set_field(q) from pinned host memory + pcfd_explicit_iterate + "
                                                           "pcfd_get_field(q) per step"},
-            "gpu_launches": int(launches) * world, "clocks": clocks, "phases": phases, "sgs": sgs,
+            "gpu_launches": int(launches) * world, "clocks": clocks, "phases": phases, "sgs": sgs, "reacting": frb,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -437,6 +447,90 @@ def sgs_bench(args, ctx, mesh, params, q0, peak, torch, stream, local_rank):
            "jacobian_ms": {k: tab0[k][0] / tab0[k][1] for k in ("k_jac_edges", "k_jac_bnodes", "k_jac_diag", "k_lu_diag") if k in tab0},
            "kernel": "k_sgs_tile (cp.async.bulk + mbarrier streamed tiles)" if "k_sgs_tile" in tab else "k_sgs_level",
            "launches_per_sweep": sum(tab[k][1] - tab0.get(k, (0, 0))[1] for k in ("k_sgs_level", "k_sgs_tile") if k in tab) / nsw}
+    c.close()
+    return out
+
+
+def fr_params_from_fixture():
+    """Chemistry tables (the reference's chemModels/5speciesAir.rxn + NASA-7 data as its ChemModel parsed them),
+    reference values and free stream of the reacting fixture the reference wrote (tools/make_golden.py)."""
+    d = dict(np.load(os.path.join(ROOT, "tests", "golden", "box4_fr_implicit.npz")))
+    meta = dict(zip([str(k) for k in d["meta_keys"]], d["meta_vals"]))
+    chem = {k: d[k] for k in ("species_mw", "species_nasa7", "rxn_A_EA_n", "rxn_flags", "rxn_species", "rxn_nup", "rxn_nupp",
+                              "rxn_tbeff")}
+    chem["dims"] = d["chem_dims"]
+    return dict(chem=chem, ref_density=meta["ref_density"], ref_velocity=meta["ref_velocity"],
+                ref_temperature=meta["ref_temperature"], ref_pressure=meta["ref_pressure"], ref_time=meta["ref_time"],
+                ref_specific_enthalpy=meta["ref_specific_enthalpy"], pref=meta["Pref"], dt=meta["dt"],
+                use_local_dt=int(meta["useLocalTimeStepping"]), rxn_on=1, qinf=d["qinf"])
+
+
+def fr_bench(args, peak, torch, stream, local_rank):
+    """Reacting 5-species air (compressibleEulerFR), implicit: 9 equations per node, 9x9 block-CRS Jacobian (FD flux +
+    FD source Jacobians, dense temporal terms), SGS.  Timed: the Jacobian refresh, one implicit iteration without it
+    (UpdateBCs, gradient, limiter, HLLC residual + finite-rate source, nsgs SGS sweeps, ApplyDQ) and the SGS sweep."""
+    from proteuscfd_b200 import capi
+    from proteuscfd_b200.cases import fr_box_case
+    n = args.fr_n or args.n
+    nsgs = 5
+    torch.cuda.empty_cache()
+    mesh, params, q, beta = fr_box_case(n, fr_params_from_fixture(), device=f"cuda:{local_rank}")
+    c = capi.Context(mesh, params, device=local_rank)
+    c.set_stream(stream.cuda_stream)
+    c.set_field(capi.F_BETA, beta)
+    c.lsq_coefficients()
+    c.set_field(capi.F_Q, q)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    c.implicit_iterate(nsgs, refresh_jac=True)    # warm-up: builds A, LU
+    torch.cuda.synchronize()
+    c.profile(on=True, reset=True)
+    reps = 3
+    e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+    e0.record(stream)
+    for _ in range(reps):
+        c.timestep(want_min=False)
+        c.jacobian()
+        c.prepare_sgs()
+    e1.record(stream)
+    eA, eB = ev(), ev()
+    eA.record(stream)
+    for _ in range(reps):
+        c.implicit_iterate(nsgs, refresh_jac=False)
+    eB.record(stream)
+    finite = bool(np.isfinite(c.get_field(capi.F_Q)).all())
+    c.blank_x()
+    nsw = 10
+    c.sgs(2, want_ddq=False)
+    e2.record(stream)
+    c.sgs(nsw, want_ddq=False)
+    e3.record(stream)
+    torch.cuda.synchronize()
+    c.profile(on=False)
+    tab = c.profile_table()
+    ms_jac = e0.elapsed_time(e1) / reps
+    ms_iter = eA.elapsed_time(eB) / reps
+    ms_sweep = e2.elapsed_time(e3) / nsw
+    kern = {k: v[0] / max(v[1], 1) for k, v in tab.items()}
+    it_kernels = ("kfr_update_bcs_edges", "kfr_gradient", "kfr_limiter", "kfr_fill_int", "kfr_clip_edges", "kfr_clip_nodes",
+                  "kfr_limiter_final", "kfr_flux_edges", "kfr_flux_bedges", "kfr_source", "kfr_residual_gather", "kfr_apply_dq")
+    ms_explicit_part = sum(kern.get(k, 0.0) for k in it_kernels)
+    nblocks = c.get_crs()[1].size
+    neqn, nterms = c.neqn, c.nterms
+    ne, nn = c.nedge, c.nnode
+    bytes_sweep = 2 * (nblocks * 8 * neqn * neqn + 4 * nblocks + 4 * (nn + 1) + 4 * neqn * nn + 8 * neqn * 3 * nn)
+    bytes_resid = 40 * ne + nn * (8 * neqn + 24 * neqn + 8 * neqn + 24 + 8) + nn * 8 * neqn
+    ms_resid = sum(kern.get(k, 0.0) for k in ("kfr_flux_edges", "kfr_flux_bedges", "kfr_source", "kfr_residual_gather"))
+    out = {"workload": f"BASELINE configs[4] on one GPU: reacting 5-species air (compressibleEulerFR), Kuhn box n={n} "
+                       f"({nn} nodes, {ne} edges, {nblocks} 9x9 blocks = {nblocks * 648 / 1e9:.1f} GB), HLLC 2nd order + LSQ + "
+                       "Venkatakrishnan + finite-rate source, implicit",
+           "jacobian_refresh_ms": ms_jac, "sgs_ms_per_sweep": ms_sweep, "sgs_sweeps_per_s": 1e3 / ms_sweep,
+           "sgs_algorithmic_bytes_per_sweep": bytes_sweep, "sgs_GBps": bytes_sweep / (ms_sweep * 1e-3) / 1e9,
+           "sgs_frac_hbm": bytes_sweep / (ms_sweep * 1e-3) / 1e9 / peak,
+           "residual_ms": ms_resid, "residual_Medges_s": ne / (ms_resid * 1e-3) / 1e6,
+           "residual_frac_hbm": bytes_resid / (ms_resid * 1e-3) / 1e9 / peak,
+           "iteration_without_refresh_ms": ms_iter, "iteration_Medges_s": ne / (ms_iter * 1e-3) / 1e6, "nsgs": nsgs,
+           "state_finite_after_run": finite, "non_sgs_kernels_ms": ms_explicit_part,
+           "kernels_ms": kern}
     c.close()
     return out
 

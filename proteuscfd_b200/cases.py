@@ -205,3 +205,64 @@ def slab_case(n, rank, nranks, jitter=0.15, mach=0.5, gamma=1.4, cfl=0.5, limite
     q[: nnode + gnode] = smooth_state(mesh["xyz"].reshape(-1, 3), mach, gamma)
     q[nnode + gnode:] = q[b_n[:, 0]]
     return mesh, params, q.reshape(-1)
+
+
+# ------------------------------------------------------------------------------------------ reacting eqnset
+UNIV_R = 8.31447215   # chem_constants.h:5
+
+
+def fr_aux_vars(Q, fr):
+    """ComputeAuxiliaryVariables of the reacting eqnset (ucs/compressibleFR.tcc:755-814) on rows of
+    [rho_i | u v w | T | P | rho | cv_i | mol_i] (set-up only: the solver recomputes them with its own arithmetic)."""
+    ch = fr["chem"]
+    ns = int(ch["dims"][0])
+    mw = np.asarray(ch["species_mw"], dtype=np.float64)
+    Rs = UNIV_R / mw
+    a = np.asarray(ch["species_nasa7"], dtype=np.float64).reshape(ns, 2, 7)
+    T = Q[:, ns + 3] * fr["ref_temperature"]
+    Q[:, ns + 5] = Q[:, :ns].sum(axis=1)
+    Q[:, ns + 4] = ((Q[:, :ns] * fr["ref_density"]) * Rs * T[:, None]).sum(axis=1) / fr["ref_pressure"]
+    s_ref = fr["ref_velocity"] ** 2 / fr["ref_temperature"]
+    hi = T > 1000.0
+    for i in range(ns):
+        c = np.where(hi[:, None], a[i, 1], a[i, 0])
+        cp = (c[:, 0] + T * (c[:, 1] + T * (c[:, 2] + T * (c[:, 3] + T * c[:, 4])))) * Rs[i]
+        Q[:, ns + 6 + i] = (cp - Rs[i]) / s_ref
+        Q[:, 2 * ns + 6 + i] = Q[:, i] / mw[i] / 1000.0
+    return Q
+
+
+def fr_box_case(n, fr, mach=0.5, jitter=0.15, cfl=5.0, limiter=2, sorder=2, colored=True, device="cpu", seed=1234,
+                amp=1.0):
+    """Reacting-eqnset counterpart of box_case: (mesh, params, q, beta).  `fr` carries the chemistry tables, the
+    reference values and the free stream (dict: chem, ref_*, pref, dt, use_local_dt, rxn_on, qinf) -- the caller
+    takes them from a case set-up or a fixture; the state is the free stream perturbed as SURVEY.md 8d prescribes."""
+    xyz, tets, tris, tags = kuhn_box(n, jitter=jitter, seed=seed)
+    if colored:
+        xyz, tets, tris = renumber(xyz, tets, tris, color_order(kuhn_box_colors(n)))
+    mesh = median_dual(xyz, tets, tris, tags, device=device)
+    lut = np.zeros(max(BOX_BC) + 1, dtype=np.int32)
+    for t, b in BOX_BC.items():
+        lut[t] = b
+    mesh["bedges_bctype"] = lut[mesh["bedges_factag"]]
+    ns = int(fr["chem"]["dims"][0])
+    nv = 3 * ns + 6
+    qinf = np.asarray(fr["qinf"], dtype=np.float64)
+    params = dict(eqnset=capi.EQNSET_COMPRESSIBLE_EULER_FR, sorder=sorder, limiter=limiter, no_cvbc=0, gamma=0.0, chi=0.0,
+                  cfl=cfl, fr=fr)
+    nn, nb = mesh["nnode"], mesh["nbnode"]
+    X = mesh["xyz"].reshape(-1, 3)
+    x, y, z = X[:, 0], X[:, 1], X[:, 2]
+    tp = 2.0 * np.pi
+    q = np.zeros((nn + nb, nv))
+    for k in range(ns):
+        q[:nn, k] = qinf[k] * (1.0 + 0.1 * amp * np.sin(tp * x) * np.cos(tp * y)) * (1.0 + 0.05 * amp * np.sin(tp * (z + 0.17 * k)))
+    q[:nn, ns + 0] = mach + 0.05 * amp * np.sin(tp * y)
+    q[:nn, ns + 1] = 0.05 * amp * np.sin(tp * z)
+    q[:nn, ns + 2] = 0.05 * amp * np.sin(tp * x)
+    q[:nn, ns + 3] = qinf[ns + 3] * (1.0 + 0.1 * amp * np.cos(tp * z))
+    fr_aux_vars(q[:nn], fr)
+    q[nn:] = q[mesh["bedges_n"].reshape(-1, 2)[:, 0]]
+    # preconditioning field: beta = max(betaMin, Mach^2) below sonic, 1 otherwise (solutionSpace.tcc:235-247)
+    beta = np.full(nn + nb, mach * mach if mach < 1.0 else 1.0)
+    return mesh, params, q.reshape(-1), beta

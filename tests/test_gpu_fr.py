@@ -184,3 +184,110 @@ def test_fr_frozen_implicit_bit_exact(oracle):
     exact(ctx.get_field(capi.F_A), A, "A (LU form)")
     exact(ctx.get_field(capi.F_X), x, "x")
     exact(ctx.get_field(capi.F_Q), q, "q")
+
+
+def fixture_fr_params(name="box4_fr_implicit", rxn_on=None):
+    g, meta = load_golden(name)
+    return dict(chem=chem_tables(g), ref_density=meta["ref_density"], ref_velocity=meta["ref_velocity"],
+                ref_temperature=meta["ref_temperature"], ref_pressure=meta["ref_pressure"], ref_time=meta["ref_time"],
+                ref_specific_enthalpy=meta["ref_specific_enthalpy"], pref=meta["Pref"], dt=meta["dt"],
+                use_local_dt=int(meta["useLocalTimeStepping"]), rxn_on=int(meta["rxnOn"]) if rxn_on is None else rxn_on,
+                qinf=g["qinf"]), g, meta
+
+
+def oracle_for_fr(lib, mesh, params, g, meta):
+    """FrOracle on a generated mesh: fixture tables / reference values, the mesh and numerics of `mesh`, `params`."""
+    gg = dict(g)
+    for k in ("edges_n", "edges_a", "bedges_n", "bedges_a", "bedges_bctype", "xyz", "vol", "ipsp", "psp"):
+        gg[k] = np.asarray(mesh[k])
+    mm = dict(meta)
+    for k in ("nnode", "gnode", "nbnode", "nedge", "nbedge", "ngedge"):
+        mm[k] = mesh[k]
+    fr = params["fr"]
+    mm.update(limiter=params["limiter"], sorder=params["sorder"], no_cvbc=params["no_cvbc"], chi=params["chi"],
+              cfl=params["cfl"], rxnOn=fr["rxn_on"], gamma=1.4)
+    return FrOracle(lib, gg, mm)
+
+
+@pytest.mark.parametrize("colored", [True, False])
+def test_fr_seeded_box_vs_oracle(oracle, colored):
+    """A 10^3 box (1331 nodes, 8.6 k edges) in the SURVEY 8d state, frozen chemistry: two implicit iterations (the
+    second re-using the LU'd Jacobian) then an explicit one, every field bit-identical to the oracle.  colored = the
+    colour-sorted numbering used at scale (8 SGS levels per direction), else lexicographic (level schedule)."""
+    from proteuscfd_b200 import capi
+    from proteuscfd_b200.cases import fr_box_case
+    fr, g, meta = fixture_fr_params(rxn_on=0)
+    mesh, params, q0, beta = fr_box_case(10, fr, colored=colored)
+    o = oracle_for_fr(oracle, mesh, params, g, meta)
+    ctx = capi.Context(mesh, params)
+    ctx.set_field(capi.F_BETA, beta)
+    ctx.lsq_coefficients()
+    ctx.set_field(capi.F_Q, q0)
+    q = q0.copy()
+    bo = beta[: mesh["nnode"] + mesh["gnode"]].copy()
+    _, sw = o.lsq()
+    ia, ja, iau = o.crs_init()
+    dt, _ = o.timestep(q, bo)
+    A = o.jacobian(q, bo, dt, ia, ja, iau)
+    pv = None
+    for it in range(2):
+        o.update_bcs(q, bo)
+        grad = o.gradient(q, sw)
+        lim = o.limiter(q, grad)
+        b = o.residual(q, grad, lim, bo)
+        if pv is None:
+            pv = o.prepare_sgs(iau, A)
+        x, _ = o.sgs(2, ia, ja, iau, A, pv, b)
+        o.apply_dq(q, x)
+        ctx.implicit_iterate(2, refresh_jac=(it == 0))
+        exact(ctx.get_field(capi.F_QGRAD), grad, f"qgrad, iteration {it}")
+        exact(ctx.get_field(capi.F_LIMITER), lim, f"limiter, iteration {it}")
+        exact(ctx.get_field(capi.F_B), b, f"b, iteration {it}")
+        exact(ctx.get_field(capi.F_X), x, f"x, iteration {it}")
+        exact(ctx.get_field(capi.F_Q), q, f"q, iteration {it}")
+    dt, _ = o.timestep(q, bo)
+    o.update_bcs(q, bo)
+    grad = o.gradient(q, sw)
+    lim = o.limiter(q, grad)
+    b = o.residual(q, grad, lim, bo)
+    o.c.cfl = 0.05
+    ctx.set_cfl(0.05)
+    dt, _ = o.timestep(q, bo)
+    x = o.explicit_solve(q, b, dt)
+    o.apply_dq(q, x)
+    ctx.explicit_iterate(refresh_dt=True)
+    exact(ctx.get_field(capi.F_TIMESTEP), dt, "timestep")
+    exact(ctx.get_field(capi.F_X), x, "explicit x")
+    exact(ctx.get_field(capi.F_Q), q, "q after the explicit iteration")
+
+
+def test_fr_reacting_box_close_to_oracle(oracle):
+    """the same box with the reactions on: residual species rows to 1e-12 of the rate scale, update to 1e-5."""
+    from proteuscfd_b200 import capi
+    from proteuscfd_b200.cases import fr_box_case
+    fr, g, meta = fixture_fr_params()
+    mesh, params, q0, beta = fr_box_case(10, fr)
+    o = oracle_for_fr(oracle, mesh, params, g, meta)
+    ctx = capi.Context(mesh, params)
+    ctx.set_field(capi.F_BETA, beta)
+    ctx.lsq_coefficients()
+    ctx.set_field(capi.F_Q, q0)
+    q = q0.copy()
+    bo = beta[: mesh["nnode"] + mesh["gnode"]].copy()
+    _, sw = o.lsq()
+    ia, ja, iau = o.crs_init()
+    dt, _ = o.timestep(q, bo)
+    A = o.jacobian(q, bo, dt, ia, ja, iau)
+    o.update_bcs(q, bo)
+    grad = o.gradient(q, sw)
+    lim = o.limiter(q, grad)
+    b = o.residual(q, grad, lim, bo)
+    pv = o.prepare_sgs(iau, A)
+    x, _ = o.sgs(3, ia, ja, iau, A, pv, b)
+    ctx.implicit_iterate(3, refresh_jac=True)
+    scale = source_scale(oracle, g, meta, q, np.asarray(mesh["vol"]))
+    species_rows_close(ctx.get_field(capi.F_B), b, scale, "b")
+    xg = ctx.get_field(capi.F_X).reshape(-1, NEQ)
+    xo = x.reshape(-1, NEQ)
+    err = np.abs(xg - xo).max(axis=0) / np.abs(xo).max(axis=0)
+    assert np.all(err <= 1e-5), f"relative error of the update per equation: {err}"
