@@ -245,14 +245,13 @@ def test_fr_seeded_box_vs_oracle(oracle, colored):
         exact(ctx.get_field(capi.F_B), b, f"b, iteration {it}")
         exact(ctx.get_field(capi.F_X), x, f"x, iteration {it}")
         exact(ctx.get_field(capi.F_Q), q, f"q, iteration {it}")
-    dt, _ = o.timestep(q, bo)
+    o.c.cfl = 0.05
+    ctx.set_cfl(0.05)
+    dt, _ = o.timestep(q, bo)       # ComputeTimesteps runs before UpdateBCs (PreTimeAdvance, solutionSpace.tcc:629-634)
     o.update_bcs(q, bo)
     grad = o.gradient(q, sw)
     lim = o.limiter(q, grad)
     b = o.residual(q, grad, lim, bo)
-    o.c.cfl = 0.05
-    ctx.set_cfl(0.05)
-    dt, _ = o.timestep(q, bo)
     x = o.explicit_solve(q, b, dt)
     o.apply_dq(q, x)
     ctx.explicit_iterate(refresh_dt=True)
