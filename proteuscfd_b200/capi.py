@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpcfd_b200.so")
+LIB_PATH = os.environ.get("PCFD_B200_LIB") or os.path.join(_HERE, "libpcfd_b200.so")   # override: tuning builds
 
 NEQN, NVARS, NTERMS = 5, 10, 9
 EQNSET_COMPRESSIBLE_EULER_FR = 0
