@@ -355,9 +355,18 @@ def main():
             d["frac_hbm"] = d["GBps"] / peak
         passes[pname] = d
     dominant = max((p for p in passes if "GBps" in passes[p]), key=lambda p: passes[p]["ms_per_step"])
+    # measured DRAM traffic of the pass's kernels (one ncu --set full capture of this workload, committed under profiles/)
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_dram_traffic.json")))["explicit_lexicographic"]
+        if args.n == 118 and world == 1:
+            traffic = sum(tr[k] for k in PASS_KERNELS[dominant] if k in kern and k in tr)
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "kernel": "+".join(k for k in PASS_KERNELS[dominant] if k in kern), "pass": dominant,
                 "achieved": passes[dominant]["GBps"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": passes[dominant]["frac_hbm"], "traffic": None,
+                "frac": passes[dominant]["frac_hbm"], "traffic": traffic,
+                "traffic_source": "profiles/r1_dram_traffic.json (ncu dram__bytes_read+write.sum per launch, same workload)" if traffic else None,
                 "bytes_per_launch": passes[dominant]["algorithmic_bytes"], "ms_per_launch": passes[dominant]["ms_per_step"],
                 "note": "algorithmic bytes = SURVEY.md 8d compulsory bytes of the pass; the Roe flux is FP64-pipe-bound "
                         "(see profiles/), so frac is reported for completeness, not as the limiter"}
