@@ -86,7 +86,7 @@ typedef struct {
 typedef struct {
   int eqnset;                /* PCFD_EQNSET_* */
   int sorder;                /* spatialOrder 1|2 */
-  int limiter;               /* 0 none, 1 Barth, 2 Venkatakrishnan */
+  int limiter;               /* 0 none, 1 Barth, 2 Venkatakrishnan, 3 modified Venkatakrishnan (limiters.tcc:534-735) */
   int no_cvbc;
   double gamma, chi, cfl;
   double qinf[10];           /* free-stream state incl. aux vars (bc.tcc: Qinf) */

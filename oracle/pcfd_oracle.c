@@ -630,7 +630,33 @@ static void limit_side(const orc_case* c, const double* q, const double* qgrad, 
   dx[1] = 0.5*(c->xyz[3*other+1] - c->xyz[3*me+1]);
   dx[2] = 0.5*(c->xyz[3*other+2] - c->xyz[3*me+2]);
   extrapolate_variables(c->chi, QL, qL, dQ, &qgrad[me*NTERMS*3], dx, ones);
-  (void)boundary_variant;
+  if(c->limiter == 3){
+    /* Kernel_VenkatMod / Bkernel_VenkatMod (limiters.tcc:534-735).  variant 0: left node of an interior edge, 2: right
+       node, 1: ghost half-edge.  eps^2 = 6 pi V K^3, K = 1.  The left branch leaves DP unset when the extrapolated
+       value equals the nodal one (:612-617); DM is then 0 and the ratio is (DP^2 + eps^2)/(DP^2 + eps^2) = 1 for any
+       finite DP, so DP = 0 reproduces it. */
+    const double Pi = 3.141592653589793;
+    double L3 = 6.0*Pi*c->vol[me], K3 = 1.0*1.0*1.0;
+    for(j = 0; j < 5; j++){
+      double DM = QL[j] - qL[j], DP = 0.0, ep2, temp;
+      if(boundary_variant == 1){
+	if(QL[j] > qL[j]) DP = qmax[me*5 + j] - QL[j];
+	else if(QL[j] <= qL[j]) DP = qmin[me*5 + j] - QL[j];
+      }
+      else if(boundary_variant == 2){
+	if(QL[j] > qL[j]) DP = qmax[me*5 + j] - qL[j];
+	if(QL[j] <= qL[j]) DP = qmin[me*5 + j] - qL[j];
+      }
+      else{
+	if(QL[j] > qL[j]) DP = qmax[me*5 + j] - qL[j];
+	else if(QL[j] < qL[j]) DP = qmin[me*5 + j] - qL[j];
+      }
+      ep2 = L3*K3;
+      temp = (DP*DP + ep2 + 2.0*DM*DP)/(DP*DP + 2.0*DM*DM + DM*DP + ep2);
+      lim[me*5 + j] = MIND(lim[me*5 + j], temp);
+    }
+    return;
+  }
   for(j = 0; j < 5; j++){
     double temp = 1.0;
     if(QL[j] > qL[j]) temp = (qmax[me*5 + j] - qL[j])/(QL[j] - qL[j]);
@@ -675,11 +701,11 @@ void orc_limiter(const orc_case* c, const double* q, const double* qgrad, double
     }
   }
 
-  if(c->limiter == 1 || c->limiter == 2){
+  if(c->limiter == 1 || c->limiter == 2 || c->limiter == 3){
     for(e = 0; e < c->nedge; e++){
       int l = c->edges_n[2*e], r = c->edges_n[2*e+1];
       limit_side(c, q, qgrad, qmin, qmax, lim, l, r, 0);
-      limit_side(c, q, qgrad, qmin, qmax, lim, r, l, 0);
+      limit_side(c, q, qgrad, qmin, qmax, lim, r, l, 2);
     }
     for(e = 0; e < nb; e++){
       int l = c->bedges_n[2*e], r = c->bedges_n[2*e+1];

@@ -45,7 +45,7 @@ typedef struct {
   const int* ipsp;           /* [nnode+1] */
   const int* psp;            /* [ipsp[nnode]] */
   double gamma, chi, cfl;
-  int limiter;               /* 0 none, 1 Barth, 2 Venkatakrishnan */
+  int limiter;               /* 0 none, 1 Barth, 2 Venkatakrishnan, 3 modified Venkatakrishnan */
   int sorder;                /* 1 or 2 */
   int no_cvbc;
   double qinf[ORC_NVARS];

@@ -654,7 +654,7 @@ static double limiter_fn(int type, double temp)
 }
 
 static void fr_limit_side(const orc_case* c, int neqn, int nvars, int nterms, const double* q, const double* qgrad,
-			  const double* qmin, const double* qmax, double* lim, int me, int other)
+			  const double* qmin, const double* qmax, double* lim, int me, int other, int variant)
 {
   int j;
   double QL[MAXE], dQ[MAXE], dx[3], ones[MAXE];
@@ -665,6 +665,31 @@ static void fr_limit_side(const orc_case* c, int neqn, int nvars, int nterms, co
   dx[1] = 0.5*(c->xyz[3*other+1] - c->xyz[3*me+1]);
   dx[2] = 0.5*(c->xyz[3*other+2] - c->xyz[3*me+2]);
   fr_extrapolate(c->chi, neqn, QL, qL, dQ, &qgrad[(size_t)me*nterms*3], dx, ones);
+  if(c->limiter == 3){
+    /* Kernel_VenkatMod / Bkernel_VenkatMod (limiters.tcc:534-735); variant 0 left, 2 right, 1 ghost half-edge; see
+       pcfd_oracle.c for the DP == unset case */
+    const double Pi = 3.141592653589793;
+    double L3 = 6.0*Pi*c->vol[me], K3 = 1.0*1.0*1.0;
+    for(j = 0; j < neqn; j++){
+      double DM = QL[j] - qL[j], DP = 0.0, ep2, temp;
+      if(variant == 1){
+	if(QL[j] > qL[j]) DP = qmax[(size_t)me*neqn + j] - QL[j];
+	else if(QL[j] <= qL[j]) DP = qmin[(size_t)me*neqn + j] - QL[j];
+      }
+      else if(variant == 2){
+	if(QL[j] > qL[j]) DP = qmax[(size_t)me*neqn + j] - qL[j];
+	if(QL[j] <= qL[j]) DP = qmin[(size_t)me*neqn + j] - qL[j];
+      }
+      else{
+	if(QL[j] > qL[j]) DP = qmax[(size_t)me*neqn + j] - qL[j];
+	else if(QL[j] < qL[j]) DP = qmin[(size_t)me*neqn + j] - qL[j];
+      }
+      ep2 = L3*K3;
+      temp = (DP*DP + ep2 + 2.0*DM*DP)/(DP*DP + 2.0*DM*DM + DM*DP + ep2);
+      lim[(size_t)me*neqn + j] = MIND(lim[(size_t)me*neqn + j], temp);
+    }
+    return;
+  }
   for(j = 0; j < neqn; j++){
     double temp = 1.0;
     if(QL[j] > qL[j]) temp = (qmax[(size_t)me*neqn + j] - qL[j])/(QL[j] - qL[j]);
@@ -702,16 +727,16 @@ void orc_fr_limiter(const orc_case* c, const orc_fr_params* p, const double* q, 
       qmin[(size_t)l*neqn+j] = MIND(qmin[(size_t)l*neqn+j], q[(size_t)r*nvars+j]);
     }
   }
-  if(c->limiter == 1 || c->limiter == 2){
+  if(c->limiter == 1 || c->limiter == 2 || c->limiter == 3){
     for(e = 0; e < c->nedge; e++){
       int l = c->edges_n[2*e], r = c->edges_n[2*e+1];
-      fr_limit_side(c, neqn, nvars, nterms, q, qgrad, qmin, qmax, lim, l, r);
-      fr_limit_side(c, neqn, nvars, nterms, q, qgrad, qmin, qmax, lim, r, l);
+      fr_limit_side(c, neqn, nvars, nterms, q, qgrad, qmin, qmax, lim, l, r, 0);
+      fr_limit_side(c, neqn, nvars, nterms, q, qgrad, qmin, qmax, lim, r, l, 2);
     }
     for(e = 0; e < nb; e++){
       int l = c->bedges_n[2*e], r = c->bedges_n[2*e+1];
       if(!is_ghost(c, r)) continue;
-      fr_limit_side(c, neqn, nvars, nterms, q, qgrad, qmin, qmax, lim, l, r);
+      fr_limit_side(c, neqn, nvars, nterms, q, qgrad, qmin, qmax, lim, l, r, 1);
     }
   }
   if(c->limiter != 0){

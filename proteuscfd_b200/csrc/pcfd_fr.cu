@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(W<NS>::NEQ * 16) kfr_limiter(DevMesh m, int ty
   if (n >= m.nnode + m.gnode) return;
   const int j = tid - n * NEQ;
   double l = 1.0;
-  if (n < m.nnode && (type == 1 || type == 2)) {
+  if (n < m.nnode && (type == 1 || type == 2 || type == 3)) {
     double qmin = 0.0, qmax = 0.0;
     const int k0 = m.adjp[n], k1 = m.adjp[n + 1];
     for (int k = k0; k < k1; k++) {
@@ -173,9 +173,23 @@ __global__ void __launch_bounds__(W<NS>::NEQ * 16) kfr_limiter(DevMesh m, int ty
       const double corr = (0.5 * chi * dQ + (1.0 - chi) * (g0 * dx[0] + g1 * dx[1] + g2 * dx[2]));
       const double QH = qn + corr * 1.0;
       double t = 1.0;
-      if (QH > qn) t = (qmax - qn) / (QH - qn);
-      else if (QH < qn) t = (qmin - qn) / (QH - qn);
-      t = limiter_fn(type, t);
+      if (type == 3) {
+        // Kernel_VenkatMod / Bkernel_VenkatMod (limiters.tcc:534-735), eps^2 = 6 pi V K^3 with K = 1.  Three spellings of
+        // delta+ in the reference: left node of an interior edge (unset when QH == qn: DM = 0 makes the ratio 1 for any
+        // finite value, 0 is used), right node, ghost half-edge (measured from the extrapolated value).
+        const double DM = QH - qn;
+        double DP = 0.0;
+        if (a.y >= m.nedge) DP = (QH > qn) ? (qmax - QH) : (qmin - QH);
+        else if (a.x < 0) DP = (QH > qn) ? (qmax - qn) : (qmin - qn);
+        else if (QH > qn) DP = qmax - qn;
+        else if (QH < qn) DP = qmin - qn;
+        const double ep2 = (6.0 * 3.141592653589793 * m.vol[n]) * (1.0 * 1.0 * 1.0);
+        t = (DP * DP + ep2 + 2.0 * DM * DP) / (DP * DP + 2.0 * DM * DM + DM * DP + ep2);
+      } else {
+        if (QH > qn) t = (qmax - qn) / (QH - qn);
+        else if (QH < qn) t = (qmin - qn) / (QH - qn);
+        t = limiter_fn(type, t);
+      }
       l = fr::mind(l, t);
     }
   }

@@ -209,15 +209,15 @@ def oracle_for_fr(lib, mesh, params, g, meta):
     return FrOracle(lib, gg, mm)
 
 
-@pytest.mark.parametrize("colored", [True, False])
-def test_fr_seeded_box_vs_oracle(oracle, colored):
+@pytest.mark.parametrize("colored,limiter", [(True, 2), (False, 2), (True, 3), (False, 1)])
+def test_fr_seeded_box_vs_oracle(oracle, colored, limiter):
     """A 10^3 box (1331 nodes, 8.6 k edges) in the SURVEY 8d state, frozen chemistry: two implicit iterations (the
     second re-using the LU'd Jacobian) then an explicit one, every field bit-identical to the oracle.  colored = the
     colour-sorted numbering used at scale (8 SGS levels per direction), else lexicographic (level schedule)."""
     from proteuscfd_b200 import capi
     from proteuscfd_b200.cases import fr_box_case
     fr, g, meta = fixture_fr_params(rxn_on=0)
-    mesh, params, q0, beta = fr_box_case(10, fr, colored=colored)
+    mesh, params, q0, beta = fr_box_case(10, fr, colored=colored, limiter=limiter)   # 2 Venkatakrishnan, 3 modified, 1 Barth
     o = oracle_for_fr(oracle, mesh, params, g, meta)
     ctx = capi.Context(mesh, params)
     ctx.set_field(capi.F_BETA, beta)

@@ -10,14 +10,14 @@ import pytest
 
 from tests.oracle_lib import Oracle, load_golden
 
-INVISCID = ["box8_explicit_venkat", "box8_explicit_barth", "box6_implicit_sgs", "box6c_implicit_sgs",
+INVISCID = ["box8_explicit_venkat", "box8_explicit_barth", "box8_explicit_venkatmod", "box6_implicit_sgs", "box6c_implicit_sgs",
             "ramp15_implicit", "cube_LowFi"]
 # laminar Navier-Stokes (compressibleNS): viscous flux + analytic viscous Jacobian + no-slip wall hooks
 NS = ["box6_ns_implicit", "box6_ns_adiabatic", "box6_sa_implicit"]
 ALL = INVISCID + NS
 INVISCID_IMPLICIT = ["box6_implicit_sgs", "box6c_implicit_sgs", "ramp15_implicit", "cube_LowFi"]
 IMPLICIT = INVISCID_IMPLICIT + NS
-EXPLICIT = ["box8_explicit_venkat", "box8_explicit_barth"]
+EXPLICIT = ["box8_explicit_venkat", "box8_explicit_barth", "box8_explicit_venkatmod"]
 
 
 def exact(a, b, what):

@@ -202,6 +202,8 @@ CASES = {
     "box8_explicit_venkat": lambda: make_case("box8_explicit_venkat", mesh=kuhn_box(8, jitter=0.15)),
     # Barth limiter on the same mesh
     "box8_explicit_barth": lambda: make_case("box8_explicit_barth", mesh=kuhn_box(8, jitter=0.15), limiter=1),
+    # modified Venkatakrishnan limiter (limiter = 3, eps^2 = 6 pi V), limiters.tcc:534-735
+    "box8_explicit_venkatmod": lambda: make_case("box8_explicit_venkatmod", mesh=kuhn_box(8, jitter=0.15), limiter=3),
     # implicit: FD Jacobian, LU, 3 SGS sweeps on natural (lexicographic) numbering
     "box6_implicit_sgs": lambda: make_case("box6_implicit_sgs", mesh=kuhn_box(6, jitter=0.15), nsgs=3, cfl=5.0),
     # implicit on a colour-sorted numbering (the multicolour schedule used at scale)
