@@ -266,7 +266,14 @@ def main():
         pobj = PObj(rank, world).BuildCommMaps(mesh["gNodeOwner"], mesh["gNodeLocalId"], group)
         dev = torch.device("cuda", local_rank)
         xch = PutExchange(ctx, pobj, dist, torch, dev, group) if args.halo == "put" else NcclExchange(ctx, pobj, dist, torch, dev)
-        hp = DistributedHotPath(ctx, xch)
+        hitflag = torch.zeros(1, device=dev, dtype=torch.int32)
+
+        def any_rank(hit):   # the (rare) pressure-clip fallback is a global decision: one 4-byte max all-reduce
+            hitflag.fill_(int(hit))
+            dist.all_reduce(hitflag, op=dist.ReduceOp.MAX)
+            return bool(hitflag.item())
+
+        hp = DistributedHotPath(ctx, xch, any_rank=any_rank)
         hp.setup()
         ctx.set_field(capi.F_Q, q0)
         step = lambda: hp.explicit_iterate(refresh_dt=True)

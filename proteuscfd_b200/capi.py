@@ -36,7 +36,7 @@ SYMBOLS = [
     "pcfd_ipc_export", "pcfd_ipc_open", "pcfd_ipc_close",
     "pcfd_turb_compute", "pcfd_halo_configure",
     "pcfd_chem_create", "pcfd_chem_destroy", "pcfd_chem_last_error", "pcfd_chem_mass_production",
-    "pcfd_create_fr", "pcfd_widths",
+    "pcfd_create_fr", "pcfd_widths", "pcfd_limiter_raw", "pcfd_residual_fused",
     "pcfd_chem_source_term", "pcfd_chem_source_term_device", "pcfd_halo_width", "pcfd_halo_send_total", "pcfd_halo_pack", "pcfd_halo_recv_ptr",
 ]
 
@@ -144,6 +144,8 @@ def load_library(path=LIB_PATH):
     lib.pcfd_create_fr.argtypes = [C.POINTER(MeshDesc), C.POINTER(Params), C.POINTER(FrParams), C.c_int,
                                    C.POINTER(C.c_void_p)]
     lib.pcfd_widths.argtypes = [C.c_void_p, _ip, _ip, _ip]
+    lib.pcfd_limiter_raw.argtypes = [C.c_void_p]
+    lib.pcfd_residual_fused.argtypes = [C.c_void_p, _dp, _ip]
     lib.pcfd_explicit_iterate.argtypes = [C.c_void_p, C.c_int, _dp]
     lib.pcfd_implicit_iterate.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp]
     lib.pcfd_launch_count.restype = C.c_longlong
@@ -350,6 +352,16 @@ class Context:
 
     def limiter(self):
         self._ck(self.lib.pcfd_limiter(self.h))
+
+    def limiter_raw(self):
+        self._ck(self.lib.pcfd_limiter_raw(self.h))
+
+    def residual_fused(self, want_norms=False):
+        """(norms or None, clip_hit): see pcfd_residual_fused."""
+        hit = C.c_int(0)
+        s = np.zeros(1 + self.neqn) if want_norms else None
+        self._ck(self.lib.pcfd_residual_fused(self.h, _d(s) if want_norms else None, C.byref(hit)))
+        return s, bool(hit.value)
 
     def residual(self, want_norms=False):
         if not want_norms:

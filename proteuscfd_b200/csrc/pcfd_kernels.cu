@@ -2398,6 +2398,37 @@ static int gradient_limiter_residual(pcfd_ctx* c, double* sumsq) {
   return pcfd_residual(c, sumsq);
 }
 
+// The two halves of the fused limiter / residual path as separate entry points, so that a multi-rank host can put the
+// limiter halo exchange between them (the clamp of negatives is element-wise, so exchanging the raw limiter and clamping
+// on both sides equals exchanging the clamped one).
+int pcfd_limiter_raw(pcfd_ctx* c) {
+  if (!c) return 1;
+  CK(cudaSetDevice(c->device));
+  if (c->fr) return fail(c, "pcfd_limiter_raw: not available for the reacting eqnset (use pcfd_limiter)");
+  PROF("k_limiter");
+  k_limiter<<<nblk((long long)c->nn * 5, 160), 160, 0, c->stream>>>(c->dm, c->prm.limiter, c->prm.chi, c->f[PCFD_F_Q],
+                                                                   c->f[PCFD_F_QGRAD], c->f[PCFD_F_LIMITER]);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int pcfd_residual_fused(pcfd_ctx* c, double* sumsq, int* clip_hit) {
+  if (!c) return 1;
+  CK(cudaSetDevice(c->device));
+  if (c->fr) return fail(c, "pcfd_residual_fused: not available for the reacting eqnset (use pcfd_residual)");
+  if (!clip_hit) return fail(c, "pcfd_residual_fused: clip_hit must not be NULL");
+  if (c->prm.sorder < 2 || c->prm.limiter == 0) {   // nothing to clip: the plain residual
+    *clip_hit = 0;
+    return pcfd_residual(c, sumsq);
+  }
+  bool hit = false;
+  if (run_flux(c, true, &hit)) return 1;
+  *clip_hit = hit ? 1 : 0;
+  if (hit) c->clip_fallbacks++;
+  if (sumsq && !hit) return run_sumsq(c, c->f[PCFD_F_B], c->nnode, sumsq);
+  return 0;
+}
+
 static int run_limiter_final(pcfd_ctx* c, const int* tclip) {
   PROF("k_limiter_final");
   k_limiter_final<<<nblk((long long)c->nn * 5, 256), 256, 0, c->stream>>>(c->nn, c->nnode, tclip, c->f[PCFD_F_LIMITER]);

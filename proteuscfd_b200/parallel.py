@@ -241,10 +241,16 @@ class DistributedHotPath:
     """SolutionSpace::NewtonIterate (ucs/solutionSpace.tcc:640-904) across ranks: the phase calls of one context
     with the reference's halo exchanges and reductions in the reference's places."""
 
-    def __init__(self, ctx, exchange, allreduce_sum=None, allreduce_min=None):
+    def __init__(self, ctx, exchange, allreduce_sum=None, allreduce_min=None, any_rank=None, fused=True):
+        """any_rank(flag) -> True if the flag is set on any rank (a max all-reduce); with it the limiter / residual
+        pair runs as pcfd_limiter_raw -> halo -> pcfd_residual_fused (one edge pass instead of two, no host sync
+        inside the limiter) and falls back to the ordered pressure-clip path only when some rank reports a clip."""
         self.ctx, self.x = ctx, exchange
         self.sum = allreduce_sum or (lambda a: a)
         self.min = allreduce_min or (lambda a: a)
+        self.any_rank = any_rank
+        self.fused = fused and any_rank is not None and ctx.neqn == capi.NEQN
+        self.clip_fallbacks = 0
 
     def setup(self):
         # Gradient::ComputeNodeLSQCoefficients ends with halos of s and sw (gradient.tcc:131-134)
@@ -258,6 +264,13 @@ class DistributedHotPath:
         self.x.update(capi.F_Q)             # :665
         c.gradient()
         self.x.update(capi.F_QGRAD)         # gradient.tcc:98
+        if self.fused:
+            c.limiter_raw()
+            self.x.update(capi.F_LIMITER)   # limiters.tcc:128 (raw values; both sides clamp)
+            norms, hit = c.residual_fused(want_norms=want_norms)
+            if not self.any_rank(hit):
+                return norms
+            self.clip_fallbacks += 1
         c.limiter()
         self.x.update(capi.F_LIMITER)       # limiters.tcc:128
         return c.residual(want_norms=want_norms)

@@ -92,8 +92,9 @@ def test_multirank_iteration_matches_reference(name):
     check(ranks, ctxs, capi.F_Q, "q1")
 
 
-@pytest.mark.parametrize("colored,implicit", [(False, False), (True, True)])
-def test_slab_partitions_vs_oracle(oracle, colored, implicit):
+@pytest.mark.parametrize("colored,implicit,fused", [(False, False, False), (True, True, False), (False, False, True),
+                                                    (True, True, True)])
+def test_slab_partitions_vs_oracle(oracle, colored, implicit, fused):
     """Partitions generated in memory (cases.slab_case, the bench's multi-GPU input): three ranks on one GPU with
     direct-put halos against the C oracle run per rank with a numpy halo exchange through the same maps."""
     from proteuscfd_b200 import capi
@@ -146,9 +147,16 @@ def test_slab_partitions_vs_oracle(oracle, colored, implicit):
         x.update(capi.F_Q)
         each(ctxs, lambda c: c.gradient())
         x.update(capi.F_QGRAD)
-        each(ctxs, lambda c: c.limiter())
-        x.update(capi.F_LIMITER)
-        each(ctxs, lambda c: c.residual())
+        if fused:
+            # pcfd_limiter_raw -> halo of the raw limiter -> pcfd_residual_fused (clamp + residual + clip test in one pass)
+            each(ctxs, lambda c: c.limiter_raw())
+            x.update(capi.F_LIMITER)
+            hits = [c.residual_fused()[1] for c in ctxs]
+            assert not any(hits), "the smooth state must not trigger the pressure clip"
+        else:
+            each(ctxs, lambda c: c.limiter())
+            x.update(capi.F_LIMITER)
+            each(ctxs, lambda c: c.residual())
         for r in range(nr):
             exact(ctxs[r].get_field(capi.F_QGRAD), grads[r], f"qgrad rank {r} it {it}")
             exact(ctxs[r].get_field(capi.F_LIMITER), lims[r], f"limiter rank {r} it {it}")
