@@ -353,69 +353,117 @@ __device__ __forceinline__ void perp_vectors(const double* n, double* v1, double
   v2[0] = v2[0] / mag; v2[1] = v2[1] / mag; v2[2] = v2[2] / mag;
 }
 
-// NOTE on __noinline__ (eigensystem, farfield_bc, inviscid_wall_bc, boundary_variables): with these inlined into the
+// NOTE on __noinline__ (farfield_bc, inviscid_wall_bc, boundary_variables): with these inlined into the
 // boundary-Jacobian kernel, nvcc 12.9 (-O3, sm_100a) overlaid the caller's perturbed left state with a temporary of
 // the inlined wall BC (the state came back with its v-component overwritten by the BC solution; the same source built
 // for the host is clean under ASan/UBSan).  As real calls each gets its own frame; they run per boundary half-edge only.
 
-// Eigensystem (compressibleFR.tcc:150-290); the per-species c2i are overwritten by the bulk c2 there (:176-180)
+// Eigensystem (compressibleFR.tcc:150-290) in closed form.  The reference fills two dense N x N arrays T, Tinv; both
+// are sparse (an identity block plus the velocity / temperature columns), so here only the scalars they are built from
+// are kept and rows are applied on the fly.  Skipping the structurally-zero entries of a row sum is exact: every
+// product with a stored 0.0 is a signed zero, and s + (+-0) == s.  The per-species c2i are overwritten by the bulk c2
+// in the reference (:176-180).
 template <int NS>
-__device__ __noinline__ void eigensystem(const Params<NS>& p, const double* Q, const double* av, double vdotn, double* eig, double* T,
-                            double* Tinv, double beta) {
-  constexpr int N = NS + 4;
-  const double nx = av[0], ny = av[1], nz = av[2];
-  const double bm1 = beta - 1.0, bp1 = beta + 1.0, oneMBeta = 1.0 - beta;
-  const double theta = theta_of<NS>(Q, av, vdotn);
-  const double rho = Q[NS + 5];
-  double R, c2, l[3], m[3];
-  fluid_props(p, Q, Q[NS + 3], R, c2);
-  const double thetaPrime = 0.5 * bp1 * theta;
-  const double cPrime = 0.5 * sqrt(theta * theta * (oneMBeta * oneMBeta) + 4.0 * beta * c2);
-  perp_vectors(av, l, m);
-  const double lx = l[0], ly = l[1], lz = l[2], mx = m[0], my = m[1], mz = m[2];
-  constexpr int uloc = NS, vloc = NS + 1, wloc = NS + 2, tloc = NS + 3;
-  for (int i = 0; i < NS + 2; i++) eig[i] = theta;
-  eig[wloc] = thetaPrime + cPrime;
-  eig[tloc] = thetaPrime - cPrime;
+struct Eigen {
+  double theta, c2, cPrime, thetaPrime, Xp, Xm, rho, bm1;
+  double l[3], m[3], n[3];
+};
+
+template <int NS>
+__device__ __forceinline__ void eigen_setup(const Params<NS>& p, const double* Q, const double* av, double vdotn, double beta,
+                                            Eigen<NS>& E) {
+  const double bp1 = beta + 1.0, oneMBeta = 1.0 - beta;
+  E.bm1 = beta - 1.0;
+  E.n[0] = av[0]; E.n[1] = av[1]; E.n[2] = av[2];
+  E.theta = theta_of<NS>(Q, av, vdotn);
+  E.rho = Q[NS + 5];
+  double R;
+  fluid_props(p, Q, Q[NS + 3], R, E.c2);
+  E.thetaPrime = 0.5 * bp1 * E.theta;
+  E.cPrime = 0.5 * sqrt(E.theta * E.theta * (oneMBeta * oneMBeta) + 4.0 * beta * E.c2);
+  perp_vectors(av, E.l, E.m);
   const double betam = oneMBeta * 0.5;
-  const double Xp = theta * betam + cPrime;
-  const double Xm = theta * betam - cPrime;
-  for (int i = 0; i < N * N; i++) T[i] = 0.0;
-  for (int i = 0; i < NS; i++) {
-    T[N * i + i] = 1.0;
-    T[N * i + wloc] = -(Q[i] * (c2 + bm1 * c2 - theta * bm1 * Xm)) / (c2 * Xm);
-    T[N * i + tloc] = (Q[i] * (c2 + bm1 * c2 - theta * bm1 * Xp)) / (c2 * Xp);
-  }
-  T[N * (NS + 0) + (NS + 0)] = lx; T[N * (NS + 0) + (NS + 1)] = mx; T[N * (NS + 0) + (NS + 2)] = nx; T[N * (NS + 0) + (NS + 3)] = -nx;
-  T[N * (NS + 1) + (NS + 0)] = ly; T[N * (NS + 1) + (NS + 1)] = my; T[N * (NS + 1) + (NS + 2)] = ny; T[N * (NS + 1) + (NS + 3)] = -ny;
-  T[N * (NS + 2) + (NS + 0)] = lz; T[N * (NS + 2) + (NS + 1)] = mz; T[N * (NS + 2) + (NS + 2)] = nz; T[N * (NS + 2) + (NS + 3)] = -nz;
-  T[N * (NS + 3) + wloc] = -rho * Xm;
-  T[N * (NS + 3) + tloc] = rho * Xp;
-  for (int i = 0; i < N * N; i++) Tinv[i] = 0.0;
-  for (int i = 0; i < NS; i++) {
+  E.Xp = E.theta * betam + E.cPrime;
+  E.Xm = E.theta * betam - E.cPrime;
+}
+// eigenvalue i (compressibleFR.tcc:199-203)
+template <int NS>
+__device__ __forceinline__ double eigen_value(const Eigen<NS>& E, int i) {
+  if (i < NS + 2) return E.theta;
+  return (i == NS + 2) ? (E.thetaPrime + E.cPrime) : (E.thetaPrime - E.cPrime);
+}
+// the non-zero entries of row i of Tinv (compressibleFR.tcc:240-273): columns u, v, w, t (+ the unit diagonal for a
+// species row); returns the number of leading species columns that are non-zero (1 for species rows, else 0)
+template <int NS>
+__device__ __forceinline__ void tinv_row(const Eigen<NS>& E, const double* Q, int i, double& du, double& dv, double& dw,
+                                         double& dt) {
+  const double lx = E.l[0], ly = E.l[1], lz = E.l[2], mx = E.m[0], my = E.m[1], mz = E.m[2];
+  const double nx = E.n[0], ny = E.n[1], nz = E.n[2];
+  const double c2 = E.c2, Xm = E.Xm, Xp = E.Xp, bm1 = E.bm1, theta = E.theta, rho = E.rho, cPrime = E.cPrime;
+  if (i < NS) {
     const double KK = -Q[i] * (c2 * (Xm + Xp) - bm1 * Xm * Xp * theta + bm1 * c2 * (Xm + Xp));
-    Tinv[i * N + i] = 1.0;
-    Tinv[i * N + uloc] = -((ly * mz - lz * my) * KK) / (c2 * Xm * Xp);
-    Tinv[i * N + vloc] = ((lx * mz - lz * mx) * KK) / (c2 * Xm * Xp);
-    Tinv[i * N + wloc] = -((lx * my - ly * mx) * KK) / (c2 * Xm * Xp);
-    Tinv[i * N + tloc] = (Q[i] * (c2 + bm1 * c2)) / (rho * c2 * Xm * Xp);
+    du = -((ly * mz - lz * my) * KK) / (c2 * Xm * Xp);
+    dv = ((lx * mz - lz * mx) * KK) / (c2 * Xm * Xp);
+    dw = -((lx * my - ly * mx) * KK) / (c2 * Xm * Xp);
+    dt = (Q[i] * (c2 + bm1 * c2)) / (rho * c2 * Xm * Xp);
+  } else if (i == NS) {
+    du = my * nz - mz * ny;
+    dv = -(mx * nz - mz * nx);
+    dw = mx * ny - my * nx;
+    dt = 0.0;
+  } else if (i == NS + 1) {
+    du = -(ly * nz - lz * ny);
+    dv = lx * nz - lz * nx;
+    dw = -(lx * ny - ly * nx);
+    dt = 0.0;
+  } else if (i == NS + 2) {
+    du = ((Xp) * (ly * mz - lz * my)) / (2.0 * cPrime);
+    dv = -((Xp) * (lx * mz - lz * mx)) / (2.0 * cPrime);
+    dw = ((Xp) * (lx * my - ly * mx)) / (2.0 * cPrime);
+    dt = 1.0 / (2.0 * rho * cPrime);
+  } else {
+    du = ((Xm) * (ly * mz - lz * my)) / (2.0 * cPrime);
+    dv = -((Xm) * (lx * mz - lz * mx)) / (2.0 * cPrime);
+    dw = ((Xm) * (lx * my - ly * mx)) / (2.0 * cPrime);
+    dt = 1.0 / (2.0 * rho * cPrime);
   }
-  Tinv[N * uloc + uloc] = my * nz - mz * ny;
-  Tinv[N * uloc + vloc] = -(mx * nz - mz * nx);
-  Tinv[N * uloc + wloc] = mx * ny - my * nx;
-  Tinv[N * uloc + tloc] = 0.0;
-  Tinv[N * vloc + uloc] = -(ly * nz - lz * ny);
-  Tinv[N * vloc + vloc] = lx * nz - lz * nx;
-  Tinv[N * vloc + wloc] = -(lx * ny - ly * nx);
-  Tinv[N * vloc + tloc] = 0.0;
-  Tinv[N * wloc + uloc] = ((Xp) * (ly * mz - lz * my)) / (2.0 * cPrime);
-  Tinv[N * wloc + vloc] = -((Xp) * (lx * mz - lz * mx)) / (2.0 * cPrime);
-  Tinv[N * wloc + wloc] = ((Xp) * (lx * my - ly * mx)) / (2.0 * cPrime);
-  Tinv[N * wloc + tloc] = 1.0 / (2.0 * rho * cPrime);
-  Tinv[N * tloc + uloc] = ((Xm) * (ly * mz - lz * my)) / (2.0 * cPrime);
-  Tinv[N * tloc + vloc] = -((Xm) * (lx * mz - lz * mx)) / (2.0 * cPrime);
-  Tinv[N * tloc + wloc] = ((Xm) * (lx * my - ly * mx)) / (2.0 * cPrime);
-  Tinv[N * tloc + tloc] = 1.0 / (2.0 * rho * cPrime);
+}
+// rhs[i] = sum_j Tinv[i][j] * val[j], j ascending from 0.0 (compressibleFR.tcc:988-993, 1090-1095)
+template <int NS>
+__device__ __forceinline__ double tinv_row_dot(const Eigen<NS>& E, const double* Q, int i, const double* val) {
+  double du, dv, dw, dt;
+  tinv_row(E, Q, i, du, dv, dw, dt);
+  double s = 0.0;
+  if (i < NS) s += 1.0 * val[i];
+  s += du * val[NS];
+  s += dv * val[NS + 1];
+  s += dw * val[NS + 2];
+  if (i != NS && i != NS + 1) s += dt * val[NS + 3];
+  return s;
+}
+// (T v)[i] in MatVecMult order (matrix.h:63-74; T: compressibleFR.tcc:213-237)
+template <int NS>
+__device__ __forceinline__ double t_row_dot(const Eigen<NS>& E, const double* Q, int i, const double* v) {
+  const double c2 = E.c2, Xm = E.Xm, Xp = E.Xp, bm1 = E.bm1, theta = E.theta, rho = E.rho;
+  if (i < NS) {
+    const double tw = -(Q[i] * (c2 + bm1 * c2 - theta * bm1 * Xm)) / (c2 * Xm);
+    const double tt = (Q[i] * (c2 + bm1 * c2 - theta * bm1 * Xp)) / (c2 * Xp);
+    double s = 1.0 * v[i];
+    s += tw * v[NS + 2];
+    s += tt * v[NS + 3];
+    return s;
+  }
+  if (i < NS + 3) {
+    const int k = i - NS;
+    double s = E.l[k] * v[NS];
+    s += E.m[k] * v[NS + 1];
+    s += E.n[k] * v[NS + 2];
+    s += -E.n[k] * v[NS + 3];
+    return s;
+  }
+  double s = -rho * Xm * v[NS + 2];
+  s += rho * Xp * v[NS + 3];
+  return s;
 }
 
 // NewtonFindTGivenP (compressibleFR.tcc:2343-2378)
@@ -443,27 +491,27 @@ constexpr int N_SUBIT = 10;   // compressibleFR.tcc:32
 
 // GetFarfieldBoundaryVariables (compressibleFR.tcc:940-1039)
 template <int NS>
-__device__ __noinline__ void farfield_bc(const Params<NS>& p, const double* QL, double* QR, const double* av, double vdotn, double beta) {
+__device__ __noinline__ void farfield_bc(const Params<NS>& p, const double* QL, double* QR, const double* av, double vdotn,
+                                         double beta) {
   constexpr int N = NS + 4, NV = 3 * NS + 6;
-  double qavg[NS + 6], eig[N], Tinv[N * N], T[N * N], rhs[N], ql[N], qinf[N];
+  double qavg[NS + 6], rhs[N], ql[N], qinf[N];
+  Eigen<NS> E;
   for (int subit = 0; subit < N_SUBIT; subit++) {
     for (int i = 0; i < N; i++) qavg[i] = 0.5 * (QL[i] + QR[i]);
     aux_pr(p, qavg);
-    eigensystem(p, qavg, av, vdotn, eig, T, Tinv, beta);
+    eigen_setup(p, qavg, av, vdotn, beta, E);
     if (p.no_cvbc) {
-      if (eig[0] >= 0.0) { for (int i = 0; i < NV; i++) QR[i] = QL[i]; }
+      if (E.theta >= 0.0) { for (int i = 0; i < NV; i++) QR[i] = QL[i]; }
       else { for (int i = 0; i < NV; i++) QR[i] = p.qinf[i]; }
     } else {
       for (int i = 0; i < N; i++) { ql[i] = QL[i]; qinf[i] = p.qinf[i]; }
       const double Tguess = ql[N - 1];
       ql[N - 1] = QL[NS + 4];
       qinf[N - 1] = p.qinf[NS + 4];
-      for (int i = 0; i < N; i++) {
-        double s = 0.0;
-        for (int j = 0; j < N; j++) s += Tinv[i * N + j] * (eig[i] >= 0.0 ? ql[j] : qinf[j]);
-        rhs[i] = s;
-      }
-      matvec<N>(T, rhs, QR);
+#pragma unroll
+      for (int i = 0; i < N; i++) rhs[i] = tinv_row_dot(E, qavg, i, (eigen_value(E, i) >= 0.0) ? ql : qinf);
+#pragma unroll
+      for (int i = 0; i < N; i++) QR[i] = t_row_dot(E, qavg, i, rhs);
       for (int i = 0; i < NS; i++) if (QR[i] < 0.0) QR[i] = 0.0;
       const double pgoal = QR[N - 1];
       QR[N - 1] = newton_T_given_P(p, QR, pgoal, Tguess);
@@ -471,34 +519,82 @@ __device__ __noinline__ void farfield_bc(const Params<NS>& p, const double* QL, 
   }
 }
 
-// GetInviscidWallBoundaryVariables (compressibleFR.tcc:1042-1134)
+// LU / LuSolve (matrix.h:110-190, 237-264) on a matrix whose element k lives at a[k * S]: one matrix per thread,
+// interleaved in shared memory (conflict-free; dynamic row indices through the permutation never leave shared memory)
+template <int N>
+__device__ __forceinline__ void lu_strided(double* a, int S, int* p, int SP) {
+  for (int i = 0; i < N; i++) p[i * SP] = i;
+  int row = 0;
+  for (int i = 0; i < N; i++) {
+    double large = 0.0;
+    for (int j = i; j < N; j++) {
+      const double v = a[(p[j * SP] * N + i) * S];
+      if (fabs(v) > fabs(large)) { large = v; row = j; }
+    }
+    const int t = p[i * SP]; p[i * SP] = p[row * SP]; p[row * SP] = t;
+    large = 1.0 / large;
+    const int pi = p[i * SP];
+    for (int j = i + 1; j < N; j++) a[(p[j * SP] * N + i) * S] *= large;
+    for (int j = i + 1; j < N; j++) {
+      const int pj = p[j * SP];
+      const double f = a[(pj * N + i) * S];
+      for (int k = i + 1; k < N; k++) a[(pj * N + k) * S] -= f * a[(pi * N + k) * S];
+    }
+  }
+}
+template <int N>
+__device__ __forceinline__ void lu_solve_strided(const double* a, int S, double* b, const int* p, int SP, double* x) {
+  for (int i = 0; i < N; i++) {
+    const int pi = p[i * SP];
+    double sum = 0.0;
+    for (int j = 0; j < i; j++) sum += a[(pi * N + j) * S] * x[j];
+    x[i] = b[pi] - sum;
+  }
+  for (int i = N - 1; i >= 0; i--) {
+    const int pi = p[i * SP];
+    double sum = 0.0;
+    for (int j = N - 1; j > i; j--) sum += a[(pi * N + j) * S] * b[j];
+    b[i] = (x[i] - sum) / a[(pi * N + i) * S];
+  }
+}
+
+// GetInviscidWallBoundaryVariables (compressibleFR.tcc:1042-1134).  sm / smi: this thread's N*N doubles and N ints of
+// shared memory at stride S (the modified Tinv of the characteristic solve and its pivot vector).
 template <int NS>
-__device__ __noinline__ void inviscid_wall_bc(const Params<NS>& p, const double* QL, double* QR, const double* av, double vdotn,
-                                 double beta) {
+__device__ __noinline__ void inviscid_wall_bc(const Params<NS>& p, const double* QL, double* QR, const double* av,
+                                              double vdotn, double beta, double* sm, int* smi, int S) {
   constexpr int N = NS + 4, NV = 3 * NS + 6;
   if (!p.no_cvbc) {
-    double qavg[NS + 6], eig[N], Tinv[N * N], T[N * N], rhs[N], scr[N], ql[N];
-    int pv[N];
+    double qavg[NS + 6], rhs[N], scr[N], ql[N];
+    Eigen<NS> E;
     for (int subit = 0; subit < N_SUBIT; subit++) {
       for (int i = 0; i < N; i++) qavg[i] = 0.5 * (QL[i] + QR[i]);
       aux_pr(p, qavg);
-      eigensystem(p, qavg, av, vdotn, eig, T, Tinv, beta);
+      eigen_setup(p, qavg, av, vdotn, beta, E);
       for (int i = 0; i < N; i++) ql[i] = QL[i];
       const double Tguess = ql[N - 1];
       ql[N - 1] = QL[NS + 4];
-      for (int i = 0; i < N; i++) {
-        double s = 0.0;
-        for (int j = 0; j < N; j++) s += Tinv[i * N + j] * ql[j];
-        rhs[i] = s;
+#pragma unroll
+      for (int i = 0; i < N; i++) rhs[i] = tinv_row_dot(E, qavg, i, ql);
+      // Tinv with its last row replaced by theta = 0 (wall velocity = flow velocity)
+      for (int k = 0; k < N * N; k++) sm[k * S] = 0.0;
+#pragma unroll
+      for (int i = 0; i < N - 1; i++) {
+        double du, dv, dw, dt;
+        tinv_row(E, qavg, i, du, dv, dw, dt);
+        if (i < NS) sm[(i * N + i) * S] = 1.0;
+        sm[(i * N + NS) * S] = du;
+        sm[(i * N + NS + 1) * S] = dv;
+        sm[(i * N + NS + 2) * S] = dw;
+        sm[(i * N + NS + 3) * S] = dt;
       }
-      for (int i = 0; i < NS; i++) Tinv[(N - 1) * N + i] = 0.0;
-      Tinv[(N - 1) * N + NS] = av[0];
-      Tinv[(N - 1) * N + NS + 1] = av[1];
-      Tinv[(N - 1) * N + NS + 2] = av[2];
-      Tinv[(N - 1) * N + NS + 3] = 0.0;
+      sm[((N - 1) * N + NS) * S] = av[0];
+      sm[((N - 1) * N + NS + 1) * S] = av[1];
+      sm[((N - 1) * N + NS + 2) * S] = av[2];
+      sm[((N - 1) * N + NS + 3) * S] = 0.0;
       rhs[N - 1] = vdotn;
-      lu<N>(Tinv, pv);
-      lu_solve<N>(Tinv, rhs, pv, scr);
+      lu_strided<N>(sm, S, smi, S);
+      lu_solve_strided<N>(sm, S, rhs, smi, S, scr);
       for (int i = 0; i < N; i++) QR[i] = rhs[i];
       const double pgoal = QR[N - 1];
       QR[N - 1] = newton_T_given_P(p, QR, pgoal, Tguess);
@@ -519,7 +615,8 @@ __device__ __noinline__ void inviscid_wall_bc(const Params<NS>& p, const double*
 
 // CalculateBoundaryVariables (bc.tcc:1058-1397) for the BC types of the reacting configs; QL and QR are full rows
 template <int NS>
-__device__ __noinline__ void boundary_variables(const Params<NS>& p, double* QL, double* QR, const double* av, int bctype, double betaL) {
+__device__ __noinline__ void boundary_variables(const Params<NS>& p, double* QL, double* QR, const double* av, int bctype,
+                                                double betaL, double* sm, int* smi, int S) {
   constexpr int N = NS + 4;
   const double vdotn = 0.0;   // static mesh
   switch (bctype) {
@@ -531,7 +628,7 @@ __device__ __noinline__ void boundary_variables(const Params<NS>& p, double* QL,
       farfield_bc(p, QL, QR, av, vdotn, betaL);
       break;
     case PCFD_BC_IMPERMEABLE_WALL: case PCFD_BC_SYMMETRY:
-      inviscid_wall_bc(p, QL, QR, av, vdotn, betaL);
+      inviscid_wall_bc(p, QL, QR, av, vdotn, betaL, sm, smi, S);
       break;
     default: break;
   }
