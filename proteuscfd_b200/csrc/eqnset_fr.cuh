@@ -519,53 +519,78 @@ __device__ __noinline__ void farfield_bc(const Params<NS>& p, const double* QL, 
   }
 }
 
-// LU / LuSolve (matrix.h:110-190, 237-264) on a matrix whose element k lives at a[k * S]: one matrix per thread,
-// interleaved in shared memory (conflict-free; dynamic row indices through the permutation never leave shared memory)
-template <int N>
-__device__ __forceinline__ void lu_strided(double* a, int S, int* p, int SP) {
-  for (int i = 0; i < N; i++) p[i * SP] = i;
-  int row = 0;
-  for (int i = 0; i < N; i++) {
+// The characteristic solve of the slip wall: LU (matrix.h:110-190) + LuSolve (:237-264) of Tinv with its last row
+// replaced by [0.., n, 0].  The species columns of that matrix hold a unit diagonal and nothing else, so the partial
+// pivoting of the reference picks row i for every species column i, its multipliers are exact zeros and the
+// elimination leaves the rest untouched: the N x N factorisation IS the pivoted LU of the trailing 4 x 4 block
+// (rows / columns u, v, w, T), and the species unknowns follow by back-substitution over the columns T, w, v, u (the
+// reference's descending order).  Same operations on the same operands, 16 matrix entries instead of (NS+4)^2.
+template <int NS>
+__device__ __forceinline__ void wall_solve(const Eigen<NS>& E, const double* Q, const double* av, double* rhs) {
+  constexpr int N = NS + 4;
+  double M[4][4];
+  int p[4] = {0, 1, 2, 3};
+#pragma unroll
+  for (int r = 0; r < 3; r++) tinv_row(E, Q, NS + r, M[r][0], M[r][1], M[r][2], M[r][3]);
+  M[3][0] = av[0]; M[3][1] = av[1]; M[3][2] = av[2]; M[3][3] = 0.0;
+  int row = 0;   // (only read if a pivot column is entirely zero, i.e. for a singular system)
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
     double large = 0.0;
-    for (int j = i; j < N; j++) {
-      const double v = a[(p[j * SP] * N + i) * S];
+#pragma unroll
+    for (int j = i; j < 4; j++) {
+      const double v = M[p[j]][i];
       if (fabs(v) > fabs(large)) { large = v; row = j; }
     }
-    const int t = p[i * SP]; p[i * SP] = p[row * SP]; p[row * SP] = t;
+    const int t = p[i]; p[i] = p[row]; p[row] = t;
     large = 1.0 / large;
-    const int pi = p[i * SP];
-    for (int j = i + 1; j < N; j++) a[(p[j * SP] * N + i) * S] *= large;
-    for (int j = i + 1; j < N; j++) {
-      const int pj = p[j * SP];
-      const double f = a[(pj * N + i) * S];
-      for (int k = i + 1; k < N; k++) a[(pj * N + k) * S] -= f * a[(pi * N + k) * S];
-    }
+#pragma unroll
+    for (int j = i + 1; j < 4; j++) M[p[j]][i] *= large;
+#pragma unroll
+    for (int j = i + 1; j < 4; j++)
+#pragma unroll
+      for (int k = i + 1; k < 4; k++) M[p[j]][k] -= M[p[j]][i] * M[p[i]][k];
   }
-}
-template <int N>
-__device__ __forceinline__ void lu_solve_strided(const double* a, int S, double* b, const int* p, int SP, double* x) {
-  for (int i = 0; i < N; i++) {
-    const int pi = p[i * SP];
+  double x[4], b[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) b[i] = rhs[NS + i];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
     double sum = 0.0;
-    for (int j = 0; j < i; j++) sum += a[(pi * N + j) * S] * x[j];
-    x[i] = b[pi] - sum;
+#pragma unroll
+    for (int j = 0; j < i; j++) sum += M[p[i]][j] * x[j];
+    x[i] = b[p[i]] - sum;
   }
-  for (int i = N - 1; i >= 0; i--) {
-    const int pi = p[i * SP];
+#pragma unroll
+  for (int i = 3; i >= 0; i--) {
     double sum = 0.0;
-    for (int j = N - 1; j > i; j--) sum += a[(pi * N + j) * S] * b[j];
-    b[i] = (x[i] - sum) / a[(pi * N + i) * S];
+#pragma unroll
+    for (int j = 3; j > i; j--) sum += M[p[i]][j] * b[j];
+    b[i] = (x[i] - sum) / M[p[i]][i];
   }
+#pragma unroll
+  for (int i = 0; i < 4; i++) rhs[NS + i] = b[i];
+#pragma unroll
+  for (int i = NS - 1; i >= 0; i--) {
+    double du, dv, dw, dt;
+    tinv_row(E, Q, i, du, dv, dw, dt);
+    double sum = 0.0;
+    sum += dt * b[3];
+    sum += dw * b[2];
+    sum += dv * b[1];
+    sum += du * b[0];
+    rhs[i] = (rhs[i] - sum) / 1.0;
+  }
+  (void)N;
 }
 
-// GetInviscidWallBoundaryVariables (compressibleFR.tcc:1042-1134).  sm / smi: this thread's N*N doubles and N ints of
-// shared memory at stride S (the modified Tinv of the characteristic solve and its pivot vector).
+// GetInviscidWallBoundaryVariables (compressibleFR.tcc:1042-1134)
 template <int NS>
 __device__ __noinline__ void inviscid_wall_bc(const Params<NS>& p, const double* QL, double* QR, const double* av,
-                                              double vdotn, double beta, double* sm, int* smi, int S) {
+                                              double vdotn, double beta) {
   constexpr int N = NS + 4, NV = 3 * NS + 6;
   if (!p.no_cvbc) {
-    double qavg[NS + 6], rhs[N], scr[N], ql[N];
+    double qavg[NS + 6], rhs[N], ql[N];
     Eigen<NS> E;
     for (int subit = 0; subit < N_SUBIT; subit++) {
       for (int i = 0; i < N; i++) qavg[i] = 0.5 * (QL[i] + QR[i]);
@@ -576,25 +601,8 @@ __device__ __noinline__ void inviscid_wall_bc(const Params<NS>& p, const double*
       ql[N - 1] = QL[NS + 4];
 #pragma unroll
       for (int i = 0; i < N; i++) rhs[i] = tinv_row_dot(E, qavg, i, ql);
-      // Tinv with its last row replaced by theta = 0 (wall velocity = flow velocity)
-      for (int k = 0; k < N * N; k++) sm[k * S] = 0.0;
-#pragma unroll
-      for (int i = 0; i < N - 1; i++) {
-        double du, dv, dw, dt;
-        tinv_row(E, qavg, i, du, dv, dw, dt);
-        if (i < NS) sm[(i * N + i) * S] = 1.0;
-        sm[(i * N + NS) * S] = du;
-        sm[(i * N + NS + 1) * S] = dv;
-        sm[(i * N + NS + 2) * S] = dw;
-        sm[(i * N + NS + 3) * S] = dt;
-      }
-      sm[((N - 1) * N + NS) * S] = av[0];
-      sm[((N - 1) * N + NS + 1) * S] = av[1];
-      sm[((N - 1) * N + NS + 2) * S] = av[2];
-      sm[((N - 1) * N + NS + 3) * S] = 0.0;
       rhs[N - 1] = vdotn;
-      lu_strided<N>(sm, S, smi, S);
-      lu_solve_strided<N>(sm, S, rhs, smi, S, scr);
+      wall_solve(E, qavg, av, rhs);
       for (int i = 0; i < N; i++) QR[i] = rhs[i];
       const double pgoal = QR[N - 1];
       QR[N - 1] = newton_T_given_P(p, QR, pgoal, Tguess);
@@ -616,7 +624,7 @@ __device__ __noinline__ void inviscid_wall_bc(const Params<NS>& p, const double*
 // CalculateBoundaryVariables (bc.tcc:1058-1397) for the BC types of the reacting configs; QL and QR are full rows
 template <int NS>
 __device__ __noinline__ void boundary_variables(const Params<NS>& p, double* QL, double* QR, const double* av, int bctype,
-                                                double betaL, double* sm, int* smi, int S) {
+                                                double betaL) {
   constexpr int N = NS + 4;
   const double vdotn = 0.0;   // static mesh
   switch (bctype) {
@@ -628,7 +636,7 @@ __device__ __noinline__ void boundary_variables(const Params<NS>& p, double* QL,
       farfield_bc(p, QL, QR, av, vdotn, betaL);
       break;
     case PCFD_BC_IMPERMEABLE_WALL: case PCFD_BC_SYMMETRY:
-      inviscid_wall_bc(p, QL, QR, av, vdotn, betaL, sm, smi, S);
+      inviscid_wall_bc(p, QL, QR, av, vdotn, betaL);
       break;
     default: break;
   }

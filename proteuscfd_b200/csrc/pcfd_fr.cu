@@ -65,10 +65,7 @@ __global__ void __launch_bounds__(64) kfr_update_bcs_edges(DevMesh m, fr::Params
   load_row<NS, NV>(q, lr.y, QR);
   load_avec(m.bea, be, av);
   if (!first) fr::aux(p, QL);
-  extern __shared__ __align__(16) unsigned char bc_smem[];
-  double* sm = reinterpret_cast<double*>(bc_smem) + threadIdx.x;
-  int* smi = reinterpret_cast<int*>(bc_smem + sizeof(double) * W<NS>::N2 * blockDim.x) + threadIdx.x;
-  fr::boundary_variables(p, QL, QR, av, m.bctype[be], beta[lr.x], sm, smi, (int)blockDim.x);
+  fr::boundary_variables(p, QL, QR, av, m.bctype[be], beta[lr.x]);
   double* qr = q + (size_t)lr.y * NV;
   for (int i = 0; i < NV; i++) qr[i] = QR[i];
   if (first) {
@@ -591,11 +588,7 @@ __global__ void __launch_bounds__(64) kfr_jac_bedges(DevMesh m, fr::Params<NS> p
   load_row<NS, NV>(q, r, QR);
   load_avec(m.bea, be, av);
   if (!first && type != PCFD_BC_PARALLEL) fr::aux(p, QL);
-  extern __shared__ __align__(16) unsigned char bc_smem[];
-  double* sm = reinterpret_cast<double*>(bc_smem) + threadIdx.x;
-  int* smi = reinterpret_cast<int*>(bc_smem + sizeof(double) * N2 * blockDim.x) + threadIdx.x;
-  const int S = (int)blockDim.x;
-  fr::boundary_variables(p, QL, QR, av, type, betaL, sm, smi, S);
+  fr::boundary_variables(p, QL, QR, av, type, betaL);
   if (type != PCFD_BC_PARALLEL) {
     double* qr = q + (size_t)r * NV;
     for (int i = 0; i < NV; i++) qr[i] = QR[i];
@@ -616,7 +609,7 @@ __global__ void __launch_bounds__(64) kfr_jac_bedges(DevMesh m, fr::Params<NS> p
     fr::numerical_flux(p, QL, QPR, av, 0.0, betaL, fR);
     if (!ghost) {
       for (int k = 0; k < NV; k++) QPR[k] = QR[k];
-      fr::boundary_variables(p, QPL, QPR, av, type, betaL, sm, smi, S);
+      fr::boundary_variables(p, QPL, QPR, av, type, betaL);
       fr::numerical_flux(p, QPL, QPR, av, 0.0, betaL, fL);
     } else {
       fr::numerical_flux(p, QPL, QR, av, 0.0, betaL, fL);
@@ -826,24 +819,10 @@ template <int NS>
 struct Impl {
   using Wd = W<NS>;
 
-  // per-thread scratch of the wall BC in shared memory: (NS+4)^2 doubles + NS+4 ints, interleaved over the block
-  static size_t bc_smem_bytes(int threads) { return (size_t)threads * (Wd::N2 * sizeof(double) + Wd::NEQ * sizeof(int)); }
-  static int bc_smem_optin() {
-    static bool done = false;
-    if (!done) {
-      if (cudaFuncSetAttribute(kfr_update_bcs_edges<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc_smem_bytes(64)) != cudaSuccess ||
-          cudaFuncSetAttribute(kfr_jac_bedges<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc_smem_bytes(64)) != cudaSuccess)
-        return 1;
-      done = true;
-    }
-    return 0;
-  }
-
   static int update_bcs(pcfd_ctx* c) {
     if (!c->nblist_bc) return 0;
-    if (bc_smem_optin()) return fail(c, "cudaFuncSetAttribute(shared memory) failed");
     PROF("kfr_update_bcs_edges");
-    kfr_update_bcs_edges<NS><<<nblk(c->nblist_bc, 64), 64, bc_smem_bytes(64), c->stream>>>(c->dm, make_params<NS>(c), c->blist, c->nblist_bc,
+    kfr_update_bcs_edges<NS><<<nblk(c->nblist_bc, 64), 64, 0, c->stream>>>(c->dm, make_params<NS>(c), c->blist, c->nblist_bc,
                                                                           c->bfirst, c->f[PCFD_F_BETA], c->f[PCFD_F_Q]);
     LAUNCH_CHECK();
     return 0;
@@ -978,9 +957,8 @@ struct Impl {
       LAUNCH_CHECK();
     }
     if (c->nblist) {
-      if (bc_smem_optin()) return fail(c, "cudaFuncSetAttribute(shared memory) failed");
-      PROF("kfr_jac_bedges");
-      kfr_jac_bedges<NS><<<nblk(c->nblist, 64), 64, bc_smem_bytes(64), c->stream>>>(c->dm, p, c->blist, c->nblist, c->bfirst, beta,
+        PROF("kfr_jac_bedges");
+      kfr_jac_bedges<NS><<<nblk(c->nblist, 64), 64, 0, c->stream>>>(c->dm, p, c->blist, c->nblist, c->bfirst, beta,
                                                                    c->f[PCFD_F_Q], c->bpos, c->bdiag, A);
       LAUNCH_CHECK();
     }
