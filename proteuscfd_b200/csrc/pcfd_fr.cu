@@ -15,6 +15,7 @@
 
 #include "pcfd_internal.cuh"
 #include "eqnset_fr.cuh"
+#include "sgs_tile.cuh"
 
 struct pcfd_fr_state {
   pcfd_fr_params host{};
@@ -992,6 +993,33 @@ struct Impl {
         for (size_t l = 0; l + 1 < off.size(); l++) {
           const int nr = off[l + 1] - off[l];
           const int warps = (nr + RPW - 1) / RPW;
+          const int cap = (dir ? c->tile_cap_b : c->tile_cap_f)[l];
+          if (cap > 0) {
+            // rows of the level are consecutive in memory (colour-sorted numbering): bulk-copy streamed tiles, 16 lanes
+            // per row (sgs_tile.cuh)
+            const int Wt = c->sgs_tile_warps;
+            const int RT = Wt * 2;
+            const int capA = (cap * Wd::N2 * 8 + 8 + 15) & ~15;
+            const size_t shm = 16 + (size_t)capA;
+            const int tiles = (nr + RT - 1) / RT;
+            const int pf = c->sgs_pf_dist >= 0 ? c->sgs_pf_dist : (int)((size_t)(24 << 20) / shm);
+            const int row0 = dir ? c->lev_first_b[l] : c->lev_first_f[l];
+            const int step = dir ? c->lev_step_b[l] : c->lev_step_f[l];
+            PROF("k_sgs_tile");
+#define PCFD_FR_TILE(WW)                                                                                               \
+  do {                                                                                                                 \
+    static size_t set_##WW = 0;                                                                                        \
+    if (shm > set_##WW) {                                                                                              \
+      CK(cudaFuncSetAttribute(k_sgs_tile_t<Wd::NEQ, WW, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));  \
+      set_##WW = shm;                                                                                                  \
+    }                                                                                                                  \
+    k_sgs_tile_t<Wd::NEQ, WW, 16><<<tiles, WW * 32, shm, c->stream>>>(row0, step, nr, c->ia, c->ja, A, c->pv, c->f[PCFD_F_B], x, pf); \
+  } while (0)
+            if (Wt == 1) PCFD_FR_TILE(1); else if (Wt == 4) PCFD_FR_TILE(4); else PCFD_FR_TILE(2);
+#undef PCFD_FR_TILE
+            LAUNCH_CHECK();
+            continue;
+          }
           PROF("kfr_sgs_level");
           kfr_sgs_level<NS, 2><<<nblk((long long)warps * 32, 128), 128, 0, c->stream>>>(rows + off[l], nr, c->ia, c->ja, c->iau, A,
                                                                                        c->pv, c->f[PCFD_F_B], x);
