@@ -388,6 +388,13 @@ def main():
     if not args.no_sgs and rank == 0 and world == 1:
         sgs = sgs_bench(args, ctx, mesh, params, q0, peak, torch, stream, local_rank)
 
+    # ---------------------------------------------------------------- SGS sweeps/s across ranks (N > 1)
+    if not args.no_sgs and world > 1:
+        try:
+            sgs = sgs_bench_multi(args, ctx, xch, rank, world, local_rank, peak, torch, dist, stream)
+        except Exception as e:
+            sgs = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     # ---------------------------------------------------------------- reacting eqnset (BASELINE configs[4] on one GPU)
     frb = None
     if not args.no_fr and rank == 0 and world == 1:
@@ -481,6 +488,102 @@ def sgs_bench(args, ctx, mesh, params, q0, peak, torch, stream, local_rank):
            "jacobian_ms": {k: tab0[k][0] / tab0[k][1] for k in ("k_jac_edges", "k_jac_bnodes", "k_jac_diag", "k_lu_diag") if k in tab0},
            "kernel": "k_sgs_tile (cp.async.bulk + mbarrier streamed tiles)" if "k_sgs_tile" in tab else "k_sgs_level",
            "launches_per_sweep": sum(tab[k][1] - tab0.get(k, (0, 0))[1] for k in ("k_sgs_level", "k_sgs_tile") if k in tab) / nsw}
+    c.close()
+    return out
+
+
+def sgs_bench_multi(args, ctx, xch, rank, world, local_rank, peak, torch, dist, stream):
+    """SGS sweeps/s and the implicit iteration on N partitions (BASELINE configs[2]/[3] layout): every rank holds one
+    z-slab with a colour-sorted numbering, its 5x5 block-CRS rows (ghost columns included) and runs the reference's
+    multi-rank solve: block-Jacobi across partitions, one halo exchange of x after every sweep (ucs/crs.tcc:88,146).
+    Times are the max over ranks; sweeps/s counts whole-domain sweeps, GB/s the bytes all ranks streamed."""
+    from proteuscfd_b200 import capi
+    from proteuscfd_b200.cases import slab_case
+    from proteuscfd_b200.parallel import DistributedHotPath, NcclExchange, PObj, PutExchange, TorchGroup
+    n = args.sgs_n or args.n
+    if hasattr(xch, "close"):
+        xch.close()
+    ctx.close()
+    torch.cuda.empty_cache()
+    dev = torch.device("cuda", local_rank)
+    mesh, params, q = slab_case(n, rank, world, cfl=5.0, colored=True, device=f"cuda:{local_rank}")
+    c = capi.Context(mesh, params, device=local_rank)
+    c.set_stream(stream.cuda_stream)
+    group = TorchGroup(dist)
+    pobj = PObj(rank, world).BuildCommMaps(mesh["gNodeOwner"], mesh["gNodeLocalId"], group)
+    x = PutExchange(c, pobj, dist, torch, dev, group) if args.halo == "put" else NcclExchange(c, pobj, dist, torch, dev)
+    hitflag = torch.zeros(1, device=dev, dtype=torch.int32)
+
+    def any_rank(hit):
+        hitflag.fill_(int(hit))
+        dist.all_reduce(hitflag, op=dist.ReduceOp.MAX)
+        return bool(hitflag.item())
+
+    hp = DistributedHotPath(c, x, any_rank=any_rank)
+    hp.setup()
+    c.set_field(capi.F_Q, q)
+    hp.implicit_iterate(2, refresh_jac=True)      # builds A and its LU; warm-up
+
+    def sync():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxms(ms):
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def total(v):
+        t = torch.tensor([v], device=dev, dtype=torch.int64)
+        dist.all_reduce(t)
+        return int(t.item())
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    c.blank_x()
+    x.update(capi.F_X)
+    for _ in range(2):
+        c.sgs(1, want_ddq=False)
+        x.update(capi.F_X)
+    nsw = 10
+    sync()
+    e0, e1 = ev(), ev()
+    e0.record(stream)
+    for _ in range(nsw):
+        c.sgs(1, want_ddq=False)
+        x.update(capi.F_X)
+    e1.record(stream)
+    sync()
+    ms = maxms(e0.elapsed_time(e1) / nsw)
+    nsgs_it, reps = 5, 5
+    c.set_field(capi.F_Q, q)
+    hp.implicit_iterate(nsgs_it, refresh_jac=False)
+    sync()
+    e2, e3 = ev(), ev()
+    e2.record(stream)
+    for _ in range(reps):
+        hp.implicit_iterate(nsgs_it, refresh_jac=False)
+    e3.record(stream)
+    sync()
+    ms_it = maxms(e2.elapsed_time(e3) / reps)
+    nblocks = int(c.get_crs()[1].size)
+    pbs = pass_bytes(c.nedge + c.ngedge, c.nnode + c.gnode, nblocks)
+    bytes_sweep = total(pass_bytes(c.nedge, c.nnode, nblocks)["sgs_sweep"])
+    bytes_it = total(pbs["gradient"] + pbs["limiter"] + pbs["residual"]) + nsgs_it * bytes_sweep
+    nn_g, nb_g = total(c.nnode), total(nblocks)
+    ne_g = total(2 * c.nedge + c.ngedge) // 2
+    out = {"sweeps_per_s": 1e3 / ms, "ms_per_sweep": ms, "nodes": nn_g, "blocks": nb_g, "block": "5x5", "n_gpus": world,
+           "what": f"one sweep = forward + backward over every partition + halo exchange of x ('{args.halo}'); block-Jacobi "
+                   "across partitions as in the reference",
+           "algorithmic_bytes_per_sweep": bytes_sweep, "GBps": bytes_sweep / (ms * 1e-3) / 1e9,
+           "frac_hbm": bytes_sweep / (ms * 1e-3) / 1e9 / (peak * world),
+           "implicit_iteration": {"what": f"UpdateBCs + gradient + limiter + residual + {nsgs_it} SGS sweeps + ApplyDQ with the "
+                                          "reference's halo exchanges, Jacobian kept",
+                                  "ms": ms_it, "Medges_s": ne_g / (ms_it * 1e-3) / 1e6, "algorithmic_bytes": bytes_it,
+                                  "GBps": bytes_it / (ms_it * 1e-3) / 1e9,
+                                  "frac_hbm": bytes_it / (ms_it * 1e-3) / 1e9 / (peak * world),
+                                  "clip_fallbacks": hp.clip_fallbacks}}
+    if hasattr(x, "close"):
+        x.close()
     c.close()
     return out
 
