@@ -78,10 +78,17 @@ int main(int argc, char* argv[])
       HDF_WriteScalar(h5, dir, "NASA7_burcat_coeff15", &hf);
       HDF_WriteArray(h5, dir, "NASA7_burcat1", lo, 7);
       HDF_WriteArray(h5, dir, "NASA7_burcat2", hi, 7);
-      // transport fits are not on the source-term path; any well-formed table will do
-      Real tr[12] = {200.0, 1000.0, 0.6, -20.0, 200.0, 1.5, 1000.0, 5000.0, 0.65, -30.0, 900.0, 1.0};
-      HDF_WriteArray(h5, dir, "k", tr, 2, 6);
-      HDF_WriteArray(h5, dir, "mu", tr, 2, 6);
+      // NASA RP-1311 transport fits (rows of [Tlo, Thi, A, B, C, D]) from the reference's chemdata/trans.inp
+      int nk = 0, nmu = 0;
+      Real kfit[18], mufit[18];
+      fin >> nk;
+      if(nk < 1 || nk > 3){ std::cerr << "bad conductivity table for " << sym << std::endl; return 2; }
+      for(int i = 0; i < nk*6; i++) fin >> kfit[i];
+      fin >> nmu;
+      if(nmu < 1 || nmu > 3){ std::cerr << "bad viscosity table for " << sym << std::endl; return 2; }
+      for(int i = 0; i < nmu*6; i++) fin >> mufit[i];
+      HDF_WriteArray(h5, dir, "k", kfit, nk, 6);
+      HDF_WriteArray(h5, dir, "mu", mufit, nmu, 6);
     }
     HDF_CloseFile(h5);
   }

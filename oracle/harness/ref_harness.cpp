@@ -236,6 +236,7 @@ static void DumpMesh(SolutionSpace<Real>* space)
   f << "ref_pressure " << param->ref_pressure << "\nref_time " << param->ref_time << "\n";
   f << "ref_length " << param->ref_length << "\nref_specific_enthalpy " << param->ref_specific_enthalpy << "\n";
   f << "rxnOn " << param->rxnOn << "\ngravity_on " << param->gravity_on << "\n";
+  f << "ref_viscosity " << param->ref_viscosity << "\nref_k " << param->ref_k << "\n";
   if(param->eqnset_id == CompressibleEulerFR || param->eqnset_id == CompressibleNSFR){
     CompressibleFREqnSet<Real>* fr = dynamic_cast<CompressibleFREqnSet<Real>*>(eqnset);
     f << "nspecies " << fr->nspecies << "\nPref " << fr->Pref << "\n";
@@ -258,6 +259,26 @@ static void DumpMesh(SolutionSpace<Real>* space)
     Dump("species_mw", mw.data(), mw.size());
     Dump("species_R", Rs.data(), Rs.size());
     Dump("species_nasa7", coeff.data(), coeff.size());
+    {
+      // transport data as Species holds it (species.h:35-49): Sutherland coefficients below the transition
+      // temperature, NASA RP-1311 fits [Tlo, Thi, A, B, C, D] above (up to 3 ranges, unused rows zero)
+      std::vector<Real> mufit(ns*18, 0.0), kfit(ns*18, 0.0), white(ns*8);
+      std::vector<Int> counts(ns*2);
+      for(Int i = 0; i < ns; i++){
+	Species<Real>& sp = chem.species[i];
+	counts[2*i] = sp.mu_coeff_curves;
+	counts[2*i+1] = sp.k_coeff_curves;
+	for(Int r = 0; r < sp.mu_coeff_curves; r++) for(Int k = 0; k < 6; k++) mufit[i*18 + r*6 + k] = sp.mu_coeff[r][k];
+	for(Int r = 0; r < sp.k_coeff_curves; r++) for(Int k = 0; k < 6; k++) kfit[i*18 + r*6 + k] = sp.k_coeff[r][k];
+	for(Int k = 0; k < 3; k++){ white[i*8 + k] = sp.mu_coeff_White[k]; white[i*8 + 4 + k] = sp.k_coeff_White[k]; }
+	white[i*8 + 3] = sp.mu_transition_White;
+	white[i*8 + 7] = sp.k_transition_White;
+      }
+      Dump("species_mu_fit", mufit.data(), mufit.size());
+      Dump("species_k_fit", kfit.data(), kfit.size());
+      Dump("species_white", white.data(), white.size());
+      Dump("species_fit_counts", counts.data(), counts.size());
+    }
     std::vector<Real> rk(nr*3), nup(nr*ns, 0.0), nupp(nr*ns, 0.0), tbeff(nr*ns, 1.0);
     std::vector<Int> flags(nr*4), order(nr*ns, -1);
     for(Int j = 0; j < nr; j++){

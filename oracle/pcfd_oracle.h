@@ -141,6 +141,14 @@ void orc_chem_source_term(const orc_chem_model* m, int n, int stride, const doub
 /* ---- reacting eqnset (CompressibleFREqnSet, compressibleFR.tcc), oracle/pcfd_oracle_fr.c.  The mesh, chi, cfl,
    limiter, sorder, no_cvbc and the VNN fields of orc_case are used; gamma and qinf[10] are not.  ns = nspecies:
    neqn = ns+4, nvars = 3ns+6 [rho_i | u v w | T | P | rho | cv_i | mol_i], nterms = 2ns+4. */
+/* species transport data as Species holds it (species.h:35-49, species.tcc:13-22, 241-310): Sutherland law below the
+   transition temperature (White), NASA RP-1311 fits [Tlo, Thi, A, B, C, D] above */
+typedef struct {
+  int nmu[ORC_CHEM_MAX_SPECIES], nk[ORC_CHEM_MAX_SPECIES];
+  double mu_fit[ORC_CHEM_MAX_SPECIES][3][6], k_fit[ORC_CHEM_MAX_SPECIES][3][6];
+  double mu_white[ORC_CHEM_MAX_SPECIES][4], k_white[ORC_CHEM_MAX_SPECIES][4];   /* ref value, T0, S, transition T */
+} orc_transport;
+
 typedef struct {
   const orc_chem_model* chem;
   double ref_density, ref_velocity, ref_temperature, ref_pressure, ref_time, ref_specific_enthalpy;  /* param.tcc:352-398 */
@@ -149,7 +157,19 @@ typedef struct {
   int use_local_dt;        /* Param::useLocalTimeStepping */
   int rxn_on;              /* Param::rxnOn */
   double qinf[3*ORC_CHEM_MAX_SPECIES + 6];
+  /* compressibleNSFR (orc_case.viscous, Re, PrT, mut are used as for compressibleNS) */
+  const orc_transport* transport;   /* NULL unless viscous */
+  double ref_viscosity, ref_k;      /* param.tcc:210-211 */
 } orc_fr_params;
+
+/* ChemModel::GetViscosity / GetThermalConductivity (chem.tcc:876-938): Wilke-mixed, dimensional (rhoi kg/m^3, T K) */
+double orc_fr_mixture_viscosity(const orc_fr_params* p, const double* rhoi, double T);
+double orc_fr_mixture_conductivity(const orc_fr_params* p, const double* rhoi, double T);
+/* CompressibleFREqnSet::ViscousFlux (compressibleFR.tcc:551-637) and ViscousJacobian (:1713-2040); Q, QL, QR full states */
+void orc_fr_viscous_flux(const orc_case* c, const orc_fr_params* p, const double* Q, const double* grad, const double* avec,
+			 double mut, double* flux);
+void orc_fr_viscous_jacobian(const orc_case* c, const orc_fr_params* p, const double* QL, const double* QR, const double* dx,
+			     double s2, const double* avec, double mut, double* aL, double* aR);
 
 void orc_fr_update_bcs(const orc_case* c, const orc_fr_params* p, double* q, const double* beta);
 void orc_fr_gradient(const orc_case* c, const orc_fr_params* p, const double* q, const double* sw, double* qgrad);

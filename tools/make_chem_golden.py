@@ -33,6 +33,32 @@ def nasa7_record(lines, i):
     return mw, hf298_over_R, low, high
 
 
+def transport_fits(sym):
+    """NASA RP-1311 viscosity (V) and conductivity (C) fits [Tlo, Thi, A, B, C, D] of a pure species from the reference's
+    chemdata/trans.inp (the tables its chemDB.py stores as /species/<sym>/mu and /species/<sym>/k)."""
+    lines = open(os.path.join(REFERENCE, "chemdata", "trans.inp"), errors="replace").read().splitlines()
+    for i, ln in enumerate(lines):
+        if ln[:16].strip() == sym and ln[16:32].strip() == "" and ln[32:36].strip().startswith("V"):
+            tag = ln[34:38]
+            nv, nc = int(tag[1]), int(tag[3])
+            mu, k = [], []
+            for l in lines[i + 1: i + 1 + nv + nc]:
+                row = [float(l[2:9]), float(l[9:19])] + [float(l[20 + 15 * j: 35 + 15 * j].replace("E ", "E+")) for j in range(4)]
+                (mu if l[1] == "V" else k).append(row)
+            return mu, k
+    raise RuntimeError(f"no transport record for {sym}")
+
+
+def write_species_table(path, tab):
+    """One line per species: symbol MW hf298/R low[7] high[7] nk k[nk][6] nmu mu[nmu][6] (read by oracle/harness/ref_chem.cpp)."""
+    with open(path, "w") as f:
+        for s, mw, hf, low, high in tab:
+            mu, k = transport_fits(s)
+            f.write(f"{s} {mw!r} {hf!r} " + " ".join(repr(v) for v in low) + " " + " ".join(repr(v) for v in high))
+            f.write(f" {len(k)} " + " ".join(repr(v) for row in k for v in row))
+            f.write(f" {len(mu)} " + " ".join(repr(v) for row in mu for v in row) + "\n")
+
+
 def species_table():
     lines = open(os.path.join(REFERENCE, "chemdata", "BURCAT_FIXED.THR"), errors="replace").read().splitlines()
     out = []
@@ -61,9 +87,7 @@ def main():
     T[:8] = [1000.0, 1000.0000001, 999.9999999, 200.5, 5999.0, 3000.0, 2000.0, 4000.0]
     states = np.concatenate([rho[:, None] * Y, T[:, None]], axis=1)
     work = tempfile.mkdtemp(prefix="pcfd_chem_")
-    with open(os.path.join(work, "species.txt"), "w") as f:
-        for s, mw, hf, low, high in tab:
-            f.write(f"{s} {mw!r} {hf!r} " + " ".join(repr(v) for v in low) + " " + " ".join(repr(v) for v in high) + "\n")
+    write_species_table(os.path.join(work, "species.txt"), tab)
     out = os.path.join(work, "out")
     # the model orders its species by first appearance in the reactions, not by the speciesInModel list: ask it
     np.zeros(0).tofile(os.path.join(work, "states.bin"))

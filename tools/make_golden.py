@@ -67,7 +67,7 @@ massFractions = [0.20, 0.02, 0.01, 0.75, 0.02]
 reactionsOn = {rxn}
 """
 
-INT_ARRAYS = {"rxn_flags", "rxn_species", "chem_dims", "edges_n", "bedges_n", "bedges_factag", "bedges_bctype", "ipsp", "psp", "gNodeOwner",
+INT_ARRAYS = {"species_fit_counts", "rxn_flags", "rxn_species", "chem_dims", "edges_n", "bedges_n", "bedges_factag", "bedges_bctype", "ipsp", "psp", "gNodeOwner",
               "gNodeLocalId", "commCountsSend", "commCountsRecv", "commOffsetsRecv", "nodePackingList",
               "ia", "ja", "iau", "pv"}
 
@@ -172,9 +172,7 @@ def fr_inputs(work, name):
     reference's HDF layer from the NASA-7 records of the reference's chemdata/BURCAT_FIXED.THR)."""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import make_chem_golden as mc
-    with open(os.path.join(work, "species.txt"), "w") as f:
-        for s, mw, hf, low, high in mc.species_table():
-            f.write(f"{s} {mw!r} {hf!r} " + " ".join(repr(v) for v in low) + " " + " ".join(repr(v) for v in high) + "\n")
+    mc.write_species_table(os.path.join(work, "species.txt"), mc.species_table())
     np.zeros(0).tofile(os.path.join(work, "states.bin"))
     run([os.path.join(REFBIN, "ref_chem"), os.path.join(REFERENCE, "chemModels", "5speciesAir"),
          os.path.join(work, "species.txt"), os.path.join(work, "states.bin"), os.path.join(work, "chemout")], work)
@@ -234,6 +232,13 @@ CASES = {
                                           cfl=0.05, extra=FR_EXTRA.format(temp=2500, pres=2000, rxn=1)),
     "box4_fr_implicit": lambda: make_case("box4_fr_implicit", mesh=kuhn_box(4, jitter=0.15), eqnset="compressibleEulerFR",
                                           nsgs=3, cfl=5.0, extra=FR_EXTRA.format(temp=3000, pres=101325, rxn=1)),
+    # the viscous reacting eqnset (compressibleNSFR): Wilke-mixed species transport (Sutherland below 1000 K, NASA
+    # RP-1311 fits of the reference's chemdata/trans.inp above), viscous flux + analytic viscous Jacobian, implicit;
+    # T_inf = 900 K with a +-10 % field so both transport branches are hit
+    "box4_nsfr_implicit": lambda: make_case("box4_nsfr_implicit", mesh=kuhn_box(4, jitter=0.15), eqnset="compressibleNSFR",
+                                            nsgs=3, cfl=5.0, refvisc=2.0e-4,   # Re = 111 (refLength 1 cm, 2 kPa)
+                                            extra=FR_EXTRA.format(temp=950, pres=2000, rxn=1)
+                                            + "refThermalConductivity = 0.05\nrefLength = 0.01\n"),
     # the reference's own unit-test fixture (unitTest/gradientTest.h:20-232): prism cube, 216 nodes
     "cube_LowFi": lambda: make_case(
         "cube_LowFi", h5=os.path.join(REFERENCE, "unitTest/meshResources/cubeStructuredSeries/cube_LowFi.0.h5"),
