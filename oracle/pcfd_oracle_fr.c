@@ -21,6 +21,7 @@
 #define MAXS ORC_CHEM_MAX_SPECIES
 #define MAXE (MAXS + 4)
 #define MAXV (3*MAXS + 6)
+#define MAXT (2*MAXS + 4)
 #define UNIV_R 8.31447215   /* chem_constants.h:5 */
 
 static double MAXD(double x, double y){ return (x > y) ? x : y; }
@@ -763,6 +764,280 @@ void orc_fr_limiter(const orc_case* c, const orc_fr_params* p, const double* q, 
   free(qmin); free(qmax);
 }
 
+/* ------------------------------------------------------------- transport + viscous terms (compressibleNSFR) */
+
+static double chem_dRmixdRhoi(const orc_fr_params* p, const double* rhoi, double rho, int i);
+
+/* Species::GetViscosity / GetThermalConductivity species.tcc:393-479: Sutherland (White) up to the transition
+   temperature, NASA RP-1311 fit above; the range search keeps the LAST range containing T (no break) */
+static double sp_transport(const double white[4], const double fit[3][6], int nfit, double T, double convFact)
+{
+  int i, range = -1;
+  if(T <= white[3]){
+    double v0 = white[0], T0 = white[1], S = white[2];
+    return v0*(pow(T/T0, 1.5))*((T0 + S)/(T + S));
+  }
+  for(i = 0; i < nfit; i++){
+    if(T >= fit[i][0] && T <= fit[i][1]) range = i;
+  }
+  if(range == -1) return NAN;      /* the reference aborts */
+  {
+    double A = fit[range][2], B = fit[range][3], Cc = fit[range][4], D = fit[range][5];
+    double logv = A*log(T) + B/T + Cc/(T*T) + D;
+    return exp(logv)*convFact;
+  }
+}
+static double sp_visc(const orc_fr_params* p, int i, double T)
+{ return sp_transport(p->transport->mu_white[i], p->transport->mu_fit[i], p->transport->nmu[i], T, 1.0e-7); }
+static double sp_cond(const orc_fr_params* p, int i, double T)
+{ return sp_transport(p->transport->k_white[i], p->transport->k_fit[i], p->transport->nk[i], T, 0.0001); }
+
+/* ChemModel::WilkesMixtureRule chem.tcc:876-916 with MassFractionToMoleFraction :941-958.  Note the species
+   VISCOSITIES weight the mixing of either property. */
+static double wilke(const orc_fr_params* p, const double* rhoi, const double* property, double T)
+{
+  int i, j, ns = p->chem->nspecies;
+  double mixtureProp = 0.0, sqrt8 = sqrt(8.0), rho = 0.0, summ = 0.0;
+  double massfrac[MAXS], molefrac[MAXS], visc[MAXS];
+  for(i = 0; i < ns; i++) rho += rhoi[i];
+  for(i = 0; i < ns; i++) massfrac[i] = rhoi[i]/rho;
+  for(i = 0; i < ns; i++){
+    molefrac[i] = (massfrac[i])/p->chem->mw[i];
+    summ += molefrac[i];
+  }
+  for(i = 0; i < ns; i++) molefrac[i] /= summ;
+  summ = 0.0;
+  for(i = 0; i < ns - 1; i++) summ += molefrac[i];
+  molefrac[ns-1] = 1.0 - summ;
+  for(i = 0; i < ns; i++) visc[i] = sp_visc(p, i, T);
+  for(i = 0; i < ns; i++){
+    double wi = 0.0, fraci = molefrac[i], MWi = p->chem->mw[i];
+    for(j = 0; j < ns; j++){
+      double fracj = molefrac[j], MWj = p->chem->mw[j];
+      double temp = (1.0 + sqrt(visc[i]/visc[j])*pow(MWj/MWi, 0.25));
+      double phi = pow((1.0 + MWi/MWj), -0.5)*temp*temp/sqrt8;
+      wi += fracj*phi;
+    }
+    mixtureProp += (fraci/wi)*property[i];
+  }
+  return mixtureProp;
+}
+
+double orc_fr_mixture_viscosity(const orc_fr_params* p, const double* rhoi, double T)
+{
+  int i, ns = p->chem->nspecies;
+  double visc[MAXS];
+  for(i = 0; i < ns; i++) visc[i] = sp_visc(p, i, T);
+  return wilke(p, rhoi, visc, T);
+}
+
+double orc_fr_mixture_conductivity(const orc_fr_params* p, const double* rhoi, double T)
+{
+  int i, ns = p->chem->nspecies;
+  double k[MAXS];
+  for(i = 0; i < ns; i++) k[i] = sp_cond(p, i, T);
+  return wilke(p, rhoi, k, T);
+}
+
+/* CompressibleFREqnSet::GetMolecularViscosity / GetThermalConductivity compressibleFR.tcc:1580-1599 */
+static double fr_molecular_viscosity(const orc_fr_params* p, const double* rhoi, double T)
+{
+  int i, ns = p->chem->nspecies;
+  double rhoidim[MAXS];
+  for(i = 0; i < ns; i++) rhoidim[i] = rhoi[i]*p->ref_density;
+  return orc_fr_mixture_viscosity(p, rhoidim, T*p->ref_temperature)/p->ref_viscosity;
+}
+static double fr_thermal_conductivity(const orc_fr_params* p, const double* rhoi, double T)
+{
+  int i, ns = p->chem->nspecies;
+  double rhoidim[MAXS];
+  for(i = 0; i < ns; i++) rhoidim[i] = rhoi[i]*p->ref_density;
+  return orc_fr_mixture_conductivity(p, rhoidim, T*p->ref_temperature)/p->ref_k;
+}
+
+/* CompressibleFREqnSet::ViscousFlux compressibleFR.tcc:551-637 (symmetry2D off) */
+void orc_fr_viscous_flux(const orc_case* c, const orc_fr_params* p, const double* Q, const double* grad, const double* avec,
+			 double mut, double* flux)
+{
+  int i, ns = p->chem->nspecies, offset = ns*3;
+  double ux = grad[offset + 0], uy = grad[offset + 1], uz = grad[offset + 2];
+  double vx = grad[offset + 3], vy = grad[offset + 4], vz = grad[offset + 5];
+  double wx = grad[offset + 6], wy = grad[offset + 7], wz = grad[offset + 8];
+  double Tx = grad[offset + 9], Ty = grad[offset + 10], Tz = grad[offset + 11];
+  double u = Q[ns], v = Q[ns+1], w = Q[ns+2];
+  const double* rhoi = &Q[0];
+  double T = Q[ns+3];
+  double cv, cp, R, gamma, c2;
+  double mu, tmut, fact = 2.0/3.0, tauxx, tauyy, tauzz, tauxy, tauxz, tauyz, tauxn, tauyn, tauzn;
+  double Re = c->Re, RK, RKT, k, Tn, kT;
+  fr_fluid_props(p, rhoi, T, &cv, &cp, &R, &gamma, &c2);
+  mu = fr_molecular_viscosity(p, rhoi, T);
+  tmut = (mu + mut);
+  tauxx = 2.0*fact*ux - fact*vy - fact*wz;
+  tauyy = 2.0*fact*vy - fact*ux - fact*wz;
+  tauzz = 2.0*fact*wz - fact*ux - fact*vy;
+  tauxy = uy + vx;
+  tauxz = uz + wx;
+  tauyz = vz + wy;
+  RK = avec[3]/Re;
+  RKT = RK*tmut;
+  k = -fr_thermal_conductivity(p, rhoi, T);
+  Tn = Tx*avec[0] + Ty*avec[1] + Tz*avec[2];
+  kT = (cp*mut)/c->PrT;
+  k -= kT;
+  tauxn = -tauxx*avec[0] - tauxy*avec[1] - tauxz*avec[2];
+  tauyn = -tauxy*avec[0] - tauyy*avec[1] - tauyz*avec[2];
+  tauzn = -tauxz*avec[0] - tauyz*avec[1] - tauzz*avec[2];
+  for(i = 0; i < ns; i++) flux[i] = 0.0;
+  flux[ns+0] = RKT*(tauxn);
+  flux[ns+1] = RKT*(tauyn);
+  flux[ns+2] = RKT*(tauzn);
+  flux[ns+3] = RKT*(tauxn*u + tauyn*v + tauzn*w) + RK*k*Tn;
+}
+
+/* one side of CompressibleFREqnSet::ViscousJacobian (compressibleFR.tcc:1796-1960 right, :1963-2010 left): D = -/+dx/s2 */
+static void fr_viscous_jac_side(const orc_fr_params* p, const double* D, const double* Qs, double u, double v, double w,
+				const double* avec, double RK, double RKT, double c1, double* a)
+{
+  int i, j, ns = p->chem->nspecies, neqn = ns + 4;
+  const double* rhois = &Qs[0];
+  double rhos = Qs[ns+5], us = Qs[ns], vs = Qs[ns+1], ws = Qs[ns+2], Ps = Qs[ns+4], Ts = Qs[ns+3];
+  double cvs, cps, Rs, gammas, c2s;
+  double Drho[3];
+  double dux, duy, duz, dvx, dvy, dvz, dwx, dwy, dwz, dfact, dtauxx, dtauyy, dtauzz, dtauxy, dtauxz, dtauyz;
+  double dtauxn, dtauyn, dtauzn, c43 = 4.0/3.0, mc23 = -2.0/3.0;
+  double dR2_drhou, dR2_drhov, dR2_drhow, dR3_drhou, dR3_drhov, dR3_drhow, dR4_drhou, dR4_drhov, dR4_drhow;
+  double dT_dP, dTdRhoi[MAXS], rhoidim[MAXS], dP_dru, dP_drv, dP_drw, dP_dret, Tn;
+  double* row;
+  fr_fluid_props(p, rhois, Ts, &cvs, &cps, &Rs, &gammas, &c2s);
+  for(i = 0; i < 3; i++) Drho[i] = D[i]/rhos;
+  dux = -u*Drho[0]; duy = -u*Drho[1]; duz = -u*Drho[2];
+  dvx = -v*Drho[0]; dvy = -v*Drho[1]; dvz = -v*Drho[2];
+  dwx = -w*Drho[0]; dwy = -w*Drho[1]; dwz = -w*Drho[2];
+  dfact = -2.0/3.0*(dux + dvy + dwz);
+  dtauxx = (2.0*dux + dfact);
+  dtauyy = (2.0*dvy + dfact);
+  dtauzz = (2.0*dwz + dfact);
+  dtauxy = duy + dvx;
+  dtauxz = duz + dwx;
+  dtauyz = dvz + dwy;
+  dtauxn = dtauxx*avec[0] + dtauxy*avec[1] + dtauxz*avec[2];
+  dtauyn = dtauxy*avec[0] + dtauyy*avec[1] + dtauyz*avec[2];
+  dtauzn = dtauxz*avec[0] + dtauyz*avec[1] + dtauzz*avec[2];
+  for(i = 0; i < ns; i++){
+    row = &a[i*neqn];
+    for(j = 0; j < neqn; j++) row[j] = 0.0;
+  }
+  row = &a[ns*neqn];
+  dR2_drhou = (c43*Drho[0]*avec[0] + Drho[1]*avec[1] + Drho[2]*avec[2]);
+  dR2_drhov = (mc23*Drho[1]*avec[0] + Drho[0]*avec[1]);
+  dR2_drhow = (mc23*Drho[2]*avec[0] + Drho[0]*avec[2]);
+  for(i = 0; i < ns; i++) row[i] = -RKT*(dtauxn);
+  row[ns+0] = -RKT*dR2_drhou;
+  row[ns+1] = -RKT*dR2_drhov;
+  row[ns+2] = -RKT*dR2_drhow;
+  row[ns+3] = 0.0;
+  row = &a[(ns+1)*neqn];
+  dR3_drhou = (mc23*Drho[0]*avec[1] + Drho[1]*avec[0]);
+  dR3_drhov = (Drho[0]*avec[0] + c43*Drho[1]*avec[1] + Drho[2]*avec[2]);
+  dR3_drhow = (mc23*Drho[2]*avec[1] + Drho[1]*avec[2]);
+  for(i = 0; i < ns; i++) row[i] = -RKT*(dtauyn);
+  row[ns+0] = -RKT*dR3_drhou;
+  row[ns+1] = -RKT*dR3_drhov;
+  row[ns+2] = -RKT*dR3_drhow;
+  row[ns+3] = 0.0;
+  row = &a[(ns+2)*neqn];
+  dR4_drhou = (mc23*Drho[0]*avec[2] + Drho[2]*avec[0]);
+  dR4_drhov = (mc23*Drho[1]*avec[2] + Drho[2]*avec[1]);
+  dR4_drhow = (Drho[0]*avec[0] + Drho[1]*avec[1] + c43*Drho[2]*avec[2]);
+  for(i = 0; i < ns; i++) row[i] = -RKT*(dtauzn);
+  row[ns+0] = -RKT*dR4_drhou;
+  row[ns+1] = -RKT*dR4_drhov;
+  row[ns+2] = -RKT*dR4_drhow;
+  row[ns+3] = 0.0;
+  /* IdealGasEOS::GetdT_dP EOS.tcc:42-45; ChemModel::dTdRhoi chem.tcc:687-704 on dimensional densities / pressure */
+  dT_dP = (1.0/(rhos*Rs));
+  {
+    double rho = 0.0, Rmix = 0.0, Pdim = Ps*p->ref_pressure, Td, dTdRho, dTdR;
+    for(i = 0; i < ns; i++) rhoidim[i] = Qs[i]*p->ref_density;
+    for(i = 0; i < ns; i++){
+      rho += rhoidim[i];
+      Rmix += rhoidim[i]*sp_R(p, i);
+    }
+    Rmix /= rho;
+    Td = Pdim/(rho*Rmix);
+    (void)Td;
+    dTdRho = (-Pdim/(Rmix*rho*rho));
+    dTdR = (-Pdim/(rho*Rmix*Rmix));
+    for(i = 0; i < ns; i++) dTdRhoi[i] = dTdR*chem_dRmixdRhoi(p, rhoidim, rho, i) + dTdRho;
+  }
+  dP_dru = Rs/cvs*us;
+  dP_drv = Rs/cvs*vs;
+  dP_drw = Rs/cvs*ws;
+  dP_dret = Rs/cvs;
+  Tn = (D[0]*avec[0] + D[1]*avec[1] + D[2]*avec[2])*c1;
+  row = &a[(ns+3)*neqn];
+  for(i = 0; i < ns; i++){
+    double dT_drho = dTdRhoi[i]/(p->ref_temperature/p->ref_density);
+    row[i] = -RKT*(dtauxn*u + dtauyn*v + dtauzn*w) + RK*Tn*dT_drho;
+  }
+  row[ns+0] = -RKT*(dR2_drhou*u + dR3_drhou*v + dR4_drhou*w) + RK*Tn*dT_dP*dP_dru;
+  row[ns+1] = -RKT*(dR2_drhov*u + dR3_drhov*v + dR4_drhov*w) + RK*Tn*dT_dP*dP_drv;
+  row[ns+2] = -RKT*(dR2_drhow*u + dR3_drhow*v + dR4_drhow*w) + RK*Tn*dT_dP*dP_drw;
+  row[ns+3] =                                                  RK*Tn*dT_dP*dP_dret;
+}
+
+/* CompressibleFREqnSet::ViscousJacobian compressibleFR.tcc:1713-2040 */
+void orc_fr_viscous_jacobian(const orc_case* c, const orc_fr_params* p, const double* QL, const double* QR, const double* dx,
+			     double s2, const double* avec, double mut, double* aL, double* aR)
+{
+  int i, ns = p->chem->nspecies, neqn = ns + 4;
+  double Q[MAXV], DxL[3], DxR[3];
+  double T, mu, tmut, RK, RKT, cv, cp, R, gamma, c2, u, v, w, k, kT, c1;
+  for(i = 0; i < neqn; i++) Q[i] = 0.5*(QL[i] + QR[i]);
+  fr_aux(p, Q);
+  T = Q[ns+3];
+  mu = fr_molecular_viscosity(p, Q, T);
+  tmut = (mu + mut);
+  RK = avec[3]/c->Re;
+  RKT = RK*tmut;
+  fr_fluid_props(p, Q, T, &cv, &cp, &R, &gamma, &c2);
+  u = 0.5*(QL[ns] + QR[ns]);
+  v = 0.5*(QL[ns+1] + QR[ns+1]);
+  w = 0.5*(QL[ns+2] + QR[ns+2]);
+  for(i = 0; i < 3; i++){
+    DxL[i] = -dx[i]/s2;
+    DxR[i] = dx[i]/s2;
+  }
+  k = fr_thermal_conductivity(p, Q, T);
+  kT = mut/c->PrT*cp;
+  c1 = -(k + kT);
+  fr_viscous_jac_side(p, DxR, QR, u, v, w, avec, RK, RKT, c1, aR);
+  fr_viscous_jac_side(p, DxL, QL, u, v, w, avec, RK, RKT, c1, aL);
+  for(i = 0; i < neqn*neqn; i++) aL[i] = -aL[i];
+}
+
+/* the face gradient of Kernel_Viscous_Flux residual.tcc:430-452 for nterms gradient terms */
+static void fr_face_gradient(const orc_case* c, int ns, const double* qL, const double* qR, const double* gradL,
+			     const double* gradR, const double* xL, const double* xR, double* grad)
+{
+  int i, j, nterms = 2*ns + 4;
+  for(i = 0; i < nterms*3; i++) grad[i] = 0.5*(gradL[i] + gradR[i]);
+  if(c->sorder > 1){
+    double dx[3], s2 = 0.0;
+    for(i = 0; i < 3; i++){
+      dx[i] = (xR[i] - xL[i]);
+      s2 += dx[i]*dx[i];
+    }
+    for(j = 0; j < nterms; j++){
+      double qdots = dx[0]*grad[j*3] + dx[1]*grad[j*3+1] + dx[2]*grad[j*3+2];
+      int loc = fr_gradloc(ns, j);
+      double dq = (qR[loc] - qL[loc] - qdots)/s2;
+      for(i = 0; i < 3; i++) grad[j*3 + i] += dq*dx[i];
+    }
+  }
+}
+
 /* ------------------------------------------------------------- residual */
 
 /* SourceTerm compressibleFR.tcc:1276-1316 (gravity off) */
@@ -830,6 +1105,41 @@ void orc_fr_residual(const orc_case* c, const orc_fr_params* p, const double* q,
     }
     fr_numerical_flux(p, QL, QR, avec, 0.0, flux, beta[l]);
     for(i = 0; i < neqn; i++) b[(size_t)l*neqn + i] += -flux[i];
+  }
+  if(c->viscous){
+    /* Kernel_Viscous_Flux residual.tcc:390-466 */
+    for(e = 0; e < c->nedge; e++){
+      int l = c->edges_n[2*e], r = c->edges_n[2*e+1];
+      const double* qL = &q[(size_t)l*nvars];
+      const double* qR = &q[(size_t)r*nvars];
+      double Qavg[MAXV], grad[MAXT*3], flux[MAXE], tmut;
+      for(i = 0; i < neqn; i++) Qavg[i] = (qL[i] + qR[i])/2.0;
+      fr_aux(p, Qavg);
+      tmut = c->mut ? 0.5*(c->mut[l] + c->mut[r]) : 0.0;
+      fr_face_gradient(c, ns, qL, qR, &qgrad[(size_t)l*nterms*3], &qgrad[(size_t)r*nterms*3], &c->xyz[3*l], &c->xyz[3*r], grad);
+      orc_fr_viscous_flux(c, p, Qavg, grad, &c->edges_a[4*e], tmut, flux);
+      for(i = 0; i < neqn; i++) b[(size_t)r*neqn + i] += flux[i];
+      for(i = 0; i < neqn; i++) b[(size_t)l*neqn + i] += -flux[i];
+    }
+    /* Bkernel_Viscous_Flux residual.tcc:468-562 */
+    for(e = 0; e < nb; e++){
+      int l = c->bedges_n[2*e], r = c->bedges_n[2*e+1];
+      const double* qL = &q[(size_t)l*nvars];
+      const double* qR = &q[(size_t)r*nvars];
+      double Qavg[MAXV], grad[MAXT*3], flux[MAXE], tmut;
+      for(i = 0; i < neqn; i++) Qavg[i] = 0.5*(qL[i] + qR[i]);
+      fr_aux(p, Qavg);
+      if(is_ghost(c, r)){
+	tmut = c->mut ? (c->mut[l] + c->mut[r])/2.0 : 0.0;
+	fr_face_gradient(c, ns, qL, qR, &qgrad[(size_t)l*nterms*3], &qgrad[(size_t)r*nterms*3], &c->xyz[3*l], &c->xyz[3*r], grad);
+      }
+      else{
+	tmut = c->mut ? c->mut[l] : 0.0;
+	memcpy(grad, &qgrad[(size_t)l*nterms*3], sizeof(double)*3*nterms);
+      }
+      orc_fr_viscous_flux(c, p, Qavg, grad, &c->bedges_a[4*e], tmut, flux);
+      for(i = 0; i < neqn; i++) b[(size_t)l*neqn + i] += -flux[i];
+    }
   }
   for(i = 0; i < c->nnode; i++){
     double source[MAXE];
@@ -1134,6 +1444,24 @@ void orc_fr_jacobian(const orc_case* c, const orc_fr_params* p, double* q, const
     }
     pL = get_block(ia, ja, A, l, l, n2);
     for(kk = 0; kk < n2; kk++) pL[kk] += tempL[kk];
+  }
+  /* Kernel_Viscous_Jac jacobian.tcc:728-767 (Bkernel_Viscous_Jac :770-848 ends with size = 0: no-op) */
+  if(c->viscous){
+    for(e = 0; e < c->nedge; e++){
+      int l = c->edges_n[2*e], r = c->edges_n[2*e+1], kk;
+      double tmut = c->mut ? (c->mut[l] + c->mut[r])/2.0 : 0.0;
+      double dx[3], s2 = 0.0, tempL[MAXE*MAXE], tempR[MAXE*MAXE];
+      double *pL, *pR;
+      for(i = 0; i < 3; i++){
+	dx[i] = (c->xyz[3*r+i] - c->xyz[3*l+i]);
+	s2 += dx[i]*dx[i];
+      }
+      orc_fr_viscous_jacobian(c, p, &q[(size_t)l*nvars], &q[(size_t)r*nvars], dx, s2, &c->edges_a[4*e], tmut, tempL, tempR);
+      pL = get_block(ia, ja, A, r, l, n2);
+      pR = get_block(ia, ja, A, l, r, n2);
+      for(kk = 0; kk < n2; kk++) pR[kk] += tempR[kk];
+      for(kk = 0; kk < n2; kk++) pL[kk] += tempL[kk];
+    }
   }
   for(e = 0; e < c->nedge; e++){
     int l = c->edges_n[2*e], r = c->edges_n[2*e+1], kk;

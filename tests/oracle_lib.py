@@ -207,13 +207,41 @@ class ChemOracle:
         return src
 
 
+class OrcTransport(C.Structure):
+    """orc_transport (oracle/pcfd_oracle.h)."""
+    _S = 16
+    _fields_ = [("nmu", C.c_int * _S), ("nk", C.c_int * _S),
+                ("mu_fit", C.c_double * 6 * 3 * _S), ("k_fit", C.c_double * 6 * 3 * _S),
+                ("mu_white", C.c_double * 4 * _S), ("k_white", C.c_double * 4 * _S)]
+
+
+def fill_transport(t, g):
+    """Species transport tables of an NSFR fixture (species_mu_fit, species_k_fit [ns,3,6]; species_white [ns,8];
+    species_fit_counts [ns,2]) into an orc_transport-shaped ctypes structure."""
+    cnt = np.asarray(g["species_fit_counts"]).reshape(-1, 2)
+    ns = len(cnt)
+    mu, k, wh = (np.asarray(g["species_mu_fit"]).reshape(ns, 3, 6), np.asarray(g["species_k_fit"]).reshape(ns, 3, 6),
+                 np.asarray(g["species_white"]).reshape(ns, 8))
+    for i in range(ns):
+        t.nmu[i], t.nk[i] = int(cnt[i, 0]), int(cnt[i, 1])
+        for r in range(3):
+            for j in range(6):
+                t.mu_fit[i][r][j] = mu[i, r, j]
+                t.k_fit[i][r][j] = k[i, r, j]
+        for j in range(4):
+            t.mu_white[i][j] = wh[i, j]
+            t.k_white[i][j] = wh[i, 4 + j]
+    return t
+
+
 class OrcFrParams(C.Structure):
     """orc_fr_params (oracle/pcfd_oracle.h)."""
     _fields_ = [("chem", C.POINTER(OrcChemModel)),
                 ("ref_density", C.c_double), ("ref_velocity", C.c_double), ("ref_temperature", C.c_double),
                 ("ref_pressure", C.c_double), ("ref_time", C.c_double), ("ref_specific_enthalpy", C.c_double),
                 ("Pref", C.c_double), ("dt_param", C.c_double), ("use_local_dt", C.c_int), ("rxn_on", C.c_int),
-                ("qinf", C.c_double * (3 * 16 + 6))]
+                ("qinf", C.c_double * (3 * 16 + 6)),
+                ("transport", C.POINTER(OrcTransport)), ("ref_viscosity", C.c_double), ("ref_k", C.c_double)]
 
 
 def chem_tables(g):
@@ -244,6 +272,10 @@ class FrOracle(Oracle):
         p.dt_param, p.use_local_dt, p.rxn_on = float(meta["dt"]), int(meta["useLocalTimeStepping"]), int(meta["rxnOn"])
         for j in range(self.nvars):
             p.qinf[j] = qinf[j]
+        if int(meta.get("viscous", 0)):
+            self.transport = fill_transport(OrcTransport(), g)
+            p.transport = C.pointer(self.transport)
+            p.ref_viscosity, p.ref_k = float(meta["ref_viscosity"]), float(meta["ref_k"])
         self.p = p
         lib.orc_fr_timestep.restype = C.c_double
         lib.orc_fr_sgs.restype = C.c_double

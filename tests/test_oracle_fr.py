@@ -10,7 +10,8 @@ import pytest
 from tests.oracle_lib import FrOracle, load_golden
 from tests.test_oracle import exact
 
-FR = ["box5_fr_explicit", "box4_fr_implicit"]
+FR = ["box5_fr_explicit", "box4_fr_implicit", "box4_nsfr_implicit"]
+IMPLICIT = ["box4_fr_implicit", "box4_nsfr_implicit"]
 
 
 @pytest.mark.parametrize("name", FR)
@@ -59,8 +60,10 @@ def test_fr_explicit_update(oracle):
     exact(q, g["q1"], "q1")
 
 
-def test_fr_jacobian_lu_sgs(oracle):
-    g, meta = load_golden("box4_fr_implicit")
+@pytest.mark.parametrize("name", IMPLICIT)
+def test_fr_jacobian_lu_sgs(oracle, name):
+    # box4_nsfr_implicit adds the analytic viscous Jacobian (compressibleFR.tcc:1713-2040) to the off-diagonal blocks
+    g, meta = load_golden(name)
     o = FrOracle(oracle, g, meta)
     ia, ja, iau = o.crs_init()
     exact(ia, g["ia"], "ia")
@@ -76,3 +79,24 @@ def test_fr_jacobian_lu_sgs(oracle):
     assert ddq == g["sgs_ddq"][0]
     o.apply_dq(q, x)
     exact(q, g["q1"], "q1")
+
+
+def test_nsfr_fixture_is_viscous():
+    # compressibleNSFR at Re = 111: the viscous flux is a visible part of b, temperatures straddle the 1000 K switch
+    # between the Sutherland law and the NASA RP-1311 fits (species.tcc:393-479)
+    g, meta = load_golden("box4_nsfr_implicit")
+    assert int(meta["viscous"]) == 1 and int(meta["eqnset_id"]) == 1 and 100.0 < meta["Re"] < 125.0
+    T = g["q0"].reshape(-1, 21)[: int(meta["nnode"]), 8] * meta["ref_temperature"]
+    assert T.min() < 1000.0 < T.max()
+    assert list(g["species_fit_counts"]) == [3, 3, 2, 2, 2, 2, 3, 3, 3, 3]      # O2, O, N, N2, NO: (mu, k) ranges
+
+
+def test_nsfr_viscous_part_of_residual(oracle):
+    # the viscous flux really is in b: the same state without it differs at the 1e-2 level of |b|
+    g, meta = load_golden("box4_nsfr_implicit")
+    o = FrOracle(oracle, g, meta)
+    b = o.residual(g["q0"].copy(), g["qgrad"], g["limiter"], g["beta"])
+    exact(b, g["b"], "b")
+    o.c.viscous = 0
+    b0 = o.residual(g["q0"].copy(), g["qgrad"], g["limiter"], g["beta"])
+    assert np.abs(b - b0).max() > 1e-3 * np.abs(b).max()
