@@ -31,10 +31,11 @@
 extern "C" {
 #endif
 
-#define PCFD_ABI_VERSION 3
+#define PCFD_ABI_VERSION 4
 
 /* eqnset ids follow eqnset_defines.h / create_functions.h:17-45 */
-enum { PCFD_EQNSET_COMPRESSIBLE_EULER_FR = 0, PCFD_EQNSET_COMPRESSIBLE_EULER = 2, PCFD_EQNSET_COMPRESSIBLE_NS = 3 };
+enum { PCFD_EQNSET_COMPRESSIBLE_EULER_FR = 0, PCFD_EQNSET_COMPRESSIBLE_NS_FR = 1, PCFD_EQNSET_COMPRESSIBLE_EULER = 2,
+       PCFD_EQNSET_COMPRESSIBLE_NS = 3 };
 
 /* BC types: bc_defines.h:4-30 (the value bc->GetBCType(factag) returns) */
 enum { PCFD_BC_PARALLEL = 0, PCFD_BC_DIRICHLET = 1, PCFD_BC_NEUMANN = 2, PCFD_BC_IMPERMEABLE_WALL = 3,
@@ -262,6 +263,15 @@ int pcfd_chem_source_term(pcfd_chem* chem, int n, int stride, const double* Q, c
  * (eqnset.tcc:163-187), dense temporal terms (:1319-1463), native <-> conservative explicit update (solve.tcc:112-130).
  * Every pcfd_* phase entry point above works on such a context; pcfd_turb_compute does not.
  */
+/* Species transport data as Species holds it (species.h:35-49; species.tcc:13-22, 241-310): Sutherland law (White) up
+   to the transition temperature, NASA RP-1311 fits above (rows [Tlo, Thi, A, B, C, D], as the reference's chemDB.py
+   stores chemdata/trans.inp under /species/<sym>/mu and /species/<sym>/k). */
+typedef struct {
+  int nmu[PCFD_CHEM_MAX_SPECIES], nk[PCFD_CHEM_MAX_SPECIES];          /* Species::mu_coeff_curves, k_coeff_curves (<= 3) */
+  double mu_fit[PCFD_CHEM_MAX_SPECIES][3][6], k_fit[PCFD_CHEM_MAX_SPECIES][3][6];
+  double mu_white[PCFD_CHEM_MAX_SPECIES][4], k_white[PCFD_CHEM_MAX_SPECIES][4];   /* value, T0, S, transition T */
+} pcfd_transport_model;
+
 typedef struct {
   pcfd_chem_model chem;      /* ChemModel tables (species order = the model's) */
   /* Param reference values (param.tcc:352-398) */
@@ -271,9 +281,14 @@ typedef struct {
   int use_local_dt;          /* Param::useLocalTimeStepping */
   int rxn_on;                /* Param::rxnOn */
   double qinf[3 * PCFD_CHEM_MAX_SPECIES + 6];   /* EqnSet::Qinf, all nvars entries */
+  /* compressibleNSFR (params->eqnset == PCFD_EQNSET_COMPRESSIBLE_NS_FR, param.tcc:401-404): viscous flux
+     (compressibleFR.tcc:551-637) and analytic viscous Jacobian (:1713-2040) with Wilke-mixed species transport
+     (chem.tcc:876-938, species.tcc:393-479).  Re and PrT come from pcfd_params; the eddy viscosity from field PCFD_F_MUT. */
+  pcfd_transport_model transport;
+  double ref_viscosity, ref_k;                  /* Param::ref_viscosity, ref_k (param.tcc:210-211) */
 } pcfd_fr_params;
 
-/* params->eqnset must be PCFD_EQNSET_COMPRESSIBLE_EULER_FR; sorder, limiter, chi, cfl, no_cvbc, enable_vnn / vnn are
+/* params->eqnset must be PCFD_EQNSET_COMPRESSIBLE_EULER_FR or PCFD_EQNSET_COMPRESSIBLE_NS_FR; sorder, limiter, chi, cfl, no_cvbc, enable_vnn / vnn are
    read from params, gamma / qinf / the viscous fields are not.  The preconditioning field "beta"
    (solutionSpace.tcc:235-247) is set with pcfd_set_field(PCFD_F_BETA). */
 int pcfd_create_fr(const pcfd_mesh_desc* mesh, const pcfd_params* params, const pcfd_fr_params* fr, int device,

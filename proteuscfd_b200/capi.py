@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("PCFD_B200_LIB") or os.path.join(_HERE, "libpcfd_b200.
 
 NEQN, NVARS, NTERMS = 5, 10, 9
 EQNSET_COMPRESSIBLE_EULER_FR = 0
+EQNSET_COMPRESSIBLE_NS_FR = 1
 EQNSET_COMPRESSIBLE_EULER = 2
 EQNSET_COMPRESSIBLE_NS = 3
 
@@ -70,13 +71,42 @@ class ChemModelDesc(C.Structure):
                 ("nup", C.c_double * _S * _R), ("nupp", C.c_double * _S * _R), ("tbeff", C.c_double * _S * _R)]
 
 
+class TransportDesc(C.Structure):
+    """pcfd_transport_model (include/pcfd.h)."""
+    _S = CHEM_MAX_SPECIES
+    _fields_ = [("nmu", C.c_int * _S), ("nk", C.c_int * _S),
+                ("mu_fit", C.c_double * 6 * 3 * _S), ("k_fit", C.c_double * 6 * 3 * _S),
+                ("mu_white", C.c_double * 4 * _S), ("k_white", C.c_double * 4 * _S)]
+
+
+def fill_transport(t, g):
+    """Fill a pcfd_transport_model-shaped ctypes struct from the flat species transport tables of a fixture / a reference
+    ChemModel: species_mu_fit, species_k_fit [ns,3,6] (rows [Tlo, Thi, A, B, C, D]); species_white [ns,8] (viscosity then
+    conductivity: value, T0, S, transition T); species_fit_counts [ns,2] (viscosity, conductivity ranges)."""
+    cnt = np.asarray(g["species_fit_counts"]).reshape(-1, 2)
+    ns = len(cnt)
+    mu, k, wh = (np.asarray(g["species_mu_fit"]).reshape(ns, 3, 6), np.asarray(g["species_k_fit"]).reshape(ns, 3, 6),
+                 np.asarray(g["species_white"]).reshape(ns, 8))
+    for i in range(ns):
+        t.nmu[i], t.nk[i] = int(cnt[i, 0]), int(cnt[i, 1])
+        for r in range(3):
+            for j in range(6):
+                t.mu_fit[i][r][j] = float(mu[i, r, j])
+                t.k_fit[i][r][j] = float(k[i, r, j])
+        for j in range(4):
+            t.mu_white[i][j] = float(wh[i, j])
+            t.k_white[i][j] = float(wh[i, 4 + j])
+    return t
+
+
 class FrParams(C.Structure):
     """pcfd_fr_params (include/pcfd.h): the reacting eqnset's chemistry tables, reference values and free stream."""
     _fields_ = [("chem", ChemModelDesc),
                 ("ref_density", C.c_double), ("ref_velocity", C.c_double), ("ref_temperature", C.c_double),
                 ("ref_pressure", C.c_double), ("ref_time", C.c_double), ("ref_specific_enthalpy", C.c_double),
                 ("pref", C.c_double), ("dt", C.c_double), ("use_local_dt", C.c_int), ("rxn_on", C.c_int),
-                ("qinf", C.c_double * (3 * CHEM_MAX_SPECIES + 6))]
+                ("qinf", C.c_double * (3 * CHEM_MAX_SPECIES + 6)),
+                ("transport", TransportDesc), ("ref_viscosity", C.c_double), ("ref_k", C.c_double)]
 
 
 def fill_chem_model(md, t):
@@ -230,6 +260,10 @@ class Context:
             for j, v in enumerate(np.asarray(fr["qinf"], dtype=np.float64).reshape(-1)):
                 fp.qinf[j] = float(v)
             pr.eqnset = EQNSET_COMPRESSIBLE_EULER_FR
+            if fr.get("transport") is not None:     # compressibleNSFR: viscous terms with Wilke-mixed species transport
+                fill_transport(fp.transport, fr["transport"])
+                fp.ref_viscosity, fp.ref_k = float(fr["ref_viscosity"]), float(fr["ref_k"])
+                pr.eqnset = EQNSET_COMPRESSIBLE_NS_FR
             rc = self.lib.pcfd_create_fr(C.byref(md), C.byref(pr), C.byref(fp), int(device), C.byref(h))
         else:
             rc = self.lib.pcfd_create(C.byref(md), C.byref(pr), int(device), C.byref(h))

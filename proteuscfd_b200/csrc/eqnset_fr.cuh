@@ -740,6 +740,259 @@ __device__ __forceinline__ double dRmixdRhoi(const Params<NS>& p, const double* 
   return d;
 }
 
+// ====================================================================== transport + viscous terms (compressibleNSFR)
+// Species transport data as Species holds it (species.h:35-49): Sutherland law (White) up to the transition
+// temperature, NASA RP-1311 fits [Tlo, Thi, A, B, C, D] above.  The two molecular-weight powers of Wilke's rule
+// (chem.tcc:908-909) do not depend on the state: they are evaluated once on the host with the C library's pow.
+template <int NS>
+struct Transport {
+  double mu_fit[NS][3][6], k_fit[NS][3][6];
+  double mu_white[NS][4], k_white[NS][4];     // reference value, T0, S, transition temperature
+  int nmu[NS], nk[NS];
+  double pw25[NS][NS];                        // pow(MW_j / MW_i, 0.25)
+  double pwm05[NS][NS];                       // pow(1 + MW_i / MW_j, -0.5)
+  double sqrt8;
+  double ref_viscosity, ref_k, Re, PrT;
+};
+
+// Species::GetViscosity / GetThermalConductivity (species.tcc:393-479); the range search keeps the last match
+__device__ __forceinline__ double sp_transport(const double* white, const double (*fit)[6], int nfit, double T, double conv) {
+  if (T <= white[3]) {
+    const double v0 = white[0], T0 = white[1], S = white[2];
+    return v0 * (pow(T / T0, 1.5)) * ((T0 + S) / (T + S));
+  }
+  int range = -1;
+  for (int i = 0; i < nfit; i++)
+    if (T >= fit[i][0] && T <= fit[i][1]) range = i;
+  if (range == -1) return nan("");   // the reference aborts
+  const double A = fit[range][2], B = fit[range][3], C = fit[range][4], D = fit[range][5];
+  const double logv = A * log(T) + B / T + C / (T * T) + D;
+  return exp(logv) * conv;
+}
+
+// ChemModel::GetViscosity / GetThermalConductivity -> WilkesMixtureRule (chem.tcc:876-938) with
+// MassFractionToMoleFraction (:941-958), through CompressibleFREqnSet::GetMolecularViscosity / GetThermalConductivity
+// (compressibleFR.tcc:1580-1599).  Both properties are mixed with the same weights (the species viscosities), so the
+// weights are formed once; rhoi and T non-dimensional, results non-dimensional.
+template <int NS>
+__device__ __forceinline__ void mixture_transport(const Params<NS>& p, const Transport<NS>& t, const double* rhoi, double T,
+                                                  double& mu, double& k) {
+  const double Td = T * p.ref_temperature;
+  double rho = 0.0, summ = 0.0, mf[NS], visc[NS], cond[NS];
+#pragma unroll
+  for (int i = 0; i < NS; i++) { mf[i] = rhoi[i] * p.ref_density; rho += mf[i]; }
+#pragma unroll
+  for (int i = 0; i < NS; i++) {
+    const double massfrac = mf[i] / rho;
+    mf[i] = (massfrac) / p.mw[i];
+    summ += mf[i];
+  }
+#pragma unroll
+  for (int i = 0; i < NS; i++) mf[i] /= summ;
+  summ = 0.0;
+#pragma unroll
+  for (int i = 0; i < NS - 1; i++) summ += mf[i];
+  mf[NS - 1] = 1.0 - summ;
+#pragma unroll
+  for (int i = 0; i < NS; i++) {
+    visc[i] = sp_transport(t.mu_white[i], t.mu_fit[i], t.nmu[i], Td, 1.0e-7);
+    cond[i] = sp_transport(t.k_white[i], t.k_fit[i], t.nk[i], Td, 0.0001);
+  }
+  double mmu = 0.0, mk = 0.0;
+#pragma unroll
+  for (int i = 0; i < NS; i++) {
+    double wi = 0.0;
+#pragma unroll
+    for (int j = 0; j < NS; j++) {
+      const double temp = (1.0 + sqrt(visc[i] / visc[j]) * t.pw25[i][j]);
+      const double phi = t.pwm05[i][j] * temp * temp / t.sqrt8;
+      wi += mf[j] * phi;
+    }
+    mmu += (mf[i] / wi) * visc[i];
+    mk += (mf[i] / wi) * cond[i];
+  }
+  mu = mmu / t.ref_viscosity;
+  k = mk / t.ref_k;
+}
+
+// GetFluidProperties as above, returning the mixture cv, cp and R (non-dimensional) the viscous terms read
+template <int NS>
+__device__ __forceinline__ void fluid_props_cvcp(const Params<NS>& p, const double* rhoi, double T, double& cv, double& cp,
+                                                 double& R) {
+  const double s_ref = (p.ref_velocity * p.ref_velocity / p.ref_temperature);
+  double rhoiDim[NS];
+#pragma unroll
+  for (int i = 0; i < NS; i++) rhoiDim[i] = rhoi[i] * p.ref_density;
+  const double Tdim = T * p.ref_temperature;
+  double RDim = 0.0, rhoDim = 0.0, cpDim = 0.0, cvDim = 0.0;
+#pragma unroll
+  for (int i = 0; i < NS; i++) rhoDim += rhoiDim[i];
+#pragma unroll
+  for (int i = 0; i < NS; i++) RDim += rhoiDim[i] * p.Rs[i];
+  RDim /= rhoDim;
+  const int rng = thermo_range(Tdim);
+#pragma unroll
+  for (int i = 0; i < NS; i++) {
+    const double X = rhoiDim[i] / rhoDim;
+    const double cpi = sp_cp(p, i, rng, Tdim);
+    cpDim += cpi * X;
+    cvDim += X * (cpi - p.Rs[i]);
+  }
+  cv = cvDim / s_ref;
+  cp = cpDim / s_ref;
+  R = RDim / s_ref;
+}
+
+// CompressibleFREqnSet::ViscousFlux (compressibleFR.tcc:551-637): Q = [rho_i, u, v, w, T] of the face, g = gradients of
+// u, v, w, T (12 doubles); f = the momentum and energy rows (the species rows are zero)
+template <int NS>
+__device__ __forceinline__ void viscous_flux(const Params<NS>& p, const Transport<NS>& t, const double* Q, const double* g,
+                                             const double* av, double mut, double* f) {
+  const double ux = g[0], uy = g[1], uz = g[2], vx = g[3], vy = g[4], vz = g[5], wx = g[6], wy = g[7], wz = g[8];
+  const double Tx = g[9], Ty = g[10], Tz = g[11];
+  const double u = Q[NS], v = Q[NS + 1], w = Q[NS + 2], T = Q[NS + 3];
+  double cv, cp, R, mu, kc;
+  fluid_props_cvcp(p, Q, T, cv, cp, R);
+  mixture_transport(p, t, Q, T, mu, kc);
+  const double tmut = (mu + mut);
+  const double fact = 2.0 / 3.0;
+  const double tauxx = 2.0 * fact * ux - fact * vy - fact * wz;
+  const double tauyy = 2.0 * fact * vy - fact * ux - fact * wz;
+  const double tauzz = 2.0 * fact * wz - fact * ux - fact * vy;
+  const double tauxy = uy + vx;
+  const double tauxz = uz + wx;
+  const double tauyz = vz + wy;
+  const double RK = av[3] / t.Re;
+  const double RKT = RK * tmut;
+  double k = -kc;
+  const double Tn = Tx * av[0] + Ty * av[1] + Tz * av[2];
+  const double kT = (cp * mut) / t.PrT;
+  k -= kT;
+  const double tauxn = -tauxx * av[0] - tauxy * av[1] - tauxz * av[2];
+  const double tauyn = -tauxy * av[0] - tauyy * av[1] - tauyz * av[2];
+  const double tauzn = -tauxz * av[0] - tauyz * av[1] - tauzz * av[2];
+  f[0] = RKT * (tauxn);
+  f[1] = RKT * (tauyn);
+  f[2] = RKT * (tauzn);
+  f[3] = RKT * (tauxn * u + tauyn * v + tauzn * w) + RK * k * Tn;
+}
+
+// the part of CompressibleFREqnSet::ViscousJacobian (compressibleFR.tcc:1713-2040) shared by both sides: averaged state,
+// its viscosity / conductivity / cp
+template <int NS>
+struct ViscJacCommon {
+  double u, v, w, RK, RKT, c1;
+};
+template <int NS>
+__device__ __forceinline__ void viscous_jac_common(const Params<NS>& p, const Transport<NS>& t, const double* QL,
+                                                   const double* QR, const double* av, double mut, ViscJacCommon<NS>& C) {
+  double Q[NS + 4];
+#pragma unroll
+  for (int i = 0; i < NS + 4; i++) Q[i] = 0.5 * (QL[i] + QR[i]);
+  const double T = Q[NS + 3];
+  double mu, k, cv, cp, R;
+  mixture_transport(p, t, Q, T, mu, k);
+  const double tmut = (mu + mut);
+  C.RK = av[3] / t.Re;
+  C.RKT = C.RK * tmut;
+  fluid_props_cvcp(p, Q, T, cv, cp, R);
+  C.u = 0.5 * (QL[NS] + QR[NS]);
+  C.v = 0.5 * (QL[NS + 1] + QR[NS + 1]);
+  C.w = 0.5 * (QL[NS + 2] + QR[NS + 2]);
+  const double kT = mut / t.PrT * cp;
+  C.c1 = -(k + kT);
+}
+
+// one side (:1796-1960 right with D = dx/s2, :1963-2010 left with D = -dx/s2): rows NS..NS+3 of the block, a[4][NS+4]
+// (the species rows are zero); Qs holds [0, NS+6) of that side's node (stored aux values P and rho)
+template <int NS>
+__device__ __forceinline__ void viscous_jac_side(const Params<NS>& p, const ViscJacCommon<NS>& C, const double* D,
+                                                 const double* Qs, const double* av, double* a) {
+  constexpr int NEQ = NS + 4;
+  const double u = C.u, v = C.v, w = C.w, RK = C.RK, RKT = C.RKT;
+  const double rhos = Qs[NS + 5], us = Qs[NS], vs = Qs[NS + 1], ws = Qs[NS + 2], Ps = Qs[NS + 4], Ts = Qs[NS + 3];
+  double cvs, cps, Rs;
+  fluid_props_cvcp(p, Qs, Ts, cvs, cps, Rs);
+  double Dr[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) Dr[i] = D[i] / rhos;
+  const double dux = -u * Dr[0], duy = -u * Dr[1], duz = -u * Dr[2];
+  const double dvx = -v * Dr[0], dvy = -v * Dr[1], dvz = -v * Dr[2];
+  const double dwx = -w * Dr[0], dwy = -w * Dr[1], dwz = -w * Dr[2];
+  const double dfact = -2.0 / 3.0 * (dux + dvy + dwz);
+  const double dtauxx = (2.0 * dux + dfact);
+  const double dtauyy = (2.0 * dvy + dfact);
+  const double dtauzz = (2.0 * dwz + dfact);
+  const double dtauxy = duy + dvx;
+  const double dtauxz = duz + dwx;
+  const double dtauyz = dvz + dwy;
+  const double dtauxn = dtauxx * av[0] + dtauxy * av[1] + dtauxz * av[2];
+  const double dtauyn = dtauxy * av[0] + dtauyy * av[1] + dtauyz * av[2];
+  const double dtauzn = dtauxz * av[0] + dtauyz * av[1] + dtauzz * av[2];
+  const double c43 = 4.0 / 3.0, mc23 = -2.0 / 3.0;
+  double* row = a;
+  const double dR2_drhou = (c43 * Dr[0] * av[0] + Dr[1] * av[1] + Dr[2] * av[2]);
+  const double dR2_drhov = (mc23 * Dr[1] * av[0] + Dr[0] * av[1]);
+  const double dR2_drhow = (mc23 * Dr[2] * av[0] + Dr[0] * av[2]);
+#pragma unroll
+  for (int i = 0; i < NS; i++) row[i] = -RKT * (dtauxn);
+  row[NS + 0] = -RKT * dR2_drhou;
+  row[NS + 1] = -RKT * dR2_drhov;
+  row[NS + 2] = -RKT * dR2_drhow;
+  row[NS + 3] = 0.0;
+  row = a + NEQ;
+  const double dR3_drhou = (mc23 * Dr[0] * av[1] + Dr[1] * av[0]);
+  const double dR3_drhov = (Dr[0] * av[0] + c43 * Dr[1] * av[1] + Dr[2] * av[2]);
+  const double dR3_drhow = (mc23 * Dr[2] * av[1] + Dr[1] * av[2]);
+#pragma unroll
+  for (int i = 0; i < NS; i++) row[i] = -RKT * (dtauyn);
+  row[NS + 0] = -RKT * dR3_drhou;
+  row[NS + 1] = -RKT * dR3_drhov;
+  row[NS + 2] = -RKT * dR3_drhow;
+  row[NS + 3] = 0.0;
+  row = a + 2 * NEQ;
+  const double dR4_drhou = (mc23 * Dr[0] * av[2] + Dr[2] * av[0]);
+  const double dR4_drhov = (mc23 * Dr[1] * av[2] + Dr[2] * av[1]);
+  const double dR4_drhow = (Dr[0] * av[0] + Dr[1] * av[1] + c43 * Dr[2] * av[2]);
+#pragma unroll
+  for (int i = 0; i < NS; i++) row[i] = -RKT * (dtauzn);
+  row[NS + 0] = -RKT * dR4_drhou;
+  row[NS + 1] = -RKT * dR4_drhov;
+  row[NS + 2] = -RKT * dR4_drhow;
+  row[NS + 3] = 0.0;
+  // IdealGasEOS::GetdT_dP (EOS.tcc:42-45); ChemModel::dTdRhoi (chem.tcc:687-704) on dimensional densities / pressure
+  const double dT_dP = (1.0 / (rhos * Rs));
+  double rhoidim[NS], dTdRhoi[NS];
+  {
+    double rho = 0.0, Rmix = 0.0;
+    const double Pdim = Ps * p.ref_pressure;
+#pragma unroll
+    for (int i = 0; i < NS; i++) rhoidim[i] = Qs[i] * p.ref_density;
+#pragma unroll
+    for (int i = 0; i < NS; i++) { rho += rhoidim[i]; Rmix += rhoidim[i] * p.Rs[i]; }
+    Rmix /= rho;
+    const double dTdRho = (-Pdim / (Rmix * rho * rho));
+    const double dTdR = (-Pdim / (rho * Rmix * Rmix));
+#pragma unroll
+    for (int i = 0; i < NS; i++) dTdRhoi[i] = dTdR * dRmixdRhoi(p, rhoidim, rho, i) + dTdRho;
+  }
+  const double dP_dru = Rs / cvs * us;
+  const double dP_drv = Rs / cvs * vs;
+  const double dP_drw = Rs / cvs * ws;
+  const double dP_dret = Rs / cvs;
+  const double Tn = (D[0] * av[0] + D[1] * av[1] + D[2] * av[2]) * C.c1;
+  row = a + 3 * NEQ;
+#pragma unroll
+  for (int i = 0; i < NS; i++) {
+    const double dT_drho = dTdRhoi[i] / (p.ref_temperature / p.ref_density);
+    row[i] = -RKT * (dtauxn * u + dtauyn * v + dtauzn * w) + RK * Tn * dT_drho;
+  }
+  row[NS + 0] = -RKT * (dR2_drhou * u + dR3_drhou * v + dR4_drhou * w) + RK * Tn * dT_dP * dP_dru;
+  row[NS + 1] = -RKT * (dR2_drhov * u + dR3_drhov * v + dR4_drhov * w) + RK * Tn * dT_dP * dP_drv;
+  row[NS + 2] = -RKT * (dR2_drhow * u + dR3_drhow * v + dR4_drhow * w) + RK * Tn * dT_dP * dP_drw;
+  row[NS + 3] = RK * Tn * dT_dP * dP_dret;
+}
+
 // ContributeTemporalTerms (compressibleFR.tcc:1319-1463) with ChemModel::dEtdP_dEtdRhoi (chem.tcc:829-858) and the
 // IdealGasEOS derivatives (EOS.tcc:42-76); A = the node's diagonal block, row-major N x N, accumulated in place
 template <int NS>

@@ -25,6 +25,9 @@ struct pcfd_fr_state {
   double *red = nullptr, *redout = nullptr;
   int bad_newton = 0;
   int* dbad = nullptr;
+  // compressibleNSFR: per-edge / per-half-edge viscous flux slots (momentum + energy rows)
+  bool viscous = false;
+  double *vflux = nullptr, *bvflux = nullptr;
 };
 
 namespace {
@@ -342,6 +345,68 @@ __global__ void __launch_bounds__(128) kfr_flux_bedges(DevMesh m, fr::Params<NS>
   for (int j = 0; j < NEQ; j++) bflux[(size_t)e * NEQ + j] = f[j];
 }
 
+// Kernel_Viscous_Flux / Bkernel_Viscous_Flux (residual.tcc:390-562) with CompressibleFREqnSet::ViscousFlux: one thread
+// per interior edge (e < nedge) or half-edge; the face gradient (average + directional correction, :430-452) is formed
+// for the four terms the flux reads (u, v, w, T); writes the momentum and energy rows of the edge's private slot
+template <int NS>
+__device__ __forceinline__ void face_gradient_uvwT(const DevMesh& m, int l, int r, bool corrected, const double* QL,
+                                                   const double* QR, const double* __restrict__ qgrad, double* g) {
+  constexpr int NT = W<NS>::NT;
+  const double* gl = qgrad + (size_t)l * NT * 3 + NS * 3;
+  const double* gr = qgrad + (size_t)r * NT * 3 + NS * 3;
+#pragma unroll
+  for (int i = 0; i < 12; i++) g[i] = 0.5 * (__ldg(gl + i) + __ldg(gr + i));
+  if (corrected) {
+    double dx[3], s2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      dx[i] = (__ldg(m.xyz + 3 * r + i) - __ldg(m.xyz + 3 * l + i));
+      s2 += dx[i] * dx[i];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const double qdots = dx[0] * g[j * 3] + dx[1] * g[j * 3 + 1] + dx[2] * g[j * 3 + 2];
+      const double dq = (QR[NS + j] - QL[NS + j] - qdots) / s2;
+#pragma unroll
+      for (int i = 0; i < 3; i++) g[j * 3 + i] += dq * dx[i];
+    }
+  }
+}
+
+template <int NS>
+__global__ void __launch_bounds__(128) kfr_vflux_edges(DevMesh m, fr::Params<NS> p, fr::Transport<NS> t,
+                                                        const double* __restrict__ q, const double* __restrict__ qgrad,
+                                                        const double* __restrict__ mut, double* __restrict__ vflux,
+                                                        double* __restrict__ bvflux) {
+  constexpr int NT = W<NS>::NT;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nb = m.nbedge + m.ngedge;
+  if (idx >= m.nedge + nb) return;
+  const bool interior = idx < m.nedge;
+  const int e = interior ? idx : idx - m.nedge;
+  const int2 lr = interior ? m.en[e] : m.ben[e];
+  const int l = lr.x, r = lr.y;
+  double av[4], QL[NS + 4], QR[NS + 4], Q[NS + 4], g[12], f[4], tmut;
+  load_avec(interior ? m.ea : m.bea, e, av);
+  load_row<NS, NS + 4>(q, l, QL);
+  load_row<NS, NS + 4>(q, r, QR);
+#pragma unroll
+  for (int i = 0; i < NS + 4; i++) Q[i] = 0.5 * (QL[i] + QR[i]);
+  if (interior || is_ghost(m, r)) {
+    tmut = 0.5 * (mut[l] + mut[r]);
+    face_gradient_uvwT<NS>(m, l, r, p.sorder > 1, QL, QR, qgrad, g);
+  } else {
+    tmut = mut[l];
+    const double* gl = qgrad + (size_t)l * NT * 3 + NS * 3;
+#pragma unroll
+    for (int i = 0; i < 12; i++) g[i] = __ldg(gl + i);
+  }
+  fr::viscous_flux(p, t, Q, g, av, tmut, f);
+  double* dst = interior ? vflux + (size_t)e * 4 : bvflux + (size_t)e * 4;
+#pragma unroll
+  for (int j = 0; j < 4; j++) dst[j] = f[j];
+}
+
 // SourceTerm (compressibleFR.tcc:1276-1316) per node -> src[n*NS]
 template <int NS>
 __global__ void __launch_bounds__(128) kfr_source(int nnode, fr::Params<NS> p, const double* __restrict__ q,
@@ -360,6 +425,8 @@ __global__ void __launch_bounds__(128) kfr_source(int nnode, fr::Params<NS> p, c
 template <int NS>
 __global__ void __launch_bounds__(W<NS>::NEQ * 16) kfr_residual_gather(DevMesh m, const double* __restrict__ flux,
                                                                         const double* __restrict__ bflux,
+                                                                        const double* __restrict__ vflux,
+                                                                        const double* __restrict__ bvflux,
                                                                         const double* __restrict__ src, double* __restrict__ b) {
   constexpr int NEQ = W<NS>::NEQ;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -372,6 +439,14 @@ __global__ void __launch_bounds__(W<NS>::NEQ * 16) kfr_residual_gather(DevMesh m
     const int2 a = m.adj[k];
     const double f = (a.y < m.nedge) ? __ldg(flux + (size_t)a.y * NEQ + j) : __ldg(bflux + (size_t)(a.y - m.nedge) * NEQ + j);
     acc += (a.x < 0) ? f : -f;
+  }
+  // the viscous passes come after both inviscid ones (residual.tcc:88-104); their species rows are zero
+  if (vflux && j >= NS) {
+    for (int k = k0; k < k1; k++) {
+      const int2 a = m.adj[k];
+      const double f = (a.y < m.nedge) ? __ldg(vflux + (size_t)a.y * 4 + (j - NS)) : __ldg(bvflux + (size_t)(a.y - m.nedge) * 4 + (j - NS));
+      acc += (a.x < 0) ? f : -f;
+    }
   }
   acc += (j < NS) ? src[(size_t)n * NS + j] : 0.0;
   b[(size_t)n * NEQ + j] = acc;
@@ -565,6 +640,49 @@ __global__ void __launch_bounds__((2 * W<NS>::NEQ + 1) * EPB, PCFD_FRJAC_MINB) k
     double* dst = A + (size_t)posLR[e] * N2 + (role - NEQ - 1);
 #pragma unroll
     for (int j = 0; j < NEQ; j++) dst[j * NEQ] = 0.0 + (f[j] - fS[slot][j]) / h;
+  }
+}
+
+// Kernel_Viscous_Jac (jacobian.tcc:728-767) with CompressibleFREqnSet::ViscousJacobian: two threads per edge, one block
+// side each (side 0: aR added to A(l,r); side 1: -aL added to A(r,l)), after the inviscid finite-difference pass.  The
+// species rows of both blocks are zero and are left alone.  (Bkernel_Viscous_Jac ends with size = 0: no boundary part.)
+template <int NS>
+__global__ void __launch_bounds__(128) kfr_vjac_edges(DevMesh m, fr::Params<NS> p, fr::Transport<NS> t,
+                                                       const double* __restrict__ q, const double* __restrict__ mut,
+                                                       const int* __restrict__ posLR, const int* __restrict__ posRL,
+                                                       double* __restrict__ A) {
+  constexpr int NEQ = W<NS>::NEQ, N2 = W<NS>::N2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = idx >> 1, side = idx & 1;
+  if (e >= m.nedge) return;
+  const int2 lr = m.en[e];
+  const int l = lr.x, r = lr.y;
+  double av[4], QL[NS + 6], QR[NS + 6], dx[3], D[3], s2 = 0.0, a[4 * NEQ];
+  load_avec(m.ea, e, av);
+  load_row<NS, NS + 6>(q, l, QL);
+  load_row<NS, NS + 6>(q, r, QR);
+  const double tmut = (mut[l] + mut[r]) / 2.0;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    dx[i] = (__ldg(m.xyz + 3 * r + i) - __ldg(m.xyz + 3 * l + i));
+    s2 += dx[i] * dx[i];
+  }
+  fr::ViscJacCommon<NS> C;
+  fr::viscous_jac_common(p, t, QL, QR, av, tmut, C);
+  if (side == 0) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) D[i] = dx[i] / s2;
+    fr::viscous_jac_side(p, C, D, QR, av, a);
+    double* dst = A + (size_t)posLR[e] * N2 + NS * NEQ;
+#pragma unroll
+    for (int k = 0; k < 4 * NEQ; k++) dst[k] += a[k];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 3; i++) D[i] = -dx[i] / s2;
+    fr::viscous_jac_side(p, C, D, QL, av, a);
+    double* dst = A + (size_t)posRL[e] * N2 + NS * NEQ;
+#pragma unroll
+    for (int k = 0; k < 4 * NEQ; k++) dst[k] += -a[k];
   }
 }
 
@@ -804,6 +922,28 @@ fr::Params<NS> make_params(const pcfd_ctx* c) {
   return p;
 }
 
+template <int NS>
+fr::Transport<NS> make_transport(const pcfd_ctx* c) {
+  const pcfd_fr_state* s = c->fr;
+  const pcfd_transport_model& tm = s->host.transport;
+  fr::Transport<NS> t{};
+  for (int i = 0; i < NS; i++) {
+    t.nmu[i] = tm.nmu[i]; t.nk[i] = tm.nk[i];
+    for (int r = 0; r < 3; r++)
+      for (int k = 0; k < 6; k++) { t.mu_fit[i][r][k] = tm.mu_fit[i][r][k]; t.k_fit[i][r][k] = tm.k_fit[i][r][k]; }
+    for (int k = 0; k < 4; k++) { t.mu_white[i][k] = tm.mu_white[i][k]; t.k_white[i][k] = tm.k_white[i][k]; }
+    for (int j = 0; j < NS; j++) {
+      const double MWi = s->host.chem.mw[i], MWj = s->host.chem.mw[j];
+      t.pw25[i][j] = pow(MWj / MWi, 0.25);          // chem.tcc:908
+      t.pwm05[i][j] = pow((1.0 + MWi / MWj), -0.5);  // chem.tcc:909
+    }
+  }
+  t.sqrt8 = sqrt(8.0);
+  t.ref_viscosity = s->host.ref_viscosity; t.ref_k = s->host.ref_k;
+  t.Re = c->prm.Re; t.PrT = c->prm.PrT;
+  return t;
+}
+
 int fr_sumsq(pcfd_ctx* c, const double* v, int nrows, int slot, double* host_out) {
   pcfd_fr_state* s = c->fr;
   PROF("kfr_sumsq_partial");
@@ -898,12 +1038,18 @@ struct Impl {
                                                                   c->f[PCFD_F_LIMITER], beta, c->bflux);
       LAUNCH_CHECK();
     }
+    if (c->fr->viscous && c->nedge + c->nb) {
+      PROF("kfr_vflux_edges");
+      kfr_vflux_edges<NS><<<nblk((long long)c->nedge + c->nb, 128), 128, 0, c->stream>>>(
+          c->dm, p, make_transport<NS>(c), c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD], c->f[PCFD_F_MUT], c->fr->vflux, c->fr->bvflux);
+      LAUNCH_CHECK();
+    }
     PROF("kfr_source");
     kfr_source<NS><<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->nnode, p, c->f[PCFD_F_Q], c->vol, c->fr->src);
     LAUNCH_CHECK();
     PROF("kfr_residual_gather");
-    kfr_residual_gather<NS><<<nblk((long long)c->nnode * Wd::NEQ, BS), BS, 0, c->stream>>>(c->dm, c->flux, c->bflux, c->fr->src,
-                                                                                          c->f[PCFD_F_B]);
+    kfr_residual_gather<NS><<<nblk((long long)c->nnode * Wd::NEQ, BS), BS, 0, c->stream>>>(
+        c->dm, c->flux, c->bflux, c->fr->viscous ? c->fr->vflux : nullptr, c->fr->bvflux, c->fr->src, c->f[PCFD_F_B]);
     LAUNCH_CHECK();
     if (sumsq) return fr_sumsq(c, c->f[PCFD_F_B], c->nnode, 0, sumsq);
     return 0;
@@ -964,6 +1110,12 @@ struct Impl {
         PROF("kfr_jac_bedges");
       kfr_jac_bedges<NS><<<nblk(c->nblist, 64), 64, 0, c->stream>>>(c->dm, p, c->blist, c->nblist, c->bfirst, beta,
                                                                    c->f[PCFD_F_Q], c->bpos, c->bdiag, A);
+      LAUNCH_CHECK();
+    }
+    if (c->fr->viscous && c->nedge) {
+      PROF("kfr_vjac_edges");
+      kfr_vjac_edges<NS><<<nblk(2LL * c->nedge, 128), 128, 0, c->stream>>>(c->dm, p, make_transport<NS>(c), c->f[PCFD_F_Q],
+                                                                          c->f[PCFD_F_MUT], c->posLR, c->posRL, A);
       LAUNCH_CHECK();
     }
     PROF("kfr_jac_diag");
@@ -1077,7 +1229,9 @@ int pcfd_create_fr(const pcfd_mesh_desc* mesh, const pcfd_params* params, const 
   pcfd_ctx* c = nullptr;
   if (!mesh || !params || !frp || !out) return fail(c, "pcfd_create_fr: null argument");
   *out = nullptr;
-  if (params->eqnset != PCFD_EQNSET_COMPRESSIBLE_EULER_FR) return fail(c, "pcfd_create_fr: eqnset must be compressibleEulerFR");
+  if (params->eqnset != PCFD_EQNSET_COMPRESSIBLE_EULER_FR && params->eqnset != PCFD_EQNSET_COMPRESSIBLE_NS_FR)
+    return fail(c, "pcfd_create_fr: eqnset must be compressibleEulerFR or compressibleNSFR");
+  const bool viscous = params->eqnset == PCFD_EQNSET_COMPRESSIBLE_NS_FR;   // param.tcc:401-404
   const int ns = frp->chem.nspecies;
   if (ns != 5) return fail(c, "pcfd_create_fr: this build carries kernels for 5 species only");
   if (frp->chem.nreactions < 0 || frp->chem.nreactions > PCFD_CHEM_MAX_REACTIONS) return fail(c, "pcfd_create_fr: bad reaction count");
@@ -1089,6 +1243,15 @@ int pcfd_create_fr(const pcfd_mesh_desc* mesh, const pcfd_params* params, const 
   if (!(frp->ref_density > 0.0 && frp->ref_velocity > 0.0 && frp->ref_temperature > 0.0 && frp->ref_pressure > 0.0 &&
         frp->ref_time > 0.0 && frp->ref_specific_enthalpy > 0.0))
     return fail(c, "pcfd_create_fr: reference values must be positive");
+  if (viscous) {
+    if (!(params->Re > 0.0 && params->PrT > 0.0 && frp->ref_viscosity > 0.0 && frp->ref_k > 0.0))
+      return fail(c, "pcfd_create_fr: compressibleNSFR needs positive Re, PrT, ref_viscosity and ref_k");
+    for (int i = 0; i < ns; i++) {
+      const pcfd_transport_model& tm = frp->transport;
+      if (tm.nmu[i] < 1 || tm.nmu[i] > 3 || tm.nk[i] < 1 || tm.nk[i] > 3)
+        return fail(c, "pcfd_create_fr: every species needs 1..3 viscosity and conductivity fit ranges");
+    }
+  }
   const int nb = mesh->nbedge + mesh->ngedge;
   for (int e = 0; e < nb; e++) {
     const int t = mesh->bedges_bctype[e];
@@ -1098,10 +1261,11 @@ int pcfd_create_fr(const pcfd_mesh_desc* mesh, const pcfd_params* params, const 
   pcfd_params prm = *params;
   prm.turb_model = 0;
   if (pcfd_internal_create(mesh, &prm, device, ns + 4, 3 * ns + 6, 2 * ns + 4, &c)) return 1;
-  c->prm.eqnset = PCFD_EQNSET_COMPRESSIBLE_EULER_FR;
+  c->prm.eqnset = params->eqnset;
   pcfd_fr_state* s = new pcfd_fr_state();
   c->fr = s;
   s->host = *frp;
+  s->viscous = viscous;
   struct Guard { pcfd_ctx* c; bool ok = false; ~Guard() { if (!ok) { pcfd_create_err() = c->err; pcfd_destroy(c); } } } guard{c};
   CK(cudaMalloc(reinterpret_cast<void**>(&s->chem_dev), sizeof(pcfd_chem_model)));
   CK(cudaMemcpy(s->chem_dev, &frp->chem, sizeof(pcfd_chem_model), cudaMemcpyHostToDevice));
@@ -1111,6 +1275,10 @@ int pcfd_create_fr(const pcfd_mesh_desc* mesh, const pcfd_params* params, const 
   if (dev_alloc(c, &s->red, (size_t)FR_RED_BLOCKS * 32)) return 1;
   if (dev_alloc(c, &s->redout, 128)) return 1;
   if (dev_alloc(c, &s->dbad, 4)) return 1;
+  if (viscous) {
+    if (dev_alloc(c, &s->vflux, (size_t)c->nedge * 4)) return 1;
+    if (dev_alloc(c, &s->bvflux, (size_t)c->nb * 4)) return 1;
+  }
   // the implicit path always needs the matrix; allocate it lazily like the perfect-gas path does (pcfd_jacobian)
   {   // beta defaults to 1 (no preconditioning) until the host sets the field
     std::vector<double> ones(c->fsize[PCFD_F_BETA], 1.0);

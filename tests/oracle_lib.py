@@ -215,25 +215,6 @@ class OrcTransport(C.Structure):
                 ("mu_white", C.c_double * 4 * _S), ("k_white", C.c_double * 4 * _S)]
 
 
-def fill_transport(t, g):
-    """Species transport tables of an NSFR fixture (species_mu_fit, species_k_fit [ns,3,6]; species_white [ns,8];
-    species_fit_counts [ns,2]) into an orc_transport-shaped ctypes structure."""
-    cnt = np.asarray(g["species_fit_counts"]).reshape(-1, 2)
-    ns = len(cnt)
-    mu, k, wh = (np.asarray(g["species_mu_fit"]).reshape(ns, 3, 6), np.asarray(g["species_k_fit"]).reshape(ns, 3, 6),
-                 np.asarray(g["species_white"]).reshape(ns, 8))
-    for i in range(ns):
-        t.nmu[i], t.nk[i] = int(cnt[i, 0]), int(cnt[i, 1])
-        for r in range(3):
-            for j in range(6):
-                t.mu_fit[i][r][j] = mu[i, r, j]
-                t.k_fit[i][r][j] = k[i, r, j]
-        for j in range(4):
-            t.mu_white[i][j] = wh[i, j]
-            t.k_white[i][j] = wh[i, 4 + j]
-    return t
-
-
 class OrcFrParams(C.Structure):
     """orc_fr_params (oracle/pcfd_oracle.h)."""
     _fields_ = [("chem", C.POINTER(OrcChemModel)),
@@ -273,6 +254,7 @@ class FrOracle(Oracle):
         for j in range(self.nvars):
             p.qinf[j] = qinf[j]
         if int(meta.get("viscous", 0)):
+            from proteuscfd_b200.capi import fill_transport   # a pure-Python table filler, no compute
             self.transport = fill_transport(OrcTransport(), g)
             p.transport = C.pointer(self.transport)
             p.ref_viscosity, p.ref_k = float(meta["ref_viscosity"]), float(meta["ref_k"])

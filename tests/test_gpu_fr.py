@@ -37,6 +37,10 @@ def fr_ctx(name, rxn_on=None):
               qinf=g["qinf"])
     params = dict(sorder=int(meta["sorder"]), limiter=int(meta["limiter"]), no_cvbc=int(meta["no_cvbc"]), gamma=0.0,
                   chi=meta["chi"], cfl=meta["cfl"], fr=fr)
+    if int(meta.get("viscous", 0)):      # compressibleNSFR: species transport tables, Re, PrT
+        fr.update(transport={k: g[k] for k in ("species_mu_fit", "species_k_fit", "species_white", "species_fit_counts")},
+                  ref_viscosity=meta["ref_viscosity"], ref_k=meta["ref_k"])
+        params.update(Re=meta["Re"], PrT=meta["PrT"])
     ctx = capi.Context(mesh, params)
     assert (ctx.neqn, ctx.nvars, ctx.nterms) == (NEQ, NV, NT)
     beta = np.ones(ctx.field_size(capi.F_BETA))

@@ -1,0 +1,141 @@
+"""The viscous reacting eqnset (compressibleNSFR) on the GPU, through the C ABI, against the fixture written by the
+reference itself (tests/golden/box4_nsfr_implicit.npz: Re = 111, temperatures on both sides of the 1000 K switch between
+the Sutherland law and the NASA RP-1311 fits).
+
+Bars, and why:
+ * BIT-EXACT: BC states, gradient, limiter, time step, LU and SGS given the same matrix, the species rows of the
+   off-diagonal Jacobian blocks (no viscous part).
+ * 1e-12 relative: the momentum / energy rows of the residual and of the off-diagonal blocks.  They carry the viscous
+   flux / analytic viscous Jacobian, whose mixture viscosity and conductivity call pow / log / exp (species.tcc:393-479):
+   CUDA libm here, glibc in the reference, 1-2 ulp apart.  The two state-independent powers of Wilke's rule
+   (chem.tcc:908-909) are evaluated on the host with the C library, like the reference.
+ * species rows of b, diagonal blocks, the implicit update: as for compressibleEulerFR (tests/test_gpu_fr.py).
+"""
+import numpy as np
+import pytest
+
+from tests.oracle_lib import FrOracle, load_golden
+from tests.test_gpu_fr import NEQ, NS, NV, fr_ctx, source_scale
+from tests.test_oracle import exact
+
+pytestmark = pytest.mark.gpu
+
+NAME = "box4_nsfr_implicit"
+
+
+def test_nsfr_update_bcs_gradient_limiter_timestep():
+    from proteuscfd_b200 import capi
+    ctx, g, _ = fr_ctx(NAME)
+    ctx.set_field(capi.F_Q, g["q_pre"])
+    ctx.update_bcs()
+    exact(ctx.get_field(capi.F_Q), g["q0"], "q after UpdateBCs")
+    ctx.lsq_coefficients()
+    ctx.gradient()
+    exact(ctx.get_field(capi.F_QGRAD), g["qgrad"], "qgrad")
+    ctx.limiter()
+    exact(ctx.get_field(capi.F_LIMITER), g["limiter"], "limiter")
+    dtmin = ctx.timestep()
+    exact(ctx.get_field(capi.F_TIMESTEP), g["timestep"], "timestep")
+    assert dtmin == g["dtmin"][0]
+
+
+def test_nsfr_residual(oracle):
+    from proteuscfd_b200 import capi
+    ctx, g, meta = fr_ctx(NAME)
+    ctx.lsq_coefficients()
+    ctx.set_field(capi.F_Q, g["q0"])
+    ctx.set_field(capi.F_QGRAD, g["qgrad"])
+    ctx.set_field(capi.F_LIMITER, g["limiter"])
+    s = ctx.residual(want_norms=True)
+    b = ctx.get_field(capi.F_B).reshape(-1, NEQ)
+    bref = g["b"].reshape(-1, NEQ)
+    # momentum / energy rows: inviscid part exact, viscous part to libm rounding -> 1e-12 of the row's magnitude
+    scale = np.abs(bref[:, NS:]).max(axis=0)
+    err = np.abs(b[:, NS:] - bref[:, NS:]) / scale
+    assert err.max() <= 1e-12, f"momentum / energy rows off by {err.max():.3e} relative"
+    sc = source_scale(oracle, g, meta, g["q0"], g["vol"])
+    errs = np.abs(b[:, :NS] - bref[:, :NS])
+    assert np.all(errs <= 1e-12 * sc + 1e-300)
+    assert np.isclose(np.sqrt(s[0]) / b.size, g["resnorm"][0], rtol=1e-12)
+    # the viscous flux is really there: the oracle without it differs at the percent level
+    o = FrOracle(oracle, g, meta)
+    o.c.viscous = 0
+    b0 = o.residual(g["q0"].copy(), g["qgrad"], g["limiter"], g["beta"]).reshape(-1, NEQ)
+    assert np.abs(b0[:, NS:] - bref[:, NS:]).max() > 1e-3 * scale.max()
+    assert np.abs(b[:, NS:] - bref[:, NS:]).max() < 1e-9 * np.abs(b0[:, NS:] - bref[:, NS:]).max()
+
+
+def test_nsfr_jacobian_lu_sgs():
+    from proteuscfd_b200 import capi
+    ctx, g, meta = fr_ctx(NAME)
+    ctx.set_field(capi.F_Q, g["q0"])
+    ctx.set_field(capi.F_TIMESTEP, g["timestep"])
+    ctx.jacobian()
+    ia, ja, iau, _ = ctx.get_crs()
+    exact(ia, g["ia"], "ia")
+    exact(ja, g["ja"], "ja")
+    A = ctx.get_field(capi.F_A).reshape(-1, NEQ, NEQ)
+    Aref = g["A"].reshape(-1, NEQ, NEQ)
+    offd = np.ones(len(A), bool)
+    offd[iau] = False
+    exact(A[offd][:, :NS, :], Aref[offd][:, :NS, :], "species rows of the off-diagonal blocks (no viscous part)")
+    blk = np.abs(Aref[offd]).reshape(-1, NEQ * NEQ).max(axis=1)[:, None, None]
+    err = np.abs(A[offd][:, NS:, :] - Aref[offd][:, NS:, :]) / blk
+    assert err.max() <= 1e-12, f"momentum / energy rows of the off-diagonal blocks off by {err.max():.3e} of the block"
+    scale = np.abs(Aref[iau]).reshape(-1, NEQ * NEQ).max(axis=1)[:, None, None]
+    assert np.all(np.abs(A[iau] - Aref[iau]) <= 2e-6 * scale)
+    # LU + SGS on the reference's own matrix and right-hand side: exact
+    ctx.set_field(capi.F_A, g["A"])
+    ctx.set_field(capi.F_B, g["b"])
+    ctx.prepare_sgs()
+    exact(ctx.get_field(capi.F_A), g["A_lu"], "A after LU")
+    exact(ctx.get_crs()[3], g["pv"], "pv")
+    ctx.blank_x()
+    ctx.sgs(int(meta["nSgs"]))
+    exact(ctx.get_field(capi.F_X), g["x"], "x")
+    ctx.apply_dq()
+    exact(ctx.get_field(capi.F_Q), g["q1"], "q1")
+
+
+def test_nsfr_implicit_iteration_close():
+    from proteuscfd_b200 import capi
+    ctx, g, meta = fr_ctx(NAME)
+    ctx.lsq_coefficients()
+    ctx.set_field(capi.F_Q, g["q_pre"])
+    ctx.implicit_iterate(int(meta["nSgs"]), refresh_jac=True)
+    x = ctx.get_field(capi.F_X).reshape(-1, NEQ)
+    xref = g["x"].reshape(-1, NEQ)
+    err = np.abs(x - xref).max(axis=0) / np.abs(xref).max(axis=0)
+    assert np.all(err <= 1e-5), f"relative error of the update per equation: {err}"
+
+
+def test_nsfr_frozen_implicit_vs_oracle(oracle):
+    """reactionsOn = 0 leaves the transport fits as the only libm calls: the whole implicit iteration then agrees with
+    the oracle to 1e-10 relative on the update (the analytic viscous Jacobian is not finite-differenced, so nothing
+    amplifies the 1-2 ulp of pow / log / exp)."""
+    from proteuscfd_b200 import capi
+    g, meta = load_golden(NAME)
+    meta = dict(meta, rxnOn=0.0)
+    o = FrOracle(oracle, g, meta)
+    ctx, _, _ = fr_ctx(NAME, rxn_on=0)
+    q = g["q_pre"].copy()
+    beta, sw = g["beta"], g["lsq_sw"]
+    ia, ja, iau = o.crs_init()
+    dt, _ = o.timestep(q, beta)
+    A = o.jacobian(q, beta, dt, ia, ja, iau)
+    o.update_bcs(q, beta)
+    grad = o.gradient(q, sw)
+    lim = o.limiter(q, grad)
+    b = o.residual(q, grad, lim, beta)
+    pv = o.prepare_sgs(iau, A)
+    x, _ = o.sgs(3, ia, ja, iau, A, pv, b)
+    o.apply_dq(q, x)
+    ctx.lsq_coefficients()
+    ctx.set_field(capi.F_Q, g["q_pre"])
+    ctx.implicit_iterate(3, refresh_jac=True)
+    xg = ctx.get_field(capi.F_X).reshape(-1, NEQ)
+    xo = x.reshape(-1, NEQ)
+    err = np.abs(xg - xo).max(axis=0) / np.abs(xo).max(axis=0)
+    assert np.all(err <= 1e-10), f"relative error of the update per equation: {err}"
+    qg = ctx.get_field(capi.F_Q).reshape(-1, NV)
+    assert np.allclose(qg, q.reshape(-1, NV), rtol=1e-10, atol=1e-14)
