@@ -403,6 +403,13 @@ def main():
         except Exception as e:
             frb = {"error": f"{type(e).__name__}: {e}"[:300]}
 
+    frv = None
+    if not args.no_fr and rank == 0 and world == 1:
+        try:
+            frv = fr_bench(args, peak, torch, stream, local_rank, viscous=True)
+        except Exception as e:
+            frv = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -428,7 +435,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": nq * 8 * world,
                     "d2h_bytes_per_step": nq * 8 * world, "what": "pcfd_set_field(q) from pinned host memory + pcfd_explicit_iterate + "
                                                           "pcfd_get_field(q) per step"},
-            "gpu_launches": int(launches) * world, "clocks": clocks, "phases": phases, "sgs": sgs, "reacting": frb,
+            "gpu_launches": int(launches) * world, "clocks": clocks, "phases": phases, "sgs": sgs, "reacting": frb, "reacting_viscous": frv,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -588,21 +595,26 @@ def sgs_bench_multi(args, ctx, xch, rank, world, local_rank, peak, torch, dist, 
     return out
 
 
-def fr_params_from_fixture():
+def fr_params_from_fixture(viscous=False):
     """Chemistry tables (the reference's chemModels/5speciesAir.rxn + NASA-7 data as its ChemModel parsed them),
-    reference values and free stream of the reacting fixture the reference wrote (tools/make_golden.py)."""
-    d = dict(np.load(os.path.join(ROOT, "tests", "golden", "box4_fr_implicit.npz")))
+    reference values and free stream of the reacting fixture the reference wrote (tools/make_golden.py); viscous: the
+    compressibleNSFR fixture, which adds the species transport tables (chemdata/trans.inp), Re and PrT."""
+    d = dict(np.load(os.path.join(ROOT, "tests", "golden", "box4_nsfr_implicit.npz" if viscous else "box4_fr_implicit.npz")))
     meta = dict(zip([str(k) for k in d["meta_keys"]], d["meta_vals"]))
     chem = {k: d[k] for k in ("species_mw", "species_nasa7", "rxn_A_EA_n", "rxn_flags", "rxn_species", "rxn_nup", "rxn_nupp",
                               "rxn_tbeff")}
     chem["dims"] = d["chem_dims"]
-    return dict(chem=chem, ref_density=meta["ref_density"], ref_velocity=meta["ref_velocity"],
+    extra = {}
+    if viscous:
+        extra = dict(transport={k: d[k] for k in ("species_mu_fit", "species_k_fit", "species_white", "species_fit_counts")},
+                     ref_viscosity=meta["ref_viscosity"], ref_k=meta["ref_k"], Re=meta["Re"], PrT=meta["PrT"])
+    return dict(chem=chem, **extra, ref_density=meta["ref_density"], ref_velocity=meta["ref_velocity"],
                 ref_temperature=meta["ref_temperature"], ref_pressure=meta["ref_pressure"], ref_time=meta["ref_time"],
                 ref_specific_enthalpy=meta["ref_specific_enthalpy"], pref=meta["Pref"], dt=meta["dt"],
                 use_local_dt=int(meta["useLocalTimeStepping"]), rxn_on=1, qinf=d["qinf"])
 
 
-def fr_bench(args, peak, torch, stream, local_rank):
+def fr_bench(args, peak, torch, stream, local_rank, viscous=False):
     """Reacting 5-species air (compressibleEulerFR), implicit: 9 equations per node, 9x9 block-CRS Jacobian (FD flux +
     FD source Jacobians, dense temporal terms), SGS.  Timed: the Jacobian refresh, one implicit iteration without it
     (UpdateBCs, gradient, limiter, HLLC residual + finite-rate source, nsgs SGS sweeps, ApplyDQ) and the SGS sweep."""
@@ -611,7 +623,7 @@ def fr_bench(args, peak, torch, stream, local_rank):
     n = args.fr_n or args.n
     nsgs = 5
     torch.cuda.empty_cache()
-    mesh, params, q, beta = fr_box_case(n, fr_params_from_fixture(), device=f"cuda:{local_rank}")
+    mesh, params, q, beta = fr_box_case(n, fr_params_from_fixture(viscous), device=f"cuda:{local_rank}")
     c = capi.Context(mesh, params, device=local_rank)
     c.set_stream(stream.cuda_stream)
     c.set_field(capi.F_BETA, beta)
@@ -649,21 +661,26 @@ def fr_bench(args, peak, torch, stream, local_rank):
     ms_sweep = e2.elapsed_time(e3) / nsw
     kern = {k: v[0] / max(v[1], 1) for k, v in tab.items()}
     it_kernels = ("kfr_update_bcs_edges", "kfr_gradient", "kfr_limiter", "kfr_fill_int", "kfr_clip_edges", "kfr_clip_nodes",
-                  "kfr_limiter_final", "kfr_flux_edges", "kfr_flux_bedges", "kfr_source", "kfr_residual_gather", "kfr_apply_dq")
+                  "kfr_limiter_final", "kfr_flux_edges", "kfr_flux_bedges", "kfr_vflux_edges", "kfr_source", "kfr_residual_gather",
+                  "kfr_apply_dq")
     ms_explicit_part = sum(kern.get(k, 0.0) for k in it_kernels)
     nblocks = c.get_crs()[1].size
     neqn, nterms = c.neqn, c.nterms
     ne, nn = c.nedge, c.nnode
     bytes_sweep = 2 * (nblocks * 8 * neqn * neqn + 4 * nblocks + 4 * (nn + 1) + 4 * neqn * nn + 8 * neqn * 3 * nn)
     bytes_resid = 40 * ne + nn * (8 * neqn + 24 * neqn + 8 * neqn + 24 + 8) + nn * 8 * neqn
-    ms_resid = sum(kern.get(k, 0.0) for k in ("kfr_flux_edges", "kfr_flux_bedges", "kfr_source", "kfr_residual_gather"))
+    if viscous:     # the viscous pass re-reads edges, q and all gradient terms, and read-modify-writes b
+        bytes_resid += 40 * ne + nn * (8 * nterms + 24 * nterms + 24 + 8) + nn * 16 * neqn
+    ms_resid = sum(kern.get(k, 0.0) for k in ("kfr_flux_edges", "kfr_flux_bedges", "kfr_vflux_edges", "kfr_source",
+                                              "kfr_residual_gather"))
     bytes_grad = 8 * ne + nn * (24 + 8 * nterms + 48 + 24 * nterms)
     bytes_lim = ((8 * ne + nn * (8 * neqn + 16 * neqn)) + (8 * ne + nn * (8 * neqn + 24 * neqn + 24 + 16 * neqn) + nn * 8 * neqn)
                  + (8 * ne + nn * (8 * neqn + 24 * neqn + 24 + 8 * neqn) + nn * 8 * neqn))
     bytes_iter = bytes_grad + bytes_lim + bytes_resid + nsgs * bytes_sweep
-    out = {"workload": f"BASELINE configs[4] on one GPU: reacting 5-species air (compressibleEulerFR), Kuhn box n={n} "
+    out = {"workload": f"BASELINE configs[4] on one GPU: reacting 5-species air ({'compressibleNSFR' if viscous else 'compressibleEulerFR'}), Kuhn box n={n} "
                        f"({nn} nodes, {ne} edges, {nblocks} 9x9 blocks = {nblocks * 648 / 1e9:.1f} GB), HLLC 2nd order + LSQ + "
-                       "Venkatakrishnan + finite-rate source, implicit",
+                       "Venkatakrishnan + finite-rate source" + (" + Wilke-mixed viscous flux / analytic viscous Jacobian" if viscous else "")
+                       + ", implicit",
            "jacobian_refresh_ms": ms_jac, "sgs_ms_per_sweep": ms_sweep, "sgs_sweeps_per_s": 1e3 / ms_sweep,
            "sgs_algorithmic_bytes_per_sweep": bytes_sweep, "sgs_GBps": bytes_sweep / (ms_sweep * 1e-3) / 1e9,
            "sgs_frac_hbm": bytes_sweep / (ms_sweep * 1e-3) / 1e9 / peak,

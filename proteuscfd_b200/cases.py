@@ -250,6 +250,8 @@ def fr_box_case(n, fr, mach=0.5, jitter=0.15, cfl=5.0, limiter=2, sorder=2, colo
     qinf = np.asarray(fr["qinf"], dtype=np.float64)
     params = dict(eqnset=capi.EQNSET_COMPRESSIBLE_EULER_FR, sorder=sorder, limiter=limiter, no_cvbc=0, gamma=0.0, chi=0.0,
                   cfl=cfl, fr=fr)
+    if fr.get("transport") is not None:     # compressibleNSFR: Re and PrT travel in pcfd_params
+        params.update(eqnset=capi.EQNSET_COMPRESSIBLE_NS_FR, Re=fr["Re"], PrT=fr.get("PrT", 0.85))
     nn, nb = mesh["nnode"], mesh["nbnode"]
     X = mesh["xyz"].reshape(-1, 3)
     x, y, z = X[:, 0], X[:, 1], X[:, 2]

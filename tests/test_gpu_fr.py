@@ -192,7 +192,11 @@ def test_fr_frozen_implicit_bit_exact(oracle):
 
 def fixture_fr_params(name="box4_fr_implicit", rxn_on=None):
     g, meta = load_golden(name)
-    return dict(chem=chem_tables(g), ref_density=meta["ref_density"], ref_velocity=meta["ref_velocity"],
+    extra = {}
+    if int(meta.get("viscous", 0)):      # compressibleNSFR: species transport tables, Re, PrT
+        extra = dict(transport={k: g[k] for k in ("species_mu_fit", "species_k_fit", "species_white", "species_fit_counts")},
+                     ref_viscosity=meta["ref_viscosity"], ref_k=meta["ref_k"], Re=meta["Re"], PrT=meta["PrT"])
+    return dict(chem=chem_tables(g), **extra, ref_density=meta["ref_density"], ref_velocity=meta["ref_velocity"],
                 ref_temperature=meta["ref_temperature"], ref_pressure=meta["ref_pressure"], ref_time=meta["ref_time"],
                 ref_specific_enthalpy=meta["ref_specific_enthalpy"], pref=meta["Pref"], dt=meta["dt"],
                 use_local_dt=int(meta["useLocalTimeStepping"]), rxn_on=int(meta["rxnOn"]) if rxn_on is None else rxn_on,
@@ -202,6 +206,9 @@ def fixture_fr_params(name="box4_fr_implicit", rxn_on=None):
 def oracle_for_fr(lib, mesh, params, g, meta):
     """FrOracle on a generated mesh: fixture tables / reference values, the mesh and numerics of `mesh`, `params`."""
     gg = dict(g)
+    gg.pop("mut", None)      # the fixture's eddy-viscosity field belongs to the fixture's mesh
+    if mesh.get("mut") is not None:
+        gg["mut"] = np.asarray(mesh["mut"], dtype=np.float64)
     for k in ("edges_n", "edges_a", "bedges_n", "bedges_a", "bedges_bctype", "xyz", "vol", "ipsp", "psp"):
         gg[k] = np.asarray(mesh[k])
     mm = dict(meta)

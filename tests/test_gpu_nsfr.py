@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 
 from tests.oracle_lib import FrOracle, load_golden
-from tests.test_gpu_fr import NEQ, NS, NV, fr_ctx, source_scale
+from tests.test_gpu_fr import NEQ, NS, NV, fixture_fr_params, fr_ctx, oracle_for_fr, source_scale
 from tests.test_oracle import exact
 
 pytestmark = pytest.mark.gpu
@@ -139,3 +139,59 @@ def test_nsfr_frozen_implicit_vs_oracle(oracle):
     assert np.all(err <= 1e-10), f"relative error of the update per equation: {err}"
     qg = ctx.get_field(capi.F_Q).reshape(-1, NV)
     assert np.allclose(qg, q.reshape(-1, NV), rtol=1e-10, atol=1e-14)
+
+
+@pytest.mark.parametrize("colored", [True, False])
+def test_nsfr_seeded_box_vs_oracle(oracle, colored):
+    """A 10^3 box in the SURVEY 8d state with a smooth, non-zero eddy-viscosity field (so the (mu + mut) and cp mut / PrT
+    terms are live), frozen chemistry: two implicit iterations (the second re-using the LU'd Jacobian), GPU vs oracle.
+    Gradient and limiter are bit-exact; residual and update to 1e-11 of the equation's magnitude (transport libm)."""
+    from proteuscfd_b200 import capi
+    from proteuscfd_b200.cases import fr_box_case
+    fr, g, meta = fixture_fr_params(NAME, rxn_on=0)
+    mesh, params, q0, beta = fr_box_case(10, fr, colored=colored)
+    ntot = mesh["nnode"] + mesh["gnode"] + mesh["nbnode"]
+    X = np.asarray(mesh["xyz"]).reshape(-1, 3)
+    mut = np.zeros(ntot)
+    mut[: len(X)] = 0.2 * (1.0 + 0.5 * np.sin(2 * np.pi * X[:, 0]) * np.cos(2 * np.pi * X[:, 2]))
+    mesh = dict(mesh, mut=mut)
+    o = oracle_for_fr(oracle, mesh, params, g, meta)
+    assert o.c.viscous == 1
+    ctx = capi.Context(mesh, params)
+    ctx.set_field(capi.F_BETA, beta)
+    ctx.set_field(capi.F_MUT, mut)
+    ctx.lsq_coefficients()
+    ctx.set_field(capi.F_Q, q0)
+    q = q0.copy()
+    bo = beta[: mesh["nnode"] + mesh["gnode"]].copy()
+    _, sw = o.lsq()
+    ia, ja, iau = o.crs_init()
+    dt, _ = o.timestep(q, bo)
+    A = o.jacobian(q, bo, dt, ia, ja, iau)
+    pv = None
+
+    def close(a, ref, what, tol):
+        a, ref = a.reshape(-1, NEQ), ref.reshape(-1, NEQ)
+        err = np.abs(a - ref).max(axis=0) / np.abs(ref).max(axis=0)
+        assert np.all(err <= tol), f"{what}: relative error per equation {err}"
+
+    for it in range(2):
+        o.update_bcs(q, bo)
+        grad = o.gradient(q, sw)
+        lim = o.limiter(q, grad)
+        b = o.residual(q, grad, lim, bo)
+        if pv is None:
+            pv = o.prepare_sgs(iau, A)
+        x, _ = o.sgs(2, ia, ja, iau, A, pv, b)
+        o.apply_dq(q, x)
+        ctx.implicit_iterate(2, refresh_jac=(it == 0))
+        if it == 0:
+            exact(ctx.get_field(capi.F_QGRAD), grad, "qgrad")
+            exact(ctx.get_field(capi.F_LIMITER), lim, "limiter")
+        close(ctx.get_field(capi.F_B), b, f"b, iteration {it}", 1e-11)
+        close(ctx.get_field(capi.F_X), x, f"x, iteration {it}", 1e-10)
+    assert np.allclose(ctx.get_field(capi.F_Q).reshape(-1, NV), q.reshape(-1, NV), rtol=1e-10, atol=1e-14)
+    # the eddy viscosity matters: the laminar oracle residual differs visibly
+    o.c.mut = None
+    b_lam = o.residual(q, grad, lim, bo).reshape(-1, NEQ)
+    assert np.abs(b_lam[:, NS:] - b.reshape(-1, NEQ)[:, NS:]).max() > 1e-4 * np.abs(b).max()
