@@ -460,6 +460,9 @@ def sgs_bench(args, ctx, mesh, params, q0, peak, torch, stream, local_rank):
     c.sgs(2, want_ddq=False)
     torch.cuda.synchronize()
     tab0 = c.profile_table()
+    # timed regions run with the per-kernel event profiling OFF (its event records sit between the launches and would
+    # serialise the programmatic dependent launch of consecutive SGS levels); a profiled pass follows for the tables
+    c.profile(on=False)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     nsw = 10
     e0.record(stream)
@@ -480,6 +483,9 @@ def sgs_bench(args, ctx, mesh, params, q0, peak, torch, stream, local_rank):
     e3.record(stream)
     torch.cuda.synchronize()
     ms_it = e2.elapsed_time(e3) / reps
+    c.profile(on=True)
+    c.implicit_iterate(nsgs_it, refresh_jac=False)
+    torch.cuda.synchronize()
     tab = c.profile_table()
     _, nblocks = c.get_crs()[1].size, c.get_crs()[1].size
     pbs = pass_bytes(c.nedge, c.nnode, nblocks)
@@ -493,8 +499,10 @@ def sgs_bench(args, ctx, mesh, params, q0, peak, torch, stream, local_rank):
                                   "ms": ms_it, "Medges_s": c.nedge / (ms_it * 1e-3) / 1e6, "algorithmic_bytes": bytes_it,
                                   "GBps": bytes_it / (ms_it * 1e-3) / 1e9, "frac_hbm": bytes_it / (ms_it * 1e-3) / 1e9 / peak},
            "jacobian_ms": {k: tab0[k][0] / tab0[k][1] for k in ("k_jac_edges", "k_jac_bnodes", "k_jac_diag", "k_lu_diag") if k in tab0},
+           "kernels_ms": {k: v[0] / max(v[1], 1) for k, v in tab.items()},
            "kernel": "k_sgs_tile (cp.async.bulk + mbarrier streamed tiles)" if "k_sgs_tile" in tab else "k_sgs_level",
-           "launches_per_sweep": sum(tab[k][1] - tab0.get(k, (0, 0))[1] for k in ("k_sgs_level", "k_sgs_tile") if k in tab) / nsw}
+           "launches_per_sweep": sum(tab[k][1] - tab0.get(k, (0, 0))[1] for k in ("k_sgs_level", "k_sgs_tile") if k in tab) / nsgs_it,
+           "pdl": "levels of a sweep launched with programmatic stream serialization (PCFD_SGS_PDL=0 disables)"}
     c.close()
     return out
 
@@ -632,7 +640,6 @@ def fr_bench(args, peak, torch, stream, local_rank, viscous=False):
     ev = lambda: torch.cuda.Event(enable_timing=True)
     c.implicit_iterate(nsgs, refresh_jac=True)    # warm-up: builds A, LU
     torch.cuda.synchronize()
-    c.profile(on=True, reset=True)
     reps = 3
     e0, e1, e2, e3 = ev(), ev(), ev(), ev()
     e0.record(stream)
@@ -653,6 +660,14 @@ def fr_bench(args, peak, torch, stream, local_rank, viscous=False):
     e2.record(stream)
     c.sgs(nsw, want_ddq=False)
     e3.record(stream)
+    torch.cuda.synchronize()
+    # per-kernel tables from a separate profiled pass (event records between launches would serialise the programmatic
+    # dependent launch of consecutive SGS levels, so the timed regions above run without them)
+    c.profile(on=True, reset=True)
+    c.timestep(want_min=False)
+    c.jacobian()
+    c.prepare_sgs()
+    c.implicit_iterate(nsgs, refresh_jac=False)
     torch.cuda.synchronize()
     c.profile(on=False)
     tab = c.profile_table()

@@ -1138,6 +1138,7 @@ struct Impl {
     constexpr int RPW = 32 / Wd::NEQ;
     const double* A = c->f[PCFD_F_A];
     double* x = c->f[PCFD_F_X];
+    bool prev_tile = false;
     for (int s = 0; s < nsgs; s++) {
       for (int dir = 0; dir < 2; dir++) {
         const std::vector<int>& off = dir ? c->lev_b : c->lev_f;
@@ -1157,6 +1158,7 @@ struct Impl {
             const int pf = c->sgs_pf_dist >= 0 ? c->sgs_pf_dist : (int)((size_t)(24 << 20) / shm);
             const int row0 = dir ? c->lev_first_b[l] : c->lev_first_f[l];
             const int step = dir ? c->lev_step_b[l] : c->lev_step_f[l];
+            const bool chain = c->sgs_pdl && !c->prof && prev_tile;   // programmatic dependent launch between levels
             PROF("k_sgs_tile");
 #define PCFD_FR_TILE(WW)                                                                                               \
   do {                                                                                                                 \
@@ -1165,13 +1167,16 @@ struct Impl {
       CK(cudaFuncSetAttribute(k_sgs_tile_t<Wd::NEQ, WW, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));  \
       set_##WW = shm;                                                                                                  \
     }                                                                                                                  \
-    k_sgs_tile_t<Wd::NEQ, WW, 16><<<tiles, WW * 32, shm, c->stream>>>(row0, step, nr, c->ia, c->ja, A, c->pv, c->f[PCFD_F_B], x, pf); \
+    CK(launch_maybe_pdl(k_sgs_tile_t<Wd::NEQ, WW, 16>, tiles, WW * 32, shm, c->stream, chain, row0, step, nr, c->ia, c->ja, A, \
+                        c->pv, c->f[PCFD_F_B], x, pf));                                                                \
   } while (0)
             if (Wt == 1) PCFD_FR_TILE(1); else if (Wt == 4) PCFD_FR_TILE(4); else PCFD_FR_TILE(2);
 #undef PCFD_FR_TILE
             LAUNCH_CHECK();
+            prev_tile = true;
             continue;
           }
+          prev_tile = false;
           PROF("kfr_sgs_level");
           kfr_sgs_level<NS, 2><<<nblk((long long)warps * 32, 128), 128, 0, c->stream>>>(rows + off[l], nr, c->ia, c->ja, c->iau, A,
                                                                                        c->pv, c->f[PCFD_F_B], x);
@@ -1180,6 +1185,7 @@ struct Impl {
       }
       // the reference halo-updates x here (crs.tcc:147-150); its |xOld - xNorm| monitor needs the last two norms
       if (ddq && s >= nsgs - 2) {
+        prev_tile = false;
         if (fr_sumsq(c, x, c->nnode, (s == nsgs - 1) ? 0 : 1, nullptr)) return 1;
       }
     }

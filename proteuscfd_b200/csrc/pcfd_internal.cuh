@@ -122,6 +122,7 @@ struct pcfd_ctx {
   // the level are not consecutive in memory -> per-lane-load kernel); PCFD_SGS_TILE_WARPS = 0 disables it
   int sgs_tile_warps = 4, sgs_tile_lpr = 16;   // PCFD_SGS_TILE_WARPS / PCFD_SGS_TILE_LPR (lanes per row: 5, 10, 16)
   int sgs_pf_dist = -1;    // PCFD_SGS_PREFETCH_TILES (-1: automatic, 0: off)
+  bool sgs_pdl = true;     // PCFD_SGS_PDL=0: plain launches between the levels of a sweep (no programmatic dependent launch)
   int sgs_ring_stages = 0, sgs_ring_ctas_per_sm = 0, ring_cap_blocks = 0, num_sms = 148;
   std::vector<int> tile_cap_f, tile_cap_b, lev_first_f, lev_first_b, lev_step_f, lev_step_b;
   std::vector<void*> allocs;

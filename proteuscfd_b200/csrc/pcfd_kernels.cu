@@ -1687,6 +1687,7 @@ static int create_impl(const pcfd_mesh_desc* mesh, const pcfd_params* params, in
   if (const char* e = getenv("PCFD_SGS_TILE_WARPS")) c->sgs_tile_warps = atoi(e);
   if (c->sgs_tile_warps != 0 && c->sgs_tile_warps != 1 && c->sgs_tile_warps != 2 && c->sgs_tile_warps != 4) c->sgs_tile_warps = 4;
   if (const char* e = getenv("PCFD_SGS_PREFETCH_TILES")) c->sgs_pf_dist = atoi(e);
+  if (const char* e = getenv("PCFD_SGS_PDL")) c->sgs_pdl = atoi(e) != 0;
   if (const char* e = getenv("PCFD_SGS_RING_STAGES")) c->sgs_ring_stages = atoi(e);
   if (const char* e = getenv("PCFD_SGS_RING_CTAS")) c->sgs_ring_ctas_per_sm = atoi(e);
   if (c->sgs_ring_stages > 0) c->sgs_tile_warps = 1;   // ring tiles are one warp's rows
@@ -2438,6 +2439,7 @@ int pcfd_sgs(pcfd_ctx* c, int nsgs, double* ddq) {
   constexpr int RPW = 32 / NEQN;
   const double* A = c->f[PCFD_F_A];
   double* x = c->f[PCFD_F_X];
+  bool prev_tile = false;   // the previous launch of this call was a k_sgs_tile level
   for (int s = 0; s < nsgs; s++) {
     for (int dir = 0; dir < 2; dir++) {
       const std::vector<int>& off = dir ? c->lev_b : c->lev_f;
@@ -2490,6 +2492,8 @@ int pcfd_sgs(pcfd_ctx* c, int nsgs, double* ddq) {
           const int pf = c->sgs_pf_dist >= 0 ? c->sgs_pf_dist : (int)((size_t)(24 << 20) / shm);
           const int row0 = dir ? c->lev_first_b[l] : c->lev_first_f[l];
           const int step = dir ? c->lev_step_b[l] : c->lev_step_f[l];
+          // programmatic dependent launch between consecutive levels of this call (never across other kernels)
+          const bool chain = c->sgs_pdl && !c->prof && prev_tile;
           PROF("k_sgs_tile");
 #define PCFD_TILE_LAUNCH(WW, LL)                                                                                      \
   do {                                                                                                                \
@@ -2498,15 +2502,18 @@ int pcfd_sgs(pcfd_ctx* c, int nsgs, double* ddq) {
       CK(cudaFuncSetAttribute(k_sgs_tile_t<NEQN, WW, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));            \
       set_##WW##_##LL = shm;                                                                                          \
     }                                                                                                                 \
-    k_sgs_tile_t<NEQN, WW, LL><<<tiles, WW * 32, shm, c->stream>>>(row0, step, nr, c->ia, c->ja, A, c->pv, c->f[PCFD_F_B], x, pf); \
+    CK(launch_maybe_pdl(k_sgs_tile_t<NEQN, WW, LL>, tiles, WW * 32, shm, c->stream, chain, row0, step, nr, c->ia, c->ja, A, \
+                        c->pv, c->f[PCFD_F_B], x, pf));                                                               \
   } while (0)
           if (LPR == 5) { if (W == 1) PCFD_TILE_LAUNCH(1, 5); else if (W == 4) PCFD_TILE_LAUNCH(4, 5); else PCFD_TILE_LAUNCH(2, 5); }
           else if (LPR == 10) { if (W == 1) PCFD_TILE_LAUNCH(1, 10); else if (W == 4) PCFD_TILE_LAUNCH(4, 10); else PCFD_TILE_LAUNCH(2, 10); }
           else { if (W == 1) PCFD_TILE_LAUNCH(1, 16); else if (W == 4) PCFD_TILE_LAUNCH(4, 16); else PCFD_TILE_LAUNCH(2, 16); }
 #undef PCFD_TILE_LAUNCH
           LAUNCH_CHECK();
+          prev_tile = true;
           continue;
         }
+        prev_tile = false;
         PROF("k_sgs_level");
         const int nb_ = nblk((long long)warps * 32, 128);
         switch (c->sgs_unroll) {
@@ -2520,6 +2527,7 @@ int pcfd_sgs(pcfd_ctx* c, int nsgs, double* ddq) {
     }
     // xNorm of the last two sweeps only (crs.tcc:149-172 uses nothing else)
     if (ddq && s >= nsgs - 2) {
+      prev_tile = false;
       PROF("k_sumsq_partial");
       k_sumsq_partial<256, NEQN><<<RED_BLOCKS, 256, 0, c->stream>>>(x, c->nnode, c->red);
       LAUNCH_CHECK();

@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_sgs_tile_t(int row0, int step, i
   const bool active = (grp < RPW) && (slot < s1);
   const unsigned gmask = (LPR == 16 ? 0xffffu : ((1u << LPR) - 1u)) << (grp * LPR);   // the row's own lanes
   int row = 0, k0 = 0, nb = 0;
-  int p[NQ];
+  int p[NQ], col[R];
   double rhs = 0.0;
   double xr[R][NQ];
   if (active) {
@@ -134,15 +134,28 @@ __global__ void __launch_bounds__(WARPS * 32) k_sgs_tile_t(int row0, int step, i
 #pragma unroll
     for (int r = 0; r < R; r++) {
       const int u = r * LPR + t;
-      if (u < nb) {
-        const double* xc = x + (size_t)__ldg(ja + k0 + 1 + u) * NQ;
-#pragma unroll
-        for (int j = 0; j < NQ; j++) xr[r][j] = xc[j];
-      }
+      col[r] = (u < nb) ? __ldg(ja + k0 + 1 + u) : 0;
     }
 #pragma unroll
     for (int j = 0; j < NQ; j++) p[j] = __ldg(pv + (size_t)row * NQ + j);
     if (t < NQ) rhs = __ldg(b + (size_t)row * NQ + t);
+  }
+  // Programmatic dependent launch (levels of one pcfd_sgs call are launched back to back with
+  // cudaLaunchAttributeProgrammaticStreamSerialization): everything above -- the bulk copy of the tile's matrix bytes,
+  // the L2 prefetch, ia / ja / pv / b -- is independent of the previous level and overlaps its tail; only x carries the
+  // dependency (read below, written at the end), so the wait sits here.  Both instructions are no-ops in a plain launch.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (active) {
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const int u = r * LPR + t;
+      if (u < nb) {
+        const double* xc = x + (size_t)col[r] * NQ;
+#pragma unroll
+        for (int j = 0; j < NQ; j++) xr[r][j] = xc[j];
+      }
+    }
   }
   __syncthreads();        // mbarrier initialised before anyone waits on it
   mbar_wait(bar, 0);
@@ -211,5 +224,22 @@ __global__ void __launch_bounds__(WARPS * 32) k_sgs_tile_t(int row0, int step, i
   x[(size_t)row * NQ + t] = out;
 }
 
+
+// launch with (pdl = true) or without the programmatic-stream-serialization attribute
+template <class... KArgs, class... Args>
+inline cudaError_t launch_maybe_pdl(void (*kernel)(KArgs...), int grid, int block, size_t shm, cudaStream_t stream, bool pdl,
+                                    Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = shm;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 }  // namespace
