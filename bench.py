@@ -395,8 +395,16 @@ def main():
         except Exception as e:
             sgs = {"error": f"{type(e).__name__}: {e}"[:300]}
 
+    # ---------------------------------------------------------------- reacting eqnset across ranks (BASELINE configs[4])
+    frm = None
+    if not args.no_fr and world > 1:
+        try:
+            frm = fr_bench_multi(args, rank, world, local_rank, peak, torch, dist, stream)
+        except Exception as e:
+            frm = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     # ---------------------------------------------------------------- reacting eqnset (BASELINE configs[4] on one GPU)
-    frb = None
+    frb = frm
     if not args.no_fr and rank == 0 and world == 1:
         try:
             frb = fr_bench(args, peak, torch, stream, local_rank)
@@ -597,6 +605,101 @@ def sgs_bench_multi(args, ctx, xch, rank, world, local_rank, peak, torch, dist, 
                                   "GBps": bytes_it / (ms_it * 1e-3) / 1e9,
                                   "frac_hbm": bytes_it / (ms_it * 1e-3) / 1e9 / (peak * world),
                                   "clip_fallbacks": hp.clip_fallbacks}}
+    if hasattr(x, "close"):
+        x.close()
+    c.close()
+    return out
+
+
+def fr_bench_multi(args, rank, world, local_rank, peak, torch, dist, stream):
+    """BASELINE configs[4] as named: reacting 5-species air (compressibleEulerFR), implicit, on N partitions (one z-slab of
+    n^3 hexes per GPU, colour-sorted numbering, 9x9 block-CRS rows with ghost columns).  One iteration = UpdateBCs,
+    gradient, limiter, HLLC residual + finite-rate source, nsgs SGS sweeps, ApplyDQ with the reference's halo
+    exchanges (q 21 wide, qgrad 42, limiter 9, x 9 after every sweep); Jacobian kept.  Max over ranks."""
+    from proteuscfd_b200 import capi
+    from proteuscfd_b200.cases import fr_slab_case
+    from proteuscfd_b200.parallel import DistributedHotPath, NcclExchange, PObj, PutExchange, TorchGroup
+    n = args.fr_n or args.n
+    nsgs, reps = 5, 3
+    torch.cuda.empty_cache()
+    dev = torch.device("cuda", local_rank)
+    mesh, params, q, beta = fr_slab_case(n, rank, world, fr_params_from_fixture(), device=f"cuda:{local_rank}")
+    c = capi.Context(mesh, params, device=local_rank)
+    c.set_stream(stream.cuda_stream)
+    c.set_field(capi.F_BETA, beta)
+    group = TorchGroup(dist)
+    pobj = PObj(rank, world).BuildCommMaps(mesh["gNodeOwner"], mesh["gNodeLocalId"], group)
+    x = PutExchange(c, pobj, dist, torch, dev, group) if args.halo == "put" else NcclExchange(c, pobj, dist, torch, dev)
+    hp = DistributedHotPath(c, x)
+    hp.setup()
+    c.set_field(capi.F_Q, q)
+    hp.implicit_iterate(nsgs, refresh_jac=True)     # builds A and its LU; warm-up
+
+    def sync():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxms(ms):
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def total(v):
+        t = torch.tensor([v], device=dev, dtype=torch.int64)
+        dist.all_reduce(t)
+        return int(t.item())
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    sync()
+    e0, e1 = ev(), ev()
+    e0.record(stream)
+    for _ in range(reps):
+        hp.implicit_iterate(nsgs, refresh_jac=False)
+    e1.record(stream)
+    sync()
+    ms_it = maxms(e0.elapsed_time(e1) / reps)
+    finite = bool(np.isfinite(c.get_field(capi.F_Q)).all())
+    c.blank_x()
+    x.update(capi.F_X)
+    nsw = 6
+    sync()
+    e2, e3 = ev(), ev()
+    e2.record(stream)
+    for _ in range(nsw):
+        c.sgs(1, want_ddq=False)
+        x.update(capi.F_X)
+    e3.record(stream)
+    sync()
+    ms_sweep = maxms(e2.elapsed_time(e3) / nsw)
+    e4, e5 = ev(), ev()
+    e4.record(stream)
+    c.timestep(want_min=False)
+    c.jacobian()
+    c.prepare_sgs()
+    e5.record(stream)
+    sync()
+    ms_jac = maxms(e4.elapsed_time(e5))
+    nblocks = int(c.get_crs()[1].size)
+    neqn, nterms = c.neqn, c.nterms
+    ne, nn, nl = c.nedge + c.ngedge, c.nnode, c.nnode + c.gnode
+    bytes_sweep = total(2 * (nblocks * 8 * neqn * neqn + 4 * nblocks + 4 * (nn + 1) + 4 * neqn * nn + 8 * neqn * 3 * nn))
+    bytes_head = (8 * ne + nl * (24 + 8 * nterms + 48 + 24 * nterms)
+                  + (8 * ne + nl * (8 * neqn + 16 * neqn)) + (8 * ne + nl * (8 * neqn + 24 * neqn + 24 + 16 * neqn) + nl * 8 * neqn)
+                  + (8 * ne + nl * (8 * neqn + 24 * neqn + 24 + 8 * neqn) + nl * 8 * neqn)
+                  + 40 * ne + nl * (8 * neqn + 24 * neqn + 8 * neqn + 24 + 8) + nn * 8 * neqn)
+    bytes_iter = total(bytes_head) + nsgs * bytes_sweep
+    nn_g, nb_g = total(nn), total(nblocks)
+    ne_g = total(2 * c.nedge + c.ngedge) // 2
+    out = {"workload": f"BASELINE configs[4]: reacting 5-species air (compressibleEulerFR), implicit, {world} z-slab partitions of an "
+                       f"n x n x {n * world} Kuhn box (n = {n}: {6 * n ** 3 * world} tets, {nn_g} nodes, {ne_g} edges, {nb_g} 9x9 blocks = "
+                       f"{nb_g * 648 / 1e9:.1f} GB) on {world} GPUs; halo exchange '{args.halo}'",
+           "n_gpus": world, "nsgs": nsgs,
+           "iteration_without_refresh_ms": ms_it, "iteration_Medges_s": ne_g / (ms_it * 1e-3) / 1e6,
+           "iteration_algorithmic_bytes": bytes_iter, "iteration_GBps": bytes_iter / (ms_it * 1e-3) / 1e9,
+           "iteration_frac_hbm": bytes_iter / (ms_it * 1e-3) / 1e9 / (peak * world),
+           "sgs_ms_per_sweep": ms_sweep, "sgs_sweeps_per_s": 1e3 / ms_sweep, "sgs_algorithmic_bytes_per_sweep": bytes_sweep,
+           "sgs_GBps": bytes_sweep / (ms_sweep * 1e-3) / 1e9, "sgs_frac_hbm": bytes_sweep / (ms_sweep * 1e-3) / 1e9 / (peak * world),
+           "jacobian_refresh_ms": ms_jac, "state_finite_after_run": finite}
     if hasattr(x, "close"):
         x.close()
     c.close()

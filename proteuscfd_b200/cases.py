@@ -268,3 +268,35 @@ def fr_box_case(n, fr, mach=0.5, jitter=0.15, cfl=5.0, limiter=2, sorder=2, colo
     # preconditioning field: beta = max(betaMin, Mach^2) below sonic, 1 otherwise (solutionSpace.tcc:235-247)
     beta = np.full(nn + nb, mach * mach if mach < 1.0 else 1.0)
     return mesh, params, q.reshape(-1), beta
+
+
+def fr_slab_case(n, rank, nranks, fr, mach=0.5, jitter=0.15, cfl=5.0, limiter=2, sorder=2, colored=True, device="cpu",
+                 seed=1234, amp=1.0):
+    """Reacting-eqnset counterpart of slab_case: partition `rank` of the n x n x (n*nranks) box in udecomp's layout with
+    the fr_box_case state (owned and ghost nodes from their coordinates, phantom nodes from their left node):
+    (mesh, params, q, beta)."""
+    mesh, _, _ = slab_case(n, rank, nranks, jitter=jitter, mach=mach, cfl=cfl, limiter=limiter, sorder=sorder, colored=colored,
+                           device=device, seed=seed)
+    ns = int(fr["chem"]["dims"][0])
+    nv = 3 * ns + 6
+    qinf = np.asarray(fr["qinf"], dtype=np.float64)
+    params = dict(eqnset=capi.EQNSET_COMPRESSIBLE_EULER_FR, sorder=sorder, limiter=limiter, no_cvbc=0, gamma=0.0, chi=0.0,
+                  cfl=cfl, fr=fr)
+    if fr.get("transport") is not None:
+        params.update(eqnset=capi.EQNSET_COMPRESSIBLE_NS_FR, Re=fr["Re"], PrT=fr.get("PrT", 0.85))
+    nn, nb = mesh["nnode"] + mesh["gnode"], mesh["nbnode"]
+    X = mesh["xyz"].reshape(-1, 3)
+    # the slab cases stretch the box along z (n*nranks hexes of the same size): keep the state periodic per unit length
+    x, y, z = X[:, 0], X[:, 1], X[:, 2]
+    tp = 2.0 * np.pi
+    q = np.zeros((nn + nb, nv))
+    for k in range(ns):
+        q[:nn, k] = qinf[k] * (1.0 + 0.1 * amp * np.sin(tp * x) * np.cos(tp * y)) * (1.0 + 0.05 * amp * np.sin(tp * (z + 0.17 * k)))
+    q[:nn, ns + 0] = mach + 0.05 * amp * np.sin(tp * y)
+    q[:nn, ns + 1] = 0.05 * amp * np.sin(tp * z)
+    q[:nn, ns + 2] = 0.05 * amp * np.sin(tp * x)
+    q[:nn, ns + 3] = qinf[ns + 3] * (1.0 + 0.1 * amp * np.cos(tp * z))
+    fr_aux_vars(q[:nn], fr)
+    q[nn:] = q[mesh["bedges_n"].reshape(-1, 2)[: mesh["nbedge"], 0]]
+    beta = np.full(nn + nb, mach * mach if mach < 1.0 else 1.0)
+    return mesh, params, q.reshape(-1), beta

@@ -196,6 +196,140 @@ def test_slab_partitions_vs_oracle(oracle, colored, implicit, fused):
             exact(ctxs[r].get_field(capi.F_Q), qs[r], f"q rank {r} it {it}")
 
 
+@pytest.mark.parametrize("colored,viscous", [(True, False), (False, False), (True, True)])
+def test_fr_slab_partitions_vs_oracle(oracle, colored, viscous):
+    """The reacting eqnset on partitions (BASELINE configs[4] is an 8-partition case): two z-slabs on one GPU with
+    direct-put halos of q (21 wide), qgrad (42), limiter and x (9), DistributedHotPath driving the iterations, against
+    the FR oracle run per rank with a numpy halo exchange through the same maps.  Frozen chemistry: one implicit
+    iteration (2 sweeps, block-Jacobi across partitions) and one explicit iteration, bit-exact; with the viscous terms
+    (compressibleNSFR) to 1e-11 (transport libm)."""
+    import ctypes as C
+    from proteuscfd_b200 import capi
+    from proteuscfd_b200.cases import fr_slab_case
+    from proteuscfd_b200.parallel import DistributedHotPath, LoopbackExchange, build_local_group_maps
+    from tests.oracle_lib import _d, _i
+    from tests.test_gpu_fr import fixture_fr_params, oracle_for_fr
+    nr, NEQ, NV, NT = 2, 9, 21, 14
+    fr, g, meta = fixture_fr_params("box4_nsfr_implicit" if viscous else "box4_fr_implicit", rxn_on=0)
+    parts = [fr_slab_case(6, r, nr, fr, colored=colored) for r in range(nr)]
+    pobjs = build_local_group_maps([(m["gNodeOwner"], m["gNodeLocalId"]) for m, _, _, _ in parts])
+    orcs = [oracle_for_fr(oracle, m, p, g, meta) for m, p, _, _ in parts]
+    ctxs = [capi.Context(m, p) for m, p, _, _ in parts]
+    x = LoopbackExchange(ctxs, build_local_group_maps([(m["gNodeOwner"], m["gNodeLocalId"]) for m, _, _, _ in parts]))
+    nn = [m["nnode"] for m, _, _, _ in parts]
+    nl = [m["nnode"] + m["gnode"] for m, _, _, _ in parts]
+
+    def halo(arrs, w):
+        packed = [pobjs[r].pack_numpy(arrs[r], w) for r in range(nr)]
+        for r in range(nr):
+            pobjs[r].unpack_numpy(arrs[r], w, nn[r], [packed[p][r] for p in range(nr)])
+
+    def same(a, ref, what):
+        if not viscous:
+            return exact(a, ref, what)
+        a, ref = np.asarray(a).reshape(-1, NEQ), np.asarray(ref).reshape(-1, NEQ)
+        err = np.abs(a - ref).max(axis=0) / np.abs(ref).max(axis=0)
+        assert np.all(err <= 1e-10), f"{what}: relative error per equation {err}"
+
+    qs = [q.copy() for _, _, q, _ in parts]
+    betas = [b[: nl[r]].copy() for r, (_, _, _, b) in enumerate(parts)]
+    sws = [o.lsq()[1] for o in orcs]
+    halo(sws, 6)
+    for r in range(nr):
+        ctxs[r].set_field(capi.F_BETA, parts[r][3])
+        ctxs[r].lsq_coefficients()
+    x.update(capi.F_LSQ_S)
+    x.update(capi.F_LSQ_SW)
+    for r in range(nr):
+        ctxs[r].set_field(capi.F_Q, qs[r])
+        exact(ctxs[r].get_field(capi.F_LSQ_SW), sws[r], f"sw rank {r}")
+
+    def oracle_head():
+        for r in range(nr):
+            orcs[r].update_bcs(qs[r], betas[r])
+        halo(qs, NV)
+        grads = [orcs[r].gradient(qs[r], sws[r]) for r in range(nr)]
+        halo(grads, NT * 3)
+        lims = [orcs[r].limiter(qs[r], grads[r]) for r in range(nr)]
+        halo(lims, NEQ)
+        return grads, lims, [orcs[r].residual(qs[r], grads[r], lims[r], betas[r]) for r in range(nr)]
+
+    # ---- implicit iteration
+    dts = [orcs[r].timestep(qs[r], betas[r])[0] for r in range(nr)]
+    crs = [o.crs_init() for o in orcs]
+    As = [orcs[r].jacobian(qs[r], betas[r], dts[r], *crs[r]) for r in range(nr)]
+    grads, lims, bs = oracle_head()
+    xs = []
+    for r in range(nr):
+        pv = orcs[r].prepare_sgs(crs[r][2], As[r])
+        xs.append((pv, np.zeros(nl[r] * NEQ)))
+    for sweep in range(2):
+        for r in range(nr):
+            orcs[r].lib.orc_fr_sgs.restype = C.c_double
+            orcs[r].lib.orc_fr_sgs(C.byref(orcs[r].c), C.byref(orcs[r].p), 1, _i(crs[r][0]), _i(crs[r][1]), _i(crs[r][2]),
+                                   _d(As[r]), _i(xs[r][0]), _d(bs[r]), _d(xs[r][1]))
+        halo([xx[1] for xx in xs], NEQ)
+    for r in range(nr):
+        orcs[r].apply_dq(qs[r], xs[r][1])
+    halo(qs, NV)
+    hps = [DistributedHotPath(c, None) for c in ctxs]
+    # the hot-path driver calls its exchange per rank; with all ranks in one process the loopback exchange moves every
+    # rank's rows at once, so the phases are stepped in lock-step here exactly as DistributedHotPath.implicit_iterate does
+    for c in ctxs:
+        c.timestep(want_min=False)
+        c.jacobian()
+        c.update_bcs()
+    x.update(capi.F_Q)
+    each(ctxs, lambda c: c.gradient())
+    x.update(capi.F_QGRAD)
+    each(ctxs, lambda c: c.limiter())
+    x.update(capi.F_LIMITER)
+    each(ctxs, lambda c: c.residual())
+    each(ctxs, lambda c: c.prepare_sgs())
+    each(ctxs, lambda c: c.blank_x())
+    x.update(capi.F_X)
+    for sweep in range(2):
+        each(ctxs, lambda c: c.sgs(1, want_ddq=False))
+        x.update(capi.F_X)
+    each(ctxs, lambda c: c.apply_dq())
+    x.update(capi.F_Q)
+    assert all(not h.fused for h in hps)          # the fused limiter/residual pair is a perfect-gas path
+    for r in range(nr):
+        exact(ctxs[r].get_field(capi.F_QGRAD), grads[r], f"qgrad rank {r}")
+        exact(ctxs[r].get_field(capi.F_LIMITER), lims[r], f"limiter rank {r}")
+        same(ctxs[r].get_field(capi.F_B), bs[r], f"b rank {r}")
+        same(ctxs[r].get_field(capi.F_X), xs[r][1], f"x rank {r}")
+        if viscous:
+            assert np.allclose(ctxs[r].get_field(capi.F_Q), qs[r], rtol=1e-10, atol=1e-14)
+        else:
+            exact(ctxs[r].get_field(capi.F_Q), qs[r], f"q rank {r} after the implicit iteration")
+    if viscous:
+        return
+    # ---- explicit iteration
+    for r in range(nr):
+        orcs[r].c.cfl = 0.05
+        ctxs[r].set_cfl(0.05)
+    dts = [orcs[r].timestep(qs[r], betas[r])[0] for r in range(nr)]
+    grads, lims, bs = oracle_head()
+    for r in range(nr):
+        xe = orcs[r].explicit_solve(qs[r], bs[r], dts[r])
+        orcs[r].apply_dq(qs[r], xe)
+    halo(qs, NV)
+    each(ctxs, lambda c: c.timestep(want_min=False))
+    each(ctxs, lambda c: c.update_bcs())
+    x.update(capi.F_Q)
+    each(ctxs, lambda c: c.gradient())
+    x.update(capi.F_QGRAD)
+    each(ctxs, lambda c: c.limiter())
+    x.update(capi.F_LIMITER)
+    each(ctxs, lambda c: c.residual())
+    each(ctxs, lambda c: c.explicit_solve())
+    x.update(capi.F_Q)
+    for r in range(nr):
+        exact(ctxs[r].get_field(capi.F_B), bs[r], f"explicit b rank {r}")
+        exact(ctxs[r].get_field(capi.F_Q), qs[r], f"q rank {r} after the explicit iteration")
+
+
 def test_nccl_two_process_exchange():
     """The real thing: one process per GPU, NCCL send/recv into the ghost segments and the direct-put exchange,
     launched with torchrun when the box has >= 2 GPUs (gpurun --gpus 2)."""

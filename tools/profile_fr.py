@@ -17,12 +17,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=118)
     ap.add_argument("--nsgs", type=int, default=1)
+    ap.add_argument("--viscous", action="store_true", help="compressibleNSFR: viscous flux / Jacobian with species transport")
     args = ap.parse_args()
     import torch
     from bench import fr_params_from_fixture
     from proteuscfd_b200 import capi
     from proteuscfd_b200.cases import fr_box_case
-    mesh, params, q, beta = fr_box_case(args.n, fr_params_from_fixture(), device="cuda:0")
+    mesh, params, q, beta = fr_box_case(args.n, fr_params_from_fixture(args.viscous), device="cuda:0")
     ctx = capi.Context(mesh, params, device=0)
     ctx.set_field(capi.F_BETA, beta)
     ctx.lsq_coefficients()
