@@ -806,7 +806,7 @@ def fr_bench(args, peak, torch, stream, local_rank, viscous=False):
            "residual_frac_hbm": bytes_resid / (ms_resid * 1e-3) / 1e9 / peak,
            "iteration_without_refresh_ms": ms_iter, "iteration_Medges_s": ne / (ms_iter * 1e-3) / 1e6, "nsgs": nsgs,
            "iteration_algorithmic_bytes": bytes_iter, "iteration_frac_hbm": bytes_iter / (ms_iter * 1e-3) / 1e9 / peak,
-           "state_finite_after_run": finite, "non_sgs_kernels_ms": ms_explicit_part,
+           "state_finite_after_run": finite, "clip_fallbacks": c.clip_fallbacks(), "non_sgs_kernels_ms": ms_explicit_part,
            "kernels_ms": kern}
     c.close()
     return out

@@ -148,13 +148,15 @@ int pcfd_prepare_sgs(pcfd_ctx* ctx);
 int pcfd_blank_x(pcfd_ctx* ctx);
 /* CRS::SGS (crs.tcc:62-173); ddq (may be NULL) receives |xOld - xNorm| */
 int pcfd_sgs(pcfd_ctx* ctx, int nsgs, double* ddq);
-/* Limiter::Compute + ComputeResiduals in two halves for multi-rank hosts (perfect-gas eqnsets).  pcfd_limiter_raw runs
+/* Limiter::Compute + ComputeResiduals in two halves for multi-rank hosts (all eqnsets).  pcfd_limiter_raw runs
    passes 1+2 of Limiter::Compute (limiters.tcc:53-110) and leaves the UNCLAMPED limiter in field PCFD_F_LIMITER; the
    host exchanges that field (limiters.tcc:128); pcfd_residual_fused then clamps it (:118-125), evaluates the residual
    and performs the test of Kernel_PressureClip (:737-815) on the way.  *clip_hit == 0: limiter and residual are final
    (the pressure clip would not have changed anything).  *clip_hit != 0 (rare; on ANY rank): discard, then every rank
    calls pcfd_limiter, exchanges the limiter and calls pcfd_residual. */
 int pcfd_limiter_raw(pcfd_ctx* ctx);
+/* how many times the fused limiter / residual pair of this context had to fall back to the ordered clip path */
+long long pcfd_clip_fallbacks(const pcfd_ctx* ctx);
 int pcfd_residual_fused(pcfd_ctx* ctx, double* sumsq, int* clip_hit);
 
 /* loop over nnode of EqnSet::ApplyDQ (solutionSpace.tcc:802-804) */

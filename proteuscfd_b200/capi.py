@@ -37,7 +37,7 @@ SYMBOLS = [
     "pcfd_ipc_export", "pcfd_ipc_open", "pcfd_ipc_close",
     "pcfd_turb_compute", "pcfd_halo_configure",
     "pcfd_chem_create", "pcfd_chem_destroy", "pcfd_chem_last_error", "pcfd_chem_mass_production",
-    "pcfd_create_fr", "pcfd_widths", "pcfd_limiter_raw", "pcfd_residual_fused",
+    "pcfd_create_fr", "pcfd_widths", "pcfd_limiter_raw", "pcfd_residual_fused", "pcfd_clip_fallbacks",
     "pcfd_chem_source_term", "pcfd_chem_source_term_device", "pcfd_halo_width", "pcfd_halo_send_total", "pcfd_halo_pack", "pcfd_halo_recv_ptr",
 ]
 
@@ -325,6 +325,11 @@ class Context:
 
     def set_cfl(self, cfl):
         self._ck(self.lib.pcfd_set_cfl(self.h, float(cfl)))
+
+    def clip_fallbacks(self):
+        """times the fused limiter / residual pair fell back to the ordered pressure-clip path"""
+        self.lib.pcfd_clip_fallbacks.restype = C.c_longlong
+        return int(self.lib.pcfd_clip_fallbacks(self.h))
 
     def launch_count(self):
         return int(self.lib.pcfd_launch_count(self.h))

@@ -121,16 +121,24 @@ __device__ __forceinline__ void fluid_props(const Params<NS>& p, const double* r
   c2 = c2Dim / (p.ref_velocity * p.ref_velocity);
 }
 
-// GetTotalEnthalpy (compressibleFR.tcc:1249-1273)
+// GetTotalEnthalpy (compressibleFR.tcc:1249-1273); hr = h rho and ke = rho |v|^2 / 2 are also what GetTotalEnergy
+// (:1219-1246) is made of: E = (hr - P) + ke
 template <int NS>
-__device__ __forceinline__ double total_enthalpy(const Params<NS>& p, const double* Q) {
+__device__ __forceinline__ double total_enthalpy(const Params<NS>& p, const double* Q, double& hr, double& ke) {
   double X[NS];
   const double T = Q[NS + 3], rho = Q[NS + 5], u = Q[NS], v = Q[NS + 1], w = Q[NS + 2];
   const double v2 = u * u + v * v + w * w;
 #pragma unroll
   for (int i = 0; i < NS; i++) X[i] = Q[i] / rho;
   const double h = chem_h(p, X, T * p.ref_temperature) / p.ref_specific_enthalpy;
-  return h * rho + 0.5 * rho * v2;
+  hr = h * rho;
+  ke = 0.5 * rho * v2;
+  return hr + ke;
+}
+template <int NS>
+__device__ __forceinline__ double total_enthalpy(const Params<NS>& p, const double* Q) {
+  double hr, ke;
+  return total_enthalpy(p, Q, hr, ke);
 }
 // GetTotalEnergy (compressibleFR.tcc:1219-1246)
 template <int NS>
@@ -155,19 +163,21 @@ __device__ __forceinline__ double theta_of(const double* Q, const double* n, dou
 // kneecap of EqnSet::NumericalFlux (eqnset.tcc:73-88) is applied here.
 template <int NS>
 __device__ __forceinline__ void numerical_flux(const Params<NS>& p, const double* QL, const double* QR, const double* av,
-                                               double vdotn, double beta, double* flux) {
+                                               double vdotn, double beta, double* flux, double* parts = nullptr) {
   const double uL = QL[NS], vL = QL[NS + 1], wL = QL[NS + 2], TL = QL[NS + 3], pL = QL[NS + 4];
   const double pgL = pL - p.Pref, rhoL = QL[NS + 5];
   double RL, c2L, RR, c2R, Rm, c2;
   fluid_props(p, QL, TL, RL, c2L);
-  const double HTL = total_enthalpy(p, QL);
+  double hrL, keL, hrR, keR;
+  const double HTL = total_enthalpy(p, QL, hrL, keL);
   const double ETL = HTL - pL;
   const double thetaL = theta_of<NS>(QL, av, vdotn);
   const double uR = QR[NS], vR = QR[NS + 1], wR = QR[NS + 2], TR = QR[NS + 3], pR = QR[NS + 4];
   const double pgR = pR - p.Pref, rhoR = QR[NS + 5];
   fluid_props(p, QR, TR, RR, c2R);
-  const double HTR = total_enthalpy(p, QR);
+  const double HTR = total_enthalpy(p, QR, hrR, keR);
   const double ETR = HTR - pR;
+  if (parts) { parts[0] = hrL; parts[1] = keL; parts[2] = hrR; parts[3] = keR; }
   const double thetaR = theta_of<NS>(QR, av, vdotn);
 
   const double rho = sqrt(rhoL * rhoR);
@@ -285,6 +295,18 @@ __device__ __forceinline__ bool bad_extrapolation(const Params<NS>& p, const dou
 #pragma unroll
   for (int i = 0; i < NS; i++) if (Q[i] < 0.0) return true;
   if (total_energy(p, Q) <= 0.0) return true;
+  if (Q[NS + 4] < 1.0e-10) return true;
+  if (Q[NS + 3] < 1.0e-10) return true;
+  return false;
+}
+
+// the same test with h rho and rho |v|^2 / 2 of the state already at hand (from the flux evaluation)
+template <int NS>
+__device__ __forceinline__ bool bad_extrapolation(const Params<NS>& p, const double* Q, double hr, double ke) {
+#pragma unroll
+  for (int i = 0; i < NS; i++) if (Q[i] < 0.0) return true;
+  const double E = hr - Q[NS + 4];
+  if (E + ke <= 0.0) return true;
   if (Q[NS + 4] < 1.0e-10) return true;
   if (Q[NS + 3] < 1.0e-10) return true;
   return false;
@@ -751,12 +773,17 @@ struct Transport {
   int nmu[NS], nk[NS];
   double pw25[NS][NS];                        // pow(MW_j / MW_i, 0.25)
   double pwm05[NS][NS];                       // pow(1 + MW_i / MW_j, -0.5)
+  double phi_ii[NS];                          // Wilke's phi for j == i: visc_i / visc_i == 1, nothing of the state is left
   double sqrt8;
   double ref_viscosity, ref_k, Re, PrT;
+  int white_uniform;                          // every species carries the same Sutherland rows (the reference's do,
+                                              // species.tcc:13-22) and mu / k share T0: one pow serves all ten fits
 };
 
-// Species::GetViscosity / GetThermalConductivity (species.tcc:393-479); the range search keeps the last match
-__device__ __forceinline__ double sp_transport(const double* white, const double (*fit)[6], int nfit, double T, double conv) {
+// Species::GetViscosity / GetThermalConductivity (species.tcc:393-479); the range search keeps the last match.
+// logT = log(T) is passed in: the same argument gives the same value, so it is formed once per state.
+__device__ __forceinline__ double sp_transport(const double* white, const double (*fit)[6], int nfit, double T, double logT,
+                                               double conv) {
   if (T <= white[3]) {
     const double v0 = white[0], T0 = white[1], S = white[2];
     return v0 * (pow(T / T0, 1.5)) * ((T0 + S) / (T + S));
@@ -766,7 +793,7 @@ __device__ __forceinline__ double sp_transport(const double* white, const double
     if (T >= fit[i][0] && T <= fit[i][1]) range = i;
   if (range == -1) return nan("");   // the reference aborts
   const double A = fit[range][2], B = fit[range][3], C = fit[range][4], D = fit[range][5];
-  const double logv = A * log(T) + B / T + C / (T * T) + D;
+  const double logv = A * logT + B / T + C / (T * T) + D;
   return exp(logv) * conv;
 }
 
@@ -793,10 +820,20 @@ __device__ __forceinline__ void mixture_transport(const Params<NS>& p, const Tra
 #pragma unroll
   for (int i = 0; i < NS - 1; i++) summ += mf[i];
   mf[NS - 1] = 1.0 - summ;
+  if (t.white_uniform && Td <= t.mu_white[0][3]) {
+    // Sutherland branch with identical rows for every species: identical operands, identical results -- one pow
+    const double p15 = pow(Td / t.mu_white[0][1], 1.5);
+    const double vm = t.mu_white[0][0] * (p15) * ((t.mu_white[0][1] + t.mu_white[0][2]) / (Td + t.mu_white[0][2]));
+    const double vk = t.k_white[0][0] * (p15) * ((t.k_white[0][1] + t.k_white[0][2]) / (Td + t.k_white[0][2]));
 #pragma unroll
-  for (int i = 0; i < NS; i++) {
-    visc[i] = sp_transport(t.mu_white[i], t.mu_fit[i], t.nmu[i], Td, 1.0e-7);
-    cond[i] = sp_transport(t.k_white[i], t.k_fit[i], t.nk[i], Td, 0.0001);
+    for (int i = 0; i < NS; i++) { visc[i] = vm; cond[i] = vk; }
+  } else {
+    const double logT = log(Td);
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+      visc[i] = sp_transport(t.mu_white[i], t.mu_fit[i], t.nmu[i], Td, logT, 1.0e-7);
+      cond[i] = sp_transport(t.k_white[i], t.k_fit[i], t.nk[i], Td, logT, 0.0001);
+    }
   }
   double mmu = 0.0, mk = 0.0;
 #pragma unroll
@@ -804,8 +841,15 @@ __device__ __forceinline__ void mixture_transport(const Params<NS>& p, const Tra
     double wi = 0.0;
 #pragma unroll
     for (int j = 0; j < NS; j++) {
-      const double temp = (1.0 + sqrt(visc[i] / visc[j]) * t.pw25[i][j]);
-      const double phi = t.pwm05[i][j] * temp * temp / t.sqrt8;
+      double phi;
+      if (j == i) {
+        phi = t.phi_ii[i];     // visc_i / visc_i == 1 exactly (a NaN viscosity still poisons wi through the other terms)
+      } else {
+        // equal viscosities (always, on the Sutherland branch): the ratio is exactly 1 and so is its square root
+        const double rt = (visc[i] == visc[j]) ? 1.0 : sqrt(visc[i] / visc[j]);
+        const double temp = (1.0 + rt * t.pw25[i][j]);
+        phi = t.pwm05[i][j] * temp * temp / t.sqrt8;
+      }
       wi += mf[j] * phi;
     }
     mmu += (mf[i] / wi) * visc[i];

@@ -28,6 +28,7 @@ struct pcfd_fr_state {
   // compressibleNSFR: per-edge / per-half-edge viscous flux slots (momentum + energy rows)
   bool viscous = false;
   double *vflux = nullptr, *bvflux = nullptr;
+  unsigned char* negflag = nullptr;         // nodes whose raw limiter has a negative component (fused clip test)
 };
 
 namespace {
@@ -271,11 +272,13 @@ __global__ void kfr_fill_int(int* p, int n, int v) {
 
 // ====================================================================== residual
 // MUSCL reconstruction of one side pair (Kernel_Inviscid_Flux, residual.tcc:192-296): QL / QR hold [0, NS+6)
-template <int NS>
-__device__ __forceinline__ void reconstruct(const DevMesh& m, const fr::Params<NS>& p, int l, int r,
+// CLAMP: `lim` is the raw limiter; negative components are clamped on the fly (limiters.tcc:118-125) and reported
+template <int NS, bool CLAMP = false>
+__device__ __forceinline__ bool reconstruct(const DevMesh& m, const fr::Params<NS>& p, int l, int r,
                                             const double* __restrict__ qgrad, const double* __restrict__ lim, double* QL,
                                             double* QR) {
   constexpr int NEQ = W<NS>::NEQ, NT = W<NS>::NT;
+  bool neg = false;
   double dQ[NEQ], dx[3], gr[NEQ * 3], lm[NEQ], qL[NEQ], qR[NEQ];
 #pragma unroll
   for (int j = 0; j < NEQ; j++) { qL[j] = QL[j]; qR[j] = QR[j]; dQ[j] = qR[j] - qL[j]; }
@@ -284,7 +287,10 @@ __device__ __forceinline__ void reconstruct(const DevMesh& m, const fr::Params<N
 #pragma unroll
   for (int j = 0; j < NEQ * 3; j++) gr[j] = __ldg(qgrad + (size_t)l * NT * 3 + j);
 #pragma unroll
-  for (int j = 0; j < NEQ; j++) lm[j] = __ldg(lim + (size_t)l * NEQ + j);
+  for (int j = 0; j < NEQ; j++) {
+    lm[j] = __ldg(lim + (size_t)l * NEQ + j);
+    if (CLAMP && lm[j] < 0.0) { lm[j] = 0.0; neg = true; }
+  }
   fr::extrapolate<NS>(p.chi, QL, qL, dQ, gr, dx, lm);
 #pragma unroll
   for (int j = 0; j < NEQ; j++) dQ[j] = -dQ[j];
@@ -293,32 +299,80 @@ __device__ __forceinline__ void reconstruct(const DevMesh& m, const fr::Params<N
 #pragma unroll
   for (int j = 0; j < NEQ * 3; j++) gr[j] = __ldg(qgrad + (size_t)r * NT * 3 + j);
 #pragma unroll
-  for (int j = 0; j < NEQ; j++) lm[j] = __ldg(lim + (size_t)r * NEQ + j);
+  for (int j = 0; j < NEQ; j++) {
+    lm[j] = __ldg(lim + (size_t)r * NEQ + j);
+    if (CLAMP && lm[j] < 0.0) { lm[j] = 0.0; neg = true; }
+  }
   fr::extrapolate<NS>(p.chi, QR, qR, dQ, gr, dx, lm);
+  return neg;
 }
 
-template <int NS>
+// DET = true is the fused fast path of the composite iterations (as k_flux_edges<true> of the perfect-gas path): `lim`
+// holds the RAW limiter of kfr_limiter (before Kernel_PressureClip and the clamp of negatives, limiters.tcc:105-125).
+// The flux uses the clamped value; the pressure-clip test of kfr_clip_edges (BadExtrapolation of the two extrapolated
+// states) is evaluated on the way -- the same states unless a raw component was negative; those edges are left to
+// kfr_clip_neg_edges.  If no edge anywhere raises *any, clip(lim) == clamp(lim) and this flux is final; otherwise the
+// caller discards it and takes the ordered clip path.
+template <int NS, bool DET>
 __global__ void __launch_bounds__(128) kfr_flux_edges(DevMesh m, fr::Params<NS> p, const double* __restrict__ q,
                                                        const double* __restrict__ qgrad, const double* __restrict__ lim,
-                                                       const double* __restrict__ beta, double* __restrict__ flux) {
+                                                       const double* __restrict__ beta, double* __restrict__ flux,
+                                                       int* __restrict__ any) {
   constexpr int NEQ = W<NS>::NEQ;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= m.nedge) return;
   const int2 lr = m.en[e];
   const int l = lr.x, r = lr.y;
-  double av[4], QL[NS + 6], QR[NS + 6], f[NEQ];
+  double av[4], QL[NS + 6], QR[NS + 6], f[NEQ], parts[4];
   load_avec(m.ea, e, av);
   load_row<NS, NS + 6>(q, l, QL);
   load_row<NS, NS + 6>(q, r, QR);
   const double avbeta = 0.5 * (beta[l] + beta[r]);
+  bool test = false;
   if (p.sorder > 1) {
-    reconstruct<NS>(m, p, l, r, qgrad, lim, QL, QR);
+    if (DET) {
+      // where a raw component is negative (local extrema: common) the clip test needs the raw-limiter states and the
+      // flux the clamped ones: those few edges are tested by kfr_clip_neg_edges instead, with a per-node flag
+      test = !reconstruct<NS, true>(m, p, l, r, qgrad, lim, QL, QR);
+    } else {
+      reconstruct<NS, false>(m, p, l, r, qgrad, lim, QL, QR);
+    }
     fr::aux_pr(p, QL);
     fr::aux_pr(p, QR);
   }
-  fr::numerical_flux(p, QL, QR, av, 0.0, avbeta, f);
+  fr::numerical_flux(p, QL, QR, av, 0.0, avbeta, f, DET ? parts : nullptr);
+  // BadExtrapolation of both states, with the enthalpy terms the flux has just formed
+  if (DET && test && (fr::bad_extrapolation(p, QL, parts[0], parts[1]) || fr::bad_extrapolation(p, QR, parts[2], parts[3]))) *any = 1;
 #pragma unroll
   for (int j = 0; j < NEQ; j++) flux[(size_t)e * NEQ + j] = f[j];
+}
+
+// nodes whose raw limiter has a negative component (owned and ghost rows)
+__global__ void kfr_negflag_nodes(int nn, int neqn, const double* __restrict__ lim, unsigned char* __restrict__ negflag) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nn) return;
+  bool neg = false;
+  for (int j = 0; j < neqn; j++) neg = neg || (lim[(size_t)n * neqn + j] < 0.0);
+  negflag[n] = neg ? 1 : 0;
+}
+
+// the pressure-clip test of kfr_clip_edges (first pass: nothing zeroed yet) for the edges that touch a flagged node,
+// with the RAW limiter as Kernel_PressureClip sees it (limiters.tcc:737-815)
+template <int NS>
+__global__ void __launch_bounds__(128) kfr_clip_neg_edges(DevMesh m, fr::Params<NS> p, const double* __restrict__ q,
+                                                           const double* __restrict__ qgrad, const double* __restrict__ lim,
+                                                           const unsigned char* __restrict__ negflag, int* __restrict__ any) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m.nedge) return;
+  const int2 lr = m.en[e];
+  if (!(negflag[lr.x] | negflag[lr.y])) return;
+  double QL[NS + 6], QR[NS + 6];
+  load_row<NS, NS + 6>(q, lr.x, QL);
+  load_row<NS, NS + 6>(q, lr.y, QR);
+  reconstruct<NS, false>(m, p, lr.x, lr.y, qgrad, lim, QL, QR);
+  fr::aux_pr(p, QL);
+  fr::aux_pr(p, QR);
+  if (fr::bad_extrapolation(p, QL) || fr::bad_extrapolation(p, QR)) *any = 1;
 }
 
 // Bkernel_Inviscid_Flux (residual.tcc:299-387)
@@ -939,6 +993,15 @@ fr::Transport<NS> make_transport(const pcfd_ctx* c) {
     }
   }
   t.sqrt8 = sqrt(8.0);
+  t.white_uniform = 1;
+  for (int i = 0; i < NS; i++) {
+    const double temp = (1.0 + sqrt(1.0) * t.pw25[i][i]);
+    t.phi_ii[i] = t.pwm05[i][i] * temp * temp / t.sqrt8;
+    for (int k = 0; k < 4; k++)
+      if (tm.mu_white[i][k] != tm.mu_white[0][k] || tm.k_white[i][k] != tm.k_white[0][k]) t.white_uniform = 0;
+  }
+  // one pow serves both properties only if they share T0 and the transition temperature
+  if (tm.mu_white[0][1] != tm.k_white[0][1] || tm.mu_white[0][3] != tm.k_white[0][3]) t.white_uniform = 0;
   t.ref_viscosity = s->host.ref_viscosity; t.ref_k = s->host.ref_k;
   t.Re = c->prm.Re; t.PrT = c->prm.PrT;
   return t;
@@ -1022,14 +1085,51 @@ struct Impl {
     LAUNCH_CHECK();
     return 0;
   }
-  static int residual(pcfd_ctx* c, double* sumsq) {
+  // Limiter::Compute without Kernel_PressureClip and the clamp: the raw limiter (first half of the fused pair)
+  static int limiter_raw(pcfd_ctx* c) {
+    constexpr int BS = Wd::NEQ * 16;
+    PROF("kfr_limiter");
+    kfr_limiter<NS><<<nblk((long long)c->nn * Wd::NEQ, BS), BS, 0, c->stream>>>(c->dm, c->prm.limiter, c->prm.chi, c->f[PCFD_F_Q],
+                                                                               c->f[PCFD_F_QGRAD], c->f[PCFD_F_LIMITER]);
+    LAUNCH_CHECK();
+    return 0;
+  }
+  static int residual(pcfd_ctx* c, double* sumsq) { return residual_impl(c, sumsq, nullptr); }
+  // clip_hit != nullptr: the fused form -- lim holds the raw limiter, the edge kernel clamps on the fly and raises
+  // dflags[2] if the pressure clip would act anywhere, kfr_limiter_final clamps in place behind it
+  static int residual_impl(pcfd_ctx* c, double* sumsq, bool* clip_hit) {
     constexpr int BS = Wd::NEQ * 16;
     const fr::Params<NS> p = make_params<NS>(c);
     const double* beta = c->f[PCFD_F_BETA];
+    const bool fused = clip_hit != nullptr;
+    if (fused) {
+      CK(cudaMemsetAsync(c->dflags + 2, 0, sizeof(int), c->stream));
+      PROF("kfr_negflag_nodes");
+      kfr_negflag_nodes<<<nblk(c->nn, 256), 256, 0, c->stream>>>(c->nn, Wd::NEQ, c->f[PCFD_F_LIMITER], c->fr->negflag);
+      LAUNCH_CHECK();
+      if (c->nedge) {
+        PROF("kfr_clip_neg_edges");
+        kfr_clip_neg_edges<NS><<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, p, c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD],
+                                                                          c->f[PCFD_F_LIMITER], c->fr->negflag, c->dflags + 2);
+        LAUNCH_CHECK();
+      }
+    }
     if (c->nedge) {
       PROF("kfr_flux_edges");
-      kfr_flux_edges<NS><<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, p, c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD],
-                                                                    c->f[PCFD_F_LIMITER], beta, c->flux);
+      if (fused)
+        kfr_flux_edges<NS, true><<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, p, c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD],
+                                                                            c->f[PCFD_F_LIMITER], beta, c->flux, c->dflags + 2);
+      else
+        kfr_flux_edges<NS, false><<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, p, c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD],
+                                                                             c->f[PCFD_F_LIMITER], beta, c->flux, nullptr);
+      LAUNCH_CHECK();
+    }
+    if (fused) {
+      CK(cudaMemcpyAsync(c->hflag, c->dflags + 2, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaEventRecord(c->ev_flag, c->stream));
+      PROF("kfr_limiter_final");
+      kfr_limiter_final<<<nblk((long long)c->nn * Wd::NEQ, 256), 256, 0, c->stream>>>(c->nn, c->nnode, Wd::NEQ, nullptr,
+                                                                                     c->f[PCFD_F_LIMITER]);
       LAUNCH_CHECK();
     }
     if (c->nb) {
@@ -1051,6 +1151,11 @@ struct Impl {
     kfr_residual_gather<NS><<<nblk((long long)c->nnode * Wd::NEQ, BS), BS, 0, c->stream>>>(
         c->dm, c->flux, c->bflux, c->fr->viscous ? c->fr->vflux : nullptr, c->fr->bvflux, c->fr->src, c->f[PCFD_F_B]);
     LAUNCH_CHECK();
+    if (fused) {
+      CK(cudaEventSynchronize(c->ev_flag));
+      *clip_hit = *c->hflag != 0;
+      if (*clip_hit) return 0;      // the caller redoes limiter + residual on the ordered clip path
+    }
     if (sumsq) return fr_sumsq(c, c->f[PCFD_F_B], c->nnode, 0, sumsq);
     return 0;
   }
@@ -1221,6 +1326,8 @@ int pcfd_fr_update_bcs(pcfd_ctx* c) { FR_DISPATCH(c, update_bcs(c)); }
 int pcfd_fr_gradient(pcfd_ctx* c) { FR_DISPATCH(c, gradient(c)); }
 int pcfd_fr_limiter(pcfd_ctx* c) { FR_DISPATCH(c, limiter(c)); }
 int pcfd_fr_residual(pcfd_ctx* c, double* sumsq) { FR_DISPATCH(c, residual(c, sumsq)); }
+int pcfd_fr_limiter_raw(pcfd_ctx* c) { FR_DISPATCH(c, limiter_raw(c)); }
+int pcfd_fr_residual_fused(pcfd_ctx* c, double* sumsq, bool* clip_hit) { FR_DISPATCH(c, residual_impl(c, sumsq, clip_hit)); }
 int pcfd_fr_timestep(pcfd_ctx* c, double* dtmin) { FR_DISPATCH(c, timestep(c, dtmin)); }
 int pcfd_fr_explicit_solve(pcfd_ctx* c) { FR_DISPATCH(c, explicit_solve(c)); }
 int pcfd_fr_apply_dq(pcfd_ctx* c) { FR_DISPATCH(c, apply_dq(c)); }
@@ -1281,6 +1388,7 @@ int pcfd_create_fr(const pcfd_mesh_desc* mesh, const pcfd_params* params, const 
   if (dev_alloc(c, &s->red, (size_t)FR_RED_BLOCKS * 32)) return 1;
   if (dev_alloc(c, &s->redout, 128)) return 1;
   if (dev_alloc(c, &s->dbad, 4)) return 1;
+  if (dev_alloc(c, &s->negflag, (size_t)c->nn)) return 1;
   if (viscous) {
     if (dev_alloc(c, &s->vflux, (size_t)c->nedge * 4)) return 1;
     if (dev_alloc(c, &s->bvflux, (size_t)c->nb * 4)) return 1;

@@ -220,6 +220,8 @@ int pcfd_fr_update_bcs(pcfd_ctx* c);
 int pcfd_fr_gradient(pcfd_ctx* c);
 int pcfd_fr_limiter(pcfd_ctx* c);
 int pcfd_fr_residual(pcfd_ctx* c, double* sumsq);
+int pcfd_fr_limiter_raw(pcfd_ctx* c);
+int pcfd_fr_residual_fused(pcfd_ctx* c, double* sumsq, bool* clip_hit);
 int pcfd_fr_timestep(pcfd_ctx* c, double* dtmin);
 int pcfd_fr_explicit_solve(pcfd_ctx* c);
 int pcfd_fr_apply_dq(pcfd_ctx* c);

@@ -2179,7 +2179,16 @@ int pcfd_limiter(pcfd_ctx* c) {
 // exists to prevent exactly that) are the ordered clip passes and the flux redone.
 static int gradient_limiter_residual(pcfd_ctx* c, double* sumsq) {
   if (c->fr) {
-    if (c->prm.sorder > 1 && (pcfd_gradient(c) || pcfd_limiter(c))) return 1;
+    if (c->prm.sorder > 1) {
+      if (pcfd_gradient(c)) return 1;
+      if (c->prm.limiter != 0 && c->fused_clip) {
+        bool hit = false;
+        if (pcfd_fr_limiter_raw(c) || pcfd_fr_residual_fused(c, sumsq, &hit)) return 1;
+        if (!hit) return 0;
+        c->clip_fallbacks++;
+      }
+      if (pcfd_limiter(c)) return 1;
+    }
     return pcfd_residual(c, sumsq);
   }
   if (c->prm.sorder > 1) {
@@ -2209,7 +2218,7 @@ static int gradient_limiter_residual(pcfd_ctx* c, double* sumsq) {
 int pcfd_limiter_raw(pcfd_ctx* c) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
-  if (c->fr) return fail(c, "pcfd_limiter_raw: not available for the reacting eqnset (use pcfd_limiter)");
+  if (c->fr) return pcfd_fr_limiter_raw(c);
   PROF("k_limiter");
   k_limiter<<<nblk((long long)c->nn * 5, 160), 160, 0, c->stream>>>(c->dm, c->prm.limiter, c->prm.chi, c->f[PCFD_F_Q],
                                                                    c->f[PCFD_F_QGRAD], c->f[PCFD_F_LIMITER]);
@@ -2217,16 +2226,23 @@ int pcfd_limiter_raw(pcfd_ctx* c) {
   return 0;
 }
 
+long long pcfd_clip_fallbacks(const pcfd_ctx* c) { return c ? c->clip_fallbacks : -1; }
+
 int pcfd_residual_fused(pcfd_ctx* c, double* sumsq, int* clip_hit) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
-  if (c->fr) return fail(c, "pcfd_residual_fused: not available for the reacting eqnset (use pcfd_residual)");
   if (!clip_hit) return fail(c, "pcfd_residual_fused: clip_hit must not be NULL");
   if (c->prm.sorder < 2 || c->prm.limiter == 0) {   // nothing to clip: the plain residual
     *clip_hit = 0;
     return pcfd_residual(c, sumsq);
   }
   bool hit = false;
+  if (c->fr) {
+    if (pcfd_fr_residual_fused(c, sumsq, &hit)) return 1;
+    *clip_hit = hit ? 1 : 0;
+    if (hit) c->clip_fallbacks++;
+    return 0;
+  }
   if (run_flux(c, true, &hit)) return 1;
   *clip_hit = hit ? 1 : 0;
   if (hit) c->clip_fallbacks++;

@@ -249,7 +249,7 @@ class DistributedHotPath:
         self.sum = allreduce_sum or (lambda a: a)
         self.min = allreduce_min or (lambda a: a)
         self.any_rank = any_rank
-        self.fused = fused and any_rank is not None and ctx.neqn == capi.NEQN
+        self.fused = fused and any_rank is not None
         self.clip_fallbacks = 0
 
     def setup(self):
