@@ -630,7 +630,14 @@ def fr_bench_multi(args, rank, world, local_rank, peak, torch, dist, stream):
     group = TorchGroup(dist)
     pobj = PObj(rank, world).BuildCommMaps(mesh["gNodeOwner"], mesh["gNodeLocalId"], group)
     x = PutExchange(c, pobj, dist, torch, dev, group) if args.halo == "put" else NcclExchange(c, pobj, dist, torch, dev)
-    hp = DistributedHotPath(c, x)
+    hitflag = torch.zeros(1, device=dev, dtype=torch.int32)
+
+    def any_rank(hit):   # the (rare) pressure-clip fallback is a global decision: one 4-byte max all-reduce
+        hitflag.fill_(int(hit))
+        dist.all_reduce(hitflag, op=dist.ReduceOp.MAX)
+        return bool(hitflag.item())
+
+    hp = DistributedHotPath(c, x, any_rank=any_rank)
     hp.setup()
     c.set_field(capi.F_Q, q)
     hp.implicit_iterate(nsgs, refresh_jac=True)     # builds A and its LU; warm-up
@@ -699,7 +706,7 @@ def fr_bench_multi(args, rank, world, local_rank, peak, torch, dist, stream):
            "iteration_frac_hbm": bytes_iter / (ms_it * 1e-3) / 1e9 / (peak * world),
            "sgs_ms_per_sweep": ms_sweep, "sgs_sweeps_per_s": 1e3 / ms_sweep, "sgs_algorithmic_bytes_per_sweep": bytes_sweep,
            "sgs_GBps": bytes_sweep / (ms_sweep * 1e-3) / 1e9, "sgs_frac_hbm": bytes_sweep / (ms_sweep * 1e-3) / 1e9 / (peak * world),
-           "jacobian_refresh_ms": ms_jac, "state_finite_after_run": finite}
+           "jacobian_refresh_ms": ms_jac, "state_finite_after_run": finite, "clip_fallbacks": hp.clip_fallbacks}
     if hasattr(x, "close"):
         x.close()
     c.close()

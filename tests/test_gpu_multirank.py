@@ -196,17 +196,18 @@ def test_slab_partitions_vs_oracle(oracle, colored, implicit, fused):
             exact(ctxs[r].get_field(capi.F_Q), qs[r], f"q rank {r} it {it}")
 
 
-@pytest.mark.parametrize("colored,viscous", [(True, False), (False, False), (True, True)])
-def test_fr_slab_partitions_vs_oracle(oracle, colored, viscous):
+@pytest.mark.parametrize("colored,viscous,fused", [(True, False, False), (False, False, False), (True, True, False),
+                                                   (True, False, True), (True, True, True)])
+def test_fr_slab_partitions_vs_oracle(oracle, colored, viscous, fused):
     """The reacting eqnset on partitions (BASELINE configs[4] is an 8-partition case): two z-slabs on one GPU with
-    direct-put halos of q (21 wide), qgrad (42), limiter and x (9), DistributedHotPath driving the iterations, against
+    direct-put halos of q (21 wide), qgrad (42), limiter and x (9), stepped as DistributedHotPath does, against
     the FR oracle run per rank with a numpy halo exchange through the same maps.  Frozen chemistry: one implicit
     iteration (2 sweeps, block-Jacobi across partitions) and one explicit iteration, bit-exact; with the viscous terms
     (compressibleNSFR) to 1e-11 (transport libm)."""
     import ctypes as C
     from proteuscfd_b200 import capi
     from proteuscfd_b200.cases import fr_slab_case
-    from proteuscfd_b200.parallel import DistributedHotPath, LoopbackExchange, build_local_group_maps
+    from proteuscfd_b200.parallel import LoopbackExchange, build_local_group_maps
     from tests.oracle_lib import _d, _i
     from tests.test_gpu_fr import fixture_fr_params, oracle_for_fr
     nr, NEQ, NV, NT = 2, 9, 21, 14
@@ -272,7 +273,6 @@ def test_fr_slab_partitions_vs_oracle(oracle, colored, viscous):
     for r in range(nr):
         orcs[r].apply_dq(qs[r], xs[r][1])
     halo(qs, NV)
-    hps = [DistributedHotPath(c, None) for c in ctxs]
     # the hot-path driver calls its exchange per rank; with all ranks in one process the loopback exchange moves every
     # rank's rows at once, so the phases are stepped in lock-step here exactly as DistributedHotPath.implicit_iterate does
     for c in ctxs:
@@ -282,9 +282,17 @@ def test_fr_slab_partitions_vs_oracle(oracle, colored, viscous):
     x.update(capi.F_Q)
     each(ctxs, lambda c: c.gradient())
     x.update(capi.F_QGRAD)
-    each(ctxs, lambda c: c.limiter())
-    x.update(capi.F_LIMITER)
-    each(ctxs, lambda c: c.residual())
+    if fused:
+        # pcfd_limiter_raw -> halo of the raw limiter -> pcfd_residual_fused (clamp + residual + clip test in one pass)
+        each(ctxs, lambda c: c.limiter_raw())
+        x.update(capi.F_LIMITER)
+        hits = [c.residual_fused()[1] for c in ctxs]
+        assert not any(hits), "the smooth state must not trigger the pressure clip"
+        assert all(c.clip_fallbacks() == 0 for c in ctxs)
+    else:
+        each(ctxs, lambda c: c.limiter())
+        x.update(capi.F_LIMITER)
+        each(ctxs, lambda c: c.residual())
     each(ctxs, lambda c: c.prepare_sgs())
     each(ctxs, lambda c: c.blank_x())
     x.update(capi.F_X)
@@ -293,7 +301,6 @@ def test_fr_slab_partitions_vs_oracle(oracle, colored, viscous):
         x.update(capi.F_X)
     each(ctxs, lambda c: c.apply_dq())
     x.update(capi.F_Q)
-    assert all(not h.fused for h in hps)          # the fused limiter/residual pair is a perfect-gas path
     for r in range(nr):
         exact(ctxs[r].get_field(capi.F_QGRAD), grads[r], f"qgrad rank {r}")
         exact(ctxs[r].get_field(capi.F_LIMITER), lims[r], f"limiter rank {r}")
