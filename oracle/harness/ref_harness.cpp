@@ -411,6 +411,24 @@ int main(int argc, char* argv[])
     eqnset->NativeToConservative(&space->qold[i*nvars]);
     eqnset->NativeToConservative(&space->qoldm1[i*nvars]);
   }
+  if(getenv("PCFD_UNSTEADY")){
+    // unsteady fixture: a third (or later) time step of a BDF run -- q^n and q^{n-1} differ from q^{n+1} and from each
+    // other, so that TemporalResidual (residual.tcc:125-179) and the cnp1 V / dt diagonal terms (jacobian.tcc:214-250)
+    // contribute; iter > 2 selects the BDF2 coefficients when timeOrder = 2
+    const Real twopi = 2.0*3.14159265358979323846;
+    space->iter = (space->iter > 3) ? space->iter : 3;
+    for(Int i = 0; i < nnode; i++){
+      Real x = m->xyz[3*i + 0], y = m->xyz[3*i + 1], z = m->xyz[3*i + 2];
+      for(Int j = 0; j < neqn; j++){
+	space->qold[i*nvars + j] *= (1.0 - 0.010*sin(twopi*(x + 0.1*j))*cos(twopi*z));
+	space->qoldm1[i*nvars + j] *= (1.0 - 0.017*cos(twopi*(y + 0.07*j))*sin(twopi*x));
+      }
+    }
+  }
+  if(mode == "dump"){
+    Dump("qold", space->qold, (size_t)nnode*nvars);
+    Dump("qoldm1", space->qoldm1, (size_t)nnode*nvars);
+  }
   // NewtonIterate head (solutionSpace.tcc:662-665)
   UpdateBCs(space);
   p->UpdateGeneralVectors(space->q, nvars);

@@ -986,6 +986,24 @@ void orc_residual(const orc_case* c, const double* q, const double* qgrad, const
   }
   /* SourceTerm (compressible.tcc:1196-1208, gravity off) adds +0.0: node loop residual.tcc:109-115 */
   for(i = 0; i < c->nnode*NEQN; i++) b[i] += 0.0;
+  /* TemporalResidual residual.tcc:125-179 (no GCL); q holds conservative variables (NativeToConservative: identity) */
+  if(c->torder && c->qold){
+    double cnp1 = 1.0, cnm1 = 0.0;
+    if(c->iter > 1 && c->torder == 2){ cnp1 = 1.5; cnm1 = -0.5; }
+    for(i = 0; i < c->nnode; i++){
+      double dt = cnp1*c->vol[i]/c->dt_param;
+      double dtm1 = cnm1*c->vol[i]/c->dt_param;
+      double dq[NEQN], dqm1[NEQN];
+      for(j = 0; j < NEQN; j++){
+	dq[j] = q[i*NVARS + j] - c->qold[i*NVARS + j];
+	dqm1[j] = c->qold[i*NVARS + j] - c->qoldm1[i*NVARS + j];
+      }
+      for(j = 0; j < NEQN; j++){
+	b[i*NEQN + j] -= dt*dq[j];
+	b[i*NEQN + j] -= dtm1*dqm1[j];
+      }
+    }
+  }
   /* Bkernel_BC_Res_Modify (residual.tcc:40-43, bc.tcc:905-1056) -> ModifyViscousWallResidual
      (compressible.tcc:1611-1631) */
   for(e = 0; e < nb; e++){
@@ -1205,10 +1223,16 @@ void orc_jacobian(const orc_case* c, double* q, const double* beta, const double
   /* source-term Jacobian (eqnset.tcc:163-187) is identically zero without gravity:
      jac[j] -= 0.0 (jacobian.tcc:199-208) */
 
-  /* ContributeTemporalTerms :214-250 -> eqnset.tcc:195-208 (steady: param->dt < 0, cnp1 = 1) */
-  for(i = 0; i < c->nnode; i++){
-    double* d = get_block(ia, ja, A, i, i);
-    for(k = 0; k < NEQN; k++) d[k*NEQN + k] += 1.0*c->vol[i]/dt[i];
+  /* ContributeTemporalTerms :214-250 -> eqnset.tcc:195-208 */
+  {
+    double cnp1 = (c->iter > 1 && c->torder == 2) ? 1.5 : 1.0;
+    for(i = 0; i < c->nnode; i++){
+      double* d = get_block(ia, ja, A, i, i);
+      for(k = 0; k < NEQN; k++){
+	if(c->use_local_dt && (c->dt_param > 0.0)) d[k*NEQN + k] += cnp1*c->vol[i]/c->dt_param + c->vol[i]/dt[i];
+	else d[k*NEQN + k] += cnp1*c->vol[i]/dt[i];
+      }
+    }
   }
 
   /* Bkernel_BC_Jac_Modify (jacobian.tcc:247-249, bc.tcc:747-903) -> ModifyViscousWallJacobian

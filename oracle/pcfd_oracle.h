@@ -56,6 +56,12 @@ typedef struct {
   const double* bedges_twall;  /* [nbedge] bcobj->twall / ref_temperature of the half-edge's surface
                                   (read for NoSlip only; < 0: adiabatic).  NULL: 1/tref (bcobj.tcc:31) */
   const double* mut;           /* field "mut" [nnode+gnode+nbnode]; NULL: zero (laminar) */
+  /* time integration (Param::dt, useLocalTimeStepping, torder; SolutionSpace::iter, qold, qoldm1).  qold == NULL:
+     q^n == q^{n+1} (first Newton iteration of a steady step): TemporalResidual contributes exact zeros and is skipped */
+  double dt_param;             /* Param::dt (< 0: steady) -- perfect-gas eqnsets; the reacting one reads orc_fr_params */
+  int use_local_dt, torder, iter;
+  const double* qold;          /* [nnode*nvars] conservative variables at t^n */
+  const double* qoldm1;        /* [nnode*nvars] ... at t^{n-1} */
 } orc_case;
 
 /* gradient.tcc:115-138, 381-542 : s and sw, each [(nnode+gnode)*6] */

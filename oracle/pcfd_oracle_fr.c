@@ -767,6 +767,7 @@ void orc_fr_limiter(const orc_case* c, const orc_fr_params* p, const double* q, 
 /* ------------------------------------------------------------- transport + viscous terms (compressibleNSFR) */
 
 static double chem_dRmixdRhoi(const orc_fr_params* p, const double* rhoi, double rho, int i);
+static void fr_native_to_conservative(const orc_fr_params* p, double* Q);
 
 /* Species::GetViscosity / GetThermalConductivity species.tcc:393-479: Sutherland (White) up to the transition
    temperature, NASA RP-1311 fit above; the range search keeps the LAST range containing T (no break) */
@@ -1146,6 +1147,26 @@ void orc_fr_residual(const orc_case* c, const orc_fr_params* p, const double* q,
     fr_source_term(p, &q[(size_t)i*nvars], c->vol[i], source);
     for(j = 0; j < neqn; j++) b[(size_t)i*neqn + j] += source[j];
   }
+  /* TemporalResidual residual.tcc:125-179 (no GCL): the stored state is native, the equations conservative */
+  if(c->torder && c->qold){
+    double cnp1 = 1.0, cnm1 = 0.0;
+    if(c->iter > 1 && c->torder == 2){ cnp1 = 1.5; cnm1 = -0.5; }
+    for(i = 0; i < c->nnode; i++){
+      double dt = cnp1*c->vol[i]/p->dt_param;
+      double dtm1 = cnm1*c->vol[i]/p->dt_param;
+      double Q[MAXV], dq[MAXE], dqm1[MAXE];
+      memcpy(Q, &q[(size_t)i*nvars], sizeof(double)*nvars);
+      fr_native_to_conservative(p, Q);
+      for(j = 0; j < neqn; j++){
+	dq[j] = Q[j] - c->qold[(size_t)i*nvars + j];
+	dqm1[j] = c->qold[(size_t)i*nvars + j] - c->qoldm1[(size_t)i*nvars + j];
+      }
+      for(j = 0; j < neqn; j++){
+	b[(size_t)i*neqn + j] -= dt*dq[j];
+	b[(size_t)i*neqn + j] -= dtm1*dqm1[j];
+      }
+    }
+  }
 }
 
 /* timestep.tcc:7-49 (local time stepping), kernels :80-143 */
@@ -1489,9 +1510,12 @@ void orc_fr_jacobian(const orc_case* c, const orc_fr_params* p, double* q, const
     }
     for(kk = 0; kk < n2; kk++) jac[kk] -= SJ[kk];
   }
-  /* ContributeTemporalTerms jacobian.tcc:214-250 (cnp1 = 1: first iteration / first order in time) */
-  for(i = 0; i < c->nnode; i++){
-    fr_temporal_terms(p, &q[(size_t)i*nvars], c->vol[i], 1.0, p->dt_param, dt[i], get_block(ia, ja, A, i, i, n2), beta[i]);
+  /* ContributeTemporalTerms jacobian.tcc:214-250 */
+  {
+    double cnp1 = (c->iter > 1 && c->torder == 2) ? 1.5 : 1.0;
+    for(i = 0; i < c->nnode; i++){
+      fr_temporal_terms(p, &q[(size_t)i*nvars], c->vol[i], cnp1, p->dt_param, dt[i], get_block(ia, ja, A, i, i, n2), beta[i]);
+    }
   }
 }
 

@@ -28,7 +28,9 @@ class OrcCase(C.Structure):
                 ("qinf", C.c_double * NVARS),
                 ("viscous", C.c_int), ("enable_vnn", C.c_int),
                 ("Re", C.c_double), ("Pr", C.c_double), ("PrT", C.c_double), ("tref", C.c_double),
-                ("mach", C.c_double), ("vnn", C.c_double), ("bedges_twall", _dp), ("mut", _dp)]
+                ("mach", C.c_double), ("vnn", C.c_double), ("bedges_twall", _dp), ("mut", _dp),
+                ("dt_param", C.c_double), ("use_local_dt", C.c_int), ("torder", C.c_int), ("iter", C.c_int),
+                ("qold", _dp), ("qoldm1", _dp)]
 
 
 def _d(a):
@@ -67,6 +69,12 @@ class Oracle:
         c.tref, c.mach, c.vnn = meta.get("ref_temperature", 300.0), meta.get("velocity", 0.0), meta.get("VNN", 20.0)
         c.bedges_twall = _d(k["bedges_twall"]) if "bedges_twall" in k and k["bedges_twall"].size else None
         c.mut = _d(k["mut"]) if "mut" in k else None
+        # time integration: the BDF terms are live only when the fixture / caller carries a q^n that differs from q
+        c.dt_param, c.use_local_dt = float(meta.get("dt", -1.0)), int(meta.get("useLocalTimeStepping", 1))
+        c.torder, c.iter = int(meta.get("torder", 1)), int(meta.get("iter", 1))
+        unsteady = float(meta.get("dt", -1.0)) > 0.0 and "qold" in k
+        c.qold = _d(k["qold"]) if unsteady else None
+        c.qoldm1 = _d(k["qoldm1"]) if unsteady else None
         self.c = c
         self.nn = c.nnode + c.gnode
         self.nnode = c.nnode

@@ -10,12 +10,13 @@ import pytest
 
 from tests.oracle_lib import Oracle, load_golden
 
+# box6_unsteady_bdf2: dual time stepping, third step of a BDF2 run (TemporalResidual with q^n, q^{n-1}; cnp1 V/dt + V/dtau)
 INVISCID = ["box8_explicit_venkat", "box8_explicit_barth", "box8_explicit_venkatmod", "box6_implicit_sgs", "box6c_implicit_sgs",
-            "ramp15_implicit", "cube_LowFi"]
+            "ramp15_implicit", "cube_LowFi", "box6_unsteady_bdf2"]
 # laminar Navier-Stokes (compressibleNS): viscous flux + analytic viscous Jacobian + no-slip wall hooks
 NS = ["box6_ns_implicit", "box6_ns_adiabatic", "box6_sa_implicit"]
 ALL = INVISCID + NS
-INVISCID_IMPLICIT = ["box6_implicit_sgs", "box6c_implicit_sgs", "ramp15_implicit", "cube_LowFi"]
+INVISCID_IMPLICIT = ["box6_implicit_sgs", "box6c_implicit_sgs", "ramp15_implicit", "cube_LowFi", "box6_unsteady_bdf2"]
 IMPLICIT = INVISCID_IMPLICIT + NS
 EXPLICIT = ["box8_explicit_venkat", "box8_explicit_barth", "box8_explicit_venkatmod"]
 
@@ -118,3 +119,14 @@ def test_resnorm_matches_reference_definition():
     g, meta = load_golden("box8_explicit_venkat")
     b = g["b"]
     assert np.isclose(np.sqrt(np.sum(b * b)) / b.size, g["resnorm"][0], rtol=1e-13)
+
+
+def test_unsteady_fixture_exercises_the_bdf_terms(oracle):
+    g, meta = load_golden("box6_unsteady_bdf2")
+    assert meta["dt"] == 0.02 and int(meta["torder"]) == 2 and int(meta["iter"]) == 3
+    o = Oracle(oracle, g, meta)
+    b = o.residual(g["q0"].copy(), g["qgrad"], g["limiter"], g["beta"])
+    exact(b, g["b"], "b")
+    o.c.qold = None     # steady form: no temporal residual
+    b0 = o.residual(g["q0"].copy(), g["qgrad"], g["limiter"], g["beta"])
+    assert np.abs(b - b0).max() > 0.1 * np.abs(b).max()

@@ -10,8 +10,8 @@ import pytest
 from tests.oracle_lib import FrOracle, load_golden
 from tests.test_oracle import exact
 
-FR = ["box5_fr_explicit", "box4_fr_implicit", "box4_nsfr_implicit"]
-IMPLICIT = ["box4_fr_implicit", "box4_nsfr_implicit"]
+FR = ["box5_fr_explicit", "box4_fr_implicit", "box4_nsfr_implicit", "box4_fr_unsteady"]
+IMPLICIT = ["box4_fr_implicit", "box4_nsfr_implicit", "box4_fr_unsteady"]
 
 
 @pytest.mark.parametrize("name", FR)

@@ -131,7 +131,7 @@ def collect(outdir, rank):
     return d
 
 
-def make_case(name, mesh=None, h5=None, bc=BOX_BC, np_ranks=1, part=None, **kw):
+def make_case(name, mesh=None, h5=None, bc=BOX_BC, np_ranks=1, part=None, unsteady=False, **kw):
     opts = dict(eqnset="compressibleEuler", sorder=2, limiter=2, nsgs=0, mach=0.5, cfl=0.5,
                 fx=1.0, fy=0.0, fz=0.0, jactype=0, refvisc=1.0, vnn=0, turb=0, extra="")
     opts.update(kw)
@@ -153,8 +153,10 @@ def make_case(name, mesh=None, h5=None, bc=BOX_BC, np_ranks=1, part=None, **kw):
                 np.savetxt(os.path.join(work, "part.txt"), part, fmt="%d")
                 env["PCFD_PARTITION_FILE"] = os.path.join(work, "part.txt")
             run([os.path.join(REFBIN, "udecomp_ref"), f"{name}.ugrid", str(np_ranks)], work, env)
-        run([os.path.join(REFBIN, "ref_harness"), os.path.join(work, name), os.path.join(work, "out"), "dump"],
-            work, {"PCFD_MPI_NP": str(np_ranks)})
+        henv = {"PCFD_MPI_NP": str(np_ranks)}
+        if unsteady:
+            henv["PCFD_UNSTEADY"] = "1"
+        run([os.path.join(REFBIN, "ref_harness"), os.path.join(work, name), os.path.join(work, "out"), "dump"], work, henv)
         os.makedirs(GOLDEN, exist_ok=True)
         for r in range(np_ranks):
             d = collect(os.path.join(work, "out"), r)
@@ -239,6 +241,13 @@ CASES = {
                                             nsgs=3, cfl=5.0, refvisc=2.0e-4,   # Re = 111 (refLength 1 cm, 2 kPa)
                                             extra=FR_EXTRA.format(temp=950, pres=2000, rxn=1)
                                             + "refThermalConductivity = 0.05\nrefLength = 0.01\n"),
+    # unsteady (dual time stepping): physical time step 0.02, BDF2 at the third step -- TemporalResidual with
+    # q^n, q^{n-1} and the cnp1 V/dt + V/dtau diagonal (perfect gas: diagonal; reacting: dense dQ/dq blocks)
+    "box6_unsteady_bdf2": lambda: make_case("box6_unsteady_bdf2", mesh=kuhn_box(6, jitter=0.15), nsgs=3, cfl=5.0, unsteady=True,
+                                            extra="timeStep = 0.02\ntimeOrder = 2\n"),
+    "box4_fr_unsteady": lambda: make_case("box4_fr_unsteady", mesh=kuhn_box(4, jitter=0.15), eqnset="compressibleEulerFR",
+                                          nsgs=3, cfl=5.0, unsteady=True,
+                                          extra=FR_EXTRA.format(temp=3000, pres=101325, rxn=1) + "timeStep = 0.02\ntimeOrder = 2\n"),
     # the reference's own unit-test fixture (unitTest/gradientTest.h:20-232): prism cube, 216 nodes
     "cube_LowFi": lambda: make_case(
         "cube_LowFi", h5=os.path.join(REFERENCE, "unitTest/meshResources/cubeStructuredSeries/cube_LowFi.0.h5"),
