@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PCFD_ABI_VERSION 4
+#define PCFD_ABI_VERSION 5
 
 /* eqnset ids follow eqnset_defines.h / create_functions.h:17-45 */
 enum { PCFD_EQNSET_COMPRESSIBLE_EULER_FR = 0, PCFD_EQNSET_COMPRESSIBLE_NS_FR = 1, PCFD_EQNSET_COMPRESSIBLE_EULER = 2,
@@ -63,7 +63,12 @@ enum {
   PCFD_F_TURB_B = 14,    /* nnode */
   PCFD_F_TURB_X = 15,    /* nnode+gnode */
   PCFD_F_TURB_A = 16,    /* nblocks */
-  PCFD_F_COUNT = 17
+  /* time integration (TemporalResidual, residual.tcc:125-179): CONSERVATIVE variables at t^n and t^{n-1}, rows of
+     nvars doubles for the owned nodes, as SolutionSpace::qold / qoldm1 hold them (solutionSpace.tcc:582-592).
+     Allocated on first use (unsteady runs only). */
+  PCFD_F_QOLD = 17,      /* nnode*nvars */
+  PCFD_F_QOLDM1 = 18,    /* nnode*nvars */
+  PCFD_F_COUNT = 19
 };
 
 /* Mesh::edges / bedges / xyz / vol / ipsp / psp as flat arrays (uns_base.h:12-37, mesh.h:199-254) */
@@ -115,6 +120,12 @@ int pcfd_destroy(pcfd_ctx* ctx);
 int pcfd_set_stream(pcfd_ctx* ctx, void* cuda_stream);
 int pcfd_synchronize(pcfd_ctx* ctx);
 int pcfd_set_cfl(pcfd_ctx* ctx, double cfl);           /* Param::UpdateCFL (solutionSpace.tcc:629) */
+/* Time integration state read by ComputeResiduals / ComputeJacobians: Param::dt (< 0: steady), Param::useLocalTimeStepping,
+   Param::torder (1 | 2) and SolutionSpace::iter (BDF2 coefficients from the second step on, residual.tcc:139-149,
+   jacobian.tcc:228-230).  Default: steady, first order, iter = 1.  TemporalResidual is evaluated once field
+   PCFD_F_QOLD has been set (before that q^n == q^{n+1} and its contribution is an exact zero); the diagonal terms
+   cnp1 V/dt + V/dtau (eqnset.tcc:195-208, compressibleFR.tcc:1326-1331) follow these values at once. */
+int pcfd_set_time_integration(pcfd_ctx* ctx, double dt, int use_local_time_stepping, int torder, int iter);
 
 size_t pcfd_field_size(const pcfd_ctx* ctx, int field); /* number of doubles */
 int pcfd_set_field(pcfd_ctx* ctx, int field, const double* host, size_t n);

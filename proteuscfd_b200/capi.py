@@ -22,6 +22,7 @@ BC_FARFIELD_VISCOUS, BC_FARFIELD, BC_SONIC_INFLOW, BC_SONIC_OUTFLOW, BC_SYMMETRY
 
 F_Q, F_QGRAD, F_LIMITER, F_B, F_X, F_TIMESTEP, F_BETA, F_LSQ_S, F_LSQ_SW, F_A, F_MUT = range(11)
 F_TVAR, F_TGRAD, F_WALLDIST, F_TURB_B, F_TURB_X, F_TURB_A = range(11, 17)
+F_QOLD, F_QOLDM1 = 17, 18     # conservative variables at t^n, t^{n-1} (nnode*nvars; unsteady runs)
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -38,6 +39,7 @@ SYMBOLS = [
     "pcfd_turb_compute", "pcfd_halo_configure",
     "pcfd_chem_create", "pcfd_chem_destroy", "pcfd_chem_last_error", "pcfd_chem_mass_production",
     "pcfd_create_fr", "pcfd_widths", "pcfd_limiter_raw", "pcfd_residual_fused", "pcfd_clip_fallbacks",
+    "pcfd_set_time_integration",
     "pcfd_chem_source_term", "pcfd_chem_source_term_device", "pcfd_halo_width", "pcfd_halo_send_total", "pcfd_halo_pack", "pcfd_halo_recv_ptr",
 ]
 
@@ -157,6 +159,7 @@ def load_library(path=LIB_PATH):
     lib.pcfd_field_device_ptr.argtypes = [C.c_void_p, C.c_int]
     lib.pcfd_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.pcfd_set_cfl.argtypes = [C.c_void_p, C.c_double]
+    lib.pcfd_set_time_integration.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int]
     lib.pcfd_crs_sizes.argtypes = [C.c_void_p, _ip, _ip]
     lib.pcfd_get_crs.argtypes = [C.c_void_p, _ip, _ip, _ip, _ip]
     lib.pcfd_residual.argtypes = [C.c_void_p, _dp]
@@ -325,6 +328,11 @@ class Context:
 
     def set_cfl(self, cfl):
         self._ck(self.lib.pcfd_set_cfl(self.h, float(cfl)))
+
+    def set_time_integration(self, dt, use_local_time_stepping=1, torder=1, it=1):
+        """Param::dt / useLocalTimeStepping / torder and SolutionSpace::iter (see pcfd_set_time_integration)."""
+        self._ck(self.lib.pcfd_set_time_integration(self.h, C.c_double(float(dt)), int(use_local_time_stepping), int(torder),
+                                                    int(it)))
 
     def clip_fallbacks(self):
         """times the fused limiter / residual pair fell back to the ordered pressure-clip path"""

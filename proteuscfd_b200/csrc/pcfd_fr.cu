@@ -506,6 +506,33 @@ __global__ void __launch_bounds__(W<NS>::NEQ * 16) kfr_residual_gather(DevMesh m
   b[(size_t)n * NEQ + j] = acc;
 }
 
+// TemporalResidual (residual.tcc:125-179, no GCL): the stored state is native, the equations are written for the
+// conservative variables (NativeToConservative, compressibleFR.tcc:2117-2130); qold / qoldm1 hold conservative rows
+template <int NS>
+__global__ void __launch_bounds__(128) kfr_temporal_residual(int nnode, fr::Params<NS> p, double cnp1, double cnm1,
+                                                              const double* __restrict__ vol, const double* __restrict__ q,
+                                                              const double* __restrict__ qold, const double* __restrict__ qoldm1,
+                                                              double* __restrict__ b) {
+  constexpr int NEQ = W<NS>::NEQ, NV = W<NS>::NV;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nnode) return;
+  double Q[NS + 6];
+  load_row<NS, NS + 6>(q, n, Q);
+  fr::native_to_conservative(p, Q);
+  const double dt = cnp1 * vol[n] / p.dt;
+  const double dtm1 = cnm1 * vol[n] / p.dt;
+#pragma unroll
+  for (int j = 0; j < NEQ; j++) {
+    const double qo = qold[(size_t)n * NV + j];
+    const double dq = Q[j] - qo;
+    const double dqm1 = qo - qoldm1[(size_t)n * NV + j];
+    double v = b[(size_t)n * NEQ + j];
+    v -= dt * dq;
+    v -= dtm1 * dqm1;
+    b[(size_t)n * NEQ + j] = v;
+  }
+}
+
 // ====================================================================== time step
 // Kernel_Timestep / Bkernel_Timestep (timestep.tcc:80-143): spectral radius x area of the averaged state, per edge
 template <int NS>
@@ -834,7 +861,7 @@ __global__ void __launch_bounds__(W<NS>::NEQ * 16) kfr_jac_diag(DevMesh m, const
 template <int NS>
 __global__ void __launch_bounds__(64) kfr_jac_node(DevMesh m, fr::Params<NS> p, const int* __restrict__ iau,
                                                     const double* __restrict__ q, const double* __restrict__ dt,
-                                                    const double* __restrict__ beta, double* A) {
+                                                    const double* __restrict__ beta, double cnp1, double* A) {
   constexpr int NEQ = W<NS>::NEQ, N2 = W<NS>::N2;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= m.nnode) return;
@@ -854,7 +881,7 @@ __global__ void __launch_bounds__(64) kfr_jac_node(DevMesh m, fr::Params<NS> p, 
       for (int j = 0; j < NS; j++) dg[j * NEQ + i] -= (sP[j] - s0[j]) / h;
     }
   }
-  fr::temporal_terms(p, Q, vol, 1.0, dt[n], dg, beta[n]);
+  fr::temporal_terms(p, Q, vol, cnp1, dt[n], dg, beta[n]);
 }
 
 // CRSMatrix::PrepareSGS (crsmatrix.tcc:840-876) -> LU (matrix.h:110-190)
@@ -1151,6 +1178,14 @@ struct Impl {
     kfr_residual_gather<NS><<<nblk((long long)c->nnode * Wd::NEQ, BS), BS, 0, c->stream>>>(
         c->dm, c->flux, c->bflux, c->fr->viscous ? c->fr->vflux : nullptr, c->fr->bvflux, c->fr->src, c->f[PCFD_F_B]);
     LAUNCH_CHECK();
+    if (c->torder && c->have_qold) {
+      const bool bdf2 = c->iter > 1 && c->torder == 2;
+      PROF("kfr_temporal_residual");
+      kfr_temporal_residual<NS><<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->nnode, p, bdf2 ? 1.5 : 1.0, bdf2 ? -0.5 : 0.0, c->vol,
+                                                                           c->f[PCFD_F_Q], c->f[PCFD_F_QOLD],
+                                                                           c->f[PCFD_F_QOLDM1], c->f[PCFD_F_B]);
+      LAUNCH_CHECK();
+    }
     if (fused) {
       CK(cudaEventSynchronize(c->ev_flag));
       *clip_hit = *c->hflag != 0;
@@ -1227,7 +1262,8 @@ struct Impl {
     kfr_jac_diag<NS><<<nblk((long long)c->nnode * Wd::NEQ, BS), BS, 0, c->stream>>>(c->dm, c->iau, c->posLR, c->posRL, c->bdiag, A);
     LAUNCH_CHECK();
     PROF("kfr_jac_node");
-    kfr_jac_node<NS><<<nblk(c->nnode, 64), 64, 0, c->stream>>>(c->dm, p, c->iau, c->f[PCFD_F_Q], c->f[PCFD_F_TIMESTEP], beta, A);
+    kfr_jac_node<NS><<<nblk(c->nnode, 64), 64, 0, c->stream>>>(c->dm, p, c->iau, c->f[PCFD_F_Q], c->f[PCFD_F_TIMESTEP], beta,
+                                                               (c->iter > 1 && c->torder == 2) ? 1.5 : 1.0, A);
     LAUNCH_CHECK();
     return 0;
   }
@@ -1315,6 +1351,12 @@ struct Impl {
   }
 
 }  // namespace
+
+void pcfd_fr_set_time(pcfd_ctx* c, double dt, int use_local) {
+  if (!c || !c->fr) return;
+  c->fr->host.dt = dt;
+  c->fr->host.use_local_dt = use_local;
+}
 
 void pcfd_fr_destroy(pcfd_ctx* c) {
   if (!c || !c->fr) return;

@@ -116,6 +116,10 @@ struct pcfd_ctx {
   std::vector<int> send_counts, send_offsets, recv_counts, recv_offsets;
   int* send_list = nullptr;
   int send_total = 0;
+  // time integration (pcfd_set_time_integration): Param::dt, useLocalTimeStepping, torder, SolutionSpace::iter
+  double time_dt = -1.0;
+  int time_local = 1, torder = 1, iter = 1;
+  bool have_qold = false;   // PCFD_F_QOLD has been set: TemporalResidual is live
   bool ludiag = false;
   int sgs_unroll = 4;      // blocks in flight per lane in k_sgs_level (PCFD_SGS_UNROLL overrides, for tuning)
   // bulk-copy (TMA) streaming variant: per level, shared-memory bytes for the matrix part of a tile (0: the rows of
@@ -221,6 +225,7 @@ int pcfd_fr_gradient(pcfd_ctx* c);
 int pcfd_fr_limiter(pcfd_ctx* c);
 int pcfd_fr_residual(pcfd_ctx* c, double* sumsq);
 int pcfd_fr_limiter_raw(pcfd_ctx* c);
+void pcfd_fr_set_time(pcfd_ctx* c, double dt, int use_local);
 int pcfd_fr_residual_fused(pcfd_ctx* c, double* sumsq, bool* clip_hit);
 int pcfd_fr_timestep(pcfd_ctx* c, double* dtmin);
 int pcfd_fr_explicit_solve(pcfd_ctx* c);

@@ -897,12 +897,43 @@ __global__ void __launch_bounds__(64) k_jac_bedges(DevMesh m, eq::BcParams bp, c
   }
 }
 
+// TemporalResidual (residual.tcc:125-179, no GCL): b -= cnp1 V/dt (Q - Q^n) and b -= cnm1 V/dt (Q^n - Q^{n-1}) on the
+// conservative variables.  It runs between the spatial residual and Bkernel_BC_Res_Modify (residual.tcc:20-43), whose
+// hard-set wall rows (already applied by the gather) are therefore re-applied here.
+__global__ void __launch_bounds__(128) k_temporal_residual(int nnode, double cnp1, double cnm1, double tdt,
+                                                            const double* __restrict__ vol, const double* __restrict__ q,
+                                                            const double* __restrict__ qold, const double* __restrict__ qoldm1,
+                                                            const unsigned char* __restrict__ wallflag, double* __restrict__ b) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nnode) return;
+  const double dt = cnp1 * vol[n] / tdt;
+  const double dtm1 = cnm1 * vol[n] / tdt;
+  double r[NEQN];
+#pragma unroll
+  for (int j = 0; j < NEQN; j++) {
+    const double qo = qold[(size_t)n * NVARS + j];
+    const double dq = q[(size_t)n * NVARS + j] - qo;
+    const double dqm1 = qo - qoldm1[(size_t)n * NVARS + j];
+    double v = b[(size_t)n * NEQN + j];
+    v -= dt * dq;
+    v -= dtm1 * dqm1;
+    r[j] = v;
+  }
+  if (wallflag) {
+    const unsigned char wf = wallflag[n];
+    if (wf & 1) { r[1] = r[2] = r[3] = r[4] = 0.0; }
+    if (wf & 2) r[0] = 0.0;
+  }
+#pragma unroll
+  for (int j = 0; j < NEQN; j++) b[(size_t)n * NEQN + j] = r[j];
+}
+
 // Kernel_Diag_NumJac (jacobian.tcc:434-456) + ContributeTemporalTerms (:214-250 ->
-// eqnset.tcc:195-208, steady: cnp1 = 1): diag(n) -= A(other,n) in edge order, then
+// eqnset.tcc:195-208): diag(n) -= A(other,n) in edge order, then
 // += vol/dt on its diagonal.
 __global__ void __launch_bounds__(128) k_jac_diag(DevMesh m, const int* __restrict__ iau, const int* __restrict__ posLR,
                                                    const int* __restrict__ posRL, const double* __restrict__ dt,
-                                                   const double* __restrict__ bdiag, double* A) {
+                                                   const double* __restrict__ bdiag, double cnp1, double tdt, double* A) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= m.nnode) return;
   double* dg = A + (size_t)iau[n] * NEQN2;
@@ -927,7 +958,8 @@ __global__ void __launch_bounds__(128) k_jac_diag(DevMesh m, const int* __restri
 #pragma unroll
     for (int kk = 0; kk < NEQN2; kk++) d[kk] += -src[kk];
   }
-  const double tt = 1.0 * m.vol[n] / dt[n];
+  // tdt > 0: unsteady with local (pseudo) time stepping: cnp1 V/dt + V/dtau; else cnp1 V/dtau (eqnset.tcc:199-206)
+  const double tt = (tdt > 0.0) ? cnp1 * m.vol[n] / tdt + m.vol[n] / dt[n] : cnp1 * m.vol[n] / dt[n];
 #pragma unroll
   for (int kk = 0; kk < NEQN; kk++) d[kk * NEQN + kk] += tt;
 #pragma unroll
@@ -1946,7 +1978,7 @@ static int create_impl(const pcfd_mesh_desc* mesh, const pcfd_params* params, in
   c->fsize[PCFD_F_TURB_A] = sa_on ? (size_t)c->nblocks : 0;
   c->fsize[PCFD_F_A] = 0;   // allocated on first use (implicit runs only)
   for (int k = 0; k < PCFD_F_COUNT; k++) {
-    if (k == PCFD_F_A) continue;
+    if (k == PCFD_F_A || k == PCFD_F_QOLD || k == PCFD_F_QOLDM1) continue;   // allocated on first use
     if (dev_alloc(c, &c->f[k], c->fsize[k] + 4)) return 1;   // slack: 16-byte rounded bulk prefetches
     CK(cudaMemset(c->f[k], 0, std::max<size_t>(c->fsize[k], 1) * sizeof(double)));
   }
@@ -2035,6 +2067,18 @@ int pcfd_profile_get(pcfd_ctx* c, int i, const char** name, double* total_ms, lo
   return 0;
 }
 
+// qold / qoldm1: unsteady runs only, allocated on first use
+static int ensure_time_fields(pcfd_ctx* c) {
+  if (c->f[PCFD_F_QOLD]) return 0;
+  for (int k : {PCFD_F_QOLD, PCFD_F_QOLDM1}) {
+    c->fsize[k] = (size_t)c->nnode * c->nvars;
+    if (dev_alloc(c, &c->f[k], c->fsize[k] + 4)) return 1;
+    CK(cudaMemsetAsync(c->f[k], 0, c->fsize[k] * sizeof(double), c->stream));
+  }
+  return 0;
+}
+static bool is_time_field(int field) { return field == PCFD_F_QOLD || field == PCFD_F_QOLDM1; }
+
 static int ensure_matrix(pcfd_ctx* c) {
   if (c->f[PCFD_F_A]) return 0;
   c->fsize[PCFD_F_A] = (size_t)c->nblocks * c->neqn * c->neqn;
@@ -2047,6 +2091,7 @@ static int ensure_matrix(pcfd_ctx* c) {
 size_t pcfd_field_size(const pcfd_ctx* c, int field) {
   if (!c || field < 0 || field >= PCFD_F_COUNT) return 0;
   if (field == PCFD_F_A) return (size_t)c->nblocks * c->neqn * c->neqn;
+  if (is_time_field(field)) return (size_t)c->nnode * c->nvars;
   return c->fsize[field];
 }
 int pcfd_set_field(pcfd_ctx* c, int field, const double* host, size_t n) {
@@ -2054,6 +2099,10 @@ int pcfd_set_field(pcfd_ctx* c, int field, const double* host, size_t n) {
   if (field < 0 || field >= PCFD_F_COUNT || !host) return fail(c, "pcfd_set_field: bad argument");
   CK(cudaSetDevice(c->device));
   if (field == PCFD_F_A) { if (ensure_matrix(c)) return 1; c->ludiag = false; }
+  if (is_time_field(field)) {
+    if (ensure_time_fields(c)) return 1;
+    if (field == PCFD_F_QOLD) c->have_qold = true;
+  }
   if (n != c->fsize[field]) return fail(c, "pcfd_set_field: size mismatch");
   CK(cudaMemcpyAsync(c->f[field], host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -2064,6 +2113,7 @@ int pcfd_get_field(pcfd_ctx* c, int field, double* host, size_t n) {
   if (field < 0 || field >= PCFD_F_COUNT || !host) return fail(c, "pcfd_get_field: bad argument");
   CK(cudaSetDevice(c->device));
   if (field == PCFD_F_A && ensure_matrix(c)) return 1;
+  if (is_time_field(field) && ensure_time_fields(c)) return 1;
   if (n != c->fsize[field]) return fail(c, "pcfd_get_field: size mismatch");
   CK(cudaMemcpyAsync(host, c->f[field], n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -2072,6 +2122,7 @@ int pcfd_get_field(pcfd_ctx* c, int field, double* host, size_t n) {
 void* pcfd_field_device_ptr(pcfd_ctx* c, int field) {
   if (!c || field < 0 || field >= PCFD_F_COUNT) return nullptr;
   if (field == PCFD_F_A) { cudaSetDevice(c->device); if (ensure_matrix(c)) return nullptr; }
+  if (is_time_field(field)) { cudaSetDevice(c->device); if (ensure_time_fields(c)) return nullptr; }
   return c->f[field];
 }
 int pcfd_crs_sizes(const pcfd_ctx* c, int* nrows, int* nblocks) {
@@ -2228,6 +2279,18 @@ int pcfd_limiter_raw(pcfd_ctx* c) {
 
 long long pcfd_clip_fallbacks(const pcfd_ctx* c) { return c ? c->clip_fallbacks : -1; }
 
+int pcfd_set_time_integration(pcfd_ctx* c, double dt, int use_local_time_stepping, int torder, int iter) {
+  if (!c) return 1;
+  if (torder != 1 && torder != 2) return fail(c, "pcfd_set_time_integration: torder must be 1 or 2 (param.tcc:167)");
+  if (dt == 0.0) return fail(c, "pcfd_set_time_integration: dt must be non-zero (negative: steady)");
+  c->time_dt = dt;
+  c->time_local = use_local_time_stepping ? 1 : 0;
+  c->torder = torder;
+  c->iter = iter;
+  if (c->fr) pcfd_fr_set_time(c, dt, c->time_local);
+  return 0;
+}
+
 int pcfd_residual_fused(pcfd_ctx* c, double* sumsq, int* clip_hit) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
@@ -2260,6 +2323,21 @@ static int run_limiter_final(pcfd_ctx* c, const int* tclip) {
 // fused = true: lim holds the raw limiter; the edge kernel clamps on the fly and raises dflags[2] if the pressure
 // clip would act anywhere, k_limiter_final then clamps in place, and *clip_hit reports the flag (one event wait that
 // overlaps with the kernels queued behind it)
+// BDF coefficients (residual.tcc:139-149, jacobian.tcc:228-230)
+static double time_cnp1(const pcfd_ctx* c) { return (c->iter > 1 && c->torder == 2) ? 1.5 : 1.0; }
+static double time_cnm1(const pcfd_ctx* c) { return (c->iter > 1 && c->torder == 2) ? -0.5 : 0.0; }
+
+// TemporalResidual, once the host has provided q^n (ComputeResiduals, residual.tcc:20-24)
+static int run_temporal(pcfd_ctx* c) {
+  if (!c->torder || !c->have_qold) return 0;
+  PROF("k_temporal_residual");
+  k_temporal_residual<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->nnode, time_cnp1(c), time_cnm1(c), c->time_dt, c->vol,
+                                                                  c->f[PCFD_F_Q], c->f[PCFD_F_QOLD], c->f[PCFD_F_QOLDM1],
+                                                                  c->viscous ? c->wallflag : nullptr, c->f[PCFD_F_B]);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 static int run_flux(pcfd_ctx* c, bool fused, bool* clip_hit) {
   if (fused) CK(cudaMemsetAsync(c->dflags + 2, 0, sizeof(int), c->stream));
   if (c->nedge) {
@@ -2303,6 +2381,7 @@ static int run_flux(pcfd_ctx* c, bool fused, bool* clip_hit) {
     k_residual_gather<true><<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->flux, c->bflux, c->vflux, c->bvflux,
                                                                         c->wallflag, c->f[PCFD_F_B]);
     LAUNCH_CHECK();
+    if (run_temporal(c)) return 1;
     if (fused) {
       CK(cudaEventSynchronize(c->ev_flag));
       *clip_hit = *c->hflag != 0;
@@ -2313,6 +2392,7 @@ static int run_flux(pcfd_ctx* c, bool fused, bool* clip_hit) {
   k_residual_gather<false><<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->flux, c->bflux, nullptr, nullptr, nullptr,
                                                                        c->f[PCFD_F_B]);
   LAUNCH_CHECK();
+  if (run_temporal(c)) return 1;
   if (fused) {
     CK(cudaEventSynchronize(c->ev_flag));
     *clip_hit = *c->hflag != 0;
@@ -2417,7 +2497,8 @@ int pcfd_jacobian(pcfd_ctx* c) {
   }
   PROF("k_jac_diag");
   k_jac_diag<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->iau, c->posLR, c->posRL, c->f[PCFD_F_TIMESTEP],
-                                                         c->bdiag, A);
+                                                         c->bdiag, time_cnp1(c), (c->time_local && c->time_dt > 0.0) ? c->time_dt : -1.0,
+                                                         A);
   LAUNCH_CHECK();
   if (c->nwall) {
     PROF("k_jac_wall");
