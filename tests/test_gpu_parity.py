@@ -33,6 +33,10 @@ def golden_ctx(name):
         mut = np.zeros(ctx.field_size(capi.F_MUT))
         mut[: g["mut"].size] = g["mut"]
         ctx.set_field(capi.F_MUT, mut)
+    if float(meta.get("dt", -1.0)) > 0.0 and "qold" in g:   # unsteady fixture: BDF terms live (tests/test_gpu_unsteady.py)
+        ctx.set_time_integration(meta["dt"], int(meta["useLocalTimeStepping"]), int(meta["torder"]), int(meta["iter"]))
+        ctx.set_field(capi.F_QOLD, g["qold"])
+        ctx.set_field(capi.F_QOLDM1, g["qoldm1"])
     return ctx, g, meta
 
 
