@@ -207,6 +207,29 @@ def slab_case(n, rank, nranks, jitter=0.15, mach=0.5, gamma=1.4, cfl=0.5, limite
     return mesh, params, q.reshape(-1)
 
 
+def partitioned_box_case(n, nranks, part=None, jitter=0.15, mach=0.5, gamma=1.4, cfl=0.5, limiter=2, sorder=2, seed=1234):
+    """The n^3 Kuhn box cut into `nranks` node partitions in udecomp's layout (partition.py): a list of
+    (mesh, params, q) per rank.  part: partition id per node (default: recursive coordinate bisection)."""
+    from .partition import rcb_partition, udecomp_partition
+    xyz, tets, tris, tags = kuhn_box(n, jitter=jitter, seed=seed)
+    if part is None:
+        part = rcb_partition(xyz, nranks)
+    lut = np.zeros(max(BOX_BC) + 1, dtype=np.int32)
+    for t, bc in BOX_BC.items():
+        lut[t] = bc
+    out = []
+    qinf = freestream(mach, gamma)
+    for mesh in udecomp_partition(xyz, tets, tris, tags, part, nranks, bc_lut=lut):
+        params = dict(eqnset=capi.EQNSET_COMPRESSIBLE_EULER, sorder=sorder, limiter=limiter, no_cvbc=0, gamma=gamma,
+                      chi=0.0, cfl=cfl, qinf=qinf)
+        nl, nb = mesh["nnode"] + mesh["gnode"], mesh["nbedge"]
+        q = np.zeros((nl + nb, 10))
+        q[:nl] = smooth_state(mesh["xyz"].reshape(-1, 3), mach, gamma)
+        q[nl:] = q[mesh["bedges_n"].reshape(-1, 2)[:nb, 0]]
+        out.append((mesh, params, q.reshape(-1)))
+    return out
+
+
 # ------------------------------------------------------------------------------------------ reacting eqnset
 UNIV_R = 8.31447215   # chem_constants.h:5
 

@@ -97,12 +97,27 @@ def test_multirank_iteration_matches_reference(name):
 def test_slab_partitions_vs_oracle(oracle, colored, implicit, fused):
     """Partitions generated in memory (cases.slab_case, the bench's multi-GPU input): three ranks on one GPU with
     direct-put halos against the C oracle run per rank with a numpy halo exchange through the same maps."""
-    from proteuscfd_b200 import capi
     from proteuscfd_b200.cases import slab_case
-    from proteuscfd_b200.parallel import LoopbackExchange, build_local_group_maps
-    from tests.oracle_lib import oracle_for
     nr = 3
     parts = [slab_case(7, r, nr, colored=colored, cfl=5.0 if implicit else 0.5) for r in range(nr)]
+    run_partitions_vs_oracle(oracle, parts, implicit, fused)
+
+
+@pytest.mark.parametrize("nr,implicit,fused", [(3, True, True), (5, False, False)])
+def test_rcb_partitions_vs_oracle(oracle, nr, implicit, fused):
+    """General (non-slab) partitions: recursive-bisection node partition of the box laid out as udecomp does
+    (proteuscfd_b200/partition.py), ranks with several neighbours each; same bit-exact bar."""
+    from proteuscfd_b200.cases import partitioned_box_case
+    parts = partitioned_box_case(7, nr, cfl=5.0 if implicit else 0.5)
+    assert max(len(np.unique(m["gNodeOwner"])) for m, _, _ in parts) >= 2
+    run_partitions_vs_oracle(oracle, parts, implicit, fused)
+
+
+def run_partitions_vs_oracle(oracle, parts, implicit, fused):
+    from proteuscfd_b200 import capi
+    from proteuscfd_b200.parallel import LoopbackExchange, build_local_group_maps
+    from tests.oracle_lib import oracle_for
+    nr = len(parts)
     pobjs = build_local_group_maps([(m["gNodeOwner"], m["gNodeLocalId"]) for m, _, _ in parts])
     orcs = [oracle_for(oracle, m, p) for m, p, _ in parts]
     ctxs = [capi.Context(m, p) for m, p, _ in parts]
