@@ -540,8 +540,32 @@ static void fr_inviscid_wall_bc(const orc_case* c, const orc_fr_params* p, const
 }
 
 /* bc.tcc:1058-1397 for the BC types of the reacting configs; the reference passes bcobj->GetQref == Qinf */
+/* CompressibleFREqnSet::GetViscousWallBoundaryVariables compressibleFR.tcc:2048-2070 */
+static void fr_viscous_wall_bc(int ns, double* QL, double* QR, const double* vel, const double* normalQ, double Twall)
+{
+  int i;
+  if(Twall < 0.0){
+    for(i = 0; i < ns; i++) QR[i] = QL[i];
+    QR[ns+3] = QL[ns+3] = normalQ[ns+3];
+  }
+  else{
+    for(i = 0; i < ns; i++) QR[i] = QL[i];
+    QR[ns+3] = QL[ns+3] = Twall;
+  }
+  QR[ns] = QL[ns] = vel[0];
+  QR[ns+1] = QL[ns+1] = vel[1];
+  QR[ns+2] = QL[ns+2] = vel[2];
+}
+
+/* bcobj->twall / ref_temperature of the half-edge's surface (bc.tcc:1283-1286); default bcobj.tcc:31 */
+static double fr_wall_temperature(const orc_case* c, const orc_fr_params* p, int e)
+{
+  return c->bedges_twall ? c->bedges_twall[e] : 1.0/p->ref_temperature;
+}
+
+/* e, q: the half-edge and the whole state array (the no-slip wall reads its most-normal neighbour, bc.tcc:1182-1206) */
 static void fr_boundary_variables(const orc_case* c, const orc_fr_params* p, double* QL, double* QR, const double* avec,
-				  int bctype, double betaL)
+				  int bctype, double betaL, int e, const double* q)
 {
   int i, ns = p->chem->nspecies, neqn = ns + 4, nvars = 3*ns + 6;
   double vdotn = 0.0;
@@ -559,6 +583,14 @@ static void fr_boundary_variables(const orc_case* c, const orc_fr_params* p, dou
   case ORC_BC_IMPERMEABLE_WALL: case ORC_BC_SYMMETRY:
     fr_inviscid_wall_bc(c, p, QL, QR, avec, vdotn, betaL);
     break;
+  case ORC_BC_NOSLIP: {   /* bc.tcc:1182-1291, static wall */
+    double vel[3] = {0.0, 0.0, 0.0}, nQ[MAXV];
+    int normalNode = orc_normal_node(c, e);
+    vel[0] += 0.0; vel[1] += 0.0; vel[2] += 0.0;   /* velw */
+    for(i = 0; i < nvars; i++) nQ[i] = q[(size_t)normalNode*nvars + i];
+    fr_viscous_wall_bc(ns, QL, QR, vel, nQ, fr_wall_temperature(c, p, e));
+    break;
+  }
   default: break;
   }
   fr_aux(p, QR);
@@ -571,7 +603,7 @@ void orc_fr_update_bcs(const orc_case* c, const orc_fr_params* p, double* q, con
   int e, nb = c->nbedge + c->ngedge, nvars = 3*p->chem->nspecies + 6;
   for(e = 0; e < nb; e++){
     int l = c->bedges_n[2*e], r = c->bedges_n[2*e+1];
-    fr_boundary_variables(c, p, &q[(size_t)l*nvars], &q[(size_t)r*nvars], &c->bedges_a[4*e], c->bedges_bctype[e], beta[l]);
+    fr_boundary_variables(c, p, &q[(size_t)l*nvars], &q[(size_t)r*nvars], &c->bedges_a[4*e], c->bedges_bctype[e], beta[l], e, q);
   }
 }
 
@@ -1167,6 +1199,13 @@ void orc_fr_residual(const orc_case* c, const orc_fr_params* p, const double* q,
       }
     }
   }
+  /* Bkernel_BC_Res_Modify (residual.tcc:40-43, bc.tcc:905-1056) -> ModifyViscousWallResidual compressibleFR.tcc:2101-2114 */
+  for(e = 0; e < nb; e++){
+    if(c->bedges_bctype[e] == ORC_BC_NOSLIP){
+      double* res = &b[(size_t)c->bedges_n[2*e]*neqn];
+      res[ns] = 0.0; res[ns+1] = 0.0; res[ns+2] = 0.0; res[ns+3] = 0.0;
+    }
+  }
 }
 
 /* timestep.tcc:7-49 (local time stepping), kernels :80-143 */
@@ -1437,7 +1476,7 @@ void orc_fr_jacobian(const orc_case* c, const orc_fr_params* p, double* q, const
     int bctype = c->bedges_bctype[e];
     double QPL[MAXV], QPR[MAXV], fluxS[MAXE], fluxL[MAXE], fluxR[MAXE], tempL[MAXE*MAXE], tempR[MAXE*MAXE];
     double *pL, betaL = beta[l];
-    fr_boundary_variables(c, p, QL, QR, avec, bctype, betaL);
+    fr_boundary_variables(c, p, QL, QR, avec, bctype, betaL, e, q);
     fr_numerical_flux(p, QL, QR, avec, 0.0, fluxS, betaL);
     for(i = 0; i < neqn; i++){
       memcpy(QPL, QL, sizeof(double)*nvars);
@@ -1448,7 +1487,7 @@ void orc_fr_jacobian(const orc_case* c, const orc_fr_params* p, double* q, const
       if(!is_ghost(c, r)){
 	memcpy(QPR, QR, sizeof(double)*nvars);
 	fr_aux(p, QPR);
-	fr_boundary_variables(c, p, QPL, QPR, avec, bctype, betaL);
+	fr_boundary_variables(c, p, QPL, QPR, avec, bctype, betaL, e, q);
 	fr_numerical_flux(p, QPL, QPR, avec, 0.0, fluxL, betaL);
       }
       else{
@@ -1515,6 +1554,23 @@ void orc_fr_jacobian(const orc_case* c, const orc_fr_params* p, double* q, const
     double cnp1 = (c->iter > 1 && c->torder == 2) ? 1.5 : 1.0;
     for(i = 0; i < c->nnode; i++){
       fr_temporal_terms(p, &q[(size_t)i*nvars], c->vol[i], cnp1, p->dt_param, dt[i], get_block(ia, ja, A, i, i, n2), beta[i]);
+    }
+  }
+  /* Bkernel_BC_Jac_Modify (jacobian.tcc:247-249, bc.tcc:747-903) -> ModifyViscousWallJacobian compressibleFR.tcc:2072-2099
+     with CRSMatrix::BlankSubRow (crsmatrix.tcc:524-541) */
+  for(e = 0; e < nb; e++){
+    if(c->bedges_bctype[e] == ORC_BC_NOSLIP){
+      int cv = c->bedges_n[2*e], sub, kk;
+      double Twall = fr_wall_temperature(c, p, e);
+      double* diag = get_block(ia, ja, A, cv, cv, n2);
+      for(sub = ns; sub < ns + 4; sub++){
+	for(kk = ia[cv]; kk < ia[cv+1]; kk++) for(j = 0; j < neqn; j++) A[(size_t)kk*n2 + sub*neqn + j] = 0.0;
+	diag[sub*neqn + sub] = 1.0;
+      }
+      if(Twall < 0.0){
+	double* off = get_block(ia, ja, A, cv, orc_normal_node(c, e), n2);
+	off[(ns+3)*neqn + ns+3] = -1.0;
+      }
     }
   }
 }

@@ -241,6 +241,16 @@ CASES = {
                                             nsgs=3, cfl=5.0, refvisc=2.0e-4,   # Re = 111 (refLength 1 cm, 2 kPa)
                                             extra=FR_EXTRA.format(temp=950, pres=2000, rxn=1)
                                             + "refThermalConductivity = 0.05\nrefLength = 0.01\n"),
+    # viscous reacting eqnset with a no-slip floor (isothermal 900 K / adiabatic): hard-set wall state from the
+    # most-normal neighbour (bc.tcc:1182-1291, compressibleFR.tcc:2048-2070), wall rows of residual and Jacobian (:2072-2114)
+    "box4_nsfr_wall": lambda: make_case("box4_nsfr_wall", mesh=kuhn_box(4, jitter=0.15), bc=ns_bc(900.0), eqnset="compressibleNSFR",
+                                        nsgs=3, cfl=5.0, refvisc=2.0e-4,
+                                        extra=FR_EXTRA.format(temp=950, pres=2000, rxn=1)
+                                        + "refThermalConductivity = 0.05\nrefLength = 0.01\n"),
+    "box4_nsfr_adiabatic": lambda: make_case("box4_nsfr_adiabatic", mesh=kuhn_box(4, jitter=0.15), bc=ns_bc(-1.0),
+                                             eqnset="compressibleNSFR", nsgs=3, cfl=5.0, refvisc=2.0e-4,
+                                             extra=FR_EXTRA.format(temp=950, pres=2000, rxn=1)
+                                             + "refThermalConductivity = 0.05\nrefLength = 0.01\n"),
     # unsteady (dual time stepping): physical time step 0.02, BDF2 at the third step -- TemporalResidual with
     # q^n, q^{n-1} and the cnp1 V/dt + V/dtau diagonal (perfect gas: diagonal; reacting: dense dQ/dq blocks)
     "box6_unsteady_bdf2": lambda: make_case("box6_unsteady_bdf2", mesh=kuhn_box(6, jitter=0.15), nsgs=3, cfl=5.0, unsteady=True,
