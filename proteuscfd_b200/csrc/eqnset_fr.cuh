@@ -667,6 +667,41 @@ __device__ __noinline__ void boundary_variables(const Params<NS>& p, double* QL,
 }
 
 // ---------------------------------------------------------------- update
+// GetViscousWallBoundaryVariables (compressibleFR.tcc:2048-2070), static wall (vel = 0 after bc.tcc:1207-1254 with no
+// movement, no bleed steps, no grid speed): species densities kept, wall velocity, wall temperature = Twall or, for an
+// adiabatic wall (Twall < 0), the temperature of the most-normal neighbour.  Rewrites QL itself (hard-set wall node).
+template <int NS>
+__device__ __forceinline__ void viscous_wall_bc(double* QL, double* QR, double normalT, double Twall) {
+#pragma unroll
+  for (int i = 0; i < NS; i++) QR[i] = QL[i];
+  if (Twall < 0.0) QR[NS + 3] = QL[NS + 3] = normalT;
+  else QR[NS + 3] = QL[NS + 3] = Twall;
+  QR[NS] = QL[NS] = 0.0;
+  QR[NS + 1] = QL[NS + 1] = 0.0;
+  QR[NS + 2] = QL[NS + 2] = 0.0;
+}
+
+// CalculateBoundaryVariables (bc.tcc:1058-1397) including the BC types that rewrite the interior state: nodes owning
+// such a half-edge are walked sequentially (kfr_update_bcs_nodes, kfr_jac_bnodes)
+template <int NS>
+__device__ __noinline__ void boundary_variables_seq(const Params<NS>& p, double* QL, double* QR, const double* av, int bctype,
+                                                    double betaL, double normalT, double Twall) {
+  constexpr int NV = 3 * NS + 6;
+  switch (bctype) {
+    case PCFD_BC_SONIC_INFLOW: case PCFD_BC_DIRICHLET:
+      for (int i = 0; i < NV; i++) QR[i] = QL[i] = p.qinf[i];
+      break;
+    case PCFD_BC_NOSLIP:
+      viscous_wall_bc<NS>(QL, QR, normalT, Twall);
+      break;
+    default:
+      boundary_variables(p, QL, QR, av, bctype, betaL);
+      return;
+  }
+  aux(p, QR);
+  aux(p, QL);
+}
+
 // ApplyDQ (compressibleFR.tcc:886-937)
 template <int NS>
 __device__ __forceinline__ void apply_dq(const Params<NS>& p, const double* dQ, double* Q) {

@@ -79,6 +79,42 @@ __global__ void __launch_bounds__(64) kfr_update_bcs_edges(DevMesh m, fr::Params
   }
 }
 
+// The same update for nodes owning a Dirichlet-type half-edge (Dirichlet, sonic inflow, no-slip: they rewrite QL itself):
+// one thread per such node, its BC half-edges in half-edge order -- the reference's sequence, since two half-edges
+// interact only through their shared left node (k_update_bcs of the perfect-gas path)
+template <int NS>
+__global__ void __launch_bounds__(64) kfr_update_bcs_nodes(DevMesh m, fr::Params<NS> p, const int* __restrict__ bnodes, int nb,
+                                                            const double* __restrict__ beta, double* q) {
+  constexpr int NV = W<NS>::NV;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nb) return;
+  const int n = bnodes[t];
+  double QL[NV];
+  load_row<NS, NV>(q, n, QL);
+  bool touched = false;
+  for (int k = m.adjp[n]; k < m.adjp[n + 1]; k++) {
+    const int2 a = m.adj[k];
+    if (a.y < m.nedge) continue;
+    const int be = a.y - m.nedge;
+    const int type = m.bctype[be];
+    if (type == PCFD_BC_PARALLEL) continue;
+    const int r = a.x & 0x7fffffff;
+    double QR[NV], av[4];
+    load_row<NS, NV>(q, r, QR);
+    load_avec(m.bea, be, av);
+    double nT = 0.0, tw = 0.0;
+    if (type == PCFD_BC_NOSLIP) { nT = q[(size_t)m.bnormal[be] * NV + NS + 3]; tw = m.btwall[be]; }
+    fr::boundary_variables_seq(p, QL, QR, av, type, beta[n], nT, tw);
+    double* qr = q + (size_t)r * NV;
+    for (int i = 0; i < NV; i++) qr[i] = QR[i];
+    touched = true;
+  }
+  if (touched) {
+    double* ql = q + (size_t)n * NV;
+    for (int i = 0; i < NV; i++) ql[i] = QL[i];
+  }
+}
+
 // ====================================================================== gradient
 // Gradient::Compute (gradient.tcc:57-112, weighted LSQ kernels :251-378, symmetry fix :545-565): ordered gather
 template <int NS>
@@ -481,7 +517,9 @@ __global__ void __launch_bounds__(W<NS>::NEQ * 16) kfr_residual_gather(DevMesh m
                                                                         const double* __restrict__ bflux,
                                                                         const double* __restrict__ vflux,
                                                                         const double* __restrict__ bvflux,
-                                                                        const double* __restrict__ src, double* __restrict__ b) {
+                                                                        const double* __restrict__ src,
+                                                                        const unsigned char* __restrict__ wallflag,
+                                                                        double* __restrict__ b) {
   constexpr int NEQ = W<NS>::NEQ;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = tid / NEQ;
@@ -503,6 +541,8 @@ __global__ void __launch_bounds__(W<NS>::NEQ * 16) kfr_residual_gather(DevMesh m
     }
   }
   acc += (j < NS) ? src[(size_t)n * NS + j] : 0.0;
+  // Bkernel_BC_Res_Modify -> ModifyViscousWallResidual (compressibleFR.tcc:2101-2114): momentum and energy rows of no-slip nodes
+  if (wallflag && j >= NS && (wallflag[n] & 1)) acc = 0.0;
   b[(size_t)n * NEQ + j] = acc;
 }
 
@@ -512,7 +552,7 @@ template <int NS>
 __global__ void __launch_bounds__(128) kfr_temporal_residual(int nnode, fr::Params<NS> p, double cnp1, double cnm1,
                                                               const double* __restrict__ vol, const double* __restrict__ q,
                                                               const double* __restrict__ qold, const double* __restrict__ qoldm1,
-                                                              double* __restrict__ b) {
+                                                              const unsigned char* __restrict__ wallflag, double* __restrict__ b) {
   constexpr int NEQ = W<NS>::NEQ, NV = W<NS>::NV;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= nnode) return;
@@ -529,6 +569,7 @@ __global__ void __launch_bounds__(128) kfr_temporal_residual(int nnode, fr::Para
     double v = b[(size_t)n * NEQ + j];
     v -= dt * dq;
     v -= dtm1 * dqm1;
+    if (wallflag && j >= NS && (wallflag[n] & 1)) v = 0.0;   // the wall hook runs after the temporal terms (residual.tcc:40-43)
     b[(size_t)n * NEQ + j] = v;
   }
 }
@@ -822,6 +863,91 @@ __global__ void __launch_bounds__(64) kfr_jac_bedges(DevMesh m, fr::Params<NS> p
   }
 }
 
+// Bkernel_NumJac for the nodes owning a Dirichlet-type half-edge: one thread per node, ALL its half-edges (ghost ones
+// included) in half-edge order with the interior state carried from one to the next (k_jac_bnodes of the perfect-gas path)
+template <int NS>
+__global__ void __launch_bounds__(64) kfr_jac_bnodes(DevMesh m, fr::Params<NS> p, const int* __restrict__ bnodes, int nb,
+                                                      const double* __restrict__ beta, double* q, const int* __restrict__ bpos,
+                                                      double* __restrict__ bdiag, double* __restrict__ A) {
+  constexpr int NEQ = W<NS>::NEQ, NV = W<NS>::NV, N2 = W<NS>::N2;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nb) return;
+  const int n = bnodes[t];
+  const double h = 1.0e-8;
+  const double betaL = beta[n];
+  double QL[NV];
+  load_row<NS, NV>(q, n, QL);
+  for (int k = m.adjp[n]; k < m.adjp[n + 1]; k++) {
+    const int2 a = m.adj[k];
+    if (a.y < m.nedge) continue;
+    const int be = a.y - m.nedge;
+    const int r = a.x & 0x7fffffff;
+    const int type = m.bctype[be];
+    const bool ghost = is_ghost(m, r);
+    double QR[NV], av[4], fS[NEQ], fL[NEQ], fR[NEQ];
+    load_row<NS, NV>(q, r, QR);
+    load_avec(m.bea, be, av);
+    double nT = 0.0, tw = 0.0;
+    if (type == PCFD_BC_NOSLIP) { nT = q[(size_t)m.bnormal[be] * NV + NS + 3]; tw = m.btwall[be]; }
+    fr::boundary_variables_seq(p, QL, QR, av, type, betaL, nT, tw);
+    if (type != PCFD_BC_PARALLEL) {
+      double* qr = q + (size_t)r * NV;
+      for (int i = 0; i < NV; i++) qr[i] = QR[i];
+    }
+    fr::numerical_flux(p, QL, QR, av, 0.0, betaL, fS);
+    double* bd = bdiag + (size_t)be * N2;
+    double* ag = ghost ? A + (size_t)bpos[be] * N2 : nullptr;
+    for (int i = 0; i < NEQ; i++) {
+      double QPL[NV], QPR[NV];
+      for (int kk = 0; kk < NV; kk++) { QPL[kk] = QL[kk]; QPR[kk] = QR[kk]; }
+      QPL[i] += h; QPR[i] += h;
+      fr::aux(p, QPL);
+      fr::aux_pr(p, QPR);
+      fr::numerical_flux(p, QL, QPR, av, 0.0, betaL, fR);
+      if (!ghost) {
+        for (int kk = 0; kk < NV; kk++) QPR[kk] = QR[kk];
+        fr::boundary_variables_seq(p, QPL, QPR, av, type, betaL, nT, tw);
+        fr::numerical_flux(p, QPL, QPR, av, 0.0, betaL, fL);
+      } else {
+        fr::numerical_flux(p, QPL, QR, av, 0.0, betaL, fL);
+      }
+      for (int j = 0; j < NEQ; j++) bd[j * NEQ + i] = (fL[j] - fS[j]) / h;
+      if (ghost) for (int j = 0; j < NEQ; j++) ag[j * NEQ + i] = 0.0 + (fR[j] - fS[j]) / h;
+    }
+  }
+  double* ql = q + (size_t)n * NV;
+  for (int i = 0; i < NV; i++) ql[i] = QL[i];
+}
+
+// Bkernel_BC_Jac_Modify (jacobian.tcc:247-249, bc.tcc:747-903) -> ModifyViscousWallJacobian (compressibleFR.tcc:2072-2099)
+// with CRSMatrix::BlankSubRow (crsmatrix.tcc:524-541): one thread per wall node, its NoSlip half-edges in order
+template <int NS>
+__global__ void kfr_jac_wall(DevMesh m, const int* __restrict__ wnodes, int nw, const int* __restrict__ ia,
+                             const int* __restrict__ ja, const int* __restrict__ iau, double* A) {
+  constexpr int NEQ = W<NS>::NEQ, N2 = W<NS>::N2;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nw) return;
+  const int n = wnodes[t];
+  const int r0 = ia[n], r1 = ia[n + 1];
+  double* diag = A + (size_t)iau[n] * N2;
+  for (int k = m.adjp[n]; k < m.adjp[n + 1]; k++) {
+    const int2 a = m.adj[k];
+    if (a.y < m.nedge) continue;
+    const int be = a.y - m.nedge;
+    if (m.bctype[be] != PCFD_BC_NOSLIP) continue;
+    for (int sub = NS; sub < NS + 4; sub++) {
+      for (int kk = r0; kk < r1; kk++)
+        for (int j = 0; j < NEQ; j++) A[(size_t)kk * N2 + sub * NEQ + j] = 0.0;
+      diag[sub * NEQ + sub] = 1.0;
+    }
+    if (m.btwall[be] < 0.0) {   // adiabatic: the wall temperature follows the most-normal neighbour
+      const int nn_ = m.bnormal[be];
+      for (int kk = r0; kk < r1; kk++)
+        if (ja[kk] == nn_) { A[(size_t)kk * N2 + (NS + 3) * NEQ + NS + 3] = -1.0; break; }
+    }
+  }
+}
+
 // Kernel_Diag_NumJac (jacobian.tcc:434-456) after the boundary terms: NEQ threads per node, one block row each
 template <int NS>
 __global__ void __launch_bounds__(W<NS>::NEQ * 16) kfr_jac_diag(DevMesh m, const int* __restrict__ iau,
@@ -1054,6 +1180,12 @@ struct Impl {
   using Wd = W<NS>;
 
   static int update_bcs(pcfd_ctx* c) {
+    if (c->nbn) {
+      PROF("kfr_update_bcs_nodes");
+      kfr_update_bcs_nodes<NS><<<nblk(c->nbn, 64), 64, 0, c->stream>>>(c->dm, make_params<NS>(c), c->bnodes, c->nbn,
+                                                                      c->f[PCFD_F_BETA], c->f[PCFD_F_Q]);
+      LAUNCH_CHECK();
+    }
     if (!c->nblist_bc) return 0;
     PROF("kfr_update_bcs_edges");
     kfr_update_bcs_edges<NS><<<nblk(c->nblist_bc, 64), 64, 0, c->stream>>>(c->dm, make_params<NS>(c), c->blist, c->nblist_bc,
@@ -1176,14 +1308,16 @@ struct Impl {
     LAUNCH_CHECK();
     PROF("kfr_residual_gather");
     kfr_residual_gather<NS><<<nblk((long long)c->nnode * Wd::NEQ, BS), BS, 0, c->stream>>>(
-        c->dm, c->flux, c->bflux, c->fr->viscous ? c->fr->vflux : nullptr, c->fr->bvflux, c->fr->src, c->f[PCFD_F_B]);
+        c->dm, c->flux, c->bflux, c->fr->viscous ? c->fr->vflux : nullptr, c->fr->bvflux, c->fr->src,
+        c->nwall ? c->wallflag : nullptr, c->f[PCFD_F_B]);
     LAUNCH_CHECK();
     if (c->torder && c->have_qold) {
       const bool bdf2 = c->iter > 1 && c->torder == 2;
       PROF("kfr_temporal_residual");
       kfr_temporal_residual<NS><<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->nnode, p, bdf2 ? 1.5 : 1.0, bdf2 ? -0.5 : 0.0, c->vol,
                                                                            c->f[PCFD_F_Q], c->f[PCFD_F_QOLD],
-                                                                           c->f[PCFD_F_QOLDM1], c->f[PCFD_F_B]);
+                                                                           c->f[PCFD_F_QOLDM1], c->nwall ? c->wallflag : nullptr,
+                                                                           c->f[PCFD_F_B]);
       LAUNCH_CHECK();
     }
     if (fused) {
@@ -1246,6 +1380,12 @@ struct Impl {
                                                                               c->posRL, A);
       LAUNCH_CHECK();
     }
+    if (c->nbn) {
+      PROF("kfr_jac_bnodes");
+      kfr_jac_bnodes<NS><<<nblk(c->nbn, 64), 64, 0, c->stream>>>(c->dm, p, c->bnodes, c->nbn, beta, c->f[PCFD_F_Q], c->bpos,
+                                                                c->bdiag, A);
+      LAUNCH_CHECK();
+    }
     if (c->nblist) {
         PROF("kfr_jac_bedges");
       kfr_jac_bedges<NS><<<nblk(c->nblist, 64), 64, 0, c->stream>>>(c->dm, p, c->blist, c->nblist, c->bfirst, beta,
@@ -1265,6 +1405,11 @@ struct Impl {
     kfr_jac_node<NS><<<nblk(c->nnode, 64), 64, 0, c->stream>>>(c->dm, p, c->iau, c->f[PCFD_F_Q], c->f[PCFD_F_TIMESTEP], beta,
                                                                (c->iter > 1 && c->torder == 2) ? 1.5 : 1.0, A);
     LAUNCH_CHECK();
+    if (c->nwall) {
+      PROF("kfr_jac_wall");
+      kfr_jac_wall<NS><<<nblk(c->nwall, 64), 64, 0, c->stream>>>(c->dm, c->wnodes, c->nwall, c->ia, c->ja, c->iau, A);
+      LAUNCH_CHECK();
+    }
     return 0;
   }
   static int prepare_sgs(pcfd_ctx* c) {
@@ -1410,8 +1555,10 @@ int pcfd_create_fr(const pcfd_mesh_desc* mesh, const pcfd_params* params, const 
   const int nb = mesh->nbedge + mesh->ngedge;
   for (int e = 0; e < nb; e++) {
     const int t = mesh->bedges_bctype[e];
-    if (t == PCFD_BC_DIRICHLET || t == PCFD_BC_SONIC_INFLOW || t == PCFD_BC_NOSLIP || t == PCFD_BC_FARFIELD_VISCOUS)
-      return fail(c, "pcfd_create_fr: Dirichlet / sonic-inflow / no-slip / viscous far-field BCs are not available for the reacting eqnset");
+    if (t == PCFD_BC_FARFIELD_VISCOUS)
+      return fail(c, "pcfd_create_fr: the viscous far-field BC is not available for the reacting eqnset");
+    if (t == PCFD_BC_NOSLIP && !mesh->bedges_twall)
+      return fail(c, "pcfd_create_fr: no-slip walls need bedges_twall (wall temperature / ref_temperature; < 0: adiabatic)");
   }
   pcfd_params prm = *params;
   prm.turb_model = 0;

@@ -30,6 +30,8 @@ def fr_ctx(name, rxn_on=None):
     mesh = {k: g[k] for k in ("edges_n", "edges_a", "bedges_n", "bedges_a", "bedges_bctype", "xyz", "vol", "ipsp", "psp")}
     for k in ("nnode", "gnode", "nbnode", "nedge", "nbedge", "ngedge"):
         mesh[k] = int(meta[k])
+    if (g["bedges_bctype"] == 4).any():      # no-slip walls: wall temperature per half-edge (< 0: adiabatic)
+        mesh["bedges_twall"] = g["bedges_twall"]
     fr = dict(chem=chem_tables(g), ref_density=meta["ref_density"], ref_velocity=meta["ref_velocity"],
               ref_temperature=meta["ref_temperature"], ref_pressure=meta["ref_pressure"], ref_time=meta["ref_time"],
               ref_specific_enthalpy=meta["ref_specific_enthalpy"], pref=meta["Pref"], dt=meta["dt"],

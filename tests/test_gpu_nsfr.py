@@ -195,3 +195,97 @@ def test_nsfr_seeded_box_vs_oracle(oracle, colored):
     o.c.mut = None
     b_lam = o.residual(q, grad, lim, bo).reshape(-1, NEQ)
     assert np.abs(b_lam[:, NS:] - b.reshape(-1, NEQ)[:, NS:]).max() > 1e-4 * np.abs(b).max()
+
+
+WALL = ["box4_nsfr_wall", "box4_nsfr_adiabatic"]
+
+
+@pytest.mark.parametrize("name", WALL)
+def test_nsfr_noslip_wall(oracle, name):
+    """No-slip floor under the viscous reacting eqnset (isothermal 900 K / adiabatic): hard-set wall state from the
+    most-normal neighbour (bc.tcc:1182-1291, compressibleFR.tcc:2048-2070) by the sequential per-node BC walk, wall rows
+    of the residual (:2101-2114) and of the Jacobian (:2072-2099), against the reference's fixtures."""
+    from proteuscfd_b200 import capi
+    ctx, g, meta = fr_ctx(name)
+    nn = int(meta["nnode"])
+    ctx.set_field(capi.F_Q, g["q_pre"])
+    ctx.update_bcs()
+    exact(ctx.get_field(capi.F_Q), g["q0"], "q after UpdateBCs (wall nodes hard-set)")
+    ctx.lsq_coefficients()
+    ctx.gradient()
+    exact(ctx.get_field(capi.F_QGRAD), g["qgrad"], "qgrad")
+    ctx.limiter()
+    exact(ctx.get_field(capi.F_LIMITER), g["limiter"], "limiter")
+    ctx.residual()
+    b = ctx.get_field(capi.F_B).reshape(-1, NEQ)
+    bref = g["b"].reshape(-1, NEQ)
+    wall = np.zeros(nn, bool)
+    wall[g["bedges_n"].reshape(-1, 2)[: int(meta["nbedge"]), 0][g["bedges_bctype"][: int(meta["nbedge"])] == 4]] = True
+    assert wall.any() and np.all(bref[wall, NS:] == 0.0)
+    assert np.all(b[wall, NS:] == 0.0), "momentum / energy rows of wall nodes must be hard zeros"
+    scale = np.abs(bref[:, NS:]).max(axis=0)
+    assert (np.abs(b[:, NS:] - bref[:, NS:]) / scale).max() <= 1e-12
+    sc = source_scale(oracle, g, meta, g["q0"], g["vol"])
+    assert np.all(np.abs(b[:, :NS] - bref[:, :NS]) <= 1e-12 * sc + 1e-300)
+    dtmin = ctx.timestep()
+    exact(ctx.get_field(capi.F_TIMESTEP), g["timestep"], "timestep")
+    assert dtmin == g["dtmin"][0]
+    # Jacobian: boundary pass by node walk, wall rows blanked with a unit diagonal (and -1 towards the normal node)
+    ctx.jacobian()
+    ia, ja, iau, _ = ctx.get_crs()
+    A = ctx.get_field(capi.F_A).reshape(-1, NEQ, NEQ)
+    Aref = g["A"].reshape(-1, NEQ, NEQ)
+    rows = np.repeat(np.arange(nn), np.diff(ia))
+    wblk = wall[rows]
+    exact(A[wblk][:, NS:, :], Aref[wblk][:, NS:, :], "wall rows of every block of a wall node")
+    offd = np.ones(len(A), bool)
+    offd[iau] = False
+    exact(A[offd][:, :NS, :], Aref[offd][:, :NS, :], "species rows of the off-diagonal blocks")
+    blk = np.abs(Aref[offd]).reshape(-1, NEQ * NEQ).max(axis=1)[:, None, None]
+    assert (np.abs(A[offd][:, NS:, :] - Aref[offd][:, NS:, :]) / blk).max() <= 1e-12
+    scale = np.abs(Aref[iau]).reshape(-1, NEQ * NEQ).max(axis=1)[:, None, None]
+    assert np.all(np.abs(A[iau] - Aref[iau]) <= 2e-6 * scale)
+    nloc = nn + int(meta["gnode"])
+    qa = ctx.get_field(capi.F_Q).reshape(-1, NV)
+    exact(qa[:nloc], g["q0"].reshape(-1, NV)[:nloc], "interior rows after the boundary Jacobian pass")
+    exact(qa[nloc:], g["q1"].reshape(-1, NV)[nloc:], "phantom rows after the boundary Jacobian pass")
+    # LU + SGS on the reference's own matrix and right-hand side: exact
+    ctx.set_field(capi.F_A, g["A"])
+    ctx.set_field(capi.F_B, g["b"])
+    ctx.prepare_sgs()
+    exact(ctx.get_field(capi.F_A), g["A_lu"], "A after LU")
+    ctx.blank_x()
+    ctx.sgs(int(meta["nSgs"]))
+    exact(ctx.get_field(capi.F_X), g["x"], "x")
+    ctx.apply_dq()
+    exact(ctx.get_field(capi.F_Q), g["q1"], "q1")
+
+
+@pytest.mark.parametrize("name", WALL)
+def test_nsfr_noslip_implicit_iteration_close(oracle, name):
+    """The whole implicit iteration through pcfd_implicit_iterate against the ORACLE stepped in the same order
+    (NewtonIterate takes the time step and the Jacobian before UpdateBCs; the harness that wrote the fixture after it, and
+    with hard-set walls that moves dt by a few percent -- so the fixture's x is not the reference point here)."""
+    from proteuscfd_b200 import capi
+    ctx, g, meta = fr_ctx(name)
+    o = FrOracle(oracle, g, meta)
+    q = g["q_pre"].copy()
+    beta, sw = g["beta"], g["lsq_sw"]
+    ia, ja, iau = o.crs_init()
+    dt, _ = o.timestep(q, beta)
+    A = o.jacobian(q, beta, dt, ia, ja, iau)
+    o.update_bcs(q, beta)
+    grad = o.gradient(q, sw)
+    lim = o.limiter(q, grad)
+    b = o.residual(q, grad, lim, beta)
+    pv = o.prepare_sgs(iau, A)
+    xo, _ = o.sgs(int(meta["nSgs"]), ia, ja, iau, A, pv, b)
+    ctx.lsq_coefficients()
+    ctx.set_field(capi.F_Q, g["q_pre"])
+    ctx.implicit_iterate(int(meta["nSgs"]), refresh_jac=True)
+    exact(ctx.get_field(capi.F_TIMESTEP), dt, "timestep")
+    exact(ctx.get_field(capi.F_LIMITER), lim, "limiter")
+    x = ctx.get_field(capi.F_X).reshape(-1, NEQ)
+    xo = xo.reshape(-1, NEQ)
+    err = np.abs(x - xo).max(axis=0) / np.abs(xo).max(axis=0)
+    assert np.all(err <= 1e-5), f"relative error of the update per equation: {err}"
