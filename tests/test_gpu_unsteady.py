@@ -88,7 +88,7 @@ def test_unsteady_composite_iteration_bit_exact():
 
 def test_unsteady_reacting(oracle):
     from proteuscfd_b200 import capi
-    from tests.test_gpu_fr import NEQ, NS, fr_ctx, source_scale, species_rows_close
+    from tests.test_gpu_fr import NEQ, fr_ctx, source_scale, species_rows_close
     ctx, g, meta = fr_ctx("box4_fr_unsteady")
     ctx.lsq_coefficients()
     ctx.set_field(capi.F_Q, g["q0"])

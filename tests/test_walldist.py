@@ -39,7 +39,6 @@ def test_partitioned_wall_distance_equals_the_serial_one():
     # serial field on its nodes
     from proteuscfd_b200.boxmesh import kuhn_box
     from proteuscfd_b200.dualmesh import median_dual
-    from proteuscfd_b200.parallel import LocalGroup
     from proteuscfd_b200.partition import rcb_partition, udecomp_partition
     xyz, tets, tris, tags = kuhn_box(5, jitter=0.15)
     lut = np.array([0, 6, 6, 9, 9, 4, 6], dtype=np.int32)      # tag 5 (zmin) = no-slip floor
@@ -56,7 +55,6 @@ def test_partitioned_wall_distance_equals_the_serial_one():
         def allgather(self, _):
             return self.items
     grp = Group([wall_points(m) for m in parts])
-    assert LocalGroup is not None
     for m in parts:
         d = wall_distance(m, group=grp)
         assert np.array_equal(d, dser[m["gid"]])
