@@ -209,6 +209,8 @@ static void DumpMesh(SolutionSpace<Real>* space)
   if(space->param->viscous){
     // eddy viscosity seen by the flow's viscous flux / Jacobian (zero unless a turbulence model initialised it)
     Dump("mut", space->GetFieldData("mut", FIELDS::STATE_NONE), (size_t)(nnode+gnode));
+    // wall distance (read by the FarFieldViscous BC and the turbulence model)
+    Dump("wallDistance", space->GetFieldData("wallDistance", FIELDS::STATE_NONE), (size_t)(nnode+gnode));
   }
 
   Param<Real>* param = space->param;

@@ -843,9 +843,24 @@ static void inviscid_wall_bc(const orc_case* c, const double* QL, double* QR, co
   }
 }
 
+/* PowerLawU ucs/powerLaw.h:11-29 */
+double orc_power_law_u(double uinf, double wallDist, double Re)
+{
+  double re = Re;
+  double x = 10.0;
+  double deltaTurb = 0.382*x/(pow(re, 0.2));
+  double delta = deltaTurb;
+  double u = uinf*pow(wallDist/delta, 1.0/7.0);
+  if(u < uinf) return u;
+  return(uinf);
+}
+
 /* bc.tcc:1058-1120 dispatch for the BC types of the hot-path configs */
+/* qref: the caller's copy of the free stream (BC_Kernel takes a fresh one per call, bc.tcc:741-744; Bkernel_NumJac takes
+   ONE per half-edge and hands it to every re-evaluation, jacobian.tcc:485-506 -- the FarFieldViscous branch scales it in
+   place, so the scaling compounds across the perturbations there); NULL: a fresh copy */
 static void boundary_variables(const orc_case* c, double* QL, double* QR, const double* avec, int bctype,
-			       int e, const double* q)
+			       int e, const double* q, double* qref)
 {
   int i;
   double vdotn = 0.0;   /* static mesh (driver.tcc:97-113 with nv == 0) */
@@ -860,6 +875,16 @@ static void boundary_variables(const orc_case* c, double* QL, double* QR, const 
   case ORC_BC_FARFIELD:
     farfield_bc(c, QL, QR, c->qinf, avec, vdotn);
     break;
+  case ORC_BC_FARFIELD_VISCOUS: {   /* bc.tcc:1092-1108: free-stream momentum scaled by a 1/7 power-law profile */
+    double fresh[NVARS], ubar = orc_power_law_u(1.0, c->walldist[c->bedges_n[2*e]], c->Re);
+    double* Qinf = qref ? qref : fresh;
+    if(!qref) for(i = 0; i < NVARS; i++) fresh[i] = c->qinf[i];
+    if(ubar < 1.0){
+      for(i = 0; i < 3; i++) Qinf[1+i] = ubar*Qinf[1+i];   /* GetMomentumLocation() == 1 */
+    }
+    farfield_bc(c, QL, QR, Qinf, avec, vdotn);
+    break;
+  }
   case ORC_BC_IMPERMEABLE_WALL: case ORC_BC_SYMMETRY:
     inviscid_wall_bc(c, QL, QR, avec, vdotn);
     break;
@@ -885,7 +910,7 @@ void orc_update_bcs(const orc_case* c, double* q, const double* beta)
   (void)beta;
   for(e = 0; e < nb; e++){
     int l = c->bedges_n[2*e], r = c->bedges_n[2*e+1];
-    boundary_variables(c, &q[l*NVARS], &q[r*NVARS], &c->bedges_a[4*e], c->bedges_bctype[e], e, q);
+    boundary_variables(c, &q[l*NVARS], &q[r*NVARS], &c->bedges_a[4*e], c->bedges_bctype[e], e, q, NULL);
   }
 }
 
@@ -1158,9 +1183,10 @@ void orc_jacobian(const orc_case* c, double* q, const double* beta, const double
     double* QL = &q[l*NVARS];
     double* QR = &q[r*NVARS];
     int bctype = c->bedges_bctype[e];
-    double QPL[NVARS], QPR[NVARS], fluxS[NEQN], fluxL[NEQN], fluxR[NEQN], tempL[25], tempR[25];
+    double QPL[NVARS], QPR[NVARS], fluxS[NEQN], fluxL[NEQN], fluxR[NEQN], tempL[25], tempR[25], Qref[NVARS];
     double *pL;
-    boundary_variables(c, QL, QR, avec, bctype, e, q);
+    for(i = 0; i < NVARS; i++) Qref[i] = c->qinf[i];
+    boundary_variables(c, QL, QR, avec, bctype, e, q, Qref);
     numerical_flux(QL, QR, avec, 0.0, gamma, fluxS);
     for(i = 0; i < NEQN; i++){
       memcpy(QPL, QL, sizeof(double)*NVARS);
@@ -1171,7 +1197,7 @@ void orc_jacobian(const orc_case* c, double* q, const double* beta, const double
       if(!is_ghost(c, r)){     /* boundaryJacEval == 0 */
 	memcpy(QPR, QR, sizeof(double)*NVARS);
 	compute_aux(QPR, gamma);
-	boundary_variables(c, QPL, QPR, avec, bctype, e, q);
+	boundary_variables(c, QPL, QPR, avec, bctype, e, q, Qref);
 	numerical_flux(QPL, QPR, avec, 0.0, gamma, fluxL);
       }
       else{

@@ -62,6 +62,7 @@ typedef struct {
   int use_local_dt, torder, iter;
   const double* qold;          /* [nnode*nvars] conservative variables at t^n */
   const double* qoldm1;        /* [nnode*nvars] ... at t^{n-1} */
+  const double* walldist;      /* field "wallDistance" [nnode+gnode]; read by the FarFieldViscous BC (bc.tcc:1092-1108) */
 } orc_case;
 
 /* gradient.tcc:115-138, 381-542 : s and sw, each [(nnode+gnode)*6] */
@@ -99,6 +100,8 @@ void orc_viscous_flux(const orc_case* c, const double* Q, const double* grad, co
 		      double* flux);
 void orc_viscous_jacobian(const orc_case* c, const double* QL, const double* QR, const double* dx, double s2,
 			  const double* avec, double mut, double* aL, double* aR);
+/* PowerLawU (ucs/powerLaw.h:11-29) */
+double orc_power_law_u(double uinf, double wallDist, double Re);
 /* most-normal neighbour of a wall node (bc.tcc:1182-1206) for half-edge e */
 int orc_normal_node(const orc_case* c, int e);
 

@@ -564,8 +564,10 @@ static double fr_wall_temperature(const orc_case* c, const orc_fr_params* p, int
 }
 
 /* e, q: the half-edge and the whole state array (the no-slip wall reads its most-normal neighbour, bc.tcc:1182-1206) */
+/* qref: see boundary_variables in pcfd_oracle.c (one free-stream copy per half-edge in Bkernel_NumJac, scaled in place by
+   the FarFieldViscous branch at every re-evaluation; NULL: a fresh copy, as in BC_Kernel) */
 static void fr_boundary_variables(const orc_case* c, const orc_fr_params* p, double* QL, double* QR, const double* avec,
-				  int bctype, double betaL, int e, const double* q)
+				  int bctype, double betaL, int e, const double* q, double* qref)
 {
   int i, ns = p->chem->nspecies, neqn = ns + 4, nvars = 3*ns + 6;
   double vdotn = 0.0;
@@ -580,6 +582,16 @@ static void fr_boundary_variables(const orc_case* c, const orc_fr_params* p, dou
   case ORC_BC_FARFIELD:
     fr_farfield_bc(c, p, QL, QR, p->qinf, avec, vdotn, betaL);
     break;
+  case ORC_BC_FARFIELD_VISCOUS: {   /* bc.tcc:1092-1108; GetMomentumLocation() == nspecies */
+    double fresh[MAXV], ubar = orc_power_law_u(1.0, c->walldist[c->bedges_n[2*e]], c->Re);
+    double* Qinf = qref ? qref : fresh;
+    if(!qref) for(i = 0; i < nvars; i++) fresh[i] = p->qinf[i];
+    if(ubar < 1.0){
+      for(i = 0; i < 3; i++) Qinf[ns+i] = ubar*Qinf[ns+i];
+    }
+    fr_farfield_bc(c, p, QL, QR, Qinf, avec, vdotn, betaL);
+    break;
+  }
   case ORC_BC_IMPERMEABLE_WALL: case ORC_BC_SYMMETRY:
     fr_inviscid_wall_bc(c, p, QL, QR, avec, vdotn, betaL);
     break;
@@ -603,7 +615,7 @@ void orc_fr_update_bcs(const orc_case* c, const orc_fr_params* p, double* q, con
   int e, nb = c->nbedge + c->ngedge, nvars = 3*p->chem->nspecies + 6;
   for(e = 0; e < nb; e++){
     int l = c->bedges_n[2*e], r = c->bedges_n[2*e+1];
-    fr_boundary_variables(c, p, &q[(size_t)l*nvars], &q[(size_t)r*nvars], &c->bedges_a[4*e], c->bedges_bctype[e], beta[l], e, q);
+    fr_boundary_variables(c, p, &q[(size_t)l*nvars], &q[(size_t)r*nvars], &c->bedges_a[4*e], c->bedges_bctype[e], beta[l], e, q, NULL);
   }
 }
 
@@ -1474,9 +1486,10 @@ void orc_fr_jacobian(const orc_case* c, const orc_fr_params* p, double* q, const
     double* QL = &q[(size_t)l*nvars];
     double* QR = &q[(size_t)r*nvars];
     int bctype = c->bedges_bctype[e];
-    double QPL[MAXV], QPR[MAXV], fluxS[MAXE], fluxL[MAXE], fluxR[MAXE], tempL[MAXE*MAXE], tempR[MAXE*MAXE];
+    double QPL[MAXV], QPR[MAXV], fluxS[MAXE], fluxL[MAXE], fluxR[MAXE], tempL[MAXE*MAXE], tempR[MAXE*MAXE], Qref[MAXV];
     double *pL, betaL = beta[l];
-    fr_boundary_variables(c, p, QL, QR, avec, bctype, betaL, e, q);
+    for(i = 0; i < nvars; i++) Qref[i] = p->qinf[i];
+    fr_boundary_variables(c, p, QL, QR, avec, bctype, betaL, e, q, Qref);
     fr_numerical_flux(p, QL, QR, avec, 0.0, fluxS, betaL);
     for(i = 0; i < neqn; i++){
       memcpy(QPL, QL, sizeof(double)*nvars);
@@ -1487,7 +1500,7 @@ void orc_fr_jacobian(const orc_case* c, const orc_fr_params* p, double* q, const
       if(!is_ghost(c, r)){
 	memcpy(QPR, QR, sizeof(double)*nvars);
 	fr_aux(p, QPR);
-	fr_boundary_variables(c, p, QPL, QPR, avec, bctype, betaL, e, q);
+	fr_boundary_variables(c, p, QPL, QPR, avec, bctype, betaL, e, q, Qref);
 	fr_numerical_flux(p, QPL, QPR, avec, 0.0, fluxL, betaL);
       }
       else{

@@ -14,7 +14,8 @@ from tests.oracle_lib import Oracle, load_golden
 INVISCID = ["box8_explicit_venkat", "box8_explicit_barth", "box8_explicit_venkatmod", "box6_implicit_sgs", "box6c_implicit_sgs",
             "ramp15_implicit", "cube_LowFi", "box6_unsteady_bdf2"]
 # laminar Navier-Stokes (compressibleNS): viscous flux + analytic viscous Jacobian + no-slip wall hooks
-NS = ["box6_ns_implicit", "box6_ns_adiabatic", "box6_sa_implicit"]
+# box6_ns_ffv: farFieldViscous side faces (power-law scaled free stream, bc.tcc:1092-1108) next to the no-slip floor
+NS = ["box6_ns_implicit", "box6_ns_adiabatic", "box6_sa_implicit", "box6_ns_ffv"]
 ALL = INVISCID + NS
 INVISCID_IMPLICIT = ["box6_implicit_sgs", "box6c_implicit_sgs", "ramp15_implicit", "cube_LowFi", "box6_unsteady_bdf2"]
 IMPLICIT = INVISCID_IMPLICIT + NS
@@ -130,3 +131,24 @@ def test_unsteady_fixture_exercises_the_bdf_terms(oracle):
     o.c.qold = None     # steady form: no temporal residual
     b0 = o.residual(g["q0"].copy(), g["qgrad"], g["limiter"], g["beta"])
     assert np.abs(b - b0).max() > 0.1 * np.abs(b).max()
+
+
+def test_far_field_viscous_fixture_scales_the_free_stream(oracle):
+    from tests.oracle_lib import C
+    g, meta = load_golden("box6_ns_ffv")
+    assert (g["bedges_bctype"] == 5).any() and (g["bedges_bctype"] == 4).any()
+    oracle.orc_power_law_u.restype = C.c_double
+    oracle.orc_power_law_u.argtypes = [C.c_double, C.c_double, C.c_double]
+    d = g["wallDistance"][: int(meta["nnode"])]
+    ubar = np.array([oracle.orc_power_law_u(1.0, float(x), float(meta["Re"])) for x in d])
+    assert ubar.min() == 0.0 and 0.5 < ubar.max() < 1.0          # the whole box sits inside the power-law layer
+    # with the plain far-field BC on the same faces the phantom states differ: the scaling is live
+    o = Oracle(oracle, g, meta)
+    q = g["q_pre"].copy()
+    o.update_bcs(q, g["beta"])
+    exact(q, g["q0"], "q after BC update")
+    g2 = dict(g, bedges_bctype=np.where(g["bedges_bctype"] == 5, 6, g["bedges_bctype"]).astype(np.int32))
+    o2 = Oracle(oracle, g2, meta)
+    q2 = g["q_pre"].copy()
+    o2.update_bcs(q2, g["beta"])
+    assert np.abs(q2 - g["q0"]).max() > 1e-3

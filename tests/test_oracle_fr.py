@@ -11,8 +11,10 @@ from tests.oracle_lib import FrOracle, load_golden
 from tests.test_oracle import exact
 
 # box4_nsfr_wall / box4_nsfr_adiabatic: no-slip floor (isothermal 900 K / adiabatic) under the viscous reacting eqnset
-FR = ["box5_fr_explicit", "box4_fr_implicit", "box4_nsfr_implicit", "box4_fr_unsteady", "box4_nsfr_wall", "box4_nsfr_adiabatic"]
-IMPLICIT = ["box4_fr_implicit", "box4_nsfr_implicit", "box4_fr_unsteady", "box4_nsfr_wall", "box4_nsfr_adiabatic"]
+# box4_nsfr_ffv: farFieldViscous side faces next to the no-slip floor
+FR = ["box5_fr_explicit", "box4_fr_implicit", "box4_nsfr_implicit", "box4_fr_unsteady", "box4_nsfr_wall", "box4_nsfr_adiabatic",
+      "box4_nsfr_ffv"]
+IMPLICIT = ["box4_fr_implicit", "box4_nsfr_implicit", "box4_fr_unsteady", "box4_nsfr_wall", "box4_nsfr_adiabatic", "box4_nsfr_ffv"]
 
 
 @pytest.mark.parametrize("name", FR)
@@ -20,7 +22,7 @@ def test_fr_fixture_is_the_reacting_eqnset(name):
     g, meta = load_golden(name)
     assert int(meta["nspecies"]) == 5 and int(meta["neqn"]) == 9 and int(meta["nvars"]) == 21 and int(meta["nterms"]) == 14
     assert int(meta["rxnOn"]) == 1 and g["beta"][0] == 0.25       # preconditioned: beta = Mach^2 (solutionSpace.tcc:238-243)
-    if "wall" in name or "adiabatic" in name:
+    if "wall" in name or "adiabatic" in name or "ffv" in name:
         noslip = g["bedges_bctype"][: int(meta["nbedge"])] == 4
         tw = g["bedges_twall"][noslip]
         assert noslip.any() and np.all(tw == tw[0]) and (tw[0] < 0.0 if "adiabatic" in name else np.isclose(tw[0], 900.0 / 950.0))

@@ -183,6 +183,18 @@ def fr_inputs(work, name):
     os.chmod(os.path.join(work, f"{name}.rxn"), 0o644)
 
 
+def ffv_bc(twall):
+    """no-slip floor with farFieldViscous side faces (free-stream momentum scaled by a 1/7 power-law profile of the wall
+    distance, bc.tcc:1092-1108), far field on top"""
+    return f"""surface #1 = farFieldViscous "xmin"
+surface #2 = farFieldViscous "xmax"
+surface #3 = symmetry "ymin"
+surface #4 = symmetry "ymax"
+surface #5 = noSlip "floor" twall = [{twall}]
+surface #6 = farField "zmax"
+"""
+
+
 def slab_part(xyz, ranks, axis=2):
     """Partition id per node: equal slabs along one axis."""
     x = np.clip(xyz[:, axis], 0.0, 1.0 - 1e-12)
@@ -251,6 +263,13 @@ CASES = {
                                              eqnset="compressibleNSFR", nsgs=3, cfl=5.0, refvisc=2.0e-4,
                                              extra=FR_EXTRA.format(temp=950, pres=2000, rxn=1)
                                              + "refThermalConductivity = 0.05\nrefLength = 0.01\n"),
+    # farFieldViscous boundaries next to a no-slip floor, laminar NS and viscous reacting
+    "box6_ns_ffv": lambda: make_case("box6_ns_ffv", mesh=kuhn_box(6, jitter=0.15), bc=ffv_bc(330.0), eqnset="compressibleNS",
+                                     nsgs=3, cfl=5.0, refvisc=0.5),
+    "box4_nsfr_ffv": lambda: make_case("box4_nsfr_ffv", mesh=kuhn_box(4, jitter=0.15), bc=ffv_bc(900.0), eqnset="compressibleNSFR",
+                                       nsgs=3, cfl=5.0, refvisc=2.0e-4,
+                                       extra=FR_EXTRA.format(temp=950, pres=2000, rxn=1)
+                                       + "refThermalConductivity = 0.05\nrefLength = 0.01\n"),
     # unsteady (dual time stepping): physical time step 0.02, BDF2 at the third step -- TemporalResidual with
     # q^n, q^{n-1} and the cnp1 V/dt + V/dtau diagonal (perfect gas: diagonal; reacting: dense dQ/dq blocks)
     "box6_unsteady_bdf2": lambda: make_case("box6_unsteady_bdf2", mesh=kuhn_box(6, jitter=0.15), nsgs=3, cfl=5.0, unsteady=True,
