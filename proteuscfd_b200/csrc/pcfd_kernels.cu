@@ -2018,6 +2018,14 @@ int pcfd_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int devic
     if (out) *out = nullptr;
     return fail(nullptr, "pcfd_create: unsupported eqnset id (the reacting eqnset is created with pcfd_create_fr)");
   }
+  if (mesh && mesh->bedges_bctype) {
+    for (int e = 0; e < mesh->nbedge + mesh->ngedge; e++) {
+      if (mesh->bedges_bctype[e] == PCFD_BC_FARFIELD_VISCOUS) {
+        if (out) *out = nullptr;
+        return fail(nullptr, "pcfd_create: the viscous far-field BC (bc.tcc:1092-1108) is not available on the GPU path yet");
+      }
+    }
+  }
   return create_impl(mesh, params, device, NEQN, NVARS, NTERMS, out);
 }
 

@@ -14,11 +14,13 @@ from tests.oracle_lib import Oracle, load_golden
 INVISCID = ["box8_explicit_venkat", "box8_explicit_barth", "box8_explicit_venkatmod", "box6_implicit_sgs", "box6c_implicit_sgs",
             "ramp15_implicit", "cube_LowFi", "box6_unsteady_bdf2"]
 # laminar Navier-Stokes (compressibleNS): viscous flux + analytic viscous Jacobian + no-slip wall hooks
-# box6_ns_ffv: farFieldViscous side faces (power-law scaled free stream, bc.tcc:1092-1108) next to the no-slip floor
-NS = ["box6_ns_implicit", "box6_ns_adiabatic", "box6_sa_implicit", "box6_ns_ffv"]
-ALL = INVISCID + NS
+NS = ["box6_ns_implicit", "box6_ns_adiabatic", "box6_sa_implicit"]      # also the list tests/test_gpu_viscous.py runs on the GPU
+# oracle only so far (the CUDA path rejects the BC type): farFieldViscous side faces (power-law scaled free stream,
+# bc.tcc:1092-1108) next to the no-slip floor
+NS_ORACLE_ONLY = ["box6_ns_ffv"]
+ALL = INVISCID + NS + NS_ORACLE_ONLY
 INVISCID_IMPLICIT = ["box6_implicit_sgs", "box6c_implicit_sgs", "ramp15_implicit", "cube_LowFi", "box6_unsteady_bdf2"]
-IMPLICIT = INVISCID_IMPLICIT + NS
+IMPLICIT = INVISCID_IMPLICIT + NS + NS_ORACLE_ONLY
 EXPLICIT = ["box8_explicit_venkat", "box8_explicit_barth", "box8_explicit_venkatmod"]
 
 
