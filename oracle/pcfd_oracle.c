@@ -1159,6 +1159,27 @@ void orc_jacobian(const orc_case* c, double* q, const double* beta, const double
     const double* QR = &q[r*NVARS];
     double QPL[NVARS], QPR[NVARS], fluxS[NEQN], fluxL[NEQN], fluxR[NEQN], tempL[25], tempR[25];
     double *pR, *pL;
+    if(c->field_jac_type == 1){
+      /* Kernel_NumJac_Centered :306-366 */
+      double fluxLd[NEQN], fluxRd[NEQN];
+      for(i = 0; i < NEQN; i++){
+	memcpy(QPL, QL, sizeof(double)*NVARS);
+	memcpy(QPR, QR, sizeof(double)*NVARS);
+	QPL[i] += h; QPR[i] += h;
+	compute_aux(QPL, gamma); compute_aux(QPR, gamma);
+	numerical_flux(QPL, QR, avec, 0.0, gamma, fluxL);
+	numerical_flux(QL, QPR, avec, 0.0, gamma, fluxR);
+	memcpy(QPL, QL, sizeof(double)*NVARS);
+	memcpy(QPR, QR, sizeof(double)*NVARS);
+	QPL[i] -= h; QPR[i] -= h;
+	compute_aux(QPL, gamma); compute_aux(QPR, gamma);
+	numerical_flux(QPL, QR, avec, 0.0, gamma, fluxLd);
+	numerical_flux(QL, QPR, avec, 0.0, gamma, fluxRd);
+	for(j = 0; j < NEQN; j++) tempL[j*NEQN + i] = (fluxLd[j] - fluxL[j])/(2.0*h);
+	for(j = 0; j < NEQN; j++) tempR[j*NEQN + i] = (fluxR[j] - fluxRd[j])/(2.0*h);
+      }
+    }
+    else{
     numerical_flux(QL, QR, avec, 0.0, gamma, fluxS);
     for(i = 0; i < NEQN; i++){
       memcpy(QPL, QL, sizeof(double)*NVARS);
@@ -1169,6 +1190,7 @@ void orc_jacobian(const orc_case* c, double* q, const double* beta, const double
       numerical_flux(QL, QPR, avec, 0.0, gamma, fluxR);
       for(j = 0; j < NEQN; j++) tempL[j*NEQN + i] = (fluxS[j] - fluxL[j])/h;
       for(j = 0; j < NEQN; j++) tempR[j*NEQN + i] = (fluxR[j] - fluxS[j])/h;
+    }
     }
     pR = get_block(ia, ja, A, l, r);
     pL = get_block(ia, ja, A, r, l);
@@ -1187,6 +1209,38 @@ void orc_jacobian(const orc_case* c, double* q, const double* beta, const double
     double *pL;
     for(i = 0; i < NVARS; i++) Qref[i] = c->qinf[i];
     boundary_variables(c, QL, QR, avec, bctype, e, q, Qref);
+    if(c->boundary_jac_type == 1){
+      /* Bkernel_NumJac_Centered :546-640, boundaryJacEval == 0: the BC is re-evaluated for the +h state only (the -h branch
+	 tests boundaryJacEval without the negation, :604) */
+      double fluxLd[NEQN], fluxRd[NEQN];
+      for(i = 0; i < NEQN; i++){
+	memcpy(QPL, QL, sizeof(double)*NVARS);
+	memcpy(QPR, QR, sizeof(double)*NVARS);
+	QPL[i] += h; QPR[i] += h;
+	compute_aux(QPL, gamma); compute_aux(QPR, gamma);
+	numerical_flux(QL, QPR, avec, 0.0, gamma, fluxR);
+	if(!is_ghost(c, r)){
+	  memcpy(QPR, QR, sizeof(double)*NVARS);
+	  compute_aux(QPR, gamma);
+	  boundary_variables(c, QPL, QPR, avec, bctype, e, q, Qref);
+	  numerical_flux(QPL, QPR, avec, 0.0, gamma, fluxL);
+	}
+	else{
+	  numerical_flux(QPL, QR, avec, 0.0, gamma, fluxL);
+	}
+	memcpy(QPL, QL, sizeof(double)*NVARS);
+	memcpy(QPR, QR, sizeof(double)*NVARS);
+	QPL[i] -= h; QPR[i] -= h;
+	compute_aux(QPL, gamma); compute_aux(QPR, gamma);
+	numerical_flux(QL, QPR, avec, 0.0, gamma, fluxRd);
+	numerical_flux(QPL, QR, avec, 0.0, gamma, fluxLd);
+	for(j = 0; j < NEQN; j++){
+	  tempL[j*NEQN + i] = (fluxL[j] - fluxLd[j])/(2.0*h);
+	  tempR[j*NEQN + i] = (fluxR[j] - fluxRd[j])/(2.0*h);
+	}
+      }
+    }
+    else{
     numerical_flux(QL, QR, avec, 0.0, gamma, fluxS);
     for(i = 0; i < NEQN; i++){
       memcpy(QPL, QL, sizeof(double)*NVARS);
@@ -1207,6 +1261,7 @@ void orc_jacobian(const orc_case* c, double* q, const double* beta, const double
 	tempL[j*NEQN + i] = (fluxL[j] - fluxS[j])/h;
 	tempR[j*NEQN + i] = (fluxR[j] - fluxS[j])/h;
       }
+    }
     }
     if(is_ghost(c, r)){
       double* pR = get_block(ia, ja, A, l, r);

@@ -18,9 +18,11 @@ NS = ["box6_ns_implicit", "box6_ns_adiabatic", "box6_sa_implicit"]      # also t
 # oracle only so far (the CUDA path rejects the BC type): farFieldViscous side faces (power-law scaled free stream,
 # bc.tcc:1092-1108) next to the no-slip floor
 NS_ORACLE_ONLY = ["box6_ns_ffv"]
-ALL = INVISCID + NS + NS_ORACLE_ONLY
+# oracle only so far: central-difference flux Jacobians (jacobianFieldType = jacobianBoundaryType = 1)
+JAC_ORACLE_ONLY = ["box6_implicit_central"]
+ALL = INVISCID + NS + NS_ORACLE_ONLY + JAC_ORACLE_ONLY
 INVISCID_IMPLICIT = ["box6_implicit_sgs", "box6c_implicit_sgs", "ramp15_implicit", "cube_LowFi", "box6_unsteady_bdf2"]
-IMPLICIT = INVISCID_IMPLICIT + NS + NS_ORACLE_ONLY
+IMPLICIT = INVISCID_IMPLICIT + NS + NS_ORACLE_ONLY + JAC_ORACLE_ONLY
 EXPLICIT = ["box8_explicit_venkat", "box8_explicit_barth", "box8_explicit_venkatmod"]
 
 
@@ -154,3 +156,22 @@ def test_far_field_viscous_fixture_scales_the_free_stream(oracle):
     q2 = g["q_pre"].copy()
     o2.update_bcs(q2, g["beta"])
     assert np.abs(q2 - g["q0"]).max() > 1e-3
+
+
+def test_central_jacobian_fixture_differs_from_the_one_sided_one(oracle):
+    g, meta = load_golden("box6_implicit_central")
+    assert int(meta["fieldJacType"]) == 1 and int(meta["boundaryJacType"]) == 1
+    o = Oracle(oracle, g, meta)
+    ia, ja, iau = o.crs_init()
+    A = o.jacobian(g["q0"].copy(), g["beta"], g["timestep"], ia, ja, iau)
+    exact(A, g["A"], "A (central differences)")
+    o.c.field_jac_type = o.c.boundary_jac_type = 0
+    A0 = o.jacobian(g["q0"].copy(), g["beta"], g["timestep"], ia, ja, iau)
+    offd = np.ones(len(ja), bool)
+    offd[iau] = False
+    A, A0 = A.reshape(-1, 25), A0.reshape(-1, 25)
+    d = np.abs(A[offd] - A0[offd]).max() / np.abs(A0[offd]).max()
+    assert 1e-12 < d < 1e-5          # interior edges: same derivative, different truncation / rounding error
+    # boundary blocks: the reference re-evaluates the BC for the +h state only (jacobian.tcc:581-612), so the "central"
+    # boundary Jacobian carries (F(BC(q+h)) - F(q-h, frozen BC)) / 2h -- reproduced as it is, far from the one-sided one
+    assert np.abs(A[iau] - A0[iau]).max() > 1e-3 * np.abs(A0[iau]).max()
