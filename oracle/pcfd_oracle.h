@@ -64,7 +64,7 @@ typedef struct {
   const double* qoldm1;        /* [nnode*nvars] ... at t^{n-1} */
   const double* walldist;      /* field "wallDistance" [nnode+gnode]; read by the FarFieldViscous BC (bc.tcc:1092-1108) */
   int field_jac_type, boundary_jac_type;   /* Param::fieldJacType / boundaryJacType: 0 one-sided FD, 1 central FD
-                                              (jacobian.tcc:306-366, 546-640); perfect-gas oracle only */
+                                              (jacobian.tcc:306-366, 546-640) */
 } orc_case;
 
 /* gradient.tcc:115-138, 381-542 : s and sw, each [(nnode+gnode)*6] */

@@ -1464,6 +1464,27 @@ void orc_fr_jacobian(const orc_case* c, const orc_fr_params* p, double* q, const
     const double* QR = &q[(size_t)r*nvars];
     double QPL[MAXV], QPR[MAXV], fluxS[MAXE], fluxL[MAXE], fluxR[MAXE], tempL[MAXE*MAXE], tempR[MAXE*MAXE];
     double *pR, *pL, avbeta = 0.5*(beta[l] + beta[r]);
+    if(c->field_jac_type == 1){
+      /* Kernel_NumJac_Centered jacobian.tcc:306-366 */
+      double fluxLd[MAXE], fluxRd[MAXE];
+      for(i = 0; i < neqn; i++){
+	memcpy(QPL, QL, sizeof(double)*nvars);
+	memcpy(QPR, QR, sizeof(double)*nvars);
+	QPL[i] += h; QPR[i] += h;
+	fr_aux(p, QPL); fr_aux(p, QPR);
+	fr_numerical_flux(p, QPL, QR, avec, 0.0, fluxL, avbeta);
+	fr_numerical_flux(p, QL, QPR, avec, 0.0, fluxR, avbeta);
+	memcpy(QPL, QL, sizeof(double)*nvars);
+	memcpy(QPR, QR, sizeof(double)*nvars);
+	QPL[i] -= h; QPR[i] -= h;
+	fr_aux(p, QPL); fr_aux(p, QPR);
+	fr_numerical_flux(p, QPL, QR, avec, 0.0, fluxLd, avbeta);
+	fr_numerical_flux(p, QL, QPR, avec, 0.0, fluxRd, avbeta);
+	for(j = 0; j < neqn; j++) tempL[j*neqn + i] = (fluxLd[j] - fluxL[j])/(2.0*h);
+	for(j = 0; j < neqn; j++) tempR[j*neqn + i] = (fluxR[j] - fluxRd[j])/(2.0*h);
+      }
+    }
+    else{
     fr_numerical_flux(p, QL, QR, avec, 0.0, fluxS, avbeta);
     for(i = 0; i < neqn; i++){
       memcpy(QPL, QL, sizeof(double)*nvars);
@@ -1474,6 +1495,7 @@ void orc_fr_jacobian(const orc_case* c, const orc_fr_params* p, double* q, const
       fr_numerical_flux(p, QL, QPR, avec, 0.0, fluxR, avbeta);
       for(j = 0; j < neqn; j++) tempL[j*neqn + i] = (fluxS[j] - fluxL[j])/h;
       for(j = 0; j < neqn; j++) tempR[j*neqn + i] = (fluxR[j] - fluxS[j])/h;
+    }
     }
     pR = get_block(ia, ja, A, l, r, n2);
     pL = get_block(ia, ja, A, r, l, n2);
@@ -1490,6 +1512,37 @@ void orc_fr_jacobian(const orc_case* c, const orc_fr_params* p, double* q, const
     double *pL, betaL = beta[l];
     for(i = 0; i < nvars; i++) Qref[i] = p->qinf[i];
     fr_boundary_variables(c, p, QL, QR, avec, bctype, betaL, e, q, Qref);
+    if(c->boundary_jac_type == 1){
+      /* Bkernel_NumJac_Centered jacobian.tcc:546-640, boundaryJacEval == 0 (BC re-evaluated for the +h state only) */
+      double fluxLd[MAXE], fluxRd[MAXE];
+      for(i = 0; i < neqn; i++){
+	memcpy(QPL, QL, sizeof(double)*nvars);
+	memcpy(QPR, QR, sizeof(double)*nvars);
+	QPL[i] += h; QPR[i] += h;
+	fr_aux(p, QPL); fr_aux(p, QPR);
+	fr_numerical_flux(p, QL, QPR, avec, 0.0, fluxR, betaL);
+	if(!is_ghost(c, r)){
+	  memcpy(QPR, QR, sizeof(double)*nvars);
+	  fr_aux(p, QPR);
+	  fr_boundary_variables(c, p, QPL, QPR, avec, bctype, betaL, e, q, Qref);
+	  fr_numerical_flux(p, QPL, QPR, avec, 0.0, fluxL, betaL);
+	}
+	else{
+	  fr_numerical_flux(p, QPL, QR, avec, 0.0, fluxL, betaL);
+	}
+	memcpy(QPL, QL, sizeof(double)*nvars);
+	memcpy(QPR, QR, sizeof(double)*nvars);
+	QPL[i] -= h; QPR[i] -= h;
+	fr_aux(p, QPL); fr_aux(p, QPR);
+	fr_numerical_flux(p, QL, QPR, avec, 0.0, fluxRd, betaL);
+	fr_numerical_flux(p, QPL, QR, avec, 0.0, fluxLd, betaL);
+	for(j = 0; j < neqn; j++){
+	  tempL[j*neqn + i] = (fluxL[j] - fluxLd[j])/(2.0*h);
+	  tempR[j*neqn + i] = (fluxR[j] - fluxRd[j])/(2.0*h);
+	}
+      }
+    }
+    else{
     fr_numerical_flux(p, QL, QR, avec, 0.0, fluxS, betaL);
     for(i = 0; i < neqn; i++){
       memcpy(QPL, QL, sizeof(double)*nvars);
@@ -1510,6 +1563,7 @@ void orc_fr_jacobian(const orc_case* c, const orc_fr_params* p, double* q, const
 	tempL[j*neqn + i] = (fluxL[j] - fluxS[j])/h;
 	tempR[j*neqn + i] = (fluxR[j] - fluxS[j])/h;
       }
+    }
     }
     if(is_ghost(c, r)){
       double* pR = get_block(ia, ja, A, l, r, n2);

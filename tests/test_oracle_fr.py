@@ -12,9 +12,11 @@ from tests.test_oracle import exact
 
 # box4_nsfr_wall / box4_nsfr_adiabatic: no-slip floor (isothermal 900 K / adiabatic) under the viscous reacting eqnset
 # box4_nsfr_ffv: farFieldViscous side faces next to the no-slip floor
+# box4_fr_central: central-difference flux Jacobians (jacobianFieldType = jacobianBoundaryType = 1)
 FR = ["box5_fr_explicit", "box4_fr_implicit", "box4_nsfr_implicit", "box4_fr_unsteady", "box4_nsfr_wall", "box4_nsfr_adiabatic",
-      "box4_nsfr_ffv"]
-IMPLICIT = ["box4_fr_implicit", "box4_nsfr_implicit", "box4_fr_unsteady", "box4_nsfr_wall", "box4_nsfr_adiabatic", "box4_nsfr_ffv"]
+      "box4_nsfr_ffv", "box4_fr_central"]
+IMPLICIT = ["box4_fr_implicit", "box4_nsfr_implicit", "box4_fr_unsteady", "box4_nsfr_wall", "box4_nsfr_adiabatic", "box4_nsfr_ffv",
+            "box4_fr_central"]
 
 
 @pytest.mark.parametrize("name", FR)

@@ -272,6 +272,8 @@ CASES = {
                                        + "refThermalConductivity = 0.05\nrefLength = 0.01\n"),
     # central-difference flux Jacobians (jacobianFieldType = jacobianBoundaryType = 1, jacobian.tcc:306-366, 546-640)
     "box6_implicit_central": lambda: make_case("box6_implicit_central", mesh=kuhn_box(6, jitter=0.15), nsgs=3, cfl=5.0, jactype=1),
+    "box4_fr_central": lambda: make_case("box4_fr_central", mesh=kuhn_box(4, jitter=0.15), eqnset="compressibleEulerFR",
+                                         nsgs=3, cfl=5.0, jactype=1, extra=FR_EXTRA.format(temp=3000, pres=101325, rxn=1)),
     # unsteady (dual time stepping): physical time step 0.02, BDF2 at the third step -- TemporalResidual with
     # q^n, q^{n-1} and the cnp1 V/dt + V/dtau diagonal (perfect gas: diagonal; reacting: dense dQ/dq blocks)
     "box6_unsteady_bdf2": lambda: make_case("box6_unsteady_bdf2", mesh=kuhn_box(6, jitter=0.15), nsgs=3, cfl=5.0, unsteady=True,
