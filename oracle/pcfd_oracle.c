@@ -564,6 +564,33 @@ void orc_gradient(const orc_case* c, const double* q, const double* sw, double* 
   int nb = c->nbedge + c->ngedge;
   int ntot = (c->nnode + c->gnode)*NTERMS*3;
   for(k = 0; k < ntot; k++) qgrad[k] = 0.0;
+  if(c->grad_type == 1){
+    /* Kernel_Green_Gauss_Gradient / Bkernel_Green_Gauss_Gradient gradient.tcc:170-248, then the division by the dual
+       volume (:83-89) */
+    for(e = 0; e < c->nedge; e++){
+      int l = c->edges_n[2*e], r = c->edges_n[2*e+1];
+      const double* avec = &c->edges_a[4*e];
+      double area = avec[3];
+      for(i = 0; i < NTERMS; i++){
+	double faceavg = 0.5*(q[l*NVARS + GRADLOC[i]] + q[r*NVARS + GRADLOC[i]]);
+	for(j = 0; j < 3; j++){
+	  qgrad[r*NTERMS*3 + 3*i + j] += -faceavg*avec[j]*area;
+	  qgrad[l*NTERMS*3 + 3*i + j] += faceavg*avec[j]*area;
+	}
+      }
+    }
+    for(e = 0; e < nb; e++){
+      int l = c->bedges_n[2*e], r = c->bedges_n[2*e+1];
+      const double* avec = &c->bedges_a[4*e];
+      double area = avec[3];
+      for(i = 0; i < NTERMS; i++){
+	double faceavg = 0.5*(q[l*NVARS + GRADLOC[i]] + q[r*NVARS + GRADLOC[i]]);
+	for(j = 0; j < 3; j++) qgrad[l*NTERMS*3 + 3*i + j] += faceavg*avec[j]*area;
+      }
+    }
+    for(i = 0; i < c->nnode; i++) for(j = 0; j < NTERMS*3; j++) qgrad[i*NTERMS*3 + j] /= c->vol[i];
+  }
+  else
   for(e = 0; e < c->nedge + nb; e++){
     int interior = e < c->nedge;
     int l = interior ? c->edges_n[2*e] : c->bedges_n[2*(e - c->nedge)];

@@ -65,6 +65,7 @@ typedef struct {
   const double* walldist;      /* field "wallDistance" [nnode+gnode]; read by the FarFieldViscous BC (bc.tcc:1092-1108) */
   int field_jac_type, boundary_jac_type;   /* Param::fieldJacType / boundaryJacType: 0 one-sided FD, 1 central FD
                                               (jacobian.tcc:306-366, 546-640) */
+  int grad_type;               /* Param::gradType: 0 weighted least squares, 1 Green-Gauss (gradient.tcc:77-90, 170-248) */
 } orc_case;
 
 /* gradient.tcc:115-138, 381-542 : s and sw, each [(nnode+gnode)*6] */

@@ -647,6 +647,34 @@ void orc_fr_gradient(const orc_case* c, const orc_fr_params* p, const double* q,
   int nb = c->nbedge + c->ngedge;
   size_t k, ntot = (size_t)(c->nnode + c->gnode)*nterms*3;
   for(k = 0; k < ntot; k++) qgrad[k] = 0.0;
+  if(c->grad_type == 1){
+    /* Green-Gauss: gradient.tcc:170-248 and the division by the dual volume (:83-89) */
+    for(e = 0; e < c->nedge; e++){
+      int l = c->edges_n[2*e], r = c->edges_n[2*e+1];
+      const double* avec = &c->edges_a[4*e];
+      double area = avec[3];
+      for(i = 0; i < nterms; i++){
+	int loc = fr_gradloc(ns, i);
+	double faceavg = 0.5*(q[(size_t)l*nvars + loc] + q[(size_t)r*nvars + loc]);
+	for(j = 0; j < 3; j++){
+	  qgrad[(size_t)r*nterms*3 + 3*i + j] += -faceavg*avec[j]*area;
+	  qgrad[(size_t)l*nterms*3 + 3*i + j] += faceavg*avec[j]*area;
+	}
+      }
+    }
+    for(e = 0; e < nb; e++){
+      int l = c->bedges_n[2*e], r = c->bedges_n[2*e+1];
+      const double* avec = &c->bedges_a[4*e];
+      double area = avec[3];
+      for(i = 0; i < nterms; i++){
+	int loc = fr_gradloc(ns, i);
+	double faceavg = 0.5*(q[(size_t)l*nvars + loc] + q[(size_t)r*nvars + loc]);
+	for(j = 0; j < 3; j++) qgrad[(size_t)l*nterms*3 + 3*i + j] += faceavg*avec[j]*area;
+      }
+    }
+    for(i = 0; i < c->nnode; i++) for(j = 0; j < nterms*3; j++) qgrad[(size_t)i*nterms*3 + j] /= c->vol[i];
+  }
+  else
   for(e = 0; e < c->nedge + nb; e++){
     int interior = e < c->nedge;
     int l = interior ? c->edges_n[2*e] : c->bedges_n[2*(e - c->nedge)];

@@ -30,7 +30,8 @@ class OrcCase(C.Structure):
                 ("Re", C.c_double), ("Pr", C.c_double), ("PrT", C.c_double), ("tref", C.c_double),
                 ("mach", C.c_double), ("vnn", C.c_double), ("bedges_twall", _dp), ("mut", _dp),
                 ("dt_param", C.c_double), ("use_local_dt", C.c_int), ("torder", C.c_int), ("iter", C.c_int),
-                ("qold", _dp), ("qoldm1", _dp), ("walldist", _dp), ("field_jac_type", C.c_int), ("boundary_jac_type", C.c_int)]
+                ("qold", _dp), ("qoldm1", _dp), ("walldist", _dp), ("field_jac_type", C.c_int), ("boundary_jac_type", C.c_int),
+                ("grad_type", C.c_int)]
 
 
 def _d(a):
@@ -77,6 +78,7 @@ class Oracle:
         c.qoldm1 = _d(k["qoldm1"]) if unsteady else None
         c.walldist = _d(k["wallDistance"]) if "wallDistance" in k else None
         c.field_jac_type, c.boundary_jac_type = int(meta.get("fieldJacType", 0)), int(meta.get("boundaryJacType", 0))
+        c.grad_type = int(meta.get("gradType", 0))
         self.c = c
         self.nn = c.nnode + c.gnode
         self.nnode = c.nnode

@@ -20,10 +20,13 @@ NS = ["box6_ns_implicit", "box6_ns_adiabatic", "box6_sa_implicit"]      # also t
 NS_ORACLE_ONLY = ["box6_ns_ffv"]
 # oracle only so far: central-difference flux Jacobians (jacobianFieldType = jacobianBoundaryType = 1)
 JAC_ORACLE_ONLY = ["box6_implicit_central"]
-ALL = INVISCID + NS + NS_ORACLE_ONLY + JAC_ORACLE_ONLY
+# oracle only so far: Green-Gauss gradients (gradientType = 1, gradient.tcc:170-248)
+GG_ORACLE_ONLY = ["box8_explicit_gg"]
+ALL = INVISCID + NS + NS_ORACLE_ONLY + JAC_ORACLE_ONLY + GG_ORACLE_ONLY
 INVISCID_IMPLICIT = ["box6_implicit_sgs", "box6c_implicit_sgs", "ramp15_implicit", "cube_LowFi", "box6_unsteady_bdf2"]
 IMPLICIT = INVISCID_IMPLICIT + NS + NS_ORACLE_ONLY + JAC_ORACLE_ONLY
-EXPLICIT = ["box8_explicit_venkat", "box8_explicit_barth", "box8_explicit_venkatmod"]
+EXPLICIT = ["box8_explicit_venkat", "box8_explicit_barth", "box8_explicit_venkatmod"]      # also run on the GPU (test_gpu_parity)
+EXPLICIT_ORACLE = EXPLICIT + GG_ORACLE_ONLY
 
 
 def exact(a, b, what):
@@ -72,7 +75,7 @@ def test_gradient_limiter_residual_timestep(oracle, name):
     assert dtmin == g["dtmin"][0]
 
 
-@pytest.mark.parametrize("name", EXPLICIT)
+@pytest.mark.parametrize("name", EXPLICIT_ORACLE)
 def test_explicit_update(oracle, name):
     g, meta = load_golden(name)
     o = Oracle(oracle, g, meta)
@@ -175,3 +178,16 @@ def test_central_jacobian_fixture_differs_from_the_one_sided_one(oracle):
     # boundary blocks: the reference re-evaluates the BC for the +h state only (jacobian.tcc:581-612), so the "central"
     # boundary Jacobian carries (F(BC(q+h)) - F(q-h, frozen BC)) / 2h -- reproduced as it is, far from the one-sided one
     assert np.abs(A[iau] - A0[iau]).max() > 1e-3 * np.abs(A0[iau]).max()
+
+
+def test_green_gauss_fixture_differs_from_least_squares(oracle):
+    g, meta = load_golden("box8_explicit_gg")
+    assert int(meta["gradType"]) == 1
+    o = Oracle(oracle, g, meta)
+    grad = o.gradient(g["q0"].copy(), g["lsq_sw"])
+    exact(grad, g["qgrad"], "qgrad (Green-Gauss)")
+    o.c.grad_type = 0
+    lsq = o.gradient(g["q0"].copy(), g["lsq_sw"])
+    nn = int(meta["nnode"])
+    d = np.abs(grad - lsq).reshape(-1, 27)[:nn].max() / np.abs(lsq).max()
+    assert 1e-3 < d        # two discretisations of the same derivative (and GG is only first-order at boundary nodes)

@@ -14,9 +14,9 @@ from tests.test_oracle import exact
 # box4_nsfr_ffv: farFieldViscous side faces next to the no-slip floor
 # box4_fr_central: central-difference flux Jacobians (jacobianFieldType = jacobianBoundaryType = 1)
 FR = ["box5_fr_explicit", "box4_fr_implicit", "box4_nsfr_implicit", "box4_fr_unsteady", "box4_nsfr_wall", "box4_nsfr_adiabatic",
-      "box4_nsfr_ffv", "box4_fr_central"]
+      "box4_nsfr_ffv", "box4_fr_central", "box4_fr_gg"]      # box4_fr_gg: Green-Gauss gradients (gradientType = 1)
 IMPLICIT = ["box4_fr_implicit", "box4_nsfr_implicit", "box4_fr_unsteady", "box4_nsfr_wall", "box4_nsfr_adiabatic", "box4_nsfr_ffv",
-            "box4_fr_central"]
+            "box4_fr_central", "box4_fr_gg"]
 
 
 @pytest.mark.parametrize("name", FR)

@@ -274,6 +274,10 @@ CASES = {
     "box6_implicit_central": lambda: make_case("box6_implicit_central", mesh=kuhn_box(6, jitter=0.15), nsgs=3, cfl=5.0, jactype=1),
     "box4_fr_central": lambda: make_case("box4_fr_central", mesh=kuhn_box(4, jitter=0.15), eqnset="compressibleEulerFR",
                                          nsgs=3, cfl=5.0, jactype=1, extra=FR_EXTRA.format(temp=3000, pres=101325, rxn=1)),
+    # Green-Gauss gradients (gradientType = 1, gradient.tcc:170-248) under both eqnset families
+    "box8_explicit_gg": lambda: make_case("box8_explicit_gg", mesh=kuhn_box(8, jitter=0.15), extra="gradientType = 1\n"),
+    "box4_fr_gg": lambda: make_case("box4_fr_gg", mesh=kuhn_box(4, jitter=0.15), eqnset="compressibleEulerFR", nsgs=3, cfl=5.0,
+                                    extra=FR_EXTRA.format(temp=3000, pres=101325, rxn=1) + "gradientType = 1\n"),
     # unsteady (dual time stepping): physical time step 0.02, BDF2 at the third step -- TemporalResidual with
     # q^n, q^{n-1} and the cnp1 V/dt + V/dtau diagonal (perfect gas: diagonal; reacting: dense dQ/dq blocks)
     "box6_unsteady_bdf2": lambda: make_case("box6_unsteady_bdf2", mesh=kuhn_box(6, jitter=0.15), nsgs=3, cfl=5.0, unsteady=True,
