@@ -392,6 +392,20 @@ def main():
                 "bytes_per_launch": passes[dominant]["algorithmic_bytes"], "ms_per_launch": passes[dominant]["ms_per_step"],
                 "note": "algorithmic bytes = SURVEY.md 8d compulsory bytes of the pass; the Roe flux is FP64-pipe-bound "
                         "(see profiles/), so frac is reported for completeness, not as the limiter"}
+    # the dominant kernel is FP64-pipe-bound, not HBM-bound: put the pipe roofline next to the HBM one.  1274 = FP64-pipe
+    # instructions per edge of k_flux_edges<true> (static SASS count, `cuobjdump -sass`: 315 DADD + 451 DMUL + 455 DFMA
+    # inside the IEEE division / sqrt sequences + 53 DSETP; the rarely taken raw-limiter branch included, so an upper
+    # bound on the dynamic count); B200: 148 SMs x 64 FP64 lanes, one instruction per lane per clock
+    try:
+        sm_mhz = float((clocks or {}).get("sm_max_mhz") or 1965.0)
+        bound_ms = 1274.0 * ne / (148 * 64 * sm_mhz * 1e6) * 1e3
+        ms_flux = kern["k_flux_edges"]["ms_per_step"]
+        roofline["fp64_pipe"] = {"kernel": "k_flux_edges", "instr_per_edge": 1274, "bound_ms": bound_ms, "ms": ms_flux,
+                                 "frac": bound_ms / ms_flux,
+                                 "how": "static SASS count of FP64-pipe instructions x edges / (148 SMs x 64 lanes x SM clock); 64 lanes per SM = "
+                                        "the nominal 37 TFLOP/s FMA peak at 1.965 GHz, not measured here"}
+    except Exception:
+        pass
     step_bytes = sum(pb[p] for p in ("gradient", "limiter", "residual", "timestep"))
     phases = {"residual_Medges_s": ne / (passes["residual"]["ms_per_step"] * 1e-3) / 1e6 if "residual" in passes else None,
               "gradient_limiter_Medges_s": ne / ((passes["gradient"]["ms_per_step"] + passes["limiter"]["ms_per_step"]) * 1e-3) / 1e6,
