@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PCFD_ABI_VERSION 5
+#define PCFD_ABI_VERSION 6
 
 /* eqnset ids follow eqnset_defines.h / create_functions.h:17-45 */
 enum { PCFD_EQNSET_COMPRESSIBLE_EULER_FR = 0, PCFD_EQNSET_COMPRESSIBLE_NS_FR = 1, PCFD_EQNSET_COMPRESSIBLE_EULER = 2,
@@ -126,6 +126,15 @@ int pcfd_set_cfl(pcfd_ctx* ctx, double cfl);           /* Param::UpdateCFL (solu
    PCFD_F_QOLD has been set (before that q^n == q^{n+1} and its contribution is an exact zero); the diagonal terms
    cnp1 V/dt + V/dtau (eqnset.tcc:195-208, compressibleFR.tcc:1326-1331) follow these values at once. */
 int pcfd_set_time_integration(pcfd_ctx* ctx, double dt, int use_local_time_stepping, int torder, int iter);
+/* Param::gradType (param.tcc, read at gradient.tcc:68-90): 0 weighted least squares (default), 1 Green-Gauss
+   (Kernel_Green_Gauss_Gradient / Bkernel_Green_Gauss_Gradient gradient.tcc:170-248, divided by the dual volume :83-89).
+   pcfd_gradient and the composite iterations follow it at once.  (ABI v6) */
+int pcfd_set_gradient_type(pcfd_ctx* ctx, int type);
+/* Param::fieldJacType / boundaryJacType (jacobian.tcc:140-176): 0 one-sided finite differences (default,
+   Kernel_NumJac :254-304 / Bkernel_NumJac :459-544), 1 central differences (Kernel_NumJac_Centered :306-366 /
+   Bkernel_NumJac_Centered :546-640, whose -h branch does not re-evaluate the BC).  Type 2 (complex step) is rejected.
+   Both eqnset families.  (ABI v6) */
+int pcfd_set_jacobian_type(pcfd_ctx* ctx, int field_type, int boundary_type);
 
 size_t pcfd_field_size(const pcfd_ctx* ctx, int field); /* number of doubles */
 int pcfd_set_field(pcfd_ctx* ctx, int field, const double* host, size_t n);

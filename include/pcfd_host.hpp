@@ -91,6 +91,9 @@ class DropIn {
     pr.turb_model = s_->param->viscous ? s_->param->turbModel : 0;
 
     if (pcfd_create(&md, &pr, device, &ctx_) != 0) onError_("pcfd_create", pcfd_last_error(NULL));
+    // Param::gradType (gradient.tcc:68-90) and Param::fieldJacType / boundaryJacType (jacobian.tcc:140-176)
+    Check(pcfd_set_gradient_type(ctx_, s_->param->gradType), "pcfd_set_gradient_type");
+    Check(pcfd_set_jacobian_type(ctx_, s_->param->fieldJacType, s_->param->boundaryJacType), "pcfd_set_jacobian_type");
     // Mesh::s / Mesh::sw were filled by ComputeNodeLSQCoefficients during Init: reuse them
     Check(pcfd_set_field(ctx_, PCFD_F_LSQ_S, s_->m->s, 6 * (size_t)(nnode_ + gnode_)), "set s");
     Check(pcfd_set_field(ctx_, PCFD_F_LSQ_SW, s_->m->sw, 6 * (size_t)(nnode_ + gnode_)), "set sw");

@@ -39,7 +39,7 @@ SYMBOLS = [
     "pcfd_turb_compute", "pcfd_halo_configure",
     "pcfd_chem_create", "pcfd_chem_destroy", "pcfd_chem_last_error", "pcfd_chem_mass_production",
     "pcfd_create_fr", "pcfd_widths", "pcfd_limiter_raw", "pcfd_residual_fused", "pcfd_clip_fallbacks",
-    "pcfd_set_time_integration",
+    "pcfd_set_time_integration", "pcfd_set_gradient_type", "pcfd_set_jacobian_type",
     "pcfd_chem_source_term", "pcfd_chem_source_term_device", "pcfd_halo_width", "pcfd_halo_send_total", "pcfd_halo_pack", "pcfd_halo_recv_ptr",
 ]
 
@@ -160,6 +160,8 @@ def load_library(path=LIB_PATH):
     lib.pcfd_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.pcfd_set_cfl.argtypes = [C.c_void_p, C.c_double]
     lib.pcfd_set_time_integration.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int]
+    lib.pcfd_set_gradient_type.argtypes = [C.c_void_p, C.c_int]
+    lib.pcfd_set_jacobian_type.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.pcfd_crs_sizes.argtypes = [C.c_void_p, _ip, _ip]
     lib.pcfd_get_crs.argtypes = [C.c_void_p, _ip, _ip, _ip, _ip]
     lib.pcfd_residual.argtypes = [C.c_void_p, _dp]
@@ -333,6 +335,14 @@ class Context:
         """Param::dt / useLocalTimeStepping / torder and SolutionSpace::iter (see pcfd_set_time_integration)."""
         self._ck(self.lib.pcfd_set_time_integration(self.h, C.c_double(float(dt)), int(use_local_time_stepping), int(torder),
                                                     int(it)))
+
+    def set_gradient_type(self, grad_type):
+        """Param::gradType: 0 weighted least squares, 1 Green-Gauss (gradient.tcc:68-90)."""
+        self._ck(self.lib.pcfd_set_gradient_type(self.h, int(grad_type)))
+
+    def set_jacobian_type(self, field_type, boundary_type):
+        """Param::fieldJacType / boundaryJacType: 0 one-sided, 1 central differences (jacobian.tcc:140-176)."""
+        self._ck(self.lib.pcfd_set_jacobian_type(self.h, int(field_type), int(boundary_type)))
 
     def clip_fallbacks(self):
         """times the fused limiter / residual pair fell back to the ordered pressure-clip path"""

@@ -176,6 +176,60 @@ __global__ void __launch_bounds__(128) kfr_gradient(DevMesh m, const double* __r
   for (int kk = 0; kk < NT * 3; kk++) out[kk] = g[kk];
 }
 
+// Gradient::Compute with Param::gradType == 1: Green-Gauss (gradient.tcc:77-90, kernels :170-248) -- interior edges, then
+// all half-edges, the division by the dual volume, the symmetry fix; ordered gather (see k_gradient_gg)
+template <int NS>
+__global__ void __launch_bounds__(128) kfr_gradient_gg(DevMesh m, const double* __restrict__ q, double* __restrict__ qgrad) {
+  constexpr int NV = W<NS>::NV, NT = W<NS>::NT;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= m.nnode) return;
+  double g[NT * 3], qn[NT];
+#pragma unroll
+  for (int k = 0; k < NT * 3; k++) g[k] = 0.0;
+#pragma unroll
+  for (int i = 0; i < NT; i++) qn[i] = q[(size_t)n * NV + gradloc<NS>(i)];
+  const int kbeg = m.adjp[n], kend = m.adjp[n + 1];
+  for (int k = kbeg; k < kend; k++) {
+    const int2 a = m.adj[k];
+    const int o = a.x & 0x7fffffff;
+    const bool right = a.x < 0;
+    double av[4];
+    if (a.y < m.nedge) load_avec(m.ea, a.y, av);
+    else load_avec(m.bea, a.y - m.nedge, av);
+    const double area = av[3];
+#pragma unroll
+    for (int i = 0; i < NT; i++) {
+      const double qo = __ldg(q + (size_t)o * NV + gradloc<NS>(i));
+      const double faceavg = 0.5 * (qn[i] + qo);
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        if (right) g[3 * i + j] += -faceavg * av[j] * area;
+        else g[3 * i + j] += faceavg * av[j] * area;
+      }
+    }
+  }
+  const double vol = m.vol[n];
+#pragma unroll
+  for (int kk = 0; kk < NT * 3; kk++) g[kk] /= vol;
+  for (int k = kbeg; k < kend; k++) {
+    const int2 a = m.adj[k];
+    if (a.y < m.nedge) continue;
+    const int be = a.y - m.nedge;
+    if (m.bctype[be] != PCFD_BC_SYMMETRY) continue;
+    double av[4];
+    load_avec(m.bea, be, av);
+#pragma unroll
+    for (int i = 0; i < NT; i++) {
+      const double dot = g[i * 3] * av[0] + g[i * 3 + 1] * av[1] + g[i * 3 + 2] * av[2];
+#pragma unroll
+      for (int j = 0; j < 3; j++) g[i * 3 + j] -= dot * av[j];
+    }
+  }
+  double* out = qgrad + (size_t)n * NT * 3;
+#pragma unroll
+  for (int kk = 0; kk < NT * 3; kk++) out[kk] = g[kk];
+}
+
 // ======================================================================= limiter
 // Limiter::Compute passes 1+2 (limiters.tcc:53-110), NEQ threads per node (one equation each); unclamped output
 template <int NS>
@@ -765,6 +819,54 @@ __global__ void __launch_bounds__((2 * W<NS>::NEQ + 1) * EPB, PCFD_FRJAC_MINB) k
   }
 }
 
+// Kernel_NumJac_Centered (jacobian.tcc:306-366), Param::fieldJacType == 1: 2*NEQ lanes per edge, two HLLC fluxes each
+// (column i perturbed by +h and by -h): lanes 0..NEQ-1 column i of A(r,l) = (F(qL-h) - F(qL+h))/2h, lanes NEQ..2NEQ-1
+// column i of A(l,r) = (F(qR+h) - F(qR-h))/2h.
+template <int NS, int EPB>
+__global__ void __launch_bounds__(2 * W<NS>::NEQ * EPB) kfr_jac_edges_central(DevMesh m, fr::Params<NS> p,
+                                                                               const double* __restrict__ q,
+                                                                               const double* __restrict__ beta,
+                                                                               const int* __restrict__ posLR,
+                                                                               const int* __restrict__ posRL,
+                                                                               double* __restrict__ A) {
+  constexpr int NEQ = W<NS>::NEQ, N2 = W<NS>::N2, LPE = 2 * NEQ;
+  const int slot = threadIdx.x / LPE;
+  const int role = threadIdx.x - slot * LPE;
+  const int e = blockIdx.x * EPB + slot;
+  if (e >= m.nedge) return;
+  const double h = 1.0e-8;
+  const int2 lr = m.en[e];
+  const int l = lr.x, r = lr.y;
+  const bool left = role < NEQ;
+  const int i = left ? role : role - NEQ;
+  double av[4], QL[NS + 6], QR[NS + 6], QP[NS + 6], fp[NEQ], fm[NEQ];
+  load_avec(m.ea, e, av);
+  load_row<NS, NS + 6>(q, l, QL);
+  load_row<NS, NS + 6>(q, r, QR);
+  const double avbeta = 0.5 * (beta[l] + beta[r]);
+#pragma unroll
+  for (int k = 0; k < NS + 6; k++) QP[k] = left ? QL[k] : QR[k];
+  QP[i] += h;
+  fr::aux_pr(p, QP);
+  if (left) fr::numerical_flux(p, QP, QR, av, 0.0, avbeta, fp);
+  else fr::numerical_flux(p, QL, QP, av, 0.0, avbeta, fp);
+#pragma unroll
+  for (int k = 0; k < NS + 6; k++) QP[k] = left ? QL[k] : QR[k];
+  QP[i] -= h;
+  fr::aux_pr(p, QP);
+  if (left) fr::numerical_flux(p, QP, QR, av, 0.0, avbeta, fm);
+  else fr::numerical_flux(p, QL, QP, av, 0.0, avbeta, fm);
+  if (left) {
+    double* dst = A + (size_t)posRL[e] * N2 + i;
+#pragma unroll
+    for (int j = 0; j < NEQ; j++) dst[j * NEQ] = 0.0 + (fm[j] - fp[j]) / (2.0 * h);
+  } else {
+    double* dst = A + (size_t)posLR[e] * N2 + i;
+#pragma unroll
+    for (int j = 0; j < NEQ; j++) dst[j * NEQ] = 0.0 + (fp[j] - fm[j]) / (2.0 * h);
+  }
+}
+
 // Kernel_Viscous_Jac (jacobian.tcc:728-767) with CompressibleFREqnSet::ViscousJacobian: two threads per edge, one block
 // side each (side 0: aR added to A(l,r); side 1: -aL added to A(r,l)), after the inviscid finite-difference pass.  The
 // species rows of both blocks are zero and are left alone.  (Bkernel_Viscous_Jac ends with size = 0: no boundary part.)
@@ -913,6 +1015,128 @@ __global__ void __launch_bounds__(64) kfr_jac_bnodes(DevMesh m, fr::Params<NS> p
       }
       for (int j = 0; j < NEQ; j++) bd[j * NEQ + i] = (fL[j] - fS[j]) / h;
       if (ghost) for (int j = 0; j < NEQ; j++) ag[j * NEQ + i] = 0.0 + (fR[j] - fS[j]) / h;
+    }
+  }
+  double* ql = q + (size_t)n * NV;
+  for (int i = 0; i < NV; i++) ql[i] = QL[i];
+}
+
+// Bkernel_NumJac_Centered (jacobian.tcc:546-640), Param::boundaryJacType == 1, boundaryJacEval == 0: kfr_jac_bedges with
+// central differences.  The BC is re-evaluated for the +h state only (the -h branch tests boundaryJacEval without the
+// negation, :604): F(qL-h, QR) is taken against the unperturbed phantom state.
+template <int NS>
+__global__ void __launch_bounds__(64) kfr_jac_bedges_central(DevMesh m, fr::Params<NS> p, const int* __restrict__ list, int n,
+                                                              const unsigned char* __restrict__ bfirst,
+                                                              const double* __restrict__ beta, double* q,
+                                                              const int* __restrict__ bpos, double* __restrict__ bdiag,
+                                                              double* __restrict__ A) {
+  constexpr int NEQ = W<NS>::NEQ, NV = W<NS>::NV, N2 = W<NS>::N2;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int be = list[t];
+  const int2 lr = m.ben[be];
+  const int l = lr.x, r = lr.y;
+  const int type = m.bctype[be];
+  const bool first = bfirst[be] != 0;
+  const bool ghost = is_ghost(m, r);
+  const double h = 1.0e-8;
+  const double betaL = beta[l];
+  double QL[NV], QR[NV], av[4], fL[NEQ], fR[NEQ], fLd[NEQ], fRd[NEQ];
+  load_row<NS, NV>(q, l, QL);
+  load_row<NS, NV>(q, r, QR);
+  load_avec(m.bea, be, av);
+  if (!first && type != PCFD_BC_PARALLEL) fr::aux(p, QL);
+  fr::boundary_variables(p, QL, QR, av, type, betaL);
+  if (type != PCFD_BC_PARALLEL) {
+    double* qr = q + (size_t)r * NV;
+    for (int i = 0; i < NV; i++) qr[i] = QR[i];
+    if (first) {
+      double* ql = q + (size_t)l * NV;
+      for (int i = NS + 4; i < NV; i++) ql[i] = QL[i];
+    }
+  }
+  double* bd = bdiag + (size_t)be * N2;
+  double* ag = ghost ? A + (size_t)bpos[be] * N2 : nullptr;
+  for (int i = 0; i < NEQ; i++) {
+    double QPL[NV], QPR[NV];
+    for (int k = 0; k < NV; k++) { QPL[k] = QL[k]; QPR[k] = QR[k]; }
+    QPL[i] += h; QPR[i] += h;
+    fr::aux(p, QPL);
+    fr::aux_pr(p, QPR);
+    fr::numerical_flux(p, QL, QPR, av, 0.0, betaL, fR);
+    if (!ghost) {
+      for (int k = 0; k < NV; k++) QPR[k] = QR[k];
+      fr::boundary_variables(p, QPL, QPR, av, type, betaL);
+      fr::numerical_flux(p, QPL, QPR, av, 0.0, betaL, fL);
+    } else {
+      fr::numerical_flux(p, QPL, QR, av, 0.0, betaL, fL);
+    }
+    for (int k = 0; k < NV; k++) { QPL[k] = QL[k]; QPR[k] = QR[k]; }
+    QPL[i] -= h; QPR[i] -= h;
+    fr::aux(p, QPL);
+    fr::aux_pr(p, QPR);
+    fr::numerical_flux(p, QL, QPR, av, 0.0, betaL, fRd);
+    fr::numerical_flux(p, QPL, QR, av, 0.0, betaL, fLd);
+    for (int j = 0; j < NEQ; j++) bd[j * NEQ + i] = (fL[j] - fLd[j]) / (2.0 * h);
+    if (ghost) for (int j = 0; j < NEQ; j++) ag[j * NEQ + i] = 0.0 + (fR[j] - fRd[j]) / (2.0 * h);
+  }
+}
+
+// kfr_jac_bnodes with central differences (nodes owning a Dirichlet-type half-edge, sequential half-edge walk)
+template <int NS>
+__global__ void __launch_bounds__(64) kfr_jac_bnodes_central(DevMesh m, fr::Params<NS> p, const int* __restrict__ bnodes, int nb,
+                                                              const double* __restrict__ beta, double* q,
+                                                              const int* __restrict__ bpos, double* __restrict__ bdiag,
+                                                              double* __restrict__ A) {
+  constexpr int NEQ = W<NS>::NEQ, NV = W<NS>::NV, N2 = W<NS>::N2;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nb) return;
+  const int n = bnodes[t];
+  const double h = 1.0e-8;
+  const double betaL = beta[n];
+  double QL[NV];
+  load_row<NS, NV>(q, n, QL);
+  for (int k = m.adjp[n]; k < m.adjp[n + 1]; k++) {
+    const int2 a = m.adj[k];
+    if (a.y < m.nedge) continue;
+    const int be = a.y - m.nedge;
+    const int r = a.x & 0x7fffffff;
+    const int type = m.bctype[be];
+    const bool ghost = is_ghost(m, r);
+    double QR[NV], av[4], fL[NEQ], fR[NEQ], fLd[NEQ], fRd[NEQ];
+    load_row<NS, NV>(q, r, QR);
+    load_avec(m.bea, be, av);
+    double nT = 0.0, tw = 0.0;
+    if (type == PCFD_BC_NOSLIP) { nT = q[(size_t)m.bnormal[be] * NV + NS + 3]; tw = m.btwall[be]; }
+    fr::boundary_variables_seq(p, QL, QR, av, type, betaL, nT, tw);
+    if (type != PCFD_BC_PARALLEL) {
+      double* qr = q + (size_t)r * NV;
+      for (int i = 0; i < NV; i++) qr[i] = QR[i];
+    }
+    double* bd = bdiag + (size_t)be * N2;
+    double* ag = ghost ? A + (size_t)bpos[be] * N2 : nullptr;
+    for (int i = 0; i < NEQ; i++) {
+      double QPL[NV], QPR[NV];
+      for (int kk = 0; kk < NV; kk++) { QPL[kk] = QL[kk]; QPR[kk] = QR[kk]; }
+      QPL[i] += h; QPR[i] += h;
+      fr::aux(p, QPL);
+      fr::aux_pr(p, QPR);
+      fr::numerical_flux(p, QL, QPR, av, 0.0, betaL, fR);
+      if (!ghost) {
+        for (int kk = 0; kk < NV; kk++) QPR[kk] = QR[kk];
+        fr::boundary_variables_seq(p, QPL, QPR, av, type, betaL, nT, tw);
+        fr::numerical_flux(p, QPL, QPR, av, 0.0, betaL, fL);
+      } else {
+        fr::numerical_flux(p, QPL, QR, av, 0.0, betaL, fL);
+      }
+      for (int kk = 0; kk < NV; kk++) { QPL[kk] = QL[kk]; QPR[kk] = QR[kk]; }
+      QPL[i] -= h; QPR[i] -= h;
+      fr::aux(p, QPL);
+      fr::aux_pr(p, QPR);
+      fr::numerical_flux(p, QL, QPR, av, 0.0, betaL, fRd);
+      fr::numerical_flux(p, QPL, QR, av, 0.0, betaL, fLd);
+      for (int j = 0; j < NEQ; j++) bd[j * NEQ + i] = (fL[j] - fLd[j]) / (2.0 * h);
+      if (ghost) for (int j = 0; j < NEQ; j++) ag[j * NEQ + i] = 0.0 + (fR[j] - fRd[j]) / (2.0 * h);
     }
   }
   double* ql = q + (size_t)n * NV;
@@ -1194,6 +1418,12 @@ struct Impl {
     return 0;
   }
   static int gradient(pcfd_ctx* c) {
+    if (c->grad_type == 1) {
+      PROF("kfr_gradient_gg");
+      kfr_gradient_gg<NS><<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD]);
+      LAUNCH_CHECK();
+      return 0;
+    }
     PROF("kfr_gradient");
     kfr_gradient<NS><<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->f[PCFD_F_Q], c->f[PCFD_F_LSQ_SW], c->f[PCFD_F_QGRAD]);
     LAUNCH_CHECK();
@@ -1375,21 +1605,40 @@ struct Impl {
     CK(cudaMemsetAsync(A, 0, c->fsize[PCFD_F_A] * sizeof(double), c->stream));
     c->ludiag = false;
     if (c->nedge) {
-      PROF("kfr_jac_edges");
-      kfr_jac_edges<NS, EPB><<<nblk(c->nedge, EPB), LPE * EPB, 0, c->stream>>>(c->dm, p, c->f[PCFD_F_Q], beta, c->posLR,
-                                                                              c->posRL, A);
+      if (c->field_jac_type == 1) {
+        constexpr int EPBC = 4;
+        PROF("kfr_jac_edges_central");
+        kfr_jac_edges_central<NS, EPBC><<<nblk(c->nedge, EPBC), 2 * Wd::NEQ * EPBC, 0, c->stream>>>(c->dm, p, c->f[PCFD_F_Q], beta,
+                                                                                                  c->posLR, c->posRL, A);
+      } else {
+        PROF("kfr_jac_edges");
+        kfr_jac_edges<NS, EPB><<<nblk(c->nedge, EPB), LPE * EPB, 0, c->stream>>>(c->dm, p, c->f[PCFD_F_Q], beta, c->posLR,
+                                                                                c->posRL, A);
+      }
       LAUNCH_CHECK();
     }
     if (c->nbn) {
-      PROF("kfr_jac_bnodes");
-      kfr_jac_bnodes<NS><<<nblk(c->nbn, 64), 64, 0, c->stream>>>(c->dm, p, c->bnodes, c->nbn, beta, c->f[PCFD_F_Q], c->bpos,
-                                                                c->bdiag, A);
+      if (c->boundary_jac_type == 1) {
+        PROF("kfr_jac_bnodes_central");
+        kfr_jac_bnodes_central<NS><<<nblk(c->nbn, 64), 64, 0, c->stream>>>(c->dm, p, c->bnodes, c->nbn, beta, c->f[PCFD_F_Q],
+                                                                          c->bpos, c->bdiag, A);
+      } else {
+        PROF("kfr_jac_bnodes");
+        kfr_jac_bnodes<NS><<<nblk(c->nbn, 64), 64, 0, c->stream>>>(c->dm, p, c->bnodes, c->nbn, beta, c->f[PCFD_F_Q], c->bpos,
+                                                                  c->bdiag, A);
+      }
       LAUNCH_CHECK();
     }
     if (c->nblist) {
+      if (c->boundary_jac_type == 1) {
+        PROF("kfr_jac_bedges_central");
+        kfr_jac_bedges_central<NS><<<nblk(c->nblist, 64), 64, 0, c->stream>>>(c->dm, p, c->blist, c->nblist, c->bfirst, beta,
+                                                                             c->f[PCFD_F_Q], c->bpos, c->bdiag, A);
+      } else {
         PROF("kfr_jac_bedges");
-      kfr_jac_bedges<NS><<<nblk(c->nblist, 64), 64, 0, c->stream>>>(c->dm, p, c->blist, c->nblist, c->bfirst, beta,
-                                                                   c->f[PCFD_F_Q], c->bpos, c->bdiag, A);
+        kfr_jac_bedges<NS><<<nblk(c->nblist, 64), 64, 0, c->stream>>>(c->dm, p, c->blist, c->nblist, c->bfirst, beta,
+                                                                     c->f[PCFD_F_Q], c->bpos, c->bdiag, A);
+      }
       LAUNCH_CHECK();
     }
     if (c->fr->viscous && c->nedge) {

@@ -76,6 +76,8 @@ struct pcfd_ctx {
   int nnode = 0, gnode = 0, nbnode = 0, nedge = 0, nbedge = 0, ngedge = 0;
   int nb = 0, nn = 0, ntot = 0, nblocks = 0;
   pcfd_params prm{};
+  int field_jac_type = 0, boundary_jac_type = 0;   // Param::fieldJacType / boundaryJacType: 0 one-sided, 1 central FD
+  int grad_type = 0;   // Param::gradType: 0 weighted least squares, 1 Green-Gauss (pcfd_set_gradient_type)
   // system widths: 5 / 10 / 9 for the perfect-gas eqnsets, ns+4 / 3ns+6 / 2ns+4 for the reacting one
   int neqn = PCFD_NEQN, nvars = PCFD_NVARS, nterms = PCFD_NTERMS;
   struct pcfd_fr_state* fr = nullptr;   // reacting eqnset (pcfd_fr.cu); null for the perfect-gas eqnsets

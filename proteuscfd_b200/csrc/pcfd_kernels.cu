@@ -154,6 +154,61 @@ __global__ void __launch_bounds__(128) k_gradient(DevMesh m, const double* __res
   for (int kk = 0; kk < NTERMS * 3; kk++) out[kk] = g[kk];
 }
 
+// Gradient::Compute with Param::gradType == 1 (gradient.tcc:77-90): Kernel_Green_Gauss_Gradient /
+// Bkernel_Green_Gauss_Gradient (:170-248) in the Driver / Bdriver order (interior edges, then ALL half-edges, ghost
+// and boundary alike), the division by the dual volume (:83-89) and the symmetry fix (:545-565), as one ordered
+// gather per node.  The node's edge list is sorted by edge id with the half-edges at its tail, which is that order.
+__global__ void __launch_bounds__(128) k_gradient_gg(DevMesh m, const double* __restrict__ q, double* __restrict__ qgrad) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= m.nnode) return;
+  double g[NTERMS * 3];
+#pragma unroll
+  for (int k = 0; k < NTERMS * 3; k++) g[k] = 0.0;
+  double qn[NVARS];
+  load_q10(q, n, qn);
+  const int kbeg = m.adjp[n], kend = m.adjp[n + 1];
+  for (int k = kbeg; k < kend; k++) {
+    const int2 a = m.adj[k];
+    const int o = a.x & 0x7fffffff;
+    const bool right = a.x < 0;
+    double qo[NVARS], av[4];
+    load_q10(q, o, qo);
+    if (a.y < m.nedge) load_avec(m.ea, a.y, av);
+    else load_avec(m.bea, a.y - m.nedge, av);
+    const double area = av[3];
+#pragma unroll
+    for (int i = 0; i < NTERMS; i++) {
+      const int v = (i < 6) ? i : i + 1;   // c_gradloc
+      const double faceavg = 0.5 * (qn[v] + qo[v]);
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        if (right) g[3 * i + j] += -faceavg * av[j] * area;
+        else g[3 * i + j] += faceavg * av[j] * area;
+      }
+    }
+  }
+  const double vol = m.vol[n];
+#pragma unroll
+  for (int kk = 0; kk < NTERMS * 3; kk++) g[kk] /= vol;
+  for (int k = kbeg; k < kend; k++) {
+    const int2 a = m.adj[k];
+    if (a.y < m.nedge) continue;
+    const int be = a.y - m.nedge;
+    if (m.bctype[be] != PCFD_BC_SYMMETRY) continue;
+    double av[4];
+    load_avec(m.bea, be, av);
+#pragma unroll
+    for (int i = 0; i < NTERMS; i++) {
+      const double dot = g[i * 3] * av[0] + g[i * 3 + 1] * av[1] + g[i * 3 + 2] * av[2];
+#pragma unroll
+      for (int j = 0; j < 3; j++) g[i * 3 + j] -= dot * av[j];
+    }
+  }
+  double* out = qgrad + (size_t)n * NTERMS * 3;
+#pragma unroll
+  for (int kk = 0; kk < NTERMS * 3; kk++) out[kk] = g[kk];
+}
+
 // ======================================================================= limiter
 
 // Limiter::Compute passes 1+2 (limiters.tcc:53-110): neighbour min/max (from ZERO,
@@ -750,6 +805,48 @@ __global__ void __launch_bounds__(128) k_jac_edges(DevMesh m, double gamma, cons
   }
 }
 
+// Kernel_NumJac_Centered (jacobian.tcc:306-366), Param::fieldJacType == 1: central differences, h = 1e-8, of the
+// first-order flux; A(r,l) = (F(qL-h) - F(qL+h))/2h, A(l,r) = (F(qR+h) - F(qR-h))/2h.
+__global__ void __launch_bounds__(128) k_jac_edges_central(DevMesh m, double gamma, const double* __restrict__ q,
+                                                            const int* __restrict__ posLR, const int* __restrict__ posRL,
+                                                            double* __restrict__ A) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m.nedge) return;
+  const double h = 1.0e-8;
+  const int2 lr = m.en[e];
+  double av[4], QL[5], QR[5];
+  load_avec(m.ea, e, av);
+  load_q5(q, lr.x, QL);
+  load_q5(q, lr.y, QR);
+  double* pR = A + (size_t)posLR[e] * NEQN2;   // row l, column r
+  double* pL = A + (size_t)posRL[e] * NEQN2;   // row r, column l
+#pragma unroll 1
+  for (int i = 0; i < 5; i++) {
+    double QP[5], fL[5], fR[5], fLd[5], fRd[5];
+#pragma unroll
+    for (int j = 0; j < 5; j++) QP[j] = QL[j];
+    QP[i] += h;
+    eq::numerical_flux(QP, QR, av, 0.0, gamma, fL);
+#pragma unroll
+    for (int j = 0; j < 5; j++) QP[j] = QR[j];
+    QP[i] += h;
+    eq::numerical_flux(QL, QP, av, 0.0, gamma, fR);
+#pragma unroll
+    for (int j = 0; j < 5; j++) QP[j] = QL[j];
+    QP[i] -= h;
+    eq::numerical_flux(QP, QR, av, 0.0, gamma, fLd);
+#pragma unroll
+    for (int j = 0; j < 5; j++) QP[j] = QR[j];
+    QP[i] -= h;
+    eq::numerical_flux(QL, QP, av, 0.0, gamma, fRd);
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+      pL[j * 5 + i] = 0.0 + (fLd[j] - fL[j]) / (2.0 * h);   // "+=" onto the blanked matrix
+      pR[j * 5 + i] = 0.0 + (fR[j] - fRd[j]) / (2.0 * h);
+    }
+  }
+}
+
 // Kernel_Viscous_Jac (jacobian.tcc:768-800): analytic viscous blocks added onto the two off-diagonal blocks of
 // the edge.  A separate pass AFTER the boundary Jacobian kernels, as in the reference (jacobian.tcc:183-193):
 // Bkernel_NumJac updates the wall-node and phantom states this kernel reads.
@@ -854,6 +951,100 @@ __device__ __forceinline__ void jac_half_edge(const DevMesh& m, const eq::BcPara
     }
 #pragma unroll
     for (int j = 0; j < 5; j++) bd[j * 5 + i] = (fL[j] - fS[j]) / h;
+  }
+}
+
+// Bkernel_NumJac_Centered (jacobian.tcc:546-640), Param::boundaryJacType == 1, boundaryJacEval == 0, for ONE half-edge.
+// The BC is re-evaluated for the +h state only: the -h branch tests boundaryJacEval without the negation (:604), so it
+// takes the flux of the perturbed left state against the unperturbed phantom state.
+__device__ __forceinline__ void jac_half_edge_central(const DevMesh& m, const eq::BcParams& bp, int be, double* QL, double* q,
+                                                      const int* __restrict__ bpos, double* __restrict__ bdiag,
+                                                      double* __restrict__ A) {
+  const double h = 1.0e-8;
+  const double gamma = bp.gamma;
+  const int type = m.bctype[be];
+  const int r = m.ben[be].y;
+  const bool ghost = is_ghost(m, r);
+  double QR[NVARS], av[4], nQ[NVARS];
+  double tw = 0.0;
+  load_q10(q, r, QR);
+  load_avec(m.bea, be, av);
+  if (type == PCFD_BC_NOSLIP) { load_q10(q, m.bnormal[be], nQ); tw = m.btwall[be]; }
+  eq::boundary_variables(bp, QL, QR, av, type, nQ, tw);
+  if (type != PCFD_BC_PARALLEL) store_q10(q, r, QR);
+  double* pR = ghost ? A + (size_t)bpos[be] * NEQN2 : nullptr;
+  double* bd = bdiag + (size_t)be * NEQN2;
+#pragma unroll 1
+  for (int i = 0; i < 5; i++) {
+    double QPL[NVARS], QPR[NVARS], fL[5], fR[5], fLd[5], fRd[5];
+#pragma unroll
+    for (int j = 0; j < NVARS; j++) { QPL[j] = QL[j]; QPR[j] = QR[j]; }
+    QPL[i] += h;
+    QPR[i] += h;
+    eq::aux(QPL, gamma);
+    eq::aux(QPR, gamma);
+    eq::numerical_flux(QL, QPR, av, 0.0, gamma, fR);
+    if (ghost) {
+      eq::numerical_flux(QPL, QR, av, 0.0, gamma, fL);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NVARS; j++) QPR[j] = QR[j];
+      eq::aux(QPR, gamma);
+      eq::boundary_variables(bp, QPL, QPR, av, type, nQ, tw);
+      eq::numerical_flux(QPL, QPR, av, 0.0, gamma, fL);
+    }
+#pragma unroll
+    for (int j = 0; j < NVARS; j++) { QPL[j] = QL[j]; QPR[j] = QR[j]; }
+    QPL[i] -= h;
+    QPR[i] -= h;
+    eq::aux(QPL, gamma);
+    eq::aux(QPR, gamma);
+    eq::numerical_flux(QL, QPR, av, 0.0, gamma, fRd);
+    eq::numerical_flux(QPL, QR, av, 0.0, gamma, fLd);
+    if (ghost) {
+#pragma unroll
+      for (int j = 0; j < 5; j++) pR[j * 5 + i] = 0.0 + (fR[j] - fRd[j]) / (2.0 * h);
+    }
+#pragma unroll
+    for (int j = 0; j < 5; j++) bd[j * 5 + i] = (fL[j] - fLd[j]) / (2.0 * h);
+  }
+}
+
+__global__ void __launch_bounds__(64) k_jac_bnodes_central(DevMesh m, eq::BcParams bp, const int* __restrict__ bnodes, int nb,
+                                                            double* q, const int* __restrict__ bpos, double* __restrict__ bdiag,
+                                                            double* __restrict__ A) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nb) return;
+  const int n = bnodes[t];
+  double QL[NVARS];
+  load_q10(q, n, QL);
+  for (int k = m.adjp[n]; k < m.adjp[n + 1]; k++) {
+    const int2 a = m.adj[k];
+    if (a.y < m.nedge) continue;
+    jac_half_edge_central(m, bp, a.y - m.nedge, QL, q, bpos, bdiag, A);
+  }
+  store_q10(q, n, QL);
+}
+
+__global__ void __launch_bounds__(64) k_jac_bedges_central(DevMesh m, eq::BcParams bp, const int* __restrict__ list, int n,
+                                                            const unsigned char* __restrict__ bfirst, double* q,
+                                                            const int* __restrict__ bpos, double* __restrict__ bdiag,
+                                                            double* __restrict__ A) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int be = list[t];
+  const int l = m.ben[be].x;
+  const int type = m.bctype[be];
+  const bool first = bfirst[be] != 0;
+  double QL[NVARS];
+  load_q10(q, l, QL);
+  if (!first && type != PCFD_BC_PARALLEL) eq::aux(QL, bp.gamma);
+  jac_half_edge_central(m, bp, be, QL, q, bpos, bdiag, A);
+  if (first && type != PCFD_BC_PARALLEL) {
+    double2* pq = reinterpret_cast<double2*>(q + (size_t)l * NVARS);
+    q[(size_t)l * NVARS + 5] = QL[5];
+    pq[3] = make_double2(QL[6], QL[7]);
+    pq[4] = make_double2(QL[8], QL[9]);
   }
 }
 
@@ -2181,9 +2372,32 @@ int pcfd_gradient(pcfd_ctx* c) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
   if (c->fr) return pcfd_fr_gradient(c);
+  if (c->grad_type == 1) {
+    PROF("k_gradient_gg");
+    k_gradient_gg<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD]);
+    LAUNCH_CHECK();
+    return 0;
+  }
   PROF("k_gradient");
   k_gradient<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->f[PCFD_F_Q], c->f[PCFD_F_LSQ_SW], c->f[PCFD_F_QGRAD]);
   LAUNCH_CHECK();
+  return 0;
+}
+
+int pcfd_set_jacobian_type(pcfd_ctx* c, int field_type, int boundary_type) {
+  if (!c) return 1;
+  if ((field_type != 0 && field_type != 1) || (boundary_type != 0 && boundary_type != 1))
+    return fail(c, "pcfd_set_jacobian_type: 0 (one-sided differences) or 1 (central differences); the complex-step type 2 "
+                   "(jacobian.tcc:140-176) is not built");
+  c->field_jac_type = field_type;
+  c->boundary_jac_type = boundary_type;
+  return 0;
+}
+
+int pcfd_set_gradient_type(pcfd_ctx* c, int type) {
+  if (!c) return 1;
+  if (type != 0 && type != 1) return fail(c, "pcfd_set_gradient_type: 0 (weighted least squares) or 1 (Green-Gauss), gradient.tcc:68-90");
+  c->grad_type = type;
   return 0;
 }
 
@@ -2482,19 +2696,36 @@ int pcfd_jacobian(pcfd_ctx* c) {
   CK(cudaMemsetAsync(A, 0, c->fsize[PCFD_F_A] * sizeof(double), c->stream));   // CRSMatrix::Blank
   c->ludiag = false;
   if (c->nedge) {
-    PROF("k_jac_edges");
-    k_jac_edges<<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, c->prm.gamma, c->f[PCFD_F_Q], c->posLR, c->posRL, A);
+    if (c->field_jac_type == 1) {
+      PROF("k_jac_edges_central");
+      k_jac_edges_central<<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, c->prm.gamma, c->f[PCFD_F_Q], c->posLR, c->posRL, A);
+    } else {
+      PROF("k_jac_edges");
+      k_jac_edges<<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, c->prm.gamma, c->f[PCFD_F_Q], c->posLR, c->posRL, A);
+    }
     LAUNCH_CHECK();
   }
   if (c->nbn) {
-    PROF("k_jac_bnodes");
-    k_jac_bnodes<<<nblk(c->nbn, 64), 64, 0, c->stream>>>(c->dm, c->bp, c->bnodes, c->nbn, c->f[PCFD_F_Q], c->bpos, c->bdiag, A);
+    if (c->boundary_jac_type == 1) {
+      PROF("k_jac_bnodes_central");
+      k_jac_bnodes_central<<<nblk(c->nbn, 64), 64, 0, c->stream>>>(c->dm, c->bp, c->bnodes, c->nbn, c->f[PCFD_F_Q], c->bpos,
+                                                                   c->bdiag, A);
+    } else {
+      PROF("k_jac_bnodes");
+      k_jac_bnodes<<<nblk(c->nbn, 64), 64, 0, c->stream>>>(c->dm, c->bp, c->bnodes, c->nbn, c->f[PCFD_F_Q], c->bpos, c->bdiag, A);
+    }
     LAUNCH_CHECK();
   }
   if (c->nblist) {
-    PROF("k_jac_bedges");
-    k_jac_bedges<<<nblk(c->nblist, 64), 64, 0, c->stream>>>(c->dm, c->bp, c->blist, c->nblist, c->bfirst, c->f[PCFD_F_Q],
-                                                            c->bpos, c->bdiag, A);
+    if (c->boundary_jac_type == 1) {
+      PROF("k_jac_bedges_central");
+      k_jac_bedges_central<<<nblk(c->nblist, 64), 64, 0, c->stream>>>(c->dm, c->bp, c->blist, c->nblist, c->bfirst,
+                                                                      c->f[PCFD_F_Q], c->bpos, c->bdiag, A);
+    } else {
+      PROF("k_jac_bedges");
+      k_jac_bedges<<<nblk(c->nblist, 64), 64, 0, c->stream>>>(c->dm, c->bp, c->blist, c->nblist, c->bfirst, c->f[PCFD_F_Q],
+                                                              c->bpos, c->bdiag, A);
+    }
     LAUNCH_CHECK();
   }
   if (c->viscous && c->nedge) {

@@ -1,0 +1,173 @@
+"""GPU parity tests of the variants added AFTER the round's GPU minutes ran out (ABI v6): Green-Gauss gradients
+(Param::gradType = 1, gradient.tcc:170-248) for both eqnset families and central-difference flux Jacobians
+(fieldJacType = boundaryJacType = 1, jacobian.tcc:306-366, 546-640) for the perfect-gas eqnsets.
+
+Status: the kernels compile for sm_100a and the oracle side of each comparison is pinned bit-exact on the same
+reference-generated fixtures (tests/test_oracle.py, tests/test_oracle_fr.py), but these tests have NOT yet run on a
+B200.  They are therefore `xfail(strict=False)`: an XPASS in the round-end log is the first verification, a failure does
+not hide behind a green suite (it is reported as xfailed, and DESIGN.md lists the variants as "GPU run pending").
+The file sorts last so that a fault in an unverified kernel cannot disturb the verified tests before it.
+
+Bar: BIT-EXACT against the fixtures the reference wrote, like tests/test_gpu_parity.py (ordered gathers, --fmad=false).
+"""
+import numpy as np
+import pytest
+
+from tests.oracle_lib import oracle_for
+from tests.test_oracle import exact
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="kernels added after the round's GPU budget was spent: first B200 run pending")]
+
+
+def test_green_gauss_gradient_fixture():
+    """qgrad, then limiter / residual / time step computed from it, against the reference's box8_explicit_gg dump."""
+    from proteuscfd_b200 import capi
+    from tests.test_gpu_parity import golden_ctx
+    ctx, g, meta = golden_ctx("box8_explicit_gg")
+    assert int(meta["gradType"]) == 1
+    ctx.set_gradient_type(1)
+    ctx.set_field(capi.F_Q, g["q0"])
+    ctx.gradient()
+    exact(ctx.get_field(capi.F_QGRAD), g["qgrad"], "qgrad (Green-Gauss)")
+    ctx.limiter()
+    exact(ctx.get_field(capi.F_LIMITER), g["limiter"], "limiter")
+    ctx.residual()
+    exact(ctx.get_field(capi.F_B), g["b"], "b")
+    ctx.timestep()
+    exact(ctx.get_field(capi.F_TIMESTEP), g["timestep"], "timestep")
+    ctx.explicit_solve()
+    exact(ctx.get_field(capi.F_Q), g["q1"], "q1")
+
+
+def test_green_gauss_explicit_iterate_vs_oracle(oracle):
+    """two explicit iterations on a seeded 16^3 box with symmetry planes (the symmetry fix follows the volume division)"""
+    from proteuscfd_b200 import capi
+    from proteuscfd_b200.cases import box_case
+    bc = {1: capi.BC_FARFIELD, 2: capi.BC_FARFIELD, 3: capi.BC_SYMMETRY, 4: capi.BC_SYMMETRY, 5: capi.BC_FARFIELD,
+          6: capi.BC_IMPERMEABLE_WALL}
+    mesh, params, q = box_case(16, bc=bc, limiter=2)
+    o = oracle_for(oracle, mesh, params)
+    o.c.grad_type = 1
+    ctx = capi.Context(mesh, params)
+    ctx.set_gradient_type(1)
+    ctx.lsq_coefficients()
+    _, sw = o.lsq()
+    ctx.set_field(capi.F_Q, q)
+    qo = q.copy()
+    beta = np.zeros(1)
+    for it in range(2):
+        dt, _ = o.timestep(qo, beta)
+        o.update_bcs(qo, beta)
+        grad = o.gradient(qo, sw)
+        lim = o.limiter(qo, grad)
+        b = o.residual(qo, grad, lim, beta)
+        o.explicit_solve(qo, b, dt)
+        ctx.explicit_iterate(refresh_dt=True)
+        exact(ctx.get_field(capi.F_QGRAD), grad, f"qgrad it{it}")
+        exact(ctx.get_field(capi.F_B), b, f"b it{it}")
+        exact(ctx.get_field(capi.F_Q), qo, f"q it{it}")
+
+
+def test_green_gauss_gradient_fr_fixture():
+    """the reacting eqnset (14 gradient terms) against the reference's box4_fr_gg dump"""
+    from proteuscfd_b200 import capi
+    from tests.test_gpu_fr import fr_ctx
+    ctx, g, meta = fr_ctx("box4_fr_gg")
+    assert int(meta["gradType"]) == 1
+    ctx.set_gradient_type(1)
+    ctx.set_field(capi.F_Q, g["q0"])
+    ctx.gradient()
+    exact(ctx.get_field(capi.F_QGRAD), g["qgrad"], "qgrad (Green-Gauss, reacting)")
+    ctx.limiter()
+    exact(ctx.get_field(capi.F_LIMITER), g["limiter"], "limiter")
+
+
+def test_central_difference_jacobian_fixture():
+    """A, its LU, the SGS update and q1 against the reference's box6_implicit_central dump"""
+    from proteuscfd_b200 import capi
+    from tests.test_gpu_parity import golden_ctx
+    ctx, g, meta = golden_ctx("box6_implicit_central")
+    assert int(meta["fieldJacType"]) == 1 and int(meta["boundaryJacType"]) == 1
+    ctx.set_jacobian_type(1, 1)
+    ctx.set_field(capi.F_Q, g["q0"])
+    ctx.set_field(capi.F_TIMESTEP, g["timestep"])
+    ctx.jacobian()
+    exact(ctx.get_field(capi.F_A), g["A"], "A (central differences)")
+    ctx.prepare_sgs()
+    exact(ctx.get_field(capi.F_A), g["A_lu"], "A_lu")
+    ctx.set_field(capi.F_B, g["b"])
+    ctx.blank_x()
+    ctx.sgs(int(meta["nSgs"]))
+    exact(ctx.get_field(capi.F_X), g["x"], "x")
+    ctx.apply_dq()
+    exact(ctx.get_field(capi.F_Q), g["q1"], "q1")
+
+
+@pytest.mark.parametrize("types", [(1, 1), (1, 0), (0, 1)])
+def test_central_difference_jacobian_vs_oracle(oracle, types):
+    """field and boundary types independently, Dirichlet-type half-edges (node walk) mixed with far field / symmetry"""
+    from proteuscfd_b200 import capi
+    from proteuscfd_b200.cases import box_case
+    bc = {1: capi.BC_SONIC_INFLOW, 2: capi.BC_SONIC_OUTFLOW, 3: capi.BC_SYMMETRY, 4: capi.BC_DIRICHLET,
+          5: capi.BC_FARFIELD, 6: capi.BC_NEUMANN}
+    mesh, params, q = box_case(10, bc=bc, cfl=5.0)
+    o = oracle_for(oracle, mesh, params)
+    o.c.field_jac_type, o.c.boundary_jac_type = types
+    ctx = capi.Context(mesh, params)
+    ctx.set_jacobian_type(*types)
+    ia, ja, iau = o.crs_init()
+    ctx.set_field(capi.F_Q, q)
+    qo = q.copy()
+    dt, _ = o.timestep(qo, np.zeros(1))
+    A = o.jacobian(qo, np.zeros(1), dt, ia, ja, iau)
+    ctx.timestep(want_min=False)
+    ctx.jacobian()
+    exact(ctx.get_field(capi.F_A), A, "A")
+    exact(ctx.get_field(capi.F_Q), qo, "q after the boundary Jacobian")
+
+
+def test_central_difference_jacobian_fr_fixture():
+    """the reacting eqnset (9x9 blocks, HLLC) against the reference's box4_fr_central dump: off-diagonal blocks (pure
+    flux Jacobian) bit-exact; diagonal blocks carry the one-sided FD source-term Jacobian (libm rounding / h, see
+    tests/test_gpu_fr.py): 2e-6 of the block's largest entry, the bar of test_fr_jacobian_lu_sgs"""
+    from proteuscfd_b200 import capi
+    from tests.test_gpu_fr import NEQ, NV, fr_ctx
+    ctx, g, meta = fr_ctx("box4_fr_central")
+    assert int(meta["fieldJacType"]) == 1 and int(meta["boundaryJacType"]) == 1
+    ctx.set_jacobian_type(1, 1)
+    ctx.set_field(capi.F_Q, g["q0"])
+    ctx.set_field(capi.F_TIMESTEP, g["timestep"])
+    ctx.jacobian()
+    _, _, iau, _ = ctx.get_crs()
+    A = ctx.get_field(capi.F_A).reshape(-1, NEQ * NEQ)
+    Aref = g["A"].reshape(-1, NEQ * NEQ)
+    offd = np.ones(len(A), bool)
+    offd[iau] = False
+    exact(A[offd], Aref[offd], "off-diagonal blocks (central flux Jacobian)")
+    scale = np.abs(Aref[iau]).max(axis=1, keepdims=True)
+    assert np.all(np.abs(A[iau] - Aref[iau]) <= 2e-6 * scale)
+    nloc = int(meta["nnode"]) + int(meta["gnode"])
+    qa = ctx.get_field(capi.F_Q).reshape(-1, NV)
+    exact(qa[nloc:], g["q1"].reshape(-1, NV)[nloc:], "phantom rows after the boundary Jacobian pass")
+
+
+def test_central_difference_jacobian_fr_frozen_vs_oracle(oracle):
+    """reactionsOn = 0 removes the libm calls: the whole central-difference Jacobian is then bit-identical to the oracle"""
+    from proteuscfd_b200 import capi
+    from tests.oracle_lib import FrOracle, load_golden
+    from tests.test_gpu_fr import fr_ctx
+    g, meta = load_golden("box4_fr_central")
+    meta = dict(meta, rxnOn=0.0)
+    o = FrOracle(oracle, g, meta)
+    ctx, _, _ = fr_ctx("box4_fr_central", rxn_on=0)
+    ctx.set_jacobian_type(1, 1)
+    q = g["q_pre"].copy()
+    ia, ja, iau = o.crs_init()
+    dt, _ = o.timestep(q, g["beta"])
+    A = o.jacobian(q, g["beta"], dt, ia, ja, iau)
+    ctx.set_field(capi.F_Q, g["q_pre"])
+    ctx.timestep(want_min=False)
+    ctx.jacobian()
+    exact(ctx.get_field(capi.F_A), A, "A")
+    exact(ctx.get_field(capi.F_Q)[: q.size], q, "q after the boundary Jacobian")
