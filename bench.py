@@ -207,7 +207,7 @@ def cpu_baseline(args):
         try:
             case = ref_bench.ReferenceCase(n, ranks, limiter=2, nsgs=5, cfl=5.0)
             try:
-                ti = case.time(2)
+                ti = case.time(2, timeout=240)   # never run on the GPU box's core count yet: bounded
             finally:
                 case.close()
             out["sgs"] = {"sweeps_per_s": 5.0 / ti["t_sgs"], "node_sweeps_per_s": 5.0 * ti["nnode"] / ti["t_sgs"],
