@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -90,6 +91,21 @@ class DropIn {
     pr.mach = s_->param->GetVelocity(s_->iter);
     pr.turb_model = s_->param->viscous ? s_->param->turbModel : 0;
 
+    const bool reacting = pr.eqnset == PCFD_EQNSET_COMPRESSIBLE_EULER_FR || pr.eqnset == PCFD_EQNSET_COMPRESSIBLE_NS_FR;
+    if (reacting) {
+      // CompressibleFREqnSet (compressibleFR.h:12-23): chemistry tables, reference values, all nvars of Qinf
+      std::vector<pcfd_fr_params> fpv(1);   // ~100 kB: keep it off the stack
+      FillFrParams(fpv[0]);
+      if (const char* path = std::getenv("PCFD_HOST_DUMP_FR_PARAMS")) {   // test hook: the struct as handed to pcfd_create_fr
+        if (FILE* f = std::fopen(path, "wb")) { std::fwrite(&fpv[0], sizeof(pcfd_fr_params), 1, f); std::fclose(f); }
+      }
+      if (pcfd_create_fr(&md, &pr, &fpv[0], device, &ctx_) != 0) onError_("pcfd_create_fr", pcfd_last_error(NULL));
+      // preconditioning field "beta" (solutionSpace.tcc:235-247); rows beyond the local + ghost nodes stay 1
+      std::vector<double> beta(pcfd_field_size(ctx_, PCFD_F_BETA), 1.0);
+      const double* hb = s_->GetFieldData("beta", FIELDS::STATE_NONE);
+      for (int i = 0; i < nnode_ + gnode_ && (size_t)i < beta.size(); i++) beta[i] = hb[i];
+      Check(pcfd_set_field(ctx_, PCFD_F_BETA, beta.data(), beta.size()), "set beta");
+    } else
     if (pcfd_create(&md, &pr, device, &ctx_) != 0) onError_("pcfd_create", pcfd_last_error(NULL));
     // Param::gradType (gradient.tcc:68-90) and Param::fieldJacType / boundaryJacType (jacobian.tcc:140-176)
     Check(pcfd_set_gradient_type(ctx_, s_->param->gradType), "pcfd_set_gradient_type");
@@ -128,7 +144,7 @@ class DropIn {
   // residual.tcc:13-63: returns [resGlobal, res_0 .. res_{neqn-1}] with the reference's norm sqrt(sum)/N
   // (parallel.h:160-219); single rank here -- with several ranks the caller all-reduces the sums first
   std::vector<double> ComputeResiduals() {
-    double ss[1 + 16];
+    double ss[1 + PCFD_CHEM_MAX_SPECIES + 4];
     Check(pcfd_residual(ctx_, ss), "ComputeResiduals");
     std::vector<double> res(1 + neqn_);
     res[0] = std::sqrt(ss[0]) / ((double)nnode_ * neqn_);
@@ -172,6 +188,63 @@ class DropIn {
   void ApplyDQ() { Check(pcfd_apply_dq(ctx_), "ApplyDQ"); }                                                // solutionSpace.tcc:802
 
  private:
+  // pcfd_fr_params from the reference's own objects: ChemModel / Species / Reaction (chem.h, species.h:35-49,
+  // reaction.h:51-95) as CompressibleFREqnSet holds them, Param's reference values (param.tcc:352-398)
+  void FillFrParams(pcfd_fr_params& fp) {
+    std::memset(&fp, 0, sizeof(fp));
+    CompressibleFREqnSet<double>* fr = dynamic_cast<CompressibleFREqnSet<double>*>(s_->eqnset);
+    if (!fr) { onError_("DropIn", "eqnset_id names a reacting eqnset but eqnset is not a CompressibleFREqnSet"); return; }
+    ChemModel<double>& chem = *fr->chem;
+    const int ns = chem.nspecies, nr = chem.nreactions;
+    if (ns > PCFD_CHEM_MAX_SPECIES || nr > PCFD_CHEM_MAX_REACTIONS) {
+      onError_("DropIn", "chemistry model exceeds PCFD_CHEM_MAX_SPECIES / PCFD_CHEM_MAX_REACTIONS");
+      return;
+    }
+    pcfd_chem_model& cm = fp.chem;
+    cm.nspecies = ns;
+    cm.nreactions = nr;
+    for (int i = 0; i < ns; i++) {
+      Species<double>& sp = chem.species[i];
+      cm.mw[i] = sp.MW;
+      for (int k = 0; k < 7; k++) { cm.nasa7[i][0][k] = sp.thermo_coeff[0][k]; cm.nasa7[i][1][k] = sp.thermo_coeff[1][k]; }
+      fp.transport.nmu[i] = sp.mu_coeff_curves;
+      fp.transport.nk[i] = sp.k_coeff_curves;
+      for (int r = 0; r < sp.mu_coeff_curves && r < 3; r++) for (int k = 0; k < 6; k++) fp.transport.mu_fit[i][r][k] = sp.mu_coeff[r][k];
+      for (int r = 0; r < sp.k_coeff_curves && r < 3; r++) for (int k = 0; k < 6; k++) fp.transport.k_fit[i][r][k] = sp.k_coeff[r][k];
+      for (int k = 0; k < 3; k++) { fp.transport.mu_white[i][k] = sp.mu_coeff_White[k]; fp.transport.k_white[i][k] = sp.k_coeff_White[k]; }
+      fp.transport.mu_white[i][3] = sp.mu_transition_White;
+      fp.transport.k_white[i][3] = sp.k_transition_White;
+    }
+    for (int j = 0; j < nr; j++) {
+      Reaction<double>& r = chem.reactions[j];
+      cm.rxn_type[j] = r.rxnType;
+      cm.third_body[j] = r.thirdBodiesPresent ? 1 : 0;
+      cm.backward_given[j] = r.backwardRateGiven ? 1 : 0;
+      cm.rxn_type_b[j] = r.backwardRateGiven ? r.rxnTypeBackward : 0;
+      cm.nsp[j] = r.GetNspecies();
+      cm.A[j] = r.A; cm.EA[j] = r.EA; cm.n[j] = r.n;
+      if (r.backwardRateGiven) { cm.Ab[j] = r.Ab; cm.EAb[j] = r.EAb; cm.nb[j] = r.nb; }
+      for (int k = 0; k < r.GetNspecies(); k++) {
+        cm.species[j][k] = r.globalIndx[k];
+        cm.nup[j][k] = r.Nup[k];
+        cm.nupp[j][k] = r.Nupp[k];
+        cm.tbeff[j][k] = (r.thirdBodiesPresent && (size_t)k < r.TBEff.size()) ? r.TBEff[k] : 1.0;
+      }
+    }
+    fp.ref_density = s_->param->ref_density;
+    fp.ref_velocity = s_->param->ref_velocity;
+    fp.ref_temperature = s_->param->ref_temperature;
+    fp.ref_pressure = s_->param->ref_pressure;
+    fp.ref_time = s_->param->ref_time;
+    fp.ref_specific_enthalpy = s_->param->ref_specific_enthalpy;
+    fp.pref = fr->Pref;
+    fp.dt = s_->param->dt;
+    fp.use_local_dt = s_->param->useLocalTimeStepping ? 1 : 0;
+    fp.rxn_on = s_->param->rxnOn ? 1 : 0;
+    for (int k = 0; k < nvars_; k++) fp.qinf[k] = s_->eqnset->Qinf[k];
+    fp.ref_viscosity = s_->param->ref_viscosity;
+    fp.ref_k = s_->param->ref_k;
+  }
   size_t NQ() const { return (size_t)(nnode_ + gnode_ + nbnode_) * nvars_; }
   void Check(int rc, const char* where) {
     if (rc != 0) onError_(where, pcfd_last_error(ctx_));

@@ -40,8 +40,9 @@ refPressure = 101325
 velocity = {mach}
 CFL = {cfl}
 flowDirection = [1.0, 0.0, 0.0]
-jacobianFieldType = 0
-jacobianBoundaryType = 0
+jacobianFieldType = {jactype}
+jacobianBoundaryType = {jactype}
+gradientType = {gradtype}
 <<<END SPACE>>>
 """
 
@@ -90,7 +91,8 @@ def block_partition(xyz, ranks):
 class ReferenceCase:
     """A box case decomposed for `ranks` reference processes, kept on disk so it can be timed repeatedly."""
 
-    def __init__(self, n, ranks, limiter=2, nsgs=0, sorder=2, mach=0.5, cfl=0.5, jitter=0.15, colored=False):
+    def __init__(self, n, ranks, limiter=2, nsgs=0, sorder=2, mach=0.5, cfl=0.5, jitter=0.15, colored=False, jactype=0,
+                 gradtype=0):
         from proteuscfd_b200.boxmesh import kuhn_box, renumber, write_ugrid
         from proteuscfd_b200.ordering import color_order, kuhn_box_colors
         self.work = tempfile.mkdtemp(prefix="pcfd_refbench_")
@@ -105,7 +107,8 @@ class ReferenceCase:
             p2[new_of_old] = part
             part = p2
         with open(os.path.join(self.work, "box.param"), "w") as f:
-            f.write(PARAM_TMPL.format(name=self.name, sorder=sorder, limiter=limiter, nsgs=nsgs, mach=mach, cfl=cfl))
+            f.write(PARAM_TMPL.format(name=self.name, sorder=sorder, limiter=limiter, nsgs=nsgs, mach=mach, cfl=cfl,
+                                     jactype=int(jactype), gradtype=int(gradtype)))
         with open(os.path.join(self.work, "box.bc"), "w") as f:
             f.write(BOX_BC)
         write_ugrid(os.path.join(self.work, "box.ugrid"), xyz, tets, tris, tags)

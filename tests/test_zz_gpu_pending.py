@@ -171,3 +171,31 @@ def test_central_difference_jacobian_fr_frozen_vs_oracle(oracle):
     ctx.jacobian()
     exact(ctx.get_field(capi.F_A), A, "A")
     exact(ctx.get_field(capi.F_Q)[: q.size], q, "q after the boundary Jacobian")
+
+
+@pytest.mark.parametrize("kind", ["explicit_green_gauss", "implicit_central"])
+def test_reference_with_dropin_matches_reference_variants(kind):
+    """end to end through include/pcfd_host.hpp (which hands Param::gradType / fieldJacType / boundaryJacType over): the
+    unmodified reference with gradientType = 1 resp. jacobianFieldType = jacobianBoundaryType = 1 against the same
+    harness with the GPU phases, every dumped array bit-identical (tests/test_dropin_reference.py for the defaults)"""
+    from oracle import ref_bench
+    if not ref_bench.available(dropin=True):
+        pytest.skip("oracle/_ref binaries not built (needs /root/reference at build time)")
+    if kind == "explicit_green_gauss":
+        case = ref_bench.ReferenceCase(10, 1, limiter=2, nsgs=0, cfl=0.5, gradtype=1)
+    else:
+        case = ref_bench.ReferenceCase(8, 1, limiter=2, nsgs=3, cfl=5.0, colored=True, jactype=1)
+    try:
+        cpu = case.dump(dropin=False)[0]
+        gpu = case.dump(dropin=True)[0]
+    finally:
+        case.close()
+    assert set(cpu) == set(gpu)
+    for name in sorted(cpu):
+        if name == "resnorm":
+            assert np.allclose(gpu[name], cpu[name], rtol=1e-13, atol=0), name
+        elif name == "sgs_ddq":
+            xn = np.sqrt(np.sum(cpu["x"] ** 2)) / max(cpu["b"].size, 1)
+            assert abs(gpu[name][0] - cpu[name][0]) <= 1e-12 * xn
+        else:
+            exact(gpu[name], cpu[name], name)
