@@ -9,6 +9,10 @@ set -u
 out=gpurun_out
 mkdir -p "$out"
 
+# 0. first B200 run of the variants written after round 1's GPU minutes were spent (Green-Gauss gradients, central-difference
+#    Jacobians, their drop-in runs): XPASS = verified, then drop the xfail marker of tests/test_zz_gpu_pending.py.  ~1 min
+timeout 300 python -m pytest tests/test_zz_gpu_pending.py -m gpu -q -rxX > "$out/pending_variants.log" 2>&1
+
 # 1. launch list of the bench command itself (explicit iteration + 5x5 SGS), duration only: ~1 min
 timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$out/launches_bench.csv" \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-fr > "$out/launches_bench.log" 2>&1
