@@ -1,0 +1,256 @@
+"""Host emulation of selected CUDA kernels: the kernel SOURCE TEXT of proteuscfd_b200/csrc (the device functions of
+eqnset_compressible.cuh, the helpers of pcfd_internal.cuh and the named kernels of pcfd_kernels.cu) is extracted, compiled
+for the host with g++ (-ffp-contract=off, the counterpart of nvcc's --fmad=false; `__global__` / `__device__` defined away,
+`threadIdx` / `blockIdx` set by a loop) and run against the C oracle.
+
+Why: Green-Gauss gradients and central-difference Jacobians were written after the round's GPU minutes were spent
+(tests/test_zz_gpu_pending.py holds their B200 tests).  This test executes the very same kernel source on the CPU, so a
+logic error in them cannot wait for the next GPU run to show.  It is TEST INFRASTRUCTURE: nothing here is reachable from
+the product, which still has no CPU path.  As a control the same emulation runs two GPU-verified kernels (k_gradient,
+k_jac_edges + jac_half_edge) and must reproduce the oracle with them too.
+
+What it cannot check: launch configuration, the half-edge work-list split (bnodes / blist / bfirst -- shared with the
+verified kernels), nvcc's code generation.  Bars: bit-exact for the gradient and for the off-diagonal Jacobian blocks;
+the diagonal blocks are summed here in numpy in a different order than k_jac_diag does it, so 1e-10 of the block scale.
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.oracle_lib import oracle_for
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "proteuscfd_b200", "csrc")
+
+PRELUDE = r"""
+#include <cmath>
+#include <cstddef>
+#include <cstring>
+struct int2 { int x, y; };
+struct double2 { double x, y; };
+static inline double2 make_double2(double a, double b) { double2 r; r.x = a; r.y = b; return r; }
+#define __device__
+#define __global__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+template <class T> static inline T __ldg(const T* p) { return *p; }
+using std::isnan;
+static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }   // explicit, exact on both sides
+struct idx3 { unsigned x, y, z; };
+static idx3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDim = {1, 1, 1};
+#include "pcfd.h"
+#include "eqnset_compressible.cuh"
+#define NEQN PCFD_NEQN
+#define NVARS PCFD_NVARS
+#define NTERMS PCFD_NTERMS
+#define NEQN2 (NEQN * NEQN)
+"""
+
+DRIVER = r"""
+extern "C" {
+struct emu_mesh {
+  int nnode, gnode, nbnode, nedge, nbedge, ngedge;
+  const int* en; const double* ea; const int* ben; const double* bea; const int* bctype; const double* xyz;
+  const double* vol; const int* adjp; const int* adj; const int* bnormal; const double* btwall;
+};
+static DevMesh dev(const emu_mesh* m) {
+  DevMesh d;
+  d.nnode = m->nnode; d.gnode = m->gnode; d.nbnode = m->nbnode; d.nedge = m->nedge; d.nbedge = m->nbedge; d.ngedge = m->ngedge;
+  d.en = (const int2*)m->en; d.ea = m->ea; d.ben = (const int2*)m->ben; d.bea = m->bea; d.bctype = m->bctype; d.xyz = m->xyz;
+  d.vol = m->vol; d.adjp = m->adjp; d.adj = (const int2*)m->adj; d.bnormal = m->bnormal; d.btwall = m->btwall;
+  return d;
+}
+#define FOR_THREADS(n) for (blockIdx.x = 0; blockIdx.x < (unsigned)(n); blockIdx.x++)
+void emu_gradient(const emu_mesh* m, int gg, const double* q, const double* sw, double* qgrad) {
+  DevMesh d = dev(m);
+  FOR_THREADS(m->nnode) { if (gg) k_gradient_gg(d, q, qgrad); else k_gradient(d, q, sw, qgrad); }
+}
+// posLR / posRL: slot e and nedge + e of a per-edge block array
+void emu_jac_edges(const emu_mesh* m, int central, double gamma, const double* q, const int* posLR, const int* posRL, double* A) {
+  DevMesh d = dev(m);
+  FOR_THREADS(m->nedge) { if (central) k_jac_edges_central(d, gamma, q, posLR, posRL, A); else k_jac_edges(d, gamma, q, posLR, posRL, A); }
+}
+// all half-edges in the reference's order, the interior state read from / written to q directly (Bdriver semantics)
+void emu_jac_bedges(const emu_mesh* m, int central, double gamma, int no_cvbc, const double* qinf, double* q, double* bdiag) {
+  DevMesh d = dev(m);
+  eq::BcParams bp;
+  bp.gamma = gamma; bp.no_cvbc = no_cvbc;
+  for (int k = 0; k < NVARS; k++) bp.qinf[k] = qinf[k];
+  for (int be = 0; be < m->nbedge + m->ngedge; be++) {
+    double* QL = q + (size_t)d.ben[be].x * NVARS;
+    if (central) jac_half_edge_central(d, bp, be, QL, q, (const int*)0, bdiag, (double*)0);
+    else jac_half_edge(d, bp, be, QL, q, (const int*)0, bdiag, (double*)0);
+  }
+}
+}
+"""
+
+
+def extract(src, name):
+    """the definition of function / struct `name`: from the start of its line group to the matching closing brace"""
+    m = re.search(r"^[^\n/]*\b" + re.escape(name) + r"\s*\(", src, re.M) if not name.startswith("struct ") else \
+        re.search(r"^" + re.escape(name) + r"\s*\{", src, re.M)
+    assert m, f"{name} not found"
+    start = m.start()
+    i = src.index("{", m.end() - 1)
+    depth = 0
+    while True:
+        c = src[i]
+        if c == "{":
+            depth += 1
+        elif c == "}":
+            depth -= 1
+            if depth == 0:
+                break
+        i += 1
+    end = i + 1
+    if name.startswith("struct "):
+        end = src.index(";", end) + 1
+    return src[start:end] + "\n"
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    work = tmp_path_factory.mktemp("host_emul")
+    internal = open(os.path.join(CSRC, "pcfd_internal.cuh")).read()
+    kernels = open(os.path.join(CSRC, "pcfd_kernels.cu")).read()
+    parts = [PRELUDE]
+    for n in ("struct DevMesh", "is_ghost", "load_avec", "lsq_weights"):
+        parts.append(extract(internal, n))
+    for n in ("load_q5", "load_q10", "store_q10", "k_gradient", "k_gradient_gg", "k_jac_edges", "k_jac_edges_central",
+              "jac_half_edge", "jac_half_edge_central"):
+        parts.append(extract(kernels, n))
+    parts.append(DRIVER)
+    cpp = work / "emul.cpp"
+    cpp.write_text("".join(parts))
+    so = work / "libemul.so"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-I", CSRC,
+                           "-I", os.path.join(ROOT, "include"), "-o", str(so), str(cpp)])
+    return C.CDLL(str(so))
+
+
+class EmuMesh(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("nnode", "gnode", "nbnode", "nedge", "nbedge", "ngedge")] + \
+               [(k, C.c_void_p) for k in ("en", "ea", "ben", "bea", "bctype", "xyz", "vol", "adjp", "adj", "bnormal", "btwall")]
+
+
+def build_mesh(mesh):
+    """emu_mesh + the node -> edge lists the library builds in pcfd_create: per node its edges sorted by edge id (interior
+    edges, then half-edges), .x = other node | 1 << 31 if the node is the edge's RIGHT node, .y = edge id"""
+    keep = {}
+    nnode, nedge = int(mesh["nnode"]), int(mesh["nedge"])
+    en = np.ascontiguousarray(mesh["edges_n"], dtype=np.int32).reshape(-1, 2)
+    ben = np.ascontiguousarray(mesh["bedges_n"], dtype=np.int32).reshape(-1, 2)
+    node = np.concatenate([en[:, 0], en[:, 1], ben[:, 0]]).astype(np.int64)
+    other = np.concatenate([en[:, 1].astype(np.int64), en[:, 0].astype(np.int64) | (1 << 31), ben[:, 1].astype(np.int64)])
+    eid = np.concatenate([np.arange(nedge), np.arange(nedge), nedge + np.arange(len(ben))]).astype(np.int64)
+    order = np.lexsort((eid, node))
+    node, other, eid = node[order], other[order], eid[order]
+    adjp = np.zeros(nnode + 1, dtype=np.int32)
+    np.add.at(adjp, node + 1, 1)
+    adjp = np.cumsum(adjp).astype(np.int32)
+    adj = np.stack([(other & 0xFFFFFFFF).astype(np.uint32).view(np.int32), eid.astype(np.int32)], axis=1)
+    m = EmuMesh()
+    for k in ("nnode", "gnode", "nbnode", "nedge", "nbedge", "ngedge"):
+        setattr(m, k, int(mesh[k]))
+    arrays = dict(en=en, ea=np.ascontiguousarray(mesh["edges_a"], dtype=np.float64), ben=ben,
+                  bea=np.ascontiguousarray(mesh["bedges_a"], dtype=np.float64),
+                  bctype=np.ascontiguousarray(mesh["bedges_bctype"], dtype=np.int32),
+                  xyz=np.ascontiguousarray(mesh["xyz"], dtype=np.float64), vol=np.ascontiguousarray(mesh["vol"], dtype=np.float64),
+                  adjp=adjp, adj=np.ascontiguousarray(adj), bnormal=np.full(len(ben), -1, dtype=np.int32),
+                  btwall=np.zeros(len(ben)))
+    for k, a in arrays.items():
+        keep[k] = a
+        setattr(m, k, a.ctypes.data)
+    return m, keep
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+BC_SETS = {
+    "farfield_symmetry_wall": None,     # the default box: far field, symmetry, impermeable wall
+    "dirichlet_types": "dirichlet",
+}
+
+
+def case(kind):
+    from proteuscfd_b200 import capi
+    from proteuscfd_b200.cases import box_case
+    if kind == "dirichlet":
+        bc = {1: capi.BC_SONIC_INFLOW, 2: capi.BC_SONIC_OUTFLOW, 3: capi.BC_SYMMETRY, 4: capi.BC_DIRICHLET,
+              5: capi.BC_FARFIELD, 6: capi.BC_NEUMANN}
+        return box_case(8, bc=bc, cfl=5.0)
+    return box_case(8, cfl=5.0)
+
+
+@pytest.mark.parametrize("gg", [0, 1])
+@pytest.mark.parametrize("kind", list(BC_SETS.values()))
+def test_gradient_kernels_on_host(emu, oracle, gg, kind):
+    mesh, params, q = case(kind)
+    o = oracle_for(oracle, mesh, params)
+    o.c.grad_type = gg
+    qo = q.copy()
+    o.update_bcs(qo, np.zeros(1))
+    _, sw = o.lsq()
+    ref = o.gradient(qo, sw)
+    m, keep = build_mesh(mesh)
+    out = np.zeros_like(ref)
+    emu.emu_gradient(C.byref(m), gg, _p(qo), _p(sw), _p(out))
+    nloc = int(mesh["nnode"]) * 27
+    assert np.abs(ref[:nloc]).max() > 0
+    assert np.array_equal(out[:nloc], ref[:nloc]), f"max diff {np.abs(out[:nloc] - ref[:nloc]).max():.3e}"
+
+
+@pytest.mark.parametrize("types", [(0, 0), (1, 1), (1, 0), (0, 1)])
+@pytest.mark.parametrize("kind", list(BC_SETS.values()))
+def test_jacobian_kernels_on_host(emu, oracle, types, kind):
+    mesh, params, q = case(kind)
+    o = oracle_for(oracle, mesh, params)
+    o.c.field_jac_type, o.c.boundary_jac_type = types
+    ia, ja, iau = o.crs_init()
+    qo = q.copy()
+    dt, _ = o.timestep(qo, np.zeros(1))
+    A = o.jacobian(qo, np.zeros(1), dt, ia, ja, iau).reshape(-1, 25)
+
+    m, keep = build_mesh(mesh)
+    nedge, nnode = int(mesh["nedge"]), int(mesh["nnode"])
+    nb = int(mesh["nbedge"]) + int(mesh["ngedge"])
+    qe = q.copy()
+    # field kernel: block slots e (row l, column r) and nedge + e (row r, column l)
+    posLR = np.arange(nedge, dtype=np.int32)
+    posRL = (nedge + np.arange(nedge)).astype(np.int32)
+    E = np.full((2 * nedge, 25), np.nan)
+    emu.emu_jac_edges(C.byref(m), types[0], C.c_double(params["gamma"]), _p(qe), _p(posLR), _p(posRL), _p(E))
+    # boundary kernel, reference order
+    bd = np.full((nb, 25), np.nan)
+    qinf = np.ascontiguousarray(params["qinf"], dtype=np.float64)
+    emu.emu_jac_bedges(C.byref(m), types[1], C.c_double(params["gamma"]), int(params["no_cvbc"]), _p(qinf), _p(qe), _p(bd))
+    assert np.isfinite(E).all() and np.isfinite(bd).all()
+    assert np.array_equal(qe, qo), "q after the boundary Jacobian pass (phantom states, aux of the boundary nodes)"
+
+    def block(row, col):
+        k = ia[row] + np.nonzero(ja[ia[row]:ia[row + 1]] == col)[0][0]
+        return A[k]
+
+    en = keep["en"]
+    for e in range(nedge):      # off-diagonal blocks: bit-exact
+        l, r = en[e]
+        assert np.array_equal(E[e], block(l, r)), f"A(l,r) of edge {e}"
+        assert np.array_equal(E[nedge + e], block(r, l)), f"A(r,l) of edge {e}"
+    # diagonal blocks: Kernel_Diag_NumJac (-sum of the column's off-diagonal blocks) + boundary terms + V/dt on the diagonal
+    D = np.zeros((nnode, 25))
+    np.add.at(D, en[:, 0], -E[nedge:])      # dL += -jacL = -A(r,l)
+    np.add.at(D, en[:, 1], -E[:nedge])      # dR += -jacR = -A(l,r)
+    np.add.at(D, keep["ben"][:, 0], bd)
+    vol = keep["vol"]
+    for i in range(5):
+        D[:, 6 * i] += vol / dt
+    ref = A[iau]
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    assert np.all(np.abs(D - ref) <= 1e-10 * scale), f"diagonal blocks off by {np.max(np.abs(D - ref) / scale):.3e} of scale"
