@@ -39,6 +39,8 @@ static inline double2 make_double2(double a, double b) { double2 r; r.x = a; r.y
 #define __launch_bounds__(...)
 template <class T> static inline T __ldg(const T* p) { return *p; }
 using std::isnan;
+#define __noinline__
+static inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, sizeof d); return d; }
 static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }   // explicit, exact on both sides
 struct idx3 { unsigned x, y, z; };
 static idx3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDim = {1, 1, 1};
@@ -96,6 +98,9 @@ def extract(src, name):
         re.search(r"^" + re.escape(name) + r"\s*\{", src, re.M)
     assert m, f"{name} not found"
     start = m.start()
+    prev = src.rfind("\n", 0, start - 1) + 1
+    if src[prev:start].startswith("template"):
+        start = prev
     i = src.index("{", m.end() - 1)
     depth = 0
     while True:
@@ -251,6 +256,264 @@ def test_jacobian_kernels_on_host(emu, oracle, types, kind):
     vol = keep["vol"]
     for i in range(5):
         D[:, 6 * i] += vol / dt
+    ref = A[iau]
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    assert np.all(np.abs(D - ref) <= 1e-10 * scale), f"diagonal blocks off by {np.max(np.abs(D - ref) / scale):.3e} of scale"
+
+
+# ------------------------------------------------------------------------------------------------ reacting eqnset
+FR_DRIVER = r"""
+extern "C" {
+struct emu_mesh {
+  int nnode, gnode, nbnode, nedge, nbedge, ngedge;
+  const int* en; const double* ea; const int* ben; const double* bea; const int* bctype; const double* xyz;
+  const double* vol; const int* adjp; const int* adj; const int* bnormal; const double* btwall;
+};
+static DevMesh dev(const emu_mesh* m) {
+  DevMesh d;
+  d.nnode = m->nnode; d.gnode = m->gnode; d.nbnode = m->nbnode; d.nedge = m->nedge; d.nbedge = m->nbedge; d.ngedge = m->ngedge;
+  d.en = (const int2*)m->en; d.ea = m->ea; d.ben = (const int2*)m->ben; d.bea = m->bea; d.bctype = m->bctype; d.xyz = m->xyz;
+  d.vol = m->vol; d.adjp = m->adjp; d.adj = (const int2*)m->adj; d.bnormal = m->bnormal; d.btwall = m->btwall;
+  return d;
+}
+// make_params of pcfd_fr.cu, from the same pcfd_fr_params / pcfd_params values
+static fr::Params<5> params(const pcfd_fr_params* h, double chi, double cfl, int no_cvbc, int sorder, int limiter) {
+  fr::Params<5> p;
+  std::memset(&p, 0, sizeof(p));
+  for (int i = 0; i < 5; i++) {
+    p.mw[i] = h->chem.mw[i];
+    p.Rs[i] = chemdev::UNIV_R / h->chem.mw[i];
+    for (int r = 0; r < 2; r++) for (int k = 0; k < 7; k++) p.nasa[i][r][k] = h->chem.nasa7[i][r][k];
+  }
+  p.ref_density = h->ref_density; p.ref_velocity = h->ref_velocity; p.ref_temperature = h->ref_temperature;
+  p.ref_pressure = h->ref_pressure; p.ref_time = h->ref_time; p.ref_specific_enthalpy = h->ref_specific_enthalpy;
+  p.Pref = h->pref; p.dt = h->dt; p.chi = chi; p.cfl = cfl;
+  p.use_local_dt = h->use_local_dt; p.rxn_on = h->rxn_on; p.no_cvbc = no_cvbc; p.sorder = sorder; p.limiter = limiter;
+  for (int i = 0; i < 21; i++) p.qinf[i] = h->qinf[i];
+  return p;
+}
+void emu_fr_gradient(const emu_mesh* m, int gg, const double* q, const double* sw, double* qgrad) {
+  DevMesh d = dev(m);
+  for (blockIdx.x = 0; blockIdx.x < (unsigned)m->nnode; blockIdx.x++) {
+    if (gg) kfr_gradient_gg<5>(d, q, qgrad); else kfr_gradient<5>(d, q, sw, qgrad);
+  }
+}
+void emu_fr_jac_edges_central(const emu_mesh* m, const pcfd_fr_params* h, double chi, double cfl, int no_cvbc, const double* q,
+                              const double* beta, const int* posLR, const int* posRL, double* A) {
+  DevMesh d = dev(m);
+  fr::Params<5> p = params(h, chi, cfl, no_cvbc, 2, 2);
+  blockDim.x = 2 * 9 * 4;
+  for (blockIdx.x = 0; blockIdx.x < (unsigned)((m->nedge + 3) / 4); blockIdx.x++)
+    for (threadIdx.x = 0; threadIdx.x < blockDim.x; threadIdx.x++) kfr_jac_edges_central<5, 4>(d, p, q, beta, posLR, posRL, A);
+  threadIdx.x = 0; blockDim.x = 1;
+}
+void emu_fr_jac_bnodes_central(const emu_mesh* m, const pcfd_fr_params* h, double chi, double cfl, int no_cvbc, const int* bnodes,
+                               int n, const double* beta, double* q, double* bdiag) {
+  DevMesh d = dev(m);
+  fr::Params<5> p = params(h, chi, cfl, no_cvbc, 2, 2);
+  for (blockIdx.x = 0; blockIdx.x < (unsigned)n; blockIdx.x++)
+    kfr_jac_bnodes_central<5>(d, p, bnodes, n, beta, q, (const int*)0, bdiag, (double*)0);
+}
+void emu_fr_jac_bedges(const emu_mesh* m, const pcfd_fr_params* h, double chi, double cfl, int no_cvbc, int central, const int* list,
+                       int n, const unsigned char* bfirst, const double* beta, double* q, double* bdiag) {
+  DevMesh d = dev(m);
+  fr::Params<5> p = params(h, chi, cfl, no_cvbc, 2, 2);
+  for (blockIdx.x = 0; blockIdx.x < (unsigned)n; blockIdx.x++) {
+    if (central) kfr_jac_bedges_central<5>(d, p, list, n, bfirst, beta, q, (const int*)0, bdiag, (double*)0);
+    else kfr_jac_bedges<5>(d, p, list, n, bfirst, beta, q, (const int*)0, bdiag, (double*)0);
+  }
+}
+}
+"""
+
+
+@pytest.fixture(scope="module")
+def emu_fr(tmp_path_factory):
+    work = tmp_path_factory.mktemp("host_emul_fr")
+    (work / "cuda_runtime.h").write_text("/* stub: the host emulation defines what the kernels use */\n")
+    internal = open(os.path.join(CSRC, "pcfd_internal.cuh")).read()
+    kernels = open(os.path.join(CSRC, "pcfd_fr.cu")).read()
+    prelude = PRELUDE.replace('#include "eqnset_compressible.cuh"', '#include "eqnset_compressible.cuh"\n#include "eqnset_fr.cuh"')
+    parts = [prelude]
+    for n in ("struct DevMesh", "is_ghost", "load_avec", "lsq_weights"):
+        parts.append(extract(internal, n))
+    for n in ("struct W", "gradloc", "load_row", "kfr_gradient", "kfr_gradient_gg", "kfr_jac_edges_central", "kfr_jac_bedges",
+              "kfr_jac_bedges_central", "kfr_jac_bnodes_central"):
+        parts.append(extract(kernels, n))
+    parts.append(FR_DRIVER)
+    cpp = work / "emul_fr.cpp"
+    cpp.write_text("".join(parts))
+    so = work / "libemul_fr.so"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-I", str(work), "-I", CSRC,
+                           "-I", os.path.join(ROOT, "include"), "-o", str(so), str(cpp)])
+    return C.CDLL(str(so))
+
+
+def fr_fixture(name, rxn_on=0):
+    from proteuscfd_b200 import capi
+    from tests.oracle_lib import chem_tables, load_golden
+    g, meta = load_golden(name)
+    meta = dict(meta, rxnOn=float(rxn_on))
+    mesh = {k: g[k] for k in ("edges_n", "edges_a", "bedges_n", "bedges_a", "bedges_bctype", "xyz", "vol")}
+    for k in ("nnode", "gnode", "nbnode", "nedge", "nbedge", "ngedge"):
+        mesh[k] = int(meta[k])
+    fp = capi.FrParams()
+    capi.fill_chem_model(fp.chem, chem_tables(g))
+    for k, mk in (("ref_density", "ref_density"), ("ref_velocity", "ref_velocity"), ("ref_temperature", "ref_temperature"),
+                  ("ref_pressure", "ref_pressure"), ("ref_time", "ref_time"), ("ref_specific_enthalpy", "ref_specific_enthalpy"),
+                  ("pref", "Pref"), ("dt", "dt")):
+        setattr(fp, k, float(meta[mk]))
+    fp.use_local_dt, fp.rxn_on = int(meta["useLocalTimeStepping"]), int(rxn_on)
+    for j, v in enumerate(g["qinf"]):
+        fp.qinf[j] = float(v)
+    return g, meta, mesh, fp
+
+
+@pytest.mark.parametrize("name,gg", [("box4_fr_implicit", 0), ("box4_fr_gg", 1)])
+def test_fr_gradient_kernels_on_host(emu_fr, name, gg):
+    """kfr_gradient (GPU-verified, control) and kfr_gradient_gg against the qgrad the REFERENCE dumped"""
+    g, meta, mesh, _ = fr_fixture(name)
+    assert int(meta["gradType"]) == gg
+    m, keep = build_mesh(mesh)
+    q0 = np.ascontiguousarray(g["q0"])
+    sw = np.ascontiguousarray(g["lsq_sw"])
+    out = np.zeros_like(g["qgrad"])
+    emu_fr.emu_fr_gradient(C.byref(m), gg, _p(q0), _p(sw), _p(out))
+    nloc = int(meta["nnode"]) * 14 * 3
+    assert np.array_equal(out[:nloc], g["qgrad"][:nloc]), f"max diff {np.abs(out[:nloc] - g['qgrad'][:nloc]).max():.3e}"
+
+
+def test_fr_central_jacobian_kernels_on_host(emu_fr, oracle):
+    """kfr_jac_edges_central: off-diagonal blocks bit-exact against the oracle (which is bit-exact on the reference's
+    box4_fr_central dump).  kfr_jac_bedges_central: the change of the diagonal blocks between the central and the
+    one-sided boundary type must equal the change of the per-node sums of the half-edge blocks, the one-sided ones coming
+    from the GPU-verified kfr_jac_bedges run through the same emulation (1e-9 of the block scale: summation order)."""
+    from tests.oracle_lib import FrOracle
+    g, meta, mesh, fp = fr_fixture("box4_fr_central", rxn_on=0)
+    NEQ, NV = 9, 21
+    nedge, nnode = int(meta["nedge"]), int(meta["nnode"])
+    nb = int(meta["nbedge"]) + int(meta["ngedge"])
+    beta = np.ascontiguousarray(g["beta"])
+    res = {}
+    for btype in (0, 1):
+        o = FrOracle(oracle, g, meta)
+        o.c.field_jac_type, o.c.boundary_jac_type = 1, btype
+        ia, ja, iau = o.crs_init()
+        q = g["q_pre"].copy()
+        dt, _ = o.timestep(q, beta)
+        res[btype] = (o.jacobian(q, beta, dt, ia, ja, iau).reshape(-1, NEQ * NEQ), q)
+    A1, q1 = res[1]
+    A0, q0 = res[0]
+
+    m, keep = build_mesh(mesh)
+    chi, cfl, no_cvbc = float(meta["chi"]), float(meta["cfl"]), int(meta["no_cvbc"])
+    posLR = np.arange(nedge, dtype=np.int32)
+    posRL = (nedge + np.arange(nedge)).astype(np.int32)
+    E = np.full((2 * nedge, NEQ * NEQ), np.nan)
+    qe = np.ascontiguousarray(g["q_pre"].copy())
+    emu_fr.emu_fr_jac_edges_central(C.byref(m), C.byref(fp), C.c_double(chi), C.c_double(cfl), no_cvbc, _p(qe), _p(beta),
+                                    _p(posLR), _p(posRL), _p(E))
+    assert np.isfinite(E).all()
+    en = keep["en"]
+
+    def block(A, row, col):
+        k = ia[row] + np.nonzero(ja[ia[row]:ia[row + 1]] == col)[0][0]
+        return A[k]
+
+    for e in range(nedge):
+        l, r = en[e]
+        assert np.array_equal(E[e], block(A1, l, r)), f"A(l,r) of edge {e}"
+        assert np.array_equal(E[nedge + e], block(A1, r, l)), f"A(r,l) of edge {e}"
+
+    # boundary kernels: every half-edge in order; bfirst = first half-edge of its node
+    ben = keep["ben"]
+    blist = np.arange(nb, dtype=np.int32)
+    bfirst = np.zeros(nb, dtype=np.uint8)
+    seen = set()
+    for be in range(nb):
+        if int(ben[be, 0]) not in seen:
+            bfirst[be] = 1
+            seen.add(int(ben[be, 0]))
+    sums = {}
+    for central in (0, 1):
+        bd = np.full((nb, NEQ * NEQ), np.nan)
+        qb = np.ascontiguousarray(g["q_pre"].copy())
+        emu_fr.emu_fr_jac_bedges(C.byref(m), C.byref(fp), C.c_double(chi), C.c_double(cfl), no_cvbc, central, _p(blist), nb,
+                                 _p(bfirst), _p(beta), _p(qb), _p(bd))
+        assert np.isfinite(bd).all()
+        assert np.array_equal(qb, q1 if central else q0), "q after the boundary Jacobian pass"
+        S = np.zeros((nnode, NEQ * NEQ))
+        np.add.at(S, ben[:, 0], bd)
+        sums[central] = S
+        if central:
+            # the node-walk variant (nodes owning a Dirichlet-type half-edge on the GPU; here: every boundary node) must
+            # produce the same half-edge blocks and the same state
+            bnodes = np.unique(ben[:, 0]).astype(np.int32)
+            bd2 = np.full((nb, NEQ * NEQ), np.nan)
+            qn = np.ascontiguousarray(g["q_pre"].copy())
+            emu_fr.emu_fr_jac_bnodes_central(C.byref(m), C.byref(fp), C.c_double(chi), C.c_double(cfl), no_cvbc, _p(bnodes),
+                                             len(bnodes), _p(beta), _p(qn), _p(bd2))
+            assert np.array_equal(bd2, bd), "kfr_jac_bnodes_central vs kfr_jac_bedges_central"
+            assert np.array_equal(qn, q1)
+    dref = A1[iau] - A0[iau]
+    demu = sums[1] - sums[0]
+    scale = np.maximum(np.abs(A1[iau]).max(axis=1, keepdims=True), np.abs(sums[1]).max(axis=1, keepdims=True))
+    assert np.abs(dref).max() > 1e-3 * scale.max(), "the two boundary types do not differ: the test would be vacuous"
+    assert np.all(np.abs(demu - dref) <= 1e-9 * scale), f"off by {np.max(np.abs(demu - dref) / scale):.3e} of scale"
+
+
+# ------------------------------------------------------------------- perfect gas, straight against the reference's dumps
+def golden_mesh(name):
+    from tests.oracle_lib import load_golden
+    g, meta = load_golden(name)
+    mesh = {k: g[k] for k in ("edges_n", "edges_a", "bedges_n", "bedges_a", "bedges_bctype", "xyz", "vol")}
+    for k in ("nnode", "gnode", "nbnode", "nedge", "nbedge", "ngedge"):
+        mesh[k] = int(meta[k])
+    return g, meta, mesh
+
+
+def test_green_gauss_kernel_on_host_vs_reference_dump(emu):
+    g, meta, mesh = golden_mesh("box8_explicit_gg")
+    assert int(meta["gradType"]) == 1
+    m, keep = build_mesh(mesh)
+    q0 = np.ascontiguousarray(g["q0"])
+    out = np.zeros_like(g["qgrad"])
+    emu.emu_gradient(C.byref(m), 1, _p(q0), _p(np.zeros(6)), _p(out))
+    nloc = int(meta["nnode"]) * 27
+    assert np.array_equal(out[:nloc], g["qgrad"][:nloc])
+
+
+def test_central_jacobian_kernels_on_host_vs_reference_dump(emu):
+    """off-diagonal blocks and the state after the boundary pass bit-exact against the reference's box6_implicit_central
+    dump; diagonal blocks to 1e-10 of their scale (numpy sums in another order than k_jac_diag)"""
+    g, meta, mesh = golden_mesh("box6_implicit_central")
+    assert int(meta["fieldJacType"]) == 1 and int(meta["boundaryJacType"]) == 1
+    m, keep = build_mesh(mesh)
+    nedge, nnode = int(meta["nedge"]), int(meta["nnode"])
+    nb = int(meta["nbedge"]) + int(meta["ngedge"])
+    ia, ja, iau = g["ia"], g["ja"], g["iau"]
+    A = g["A"].reshape(-1, 25)
+    qe = np.ascontiguousarray(g["q0"].copy())
+    posLR = np.arange(nedge, dtype=np.int32)
+    posRL = (nedge + np.arange(nedge)).astype(np.int32)
+    E = np.full((2 * nedge, 25), np.nan)
+    gamma = float(meta["gamma"])
+    emu.emu_jac_edges(C.byref(m), 1, C.c_double(gamma), _p(qe), _p(posLR), _p(posRL), _p(E))
+    bd = np.full((nb, 25), np.nan)
+    qinf = np.ascontiguousarray(g["qinf"], dtype=np.float64)
+    emu.emu_jac_bedges(C.byref(m), 1, C.c_double(gamma), int(meta["no_cvbc"]), _p(qinf), _p(qe), _p(bd))
+    en = keep["en"]
+    for e in range(nedge):
+        l, r = en[e]
+        kLR = ia[l] + np.nonzero(ja[ia[l]:ia[l + 1]] == r)[0][0]
+        kRL = ia[r] + np.nonzero(ja[ia[r]:ia[r + 1]] == l)[0][0]
+        assert np.array_equal(E[e], A[kLR]) and np.array_equal(E[nedge + e], A[kRL]), f"edge {e}"
+    D = np.zeros((nnode, 25))
+    np.add.at(D, en[:, 0], -E[nedge:])
+    np.add.at(D, en[:, 1], -E[:nedge])
+    np.add.at(D, keep["ben"][:, 0], bd)
+    for i in range(5):
+        D[:, 6 * i] += g["vol"] / g["timestep"]
     ref = A[iau]
     scale = np.abs(ref).max(axis=1, keepdims=True)
     assert np.all(np.abs(D - ref) <= 1e-10 * scale), f"diagonal blocks off by {np.max(np.abs(D - ref) / scale):.3e} of scale"

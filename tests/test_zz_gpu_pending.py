@@ -3,7 +3,8 @@
 (fieldJacType = boundaryJacType = 1, jacobian.tcc:306-366, 546-640) for the perfect-gas eqnsets.
 
 Status: the kernels compile for sm_100a and the oracle side of each comparison is pinned bit-exact on the same
-reference-generated fixtures (tests/test_oracle.py, tests/test_oracle_fr.py), but these tests have NOT yet run on a
+reference-generated fixtures (tests/test_oracle.py, tests/test_oracle_fr.py); the kernel source itself, compiled for the
+host, reproduces those fixtures bit for bit (tests/test_host_emulation.py) -- but these tests have NOT yet run on a
 B200.  They are therefore `xfail(strict=False)`: an XPASS in the round-end log is the first verification, a failure does
 not hide behind a green suite (it is reported as xfailed, and DESIGN.md lists the variants as "GPU run pending").
 The file sorts last so that a fault in an unverified kernel cannot disturb the verified tests before it.
