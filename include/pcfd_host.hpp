@@ -8,9 +8,12 @@
 // (space->qgrad, space->limiter->l, space->crs->b/x, space->crs->A->M/pv, field "timestep",
 // space->q), so the rest of ucs.x (norms, output, forces, restart) is untouched.
 //
-// The template is duck-typed: it only needs the public members it names, so it also
-// compiles against a mock (tests/cpp/mock_space.hpp).  C++11, like the reference
-// (make.opts:44).  Error behaviour follows the reference: a failed call is fatal
+// The template only needs the public members it names; for the reacting eqnsets it also names the
+// reference's CompressibleFREqnSet / ChemModel / Species / Reaction (compressibleFR.h, chem.h), so it
+// is included where solutionSpace.tcc's own includes are in scope.  It is compiled into the real
+// reference by oracle/Makefile (ref_harness_gpu).  Test hook: with PCFD_HOST_DUMP_FR_PARAMS=<file> in
+// the environment the pcfd_fr_params handed to pcfd_create_fr is also written to <file>
+// (tests/test_dropin_fr_params.py).  C++11, like the reference (make.opts:44).  Error behaviour follows the reference: a failed call is fatal
 // (`Abort << ...`, ucs/exceptions.h:30-49); here the handler is pluggable and defaults to
 // printing pcfd_last_error and calling std::abort().
 #ifndef PCFD_HOST_HPP
