@@ -88,6 +88,19 @@ void emu_jac_bedges(const emu_mesh* m, int central, double gamma, int no_cvbc, c
     else jac_half_edge(d, bp, be, QL, q, (const int*)0, bdiag, (double*)0);
   }
 }
+// the same with the block positions of A(l, ghost) for the parallel half-edges of a partition
+void emu_jac_bedges_pos(const emu_mesh* m, int central, double gamma, int no_cvbc, const double* qinf, double* q, const int* bpos,
+                        double* bdiag, double* A) {
+  DevMesh d = dev(m);
+  eq::BcParams bp;
+  bp.gamma = gamma; bp.no_cvbc = no_cvbc;
+  for (int k = 0; k < NVARS; k++) bp.qinf[k] = qinf[k];
+  for (int be = 0; be < m->nbedge + m->ngedge; be++) {
+    double* QL = q + (size_t)d.ben[be].x * NVARS;
+    if (central) jac_half_edge_central(d, bp, be, QL, q, bpos, bdiag, A);
+    else jac_half_edge(d, bp, be, QL, q, bpos, bdiag, A);
+  }
+}
 }
 """
 
@@ -517,3 +530,53 @@ def test_central_jacobian_kernels_on_host_vs_reference_dump(emu):
     ref = A[iau]
     scale = np.abs(ref).max(axis=1, keepdims=True)
     assert np.all(np.abs(D - ref) <= 1e-10 * scale), f"diagonal blocks off by {np.max(np.abs(D - ref) / scale):.3e} of scale"
+
+
+# ------------------------------------------------------------------------- a partition: ghost nodes and ghost half-edges
+@pytest.mark.parametrize("name", ["box9_3rank_implicit_r1of3", "box8_2rank_explicit_r0of2"])
+def test_variants_on_a_partition_on_host(emu, oracle, name):
+    """rank-local mesh of a reference multi-rank run: Green-Gauss over the parallel half-edges, and the ghost branch of the
+    central boundary Jacobian (A(l, ghost) blocks), against the oracle with the variant switched on"""
+    from tests.oracle_lib import Oracle, load_golden
+    g, meta = load_golden(name)
+    assert int(meta["gnode"]) > 0 and int(meta["ngedge"]) > 0
+    mesh = {k: g[k] for k in ("edges_n", "edges_a", "bedges_n", "bedges_a", "bedges_bctype", "xyz", "vol")}
+    for k in ("nnode", "gnode", "nbnode", "nedge", "nbedge", "ngedge"):
+        mesh[k] = int(meta[k])
+    m, keep = build_mesh(mesh)
+    nnode, nedge = mesh["nnode"], mesh["nedge"]
+    nb = mesh["nbedge"] + mesh["ngedge"]
+
+    o = Oracle(oracle, g, meta)
+    o.c.grad_type = 1
+    q0 = np.ascontiguousarray(g["q0"].copy())
+    ref = o.gradient(q0, np.ascontiguousarray(g["lsq_sw"]))
+    out = np.zeros_like(ref)
+    emu.emu_gradient(C.byref(m), 1, _p(q0), _p(np.zeros(6)), _p(out))
+    assert np.array_equal(out[: nnode * 27], ref[: nnode * 27]), "Green-Gauss on a partition"
+
+    o = Oracle(oracle, g, meta)
+    o.c.field_jac_type = o.c.boundary_jac_type = 1
+    ia, ja, iau = o.crs_init()
+    qo = g["q0"].copy()
+    dt, _ = o.timestep(qo, np.zeros(1))
+    A = o.jacobian(qo, np.zeros(1), dt, ia, ja, iau).reshape(-1, 25)
+    ben = keep["ben"]
+    bpos = np.full(nb, -1, dtype=np.int32)
+    nghost = 0
+    for be in range(nb):
+        l, r = int(ben[be, 0]), int(ben[be, 1])
+        if nnode <= r < nnode + mesh["gnode"]:
+            bpos[be] = ia[l] + np.nonzero(ja[ia[l]:ia[l + 1]] == r)[0][0]
+            nghost += 1
+    assert nghost > 0
+    Ae = np.zeros_like(A)
+    bd = np.full((nb, 25), np.nan)
+    qe = np.ascontiguousarray(g["q0"].copy())
+    qinf = np.ascontiguousarray(g["qinf"], dtype=np.float64)
+    emu.emu_jac_bedges_pos(C.byref(m), 1, C.c_double(float(meta["gamma"])), int(meta["no_cvbc"]), _p(qinf), _p(qe), _p(bpos),
+                           _p(bd), _p(Ae))
+    assert np.array_equal(qe, qo)
+    for be in range(nb):
+        if bpos[be] >= 0:
+            assert np.array_equal(Ae[bpos[be]], A[bpos[be]]), f"A(l, ghost) of half-edge {be}"

@@ -200,3 +200,20 @@ def test_reference_with_dropin_matches_reference_variants(kind):
             assert abs(gpu[name][0] - cpu[name][0]) <= 1e-12 * xn
         else:
             exact(gpu[name], cpu[name], name)
+
+
+def test_variant_setters_reject_what_is_not_built():
+    """complex-step Jacobians (type 2, jacobian.tcc:150-176 -- they need the reference's complex EqnSet instantiation)
+    and unknown gradient types are refused with an error, never silently mapped to another kernel"""
+    from proteuscfd_b200 import capi
+    from proteuscfd_b200.cases import box_case
+    mesh, params, q = box_case(4)
+    ctx = capi.Context(mesh, params)
+    with pytest.raises(capi.PcfdError, match="complex"):
+        ctx.set_jacobian_type(2, 0)
+    with pytest.raises(capi.PcfdError, match="complex"):
+        ctx.set_jacobian_type(0, 2)
+    with pytest.raises(capi.PcfdError, match="Green-Gauss"):
+        ctx.set_gradient_type(2)
+    ctx.set_jacobian_type(1, 0)
+    ctx.set_gradient_type(1)
