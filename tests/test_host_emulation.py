@@ -327,6 +327,16 @@ void emu_fr_jac_bnodes_central(const emu_mesh* m, const pcfd_fr_params* h, doubl
   for (blockIdx.x = 0; blockIdx.x < (unsigned)n; blockIdx.x++)
     kfr_jac_bnodes_central<5>(d, p, bnodes, n, beta, q, (const int*)0, bdiag, (double*)0);
 }
+void emu_fr_jac_bedges_pos(const emu_mesh* m, const pcfd_fr_params* h, double chi, double cfl, int no_cvbc, int central,
+                           const int* list, int n, const unsigned char* bfirst, const double* beta, double* q, const int* bpos,
+                           double* bdiag, double* A) {
+  DevMesh d = dev(m);
+  fr::Params<5> p = params(h, chi, cfl, no_cvbc, 2, 2);
+  for (blockIdx.x = 0; blockIdx.x < (unsigned)n; blockIdx.x++) {
+    if (central) kfr_jac_bedges_central<5>(d, p, list, n, bfirst, beta, q, bpos, bdiag, A);
+    else kfr_jac_bedges<5>(d, p, list, n, bfirst, beta, q, bpos, bdiag, A);
+  }
+}
 void emu_fr_jac_bedges(const emu_mesh* m, const pcfd_fr_params* h, double chi, double cfl, int no_cvbc, int central, const int* list,
                        int n, const unsigned char* bfirst, const double* beta, double* q, double* bdiag) {
   DevMesh d = dev(m);
@@ -580,3 +590,70 @@ def test_variants_on_a_partition_on_host(emu, oracle, name):
     for be in range(nb):
         if bpos[be] >= 0:
             assert np.array_equal(Ae[bpos[be]], A[bpos[be]]), f"A(l, ghost) of half-edge {be}"
+
+
+@pytest.mark.parametrize("rank", [0, 1])
+def test_fr_variants_on_a_partition_on_host(emu_fr, oracle, rank):
+    """the reacting eqnset on one of two z-slab partitions (udecomp layout, ghost nodes and parallel half-edges):
+    kfr_gradient_gg over the parallel half-edges and the ghost branch of kfr_jac_bedges_central (A(l, ghost) blocks, with
+    the GPU-verified one-sided kernel as control) against the FR oracle with the variant switched on"""
+    from proteuscfd_b200 import capi
+    from proteuscfd_b200.cases import fr_slab_case
+    from tests.test_gpu_fr import fixture_fr_params, oracle_for_fr
+    NEQ = 9
+    fr, g, meta = fixture_fr_params("box4_fr_implicit", rxn_on=0)
+    mesh, params, q, beta = fr_slab_case(4, rank, 2, fr, colored=False)
+    assert mesh["gnode"] > 0 and mesh["ngedge"] > 0
+    nnode = mesh["nnode"]
+    nb = mesh["nbedge"] + mesh["ngedge"]
+    m, keep = build_mesh(mesh)
+    fp = capi.FrParams()
+    capi.fill_chem_model(fp.chem, fr["chem"])
+    for k in ("ref_density", "ref_velocity", "ref_temperature", "ref_pressure", "ref_time", "ref_specific_enthalpy", "pref", "dt"):
+        setattr(fp, k, float(fr[k]))
+    fp.use_local_dt, fp.rxn_on = int(fr.get("use_local_dt", 1)), 0
+    for j, v in enumerate(np.asarray(fr["qinf"]).reshape(-1)):
+        fp.qinf[j] = float(v)
+    beta = np.ascontiguousarray(beta)
+
+    o = oracle_for_fr(oracle, mesh, params, g, meta)
+    o.c.grad_type = 1
+    q0 = np.ascontiguousarray(q.copy())
+    o.update_bcs(q0, beta)
+    ref = o.gradient(q0, np.zeros((nnode + mesh["gnode"]) * 6))
+    out = np.zeros_like(ref)
+    emu_fr.emu_fr_gradient(C.byref(m), 1, _p(q0), _p(np.zeros(6)), _p(out))
+    assert np.abs(ref[: nnode * 42]).max() > 0
+    assert np.array_equal(out[: nnode * 42], ref[: nnode * 42]), "Green-Gauss (reacting) on a partition"
+
+    ben = keep["ben"]
+    blist = np.arange(nb, dtype=np.int32)
+    bfirst = np.zeros(nb, dtype=np.uint8)
+    seen = set()
+    for be in range(nb):
+        if int(ben[be, 0]) not in seen:
+            bfirst[be] = 1
+            seen.add(int(ben[be, 0]))
+    for central in (0, 1):
+        o = oracle_for_fr(oracle, mesh, params, g, meta)
+        o.c.field_jac_type, o.c.boundary_jac_type = 0, central
+        ia, ja, iau = o.crs_init()
+        qo = q.copy()
+        dt, _ = o.timestep(qo, beta)
+        A = o.jacobian(qo, beta, dt, ia, ja, iau).reshape(-1, NEQ * NEQ)
+        bpos = np.full(nb, -1, dtype=np.int32)
+        for be in range(nb):
+            l, r = int(ben[be, 0]), int(ben[be, 1])
+            if nnode <= r < nnode + mesh["gnode"]:
+                bpos[be] = ia[l] + np.nonzero(ja[ia[l]:ia[l + 1]] == r)[0][0]
+        assert (bpos >= 0).sum() > 0
+        Ae = np.zeros_like(A)
+        bd = np.full((nb, NEQ * NEQ), np.nan)
+        qe = np.ascontiguousarray(q.copy())
+        emu_fr.emu_fr_jac_bedges_pos(C.byref(m), C.byref(fp), C.c_double(params["chi"]), C.c_double(params["cfl"]),
+                                     int(params["no_cvbc"]), central, _p(blist), nb, _p(bfirst), _p(beta), _p(qe), _p(bpos),
+                                     _p(bd), _p(Ae))
+        assert np.array_equal(qe, qo), f"q after the boundary Jacobian pass (central={central})"
+        for be in range(nb):
+            if bpos[be] >= 0:
+                assert np.array_equal(Ae[bpos[be]], A[bpos[be]]), f"A(l, ghost) of half-edge {be} (central={central})"
