@@ -197,6 +197,14 @@ int pcfd_implicit_iterate(pcfd_ctx* ctx, int refresh_jac, int nsgs, double* sums
    sweeps (nsgs == 0: explicit update), nu~ update with the clip at zero, eddy viscosity into field "mut".
    Reads q, qgrad and timestep as the flow iteration left them.  sumsq (may be NULL) receives sum(b^2). */
 int pcfd_turb_compute(pcfd_ctx* ctx, int nsgs, double* sumsq);
+/* The same computation cut at the reference's exchange points (turb.tcc:183-325), for runs on partitions: the caller
+   exchanges the named field after each phase (pcfd_halo_pack / pcfd_halo_recv_ptr know them).
+     0 blank + turbulence BCs -> halo PCFD_F_TVAR (:185);  1 gradient of tvar -> halo PCFD_F_TGRAD (gradient.tcc:98);
+     2 assembly, wall rows, sumsq = sum(b^2) of this rank's nodes (may be NULL), inverse diagonal;
+     3 ONE symmetric sweep -> halo PCFD_F_TURB_X (crs.tcc:146), repeated nSgs times;
+     4 tvar += x -> halo PCFD_F_TVAR (:325);  5 eddy viscosity (local + ghost nodes).
+   Phases 0..5 in order with nSgs repeats of phase 3 and no exchange are pcfd_turb_compute(ctx, nSgs, sumsq).  (ABI v6) */
+int pcfd_turb_phase(pcfd_ctx* ctx, int phase, double* sumsq);
 
 /* ---- halo exchange: PObj (parallel.tcc).  The send lists are persistent (the reference re-sends the index
    lists on every call, parallel.tcc:809-827).  send_list = PObj::nodePackingList concatenated in peer order

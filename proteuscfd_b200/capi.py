@@ -36,7 +36,7 @@ SYMBOLS = [
     "pcfd_apply_dq", "pcfd_explicit_iterate", "pcfd_implicit_iterate", "pcfd_launch_count",
     "pcfd_profile_enable", "pcfd_profile_reset", "pcfd_profile_count", "pcfd_profile_get",
     "pcfd_ipc_export", "pcfd_ipc_open", "pcfd_ipc_close",
-    "pcfd_turb_compute", "pcfd_halo_configure",
+    "pcfd_turb_compute", "pcfd_turb_phase", "pcfd_halo_configure",
     "pcfd_chem_create", "pcfd_chem_destroy", "pcfd_chem_last_error", "pcfd_chem_mass_production",
     "pcfd_create_fr", "pcfd_widths", "pcfd_limiter_raw", "pcfd_residual_fused", "pcfd_clip_fallbacks",
     "pcfd_set_time_integration", "pcfd_set_gradient_type", "pcfd_set_jacobian_type",
@@ -463,6 +463,16 @@ class Context:
             return None
         d = C.c_double()
         self._ck(self.lib.pcfd_turb_compute(self.h, int(nsgs), C.byref(d)))
+        return d.value
+
+    def turb_phase(self, phase, want_norm=False):
+        """one phase of TurbulenceModel::Compute between the reference's exchange points (see pcfd_turb_phase)"""
+        self.lib.pcfd_turb_phase.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        if not want_norm:
+            self._ck(self.lib.pcfd_turb_phase(self.h, int(phase), None))
+            return None
+        d = C.c_double()
+        self._ck(self.lib.pcfd_turb_phase(self.h, int(phase), C.byref(d)))
         return d.value
 
     def apply_dq(self):

@@ -3055,6 +3055,99 @@ int pcfd_turb_compute(pcfd_ctx* c, int nsgs, double* sumsq) {
   return 0;
 }
 
+// TurbulenceModel::Compute cut at the reference's exchange points (turb.tcc:183-325) for runs on partitions: the same
+// kernels, in the same order, as pcfd_turb_compute; the caller exchanges the named field after each phase.
+//   0  blank the system, turbulence BCs                                  -> halo of tvar        (turb.tcc:185)
+//   1  LSQ gradient of tvar                                              -> halo of tgrad       (gradient.tcc:98)
+//   2  convective / diffusive / source terms, wall rows, sum of b^2 (sumsq, may be NULL), inverse diagonal
+//   3  ONE symmetric Gauss-Seidel sweep (forward + backward)             -> halo of turb_x      (crs.tcc:146)
+//   4  tvar += x                                                         -> halo of tvar        (turb.tcc:325)
+//   5  eddy viscosity of the local and ghost nodes
+int pcfd_turb_phase(pcfd_ctx* c, int phase, double* sumsq) {
+  if (!c) return 1;
+  if (c->fr) return fail(c, "pcfd_turb_phase: not available for the reacting eqnset");
+  if (c->prm.turb_model != 1) return fail(c, "pcfd_turb_phase: the context was created without a turbulence model");
+  CK(cudaSetDevice(c->device));
+  double *tvar = c->f[PCFD_F_TVAR], *tgrad = c->f[PCFD_F_TGRAD], *tb = c->f[PCFD_F_TURB_B], *tx = c->f[PCFD_F_TURB_X],
+         *tA = c->f[PCFD_F_TURB_A];
+  switch (phase) {
+    case 0:
+      CK(cudaMemsetAsync(tA, 0, c->fsize[PCFD_F_TURB_A] * sizeof(double), c->stream));
+      CK(cudaMemsetAsync(tx, 0, c->fsize[PCFD_F_TURB_X] * sizeof(double), c->stream));
+      if (c->ntbnodes) {
+        PROF("k_turb_bcs");
+        k_turb_bcs<<<nblk(c->ntbnodes, 128), 128, 0, c->stream>>>(c->dm, c->tbnodes, c->ntbnodes, tvar);
+        LAUNCH_CHECK();
+      }
+      return 0;
+    case 1:
+      PROF("k_turb_gradient");
+      k_turb_gradient<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, tvar, c->f[PCFD_F_LSQ_S], tgrad);
+      LAUNCH_CHECK();
+      return 0;
+    case 2:
+      if (c->nedge) {
+        PROF("k_turb_edges");
+        k_turb_edges<<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, c->vp, c->f[PCFD_F_Q], tvar, tgrad, c->posLR, c->posRL,
+                                                                 c->tslots, tA);
+        LAUNCH_CHECK();
+      }
+      if (c->nb) {
+        PROF("k_turb_bedges");
+        k_turb_bedges<<<nblk(c->nb, 128), 128, 0, c->stream>>>(c->dm, c->vp, c->f[PCFD_F_Q], tvar, tgrad, c->bpos, c->tbslots, tA);
+        LAUNCH_CHECK();
+      }
+      PROF("k_turb_node");
+      k_turb_node<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->vp, c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD], tvar,
+                                                              c->f[PCFD_F_WALLDIST], c->f[PCFD_F_TIMESTEP], c->tslots,
+                                                              c->tbslots, c->iau, c->posLR, c->posRL, tb, tA);
+      LAUNCH_CHECK();
+      if (c->nwall) {
+        PROF("k_turb_wall");
+        k_turb_wall<<<nblk(c->nwall, 128), 128, 0, c->stream>>>(c->wnodes, c->nwall, c->ia, c->iau, tb, tx, tA);
+        LAUNCH_CHECK();
+      }
+      if (sumsq) {
+        PROF("k_sumsq_partial");
+        k_sumsq_partial<256, 1><<<RED_BLOCKS, 256, 0, c->stream>>>(tb, c->nnode, c->red);
+        LAUNCH_CHECK();
+        PROF("k_sumsq_final");
+        k_sumsq_final<256, 1><<<1, 256, 0, c->stream>>>(c->red, RED_BLOCKS, c->redout);
+        LAUNCH_CHECK();
+        CK(cudaMemcpyAsync(sumsq, c->redout, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      }
+      PROF("k_turb_invdiag");
+      k_turb_invdiag<<<nblk(c->nnode, 256), 256, 0, c->stream>>>(c->nnode, c->iau, tA);
+      LAUNCH_CHECK();
+      if (sumsq) CK(cudaStreamSynchronize(c->stream));
+      return 0;
+    case 3:
+      for (int dir = 0; dir < 2; dir++) {
+        const std::vector<int>& off = dir ? c->lev_b : c->lev_f;
+        const int* rows = dir ? c->rows_b : c->rows_f;
+        for (size_t l = 0; l + 1 < off.size(); l++) {
+          const int nr = off[l + 1] - off[l];
+          PROF("k_sgs_scalar_level");
+          k_sgs_scalar_level<<<nblk(nr, 128), 128, 0, c->stream>>>(rows + off[l], nr, c->ia, c->ja, tA, tb, tx);
+          LAUNCH_CHECK();
+        }
+      }
+      return 0;
+    case 4:
+      PROF("k_turb_update");
+      k_turb_update<<<nblk(c->nnode, 256), 256, 0, c->stream>>>(c->nnode, tx, tvar);
+      LAUNCH_CHECK();
+      return 0;
+    case 5:
+      PROF("k_turb_mut");
+      k_turb_mut<<<nblk(c->nn, 256), 256, 0, c->stream>>>(c->nn, c->vp, c->f[PCFD_F_Q], tvar, c->f[PCFD_F_MUT]);
+      LAUNCH_CHECK();
+      return 0;
+    default:
+      return fail(c, "pcfd_turb_phase: phase must be 0..5");
+  }
+}
+
 int pcfd_explicit_iterate(pcfd_ctx* c, int refresh_dt, double* sumsq) {
   if (!c) return 1;
   if (refresh_dt && pcfd_timestep(c, nullptr)) return 1;

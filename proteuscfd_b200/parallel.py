@@ -275,6 +275,26 @@ class DistributedHotPath:
         self.x.update(capi.F_LIMITER)       # limiters.tcc:128
         return c.residual(want_norms=want_norms)
 
+    def turb_compute(self, nsgs, want_norm=False):
+        """TurbulenceModel::Compute (ucs/turb.tcc:163-339, Spalart-Allmaras) across ranks: the phases of pcfd_turb_phase
+        with the reference's exchanges in the reference's places; returns the all-reduced sum(b^2) when asked.
+        Block-Jacobi across partitions, like CRS::SGS (ghost values of x lag one sweep)."""
+        c = self.ctx
+        c.turb_phase(0)
+        self.x.update(capi.F_TVAR)          # turb.tcc:185
+        c.turb_phase(1)
+        self.x.update(capi.F_TGRAD)         # gradient.tcc:98
+        s = c.turb_phase(2, want_norm=want_norm)
+        if want_norm:
+            s = self.sum(s)                 # ParallelL2Norm, turb.tcc:256
+        for _ in range(nsgs):
+            c.turb_phase(3)
+            self.x.update(capi.F_TURB_X)    # crs.tcc:146
+        c.turb_phase(4)
+        self.x.update(capi.F_TVAR)          # turb.tcc:325
+        c.turb_phase(5)
+        return s
+
     def explicit_iterate(self, refresh_dt=True):
         c = self.ctx
         if refresh_dt:

@@ -5,7 +5,8 @@ GPU, no numerics."""
 from proteuscfd_b200 import capi
 from proteuscfd_b200.parallel import DistributedHotPath
 
-NAMES = {capi.F_Q: "q", capi.F_QGRAD: "qgrad", capi.F_LIMITER: "limiter", capi.F_X: "x", capi.F_LSQ_S: "s", capi.F_LSQ_SW: "sw"}
+NAMES = {capi.F_Q: "q", capi.F_QGRAD: "qgrad", capi.F_LIMITER: "limiter", capi.F_X: "x", capi.F_LSQ_S: "s", capi.F_LSQ_SW: "sw",
+         capi.F_TVAR: "tvar", capi.F_TGRAD: "tgrad", capi.F_TURB_X: "turb_x"}
 
 
 class Recorder:
@@ -22,6 +23,10 @@ class Recorder:
         hit = self.clip_hits[self.nfused] if self.nfused < len(self.clip_hits) else False
         self.nfused += 1
         return None, hit
+
+    def turb_phase(self, phase, want_norm=False):
+        self.log.append(f"turb_phase{phase}")
+        return 2.0 if want_norm else None
 
     def __getattr__(self, name):
         def call(*a, **k):
@@ -70,3 +75,18 @@ def test_clip_hit_on_any_rank_falls_back_to_the_ordered_path():
     i = log.index("residual_fused")
     assert log[i + 1: i + 4] == ["limiter", "halo:limiter", "residual"]
     assert hp.clip_fallbacks == 1 and log.count("gradient") == 1       # the gradient is not redone
+
+
+def test_turbulence_compute_follows_the_reference_exchange_points():
+    """TurbulenceModel::Compute (ucs/turb.tcc:163-339): UpdateBCs, halo of tvar (:185), gradient + its halo (:192,
+    gradient.tcc:98), assembly and the all-reduced residual (:256), nSgs sweeps with a halo of x each (crs.tcc:146), the
+    update and the halo of tvar (:325), then the eddy viscosity"""
+    log = []
+    ctx = Recorder(log)
+    hp = DistributedHotPath(ctx, ctx, allreduce_sum=lambda v: 3.0 * v)
+    s = hp.turb_compute(2, want_norm=True)
+    assert log == ["turb_phase0", "halo:tvar", "turb_phase1", "halo:tgrad", "turb_phase2", "turb_phase3", "halo:turb_x",
+                   "turb_phase3", "halo:turb_x", "turb_phase4", "halo:tvar", "turb_phase5"]
+    assert s == 6.0      # the residual sum of squares goes through the all-reduce
+    log.clear()
+    assert hp.turb_compute(1) is None and log.count("turb_phase3") == 1

@@ -217,3 +217,36 @@ def test_variant_setters_reject_what_is_not_built():
         ctx.set_gradient_type(2)
     ctx.set_jacobian_type(1, 0)
     ctx.set_gradient_type(1)
+
+
+def test_turb_phases_equal_turb_compute():
+    """pcfd_turb_phase 0..5 (nSgs repeats of phase 3, no exchange) relaunch the kernels of pcfd_turb_compute in the same
+    order: on one partition every turbulence field and the residual sum must come out bit-identical"""
+    from proteuscfd_b200 import capi
+    from tests.test_gpu_parity import golden_ctx
+    res = []
+    for phased in (False, True):
+        ctx, g, meta = golden_ctx("box6_sa_implicit")
+        ctx.set_field(capi.F_Q, g["turb_q"])             # the set-up of test_spalart_allmaras_compute_vs_reference
+        ctx.set_field(capi.F_QGRAD, g["turb_qgrad"])
+        ctx.set_field(capi.F_TIMESTEP, g["turb_dt"])
+        ctx.set_field(capi.F_LSQ_S, g["lsq_s"])
+        ctx.set_field(capi.F_WALLDIST, g["wallDistance"])
+        ctx.set_field(capi.F_TVAR, g["turb_tvar0"])
+        nsgs = 3
+        if phased:
+            ctx.turb_phase(0)
+            ctx.turb_phase(1)
+            s = ctx.turb_phase(2, want_norm=True)
+            for _ in range(nsgs):
+                ctx.turb_phase(3)
+            ctx.turb_phase(4)
+            ctx.turb_phase(5)
+        else:
+            s = ctx.turb_compute(nsgs, want_norm=True)
+        res.append((s, ctx.get_field(capi.F_TVAR), ctx.get_field(capi.F_MUT), ctx.get_field(capi.F_TURB_X),
+                    ctx.get_field(capi.F_TGRAD)))
+    assert res[0][0] == res[1][0]
+    for a, b, what in zip(res[0][1:], res[1][1:], ("tvar", "mut", "turb_x", "tgrad")):
+        exact(b, a, what)
+    assert np.abs(res[0][3]).max() > 0
