@@ -23,6 +23,10 @@ timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --c
 timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file "$out/launches_pg.csv" \
     --profile-from-start off python tools/profile_run.py --n 118 --nsgs 2 > "$out/launches_pg.log" 2>&1
 
+# 2b. the session-6 variants (Green-Gauss gradient, central-difference Jacobian refresh): duration-only launch list, ~40 s
+timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file "$out/launches_pg_variants.csv" \
+    --profile-from-start off python tools/profile_run.py --n 118 --nsgs 2 --green-gauss --jac-central > "$out/launches_pg_variants.log" 2>&1
+
 # 3. --set full of the kernels that carry the headline numbers (one launch each; the SGS tile kernel twice): ~2 min
 timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off \
     -k regex:"k_flux_edges|k_gradient|k_limiter|k_residual_gather|k_timestep" -c 6 -o "$out/prof_explicit" \

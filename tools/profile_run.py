@@ -19,12 +19,18 @@ def main():
     ap.add_argument("--nsgs", type=int, default=1)
     ap.add_argument("--explicit-only", action="store_true")
     ap.add_argument("--natural", action="store_true", help="lexicographic node numbering (the explicit bench case)")
+    ap.add_argument("--green-gauss", action="store_true", help="Param::gradType = 1 (k_gradient_gg)")
+    ap.add_argument("--jac-central", action="store_true", help="fieldJacType = boundaryJacType = 1 (k_jac_*_central)")
     args = ap.parse_args()
     import torch
     from proteuscfd_b200 import capi
     from proteuscfd_b200.cases import box_case
     mesh, params, q = box_case(args.n, colored=not args.natural, device="cuda:0")
     ctx = capi.Context(mesh, params, device=0)
+    if args.green_gauss:
+        ctx.set_gradient_type(1)
+    if args.jac_central:
+        ctx.set_jacobian_type(1, 1)
     ctx.lsq_coefficients()
     ctx.set_field(capi.F_Q, q)
     ctx.explicit_iterate(refresh_dt=True)      # warm-up
