@@ -1,6 +1,8 @@
 """GPU parity tests of the variants added AFTER the round's GPU minutes ran out (ABI v6): Green-Gauss gradients
 (Param::gradType = 1, gradient.tcc:170-248) for both eqnset families and central-difference flux Jacobians
-(fieldJacType = boundaryJacType = 1, jacobian.tcc:306-366, 546-640) for the perfect-gas eqnsets.
+(fieldJacType = boundaryJacType = 1, jacobian.tcc:306-366, 546-640) for both families, their end-to-end drop-in runs through
+include/pcfd_host.hpp, the error behaviour of the two setters, and pcfd_turb_phase (Spalart-Allmaras cut at the reference's
+exchange points) against the monolithic pcfd_turb_compute.
 
 Status: the kernels compile for sm_100a and the oracle side of each comparison is pinned bit-exact on the same
 reference-generated fixtures (tests/test_oracle.py, tests/test_oracle_fr.py); the kernel source itself, compiled for the
