@@ -1541,14 +1541,23 @@ static double sa_eddy_viscosity(double rho, double nu, double nut)
   return rho*nut*fv1;
 }
 
-double orc_turb_sa(const orc_case* c, int nsgs, const double* q, const double* qgrad, const double* s,
-		   const double* dist, const double* dt, const int* ia, const int* ja, const int* iau,
-		   double* tvar, double* tgrad, double* b, double* A, double* x, double* mut)
+/* One phase of the model update, cut at the reference's exchange points (turb.tcc:183-325) so that a test can replay a
+   multi-rank run rank by rank with the halos in between:
+     0 blank the system + BCs                 -> halo of tvar  (turb.tcc:185)
+     1 gradient of tvar                       -> halo of tgrad (gradient.tcc:98)
+     2 assembly, residual norm (returned: sum of b^2), inverse diagonal when nsgs > 0
+     3 ONE symmetric Gauss-Seidel sweep (nsgs > 0) or the explicit update (nsgs == 0) -> halo of x (crs.tcc:146)
+     4 update + clip                          -> halo of tvar  (turb.tcc:325)
+     5 eddy viscosity of local and ghost nodes */
+double orc_turb_sa_phase(const orc_case* c, int phase, int nsgs, const double* q, const double* qgrad, const double* s,
+			 const double* dist, const double* dt, const int* ia, const int* ja, const int* iau,
+			 double* tvar, double* tgrad, double* b, double* A, double* x, double* mut)
 {
-  int e, i, k, isgs, dir;
+  int e, i, k, dir;
   int nnode = c->nnode, nn = c->nnode + c->gnode, nb = c->nbedge + c->ngedge;
   double Re = c->Re/c->mach;   /* CompressibleEqnSet::GetRe, compressible.tcc:1190-1199 */
-  double resid;
+  double resid = 0.0;
+  if(phase == 0){
   /* crs.BlankSystem (crs.tcc:417-425) */
   for(k = 0; k < ia[nnode]; k++) A[k] = 0.0;
   for(i = 0; i < nn; i++) x[i] = 0.0;
@@ -1563,7 +1572,8 @@ double orc_turb_sa(const orc_case* c, int nsgs, const double* q, const double* q
     else if(t == ORC_BC_SYMMETRY || t == ORC_BC_IMPERMEABLE_WALL) tvar[r] = tvar[l];
     else tvar[r] = SA_TINF;
   }
-
+  }
+  else if(phase == 1){
   /* unweighted LSQ gradient of tvar (turb.tcc:186-190; gradient.tcc:57-112, 251-378, 545-565) */
   for(i = 0; i < nn*3; i++) tgrad[i] = 0.0;
   for(e = 0; e < c->nedge + nb; e++){
@@ -1589,7 +1599,8 @@ double orc_turb_sa(const orc_case* c, int nsgs, const double* q, const double* q
       for(j = 0; j < 3; j++) tgrad[l*3 + j] -= dot*avec[j];
     }
   }
-
+  }
+  else if(phase == 2){
   /* Convective: Kernel_Convective turb.tcc:342-449, Bkernel_Convective :451-561 (first order) */
   for(e = 0; e < c->nedge; e++){
     int l = c->edges_n[2*e], r = c->edges_n[2*e+1];
@@ -1721,11 +1732,14 @@ double orc_turb_sa(const orc_case* c, int nsgs, const double* q, const double* q
   {
     double ss = 0.0;
     for(i = 0; i < nnode; i++) ss += b[i]*b[i];
-    resid = sqrt(ss)/(double)nnode;
+    resid = ss;
   }
-  if(nsgs > 0){
+  if(nsgs > 0)
     for(i = 0; i < nnode; i++) A[iau[i]] = 1.0/A[iau[i]];   /* PrepareSGS, crsmatrix.tcc:852-858 */
-    for(isgs = 0; isgs < nsgs; isgs++){
+  }
+  else if(phase == 3){
+  if(nsgs > 0){
+    {
       for(dir = 0; dir < 2; dir++){
 	for(k = 0; k < nnode; k++){
 	  int indx;
@@ -1744,18 +1758,39 @@ double orc_turb_sa(const orc_case* c, int nsgs, const double* q, const double* q
   else{
     for(i = 0; i < nnode; i++) x[i] = b[i]*dt[i]/c->vol[i];
   }
+  }
+  else if(phase == 4){
   /* update + clip (turb.tcc:306-320) */
   for(i = 0; i < nnode; i++){
     tvar[i] += x[i];
     if(tvar[i] < 0.0) tvar[i] = 0.0;
   }
+  }
+  else if(phase == 5){
   /* eddy viscosity (turb.tcc:324-336) */
   for(i = 0; i < nn; i++){
     const double* Q = &q[i*NVARS];
     double rho = Q[0], mu = compute_viscosity(c, Q), nu = mu/rho;
     mut[i] = sa_eddy_viscosity(rho, nu, tvar[i]);
   }
+  }
   return resid;
+}
+
+double orc_turb_sa(const orc_case* c, int nsgs, const double* q, const double* qgrad, const double* s,
+		   const double* dist, const double* dt, const int* ia, const int* ja, const int* iau,
+		   double* tvar, double* tgrad, double* b, double* A, double* x, double* mut)
+{
+  int ph, isgs;
+  double ss = 0.0;
+  for(ph = 0; ph <= 5; ph++){
+    int reps = (ph == 3 && nsgs > 0) ? nsgs : 1;
+    for(isgs = 0; isgs < reps; isgs++){
+      double r = orc_turb_sa_phase(c, ph, nsgs, q, qgrad, s, dist, dt, ia, ja, iau, tvar, tgrad, b, A, x, mut);
+      if(ph == 2) ss = r;
+    }
+  }
+  return sqrt(ss)/(double)c->nnode;
 }
 
 /* ------------------------------------------------ finite-rate chemistry */

@@ -117,6 +117,11 @@ int orc_normal_node(const orc_case* c, int e);
 double orc_turb_sa(const orc_case* c, int nsgs, const double* q, const double* qgrad, const double* s,
 		   const double* dist, const double* dt, const int* ia, const int* ja, const int* iau,
 		   double* tvar, double* tgrad, double* b, double* A, double* x, double* mut);
+/* the same update one phase at a time (0..5, see pcfd_oracle.c), for per-rank replays with halos in between; phase 2
+   returns the sum of b^2 */
+double orc_turb_sa_phase(const orc_case* c, int phase, int nsgs, const double* q, const double* qgrad, const double* s,
+		   const double* dist, const double* dt, const int* ia, const int* ja, const int* iau,
+		   double* tvar, double* tgrad, double* b, double* A, double* x, double* mut);
 
 /* compressible.tcc:93-230 -- exposed for unit tests */
 void orc_roe_flux(const double* QL, const double* QR, const double* avec, double vdotn, double gamma,

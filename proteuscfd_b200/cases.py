@@ -63,7 +63,7 @@ def smooth_state(xyz, mach, gamma, amp=1.0):
 
 def box_case(n, jitter=0.15, mach=0.5, gamma=1.4, cfl=0.5, limiter=2, sorder=2, colored=False, ramp_deg=0.0,
              bc=None, device="cpu", amp=1.0, seed=1234, viscous=False, reynolds=400.0, twall=1.1, tref=300.0,
-             enable_vnn=0):
+             enable_vnn=0, turb=False):
     """Return (mesh dict, params dict, q [(nnode+nbnode)*10]) for an n^3-hex Kuhn box.  viscous=True selects the
     compressibleNS eqnset with a no-slip floor (wall temperature `twall`, non-dimensional; < 0: adiabatic)."""
     xyz, tets, tris, tags = kuhn_box(n, jitter=jitter, seed=seed, ramp_deg=ramp_deg)
@@ -81,7 +81,7 @@ def box_case(n, jitter=0.15, mach=0.5, gamma=1.4, cfl=0.5, limiter=2, sorder=2, 
                   chi=0.0, cfl=cfl, qinf=qinf)
     if viscous:
         params.update(eqnset=capi.EQNSET_COMPRESSIBLE_NS, viscous=1, Re=reynolds, Pr=0.72, PrT=0.85, tref=tref, mach=mach,
-                      enable_vnn=enable_vnn, vnn=20.0)
+                      enable_vnn=enable_vnn, vnn=20.0, turb_model=1 if turb else 0)
         mesh["bedges_twall"] = np.where(mesh["bedges_bctype"] == capi.BC_NOSLIP, twall, 1.0 / tref)
     nn, nb = mesh["nnode"], mesh["nbnode"]
     q = np.zeros((nn + nb, 10))
@@ -116,7 +116,8 @@ def _owned_order(n, k0, k1, colored):
 
 
 def slab_case(n, rank, nranks, jitter=0.15, mach=0.5, gamma=1.4, cfl=0.5, limiter=2, sorder=2, colored=False,
-              device="cpu", seed=1234):
+              device="cpu", seed=1234, bc=None, viscous=False, reynolds=400.0, twall=1.1, tref=300.0, turb=False,
+              enable_vnn=0):
     """Partition `rank` of a box of n x n x (n*nranks) hexes cut into z-slabs, in the layout udecomp writes
     (ucs/decomp.cpp:122-273): owned nodes first, ghost nodes grouped by owning rank, cut edges as ghost half-edges
     carrying the full dual face, `gNodeOwner` / `gNodeLocalId` for the halo maps.  Every rank builds only its own
@@ -186,9 +187,10 @@ def slab_case(n, rank, nranks, jitter=0.15, mach=0.5, gamma=1.4, cfl=0.5, limite
     ipsp[1:] = np.cumsum(np.bincount(pa, minlength=nnode))
     inv = np.empty(nnode + gnode, dtype=np.int64)
     inv[new[new >= 0]] = np.nonzero(new >= 0)[0]
-    lut = np.zeros(max(BOX_BC) + 1, dtype=np.int32)
-    for t, bc in BOX_BC.items():
-        lut[t] = bc
+    table = bc or (NS_BC if viscous else BOX_BC)
+    lut = np.zeros(max(table) + 1, dtype=np.int32)
+    for t, b_ in table.items():
+        lut[t] = b_
     mesh = dict(
         nnode=nnode, gnode=gnode, nbnode=nbedge, nedge=len(edges_n), nbedge=nbedge, ngedge=len(gh_n),
         edges_n=edges_n.astype(np.int32).reshape(-1), edges_a=np.ascontiguousarray(edges_a).reshape(-1),
@@ -201,6 +203,10 @@ def slab_case(n, rank, nranks, jitter=0.15, mach=0.5, gamma=1.4, cfl=0.5, limite
     qinf = freestream(mach, gamma)
     params = dict(eqnset=capi.EQNSET_COMPRESSIBLE_EULER, sorder=sorder, limiter=limiter, no_cvbc=0, gamma=gamma,
                   chi=0.0, cfl=cfl, qinf=qinf)
+    if viscous:     # compressibleNS (+ Spalart-Allmaras): as box_case
+        params.update(eqnset=capi.EQNSET_COMPRESSIBLE_NS, viscous=1, Re=reynolds, Pr=0.72, PrT=0.85, tref=tref, mach=mach,
+                      enable_vnn=enable_vnn, vnn=20.0, turb_model=1 if turb else 0)
+        mesh["bedges_twall"] = np.where(mesh["bedges_bctype"][:nbedge] == capi.BC_NOSLIP, twall, 1.0 / tref)
     q = np.zeros((nnode + gnode + nbedge, 10))
     q[: nnode + gnode] = smooth_state(mesh["xyz"].reshape(-1, 3), mach, gamma)
     q[nnode + gnode:] = q[b_n[:, 0]]

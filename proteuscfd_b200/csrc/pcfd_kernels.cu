@@ -1803,6 +1803,11 @@ __global__ void k_fill_int(int* p, int n, int v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
+// p[i] = *src if src is given, else v
+__global__ void k_fill_double(double* p, int n, double v, const double* __restrict__ src) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = src ? src[0] : v;
+}
 
 }  // namespace
 
@@ -2645,14 +2650,48 @@ int pcfd_residual(pcfd_ctx* c, double* sumsq) {
   return 0;
 }
 
+// ComputeTimesteps without local time stepping (timestep.tcc:47-74): Param::dt in every cell when it is positive,
+// otherwise the smallest CFL (and VNN) limited step of THIS rank's cells in every cell (the reference takes no
+// minimum across ranks here; the all-reduce of solutionSpace.tcc:712-714 only feeds the residual file).
+static int timestep_global(pcfd_ctx* c, double* dtmin) {
+  double* dt = c->f[PCFD_F_TIMESTEP];
+  if (c->time_dt > 0.0) {
+    PROF("k_fill_double");
+    k_fill_double<<<nblk(c->nnode, 256), 256, 0, c->stream>>>(dt, c->nnode, c->time_dt, nullptr);
+    LAUNCH_CHECK();
+    if (dtmin) *dtmin = c->time_dt;
+    return 0;
+  }
+  PROF("k_min_partial");
+  k_min_partial<256><<<RED_BLOCKS, 256, 0, c->stream>>>(dt, c->nnode, c->red);
+  LAUNCH_CHECK();
+  PROF("k_min_final");
+  k_min_final<256><<<1, 256, 0, c->stream>>>(c->red, RED_BLOCKS, c->redout + 8);
+  LAUNCH_CHECK();
+  PROF("k_fill_double");
+  k_fill_double<<<nblk(c->nnode, 256), 256, 0, c->stream>>>(dt, c->nnode, 0.0, c->redout + 8);
+  LAUNCH_CHECK();
+  if (dtmin) {
+    CK(cudaMemcpyAsync(dtmin, c->redout + 8, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+
 int pcfd_timestep(pcfd_ctx* c, double* dtmin) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
-  if (c->fr) return pcfd_fr_timestep(c, dtmin);
+  const bool global_dt = !c->time_local;
+  if (global_dt && c->time_dt > 0.0) return timestep_global(c, dtmin);   // no eigenvalue pass at all (timestep.tcc:50-54)
+  if (c->fr) {
+    if (pcfd_fr_timestep(c, global_dt ? nullptr : dtmin)) return 1;
+    return global_dt ? timestep_global(c, dtmin) : 0;
+  }
   PROF("k_timestep");
   k_timestep<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->prm.gamma, c->prm.cfl, c->f[PCFD_F_Q], c->vnn23,
                                                          c->f[PCFD_F_TIMESTEP]);
   LAUNCH_CHECK();
+  if (global_dt) return timestep_global(c, dtmin);
   if (dtmin) {
     PROF("k_min_partial");
     k_min_partial<256><<<RED_BLOCKS, 256, 0, c->stream>>>(c->f[PCFD_F_TIMESTEP], c->nnode, c->red);

@@ -161,6 +161,12 @@ class NcclExchange:
     def __init__(self, ctx, pobj, dist, torch, device):
         self.ctx, self.p, self.dist, self.torch = ctx, pobj, dist, torch
         pobj.attach(ctx)
+        # the pack kernel and ncclSend must share a stream: the context launches on torch's current one from here on
+        cur = torch.cuda.current_stream(device).cuda_stream
+        if cur == 0:
+            raise RuntimeError("NcclExchange: make a non-default torch stream current first (the context cannot launch on "
+                               "the legacy default stream; pcfd_set_stream(NULL) selects its own stream)")
+        ctx.set_stream(cur)
         self.device = device
         self.stage = {}
         self.views = {}
@@ -202,10 +208,13 @@ class PutExchange:
     about to be overwritten, the second that every put has landed before anyone reads."""
 
     FIELDS = (capi.F_Q, capi.F_QGRAD, capi.F_LIMITER, capi.F_X, capi.F_LSQ_S, capi.F_LSQ_SW)
+    TURB_FIELDS = (capi.F_TVAR, capi.F_TGRAD, capi.F_TURB_X)    # allocated only with a turbulence model
 
     def __init__(self, ctx, pobj, dist, torch, device, group):
         self.ctx, self.p, self.dist, self.torch = ctx, pobj, dist, torch
         pobj.attach(ctx)
+        if ctx.field_size(capi.F_TVAR) > 0:
+            self.FIELDS = self.FIELDS + self.TURB_FIELDS
         self.token = torch.zeros(1, device=device)
         mine = {"nnode": ctx.nnode, "recv_offsets": [int(o) for o in pobj.commOffsetsRecv],
                 "handles": {f: ctx.ipc_export(f) for f in self.FIELDS}}
@@ -226,6 +235,8 @@ class PutExchange:
         self.dist.all_reduce(self.token)     # on the current stream: orders the puts against the peers' kernels
 
     def update(self, field):
+        if field not in self.dst:
+            raise KeyError(f"PutExchange: field {field} was not exported (not allocated in this context)")
         self._barrier()
         for peer, dst in self.dst[field].items():
             self.ctx.halo_pack(field, dst, peer=peer)

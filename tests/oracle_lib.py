@@ -156,6 +156,19 @@ class Oracle:
         return out
 
 
+    def turb_sa_phase(self, phase, nsgs, q, qgrad, s, dist, dt, ia, ja, iau, st):
+        """One phase (0..5) of the same update on the state dict `st` (tvar, tgrad, b, A, x, mut: allocated by
+        turb_sa_state); phase 2 returns the sum of b^2."""
+        self.lib.orc_turb_sa_phase.restype = C.c_double
+        return self.lib.orc_turb_sa_phase(C.byref(self.c), int(phase), int(nsgs), _d(q), _d(qgrad), _d(s), _d(dist), _d(dt),
+                                          _i(ia), _i(ja), _i(iau), _d(st["tvar"]), _d(st["tgrad"]), _d(st["b"]), _d(st["A"]),
+                                          _d(st["x"]), _d(st["mut"]))
+
+    def turb_sa_state(self, tvar):
+        return dict(tvar=tvar, tgrad=np.zeros(self.nn * 3), b=np.zeros(self.nnode), A=np.zeros(self.nblocks),
+                    x=np.zeros(self.nn), mut=np.zeros(self.nn))
+
+
 def oracle_for(lib, mesh, params):
     """Bind the C oracle to a mesh/params pair in the C-ABI dict form (proteuscfd_b200.cases)."""
     g = {k: np.asarray(mesh[k]) for k in ("edges_n", "edges_a", "bedges_n", "bedges_a", "bedges_bctype", "xyz", "vol",

@@ -148,6 +148,30 @@ def test_fr_jacobian_lu_sgs():
     exact(ctx.get_field(capi.F_Q), g["q1"], "q1")
 
 
+def test_fr_reactions_on_update_with_reference_matrix():
+    """Pins the split claimed in the module docstring: with reactions ON, the only thing that keeps the implicit update
+    away from the north-star 1e-12 is the reference's finite-difference source Jacobian (libm rounding / h) in the
+    diagonal blocks.  Here the fixture's A is injected and everything else is ours (BCs, gradient, limiter, HLLC residual
+    + finite-rate source from q_pre, LU, SGS): x must then agree to 1e-12 of each equation's largest update."""
+    from proteuscfd_b200 import capi
+    ctx, g, meta = fr_ctx("box4_fr_implicit")
+    assert int(meta["rxnOn"]) == 1
+    ctx.lsq_coefficients()
+    ctx.set_field(capi.F_Q, g["q_pre"])
+    ctx.update_bcs()
+    ctx.gradient()
+    ctx.limiter()
+    ctx.residual()
+    ctx.set_field(capi.F_A, g["A"])
+    ctx.prepare_sgs()
+    ctx.blank_x()
+    ctx.sgs(int(meta["nSgs"]), want_ddq=False)
+    x = ctx.get_field(capi.F_X).reshape(-1, NEQ)
+    xref = g["x"].reshape(-1, NEQ)
+    err = np.abs(x - xref).max(axis=0) / np.abs(xref).max(axis=0)
+    assert np.all(err <= 1e-12), f"relative error of the update per equation with the reference's A: {err}"
+
+
 def test_fr_implicit_iteration_close():
     """the whole implicit iteration from q_pre, own residual and own Jacobian: 1e-5 relative on the update."""
     from proteuscfd_b200 import capi

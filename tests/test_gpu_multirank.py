@@ -372,3 +372,114 @@ def test_nccl_two_process_exchange():
                         "box8_2rank_explicit", "put"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("RANK_OK") == 2, r.stdout[-3000:]
+
+
+@pytest.mark.parametrize("nr,wall_tag", [(2, 5), (3, 3)])
+def test_sa_slab_partitions_vs_oracle(oracle, nr, wall_tag):
+    """Spalart-Allmaras across partitions (BASELINE configs[3]; TurbulenceModel::Compute, ucs/turb.tcc:163-339 with its
+    exchanges at :185, gradient.tcc:98, crs.tcc:146, :325): z-slabs of a laminar-NS + SA box on one GPU, stepped through
+    DistributedHotPath.turb_compute's phase / halo order with direct-put halos, against the oracle's
+    orc_turb_sa_phase replayed per rank with a numpy halo through the same maps.  wall_tag 5: the no-slip floor lives
+    in rank 0 only (the other ranks' wall distance comes from rank 0's wall nodes); 3: every slab owns a strip of wall.
+    tgrad and the matrix pattern bit-exact, everything downstream of Sutherland's law / the source term's libm calls to
+    1e-12 per node (tests/test_gpu_viscous.py)."""
+    from proteuscfd_b200 import capi
+    from proteuscfd_b200.cases import NS_BC, slab_case
+    from proteuscfd_b200.parallel import LoopbackExchange, build_local_group_maps
+    from proteuscfd_b200.walldist import nearest_distance, wall_points
+    from tests.oracle_lib import oracle_for
+    from tests.test_gpu_viscous import close_per_node
+    nsgs = 3
+    bc = dict(NS_BC)
+    bc[5] = capi.BC_SYMMETRY
+    bc[wall_tag] = capi.BC_NOSLIP
+    parts = [slab_case(6, r, nr, viscous=True, turb=True, colored=True, cfl=5.0, bc=bc) for r in range(nr)]
+    maps = [(m["gNodeOwner"], m["gNodeLocalId"]) for m, _, _ in parts]
+    pobjs = build_local_group_maps(maps)
+    orcs = [oracle_for(oracle, m, p) for m, p, _ in parts]
+    ctxs = [capi.Context(m, p) for m, p, _ in parts]
+    x = LoopbackExchange(ctxs, build_local_group_maps(maps))
+    nn = [m["nnode"] for m, _, _ in parts]
+    nl = [m["nnode"] + m["gnode"] for m, _, _ in parts]
+
+    def halo(arrs, w):
+        packed = [pobjs[r].pack_numpy(arrs[r], w) for r in range(nr)]
+        for r in range(nr):
+            pobjs[r].unpack_numpy(arrs[r], w, nn[r], [packed[p][r] for p in range(nr)])
+
+    # wall distance: nearest viscous wall node of ANY rank (walldist.tcc:24-113)
+    pts = np.concatenate([wall_points(m) for m, _, _ in parts])
+    assert len(pts) > 0
+    dist = [nearest_distance(m["xyz"].reshape(-1, 3)[: nl[r]], pts) for r, (m, _, _) in enumerate(parts)]
+    # the flow side of the model's inputs from the oracle (bit-exact against the GPU elsewhere in this file)
+    beta = np.zeros(1)
+    qs = [q.copy() for _, _, q in parts]
+    ss_, sws = zip(*[o.lsq() for o in orcs])
+    ss_, sws = list(ss_), list(sws)
+    halo(ss_, 6)
+    halo(sws, 6)
+    for r in range(nr):
+        orcs[r].update_bcs(qs[r], beta)
+    halo(qs, 10)
+    dts = [orcs[r].timestep(qs[r], beta)[0] for r in range(nr)]
+    grads = [orcs[r].gradient(qs[r], sws[r]) for r in range(nr)]
+    halo(grads, 27)
+    crs = [o.crs_init() for o in orcs]
+    rng = np.random.default_rng(7)
+    sts = []
+    for r, (m, _, _) in enumerate(parts):
+        # nu~ = free-stream value modulated smoothly in space (consistent across ranks: a function of the coordinates)
+        X = m["xyz"].reshape(-1, 3)[: nl[r]]
+        tv = np.zeros(nl[r] + m["nbnode"])
+        tv[: nl[r]] = 1.341946 * (1.0 + 0.3 * np.sin(2 * np.pi * X[:, 0]) * np.cos(2 * np.pi * X[:, 2]) + 0.2 * X[:, 1])
+        sts.append(orcs[r].turb_sa_state(tv))
+        c = ctxs[r]
+        c.set_field(capi.F_Q, qs[r])
+        c.set_field(capi.F_QGRAD, grads[r])
+        c.set_field(capi.F_TIMESTEP, dts[r])
+        c.set_field(capi.F_LSQ_S, ss_[r])
+        c.set_field(capi.F_WALLDIST, dist[r])
+        c.set_field(capi.F_TVAR, tv.copy())
+
+    def ophase(ph):
+        return [orcs[r].turb_sa_phase(ph, nsgs, qs[r], grads[r], ss_[r], dist[r], dts[r], *crs[r], sts[r]) for r in range(nr)]
+
+    # ---- oracle, rank by rank, halos at the reference's exchange points
+    ophase(0)
+    halo([s["tvar"] for s in sts], 1)
+    ophase(1)
+    halo([s["tgrad"] for s in sts], 3)
+    osum = sum(ophase(2))
+    for _ in range(nsgs):
+        ophase(3)
+        halo([s["x"] for s in sts], 1)
+    ophase(4)
+    halo([s["tvar"] for s in sts], 1)
+    ophase(5)
+    # ---- GPU: the order of DistributedHotPath.turb_compute, all ranks in lock-step
+    each(ctxs, lambda c: c.turb_phase(0))
+    x.update(capi.F_TVAR)
+    each(ctxs, lambda c: c.turb_phase(1))
+    x.update(capi.F_TGRAD)
+    gsum = sum(c.turb_phase(2, want_norm=True) for c in ctxs)
+    for _ in range(nsgs):
+        each(ctxs, lambda c: c.turb_phase(3))
+        x.update(capi.F_TURB_X)
+    each(ctxs, lambda c: c.turb_phase(4))
+    x.update(capi.F_TVAR)
+    each(ctxs, lambda c: c.turb_phase(5))
+    assert np.isclose(gsum, osum, rtol=1e-11)
+    moved = 0.0
+    for r in range(nr):
+        c, s = ctxs[r], sts[r]
+        exact(c.get_field(capi.F_TGRAD), s["tgrad"], f"tgrad rank {r} (ghost rows included)")
+        close_per_node(c.get_field(capi.F_TURB_B), s["b"], 1, f"turbulence residual rank {r}")
+        close_per_node(c.get_field(capi.F_TURB_A), s["A"], 1, f"turbulence matrix rank {r} (ghost columns included)")
+        close_per_node(c.get_field(capi.F_TURB_X), s["x"], 1, f"turbulence update rank {r} (ghost rows included)")
+        close_per_node(c.get_field(capi.F_TVAR)[: nl[r]], s["tvar"][: nl[r]], 1, f"nu~ rank {r}")
+        close_per_node(c.get_field(capi.F_MUT)[: nl[r]], s["mut"], 1, f"eddy viscosity rank {r}")
+        moved = max(moved, np.abs(s["x"][: nn[r]]).max())
+        # the ghost columns of the scalar matrix are live: the test would not notice a dropped halo otherwise
+        ia, ja, _ = crs[r]
+        assert np.abs(s["A"][ja >= nn[r]]).max() > 0
+    assert moved > 1e-6

@@ -117,3 +117,35 @@ def test_unsteady_reacting(oracle):
     ctx.blank_x()
     ctx.sgs(int(meta["nSgs"]))
     exact(ctx.get_field(capi.F_X), g["x"], "x")
+
+
+@pytest.mark.parametrize("family", ["pg", "fr"])
+def test_global_time_step_branches(family):
+    """ComputeTimesteps without local time stepping (timestep.tcc:47-74): Param::dt everywhere when it is positive; the
+    rank's smallest CFL-limited step everywhere otherwise.  min() is exact, so the second branch is compared with the
+    minimum of the local-time-stepping field, and the diagonal of A with the field actually used."""
+    from proteuscfd_b200 import capi
+    if family == "pg":
+        ctx, g, meta = pg_ctx("box6_unsteady_bdf2")
+    else:
+        from tests.test_gpu_fr import fr_ctx
+        ctx, g, meta = fr_ctx("box4_fr_unsteady")
+    ctx.lsq_coefficients()
+    ctx.set_field(capi.F_Q, g["q0"])
+    ctx.set_time_integration(-1.0, 1, 1, 1)
+    dtmin_local = ctx.timestep()
+    local = ctx.get_field(capi.F_TIMESTEP)
+    assert dtmin_local == local.min() and local.max() > local.min()
+    ctx.set_time_integration(-1.0, 0, 1, 1)          # steady, global step: min over the rank's cells
+    assert ctx.timestep() == dtmin_local
+    exact(ctx.get_field(capi.F_TIMESTEP), np.full_like(local, dtmin_local), "timestep (global minimum)")
+    ctx.set_time_integration(0.0125, 0, 1, 1)        # unsteady, prescribed global step
+    assert ctx.timestep() == 0.0125
+    exact(ctx.get_field(capi.F_TIMESTEP), np.full_like(local, 0.0125), "timestep (Param::dt)")
+    if family == "pg":
+        # explicit update advances every cell with that step (solve.tcc:71-98)
+        ctx.update_bcs(); ctx.gradient(); ctx.limiter(); ctx.residual()
+        b = ctx.get_field(capi.F_B).reshape(-1, 5)
+        ctx.explicit_solve()
+        x = ctx.get_field(capi.F_X).reshape(-1, 5)[: b.shape[0]]
+        exact(x, b * 0.0125 / g["vol"][:, None], "explicit dq with the global step")

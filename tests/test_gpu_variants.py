@@ -1,15 +1,10 @@
-"""GPU parity tests of the variants added AFTER the round's GPU minutes ran out (ABI v6): Green-Gauss gradients
-(Param::gradType = 1, gradient.tcc:170-248) for both eqnset families and central-difference flux Jacobians
-(fieldJacType = boundaryJacType = 1, jacobian.tcc:306-366, 546-640) for both families, their end-to-end drop-in runs through
-include/pcfd_host.hpp, the error behaviour of the two setters, and pcfd_turb_phase (Spalart-Allmaras cut at the reference's
-exchange points) against the monolithic pcfd_turb_compute.
+"""GPU parity tests of the variants of ABI v6: Green-Gauss gradients (Param::gradType = 1, gradient.tcc:170-248) for both
+eqnset families and central-difference flux Jacobians (fieldJacType = boundaryJacType = 1, jacobian.tcc:306-366, 546-640)
+for both families, their end-to-end drop-in runs through include/pcfd_host.hpp, the error behaviour of the two setters,
+and pcfd_turb_phase (Spalart-Allmaras cut at the reference's exchange points) against the monolithic pcfd_turb_compute.
 
-Status: the kernels compile for sm_100a and the oracle side of each comparison is pinned bit-exact on the same
-reference-generated fixtures (tests/test_oracle.py, tests/test_oracle_fr.py); the kernel source itself, compiled for the
-host, reproduces those fixtures bit for bit (tests/test_host_emulation.py) -- but these tests have NOT yet run on a
-B200.  They are therefore `xfail(strict=False)`: an XPASS in the round-end log is the first verification, a failure does
-not hide behind a green suite (it is reported as xfailed, and DESIGN.md lists the variants as "GPU run pending").
-The file sorts last so that a fault in an unverified kernel cannot disturb the verified tests before it.
+First B200 run: the driver's round-1 GPU test pass (GPUTEST_r01.json, 13 xpassed); the xfail marker the file carried
+until then is gone, so a regression now fails the suite.
 
 Bar: BIT-EXACT against the fixtures the reference wrote, like tests/test_gpu_parity.py (ordered gathers, --fmad=false).
 """
@@ -19,8 +14,7 @@ import pytest
 from tests.oracle_lib import oracle_for
 from tests.test_oracle import exact
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="kernels added after the round's GPU budget was spent: first B200 run pending")]
+pytestmark = pytest.mark.gpu
 
 
 def test_green_gauss_gradient_fixture():
