@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PCFD_ABI_VERSION 6
+#define PCFD_ABI_VERSION 7
 
 /* eqnset ids follow eqnset_defines.h / create_functions.h:17-45 */
 enum { PCFD_EQNSET_COMPRESSIBLE_EULER_FR = 0, PCFD_EQNSET_COMPRESSIBLE_NS_FR = 1, PCFD_EQNSET_COMPRESSIBLE_EULER = 2,
@@ -225,6 +225,34 @@ void* pcfd_halo_recv_ptr(pcfd_ctx* ctx, int field, int peer);
 int pcfd_ipc_export(pcfd_ctx* ctx, int field, void* handle64);
 int pcfd_ipc_open(pcfd_ctx* ctx, const void* handle64, void** devptr);
 int pcfd_ipc_close(pcfd_ctx* ctx, void* devptr);
+
+/* ---- collective-free exchange between one-process-per-GPU ranks (ABI v7): the device-resident replacement of
+   PObj::UpdateGeneralVectors (parallel.tcc:779-873).  After pcfd_halo_configure every rank exports one fixed-size blob
+   (CUDA-IPC handles of its exchangeable fields and of a flag page, its node count and receive offsets); the host
+   all-gathers the blobs with its own transport (MPI_Allgather in ucs.x) and hands the table, in rank order, to
+   pcfd_comm_connect.  From then on
+     pcfd_comm_post(field)   ONE kernel: neighbour handshake on epoch flags, gather of nodePackingList rows, stores
+                             straight into the neighbours' ghost segments over NVLink, done flags;
+     pcfd_comm_wait(field)   a one-block kernel that waits for the neighbours' done flags of that post;
+     pcfd_comm_update(field) = post + wait (what UpdateGeneralVectors does).
+   Nothing in them synchronises the host or calls a collective; ghost-independent work queued between post and wait
+   overlaps the transfer.  While connected, pcfd_lsq_coefficients, pcfd_explicit_iterate, pcfd_implicit_iterate and
+   pcfd_turb_compute run the reference's multi-rank sequence themselves (exchanges at solutionSpace.tcc:665, 857,
+   gradient.tcc:98,131-134, limiters.tcc:128, crs.tcc:88,146, turb.tcc:185,325), the pressure-clip decision being taken
+   globally through pcfd_comm_allgather's flag words.  Blobs published by contexts of the SAME process are wired with
+   plain pointers (several ranks as threads of one process: the tests' single-GPU harness). */
+#define PCFD_COMM_MAX_RANKS 64
+size_t pcfd_comm_blob_size(void);
+int pcfd_comm_export(pcfd_ctx* ctx, void* blob);
+int pcfd_comm_connect(pcfd_ctx* ctx, const void* blobs /* nranks * pcfd_comm_blob_size() bytes, rank order */);
+int pcfd_comm_disconnect(pcfd_ctx* ctx);
+int pcfd_comm_connected(const pcfd_ctx* ctx);
+int pcfd_comm_post(pcfd_ctx* ctx, int field);
+int pcfd_comm_wait(pcfd_ctx* ctx, int field);
+int pcfd_comm_update(pcfd_ctx* ctx, int field);
+/* the reference's small reductions (ParallelL2Norm parallel.h:160-219, MPI_MIN of dtmin solutionSpace.tcc:712-714):
+   every rank contributes n <= 8 doubles, out[r*n + k] = value k of rank r (host buffers; waits for the stream) */
+int pcfd_comm_allgather(pcfd_ctx* ctx, const double* vals, int n, double* out);
 
 /* number of CUDA kernels this context has launched since creation */
 long long pcfd_launch_count(const pcfd_ctx* ctx);

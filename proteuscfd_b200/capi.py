@@ -41,6 +41,8 @@ SYMBOLS = [
     "pcfd_create_fr", "pcfd_widths", "pcfd_limiter_raw", "pcfd_residual_fused", "pcfd_clip_fallbacks",
     "pcfd_set_time_integration", "pcfd_set_gradient_type", "pcfd_set_jacobian_type",
     "pcfd_chem_source_term", "pcfd_chem_source_term_device", "pcfd_halo_width", "pcfd_halo_send_total", "pcfd_halo_pack", "pcfd_halo_recv_ptr",
+    "pcfd_comm_blob_size", "pcfd_comm_export", "pcfd_comm_connect", "pcfd_comm_disconnect", "pcfd_comm_connected",
+    "pcfd_comm_post", "pcfd_comm_wait", "pcfd_comm_update", "pcfd_comm_allgather",
 ]
 
 
@@ -198,6 +200,16 @@ def load_library(path=LIB_PATH):
     lib.pcfd_halo_pack.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.pcfd_halo_recv_ptr.restype = C.c_void_p
     lib.pcfd_halo_recv_ptr.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.pcfd_comm_blob_size.restype = C.c_size_t
+    lib.pcfd_comm_blob_size.argtypes = []
+    lib.pcfd_comm_export.argtypes = [C.c_void_p, C.c_void_p]
+    lib.pcfd_comm_connect.argtypes = [C.c_void_p, C.c_void_p]
+    lib.pcfd_comm_disconnect.argtypes = [C.c_void_p]
+    lib.pcfd_comm_connected.argtypes = [C.c_void_p]
+    for name in ("pcfd_comm_post", "pcfd_comm_wait", "pcfd_comm_update"):
+        getattr(lib, name).argtypes = [C.c_void_p, C.c_int]
+    lib.pcfd_comm_allgather.argtypes = [C.c_void_p, _dp, C.c_int, _dp]
+    lib.pcfd_turb_phase.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     for name in ("pcfd_destroy", "pcfd_synchronize", "pcfd_lsq_coefficients", "pcfd_update_bcs", "pcfd_gradient",
                  "pcfd_limiter", "pcfd_explicit_solve", "pcfd_jacobian", "pcfd_prepare_sgs", "pcfd_blank_x",
                  "pcfd_apply_dq"):
@@ -383,6 +395,38 @@ class Context:
     def ipc_close(self, ptr):
         self._ck(self.lib.pcfd_ipc_close(self.h, C.c_void_p(ptr)))
 
+    # -- collective-free exchange (pcfd_comm_*): blobs travel through whatever the host has
+    def comm_export(self):
+        buf = C.create_string_buffer(int(self.lib.pcfd_comm_blob_size()))
+        self._ck(self.lib.pcfd_comm_export(self.h, buf))
+        return buf.raw
+
+    def comm_connect(self, blobs):
+        """blobs: every rank's comm_export() in rank order"""
+        joined = b"".join(blobs)
+        self._ck(self.lib.pcfd_comm_connect(self.h, C.c_char_p(joined)))
+
+    def comm_disconnect(self):
+        self._ck(self.lib.pcfd_comm_disconnect(self.h))
+
+    def comm_connected(self):
+        return bool(self.lib.pcfd_comm_connected(self.h))
+
+    def comm_post(self, field):
+        self._ck(self.lib.pcfd_comm_post(self.h, field))
+
+    def comm_wait(self, field):
+        self._ck(self.lib.pcfd_comm_wait(self.h, field))
+
+    def comm_update(self, field):
+        self._ck(self.lib.pcfd_comm_update(self.h, field))
+
+    def comm_allgather(self, vals, nranks):
+        v = np.ascontiguousarray(vals, dtype=np.float64).reshape(-1)
+        out = np.zeros(nranks * v.size)
+        self._ck(self.lib.pcfd_comm_allgather(self.h, _d(v), int(v.size), _d(out)))
+        return out.reshape(nranks, v.size)
+
     def profile(self, on=True, reset=False):
         if reset:
             self._ck(self.lib.pcfd_profile_reset(self.h))
@@ -467,7 +511,6 @@ class Context:
 
     def turb_phase(self, phase, want_norm=False):
         """one phase of TurbulenceModel::Compute between the reference's exchange points (see pcfd_turb_phase)"""
-        self.lib.pcfd_turb_phase.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         if not want_norm:
             self._ck(self.lib.pcfd_turb_phase(self.h, int(phase), None))
             return None

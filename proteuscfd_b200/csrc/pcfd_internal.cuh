@@ -81,6 +81,7 @@ struct pcfd_ctx {
   // system widths: 5 / 10 / 9 for the perfect-gas eqnsets, ns+4 / 3ns+6 / 2ns+4 for the reacting one
   int neqn = PCFD_NEQN, nvars = PCFD_NVARS, nterms = PCFD_NTERMS;
   struct pcfd_fr_state* fr = nullptr;   // reacting eqnset (pcfd_fr.cu); null for the perfect-gas eqnsets
+  struct pcfd_comm* comm = nullptr;     // flag-based direct-put exchange between ranks (pcfd_comm.cuh); null: single rank
   DevMesh dm{};
   eq::BcParams bp{};
   double* f[PCFD_F_COUNT] = {};
@@ -123,6 +124,7 @@ struct pcfd_ctx {
   int time_local = 1, torder = 1, iter = 1;
   bool have_qold = false;   // PCFD_F_QOLD has been set: TemporalResidual is live
   bool ludiag = false;
+  double sgs_prev_norm = 0.0;   // xNorm of the last-but-one sweep when the sweeps of a solve are separate calls (multi-rank)
   int sgs_unroll = 4;      // blocks in flight per lane in k_sgs_level (PCFD_SGS_UNROLL overrides, for tuning)
   // bulk-copy (TMA) streaming variant: per level, shared-memory bytes for the matrix part of a tile (0: the rows of
   // the level are not consecutive in memory -> per-lane-load kernel); PCFD_SGS_TILE_WARPS = 0 disables it
@@ -214,6 +216,19 @@ int dev_upload(pcfd_ctx* c, T** p, const T* host, size_t n) {
   return 0;
 }
 inline int nblk(long long n, int bs) { return (int)std::max<long long>(1, (n + bs - 1) / bs); }
+
+// doubles per node of an exchangeable field (0: the field has no ghost rows)
+inline int field_width(const pcfd_ctx* c, int field) {
+  switch (field) {
+    case PCFD_F_Q: return c->nvars;
+    case PCFD_F_QGRAD: return c->nterms * 3;
+    case PCFD_F_LIMITER: case PCFD_F_X: return c->neqn;
+    case PCFD_F_LSQ_S: case PCFD_F_LSQ_SW: return 6;
+    case PCFD_F_BETA: case PCFD_F_MUT: case PCFD_F_TVAR: case PCFD_F_TURB_X: case PCFD_F_WALLDIST: return 1;
+    case PCFD_F_TGRAD: return 3;
+    default: return 0;
+  }
+}
 
 }  // namespace
 

@@ -1870,6 +1870,8 @@ std::vector<int> contiguous_ranges(int n, const int* ia, const int* ja) {
 
 }  // namespace
 
+#include "pcfd_comm.cuh"
+
 // ======================================================================= C ABI
 extern "C" {
 
@@ -1881,6 +1883,13 @@ int pcfd_destroy(pcfd_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   if (c->fr) pcfd_fr_destroy(c);
+  if (c->comm) {
+    pcfd_comm_disconnect(c);
+    if (c->comm->hgout) cudaFreeHost(c->comm->hgout);
+    if (c->comm->ev) cudaEventDestroy(c->comm->ev);
+    delete c->comm;
+    c->comm = nullptr;
+  }
   for (void* p : c->allocs) cudaFree(p);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->hflag) cudaFreeHost(c->hflag);
@@ -2234,6 +2243,7 @@ int pcfd_synchronize(pcfd_ctx* c) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->stream));
+  if (comm_on(c)) return comm_check_err(c);
   return 0;
 }
 int pcfd_set_cfl(pcfd_ctx* c, double cfl) {
@@ -2352,6 +2362,10 @@ int pcfd_lsq_coefficients(pcfd_ctx* c) {
   PROF("k_lsq_coeff");
   k_lsq_coeff<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->f[PCFD_F_LSQ_S], c->f[PCFD_F_LSQ_SW]);
   LAUNCH_CHECK();
+  if (comm_on(c)) {   // gradient.tcc:131-134: halos of s and sw
+    if (comm_update(c, PCFD_F_LSQ_S)) return 1;
+    return comm_update(c, PCFD_F_LSQ_SW);
+  }
   return 0;
 }
 
@@ -2456,27 +2470,39 @@ int pcfd_limiter(pcfd_ctx* c) {
 // rides along in the edge-flux kernel (k_flux_edges<true>); only when some edge actually clips (rare: the limiter
 // exists to prevent exactly that) are the ordered clip passes and the flux redone.
 static int gradient_limiter_residual(pcfd_ctx* c, double* sumsq) {
+  const bool dist = comm_on(c);
   if (c->fr) {
     if (c->prm.sorder > 1) {
       if (pcfd_gradient(c)) return 1;
+      if (dist && comm_update(c, PCFD_F_QGRAD)) return 1;          // gradient.tcc:98
       if (c->prm.limiter != 0 && c->fused_clip) {
         bool hit = false;
-        if (pcfd_fr_limiter_raw(c) || pcfd_fr_residual_fused(c, sumsq, &hit)) return 1;
+        if (pcfd_fr_limiter_raw(c)) return 1;
+        if (dist && comm_update(c, PCFD_F_LIMITER)) return 1;      // limiters.tcc:128 (raw values; both sides clamp)
+        if (pcfd_fr_residual_fused(c, sumsq, &hit)) return 1;
+        if (dist) {   // one decision for all ranks
+          double mine = hit ? 1.0 : 0.0, all[COMM_MAXR];
+          if (pcfd_comm_allgather(c, &mine, 1, all)) return 1;
+          for (int r = 0; r < c->nranks; r++) hit = hit || all[r] != 0.0;
+        }
         if (!hit) return 0;
         c->clip_fallbacks++;
       }
       if (pcfd_limiter(c)) return 1;
+      if (dist && comm_update(c, PCFD_F_LIMITER)) return 1;
     }
     return pcfd_residual(c, sumsq);
   }
   if (c->prm.sorder > 1) {
     if (pcfd_gradient(c)) return 1;
+    if (dist && comm_post(c, PCFD_F_QGRAD)) return 1;              // gradient.tcc:98; waited for inside run_flux
     const int type = c->prm.limiter;
     if (type != 0 && c->fused_clip) {
       PROF("k_limiter");
       k_limiter<<<nblk((long long)c->nn * 5, 160), 160, 0, c->stream>>>(c->dm, type, c->prm.chi, c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD],
                                                          c->f[PCFD_F_LIMITER]);
       LAUNCH_CHECK();
+      if (dist && comm_post(c, PCFD_F_LIMITER)) return 1;          // limiters.tcc:128 (raw values; both sides clamp)
       bool hit = false;
       if (run_flux(c, true, &hit)) return 1;
       if (!hit) {
@@ -2484,8 +2510,11 @@ static int gradient_limiter_residual(pcfd_ctx* c, double* sumsq) {
         return 0;
       }
       c->clip_fallbacks++;
+    } else if (dist && comm_wait(c, PCFD_F_QGRAD)) {
+      return 1;
     }
     if (pcfd_limiter(c)) return 1;
+    if (dist && comm_update(c, PCFD_F_LIMITER)) return 1;
   }
   return pcfd_residual(c, sumsq);
 }
@@ -2565,7 +2594,26 @@ static int run_temporal(pcfd_ctx* c) {
   return 0;
 }
 
+// Across ranks (comm connected, fused): the caller has POSTED the halos of qgrad and of the raw limiter; the interior
+// edge kernel -- ghost-independent -- runs while they are in flight, every rank's clip flag goes round through the
+// flag page (no collective), and the waits come just before the first kernel that reads ghost rows.  *clip_hit is
+// the GLOBAL decision (limiters.tcc:112-117 runs on every rank or on none).
+// the host reads the clip flag(s) while the kernels queued behind the copy keep the GPU busy
+static int flux_clip_decision(pcfd_ctx* c, bool dist, bool* clip_hit) {
+  if (!dist) {
+    CK(cudaEventSynchronize(c->ev_flag));
+    *clip_hit = *c->hflag != 0;
+    return 0;
+  }
+  CK(cudaEventSynchronize(c->comm->ev));
+  bool hit = false;
+  for (int r = 0; r < c->nranks; r++) hit = hit || c->comm->hgout[r * COMM_GW] != 0.0;
+  *clip_hit = hit;
+  return 0;
+}
+
 static int run_flux(pcfd_ctx* c, bool fused, bool* clip_hit) {
+  const bool dist = fused && comm_on(c);
   if (fused) CK(cudaMemsetAsync(c->dflags + 2, 0, sizeof(int), c->stream));
   if (c->nedge) {
     PROF("k_flux_edges");
@@ -2579,7 +2627,11 @@ static int run_flux(pcfd_ctx* c, bool fused, bool* clip_hit) {
                                                                       c->f[PCFD_F_LIMITER], c->flux, nullptr);
     LAUNCH_CHECK();
   }
-  if (fused) {
+  if (dist) {
+    if (comm_gather_enqueue(c, nullptr, c->dflags + 2, 1)) return 1;
+    if (comm_wait(c, PCFD_F_QGRAD) || comm_wait(c, PCFD_F_LIMITER)) return 1;
+    if (run_limiter_final(c, nullptr)) return 1;
+  } else if (fused) {
     CK(cudaMemcpyAsync(c->hflag, c->dflags + 2, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaEventRecord(c->ev_flag, c->stream));
     if (run_limiter_final(c, nullptr)) return 1;
@@ -2609,10 +2661,7 @@ static int run_flux(pcfd_ctx* c, bool fused, bool* clip_hit) {
                                                                         c->wallflag, c->f[PCFD_F_B]);
     LAUNCH_CHECK();
     if (run_temporal(c)) return 1;
-    if (fused) {
-      CK(cudaEventSynchronize(c->ev_flag));
-      *clip_hit = *c->hflag != 0;
-    }
+    if (fused) return flux_clip_decision(c, dist, clip_hit);
     return 0;
   }
   PROF("k_residual_gather");
@@ -2620,10 +2669,7 @@ static int run_flux(pcfd_ctx* c, bool fused, bool* clip_hit) {
                                                                        c->f[PCFD_F_B]);
   LAUNCH_CHECK();
   if (run_temporal(c)) return 1;
-  if (fused) {
-    CK(cudaEventSynchronize(c->ev_flag));
-    *clip_hit = *c->hflag != 0;
-  }
+  if (fused) return flux_clip_decision(c, dist, clip_hit);
   return 0;
 }
 
@@ -2923,18 +2969,6 @@ int pcfd_sgs(pcfd_ctx* c, int nsgs, double* ddq) {
   return 0;
 }
 
-static int field_width(const pcfd_ctx* c, int field) {
-  switch (field) {
-    case PCFD_F_Q: return c->nvars;
-    case PCFD_F_QGRAD: return c->nterms * 3;
-    case PCFD_F_LIMITER: case PCFD_F_X: return c->neqn;
-    case PCFD_F_LSQ_S: case PCFD_F_LSQ_SW: return 6;
-    case PCFD_F_BETA: case PCFD_F_MUT: case PCFD_F_TVAR: case PCFD_F_TURB_X: case PCFD_F_WALLDIST: return 1;
-    case PCFD_F_TGRAD: return 3;
-    default: return 0;
-  }
-}
-
 int pcfd_halo_configure(pcfd_ctx* c, int rank, int nranks, const int* send_counts, const int* send_list,
                         const int* recv_counts) {
   if (!c) return 1;
@@ -3022,6 +3056,18 @@ int pcfd_turb_compute(pcfd_ctx* c, int nsgs, double* sumsq) {
   if (c->fr) return fail(c, "pcfd_turb_compute: not available for the reacting eqnset");
   if (c->prm.turb_model != 1) return fail(c, "pcfd_turb_compute: the context was created without a turbulence model");
   CK(cudaSetDevice(c->device));
+  if (comm_on(c)) {
+    // across ranks: the phases of pcfd_turb_phase with the reference's exchanges (turb.tcc:185, gradient.tcc:98,
+    // crs.tcc:146, turb.tcc:325); block-Jacobi across partitions like CRS::SGS; sumsq = this rank's sum of b^2
+    if (nsgs <= 0) return fail(c, "pcfd_turb_compute: nsgs == 0 (explicit turbulence update) is not implemented");
+    if (pcfd_turb_phase(c, 0, nullptr) || comm_update(c, PCFD_F_TVAR)) return 1;
+    if (pcfd_turb_phase(c, 1, nullptr) || comm_update(c, PCFD_F_TGRAD)) return 1;
+    if (pcfd_turb_phase(c, 2, sumsq)) return 1;
+    for (int s = 0; s < nsgs; s++)
+      if (pcfd_turb_phase(c, 3, nullptr) || comm_update(c, PCFD_F_TURB_X)) return 1;
+    if (pcfd_turb_phase(c, 4, nullptr) || comm_update(c, PCFD_F_TVAR)) return 1;
+    return pcfd_turb_phase(c, 5, nullptr);
+  }
   double *tvar = c->f[PCFD_F_TVAR], *tgrad = c->f[PCFD_F_TGRAD], *tb = c->f[PCFD_F_TURB_B], *tx = c->f[PCFD_F_TURB_X],
          *tA = c->f[PCFD_F_TURB_A];
   // crs.BlankSystem (crs.tcc:417-425); every interior off-diagonal and every diagonal entry is overwritten below
@@ -3187,26 +3233,57 @@ int pcfd_turb_phase(pcfd_ctx* c, int phase, double* sumsq) {
   }
 }
 
+// One iteration of SolutionSpace::NewtonIterate (solutionSpace.tcc:640-904).  Across ranks (pcfd_comm_connect) the
+// reference's halo exchanges run in the reference's places; sumsq / ddq stay THIS rank's sums (the host finishes the
+// norms with pcfd_comm_allgather, as ParallelL2Norm does with MPI_Allreduce).
 int pcfd_explicit_iterate(pcfd_ctx* c, int refresh_dt, double* sumsq) {
   if (!c) return 1;
+  const bool dist = comm_on(c);
   if (refresh_dt && pcfd_timestep(c, nullptr)) return 1;
   if (pcfd_update_bcs(c)) return 1;
+  if (dist && comm_update(c, PCFD_F_Q)) return 1;                  // solutionSpace.tcc:665
   if (gradient_limiter_residual(c, sumsq)) return 1;
-  return pcfd_explicit_solve(c);
+  if (pcfd_explicit_solve(c)) return 1;
+  if (dist && comm_update(c, PCFD_F_Q)) return 1;                  // :857
+  return 0;
 }
 
 int pcfd_implicit_iterate(pcfd_ctx* c, int refresh_jac, int nsgs, double* sumsq, double* ddq) {
   if (!c) return 1;
+  const bool dist = comm_on(c);
   if (refresh_jac) {
     if (pcfd_timestep(c, nullptr)) return 1;   // PreIterate / PreTimeAdvance (solutionSpace.tcc:510, 629-634)
     if (pcfd_jacobian(c)) return 1;
   }
   if (pcfd_update_bcs(c)) return 1;
+  if (dist && comm_update(c, PCFD_F_Q)) return 1;                  // solutionSpace.tcc:665
   if (gradient_limiter_residual(c, sumsq)) return 1;
   if (pcfd_prepare_sgs(c)) return 1;
   if (pcfd_blank_x(c)) return 1;
-  if (pcfd_sgs(c, nsgs, ddq)) return 1;
+  if (!dist) {
+    if (pcfd_sgs(c, nsgs, ddq)) return 1;
+  } else {
+    // CRS::SGS across ranks (crs.tcc:62-173): block-Jacobi at partition boundaries, a halo of x before the first
+    // sweep (:88) and after every sweep (:146); ddq from the last two sweeps of this rank's rows
+    if (comm_update(c, PCFD_F_X)) return 1;
+    for (int sweep = 0; sweep < nsgs; sweep++) {
+      const bool last = sweep == nsgs - 1;
+      if (ddq && sweep >= nsgs - 2 && nsgs >= 2) {
+        // every sweep is its own pcfd_sgs call here (the halo of x sits between them), so |xOld - xNorm| is put
+        // together from the norms of the closing two sweeps
+        double d1 = 0.0;
+        if (pcfd_sgs(c, 1, &d1)) return 1;          // d1 = |0 - xNorm| of this sweep
+        if (!last) c->sgs_prev_norm = d1; else *ddq = fabs(c->sgs_prev_norm - d1);
+      } else {
+        double d1 = 0.0;
+        if (pcfd_sgs(c, 1, (ddq && last) ? &d1 : nullptr)) return 1;
+        if (ddq && last) *ddq = d1;
+      }
+      if (comm_update(c, PCFD_F_X)) return 1;
+    }
+  }
   if (pcfd_apply_dq(c)) return 1;
+  if (dist && comm_update(c, PCFD_F_Q)) return 1;                  // solutionSpace.tcc:857
   // NewtonIterate updates the turbulence model after the flow update (solutionSpace.tcc:862-866)
   if (c->prm.turb_model == 1) return pcfd_turb_compute(c, nsgs, nullptr);
   return 0;

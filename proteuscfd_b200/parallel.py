@@ -248,6 +248,91 @@ class PutExchange:
         self.opened = []
 
 
+class ThreadGroup:
+    """Several ranks as THREADS of one process (one context each, one GPU or several): the collective calls of
+    TorchGroup on a threading.Barrier.  ctypes releases the GIL inside the library, so a rank blocked in a stream
+    synchronisation does not stop the others -- the same relation MPI ranks have."""
+
+    def __init__(self, nranks):
+        import threading
+        self.nranks = nranks
+        self._bar = threading.Barrier(nranks)
+        self._slots = [None] * nranks
+
+    def allgather(self, rank, obj):
+        self._slots[rank] = obj
+        self._bar.wait()
+        out = list(self._slots)
+        self._bar.wait()
+        return out
+
+    def view(self, rank):
+        return _ThreadGroupRank(self, rank)
+
+    def run(self, fn):
+        """fn(rank, group_view) on one thread per rank; re-raises the first failure."""
+        import threading
+        errs = [None] * self.nranks
+
+        def body(r):
+            try:
+                fn(r, self.view(r))
+            except BaseException as e:      # noqa: BLE001 -- reported to the caller below
+                errs[r] = e
+                self._bar.abort()
+
+        ts = [threading.Thread(target=body, args=(r,)) for r in range(self.nranks)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        real = [e for e in errs if e is not None and not isinstance(e, __import__("threading").BrokenBarrierError)]
+        if real:
+            raise real[0]
+        if any(errs):
+            raise [e for e in errs if e is not None][0]
+
+
+class _ThreadGroupRank:
+    def __init__(self, group, rank):
+        self.g, self.rank, self.nranks = group, rank, group.nranks
+
+    def allgather(self, obj):
+        return self.g.allgather(self.rank, obj)
+
+    def alltoall_lists(self, wants):
+        gathered = self.g.allgather(self.rank, [np.asarray(w, dtype=np.int32) for w in wants])
+        return [gathered[p][self.rank] for p in range(self.nranks)]
+
+
+class CommExchange:
+    """The library's own exchange (pcfd_comm_*, csrc/pcfd_comm.cuh): every rank publishes one blob (CUDA-IPC handles of
+    its fields and of its flag page), `group.allgather` moves the blobs, and from pcfd_comm_connect on an exchange is a
+    put kernel + a wait kernel with epoch flags in peer memory -- no collective, no host synchronisation.  Connecting
+    also switches the composite entry points (pcfd_explicit_iterate, pcfd_implicit_iterate, pcfd_turb_compute,
+    pcfd_lsq_coefficients) to the reference's multi-rank sequence."""
+
+    def __init__(self, ctx, pobj, group):
+        self.ctx, self.p = ctx, pobj
+        pobj.attach(ctx)
+        ctx.comm_connect(group.allgather(ctx.comm_export()))
+
+    def update(self, field):
+        self.ctx.comm_update(field)
+
+    def post(self, field):
+        self.ctx.comm_post(field)
+
+    def wait(self, field):
+        self.ctx.comm_wait(field)
+
+    def allgather(self, vals):
+        return self.ctx.comm_allgather(vals, self.p.np)
+
+    def close(self):
+        self.ctx.comm_disconnect()
+
+
 class DistributedHotPath:
     """SolutionSpace::NewtonIterate (ucs/solutionSpace.tcc:640-904) across ranks: the phase calls of one context
     with the reference's halo exchanges and reductions in the reference's places."""
