@@ -247,6 +247,9 @@ int pcfd_comm_export(pcfd_ctx* ctx, void* blob);
 int pcfd_comm_connect(pcfd_ctx* ctx, const void* blobs /* nranks * pcfd_comm_blob_size() bytes, rank order */);
 int pcfd_comm_disconnect(pcfd_ctx* ctx);
 int pcfd_comm_connected(const pcfd_ctx* ctx);
+/* diagnostics: out[0..nranks) = ready epochs, out[nranks..2 nranks) = done epochs seen from each rank, out[2 nranks] = 1
+   if a flag wait of this rank ran into its time limit (20 s; PCFD_COMM_SPIN_SECONDS overrides at connect time) */
+int pcfd_comm_debug_flags(pcfd_ctx* ctx, unsigned long long* out);
 int pcfd_comm_post(pcfd_ctx* ctx, int field);
 int pcfd_comm_wait(pcfd_ctx* ctx, int field);
 int pcfd_comm_update(pcfd_ctx* ctx, int field);

@@ -42,7 +42,7 @@ SYMBOLS = [
     "pcfd_set_time_integration", "pcfd_set_gradient_type", "pcfd_set_jacobian_type",
     "pcfd_chem_source_term", "pcfd_chem_source_term_device", "pcfd_halo_width", "pcfd_halo_send_total", "pcfd_halo_pack", "pcfd_halo_recv_ptr",
     "pcfd_comm_blob_size", "pcfd_comm_export", "pcfd_comm_connect", "pcfd_comm_disconnect", "pcfd_comm_connected",
-    "pcfd_comm_post", "pcfd_comm_wait", "pcfd_comm_update", "pcfd_comm_allgather",
+    "pcfd_comm_post", "pcfd_comm_wait", "pcfd_comm_update", "pcfd_comm_allgather", "pcfd_comm_debug_flags",
 ]
 
 
@@ -405,6 +405,13 @@ class Context:
         """blobs: every rank's comm_export() in rank order"""
         joined = b"".join(blobs)
         self._ck(self.lib.pcfd_comm_connect(self.h, C.c_char_p(joined)))
+
+    def comm_debug_flags(self, nranks):
+        out = (C.c_ulonglong * (2 * nranks + 1))()
+        self.lib.pcfd_comm_debug_flags.argtypes = [C.c_void_p, C.c_void_p]
+        self._ck(self.lib.pcfd_comm_debug_flags(self.h, out))
+        v = list(out)
+        return dict(ready=v[:nranks], done=v[nranks:2 * nranks], err=v[2 * nranks])
 
     def comm_disconnect(self):
         self._ck(self.lib.pcfd_comm_disconnect(self.h))

@@ -30,7 +30,7 @@ namespace {
 constexpr int COMM_MAXR = PCFD_COMM_MAX_RANKS;
 constexpr int COMM_GW = 8;                      // doubles per rank in the small all-gather
 constexpr unsigned COMM_MAGIC = 0x70636664u;    // "pcfd"
-constexpr unsigned long long COMM_SPIN_LIMIT_NS = 20ull * 1000ull * 1000ull * 1000ull;
+constexpr unsigned long long COMM_SPIN_LIMIT_NS = 20ull * 1000ull * 1000ull * 1000ull;   // PCFD_COMM_SPIN_SECONDS overrides
 
 // layout of a rank's flag page (device memory, written by the peers)
 struct CommFlags {
@@ -58,6 +58,7 @@ struct CommBlob {
 // per-rank device tables read by the kernels
 struct CommTable {
   int npeers_send, npeers_recv, nranks, me;
+  unsigned long long spin_limit_ns;
   int send_peer[COMM_MAXR];                     // ranks this rank sends rows to
   int send_off[COMM_MAXR + 1];                  // prefix of their row counts in send_list
   int recv_peer[COMM_MAXR];                     // ranks this rank receives rows from
@@ -79,14 +80,15 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 // spin until *p >= want; false (and the error word raised) after COMM_SPIN_LIMIT_NS
-__device__ __forceinline__ bool spin_until(const unsigned long long* p, unsigned long long want, int* err) {
+__device__ __forceinline__ bool spin_until(const unsigned long long* p, unsigned long long want, int* err,
+                                           unsigned long long limit_ns) {
   if (ld_acquire_sys(p) >= want) return true;
   const unsigned long long t0 = global_ns();
   unsigned backoff = 32;
   while (ld_acquire_sys(p) < want) {
     __nanosleep(backoff);
     if (backoff < 1024) backoff *= 2;
-    if (global_ns() - t0 > COMM_SPIN_LIMIT_NS) { *err = 1; return false; }
+    if (global_ns() - t0 > limit_ns) { *err = 1; return false; }
   }
   return true;
 }
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(256) k_comm_put(const CommTable* __restrict__ 
     // the ranks that write into MY ghost rows learn that I am done reading the old ones
     st_release_sys(&tb->peer_flags[tb->recv_peer[threadIdx.x]]->ready[me], epoch);
   }
-  if (threadIdx.x < np) spin_until(&mine->ready[tb->send_peer[threadIdx.x]], epoch, &mine->err);
+  if (threadIdx.x < np) spin_until(&mine->ready[tb->send_peer[threadIdx.x]], epoch, &mine->err, tb->spin_limit_ns);
   __syncthreads();
   const long long total = (long long)tb->send_off[np] * n;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(256) k_comm_put(const CommTable* __restrict__ 
 
 __global__ void k_comm_wait(const CommTable* __restrict__ tb, unsigned long long epoch) {
   CommFlags* mine = tb->peer_flags[tb->me];
-  if (threadIdx.x < tb->npeers_recv) spin_until(&mine->done[tb->recv_peer[threadIdx.x]], epoch, &mine->err);
+  if (threadIdx.x < tb->npeers_recv) spin_until(&mine->done[tb->recv_peer[threadIdx.x]], epoch, &mine->err, tb->spin_limit_ns);
 }
 
 // small all-gather: every rank writes its n values (doubles, or one int flag) into slot [parity][me] of every rank
@@ -141,7 +143,7 @@ __global__ void k_comm_gwait(const CommTable* __restrict__ tb, int n, unsigned l
   const int r = threadIdx.x, par = (int)(gepoch & 1ull);
   if (r >= tb->nranks) return;
   CommFlags* mine = tb->peer_flags[tb->me];
-  spin_until(&mine->gtag[par][r], gepoch, &mine->err);
+  spin_until(&mine->gtag[par][r], gepoch, &mine->err, tb->spin_limit_ns);
   for (int k = 0; k < n; k++) out[r * COMM_GW + k] = mine->gval[par][r][k];
 }
 
@@ -274,6 +276,8 @@ int pcfd_comm_connect(pcfd_ctx* c, const void* blobs) {
   CommTable& t = m->h;
   memset(&t, 0, sizeof(t));
   t.nranks = R; t.me = me;
+  t.spin_limit_ns = COMM_SPIN_LIMIT_NS;
+  if (const char* e = getenv("PCFD_COMM_SPIN_SECONDS")) t.spin_limit_ns = (unsigned long long)(atof(e) * 1e9);
   auto open = [&](const CommBlob& b, const cudaIpcMemHandle_t& h, void* raw, void** out) -> int {
     if (b.pid == (int)getpid() && b.token == comm_token()) { *out = raw; return 0; }   // same process: plain pointer
     CK(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
@@ -322,6 +326,17 @@ int pcfd_comm_disconnect(pcfd_ctx* c) {
 }
 
 int pcfd_comm_connected(const pcfd_ctx* c) { return c && comm_on(c) ? 1 : 0; }
+
+/* diagnostics: ready[r], done[r] of this rank's flag page for r < nranks, then the error word (2*nranks + 1 values) */
+int pcfd_comm_debug_flags(pcfd_ctx* c, unsigned long long* out) {
+  if (!c || !c->comm || !out) return 1;
+  CK(cudaSetDevice(c->device));
+  CommFlags h;
+  CK(cudaMemcpy(&h, c->comm->flags, sizeof(h), cudaMemcpyDeviceToHost));
+  for (int r = 0; r < c->nranks; r++) { out[r] = h.ready[r]; out[c->nranks + r] = h.done[r]; }
+  out[2 * c->nranks] = (unsigned long long)h.err;
+  return 0;
+}
 
 int pcfd_comm_post(pcfd_ctx* c, int field) {
   if (!c) return 1;

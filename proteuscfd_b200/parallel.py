@@ -316,6 +316,9 @@ class CommExchange:
         self.ctx, self.p = ctx, pobj
         pobj.attach(ctx)
         ctx.comm_connect(group.allgather(ctx.comm_export()))
+        # nobody posts before everybody is connected (with the ranks as threads of one process a synchronous CUDA call
+        # of a rank that is still connecting would otherwise wait for a peer's put kernel that waits for that rank)
+        group.allgather(None)
 
     def update(self, field):
         self.ctx.comm_update(field)

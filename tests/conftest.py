@@ -3,6 +3,12 @@ import sys
 
 import pytest
 
+# Ranks-as-threads tests (tests/test_gpu_comm.py) co-run kernels of several contexts on one GPU: a put kernel of one rank
+# waits for a flag another rank's kernel raises.  With CUDA's default LAZY module loading the first launch of a kernel
+# synchronises the context, i.e. it would wait for that spinning put kernel (the case the CUDA programming guide warns
+# about under "Lazy Loading / concurrent execution").  Load everything up front.  One process per GPU is not affected.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -33,6 +33,9 @@ def run_threads(parts, body):
     def fn(rank, group):
         mesh, params = parts[rank][0], parts[rank][1]
         ctx = capi.Context(mesh, params)
+        # allocate-on-first-use fields now: a cudaMalloc inside an iteration synchronises the DEVICE, i.e. (ranks as
+        # threads sharing one GPU) it would wait for a peer's put kernel that is waiting for this very rank
+        ctx.device_ptr(capi.F_A)
         pobj = PObj(rank, nr).BuildCommMaps(mesh["gNodeOwner"], mesh["gNodeLocalId"], group)
         x = CommExchange(ctx, pobj, group)
         try:
