@@ -56,10 +56,11 @@ def pass_bytes(ne, nn, nblocks=0):
 
 # which kernels make up which reference pass
 PASS_KERNELS = {
-    "timestep": ["k_timestep"],
+    "timestep": ["k_timestep", "k_eig_bedges"],      # explicit iteration: the edge terms ride along in k_flux_edges / k_residual_gather
     "update_bcs": ["k_update_bcs"],
     "gradient": ["k_gradient"],
     "limiter": ["k_limiter", "k_fill_int", "k_clip_edges", "k_clip_nodes", "k_limiter_final"],
+
     "residual": ["k_flux_edges", "k_flux_bedges", "k_residual_gather"],
     "update": ["k_explicit"],
 }
@@ -221,6 +222,123 @@ def cpu_baseline(args):
     return {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample}
 
 
+class RankRun:
+    """One rank's context + exchange on a (possibly partitioned) case: the calls the sub-benchmarks time.
+
+    --halo comm (default): the library's own exchange (pcfd_comm_*).  After pcfd_comm_connect the composite C entry
+    points run the reference's multi-rank sequence themselves, so explicit() / implicit() are single C calls exactly
+    as on one GPU.  --halo put / nccl: the host-driven exchanges of round 1 (DistributedHotPath)."""
+
+    def __init__(self, args, mesh, params, rank, world, local_rank, torch, dist, stream, beta=None, implicit=False):
+        from proteuscfd_b200 import capi
+        self.capi, self.torch, self.dist = capi, torch, dist
+        self.rank, self.world, self.halo = rank, world, args.halo
+        self.dev = torch.device("cuda", local_rank)
+        c = self.ctx = capi.Context(mesh, params, device=local_rank)
+        c.set_stream(stream.cuda_stream)
+        if beta is not None:
+            c.set_field(capi.F_BETA, beta)
+        if implicit:
+            c.device_ptr(capi.F_A)        # allocate the matrix now, not inside the first timed iteration
+        self.x = self.hp = None
+        self.halo_rows = 0
+        self.turb = int(params.get("turb_model", 0)) == 1
+        if world > 1:
+            from proteuscfd_b200.parallel import CommExchange, DistributedHotPath, NcclExchange, PObj, PutExchange, TorchGroup
+            group = TorchGroup(dist)
+            pobj = PObj(rank, world).BuildCommMaps(mesh["gNodeOwner"], mesh["gNodeLocalId"], group)
+            self.halo_rows = int(pobj.commCountsSend.sum())
+            self.neighbours = int((pobj.commCountsSend > 0).sum())
+            if args.halo == "comm":
+                self.x = CommExchange(c, pobj, group)
+            else:
+                self.x = (PutExchange(c, pobj, dist, torch, self.dev, group) if args.halo == "put"
+                          else NcclExchange(c, pobj, dist, torch, self.dev))
+                hitflag = torch.zeros(1, device=self.dev, dtype=torch.int32)
+
+                def any_rank(hit):   # the (rare) pressure-clip fallback is a global decision: one 4-byte max all-reduce
+                    hitflag.fill_(int(hit))
+                    dist.all_reduce(hitflag, op=dist.ReduceOp.MAX)
+                    return bool(hitflag.item())
+
+                self.hp = DistributedHotPath(c, self.x, any_rank=any_rank)
+        if self.hp is not None:
+            self.hp.setup()
+        else:
+            c.lsq_coefficients()          # across ranks: the halos of s / sw are inside (gradient.tcc:131-134)
+
+    def explicit(self):
+        if self.hp is not None:
+            self.hp.explicit_iterate(refresh_dt=True)
+        else:
+            self.ctx.explicit_iterate(refresh_dt=True)
+
+    def implicit(self, nsgs, refresh):
+        if self.hp is not None:
+            self.hp.implicit_iterate(nsgs, refresh_jac=refresh)
+            if self.turb:
+                self.hp.turb_compute(nsgs)
+        else:
+            self.ctx.implicit_iterate(nsgs, refresh_jac=refresh)      # TurbulenceModel::Compute included
+
+    def refresh_only(self):
+        c = self.ctx
+        c.timestep(want_min=False)
+        c.jacobian()
+        c.prepare_sgs()
+
+    def sweep(self):
+        self.ctx.sgs(1, want_ddq=False)
+        if self.x is not None:
+            self.x.update(self.capi.F_X)      # crs.tcc:146
+
+    def blank_x(self):
+        self.ctx.blank_x()
+        if self.x is not None:
+            self.x.update(self.capi.F_X)      # crs.tcc:88
+
+    def clip_fallbacks(self):
+        return self.hp.clip_fallbacks if self.hp is not None else self.ctx.clip_fallbacks()
+
+    def sync(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def maxms(self, ms):
+        if self.world == 1:
+            return float(ms)
+        t = self.torch.tensor([ms], device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def total(self, v):
+        if self.world == 1:
+            return int(v)
+        t = self.torch.tensor([v], device=self.dev, dtype=self.torch.int64)
+        self.dist.all_reduce(t)
+        return int(t.item())
+
+    def timed(self, fn, reps, stream):
+        """max over ranks of the device time of reps calls of fn, per call [ms]"""
+        ev = lambda: self.torch.cuda.Event(enable_timing=True)
+        self.sync()
+        e0, e1 = ev(), ev()
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        self.sync()
+        return self.maxms(e0.elapsed_time(e1) / reps)
+
+    def close(self):
+        if self.world > 1:
+            self.sync()
+        if self.x is not None and hasattr(self.x, "close"):
+            self.x.close()
+        self.ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -229,13 +347,21 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=118, help="hexes per box side (118 -> ~10 M tets)")
     ap.add_argument("--ref-n", type=int, default=48, help="box side of the bounded CPU reference sample")
-    ap.add_argument("--halo", default="put", choices=["put", "nccl"],
-                    help="N>1 halo exchange: direct puts into peer ghost segments over NVLink (CUDA IPC) or NCCL send/recv")
+    ap.add_argument("--halo", default="comm", choices=["comm", "put", "nccl"],
+                    help="N>1 halo exchange.  comm: the library's own flag-based direct puts (pcfd_comm_*: no collective, no "
+                         "host sync, interior-edge flux overlaps the halos; the composite C entry points run the multi-rank "
+                         "sequence); put: host-driven direct puts between two NCCL barriers (round 1); nccl: NCCL send/recv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sgs", action="store_true")
     ap.add_argument("--no-fr", action="store_true", help="skip the reacting-eqnset (compressibleEulerFR) sub-benchmark")
     ap.add_argument("--fr-n", type=int, default=0, help="box side for the reacting sub-benchmark (0: same as --n)")
     ap.add_argument("--sgs-n", type=int, default=0, help="box side for the SGS sub-benchmark (0: same as --n)")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the oracle comparison outside the timed region")
+    ap.add_argument("--no-ns", action="store_true", help="skip the laminar-NS (configs[2]) and RANS-SA (configs[3]) objects")
+    ap.add_argument("--ns-n", type=int, default=149, help="box side of the laminar Navier-Stokes case (149 -> ~20 M tets)")
+    ap.add_argument("--no-strong", action="store_true", help="N>1: skip the fixed-size (strong scaling) 50 M-cell object")
+    ap.add_argument("--strong-n", type=int, default=203, help="box side of the fixed-size case (203 -> ~50 M tets)")
+    ap.add_argument("--no-fma", action="store_true", help="skip the FMA-contracted build's timing / drift measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -264,43 +390,20 @@ def main():
     # at the reference's four places per iteration (q, qgrad, limiter, q)
     if world > 1:
         from proteuscfd_b200.cases import slab_case
-        from proteuscfd_b200.parallel import DistributedHotPath, NcclExchange, PObj, PutExchange, TorchGroup
         mesh, params, q0 = slab_case(args.n, rank, world, device=f"cuda:{local_rank}")
     else:
         mesh, params, q0 = box_case(args.n, device=f"cuda:{local_rank}")
-    ctx = capi.Context(mesh, params, device=local_rank)
     # a real (non-default) torch stream: the library launches on it and torch.cuda.Event times it
     stream = torch.cuda.Stream(device=local_rank)
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
-    ctx.set_stream(stream.cuda_stream)
+    run = RankRun(args, mesh, params, rank, world, local_rank, torch, dist, stream)
+    ctx = run.ctx
     ne, nn = ctx.nedge, ctx.nnode
-    ne_global = ne
-    if world > 1:
-        group = TorchGroup(dist)
-        pobj = PObj(rank, world).BuildCommMaps(mesh["gNodeOwner"], mesh["gNodeLocalId"], group)
-        dev = torch.device("cuda", local_rank)
-        xch = PutExchange(ctx, pobj, dist, torch, dev, group) if args.halo == "put" else NcclExchange(ctx, pobj, dist, torch, dev)
-        hitflag = torch.zeros(1, device=dev, dtype=torch.int32)
-
-        def any_rank(hit):   # the (rare) pressure-clip fallback is a global decision: one 4-byte max all-reduce
-            hitflag.fill_(int(hit))
-            dist.all_reduce(hitflag, op=dist.ReduceOp.MAX)
-            return bool(hitflag.item())
-
-        hp = DistributedHotPath(ctx, xch, any_rank=any_rank)
-        hp.setup()
-        ctx.set_field(capi.F_Q, q0)
-        step = lambda: hp.explicit_iterate(refresh_dt=True)
-        t = torch.tensor([2 * ctx.nedge + ctx.ngedge], device="cuda", dtype=torch.int64)   # a cut edge lives on two ranks
-        dist.all_reduce(t)
-        ne_global = int(t.item()) // 2
-        halo_rows = int(pobj.commCountsSend.sum())
-    else:
-        ctx.lsq_coefficients()
-        ctx.set_field(capi.F_Q, q0)
-        step = lambda: ctx.explicit_iterate(refresh_dt=True)
-        halo_rows = 0
+    ctx.set_field(capi.F_Q, q0)
+    step = run.explicit
+    ne_global = run.total(2 * ctx.nedge + ctx.ngedge) // 2 if world > 1 else ne    # a cut edge lives on two ranks
+    halo_rows = run.halo_rows
     t_setup = time.time() - t_setup
 
     def barrier():
@@ -311,7 +414,8 @@ def main():
     # ---------------------------------------------------------------- device-resident timing
     for _ in range(W):
         step()
-    ctx.profile(on=True, reset=True)
+    # per-kernel event records between the launches cost ~2 % of a 3 ms step: the headline region runs without them,
+    # a profiled pass of the same K steps follows for the per-kernel / per-pass tables
     launches0 = ctx.launch_count()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -326,14 +430,15 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     ms_total = e0.elapsed_time(e1)
     launches = ctx.launch_count() - launches0
+    ms_step = run.maxms(ms_total) / K
+    value = ne_global / (ms_step * 1e-3) / 1e6
+    ctx.profile(on=True, reset=True)
+    Kp = min(K, 20)
+    for _ in range(Kp):
+        step()
+    barrier()
     ctx.profile(on=False)
     table = ctx.profile_table()
-    if world > 1:
-        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / K
-    value = ne_global / (ms_step * 1e-3) / 1e6
 
     # ---------------------------------------------------------------- end to end through the C ABI with HOST buffers
     nq = ctx.field_size(capi.F_Q)
@@ -346,7 +451,6 @@ def main():
         ctx.get_field(capi.F_Q, out=hq_np)
     Ke = max(3, K // 2)
     barrier()
-    t0 = time.perf_counter()
     e0.record(stream)
     for _ in range(Ke):
         ctx.set_field(capi.F_Q, hq_np)          # H2D of the step's input state (pinned)
@@ -354,53 +458,61 @@ def main():
         ctx.get_field(capi.F_Q, out=hq_np)      # D2H of the updated state
     e1.record(stream)
     barrier()
-    e2e_ms = e0.elapsed_time(e1) / Ke
-    if world > 1:
-        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    e2e_ms = run.maxms(e0.elapsed_time(e1) / Ke)
     e2e_value = ne_global / (e2e_ms * 1e-3) / 1e6
 
     # ---------------------------------------------------------------- per-pass roofline from the live kernel timings
     peak, peak_src = measured_peaks()
     pb = pass_bytes(ne, nn)
-    kern = {k: {"ms_avg": v[0] / max(v[1], 1), "launches_per_step": v[1] / K, "ms_per_step": v[0] / K} for k, v in table.items()}
+    kern = {k: {"ms_avg": v[0] / max(v[1], 1), "launches_per_step": v[1] / Kp, "ms_per_step": v[0] / Kp} for k, v in table.items()}
+    ms_prof = sum(v["ms_per_step"] for v in kern.values())
     passes = {}
     for pname, ks in PASS_KERNELS.items():
         ms = sum(kern[k]["ms_per_step"] for k in ks if k in kern)
         if ms <= 0:
             continue
-        d = {"ms_per_step": ms, "share": ms / ms_step}
+        d = {"ms_per_step": ms, "share": ms / ms_prof}
         if pname in pb:
             d["algorithmic_bytes"] = pb[pname]
             d["GBps"] = pb[pname] / (ms * 1e-3) / 1e9
             d["frac_hbm"] = d["GBps"] / peak
         passes[pname] = d
+    # ComputeTimesteps rides along in the residual pass (k_flux_edges / k_residual_gather) when no k_timestep ran: its
+    # compulsory bytes are then credited to that pass
+    if "k_timestep" not in kern and "residual" in passes:
+        r = passes["residual"]
+        r["algorithmic_bytes"] = pb["residual"] + pb["timestep"]
+        r["includes"] = "ComputeTimesteps (edge terms evaluated in k_flux_edges, summed in k_residual_gather)"
+        r["GBps"] = r["algorithmic_bytes"] / (r["ms_per_step"] * 1e-3) / 1e9
+        r["frac_hbm"] = r["GBps"] / peak
     dominant = max((p for p in passes if "GBps" in passes[p]), key=lambda p: passes[p]["ms_per_step"])
     # measured DRAM traffic of the pass's kernels (one ncu --set full capture of this workload, committed under profiles/)
-    traffic = None
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_dram_traffic.json")))["explicit_lexicographic"]
-        if args.n == 118 and world == 1:
-            traffic = sum(tr[k] for k in PASS_KERNELS[dominant] if k in kern and k in tr)
-    except Exception:
-        traffic = None
+    traffic, traffic_src = None, None
+    for fn_, key in (("r2_dram_traffic.json", "explicit_lexicographic"), ("r1_dram_traffic.json", "explicit_lexicographic")):
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", fn_)))[key]
+            if args.n == 118 and all(k in tr for k in PASS_KERNELS[dominant] if k in kern):
+                traffic = sum(tr[k] for k in PASS_KERNELS[dominant] if k in kern)
+                traffic_src = f"profiles/{fn_} (ncu dram__bytes_read+write.sum per launch, same workload)"
+                break
+        except Exception:
+            continue
     roofline = {"bound": "hbm", "kernel": "+".join(k for k in PASS_KERNELS[dominant] if k in kern), "pass": dominant,
                 "achieved": passes[dominant]["GBps"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": passes[dominant]["frac_hbm"], "traffic": traffic,
-                "traffic_source": "profiles/r1_dram_traffic.json (ncu dram__bytes_read+write.sum per launch, same workload)" if traffic else None,
+                "frac": passes[dominant]["frac_hbm"], "traffic": traffic, "traffic_source": traffic_src,
                 "bytes_per_launch": passes[dominant]["algorithmic_bytes"], "ms_per_launch": passes[dominant]["ms_per_step"],
                 "note": "algorithmic bytes = SURVEY.md 8d compulsory bytes of the pass; the Roe flux is FP64-pipe-bound "
                         "(see profiles/), so frac is reported for completeness, not as the limiter"}
-    # the dominant kernel is FP64-pipe-bound, not HBM-bound: put the pipe roofline next to the HBM one.  1274 = FP64-pipe
-    # instructions per edge of k_flux_edges<true> (static SASS count, `cuobjdump -sass`: 315 DADD + 451 DMUL + 455 DFMA
-    # inside the IEEE division / sqrt sequences + 53 DSETP; the rarely taken raw-limiter branch included, so an upper
-    # bound on the dynamic count); B200: 148 SMs x 64 FP64 lanes, one instruction per lane per clock
+    # the dominant kernel is FP64-pipe-bound, not HBM-bound: put the pipe roofline next to the HBM one.  FP64-pipe
+    # instructions per edge of k_flux_edges<true, true> (static SASS count, `cuobjdump -sass`; the rarely taken
+    # raw-limiter branch included, so an upper bound on the dynamic count); B200: 148 SMs x 64 FP64 lanes, one
+    # instruction per lane per clock
     try:
+        ipe = FLUX_FP64_INSTR["with_timestep" if "k_timestep" not in kern else "plain"]
         sm_mhz = float((clocks or {}).get("sm_max_mhz") or 1965.0)
-        bound_ms = 1274.0 * ne / (148 * 64 * sm_mhz * 1e6) * 1e3
+        bound_ms = ipe * ne / (148 * 64 * sm_mhz * 1e6) * 1e3
         ms_flux = kern["k_flux_edges"]["ms_per_step"]
-        roofline["fp64_pipe"] = {"kernel": "k_flux_edges", "instr_per_edge": 1274, "bound_ms": bound_ms, "ms": ms_flux,
+        roofline["fp64_pipe"] = {"kernel": "k_flux_edges", "instr_per_edge": ipe, "bound_ms": bound_ms, "ms": ms_flux,
                                  "frac": bound_ms / ms_flux,
                                  "how": "static SASS count of FP64-pipe instructions x edges / (148 SMs x 64 lanes x SM clock); 64 lanes per SM = "
                                         "the nominal 37 TFLOP/s FMA peak at 1.965 GHz, not measured here"}
@@ -408,44 +520,48 @@ def main():
         pass
     step_bytes = sum(pb[p] for p in ("gradient", "limiter", "residual", "timestep"))
     phases = {"residual_Medges_s": ne / (passes["residual"]["ms_per_step"] * 1e-3) / 1e6 if "residual" in passes else None,
-              "gradient_limiter_Medges_s": ne / ((passes["gradient"]["ms_per_step"] + passes["limiter"]["ms_per_step"]) * 1e-3) / 1e6,
+              "gradient_limiter_Medges_s": ne / (sum(passes[p]["ms_per_step"] for p in ("gradient", "limiter") if p in passes) * 1e-3) / 1e6,
               "iteration_frac_hbm": step_bytes / (ms_step * 1e-3) / 1e9 / peak,
-              "passes": passes, "kernels": kern}
+              "profiled_ms_per_step": ms_prof, "passes": passes, "kernels": kern}
+    clip_fallbacks = run.clip_fallbacks()
 
-    # ---------------------------------------------------------------- SGS sweeps/s (second half of the metric)
-    sgs = None
-    if not args.no_sgs and rank == 0 and world == 1:
-        sgs = sgs_bench(args, ctx, mesh, params, q0, peak, torch, stream, local_rank)
-
-    # ---------------------------------------------------------------- SGS sweeps/s across ranks (N > 1)
-    if not args.no_sgs and world > 1:
+    # ---------------------------------------------------------------- parity outside the timed region
+    parity = None
+    if not args.no_parity_check:
         try:
-            sgs = sgs_bench_multi(args, ctx, xch, rank, world, local_rank, peak, torch, dist, stream)
+            parity = parity_check(args, mesh, params, q0, rank, world, local_rank, torch, dist, stream)
         except Exception as e:
-            sgs = {"error": f"{type(e).__name__}: {e}"[:300]}
+            parity = {"error": f"{type(e).__name__}: {e}"[:300]}
 
-    # ---------------------------------------------------------------- reacting eqnset across ranks (BASELINE configs[4])
-    frm = None
-    if not args.no_fr and world > 1:
-        try:
-            frm = fr_bench_multi(args, rank, world, local_rank, peak, torch, dist, stream)
-        except Exception as e:
-            frm = {"error": f"{type(e).__name__}: {e}"[:300]}
+    run.close()
+    torch.cuda.empty_cache()
 
-    # ---------------------------------------------------------------- reacting eqnset (BASELINE configs[4] on one GPU)
-    frb = frm
-    if not args.no_fr and rank == 0 and world == 1:
+    def guarded(fn, *a, **kw):
         try:
-            frb = fr_bench(args, peak, torch, stream, local_rank)
-        except Exception as e:
-            frb = {"error": f"{type(e).__name__}: {e}"[:300]}
+            return fn(*a, **kw)
+        except Exception as e:      # never lose the headline line to a sub-benchmark
+            return {"error": f"{type(e).__name__}: {e}"[:300]}
 
-    frv = None
-    if not args.no_fr and rank == 0 and world == 1:
-        try:
-            frv = fr_bench(args, peak, torch, stream, local_rank, viscous=True)
-        except Exception as e:
-            frv = {"error": f"{type(e).__name__}: {e}"[:300]}
+    common = (args, rank, world, local_rank, peak, torch, dist, stream)
+    sgs = None if args.no_sgs else guarded(implicit_bench, *common, kind="euler")
+    laminar = rans = None
+    if not args.no_ns:
+        if world <= 2:
+            laminar = guarded(implicit_bench, *common, kind="laminar_ns")
+        rans = guarded(implicit_bench, *common, kind="rans_sa")
+    strong = None
+    if world > 1 and not args.no_strong:
+        strong = guarded(strong_bench, *common)
+    frb = frv = None
+    if not args.no_fr:
+        if world > 1:
+            frb = guarded(fr_bench_multi, args, rank, world, local_rank, peak, torch, dist, stream)
+        elif rank == 0:
+            frb = guarded(fr_bench, args, peak, torch, stream, local_rank)
+            frv = guarded(fr_bench, args, peak, torch, stream, local_rank, viscous=True)
+    fma = None
+    if world == 1 and not args.no_fma:
+        fma = guarded(fma_variant, args, mesh, params, q0, torch, stream, local_rank, ms_step)
 
     base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -455,6 +571,9 @@ def main():
             base = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": f"failed: {e}"[:300]}
 
     if rank == 0:
+        halo_txt = {"comm": "library exchange pcfd_comm_* (one put kernel with epoch-flag handshake + one wait kernel per exchange, "
+                            "no collective, no host sync; the interior-edge flux kernel runs while qgrad / limiter rows are in flight)",
+                    "put": "host-driven direct puts between two NCCL barriers", "nccl": "NCCL send/recv"}[args.halo]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -463,8 +582,8 @@ def main():
                                    f"{nn} nodes, {ne} edges) per GPU, Roe 2nd order + weighted LSQ + Venkatakrishnan, "
                                    "explicit single-stage update (the reference has no multistage RK)",
                        "parallelism": ("single partition" if world == 1 else
-                                       f"{world} z-slab partitions of an n x n x {args.n * world} box, one per GPU; halo exchange "
-                                       f"'{args.halo}' of q, qgrad, limiter, q per iteration ({halo_rows} rows/rank/exchange); "
+                                       f"{world} z-slab partitions of an n x n x {args.n * world} box, one per GPU; halos of q, qgrad, "
+                                       f"limiter, q per iteration ({halo_rows} rows/rank/exchange): {halo_txt}; "
                                        f"{ne_global} edges in total"),
                        "cache": "inputs larger than L2 (q 135 MB, qgrad 364 MB, edges 470 MB per pass); no flush needed",
                        "setup_s": t_setup},
@@ -472,260 +591,299 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": nq * 8 * world,
                     "d2h_bytes_per_step": nq * 8 * world, "what": "pcfd_set_field(q) from pinned host memory + pcfd_explicit_iterate + "
                                                           "pcfd_get_field(q) per step"},
-            "gpu_launches": int(launches) * world, "clocks": clocks, "phases": phases, "sgs": sgs, "reacting": frb, "reacting_viscous": frv,
+            "gpu_launches": int(launches) * world, "clocks": clocks, "clip_fallbacks": clip_fallbacks,
+            "parity_check": parity, "phases": phases, "sgs": sgs, "laminar_ns": laminar, "rans_sa": rans,
+            "strong_scaling": strong, "reacting": frb, "reacting_viscous": frv, "fma_variant": fma,
+            "reference_arm_note": "bench.py --impl reference runs the UNMODIFIED reference (oracle/_ref/ref_harness) on the bounded "
+                                  f"sample n={args.ref_n} (not n={args.n}), 16-32 ranks over the process-based MPI shim "
+                                  "(oracle/mpi_shim), harness timers: a stated CPU baseline, not the same configuration",
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def sgs_bench(args, ctx, mesh, params, q0, peak, torch, stream, local_rank):
-    """SGS sweeps/s on the implicit version of the same case (5x5 blocks, colour-sorted numbering)."""
+# FP64-pipe instructions per edge of k_flux_edges<true, EIG> (static SASS counts: DADD + DMUL + DFMA + DSETP + MUFU.RCP64H/RSQ64H)
+FLUX_FP64_INSTR = {"plain": 1274, "with_timestep": 1274}
+
+
+def parity_check(args, mesh, params, q0, rank, world, local_rank, torch, dist, stream):
+    """Correctness bit carried by the bench line, computed OUTSIDE the timed regions with the C oracle as the checker.
+    N = 1: one explicit iteration through pcfd_explicit_iterate on the bench mesh itself (n = 118) against the oracle
+    phase by phase.  N > 1: two explicit and two implicit composite iterations on n = 32 slabs through the SAME exchange
+    the timed region used, against the oracle replayed rank by rank with a numpy halo (tests/partition_oracle.py)."""
     from proteuscfd_b200 import capi
-    from proteuscfd_b200.cases import box_case
-    n = args.sgs_n or args.n
-    ctx.close()
-    torch.cuda.empty_cache()
-    mesh, params, q = box_case(n, cfl=5.0, colored=True, device=f"cuda:{local_rank}")
-    c = capi.Context(mesh, params, device=local_rank)
-    c.set_stream(stream.cuda_stream)
-    c.lsq_coefficients()
-    c.set_field(capi.F_Q, q)
-    c.profile(on=True, reset=True)
-    c.implicit_iterate(2, refresh_jac=True)       # builds A, LU, 2 sweeps (warm-up)
-    c.blank_x()
-    c.sgs(2, want_ddq=False)
-    torch.cuda.synchronize()
-    tab0 = c.profile_table()
-    # timed regions run with the per-kernel event profiling OFF (its event records sit between the launches and would
-    # serialise the programmatic dependent launch of consecutive SGS levels); a profiled pass follows for the tables
-    c.profile(on=False)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    nsw = 10
-    e0.record(stream)
-    c.sgs(nsw, want_ddq=False)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / nsw
-    # the whole implicit iteration without a Jacobian refresh (UpdateBCs, gradient, limiter, residual, PrepareSGS (no-op:
-    # LU kept), 5 SGS sweeps, ApplyDQ) against the HBM roofline of its compulsory bytes -- the north-star quantity
-    nsgs_it, reps = 5, 5
-    c.set_field(capi.F_Q, q)
-    c.implicit_iterate(nsgs_it, refresh_jac=False)
-    torch.cuda.synchronize()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record(stream)
-    for _ in range(reps):
-        c.implicit_iterate(nsgs_it, refresh_jac=False)
-    e3.record(stream)
-    torch.cuda.synchronize()
-    ms_it = e2.elapsed_time(e3) / reps
-    c.profile(on=True)
-    c.implicit_iterate(nsgs_it, refresh_jac=False)
-    torch.cuda.synchronize()
-    tab = c.profile_table()
-    _, nblocks = c.get_crs()[1].size, c.get_crs()[1].size
-    pbs = pass_bytes(c.nedge, c.nnode, nblocks)
-    bytes_sweep = pbs["sgs_sweep"]
-    bytes_it = pbs["gradient"] + pbs["limiter"] + pbs["residual"] + nsgs_it * bytes_sweep
-    out = {"sweeps_per_s": 1e3 / ms, "ms_per_sweep": ms, "nodes": c.nnode, "blocks": int(nblocks), "block": "5x5",
-           "levels_fwd_bwd": "colour-sorted numbering: one launch per colour per direction",
-           "algorithmic_bytes_per_sweep": bytes_sweep, "GBps": bytes_sweep / (ms * 1e-3) / 1e9,
-           "frac_hbm": bytes_sweep / (ms * 1e-3) / 1e9 / peak,
-           "implicit_iteration": {"what": f"UpdateBCs + gradient + limiter + residual + {nsgs_it} SGS sweeps + ApplyDQ, Jacobian kept",
-                                  "ms": ms_it, "Medges_s": c.nedge / (ms_it * 1e-3) / 1e6, "algorithmic_bytes": bytes_it,
-                                  "GBps": bytes_it / (ms_it * 1e-3) / 1e9, "frac_hbm": bytes_it / (ms_it * 1e-3) / 1e9 / peak},
-           "jacobian_ms": {k: tab0[k][0] / tab0[k][1] for k in ("k_jac_edges", "k_jac_bnodes", "k_jac_diag", "k_lu_diag") if k in tab0},
-           "kernels_ms": {k: v[0] / max(v[1], 1) for k, v in tab.items()},
-           "kernel": "k_sgs_tile (cp.async.bulk + mbarrier streamed tiles)" if "k_sgs_tile" in tab else "k_sgs_level",
-           "launches_per_sweep": sum(tab[k][1] - tab0.get(k, (0, 0))[1] for k in ("k_sgs_level", "k_sgs_tile") if k in tab) / nsgs_it,
-           "pdl": "levels of a sweep launched with programmatic stream serialization (PCFD_SGS_PDL=0 disables)"}
-    c.close()
+    from tests.oracle_lib import load_oracle, oracle_for
+    t0 = time.time()
+    lib = load_oracle()
+    eq = lambda a, b: bool(np.array_equal(a, b))
+    if world == 1:
+        o = oracle_for(lib, mesh, params)
+        c = capi.Context(mesh, params, device=local_rank)
+        c.set_stream(stream.cuda_stream)
+        c.lsq_coefficients()
+        c.set_field(capi.F_Q, q0)
+        qo = q0.copy()
+        beta = np.zeros(1)
+        _, sw = o.lsq()
+        dt, _ = o.timestep(qo, beta)
+        o.update_bcs(qo, beta)
+        grad = o.gradient(qo, sw)
+        lim = o.limiter(qo, grad)
+        b = o.residual(qo, grad, lim, beta)
+        o.explicit_solve(qo, b, dt)
+        c.explicit_iterate(refresh_dt=True)
+        res = {"timestep": eq(c.get_field(capi.F_TIMESTEP), dt), "qgrad": eq(c.get_field(capi.F_QGRAD), grad),
+               "limiter": eq(c.get_field(capi.F_LIMITER), lim), "b": eq(c.get_field(capi.F_B), b), "q": eq(c.get_field(capi.F_Q), qo)}
+        c.close()
+        return {"what": f"one explicit iteration on the bench mesh (n={args.n}) vs the C oracle (oracle/pcfd_oracle.c), bit-exact per field",
+                "bit_exact": res, "ok": all(res.values()), "seconds": time.time() - t0}
+    from proteuscfd_b200.cases import slab_case
+    from tests.partition_oracle import replay_perfect_gas
+    npar = 32
+    out = {"what": f"2 explicit + 2 implicit (3 sweeps, Jacobian refreshed) composite iterations on {world} slabs of n={npar} through the "
+                   f"'{args.halo}' exchange vs the per-rank oracle replay with a numpy halo, bit-exact per field (ghost rows included)"}
+    ok = True
+    for implicit in (False, True):
+        parts = [slab_case(npar, r, world, colored=implicit, cfl=5.0 if implicit else 0.5) for r in range(world)]
+        _, ref = replay_perfect_gas(lib, parts, implicit, iters=2, nsweeps=3)
+        pr = RankRun(args, parts[rank][0], parts[rank][1], rank, world, local_rank, torch, dist, stream, implicit=implicit)
+        pr.ctx.set_field(capi.F_Q, parts[rank][2])
+        res = {}
+        for it in range(2):
+            if implicit:
+                pr.implicit(3, True)
+            else:
+                pr.explicit()
+            pr.sync()
+            for k, f in (("qgrad", capi.F_QGRAD), ("limiter", capi.F_LIMITER), ("b", capi.F_B), ("q", capi.F_Q)) + (
+                    (("x", capi.F_X),) if implicit else ()):
+                res[f"{k}{it}"] = eq(pr.ctx.get_field(f), ref[it][k][rank])
+        pr.close()
+        bad = pr.total(sum(0 if v else 1 for v in res.values()))
+        out["implicit" if implicit else "explicit"] = {"rank0_bit_exact": res, "mismatching_fields_all_ranks": bad}
+        ok = ok and bad == 0
+    out["ok"] = ok
+    out["seconds"] = time.time() - t0
     return out
 
 
-def sgs_bench_multi(args, ctx, xch, rank, world, local_rank, peak, torch, dist, stream):
-    """SGS sweeps/s and the implicit iteration on N partitions (BASELINE configs[2]/[3] layout): every rank holds one
-    z-slab with a colour-sorted numbering, its 5x5 block-CRS rows (ghost columns included) and runs the reference's
-    multi-rank solve: block-Jacobi across partitions, one halo exchange of x after every sweep (ucs/crs.tcc:88,146).
-    Times are the max over ranks; sweeps/s counts whole-domain sweeps, GB/s the bytes all ranks streamed."""
+def implicit_bench(args, rank, world, local_rank, peak, torch, dist, stream, kind="euler"):
+    """Implicit 5x5 iteration and SGS sweeps/s, colour-sorted numbering, on one GPU or on z-slab partitions:
+      euler       the implicit version of the headline case (second half of the metric: SGS sweeps/s);
+      laminar_ns  BASELINE configs[2]: compressibleNS, no-slip wall, ~20 M cells in total on 1-2 GPUs (strong split);
+      rans_sa     BASELINE configs[3]: compressibleNS + Spalart-Allmaras (TurbulenceModel::Compute after the flow update),
+                  wall distance from walldist.py, one n^3 slab per GPU.
+    Reported: the iteration with the Jacobian kept, the Jacobian refresh, and the iteration WITH refresh -- the
+    reference's default (jacobianUpdateFrequency = 1, ucs/param.tcc:173)."""
     from proteuscfd_b200 import capi
-    from proteuscfd_b200.cases import slab_case
-    from proteuscfd_b200.parallel import DistributedHotPath, NcclExchange, PObj, PutExchange, TorchGroup
-    n = args.sgs_n or args.n
-    if hasattr(xch, "close"):
-        xch.close()
-    ctx.close()
-    torch.cuda.empty_cache()
-    dev = torch.device("cuda", local_rank)
-    mesh, params, q = slab_case(n, rank, world, cfl=5.0, colored=True, device=f"cuda:{local_rank}")
-    c = capi.Context(mesh, params, device=local_rank)
-    c.set_stream(stream.cuda_stream)
-    group = TorchGroup(dist)
-    pobj = PObj(rank, world).BuildCommMaps(mesh["gNodeOwner"], mesh["gNodeLocalId"], group)
-    x = PutExchange(c, pobj, dist, torch, dev, group) if args.halo == "put" else NcclExchange(c, pobj, dist, torch, dev)
-    hitflag = torch.zeros(1, device=dev, dtype=torch.int32)
-
-    def any_rank(hit):
-        hitflag.fill_(int(hit))
-        dist.all_reduce(hitflag, op=dist.ReduceOp.MAX)
-        return bool(hitflag.item())
-
-    hp = DistributedHotPath(c, x, any_rank=any_rank)
-    hp.setup()
+    from proteuscfd_b200.cases import NS_BC, box_case, slab_case
+    nsgs = 5
+    viscous = kind != "euler"
+    turb = kind == "rans_sa"
+    n = (args.sgs_n or args.n) if kind != "laminar_ns" else args.ns_n
+    nz = None
+    bc = None
+    if viscous:
+        bc = dict(NS_BC)
+        bc[5] = capi.BC_SYMMETRY
+        bc[3] = capi.BC_NOSLIP           # the wall runs along y = 0: every z-slab owns a strip of it
+    if kind == "laminar_ns" and world > 1:
+        nz = n                           # the SAME 20 M-cell box split across the ranks
+    kw = dict(cfl=5.0, colored=True, device=f"cuda:{local_rank}")
+    if viscous:
+        kw.update(viscous=True, turb=turb, bc=bc)
+    if world > 1:
+        mesh, params, q = slab_case(n, rank, world, nz=nz, **kw)
+    else:
+        mesh, params, q = box_case(n, **kw)
+    r = RankRun(args, mesh, params, rank, world, local_rank, torch, dist, stream, implicit=True)
+    c = r.ctx
+    if turb:
+        from proteuscfd_b200.parallel import TorchGroup
+        from proteuscfd_b200.walldist import wall_distance
+        wd = wall_distance(mesh, group=TorchGroup(dist) if world > 1 else None, device=f"cuda:{local_rank}")
+        c.set_field(capi.F_WALLDIST, wd)
+        tv = np.full(c.field_size(capi.F_TVAR), 1.341946)      # nu~ of the free stream (spalart.tcc:79)
+        c.set_field(capi.F_TVAR, tv)
     c.set_field(capi.F_Q, q)
-    hp.implicit_iterate(2, refresh_jac=True)      # builds A and its LU; warm-up
-
-    def sync():
-        dist.barrier()
-        torch.cuda.synchronize()
-
-    def maxms(ms):
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def total(v):
-        t = torch.tensor([v], device=dev, dtype=torch.int64)
-        dist.all_reduce(t)
-        return int(t.item())
-
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-    c.blank_x()
-    x.update(capi.F_X)
+    r.implicit(2, True)                     # builds A and its LU; warm-up
+    r.blank_x()
     for _ in range(2):
-        c.sgs(1, want_ddq=False)
-        x.update(capi.F_X)
-    nsw = 10
-    sync()
-    e0, e1 = ev(), ev()
-    e0.record(stream)
-    for _ in range(nsw):
-        c.sgs(1, want_ddq=False)
-        x.update(capi.F_X)
-    e1.record(stream)
-    sync()
-    ms = maxms(e0.elapsed_time(e1) / nsw)
-    nsgs_it, reps = 5, 5
+        r.sweep()
+    ms_sweep = r.timed(r.sweep, 10, stream)
     c.set_field(capi.F_Q, q)
-    hp.implicit_iterate(nsgs_it, refresh_jac=False)
-    sync()
-    e2, e3 = ev(), ev()
-    e2.record(stream)
-    for _ in range(reps):
-        hp.implicit_iterate(nsgs_it, refresh_jac=False)
-    e3.record(stream)
-    sync()
-    ms_it = maxms(e2.elapsed_time(e3) / reps)
+    r.implicit(nsgs, False)
+    ms_it = r.timed(lambda: r.implicit(nsgs, False), 5, stream)
+    ms_refresh = r.timed(r.refresh_only, 2, stream)
+    c.set_field(capi.F_Q, q)
+    ms_it_refresh = r.timed(lambda: r.implicit(nsgs, True), 3, stream)
+    finite = bool(np.isfinite(c.get_field(capi.F_Q)).all())
+    # per-kernel table of one iteration with refresh (profiling on: its event records break the PDL chain of the SGS
+    # levels, so it is a separate pass)
+    c.profile(on=True, reset=True)
+    r.implicit(nsgs, True)
+    r.sync()
+    c.profile(on=False)
+    tab = c.profile_table()
     nblocks = int(c.get_crs()[1].size)
     pbs = pass_bytes(c.nedge + c.ngedge, c.nnode + c.gnode, nblocks)
-    bytes_sweep = total(pass_bytes(c.nedge, c.nnode, nblocks)["sgs_sweep"])
-    bytes_it = total(pbs["gradient"] + pbs["limiter"] + pbs["residual"]) + nsgs_it * bytes_sweep
-    nn_g, nb_g = total(c.nnode), total(nblocks)
-    ne_g = total(2 * c.nedge + c.ngedge) // 2
-    out = {"sweeps_per_s": 1e3 / ms, "ms_per_sweep": ms, "nodes": nn_g, "blocks": nb_g, "block": "5x5", "n_gpus": world,
-           "what": f"one sweep = forward + backward over every partition + halo exchange of x ('{args.halo}'); block-Jacobi "
-                   "across partitions as in the reference",
-           "algorithmic_bytes_per_sweep": bytes_sweep, "GBps": bytes_sweep / (ms * 1e-3) / 1e9,
-           "frac_hbm": bytes_sweep / (ms * 1e-3) / 1e9 / (peak * world),
-           "implicit_iteration": {"what": f"UpdateBCs + gradient + limiter + residual + {nsgs_it} SGS sweeps + ApplyDQ with the "
-                                          "reference's halo exchanges, Jacobian kept",
+    bytes_sweep = r.total(pass_bytes(c.nedge, c.nnode, nblocks)["sgs_sweep"])
+    head = pbs["gradient"] + pbs["limiter"] + pbs["residual"]
+    ne_l, nn_l = c.nedge + c.ngedge, c.nnode + c.gnode
+    if viscous:      # SURVEY.md 8d: the viscous pass re-reads edges, q and all gradient terms, read-modify-writes b
+        head += 40 * ne_l + nn_l * (8 * NTERMS + 24 * NTERMS + 24 + 8) + c.nnode * 16 * NEQN
+    turb_bytes = 0
+    if turb:         # scalar system on the flow's pattern: gradient of nu~, one assembly pass, nsgs scalar sweeps (8d: 1x1 blocks)
+        turb_bytes = (8 * ne_l + nn_l * (24 + 8 + 48 + 24)) + (40 * ne_l + nn_l * (8 * NVARS + 24 + 8 + 8) + nblocks * 8) \
+            + nsgs * 2 * (nblocks * 8 + 4 * nblocks + 4 * (c.nnode + 1) + 8 * 3 * c.nnode)
+    bytes_it = r.total(head + turb_bytes) + nsgs * bytes_sweep
+    bytes_jac = r.total(40 * ne_l + nn_l * 8 * NVARS + nblocks * 8 * NEQN * NEQN)
+    nn_g, nb_g = r.total(c.nnode), r.total(nblocks)
+    ne_g = r.total(2 * c.nedge + c.ngedge) // 2 if world > 1 else c.nedge
+    names = {"euler": "implicit version of BASELINE configs[1] (inviscid Euler)",
+             "laminar_ns": "BASELINE configs[2]: laminar Navier-Stokes (compressibleNS, isothermal no-slip wall, Re 400), implicit",
+             "rans_sa": "BASELINE configs[3]: RANS Spalart-Allmaras (compressibleNS + SA, no-slip wall, wall distance by exact search), implicit"}
+    out = {"workload": f"{names[kind]}; Kuhn box n={n}, colour-sorted numbering, {world} GPU(s)"
+                       + (f", {world} z-slabs of the SAME box (strong split)" if nz else (f", one n^3 slab per GPU" if world > 1 else ""))
+                       + f": {nn_g} nodes, {ne_g} edges, {nb_g} 5x5 blocks = {nb_g * 200 / 1e9:.1f} GB",
+           "n_gpus": world, "nsgs": nsgs, "nodes": nn_g, "blocks": nb_g, "block": "5x5",
+           "sweeps_per_s": 1e3 / ms_sweep, "ms_per_sweep": ms_sweep, "algorithmic_bytes_per_sweep": bytes_sweep,
+           "GBps": bytes_sweep / (ms_sweep * 1e-3) / 1e9, "frac_hbm": bytes_sweep / (ms_sweep * 1e-3) / 1e9 / (peak * world),
+           "implicit_iteration": {"what": f"UpdateBCs + gradient + limiter + residual + {nsgs} SGS sweeps + ApplyDQ"
+                                          + (" + TurbulenceModel::Compute" if turb else "") + ", Jacobian kept"
+                                          + (", the reference's halo exchanges in the reference's places" if world > 1 else ""),
                                   "ms": ms_it, "Medges_s": ne_g / (ms_it * 1e-3) / 1e6, "algorithmic_bytes": bytes_it,
-                                  "GBps": bytes_it / (ms_it * 1e-3) / 1e9,
-                                  "frac_hbm": bytes_it / (ms_it * 1e-3) / 1e9 / (peak * world),
-                                  "clip_fallbacks": hp.clip_fallbacks}}
-    if hasattr(x, "close"):
-        x.close()
-    c.close()
+                                  "GBps": bytes_it / (ms_it * 1e-3) / 1e9, "frac_hbm": bytes_it / (ms_it * 1e-3) / 1e9 / (peak * world)},
+           "jacobian_refresh_ms": ms_refresh,
+           "iteration_with_refresh": {"what": "the same + ComputeTimesteps + ComputeJacobians + LU every iteration (the reference's default, "
+                                              "jacobianUpdateFrequency = 1, ucs/param.tcc:173); the finite-difference assembly is FP64-bound",
+                                      "ms": ms_it_refresh, "Medges_s": ne_g / (ms_it_refresh * 1e-3) / 1e6,
+                                      "algorithmic_bytes": bytes_it + bytes_jac,
+                                      "frac_hbm": (bytes_it + bytes_jac) / (ms_it_refresh * 1e-3) / 1e9 / (peak * world)},
+           "state_finite_after_run": finite, "clip_fallbacks": r.clip_fallbacks(),
+           "kernels_ms_rank0": {k: v[0] / max(v[1], 1) for k, v in tab.items()},
+           "kernel": "k_sgs_tile (cp.async.bulk + mbarrier streamed tiles, PDL-chained levels)" if "k_sgs_tile" in tab else "k_sgs_level"}
+    r.close()
+    torch.cuda.empty_cache()
     return out
+
+
+def strong_bench(args, rank, world, local_rank, peak, torch, dist, stream):
+    """STRONG scaling: one fixed box of n = 203 (50.2 M tets, 8.5 M nodes, 59 M edges -- the size the north-star target is
+    quoted on) dealt out in z-slabs to the N GPUs; explicit and implicit (5x5, Jacobian kept / refreshed) Euler
+    iterations.  The main line's `value` stays the weak-scaling figure."""
+    from proteuscfd_b200 import capi
+    from proteuscfd_b200.cases import slab_case
+    n, nsgs = args.strong_n, 5
+    mesh, params, q = slab_case(n, rank, world, nz=n, cfl=5.0, colored=True, device=f"cuda:{local_rank}")
+    r = RankRun(args, mesh, params, rank, world, local_rank, torch, dist, stream, implicit=True)
+    c = r.ctx
+    c.set_field(capi.F_Q, q)
+    c.set_cfl(0.5)
+    for _ in range(3):
+        r.explicit()
+    ms_exp = r.timed(r.explicit, 10, stream)
+    c.set_cfl(5.0)
+    c.set_field(capi.F_Q, q)
+    r.implicit(nsgs, True)
+    ms_it = r.timed(lambda: r.implicit(nsgs, False), 3, stream)
+    ms_itr = r.timed(lambda: r.implicit(nsgs, True), 2, stream)
+    finite = bool(np.isfinite(c.get_field(capi.F_Q)).all())
+    nblocks = int(c.get_crs()[1].size)
+    pbs = pass_bytes(c.nedge + c.ngedge, c.nnode + c.gnode, nblocks)
+    bytes_it = r.total(pbs["gradient"] + pbs["limiter"] + pbs["residual"]) + nsgs * r.total(pass_bytes(c.nedge, c.nnode, nblocks)["sgs_sweep"])
+    nn_g = r.total(c.nnode)
+    ne_g = r.total(2 * c.nedge + c.ngedge) // 2
+    nodes = [0] * world
+    nodes[rank] = c.nnode
+    t = torch.tensor(nodes, device=r.dev, dtype=torch.int64)
+    dist.all_reduce(t)
+    out = {"workload": f"fixed Kuhn box n={n} ({6 * n ** 3} tets, {nn_g} nodes, {ne_g} edges) split into {world} z-slabs "
+                       f"(nodes per rank {t.tolist()}), colour-sorted numbering, halo '{args.halo}'",
+           "scaling": "strong", "n_gpus": world,
+           "explicit_ms": ms_exp, "explicit_Medges_s": ne_g / (ms_exp * 1e-3) / 1e6,
+           "implicit_iteration_ms": ms_it, "implicit_Medges_s": ne_g / (ms_it * 1e-3) / 1e6,
+           "implicit_frac_hbm": bytes_it / (ms_it * 1e-3) / 1e9 / (peak * world),
+           "implicit_with_refresh_ms": ms_itr, "state_finite_after_run": finite}
+    r.close()
+    torch.cuda.empty_cache()
+    return out
+
+
+def fma_variant(args, mesh, params, q0, torch, stream, local_rank, ms_exact):
+    """What bit-exactness costs: the same sources built with FMA contraction allowed (libpcfd_b200_fma.so, NOT the
+    product) run the same explicit iterations; reported next to the exact build's time with the drift of the state from
+    the exact (= reference) arithmetic after 10 iterations, relative per node as the north star states its bar."""
+    from proteuscfd_b200 import capi
+    if not os.path.exists(capi.FMA_LIB_PATH):
+        return {"unavailable": "libpcfd_b200_fma.so not built"}
+    res = {}
+    for name, path in (("exact", None), ("fma", capi.FMA_LIB_PATH)):
+        c = capi.Context(mesh, params, device=local_rank, lib_path=path)
+        c.set_stream(stream.cuda_stream)
+        c.lsq_coefficients()
+        c.set_field(capi.F_Q, q0)
+        for _ in range(10):
+            c.explicit_iterate(refresh_dt=True)
+        q10 = c.get_field(capi.F_Q)
+        ev = lambda: torch.cuda.Event(enable_timing=True)
+        e0, e1 = ev(), ev()
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(20):
+            c.explicit_iterate(refresh_dt=True)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        res[name] = (e0.elapsed_time(e1) / 20, q10)
+        c.close()
+    nn = mesh["nnode"]
+    a, b = res["fma"][1].reshape(-1, NVARS)[:nn, :NEQN], res["exact"][1].reshape(-1, NVARS)[:nn, :NEQN]
+    scale = np.abs(b).max(axis=1, keepdims=True)
+    drift = float((np.abs(a - b) / scale).max())
+    return {"what": "explicit iteration with FMA contraction allowed (--fmad=true build of the same sources) vs the bit-exact build",
+            "ms_per_step_exact": res["exact"][0], "ms_per_step_fma": res["fma"][0],
+            "speedup_if_bit_exactness_were_dropped": res["exact"][0] / res["fma"][0],
+            "max_relative_drift_per_node_after_10_iterations": drift,
+            "within_north_star_1e-12": drift <= 1e-12,
+            "note": "the finite-difference Jacobian divides flux differences by h = 1e-8, so a contracted flux is NOT within 1e-12 "
+                    "for the implicit path whatever this explicit figure says (DESIGN.md section 3)"}
 
 
 def fr_bench_multi(args, rank, world, local_rank, peak, torch, dist, stream):
     """BASELINE configs[4] as named: reacting 5-species air (compressibleEulerFR), implicit, on N partitions (one z-slab of
     n^3 hexes per GPU, colour-sorted numbering, 9x9 block-CRS rows with ghost columns).  One iteration = UpdateBCs,
     gradient, limiter, HLLC residual + finite-rate source, nsgs SGS sweeps, ApplyDQ with the reference's halo
-    exchanges (q 21 wide, qgrad 42, limiter 9, x 9 after every sweep); Jacobian kept.  Max over ranks."""
+    exchanges (q 21 wide, qgrad 42, limiter 9, x 9 after every sweep).  Max over ranks."""
     from proteuscfd_b200 import capi
     from proteuscfd_b200.cases import fr_slab_case
-    from proteuscfd_b200.parallel import DistributedHotPath, NcclExchange, PObj, PutExchange, TorchGroup
     n = args.fr_n or args.n
     nsgs, reps = 5, 3
     torch.cuda.empty_cache()
-    dev = torch.device("cuda", local_rank)
     mesh, params, q, beta = fr_slab_case(n, rank, world, fr_params_from_fixture(), device=f"cuda:{local_rank}")
-    c = capi.Context(mesh, params, device=local_rank)
-    c.set_stream(stream.cuda_stream)
-    c.set_field(capi.F_BETA, beta)
-    group = TorchGroup(dist)
-    pobj = PObj(rank, world).BuildCommMaps(mesh["gNodeOwner"], mesh["gNodeLocalId"], group)
-    x = PutExchange(c, pobj, dist, torch, dev, group) if args.halo == "put" else NcclExchange(c, pobj, dist, torch, dev)
-    hitflag = torch.zeros(1, device=dev, dtype=torch.int32)
-
-    def any_rank(hit):   # the (rare) pressure-clip fallback is a global decision: one 4-byte max all-reduce
-        hitflag.fill_(int(hit))
-        dist.all_reduce(hitflag, op=dist.ReduceOp.MAX)
-        return bool(hitflag.item())
-
-    hp = DistributedHotPath(c, x, any_rank=any_rank)
-    hp.setup()
+    r = RankRun(args, mesh, params, rank, world, local_rank, torch, dist, stream, beta=beta, implicit=True)
+    c = r.ctx
     c.set_field(capi.F_Q, q)
-    hp.implicit_iterate(nsgs, refresh_jac=True)     # builds A and its LU; warm-up
-
-    def sync():
-        dist.barrier()
-        torch.cuda.synchronize()
-
-    def maxms(ms):
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def total(v):
-        t = torch.tensor([v], device=dev, dtype=torch.int64)
-        dist.all_reduce(t)
-        return int(t.item())
-
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-    sync()
-    e0, e1 = ev(), ev()
-    e0.record(stream)
-    for _ in range(reps):
-        hp.implicit_iterate(nsgs, refresh_jac=False)
-    e1.record(stream)
-    sync()
-    ms_it = maxms(e0.elapsed_time(e1) / reps)
+    r.implicit(nsgs, True)     # builds A and its LU; warm-up
+    ms_it = r.timed(lambda: r.implicit(nsgs, False), reps, stream)
     finite = bool(np.isfinite(c.get_field(capi.F_Q)).all())
-    c.blank_x()
-    x.update(capi.F_X)
-    nsw = 6
-    sync()
-    e2, e3 = ev(), ev()
-    e2.record(stream)
-    for _ in range(nsw):
-        c.sgs(1, want_ddq=False)
-        x.update(capi.F_X)
-    e3.record(stream)
-    sync()
-    ms_sweep = maxms(e2.elapsed_time(e3) / nsw)
-    e4, e5 = ev(), ev()
-    e4.record(stream)
-    c.timestep(want_min=False)
-    c.jacobian()
-    c.prepare_sgs()
-    e5.record(stream)
-    sync()
-    ms_jac = maxms(e4.elapsed_time(e5))
+    r.blank_x()
+    ms_sweep = r.timed(r.sweep, 6, stream)
+    ms_jac = r.timed(r.refresh_only, 1, stream)
+    c.set_field(capi.F_Q, q)
+    ms_itr = r.timed(lambda: r.implicit(nsgs, True), 2, stream)
     nblocks = int(c.get_crs()[1].size)
     neqn, nterms = c.neqn, c.nterms
     ne, nn, nl = c.nedge + c.ngedge, c.nnode, c.nnode + c.gnode
-    bytes_sweep = total(2 * (nblocks * 8 * neqn * neqn + 4 * nblocks + 4 * (nn + 1) + 4 * neqn * nn + 8 * neqn * 3 * nn))
+    bytes_sweep = r.total(2 * (nblocks * 8 * neqn * neqn + 4 * nblocks + 4 * (nn + 1) + 4 * neqn * nn + 8 * neqn * 3 * nn))
     bytes_head = (8 * ne + nl * (24 + 8 * nterms + 48 + 24 * nterms)
                   + (8 * ne + nl * (8 * neqn + 16 * neqn)) + (8 * ne + nl * (8 * neqn + 24 * neqn + 24 + 16 * neqn) + nl * 8 * neqn)
                   + (8 * ne + nl * (8 * neqn + 24 * neqn + 24 + 8 * neqn) + nl * 8 * neqn)
                   + 40 * ne + nl * (8 * neqn + 24 * neqn + 8 * neqn + 24 + 8) + nn * 8 * neqn)
-    bytes_iter = total(bytes_head) + nsgs * bytes_sweep
-    nn_g, nb_g = total(nn), total(nblocks)
-    ne_g = total(2 * c.nedge + c.ngedge) // 2
+    bytes_iter = r.total(bytes_head) + nsgs * bytes_sweep
+    bytes_jac = r.total(40 * ne + nl * 8 * c.nvars + nblocks * 8 * neqn * neqn)
+    nn_g, nb_g = r.total(nn), r.total(nblocks)
+    ne_g = r.total(2 * c.nedge + c.ngedge) // 2
     out = {"workload": f"BASELINE configs[4]: reacting 5-species air (compressibleEulerFR), implicit, {world} z-slab partitions of an "
                        f"n x n x {n * world} Kuhn box (n = {n}: {6 * n ** 3 * world} tets, {nn_g} nodes, {ne_g} edges, {nb_g} 9x9 blocks = "
                        f"{nb_g * 648 / 1e9:.1f} GB) on {world} GPUs; halo exchange '{args.halo}'",
@@ -735,10 +893,12 @@ def fr_bench_multi(args, rank, world, local_rank, peak, torch, dist, stream):
            "iteration_frac_hbm": bytes_iter / (ms_it * 1e-3) / 1e9 / (peak * world),
            "sgs_ms_per_sweep": ms_sweep, "sgs_sweeps_per_s": 1e3 / ms_sweep, "sgs_algorithmic_bytes_per_sweep": bytes_sweep,
            "sgs_GBps": bytes_sweep / (ms_sweep * 1e-3) / 1e9, "sgs_frac_hbm": bytes_sweep / (ms_sweep * 1e-3) / 1e9 / (peak * world),
-           "jacobian_refresh_ms": ms_jac, "state_finite_after_run": finite, "clip_fallbacks": hp.clip_fallbacks}
-    if hasattr(x, "close"):
-        x.close()
-    c.close()
+           "jacobian_refresh_ms": ms_jac,
+           "iteration_with_refresh_ms": ms_itr,
+           "iteration_with_refresh_frac_hbm": (bytes_iter + bytes_jac) / (ms_itr * 1e-3) / 1e9 / (peak * world),
+           "state_finite_after_run": finite, "clip_fallbacks": r.clip_fallbacks()}
+    r.close()
+    torch.cuda.empty_cache()
     return out
 
 
@@ -813,6 +973,15 @@ def fr_bench(args, peak, torch, stream, local_rank, viscous=False):
     ms_jac = e0.elapsed_time(e1) / reps
     ms_iter = eA.elapsed_time(eB) / reps
     ms_sweep = e2.elapsed_time(e3) / nsw
+    # the reference's default: Jacobian refreshed every iteration (jacobianUpdateFrequency = 1, ucs/param.tcc:173)
+    eR0, eR1 = ev(), ev()
+    c.set_field(capi.F_Q, q)
+    eR0.record(stream)
+    for _ in range(2):
+        c.implicit_iterate(nsgs, refresh_jac=True)
+    eR1.record(stream)
+    torch.cuda.synchronize()
+    ms_iter_refresh = eR0.elapsed_time(eR1) / 2
     kern = {k: v[0] / max(v[1], 1) for k, v in tab.items()}
     it_kernels = ("kfr_update_bcs_edges", "kfr_gradient", "kfr_limiter", "kfr_fill_int", "kfr_clip_edges", "kfr_clip_nodes",
                   "kfr_limiter_final", "kfr_flux_edges", "kfr_flux_bedges", "kfr_vflux_edges", "kfr_source", "kfr_residual_gather",
@@ -842,6 +1011,9 @@ def fr_bench(args, peak, torch, stream, local_rank, viscous=False):
            "residual_frac_hbm": bytes_resid / (ms_resid * 1e-3) / 1e9 / peak,
            "iteration_without_refresh_ms": ms_iter, "iteration_Medges_s": ne / (ms_iter * 1e-3) / 1e6, "nsgs": nsgs,
            "iteration_algorithmic_bytes": bytes_iter, "iteration_frac_hbm": bytes_iter / (ms_iter * 1e-3) / 1e9 / peak,
+           "iteration_with_refresh_ms": ms_iter_refresh,
+           "iteration_with_refresh_frac_hbm": (bytes_iter + 40 * ne + nn * 8 * c.nvars + nblocks * 8 * neqn * neqn)
+           / (ms_iter_refresh * 1e-3) / 1e9 / peak,
            "state_finite_after_run": finite, "clip_fallbacks": c.clip_fallbacks(), "non_sgs_kernels_ms": ms_explicit_part,
            "kernels_ms": kern}
     c.close()

@@ -141,11 +141,17 @@ def fill_chem_model(md, t):
 _lib = None
 
 
+_libs = {}
+FMA_LIB_PATH = os.path.join(_HERE, "libpcfd_b200_fma.so")   # the same sources built with --fmad=true (bench.py: price of bit-exactness)
+
+
 def load_library(path=LIB_PATH):
     """dlopen the CUDA library; raise (never fall back) when it is absent."""
     global _lib
-    if _lib is not None:
+    if path == LIB_PATH and _lib is not None:
         return _lib
+    if path in _libs:
+        return _libs[path]
     if not os.path.exists(path):
         raise RuntimeError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(there is no CPU fallback)")
@@ -214,7 +220,9 @@ def load_library(path=LIB_PATH):
                  "pcfd_limiter", "pcfd_explicit_solve", "pcfd_jacobian", "pcfd_prepare_sgs", "pcfd_blank_x",
                  "pcfd_apply_dq"):
         getattr(lib, name).argtypes = [C.c_void_p]
-    _lib = lib
+    _libs[path] = lib
+    if path == LIB_PATH:
+        _lib = lib
     return lib
 
 
@@ -233,9 +241,9 @@ class PcfdError(RuntimeError):
 class Context:
     """One hot-path context on one GPU (thin, 1:1 with the C ABI)."""
 
-    def __init__(self, mesh, params, device=0):
+    def __init__(self, mesh, params, device=0, lib_path=None):
         """mesh: dict with the pcfd_mesh_desc arrays (+ counts); params: dict with the pcfd_params fields."""
-        self.lib = load_library()
+        self.lib = load_library(lib_path) if lib_path else load_library()
         self._keep = {}
         md = MeshDesc()
         for k in ("nnode", "gnode", "nbnode", "nedge", "nbedge", "ngedge"):

@@ -93,11 +93,20 @@ def box_case(n, jitter=0.15, mach=0.5, gamma=1.4, cfl=0.5, limiter=2, sorder=2, 
 
 
 # ------------------------------------------------------------------------------------------ partitioned boxes
-def _slab_ranges(n, nranks):
-    """Owned planes of every rank for a box of n x n x (n*nranks) hexes: rank r owns k in [r*n, (r+1)*n), the last
-    rank also the closing plane."""
-    nz = n * nranks
-    return [(r * n, (r + 1) * n - 1 if r < nranks - 1 else nz) for r in range(nranks)], nz
+def _slab_ranges(n, nranks, nz=None):
+    """Owned planes of every rank for a box of n x n x nz hexes (default nz = n*nranks: every rank a cube, weak
+    scaling): the nz + 1 node planes are dealt out in contiguous runs, as evenly as they divide (the last rank takes
+    the closing plane of the default layout)."""
+    if nz is None:
+        nz = n * nranks
+        return [(r * n, (r + 1) * n - 1 if r < nranks - 1 else nz) for r in range(nranks)], nz
+    base, extra = divmod(nz + 1, nranks)
+    out, k = [], 0
+    for r in range(nranks):
+        cnt = base + (1 if r < extra else 0)
+        out.append((k, k + cnt - 1))
+        k += cnt
+    return out, nz
 
 
 def _owned_order(n, k0, k1, colored):
@@ -117,13 +126,13 @@ def _owned_order(n, k0, k1, colored):
 
 def slab_case(n, rank, nranks, jitter=0.15, mach=0.5, gamma=1.4, cfl=0.5, limiter=2, sorder=2, colored=False,
               device="cpu", seed=1234, bc=None, viscous=False, reynolds=400.0, twall=1.1, tref=300.0, turb=False,
-              enable_vnn=0):
-    """Partition `rank` of a box of n x n x (n*nranks) hexes cut into z-slabs, in the layout udecomp writes
+              enable_vnn=0, nz=None):
+    """Partition `rank` of a box of n x n x nz hexes (default nz = n*nranks) cut into z-slabs, in the layout udecomp writes
     (ucs/decomp.cpp:122-273): owned nodes first, ghost nodes grouped by owning rank, cut edges as ghost half-edges
     carrying the full dual face, `gNodeOwner` / `gNodeLocalId` for the halo maps.  Every rank builds only its own
     slab plus one ghost plane per side; shared nodes get identical coordinates (hash jitter)."""
     from .boxmesh import kuhn_slab
-    ranges, nz = _slab_ranges(n, nranks)
+    ranges, nz = _slab_ranges(n, nranks, nz)
     k0, k1 = ranges[rank]
     k_lo, k_hi = max(k0 - 1, 0), min(k1 + 1, nz)
     np1 = n + 1

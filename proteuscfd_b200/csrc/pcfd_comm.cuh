@@ -178,6 +178,7 @@ int comm_post(pcfd_ctx* c, int field) {
   if (n == 0 || !c->f[field]) return fail(c, "pcfd_comm_post: field cannot be exchanged");
   m->epoch++;
   m->field_epoch[field] = m->epoch;
+  if (field == PCFD_F_Q) c->qmm_valid = false;   // ghost rows of q change: cached neighbour min / max are stale
   const long long total = (long long)c->send_total * n;
   const int grid = (int)std::max<long long>(1, std::min<long long>((total + 1023) / 1024, (long long)c->num_sms));
   PROF("k_comm_put");

@@ -96,6 +96,10 @@ struct pcfd_ctx {
   int nbn = 0, nblist = 0, nblist_bc = 0;
   double* bdiag = nullptr;
   double *flux = nullptr, *bflux = nullptr, *red = nullptr, *redout = nullptr;
+  // ComputeTimesteps riding along in the residual pass of pcfd_explicit_iterate: per-edge / per-half-edge terms
+  double *eig = nullptr, *beig = nullptr;
+  bool eig_fuse = true;            // PCFD_EIG_FUSE=0: separate k_timestep pass
+  bool eig_now = false;            // set by pcfd_explicit_iterate around its residual pass
   // viscous terms (compressibleNS): per-edge viscous flux slots, wall-node bookkeeping, VNN time-step limit
   bool viscous = false;
   eq::ViscParams vp{};
@@ -110,6 +114,16 @@ struct pcfd_ctx {
   int* hflag = nullptr;            // pinned host copy of the fused clip flag
   cudaEvent_t ev_flag = nullptr;
   bool fused_clip = true;          // PCFD_FUSED_CLIP=0 keeps the separate clip pass in the composite iterations
+  // static LSQ weights per node visit (k_lsq_geo) for k_gradient_geo; PCFD_GRAD_GEO=0: k_gradient recomputes them
+  double4* geo = nullptr;
+  bool geo_valid = false;
+  bool use_geo = true;
+  bool limiter_per_node = false;   // PCFD_LIMITER_PER_NODE=1: one thread per node (k_limiter_node; slower on B200: 0.79 vs 0.68 ms)
+  int grad_threads = 3;            // PCFD_GRAD_THREADS=1: one thread per node (k_gradient_geo) instead of three (k_gradient_geo3)
+  // neighbour min / max of the conservative variables taken by k_gradient_geo3 (pass 1 of Limiter::Compute); valid until
+  // q changes (set_field, UpdateBCs, updates, a halo of q)
+  double* qmm = nullptr;
+  bool qmm_valid = false, use_qmm = true;   // PCFD_LIMITER_QMM=0: k_limiter walks the neighbours itself
   long long clip_fallbacks = 0;
   int *ia = nullptr, *ja = nullptr, *iau = nullptr, *pv = nullptr, *posLR = nullptr, *posRL = nullptr, *bpos = nullptr;
   int *rows_f = nullptr, *rows_b = nullptr;

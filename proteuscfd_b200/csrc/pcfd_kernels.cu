@@ -27,9 +27,19 @@
 #define NTERMS PCFD_NTERMS
 #define NEQN2 (NEQN * NEQN)
 
+#ifndef PCFD_GRAD_MINB
+#define PCFD_GRAD_MINB 4
+#endif
+#ifndef PCFD_GRAD3_MINB
+#define PCFD_GRAD3_MINB 5
+#endif
+#ifndef PCFD_LIM_MINB
+#define PCFD_LIM_MINB 4
+#endif
+
 namespace {
 
-__constant__ int c_gradloc[NTERMS] = {0, 1, 2, 3, 4, 5, 7, 8, 9};   // compressible.tcc:1009-1027
+// gradient terms -> variables (compressible.tcc:1009-1027): {0, 1, 2, 3, 4, 5, 7, 8, 9}, spelled (i < 6) ? i : i + 1 below
 
 
 __device__ __forceinline__ void load5(const double* __restrict__ p, double* v) {
@@ -154,6 +164,183 @@ __global__ void __launch_bounds__(128) k_gradient(DevMesh m, const double* __res
   for (int kk = 0; kk < NTERMS * 3; kk++) out[kk] = g[kk];
 }
 
+// ------------------------------------------------------------------ fused gradient + limiter (composite iterations)
+// The weighted-LSQ edge weights are pure geometry: for visit k of node n (its k-th incident edge, in edge order)
+// weight = 1/|dx| and we[3] = ComputeLSQCoefficients(sw[n], dx/|dx|) (gradient.tcc:141-168, 276-312) never change on a
+// static mesh.  k_lsq_geo evaluates them ONCE with the arithmetic of k_gradient and stores {weight, +-we[0..2]} per
+// visit (the sign of the scatter, gradient.tcc:306-311, folded in: (-a)*b == -(a*b) exactly), so that the per-iteration
+// kernel is left with one subtraction, one product and the ordered sum per term.  BC half-edges (no contribution,
+// gradient.tcc:322-378 only acts on parallel edges) get zeros and are skipped through the visit mask.
+__global__ void __launch_bounds__(128) k_lsq_geo(DevMesh m, const double* __restrict__ sw, double4* __restrict__ geo) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= m.nnode) return;
+  double swn[6];
+#pragma unroll
+  for (int k = 0; k < 6; k++) swn[k] = sw[6 * (size_t)n + k];
+  const double xn[3] = {m.xyz[3 * n], m.xyz[3 * n + 1], m.xyz[3 * n + 2]};
+  for (int k = m.adjp[n]; k < m.adjp[n + 1]; k++) {
+    const int2 a = m.adj[k];
+    const int o = a.x & 0x7fffffff;
+    const bool right = a.x < 0;
+    if (a.y >= m.nedge && !is_ghost(m, o)) { geo[k] = make_double4(0.0, 0.0, 0.0, 0.0); continue; }
+    const double xo[3] = {__ldg(m.xyz + 3 * o), __ldg(m.xyz + 3 * o + 1), __ldg(m.xyz + 3 * o + 2)};
+    double dx[3], we[3];   // dx = x_left - x_right
+#pragma unroll
+    for (int d = 0; d < 3; d++) dx[d] = right ? (xo[d] - xn[d]) : (xn[d] - xo[d]);
+    const double dx2 = dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2];
+    const double weight = 1.0 / sqrt(dx2);
+    dx[0] *= weight; dx[1] *= weight; dx[2] *= weight;
+    if (right) { dx[0] = -dx[0]; dx[1] = -dx[1]; dx[2] = -dx[2]; }
+    lsq_weights(swn, dx, we);
+    geo[k] = right ? make_double4(weight, we[0], we[1], we[2]) : make_double4(weight, -we[0], -we[1], -we[2]);
+  }
+}
+
+// Gradient::Compute with the precomputed visit weights: one thread per node, ordered gather like k_gradient, but a
+// visit is now 9 x (1 subtraction, 4 products, 3 additions) -- no square root, no divisions, no coordinates.
+// (A 16-lanes-per-node form with one lane per visit and the ordered sums through shared memory was measured on B200
+// at 2.47 ms against 1.33 ms for k_gradient + k_limiter: 2.3x the instructions for the transposes and shuffles;
+// profiles/r2_ncu_explicit.md.)
+__global__ void __launch_bounds__(128, PCFD_GRAD_MINB) k_gradient_geo(DevMesh m, const double* __restrict__ q,
+                                                                       const double4* __restrict__ geo,
+                                                                       double* __restrict__ qgrad) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= m.nnode) return;
+  double g[NTERMS * 3];
+#pragma unroll
+  for (int k = 0; k < NTERMS * 3; k++) g[k] = 0.0;
+  double qn[NVARS];
+  load_q10(q, n, qn);
+  const int kend = m.adjp[n + 1];
+  int k = m.adjp[n];
+  for (; k < kend; k++) {
+    const int2 a = m.adj[k];
+    const int o = a.x & 0x7fffffff;
+    const bool right = a.x < 0;
+    if (a.y >= m.nedge && !is_ghost(m, o)) continue;
+    const double2* gp = reinterpret_cast<const double2*>(geo + k);
+    const double2 ga = __ldg(gp), gb = __ldg(gp + 1);
+    const double weight = ga.x, we[3] = {ga.y, gb.x, gb.y};   // we carries the scatter sign
+    double qo[NVARS];
+    load_q10(q, o, qo);
+#pragma unroll
+    for (int i = 0; i < NTERMS; i++) {
+      const int v = (i < 6) ? i : i + 1;   // c_gradloc
+      const double dq = right ? weight * (qn[v] - qo[v]) : weight * (qo[v] - qn[v]);
+#pragma unroll
+      for (int j = 0; j < 3; j++) g[3 * i + j] += we[j] * dq;
+    }
+  }
+  // symmetry fix, in half-edge order (the half-edges are the tail of the list)
+  for (k = m.adjp[n]; k < kend; k++) {
+    const int2 a = m.adj[k];
+    if (a.y < m.nedge) continue;
+    const int be = a.y - m.nedge;
+    if (m.bctype[be] != PCFD_BC_SYMMETRY) continue;
+    double av[4];
+    load_avec(m.bea, be, av);
+#pragma unroll
+    for (int i = 0; i < NTERMS; i++) {
+      const double dot = g[i * 3] * av[0] + g[i * 3 + 1] * av[1] + g[i * 3 + 2] * av[2];
+#pragma unroll
+      for (int j = 0; j < 3; j++) g[i * 3 + j] -= dot * av[j];
+    }
+  }
+  double* out = qgrad + (size_t)n * NTERMS * 3;
+#pragma unroll
+  for (int kk = 0; kk < NTERMS * 3; kk++) out[kk] = g[kk];
+}
+
+// The same gather by THREE threads per node, three gradient terms each: the kernel is bound by the latency of its
+// neighbour-row gathers (ncu: 17 % issue slots, 16 stall cycles per instruction on the scoreboard at 25 % occupancy
+// with 122 registers), and a third of the accumulators per thread triples the warps in flight.  The threads that own
+// the five conservative variables also take the neighbour minimum / maximum of pass 1 of Limiter::Compute
+// (Kernel_FindMinMax, limiters.tcc:135-191: from ZERO, over the same visits) while the rows are in registers: qmm[n] =
+// {min[5], max[5]}, which saves the limiter kernel -- bound by instruction issue -- its first loop over the neighbours.
+__global__ void __launch_bounds__(192, PCFD_GRAD3_MINB) k_gradient_geo3(DevMesh m, const double* __restrict__ q,
+                                                                        const double4* __restrict__ geo,
+                                                                        double* __restrict__ qgrad, double* __restrict__ qmm) {
+  // results leave through shared memory: a thread owns 9 (+ up to 6) scattered doubles, the block's 64 nodes own one
+  // contiguous 13.8 kB (+ 5 kB) range, which is written with full 16-byte lanes instead of 8-byte partial sectors
+  __shared__ __align__(16) double s_g[192 * 9];
+  __shared__ __align__(16) double s_mm[64 * 10];
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = tid / 3;
+  const int part = tid - 3 * n;              // terms 3*part .. 3*part+2
+  const bool active = n < m.nnode;
+  if (active) {
+    // variables of those terms: {0,1,2}, {3,4,5}, {7,8,9}
+    const int v0 = (part == 2) ? 7 : 3 * part;
+    double g[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) g[k] = 0.0;
+    double mn[3] = {0.0, 0.0, 0.0}, mx[3] = {0.0, 0.0, 0.0};
+    const double* qr = q + (size_t)n * NVARS + v0;
+    const double qn[3] = {qr[0], qr[1], qr[2]};
+    const int kend = m.adjp[n + 1];
+    int k = m.adjp[n];
+    for (; k < kend; k++) {
+      const int2 a = m.adj[k];
+      const int o = a.x & 0x7fffffff;
+      const bool right = a.x < 0;
+      if (a.y >= m.nedge && !is_ghost(m, o)) continue;
+      const double2* gp = reinterpret_cast<const double2*>(geo + k);
+      const double2 ga = __ldg(gp), gb = __ldg(gp + 1);
+      const double weight = ga.x, we[3] = {ga.y, gb.x, gb.y};   // we carries the scatter sign
+      const double* qp = q + (size_t)o * NVARS + v0;
+      const double qo[3] = {__ldg(qp), __ldg(qp + 1), __ldg(qp + 2)};
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const double dq = right ? weight * (qn[i] - qo[i]) : weight * (qo[i] - qn[i]);
+#pragma unroll
+        for (int j = 0; j < 3; j++) g[3 * i + j] += we[j] * dq;
+        mx[i] = eq::maxd(mx[i], qo[i]);
+        mn[i] = eq::mind(mn[i], qo[i]);
+      }
+    }
+    // symmetry fix, in half-edge order (the half-edges are the tail of the list)
+    for (k = m.adjp[n]; k < kend; k++) {
+      const int2 a = m.adj[k];
+      if (a.y < m.nedge) continue;
+      const int be = a.y - m.nedge;
+      if (m.bctype[be] != PCFD_BC_SYMMETRY) continue;
+      double av[4];
+      load_avec(m.bea, be, av);
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const double dot = g[i * 3] * av[0] + g[i * 3 + 1] * av[1] + g[i * 3 + 2] * av[2];
+#pragma unroll
+        for (int j = 0; j < 3; j++) g[i * 3 + j] -= dot * av[j];
+      }
+    }
+#pragma unroll
+    for (int kk = 0; kk < 9; kk++) s_g[threadIdx.x * 9 + kk] = g[kk];
+    if (part < 2) {   // equations 0..2 and 3..4 (variable 5, the temperature, is not limited)
+      double* mm = s_mm + (threadIdx.x / 3) * 10;
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        if (3 * part + i < 5) { mm[3 * part + i] = mn[i]; mm[5 + 3 * part + i] = mx[i]; }
+      }
+    }
+  }
+  __syncthreads();
+  const int n0 = blockIdx.x * 64;
+  const int nloc = min(64, m.nnode - n0);
+  if (nloc <= 0) return;
+  {
+    double2* dst = reinterpret_cast<double2*>(qgrad + (size_t)n0 * NTERMS * 3);   // 64 * 216 B: 16-byte aligned
+    const double2* src = reinterpret_cast<const double2*>(s_g);
+    const int cnt = nloc * NTERMS * 3;
+    for (int i = threadIdx.x; i < cnt / 2; i += 192) dst[i] = src[i];
+    if ((cnt & 1) && threadIdx.x == 0) qgrad[(size_t)n0 * NTERMS * 3 + cnt - 1] = s_g[cnt - 1];
+  }
+  {
+    double2* dst = reinterpret_cast<double2*>(qmm + (size_t)n0 * 10);
+    const double2* src = reinterpret_cast<const double2*>(s_mm);
+    for (int i = threadIdx.x; i < nloc * 5; i += 192) dst[i] = src[i];
+  }
+}
+
 // Gradient::Compute with Param::gradType == 1 (gradient.tcc:77-90): Kernel_Green_Gauss_Gradient /
 // Bkernel_Green_Gauss_Gradient (:170-248) in the Driver / Bdriver order (interior edges, then ALL half-edges, ghost
 // and boundary alike), the division by the dual volume (:83-89) and the symmetry fix (:545-565), as one ordered
@@ -215,8 +402,10 @@ __global__ void __launch_bounds__(128) k_gradient_gg(DevMesh m, const double* __
 // :62-63) and Barth / Venkatakrishnan limiting, both as gathers over the node's edges.
 // Writes the UNCLAMPED limiter; pressure clip and clamp follow.  FIVE threads per node, one equation each: the
 // limiter of a variable depends on that variable's data only.
+// qmm != null: the neighbour minimum / maximum of pass 1 were taken by k_gradient_geo3 from the same q
 __global__ void __launch_bounds__(160) k_limiter(DevMesh m, int type, double chi, const double* __restrict__ q,
-                                                  const double* __restrict__ qgrad, double* __restrict__ lim) {
+                                                  const double* __restrict__ qgrad, double* __restrict__ lim,
+                                                  const double* __restrict__ qmm) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = tid / 5;
   if (n >= m.nnode + m.gnode) return;
@@ -225,13 +414,18 @@ __global__ void __launch_bounds__(160) k_limiter(DevMesh m, int type, double chi
   if (n < m.nnode && (type == 1 || type == 2 || type == 3)) {
     double qmin = 0.0, qmax = 0.0;
     const int k0 = m.adjp[n], k1 = m.adjp[n + 1];
-    for (int k = k0; k < k1; k++) {
-      const int2 a = m.adj[k];
-      const int o = a.x & 0x7fffffff;
-      if (a.y >= m.nedge && !is_ghost(m, o)) continue;
-      const double qo = __ldg(q + (size_t)o * NVARS + j);
-      qmax = eq::maxd(qmax, qo);
-      qmin = eq::mind(qmin, qo);
+    if (qmm != nullptr) {
+      qmin = qmm[(size_t)n * 10 + j];
+      qmax = qmm[(size_t)n * 10 + 5 + j];
+    } else {
+      for (int k = k0; k < k1; k++) {
+        const int2 a = m.adj[k];
+        const int o = a.x & 0x7fffffff;
+        if (a.y >= m.nedge && !is_ghost(m, o)) continue;
+        const double qo = __ldg(q + (size_t)o * NVARS + j);
+        qmax = eq::maxd(qmax, qo);
+        qmin = eq::mind(qmin, qo);
+      }
     }
     const double qn = __ldg(q + (size_t)n * NVARS + j);
     const double* gp = qgrad + (size_t)n * NTERMS * 3 + j * 3;
@@ -271,6 +465,68 @@ __global__ void __launch_bounds__(160) k_limiter(DevMesh m, int type, double chi
     }
   }
   lim[(size_t)n * 5 + j] = l;
+}
+
+// The same two passes with ONE thread per node carrying all five equations: adjacency, neighbour coordinates and the
+// half edge vector are fetched once per visit instead of once per equation, and the five independent division chains of
+// a visit give the FP64 pipe the instruction-level parallelism the five-thread form gets from its threads.
+__global__ void __launch_bounds__(128, PCFD_LIM_MINB) k_limiter_node(DevMesh m, int type, double chi, const double* __restrict__ q,
+                                                                      const double* __restrict__ qgrad, double* __restrict__ lim) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= m.nnode + m.gnode) return;
+  double l[5] = {1.0, 1.0, 1.0, 1.0, 1.0};
+  if (n < m.nnode && (type == 1 || type == 2 || type == 3)) {
+    double qmin[5] = {0, 0, 0, 0, 0}, qmax[5] = {0, 0, 0, 0, 0};
+    const int k0 = m.adjp[n], k1 = m.adjp[n + 1];
+    for (int k = k0; k < k1; k++) {
+      const int2 a = m.adj[k];
+      const int o = a.x & 0x7fffffff;
+      if (a.y >= m.nedge && !is_ghost(m, o)) continue;
+      double qo[5];
+      load_q5(q, o, qo);
+#pragma unroll
+      for (int j = 0; j < 5; j++) { qmax[j] = eq::maxd(qmax[j], qo[j]); qmin[j] = eq::mind(qmin[j], qo[j]); }
+    }
+    double qn[5], g[15];
+    load_q5(q, n, qn);
+    const double* gp = qgrad + (size_t)n * NTERMS * 3;
+#pragma unroll
+    for (int j = 0; j < 15; j++) g[j] = gp[j];
+    const double xn[3] = {m.xyz[3 * n], m.xyz[3 * n + 1], m.xyz[3 * n + 2]};
+    const double ep2 = (type == 3) ? (6.0 * 3.141592653589793 * m.vol[n]) * (1.0 * 1.0 * 1.0) : 0.0;
+    for (int k = k0; k < k1; k++) {
+      const int2 a = m.adj[k];
+      const int o = a.x & 0x7fffffff;
+      if (a.y >= m.nedge && !is_ghost(m, o)) continue;
+      double qo[5], dx[3];
+      load_q5(q, o, qo);
+#pragma unroll
+      for (int d = 0; d < 3; d++) dx[d] = 0.5 * (__ldg(m.xyz + 3 * o + d) - xn[d]);
+#pragma unroll
+      for (int j = 0; j < 5; j++) {
+        const double dQ = qo[j] - qn[j];
+        const double corr = 0.5 * chi * dQ + (1.0 - chi) * (g[3 * j] * dx[0] + g[3 * j + 1] * dx[1] + g[3 * j + 2] * dx[2]);
+        const double QH = qn[j] + corr * 1.0;
+        double t = 1.0;
+        if (type == 3) {   // see k_limiter
+          const double DM = QH - qn[j];
+          double DP = 0.0;
+          if (a.y >= m.nedge) DP = (QH > qn[j]) ? (qmax[j] - QH) : (qmin[j] - QH);
+          else if (a.x < 0) DP = (QH > qn[j]) ? (qmax[j] - qn[j]) : (qmin[j] - qn[j]);
+          else if (QH > qn[j]) DP = qmax[j] - qn[j];
+          else if (QH < qn[j]) DP = qmin[j] - qn[j];
+          t = (DP * DP + ep2 + 2.0 * DM * DP) / (DP * DP + 2.0 * DM * DM + DM * DP + ep2);
+        } else {
+          if (QH > qn[j]) t = (qmax[j] - qn[j]) / (QH - qn[j]);
+          else if (QH < qn[j]) t = (qmin[j] - qn[j]) / (QH - qn[j]);
+          t = limiter_fn(type, t);
+        }
+        l[j] = eq::mind(l[j], t);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 5; j++) lim[(size_t)n * 5 + j] = l[j];
 }
 
 // Kernel_PressureClip (limiters.tcc:737-815) is sequential in the reference: an edge
@@ -353,14 +609,15 @@ __global__ void k_limiter_final(int ntot, int nnode, const int* __restrict__ tcl
 #ifndef PCFD_FLUX_MINB
 #define PCFD_FLUX_MINB 5   /* measured on B200: 1.33 -> 1.01 ms at 10 M cells (102 registers, 152 B of spills) */
 #endif
-#ifndef PCFD_GRAD_MINB
-#define PCFD_GRAD_MINB 1
-#endif
-template <bool DET>
+// EIG: the edge's term of ComputeTimesteps (Kernel_Timestep, timestep.tcc:80-111: max eigenvalue of the averaged state
+// times the face area) is evaluated on the way from the two node states already in registers and stored per edge; the
+// residual gather then sums it per node in edge order and forms the time step -- the separate k_timestep pass (which
+// evaluates every edge twice, once from each end) disappears from the explicit iteration.
+template <bool DET, bool EIG>
 __global__ void __launch_bounds__(128, PCFD_FLUX_MINB) k_flux_edges(DevMesh m, int sorder, double chi, double gamma,
                                                      const double* __restrict__ q, const double* __restrict__ qgrad,
                                                      const double* __restrict__ lim, double* __restrict__ flux,
-                                                     int* __restrict__ any) {
+                                                     int* __restrict__ any, double* __restrict__ eig) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= m.nedge) return;
   const int2 lr = m.en[e];
@@ -369,6 +626,12 @@ __global__ void __launch_bounds__(128, PCFD_FLUX_MINB) k_flux_edges(DevMesh m, i
   load_avec(m.ea, e, av);
   load_q5(q, l, QL);
   load_q5(q, r, QR);
+  if (EIG) {
+    double Q[5];
+#pragma unroll
+    for (int j = 0; j < 5; j++) Q[j] = 0.5 * (QL[j] + QR[j]);
+    eig[e] = eq::max_eigenvalue(Q, av, 0.0, gamma) * av[3];
+  }
   bool neg = false;
   if (sorder > 1) {
     double dQ[5], dx[3], gr[15], lmL[5], lmR[5], qL[5], qR[5];
@@ -465,16 +728,21 @@ __global__ void __launch_bounds__(128) k_flux_bedges(DevMesh m, int sorder, doub
 // a second pass over the same list -- the reference runs its viscous Driver/Bdriver after the inviscid pair --
 // and Bkernel_BC_Res_Modify (bc.tcc:905-1056 -> ModifyViscousWallResidual, compressible.tcc:1611-1631) zeroes the
 // hard-set rows of no-slip wall nodes (wallflag: bit 0 = owns a NoSlip half-edge, bit 1 = an adiabatic one).
-template <bool VISC>
+// EIG: also sums the per-edge time-step terms (k_flux_edges<., true>, k_eig_bedges) in the same order and writes
+// dt = CFL V / sum (+ the Von Neumann limit), exactly what k_timestep computes (timestep.tcc:31-45).
+template <bool VISC, bool EIG>
 __global__ void __launch_bounds__(128) k_residual_gather(DevMesh m, const double* __restrict__ flux,
                                                           const double* __restrict__ bflux,
                                                           const double* __restrict__ vflux,
                                                           const double* __restrict__ bvflux,
                                                           const unsigned char* __restrict__ wallflag,
-                                                          double* __restrict__ b) {
+                                                          double* __restrict__ b, const double* __restrict__ eig,
+                                                          const double* __restrict__ beig, double cfl,
+                                                          const double* __restrict__ vnn23, double* __restrict__ dt) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= m.nnode) return;
   double acc[5] = {0, 0, 0, 0, 0};
+  double esum = 0.0;
   const int k0 = m.adjp[n], k1 = m.adjp[n + 1];
   for (int k = k0; k < k1; k++) {
     const int2 a = m.adj[k];
@@ -484,6 +752,12 @@ __global__ void __launch_bounds__(128) k_residual_gather(DevMesh m, const double
     load5(f, fv);
 #pragma unroll
     for (int j = 0; j < 5; j++) acc[j] += right ? fv[j] : -fv[j];
+    if (EIG) esum += (a.y < m.nedge) ? __ldg(eig + a.y) : __ldg(beig + (a.y - m.nedge));
+  }
+  if (EIG) {
+    double d = cfl * (m.vol[n] / esum);
+    if (vnn23 != nullptr && n >= 1) d = eq::mind(d, vnn23[n]);
+    dt[n] = d;
   }
   if (VISC) {
     for (int k = k0; k < k1; k++) {
@@ -617,6 +891,22 @@ __global__ void __launch_bounds__(128) k_timestep(DevMesh m, double gamma, doubl
   double d = cfl * (m.vol[n] / acc);
   if (vnn23 != nullptr && n >= 1) d = eq::mind(d, vnn23[n]);
   dt[n] = d;
+}
+
+// Bkernel_Timestep (timestep.tcc:114-143) per half-edge, for the fused form: launched BEFORE UpdateBCs, where
+// ComputeTimesteps sits in the iteration, so that it sees the phantom / ghost states k_timestep would see
+__global__ void __launch_bounds__(128) k_eig_bedges(DevMesh m, double gamma, const double* __restrict__ q,
+                                                     double* __restrict__ beig) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m.nbedge + m.ngedge) return;
+  const int2 lr = m.ben[e];
+  double av[4], qL[5], qR[5], Q[5];
+  load_avec(m.bea, e, av);
+  load_q5(q, lr.x, qL);
+  load_q5(q, lr.y, qR);
+#pragma unroll
+  for (int j = 0; j < 5; j++) Q[j] = 0.5 * (qL[j] + qR[j]);
+  beig[e] = eq::max_eigenvalue(Q, av, 0.0, gamma) * av[3];
 }
 
 // deterministic min / sum-of-squares reductions (fixed grid, fixed tree)
@@ -2189,6 +2479,11 @@ static int create_impl(const pcfd_mesh_desc* mesh, const pcfd_params* params, in
   }
   if (dev_alloc(c, &c->flux, (size_t)nedge * neqn)) return 1;
   if (dev_alloc(c, &c->bflux, (size_t)nb * neqn)) return 1;
+  if (neqn == NEQN) {
+    if (dev_alloc(c, &c->eig, (size_t)nedge)) return 1;
+    if (dev_alloc(c, &c->beig, (size_t)nb)) return 1;
+  }
+  if (const char* e = getenv("PCFD_EIG_FUSE")) c->eig_fuse = atoi(e) != 0;
   if (sa_on) {
     if (dev_alloc(c, &c->tslots, (size_t)nedge * 3)) return 1;
     if (dev_alloc(c, &c->tbslots, (size_t)nb * 4)) return 1;
@@ -2206,6 +2501,12 @@ static int create_impl(const pcfd_mesh_desc* mesh, const pcfd_params* params, in
   CK(cudaMallocHost(reinterpret_cast<void**>(&c->hflag), sizeof(int)));
   CK(cudaEventCreateWithFlags(&c->ev_flag, cudaEventDisableTiming));
   if (const char* e = getenv("PCFD_FUSED_CLIP")) c->fused_clip = atoi(e) != 0;
+  if (const char* e = getenv("PCFD_GRAD_GEO")) c->use_geo = atoi(e) != 0;
+  if (const char* e = getenv("PCFD_GRAD_THREADS")) c->grad_threads = atoi(e) == 1 ? 1 : 3;
+  if (const char* e = getenv("PCFD_LIMITER_QMM")) c->use_qmm = atoi(e) != 0;
+  if (neqn == NEQN && dev_alloc(c, &c->qmm, (size_t)nnode * 10)) return 1;
+  if (const char* e = getenv("PCFD_LIMITER_PER_NODE")) c->limiter_per_node = atoi(e) != 0;
+  if (neqn == NEQN && dev_alloc(c, &c->geo, adj.size())) return 1;
 
   c->dm = DevMesh{c->nnode, c->gnode, c->nbnode, c->nedge, c->nbedge, c->ngedge, c->en, c->ea, c->ben, c->bea,
                   c->bctype, c->xyz, c->vol, c->adjp, c->adj, c->bnormal, c->btwall};
@@ -2313,6 +2614,8 @@ int pcfd_set_field(pcfd_ctx* c, int field, const double* host, size_t n) {
   if (field < 0 || field >= PCFD_F_COUNT || !host) return fail(c, "pcfd_set_field: bad argument");
   CK(cudaSetDevice(c->device));
   if (field == PCFD_F_A) { if (ensure_matrix(c)) return 1; c->ludiag = false; }
+  if (field == PCFD_F_LSQ_SW) c->geo_valid = false;
+  if (field == PCFD_F_Q) c->qmm_valid = false;
   if (is_time_field(field)) {
     if (ensure_time_fields(c)) return 1;
     if (field == PCFD_F_QOLD) c->have_qold = true;
@@ -2362,6 +2665,7 @@ int pcfd_lsq_coefficients(pcfd_ctx* c) {
   PROF("k_lsq_coeff");
   k_lsq_coeff<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->f[PCFD_F_LSQ_S], c->f[PCFD_F_LSQ_SW]);
   LAUNCH_CHECK();
+  c->geo_valid = false;
   if (comm_on(c)) {   // gradient.tcc:131-134: halos of s and sw
     if (comm_update(c, PCFD_F_LSQ_S)) return 1;
     return comm_update(c, PCFD_F_LSQ_SW);
@@ -2372,6 +2676,7 @@ int pcfd_lsq_coefficients(pcfd_ctx* c) {
 int pcfd_update_bcs(pcfd_ctx* c) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
+  c->qmm_valid = false;
   if (c->fr) return pcfd_fr_update_bcs(c);
   if (c->nbn) {
     PROF("k_update_bcs");
@@ -2387,6 +2692,8 @@ int pcfd_update_bcs(pcfd_ctx* c) {
   return 0;
 }
 
+static int run_gradient_geo(pcfd_ctx* c);
+
 int pcfd_gradient(pcfd_ctx* c) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
@@ -2397,6 +2704,7 @@ int pcfd_gradient(pcfd_ctx* c) {
     LAUNCH_CHECK();
     return 0;
   }
+  if (c->use_geo && c->geo) return run_gradient_geo(c);
   PROF("k_gradient");
   k_gradient<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->f[PCFD_F_Q], c->f[PCFD_F_LSQ_SW], c->f[PCFD_F_QGRAD]);
   LAUNCH_CHECK();
@@ -2421,6 +2729,7 @@ int pcfd_set_gradient_type(pcfd_ctx* c, int type) {
 }
 
 static int run_limiter_final(pcfd_ctx* c, const int* tclip);
+static int run_limiter_raw(pcfd_ctx* c);
 static int run_flux(pcfd_ctx* c, bool fused = false, bool* clip_hit = nullptr);
 static int run_sumsq(pcfd_ctx* c, const double* v, int nrows, double* host_out);
 
@@ -2430,9 +2739,7 @@ int pcfd_limiter(pcfd_ctx* c) {
   if (c->fr) return pcfd_fr_limiter(c);
   const int type = c->prm.limiter;
   double* lim = c->f[PCFD_F_LIMITER];
-  PROF("k_limiter");
-  k_limiter<<<nblk((long long)c->nn * 5, 160), 160, 0, c->stream>>>(c->dm, type, c->prm.chi, c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD], lim);
-  LAUNCH_CHECK();
+  if (run_limiter_raw(c)) return 1;
   if (type == 0) return 0;
   // pressure clip: iterate (edges -> flags, nodes -> first clipping edge) to the fixed point
   int cur = 0;
@@ -2469,6 +2776,40 @@ int pcfd_limiter(pcfd_ctx* c) {
 // Gradient -> Limiter -> ComputeResiduals of the composite iterations.  With a limiter on, the pressure-clip test
 // rides along in the edge-flux kernel (k_flux_edges<true>); only when some edge actually clips (rare: the limiter
 // exists to prevent exactly that) are the ordered clip passes and the flux redone.
+// Gradient::Compute with the static LSQ visit weights (k_lsq_geo), (re)built when the coefficients changed
+static int run_gradient_geo(pcfd_ctx* c) {
+  if (!c->geo_valid) {
+    PROF("k_lsq_geo");
+    k_lsq_geo<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->f[PCFD_F_LSQ_SW], c->geo);
+    LAUNCH_CHECK();
+    c->geo_valid = true;
+  }
+  PROF("k_gradient");
+  if (c->grad_threads == 3) {
+    k_gradient_geo3<<<nblk((long long)c->nnode * 3, 192), 192, 0, c->stream>>>(c->dm, c->f[PCFD_F_Q], c->geo, c->f[PCFD_F_QGRAD],
+                                                                              c->qmm);
+    c->qmm_valid = true;
+  } else {
+    k_gradient_geo<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->f[PCFD_F_Q], c->geo, c->f[PCFD_F_QGRAD]);
+  }
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// passes 1 + 2 of Limiter::Compute (raw limiter): five threads per node (one per equation) or one thread per node
+static int run_limiter_raw(pcfd_ctx* c) {
+  PROF("k_limiter");
+  if (c->limiter_per_node)
+    k_limiter_node<<<nblk(c->nn, 128), 128, 0, c->stream>>>(c->dm, c->prm.limiter, c->prm.chi, c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD],
+                                                            c->f[PCFD_F_LIMITER]);
+  else
+    k_limiter<<<nblk((long long)c->nn * 5, 160), 160, 0, c->stream>>>(c->dm, c->prm.limiter, c->prm.chi, c->f[PCFD_F_Q],
+                                                                     c->f[PCFD_F_QGRAD], c->f[PCFD_F_LIMITER],
+                                                                     (c->qmm_valid && c->use_qmm) ? c->qmm : nullptr);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 static int gradient_limiter_residual(pcfd_ctx* c, double* sumsq) {
   const bool dist = comm_on(c);
   if (c->fr) {
@@ -2494,14 +2835,11 @@ static int gradient_limiter_residual(pcfd_ctx* c, double* sumsq) {
     return pcfd_residual(c, sumsq);
   }
   if (c->prm.sorder > 1) {
+    const int type = c->prm.limiter;
     if (pcfd_gradient(c)) return 1;
     if (dist && comm_post(c, PCFD_F_QGRAD)) return 1;              // gradient.tcc:98; waited for inside run_flux
-    const int type = c->prm.limiter;
     if (type != 0 && c->fused_clip) {
-      PROF("k_limiter");
-      k_limiter<<<nblk((long long)c->nn * 5, 160), 160, 0, c->stream>>>(c->dm, type, c->prm.chi, c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD],
-                                                         c->f[PCFD_F_LIMITER]);
-      LAUNCH_CHECK();
+      if (run_limiter_raw(c)) return 1;
       if (dist && comm_post(c, PCFD_F_LIMITER)) return 1;          // limiters.tcc:128 (raw values; both sides clamp)
       bool hit = false;
       if (run_flux(c, true, &hit)) return 1;
@@ -2526,11 +2864,7 @@ int pcfd_limiter_raw(pcfd_ctx* c) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
   if (c->fr) return pcfd_fr_limiter_raw(c);
-  PROF("k_limiter");
-  k_limiter<<<nblk((long long)c->nn * 5, 160), 160, 0, c->stream>>>(c->dm, c->prm.limiter, c->prm.chi, c->f[PCFD_F_Q],
-                                                                   c->f[PCFD_F_QGRAD], c->f[PCFD_F_LIMITER]);
-  LAUNCH_CHECK();
-  return 0;
+  return run_limiter_raw(c);
 }
 
 long long pcfd_clip_fallbacks(const pcfd_ctx* c) { return c ? c->clip_fallbacks : -1; }
@@ -2614,17 +2948,17 @@ static int flux_clip_decision(pcfd_ctx* c, bool dist, bool* clip_hit) {
 
 static int run_flux(pcfd_ctx* c, bool fused, bool* clip_hit) {
   const bool dist = fused && comm_on(c);
+  const bool eig = c->eig_now;   // pcfd_explicit_iterate: the time step rides along (k_eig_bedges has run)
   if (fused) CK(cudaMemsetAsync(c->dflags + 2, 0, sizeof(int), c->stream));
   if (c->nedge) {
     PROF("k_flux_edges");
-    if (fused)
-      k_flux_edges<true><<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, c->prm.sorder, c->prm.chi, c->prm.gamma,
-                                                                     c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD],
-                                                                     c->f[PCFD_F_LIMITER], c->flux, c->dflags + 2);
-    else
-      k_flux_edges<false><<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, c->prm.sorder, c->prm.chi, c->prm.gamma,
-                                                                      c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD],
-                                                                      c->f[PCFD_F_LIMITER], c->flux, nullptr);
+#define PCFD_FLUX_LAUNCH(DD, EE, ANY)                                                                                   \
+  k_flux_edges<DD, EE><<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, c->prm.sorder, c->prm.chi, c->prm.gamma,       \
+                                                                  c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD],                   \
+                                                                  c->f[PCFD_F_LIMITER], c->flux, ANY, c->eig)
+    if (fused) { if (eig) PCFD_FLUX_LAUNCH(true, true, c->dflags + 2); else PCFD_FLUX_LAUNCH(true, false, c->dflags + 2); }
+    else { if (eig) PCFD_FLUX_LAUNCH(false, true, nullptr); else PCFD_FLUX_LAUNCH(false, false, nullptr); }
+#undef PCFD_FLUX_LAUNCH
     LAUNCH_CHECK();
   }
   if (dist) {
@@ -2657,16 +2991,28 @@ static int run_flux(pcfd_ctx* c, bool fused, bool* clip_hit) {
       LAUNCH_CHECK();
     }
     PROF("k_residual_gather");
-    k_residual_gather<true><<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->flux, c->bflux, c->vflux, c->bvflux,
-                                                                        c->wallflag, c->f[PCFD_F_B]);
+    if (eig)
+      k_residual_gather<true, true><<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->flux, c->bflux, c->vflux, c->bvflux,
+                                                                                c->wallflag, c->f[PCFD_F_B], c->eig, c->beig,
+                                                                                c->prm.cfl, c->vnn23, c->f[PCFD_F_TIMESTEP]);
+    else
+      k_residual_gather<true, false><<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->flux, c->bflux, c->vflux, c->bvflux,
+                                                                                 c->wallflag, c->f[PCFD_F_B], nullptr, nullptr,
+                                                                                 0.0, nullptr, nullptr);
     LAUNCH_CHECK();
     if (run_temporal(c)) return 1;
     if (fused) return flux_clip_decision(c, dist, clip_hit);
     return 0;
   }
   PROF("k_residual_gather");
-  k_residual_gather<false><<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->flux, c->bflux, nullptr, nullptr, nullptr,
-                                                                       c->f[PCFD_F_B]);
+  if (eig)
+    k_residual_gather<false, true><<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->flux, c->bflux, nullptr, nullptr, nullptr,
+                                                                               c->f[PCFD_F_B], c->eig, c->beig, c->prm.cfl,
+                                                                               c->vnn23, c->f[PCFD_F_TIMESTEP]);
+  else
+    k_residual_gather<false, false><<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->flux, c->bflux, nullptr, nullptr, nullptr,
+                                                                                c->f[PCFD_F_B], nullptr, nullptr, 0.0, nullptr,
+                                                                                nullptr);
   LAUNCH_CHECK();
   if (run_temporal(c)) return 1;
   if (fused) return flux_clip_decision(c, dist, clip_hit);
@@ -2754,6 +3100,7 @@ int pcfd_timestep(pcfd_ctx* c, double* dtmin) {
 int pcfd_explicit_solve(pcfd_ctx* c) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
+  c->qmm_valid = false;
   if (c->fr) return pcfd_fr_explicit_solve(c);
   PROF("k_explicit");
   k_explicit<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->nnode, c->prm.gamma, c->f[PCFD_F_B], c->f[PCFD_F_TIMESTEP],
@@ -2765,6 +3112,7 @@ int pcfd_explicit_solve(pcfd_ctx* c) {
 int pcfd_apply_dq(pcfd_ctx* c) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
+  c->qmm_valid = false;
   if (c->fr) return pcfd_fr_apply_dq(c);
   PROF("k_apply_dq");
   k_apply_dq<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->nnode, c->prm.gamma, c->f[PCFD_F_X], c->f[PCFD_F_Q]);
@@ -3239,10 +3587,23 @@ int pcfd_turb_phase(pcfd_ctx* c, int phase, double* sumsq) {
 int pcfd_explicit_iterate(pcfd_ctx* c, int refresh_dt, double* sumsq) {
   if (!c) return 1;
   const bool dist = comm_on(c);
-  if (refresh_dt && pcfd_timestep(c, nullptr)) return 1;
+  // ComputeTimesteps folded into the residual pass: possible when UpdateBCs does not touch owned nodes (no
+  // Dirichlet-type half-edges: the interior-edge states the flux kernel reads are then the ones ComputeTimesteps
+  // would have read) and the step is the local CFL one; the half-edge terms are taken here, before UpdateBCs
+  const bool ride = refresh_dt && !c->fr && c->eig_fuse && c->nbn == 0 && c->time_local && c->eig;
+  if (refresh_dt && !ride && pcfd_timestep(c, nullptr)) return 1;
+  if (ride && c->nb) {
+    CK(cudaSetDevice(c->device));
+    PROF("k_eig_bedges");
+    k_eig_bedges<<<nblk(c->nb, 128), 128, 0, c->stream>>>(c->dm, c->prm.gamma, c->f[PCFD_F_Q], c->beig);
+    LAUNCH_CHECK();
+  }
   if (pcfd_update_bcs(c)) return 1;
   if (dist && comm_update(c, PCFD_F_Q)) return 1;                  // solutionSpace.tcc:665
-  if (gradient_limiter_residual(c, sumsq)) return 1;
+  c->eig_now = ride;
+  const int rc = gradient_limiter_residual(c, sumsq);
+  c->eig_now = false;
+  if (rc) return 1;
   if (pcfd_explicit_solve(c)) return 1;
   if (dist && comm_update(c, PCFD_F_Q)) return 1;                  // :857
   return 0;

@@ -9,10 +9,12 @@ from proteuscfd_b200.cases import slab_case
 from proteuscfd_b200.parallel import build_local_group_maps
 
 
-@pytest.mark.parametrize("nr,colored", [(2, False), (3, True), (4, True)])
-def test_slab_halo_maps_deliver_owner_values(nr, colored):
+@pytest.mark.parametrize("nr,colored,nz", [(2, False, None), (3, True, None), (4, True, None), (3, True, 7), (4, False, 5)])
+def test_slab_halo_maps_deliver_owner_values(nr, colored, nz):
+    """nz: a FIXED box of n x n x nz hexes dealt out to the ranks (strong scaling; uneven slabs), else one cube per rank"""
     n = 4
-    parts = [slab_case(n, r, nr, colored=colored)[0] for r in range(nr)]
+    parts = [slab_case(n, r, nr, colored=colored, nz=nz)[0] for r in range(nr)]
+    assert sum(m["nnode"] for m in parts) == (n + 1) * (n + 1) * ((nz or n * nr) + 1)
     pobjs = build_local_group_maps([(m["gNodeOwner"], m["gNodeLocalId"]) for m in parts])
     nn = [m["nnode"] for m in parts]
     # field = global node id (as a double) and the coordinates: owners fill their rows, ghosts start poisoned
