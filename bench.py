@@ -604,7 +604,7 @@ def main():
 
 
 # FP64-pipe instructions per edge of k_flux_edges<true, EIG> (static SASS counts: DADD + DMUL + DFMA + DSETP + MUFU.RCP64H/RSQ64H)
-FLUX_FP64_INSTR = {"plain": 1274, "with_timestep": 1274}
+FLUX_FP64_INSTR = {"plain": 1274, "with_timestep": 1347}    # 315+451+455+53 | 331+474+488+54
 
 
 def parity_check(args, mesh, params, q0, rank, world, local_rank, torch, dist, stream):

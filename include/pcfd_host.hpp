@@ -103,6 +103,7 @@ class DropIn {
         if (FILE* f = std::fopen(path, "wb")) { std::fwrite(&fpv[0], sizeof(pcfd_fr_params), 1, f); std::fclose(f); }
       }
       if (pcfd_create_fr(&md, &pr, &fpv[0], device, &ctx_) != 0) onError_("pcfd_create_fr", pcfd_last_error(NULL));
+      if (!ctx_) return;
       // preconditioning field "beta" (solutionSpace.tcc:235-247); rows beyond the local + ghost nodes stay 1
       std::vector<double> beta(pcfd_field_size(ctx_, PCFD_F_BETA), 1.0);
       const double* hb = s_->GetFieldData("beta", FIELDS::STATE_NONE);
@@ -110,6 +111,12 @@ class DropIn {
       Check(pcfd_set_field(ctx_, PCFD_F_BETA, beta.data(), beta.size()), "set beta");
     } else
     if (pcfd_create(&md, &pr, device, &ctx_) != 0) onError_("pcfd_create", pcfd_last_error(NULL));
+    if (!ctx_) return;   // a non-aborting handler gets here: leave an empty shim rather than touch a null context
+    // Param::dt / useLocalTimeStepping / torder / iter as they stand now (steady runs: dt < 0); PushTimeIntegration
+    // refreshes them per step
+    if (s_->param->dt != 0.0)
+      Check(pcfd_set_time_integration(ctx_, s_->param->dt, s_->param->useLocalTimeStepping ? 1 : 0,
+                                      (s_->param->torder == 2) ? 2 : 1, s_->iter), "pcfd_set_time_integration");
     // Param::gradType (gradient.tcc:68-90) and Param::fieldJacType / boundaryJacType (jacobian.tcc:140-176)
     Check(pcfd_set_gradient_type(ctx_, s_->param->gradType), "pcfd_set_gradient_type");
     Check(pcfd_set_jacobian_type(ctx_, s_->param->fieldJacType, s_->param->boundaryJacType), "pcfd_set_jacobian_type");
@@ -117,7 +124,7 @@ class DropIn {
     Check(pcfd_set_field(ctx_, PCFD_F_LSQ_S, s_->m->s, 6 * (size_t)(nnode_ + gnode_)), "set s");
     Check(pcfd_set_field(ctx_, PCFD_F_LSQ_SW, s_->m->sw, 6 * (size_t)(nnode_ + gnode_)), "set sw");
   }
-  ~DropIn() { pcfd_destroy(ctx_); }
+  ~DropIn() { if (ctx_) pcfd_destroy(ctx_); }
 
   pcfd_ctx* Context() { return ctx_; }
 
@@ -189,6 +196,71 @@ class DropIn {
   }
   void ExplicitSolve() { Check(pcfd_explicit_solve(ctx_), "ExplicitSolve"); }                              // solve.tcc:71
   void ApplyDQ() { Check(pcfd_apply_dq(ctx_), "ApplyDQ"); }                                                // solutionSpace.tcc:802
+
+#ifndef PCFD_HOST_NO_MPI
+  // ---- several ranks, one process (and one GPU) each.  PObj keeps its comm maps private, so ConnectRanks rebuilds them
+  // the way PObj::BuildCommMaps does (parallel.tcc:461-554) from the mesh's public ghost tables (Mesh::gNodeOwner /
+  // gNodeLocalId, mesh.h:205-210) with the host's own MPI: receive counts per owner, MPI_Alltoall for the send counts,
+  // the requested local ids point to point.  The device-resident exchange then needs ONE more collective, ever: an
+  // MPI_Allgather of the pcfd_comm blobs (CUDA-IPC handles of the fields and of a flag page); after pcfd_comm_connect
+  // every PObj::UpdateGeneralVectors(v, n) of the hot path becomes UpdateGeneralVectors(PCFD_F_*): a put kernel and a
+  // wait kernel, no MPI, no host copy (parallel.tcc:779-873).
+  void ConnectRanks() {
+    int rank = 0, np = 1;
+    MPI_Comm_rank(MPI_COMM_WORLD, &rank);
+    MPI_Comm_size(MPI_COMM_WORLD, &np);
+    std::vector<int> recvc(np, 0), sendc(np, 0), roff(np + 1, 0), soff(np + 1, 0);
+    for (int g = 0; g < gnode_; g++) recvc[s_->m->gNodeOwner[g]]++;                    // parallel.tcc:482-484
+    MPI_Alltoall(recvc.data(), 1, MPI_INT, sendc.data(), 1, MPI_INT, MPI_COMM_WORLD);  // :497
+    for (int p = 0; p < np; p++) { roff[p + 1] = roff[p] + recvc[p]; soff[p + 1] = soff[p] + sendc[p]; }
+    std::vector<int> list((size_t)(soff[np] > 0 ? soff[np] : 1));
+    std::vector<MPI_Request> rq((size_t)np), sq((size_t)np);
+    for (int p = 0; p < np; p++)                                                       // :523-541: who wants which of my nodes
+      if (sendc[p]) MPI_Irecv(&list[soff[p]], sendc[p], MPI_INT, p, 0, MPI_COMM_WORLD, &rq[p]);
+    for (int p = 0; p < np; p++)
+      if (recvc[p]) MPI_Isend(&s_->m->gNodeLocalId[roff[p]], recvc[p], MPI_INT, p, 0, MPI_COMM_WORLD, &sq[p]);
+    for (int p = 0; p < np; p++) {
+      if (sendc[p]) MPI_Wait(&rq[p], MPI_STATUS_IGNORE);
+      if (recvc[p]) MPI_Wait(&sq[p], MPI_STATUS_IGNORE);
+    }
+    Check(pcfd_halo_configure(ctx_, rank, np, sendc.data(), list.data(), recvc.data()), "pcfd_halo_configure");
+    if (np == 1) return;
+    const size_t bs = pcfd_comm_blob_size();
+    std::vector<char> mine(bs), all(bs * (size_t)np);
+    Check(pcfd_comm_export(ctx_, mine.data()), "pcfd_comm_export");
+    MPI_Allgather(mine.data(), (int)bs, MPI_BYTE, all.data(), (int)bs, MPI_BYTE, MPI_COMM_WORLD);
+    Check(pcfd_comm_connect(ctx_, all.data()), "pcfd_comm_connect");
+    MPI_Barrier(MPI_COMM_WORLD);       // nobody posts before everybody is connected
+  }
+  // PObj::UpdateGeneralVectors(v, n) for a device-resident field (PCFD_F_Q, _QGRAD, _LIMITER, _X, _LSQ_S, _LSQ_SW, ...)
+  void UpdateGeneralVectors(int field) { Check(pcfd_comm_update(ctx_, field), "UpdateGeneralVectors"); }
+  // the two halves, for ghost-independent work in between
+  void PostHalo(int field) { Check(pcfd_comm_post(ctx_, field), "PostHalo"); }
+  void WaitHalo(int field) { Check(pcfd_comm_wait(ctx_, field), "WaitHalo"); }
+  // ParallelL2Norm / StridedParallelL2Norm (parallel.h:160-219) of the residual across ranks: sums of squares from
+  // ComputeResidualSums all-reduced with the host's MPI
+  std::vector<double> ComputeResidualsParallel() {
+    double ss[1 + PCFD_CHEM_MAX_SPECIES + 4];
+    Check(pcfd_residual(ctx_, ss), "ComputeResiduals");
+    int nn = nnode_;
+    MPI_Allreduce(MPI_IN_PLACE, ss, 1 + neqn_, MPI_DOUBLE, MPI_SUM, MPI_COMM_WORLD);
+    MPI_Allreduce(MPI_IN_PLACE, &nn, 1, MPI_INT, MPI_SUM, MPI_COMM_WORLD);
+    std::vector<double> res(1 + neqn_);
+    res[0] = std::sqrt(ss[0]) / ((double)nn * neqn_);
+    for (int k = 0; k < neqn_; k++) res[1 + k] = std::sqrt(ss[1 + k]) / (double)nn;
+    return res;
+  }
+#endif
+  // Param::dt, useLocalTimeStepping, torder and SolutionSpace::iter change from step to step: hand them over before
+  // ComputeResiduals / ComputeJacobians of an unsteady run, together with q^n and q^{n-1} (solutionSpace.tcc:582-592)
+  void PushTimeIntegration(bool with_history) {
+    Check(pcfd_set_time_integration(ctx_, s_->param->dt, s_->param->useLocalTimeStepping ? 1 : 0, s_->param->torder, s_->iter),
+          "pcfd_set_time_integration");
+    if (with_history) {
+      Check(pcfd_set_field(ctx_, PCFD_F_QOLD, s_->qold, (size_t)nnode_ * nvars_), "push qold");
+      Check(pcfd_set_field(ctx_, PCFD_F_QOLDM1, s_->qoldm1, (size_t)nnode_ * nvars_), "push qoldm1");
+    }
+  }
 
  private:
   // pcfd_fr_params from the reference's own objects: ChemModel / Species / Reaction (chem.h, species.h:35-49,

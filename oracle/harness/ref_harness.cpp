@@ -446,6 +446,10 @@ int main(int argc, char* argv[])
     DumpMesh(space);
     Dump("q0", space->q, (size_t)(nnode+gnode+nbnode)*nvars);
     pcfd::DropIn<SolutionSpace<Real> > gpu(space, 0);
+    // several ranks: halo maps from the mesh's ghost tables, CUDA-IPC connection of the ranks' device contexts; every
+    // p->UpdateGeneralVectors of the CPU branch below becomes gpu.UpdateGeneralVectors(field) on device-resident data
+    const bool multi = p->GetNp() > 1;
+    if(multi) gpu.ConnectRanks();
     gpu.PushQ();
 
     Real dtmin = gpu.ComputeTimesteps();
@@ -454,16 +458,18 @@ int main(int argc, char* argv[])
     Dump("dtmin", &dtmin, 1);
 
     gpu.GradientCompute();
+    if(multi) gpu.UpdateGeneralVectors(PCFD_F_QGRAD);        // gradient.tcc:98
     gpu.PullGradient();
     Dump("qgrad", space->qgrad, (size_t)(nnode+gnode)*nterms*3);
 
     if(param->limiter){
       gpu.LimiterCompute();
+      if(multi) gpu.UpdateGeneralVectors(PCFD_F_LIMITER);    // limiters.tcc:128
       gpu.PullLimiter();
     }
     Dump("limiter", space->limiter->l, (size_t)(nnode+gnode)*neqn);
 
-    std::vector<Real> res = gpu.ComputeResiduals();
+    std::vector<Real> res = multi ? gpu.ComputeResidualsParallel() : gpu.ComputeResiduals();
     gpu.PullB();
     Dump("b", space->crs->b, (size_t)nnode*neqn);
     Dump("resnorm", res.data(), res.size());
@@ -481,7 +487,16 @@ int main(int argc, char* argv[])
       Dump("A_lu", A->M, (size_t)A->nblocks*neqn*neqn);
       Dump("pv", A->pv, (size_t)nnode*neqn);
       gpu.BlankX();
-      Real ddq = gpu.SGS(param->nSgs);
+      Real ddq = 0.0;
+      if(multi){
+	// CRS::SGS across ranks (crs.tcc:88,146): a halo of x before the first and after every sweep
+	gpu.UpdateGeneralVectors(PCFD_F_X);
+	for(Int isgs = 0; isgs < param->nSgs; isgs++){
+	  ddq = gpu.SGS(1);
+	  gpu.UpdateGeneralVectors(PCFD_F_X);
+	}
+      }
+      else ddq = gpu.SGS(param->nSgs);
       gpu.PullX();
       Dump("x", space->crs->x, (size_t)(nnode+gnode)*neqn);
       Dump("sgs_ddq", &ddq, 1);
@@ -492,8 +507,9 @@ int main(int argc, char* argv[])
       gpu.PullX();
       Dump("x", space->crs->x, (size_t)nnode*neqn);
     }
+    if(multi) gpu.UpdateGeneralVectors(PCFD_F_Q);            // solutionSpace.tcc:857, on the device
     gpu.PullQ();
-    p->UpdateGeneralVectors(space->q, nvars);
+    if(!multi) p->UpdateGeneralVectors(space->q, nvars);
     Dump("q1", space->q, (size_t)(nnode+gnode+nbnode)*nvars);
   }
 #else

@@ -411,9 +411,10 @@ __device__ __forceinline__ void viscous_wall_bc(double gamma, double* QL, double
 }
 
 // compressible.tcc:1246-1372 characteristic far field (static mesh, 10 sub-iterations)
-__device__ __forceinline__ void farfield_bc(const BcParams& p, const double* QL, double* QR, const double* n, double vdotn) {
+// Qinf: the free stream the caller hands over (p.qinf, or the power-law scaled copy of the viscous far field)
+__device__ __forceinline__ void farfield_bc(const BcParams& p, const double* QL, double* QR, const double* n, double vdotn,
+                                            const double* Qinf) {
   const double gamma = p.gamma;
-  const double* Qinf = p.qinf;
   for (int subit = 0; subit < 10; subit++) {
     const double u = vdotn * n[0], v = vdotn * n[1], w = vdotn * n[2];
     double avg[5];
@@ -503,10 +504,30 @@ __device__ __forceinline__ void inviscid_wall_bc(const BcParams& p, const double
 
 // bc.tcc:1058-1120 + :1392-1396 CalculateBoundaryVariables for the BC types of the
 // hot-path configs; QL and QR are full nvars states.
+// Proteus_FarFieldViscous (bc.tcc:1092-1108): the momentum of the free stream is scaled by ubar = PowerLawU(1, wall
+// distance of the left node, Re) (powerLaw.h:11-29; formed on the host with the C library's pow, pcfd_set_field of
+// PCFD_F_WALLDIST) when ubar < 1.  qref: the caller's copy of Qinf, scaled IN PLACE as the reference does -- BC_Kernel
+// takes a fresh copy per call (bc.tcc:741-744: pass NULL), Bkernel_NumJac hands ONE copy to all its re-evaluations
+// (jacobian.tcc:485-506), so the scaling compounds from perturbation to perturbation there.
 __device__ __forceinline__ void boundary_variables(const BcParams& p, double* QL, double* QR, const double* n, int bctype,
-                                                   const double* normalQ = nullptr, double twall = 0.0) {
+                                                   const double* normalQ = nullptr, double twall = 0.0, double ubar = 1.0,
+                                                   double* qref = nullptr) {
   const double vdotn = 0.0;   // static mesh: driver.tcc:97-113 with Mesh::nv == 0
   switch (bctype) {
+    case PCFD_BC_FARFIELD_VISCOUS: {
+      double fresh[PCFD_NVARS];
+      double* Qinf = qref ? qref : fresh;
+      if (!qref) {
+#pragma unroll
+        for (int i = 0; i < PCFD_NVARS; i++) fresh[i] = p.qinf[i];
+      }
+      if (ubar < 1.0) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) Qinf[1 + i] = ubar * Qinf[1 + i];   // GetMomentumLocation() == 1
+      }
+      farfield_bc(p, QL, QR, n, vdotn, Qinf);
+      break;
+    }
     case PCFD_BC_PARALLEL:
       return;
     case PCFD_BC_SONIC_INFLOW:
@@ -520,7 +541,7 @@ __device__ __forceinline__ void boundary_variables(const BcParams& p, double* QL
       for (int i = 0; i < PCFD_NEQN; i++) QR[i] = QL[i];
       break;
     case PCFD_BC_FARFIELD:
-      farfield_bc(p, QL, QR, n, vdotn);
+      farfield_bc(p, QL, QR, n, vdotn, p.qinf);
       break;
     case PCFD_BC_IMPERMEABLE_WALL:
     case PCFD_BC_SYMMETRY:

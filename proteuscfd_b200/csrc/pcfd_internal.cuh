@@ -33,6 +33,7 @@ struct DevMesh {
   const int2* adj;       // (.x = other node | role<<31 (1 = this node is the RIGHT node), .y = edge id; >= nedge: half-edge)
   const int* bnormal;    // [nbedge] most-normal neighbour of the wall node (NoSlip half-edges, else -1)
   const double* btwall;  // [nbedge] non-dimensional wall temperature of the half-edge's surface (< 0: adiabatic)
+  const double* bubar;   // [nbedge] PowerLawU(1, wall distance of the left node, Re) of FarFieldViscous half-edges (else 1)
 };
 
 __device__ __forceinline__ bool is_ghost(const DevMesh& m, int n) { return n >= m.nnode && n < m.nnode + m.gnode; }
@@ -105,6 +106,10 @@ struct pcfd_ctx {
   eq::ViscParams vp{};
   double *vflux = nullptr, *bvflux = nullptr, *btwall = nullptr, *vnn23 = nullptr;
   int *bnormal = nullptr, *wnodes = nullptr, *tbnodes = nullptr;
+  // Proteus_FarFieldViscous (bc.tcc:1092-1108): half-edges of that type, their left nodes, the device table of ubar
+  std::vector<int> ffv_edges, ffv_left;
+  double* bubar = nullptr;
+  bool ffv_ready = false;          // PCFD_F_WALLDIST has been set since the table was last built
   int ntbnodes = 0;
   double *tslots = nullptr, *tbslots = nullptr;   // Spalart-Allmaras per-edge / per-half-edge slots
   unsigned char* wallflag = nullptr;

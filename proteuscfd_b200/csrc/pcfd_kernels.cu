@@ -1025,7 +1025,7 @@ __global__ void __launch_bounds__(128) k_update_bcs(DevMesh m, eq::BcParams bp, 
     load_avec(m.bea, be, av);
     double tw = 0.0;
     if (type == PCFD_BC_NOSLIP) { load_q10(q, m.bnormal[be], nQ); tw = m.btwall[be]; }
-    eq::boundary_variables(bp, QL, QR, av, type, nQ, tw);
+    eq::boundary_variables(bp, QL, QR, av, type, nQ, tw, (type == PCFD_BC_FARFIELD_VISCOUS) ? m.bubar[be] : 1.0);
     store_q10(q, r, QR);
     touched = true;
   }
@@ -1049,7 +1049,8 @@ __global__ void __launch_bounds__(128) k_update_bcs_edges(DevMesh m, eq::BcParam
   load_q10(q, lr.y, QR);
   load_avec(m.bea, be, av);
   if (!first) eq::aux(QL, bp.gamma);
-  eq::boundary_variables(bp, QL, QR, av, m.bctype[be]);
+  const int type = m.bctype[be];
+  eq::boundary_variables(bp, QL, QR, av, type, nullptr, 0.0, (type == PCFD_BC_FARFIELD_VISCOUS) ? m.bubar[be] : 1.0);
   store_q10(q, lr.y, QR);
   if (first) {   // only aux of QL can have changed
     double2* pq = reinterpret_cast<double2*>(q + (size_t)lr.x * NVARS);
@@ -1213,7 +1214,15 @@ __device__ __forceinline__ void jac_half_edge(const DevMesh& m, const eq::BcPara
   load_q10(q, r, QR);
   load_avec(m.bea, be, av);
   if (type == PCFD_BC_NOSLIP) { load_q10(q, m.bnormal[be], nQ); tw = m.btwall[be]; }
-  eq::boundary_variables(bp, QL, QR, av, type, nQ, tw);
+  // viscous far field: ONE copy of the free stream for this half-edge, scaled in place by every evaluation below
+  const bool ffv = type == PCFD_BC_FARFIELD_VISCOUS;
+  const double ubar = ffv ? m.bubar[be] : 1.0;
+  double Qref[NVARS];
+  if (ffv) {
+#pragma unroll
+    for (int j = 0; j < NVARS; j++) Qref[j] = bp.qinf[j];
+  }
+  eq::boundary_variables(bp, QL, QR, av, type, nQ, tw, ubar, ffv ? Qref : nullptr);
   if (type != PCFD_BC_PARALLEL) store_q10(q, r, QR);
   eq::numerical_flux(QL, QR, av, 0.0, gamma, fS);
   double* pR = ghost ? A + (size_t)bpos[be] * NEQN2 : nullptr;
@@ -1236,7 +1245,7 @@ __device__ __forceinline__ void jac_half_edge(const DevMesh& m, const eq::BcPara
 #pragma unroll
       for (int j = 0; j < NVARS; j++) QPR[j] = QR[j];
       eq::aux(QPR, gamma);
-      eq::boundary_variables(bp, QPL, QPR, av, type, nQ, tw);
+      eq::boundary_variables(bp, QPL, QPR, av, type, nQ, tw, ubar, ffv ? Qref : nullptr);
       eq::numerical_flux(QPL, QPR, av, 0.0, gamma, fL);
     }
 #pragma unroll
@@ -1260,7 +1269,15 @@ __device__ __forceinline__ void jac_half_edge_central(const DevMesh& m, const eq
   load_q10(q, r, QR);
   load_avec(m.bea, be, av);
   if (type == PCFD_BC_NOSLIP) { load_q10(q, m.bnormal[be], nQ); tw = m.btwall[be]; }
-  eq::boundary_variables(bp, QL, QR, av, type, nQ, tw);
+  // viscous far field: ONE copy of the free stream for this half-edge, scaled in place by every evaluation below
+  const bool ffv = type == PCFD_BC_FARFIELD_VISCOUS;
+  const double ubar = ffv ? m.bubar[be] : 1.0;
+  double Qref[NVARS];
+  if (ffv) {
+#pragma unroll
+    for (int j = 0; j < NVARS; j++) Qref[j] = bp.qinf[j];
+  }
+  eq::boundary_variables(bp, QL, QR, av, type, nQ, tw, ubar, ffv ? Qref : nullptr);
   if (type != PCFD_BC_PARALLEL) store_q10(q, r, QR);
   double* pR = ghost ? A + (size_t)bpos[be] * NEQN2 : nullptr;
   double* bd = bdiag + (size_t)be * NEQN2;
@@ -1280,7 +1297,7 @@ __device__ __forceinline__ void jac_half_edge_central(const DevMesh& m, const eq
 #pragma unroll
       for (int j = 0; j < NVARS; j++) QPR[j] = QR[j];
       eq::aux(QPR, gamma);
-      eq::boundary_variables(bp, QPL, QPR, av, type, nQ, tw);
+      eq::boundary_variables(bp, QPL, QPR, av, type, nQ, tw, ubar, ffv ? Qref : nullptr);
       eq::numerical_flux(QPL, QPR, av, 0.0, gamma, fL);
     }
 #pragma unroll
@@ -2319,6 +2336,14 @@ static int create_impl(const pcfd_mesh_desc* mesh, const pcfd_params* params, in
     wallflag[left] |= 1;
     if (btwall[e] < 0.0) wallflag[left] |= 2;
   }
+  std::vector<double> bubar(std::max(c->nbedge, 1), 1.0);
+  for (int e = 0; e < c->nbedge; e++) {
+    if (mesh->bedges_bctype[e] != PCFD_BC_FARFIELD_VISCOUS) continue;
+    if (!viscous && params->eqnset != PCFD_EQNSET_COMPRESSIBLE_NS_FR)
+      return fail(c, "pcfd_create: the viscous far-field BC needs a viscous eqnset (Re and the wall distance)");
+    c->ffv_edges.push_back(e);
+    c->ffv_left.push_back(mesh->bedges_n[2 * e]);
+  }
   std::sort(wnodes.begin(), wnodes.end());
   for (int e = 0; e < c->nbedge; e++) {
     // an adiabatic wall copies rho and rho*E from the normal node (compressible.tcc:1548-1554): in the
@@ -2436,6 +2461,7 @@ static int create_impl(const pcfd_mesh_desc* mesh, const pcfd_params* params, in
   if (dev_upload(c, &c->bfirst, bfirst.data(), bfirst.size())) return 1;
   if (dev_upload(c, &c->bnormal, bnormal.data(), bnormal.size())) return 1;
   if (dev_upload(c, &c->btwall, btwall.data(), btwall.size())) return 1;
+  if (dev_upload(c, &c->bubar, bubar.data(), bubar.size())) return 1;
   if (dev_upload(c, &c->wallflag, wallflag.data(), wallflag.size())) return 1;
   if (dev_upload(c, &c->wnodes, wnodes.data(), wnodes.size())) return 1;
   if (dev_upload(c, &c->tbnodes, tbnodes.data(), tbnodes.size())) return 1;
@@ -2467,7 +2493,7 @@ static int create_impl(const pcfd_mesh_desc* mesh, const pcfd_params* params, in
   const bool sa_on = params->turb_model == 1;
   c->fsize[PCFD_F_TVAR] = sa_on ? (size_t)c->ntot : 0;
   c->fsize[PCFD_F_TGRAD] = sa_on ? (size_t)c->nn * 3 : 0;
-  c->fsize[PCFD_F_WALLDIST] = sa_on ? (size_t)c->nn : 0;
+  c->fsize[PCFD_F_WALLDIST] = (sa_on || !c->ffv_edges.empty()) ? (size_t)c->nn : 0;
   c->fsize[PCFD_F_TURB_B] = sa_on ? (size_t)nnode : 0;
   c->fsize[PCFD_F_TURB_X] = sa_on ? (size_t)c->nn : 0;
   c->fsize[PCFD_F_TURB_A] = sa_on ? (size_t)c->nblocks : 0;
@@ -2509,7 +2535,7 @@ static int create_impl(const pcfd_mesh_desc* mesh, const pcfd_params* params, in
   if (neqn == NEQN && dev_alloc(c, &c->geo, adj.size())) return 1;
 
   c->dm = DevMesh{c->nnode, c->gnode, c->nbnode, c->nedge, c->nbedge, c->ngedge, c->en, c->ea, c->ben, c->bea,
-                  c->bctype, c->xyz, c->vol, c->adjp, c->adj, c->bnormal, c->btwall};
+                  c->bctype, c->xyz, c->vol, c->adjp, c->adj, c->bnormal, c->btwall, c->bubar};
   c->bp.gamma = params->gamma;
   c->bp.no_cvbc = params->no_cvbc;
   for (int i = 0; i < NVARS; i++) c->bp.qinf[i] = params->qinf[i];
@@ -2523,14 +2549,6 @@ int pcfd_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int devic
   if (params && params->eqnset != PCFD_EQNSET_COMPRESSIBLE_EULER && params->eqnset != PCFD_EQNSET_COMPRESSIBLE_NS) {
     if (out) *out = nullptr;
     return fail(nullptr, "pcfd_create: unsupported eqnset id (the reacting eqnset is created with pcfd_create_fr)");
-  }
-  if (mesh && mesh->bedges_bctype) {
-    for (int e = 0; e < mesh->nbedge + mesh->ngedge; e++) {
-      if (mesh->bedges_bctype[e] == PCFD_BC_FARFIELD_VISCOUS) {
-        if (out) *out = nullptr;
-        return fail(nullptr, "pcfd_create: the viscous far-field BC (bc.tcc:1092-1108) is not available on the GPU path yet");
-      }
-    }
   }
   return create_impl(mesh, params, device, NEQN, NVARS, NTERMS, out);
 }
@@ -2623,6 +2641,18 @@ int pcfd_set_field(pcfd_ctx* c, int field, const double* host, size_t n) {
   if (n != c->fsize[field]) return fail(c, "pcfd_set_field: size mismatch");
   CK(cudaMemcpyAsync(c->f[field], host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  if (field == PCFD_F_WALLDIST && !c->ffv_edges.empty()) {
+    // PowerLawU(1, d, Re) (powerLaw.h:11-29) per FarFieldViscous half-edge, with the C library's pow like the reference
+    std::vector<double> ub(c->ffv_edges.size());
+    for (size_t k = 0; k < ub.size(); k++) {
+      const double deltaTurb = 0.382 * 10.0 / (std::pow(c->prm.Re, 0.2));
+      const double u = 1.0 * std::pow(host[c->ffv_left[k]] / deltaTurb, 1.0 / 7.0);
+      ub[k] = (u < 1.0) ? u : 1.0;
+    }
+    for (size_t k = 0; k < ub.size(); k++)
+      CK(cudaMemcpy(c->bubar + c->ffv_edges[k], &ub[k], sizeof(double), cudaMemcpyHostToDevice));
+    c->ffv_ready = true;
+  }
   return 0;
 }
 int pcfd_get_field(pcfd_ctx* c, int field, double* host, size_t n) {
@@ -2677,6 +2707,8 @@ int pcfd_update_bcs(pcfd_ctx* c) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
   c->qmm_valid = false;
+  if (!c->ffv_edges.empty() && !c->ffv_ready)
+    return fail(c, "pcfd_update_bcs: the viscous far-field BC needs field PCFD_F_WALLDIST (pcfd_set_field) first");
   if (c->fr) return pcfd_fr_update_bcs(c);
   if (c->nbn) {
     PROF("k_update_bcs");
@@ -3124,6 +3156,8 @@ int pcfd_jacobian(pcfd_ctx* c) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
   if (ensure_matrix(c)) return 1;
+  if (!c->ffv_edges.empty() && !c->ffv_ready)
+    return fail(c, "pcfd_jacobian: the viscous far-field BC needs field PCFD_F_WALLDIST (pcfd_set_field) first");
   if (c->fr) return pcfd_fr_jacobian(c);
   double* A = c->f[PCFD_F_A];
   CK(cudaMemsetAsync(A, 0, c->fsize[PCFD_F_A] * sizeof(double), c->stream));   // CRSMatrix::Blank

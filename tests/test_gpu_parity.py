@@ -29,6 +29,10 @@ def golden_ctx(name):
                       tref=meta["ref_temperature"], mach=meta["velocity"], enable_vnn=int(meta["enableVNN"]),
                       vnn=meta["VNN"], turb_model=int(meta.get("turbModel", 0)))
     ctx = capi.Context(mesh, params)
+    if "wallDistance" in g and ctx.field_size(capi.F_WALLDIST) > 0:   # SA model / viscous far-field BC (power-law profile)
+        wd = np.zeros(ctx.field_size(capi.F_WALLDIST))
+        wd[: min(wd.size, g["wallDistance"].size)] = g["wallDistance"][: wd.size]
+        ctx.set_field(capi.F_WALLDIST, wd)
     if "mut" in g:   # eddy viscosity the flow's viscous terms saw in the reference run
         mut = np.zeros(ctx.field_size(capi.F_MUT))
         mut[: g["mut"].size] = g["mut"]

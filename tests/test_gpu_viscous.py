@@ -13,7 +13,7 @@ import pytest
 
 from tests.oracle_lib import oracle_for
 from tests.test_gpu_parity import golden_ctx
-from tests.test_oracle import NS, exact
+from tests.test_oracle import NS, NS_FFV, exact
 
 pytestmark = pytest.mark.gpu
 
@@ -33,7 +33,7 @@ def close_per_node(a, b, width, what):
     return float((a == b).mean())
 
 
-@pytest.mark.parametrize("name", NS)
+@pytest.mark.parametrize("name", NS + NS_FFV)
 def test_ns_bcs_gradient_limiter_timestep_bit_exact(name):
     from proteuscfd_b200 import capi
     ctx, g, _ = golden_ctx(name)
@@ -51,7 +51,7 @@ def test_ns_bcs_gradient_limiter_timestep_bit_exact(name):
     assert dtmin == g["dtmin"][0]
 
 
-@pytest.mark.parametrize("name", NS)
+@pytest.mark.parametrize("name", NS + NS_FFV)
 def test_ns_residual(name):
     from proteuscfd_b200 import capi
     ctx, g, _ = golden_ctx(name)
@@ -65,7 +65,7 @@ def test_ns_residual(name):
     assert np.isclose(np.sqrt(s[0]) / b.size, g["resnorm"][0], rtol=1e-12)
 
 
-@pytest.mark.parametrize("name", NS)
+@pytest.mark.parametrize("name", NS + NS_FFV)
 def test_ns_jacobian_lu_sgs(name):
     from proteuscfd_b200 import capi
     ctx, g, meta = golden_ctx(name)
@@ -137,3 +137,28 @@ def test_spalart_allmaras_compute_vs_reference():
     nn = g["turb_mut"].size
     close_per_node(ctx.get_field(capi.F_MUT)[:nn], g["turb_mut"], 1, "eddy viscosity")
     assert np.isclose(np.sqrt(ss) / ctx.nnode, g["turb_res"][0], rtol=1e-12)
+
+
+def test_far_field_viscous_needs_the_wall_distance():
+    """Proteus_FarFieldViscous (bc.tcc:1092-1108) scales the free stream by PowerLawU(wall distance): UpdateBCs and the
+    boundary Jacobian refuse to run before field PCFD_F_WALLDIST has been handed over; an inviscid context rejects the
+    BC type at creation"""
+    from proteuscfd_b200 import capi
+    from tests.oracle_lib import load_golden
+    g, meta = load_golden("box6_ns_ffv")
+    mesh = {k: g[k] for k in ("edges_n", "edges_a", "bedges_n", "bedges_a", "bedges_bctype", "xyz", "vol", "ipsp", "psp")}
+    for k in ("nnode", "gnode", "nbnode", "nedge", "nbedge", "ngedge"):
+        mesh[k] = int(meta[k])
+    mesh["bedges_twall"] = g["bedges_twall"]
+    params = dict(sorder=2, limiter=2, no_cvbc=0, gamma=meta["gamma"], chi=0.0, cfl=5.0, qinf=g["qinf"])
+    with pytest.raises(capi.PcfdError):
+        capi.Context(mesh, params)                       # compressibleEuler: no Re, no wall distance
+    params.update(eqnset=capi.EQNSET_COMPRESSIBLE_NS, Re=meta["Re"], Pr=meta["Pr"], PrT=meta["PrT"],
+                  tref=meta["ref_temperature"], mach=meta["velocity"])
+    ctx = capi.Context(mesh, params)
+    ctx.set_field(capi.F_Q, g["q_pre"])
+    with pytest.raises(capi.PcfdError):
+        ctx.update_bcs()
+    ctx.set_field(capi.F_WALLDIST, g["wallDistance"][: ctx.field_size(capi.F_WALLDIST)])
+    ctx.update_bcs()
+    exact(ctx.get_field(capi.F_Q), g["q0"], "q after UpdateBCs")
