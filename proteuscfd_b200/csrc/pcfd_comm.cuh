@@ -93,10 +93,10 @@ __device__ __forceinline__ bool spin_until(const unsigned long long* p, unsigned
   return true;
 }
 
-// post of one field: ready handshake, gather + put, done flags.  counter: zeroed int in local memory.
-__global__ void __launch_bounds__(256) k_comm_put(const CommTable* __restrict__ tb, int field, int n,
-                                                  const int* __restrict__ list, const double* __restrict__ v,
-                                                  unsigned long long epoch, int* counter) {
+// post of one or two fields: ready handshake, gather + put, done flags.  counter: zeroed int in local memory.
+struct PutField { int field, n; const double* v; };
+__global__ void __launch_bounds__(256) k_comm_put(const CommTable* __restrict__ tb, PutField f0, PutField f1,
+                                                  const int* __restrict__ list, unsigned long long epoch, int* counter) {
   __shared__ int s_last;
   const int me = tb->me, np = tb->npeers_send;
   CommFlags* mine = tb->peer_flags[me];
@@ -106,12 +106,17 @@ __global__ void __launch_bounds__(256) k_comm_put(const CommTable* __restrict__ 
   }
   if (threadIdx.x < np) spin_until(&mine->ready[tb->send_peer[threadIdx.x]], epoch, &mine->err, tb->spin_limit_ns);
   __syncthreads();
-  const long long total = (long long)tb->send_off[np] * n;
+  const int rows = tb->send_off[np];
+  const long long total0 = (long long)rows * f0.n, total = total0 + (long long)rows * f1.n;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int j = (int)(t / n), cidx = (int)(t - (long long)j * n);
+    const bool second = t >= total0;
+    const long long tt = second ? t - total0 : t;
+    const int n = second ? f1.n : f0.n;
+    const int j = (int)(tt / n), cidx = (int)(tt - (long long)j * n);
     int s = 0;
     while (j >= tb->send_off[s + 1]) s++;
-    tb->dst[field][s][(size_t)(j - tb->send_off[s]) * n + cidx] = v[(size_t)list[j] * n + cidx];
+    const double* v = second ? f1.v : f0.v;
+    tb->dst[second ? f1.field : f0.field][s][(size_t)(j - tb->send_off[s]) * n + cidx] = v[(size_t)list[j] * n + cidx];
   }
   __threadfence_system();
   __syncthreads();
@@ -151,6 +156,12 @@ __global__ void k_comm_gwait(const CommTable* __restrict__ tb, int n, unsigned l
 
 struct pcfd_comm {
   bool connected = false;
+  // the halo of q at solutionSpace.tcc:665 repeats the one at :857 bit for bit when nothing wrote owned rows of q in
+  // between: UpdateBCs only writes phantom rows unless a rank owns Dirichlet-type (hard-set) half-edges.  ghost_q_fresh:
+  // the ghost rows of q hold what the owners hold (every rank runs the same call sequence, so the flag agrees across
+  // ranks); no_hardset: no rank owns hard-set BC nodes (from the blobs).  PCFD_COMM_ELIDE=0 keeps every exchange.
+  bool ghost_q_fresh = false, no_hardset = false, elide = true;
+  long long elided = 0;
   CommFlags* flags = nullptr;                   // own flag page
   CommTable* table = nullptr;                   // device copy
   CommTable h{};                                // host copy
@@ -172,17 +183,26 @@ inline unsigned long long comm_token() {
 
 inline bool comm_on(const pcfd_ctx* c) { return c->comm && c->comm->connected; }
 
-int comm_post(pcfd_ctx* c, int field) {
+// field2 >= 0: a second field travels in the same kernel (one handshake, one epoch): qgrad + limiter
+int comm_post(pcfd_ctx* c, int field, int field2 = -1) {
   pcfd_comm* m = c->comm;
   const int n = field_width(c, field);
   if (n == 0 || !c->f[field]) return fail(c, "pcfd_comm_post: field cannot be exchanged");
+  const int n2 = field2 >= 0 ? field_width(c, field2) : 0;
+  if (field2 >= 0 && (n2 == 0 || !c->f[field2])) return fail(c, "pcfd_comm_post: second field cannot be exchanged");
   m->epoch++;
   m->field_epoch[field] = m->epoch;
-  if (field == PCFD_F_Q) c->qmm_valid = false;   // ghost rows of q change: cached neighbour min / max are stale
-  const long long total = (long long)c->send_total * n;
+  if (field2 >= 0) m->field_epoch[field2] = m->epoch;
+  if (field == PCFD_F_Q || field2 == PCFD_F_Q) {
+    c->qmm_valid = false;   // ghost rows of q change: cached neighbour min / max are stale
+    m->ghost_q_fresh = true;
+  }
+  const long long total = (long long)c->send_total * (n + n2);
   const int grid = (int)std::max<long long>(1, std::min<long long>((total + 1023) / 1024, (long long)c->num_sms));
   PROF("k_comm_put");
-  k_comm_put<<<grid, 256, 0, c->stream>>>(m->table, field, n, c->send_list, c->f[field], m->epoch, m->counter);
+  k_comm_put<<<grid, 256, 0, c->stream>>>(m->table, PutField{field, n, c->f[field]},
+                                          PutField{field2 >= 0 ? field2 : field, n2, field2 >= 0 ? c->f[field2] : nullptr},
+                                          c->send_list, m->epoch, m->counter);
   LAUNCH_CHECK();
   return 0;
 }
@@ -285,9 +305,12 @@ int pcfd_comm_connect(pcfd_ctx* c, const void* blobs) {
     m->opened.push_back(*out);
     return 0;
   };
+  bool hardset = false;
+  if (const char* e = getenv("PCFD_COMM_ELIDE")) m->elide = atoi(e) != 0;
   for (int r = 0; r < R; r++) {
     const CommBlob& b = B[r];
     if (b.magic != COMM_MAGIC || b.rank != r || b.nranks != R) return fail(c, "pcfd_comm_connect: blob table is not in rank order");
+    hardset = hardset || b.nbn > 0;
     if (r == me) { t.peer_flags[r] = m->flags; continue; }
     void* p = nullptr;
     if (open(b, b.flags, b.raw_flags, &p)) return 1;
@@ -312,6 +335,8 @@ int pcfd_comm_connect(pcfd_ctx* c, const void* blobs) {
   }
   if (t.send_off[t.npeers_send] != c->send_total) return fail(c, "pcfd_comm_connect: send counts do not add up");
   CK(cudaMemcpy(m->table, &t, sizeof(t), cudaMemcpyHostToDevice));
+  m->no_hardset = !hardset;
+  m->ghost_q_fresh = false;
   m->connected = true;
   return 0;
 }

@@ -2633,7 +2633,7 @@ int pcfd_set_field(pcfd_ctx* c, int field, const double* host, size_t n) {
   CK(cudaSetDevice(c->device));
   if (field == PCFD_F_A) { if (ensure_matrix(c)) return 1; c->ludiag = false; }
   if (field == PCFD_F_LSQ_SW) c->geo_valid = false;
-  if (field == PCFD_F_Q) c->qmm_valid = false;
+  if (field == PCFD_F_Q) { c->qmm_valid = false; if (c->comm) c->comm->ghost_q_fresh = false; }
   if (is_time_field(field)) {
     if (ensure_time_fields(c)) return 1;
     if (field == PCFD_F_QOLD) c->have_qold = true;
@@ -2707,6 +2707,7 @@ int pcfd_update_bcs(pcfd_ctx* c) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
   c->qmm_valid = false;
+  if (c->comm && !c->comm->no_hardset) c->comm->ghost_q_fresh = false;   // hard-set BC nodes: owned rows change
   if (!c->ffv_edges.empty() && !c->ffv_ready)
     return fail(c, "pcfd_update_bcs: the viscous far-field BC needs field PCFD_F_WALLDIST (pcfd_set_field) first");
   if (c->fr) return pcfd_fr_update_bcs(c);
@@ -2869,10 +2870,11 @@ static int gradient_limiter_residual(pcfd_ctx* c, double* sumsq) {
   if (c->prm.sorder > 1) {
     const int type = c->prm.limiter;
     if (pcfd_gradient(c)) return 1;
-    if (dist && comm_post(c, PCFD_F_QGRAD)) return 1;              // gradient.tcc:98; waited for inside run_flux
     if (type != 0 && c->fused_clip) {
       if (run_limiter_raw(c)) return 1;
-      if (dist && comm_post(c, PCFD_F_LIMITER)) return 1;          // limiters.tcc:128 (raw values; both sides clamp)
+      // gradient.tcc:98 and limiters.tcc:128 (raw values; both sides clamp) in ONE put: the limiter of the owned nodes
+      // does not read ghost gradients, so both halos can leave together; waited for inside run_flux
+      if (dist && comm_post(c, PCFD_F_QGRAD, PCFD_F_LIMITER)) return 1;
       bool hit = false;
       if (run_flux(c, true, &hit)) return 1;
       if (!hit) {
@@ -2880,7 +2882,7 @@ static int gradient_limiter_residual(pcfd_ctx* c, double* sumsq) {
         return 0;
       }
       c->clip_fallbacks++;
-    } else if (dist && comm_wait(c, PCFD_F_QGRAD)) {
+    } else if (dist && comm_update(c, PCFD_F_QGRAD)) {              // gradient.tcc:98
       return 1;
     }
     if (pcfd_limiter(c)) return 1;
@@ -2964,6 +2966,15 @@ static int run_temporal(pcfd_ctx* c) {
 // edge kernel -- ghost-independent -- runs while they are in flight, every rank's clip flag goes round through the
 // flag page (no collective), and the waits come just before the first kernel that reads ghost rows.  *clip_hit is
 // the GLOBAL decision (limiters.tcc:112-117 runs on every rank or on none).
+// The halo of q after UpdateBCs (solutionSpace.tcc:665).  Elided when it would deliver, bit for bit, the rows the last
+// halo of q delivered: nothing has written owned rows of q since (no explicit / implicit update, no pcfd_set_field,
+// and no rank owns hard-set BC nodes, so UpdateBCs only wrote phantom rows).
+static int comm_q_after_bcs(pcfd_ctx* c) {
+  pcfd_comm* m = c->comm;
+  if (m->elide && m->ghost_q_fresh && m->no_hardset) { m->elided++; return 0; }
+  return comm_update(c, PCFD_F_Q);
+}
+
 // the host reads the clip flag(s) while the kernels queued behind the copy keep the GPU busy
 static int flux_clip_decision(pcfd_ctx* c, bool dist, bool* clip_hit) {
   if (!dist) {
@@ -2995,7 +3006,8 @@ static int run_flux(pcfd_ctx* c, bool fused, bool* clip_hit) {
   }
   if (dist) {
     if (comm_gather_enqueue(c, nullptr, c->dflags + 2, 1)) return 1;
-    if (comm_wait(c, PCFD_F_QGRAD) || comm_wait(c, PCFD_F_LIMITER)) return 1;
+    if (comm_wait(c, PCFD_F_QGRAD)) return 1;
+    if (c->comm->field_epoch[PCFD_F_LIMITER] != c->comm->field_epoch[PCFD_F_QGRAD] && comm_wait(c, PCFD_F_LIMITER)) return 1;
     if (run_limiter_final(c, nullptr)) return 1;
   } else if (fused) {
     CK(cudaMemcpyAsync(c->hflag, c->dflags + 2, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -3133,6 +3145,7 @@ int pcfd_explicit_solve(pcfd_ctx* c) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
   c->qmm_valid = false;
+  if (c->comm) c->comm->ghost_q_fresh = false;
   if (c->fr) return pcfd_fr_explicit_solve(c);
   PROF("k_explicit");
   k_explicit<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->nnode, c->prm.gamma, c->f[PCFD_F_B], c->f[PCFD_F_TIMESTEP],
@@ -3145,6 +3158,7 @@ int pcfd_apply_dq(pcfd_ctx* c) {
   if (!c) return 1;
   CK(cudaSetDevice(c->device));
   c->qmm_valid = false;
+  if (c->comm) c->comm->ghost_q_fresh = false;
   if (c->fr) return pcfd_fr_apply_dq(c);
   PROF("k_apply_dq");
   k_apply_dq<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->nnode, c->prm.gamma, c->f[PCFD_F_X], c->f[PCFD_F_Q]);
@@ -3158,6 +3172,7 @@ int pcfd_jacobian(pcfd_ctx* c) {
   if (ensure_matrix(c)) return 1;
   if (!c->ffv_edges.empty() && !c->ffv_ready)
     return fail(c, "pcfd_jacobian: the viscous far-field BC needs field PCFD_F_WALLDIST (pcfd_set_field) first");
+  if (c->comm && !c->comm->no_hardset) c->comm->ghost_q_fresh = false;
   if (c->fr) return pcfd_fr_jacobian(c);
   double* A = c->f[PCFD_F_A];
   CK(cudaMemsetAsync(A, 0, c->fsize[PCFD_F_A] * sizeof(double), c->stream));   // CRSMatrix::Blank
@@ -3633,7 +3648,7 @@ int pcfd_explicit_iterate(pcfd_ctx* c, int refresh_dt, double* sumsq) {
     LAUNCH_CHECK();
   }
   if (pcfd_update_bcs(c)) return 1;
-  if (dist && comm_update(c, PCFD_F_Q)) return 1;                  // solutionSpace.tcc:665
+  if (dist && comm_q_after_bcs(c)) return 1;                       // solutionSpace.tcc:665
   c->eig_now = ride;
   const int rc = gradient_limiter_residual(c, sumsq);
   c->eig_now = false;
@@ -3651,7 +3666,7 @@ int pcfd_implicit_iterate(pcfd_ctx* c, int refresh_jac, int nsgs, double* sumsq,
     if (pcfd_jacobian(c)) return 1;
   }
   if (pcfd_update_bcs(c)) return 1;
-  if (dist && comm_update(c, PCFD_F_Q)) return 1;                  // solutionSpace.tcc:665
+  if (dist && comm_q_after_bcs(c)) return 1;                       // solutionSpace.tcc:665
   if (gradient_limiter_residual(c, sumsq)) return 1;
   if (pcfd_prepare_sgs(c)) return 1;
   if (pcfd_blank_x(c)) return 1;
@@ -3660,7 +3675,8 @@ int pcfd_implicit_iterate(pcfd_ctx* c, int refresh_jac, int nsgs, double* sumsq,
   } else {
     // CRS::SGS across ranks (crs.tcc:62-173): block-Jacobi at partition boundaries, a halo of x before the first
     // sweep (:88) and after every sweep (:146); ddq from the last two sweeps of this rank's rows
-    if (comm_update(c, PCFD_F_X)) return 1;
+    // crs.tcc:88: BlankX has just zeroed x, ghost rows included, on every rank: the halo would move zeros onto zeros
+    if (!c->comm->elide && comm_update(c, PCFD_F_X)) return 1;
     for (int sweep = 0; sweep < nsgs; sweep++) {
       const bool last = sweep == nsgs - 1;
       if (ddq && sweep >= nsgs - 2 && nsgs >= 2) {
