@@ -514,7 +514,8 @@ constexpr int N_SUBIT = 10;   // compressibleFR.tcc:32
 // GetFarfieldBoundaryVariables (compressibleFR.tcc:940-1039)
 template <int NS>
 __device__ __noinline__ void farfield_bc(const Params<NS>& p, const double* QL, double* QR, const double* av, double vdotn,
-                                         double beta) {
+                                         double beta, const double* Qinf) {
+  // Qinf: the free stream handed over by the caller (p.qinf, or the power-law scaled copy of the viscous far field)
   constexpr int N = NS + 4, NV = 3 * NS + 6;
   double qavg[NS + 6], rhs[N], ql[N], qinf[N];
   Eigen<NS> E;
@@ -524,12 +525,12 @@ __device__ __noinline__ void farfield_bc(const Params<NS>& p, const double* QL, 
     eigen_setup(p, qavg, av, vdotn, beta, E);
     if (p.no_cvbc) {
       if (E.theta >= 0.0) { for (int i = 0; i < NV; i++) QR[i] = QL[i]; }
-      else { for (int i = 0; i < NV; i++) QR[i] = p.qinf[i]; }
+      else { for (int i = 0; i < NV; i++) QR[i] = Qinf[i]; }
     } else {
-      for (int i = 0; i < N; i++) { ql[i] = QL[i]; qinf[i] = p.qinf[i]; }
+      for (int i = 0; i < N; i++) { ql[i] = QL[i]; qinf[i] = Qinf[i]; }
       const double Tguess = ql[N - 1];
       ql[N - 1] = QL[NS + 4];
-      qinf[N - 1] = p.qinf[NS + 4];
+      qinf[N - 1] = Qinf[NS + 4];
 #pragma unroll
       for (int i = 0; i < N; i++) rhs[i] = tinv_row_dot(E, qavg, i, (eigen_value(E, i) >= 0.0) ? ql : qinf);
 #pragma unroll
@@ -644,18 +645,27 @@ __device__ __noinline__ void inviscid_wall_bc(const Params<NS>& p, const double*
 }
 
 // CalculateBoundaryVariables (bc.tcc:1058-1397) for the BC types of the reacting configs; QL and QR are full rows
+// Proteus_FarFieldViscous (bc.tcc:1092-1108): see eq::boundary_variables; GetMomentumLocation() == nspecies here
 template <int NS>
 __device__ __noinline__ void boundary_variables(const Params<NS>& p, double* QL, double* QR, const double* av, int bctype,
-                                                double betaL) {
-  constexpr int N = NS + 4;
+                                                double betaL, double ubar = 1.0, double* qref = nullptr) {
+  constexpr int N = NS + 4, NV = 3 * NS + 6;
   const double vdotn = 0.0;   // static mesh
   switch (bctype) {
     case PCFD_BC_PARALLEL: return;
+    case PCFD_BC_FARFIELD_VISCOUS: {
+      double fresh[NV];
+      double* Qinf = qref ? qref : fresh;
+      if (!qref) for (int i = 0; i < NV; i++) fresh[i] = p.qinf[i];
+      if (ubar < 1.0) for (int i = 0; i < 3; i++) Qinf[NS + i] = ubar * Qinf[NS + i];
+      farfield_bc(p, QL, QR, av, vdotn, betaL, Qinf);
+      break;
+    }
     case PCFD_BC_SONIC_OUTFLOW: case PCFD_BC_NEUMANN:
       for (int i = 0; i < N; i++) QR[i] = QL[i];
       break;
     case PCFD_BC_FARFIELD:
-      farfield_bc(p, QL, QR, av, vdotn, betaL);
+      farfield_bc(p, QL, QR, av, vdotn, betaL, p.qinf);
       break;
     case PCFD_BC_IMPERMEABLE_WALL: case PCFD_BC_SYMMETRY:
       inviscid_wall_bc(p, QL, QR, av, vdotn, betaL);
@@ -685,7 +695,8 @@ __device__ __forceinline__ void viscous_wall_bc(double* QL, double* QR, double n
 // such a half-edge are walked sequentially (kfr_update_bcs_nodes, kfr_jac_bnodes)
 template <int NS>
 __device__ __noinline__ void boundary_variables_seq(const Params<NS>& p, double* QL, double* QR, const double* av, int bctype,
-                                                    double betaL, double normalT, double Twall) {
+                                                    double betaL, double normalT, double Twall, double ubar = 1.0,
+                                                    double* qref = nullptr) {
   constexpr int NV = 3 * NS + 6;
   switch (bctype) {
     case PCFD_BC_SONIC_INFLOW: case PCFD_BC_DIRICHLET:
@@ -695,7 +706,7 @@ __device__ __noinline__ void boundary_variables_seq(const Params<NS>& p, double*
       viscous_wall_bc<NS>(QL, QR, normalT, Twall);
       break;
     default:
-      boundary_variables(p, QL, QR, av, bctype, betaL);
+      boundary_variables(p, QL, QR, av, bctype, betaL, ubar, qref);
       return;
   }
   aux(p, QR);

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(64) kfr_update_bcs_edges(DevMesh m, fr::Params
   load_row<NS, NV>(q, lr.y, QR);
   load_avec(m.bea, be, av);
   if (!first) fr::aux(p, QL);
-  fr::boundary_variables(p, QL, QR, av, m.bctype[be], beta[lr.x]);
+  fr::boundary_variables(p, QL, QR, av, m.bctype[be], beta[lr.x], (m.bctype[be] == PCFD_BC_FARFIELD_VISCOUS) ? m.bubar[be] : 1.0);
   double* qr = q + (size_t)lr.y * NV;
   for (int i = 0; i < NV; i++) qr[i] = QR[i];
   if (first) {
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(64) kfr_update_bcs_nodes(DevMesh m, fr::Params
     load_avec(m.bea, be, av);
     double nT = 0.0, tw = 0.0;
     if (type == PCFD_BC_NOSLIP) { nT = q[(size_t)m.bnormal[be] * NV + NS + 3]; tw = m.btwall[be]; }
-    fr::boundary_variables_seq(p, QL, QR, av, type, beta[n], nT, tw);
+    fr::boundary_variables_seq(p, QL, QR, av, type, beta[n], nT, tw, (type == PCFD_BC_FARFIELD_VISCOUS) ? m.bubar[be] : 1.0);
     double* qr = q + (size_t)r * NV;
     for (int i = 0; i < NV; i++) qr[i] = QR[i];
     touched = true;
@@ -934,7 +934,12 @@ __global__ void __launch_bounds__(64) kfr_jac_bedges(DevMesh m, fr::Params<NS> p
   load_row<NS, NV>(q, r, QR);
   load_avec(m.bea, be, av);
   if (!first && type != PCFD_BC_PARALLEL) fr::aux(p, QL);
-  fr::boundary_variables(p, QL, QR, av, type, betaL);
+  // viscous far field: ONE copy of the free stream per half-edge, scaled in place by every evaluation (jacobian.tcc:485-506)
+  const bool ffv = type == PCFD_BC_FARFIELD_VISCOUS;
+  const double ubar = ffv ? m.bubar[be] : 1.0;
+  double Qref[NV];
+  if (ffv) for (int i = 0; i < NV; i++) Qref[i] = p.qinf[i];
+  fr::boundary_variables(p, QL, QR, av, type, betaL, ubar, ffv ? Qref : nullptr);
   if (type != PCFD_BC_PARALLEL) {
     double* qr = q + (size_t)r * NV;
     for (int i = 0; i < NV; i++) qr[i] = QR[i];
@@ -955,7 +960,7 @@ __global__ void __launch_bounds__(64) kfr_jac_bedges(DevMesh m, fr::Params<NS> p
     fr::numerical_flux(p, QL, QPR, av, 0.0, betaL, fR);
     if (!ghost) {
       for (int k = 0; k < NV; k++) QPR[k] = QR[k];
-      fr::boundary_variables(p, QPL, QPR, av, type, betaL);
+      fr::boundary_variables(p, QPL, QPR, av, type, betaL, ubar, ffv ? Qref : nullptr);
       fr::numerical_flux(p, QPL, QPR, av, 0.0, betaL, fL);
     } else {
       fr::numerical_flux(p, QPL, QR, av, 0.0, betaL, fL);
@@ -991,7 +996,11 @@ __global__ void __launch_bounds__(64) kfr_jac_bnodes(DevMesh m, fr::Params<NS> p
     load_avec(m.bea, be, av);
     double nT = 0.0, tw = 0.0;
     if (type == PCFD_BC_NOSLIP) { nT = q[(size_t)m.bnormal[be] * NV + NS + 3]; tw = m.btwall[be]; }
-    fr::boundary_variables_seq(p, QL, QR, av, type, betaL, nT, tw);
+    const bool ffv = type == PCFD_BC_FARFIELD_VISCOUS;
+    const double ubar = ffv ? m.bubar[be] : 1.0;
+    double Qref[NV];
+    if (ffv) for (int i = 0; i < NV; i++) Qref[i] = p.qinf[i];
+    fr::boundary_variables_seq(p, QL, QR, av, type, betaL, nT, tw, ubar, ffv ? Qref : nullptr);
     if (type != PCFD_BC_PARALLEL) {
       double* qr = q + (size_t)r * NV;
       for (int i = 0; i < NV; i++) qr[i] = QR[i];
@@ -1008,7 +1017,7 @@ __global__ void __launch_bounds__(64) kfr_jac_bnodes(DevMesh m, fr::Params<NS> p
       fr::numerical_flux(p, QL, QPR, av, 0.0, betaL, fR);
       if (!ghost) {
         for (int kk = 0; kk < NV; kk++) QPR[kk] = QR[kk];
-        fr::boundary_variables_seq(p, QPL, QPR, av, type, betaL, nT, tw);
+        fr::boundary_variables_seq(p, QPL, QPR, av, type, betaL, nT, tw, ubar, ffv ? Qref : nullptr);
         fr::numerical_flux(p, QPL, QPR, av, 0.0, betaL, fL);
       } else {
         fr::numerical_flux(p, QPL, QR, av, 0.0, betaL, fL);
@@ -1046,7 +1055,12 @@ __global__ void __launch_bounds__(64) kfr_jac_bedges_central(DevMesh m, fr::Para
   load_row<NS, NV>(q, r, QR);
   load_avec(m.bea, be, av);
   if (!first && type != PCFD_BC_PARALLEL) fr::aux(p, QL);
-  fr::boundary_variables(p, QL, QR, av, type, betaL);
+  // viscous far field: ONE copy of the free stream per half-edge, scaled in place by every evaluation (jacobian.tcc:485-506)
+  const bool ffv = type == PCFD_BC_FARFIELD_VISCOUS;
+  const double ubar = ffv ? m.bubar[be] : 1.0;
+  double Qref[NV];
+  if (ffv) for (int i = 0; i < NV; i++) Qref[i] = p.qinf[i];
+  fr::boundary_variables(p, QL, QR, av, type, betaL, ubar, ffv ? Qref : nullptr);
   if (type != PCFD_BC_PARALLEL) {
     double* qr = q + (size_t)r * NV;
     for (int i = 0; i < NV; i++) qr[i] = QR[i];
@@ -1066,7 +1080,7 @@ __global__ void __launch_bounds__(64) kfr_jac_bedges_central(DevMesh m, fr::Para
     fr::numerical_flux(p, QL, QPR, av, 0.0, betaL, fR);
     if (!ghost) {
       for (int k = 0; k < NV; k++) QPR[k] = QR[k];
-      fr::boundary_variables(p, QPL, QPR, av, type, betaL);
+      fr::boundary_variables(p, QPL, QPR, av, type, betaL, ubar, ffv ? Qref : nullptr);
       fr::numerical_flux(p, QPL, QPR, av, 0.0, betaL, fL);
     } else {
       fr::numerical_flux(p, QPL, QR, av, 0.0, betaL, fL);
@@ -1108,7 +1122,11 @@ __global__ void __launch_bounds__(64) kfr_jac_bnodes_central(DevMesh m, fr::Para
     load_avec(m.bea, be, av);
     double nT = 0.0, tw = 0.0;
     if (type == PCFD_BC_NOSLIP) { nT = q[(size_t)m.bnormal[be] * NV + NS + 3]; tw = m.btwall[be]; }
-    fr::boundary_variables_seq(p, QL, QR, av, type, betaL, nT, tw);
+    const bool ffv = type == PCFD_BC_FARFIELD_VISCOUS;
+    const double ubar = ffv ? m.bubar[be] : 1.0;
+    double Qref[NV];
+    if (ffv) for (int i = 0; i < NV; i++) Qref[i] = p.qinf[i];
+    fr::boundary_variables_seq(p, QL, QR, av, type, betaL, nT, tw, ubar, ffv ? Qref : nullptr);
     if (type != PCFD_BC_PARALLEL) {
       double* qr = q + (size_t)r * NV;
       for (int i = 0; i < NV; i++) qr[i] = QR[i];
@@ -1124,7 +1142,7 @@ __global__ void __launch_bounds__(64) kfr_jac_bnodes_central(DevMesh m, fr::Para
       fr::numerical_flux(p, QL, QPR, av, 0.0, betaL, fR);
       if (!ghost) {
         for (int kk = 0; kk < NV; kk++) QPR[kk] = QR[kk];
-        fr::boundary_variables_seq(p, QPL, QPR, av, type, betaL, nT, tw);
+        fr::boundary_variables_seq(p, QPL, QPR, av, type, betaL, nT, tw, ubar, ffv ? Qref : nullptr);
         fr::numerical_flux(p, QPL, QPR, av, 0.0, betaL, fL);
       } else {
         fr::numerical_flux(p, QPL, QR, av, 0.0, betaL, fL);
@@ -1804,8 +1822,8 @@ int pcfd_create_fr(const pcfd_mesh_desc* mesh, const pcfd_params* params, const 
   const int nb = mesh->nbedge + mesh->ngedge;
   for (int e = 0; e < nb; e++) {
     const int t = mesh->bedges_bctype[e];
-    if (t == PCFD_BC_FARFIELD_VISCOUS)
-      return fail(c, "pcfd_create_fr: the viscous far-field BC is not available for the reacting eqnset");
+    if (t == PCFD_BC_FARFIELD_VISCOUS && !viscous)
+      return fail(c, "pcfd_create_fr: the viscous far-field BC needs compressibleNSFR (Re and the wall distance)");
     if (t == PCFD_BC_NOSLIP && !mesh->bedges_twall)
       return fail(c, "pcfd_create_fr: no-slip walls need bedges_twall (wall temperature / ref_temperature; < 0: adiabatic)");
   }

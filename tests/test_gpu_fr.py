@@ -48,6 +48,10 @@ def fr_ctx(name, rxn_on=None):
     beta = np.ones(ctx.field_size(capi.F_BETA))
     beta[: g["beta"].size] = g["beta"]
     ctx.set_field(capi.F_BETA, beta)
+    if "wallDistance" in g and ctx.field_size(capi.F_WALLDIST) > 0:      # viscous far-field BC: power-law profile
+        wd = np.zeros(ctx.field_size(capi.F_WALLDIST))
+        wd[: min(wd.size, g["wallDistance"].size)] = g["wallDistance"][: wd.size]
+        ctx.set_field(capi.F_WALLDIST, wd)
     return ctx, g, meta
 
 

@@ -197,7 +197,9 @@ def test_nsfr_seeded_box_vs_oracle(oracle, colored):
     assert np.abs(b_lam[:, NS:] - b.reshape(-1, NEQ)[:, NS:]).max() > 1e-4 * np.abs(b).max()
 
 
-WALL = ["box4_nsfr_wall", "box4_nsfr_adiabatic"]
+# box4_nsfr_ffv: farFieldViscous side faces (free stream scaled by the power-law profile of the wall distance,
+# bc.tcc:1092-1108, with the compounding copy of Bkernel_NumJac) next to the no-slip floor
+WALL = ["box4_nsfr_wall", "box4_nsfr_adiabatic", "box4_nsfr_ffv"]
 
 
 @pytest.mark.parametrize("name", WALL)
