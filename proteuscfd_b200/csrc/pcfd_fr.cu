@@ -970,6 +970,10 @@ __global__ void __launch_bounds__(64) kfr_jac_bedges(DevMesh m, fr::Params<NS> p
   }
 }
 
+// (Round 2: a form with NEQ + 1 lanes per half-edge -- lane 0 the reference state, shared through shared memory, lane
+// i + 1 perturbation i -- is bit-exact but SLOWER on B200: 34.5 ms against 21.1 ms at 10 M cells.  The pass is bound by
+// the local-memory traffic of the boundary-state evaluation itself (ten sub-iterations of the 9x9 eigensystem, ~2 kB of
+// stack per thread), and ten times the threads make that worse; profiles/r2_ncu_explicit.md.)
 // Bkernel_NumJac for the nodes owning a Dirichlet-type half-edge: one thread per node, ALL its half-edges (ghost ones
 // included) in half-edge order with the interior state carried from one to the next (k_jac_bnodes of the perfect-gas path)
 template <int NS>
