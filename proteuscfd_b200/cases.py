@@ -9,7 +9,7 @@ import numpy as np
 from . import capi
 from .boxmesh import kuhn_box, renumber
 from .dualmesh import median_dual
-from .ordering import color_order, kuhn_box_colors
+from .ordering import color_order, kuhn_box_brick_order, kuhn_box_colors
 
 # tag -> BC type (the layout tools/make_golden.py uses for the box fixtures)
 BOX_BC = {1: capi.BC_FARFIELD, 2: capi.BC_FARFIELD, 3: capi.BC_SYMMETRY, 4: capi.BC_IMPERMEABLE_WALL,
@@ -63,13 +63,16 @@ def smooth_state(xyz, mach, gamma, amp=1.0):
 
 def box_case(n, jitter=0.15, mach=0.5, gamma=1.4, cfl=0.5, limiter=2, sorder=2, colored=False, ramp_deg=0.0,
              bc=None, device="cpu", amp=1.0, seed=1234, viscous=False, reynolds=400.0, twall=1.1, tref=300.0,
-             enable_vnn=0, turb=False):
+             enable_vnn=0, turb=False, brick=None):
     """Return (mesh dict, params dict, q [(nnode+nbnode)*10]) for an n^3-hex Kuhn box.  viscous=True selects the
     compressibleNS eqnset with a no-slip floor (wall temperature `twall`, non-dimensional; < 0: adiabatic)."""
     xyz, tets, tris, tags = kuhn_box(n, jitter=jitter, seed=seed, ramp_deg=ramp_deg)
     if colored:
         # colour-sorted numbering: sequential SGS == multicolour SGS (ordering.py)
         xyz, tets, tris = renumber(xyz, tets, tris, color_order(kuhn_box_colors(n)))
+    elif brick:
+        # brick-wise numbering: locality for the neighbour-row gathers (ordering.kuhn_box_brick_order)
+        xyz, tets, tris = renumber(xyz, tets, tris, kuhn_box_brick_order(n, brick))
     mesh = median_dual(xyz, tets, tris, tags, device=device)
     table = bc or (RAMP_BC if ramp_deg else (NS_BC if viscous else BOX_BC))
     lut = np.zeros(max(table) + 1, dtype=np.int32)
