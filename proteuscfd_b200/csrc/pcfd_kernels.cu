@@ -2077,16 +2077,26 @@ __global__ void k_turb_invdiag(int nnode, const int* __restrict__ iau, double* A
 __global__ void __launch_bounds__(128) k_sgs_scalar_level(const int* __restrict__ rows, int nrows, const int* __restrict__ ia,
                                                            const int* __restrict__ ja, const double* __restrict__ A,
                                                            const double* __restrict__ b, double* x) {
+  // consecutive levels are chained by programmatic dependent launch (as the block sweeps, sgs_tile.cuh): the next
+  // level may start its prologue (row, extents, right-hand side, inverse diagonal: nothing a level writes) while this
+  // one drains; x -- the only thing a level inherits -- is read after griddepcontrol.wait
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int row = 0, k0 = 0, k1 = 0;
+  double rhs = 0.0, dinv = 0.0;
+  if (t < nrows) {
+    row = rows[t];
+    k0 = ia[row]; k1 = ia[row + 1];
+    rhs = b[row];
+    dinv = A[k0];
+  }
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (t >= nrows) return;
-  const int row = rows[t];
-  const int k0 = ia[row], k1 = ia[row + 1];
-  double rhs = b[row];
   for (int k = k0 + 1; k < k1; k++) {
     const double vout = __ldcs(A + k) * x[__ldg(ja + k)];
     rhs -= vout;
   }
-  x[row] = A[k0] * rhs;
+  x[row] = dinv * rhs;
 }
 
 // tvar += x with the clip at zero (turb.tcc:306-320), then mut = rho nu~ fv1 for local and ghost nodes (:324-336)
@@ -3512,6 +3522,7 @@ int pcfd_turb_compute(pcfd_ctx* c, int nsgs, double* sumsq) {
     PROF("k_turb_invdiag");
     k_turb_invdiag<<<nblk(c->nnode, 256), 256, 0, c->stream>>>(c->nnode, c->iau, tA);
     LAUNCH_CHECK();
+    bool chained = false;   // the first level follows an ordinary kernel: plain launch
     for (int s = 0; s < nsgs; s++) {
       for (int dir = 0; dir < 2; dir++) {
         const std::vector<int>& off = dir ? c->lev_b : c->lev_f;
@@ -3519,7 +3530,9 @@ int pcfd_turb_compute(pcfd_ctx* c, int nsgs, double* sumsq) {
         for (size_t l = 0; l + 1 < off.size(); l++) {
           const int nr = off[l + 1] - off[l];
           PROF("k_sgs_scalar_level");
-          k_sgs_scalar_level<<<nblk(nr, 128), 128, 0, c->stream>>>(rows + off[l], nr, c->ia, c->ja, tA, tb, tx);
+          CK(launch_maybe_pdl(k_sgs_scalar_level, nblk(nr, 128), 128, 0, c->stream, c->sgs_pdl && !c->prof && chained,
+                              rows + off[l], nr, c->ia, c->ja, (const double*)tA, (const double*)tb, tx));
+          chained = true;
           LAUNCH_CHECK();
         }
       }
@@ -3603,18 +3616,22 @@ int pcfd_turb_phase(pcfd_ctx* c, int phase, double* sumsq) {
       LAUNCH_CHECK();
       if (sumsq) CK(cudaStreamSynchronize(c->stream));
       return 0;
-    case 3:
+    case 3: {
+      bool chained = false;
       for (int dir = 0; dir < 2; dir++) {
         const std::vector<int>& off = dir ? c->lev_b : c->lev_f;
         const int* rows = dir ? c->rows_b : c->rows_f;
         for (size_t l = 0; l + 1 < off.size(); l++) {
           const int nr = off[l + 1] - off[l];
           PROF("k_sgs_scalar_level");
-          k_sgs_scalar_level<<<nblk(nr, 128), 128, 0, c->stream>>>(rows + off[l], nr, c->ia, c->ja, tA, tb, tx);
+          CK(launch_maybe_pdl(k_sgs_scalar_level, nblk(nr, 128), 128, 0, c->stream, c->sgs_pdl && !c->prof && chained,
+                              rows + off[l], nr, c->ia, c->ja, (const double*)tA, (const double*)tb, tx));
+          chained = true;
           LAUNCH_CHECK();
         }
       }
       return 0;
+    }
     case 4:
       PROF("k_turb_update");
       k_turb_update<<<nblk(c->nnode, 256), 256, 0, c->stream>>>(c->nnode, tx, tvar);
