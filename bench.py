@@ -336,6 +336,8 @@ class RankRun:
             self.sync()
         if self.x is not None and hasattr(self.x, "close"):
             self.x.close()
+        if self.world > 1:
+            self.sync()          # every rank has unmapped its peers before anybody frees the exported memory
         self.ctx.close()
 
 
@@ -362,9 +364,6 @@ def main():
     ap.add_argument("--no-strong", action="store_true", help="N>1: skip the fixed-size (strong scaling) 50 M-cell object")
     ap.add_argument("--strong-n", type=int, default=203, help="box side of the fixed-size case (203 -> ~50 M tets)")
     ap.add_argument("--no-fma", action="store_true", help="skip the FMA-contracted build's timing / drift measurement")
-    ap.add_argument("--order", default="lex", choices=["lex", "brick"],
-                    help="N=1 node numbering of the explicit case: lexicographic (the generator's) or 4x4x8-node bricks (locality "
-                         "ordering in the role the reference gives RCM)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -395,7 +394,7 @@ def main():
         from proteuscfd_b200.cases import slab_case
         mesh, params, q0 = slab_case(args.n, rank, world, device=f"cuda:{local_rank}")
     else:
-        mesh, params, q0 = box_case(args.n, device=f"cuda:{local_rank}", brick=(4, 4, 8) if args.order == "brick" else None)
+        mesh, params, q0 = box_case(args.n, device=f"cuda:{local_rank}")
     # a real (non-default) torch stream: the library launches on it and torch.cuda.Event times it
     stream = torch.cuda.Stream(device=local_rank)
     torch.cuda.set_stream(stream)

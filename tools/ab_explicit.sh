@@ -1,22 +1,20 @@
 #!/usr/bin/env bash
-# A/B of the explicit-iteration kernel variants on one box (env switches of libpcfd_b200.so), bench line per variant
+# A/B of the explicit-iteration variants on one box (env switches of libpcfd_b200.so / bench options), one line per variant
 set -u
 out=gpurun_out
 run() {
   name=$1; shift
-  env "$@" timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-fr --no-sgs > "$out/ab_$name.json" 2> "$out/ab_$name.err"
+  env "$@" > "$out/ab_$name.json" 2> "$out/ab_$name.err"
   python - "$out/ab_$name.json" "$name" <<'PY'
 import json, sys
 try:
     d = json.load(open(sys.argv[1]))
     k = d["phases"]["kernels"]
-    print(sys.argv[2], "ms/step %.4f" % d["ms_per_step"], " ".join(f"{n}={v['ms_per_step']:.4f}" for n, v in k.items()))
+    print(sys.argv[2], "ms/step %.4f" % d["ms_per_step"], "parity", (d.get("parity_check") or {}).get("ok"), " ".join(f"{n}={v['ms_per_step']:.4f}" for n, v in k.items()))
 except Exception as e:
     print(sys.argv[2], "FAILED", e)
 PY
 }
-run base PCFD_GRAD_GEO=0 PCFD_EIG_FUSE=0
-run geo1 PCFD_GRAD_THREADS=1 PCFD_EIG_FUSE=0
-run geo3_noqmm PCFD_LIMITER_QMM=0 PCFD_EIG_FUSE=0
-run geo3_qmm PCFD_EIG_FUSE=0
-run all
+B="timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-fr --no-sgs --no-ns --no-fma"
+run lex $B
+run brick $B --order brick
