@@ -168,6 +168,15 @@ int pcfd_prepare_sgs(pcfd_ctx* ctx);
 int pcfd_blank_x(pcfd_ctx* ctx);
 /* CRS::SGS (crs.tcc:62-173); ddq (may be NULL) receives |xOld - xNorm| */
 int pcfd_sgs(pcfd_ctx* ctx, int nsgs, double* ddq);
+/* CRS::GMRES (crs.tcc:176-415): restarted GMRES (restarts x nsearch directions) with right preconditioning on the
+   block-CRS system of the context: A = field PCFD_F_A as ASSEMBLED (before pcfd_prepare_sgs factors its diagonal in
+   place; an error otherwise), b = PCFD_F_B, x = PCFD_F_X (initial guess in, solution out).  precond_type as
+   CRS::Preconditioner (:555-590): 0 none, 1 diagonal, 2 block diagonal (LU); 3 (ILU0) and 4 (SGS) are rejected.
+   dq_norm (may be NULL) receives the reference's return value |g[idir]|.  On connected contexts the vector that
+   needs a halo before every product travels through pcfd_comm and the dot products are summed across ranks.  The
+   reference's flow solver keeps this solver behind a comment (solutionSpace.tcc:734-750); move.tcc:714 calls it. (ABI v7) */
+int pcfd_gmres(pcfd_ctx* ctx, int restarts, int nsearch, int precond_type, double* dq_norm);
+
 /* Limiter::Compute + ComputeResiduals in two halves for multi-rank hosts (all eqnsets).  pcfd_limiter_raw runs
    passes 1+2 of Limiter::Compute (limiters.tcc:53-110) and leaves the UNCLAMPED limiter in field PCFD_F_LIMITER; the
    host exchanges that field (limiters.tcc:128); pcfd_residual_fused then clamps it (:118-125), evaluates the residual

@@ -540,6 +540,22 @@ int main(int argc, char* argv[])
       Dump("ja", A->ja, (size_t)A->nblocks);
       Dump("iau", A->iau, (size_t)nnode);
       Dump("A", A->M, (size_t)A->nblocks*neqn*neqn);
+      if(getenv("PCFD_GMRES")){
+	// CRS::GMRES (crs.tcc:176-415) on the assembled system, BEFORE the diagonal is factored in place: restarted GMRES
+	// with right preconditioning (PCFD_GMRES = the reference's precondType: 0 none, 1 diagonal, 2 block diagonal)
+	Int ptype = atoi(getenv("PCFD_GMRES"));
+	Int ndir = getenv("PCFD_GMRES_NDIR") ? atoi(getenv("PCFD_GMRES_NDIR")) : 10;
+	Int nrest = getenv("PCFD_GMRES_RESTARTS") ? atoi(getenv("PCFD_GMRES_RESTARTS")) : 1;
+	size_t nx = (size_t)(nnode+gnode)*neqn;
+	Real* xg = new Real[nx];
+	for(size_t k = 0; k < nx; k++) xg[k] = 0.0;
+	Real dq = space->crs->GMRES(nrest, ndir, ptype, NULL, xg, NULL);
+	Real cfg[3] = {(Real)ptype, (Real)ndir, (Real)nrest};
+	Dump("gmres_x", xg, nx);
+	Dump("gmres_dq", &dq, 1);
+	Dump("gmres_cfg", cfg, 3);
+	delete [] xg;
+      }
       A->PrepareSGS();
       Dump("A_lu", A->M, (size_t)A->nblocks*neqn*neqn);
       Dump("pv", A->pv, (size_t)nnode*neqn);

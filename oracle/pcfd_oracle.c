@@ -1372,6 +1372,10 @@ void orc_jacobian(const orc_case* c, double* q, const double* beta, const double
   }
 }
 
+#ifndef ORC_MAX_NEQN
+#define ORC_MAX_NEQN 32
+#endif
+
 /* matrix.h:110-190 */
 static int lu(double* a, int* p, int n)
 {
@@ -1411,6 +1415,137 @@ static void lu_solve(const double* a, double* b, const int* p, double* x, int n)
     for(j = n-1; j > i; j--) sum += a[p[i]*n + j]*b[j];
     b[i] = (x[i] - sum)/a[p[i]*n + i];
   }
+}
+
+/* CRS::GMRES (crs.tcc:176-415), single rank: restarted GMRES with right preconditioning; Preconditioner / PrecondBackSolve
+   (:555-641) types 0 (none), 1 (diagonal of the diagonal blocks), 2 (block diagonal, LU with the permutation vector).
+   A is the assembled matrix BEFORE CRSMatrix::PrepareSGS; x holds the initial guess and receives the solution
+   ((nnode+gnode)*neqn); returns |g[idir]|, the reference's dqNorm. */
+static void gm_matvec(int nnode, int gnode, int neqn, const int* ia, const int* ja, const double* A, const double* vin, double* vout)
+{
+  int i, j, k, indx, n2 = neqn*neqn;
+  double temp[ORC_MAX_NEQN];
+  for(i = 0; i < neqn*(nnode+gnode); i++) vout[i] = 0.0;   /* CRS::MatVecMultiply crs.tcc:484-508 */
+  for(i = 0; i < nnode; i++){
+    for(indx = ia[i]; indx < ia[i+1]; indx++){
+      const double* a1 = &A[(size_t)indx*n2];
+      const double* v1 = &vin[(size_t)ja[indx]*neqn];
+      for(j = 0; j < neqn; j++){   /* MatVecMult matrix.h:63-74 */
+	temp[j] = a1[j*neqn + 0]*v1[0];
+	for(k = 1; k < neqn; k++) temp[j] += a1[j*neqn + k]*v1[k];
+      }
+      for(j = 0; j < neqn; j++) vout[i*neqn + j] += temp[j];
+    }
+  }
+}
+
+static void gm_precond_solve(int type, int nnode, int neqn, const double* N, const int* pv, double* x, const double* b)
+{
+  int i, j, n2 = neqn*neqn;
+  double temp[ORC_MAX_NEQN];
+  if(type == 0){ memcpy(x, b, sizeof(double)*(size_t)nnode*neqn); return; }
+  for(i = 0; i < nnode; i++){
+    const double* ptr = &N[(size_t)i*n2];
+    if(type == 1){
+      for(j = 0; j < neqn; j++) x[i*neqn + j] = b[i*neqn + j]/ptr[j*neqn + j];
+    }
+    else{
+      memcpy(&x[i*neqn], &b[i*neqn], sizeof(double)*neqn);
+      lu_solve(ptr, &x[i*neqn], &pv[i*neqn], temp, neqn);
+    }
+  }
+}
+
+double orc_gmres(int nnode, int gnode, int neqn, int restarts, int nSearchDir, int precondType, const int* ia,
+		 const int* ja, const int* iau, const double* A, const double* b, double* x)
+{
+  const double smallnum = 1.0e-15;
+  int i, ii, j, jj, irestart, idir = 0, hpos, n2 = neqn*neqn, nloc = neqn*nnode;
+  size_t vstride = (size_t)neqn*(nnode+gnode);
+  double* vdat = (double*)calloc((size_t)(nSearchDir+1)*vstride, sizeof(double));
+  double* vtemp = (double*)calloc(vstride, sizeof(double));
+  double* uk = (double*)calloc(vstride, sizeof(double));
+  double* g = (double*)calloc(nSearchDir+2, sizeof(double));
+  double* Q = (double*)calloc((size_t)2*(nSearchDir+1), sizeof(double));
+  double* H = (double*)calloc((size_t)(nSearchDir+2)*(nSearchDir+2), sizeof(double));
+  int* Hoffset = (int*)calloc(nSearchDir+1, sizeof(int));
+  double* N = NULL;
+  int* pv = NULL;
+  double dot1_g, cosv, sinv, a1, a2, alpha, temp1, temp2, dqNorm;
+  if(precondType == 1 || precondType == 2){   /* BuildBlockDiagPrecond crsmatrix.tcc:190-240 (+ PrepareSGS for type 2) */
+    N = (double*)malloc(sizeof(double)*(size_t)nnode*n2);
+    pv = (int*)calloc((size_t)nnode*neqn, sizeof(int));
+    for(i = 0; i < nnode; i++) memcpy(&N[(size_t)i*n2], &A[(size_t)iau[i]*n2], sizeof(double)*n2);
+    if(precondType == 2) for(i = 0; i < nnode; i++) lu(&N[(size_t)i*n2], &pv[i*neqn], neqn);
+  }
+  for(irestart = 0; irestart < restarts; irestart++){
+    double* v0 = vdat;
+    gm_matvec(nnode, gnode, neqn, ia, ja, A, x, v0);
+    for(i = 0; i < nloc; i++) v0[i] = b[i] - v0[i];
+    dot1_g = 0.0;
+    for(i = 0; i < nloc; i++) dot1_g += v0[i]*v0[i];
+    dot1_g = sqrt(dot1_g);
+    if(dot1_g < smallnum){ idir = 0; break; }
+    for(i = 0; i < nloc; i++) v0[i] /= dot1_g;
+    for(i = 0; i < nSearchDir+2; i++) g[i] = 0.0;
+    g[0] = dot1_g;
+    hpos = 0;
+    for(idir = 0; idir < nSearchDir; idir++){
+      double* vk = vdat + (size_t)idir*vstride;
+      Hoffset[idir] = hpos;
+      gm_precond_solve(precondType, nnode, neqn, N, pv, vtemp, vk);
+      for(i = 0; i < (int)vstride; i++) uk[i] = 0.0;
+      gm_matvec(nnode, gnode, neqn, ia, ja, A, vtemp, uk);
+      for(j = 0; j <= idir; j++){
+	const double* vj = vdat + (size_t)j*vstride;
+	dot1_g = 0.0;
+	for(i = 0; i < nloc; i++) dot1_g += uk[i]*vj[i];
+	H[hpos++] = dot1_g;
+	for(i = 0; i < nloc; i++) uk[i] -= (dot1_g*vj[i]);
+      }
+      dot1_g = 0.0;
+      for(i = 0; i < nloc; i++) dot1_g += uk[i]*uk[i];
+      dot1_g = sqrt(dot1_g);
+      H[hpos++] = dot1_g;
+      if(dot1_g < smallnum) break;
+      {
+	double* vn = vdat + (size_t)(idir+1)*vstride;
+	for(i = 0; i < nloc; i++) vn[i] = uk[i]/dot1_g;
+      }
+      for(jj = 0; jj < idir; jj++){
+	cosv = Q[jj*2 + 0]; sinv = Q[jj*2 + 1];
+	temp1 = H[Hoffset[idir] + jj]; temp2 = H[Hoffset[idir] + jj + 1];
+	H[Hoffset[idir] + jj] = cosv*temp1 + sinv*temp2;
+	H[Hoffset[idir] + jj + 1] = -sinv*temp1 + cosv*temp2;
+      }
+      a2 = H[Hoffset[idir] + idir + 1];
+      a1 = H[Hoffset[idir] + idir];
+      alpha = sqrt(a1*a1 + a2*a2);
+      cosv = a1/alpha; sinv = a2/alpha;
+      Q[idir*2 + 0] = cosv; Q[idir*2 + 1] = sinv;
+      H[Hoffset[idir] + idir] = alpha;
+      H[Hoffset[idir] + idir + 1] = 0.0;
+      temp1 = g[idir]; temp2 = g[idir+1];
+      g[idir] = cosv*temp1 + sinv*temp2;
+      g[idir+1] = -sinv*temp1 + cosv*temp2;
+    }
+    for(jj = idir-1; jj >= 0; jj--){
+      temp1 = 0.0;
+      for(ii = jj+1; ii <= idir-1; ii++) temp1 += H[Hoffset[ii] + jj]*g[ii];
+      g[jj] -= temp1;
+      g[jj] /= H[Hoffset[jj] + jj];
+    }
+    for(ii = 0; ii < nloc; ii++) uk[ii] = 0.0;
+    for(jj = 0; jj <= idir-1; jj++){
+      const double* vj = vdat + (size_t)jj*vstride;
+      for(ii = 0; ii < nloc; ii++) uk[ii] += (vj[ii]*g[jj]);
+    }
+    gm_precond_solve(precondType, nnode, neqn, N, pv, vtemp, uk);
+    for(i = 0; i < nloc; i++) x[i] += vtemp[i];
+  }
+  dqNorm = g[idir-1+1];
+  free(vdat); free(vtemp); free(uk); free(g); free(Q); free(H); free(Hoffset); free(N); free(pv);
+  return fabs(dqNorm);
 }
 
 /* crsmatrix.tcc:840-876 */

@@ -210,4 +210,10 @@ void orc_fr_hllc_flux(const orc_fr_params* p, const double* QL, const double* QR
 #ifdef __cplusplus
 }
 #endif
+/* CRS::GMRES (crs.tcc:176-415) on one rank: restarts x nSearchDir, right preconditioner type 0 / 1 / 2 (none, diagonal,
+   block diagonal LU; crs.tcc:555-641); any block size neqn <= 32.  A: assembled matrix before PrepareSGS; x: initial guess
+   in, solution out, (nnode+gnode)*neqn; returns the reference's dqNorm. */
+double orc_gmres(int nnode, int gnode, int neqn, int restarts, int nSearchDir, int precondType, const int* ia,
+		 const int* ja, const int* iau, const double* A, const double* b, double* x);
+
 #endif

@@ -42,7 +42,7 @@ SYMBOLS = [
     "pcfd_set_time_integration", "pcfd_set_gradient_type", "pcfd_set_jacobian_type",
     "pcfd_chem_source_term", "pcfd_chem_source_term_device", "pcfd_halo_width", "pcfd_halo_send_total", "pcfd_halo_pack", "pcfd_halo_recv_ptr",
     "pcfd_comm_blob_size", "pcfd_comm_export", "pcfd_comm_connect", "pcfd_comm_disconnect", "pcfd_comm_connected",
-    "pcfd_comm_post", "pcfd_comm_wait", "pcfd_comm_update", "pcfd_comm_allgather", "pcfd_comm_debug_flags",
+    "pcfd_comm_post", "pcfd_comm_wait", "pcfd_comm_update", "pcfd_comm_allgather", "pcfd_comm_debug_flags", "pcfd_gmres",
 ]
 
 
@@ -216,6 +216,7 @@ def load_library(path=LIB_PATH):
         getattr(lib, name).argtypes = [C.c_void_p, C.c_int]
     lib.pcfd_comm_allgather.argtypes = [C.c_void_p, _dp, C.c_int, _dp]
     lib.pcfd_turb_phase.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.pcfd_gmres.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp]
     for name in ("pcfd_destroy", "pcfd_synchronize", "pcfd_lsq_coefficients", "pcfd_update_bcs", "pcfd_gradient",
                  "pcfd_limiter", "pcfd_explicit_solve", "pcfd_jacobian", "pcfd_prepare_sgs", "pcfd_blank_x",
                  "pcfd_apply_dq"):
@@ -513,6 +514,12 @@ class Context:
             return None
         d = C.c_double()
         self._ck(self.lib.pcfd_sgs(self.h, int(nsgs), C.byref(d)))
+        return d.value
+
+    def gmres(self, restarts, nsearch, precond_type):
+        """CRS::GMRES on the context's A (assembled, not factored), b and x; returns the reference's dqNorm"""
+        d = C.c_double()
+        self._ck(self.lib.pcfd_gmres(self.h, int(restarts), int(nsearch), int(precond_type), C.byref(d)))
         return d.value
 
     def turb_compute(self, nsgs, want_norm=False):

@@ -143,6 +143,10 @@ struct pcfd_ctx {
   int time_local = 1, torder = 1, iter = 1;
   bool have_qold = false;   // PCFD_F_QOLD has been set: TemporalResidual is live
   bool ludiag = false;
+  // scratch of pcfd_gmres (Krylov vectors, block-diagonal preconditioner), grown on demand
+  double* gm_buf = nullptr;
+  int* gm_pv = nullptr;
+  size_t gm_cap = 0;
   double sgs_prev_norm = 0.0;   // xNorm of the last-but-one sweep when the sweeps of a solve are separate calls (multi-rank)
   int sgs_unroll = 4;      // blocks in flight per lane in k_sgs_level (PCFD_SGS_UNROLL overrides, for tuning)
   // bulk-copy (TMA) streaming variant: per level, shared-memory bytes for the matrix part of a tile (0: the rows of

@@ -2188,6 +2188,7 @@ std::vector<int> contiguous_ranges(int n, const int* ia, const int* ja) {
 }  // namespace
 
 #include "pcfd_comm.cuh"
+#include "pcfd_gmres.cuh"
 
 // ======================================================================= C ABI
 extern "C" {
@@ -2208,6 +2209,8 @@ int pcfd_destroy(pcfd_ctx* c) {
     c->comm = nullptr;
   }
   for (void* p : c->allocs) cudaFree(p);
+  if (c->gm_buf) cudaFree(c->gm_buf);
+  if (c->gm_pv) cudaFree(c->gm_pv);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->hflag) cudaFreeHost(c->hflag);
   if (c->ev_flag) cudaEventDestroy(c->ev_flag);

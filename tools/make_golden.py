@@ -131,7 +131,7 @@ def collect(outdir, rank):
     return d
 
 
-def make_case(name, mesh=None, h5=None, bc=BOX_BC, np_ranks=1, part=None, unsteady=False, **kw):
+def make_case(name, mesh=None, h5=None, bc=BOX_BC, np_ranks=1, part=None, unsteady=False, gmres=None, **kw):
     opts = dict(eqnset="compressibleEuler", sorder=2, limiter=2, nsgs=0, mach=0.5, cfl=0.5,
                 fx=1.0, fy=0.0, fz=0.0, jactype=0, refvisc=1.0, vnn=0, turb=0, extra="")
     opts.update(kw)
@@ -156,6 +156,8 @@ def make_case(name, mesh=None, h5=None, bc=BOX_BC, np_ranks=1, part=None, unstea
         henv = {"PCFD_MPI_NP": str(np_ranks)}
         if unsteady:
             henv["PCFD_UNSTEADY"] = "1"
+        if gmres is not None:      # (precondType, search directions, restarts): also run CRS::GMRES on the assembled system
+            henv.update(PCFD_GMRES=str(gmres[0]), PCFD_GMRES_NDIR=str(gmres[1]), PCFD_GMRES_RESTARTS=str(gmres[2]))
         run([os.path.join(REFBIN, "ref_harness"), os.path.join(work, name), os.path.join(work, "out"), "dump"], work, henv)
         os.makedirs(GOLDEN, exist_ok=True)
         for r in range(np_ranks):
@@ -285,6 +287,11 @@ CASES = {
     "box4_fr_unsteady": lambda: make_case("box4_fr_unsteady", mesh=kuhn_box(4, jitter=0.15), eqnset="compressibleEulerFR",
                                           nsgs=3, cfl=5.0, unsteady=True,
                                           extra=FR_EXTRA.format(temp=3000, pres=101325, rxn=1) + "timeStep = 0.02\ntimeOrder = 2\n"),
+    # CRS::GMRES (crs.tcc:176-415) on the assembled implicit system: block-diagonal (LU) right preconditioner, 8 search
+    # directions, 2 restarts (perfect gas 5x5); diagonal preconditioner, 6 directions, 1 restart (reacting 9x9)
+    "box6_gmres": lambda: make_case("box6_gmres", mesh=kuhn_box(6, jitter=0.15), nsgs=3, cfl=5.0, gmres=(2, 8, 2)),
+    "box4_fr_gmres": lambda: make_case("box4_fr_gmres", mesh=kuhn_box(4, jitter=0.15), eqnset="compressibleEulerFR",
+                                       nsgs=3, cfl=5.0, gmres=(1, 6, 1), extra=FR_EXTRA.format(temp=3000, pres=101325, rxn=1)),
     # the reference's own unit-test fixture (unitTest/gradientTest.h:20-232): prism cube, 216 nodes
     "cube_LowFi": lambda: make_case(
         "cube_LowFi", h5=os.path.join(REFERENCE, "unitTest/meshResources/cubeStructuredSeries/cube_LowFi.0.h5"),
