@@ -766,6 +766,26 @@ def implicit_bench(args, rank, world, local_rank, peak, torch, dist, stream, kin
            "state_finite_after_run": finite, "clip_fallbacks": r.clip_fallbacks(),
            "kernels_ms_rank0": {k: v[0] / max(v[1], 1) for k, v in tab.items()},
            "kernel": "k_sgs_tile (cp.async.bulk + mbarrier streamed tiles, PDL-chained levels)" if "k_sgs_tile" in tab else "k_sgs_level"}
+    if kind == "euler":
+        # CRS::GMRES (10 directions, block-diagonal LU right preconditioner) on the freshly assembled system
+        try:
+            c.timestep(want_min=False)
+            c.jacobian()
+            c.blank_x()
+            c.gmres(1, 10, 2)                       # allocates the Krylov scratch
+            c.blank_x()
+            r.sync()
+            t0 = time.perf_counter()
+            dq = c.gmres(1, 10, 2)
+            r.sync()
+            ms_g = r.maxms((time.perf_counter() - t0) * 1e3)
+            bytes_g = r.total(11 * (nblocks * 8 * NEQN * NEQN + 4 * nblocks))      # 11 block-CRS products stream the matrix
+            out["gmres"] = {"what": "pcfd_gmres(1 restart, 10 directions, block-diagonal LU preconditioner): 11 block-CRS products, 10 "
+                                    "preconditioner solves, 65 dot products (each a host round trip), wall clock incl. those",
+                            "ms": ms_g, "dq_norm": dq, "matrix_stream_GBps": bytes_g / (ms_g * 1e-3) / 1e9,
+                            "matrix_stream_frac_hbm": bytes_g / (ms_g * 1e-3) / 1e9 / (peak * world)}
+        except Exception as e:
+            out["gmres"] = {"error": f"{type(e).__name__}: {e}"[:200]}
     r.close()
     torch.cuda.empty_cache()
     return out

@@ -238,10 +238,15 @@ int comm_gather_enqueue(pcfd_ctx* c, const double* dvals, const int* dints, int 
   return 0;
 }
 
+// the error word, read through the context's own stream into pinned memory: a synchronous cudaMemcpy would go through
+// the legacy default stream and can wait for kernels of OTHER contexts on the device (ranks as threads: a peer's put
+// kernel that is spinning for this very rank)
 int comm_check_err(pcfd_ctx* c) {
-  int e = 0;
-  CK(cudaMemcpy(&e, &c->comm->flags->err, sizeof(int), cudaMemcpyDeviceToHost));
-  if (e) return fail(c, "pcfd_comm: a peer did not answer within the time limit (flag spin timed out)");
+  pcfd_comm* m = c->comm;
+  int* herr = reinterpret_cast<int*>(m->hgout + (size_t)COMM_MAXR * COMM_GW);
+  CK(cudaMemcpyAsync(herr, &m->flags->err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (*herr) return fail(c, "pcfd_comm: a peer did not answer within the time limit (flag spin timed out)");
   return 0;
 }
 
@@ -266,7 +271,7 @@ int pcfd_comm_export(pcfd_ctx* c, void* blob) {
     if (dev_alloc(c, &m->counter, 4)) return 1;
     CK(cudaMemset(m->counter, 0, 4 * sizeof(int)));
     if (dev_alloc(c, &m->gout, (size_t)COMM_MAXR * COMM_GW)) return 1;
-    CK(cudaMallocHost(reinterpret_cast<void**>(&m->hgout), sizeof(double) * COMM_MAXR * COMM_GW));
+    CK(cudaMallocHost(reinterpret_cast<void**>(&m->hgout), sizeof(double) * (COMM_MAXR * COMM_GW + 16)));   // + error word, upload slot
     CK(cudaEventCreateWithFlags(&m->ev, cudaEventDisableTiming));
   }
   CommBlob b;
@@ -392,7 +397,10 @@ int pcfd_comm_allgather(pcfd_ctx* c, const double* vals, int n, double* out) {
   pcfd_comm* m = c->comm;
   double* stage = m->gout + (size_t)(COMM_MAXR - 1) * COMM_GW;   // tail of gout doubles as the upload slot
   if (c->nranks == COMM_MAXR) return fail(c, "pcfd_comm_allgather: staging slot unavailable at the maximum rank count");
-  CK(cudaMemcpyAsync(stage, vals, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  double* hstage = m->hgout + (size_t)COMM_MAXR * COMM_GW + 1;      // pinned: no staging through the driver's own buffers
+  CK(cudaStreamSynchronize(c->stream));                             // (a previous gather's result may still be in flight)
+  for (int k = 0; k < n; k++) hstage[k] = vals[k];
+  CK(cudaMemcpyAsync(stage, hstage, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   if (comm_gather_enqueue(c, stage, nullptr, n)) return 1;
   CK(cudaEventSynchronize(m->ev));
   for (int r = 0; r < c->nranks; r++)

@@ -147,9 +147,10 @@ int gm_dot(pcfd_ctx* c, const double* a, const double* b, int n, double* out) {
   PROF("k_gm_dot_final");
   k_gm_dot_final<256><<<1, 256, 0, c->stream>>>(c->red, RED_BLOCKS, c->redout + 12);
   LAUNCH_CHECK();
-  double local = 0.0;
-  CK(cudaMemcpyAsync(&local, c->redout + 12, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  double* hd = reinterpret_cast<double*>(c->hflag) + 1;   // pinned (c->hflag is a 64-byte pinned block)
+  CK(cudaMemcpyAsync(hd, c->redout + 12, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  double local = *hd;
   if (comm_on(c)) {
     double all[COMM_MAXR];
     if (pcfd_comm_allgather(c, &local, 1, all)) return 1;

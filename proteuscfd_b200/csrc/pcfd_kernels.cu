@@ -2537,7 +2537,7 @@ static int create_impl(const pcfd_mesh_desc* mesh, const pcfd_params* params, in
   if (dev_alloc(c, &c->tclip[0], (size_t)nnode)) return 1;
   if (dev_alloc(c, &c->tclip[1], (size_t)nnode)) return 1;
   if (dev_alloc(c, &c->dflags, 4)) return 1;
-  CK(cudaMallocHost(reinterpret_cast<void**>(&c->hflag), sizeof(int)));
+  CK(cudaMallocHost(reinterpret_cast<void**>(&c->hflag), 64));   // clip flag (int) + small pinned scratch
   CK(cudaEventCreateWithFlags(&c->ev_flag, cudaEventDisableTiming));
   if (const char* e = getenv("PCFD_FUSED_CLIP")) c->fused_clip = atoi(e) != 0;
   if (const char* e = getenv("PCFD_GRAD_GEO")) c->use_geo = atoi(e) != 0;

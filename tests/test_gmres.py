@@ -143,7 +143,9 @@ def test_gpu_gmres_across_ranks_vs_oracle(oracle):
         ia, ja, iau, _ = ctx.get_crs()
         return dict(dq=dq, x=ctx.get_field(capi.F_X), A=ctx.get_field(capi.F_A), b=ctx.get_field(capi.F_B), ia=ia, ja=ja)
 
-    got = run_threads(parts, body)
+    # the Krylov scratch is allocated on first use: do that before the ranks connect (a cudaMalloc synchronises the device,
+    # which the thread ranks share)
+    got = run_threads(parts, body, prepare=lambda ctx: ctx.gmres(1, 20, 0))
     assert len({g["dq"] for g in got}) == 1, "every rank must see the same (global) Hessenberg system"
     from proteuscfd_b200.parallel import build_local_group_maps
     pobjs = build_local_group_maps([(m["gNodeOwner"], m["gNodeLocalId"]) for m, _, _ in parts])

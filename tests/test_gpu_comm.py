@@ -23,8 +23,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def run_threads(parts, body):
-    """one thread per rank: context, halo maps over the thread group, CommExchange; body(rank, ctx, x) -> result"""
+def run_threads(parts, body, prepare=None):
+    """one thread per rank: context, halo maps over the thread group, CommExchange; body(rank, ctx, x) -> result.
+    prepare(ctx): anything that allocates device memory on first use, run BEFORE the ranks connect (see below)"""
     from proteuscfd_b200 import capi
     from proteuscfd_b200.parallel import CommExchange, PObj, ThreadGroup
     nr = len(parts)
@@ -36,6 +37,8 @@ def run_threads(parts, body):
         # allocate-on-first-use fields now: a cudaMalloc inside an iteration synchronises the DEVICE, i.e. (ranks as
         # threads sharing one GPU) it would wait for a peer's put kernel that is waiting for this very rank
         ctx.device_ptr(capi.F_A)
+        if prepare is not None:
+            prepare(ctx)
         pobj = PObj(rank, nr).BuildCommMaps(mesh["gNodeOwner"], mesh["gNodeLocalId"], group)
         x = CommExchange(ctx, pobj, group)
         try:
