@@ -1684,13 +1684,14 @@ static double sa_eddy_viscosity(double rho, double nu, double nut)
      3 ONE symmetric Gauss-Seidel sweep (nsgs > 0) or the explicit update (nsgs == 0) -> halo of x (crs.tcc:146)
      4 update + clip                          -> halo of tvar  (turb.tcc:325)
      5 eddy viscosity of local and ghost nodes */
-double orc_turb_sa_phase(const orc_case* c, int phase, int nsgs, const double* q, const double* qgrad, const double* s,
-			 const double* dist, const double* dt, const int* ia, const int* ja, const int* iau,
-			 double* tvar, double* tgrad, double* b, double* A, double* x, double* mut)
+double orc_turb_sa_phase_gas(const orc_case* c, const orc_gas* gas, int phase, int nsgs, const double* q, const double* qgrad,
+			     const double* s, const double* dist, const double* dt, const int* ia, const int* ja, const int* iau,
+			     double* tvar, double* tgrad, double* b, double* A, double* x, double* mut)
 {
   int e, i, k, dir;
   int nnode = c->nnode, nn = c->nnode + c->gnode, nb = c->nbedge + c->ngedge;
-  double Re = c->Re/c->mach;   /* CompressibleEqnSet::GetRe, compressible.tcc:1190-1199 */
+  const int NV = gas->nvars;       /* row width of q */
+  double Re = gas->Re;             /* EqnSet::GetRe() */
   double resid = 0.0;
   if(phase == 0){
   /* crs.BlankSystem (crs.tcc:417-425) */
@@ -1740,9 +1741,8 @@ double orc_turb_sa_phase(const orc_case* c, int phase, int nsgs, const double* q
   for(e = 0; e < c->nedge; e++){
     int l = c->edges_n[2*e], r = c->edges_n[2*e+1];
     const double* avec = &c->edges_a[4*e];
-    double qa[NEQN], theta, area = avec[3], tempR;
-    for(i = 0; i < NEQN; i++) qa[i] = 0.5*(q[l*NVARS + i] + q[r*NVARS + i]);
-    theta = get_theta(qa, avec, 0.0);
+    double theta, area = avec[3], tempR;
+    theta = gas->theta_avg(gas, &q[(size_t)l*NV], &q[(size_t)r*NV], avec);
     if(theta > 0.0){
       tempR = theta*area;
       *get_entry(ia, ja, A, r, l) -= tempR;
@@ -1759,9 +1759,8 @@ double orc_turb_sa_phase(const orc_case* c, int phase, int nsgs, const double* q
   for(e = 0; e < nb; e++){
     int l = c->bedges_n[2*e], r = c->bedges_n[2*e+1];
     const double* avec = &c->bedges_a[4*e];
-    double qa[NEQN], theta, area = avec[3], tempR;
-    for(i = 0; i < NEQN; i++) qa[i] = 0.5*(q[l*NVARS + i] + q[r*NVARS + i]);
-    theta = get_theta(qa, avec, 0.0);
+    double theta, area = avec[3], tempR;
+    theta = gas->theta_avg(gas, &q[(size_t)l*NV], &q[(size_t)r*NV], avec);
     if(theta > 0.0){
       tempR = theta*area;
       A[iau[l]] += tempR;
@@ -1779,7 +1778,7 @@ double orc_turb_sa_phase(const orc_case* c, int phase, int nsgs, const double* q
   for(e = 0; e < c->nedge; e++){
     int l = c->edges_n[2*e], r = c->edges_n[2*e+1];
     const double* avec = &c->edges_a[4*e];
-    double de[3], ds2 = 0.0, dxx, dyy, dzz, d, dgrad, qavg[NVARS], rho, mu, nu, tg[3];
+    double de[3], ds2 = 0.0, dxx, dyy, dzz, d, dgrad, rho, nu, tg[3];
     double tresL, tresR, tjacL, tjacR;
     for(i = 0; i < 3; i++){
       de[i] = c->xyz[3*r+i] - c->xyz[3*l+i];
@@ -1788,11 +1787,7 @@ double orc_turb_sa_phase(const orc_case* c, int phase, int nsgs, const double* q
     dxx = de[0]*avec[0]; dyy = de[1]*avec[1]; dzz = de[2]*avec[2];
     d = dxx + dyy + dzz;
     dgrad = d/ds2;
-    for(i = 0; i < NEQN; i++) qavg[i] = 0.5*(q[l*NVARS + i] + q[r*NVARS + i]);
-    compute_aux(qavg, c->gamma);
-    rho = qavg[0];
-    mu = compute_viscosity(c, qavg);
-    nu = mu/rho;
+    gas->rho_nu_avg(gas, &q[(size_t)l*NV], &q[(size_t)r*NV], &rho, &nu);
     for(i = 0; i < 3; i++) tg[i] = 0.5*(tgrad[l*3 + i] + tgrad[r*3 + i]);
     sa_diffusive(Re, nu, tg, tvar[l], tvar[r], avec, dgrad, &tresL, &tresR, &tjacL, &tjacR);
     b[l] += tresL;
@@ -1803,12 +1798,8 @@ double orc_turb_sa_phase(const orc_case* c, int phase, int nsgs, const double* q
   for(e = 0; e < nb; e++){
     int l = c->bedges_n[2*e], r = c->bedges_n[2*e+1];
     const double* avec = &c->bedges_a[4*e];
-    double qavg[NVARS], rho, mu, nu, tg[3], dgrad = 0.0, tresL, tresR, tjacL, tjacR;
-    for(i = 0; i < NEQN; i++) qavg[i] = 0.5*(q[l*NVARS + i] + q[r*NVARS + i]);
-    compute_aux(qavg, c->gamma);
-    rho = qavg[0];
-    mu = compute_viscosity(c, qavg);
-    nu = mu/rho;
+    double rho, nu, tg[3], dgrad = 0.0, tresL, tresR, tjacL, tjacR;
+    gas->rho_nu_avg(gas, &q[(size_t)l*NV], &q[(size_t)r*NV], &rho, &nu);
     if(is_ghost(c, r)){
       double de[3], ds2 = 0.0, dxx, dyy, dzz, d, qdots, dq;
       for(i = 0; i < 3; i++){
@@ -1835,12 +1826,12 @@ double orc_turb_sa_phase(const orc_case* c, int phase, int nsgs, const double* q
     else A[iau[l]] += tjacL;
   }
 
-  /* source terms (turb.tcc:207-233); vgrad = qgrad + GetVelocityGradLocation()*3 = +3 (compressible.tcc:1217) */
+  /* source terms (turb.tcc:207-233); vgrad = qgrad + GetVelocityGradLocation()*3 (compressible.tcc:1217: +3; FR: +3 ns) */
   for(i = 0; i < nnode; i++){
-    const double* Q = &q[i*NVARS];
-    double rho = Q[0], mu = compute_viscosity(c, Q), nu = mu/rho, tres, tjac;
+    double rho, nu, tres, tjac;
+    gas->rho_nu_node(gas, &q[(size_t)i*NV], &rho, &nu);
     if(dist[i] < 1.0e-16) continue;
-    sa_source(Re, nu, dist[i], &qgrad[i*NTERMS*3 + 3], tvar[i], c->vol[i], &tres, &tjac);
+    sa_source(Re, nu, dist[i], &qgrad[(size_t)i*gas->nterms*3 + gas->vloc], tvar[i], c->vol[i], &tres, &tjac);
     b[i] += tres;
     A[iau[i]] += tjac;
   }
@@ -1904,12 +1895,54 @@ double orc_turb_sa_phase(const orc_case* c, int phase, int nsgs, const double* q
   else if(phase == 5){
   /* eddy viscosity (turb.tcc:324-336) */
   for(i = 0; i < nn; i++){
-    const double* Q = &q[i*NVARS];
-    double rho = Q[0], mu = compute_viscosity(c, Q), nu = mu/rho;
+    double rho, nu;
+    gas->rho_nu_node(gas, &q[(size_t)i*NV], &rho, &nu);
     mut[i] = sa_eddy_viscosity(rho, nu, tvar[i]);
   }
   }
   return resid;
+}
+
+
+/* ---- the eqnset behind the turbulence model (TurbulenceModel talks to EqnSet through GetTheta, ComputeAuxiliaryVariables,
+   GetDensity, ComputeViscosity, GetRe, GetVelocityGradLocation): perfect gas here, the reacting eqnset in pcfd_oracle_fr.c */
+static double pg_theta_avg(const orc_gas* g, const double* qL, const double* qR, const double* avec)
+{
+  double qa[NEQN];
+  int i;
+  (void)g;
+  for(i = 0; i < NEQN; i++) qa[i] = 0.5*(qL[i] + qR[i]);
+  return get_theta(qa, avec, 0.0);
+}
+static void pg_rho_nu_avg(const orc_gas* g, const double* qL, const double* qR, double* rho, double* nu)
+{
+  const orc_case* c = (const orc_case*)g->ctx;
+  double qavg[NVARS], mu;
+  int i;
+  for(i = 0; i < NEQN; i++) qavg[i] = 0.5*(qL[i] + qR[i]);
+  compute_aux(qavg, c->gamma);
+  *rho = qavg[0];
+  mu = compute_viscosity(c, qavg);
+  *nu = mu/(*rho);
+}
+static void pg_rho_nu_node(const orc_gas* g, const double* Q, double* rho, double* nu)
+{
+  const orc_case* c = (const orc_case*)g->ctx;
+  double mu = compute_viscosity(c, Q);
+  *rho = Q[0];
+  *nu = mu/(*rho);
+}
+
+double orc_turb_sa_phase(const orc_case* c, int phase, int nsgs, const double* q, const double* qgrad, const double* s,
+			 const double* dist, const double* dt, const int* ia, const int* ja, const int* iau,
+			 double* tvar, double* tgrad, double* b, double* A, double* x, double* mut)
+{
+  orc_gas gas;
+  gas.nvars = NVARS; gas.nterms = NTERMS; gas.vloc = 3;
+  gas.Re = c->Re/c->mach;   /* CompressibleEqnSet::GetRe, compressible.tcc:1190-1199 */
+  gas.ctx = c;
+  gas.theta_avg = pg_theta_avg; gas.rho_nu_avg = pg_rho_nu_avg; gas.rho_nu_node = pg_rho_nu_node;
+  return orc_turb_sa_phase_gas(c, &gas, phase, nsgs, q, qgrad, s, dist, dt, ia, ja, iau, tvar, tgrad, b, A, x, mut);
 }
 
 double orc_turb_sa(const orc_case* c, int nsgs, const double* q, const double* qgrad, const double* s,

@@ -117,6 +117,19 @@ int orc_normal_node(const orc_case* c, int e);
 double orc_turb_sa(const orc_case* c, int nsgs, const double* q, const double* qgrad, const double* s,
 		   const double* dist, const double* dt, const int* ia, const int* ja, const int* iau,
 		   double* tvar, double* tgrad, double* b, double* A, double* x, double* mut);
+/* the eqnset as TurbulenceModel sees it (EqnSet::GetTheta / ComputeAuxiliaryVariables / GetDensity / ComputeViscosity /
+   GetRe / GetVelocityGradLocation): perfect gas in pcfd_oracle.c, compressibleNSFR in pcfd_oracle_fr.c */
+typedef struct orc_gas {
+  int nvars, nterms, vloc;      /* row widths of q and qgrad/3, offset of the velocity gradient in a qgrad row */
+  double Re;
+  const void* ctx;
+  double (*theta_avg)(const struct orc_gas* g, const double* qL, const double* qR, const double* avec);
+  void (*rho_nu_avg)(const struct orc_gas* g, const double* qL, const double* qR, double* rho, double* nu);
+  void (*rho_nu_node)(const struct orc_gas* g, const double* Q, double* rho, double* nu);
+} orc_gas;
+double orc_turb_sa_phase_gas(const orc_case* c, const orc_gas* gas, int phase, int nsgs, const double* q, const double* qgrad,
+			     const double* s, const double* dist, const double* dt, const int* ia, const int* ja, const int* iau,
+			     double* tvar, double* tgrad, double* b, double* A, double* x, double* mut);
 /* the same update one phase at a time (0..5, see pcfd_oracle.c), for per-rank replays with halos in between; phase 2
    returns the sum of b^2 */
 double orc_turb_sa_phase(const orc_case* c, int phase, int nsgs, const double* q, const double* qgrad, const double* s,
@@ -210,6 +223,16 @@ void orc_fr_hllc_flux(const orc_fr_params* p, const double* QL, const double* QR
 #ifdef __cplusplus
 }
 #endif
+/* Spalart-Allmaras under compressibleNSFR: the eqnset-agnostic TurbulenceModel::Compute of pcfd_oracle.c with the reacting
+   eqnset's accessors (Wilke-mixed viscosity, density from the aux variables, native velocities); arrays as orc_turb_sa with
+   q rows of 3 ns + 6 and qgrad rows of (2 ns + 4) x 3 doubles */
+double orc_fr_turb_sa_phase(const orc_case* c, const orc_fr_params* p, int phase, int nsgs, const double* q, const double* qgrad,
+			    const double* s, const double* dist, const double* dt, const int* ia, const int* ja, const int* iau,
+			    double* tvar, double* tgrad, double* b, double* A, double* x, double* mut);
+double orc_fr_turb_sa(const orc_case* c, const orc_fr_params* p, int nsgs, const double* q, const double* qgrad, const double* s,
+		      const double* dist, const double* dt, const int* ia, const int* ja, const int* iau,
+		      double* tvar, double* tgrad, double* b, double* A, double* x, double* mut);
+
 /* CRS::GMRES (crs.tcc:176-415) on one rank: restarts x nSearchDir, right preconditioner type 0 / 1 / 2 (none, diagonal,
    block diagonal LU; crs.tcc:555-641); any block size neqn <= 32.  A: assembled matrix before PrepareSGS; x: initial guess
    in, solution out, (nnode+gnode)*neqn; returns the reference's dqNorm. */

@@ -1716,3 +1716,67 @@ void orc_fr_hllc_flux(const orc_fr_params* p, const double* QL, const double* QR
 {
   fr_numerical_flux(p, QL, QR, avec, vdotn, flux, beta);
 }
+
+
+/* ---- Spalart-Allmaras under the viscous reacting eqnset (turbulenceModel = 1 with compressibleNSFR): TurbulenceModel::
+   Compute (turb.tcc:163-339) is eqnset-agnostic; what it asks of CompressibleFREqnSet: GetTheta (:1640-1650: native
+   velocities), ComputeAuxiliaryVariables on the averaged native state (:755-814), GetDensity (:640: the aux entry),
+   ComputeViscosity (:1572-1587: Wilke-mixed species viscosity / ref_viscosity), EqnSet::GetRe (eqnset.h:137: Param::Re),
+   GetVelocityGradLocation (:681: nspecies). */
+static double frg_theta_avg(const orc_gas* g, const double* qL, const double* qR, const double* avec)
+{
+  const orc_fr_params* p = (const orc_fr_params*)g->ctx;
+  int i, ns = p->chem->nspecies, neqn = ns + 4;
+  double qa[MAXV];
+  for(i = 0; i < neqn; i++) qa[i] = 0.5*(qL[i] + qR[i]);
+  return fr_theta(ns, qa, avec, 0.0);
+}
+static void frg_rho_nu_avg(const orc_gas* g, const double* qL, const double* qR, double* rho, double* nu)
+{
+  const orc_fr_params* p = (const orc_fr_params*)g->ctx;
+  int i, ns = p->chem->nspecies, neqn = ns + 4;
+  double qavg[MAXV], mu;
+  for(i = 0; i < g->nvars; i++) qavg[i] = 0.0;
+  for(i = 0; i < neqn; i++) qavg[i] = 0.5*(qL[i] + qR[i]);
+  fr_aux(p, qavg);
+  *rho = qavg[ns+5];
+  mu = fr_molecular_viscosity(p, qavg, qavg[ns+3]);
+  *nu = mu/(*rho);
+}
+static void frg_rho_nu_node(const orc_gas* g, const double* Q, double* rho, double* nu)
+{
+  const orc_fr_params* p = (const orc_fr_params*)g->ctx;
+  int ns = p->chem->nspecies;
+  double mu = fr_molecular_viscosity(p, Q, Q[ns+3]);
+  *rho = Q[ns+5];
+  *nu = mu/(*rho);
+}
+
+double orc_fr_turb_sa_phase(const orc_case* c, const orc_fr_params* p, int phase, int nsgs, const double* q, const double* qgrad,
+			    const double* s, const double* dist, const double* dt, const int* ia, const int* ja, const int* iau,
+			    double* tvar, double* tgrad, double* b, double* A, double* x, double* mut)
+{
+  int ns = p->chem->nspecies;
+  orc_gas gas;
+  gas.nvars = 3*ns + 6; gas.nterms = 2*ns + 4; gas.vloc = 3*ns;
+  gas.Re = c->Re;
+  gas.ctx = p;
+  gas.theta_avg = frg_theta_avg; gas.rho_nu_avg = frg_rho_nu_avg; gas.rho_nu_node = frg_rho_nu_node;
+  return orc_turb_sa_phase_gas(c, &gas, phase, nsgs, q, qgrad, s, dist, dt, ia, ja, iau, tvar, tgrad, b, A, x, mut);
+}
+
+double orc_fr_turb_sa(const orc_case* c, const orc_fr_params* p, int nsgs, const double* q, const double* qgrad, const double* s,
+		      const double* dist, const double* dt, const int* ia, const int* ja, const int* iau,
+		      double* tvar, double* tgrad, double* b, double* A, double* x, double* mut)
+{
+  int ph, isgs;
+  double ss = 0.0;
+  for(ph = 0; ph <= 5; ph++){
+    int reps = (ph == 3 && nsgs > 0) ? nsgs : 1;
+    for(isgs = 0; isgs < reps; isgs++){
+      double r = orc_fr_turb_sa_phase(c, p, ph, nsgs, q, qgrad, s, dist, dt, ia, ja, iau, tvar, tgrad, b, A, x, mut);
+      if(ph == 2) ss = r;
+    }
+  }
+  return sqrt(ss)/(double)c->nnode;
+}

@@ -653,6 +653,47 @@ __global__ void __launch_bounds__(128) kfr_eig_edges(DevMesh m, fr::Params<NS> p
   else beig[t - m.nedge] = me * av[3];
 }
 
+// What TurbulenceModel::Compute (turb.tcc:163-339) asks of the eqnset, evaluated once per call for the Spalart-Allmaras
+// kernels of pcfd_kernels.cu (which are eqnset-agnostic beyond these numbers): per interior edge / half-edge theta =
+// GetTheta of the averaged native state (compressibleFR.tcc:1640-1650) and nu = ComputeViscosity / GetDensity of the averaged
+// state after ComputeAuxiliaryVariables (turb.tcc:600-612, :684-692; Wilke-mixed species viscosity, :1572-1587); per local
+// and ghost node rho and nu of the stored state (turb.tcc:213-217, 329-334).  props_e / props_b: {theta, nu}; props_n: {rho, nu}.
+template <int NS>
+__global__ void __launch_bounds__(128) kfr_turb_props(DevMesh m, fr::Params<NS> p, fr::Transport<NS> t,
+                                                       const double* __restrict__ q, double* __restrict__ props_e,
+                                                       double* __restrict__ props_b, double* __restrict__ props_n) {
+  constexpr int NEQ = W<NS>::NEQ, NV = W<NS>::NV;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nb = m.nbedge + m.ngedge, nn = m.nnode + m.gnode;
+  if (i < m.nedge + nb) {
+    const bool interior = i < m.nedge;
+    const int2 lr = interior ? m.en[i] : m.ben[i - m.nedge];
+    double av[4], QL[NEQ], QR[NEQ], Q[NS + 6], mu, kc;
+    load_avec(interior ? m.ea : m.bea, interior ? i : i - m.nedge, av);
+    load_row<NS, NEQ>(q, lr.x, QL);
+    load_row<NS, NEQ>(q, lr.y, QR);
+#pragma unroll
+    for (int k = 0; k < NEQ; k++) Q[k] = 0.5 * (QL[k] + QR[k]);
+    const double theta = fr::theta_of<NS>(Q, av, 0.0);
+    fr::aux_pr(p, Q);
+    fr::mixture_transport(p, t, Q, Q[NS + 3], mu, kc);
+    double* out = interior ? props_e + 2 * (size_t)i : props_b + 2 * (size_t)(i - m.nedge);
+    out[0] = theta;
+    out[1] = mu / Q[NS + 5];
+    return;
+  }
+  const int n = i - (m.nedge + nb);
+  if (n >= nn) return;
+  const double* Q = q + (size_t)n * NV;
+  double rhoi[NS], mu, kc;
+#pragma unroll
+  for (int k = 0; k < NS; k++) rhoi[k] = Q[k];
+  fr::mixture_transport(p, t, rhoi, Q[NS + 3], mu, kc);
+  const double rho = Q[NS + 5];
+  props_n[2 * (size_t)n] = rho;
+  props_n[2 * (size_t)n + 1] = mu / rho;
+}
+
 // ComputeTimesteps (timestep.tcc:7-49): dt = CFL * vol / sum, VNN limit from node 1 on
 __global__ void __launch_bounds__(128) kfr_timestep(DevMesh m, double cfl, const double* __restrict__ eig,
                                                      const double* __restrict__ beig, const double* __restrict__ vnn23,
@@ -1602,6 +1643,15 @@ struct Impl {
     }
     return 0;
   }
+  static int turb_props(pcfd_ctx* c) {
+    if (!c->fr->viscous) return fail(c, "pcfd_turb_compute: Spalart-Allmaras under the reacting eqnset needs compressibleNSFR");
+    const long long nthreads = (long long)c->nedge + c->nb + c->nn;
+    PROF("kfr_turb_props");
+    kfr_turb_props<NS><<<nblk(nthreads, 128), 128, 0, c->stream>>>(c->dm, make_params<NS>(c), make_transport<NS>(c), c->f[PCFD_F_Q],
+                                                                   c->tprop_e, c->tprop_b, c->tprop_n);
+    LAUNCH_CHECK();
+    return 0;
+  }
   static int explicit_solve(pcfd_ctx* c) {
     pcfd_fr_state* s = c->fr;
     CK(cudaMemsetAsync(s->dbad, 0, sizeof(int), c->stream));
@@ -1787,6 +1837,7 @@ int pcfd_fr_residual(pcfd_ctx* c, double* sumsq) { FR_DISPATCH(c, residual(c, su
 int pcfd_fr_limiter_raw(pcfd_ctx* c) { FR_DISPATCH(c, limiter_raw(c)); }
 int pcfd_fr_residual_fused(pcfd_ctx* c, double* sumsq, bool* clip_hit) { FR_DISPATCH(c, residual_impl(c, sumsq, clip_hit)); }
 int pcfd_fr_timestep(pcfd_ctx* c, double* dtmin) { FR_DISPATCH(c, timestep(c, dtmin)); }
+int pcfd_fr_turb_props(pcfd_ctx* c) { FR_DISPATCH(c, turb_props(c)); }
 int pcfd_fr_explicit_solve(pcfd_ctx* c) { FR_DISPATCH(c, explicit_solve(c)); }
 int pcfd_fr_apply_dq(pcfd_ctx* c) { FR_DISPATCH(c, apply_dq(c)); }
 int pcfd_fr_jacobian(pcfd_ctx* c) { FR_DISPATCH(c, jacobian(c)); }
@@ -1831,8 +1882,9 @@ int pcfd_create_fr(const pcfd_mesh_desc* mesh, const pcfd_params* params, const 
     if (t == PCFD_BC_NOSLIP && !mesh->bedges_twall)
       return fail(c, "pcfd_create_fr: no-slip walls need bedges_twall (wall temperature / ref_temperature; < 0: adiabatic)");
   }
+  if (params->turb_model == 1 && !viscous)
+    return fail(c, "pcfd_create_fr: Spalart-Allmaras needs compressibleNSFR");
   pcfd_params prm = *params;
-  prm.turb_model = 0;
   if (pcfd_internal_create(mesh, &prm, device, ns + 4, 3 * ns + 6, 2 * ns + 4, &c)) return 1;
   c->prm.eqnset = params->eqnset;
   pcfd_fr_state* s = new pcfd_fr_state();

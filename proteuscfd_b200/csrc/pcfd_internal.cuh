@@ -112,6 +112,8 @@ struct pcfd_ctx {
   bool ffv_ready = false;          // PCFD_F_WALLDIST has been set since the table was last built
   int ntbnodes = 0;
   double *tslots = nullptr, *tbslots = nullptr;   // Spalart-Allmaras per-edge / per-half-edge slots
+  // SA under the reacting eqnset: {theta, nu} per edge / half-edge and {rho, nu} per local + ghost node (kfr_turb_props)
+  double *tprop_e = nullptr, *tprop_b = nullptr, *tprop_n = nullptr;
   unsigned char* wallflag = nullptr;
   int nwall = 0;
   unsigned char* clipflag = nullptr;
@@ -268,6 +270,7 @@ int pcfd_fr_limiter_raw(pcfd_ctx* c);
 void pcfd_fr_set_time(pcfd_ctx* c, double dt, int use_local);
 int pcfd_fr_residual_fused(pcfd_ctx* c, double* sumsq, bool* clip_hit);
 int pcfd_fr_timestep(pcfd_ctx* c, double* dtmin);
+int pcfd_fr_turb_props(pcfd_ctx* c);
 int pcfd_fr_explicit_solve(pcfd_ctx* c);
 int pcfd_fr_apply_dq(pcfd_ctx* c);
 int pcfd_fr_jacobian(pcfd_ctx* c);

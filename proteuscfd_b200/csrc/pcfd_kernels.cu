@@ -1900,7 +1900,16 @@ __global__ void __launch_bounds__(128) k_turb_gradient(DevMesh m, const double* 
 
 // Kernel_Convective (turb.tcc:342-449) + Kernel_Diffusive (:563-650) for one interior edge.  slots[e] =
 // {convective flux, diffusive resL, diffusive resR}; the two off-diagonal entries are final after this kernel.
-__global__ void __launch_bounds__(128) k_turb_edges(DevMesh m, eq::ViscParams vp, const double* __restrict__ q,
+// What the model asks of the eqnset (GetTheta, ComputeViscosity / GetDensity of the averaged state, GetRe, the place of the
+// velocity gradient): evaluated here for the perfect gas (PROPS == false), read from the tables kfr_turb_props wrote
+// for the reacting eqnset (PROPS == true).
+struct TurbGas {
+  double Re;                  // EqnSet::GetRe(): Re / Mach for the perfect gas (compressible.tcc), Param::Re otherwise (eqnset.h:137)
+  int gstride, goff;          // qgrad row width and GetVelocityGradLocation()*3
+  const double *pe, *pb, *pn; // {theta, nu} per edge, per half-edge; {rho, nu} per node (PROPS only)
+};
+template <bool PROPS>
+__global__ void __launch_bounds__(128) k_turb_edges(DevMesh m, eq::ViscParams vp, TurbGas tg_, const double* __restrict__ q,
                                                      const double* __restrict__ tvar, const double* __restrict__ tgrad,
                                                      const int* __restrict__ posLR, const int* __restrict__ posRL,
                                                      double* __restrict__ slots, double* __restrict__ A) {
@@ -1908,14 +1917,22 @@ __global__ void __launch_bounds__(128) k_turb_edges(DevMesh m, eq::ViscParams vp
   if (e >= m.nedge) return;
   const int2 lr = m.en[e];
   const int l = lr.x, r = lr.y;
-  double av[4], qL[5], qR[5], qa[5];
+  double av[4], theta, nu;
   load_avec(m.ea, e, av);
-  load_q5(q, l, qL);
-  load_q5(q, r, qR);
+  if constexpr (PROPS) {
+    theta = __ldg(tg_.pe + 2 * (size_t)e);
+    nu = __ldg(tg_.pe + 2 * (size_t)e + 1);
+  } else {
+    double qL[5], qR[5], qa[5];
+    load_q5(q, l, qL);
+    load_q5(q, r, qR);
 #pragma unroll
-  for (int i = 0; i < 5; i++) qa[i] = 0.5 * (qL[i] + qR[i]);
+    for (int i = 0; i < 5; i++) qa[i] = 0.5 * (qL[i] + qR[i]);
+    theta = eq::theta(qa, av, 0.0);
+    const double T = vp.gamma * eq::pressure(qa, vp.gamma) / qa[0];
+    nu = eq::viscosity(vp, T) / qa[0];
+  }
   const double tL = __ldg(tvar + l), tR = __ldg(tvar + r);
-  const double theta = eq::theta(qa, av, 0.0);
   const double ta = theta * av[3];
   double aRL = 0.0, aLR = 0.0, conv;   // A(r,l), A(l,r)
   if (theta > 0.0) { aRL -= ta; conv = ta * tL; }
@@ -1928,12 +1945,10 @@ __global__ void __launch_bounds__(128) k_turb_edges(DevMesh m, eq::ViscParams vp
   }
   const double dsum = de[0] * av[0] + de[1] * av[1] + de[2] * av[2];
   const double dgrad = dsum / ds2;
-  const double T = vp.gamma * eq::pressure(qa, vp.gamma) / qa[0];
-  const double nu = eq::viscosity(vp, T) / qa[0];
 #pragma unroll
   for (int d = 0; d < 3; d++) tg[d] = 0.5 * (__ldg(tgrad + (size_t)l * 3 + d) + __ldg(tgrad + (size_t)r * 3 + d));
   double resL, resR, jacL, jacR;
-  sa::diffusive(vp.Re / vp.mach, nu, tg, tL, tR, av, dgrad, &resL, &resR, &jacL, &jacR);
+  sa::diffusive(tg_.Re, nu, tg, tL, tR, av, dgrad, &resL, &resR, &jacL, &jacR);
   aRL -= jacL;
   aLR -= jacR;
   A[posRL[e]] = aRL;
@@ -1945,7 +1960,8 @@ __global__ void __launch_bounds__(128) k_turb_edges(DevMesh m, eq::ViscParams vp
 
 // Bkernel_Convective (turb.tcc:451-561) + Bkernel_Diffusive (:653-755) for one half-edge.  bslots[be] =
 // {convective flux, diffusive resL, convective diagonal term, diffusive diagonal term}
-__global__ void __launch_bounds__(128) k_turb_bedges(DevMesh m, eq::ViscParams vp, const double* __restrict__ q,
+template <bool PROPS>
+__global__ void __launch_bounds__(128) k_turb_bedges(DevMesh m, eq::ViscParams vp, TurbGas tg_, const double* __restrict__ q,
                                                       const double* __restrict__ tvar, const double* __restrict__ tgrad,
                                                       const int* __restrict__ bpos, double* __restrict__ bslots,
                                                       double* __restrict__ A) {
@@ -1954,20 +1970,26 @@ __global__ void __launch_bounds__(128) k_turb_bedges(DevMesh m, eq::ViscParams v
   const int2 lr = m.ben[be];
   const int l = lr.x, r = lr.y;
   const bool ghost = is_ghost(m, r);
-  double av[4], qL[5], qR[5], qa[5];
+  double av[4], theta, nu;
   load_avec(m.bea, be, av);
-  load_q5(q, l, qL);
-  load_q5(q, r, qR);
+  if constexpr (PROPS) {
+    theta = __ldg(tg_.pb + 2 * (size_t)be);
+    nu = __ldg(tg_.pb + 2 * (size_t)be + 1);
+  } else {
+    double qL[5], qR[5], qa[5];
+    load_q5(q, l, qL);
+    load_q5(q, r, qR);
 #pragma unroll
-  for (int i = 0; i < 5; i++) qa[i] = 0.5 * (qL[i] + qR[i]);
+    for (int i = 0; i < 5; i++) qa[i] = 0.5 * (qL[i] + qR[i]);
+    theta = eq::theta(qa, av, 0.0);
+    const double T = vp.gamma * eq::pressure(qa, vp.gamma) / qa[0];
+    nu = eq::viscosity(vp, T) / qa[0];
+  }
   const double tL = tvar[l], tR = tvar[r];
-  const double theta = eq::theta(qa, av, 0.0);
   const double ta = theta * av[3];
   double conv, dconv = 0.0, aLR = 0.0;
   if (theta > 0.0) { dconv = ta; conv = ta * tL; }
   else { if (ghost) aLR += ta; conv = ta * tR; }
-  const double T = vp.gamma * eq::pressure(qa, vp.gamma) / qa[0];
-  const double nu = eq::viscosity(vp, T) / qa[0];
   double tg[3], dgrad = 0.0;   // the reference leaves dgrad unset on physical boundaries (turb.tcc:669, 731)
   if (ghost) {
     double de[3], ds2 = 0.0;
@@ -1989,7 +2011,7 @@ __global__ void __launch_bounds__(128) k_turb_bedges(DevMesh m, eq::ViscParams v
     for (int d = 0; d < 3; d++) tg[d] = tgrad[(size_t)l * 3 + d];
   }
   double resL, resR, jacL, jacR;
-  sa::diffusive(vp.Re / vp.mach, nu, tg, tL, tR, av, dgrad, &resL, &resR, &jacL, &jacR);
+  sa::diffusive(tg_.Re, nu, tg, tL, tR, av, dgrad, &resL, &resR, &jacL, &jacR);
   double ddiff = 0.0;
   if (ghost) { aLR -= jacR; A[bpos[be]] = aLR; }
   else ddiff = jacL;
@@ -2001,7 +2023,8 @@ __global__ void __launch_bounds__(128) k_turb_bedges(DevMesh m, eq::ViscParams v
 
 // per node, in the reference's order: convective edges, convective half-edges, diffusive edges, diffusive half-edges,
 // source (turb.tcc:207-233), Kernel_Diag_NumJac (:241-243), temporal term (:246-252)
-__global__ void __launch_bounds__(128) k_turb_node(DevMesh m, eq::ViscParams vp, const double* __restrict__ q,
+template <bool PROPS>
+__global__ void __launch_bounds__(128) k_turb_node(DevMesh m, eq::ViscParams vp, TurbGas tg_, const double* __restrict__ q,
                                                     const double* __restrict__ qgrad, const double* __restrict__ tvar,
                                                     const double* __restrict__ dist, const double* __restrict__ dt,
                                                     const double* __restrict__ slots, const double* __restrict__ bslots,
@@ -2035,13 +2058,18 @@ __global__ void __launch_bounds__(128) k_turb_node(DevMesh m, eq::ViscParams vp,
   }
   const double d = dist[n];
   if (!(d < 1.0e-16)) {
-    double Q[NVARS];
-    load_q10(q, n, Q);
-    const double nu = eq::viscosity(vp, Q[5]) / Q[0];
+    double nu;
+    if constexpr (PROPS) {
+      nu = __ldg(tg_.pn + 2 * (size_t)n + 1);
+    } else {
+      double Q[NVARS];
+      load_q10(q, n, Q);
+      nu = eq::viscosity(vp, Q[5]) / Q[0];
+    }
     double vg[9], tres, tjac;
 #pragma unroll
-    for (int i = 0; i < 9; i++) vg[i] = __ldg(qgrad + (size_t)n * NTERMS * 3 + 3 + i);   // GetVelocityGradLocation()*3
-    sa::source(vp.Re / vp.mach, nu, d, vg, tvar[n], m.vol[n], &tres, &tjac);
+    for (int i = 0; i < 9; i++) vg[i] = __ldg(qgrad + (size_t)n * tg_.gstride + tg_.goff + i);   // GetVelocityGradLocation()*3
+    sa::source(tg_.Re, nu, d, vg, tvar[n], m.vol[n], &tres, &tjac);
     res += tres;
     diag += tjac;
   }
@@ -2107,12 +2135,19 @@ __global__ void k_turb_update(int nnode, const double* __restrict__ x, double* t
   if (t < 0.0) t = 0.0;
   tvar[n] = t;
 }
-__global__ void k_turb_mut(int nn_, eq::ViscParams vp, const double* __restrict__ q, const double* __restrict__ tvar,
+template <bool PROPS>
+__global__ void k_turb_mut(int nn_, eq::ViscParams vp, TurbGas tg_, const double* __restrict__ q, const double* __restrict__ tvar,
                            double* __restrict__ mut) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= nn_) return;
-  const double rho = q[(size_t)n * NVARS], T = q[(size_t)n * NVARS + 5];
-  const double nu = eq::viscosity(vp, T) / rho;
+  double rho, nu;
+  if constexpr (PROPS) {
+    rho = tg_.pn[2 * (size_t)n];
+    nu = tg_.pn[2 * (size_t)n + 1];
+  } else {
+    rho = q[(size_t)n * NVARS];
+    nu = eq::viscosity(vp, q[(size_t)n * NVARS + 5]) / rho;
+  }
   mut[n] = sa::eddy_viscosity(rho, nu, tvar[n]);
 }
 
@@ -2374,7 +2409,8 @@ static int create_impl(const pcfd_mesh_desc* mesh, const pcfd_params* params, in
   }
   c->ntbnodes = (int)tbnodes.size();
   if (params->turb_model != 0 && params->turb_model != 1) return fail(c, "pcfd_create: unknown turbulence model");
-  if (params->turb_model == 1 && !viscous) return fail(c, "pcfd_create: Spalart-Allmaras needs the compressibleNS eqnset");
+  if (params->turb_model == 1 && !viscous && params->eqnset != PCFD_EQNSET_COMPRESSIBLE_NS_FR)
+    return fail(c, "pcfd_create: Spalart-Allmaras needs a viscous eqnset (compressibleNS or compressibleNSFR)");
   c->viscous = viscous;
   c->vp = eq::ViscParams{params->gamma, params->Re, params->Pr, params->PrT, params->tref, params->mach};
   std::vector<double> vnn23;
@@ -2526,6 +2562,11 @@ static int create_impl(const pcfd_mesh_desc* mesh, const pcfd_params* params, in
   if (sa_on) {
     if (dev_alloc(c, &c->tslots, (size_t)nedge * 3)) return 1;
     if (dev_alloc(c, &c->tbslots, (size_t)nb * 4)) return 1;
+    if (neqn != NEQN) {   // reacting eqnset: tables of kfr_turb_props
+      if (dev_alloc(c, &c->tprop_e, (size_t)nedge * 2)) return 1;
+      if (dev_alloc(c, &c->tprop_b, (size_t)nb * 2)) return 1;
+      if (dev_alloc(c, &c->tprop_n, (size_t)c->nn * 2)) return 1;
+    }
   }
   if (viscous) {
     if (dev_alloc(c, &c->vflux, (size_t)nedge * 4)) return 1;
@@ -3461,9 +3502,57 @@ int pcfd_ipc_close(pcfd_ctx* c, void* devptr) {
   return 0;
 }
 
+// the Spalart-Allmaras kernels for the context's eqnset (q only matters to the perfect-gas instantiation; the reacting one
+// reads the tables pcfd_fr_turb_props filled from the same q, so the two must not be separated by a change of q)
+static TurbGas turb_gas(const pcfd_ctx* c) {
+  TurbGas g;
+  if (c->fr) {
+    g.Re = c->prm.Re;
+    g.gstride = c->nterms * 3;
+    g.goff = (c->neqn - 4) * 3;   // GetVelocityGradLocation() = nspecies (compressibleFR.tcc:681)
+  } else {
+    g.Re = c->vp.Re / c->vp.mach;
+    g.gstride = NTERMS * 3;
+    g.goff = 3;
+  }
+  g.pe = c->tprop_e; g.pb = c->tprop_b; g.pn = c->tprop_n;
+  return g;
+}
+static void turb_launch_edges(pcfd_ctx* c, const double* tvar, const double* tgrad, double* tA) {
+  if (c->fr)
+    k_turb_edges<true><<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, c->vp, turb_gas(c), c->f[PCFD_F_Q], tvar, tgrad, c->posLR,
+                                                                   c->posRL, c->tslots, tA);
+  else
+    k_turb_edges<false><<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, c->vp, turb_gas(c), c->f[PCFD_F_Q], tvar, tgrad, c->posLR,
+                                                                    c->posRL, c->tslots, tA);
+}
+static void turb_launch_bedges(pcfd_ctx* c, const double* tvar, const double* tgrad, double* tA) {
+  if (c->fr)
+    k_turb_bedges<true><<<nblk(c->nb, 128), 128, 0, c->stream>>>(c->dm, c->vp, turb_gas(c), c->f[PCFD_F_Q], tvar, tgrad, c->bpos,
+                                                                 c->tbslots, tA);
+  else
+    k_turb_bedges<false><<<nblk(c->nb, 128), 128, 0, c->stream>>>(c->dm, c->vp, turb_gas(c), c->f[PCFD_F_Q], tvar, tgrad, c->bpos,
+                                                                  c->tbslots, tA);
+}
+static void turb_launch_node(pcfd_ctx* c, const double* tvar, double* tb, double* tA) {
+  if (c->fr)
+    k_turb_node<true><<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->vp, turb_gas(c), c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD], tvar,
+                                                                  c->f[PCFD_F_WALLDIST], c->f[PCFD_F_TIMESTEP], c->tslots,
+                                                                  c->tbslots, c->iau, c->posLR, c->posRL, tb, tA);
+  else
+    k_turb_node<false><<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->vp, turb_gas(c), c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD], tvar,
+                                                                   c->f[PCFD_F_WALLDIST], c->f[PCFD_F_TIMESTEP], c->tslots,
+                                                                   c->tbslots, c->iau, c->posLR, c->posRL, tb, tA);
+}
+static void turb_launch_mut(pcfd_ctx* c, const double* tvar) {
+  if (c->fr)
+    k_turb_mut<true><<<nblk(c->nn, 256), 256, 0, c->stream>>>(c->nn, c->vp, turb_gas(c), c->f[PCFD_F_Q], tvar, c->f[PCFD_F_MUT]);
+  else
+    k_turb_mut<false><<<nblk(c->nn, 256), 256, 0, c->stream>>>(c->nn, c->vp, turb_gas(c), c->f[PCFD_F_Q], tvar, c->f[PCFD_F_MUT]);
+}
+
 int pcfd_turb_compute(pcfd_ctx* c, int nsgs, double* sumsq) {
   if (!c) return 1;
-  if (c->fr) return fail(c, "pcfd_turb_compute: not available for the reacting eqnset");
   if (c->prm.turb_model != 1) return fail(c, "pcfd_turb_compute: the context was created without a turbulence model");
   CK(cudaSetDevice(c->device));
   if (comm_on(c)) {
@@ -3491,21 +3580,19 @@ int pcfd_turb_compute(pcfd_ctx* c, int nsgs, double* sumsq) {
   PROF("k_turb_gradient");
   k_turb_gradient<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, tvar, c->f[PCFD_F_LSQ_S], tgrad);
   LAUNCH_CHECK();
+  if (c->fr && pcfd_fr_turb_props(c)) return 1;
   if (c->nedge) {
     PROF("k_turb_edges");
-    k_turb_edges<<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, c->vp, c->f[PCFD_F_Q], tvar, tgrad, c->posLR, c->posRL,
-                                                             c->tslots, tA);
+    turb_launch_edges(c, tvar, tgrad, tA);
     LAUNCH_CHECK();
   }
   if (c->nb) {
     PROF("k_turb_bedges");
-    k_turb_bedges<<<nblk(c->nb, 128), 128, 0, c->stream>>>(c->dm, c->vp, c->f[PCFD_F_Q], tvar, tgrad, c->bpos, c->tbslots, tA);
+    turb_launch_bedges(c, tvar, tgrad, tA);
     LAUNCH_CHECK();
   }
   PROF("k_turb_node");
-  k_turb_node<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->vp, c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD], tvar,
-                                                          c->f[PCFD_F_WALLDIST], c->f[PCFD_F_TIMESTEP], c->tslots,
-                                                          c->tbslots, c->iau, c->posLR, c->posRL, tb, tA);
+  turb_launch_node(c, tvar, tb, tA);
   LAUNCH_CHECK();
   if (c->nwall) {
     PROF("k_turb_wall");
@@ -3547,7 +3634,7 @@ int pcfd_turb_compute(pcfd_ctx* c, int nsgs, double* sumsq) {
   k_turb_update<<<nblk(c->nnode, 256), 256, 0, c->stream>>>(c->nnode, tx, tvar);
   LAUNCH_CHECK();
   PROF("k_turb_mut");
-  k_turb_mut<<<nblk(c->nn, 256), 256, 0, c->stream>>>(c->nn, c->vp, c->f[PCFD_F_Q], tvar, c->f[PCFD_F_MUT]);
+  turb_launch_mut(c, tvar);
   LAUNCH_CHECK();
   if (sumsq) CK(cudaStreamSynchronize(c->stream));
   return 0;
@@ -3563,7 +3650,6 @@ int pcfd_turb_compute(pcfd_ctx* c, int nsgs, double* sumsq) {
 //   5  eddy viscosity of the local and ghost nodes
 int pcfd_turb_phase(pcfd_ctx* c, int phase, double* sumsq) {
   if (!c) return 1;
-  if (c->fr) return fail(c, "pcfd_turb_phase: not available for the reacting eqnset");
   if (c->prm.turb_model != 1) return fail(c, "pcfd_turb_phase: the context was created without a turbulence model");
   CK(cudaSetDevice(c->device));
   double *tvar = c->f[PCFD_F_TVAR], *tgrad = c->f[PCFD_F_TGRAD], *tb = c->f[PCFD_F_TURB_B], *tx = c->f[PCFD_F_TURB_X],
@@ -3584,21 +3670,19 @@ int pcfd_turb_phase(pcfd_ctx* c, int phase, double* sumsq) {
       LAUNCH_CHECK();
       return 0;
     case 2:
+      if (c->fr && pcfd_fr_turb_props(c)) return 1;
       if (c->nedge) {
         PROF("k_turb_edges");
-        k_turb_edges<<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, c->vp, c->f[PCFD_F_Q], tvar, tgrad, c->posLR, c->posRL,
-                                                                 c->tslots, tA);
+        turb_launch_edges(c, tvar, tgrad, tA);
         LAUNCH_CHECK();
       }
       if (c->nb) {
         PROF("k_turb_bedges");
-        k_turb_bedges<<<nblk(c->nb, 128), 128, 0, c->stream>>>(c->dm, c->vp, c->f[PCFD_F_Q], tvar, tgrad, c->bpos, c->tbslots, tA);
+        turb_launch_bedges(c, tvar, tgrad, tA);
         LAUNCH_CHECK();
       }
       PROF("k_turb_node");
-      k_turb_node<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->dm, c->vp, c->f[PCFD_F_Q], c->f[PCFD_F_QGRAD], tvar,
-                                                              c->f[PCFD_F_WALLDIST], c->f[PCFD_F_TIMESTEP], c->tslots,
-                                                              c->tbslots, c->iau, c->posLR, c->posRL, tb, tA);
+      turb_launch_node(c, tvar, tb, tA);
       LAUNCH_CHECK();
       if (c->nwall) {
         PROF("k_turb_wall");
@@ -3642,7 +3726,7 @@ int pcfd_turb_phase(pcfd_ctx* c, int phase, double* sumsq) {
       return 0;
     case 5:
       PROF("k_turb_mut");
-      k_turb_mut<<<nblk(c->nn, 256), 256, 0, c->stream>>>(c->nn, c->vp, c->f[PCFD_F_Q], tvar, c->f[PCFD_F_MUT]);
+      turb_launch_mut(c, tvar);
       LAUNCH_CHECK();
       return 0;
     default:

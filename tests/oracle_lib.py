@@ -329,6 +329,16 @@ class FrOracle(Oracle):
         self.lib.orc_fr_prepare_sgs(C.byref(self.c), C.byref(self.p), _i(iau), _d(A), _i(pv))
         return pv
 
+    def turb_sa(self, nsgs, q, qgrad, s, dist, dt, ia, ja, iau, tvar):
+        """TurbulenceModel::Compute of the Spalart-Allmaras model under compressibleNSFR; tvar is updated in place."""
+        out = dict(tgrad=np.zeros(self.nn * 3), b=np.zeros(self.nnode), A=np.zeros(self.nblocks), x=np.zeros(self.nn),
+                   mut=np.zeros(self.nn))
+        self.lib.orc_fr_turb_sa.restype = C.c_double
+        out["res"] = self.lib.orc_fr_turb_sa(C.byref(self.c), C.byref(self.p), int(nsgs), _d(q), _d(qgrad), _d(s), _d(dist),
+                                             _d(dt), _i(ia), _i(ja), _i(iau), _d(tvar), _d(out["tgrad"]), _d(out["b"]),
+                                             _d(out["A"]), _d(out["x"]), _d(out["mut"]))
+        return out
+
     def sgs(self, nsgs, ia, ja, iau, A, pv, b):
         x = np.zeros(self.nn * self.neqn)
         d = self.lib.orc_fr_sgs(C.byref(self.c), C.byref(self.p), nsgs, _i(ia), _i(ja), _i(iau), _d(A), _i(pv), _d(b), _d(x))

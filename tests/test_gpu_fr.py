@@ -42,7 +42,7 @@ def fr_ctx(name, rxn_on=None):
     if int(meta.get("viscous", 0)):      # compressibleNSFR: species transport tables, Re, PrT
         fr.update(transport={k: g[k] for k in ("species_mu_fit", "species_k_fit", "species_white", "species_fit_counts")},
                   ref_viscosity=meta["ref_viscosity"], ref_k=meta["ref_k"])
-        params.update(Re=meta["Re"], PrT=meta["PrT"])
+        params.update(Re=meta["Re"], PrT=meta["PrT"], turb_model=int(meta.get("turbModel", 0)))
     ctx = capi.Context(mesh, params)
     assert (ctx.neqn, ctx.nvars, ctx.nterms) == (NEQ, NV, NT)
     beta = np.ones(ctx.field_size(capi.F_BETA))

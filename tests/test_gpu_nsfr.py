@@ -291,3 +291,86 @@ def test_nsfr_noslip_implicit_iteration_close(oracle, name):
     xo = xo.reshape(-1, NEQ)
     err = np.abs(x - xo).max(axis=0) / np.abs(xo).max(axis=0)
     assert np.all(err <= 1e-5), f"relative error of the update per equation: {err}"
+
+
+def _sa_fr_ctx():
+    from proteuscfd_b200 import capi
+    ctx, g, meta = fr_ctx("box4_nsfr_sa")
+    assert int(meta["turbModel"]) == 1
+    ctx.set_field(capi.F_Q, g["turb_q"])
+    ctx.set_field(capi.F_QGRAD, g["turb_qgrad"])
+    ctx.set_field(capi.F_TIMESTEP, g["turb_dt"])
+    ctx.set_field(capi.F_LSQ_S, g["lsq_s"])
+    ctx.set_field(capi.F_TVAR, g["turb_tvar0"])
+    return ctx, g, meta
+
+
+def test_spalart_allmaras_under_nsfr_vs_reference():
+    """turbulenceModel = 1 with compressibleNSFR: pcfd_turb_compute against the reference's own TurbulenceModel::Compute
+    run under the reacting eqnset (tests/golden/box4_nsfr_sa.npz: Wilke-mixed molecular viscosity, density from the aux
+    variables, native velocities, Re = Param::Re, velocity gradient at row nspecies).  The LSQ gradient of nu~ is
+    bit-exact; everything downstream of the species viscosity fits and the source term's exp / pow carries 1e-12."""
+    from proteuscfd_b200 import capi
+    from tests.test_gpu_viscous import close_per_node
+    ctx, g, meta = _sa_fr_ctx()
+    ss = ctx.turb_compute(int(meta["nSgs"]), want_norm=True)
+    exact(ctx.get_field(capi.F_TGRAD), g["turb_tgrad"], "tgrad")
+    close_per_node(ctx.get_field(capi.F_TURB_B), g["turb_b"], 1, "turbulence residual b")
+    close_per_node(ctx.get_field(capi.F_TURB_A), g["turb_A"], 1, "turbulence matrix (inverted diagonal)")
+    close_per_node(ctx.get_field(capi.F_TURB_X), g["turb_x"], 1, "turbulence update x")
+    close_per_node(ctx.get_field(capi.F_TVAR), g["turb_tvar1"], 1, "nu~ after the update")
+    nn = g["turb_mut"].size
+    close_per_node(ctx.get_field(capi.F_MUT)[:nn], g["turb_mut"], 1, "eddy viscosity")
+    assert np.isclose(np.sqrt(ss) / ctx.nnode, g["turb_res"][0], rtol=1e-12)
+    assert np.abs(g["turb_x"]).max() > 0.1
+
+
+def test_spalart_allmaras_under_nsfr_phases_equal_the_monolithic_call():
+    """pcfd_turb_phase 0..5 (the cut at the reference's exchange points) is the same kernels in the same order"""
+    from proteuscfd_b200 import capi
+    ctx, g, meta = _sa_fr_ctx()
+    ctx.turb_compute(int(meta["nSgs"]))
+    ref = {f: ctx.get_field(f).copy() for f in (capi.F_TVAR, capi.F_TGRAD, capi.F_TURB_B, capi.F_TURB_A, capi.F_TURB_X, capi.F_MUT)}
+    ctx2, _, _ = _sa_fr_ctx()
+    for ph in (0, 1, 2):
+        ctx2.turb_phase(ph)
+    for _ in range(int(meta["nSgs"])):
+        ctx2.turb_phase(3)
+    ctx2.turb_phase(4)
+    ctx2.turb_phase(5)
+    for f, v in ref.items():
+        exact(ctx2.get_field(f), v, f"field {f}")
+
+
+def test_spalart_allmaras_needs_a_viscous_reacting_eqnset():
+    from proteuscfd_b200 import capi
+    fr, g, meta = fixture_fr_params("box4_fr_implicit")
+    mesh = {k: g[k] for k in ("edges_n", "edges_a", "bedges_n", "bedges_a", "bedges_bctype", "xyz", "vol", "ipsp", "psp")}
+    for k in ("nnode", "gnode", "nbnode", "nedge", "nbedge", "ngedge"):
+        mesh[k] = int(meta[k])
+    params = dict(sorder=2, limiter=0, no_cvbc=0, gamma=0.0, chi=0.0, cfl=1.0, turb_model=1, fr=fr)
+    with pytest.raises(capi.PcfdError, match="Spalart-Allmaras needs compressibleNSFR"):
+        capi.Context(mesh, params)
+
+
+def test_nsfr_sa_implicit_iteration_updates_the_model(oracle):
+    """pcfd_implicit_iterate on a compressibleNSFR + SA context runs TurbulenceModel::Compute after the flow update
+    (solutionSpace.tcc:862-866): nu~ and mu_t afterwards equal a separate pcfd_turb_compute on the same state, and the
+    oracle's model update from the GPU's own flow state agrees to 1e-12."""
+    from proteuscfd_b200 import capi
+    from tests.test_gpu_viscous import close_per_node
+    ctx, g, meta = fr_ctx("box4_nsfr_sa")
+    nsgs = int(meta["nSgs"])
+    ctx.lsq_coefficients()
+    ctx.set_field(capi.F_Q, g["q_pre"])
+    ctx.set_field(capi.F_TVAR, g["turb_tvar0"])
+    mut0 = np.zeros(ctx.field_size(capi.F_MUT)); mut0[: g["mut"].size] = g["mut"]
+    ctx.set_field(capi.F_MUT, mut0)
+    ctx.implicit_iterate(nsgs, refresh_jac=True)
+    q, qgrad, dt = ctx.get_field(capi.F_Q), ctx.get_field(capi.F_QGRAD), ctx.get_field(capi.F_TIMESTEP)
+    o = FrOracle(oracle, g, meta)
+    ia, ja, iau = o.crs_init()
+    tvar = g["turb_tvar0"].copy()
+    out = o.turb_sa(nsgs, q[: g["turb_q"].size], qgrad, ctx.get_field(capi.F_LSQ_S), g["wallDistance"], dt, ia, ja, iau, tvar)
+    close_per_node(ctx.get_field(capi.F_TVAR)[: tvar.size], tvar, 1, "nu~ after the iteration")
+    close_per_node(ctx.get_field(capi.F_MUT)[: out["mut"].size], out["mut"], 1, "eddy viscosity after the iteration")

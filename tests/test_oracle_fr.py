@@ -14,7 +14,8 @@ from tests.test_oracle import exact
 # box4_nsfr_ffv: farFieldViscous side faces next to the no-slip floor
 # box4_fr_central: central-difference flux Jacobians (jacobianFieldType = jacobianBoundaryType = 1)
 FR = ["box5_fr_explicit", "box4_fr_implicit", "box4_nsfr_implicit", "box4_fr_unsteady", "box4_nsfr_wall", "box4_nsfr_adiabatic",
-      "box4_nsfr_ffv", "box4_fr_central", "box4_fr_gg"]      # box4_fr_gg: Green-Gauss gradients (gradientType = 1)
+      "box4_nsfr_ffv", "box4_fr_central", "box4_fr_gg",      # box4_fr_gg: Green-Gauss gradients (gradientType = 1)
+      "box4_nsfr_sa"]                                        # Spalart-Allmaras under compressibleNSFR
 IMPLICIT = ["box4_fr_implicit", "box4_nsfr_implicit", "box4_fr_unsteady", "box4_nsfr_wall", "box4_nsfr_adiabatic", "box4_nsfr_ffv",
             "box4_fr_central", "box4_fr_gg"]
 
@@ -109,3 +110,21 @@ def test_nsfr_viscous_part_of_residual(oracle):
     o.c.viscous = 0
     b0 = o.residual(g["q0"].copy(), g["qgrad"], g["limiter"], g["beta"])
     assert np.abs(b - b0).max() > 1e-3 * np.abs(b).max()
+
+
+def test_spalart_allmaras_under_the_reacting_eqnset(oracle):
+    """turbulenceModel = 1 with compressibleNSFR: the eqnset-agnostic TurbulenceModel::Compute (turb.tcc:163-339) with
+    the reacting eqnset's accessors (Wilke-mixed molecular viscosity, density from the aux variables, native velocities,
+    Re = Param::Re), against the reference's own run (tests/golden/box4_nsfr_sa.npz).  Same libm: bit-exact."""
+    g, meta = load_golden("box4_nsfr_sa")
+    assert int(meta["turbModel"]) == 1 and int(meta["viscous"]) == 1
+    o = FrOracle(oracle, g, meta)
+    ia, ja, iau = o.crs_init()
+    tvar = g["turb_tvar0"].copy()
+    out = o.turb_sa(int(meta["nSgs"]), g["turb_q"], g["turb_qgrad"], g["lsq_s"], g["wallDistance"], g["turb_dt"], ia, ja,
+                    iau, tvar)
+    for k in ("tgrad", "b", "A", "x", "mut"):
+        exact(out[k], g["turb_" + k], "turb " + k)
+    exact(tvar, g["turb_tvar1"], "tvar after the update")
+    assert out["res"] == g["turb_res"][0]
+    assert np.abs(g["turb_x"]).max() > 0.1 and np.abs(g["turb_mut"]).max() > 0

@@ -287,6 +287,12 @@ CASES = {
     "box4_fr_unsteady": lambda: make_case("box4_fr_unsteady", mesh=kuhn_box(4, jitter=0.15), eqnset="compressibleEulerFR",
                                           nsgs=3, cfl=5.0, unsteady=True,
                                           extra=FR_EXTRA.format(temp=3000, pres=101325, rxn=1) + "timeStep = 0.02\ntimeOrder = 2\n"),
+    # Spalart-Allmaras under the viscous reacting eqnset (turbulenceModel = 1 with compressibleNSFR): the eqnset-agnostic
+    # TurbulenceModel::Compute with Wilke-mixed molecular viscosity, no-slip floor
+    "box4_nsfr_sa": lambda: make_case("box4_nsfr_sa", mesh=kuhn_box(4, jitter=0.15), bc=ns_bc(900.0), eqnset="compressibleNSFR",
+                                      nsgs=3, cfl=5.0, refvisc=2.0e-4, turb=1,
+                                      extra=FR_EXTRA.format(temp=950, pres=2000, rxn=1)
+                                      + "refThermalConductivity = 0.05\nrefLength = 0.01\n"),
     # CRS::GMRES (crs.tcc:176-415) on the assembled implicit system: block-diagonal (LU) right preconditioner, 8 search
     # directions, 2 restarts (perfect gas 5x5); diagonal preconditioner, 6 directions, 1 restart (reacting 9x9)
     "box6_gmres": lambda: make_case("box6_gmres", mesh=kuhn_box(6, jitter=0.15), nsgs=3, cfl=5.0, gmres=(2, 8, 2)),
