@@ -307,6 +307,55 @@ static void DumpMesh(SolutionSpace<Real>* space)
 }
 
 
+// Forces / surface post-processing (PCFD_FORCES set; bodies come from the "body #k = [...]" lines of the .bc file): the
+// reference's own ComputeSurfaceAreas (forces.tcc:199-262) and Forces::Compute (:317-418: FORCE_Kernel, YpCf_Kernel,
+// ComputeCl) on the state and gradient the iteration left behind
+static void DumpForces(SolutionSpace<Real>* space)
+{
+  if(!getenv("PCFD_FORCES")) return;
+  Mesh<Real>* m = space->m;
+  Param<Real>* param = space->param;
+  Forces<Real>* f = space->forces;
+  Int nnode = m->GetNumNodes(), gnode = m->GetNumParallelNodes(), nbnode = m->GetNumBoundaryNodes();
+  Int nbedge = m->GetNumBoundaryEdges();
+  Int nvars = space->eqnset->neqn + space->eqnset->nauxvars;
+  if(f->num_bodies >= 1){
+    f->bodies[1].momentPt[0] = 0.25; f->bodies[1].momentPt[1] = 0.1; f->bodies[1].momentPt[2] = -0.05;
+  }
+  if(f->num_bodies >= 2){
+    f->bodies[2].momentAxis[0] = 0.0; f->bodies[2].momentAxis[1] = 1.0; f->bodies[2].momentAxis[2] = 0.0;
+  }
+  Dump("forces_q", space->q, (size_t)(nnode+gnode+nbnode)*nvars);
+  Dump("forces_qgrad", space->qgrad, (size_t)(nnode+gnode)*space->grad->GetNterms()*3);
+  Dump("forces_cg", m->cg, (size_t)(nnode+gnode+nbnode)*3);
+  ComputeSurfaceAreas(space, 0);
+  f->Compute();
+  Dump("forces_cp", f->cp, (size_t)nbedge);
+  Dump("forces_yp", f->yp, (size_t)nbedge);
+  Dump("forces_cf", f->cf, (size_t)nbedge);
+  Dump("forces_surfArea", f->surfArea, (size_t)(f->num_bcs+1)*3);
+  std::vector<int> lists;
+  std::vector<Real> body, geom;
+  for(Int i = 1; i <= f->num_bodies; i++){
+    CompositeBody<Real>& b = f->bodies[i];
+    lists.push_back(b.nsurfs);
+    for(Int k = 0; k < b.nsurfs; k++) lists.push_back(b.list[k]);
+    for(Int k = 0; k < 3; k++) body.push_back(b.forces[k]);
+    for(Int k = 0; k < 3; k++) body.push_back(b.vforces[k]);
+    for(Int k = 0; k < 3; k++) body.push_back(b.moments[k]);
+    for(Int k = 0; k < 3; k++) body.push_back(b.vmoments[k]);
+    for(Int k = 0; k < 3; k++) body.push_back(b.surfArea[k]);
+    body.push_back(b.cl); body.push_back(b.cd); body.push_back(b.cm);
+    for(Int k = 0; k < 3; k++) geom.push_back(b.momentPt[k]);
+    for(Int k = 0; k < 3; k++) geom.push_back(b.momentAxis[k]);
+  }
+  Dump("forces_body_lists", lists.data(), lists.size());
+  Dump("forces_body", body.data(), body.size());
+  Dump("forces_body_geom", geom.data(), geom.size());
+  Real dirs[6] = {param->liftdir[0], param->liftdir[1], param->liftdir[2], param->dragdir[0], param->dragdir[1], param->dragdir[2]};
+  Dump("forces_dirs", dirs, 6);
+}
+
 // Spalart-Allmaras (turbulenceModel = 1): inject a smooth positive nu~ field and run the reference's own
 // TurbulenceModel::Compute (turb.tcc:163-339) on the state the flow iteration left behind
 static void DumpTurbulence(SolutionSpace<Real>* space)
@@ -581,6 +630,7 @@ int main(int argc, char* argv[])
     p->UpdateGeneralVectors(space->q, nvars);
     Dump("q1", space->q, (size_t)(nnode+gnode+nbnode)*nvars);
     DumpTurbulence(space);
+    DumpForces(space);
   }
 #endif
   else if(mode == "time"){

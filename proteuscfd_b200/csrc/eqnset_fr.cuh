@@ -158,39 +158,61 @@ __device__ __forceinline__ double theta_of(const double* Q, const double* n, dou
   return (Q[NS] * n[0] + Q[NS + 1] * n[1] + Q[NS + 2] * n[2] + vdotn);
 }
 
-// HLLCFlux (compressibleFR.tcc:301-548; RoeFlux :293-298 forwards here).  QL / QR need entries [0, NS+6).  The
-// Roe-averaged state only feeds GetFluidProperties (rho_i, T), so its auxiliary variables are not formed.  The NaN
-// kneecap of EqnSet::NumericalFlux (eqnset.tcc:73-88) is applied here.
+// HLLCFlux (compressibleFR.tcc:301-548; RoeFlux :293-298 forwards here), cut into the pieces the finite-difference
+// Jacobian can share between its perturbed evaluations (kfr_jac_edges): what depends on ONE state only
+// (hllc_side_thermo), what depends on the densities and temperatures of both (hllc_roe_c2), and the rest (hllc_assemble).
+// numerical_flux is their composition; every piece does the reference's operations in the reference's order.
+
+// the speed of sound squared (GetFluidProperties) and h rho (GetTotalEnthalpy) of one state; Q needs rho at [NS+5]
 template <int NS>
-__device__ __forceinline__ void numerical_flux(const Params<NS>& p, const double* QL, const double* QR, const double* av,
-                                               double vdotn, double beta, double* flux, double* parts = nullptr) {
-  const double uL = QL[NS], vL = QL[NS + 1], wL = QL[NS + 2], TL = QL[NS + 3], pL = QL[NS + 4];
+__device__ __forceinline__ void hllc_side_thermo(const Params<NS>& p, const double* Q, double& c2, double& hr) {
+  double R, X[NS];
+  fluid_props(p, Q, Q[NS + 3], R, c2);
+  const double rho = Q[NS + 5];
+#pragma unroll
+  for (int i = 0; i < NS; i++) X[i] = Q[i] / rho;
+  const double h = chem_h(p, X, Q[NS + 3] * p.ref_temperature) / p.ref_specific_enthalpy;
+  hr = h * rho;
+}
+// the speed of sound squared of the Roe-averaged state: a function of rho_i, T and rho of both sides, not of the velocities
+template <int NS>
+__device__ __forceinline__ double hllc_roe_c2(const Params<NS>& p, const double* QL, const double* QR) {
+  const double rhoL = QL[NS + 5], rhoR = QR[NS + 5];
+  const double rho = sqrt(rhoL * rhoR);
+  const double sigma = rho / (rhoL + rho);
+  double roeQ[NS], Rm, c2;
+#pragma unroll
+  for (int i = 0; i < NS; i++) roeQ[i] = QL[i] + sigma * (QR[i] - QL[i]);
+  const double T = QL[NS + 3] + sigma * (QR[NS + 3] - QL[NS + 3]);
+  fluid_props(p, roeQ, T, Rm, c2);
+  return c2;
+}
+// QL / QR need entries [0, NS+6).  The Roe-averaged state only feeds GetFluidProperties (rho_i, T), so its auxiliary
+// variables are not formed.  The NaN kneecap of EqnSet::NumericalFlux (eqnset.tcc:73-88) is applied here.
+template <int NS>
+__device__ __forceinline__ void hllc_assemble(const Params<NS>& p, const double* QL, const double* QR, const double* av,
+                                              double vdotn, double beta, double c2L, double hrL, double c2R, double hrR,
+                                              double c2, double* flux, double* parts = nullptr) {
+  const double uL = QL[NS], vL = QL[NS + 1], wL = QL[NS + 2], pL = QL[NS + 4];
   const double pgL = pL - p.Pref, rhoL = QL[NS + 5];
-  double RL, c2L, RR, c2R, Rm, c2;
-  fluid_props(p, QL, TL, RL, c2L);
-  double hrL, keL, hrR, keR;
-  const double HTL = total_enthalpy(p, QL, hrL, keL);
+  const double keL = 0.5 * rhoL * (uL * uL + vL * vL + wL * wL);
+  const double HTL = hrL + keL;
   const double ETL = HTL - pL;
   const double thetaL = theta_of<NS>(QL, av, vdotn);
-  const double uR = QR[NS], vR = QR[NS + 1], wR = QR[NS + 2], TR = QR[NS + 3], pR = QR[NS + 4];
+  const double uR = QR[NS], vR = QR[NS + 1], wR = QR[NS + 2], pR = QR[NS + 4];
   const double pgR = pR - p.Pref, rhoR = QR[NS + 5];
-  fluid_props(p, QR, TR, RR, c2R);
-  const double HTR = total_enthalpy(p, QR, hrR, keR);
+  const double keR = 0.5 * rhoR * (uR * uR + vR * vR + wR * wR);
+  const double HTR = hrR + keR;
   const double ETR = HTR - pR;
   if (parts) { parts[0] = hrL; parts[1] = keL; parts[2] = hrR; parts[3] = keR; }
   const double thetaR = theta_of<NS>(QR, av, vdotn);
 
   const double rho = sqrt(rhoL * rhoR);
   const double sigma = rho / (rhoL + rho);
-  double roeQ[NS + 4];
-#pragma unroll
-  for (int i = 0; i < NS; i++) roeQ[i] = QL[i] + sigma * (QR[i] - QL[i]);
-  roeQ[NS + 0] = uL + sigma * (uR - uL);
-  roeQ[NS + 1] = vL + sigma * (vR - vL);
-  roeQ[NS + 2] = wL + sigma * (wR - wL);
-  roeQ[NS + 3] = TL + sigma * (TR - TL);
-  double theta = theta_of<NS>(roeQ, av, vdotn);
-  fluid_props(p, roeQ, roeQ[NS + 3], Rm, c2);
+  const double uRoe = uL + sigma * (uR - uL);
+  const double vRoe = vL + sigma * (vR - vL);
+  const double wRoe = wL + sigma * (wR - wL);
+  double theta = (uRoe * av[0] + vRoe * av[1] + wRoe * av[2] + vdotn);
 
   const double oneMBeta = 1.0 - beta;
   const double thetaPrime = theta * (1.0 + beta) * 0.5;
@@ -260,6 +282,15 @@ __device__ __forceinline__ void numerical_flux(const Params<NS>& p, const double
   flux[NS + 3] = area * (Et * theta + pStar * thetabar) + p.Pref * thetabar * area;
 #pragma unroll
   for (int i = 0; i < NS + 4; i++) if (isnan(flux[i])) flux[i] = 0.0;
+}
+template <int NS>
+__device__ __forceinline__ void numerical_flux(const Params<NS>& p, const double* QL, const double* QR, const double* av,
+                                               double vdotn, double beta, double* flux, double* parts = nullptr) {
+  double c2L, hrL, c2R, hrR;
+  hllc_side_thermo(p, QL, c2L, hrL);
+  hllc_side_thermo(p, QR, c2R, hrR);
+  const double c2 = hllc_roe_c2(p, QL, QR);
+  hllc_assemble(p, QL, QR, av, vdotn, beta, c2L, hrL, c2R, hrR, c2, flux, parts);
 }
 
 // MaxEigenvalue (compressibleFR.tcc:1603-1637)

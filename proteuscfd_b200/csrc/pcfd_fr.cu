@@ -809,54 +809,106 @@ __global__ void __launch_bounds__(128) kfr_apply_dq(int nnode, fr::Params<NS> p,
 }
 
 // ====================================================================== Jacobian
-// Kernel_NumJac (jacobian.tcc:254-304): one-sided finite differences (h = 1e-8) of the FIRST-ORDER flux.  2*NEQ+1
-// lanes per edge, one HLLC flux each: lane 0 the reference state, lanes 1..NEQ the left perturbations (column i of
-// A(r,l) = (F_S - F_L,i)/h), lanes NEQ+1..2NEQ the right ones (column i of A(l,r) = (F_R,i - F_S)/h).
-#ifndef PCFD_FRJAC_MINB
-#define PCFD_FRJAC_MINB 4   /* measured on B200: 37.1 -> 33.8 ms at 10 M cells */
-#endif
-template <int NS, int EPB>
-__global__ void __launch_bounds__((2 * W<NS>::NEQ + 1) * EPB, PCFD_FRJAC_MINB) kfr_jac_edges(DevMesh m, fr::Params<NS> p,
-                                                                             const double* __restrict__ q,
-                                                                             const double* __restrict__ beta,
-                                                                             const int* __restrict__ posLR,
-                                                                             const int* __restrict__ posRL,
-                                                                             double* __restrict__ A) {
-  constexpr int NEQ = W<NS>::NEQ, N2 = W<NS>::N2, LPE = 2 * NEQ + 1;
-  __shared__ double fS[EPB][NEQ];
-  const int slot = threadIdx.x / LPE;
-  const int role = threadIdx.x - slot * LPE;
-  const int e = blockIdx.x * EPB + slot;
-  const bool live = e < m.nedge;
+// Kernel_NumJac (jacobian.tcc:254-304): one-sided finite differences (h = 1e-8) of the FIRST-ORDER flux: column i of
+// A(r,l) = (F_S - F_L,i)/h, column i of A(l,r) = (F_R,i - F_S)/h, 2*NEQ+1 HLLC fluxes per edge.  Most of a flux is
+// thermodynamics of ONE state (speed of sound, enthalpy: ~25 IEEE divisions) or of the Roe average of the densities
+// and temperatures (~10), and most of the 19 evaluations repeat them: a perturbation of the left state leaves the
+// right state's alone, a velocity perturbation leaves all three alone.  So per edge
+//   phase A   2*(NS+2) one-state evaluations    (unperturbed, rho_i + h, T + h; per side)
+//   phase B   2*(NS+1)+1 Roe-average evaluations (unperturbed, rho_i + h or T + h on one side)
+//   phase C0  the unperturbed flux, phase C the 2*NEQ perturbed ones (hllc_assemble from the tables of A and B)
+// i.e. 14 + 13 + 19 small pieces instead of 19 x (2 + 1 + 1) for five species; the values are the ones the plain
+// evaluation computes (same operations on the same inputs), so A is bit-identical (tests/test_gpu_fr.py).
+// Work distribution: a warp owns G consecutive edges and walks each phase's task list 32 tasks at a time (G = 16: 7 / 7
+// / 1 / 9 passes with full warps except the last), tables in shared memory, __syncwarp between phases -- no block
+// barrier: a block-wide form of the same phases (one thread per task, __syncthreads) spent its time in barrier stalls
+// (profiles/r2_ncu_frjac.md).
+template <int NS>
+__device__ __forceinline__ void jac_perturb(double* Q, int idx, double h) {
+#pragma unroll
+  for (int i = 0; i < NS + 4; i++) if (i == idx) Q[i] += h;   // selects, not a dynamically indexed (local-memory) array
+}
+template <int NS, int G>
+__global__ void __launch_bounds__(128, 4)
+    kfr_jac_edges(DevMesh m, fr::Params<NS> p, const double* __restrict__ q, const double* __restrict__ beta,
+                  const int* __restrict__ posLR, const int* __restrict__ posRL, double* __restrict__ A) {
+  constexpr int NEQ = W<NS>::NEQ, N2 = W<NS>::N2;
+  constexpr int NTH = NS + 2;              // one-state evaluations per side: 0 unperturbed, 1..NS rho_i + h, NS+1 T + h
+  constexpr int NROE = 2 * (NS + 1) + 1;   // Roe-average evaluations: 0 unperturbed, then left j = 1..NS+1, then right
+  constexpr int WPB = 4;
+  __shared__ double sC2[WPB][G][2 * NTH], sHr[WPB][G][2 * NTH], sRoe[WPB][G][NROE], fS[WPB][G][NEQ];
   const double h = 1.0e-8;
-  double f[NEQ];
-  int l = 0, r = 0;
-  if (live) {
-    const int2 lr = m.en[e];
-    l = lr.x; r = lr.y;
-    double av[4], QL[NS + 6], QR[NS + 6];
-    load_avec(m.ea, e, av);
-    load_row<NS, NS + 6>(q, l, QL);
-    load_row<NS, NS + 6>(q, r, QR);
-    const double avbeta = 0.5 * (beta[l] + beta[r]);
-    if (role >= 1 && role <= NEQ) { QL[role - 1] += h; fr::aux_pr(p, QL); }
-    else if (role > NEQ) { QR[role - NEQ - 1] += h; fr::aux_pr(p, QR); }
-    fr::numerical_flux(p, QL, QR, av, 0.0, avbeta, f);
-    if (role == 0) {
-#pragma unroll
-      for (int j = 0; j < NEQ; j++) fS[slot][j] = f[j];
-    }
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e0 = (blockIdx.x * WPB + w) * G;
+  if (e0 >= m.nedge) return;
+  const int ne = (m.nedge - e0 < G) ? m.nedge - e0 : G;
+  for (int t = lane; t < ne * 2 * NTH; t += 32) {
+    const int slot = t / (2 * NTH), k = t - slot * (2 * NTH);
+    const int side = (k >= NTH) ? 1 : 0, j = k - side * NTH;
+    const int2 lr = m.en[e0 + slot];
+    double Q[NS + 6], c2, hr;
+    load_row<NS, NS + 6>(q, side ? lr.y : lr.x, Q);
+    jac_perturb<NS>(Q, (j == 0) ? -1 : ((j <= NS) ? j - 1 : NS + 3), h);
+    if (j) fr::aux_pr(p, Q);
+    fr::hllc_side_thermo(p, Q, c2, hr);
+    sC2[w][slot][k] = c2;
+    sHr[w][slot][k] = hr;
   }
-  __syncthreads();
-  if (!live || role == 0) return;
-  if (role <= NEQ) {
-    double* dst = A + (size_t)posRL[e] * N2 + (role - 1);
+  for (int t = lane; t < ne * NROE; t += 32) {
+    const int slot = t / NROE, k = t - slot * NROE;
+    const int2 lr = m.en[e0 + slot];
+    double QL[NS + 6], QR[NS + 6];
+    load_row<NS, NS + 6>(q, lr.x, QL);
+    load_row<NS, NS + 6>(q, lr.y, QR);
+    if (k >= 1 && k <= NS + 1) { jac_perturb<NS>(QL, (k <= NS) ? k - 1 : NS + 3, h); fr::aux_pr(p, QL); }
+    else if (k > NS + 1) { const int j = k - (NS + 1); jac_perturb<NS>(QR, (j <= NS) ? j - 1 : NS + 3, h); fr::aux_pr(p, QR); }
+    sRoe[w][slot][k] = fr::hllc_roe_c2(p, QL, QR);
+  }
+  __syncwarp();
+  if (lane < ne) {   // the unperturbed flux of each edge
+    const int slot = lane, e = e0 + slot;
+    const int2 lr = m.en[e];
+    double av[4], QL[NS + 6], QR[NS + 6], f[NEQ];
+    load_avec(m.ea, e, av);
+    load_row<NS, NS + 6>(q, lr.x, QL);
+    load_row<NS, NS + 6>(q, lr.y, QR);
+    const double avbeta = 0.5 * (beta[lr.x] + beta[lr.y]);
+    fr::hllc_assemble(p, QL, QR, av, 0.0, avbeta, sC2[w][slot][0], sHr[w][slot][0], sC2[w][slot][NTH], sHr[w][slot][NTH],
+                      sRoe[w][slot][0], f);
 #pragma unroll
-    for (int j = 0; j < NEQ; j++) dst[j * NEQ] = 0.0 + (fS[slot][j] - f[j]) / h;
-  } else {
-    double* dst = A + (size_t)posLR[e] * N2 + (role - NEQ - 1);
+    for (int j = 0; j < NEQ; j++) fS[w][slot][j] = f[j];
+  }
+  __syncwarp();
+  for (int t = lane; t < ne * 2 * NEQ; t += 32) {
+    const int slot = t / (2 * NEQ), role = t - slot * (2 * NEQ);   // role < NEQ: left column role; else right column role - NEQ
+    const int e = e0 + slot;
+    const bool right = role >= NEQ;
+    const int i = right ? role - NEQ : role;
+    const int2 lr = m.en[e];
+    double av[4], QL[NS + 6], QR[NS + 6], QP[NS + 6], f[NEQ];
+    load_avec(m.ea, e, av);
+    load_row<NS, NS + 6>(q, lr.x, QL);
+    load_row<NS, NS + 6>(q, lr.y, QR);
+    const double avbeta = 0.5 * (beta[lr.x] + beta[lr.y]);
 #pragma unroll
-    for (int j = 0; j < NEQ; j++) dst[j * NEQ] = 0.0 + (f[j] - fS[slot][j]) / h;
+    for (int k = 0; k < NS + 6; k++) QP[k] = right ? QR[k] : QL[k];
+    jac_perturb<NS>(QP, i, h);
+    fr::aux_pr(p, QP);
+#pragma unroll
+    for (int k = 0; k < NS + 6; k++) { if (right) QR[k] = QP[k]; else QL[k] = QP[k]; }
+    // which table entries the perturbed side reads; velocity perturbations read the unperturbed ones
+    const int jt = (i < NS) ? i + 1 : ((i == NS + 3) ? NS + 1 : 0);
+    const int jl = right ? 0 : jt, jr = right ? jt : 0;
+    const int kroe = (jt == 0) ? 0 : (right ? NS + 1 + jt : jt);
+    fr::hllc_assemble(p, QL, QR, av, 0.0, avbeta, sC2[w][slot][jl], sHr[w][slot][jl], sC2[w][slot][NTH + jr],
+                      sHr[w][slot][NTH + jr], sRoe[w][slot][kroe], f);
+    double* dst = A + (size_t)(right ? posLR[e] : posRL[e]) * N2 + i;
+#pragma unroll
+    for (int j = 0; j < NEQ; j++) {
+      const double fs = fS[w][slot][j];
+      const double num = right ? (f[j] - fs) : (fs - f[j]);
+      dst[j * NEQ] = 0.0 + num / h;
+    }
   }
 }
 
@@ -997,13 +1049,14 @@ __global__ void __launch_bounds__(64) kfr_jac_bedges(DevMesh m, fr::Params<NS> p
     for (int k = 0; k < NV; k++) { QPL[k] = QL[k]; QPR[k] = QR[k]; }
     QPL[i] += h; QPR[i] += h;
     fr::aux(p, QPL);
-    fr::aux_pr(p, QPR);
-    fr::numerical_flux(p, QL, QPR, av, 0.0, betaL, fR);
     if (!ghost) {
+      // the reference also evaluates F(qL, qR + h) here and throws it away (only ghost half-edges own an A(l, r) block)
       for (int k = 0; k < NV; k++) QPR[k] = QR[k];
       fr::boundary_variables(p, QPL, QPR, av, type, betaL, ubar, ffv ? Qref : nullptr);
       fr::numerical_flux(p, QPL, QPR, av, 0.0, betaL, fL);
     } else {
+      fr::aux_pr(p, QPR);
+      fr::numerical_flux(p, QL, QPR, av, 0.0, betaL, fR);
       fr::numerical_flux(p, QPL, QR, av, 0.0, betaL, fL);
     }
     for (int j = 0; j < NEQ; j++) bd[j * NEQ + i] = (fL[j] - fS[j]) / h;
@@ -1684,8 +1737,9 @@ struct Impl {
                                                                                                   c->posLR, c->posRL, A);
       } else {
         PROF("kfr_jac_edges");
-        kfr_jac_edges<NS, EPB><<<nblk(c->nedge, EPB), LPE * EPB, 0, c->stream>>>(c->dm, p, c->f[PCFD_F_Q], beta, c->posLR,
-                                                                                c->posRL, A);
+        constexpr int G = 16, WPB = 4;   // edges per warp, warps per block (see the kernel)
+        kfr_jac_edges<NS, G><<<nblk(c->nedge, G * WPB), 32 * WPB, 0, c->stream>>>(c->dm, p, c->f[PCFD_F_Q], beta, c->posLR,
+                                                                                 c->posRL, A);
       }
       LAUNCH_CHECK();
     }

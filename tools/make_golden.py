@@ -67,7 +67,7 @@ massFractions = [0.20, 0.02, 0.01, 0.75, 0.02]
 reactionsOn = {rxn}
 """
 
-INT_ARRAYS = {"species_fit_counts", "rxn_flags", "rxn_species", "chem_dims", "edges_n", "bedges_n", "bedges_factag", "bedges_bctype", "ipsp", "psp", "gNodeOwner",
+INT_ARRAYS = {"forces_body_lists", "species_fit_counts", "rxn_flags", "rxn_species", "chem_dims", "edges_n", "bedges_n", "bedges_factag", "bedges_bctype", "ipsp", "psp", "gNodeOwner",
               "gNodeLocalId", "commCountsSend", "commCountsRecv", "commOffsetsRecv", "nodePackingList",
               "ia", "ja", "iau", "pv"}
 
@@ -131,7 +131,7 @@ def collect(outdir, rank):
     return d
 
 
-def make_case(name, mesh=None, h5=None, bc=BOX_BC, np_ranks=1, part=None, unsteady=False, gmres=None, **kw):
+def make_case(name, mesh=None, h5=None, bc=BOX_BC, np_ranks=1, part=None, unsteady=False, gmres=None, forces=False, **kw):
     opts = dict(eqnset="compressibleEuler", sorder=2, limiter=2, nsgs=0, mach=0.5, cfl=0.5,
                 fx=1.0, fy=0.0, fz=0.0, jactype=0, refvisc=1.0, vnn=0, turb=0, extra="")
     opts.update(kw)
@@ -156,6 +156,8 @@ def make_case(name, mesh=None, h5=None, bc=BOX_BC, np_ranks=1, part=None, unstea
         henv = {"PCFD_MPI_NP": str(np_ranks)}
         if unsteady:
             henv["PCFD_UNSTEADY"] = "1"
+        if forces:                 # Forces::Compute on the bodies the .bc file declares
+            henv["PCFD_FORCES"] = "1"
         if gmres is not None:      # (precondType, search directions, restarts): also run CRS::GMRES on the assembled system
             henv.update(PCFD_GMRES=str(gmres[0]), PCFD_GMRES_NDIR=str(gmres[1]), PCFD_GMRES_RESTARTS=str(gmres[2]))
         run([os.path.join(REFBIN, "ref_harness"), os.path.join(work, name), os.path.join(work, "out"), "dump"], work, henv)
@@ -298,6 +300,17 @@ CASES = {
     "box6_gmres": lambda: make_case("box6_gmres", mesh=kuhn_box(6, jitter=0.15), nsgs=3, cfl=5.0, gmres=(2, 8, 2)),
     "box4_fr_gmres": lambda: make_case("box4_fr_gmres", mesh=kuhn_box(4, jitter=0.15), eqnset="compressibleEulerFR",
                                        nsgs=3, cfl=5.0, gmres=(1, 6, 1), extra=FR_EXTRA.format(temp=3000, pres=101325, rxn=1)),
+    # Forces::Compute / ComputeSurfaceAreas (forces.tcc): pressure and viscous forces, moments, cp / y+ / cf per
+    # half-edge, lift / drag / moment coefficients of two composite bodies (the no-slip floor; three far-field faces)
+    "box6_ns_forces": lambda: make_case("box6_ns_forces", mesh=kuhn_box(6, jitter=0.15),
+                                        bc=ns_bc(330.0) + "\nbody #1 = [5]\nbody #2 = [1,2,6]\n", eqnset="compressibleNS",
+                                        nsgs=3, cfl=5.0, refvisc=0.5, forces=True,
+                                        extra="liftDirection = [0.0, 0.2, 1.0]\ndragDirection = [1.0, 0.1, 0.0]\n"),
+    "box4_nsfr_forces": lambda: make_case("box4_nsfr_forces", mesh=kuhn_box(4, jitter=0.15),
+                                          bc=ns_bc(900.0) + "\nbody #1 = [5]\nbody #2 = [1,2,6]\n", eqnset="compressibleNSFR",
+                                          nsgs=3, cfl=5.0, refvisc=2.0e-4, forces=True,
+                                          extra=FR_EXTRA.format(temp=950, pres=2000, rxn=1)
+                                          + "refThermalConductivity = 0.05\nrefLength = 0.01\n"),
     # the reference's own unit-test fixture (unitTest/gradientTest.h:20-232): prism cube, 216 nodes
     "cube_LowFi": lambda: make_case(
         "cube_LowFi", h5=os.path.join(REFERENCE, "unitTest/meshResources/cubeStructuredSeries/cube_LowFi.0.h5"),

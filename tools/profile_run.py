@@ -21,10 +21,29 @@ def main():
     ap.add_argument("--natural", action="store_true", help="lexicographic node numbering (the explicit bench case)")
     ap.add_argument("--green-gauss", action="store_true", help="Param::gradType = 1 (k_gradient_gg)")
     ap.add_argument("--jac-central", action="store_true", help="fieldJacType = boundaryJacType = 1 (k_jac_*_central)")
+    ap.add_argument("--fr", action="store_true", help="reacting eqnset: one Jacobian refresh (kfr_jac_*), nothing else")
+    ap.add_argument("--fr-viscous", action="store_true", help="with --fr: compressibleNSFR")
     args = ap.parse_args()
     import torch
     from proteuscfd_b200 import capi
     from proteuscfd_b200.cases import box_case
+    if args.fr:
+        import bench
+        from proteuscfd_b200.cases import fr_box_case
+        mesh, params, q, beta = fr_box_case(args.n, bench.fr_params_from_fixture(args.fr_viscous), device="cuda:0")
+        ctx = capi.Context(mesh, params, device=0)
+        ctx.set_field(capi.F_BETA, beta)
+        ctx.lsq_coefficients()
+        ctx.set_field(capi.F_Q, q)
+        ctx.timestep(want_min=False)
+        ctx.jacobian()           # warm-up (allocates A)
+        ctx.synchronize()
+        torch.cuda.profiler.start()
+        ctx.jacobian()
+        ctx.synchronize()
+        torch.cuda.profiler.stop()
+        print("profiled launches done; total launches", ctx.launch_count())
+        return
     mesh, params, q = box_case(args.n, colored=not args.natural, device="cuda:0")
     ctx = capi.Context(mesh, params, device=0)
     if args.green_gauss:
