@@ -2096,3 +2096,173 @@ void orc_chem_source_term(const orc_chem_model* m, int n, int stride, const doub
     }
   }
 }
+
+
+/* ---- surface forces: ComputeSurfaceAreas (forces.tcc:199-312), FORCE_Kernel (:123-196), YpCf_Kernel (:400-478),
+   Forces::ComputeCl (:326-369).  The half-edge loops are BdriverNoScatter's: eid = 0 .. nbedge+ngedge-1 in order, every
+   sum in that order. */
+static int body_has(const orc_forces_desc* d, int body, int factag)
+{
+  int k;
+  for(k = d->body_offsets[body]; k < d->body_offsets[body+1]; k++) if(d->body_factags[k] == factag) return 1;
+  return 0;
+}
+
+void orc_surface_areas(const orc_case* c, const orc_forces_desc* d, double* surf_area, double* body_area)
+{
+  int e, i, j, nb = c->nbedge + c->ngedge;
+  for(i = 0; i < 3*(d->num_bcs+1); i++) surf_area[i] = 0.0;
+  for(i = 0; i < 3*d->nbodies; i++) body_area[i] = 0.0;
+  for(e = 0; e < nb; e++){
+    const double* avec = &c->bedges_a[4*e];
+    int factag = d->bedges_factag[e];
+    if(c->bedges_bctype[e] == ORC_BC_PARALLEL) continue;
+    surf_area[factag*3 + 0] += fabs(avec[0]*avec[3]);
+    surf_area[factag*3 + 1] += fabs(avec[1]*avec[3]);
+    surf_area[factag*3 + 2] += fabs(avec[2]*avec[3]);
+    for(i = 0; i < d->nbodies; i++){
+      if(body_has(d, i, factag)){
+	double dot = d->liftdir[0]*avec[0] + d->liftdir[1]*avec[1] + d->liftdir[2]*avec[2];
+	if(dot >= 0.0){
+	  for(j = 0; j < 3; j++) body_area[i*3 + j] += fabs(dot*avec[j]*avec[3]);
+	}
+      }
+    }
+  }
+}
+
+/* ComputeStressVector (compressible.tcc:1113-1153, compressibleFR.tcc:2204-2242): vgrad points at the velocity-gradient
+   rows of the node, reScale = Re/Mach (perfect gas) or Re */
+static void stress_vector(const double* vg, const double* avec, double mu, double reScale, double* stress)
+{
+  double ux = vg[0], uy = vg[1], uz = vg[2], vx = vg[3], vy = vg[4], vz = vg[5], wx = vg[6], wy = vg[7], wz = vg[8];
+  double div = -2.0/3.0*(ux + vy + wz);
+  double tauxx = 2.0*ux + div, tauyy = 2.0*vy + div, tauzz = 2.0*wz + div;
+  double tauxy = uy + vx, tauxz = uz + wx, tauyz = vz + wy;
+  double tauxn = tauxx*avec[0] + tauxy*avec[1] + tauxz*avec[2];
+  double tauyn = tauxy*avec[0] + tauyy*avec[1] + tauyz*avec[2];
+  double tauzn = tauxz*avec[0] + tauyz*avec[1] + tauzz*avec[2];
+  stress[0] = -(mu/reScale)*tauxn;
+  stress[1] = -(mu/reScale)*tauyn;
+  stress[2] = -(mu/reScale)*tauzn;
+}
+
+static void cross3(const double* a, const double* b, double* r)
+{
+  r[0] = a[1]*b[2] - b[1]*a[2];
+  r[1] = a[2]*b[0] - b[2]*a[0];
+  r[2] = a[0]*b[1] - b[0]*a[1];
+}
+
+void orc_forces_gas(const orc_case* c, const orc_gas* gas, const orc_forces_desc* d, const double* q, const double* qgrad,
+		    const double* body_area, double* cp, double* yp, double* cf, double* body, double* coef)
+{
+  int e, i, j, nb = c->nbedge + c->ngedge, NV = gas->nvars;
+  for(i = 0; i < 12*d->nbodies; i++) body[i] = 0.0;
+  for(e = 0; e < c->nbedge; e++) yp[e] = cf[e] = 0.0;
+  /* FORCE_Kernel */
+  for(e = 0; e < nb; e++){
+    int l = c->bedges_n[2*e], r = c->bedges_n[2*e+1];
+    const double* avec = &c->bedges_a[4*e];
+    const double* Qs = &q[(size_t)l*NV];
+    int factag = d->bedges_factag[e];
+    double pr;
+    if(is_ghost(c, r)) continue;
+    cp[e] = gas->cp_of(gas, Qs);
+    pr = gas->pressure_of(gas, Qs);
+    for(i = 0; i < d->nbodies; i++){
+      double rpos[3], tf[3], rm[3];
+      double* B = &body[12*i];
+      if(!body_has(d, i, factag)) continue;
+      for(j = 0; j < 3; j++) rpos[j] = d->cg[(size_t)r*3 + j] - d->moment_pt[3*i + j];
+      for(j = 0; j < 3; j++) tf[j] = pr*avec[j]*avec[3];
+      cross3(rpos, tf, rm);
+      for(j = 0; j < 3; j++){ B[j] += tf[j]; B[6+j] += rm[j]; }
+      if(c->bedges_bctype[e] == ORC_BC_NOSLIP && c->viscous){
+	double mu, rho, stress[3];
+	gas->mu_rho_node(gas, Qs, &mu, &rho);
+	stress_vector(&qgrad[(size_t)l*gas->nterms*3 + gas->vloc], avec, mu, gas->Re, stress);
+	for(j = 0; j < 3; j++) tf[j] = stress[j]*avec[3];
+	cross3(rpos, tf, rm);
+	for(j = 0; j < 3; j++){ B[3+j] += tf[j]; B[9+j] += rm[j]; }
+      }
+    }
+  }
+  /* YpCf_Kernel */
+  for(e = 0; e < nb; e++){
+    int l = c->bedges_n[2*e], r = c->bedges_n[2*e+1];
+    const double* avec = &c->bedges_a[4*e];
+    const double* Qs = &q[(size_t)l*NV];
+    if(is_ghost(c, r)) continue;
+    if(c->bedges_bctype[e] == ORC_BC_NOSLIP && c->viscous){
+      const double* wallx = &c->xyz[3*l];
+      double dist = 0.0, dotmax = 0.0, mu, rho, nu, stress[3], tauw;
+      int k;
+      for(k = c->ipsp[l]; k < c->ipsp[l+1]; k++){
+	const double* ptx = &c->xyz[3*c->psp[k]];
+	double dx[3], mag, dot;
+	for(j = 0; j < 3; j++) dx[j] = ptx[j] - wallx[j];
+	mag = sqrt(dx[0]*dx[0] + dx[1]*dx[1] + dx[2]*dx[2]);
+	for(j = 0; j < 3; j++) dx[j] = dx[j]/mag;
+	dot = -(dx[0]*avec[0] + dx[1]*avec[1] + dx[2]*avec[2]);
+	if(dot >= dotmax){
+	  double ex = ptx[0] - wallx[0], ey = ptx[1] - wallx[1], ez = ptx[2] - wallx[2];
+	  dist = sqrt(ex*ex + ey*ey + ez*ez);
+	  dotmax = dot;
+	}
+      }
+      gas->mu_rho_node(gas, Qs, &mu, &rho);
+      nu = mu/rho;
+      stress_vector(&qgrad[(size_t)l*gas->nterms*3 + gas->vloc], avec, mu, gas->Re, stress);
+      tauw = sqrt(stress[0]*stress[0] + stress[1]*stress[1] + stress[2]*stress[2]);
+      yp[e] = dist*sqrt(tauw/rho)/nu*gas->Re;
+      cf[e] = tauw/(0.5*rho*gas->V*gas->V);
+    }
+  }
+  /* ComputeCl */
+  for(i = 0; i < d->nbodies; i++){
+    const double* B = &body[12*i];
+    const double* ax = &d->moment_axis[3*i];
+    const double* ar = &body_area[3*i];
+    double v2 = gas->V*gas->V;
+    double lift = d->liftdir[0]*B[0] + d->liftdir[1]*B[1] + d->liftdir[2]*B[2];
+    double drag = d->dragdir[0]*B[0] + d->dragdir[1]*B[1] + d->dragdir[2]*B[2];
+    double moment = ax[0]*B[6] + ax[1]*B[7] + ax[2]*B[8];
+    double amag;
+    lift += d->liftdir[0]*B[3] + d->liftdir[1]*B[4] + d->liftdir[2]*B[5];
+    drag += d->dragdir[0]*B[3] + d->dragdir[1]*B[4] + d->dragdir[2]*B[5];
+    moment += ax[0]*B[9] + ax[1]*B[10] + ax[2]*B[11];
+    amag = sqrt(ar[0]*ar[0] + ar[1]*ar[1] + ar[2]*ar[2]);
+    coef[3*i + 0] = lift/(0.5*gas->rho_inf*v2*amag);
+    coef[3*i + 1] = drag/(0.5*gas->rho_inf*v2*amag);
+    coef[3*i + 2] = -moment/(0.5*gas->rho_inf*v2*amag*1.0);
+  }
+}
+
+/* perfect gas: GetCp (compressible.tcc:1174-1180), GetPressure (:1156), ComputeViscosity / GetDensity */
+static double pg_cp_of(const orc_gas* g, const double* Q)
+{
+  const orc_case* c = (const orc_case*)g->ctx;
+  double P = Q[6], Mach = c->mach;
+  return ((P - 1.0/c->gamma)/(0.5*Mach*Mach));
+}
+static double pg_pressure_of(const orc_gas* g, const double* Q){ (void)g; return Q[6]; }
+static void pg_mu_rho_node(const orc_gas* g, const double* Q, double* mu, double* rho)
+{
+  const orc_case* c = (const orc_case*)g->ctx;
+  *mu = compute_viscosity(c, Q);
+  *rho = Q[0];
+}
+
+void orc_forces(const orc_case* c, const orc_forces_desc* d, const double* q, const double* qgrad,
+		const double* body_area, double* cp, double* yp, double* cf, double* body, double* coef)
+{
+  orc_gas gas;
+  gas.nvars = NVARS; gas.nterms = NTERMS; gas.vloc = 3;
+  gas.Re = c->viscous ? c->Re/c->mach : 1.0;
+  gas.ctx = c;
+  gas.theta_avg = pg_theta_avg; gas.rho_nu_avg = pg_rho_nu_avg; gas.rho_nu_node = pg_rho_nu_node;
+  gas.V = c->mach; gas.rho_inf = c->qinf[0];
+  gas.cp_of = pg_cp_of; gas.pressure_of = pg_pressure_of; gas.mu_rho_node = pg_mu_rho_node;
+  orc_forces_gas(c, &gas, d, q, qgrad, body_area, cp, yp, cf, body, coef);
+}

@@ -126,7 +126,33 @@ typedef struct orc_gas {
   double (*theta_avg)(const struct orc_gas* g, const double* qL, const double* qR, const double* avec);
   void (*rho_nu_avg)(const struct orc_gas* g, const double* qL, const double* qR, double* rho, double* nu);
   void (*rho_nu_node)(const struct orc_gas* g, const double* Q, double* rho, double* nu);
+  /* what Forces asks in addition (forces.tcc:123-196, 400-478): Param::GetVelocity, GetDensity(Qinf), EqnSet::GetCp,
+     GetPressure, ComputeViscosity + GetDensity of a stored state; set by orc_forces / orc_fr_forces only */
+  double V, rho_inf;
+  double (*cp_of)(const struct orc_gas* g, const double* Q);
+  double (*pressure_of)(const struct orc_gas* g, const double* Q);
+  void (*mu_rho_node)(const struct orc_gas* g, const double* Q, double* mu, double* rho);
 } orc_gas;
+
+/* ---- surface forces: ComputeSurfaceAreas (forces.tcc:199-312), Forces::Compute (:315-478).
+   Composite bodies as the .bc file declares them ("body #k = [factags]", composite.tcc), 0-based here. */
+typedef struct {
+  int nbodies, num_bcs;            /* num_bcs = bc->largest_bc_id */
+  const int* body_offsets;         /* [nbodies+1] into body_factags */
+  const int* body_factags;
+  const double* moment_pt;         /* [3*nbodies] CompositeBody::momentPt */
+  const double* moment_axis;       /* [3*nbodies] CompositeBody::momentAxis */
+  const int* bedges_factag;        /* [nbedge+ngedge] */
+  const double* cg;                /* Mesh::cg [(nnode+gnode+nbnode)*3]: phantom nodes carry the face-piece centroid */
+  double liftdir[3], dragdir[3];   /* Param::liftdir / dragdir, as given (not normalised) */
+} orc_forces_desc;
+/* surf_area [(num_bcs+1)*3], body_area [nbodies*3] */
+void orc_surface_areas(const orc_case* c, const orc_forces_desc* d, double* surf_area, double* body_area);
+/* cp, yp, cf [nbedge]; body [nbodies*12] = forces, vforces, moments, vmoments; coef [nbodies*3] = cl, cd, cm */
+void orc_forces_gas(const orc_case* c, const orc_gas* gas, const orc_forces_desc* d, const double* q, const double* qgrad,
+		    const double* body_area, double* cp, double* yp, double* cf, double* body, double* coef);
+void orc_forces(const orc_case* c, const orc_forces_desc* d, const double* q, const double* qgrad,
+		const double* body_area, double* cp, double* yp, double* cf, double* body, double* coef);
 double orc_turb_sa_phase_gas(const orc_case* c, const orc_gas* gas, int phase, int nsgs, const double* q, const double* qgrad,
 			     const double* s, const double* dist, const double* dt, const int* ia, const int* ja, const int* iau,
 			     double* tvar, double* tgrad, double* b, double* A, double* x, double* mut);
@@ -206,6 +232,9 @@ void orc_fr_gradient(const orc_case* c, const orc_fr_params* p, const double* q,
 void orc_fr_limiter(const orc_case* c, const orc_fr_params* p, const double* q, const double* qgrad, double* lim);
 void orc_fr_residual(const orc_case* c, const orc_fr_params* p, const double* q, const double* qgrad,
 		     const double* lim, const double* beta, double* b);
+/* Forces::Compute under the reacting eqnset; V = Param::velocity */
+void orc_fr_forces(const orc_case* c, const orc_fr_params* p, const orc_forces_desc* d, double V, const double* q,
+		   const double* qgrad, const double* body_area, double* cp, double* yp, double* cf, double* body, double* coef);
 double orc_fr_timestep(const orc_case* c, const orc_fr_params* p, const double* q, const double* beta, double* dt);
 /* returns the number of nodes whose ConservativeToNative Newton iteration did not converge (the reference aborts) */
 int orc_fr_explicit_solve(const orc_case* c, const orc_fr_params* p, double* q, const double* b, const double* dt,

@@ -1780,3 +1780,40 @@ double orc_fr_turb_sa(const orc_case* c, const orc_fr_params* p, int nsgs, const
   }
   return sqrt(ss)/(double)c->nnode;
 }
+
+
+/* ---- surface forces under the reacting eqnset: GetCp (compressibleFR.tcc:672-678: (P - Pinf)/(V^2/2)), GetPressure,
+   ComputeViscosity (Wilke-mixed), GetDensity, ComputeStressVector (:2204-2242: mu/Re), GetCf (:2245-2250) */
+static double frg_cp_of(const orc_gas* g, const double* Q)
+{
+  const orc_fr_params* p = (const orc_fr_params*)g->ctx;
+  int ns = p->chem->nspecies;
+  double P = Q[ns+4], Pinf = p->qinf[ns+4];
+  return ((P - Pinf)/(0.5*g->V*g->V));
+}
+static double frg_pressure_of(const orc_gas* g, const double* Q)
+{
+  const orc_fr_params* p = (const orc_fr_params*)g->ctx;
+  return Q[p->chem->nspecies+4];
+}
+static void frg_mu_rho_node(const orc_gas* g, const double* Q, double* mu, double* rho)
+{
+  const orc_fr_params* p = (const orc_fr_params*)g->ctx;
+  int ns = p->chem->nspecies;
+  *mu = fr_molecular_viscosity(p, Q, Q[ns+3]);
+  *rho = Q[ns+5];
+}
+
+void orc_fr_forces(const orc_case* c, const orc_fr_params* p, const orc_forces_desc* d, double V, const double* q,
+		   const double* qgrad, const double* body_area, double* cp, double* yp, double* cf, double* body, double* coef)
+{
+  int ns = p->chem->nspecies;
+  orc_gas gas;
+  gas.nvars = 3*ns + 6; gas.nterms = 2*ns + 4; gas.vloc = 3*ns;
+  gas.Re = c->Re;
+  gas.ctx = p;
+  gas.theta_avg = frg_theta_avg; gas.rho_nu_avg = frg_rho_nu_avg; gas.rho_nu_node = frg_rho_nu_node;
+  gas.V = V; gas.rho_inf = p->qinf[ns+5];
+  gas.cp_of = frg_cp_of; gas.pressure_of = frg_pressure_of; gas.mu_rho_node = frg_mu_rho_node;
+  orc_forces_gas(c, &gas, d, q, qgrad, body_area, cp, yp, cf, body, coef);
+}

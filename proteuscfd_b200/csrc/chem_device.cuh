@@ -104,4 +104,46 @@ static __device__ void mass_production(const pcfd_chem_model* __restrict__ m, co
   }
 }
 
+// The same sum with the rate constants handed in: the finite-difference source Jacobian (kfr_jac_node) perturbs one
+// density at a time at a fixed temperature, so Kf / Kb (all the exp / pow / log of the model) are evaluated once per
+// temperature instead of once per perturbation.  Same operations on the same values as mass_production.
+static __device__ void rate_constants(const pcfd_chem_model* __restrict__ m, double T, double* Kf, double* Kb) {
+  const int nr = m->nreactions;
+  for (int j = 0; j < nr; j++) {
+    Kf[j] = rate_constant(m->rxn_type[j], m->A[j], m->EA[j], m->n[j], T);
+    if (m->backward_given[j]) Kb[j] = rate_constant(m->rxn_type_b[j], m->Ab[j], m->EAb[j], m->nb[j], T);
+    else Kb[j] = Kf[j] / equilibrium_constant(m, j, T);
+  }
+}
+static __device__ void mass_production_rates(const pcfd_chem_model* __restrict__ m, const double* rhoi, const double* Kf,
+                                             const double* Kb, double* wdot) {
+  const int ns = m->nspecies, nr = m->nreactions;
+  double X[PCFD_CHEM_MAX_SPECIES];
+  for (int k = 0; k < ns; k++) X[k] = rhoi[k] / m->mw[k];
+  for (int i = 0; i < ns; i++) wdot[i] = 0.0;
+  for (int j = 0; j < nr; j++) {
+    double prod_form = 1.0, prod_dest = 1.0;
+    for (int k = 0; k < m->nsp[j]; k++) {
+      const double x = X[m->species[j][k]];
+      prod_form *= pow_stoich(x, m->nup[j][k]);
+      prod_dest *= pow_stoich(x, m->nupp[j][k]);
+    }
+    double Mconc = 1.0;
+    if (m->third_body[j]) {
+      Mconc = 0.0;
+      for (int k = 0; k < ns; k++) Mconc += X[k];
+      for (int k = 0; k < m->nsp[j]; k++) Mconc += (m->tbeff[j][k] - 1.0) * X[m->species[j][k]];
+    }
+    const double net = Kf[j] * prod_form - Kb[j] * prod_dest;
+    for (int k = 0; k < m->nsp[j]; k++) {
+      const double nu_ir = m->nupp[j][k] - m->nup[j][k];
+      if (nu_ir == 0.0) continue;
+      const int g = m->species[j][k];
+      double w = nu_ir * Mconc * net;
+      w *= m->mw[g];
+      wdot[g] += w;
+    }
+  }
+}
+
 }  // namespace chemdev

@@ -807,6 +807,22 @@ __device__ bool conservative_to_native(const Params<NS>& p, double* Q) {
   return j != 20;
 }
 
+// SourceTerm with the rate constants of the state's temperature handed in (chemdev::rate_constants); rxn_on assumed
+template <int NS>
+__device__ __forceinline__ void source_term_rates(const Params<NS>& p, const double* Q, double vol, const double* Kf,
+                                                  const double* Kb, double* source) {
+  double rhoi[PCFD_CHEM_MAX_SPECIES], wdot[PCFD_CHEM_MAX_SPECIES];
+#pragma unroll
+  for (int i = 0; i < NS; i++) rhoi[i] = Q[i] * p.ref_density;
+  chemdev::mass_production_rates(p.chem, rhoi, Kf, Kb, wdot);
+#pragma unroll
+  for (int i = 0; i < NS; i++) {
+    double w = wdot[i];
+    w /= (p.ref_density / p.ref_time);
+    source[i] = vol * w;
+  }
+}
+
 // SourceTerm (compressibleFR.tcc:1276-1316), species rows only (the others are zero; gravity off)
 template <int NS>
 __device__ __forceinline__ void source_term(const Params<NS>& p, const double* Q, double vol, double* source) {

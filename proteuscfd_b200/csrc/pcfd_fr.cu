@@ -1337,14 +1337,30 @@ __global__ void __launch_bounds__(64) kfr_jac_node(DevMesh m, fr::Params<NS> p, 
   double* dg = A + (size_t)iau[n] * N2;
   const double vol = m.vol[n];
   if (p.rxn_on) {
-    fr::source_term(p, Q, vol, s0);
-    for (int i = 0; i < NEQ; i++) {
+    // NEQ + 1 source terms in the reference.  The source is a function of rho_i and T alone: a density perturbation
+    // keeps the temperature, hence every rate constant (all the exp / pow / log of the model) of the unperturbed
+    // evaluation; a velocity perturbation reproduces the unperturbed source bit for bit, so its column is
+    // (s - s)/h = +0 and the subtraction leaves the block as it is; only T + h needs new rate constants.
+    double Kf[PCFD_CHEM_MAX_REACTIONS], Kb[PCFD_CHEM_MAX_REACTIONS];
+    chemdev::rate_constants(p.chem, Q[NS + 3] * p.ref_temperature, Kf, Kb);
+    fr::source_term_rates(p, Q, vol, Kf, Kb, s0);
+    for (int i = 0; i < NS; i++) {
       double QP[NS + 4];
 #pragma unroll
       for (int k = 0; k < NS + 4; k++) QP[k] = Q[k];
-      QP[i] += h;
-      fr::source_term(p, QP, vol, sP);
+#pragma unroll
+      for (int k = 0; k < NS; k++) if (k == i) QP[k] += h;
+      fr::source_term_rates(p, QP, vol, Kf, Kb, sP);
       for (int j = 0; j < NS; j++) dg[j * NEQ + i] -= (sP[j] - s0[j]) / h;
+    }
+    {
+      double QP[NS + 4];
+#pragma unroll
+      for (int k = 0; k < NS + 4; k++) QP[k] = Q[k];
+      QP[NS + 3] += h;
+      chemdev::rate_constants(p.chem, QP[NS + 3] * p.ref_temperature, Kf, Kb);
+      fr::source_term_rates(p, QP, vol, Kf, Kb, sP);
+      for (int j = 0; j < NS; j++) dg[j * NEQ + (NS + 3)] -= (sP[j] - s0[j]) / h;
     }
   }
   fr::temporal_terms(p, Q, vol, cnp1, dt[n], dg, beta[n]);

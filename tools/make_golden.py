@@ -305,12 +305,13 @@ CASES = {
     "box6_ns_forces": lambda: make_case("box6_ns_forces", mesh=kuhn_box(6, jitter=0.15),
                                         bc=ns_bc(330.0) + "\nbody #1 = [5]\nbody #2 = [1,2,6]\n", eqnset="compressibleNS",
                                         nsgs=3, cfl=5.0, refvisc=0.5, forces=True,
-                                        extra="liftDirection = [0.0, 0.2, 1.0]\ndragDirection = [1.0, 0.1, 0.0]\n"),
+                                        extra="liftDirection = [0.3, 0.2, -1.0]\ndragDirection = [1.0, 0.1, 0.0]\n"),
     "box4_nsfr_forces": lambda: make_case("box4_nsfr_forces", mesh=kuhn_box(4, jitter=0.15),
                                           bc=ns_bc(900.0) + "\nbody #1 = [5]\nbody #2 = [1,2,6]\n", eqnset="compressibleNSFR",
                                           nsgs=3, cfl=5.0, refvisc=2.0e-4, forces=True,
                                           extra=FR_EXTRA.format(temp=950, pres=2000, rxn=1)
-                                          + "refThermalConductivity = 0.05\nrefLength = 0.01\n"),
+                                          + "refThermalConductivity = 0.05\nrefLength = 0.01\n"
+                                          + "liftDirection = [0.3, 0.2, -1.0]\ndragDirection = [1.0, 0.1, 0.0]\n"),
     # the reference's own unit-test fixture (unitTest/gradientTest.h:20-232): prism cube, 216 nodes
     "cube_LowFi": lambda: make_case(
         "cube_LowFi", h5=os.path.join(REFERENCE, "unitTest/meshResources/cubeStructuredSeries/cube_LowFi.0.h5"),
