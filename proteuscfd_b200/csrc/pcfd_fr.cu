@@ -31,6 +31,11 @@ struct pcfd_fr_state {
   unsigned char* negflag = nullptr;         // nodes whose raw limiter has a negative component (fused clip test)
 };
 
+// Register caps: measured on B200 at 10 M cells (tools/ab_occ.sh, profiles/r2_ncu_frjac.md).  A cap that doubles the resident
+// warps pays where a kernel waits on FP64 latency with 8 warps per SM (kfr_jac_bedges 18.6 -> 14.6 ms at 128 registers,
+// kfr_jac_node, kfr_vflux_edges, kfr_vjac_edges, kfr_update_bcs_edges a few per cent); kfr_flux_edges / kfr_clip_edges /
+// kfr_gradient are best left to ptxas' own choice (96 registers: 2.32 ms, 128: 2.22 ms, 212: 3.17 ms for the flux kernel).
+
 namespace {
 
 constexpr int FR_RED_BLOCKS = 296;
@@ -56,7 +61,7 @@ __device__ __forceinline__ void load_row(const double* __restrict__ q, int n, do
 // ComputeAuxiliaryVariables(QL) at the end of each call: the first half-edge sees the stored aux values, every later
 // one sees them recomputed -- which a thread reproduces locally (same argument as k_update_bcs_edges).
 template <int NS>
-__global__ void __launch_bounds__(64) kfr_update_bcs_edges(DevMesh m, fr::Params<NS> p, const int* __restrict__ list, int n,
+__global__ void __launch_bounds__(64, 8) kfr_update_bcs_edges(DevMesh m, fr::Params<NS> p, const int* __restrict__ list, int n,
                                                             const unsigned char* __restrict__ bfirst,
                                                             const double* __restrict__ beta, double* q) {
   constexpr int NV = W<NS>::NV;
@@ -518,7 +523,7 @@ __device__ __forceinline__ void face_gradient_uvwT(const DevMesh& m, int l, int 
 }
 
 template <int NS>
-__global__ void __launch_bounds__(128) kfr_vflux_edges(DevMesh m, fr::Params<NS> p, fr::Transport<NS> t,
+__global__ void __launch_bounds__(128, 5) kfr_vflux_edges(DevMesh m, fr::Params<NS> p, fr::Transport<NS> t,
                                                         const double* __restrict__ q, const double* __restrict__ qgrad,
                                                         const double* __restrict__ mut, double* __restrict__ vflux,
                                                         double* __restrict__ bvflux) {
@@ -964,7 +969,7 @@ __global__ void __launch_bounds__(2 * W<NS>::NEQ * EPB) kfr_jac_edges_central(De
 // side each (side 0: aR added to A(l,r); side 1: -aL added to A(r,l)), after the inviscid finite-difference pass.  The
 // species rows of both blocks are zero and are left alone.  (Bkernel_Viscous_Jac ends with size = 0: no boundary part.)
 template <int NS>
-__global__ void __launch_bounds__(128) kfr_vjac_edges(DevMesh m, fr::Params<NS> p, fr::Transport<NS> t,
+__global__ void __launch_bounds__(128, 5) kfr_vjac_edges(DevMesh m, fr::Params<NS> p, fr::Transport<NS> t,
                                                        const double* __restrict__ q, const double* __restrict__ mut,
                                                        const int* __restrict__ posLR, const int* __restrict__ posRL,
                                                        double* __restrict__ A) {
@@ -1006,8 +1011,8 @@ __global__ void __launch_bounds__(128) kfr_vjac_edges(DevMesh m, fr::Params<NS> 
 // Bkernel_NumJac (jacobian.tcc:459-544), boundaryJacEval == 0: one thread per half-edge; the boundary state is
 // recomputed for every perturbation of the interior state.  Writes q exactly as the reference does (phantom state,
 // aux of the left node), the diagonal contribution into the half-edge's bdiag slot and -- ghost half-edges -- A(l,ghost).
-template <int NS>
-__global__ void __launch_bounds__(64) kfr_jac_bedges(DevMesh m, fr::Params<NS> p, const int* __restrict__ list, int n,
+template <int NS, int MINB>
+__global__ void __launch_bounds__(64, MINB) kfr_jac_bedges(DevMesh m, fr::Params<NS> p, const int* __restrict__ list, int n,
                                                       const unsigned char* __restrict__ bfirst, const double* __restrict__ beta,
                                                       double* q, const int* __restrict__ bpos, double* __restrict__ bdiag,
                                                       double* __restrict__ A) {
@@ -1325,7 +1330,7 @@ __global__ void __launch_bounds__(W<NS>::NEQ * 16) kfr_jac_diag(DevMesh m, const
 // per node: the source-term Jacobian (EqnSet::SourceTermJacobian, eqnset.tcc:163-187: one-sided FD on the native
 // variables, subtracted from the diagonal block, jacobian.tcc:199-208) and ContributeTemporalTerms (:214-250)
 template <int NS>
-__global__ void __launch_bounds__(64) kfr_jac_node(DevMesh m, fr::Params<NS> p, const int* __restrict__ iau,
+__global__ void __launch_bounds__(64, 8) kfr_jac_node(DevMesh m, fr::Params<NS> p, const int* __restrict__ iau,
                                                     const double* __restrict__ q, const double* __restrict__ dt,
                                                     const double* __restrict__ beta, double cnp1, double* A) {
   constexpr int NEQ = W<NS>::NEQ, N2 = W<NS>::N2;
@@ -1778,8 +1783,13 @@ struct Impl {
                                                                              c->f[PCFD_F_Q], c->bpos, c->bdiag, A);
       } else {
         PROF("kfr_jac_bedges");
-        kfr_jac_bedges<NS><<<nblk(c->nblist, 64), 64, 0, c->stream>>>(c->dm, p, c->blist, c->nblist, c->bfirst, beta,
-                                                                     c->f[PCFD_F_Q], c->bpos, c->bdiag, A);
+        static const int minb = getenv("PCFD_FRJACB_MINB") ? atoi(getenv("PCFD_FRJACB_MINB")) : 8;
+        if (minb == 8)   // 128 registers, 16 warps per SM: 14.6 ms at 10 M cells against 18.6 ms with 255 registers / 8 warps
+          kfr_jac_bedges<NS, 8><<<nblk(c->nblist, 64), 64, 0, c->stream>>>(c->dm, p, c->blist, c->nblist, c->bfirst, beta,
+                                                                          c->f[PCFD_F_Q], c->bpos, c->bdiag, A);
+        else
+          kfr_jac_bedges<NS, 4><<<nblk(c->nblist, 64), 64, 0, c->stream>>>(c->dm, p, c->blist, c->nblist, c->bfirst, beta,
+                                                                          c->f[PCFD_F_Q], c->bpos, c->bdiag, A);
       }
       LAUNCH_CHECK();
     }

@@ -48,8 +48,62 @@ def load_golden(name):
     return d, meta
 
 
-class Oracle:
+class OrcForcesDesc(C.Structure):
+    """orc_forces_desc (oracle/pcfd_oracle.h)"""
+    _fields_ = [("nbodies", C.c_int), ("num_bcs", C.c_int), ("body_offsets", _ip), ("body_factags", _ip),
+                ("moment_pt", _dp), ("moment_axis", _dp), ("bedges_factag", _ip), ("cg", _dp),
+                ("liftdir", C.c_double * 3), ("dragdir", C.c_double * 3)]
+
+
+def bodies_from_fixture(g):
+    """The composite bodies of a forces fixture in the flat form of the C ABI: (offsets, factags, moment_pt, moment_axis)."""
+    lists = g["forces_body_lists"]
+    offs, tags, i = [0], [], 0
+    while i < lists.size:
+        n = int(lists[i])
+        tags += [int(t) for t in lists[i + 1: i + 1 + n]]
+        offs.append(len(tags))
+        i += 1 + n
+    geom = g["forces_body_geom"].reshape(-1, 6)
+    return (np.array(offs, dtype=np.int32), np.array(tags, dtype=np.int32), np.ascontiguousarray(geom[:, :3]).ravel(),
+            np.ascontiguousarray(geom[:, 3:]).ravel())
+
+
+class ForcesMixin:
+    """orc_surface_areas / orc_forces* on a forces fixture (keys forces_*)."""
+
+    def forces_desc(self, g):
+        offs, tags, mpt, max_ = bodies_from_fixture(g)
+        keep = dict(offs=offs, tags=tags, mpt=mpt, max=max_, factag=np.ascontiguousarray(g["bedges_factag"], dtype=np.int32),
+                    cg=np.ascontiguousarray(g["forces_cg"]))
+        d = OrcForcesDesc()
+        d.nbodies, d.num_bcs = offs.size - 1, g["forces_surfArea"].size // 3 - 1
+        d.body_offsets, d.body_factags = _i(offs), _i(tags)
+        d.moment_pt, d.moment_axis = _d(mpt), _d(max_)
+        d.bedges_factag, d.cg = _i(keep["factag"]), _d(keep["cg"])
+        for j in range(3):
+            d.liftdir[j], d.dragdir[j] = g["forces_dirs"][j], g["forces_dirs"][3 + j]
+        self._forces_keep = keep
+        return d
+
+    def surface_areas(self, d):
+        sa, ba = np.zeros(3 * (d.num_bcs + 1)), np.zeros(3 * d.nbodies)
+        self.lib.orc_surface_areas(C.byref(self.c), C.byref(d), _d(sa), _d(ba))
+        return sa, ba
+
+    def _forces_out(self, d):
+        nbe = self.c.nbedge
+        return dict(cp=np.zeros(nbe), yp=np.zeros(nbe), cf=np.zeros(nbe), body=np.zeros(12 * d.nbodies), coef=np.zeros(3 * d.nbodies))
+
+
+class Oracle(ForcesMixin):
     """One mesh + parameter set bound to the C oracle."""
+
+    def forces(self, d, q, qgrad, body_area):
+        o = self._forces_out(d)
+        self.lib.orc_forces(C.byref(self.c), C.byref(d), _d(q), _d(qgrad), _d(body_area), _d(o["cp"]), _d(o["yp"]), _d(o["cf"]),
+                            _d(o["body"]), _d(o["coef"]))
+        return o
 
     def __init__(self, lib, g, meta):
         self.lib = lib
@@ -328,6 +382,12 @@ class FrOracle(Oracle):
         pv = np.zeros(self.nnode * self.neqn, dtype=np.int32)
         self.lib.orc_fr_prepare_sgs(C.byref(self.c), C.byref(self.p), _i(iau), _d(A), _i(pv))
         return pv
+
+    def forces(self, d, q, qgrad, body_area, V):
+        o = self._forces_out(d)
+        self.lib.orc_fr_forces(C.byref(self.c), C.byref(self.p), C.byref(d), C.c_double(V), _d(q), _d(qgrad), _d(body_area),
+                               _d(o["cp"]), _d(o["yp"]), _d(o["cf"]), _d(o["body"]), _d(o["coef"]))
+        return o
 
     def turb_sa(self, nsgs, q, qgrad, s, dist, dt, ia, ja, iau, tvar):
         """TurbulenceModel::Compute of the Spalart-Allmaras model under compressibleNSFR; tvar is updated in place."""
