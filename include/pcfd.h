@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PCFD_ABI_VERSION 7
+#define PCFD_ABI_VERSION 8
 
 /* eqnset ids follow eqnset_defines.h / create_functions.h:17-45 */
 enum { PCFD_EQNSET_COMPRESSIBLE_EULER_FR = 0, PCFD_EQNSET_COMPRESSIBLE_NS_FR = 1, PCFD_EQNSET_COMPRESSIBLE_EULER = 2,
@@ -176,6 +176,34 @@ int pcfd_sgs(pcfd_ctx* ctx, int nsgs, double* ddq);
    needs a halo before every product travels through pcfd_comm and the dot products are summed across ranks.  The
    reference's flow solver keeps this solver behind a comment (solutionSpace.tcc:734-750); move.tcc:714 calls it. (ABI v7) */
 int pcfd_gmres(pcfd_ctx* ctx, int restarts, int nsearch, int precond_type, double* dq_norm);
+
+/* Forces (ucs/forces.tcc; called once per iteration at solutionSpace.tcc:884 and :924).  (ABI v8)
+   pcfd_forces_configure takes the composite bodies the .bc file declares ("body #k = [factags]", composite.tcc:78-170;
+   0-based here, at most 32), Param::liftdir / dragdir / velocity, the factag of every BC half-edge and Mesh::cg, and
+   evaluates ComputeSurfaceAreas (forces.tcc:199-312) for this rank's half-edges (pcfd_forces_areas reads the result:
+   surf_area [(num_bcs+1)*3] per factag, body_area [nbodies*3]; a multi-rank host sums them as the reference does).
+   pcfd_forces_compute = Forces::Compute on the device-resident q and qgrad: FORCE_Kernel (:123-196), YpCf_Kernel
+   (:400-478), ComputeCl (:326-369).  body (may be NULL) [nbodies*12] = forces, vforces, moments, vmoments of each body;
+   coef (may be NULL) [nbodies*3] = cl, cd, cm.  On connected contexts (pcfd_comm_connect) the sums and the body areas
+   are added over the ranks in rank order.  cp / y+ / cf per BC half-edge [nbedge]: pcfd_forces_get.  The per-half-edge
+   terms follow the reference's arithmetic; the body sums are tree sums (same on every run; they differ from the
+   reference's sequential += by summation order only). */
+typedef struct {
+  int nbodies, num_bcs;            /* num_bcs = BoundaryConditions::largest_bc_id */
+  const int* body_offsets;         /* [nbodies+1] into body_factags */
+  const int* body_factags;
+  const double* moment_pt;         /* [3*nbodies] CompositeBody::momentPt */
+  const double* moment_axis;       /* [3*nbodies] CompositeBody::momentAxis */
+  const int* bedges_factag;        /* [nbedge] */
+  const double* cg;                /* Mesh::cg [(nnode+gnode+nbnode)*3] */
+  double liftdir[3], dragdir[3];   /* as given in the .param file (not normalised) */
+  double velocity;                 /* Param::GetVelocity(iter) */
+} pcfd_forces_desc;
+enum { PCFD_SURF_CP = 0, PCFD_SURF_YPLUS = 1, PCFD_SURF_CF = 2 };
+int pcfd_forces_configure(pcfd_ctx* ctx, const pcfd_forces_desc* desc);
+int pcfd_forces_areas(pcfd_ctx* ctx, double* surf_area, double* body_area);
+int pcfd_forces_compute(pcfd_ctx* ctx, double* body, double* coef);
+int pcfd_forces_get(pcfd_ctx* ctx, int which, double* out);
 
 /* Limiter::Compute + ComputeResiduals in two halves for multi-rank hosts (all eqnsets).  pcfd_limiter_raw runs
    passes 1+2 of Limiter::Compute (limiters.tcc:53-110) and leaves the UNCLAMPED limiter in field PCFD_F_LIMITER; the

@@ -43,7 +43,18 @@ SYMBOLS = [
     "pcfd_chem_source_term", "pcfd_chem_source_term_device", "pcfd_halo_width", "pcfd_halo_send_total", "pcfd_halo_pack", "pcfd_halo_recv_ptr",
     "pcfd_comm_blob_size", "pcfd_comm_export", "pcfd_comm_connect", "pcfd_comm_disconnect", "pcfd_comm_connected",
     "pcfd_comm_post", "pcfd_comm_wait", "pcfd_comm_update", "pcfd_comm_allgather", "pcfd_comm_debug_flags", "pcfd_gmres",
+    "pcfd_forces_configure", "pcfd_forces_areas", "pcfd_forces_compute", "pcfd_forces_get",
 ]
+
+
+class ForcesDesc(C.Structure):
+    """pcfd_forces_desc (include/pcfd.h)"""
+    _fields_ = [("nbodies", C.c_int), ("num_bcs", C.c_int), ("body_offsets", _ip), ("body_factags", _ip),
+                ("moment_pt", _dp), ("moment_axis", _dp), ("bedges_factag", _ip), ("cg", _dp),
+                ("liftdir", C.c_double * 3), ("dragdir", C.c_double * 3), ("velocity", C.c_double)]
+
+
+SURF_CP, SURF_YPLUS, SURF_CF = 0, 1, 2
 
 
 class MeshDesc(C.Structure):
@@ -217,6 +228,10 @@ def load_library(path=LIB_PATH):
     lib.pcfd_comm_allgather.argtypes = [C.c_void_p, _dp, C.c_int, _dp]
     lib.pcfd_turb_phase.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.pcfd_gmres.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp]
+    lib.pcfd_forces_configure.argtypes = [C.c_void_p, C.POINTER(ForcesDesc)]
+    lib.pcfd_forces_areas.argtypes = [C.c_void_p, _dp, _dp]
+    lib.pcfd_forces_compute.argtypes = [C.c_void_p, _dp, _dp]
+    lib.pcfd_forces_get.argtypes = [C.c_void_p, C.c_int, _dp]
     for name in ("pcfd_destroy", "pcfd_synchronize", "pcfd_lsq_coefficients", "pcfd_update_bcs", "pcfd_gradient",
                  "pcfd_limiter", "pcfd_explicit_solve", "pcfd_jacobian", "pcfd_prepare_sgs", "pcfd_blank_x",
                  "pcfd_apply_dq"):
@@ -521,6 +536,43 @@ class Context:
         d = C.c_double()
         self._ck(self.lib.pcfd_gmres(self.h, int(restarts), int(nsearch), int(precond_type), C.byref(d)))
         return d.value
+
+    def forces_configure(self, body_offsets, body_factags, moment_pt, moment_axis, bedges_factag, cg, liftdir, dragdir,
+                         velocity, num_bcs):
+        """Composite bodies + surface data for Forces (pcfd_forces_configure); also evaluates ComputeSurfaceAreas."""
+        keep = [np.ascontiguousarray(body_offsets, dtype=np.int32), np.ascontiguousarray(body_factags, dtype=np.int32),
+                np.ascontiguousarray(moment_pt, dtype=np.float64), np.ascontiguousarray(moment_axis, dtype=np.float64),
+                np.ascontiguousarray(bedges_factag, dtype=np.int32), np.ascontiguousarray(cg, dtype=np.float64)]
+        d = ForcesDesc()
+        d.nbodies, d.num_bcs = keep[0].size - 1, int(num_bcs)
+        d.body_offsets, d.body_factags = keep[0].ctypes.data_as(_ip), keep[1].ctypes.data_as(_ip)
+        d.moment_pt, d.moment_axis = keep[2].ctypes.data_as(_dp), keep[3].ctypes.data_as(_dp)
+        d.bedges_factag, d.cg = keep[4].ctypes.data_as(_ip), keep[5].ctypes.data_as(_dp)
+        for j in range(3):
+            d.liftdir[j], d.dragdir[j] = float(liftdir[j]), float(dragdir[j])
+        d.velocity = float(velocity)
+        if keep[4].size < self.nbedge or keep[5].size < 3 * (self.nnode + self.gnode + self.nbnode):
+            raise ValueError("forces_configure: bedges_factag needs nbedge entries, cg (nnode+gnode+nbnode)*3")
+        self._ck(self.lib.pcfd_forces_configure(self.h, C.byref(d)))
+        self._forces_shape = (d.nbodies, d.num_bcs)
+
+    def forces_areas(self):
+        nb, nbc = self._forces_shape
+        sa, ba = np.zeros(3 * (nbc + 1)), np.zeros(3 * nb)
+        self._ck(self.lib.pcfd_forces_areas(self.h, sa.ctypes.data_as(_dp), ba.ctypes.data_as(_dp)))
+        return sa, ba
+
+    def forces_compute(self):
+        """Forces::Compute: (body [nbodies, 12] = forces, vforces, moments, vmoments; coef [nbodies, 3] = cl, cd, cm)"""
+        nb, _ = self._forces_shape
+        body, coef = np.zeros(12 * nb), np.zeros(3 * nb)
+        self._ck(self.lib.pcfd_forces_compute(self.h, body.ctypes.data_as(_dp), coef.ctypes.data_as(_dp)))
+        return body.reshape(nb, 12), coef.reshape(nb, 3)
+
+    def forces_get(self, which):
+        out = np.zeros(max(self.nbedge, 1))
+        self._ck(self.lib.pcfd_forces_get(self.h, int(which), out.ctypes.data_as(_dp)))
+        return out[: self.nbedge]
 
     def turb_compute(self, nsgs, want_norm=False):
         """TurbulenceModel::Compute (Spalart-Allmaras); returns sum(b^2) of the turbulence residual when asked."""

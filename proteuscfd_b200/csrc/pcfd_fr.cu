@@ -699,6 +699,29 @@ __global__ void __launch_bounds__(128) kfr_turb_props(DevMesh m, fr::Params<NS> 
   props_n[2 * (size_t)n + 1] = mu / rho;
 }
 
+// What Forces asks of the eqnset for the surface node of a BC half-edge (pcfd_forces.cuh): GetPressure, GetCp
+// (compressibleFR.tcc:672-678: (P - Pinf) / (V^2 / 2)), ComputeViscosity (Wilke-mixed) and GetDensity
+template <int NS>
+__global__ void __launch_bounds__(128) kfr_surface_props(DevMesh m, fr::Params<NS> p, fr::Transport<NS> t, double V, bool viscous,
+                                                          const double* __restrict__ q, double* __restrict__ props) {
+  constexpr int NV = W<NS>::NV;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m.nbedge) return;
+  const double* Q = q + (size_t)m.ben[e].x * NV;
+  const double P = Q[NS + 4], Pinf = p.qinf[NS + 4];
+  double mu = 0.0, kc;
+  if (viscous) {
+    double rhoi[NS];
+#pragma unroll
+    for (int k = 0; k < NS; k++) rhoi[k] = Q[k];
+    fr::mixture_transport(p, t, rhoi, Q[NS + 3], mu, kc);
+  }
+  props[4 * (size_t)e] = P;
+  props[4 * (size_t)e + 1] = ((P - Pinf) / (0.5 * V * V));
+  props[4 * (size_t)e + 2] = mu;
+  props[4 * (size_t)e + 3] = Q[NS + 5];
+}
+
 // ComputeTimesteps (timestep.tcc:7-49): dt = CFL * vol / sum, VNN limit from node 1 on
 __global__ void __launch_bounds__(128) kfr_timestep(DevMesh m, double cfl, const double* __restrict__ eig,
                                                      const double* __restrict__ beig, const double* __restrict__ vnn23,
@@ -1011,7 +1034,7 @@ __global__ void __launch_bounds__(128, 5) kfr_vjac_edges(DevMesh m, fr::Params<N
 // Bkernel_NumJac (jacobian.tcc:459-544), boundaryJacEval == 0: one thread per half-edge; the boundary state is
 // recomputed for every perturbation of the interior state.  Writes q exactly as the reference does (phantom state,
 // aux of the left node), the diagonal contribution into the half-edge's bdiag slot and -- ghost half-edges -- A(l,ghost).
-template <int NS, int MINB>
+template <int NS, int MINB = 8>
 __global__ void __launch_bounds__(64, MINB) kfr_jac_bedges(DevMesh m, fr::Params<NS> p, const int* __restrict__ list, int n,
                                                       const unsigned char* __restrict__ bfirst, const double* __restrict__ beta,
                                                       double* q, const int* __restrict__ bpos, double* __restrict__ bdiag,
@@ -1717,6 +1740,16 @@ struct Impl {
     }
     return 0;
   }
+  static int surface_props(pcfd_ctx* c, double V, double* props, double* rho_inf, bool* viscous) {
+    *viscous = c->fr->viscous;
+    *rho_inf = c->fr->host.qinf[NS + 5];
+    if (!c->nbedge) return 0;
+    PROF("kfr_surface_props");
+    kfr_surface_props<NS><<<nblk(c->nbedge, 128), 128, 0, c->stream>>>(c->dm, make_params<NS>(c), make_transport<NS>(c), V,
+                                                                      c->fr->viscous, c->f[PCFD_F_Q], props);
+    LAUNCH_CHECK();
+    return 0;
+  }
   static int turb_props(pcfd_ctx* c) {
     if (!c->fr->viscous) return fail(c, "pcfd_turb_compute: Spalart-Allmaras under the reacting eqnset needs compressibleNSFR");
     const long long nthreads = (long long)c->nedge + c->nb + c->nn;
@@ -1918,6 +1951,9 @@ int pcfd_fr_limiter_raw(pcfd_ctx* c) { FR_DISPATCH(c, limiter_raw(c)); }
 int pcfd_fr_residual_fused(pcfd_ctx* c, double* sumsq, bool* clip_hit) { FR_DISPATCH(c, residual_impl(c, sumsq, clip_hit)); }
 int pcfd_fr_timestep(pcfd_ctx* c, double* dtmin) { FR_DISPATCH(c, timestep(c, dtmin)); }
 int pcfd_fr_turb_props(pcfd_ctx* c) { FR_DISPATCH(c, turb_props(c)); }
+int pcfd_fr_surface_props(pcfd_ctx* c, double V, double* props, double* rho_inf, bool* viscous) {
+  FR_DISPATCH(c, surface_props(c, V, props, rho_inf, viscous));
+}
 int pcfd_fr_explicit_solve(pcfd_ctx* c) { FR_DISPATCH(c, explicit_solve(c)); }
 int pcfd_fr_apply_dq(pcfd_ctx* c) { FR_DISPATCH(c, apply_dq(c)); }
 int pcfd_fr_jacobian(pcfd_ctx* c) { FR_DISPATCH(c, jacobian(c)); }

@@ -83,6 +83,7 @@ struct pcfd_ctx {
   int neqn = PCFD_NEQN, nvars = PCFD_NVARS, nterms = PCFD_NTERMS;
   struct pcfd_fr_state* fr = nullptr;   // reacting eqnset (pcfd_fr.cu); null for the perfect-gas eqnsets
   struct pcfd_comm* comm = nullptr;     // flag-based direct-put exchange between ranks (pcfd_comm.cuh); null: single rank
+  struct pcfd_forces* forces = nullptr; // surface forces (pcfd_forces.cuh); null until pcfd_forces_configure
   DevMesh dm{};
   eq::BcParams bp{};
   double* f[PCFD_F_COUNT] = {};
@@ -271,6 +272,8 @@ void pcfd_fr_set_time(pcfd_ctx* c, double dt, int use_local);
 int pcfd_fr_residual_fused(pcfd_ctx* c, double* sumsq, bool* clip_hit);
 int pcfd_fr_timestep(pcfd_ctx* c, double* dtmin);
 int pcfd_fr_turb_props(pcfd_ctx* c);
+// {p, cp, mu, rho} of the surface node of every BC half-edge (Forces, pcfd_forces.cuh); also GetDensity(Qinf), viscous
+int pcfd_fr_surface_props(pcfd_ctx* c, double V, double* props, double* rho_inf, bool* viscous);
 int pcfd_fr_explicit_solve(pcfd_ctx* c);
 int pcfd_fr_apply_dq(pcfd_ctx* c);
 int pcfd_fr_jacobian(pcfd_ctx* c);

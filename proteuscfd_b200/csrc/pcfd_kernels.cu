@@ -2224,6 +2224,7 @@ std::vector<int> contiguous_ranges(int n, const int* ia, const int* ja) {
 
 #include "pcfd_comm.cuh"
 #include "pcfd_gmres.cuh"
+#include "pcfd_forces.cuh"
 
 // ======================================================================= C ABI
 extern "C" {
@@ -2236,6 +2237,7 @@ int pcfd_destroy(pcfd_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   if (c->fr) pcfd_fr_destroy(c);
+  forces_free(c);
   if (c->comm) {
     pcfd_comm_disconnect(c);
     if (c->comm->hgout) cudaFreeHost(c->comm->hgout);
