@@ -194,6 +194,57 @@ class DropIn {
     double* dst = s_->GetFieldData("mut", FIELDS::STATE_NONE);
     for (int i = 0; i < nnode_ + gnode_; i++) dst[i] = mut[i];
   }
+  // Forces::Compute (forces.tcc:315-324, called at solutionSpace.tcc:884, 924) on the device-resident q and qgrad: body
+  // sums, coefficients and the per-half-edge cp / y+ / cf land where the reference keeps them (Forces::bodies, cp, yp, cf;
+  // scalar fields CL / CM).  The bodies, Param::liftdir / dragdir and Mesh::cg are handed over on the first call
+  // (pcfd_forces_configure also evaluates ComputeSurfaceAreas; the areas are written to Forces::surfArea / bodies[].surfArea
+  // -- single rank: as they are, several ranks: the host sums them as forces.tcc:236-243 does).
+  void ComputeForces() {
+    auto* f = s_->forces;
+    auto* m = s_->m;
+    const int nbodies = f->num_bodies, nbedge = m->GetNumBoundaryEdges();
+    if (nbodies < 1) return;
+    if (!forces_ready_) {
+      std::vector<int> offs(1, 0), tags, factag((size_t)std::max(nbedge, 1));
+      std::vector<double> mpt, max_;
+      for (int i = 1; i <= nbodies; i++) {
+        for (int k = 0; k < f->bodies[i].nsurfs; k++) tags.push_back(f->bodies[i].list[k]);
+        offs.push_back((int)tags.size());
+        for (int k = 0; k < 3; k++) { mpt.push_back(f->bodies[i].momentPt[k]); max_.push_back(f->bodies[i].momentAxis[k]); }
+      }
+      if (tags.empty()) tags.push_back(-1);
+      for (int e = 0; e < nbedge; e++) factag[e] = m->bedges[e].factag;
+      pcfd_forces_desc d;
+      d.nbodies = nbodies; d.num_bcs = f->num_bcs;
+      d.body_offsets = offs.data(); d.body_factags = tags.data();
+      d.moment_pt = mpt.data(); d.moment_axis = max_.data();
+      d.bedges_factag = factag.data(); d.cg = m->cg;
+      for (int k = 0; k < 3; k++) { d.liftdir[k] = s_->param->liftdir[k]; d.dragdir[k] = s_->param->dragdir[k]; }
+      d.velocity = s_->param->GetVelocity(s_->iter);
+      Check(pcfd_forces_configure(ctx_, &d), "pcfd_forces_configure");
+      std::vector<double> ba((size_t)3 * nbodies);
+      Check(pcfd_forces_areas(ctx_, f->surfArea, ba.data()), "pcfd_forces_areas");
+      for (int i = 1; i <= nbodies; i++)
+        for (int k = 0; k < 3; k++) f->bodies[i].surfArea[k] = ba[(size_t)3 * (i - 1) + k];
+      forces_ready_ = true;
+    }
+    std::vector<double> body((size_t)12 * nbodies), coef((size_t)3 * nbodies);
+    Check(pcfd_forces_compute(ctx_, body.data(), coef.data()), "Forces::Compute");
+    for (int i = 1; i <= nbodies; i++) {
+      const double* B = &body[(size_t)12 * (i - 1)];
+      for (int k = 0; k < 3; k++) {
+        f->bodies[i].forces[k] = B[k]; f->bodies[i].vforces[k] = B[3 + k];
+        f->bodies[i].moments[k] = B[6 + k]; f->bodies[i].vmoments[k] = B[9 + k];
+      }
+      f->bodies[i].cl = coef[(size_t)3 * (i - 1)]; f->bodies[i].cd = coef[(size_t)3 * (i - 1) + 1];
+      f->bodies[i].cm = coef[(size_t)3 * (i - 1) + 2];
+    }
+    Check(pcfd_forces_get(ctx_, PCFD_SURF_CP, f->cp), "pull cp");
+    Check(pcfd_forces_get(ctx_, PCFD_SURF_YPLUS, f->yp), "pull y+");
+    Check(pcfd_forces_get(ctx_, PCFD_SURF_CF, f->cf), "pull cf");
+    s_->GetScalarField("CL").SetField(f->bodies[1].cl);
+    s_->GetScalarField("CM").SetField(f->bodies[1].cm);
+  }
   void ExplicitSolve() { Check(pcfd_explicit_solve(ctx_), "ExplicitSolve"); }                              // solve.tcc:71
   void ApplyDQ() { Check(pcfd_apply_dq(ctx_), "ApplyDQ"); }                                                // solutionSpace.tcc:802
 
@@ -330,6 +381,7 @@ class DropIn {
   Space* s_;
   pcfd_ctx* ctx_;
   ErrorHandler onError_;
+  bool forces_ready_ = false;
   int nnode_, gnode_, nbnode_, nedge_, nbedge_, ngedge_, neqn_, nvars_, nterms_;
 };
 

@@ -310,26 +310,23 @@ static void DumpMesh(SolutionSpace<Real>* space)
 // Forces / surface post-processing (PCFD_FORCES set; bodies come from the "body #k = [...]" lines of the .bc file): the
 // reference's own ComputeSurfaceAreas (forces.tcc:199-262) and Forces::Compute (:317-418: FORCE_Kernel, YpCf_Kernel,
 // ComputeCl) on the state and gradient the iteration left behind
-static void DumpForces(SolutionSpace<Real>* space)
+static void InjectForcesGeometry(SolutionSpace<Real>* space)
 {
-  if(!getenv("PCFD_FORCES")) return;
-  Mesh<Real>* m = space->m;
-  Param<Real>* param = space->param;
   Forces<Real>* f = space->forces;
-  Int nnode = m->GetNumNodes(), gnode = m->GetNumParallelNodes(), nbnode = m->GetNumBoundaryNodes();
-  Int nbedge = m->GetNumBoundaryEdges();
-  Int nvars = space->eqnset->neqn + space->eqnset->nauxvars;
   if(f->num_bodies >= 1){
     f->bodies[1].momentPt[0] = 0.25; f->bodies[1].momentPt[1] = 0.1; f->bodies[1].momentPt[2] = -0.05;
   }
   if(f->num_bodies >= 2){
     f->bodies[2].momentAxis[0] = 0.0; f->bodies[2].momentAxis[1] = 1.0; f->bodies[2].momentAxis[2] = 0.0;
   }
-  Dump("forces_q", space->q, (size_t)(nnode+gnode+nbnode)*nvars);
-  Dump("forces_qgrad", space->qgrad, (size_t)(nnode+gnode)*space->grad->GetNterms()*3);
-  Dump("forces_cg", m->cg, (size_t)(nnode+gnode+nbnode)*3);
-  ComputeSurfaceAreas(space, 0);
-  f->Compute();
+}
+
+static void DumpForcesResult(SolutionSpace<Real>* space)
+{
+  Mesh<Real>* m = space->m;
+  Param<Real>* param = space->param;
+  Forces<Real>* f = space->forces;
+  Int nbedge = m->GetNumBoundaryEdges();
   Dump("forces_cp", f->cp, (size_t)nbedge);
   Dump("forces_yp", f->yp, (size_t)nbedge);
   Dump("forces_cf", f->cf, (size_t)nbedge);
@@ -354,6 +351,21 @@ static void DumpForces(SolutionSpace<Real>* space)
   Dump("forces_body_geom", geom.data(), geom.size());
   Real dirs[6] = {param->liftdir[0], param->liftdir[1], param->liftdir[2], param->dragdir[0], param->dragdir[1], param->dragdir[2]};
   Dump("forces_dirs", dirs, 6);
+}
+
+static void DumpForces(SolutionSpace<Real>* space)
+{
+  if(!getenv("PCFD_FORCES")) return;
+  Mesh<Real>* m = space->m;
+  Int nnode = m->GetNumNodes(), gnode = m->GetNumParallelNodes(), nbnode = m->GetNumBoundaryNodes();
+  Int nvars = space->eqnset->neqn + space->eqnset->nauxvars;
+  InjectForcesGeometry(space);
+  Dump("forces_q", space->q, (size_t)(nnode+gnode+nbnode)*nvars);
+  Dump("forces_qgrad", space->qgrad, (size_t)(nnode+gnode)*space->grad->GetNterms()*3);
+  Dump("forces_cg", m->cg, (size_t)(nnode+gnode+nbnode)*3);
+  ComputeSurfaceAreas(space, 0);
+  space->forces->Compute();
+  DumpForcesResult(space);
 }
 
 // Spalart-Allmaras (turbulenceModel = 1): inject a smooth positive nu~ field and run the reference's own
@@ -560,6 +572,15 @@ int main(int argc, char* argv[])
     gpu.PullQ();
     if(!multi) p->UpdateGeneralVectors(space->q, nvars);
     Dump("q1", space->q, (size_t)(nnode+gnode+nbnode)*nvars);
+    if(getenv("PCFD_FORCES") && !multi){
+      // Forces::Compute (solutionSpace.tcc:884) on the device-resident state
+      InjectForcesGeometry(space);
+      Dump("forces_q", space->q, (size_t)(nnode+gnode+nbnode)*nvars);
+      Dump("forces_qgrad", space->qgrad, (size_t)(nnode+gnode)*space->grad->GetNterms()*3);
+      Dump("forces_cg", m->cg, (size_t)(nnode+gnode+nbnode)*3);
+      gpu.ComputeForces();
+      DumpForcesResult(space);
+    }
   }
 #else
   if(mode == "dump"){

@@ -43,7 +43,7 @@ flowDirection = [1.0, 0.0, 0.0]
 jacobianFieldType = {jactype}
 jacobianBoundaryType = {jactype}
 gradientType = {gradtype}
-<<<END SPACE>>>
+{extra}<<<END SPACE>>>
 """
 
 BOX_BC = """surface #1 = farField "xmin"
@@ -92,7 +92,7 @@ class ReferenceCase:
     """A box case decomposed for `ranks` reference processes, kept on disk so it can be timed repeatedly."""
 
     def __init__(self, n, ranks, limiter=2, nsgs=0, sorder=2, mach=0.5, cfl=0.5, jitter=0.15, colored=False, jactype=0,
-                 gradtype=0):
+                 gradtype=0, forces=False):
         from proteuscfd_b200.boxmesh import kuhn_box, renumber, write_ugrid
         from proteuscfd_b200.ordering import color_order, kuhn_box_colors
         self.work = tempfile.mkdtemp(prefix="pcfd_refbench_")
@@ -108,9 +108,12 @@ class ReferenceCase:
             part = p2
         with open(os.path.join(self.work, "box.param"), "w") as f:
             f.write(PARAM_TMPL.format(name=self.name, sorder=sorder, limiter=limiter, nsgs=nsgs, mach=mach, cfl=cfl,
-                                     jactype=int(jactype), gradtype=int(gradtype)))
+                                     jactype=int(jactype), gradtype=int(gradtype),
+                                     extra="liftDirection = [0.3, 1.0, 0.2]\ndragDirection = [1.0, 0.1, 0.0]\n" if forces else ""))
+        self.forces = bool(forces)
         with open(os.path.join(self.work, "box.bc"), "w") as f:
-            f.write(BOX_BC)
+            # forces: two composite bodies (the impermeable wall; three far-field faces) for Forces::Compute
+            f.write(BOX_BC + ("\nbody #1 = [4]\nbody #2 = [1,2,6]\n" if forces else ""))
         write_ugrid(os.path.join(self.work, "box.ugrid"), xyz, tets, tris, tags)
         env = {}
         if self.ranks > 1:
@@ -128,15 +131,18 @@ class ReferenceCase:
             return json.load(f)
 
     INT_ARRAYS = {"edges_n", "bedges_n", "bedges_factag", "bedges_bctype", "ipsp", "psp", "gNodeOwner", "gNodeLocalId",
-                  "commCountsSend", "commCountsRecv", "commOffsetsRecv", "nodePackingList", "ia", "ja", "iau", "pv"}
+                  "commCountsSend", "commCountsRecv", "commOffsetsRecv", "nodePackingList", "ia", "ja", "iau", "pv",
+                  "forces_body_lists"}
 
     def dump(self, dropin=False, timeout=600):
         """One pass with every intermediate array dumped; dropin=True runs oracle/_ref/ref_harness_gpu, the same
         harness with the phase calls replaced by include/pcfd_host.hpp (needs a B200).  Returns {rank: {name: array}}."""
         binary = "ref_harness_gpu" if dropin else "ref_harness"
         out = os.path.join(self.work, "out_gpu" if dropin else "out_cpu")
-        _run([os.path.join(REFBIN, binary), os.path.join(self.work, self.name), out, "dump"], self.work,
-             {"PCFD_MPI_NP": str(self.ranks)}, timeout=timeout)
+        env = {"PCFD_MPI_NP": str(self.ranks)}
+        if self.forces:
+            env["PCFD_FORCES"] = "1"
+        _run([os.path.join(REFBIN, binary), os.path.join(self.work, self.name), out, "dump"], self.work, env, timeout=timeout)
         res = {}
         for r in range(self.ranks):
             d = {}

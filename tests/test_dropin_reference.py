@@ -68,3 +68,28 @@ def test_reference_with_dropin_two_ranks(kind):
                 continue
             else:
                 exact(gpu[r][name], cpu[r][name], f"{name} rank {r}")
+
+
+def test_reference_forces_through_the_dropin():
+    """Forces::Compute (solutionSpace.tcc:884) through pcfd::DropIn::ComputeForces: composite bodies from the .bc file,
+    Param::liftdir / dragdir, Mesh::cg and the half-edge factags taken from the reference's own objects, results written
+    back into Forces::bodies / cp -- against the same harness calling the reference's ComputeSurfaceAreas + Forces::Compute.
+    Areas and cp bit-identical; body sums 1e-12 of their scale (tree sum against sequential +=)."""
+    from oracle import ref_bench
+    if not ref_bench.available(dropin=True):
+        pytest.skip("oracle/_ref binaries not built (needs /root/reference at build time)")
+    case = ref_bench.ReferenceCase(8, 1, limiter=2, nsgs=3, cfl=5.0, colored=True, forces=True)
+    try:
+        cpu = case.dump(dropin=False)[0]
+        gpu = case.dump(dropin=True)[0]
+    finally:
+        case.close()
+    for name in ("forces_q", "forces_qgrad", "forces_cg", "forces_cp", "forces_surfArea", "forces_body_lists", "forces_body_geom",
+                 "forces_dirs", "forces_yp", "forces_cf"):
+        exact(gpu[name], cpu[name], name)
+    b_cpu, b_gpu = cpu["forces_body"].reshape(-1, 18), gpu["forces_body"].reshape(-1, 18)
+    exact(b_gpu[:, 12:15], b_cpu[:, 12:15], "projected body areas")
+    scale = np.abs(cpu["forces_q"]).max() * 6.0      # |p| x total surface area of the unit box
+    assert np.abs(b_cpu[:, :3]).max() > 1e-3
+    assert np.all(np.abs(b_gpu[:, :12] - b_cpu[:, :12]) <= 1e-12 * scale)
+    assert np.allclose(b_gpu[:, 15:18], b_cpu[:, 15:18], rtol=1e-10)
