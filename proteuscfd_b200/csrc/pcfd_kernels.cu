@@ -1063,7 +1063,8 @@ __global__ void __launch_bounds__(128) k_update_bcs_edges(DevMesh m, eq::BcParam
 // ====================================================================== Jacobian
 // Kernel_NumJac (jacobian.tcc:254-304): one-sided finite differences, h = 1e-8, of the
 // FIRST-ORDER flux; writes A(l,r) = dF/dqR and A(r,l) = -dF/dqL into their slots.
-__global__ void __launch_bounds__(128) k_jac_edges(DevMesh m, double gamma, const double* __restrict__ q,
+template <int MINB = 2>
+__global__ void __launch_bounds__(128, MINB) k_jac_edges(DevMesh m, double gamma, const double* __restrict__ q,
                                                     const int* __restrict__ posLR, const int* __restrict__ posRL,
                                                     double* __restrict__ A) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -3239,7 +3240,12 @@ int pcfd_jacobian(pcfd_ctx* c) {
       k_jac_edges_central<<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, c->prm.gamma, c->f[PCFD_F_Q], c->posLR, c->posRL, A);
     } else {
       PROF("k_jac_edges");
-      k_jac_edges<<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, c->prm.gamma, c->f[PCFD_F_Q], c->posLR, c->posRL, A);
+      // register cap, measured at 10 M cells (tools/ab_pgjac.sh): 224 registers / 8 warps per SM 13.30 ms, 168: 12.47,
+      // 128 (16 warps): 11.44, 96: 13.44 -- the kernel waits on FP64 latency, not on the pipe
+      static const int minb = getenv("PCFD_JAC_MINB") ? atoi(getenv("PCFD_JAC_MINB")) : 4;
+      const dim3 g(nblk(c->nedge, 128));
+      if (minb == 4) k_jac_edges<4><<<g, 128, 0, c->stream>>>(c->dm, c->prm.gamma, c->f[PCFD_F_Q], c->posLR, c->posRL, A);
+      else k_jac_edges<2><<<g, 128, 0, c->stream>>>(c->dm, c->prm.gamma, c->f[PCFD_F_Q], c->posLR, c->posRL, A);
     }
     LAUNCH_CHECK();
   }
