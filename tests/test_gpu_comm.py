@@ -25,7 +25,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def run_threads(parts, body, prepare=None):
     """one thread per rank: context, halo maps over the thread group, CommExchange; body(rank, ctx, x) -> result.
-    prepare(ctx): anything that allocates device memory on first use, run BEFORE the ranks connect (see below)"""
+    prepare(ctx) or prepare(rank, ctx): anything that allocates device memory on first use, run BEFORE the ranks connect"""
     from proteuscfd_b200 import capi
     from proteuscfd_b200.parallel import CommExchange, PObj, ThreadGroup
     nr = len(parts)
@@ -38,7 +38,7 @@ def run_threads(parts, body, prepare=None):
         # threads sharing one GPU) it would wait for a peer's put kernel that is waiting for this very rank
         ctx.device_ptr(capi.F_A)
         if prepare is not None:
-            prepare(ctx)
+            prepare(ctx) if prepare.__code__.co_argcount == 1 else prepare(rank, ctx)
         pobj = PObj(rank, nr).BuildCommMaps(mesh["gNodeOwner"], mesh["gNodeLocalId"], group)
         x = CommExchange(ctx, pobj, group)
         try:
@@ -299,3 +299,59 @@ def test_comm_two_processes_over_cuda_ipc(implicit):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("RANK_OK") == 2, r.stdout[-3000:]
+
+
+def test_comm_forces_are_summed_over_the_ranks(oracle):
+    """Forces::Compute on partitions: every rank integrates its own BC half-edges, the body sums and the projected body
+    areas are added over the ranks (forces.tcc:236-243, 383-388: MPI_Allreduce; here pcfd_comm in rank order) and every
+    rank ends up with the same coefficients.  Against the oracle's per-rank sums added in the same order."""
+    from proteuscfd_b200 import capi
+    from proteuscfd_b200.cases import slab_case
+    from tests.oracle_lib import oracle_for
+    nr = 3
+    parts = [slab_case(6, r, nr, colored=True, cfl=5.0, viscous=True) for r in range(nr)]
+    tags = [capi.BC_NOSLIP, capi.BC_FARFIELD]       # the surrogate "factag" of a half-edge is its BC type here
+    V = 0.5
+    fix = []
+    for mesh, params, q in parts:
+        nloc, nbe = mesh["nnode"] + mesh["gnode"], mesh["nbedge"]
+        bn = mesh["bedges_n"].reshape(-1, 2)[:nbe]
+        cg = np.zeros((nloc + mesh["nbnode"], 3))
+        cg[bn[:, 1]] = mesh["xyz"].reshape(-1, 3)[bn[:, 0]] + 0.01
+        fix.append(dict(forces_body_lists=np.array([1, tags[0], 1, tags[1]], dtype=np.int32),
+                        forces_body_geom=np.array([0.2, 0.1, 0.0, 0, 0, 1, 0.0, 0.0, 0.0, 0, 1, 0], dtype=np.float64),
+                        bedges_factag=mesh["bedges_bctype"].astype(np.int32), forces_cg=cg.reshape(-1),
+                        forces_surfArea=np.zeros(3 * 10), forces_dirs=np.array([0.3, 0.2, -1.0, 1.0, 0.1, 0.0])))
+    rng = np.random.default_rng(3)
+    grads = [rng.standard_normal((m["nnode"] + m["gnode"]) * 27) * 0.1 for m, _, _ in parts]
+
+    def prepare(rank, ctx):
+        from tests.oracle_lib import bodies_from_fixture
+        g = fix[rank]
+        offs, tg, mpt, max_ = bodies_from_fixture(g)
+        ctx.forces_configure(offs, tg, mpt, max_, g["bedges_factag"], g["forces_cg"], g["forces_dirs"][:3], g["forces_dirs"][3:], V, 9)
+
+    def body(rank, ctx, x):
+        ctx.set_field(capi.F_Q, parts[rank][2])
+        ctx.set_field(capi.F_QGRAD, grads[rank])
+        b, c = ctx.forces_compute()
+        return b, c, ctx.forces_areas()[1]
+
+    got = run_threads(parts, body, prepare=prepare)
+    sums, areas, rho_inf = np.zeros(24), np.zeros(6), None
+    scale = 0.0
+    for r, (mesh, params, q) in enumerate(parts):
+        o = oracle_for(oracle, mesh, dict(params, viscous=1))
+        d = o.forces_desc(fix[r])
+        _, ba = o.surface_areas(d)
+        exact(got[r][2], ba, f"rank {r}: local projected areas")
+        o.c.mach = V
+        out = o.forces(d, q, grads[r], ba)
+        sums += out["body"]
+        areas += ba
+        scale += np.abs(q).max() * np.abs(mesh["bedges_a"].reshape(-1, 4)[: mesh["nbedge"], 3]).sum()
+    for r in range(nr):
+        assert np.all(np.abs(got[r][0].ravel() - sums) <= 1e-12 * scale)
+        exact(got[r][0], got[0][0], "every rank holds the same sums")
+        exact(got[r][1], got[0][1], "every rank holds the same coefficients")
+    assert np.abs(sums[3:6]).max() > 0 and np.isfinite(got[0][1]).all()
