@@ -136,6 +136,9 @@ struct pcfd_ctx {
   int *ia = nullptr, *ja = nullptr, *iau = nullptr, *pv = nullptr, *posLR = nullptr, *posRL = nullptr, *bpos = nullptr;
   int *rows_f = nullptr, *rows_b = nullptr;
   std::vector<int> lev_f, lev_b;   // level offsets into rows_f / rows_b
+  int *dlev_f = nullptr, *dlev_b = nullptr;   // the same on the device (Spalart-Allmaras contexts: k_sgs_scalar_sweeps)
+  bool turb_persist = true;        // PCFD_TURB_PERSIST=0: one launch per level for the scalar sweeps
+  int turb_grid = 0;
   // halo maps (PObj::BuildCommMaps, parallel.tcc:461-554): what this rank sends to / receives from each peer
   int rank = 0, nranks = 1;
   std::vector<int> send_counts, send_offsets, recv_counts, recv_offsets;

@@ -19,6 +19,8 @@
 //
 // Compile with --fmad=false (see eqnset_compressible.cuh for why).
 
+#include <cooperative_groups.h>
+
 #include "pcfd_internal.cuh"
 #include "sgs_tile.cuh"
 
@@ -2128,6 +2130,43 @@ __global__ void __launch_bounds__(128) k_sgs_scalar_level(const int* __restrict_
   x[row] = dinv * rhs;
 }
 
+// The same sweeps as ONE cooperative launch: a level of the scalar system is ~0.1 M rows of ~15 entries -- 3 us of data
+// behind ~20 us of launch latency and ramp -- and TurbulenceModel::Compute runs 2 x levels x nSgs of them (80 at 10 M
+// cells).  Every block walks the levels of `nsweeps` forward + backward sweeps with a grid barrier in between; x is read
+// through L2 (ld.global.cg): a value another SM wrote one level ago must not come from this SM's L1.  Row arithmetic and
+// order are those of k_sgs_scalar_level.
+__global__ void __launch_bounds__(256) k_sgs_scalar_sweeps(const int* __restrict__ rows_f, const int* __restrict__ rows_b,
+                                                            const int* __restrict__ lev_f, int nlev_f,
+                                                            const int* __restrict__ lev_b, int nlev_b, int nsweeps,
+                                                            const int* __restrict__ ia, const int* __restrict__ ja,
+                                                            const double* __restrict__ A, const double* __restrict__ b,
+                                                            double* x) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (int s = 0; s < nsweeps; s++) {
+    for (int dir = 0; dir < 2; dir++) {
+      const int* rows = dir ? rows_b : rows_f;
+      const int* lev = dir ? lev_b : lev_f;
+      const int nlev = dir ? nlev_b : nlev_f;
+      for (int l = 0; l < nlev; l++) {
+        const int r0 = lev[l], r1 = lev[l + 1];
+        for (int t = r0 + tid; t < r1; t += nth) {
+          const int row = rows[t];
+          const int k0 = ia[row], k1 = ia[row + 1];
+          double rhs = b[row];
+          const double dinv = A[k0];
+          for (int k = k0 + 1; k < k1; k++) {
+            const double vout = __ldcs(A + k) * __ldcg(x + __ldg(ja + k));
+            rhs -= vout;
+          }
+          x[row] = dinv * rhs;
+        }
+        grid.sync();
+      }
+    }
+  }
+}
+
 // tvar += x with the clip at zero (turb.tcc:306-320), then mut = rho nu~ fv1 for local and ghost nodes (:324-336)
 __global__ void k_turb_update(int nnode, const double* __restrict__ x, double* tvar) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2563,6 +2602,9 @@ static int create_impl(const pcfd_mesh_desc* mesh, const pcfd_params* params, in
   }
   if (const char* e = getenv("PCFD_EIG_FUSE")) c->eig_fuse = atoi(e) != 0;
   if (sa_on) {
+    if (dev_upload(c, &c->dlev_f, c->lev_f.data(), c->lev_f.size())) return 1;
+    if (dev_upload(c, &c->dlev_b, c->lev_b.data(), c->lev_b.size())) return 1;
+    if (const char* e = getenv("PCFD_TURB_PERSIST")) c->turb_persist = atoi(e) != 0;
     if (dev_alloc(c, &c->tslots, (size_t)nedge * 3)) return 1;
     if (dev_alloc(c, &c->tbslots, (size_t)nb * 4)) return 1;
     if (neqn != NEQN) {   // reacting eqnset: tables of kfr_turb_props
@@ -3510,6 +3552,42 @@ int pcfd_ipc_close(pcfd_ctx* c, void* devptr) {
   return 0;
 }
 
+// nsweeps symmetric Gauss-Seidel sweeps of the scalar (turbulence) system: one cooperative launch (k_sgs_scalar_sweeps)
+// or, with PCFD_TURB_PERSIST=0 / while profiling per kernel, one launch per level
+static int turb_sweeps(pcfd_ctx* c, int nsweeps, const double* tA, const double* tb, double* tx) {
+  if (c->turb_persist && !c->prof) {
+    if (c->turb_grid == 0) {
+      int per_sm = 0, sms = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sgs_scalar_sweeps, 256, 0));
+      CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+      c->turb_grid = std::max(1, std::min(per_sm, 4)) * sms;
+    }
+    int nlev_f = (int)c->lev_f.size() - 1, nlev_b = (int)c->lev_b.size() - 1;
+    const int *rows_f = c->rows_f, *rows_b = c->rows_b, *lev_f = c->dlev_f, *lev_b = c->dlev_b, *ia = c->ia, *ja = c->ja;
+    void* args[] = {&rows_f, &rows_b, &lev_f, &nlev_f, &lev_b, &nlev_b, &nsweeps, &ia, &ja, &tA, &tb, &tx};
+    PROF("k_sgs_scalar_sweeps");
+    CK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_sgs_scalar_sweeps), dim3(c->turb_grid), dim3(256), args, 0, c->stream));
+    LAUNCH_CHECK();
+    return 0;
+  }
+  bool chained = false;   // the first level follows an ordinary kernel: plain launch
+  for (int s = 0; s < nsweeps; s++) {
+    for (int dir = 0; dir < 2; dir++) {
+      const std::vector<int>& off = dir ? c->lev_b : c->lev_f;
+      const int* rows = dir ? c->rows_b : c->rows_f;
+      for (size_t l = 0; l + 1 < off.size(); l++) {
+        const int nr = off[l + 1] - off[l];
+        PROF("k_sgs_scalar_level");
+        CK(launch_maybe_pdl(k_sgs_scalar_level, nblk(nr, 128), 128, 0, c->stream, c->sgs_pdl && !c->prof && chained,
+                            rows + off[l], nr, c->ia, c->ja, tA, tb, tx));
+        chained = true;
+        LAUNCH_CHECK();
+      }
+    }
+  }
+  return 0;
+}
+
 // the Spalart-Allmaras kernels for the context's eqnset (q only matters to the perfect-gas instantiation; the reacting one
 // reads the tables pcfd_fr_turb_props filled from the same q, so the two must not be separated by a change of q)
 static TurbGas turb_gas(const pcfd_ctx* c) {
@@ -3620,21 +3698,7 @@ int pcfd_turb_compute(pcfd_ctx* c, int nsgs, double* sumsq) {
     PROF("k_turb_invdiag");
     k_turb_invdiag<<<nblk(c->nnode, 256), 256, 0, c->stream>>>(c->nnode, c->iau, tA);
     LAUNCH_CHECK();
-    bool chained = false;   // the first level follows an ordinary kernel: plain launch
-    for (int s = 0; s < nsgs; s++) {
-      for (int dir = 0; dir < 2; dir++) {
-        const std::vector<int>& off = dir ? c->lev_b : c->lev_f;
-        const int* rows = dir ? c->rows_b : c->rows_f;
-        for (size_t l = 0; l + 1 < off.size(); l++) {
-          const int nr = off[l + 1] - off[l];
-          PROF("k_sgs_scalar_level");
-          CK(launch_maybe_pdl(k_sgs_scalar_level, nblk(nr, 128), 128, 0, c->stream, c->sgs_pdl && !c->prof && chained,
-                              rows + off[l], nr, c->ia, c->ja, (const double*)tA, (const double*)tb, tx));
-          chained = true;
-          LAUNCH_CHECK();
-        }
-      }
-    }
+    if (turb_sweeps(c, nsgs, tA, tb, tx)) return 1;
   } else {
     return fail(c, "pcfd_turb_compute: nsgs == 0 (explicit turbulence update) is not implemented");
   }
@@ -3711,22 +3775,8 @@ int pcfd_turb_phase(pcfd_ctx* c, int phase, double* sumsq) {
       LAUNCH_CHECK();
       if (sumsq) CK(cudaStreamSynchronize(c->stream));
       return 0;
-    case 3: {
-      bool chained = false;
-      for (int dir = 0; dir < 2; dir++) {
-        const std::vector<int>& off = dir ? c->lev_b : c->lev_f;
-        const int* rows = dir ? c->rows_b : c->rows_f;
-        for (size_t l = 0; l + 1 < off.size(); l++) {
-          const int nr = off[l + 1] - off[l];
-          PROF("k_sgs_scalar_level");
-          CK(launch_maybe_pdl(k_sgs_scalar_level, nblk(nr, 128), 128, 0, c->stream, c->sgs_pdl && !c->prof && chained,
-                              rows + off[l], nr, c->ia, c->ja, (const double*)tA, (const double*)tb, tx));
-          chained = true;
-          LAUNCH_CHECK();
-        }
-      }
-      return 0;
-    }
+    case 3:
+      return turb_sweeps(c, 1, tA, tb, tx);
     case 4:
       PROF("k_turb_update");
       k_turb_update<<<nblk(c->nnode, 256), 256, 0, c->stream>>>(c->nnode, tx, tvar);
