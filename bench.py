@@ -312,6 +312,13 @@ class RankRun:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
+    def maxi(self, v):
+        if self.world == 1:
+            return int(v)
+        t = self.torch.tensor([v], device=self.dev, dtype=self.torch.int64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return int(t.item())
+
     def total(self, v):
         if self.world == 1:
             return int(v)
@@ -665,6 +672,34 @@ def parity_check(args, mesh, params, q0, rank, world, local_rank, torch, dist, s
         bad = pr.total(sum(0 if v else 1 for v in res.values()))
         out["implicit" if implicit else "explicit"] = {"rank0_bit_exact": res, "mismatching_fields_all_ranks": bad}
         ok = ok and bad == 0
+    # multi-neighbour halos: recursive-coordinate-bisection partitions of one box (udecomp layout, partition.py), every rank
+    # with several peers and corner ghosts -- the same composite iterations through the same exchange
+    from proteuscfd_b200.cases import partitioned_box_case
+    nrcb = 20
+    peers = 0
+    for implicit in (False, True):
+        parts = partitioned_box_case(nrcb, world, cfl=5.0 if implicit else 0.5)
+        _, ref = replay_perfect_gas(lib, parts, implicit, iters=2, nsweeps=3)
+        pr = RankRun(args, parts[rank][0], parts[rank][1], rank, world, local_rank, torch, dist, stream, implicit=implicit)
+        pr.ctx.set_field(capi.F_Q, parts[rank][2])
+        peers = int(np.unique(parts[rank][0]["gNodeOwner"]).size)
+        res = {}
+        for it in range(2):
+            if implicit:
+                pr.implicit(3, True)
+            else:
+                pr.explicit()
+            pr.sync()
+            for k, f in (("qgrad", capi.F_QGRAD), ("limiter", capi.F_LIMITER), ("b", capi.F_B), ("q", capi.F_Q)) + (
+                    (("x", capi.F_X),) if implicit else ()):
+                res[f"{k}{it}"] = eq(pr.ctx.get_field(f), ref[it][k][rank])
+        maxp = pr.maxi(peers)
+        pr.close()
+        bad = pr.total(sum(0 if v else 1 for v in res.values()))
+        out["rcb_implicit" if implicit else "rcb_explicit"] = {"rank0_bit_exact": res, "mismatching_fields_all_ranks": bad}
+        ok = ok and bad == 0
+    out["rcb"] = {"what": f"the same on {world} recursive-coordinate-bisection partitions of an n={nrcb} box (multi-neighbour halos)",
+                  "peers_of_rank0": peers, "max_peers": maxp}
     out["ok"] = ok
     out["seconds"] = time.time() - t0
     return out
