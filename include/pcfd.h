@@ -214,6 +214,9 @@ int pcfd_forces_get(pcfd_ctx* ctx, int which, double* out);
 int pcfd_limiter_raw(pcfd_ctx* ctx);
 /* how many times the fused limiter / residual pair of this context had to fall back to the ordered clip path */
 long long pcfd_clip_fallbacks(const pcfd_ctx* ctx);
+/* nodes whose update pcfd_apply_dq zeroed since creation because a component was NaN / Inf -- what NewtonIterate does
+   before ApplyDQ (solutionSpace.tcc:771-796; the reference prints the count); waits for the stream; -1 on error. (ABI v8) */
+long long pcfd_zeroed_updates(pcfd_ctx* ctx);
 int pcfd_residual_fused(pcfd_ctx* ctx, double* sumsq, int* clip_hit);
 
 /* loop over nnode of EqnSet::ApplyDQ (solutionSpace.tcc:802-804) */

@@ -43,7 +43,7 @@ SYMBOLS = [
     "pcfd_chem_source_term", "pcfd_chem_source_term_device", "pcfd_halo_width", "pcfd_halo_send_total", "pcfd_halo_pack", "pcfd_halo_recv_ptr",
     "pcfd_comm_blob_size", "pcfd_comm_export", "pcfd_comm_connect", "pcfd_comm_disconnect", "pcfd_comm_connected",
     "pcfd_comm_post", "pcfd_comm_wait", "pcfd_comm_update", "pcfd_comm_allgather", "pcfd_comm_debug_flags", "pcfd_gmres",
-    "pcfd_forces_configure", "pcfd_forces_areas", "pcfd_forces_compute", "pcfd_forces_get",
+    "pcfd_forces_configure", "pcfd_forces_areas", "pcfd_forces_compute", "pcfd_forces_get", "pcfd_zeroed_updates",
 ]
 
 
@@ -228,6 +228,8 @@ def load_library(path=LIB_PATH):
     lib.pcfd_comm_allgather.argtypes = [C.c_void_p, _dp, C.c_int, _dp]
     lib.pcfd_turb_phase.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.pcfd_gmres.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp]
+    lib.pcfd_zeroed_updates.argtypes = [C.c_void_p]
+    lib.pcfd_zeroed_updates.restype = C.c_longlong
     lib.pcfd_forces_configure.argtypes = [C.c_void_p, C.POINTER(ForcesDesc)]
     lib.pcfd_forces_areas.argtypes = [C.c_void_p, _dp, _dp]
     lib.pcfd_forces_compute.argtypes = [C.c_void_p, _dp, _dp]
@@ -536,6 +538,10 @@ class Context:
         d = C.c_double()
         self._ck(self.lib.pcfd_gmres(self.h, int(restarts), int(nsearch), int(precond_type), C.byref(d)))
         return d.value
+
+    def zeroed_updates(self):
+        """nodes whose NaN / Inf update apply_dq zeroed (NewtonIterate, solutionSpace.tcc:771-796)"""
+        return int(self.lib.pcfd_zeroed_updates(self.h))
 
     def forces_configure(self, body_offsets, body_factags, moment_pt, moment_axis, bedges_factag, cg, liftdir, dragdir,
                          velocity, num_bcs):

@@ -822,14 +822,21 @@ __global__ void __launch_bounds__(128) kfr_explicit(int nnode, fr::Params<NS> p,
 
 // the ApplyDQ loop of NewtonIterate (solutionSpace.tcc:802-804)
 template <int NS>
-__global__ void __launch_bounds__(128) kfr_apply_dq(int nnode, fr::Params<NS> p, const double* __restrict__ x, double* q) {
+__global__ void __launch_bounds__(128) kfr_apply_dq(int nnode, fr::Params<NS> p, double* __restrict__ x, double* q,
+                                                     int* __restrict__ zeroed) {
   constexpr int NEQ = W<NS>::NEQ, NV = W<NS>::NV;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= nnode) return;
   double Q[NV], dQ[NEQ];
   load_row<NS, NEQ>(q, n, Q);
+  bool bad = false;
 #pragma unroll
-  for (int j = 0; j < NEQ; j++) dQ[j] = x[(size_t)n * NEQ + j];
+  for (int j = 0; j < NEQ; j++) { dQ[j] = x[(size_t)n * NEQ + j]; bad = bad || !isfinite(dQ[j]); }
+  if (bad) {   // solutionSpace.tcc:771-796: the whole update of the node is zeroed, in crs->x as well
+#pragma unroll
+    for (int j = 0; j < NEQ; j++) { dQ[j] = 0.0; x[(size_t)n * NEQ + j] = 0.0; }
+    atomicAdd(zeroed, 1);
+  }
   fr::apply_dq(p, dQ, Q);
   double* out = q + (size_t)n * NV;
 #pragma unroll
@@ -1775,7 +1782,8 @@ struct Impl {
   }
   static int apply_dq(pcfd_ctx* c) {
     PROF("kfr_apply_dq");
-    kfr_apply_dq<NS><<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->nnode, make_params<NS>(c), c->f[PCFD_F_X], c->f[PCFD_F_Q]);
+    kfr_apply_dq<NS><<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->nnode, make_params<NS>(c), c->f[PCFD_F_X], c->f[PCFD_F_Q],
+                                                                c->dzeroed);
     LAUNCH_CHECK();
     return 0;
   }

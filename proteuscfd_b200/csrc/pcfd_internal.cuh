@@ -133,6 +133,7 @@ struct pcfd_ctx {
   double* qmm = nullptr;
   bool qmm_valid = false, use_qmm = true;   // PCFD_LIMITER_QMM=0: k_limiter walks the neighbours itself
   long long clip_fallbacks = 0;
+  int* dzeroed = nullptr;          // nodes whose NaN / Inf update ApplyDQ zeroed (solutionSpace.tcc:771-796), device counter
   int *ia = nullptr, *ja = nullptr, *iau = nullptr, *pv = nullptr, *posLR = nullptr, *posRL = nullptr, *bpos = nullptr;
   int *rows_f = nullptr, *rows_b = nullptr;
   std::vector<int> lev_f, lev_b;   // level offsets into rows_f / rows_b

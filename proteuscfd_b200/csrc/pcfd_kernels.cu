@@ -993,11 +993,21 @@ __global__ void k_explicit(int nnode, double gamma, const double* __restrict__ b
   eq::apply_dq(dq, Q, gamma);
   store_q10(q, n, Q);
 }
-__global__ void k_apply_dq(int nnode, double gamma, const double* __restrict__ x, double* __restrict__ q) {
+// NewtonIterate first zeroes the whole update of a node with a NaN / Inf component, in crs->x as well
+// (solutionSpace.tcc:771-796); zeroed nodes are counted (pcfd_zeroed_updates)
+__global__ void k_apply_dq(int nnode, double gamma, double* __restrict__ x, double* __restrict__ q, int* __restrict__ zeroed) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= nnode) return;
   double dq[5], Q[NVARS];
   load5(x + (size_t)n * 5, dq);
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < 5; j++) bad = bad || !isfinite(dq[j]);
+  if (bad) {
+#pragma unroll
+    for (int j = 0; j < 5; j++) { dq[j] = 0.0; x[(size_t)n * 5 + j] = 0.0; }
+    atomicAdd(zeroed, 1);
+  }
   load_q10(q, n, Q);
   eq::apply_dq(dq, Q, gamma);
   store_q10(q, n, Q);
@@ -2099,9 +2109,13 @@ __global__ void k_turb_wall(const int* __restrict__ wnodes, int nw, const int* _
   for (int k = ia[n]; k < ia[n + 1]; k++) A[k] = 0.0;
   A[iau[n]] = 1.0;
 }
-__global__ void k_turb_invdiag(int nnode, const int* __restrict__ iau, double* A) {
+// ... and the clip of NaN / Inf entries of the right-hand side (turb.tcc:259-276: done when the residual norm is not
+// finite, i.e. when such an entry exists; the norm itself is taken before, as there)
+__global__ void k_turb_invdiag(int nnode, const int* __restrict__ iau, double* A, double* b) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n < nnode) A[iau[n]] = 1.0 / A[iau[n]];
+  if (n >= nnode) return;
+  A[iau[n]] = 1.0 / A[iau[n]];
+  if (!isfinite(b[n])) b[n] = 0.0;
 }
 
 // one level of CRS::SGS for neqn == 1 (crs.tcc:109-113): x = Dinv * (b - sum A_k x_k), ja order
@@ -2168,9 +2182,10 @@ __global__ void __launch_bounds__(256) k_sgs_scalar_sweeps(const int* __restrict
 }
 
 // tvar += x with the clip at zero (turb.tcc:306-320), then mut = rho nu~ fv1 for local and ghost nodes (:324-336)
-__global__ void k_turb_update(int nnode, const double* __restrict__ x, double* tvar) {
+__global__ void k_turb_update(int nnode, double* __restrict__ x, double* tvar) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= nnode) return;
+  if (!isfinite(x[n])) x[n] = 0.0;   // turb.tcc:283-301: NaN / Inf entries of the update are clipped to zero
   double t = tvar[n] + x[n];
   if (t < 0.0) t = 0.0;
   tvar[n] = t;
@@ -2617,6 +2632,8 @@ static int create_impl(const pcfd_mesh_desc* mesh, const pcfd_params* params, in
     if (dev_alloc(c, &c->vflux, (size_t)nedge * 4)) return 1;
     if (dev_alloc(c, &c->bvflux, (size_t)nb * 4)) return 1;
   }
+  if (dev_alloc(c, &c->dzeroed, 4)) return 1;
+  CK(cudaMemset(c->dzeroed, 0, 4 * sizeof(int)));
   if (dev_alloc(c, &c->red, (size_t)RED_BLOCKS * 8)) return 1;
   if (dev_alloc(c, &c->redout, 16)) return 1;
   if (dev_alloc(c, &c->clipflag, (size_t)nedge)) return 1;
@@ -2670,6 +2687,15 @@ int pcfd_set_cfl(pcfd_ctx* c, double cfl) {
   return 0;
 }
 long long pcfd_launch_count(const pcfd_ctx* c) { return c ? c->launches : 0; }
+
+long long pcfd_zeroed_updates(pcfd_ctx* c) {
+  if (!c) return -1;
+  int h = 0;
+  if (cudaSetDevice(c->device) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess ||
+      cudaMemcpy(&h, c->dzeroed, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return -1;
+  return h;
+}
 
 int pcfd_profile_enable(pcfd_ctx* c, int on) {
   if (!c) return 1;
@@ -3260,7 +3286,7 @@ int pcfd_apply_dq(pcfd_ctx* c) {
   if (c->comm) c->comm->ghost_q_fresh = false;
   if (c->fr) return pcfd_fr_apply_dq(c);
   PROF("k_apply_dq");
-  k_apply_dq<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->nnode, c->prm.gamma, c->f[PCFD_F_X], c->f[PCFD_F_Q]);
+  k_apply_dq<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->nnode, c->prm.gamma, c->f[PCFD_F_X], c->f[PCFD_F_Q], c->dzeroed);
   LAUNCH_CHECK();
   return 0;
 }
@@ -3696,7 +3722,7 @@ int pcfd_turb_compute(pcfd_ctx* c, int nsgs, double* sumsq) {
   }
   if (nsgs > 0) {
     PROF("k_turb_invdiag");
-    k_turb_invdiag<<<nblk(c->nnode, 256), 256, 0, c->stream>>>(c->nnode, c->iau, tA);
+    k_turb_invdiag<<<nblk(c->nnode, 256), 256, 0, c->stream>>>(c->nnode, c->iau, tA, tb);
     LAUNCH_CHECK();
     if (turb_sweeps(c, nsgs, tA, tb, tx)) return 1;
   } else {
@@ -3771,7 +3797,7 @@ int pcfd_turb_phase(pcfd_ctx* c, int phase, double* sumsq) {
         CK(cudaMemcpyAsync(sumsq, c->redout, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
       }
       PROF("k_turb_invdiag");
-      k_turb_invdiag<<<nblk(c->nnode, 256), 256, 0, c->stream>>>(c->nnode, c->iau, tA);
+      k_turb_invdiag<<<nblk(c->nnode, 256), 256, 0, c->stream>>>(c->nnode, c->iau, tA, tb);
       LAUNCH_CHECK();
       if (sumsq) CK(cudaStreamSynchronize(c->stream));
       return 0;

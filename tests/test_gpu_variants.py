@@ -246,3 +246,40 @@ def test_turb_phases_equal_turb_compute():
     for a, b, what in zip(res[0][1:], res[1][1:], ("tvar", "mut", "turb_x", "tgrad")):
         exact(b, a, what)
     assert np.abs(res[0][3]).max() > 0
+
+
+@pytest.mark.parametrize("family", ["perfect_gas", "reacting"])
+def test_apply_dq_zeroes_the_update_of_a_node_with_a_non_finite_component(family):
+    """NewtonIterate (solutionSpace.tcc:771-796): a node whose update has a NaN / Inf component gets its WHOLE update
+    zeroed (in crs->x too) before ApplyDQ; the other nodes are updated as usual."""
+    from proteuscfd_b200 import capi
+    if family == "perfect_gas":
+        from tests.test_gpu_parity import golden_ctx
+        ctx, g, meta = golden_ctx("box6_implicit_sgs")
+    else:
+        from tests.test_gpu_fr import fr_ctx
+        ctx, g, meta = fr_ctx("box4_fr_implicit")
+    neqn, nvars = ctx.neqn, ctx.nvars
+    x = g["x"].copy()
+    ctx.set_field(capi.F_Q, g["q0"])
+    ctx.set_field(capi.F_X, x)
+    ctx.apply_dq()
+    qref = ctx.get_field(capi.F_Q).reshape(-1, nvars)
+    assert ctx.zeroed_updates() == 0
+    bad = x.reshape(-1, neqn).copy()
+    bad[3, 1] = np.nan
+    bad[7, neqn - 1] = np.inf
+    ctx.set_field(capi.F_Q, g["q0"])
+    ctx.set_field(capi.F_X, bad.reshape(-1))
+    ctx.apply_dq()
+    q = ctx.get_field(capi.F_Q).reshape(-1, nvars)
+    q0 = g["q0"].reshape(-1, nvars)
+    xs = ctx.get_field(capi.F_X).reshape(-1, neqn)
+    assert ctx.zeroed_updates() == 2
+    for n in (3, 7):
+        assert np.all(xs[n] == 0.0)
+        assert np.array_equal(q[n, :neqn], q0[n, :neqn])
+    keep = np.ones(ctx.nnode, dtype=bool)
+    keep[[3, 7]] = False
+    assert np.array_equal(q[: ctx.nnode][keep], qref[: ctx.nnode][keep])
+    assert np.array_equal(xs[: ctx.nnode][keep], x.reshape(-1, neqn)[: ctx.nnode][keep])
