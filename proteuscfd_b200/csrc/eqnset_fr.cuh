@@ -359,9 +359,10 @@ __device__ __forceinline__ void lu(double* a, int* p) {
   for (int i = 0; i < N; i++) p[i] = i;
   int row = 0;
   for (int i = 0; i < N; i++) {
-    double large = 0.0;
+    double large = 0.0, lmag = 0.0;   // |large| carried explicitly: see k_lu_diag_lanes (nvcc 12.9 drops the abs otherwise)
     for (int j = i; j < N; j++) {
-      if (fabs(a[p[j] * N + i]) > fabs(large)) { large = a[p[j] * N + i]; row = j; }
+      const double v = a[p[j] * N + i], vmag = fabs(v);
+      if (vmag > lmag) { large = v; lmag = vmag; row = j; }
     }
     const int t = p[i]; p[i] = p[row]; p[row] = t;
     large = 1.0 / large;
@@ -590,11 +591,13 @@ __device__ __forceinline__ void wall_solve(const Eigen<NS>& E, const double* Q, 
   int row = 0;   // (only read if a pivot column is entirely zero, i.e. for a singular system)
 #pragma unroll
   for (int i = 0; i < 4; i++) {
-    double large = 0.0;
+    // |large| is carried explicitly: with `fabs(v) > fabs(large)` nvcc 12.9 emitted the second comparison of every pivot
+    // step as DSETP.GT |v|, large -- abs on large dropped (see k_lu_diag_lanes, pcfd_internal.cuh)
+    double large = 0.0, lmag = 0.0;
 #pragma unroll
     for (int j = i; j < 4; j++) {
-      const double v = M[p[j]][i];
-      if (fabs(v) > fabs(large)) { large = v; row = j; }
+      const double v = M[p[j]][i], vmag = fabs(v);
+      if (vmag > lmag) { large = v; lmag = vmag; row = j; }
     }
     const int t = p[i]; p[i] = p[row]; p[row] = t;
     large = 1.0 / large;

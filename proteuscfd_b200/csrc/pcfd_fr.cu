@@ -1404,21 +1404,7 @@ __global__ void __launch_bounds__(64, 8) kfr_jac_node(DevMesh m, fr::Params<NS> 
   fr::temporal_terms(p, Q, vol, cnp1, dt[n], dg, beta[n]);
 }
 
-// CRSMatrix::PrepareSGS (crsmatrix.tcc:840-876) -> LU (matrix.h:110-190)
-template <int NS>
-__global__ void __launch_bounds__(64) kfr_lu_diag(int nnode, const int* __restrict__ iau, double* __restrict__ A,
-                                                   int* __restrict__ pv) {
-  constexpr int NEQ = W<NS>::NEQ, N2 = W<NS>::N2;
-  const int nd = blockIdx.x * blockDim.x + threadIdx.x;
-  if (nd >= nnode) return;
-  double* g = A + (size_t)iau[nd] * N2;
-  double a[N2];
-  int pp[NEQ];
-  for (int k = 0; k < N2; k++) a[k] = g[k];
-  fr::lu<NEQ>(a, pp);
-  for (int k = 0; k < N2; k++) g[k] = a[k];
-  for (int i = 0; i < NEQ; i++) pv[(size_t)nd * NEQ + i] = pp[i];
-}
+// CRSMatrix::PrepareSGS (crsmatrix.tcc:840-876) -> LU (matrix.h:110-190): k_lu_diag_lanes<NEQ> (pcfd_internal.cuh)
 
 // ========================================================================== SGS
 // One level of CRS::SGS (crs.tcc:90-145): NEQ lanes per row (3 rows per warp for 9x9 blocks), lane i owns block-row i,
@@ -1861,7 +1847,9 @@ struct Impl {
   static int prepare_sgs(pcfd_ctx* c) {
     if (c->ludiag) return 0;
     PROF("kfr_lu_diag");
-    kfr_lu_diag<NS><<<nblk(c->nnode, 64), 64, 0, c->stream>>>(c->nnode, c->iau, c->f[PCFD_F_A], c->pv);
+    constexpr int RPW = 32 / Wd::NEQ;
+    k_lu_diag_lanes<Wd::NEQ><<<nblk((long long)((c->nnode + RPW - 1) / RPW) * 32, 128), 128, 0, c->stream>>>(c->nnode, c->iau,
+                                                                                                        c->f[PCFD_F_A], c->pv);
     LAUNCH_CHECK();
     c->ludiag = true;
     return 0;

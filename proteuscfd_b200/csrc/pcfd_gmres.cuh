@@ -52,10 +52,11 @@ __global__ void __launch_bounds__(128) k_gm_precond_build(int nnode, int type, c
   for (int i = 0; i < N; i++) p[i] = i;
   if (type == 2) {
     for (int i = 0; i < N; i++) {
-      double large = 0.0;
+      double large = 0.0, lmag = 0.0;   // |large| carried explicitly: see k_lu_diag_lanes (nvcc 12.9 drops the abs otherwise)
       int row = 0;
       for (int j = i; j < N; j++) {
-        if (fabs(a[p[j] * N + i]) > fabs(large)) { large = a[p[j] * N + i]; row = j; }
+        const double v = a[p[j] * N + i], vmag = fabs(v);
+        if (vmag > lmag) { large = v; lmag = vmag; row = j; }
       }
       const int tmp = p[i]; p[i] = p[row]; p[row] = tmp;
       large = 1.0 / large;

@@ -264,6 +264,80 @@ inline int field_width(const pcfd_ctx* c, int field) {
 
 // ---- the reacting eqnset's side of every phase entry point (pcfd_fr.cu); the C ABI functions in pcfd_kernels.cu
 // forward to these when ctx->fr is set
+// CRSMatrix::PrepareSGS (crsmatrix.tcc:840-876) -> LU (matrix.h:110-190) of every diagonal block, N lanes per node: lane r
+// holds row r of the block in registers (one thread per node kept the N x N block and the dynamically indexed
+// permutation in local memory: 11.8 GB of DRAM traffic for 2.2 GB of 9x9 blocks in the round-1 ncu capture).  The
+// permutation lives as its inverse, one integer per lane (pos: where in p this row stands); the pivot search walks the
+// positions i..N-1 in order with the reference's strict '>' on |a| (first maximum wins, `row` persists when a column is
+// all zero), values fetched by shuffle from the lane that stands at that position; the pivot row is broadcast entry by
+// entry.  Same operations on every entry as the sequential routine, so the factors and pv are bit-identical.
+template <int N>
+__global__ void __launch_bounds__(128) k_lu_diag_lanes(int nnode, const int* __restrict__ iau, double* __restrict__ A,
+                                                        int* __restrict__ pv) {
+  constexpr int RPW = 32 / N;   // nodes per warp
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int grp = lane / N, r = lane - grp * N;
+  const int nd = warp * RPW + grp;
+  const bool live = grp < RPW && nd < nnode;
+  const int base = grp * N;     // first lane of this node's group
+  double a[N];
+  double* g = nullptr;
+  if (live) {
+    g = A + (size_t)iau[nd] * N * N + (size_t)r * N;
+#pragma unroll
+    for (int k = 0; k < N; k++) a[k] = g[k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < N; k++) a[k] = 0.0;
+  }
+  int pos = r;                  // p[pos] == r
+  int row = 0;
+  // Every update below is a select, not a branch: the node groups of a warp take different decisions, and the shuffles
+  // that follow want all lanes in the same static instruction.
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    __syncwarp(full);
+    // the reference's scan over the positions i..N-1: the value of column i is fetched from the lane that stands at
+    // position j (found by ballot); strict '>' on the magnitudes.  |large| is carried next to large: with
+    // `fabs(x) > fabs(large)` nvcc 12.9 emitted the second comparison of every step as DSETP.GT |x|, large -- the abs on
+    // large dropped -- and a negative first candidate lost against any second one (caught by the cube fixture, cuobjdump -sass)
+    const double mine = a[i];
+    double large = 0.0, lmag = 0.0;
+#pragma unroll
+    for (int j = i; j < N; j++) {
+      const unsigned at = __ballot_sync(full, live && pos == j);
+      const int src = __ffs((at >> base) & ((1u << N) - 1u)) - 1;
+      const double x = __shfl_sync(full, mine, base + (src < 0 ? 0 : src));
+      const double xmag = fabs(x);
+      const bool gt = xmag > lmag;
+      large = gt ? x : large;
+      lmag = gt ? xmag : lmag;
+      row = gt ? j : row;
+    }
+    // swap p[i] and p[row]
+    pos = (pos == i) ? row : ((pos == row) ? i : pos);
+    large = 1.0 / large;
+    const unsigned atp = __ballot_sync(full, live && pos == i);
+    const int piv = __ffs((atp >> base) & ((1u << N) - 1u)) - 1;
+    const bool below = pos > i;
+    const double scaled = a[i] * large;
+    a[i] = below ? scaled : a[i];
+#pragma unroll
+    for (int k = i + 1; k < N; k++) {
+      const double pk = __shfl_sync(full, a[k], base + (piv < 0 ? 0 : piv));
+      const double upd = a[k] - a[i] * pk;
+      a[k] = below ? upd : a[k];
+    }
+  }
+  if (live) {
+#pragma unroll
+    for (int k = 0; k < N; k++) g[k] = a[k];
+    pv[(size_t)nd * N + pos] = r;
+  }
+}
+
 int pcfd_internal_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int device, int neqn, int nvars,
                          int nterms, pcfd_ctx** out);
 void pcfd_fr_destroy(pcfd_ctx* c);

@@ -1478,36 +1478,7 @@ __global__ void __launch_bounds__(128) k_jac_diag(DevMesh m, const int* __restri
   for (int k = 0; k < NEQN2; k++) dg[k] = d[k];
 }
 
-// CRSMatrix::PrepareSGS (crsmatrix.tcc:840-876) -> LU (matrix.h:110-190): partial
-// pivoting through a permutation vector, rows are not swapped in memory.
-__global__ void __launch_bounds__(128) k_lu_diag(int nnode, const int* __restrict__ iau, double* __restrict__ A,
-                                                  int* __restrict__ pv) {
-  const int nd = blockIdx.x * blockDim.x + threadIdx.x;
-  if (nd >= nnode) return;
-  double* g = A + (size_t)iau[nd] * NEQN2;
-  double a[NEQN2];
-  int p[NEQN];
-#pragma unroll
-  for (int k = 0; k < NEQN2; k++) a[k] = g[k];
-#pragma unroll
-  for (int i = 0; i < NEQN; i++) p[i] = i;
-  for (int i = 0; i < NEQN; i++) {
-    double large = 0.0;
-    int row = 0;
-    for (int j = i; j < NEQN; j++) {
-      if (fabs(a[p[j] * NEQN + i]) > fabs(large)) { large = a[p[j] * NEQN + i]; row = j; }
-    }
-    const int tmp = p[i]; p[i] = p[row]; p[row] = tmp;
-    large = 1.0 / large;
-    for (int j = i + 1; j < NEQN; j++) a[p[j] * NEQN + i] *= large;
-    for (int j = i + 1; j < NEQN; j++)
-      for (int k = i + 1; k < NEQN; k++) a[p[j] * NEQN + k] -= a[p[j] * NEQN + i] * a[p[i] * NEQN + k];
-  }
-#pragma unroll
-  for (int k = 0; k < NEQN2; k++) g[k] = a[k];
-#pragma unroll
-  for (int i = 0; i < NEQN; i++) pv[(size_t)nd * NEQN + i] = p[i];
-}
+// PrepareSGS: k_lu_diag_lanes<NEQN> (pcfd_internal.cuh)
 
 // ========================================================================== SGS
 // One level of CRS::SGS (crs.tcc:90-145).  NEQN lanes cooperate on one row: lane i
@@ -3368,7 +3339,7 @@ int pcfd_prepare_sgs(pcfd_ctx* c) {
   if (c->fr) return pcfd_fr_prepare_sgs(c);
   if (c->ludiag) return 0;   // CRSMatrix::ludiag (crsmatrix.tcc:844)
   PROF("k_lu_diag");
-  k_lu_diag<<<nblk(c->nnode, 128), 128, 0, c->stream>>>(c->nnode, c->iau, c->f[PCFD_F_A], c->pv);
+  k_lu_diag_lanes<NEQN><<<nblk((long long)((c->nnode + 5) / 6) * 32, 128), 128, 0, c->stream>>>(c->nnode, c->iau, c->f[PCFD_F_A], c->pv);
   LAUNCH_CHECK();
   c->ludiag = true;
   return 0;
