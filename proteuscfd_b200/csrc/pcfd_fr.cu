@@ -1778,7 +1778,7 @@ struct Impl {
     const fr::Params<NS> p = make_params<NS>(c);
     double* A = c->f[PCFD_F_A];
     const double* beta = c->f[PCFD_F_BETA];
-    CK(cudaMemsetAsync(A, 0, c->fsize[PCFD_F_A] * sizeof(double), c->stream));
+    // no memset of A: every block is written in full before anything is added to it (see pcfd_jacobian, pcfd_kernels.cu)
     c->ludiag = false;
     if (c->nedge) {
       if (c->field_jac_type == 1) {

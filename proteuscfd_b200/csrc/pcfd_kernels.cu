@@ -3272,7 +3272,10 @@ int pcfd_jacobian(pcfd_ctx* c) {
   if (c->comm && !c->comm->no_hardset) c->comm->ghost_q_fresh = false;
   if (c->fr) return pcfd_fr_jacobian(c);
   double* A = c->f[PCFD_F_A];
-  CK(cudaMemsetAsync(A, 0, c->fsize[PCFD_F_A] * sizeof(double), c->stream));   // CRSMatrix::Blank
+  // CRSMatrix::Blank: nothing to do.  Every block of A is written in full below -- interior off-diagonals by k_jac_edges,
+  // A(l, ghost) by the ghost half-edges of k_jac_bedges / k_jac_bnodes, diagonals by k_jac_diag -- before anything is
+  // added to it; a memset of the whole matrix (5 GB at 10 M cells: 0.9 ms; 16 GB for 9x9 blocks: 2.7 ms) bought nothing
+  // (tests/test_gpu_variants.py poisons the matrix with NaN before the refresh)
   c->ludiag = false;
   if (c->nedge) {
     if (c->field_jac_type == 1) {

@@ -283,3 +283,39 @@ def test_apply_dq_zeroes_the_update_of_a_node_with_a_non_finite_component(family
     keep[[3, 7]] = False
     assert np.array_equal(q[: ctx.nnode][keep], qref[: ctx.nnode][keep])
     assert np.array_equal(xs[: ctx.nnode][keep], x.reshape(-1, neqn)[: ctx.nnode][keep])
+
+
+@pytest.mark.parametrize("name", ["box6_implicit_sgs", "box6_implicit_central", "box6_ns_implicit", "box6_sa_implicit",
+                                  "box9_3rank_implicit_r1of3", "cube_LowFi"])
+def test_jacobian_overwrites_every_block_perfect_gas(name):
+    """pcfd_jacobian does not blank the matrix first (CRSMatrix::Blank would stream 5-16 GB for nothing): every block is
+    written in full before anything is added to it.  Poison the matrix with NaN, refresh, compare with the reference's A."""
+    from proteuscfd_b200 import capi
+    from tests.test_gpu_parity import golden_ctx
+    ctx, g, meta = golden_ctx(name)
+    ctx.set_jacobian_type(int(meta.get("fieldJacType", 0)), int(meta.get("boundaryJacType", 0)))
+    ctx.set_field(capi.F_Q, g["q0"])
+    ctx.set_field(capi.F_TIMESTEP, g["timestep"])
+    ctx.set_field(capi.F_A, np.full(g["A"].size, np.nan))
+    ctx.jacobian()
+    A = ctx.get_field(capi.F_A)
+    assert np.isfinite(A).all(), f"{int((~np.isfinite(A)).sum())} entries of A were not overwritten"
+    exact(A, g["A"], "A after a refresh on a poisoned matrix")
+
+
+@pytest.mark.parametrize("name", ["box4_fr_implicit", "box4_nsfr_wall", "box4_fr_central"])
+def test_jacobian_overwrites_every_block_reacting(name):
+    from proteuscfd_b200 import capi
+    from tests.test_gpu_fr import fr_ctx
+    ctx, g, meta = fr_ctx(name)
+    ctx.set_jacobian_type(int(meta.get("fieldJacType", 0)), int(meta.get("boundaryJacType", 0)))
+    ctx.set_field(capi.F_Q, g["q0"])
+    ctx.set_field(capi.F_TIMESTEP, g["timestep"])
+    ctx.jacobian()
+    ref = ctx.get_field(capi.F_A).copy()
+    ctx.set_field(capi.F_Q, g["q0"])
+    ctx.set_field(capi.F_A, np.full(ref.size, np.nan))
+    ctx.jacobian()
+    A = ctx.get_field(capi.F_A)
+    assert np.isfinite(A).all(), f"{int((~np.isfinite(A)).sum())} entries of A were not overwritten"
+    exact(A, ref, "A after a refresh on a poisoned matrix")
