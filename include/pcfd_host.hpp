@@ -245,6 +245,29 @@ class DropIn {
     s_->GetScalarField("CL").SetField(f->bodies[1].cl);
     s_->GetScalarField("CM").SetField(f->bodies[1].cm);
   }
+  // The body of SolutionSpace::NewtonIterate as ONE library call each (solutionSpace.tcc:640-904): the phases above in the
+  // reference's order, state resident on the device, halos inside when the ranks are connected.  Returns what the
+  // phase-wise calls return: this rank's sum of b^2 (and, implicit, |xOld - xNorm| of the last two sweeps through ddq).
+  double NewtonIterateExplicit(bool refreshTimesteps) {
+    double ss = 0.0;
+    Check(pcfd_explicit_iterate(ctx_, refreshTimesteps ? 1 : 0, &ss), "NewtonIterate (explicit)");
+    return ss;
+  }
+  double NewtonIterateImplicit(int nSgs, bool refreshJacobian, double* ddq = NULL) {
+    double ss = 0.0, d = 0.0;
+    Check(pcfd_implicit_iterate(ctx_, refreshJacobian ? 1 : 0, nSgs, &ss, &d), "NewtonIterate (implicit)");
+    if (ddq) *ddq = d;
+    return ss;
+  }
+  // CRS::GMRES(restarts, nSearchDir, precondType, ...) (crs.tcc:176-415) on the matrix of ComputeJacobians (not yet
+  // factored by PrepareSGS), b and x of the context; precondType 0 none, 1 diagonal, 2 block diagonal
+  double GMRES(int restarts, int nSearchDir, int precondType) {
+    double dq = 0.0;
+    Check(pcfd_gmres(ctx_, restarts, nSearchDir, precondType, &dq), "CRS::GMRES");
+    return dq;
+  }
+  // nodes whose NaN / Inf update ApplyDQ zeroed so far (solutionSpace.tcc:771-796 prints this count)
+  long long ZeroedUpdates() { return pcfd_zeroed_updates(ctx_); }
   void ExplicitSolve() { Check(pcfd_explicit_solve(ctx_), "ExplicitSolve"); }                              // solve.tcc:71
   void ApplyDQ() { Check(pcfd_apply_dq(ctx_), "ApplyDQ"); }                                                // solutionSpace.tcc:802
 
