@@ -40,6 +40,7 @@ def main():
         ctx.synchronize()
         torch.cuda.profiler.start()
         ctx.jacobian()
+        ctx.prepare_sgs()
         ctx.synchronize()
         torch.cuda.profiler.stop()
         print("profiled launches done; total launches", ctx.launch_count())
