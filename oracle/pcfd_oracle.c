@@ -1418,7 +1418,8 @@ static void lu_solve(const double* a, double* b, const int* p, double* x, int n)
 }
 
 /* CRS::GMRES (crs.tcc:176-415), single rank: restarted GMRES with right preconditioning; Preconditioner / PrecondBackSolve
-   (:555-641) types 0 (none), 1 (diagonal of the diagonal blocks), 2 (block diagonal, LU with the permutation vector).
+   (:555-641) types 0 (none), 1 (diagonal of the diagonal blocks), 2 (block diagonal, LU with the permutation vector),
+   4 (six SGS sweeps on a copy of the matrix, the previous preconditioned vector as the initial guess).
    A is the assembled matrix BEFORE CRSMatrix::PrepareSGS; x holds the initial guess and receives the solution
    ((nnode+gnode)*neqn); returns |g[idir]|, the reference's dqNorm. */
 static void gm_matvec(int nnode, int gnode, int neqn, const int* ia, const int* ja, const double* A, const double* vin, double* vout)
@@ -1456,6 +1457,34 @@ static void gm_precond_solve(int type, int nnode, int neqn, const double* N, con
   }
 }
 
+/* PrecondBackSolve type 4 (crs.tcc:629-632): CRS::SGS(6, N, x, b) on the copy N of A whose diagonal blocks PrepareSGS has
+   factored (crs.tcc:62-173 for any neqn, one rank); x comes in as the initial guess */
+static void gm_sgs(int nnode, int neqn, int nsgs, const int* ia, const int* ja, const int* iau, const double* N, const int* pv,
+		   const double* b, double* x)
+{
+  int isgs, i, j, k, kk, indx, dir, n2 = neqn*neqn;
+  double rhs[ORC_MAX_NEQN], vout[ORC_MAX_NEQN], temp[ORC_MAX_NEQN];
+  for(isgs = 0; isgs < nsgs; isgs++){
+    for(dir = 0; dir < 2; dir++){
+      for(k = 0; k < nnode; k++){
+	i = dir ? (nnode - 1 - k) : k;
+	memcpy(rhs, &b[(size_t)i*neqn], sizeof(double)*neqn);
+	for(indx = ia[i]+1; indx < ia[i+1]; indx++){
+	  const double* a1 = &N[(size_t)indx*n2];
+	  const double* v1 = &x[(size_t)ja[indx]*neqn];
+	  for(j = 0; j < neqn; j++){
+	    vout[j] = a1[j*neqn + 0]*v1[0];
+	    for(kk = 1; kk < neqn; kk++) vout[j] += a1[j*neqn + kk]*v1[kk];
+	  }
+	  for(j = 0; j < neqn; j++) rhs[j] -= vout[j];
+	}
+	lu_solve(&N[(size_t)iau[i]*n2], rhs, &pv[i*neqn], temp, neqn);
+	memcpy(&x[(size_t)i*neqn], rhs, sizeof(double)*neqn);
+      }
+    }
+  }
+}
+
 double orc_gmres(int nnode, int gnode, int neqn, int restarts, int nSearchDir, int precondType, const int* ia,
 		 const int* ja, const int* iau, const double* A, const double* b, double* x)
 {
@@ -1478,6 +1507,13 @@ double orc_gmres(int nnode, int gnode, int neqn, int restarts, int nSearchDir, i
     for(i = 0; i < nnode; i++) memcpy(&N[(size_t)i*n2], &A[(size_t)iau[i]*n2], sizeof(double)*n2);
     if(precondType == 2) for(i = 0; i < nnode; i++) lu(&N[(size_t)i*n2], &pv[i*neqn], neqn);
   }
+  if(precondType == 4){   /* CopyMatrixStructure + PrepareSGS (crs.tcc:577-581): the whole matrix, diagonal blocks factored */
+    size_t nblocks = (size_t)ia[nnode];
+    N = (double*)malloc(sizeof(double)*nblocks*n2);
+    pv = (int*)calloc((size_t)nnode*neqn, sizeof(int));
+    memcpy(N, A, sizeof(double)*nblocks*n2);
+    for(i = 0; i < nnode; i++) lu(&N[(size_t)iau[i]*n2], &pv[i*neqn], neqn);
+  }
   for(irestart = 0; irestart < restarts; irestart++){
     double* v0 = vdat;
     gm_matvec(nnode, gnode, neqn, ia, ja, A, x, v0);
@@ -1493,7 +1529,8 @@ double orc_gmres(int nnode, int gnode, int neqn, int restarts, int nSearchDir, i
     for(idir = 0; idir < nSearchDir; idir++){
       double* vk = vdat + (size_t)idir*vstride;
       Hoffset[idir] = hpos;
-      gm_precond_solve(precondType, nnode, neqn, N, pv, vtemp, vk);
+      if(precondType == 4) gm_sgs(nnode, neqn, 6, ia, ja, iau, N, pv, vk, vtemp);
+      else gm_precond_solve(precondType, nnode, neqn, N, pv, vtemp, vk);
       for(i = 0; i < (int)vstride; i++) uk[i] = 0.0;
       gm_matvec(nnode, gnode, neqn, ia, ja, A, vtemp, uk);
       for(j = 0; j <= idir; j++){
@@ -1540,7 +1577,8 @@ double orc_gmres(int nnode, int gnode, int neqn, int restarts, int nSearchDir, i
       const double* vj = vdat + (size_t)jj*vstride;
       for(ii = 0; ii < nloc; ii++) uk[ii] += (vj[ii]*g[jj]);
     }
-    gm_precond_solve(precondType, nnode, neqn, N, pv, vtemp, uk);
+    if(precondType == 4) gm_sgs(nnode, neqn, 6, ia, ja, iau, N, pv, uk, vtemp);
+    else gm_precond_solve(precondType, nnode, neqn, N, pv, vtemp, uk);
     for(i = 0; i < nloc; i++) x[i] += vtemp[i];
   }
   dqNorm = g[idir-1+1];

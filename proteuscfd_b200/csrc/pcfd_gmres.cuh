@@ -190,14 +190,46 @@ int gmres_impl(pcfd_ctx* c, int restarts, int nSearchDir, int precondType, doubl
   double* xs = uk + vstride;
   double* Nd = xs + vstride;
   double* vtemp = c->f[PCFD_F_X];      // exchangeable: the library's halo applies to it as it is
-  const double* A = c->f[PCFD_F_A];
-  const double* b = c->f[PCFD_F_B];
+  double* const A = c->f[PCFD_F_A];
+  double* const b = c->f[PCFD_F_B];
+  int* const pvA = c->pv;
+  if (precondType == 4) {
+    // Preconditioner type 4 (crs.tcc:577-581): CopyMatrixStructure + PrepareSGS -- a copy of the whole matrix with its
+    // diagonal blocks factored; every application is CRS::SGS(6, N, vtemp, rhs) (:629-632), the previous preconditioned
+    // vector being the initial guess.  The sweeps are the context's own (pcfd_sgs) with its matrix / permutation /
+    // right-hand-side pointers switched to the copy for the duration of the call.
+    const size_t nA = c->fsize[PCFD_F_A];
+    if (c->gm_ncap < nA) {
+      if (c->gm_n) CK(cudaFree(c->gm_n));
+      if (c->gm_npv) CK(cudaFree(c->gm_npv));
+      c->gm_n = nullptr; c->gm_npv = nullptr; c->gm_ncap = 0;
+      CK(cudaMalloc(reinterpret_cast<void**>(&c->gm_n), (nA + 2) * sizeof(double)));
+      CK(cudaMalloc(reinterpret_cast<void**>(&c->gm_npv), (size_t)nnode * N * sizeof(int)));
+      c->gm_ncap = nA;
+    }
+    CK(cudaMemcpyAsync(c->gm_n, A, nA * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    constexpr int RPW = 32 / N;
+    PROF("k_lu_diag");
+    k_lu_diag_lanes<N><<<nblk((long long)((nnode + RPW - 1) / RPW) * 32, 128), 128, 0, c->stream>>>(nnode, c->iau, c->gm_n, c->gm_npv);
+    LAUNCH_CHECK();
+  }
   if (precondType == 1 || precondType == 2) {
     PROF("k_gm_precond_build");
     k_gm_precond_build<N><<<nblk(nnode, 128), 128, 0, c->stream>>>(nnode, precondType, c->iau, A, Nd, c->gm_pv);
     LAUNCH_CHECK();
   }
-  auto precond = [&](const double* rhs, double* out) -> int {   // N out = rhs
+  auto precond = [&](double* rhs, double* out) -> int {   // N out = rhs
+    if (precondType == 4) {   // out is vtemp = field x at both call sites: its halo is the library's
+      c->f[PCFD_F_A] = c->gm_n; c->pv = c->gm_npv; c->f[PCFD_F_B] = rhs;
+      int rc = 0;
+      if (dist) rc = comm_update(c, PCFD_F_X);                     // crs.tcc:88
+      for (int s = 0; s < 6 && !rc; s++) {
+        rc = pcfd_sgs(c, 1, nullptr);
+        if (!rc && dist) rc = comm_update(c, PCFD_F_X);            // crs.tcc:146
+      }
+      c->f[PCFD_F_A] = A; c->pv = pvA; c->f[PCFD_F_B] = b;
+      return rc;
+    }
     if (precondType == 0) {
       CK(cudaMemcpyAsync(out, rhs, (size_t)nloc * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
       return 0;
@@ -217,6 +249,8 @@ int gmres_impl(pcfd_ctx* c, int restarts, int nSearchDir, int precondType, doubl
   // initial guess: x with its ghost rows current (crs.tcc:249), kept in scratch from here on
   if (dist && comm_update(c, PCFD_F_X)) return 1;
   CK(cudaMemcpyAsync(xs, c->f[PCFD_F_X], vstride * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  if (precondType == 4)   // vtemp starts blank (AllocateBlankVector, crs.tcc:216): the first SGS application starts from zero
+    CK(cudaMemsetAsync(vtemp, 0, vstride * sizeof(double), c->stream));
   std::vector<double> g((size_t)nSearchDir + 2, 0.0), Q((size_t)2 * (nSearchDir + 1), 0.0),
       H((size_t)(nSearchDir + 2) * (nSearchDir + 2), 0.0);
   std::vector<int> Hoffset((size_t)nSearchDir + 1, 0);
@@ -277,10 +311,12 @@ int gmres_impl(pcfd_ctx* c, int restarts, int nSearchDir, int precondType, doubl
       if (gm_vec(c, GM_ACCUM, nloc, g[jj], vdat + (size_t)jj * vstride, nullptr, uk)) return 1;
     if (precond(uk, vtemp)) return 1;
     if (gm_vec(c, GM_ADD, nloc, 0.0, vtemp, nullptr, xs)) return 1;
-    if (dist) {   // p->UpdateGeneralVectors(x): through the exchangeable field
+    if (dist) {   // p->UpdateGeneralVectors(x): through the exchangeable field (vtemp, the next SGS guess, kept aside)
+      if (precondType == 4) CK(cudaMemcpyAsync(uk, vtemp, vstride * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
       CK(cudaMemcpyAsync(c->f[PCFD_F_X], xs, vstride * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
       if (comm_update(c, PCFD_F_X)) return 1;
       CK(cudaMemcpyAsync(xs, c->f[PCFD_F_X], vstride * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+      if (precondType == 4) CK(cudaMemcpyAsync(vtemp, uk, vstride * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     }
   }
   CK(cudaMemcpyAsync(c->f[PCFD_F_X], xs, vstride * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
@@ -294,9 +330,9 @@ int gmres_impl(pcfd_ctx* c, int restarts, int nSearchDir, int precondType, doubl
 extern "C" int pcfd_gmres(pcfd_ctx* c, int restarts, int nsearch, int precond_type, double* dq_norm) {
   if (!c) return 1;
   if (restarts < 1 || nsearch < 1 || nsearch > 200) return fail(c, "pcfd_gmres: restarts >= 1, 1 <= search directions <= 200");
-  if (precond_type < 0 || precond_type > 2)
-    return fail(c, "pcfd_gmres: preconditioner 0 (none), 1 (diagonal) or 2 (block diagonal); ILU0 (3) and SGS (4) of "
-                   "crs.tcc:555-590 are not built");
+  if (precond_type < 0 || precond_type > 4 || precond_type == 3)
+    return fail(c, "pcfd_gmres: preconditioner 0 (none), 1 (diagonal), 2 (block diagonal) or 4 (SGS); the local ILU0 (3) of "
+                   "crs.tcc:571-575 is not built");
   CK(cudaSetDevice(c->device));
   if (!c->f[PCFD_F_A]) return fail(c, "pcfd_gmres: no matrix (pcfd_jacobian or pcfd_set_field(PCFD_F_A) first)");
   if (c->ludiag) return fail(c, "pcfd_gmres: the diagonal blocks have been factored in place (pcfd_prepare_sgs); GMRES needs the assembled matrix");

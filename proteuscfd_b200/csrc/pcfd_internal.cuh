@@ -154,6 +154,9 @@ struct pcfd_ctx {
   double* gm_buf = nullptr;
   int* gm_pv = nullptr;
   size_t gm_cap = 0;
+  double* gm_n = nullptr;          // GMRES preconditioner type 4: copy of the matrix with factored diagonal blocks
+  int* gm_npv = nullptr;
+  size_t gm_ncap = 0;
   double sgs_prev_norm = 0.0;   // xNorm of the last-but-one sweep when the sweeps of a solve are separate calls (multi-rank)
   int sgs_unroll = 4;      // blocks in flight per lane in k_sgs_level (PCFD_SGS_UNROLL overrides, for tuning)
   // bulk-copy (TMA) streaming variant: per level, shared-memory bytes for the matrix part of a tile (0: the rows of

@@ -2275,6 +2275,8 @@ int pcfd_destroy(pcfd_ctx* c) {
   for (void* p : c->allocs) cudaFree(p);
   if (c->gm_buf) cudaFree(c->gm_buf);
   if (c->gm_pv) cudaFree(c->gm_pv);
+  if (c->gm_n) cudaFree(c->gm_n);
+  if (c->gm_npv) cudaFree(c->gm_npv);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->hflag) cudaFreeHost(c->hflag);
   if (c->ev_flag) cudaEventDestroy(c->ev_flag);

@@ -2,7 +2,8 @@
 
 CPU: the C restatement (oracle/pcfd_oracle.c: orc_gmres) against the solution the REFERENCE's own CRS::GMRES produced
 (tests/golden/box6_gmres.npz: 5x5 blocks, block-diagonal LU preconditioner, 8 directions, 2 restarts;
-box4_fr_gmres.npz: 9x9 blocks, diagonal preconditioner, 6 directions) -- bit-exact, x and the returned norm.
+box4_fr_gmres.npz: 9x9 blocks, diagonal preconditioner, 6 directions; box6_gmres_sgs / box4_fr_gmres_sgs: the SGS
+preconditioner, six sweeps on a copy of the matrix per application) -- bit-exact, x and the returned norm.
 GPU: pcfd_gmres through the C ABI with the fixture's A and b against the same vectors.  The matrix-vector product,
 the preconditioner and the vector updates keep the reference's arithmetic per entry; the dot products are fixed-tree
 parallel sums instead of the reference's sequential ones, so the bar is the north star's 1e-12 relative (of the largest
@@ -14,7 +15,7 @@ import pytest
 
 from tests.oracle_lib import _d, _i, load_golden, load_oracle
 
-CASES = [("box6_gmres", 5), ("box4_fr_gmres", 9)]
+CASES = [("box6_gmres", 5), ("box4_fr_gmres", 9), ("box6_gmres_sgs", 5), ("box4_fr_gmres_sgs", 9)]
 
 
 def run_oracle(lib, g, meta, neqn, cfg=None, x0=None):
@@ -94,7 +95,7 @@ def test_gpu_gmres_variants_and_errors():
     lib = load_oracle()
     ctx.set_field(capi.F_A, g["A"])
     ctx.set_field(capi.F_B, g["b"])
-    for cfg in ((0, 5, 1), (1, 7, 2), (2, 12, 1)):
+    for cfg in ((0, 5, 1), (1, 7, 2), (2, 12, 1), (4, 3, 2)):
         ref, dq_ref = run_oracle(lib, g, meta, 5, cfg=cfg)
         ctx.blank_x()
         dq = ctx.gmres(cfg[2], cfg[1], cfg[0])
@@ -108,14 +109,15 @@ def test_gpu_gmres_variants_and_errors():
     ctx.gmres(1, 6, 2)
     assert np.abs(ctx.get_field(capi.F_X) - ref).max() <= 1e-11 * np.abs(ref).max()
     with pytest.raises(capi.PcfdError):
-        ctx.gmres(1, 5, 4)              # SGS preconditioner: not built
+        ctx.gmres(1, 5, 3)              # ILU0 preconditioner: not built
     ctx.prepare_sgs()
     with pytest.raises(capi.PcfdError):
         ctx.gmres(1, 5, 2)              # diagonal already factored in place
 
 
 @pytest.mark.gpu
-def test_gpu_gmres_across_ranks_vs_oracle(oracle):
+@pytest.mark.parametrize("cfg", [(3, 20, 2), (3, 8, 4)])
+def test_gpu_gmres_across_ranks_vs_oracle(oracle, cfg):
     """three slabs as thread ranks: the halo of the preconditioned vector before every product (crs.tcc:300) and the
     rank-ordered sums of the dot products through the library exchange.  Checked through the algebra: every rank sees
     the same (global) Hessenberg system, A x = b holds on every rank's rows -- ghost columns included -- to the GMRES
@@ -139,13 +141,18 @@ def test_gpu_gmres_across_ranks_vs_oracle(oracle):
         x.update(capi.F_LIMITER)
         ctx.residual()
         ctx.blank_x()
-        dq = ctx.gmres(3, 20, 2)
+        dq = ctx.gmres(*cfg)
         ia, ja, iau, _ = ctx.get_crs()
         return dict(dq=dq, x=ctx.get_field(capi.F_X), A=ctx.get_field(capi.F_A), b=ctx.get_field(capi.F_B), ia=ia, ja=ja)
 
     # the Krylov scratch is allocated on first use: do that before the ranks connect (a cudaMalloc synchronises the device,
     # which the thread ranks share)
-    got = run_threads(parts, body, prepare=lambda ctx: ctx.gmres(1, 20, 0))
+    def prepare(ctx):
+        ctx.gmres(1, 20, 0)
+        if cfg[2] == 4:
+            ctx.gmres(1, 2, 4)      # the preconditioner's copy of the matrix as well
+
+    got = run_threads(parts, body, prepare=prepare)
     assert len({g["dq"] for g in got}) == 1, "every rank must see the same (global) Hessenberg system"
     from proteuscfd_b200.parallel import build_local_group_maps
     pobjs = build_local_group_maps([(m["gNodeOwner"], m["gNodeLocalId"]) for m, _, _ in parts])
