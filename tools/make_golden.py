@@ -298,10 +298,13 @@ CASES = {
     # CRS::GMRES (crs.tcc:176-415) on the assembled implicit system: block-diagonal (LU) right preconditioner, 8 search
     # directions, 2 restarts (perfect gas 5x5); diagonal preconditioner, 6 directions, 1 restart (reacting 9x9)
     "box6_gmres": lambda: make_case("box6_gmres", mesh=kuhn_box(6, jitter=0.15), nsgs=3, cfl=5.0, gmres=(2, 8, 2)),
-    # SGS-preconditioned GMRES (precondType 4: six sweeps on a copy of the matrix per application, crs.tcc:577-581, 629-632)
-    "box6_gmres_sgs": lambda: make_case("box6_gmres_sgs", mesh=kuhn_box(6, jitter=0.15), nsgs=3, cfl=5.0, gmres=(4, 5, 2)),
+    # SGS-preconditioned GMRES (precondType 4: six sweeps on a copy of the matrix per application, crs.tcc:577-581, 629-632).
+    # Two directions: with this preconditioner the residual is at round-off after two, and every further direction of
+    # the reference's GMRES is normalised round-off (its breakdown test is |h| < 1e-15) -- x then moves by 1e-9 .. 1e-5
+    # with the summation order of a dot product, which pins nothing
+    "box6_gmres_sgs": lambda: make_case("box6_gmres_sgs", mesh=kuhn_box(6, jitter=0.15), nsgs=3, cfl=5.0, gmres=(4, 2, 2)),
     "box4_fr_gmres_sgs": lambda: make_case("box4_fr_gmres_sgs", mesh=kuhn_box(4, jitter=0.15), eqnset="compressibleEulerFR",
-                                           nsgs=3, cfl=5.0, gmres=(4, 4, 1), extra=FR_EXTRA.format(temp=3000, pres=101325, rxn=1)),
+                                           nsgs=3, cfl=5.0, gmres=(4, 2, 1), extra=FR_EXTRA.format(temp=3000, pres=101325, rxn=1)),
     "box4_fr_gmres": lambda: make_case("box4_fr_gmres", mesh=kuhn_box(4, jitter=0.15), eqnset="compressibleEulerFR",
                                        nsgs=3, cfl=5.0, gmres=(1, 6, 1), extra=FR_EXTRA.format(temp=3000, pres=101325, rxn=1)),
     # Forces::Compute / ComputeSurfaceAreas (forces.tcc): pressure and viscous forces, moments, cp / y+ / cf per
