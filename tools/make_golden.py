@@ -303,6 +303,10 @@ CASES = {
     # the reference's GMRES is normalised round-off (its breakdown test is |h| < 1e-15) -- x then moves by 1e-9 .. 1e-5
     # with the summation order of a dot product, which pins nothing
     "box6_gmres_sgs": lambda: make_case("box6_gmres_sgs", mesh=kuhn_box(6, jitter=0.15), nsgs=3, cfl=5.0, gmres=(4, 2, 2)),
+    # the same on two reference ranks: block-Jacobi sweeps with a halo of the iterate after every sweep (crs.tcc:88,146), the
+    # preconditioned vector exchanged before every product (:300), dot products through MPI_Allreduce
+    "box8_2rank_gmres_sgs": lambda: make_case("box8_2rank_gmres_sgs", mesh=kuhn_box(8, jitter=0.15), np_ranks=2,
+                                              part=slab_part(kuhn_box(8, jitter=0.15)[0], 2), nsgs=3, cfl=5.0, gmres=(4, 2, 2)),
     "box4_fr_gmres_sgs": lambda: make_case("box4_fr_gmres_sgs", mesh=kuhn_box(4, jitter=0.15), eqnset="compressibleEulerFR",
                                            nsgs=3, cfl=5.0, gmres=(4, 2, 1), extra=FR_EXTRA.format(temp=3000, pres=101325, rxn=1)),
     "box4_fr_gmres": lambda: make_case("box4_fr_gmres", mesh=kuhn_box(4, jitter=0.15), eqnset="compressibleEulerFR",
