@@ -1774,7 +1774,7 @@ struct Impl {
     return 0;
   }
   static int jacobian(pcfd_ctx* c) {
-    constexpr int EPB = 8, LPE = 2 * Wd::NEQ + 1, BS = Wd::NEQ * 16;
+    constexpr int BS = Wd::NEQ * 16;
     const fr::Params<NS> p = make_params<NS>(c);
     double* A = c->f[PCFD_F_A];
     const double* beta = c->f[PCFD_F_BETA];
