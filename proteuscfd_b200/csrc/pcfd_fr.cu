@@ -31,7 +31,7 @@ struct pcfd_fr_state {
   unsigned char* negflag = nullptr;         // nodes whose raw limiter has a negative component (fused clip test)
 };
 
-// Register caps: measured on B200 at 10 M cells (tools/ab_occ.sh, profiles/r2_ncu_frjac.md).  A cap that doubles the resident
+// Register caps: measured on B200 at 10 M cells (tools/time_frjac.py, profiles/r2_ncu_frjac.md).  A cap that doubles the resident
 // warps pays where a kernel waits on FP64 latency with 8 warps per SM (kfr_jac_bedges 18.6 -> 14.6 ms at 128 registers,
 // kfr_jac_node, kfr_vflux_edges, kfr_vjac_edges, kfr_update_bcs_edges a few per cent); kfr_flux_edges / kfr_clip_edges /
 // kfr_gradient are best left to ptxas' own choice (96 registers: 2.32 ms, 128: 2.22 ms, 212: 3.17 ms for the flux kernel).

@@ -3285,7 +3285,7 @@ int pcfd_jacobian(pcfd_ctx* c) {
       k_jac_edges_central<<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, c->prm.gamma, c->f[PCFD_F_Q], c->posLR, c->posRL, A);
     } else {
       PROF("k_jac_edges");
-      // register cap, measured at 10 M cells (tools/ab_pgjac.sh): 224 registers / 8 warps per SM 13.30 ms, 168: 12.47,
+      // register cap, measured at 10 M cells (tools/time_pgjac.py with PCFD_JAC_MINB): 224 registers / 8 warps per SM 13.30 ms, 168: 12.47,
       // 128 (16 warps): 11.44, 96: 13.44 -- the kernel waits on FP64 latency, not on the pipe
       static const int minb = getenv("PCFD_JAC_MINB") ? atoi(getenv("PCFD_JAC_MINB")) : 4;
       const dim3 g(nblk(c->nedge, 128));
