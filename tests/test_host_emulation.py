@@ -657,3 +657,90 @@ def test_fr_variants_on_a_partition_on_host(emu_fr, oracle, rank):
         for be in range(nb):
             if bpos[be] >= 0:
                 assert np.array_equal(Ae[bpos[be]], A[bpos[be]]), f"A(l, ghost) of half-edge {be} (central={central})"
+
+
+# ------------------------------------------------------------------------------------------------ surface forces
+FORCES_DRIVER = r"""
+extern "C" {
+void emu_forces(const emu_mesh* m, double gamma, double Re, double Pr, double PrT, double tref, double mach, double V,
+                int viscous, const double* q, const double* qgrad, const int* ia, const int* ja, double* props,
+                double* terms, double* cp, double* yp, double* cf) {
+  DevMesh d = dev(m);
+  eq::ViscParams vp{gamma, Re, Pr, PrT, tref, mach};
+  FOR_THREADS(m->nbedge) k_surface_props(d, vp, gamma, V, viscous != 0, q, props);
+  FOR_THREADS(m->nbedge) k_forces_bedges(d, props, qgrad, NTERMS * 3, 3, viscous ? Re / mach : 1.0, V, viscous != 0, ia, ja,
+                                         terms, cp, yp, cf);
+}
+}
+"""
+
+
+@pytest.fixture(scope="module")
+def emu_forces(tmp_path_factory):
+    work = tmp_path_factory.mktemp("host_emul_forces")
+    internal = open(os.path.join(CSRC, "pcfd_internal.cuh")).read()
+    forces = open(os.path.join(CSRC, "pcfd_forces.cuh")).read()
+    parts = [PRELUDE]
+    for n in ("struct DevMesh", "is_ghost", "load_avec"):
+        parts.append(extract(internal, n))
+    for n in ("k_surface_props", "stress_vector", "k_forces_bedges"):
+        parts.append(extract(forces, n))
+    # the emu_mesh / dev() / FOR_THREADS part of the common driver, then the forces entry
+    head = DRIVER[: DRIVER.index("void emu_gradient")] + "}\n"
+    parts.append(head)
+    parts.append(FORCES_DRIVER)
+    cpp = work / "emul_forces.cpp"
+    cpp.write_text("".join(parts))
+    so = work / "libemul_forces.so"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-I", CSRC,
+                           "-I", os.path.join(ROOT, "include"), "-o", str(so), str(cpp)])
+    return C.CDLL(str(so))
+
+
+def test_forces_kernels_on_host_vs_reference_dump(emu_forces):
+    """k_surface_props + k_forces_bedges (csrc/pcfd_forces.cuh), executed from their source text on the host, against the
+    reference's own Forces::Compute (tests/golden/box6_ns_forces.npz).  With glibc's pow behind Sutherland's law on both
+    sides: cp, y+, cf bit-exact, and the per-half-edge force terms summed in half-edge order reproduce the reference's body
+    sums bit for bit (on the GPU that sum is a tree: tests/test_gpu_forces.py)."""
+    from tests.oracle_lib import bodies_from_fixture, load_golden
+    g, meta = load_golden("box6_ns_forces")
+    mesh = {k: g[k] for k in ("edges_n", "edges_a", "bedges_n", "bedges_a", "bedges_bctype", "xyz", "vol")}
+    for k in ("nnode", "gnode", "nbnode", "nedge", "nbedge", "ngedge"):
+        mesh[k] = int(meta[k])
+    m, keep = build_mesh(mesh)
+    nbe = mesh["nbedge"]
+    q, qgrad = np.ascontiguousarray(g["forces_q"]), np.ascontiguousarray(g["forces_qgrad"])
+    ia, ja = np.ascontiguousarray(g["ia"], dtype=np.int32), np.ascontiguousarray(g["ja"], dtype=np.int32)
+    props, terms = np.zeros(4 * nbe), np.zeros(6 * nbe)
+    cp, yp, cf = np.zeros(nbe), np.zeros(nbe), np.zeros(nbe)
+    V = float(meta["velocity"])
+    emu_forces.emu_forces(C.byref(m), C.c_double(meta["gamma"]), C.c_double(meta["Re"]), C.c_double(meta["Pr"]),
+                          C.c_double(meta["PrT"]), C.c_double(meta["ref_temperature"]), C.c_double(V), C.c_double(V), 1,
+                          _p(q), _p(qgrad), _p(ia), _p(ja), _p(props), _p(terms), _p(cp), _p(yp), _p(cf))
+    assert np.array_equal(cp, g["forces_cp"]), "cp"
+    assert np.array_equal(yp, g["forces_yp"]), "y+"
+    assert np.array_equal(cf, g["forces_cf"]), "cf"
+    assert np.abs(yp).max() > 0
+    # FORCE_Kernel's sequential += over the half-edges of each body
+    offs, tags, mpt, _ = bodies_from_fixture(g)
+    ref = g["forces_body"].reshape(-1, 18)
+    T = terms.reshape(-1, 6)
+    right = keep["ben"][:nbe, 1]
+    cg = g["forces_cg"].reshape(-1, 3)
+    for b in range(offs.size - 1):
+        mine = set(int(t) for t in tags[offs[b]: offs[b + 1]])
+        acc = np.zeros(12)
+        noslip = g["bedges_bctype"][:nbe] == 4
+        for e in range(nbe):
+            if int(g["bedges_factag"][e]) not in mine:
+                continue
+            r = cg[right[e]] - mpt[3 * b: 3 * b + 3]
+            for s in range(2):
+                if s == 1 and not noslip[e]:
+                    continue
+                f = T[e, 3 * s: 3 * s + 3]
+                acc[3 * s: 3 * s + 3] += f
+                acc[6 + 3 * s] += r[1] * f[2] - f[1] * r[2]
+                acc[6 + 3 * s + 1] += r[2] * f[0] - f[2] * r[0]
+                acc[6 + 3 * s + 2] += r[0] * f[1] - f[0] * r[1]
+        assert np.array_equal(acc, ref[b, :12]), f"body {b}: {acc - ref[b, :12]}"
