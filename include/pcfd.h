@@ -206,6 +206,13 @@ int pcfd_forces_areas(pcfd_ctx* ctx, double* surf_area, double* body_area);
 int pcfd_forces_compute(pcfd_ctx* ctx, double* body, double* coef);
 int pcfd_forces_get(pcfd_ctx* ctx, int which, double* out);
 
+/* ComputeWallDistOct (ucs/walldist.tcc:116-199): fills field PCFD_F_WALLDIST [nnode+gnode] with the distance of every
+   local node to the nearest of `points` [npoints*3] -- the viscous wall nodes of ALL ranks (the left nodes of the no-slip
+   half-edges; the reference gathers them with MPI, walldist.tcc:24-113, and so does the host here).  Exact search with the
+   reference's `Distance` arithmetic: equals the reference's field wherever its octree returns the true nearest node.
+   npoints == 0: +inf everywhere.  Needs a context with that field (turbulence model or viscous far-field BC).  (ABI v8) */
+int pcfd_wall_distance(pcfd_ctx* ctx, const double* points, int npoints);
+
 /* Limiter::Compute + ComputeResiduals in two halves for multi-rank hosts (all eqnsets).  pcfd_limiter_raw runs
    passes 1+2 of Limiter::Compute (limiters.tcc:53-110) and leaves the UNCLAMPED limiter in field PCFD_F_LIMITER; the
    host exchanges that field (limiters.tcc:128); pcfd_residual_fused then clamps it (:118-125), evaluates the residual

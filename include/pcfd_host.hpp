@@ -194,6 +194,38 @@ class DropIn {
     double* dst = s_->GetFieldData("mut", FIELDS::STATE_NONE);
     for (int i = 0; i < nnode_ + gnode_; i++) dst[i] = mut[i];
   }
+  // ComputeWallDistOct (walldist.tcc:116-199; SolutionSpace::Init for viscous runs): the field "wallDistance" from an exact
+  // search on the device.  The viscous wall nodes -- left nodes of the no-slip half-edges, half-edge order -- of all ranks
+  // are gathered with the host's MPI as SyncParallelPoint does (walldist.tcc:24-113).
+  void ComputeWallDistance() {
+    auto* m = s_->m;
+    std::vector<double> pts;
+    for (int e = 0; e < m->GetNumBoundaryEdges(); e++) {
+      if (s_->bc->GetBCType(m->bedges[e].factag) != Proteus_NoSlip) continue;
+      const int l = m->bedges[e].n[0];
+      for (int k = 0; k < 3; k++) pts.push_back(m->xyz[l * 3 + k]);
+    }
+#ifndef PCFD_HOST_NO_MPI
+    int np = 1;
+    MPI_Comm_size(MPI_COMM_WORLD, &np);
+    if (np > 1) {
+      // (MPI_Allgather on padded blocks: the reference itself uses no MPI_Allgatherv, nor does the test shim provide one)
+      int mine = (int)pts.size(), maxc = 0;
+      std::vector<int> counts(np);
+      MPI_Allgather(&mine, 1, MPI_INT, &counts[0], 1, MPI_INT, MPI_COMM_WORLD);
+      for (int r = 0; r < np; r++) maxc = std::max(maxc, counts[r]);
+      std::vector<double> padded((size_t)std::max(maxc, 1), 0.0), blocks((size_t)std::max(maxc, 1) * np), all;
+      std::copy(pts.begin(), pts.end(), padded.begin());
+      MPI_Allgather(&padded[0], std::max(maxc, 1), MPI_DOUBLE, &blocks[0], std::max(maxc, 1), MPI_DOUBLE, MPI_COMM_WORLD);
+      for (int r = 0; r < np; r++)
+        all.insert(all.end(), blocks.begin() + (size_t)r * std::max(maxc, 1), blocks.begin() + (size_t)r * std::max(maxc, 1) + counts[r]);
+      pts.swap(all);
+    }
+#endif
+    Check(pcfd_wall_distance(ctx_, pts.empty() ? NULL : &pts[0], (int)(pts.size() / 3)), "ComputeWallDistOct");
+    Check(pcfd_get_field(ctx_, PCFD_F_WALLDIST, s_->GetFieldData("wallDistance", FIELDS::STATE_NONE),
+                         (size_t)(nnode_ + gnode_)), "pull wallDistance");
+  }
   // Forces::Compute (forces.tcc:315-324, called at solutionSpace.tcc:884, 924) on the device-resident q and qgrad: body
   // sums, coefficients and the per-half-edge cp / y+ / cf land where the reference keeps them (Forces::bodies, cp, yp, cf;
   // scalar fields CL / CM).  The bodies, Param::liftdir / dragdir and Mesh::cg are handed over on the first call

@@ -44,6 +44,7 @@ SYMBOLS = [
     "pcfd_comm_blob_size", "pcfd_comm_export", "pcfd_comm_connect", "pcfd_comm_disconnect", "pcfd_comm_connected",
     "pcfd_comm_post", "pcfd_comm_wait", "pcfd_comm_update", "pcfd_comm_allgather", "pcfd_comm_debug_flags", "pcfd_gmres",
     "pcfd_forces_configure", "pcfd_forces_areas", "pcfd_forces_compute", "pcfd_forces_get", "pcfd_zeroed_updates",
+    "pcfd_wall_distance",
 ]
 
 
@@ -228,6 +229,7 @@ def load_library(path=LIB_PATH):
     lib.pcfd_comm_allgather.argtypes = [C.c_void_p, _dp, C.c_int, _dp]
     lib.pcfd_turb_phase.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.pcfd_gmres.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp]
+    lib.pcfd_wall_distance.argtypes = [C.c_void_p, _dp, C.c_int]
     lib.pcfd_zeroed_updates.argtypes = [C.c_void_p]
     lib.pcfd_zeroed_updates.restype = C.c_longlong
     lib.pcfd_forces_configure.argtypes = [C.c_void_p, C.POINTER(ForcesDesc)]
@@ -538,6 +540,12 @@ class Context:
         d = C.c_double()
         self._ck(self.lib.pcfd_gmres(self.h, int(restarts), int(nsearch), int(precond_type), C.byref(d)))
         return d.value
+
+    def wall_distance(self, points):
+        """ComputeWallDistOct: field F_WALLDIST = distance of every local node to the nearest of `points` [n, 3] (the viscous
+        wall nodes of all ranks)"""
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        self._ck(self.lib.pcfd_wall_distance(self.h, pts.ctypes.data_as(_dp), int(pts.shape[0])))
 
     def zeroed_updates(self):
         """nodes whose NaN / Inf update apply_dq zeroed (NewtonIterate, solutionSpace.tcc:771-796)"""

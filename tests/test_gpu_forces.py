@@ -105,3 +105,28 @@ def test_forces_need_configuration():
     with pytest.raises(capi.PcfdError, match="pcfd_forces_configure has not been called"):
         ctx._forces_shape = (1, 1)
         ctx.forces_compute()
+
+
+def test_wall_distance_on_the_device_vs_reference_field():
+    """pcfd_wall_distance (ComputeWallDistOct, ucs/walldist.tcc:116-199) against the `wallDistance` field of the reference's
+    Spalart-Allmaras fixture, bit-exact, and against the torch search of walldist.py on a larger seeded box"""
+    from proteuscfd_b200 import capi
+    from proteuscfd_b200.cases import NS_BC, box_case
+    from proteuscfd_b200.walldist import wall_distance, wall_points
+    from tests.test_gpu_parity import golden_ctx
+    ctx, g, meta = golden_ctx("box6_sa_implicit")
+    mesh = {k: g[k] for k in ("bedges_n", "bedges_bctype", "xyz")}
+    for k in ("nnode", "gnode", "nbedge", "ngedge"):
+        mesh[k] = int(meta[k])
+    ctx.wall_distance(wall_points(mesh))
+    nn = mesh["nnode"] + mesh["gnode"]
+    exact(ctx.get_field(capi.F_WALLDIST)[:nn], g["wallDistance"][:nn], "wallDistance")
+    mesh2, params2, q2 = box_case(20, cfl=5.0, colored=True, viscous=True, turb=True, bc=dict(NS_BC))
+    ctx2 = capi.Context(mesh2, params2)
+    ctx2.wall_distance(wall_points(mesh2))
+    exact(ctx2.get_field(capi.F_WALLDIST)[: mesh2["nnode"]], wall_distance(mesh2)[: mesh2["nnode"]], "wallDistance, n = 20")
+    ctx2.wall_distance(np.zeros((0, 3)))
+    assert np.isinf(ctx2.get_field(capi.F_WALLDIST)).all()
+    ctx3, _, _ = golden_ctx("box6_implicit_sgs")
+    with pytest.raises(capi.PcfdError, match="no wall-distance field"):
+        ctx3.wall_distance(np.zeros((1, 3)))

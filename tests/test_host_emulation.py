@@ -744,3 +744,34 @@ def test_forces_kernels_on_host_vs_reference_dump(emu_forces):
                 acc[6 + 3 * s + 1] += r[2] * f[0] - f[2] * r[0]
                 acc[6 + 3 * s + 2] += r[0] * f[1] - f[0] * r[1]
         assert np.array_equal(acc, ref[b, :12]), f"body {b}: {acc - ref[b, :12]}"
+
+
+def test_wall_distance_kernel_on_host_vs_reference_field(tmp_path):
+    """k_wall_distance (csrc/pcfd_forces.cuh) from its source text on the host against the `wallDistance` field the reference's
+    octree search produced for its Spalart-Allmaras fixture (ComputeWallDistOct, ucs/walldist.tcc:116-199): bit-exact."""
+    from proteuscfd_b200.walldist import wall_points
+    from tests.oracle_lib import load_golden
+    forces = open(os.path.join(CSRC, "pcfd_forces.cuh")).read()
+    src = PRELUDE + extract(forces, "k_wall_distance") + r"""
+extern "C" void emu_wall_distance(int nn, const double* xyz, int npts, const double* pts, double* dist) {
+  for (blockIdx.x = 0; blockIdx.x < (unsigned)nn; blockIdx.x++) k_wall_distance(nn, xyz, npts, pts, dist);
+}
+"""
+    cpp = tmp_path / "emul_wd.cpp"
+    cpp.write_text(src)
+    so = tmp_path / "libemul_wd.so"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-I", CSRC,
+                           "-I", os.path.join(ROOT, "include"), "-o", str(so), str(cpp)])
+    lib = C.CDLL(str(so))
+    g, meta = load_golden("box6_sa_implicit")
+    mesh = {k: g[k] for k in ("bedges_n", "bedges_bctype", "xyz")}
+    for k in ("nnode", "gnode", "nbedge", "ngedge"):
+        mesh[k] = int(meta[k])
+    pts = wall_points(mesh)
+    nn = mesh["nnode"] + mesh["gnode"]
+    xyz = np.ascontiguousarray(g["xyz"][: 3 * nn])
+    out = np.zeros(nn)
+    lib.emu_wall_distance(nn, _p(xyz), int(pts.shape[0]), _p(np.ascontiguousarray(pts)), _p(out))
+    assert np.array_equal(out, g["wallDistance"][:nn])
+    lib.emu_wall_distance(nn, _p(xyz), 0, _p(np.zeros(3)), _p(out))
+    assert np.isinf(out).all()
