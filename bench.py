@@ -737,10 +737,18 @@ def implicit_bench(args, rank, world, local_rank, peak, torch, dist, stream, kin
     r = RankRun(args, mesh, params, rank, world, local_rank, torch, dist, stream, implicit=True)
     c = r.ctx
     if turb:
+        # ComputeWallDistOct on the device (pcfd_wall_distance): every rank's viscous wall nodes, gathered like
+        # SyncParallelPoint does, against every local node
         from proteuscfd_b200.parallel import TorchGroup
-        from proteuscfd_b200.walldist import wall_distance
-        wd = wall_distance(mesh, group=TorchGroup(dist) if world > 1 else None, device=f"cuda:{local_rank}")
-        c.set_field(capi.F_WALLDIST, wd)
+        from proteuscfd_b200.walldist import wall_points
+        pts = wall_points(mesh)
+        if world > 1:
+            pts = np.concatenate([np.asarray(p_, dtype=np.float64).reshape(-1, 3) for p_ in TorchGroup(dist).allgather(pts)])
+        t_wd = time.time()
+        c.wall_distance(pts)
+        c.synchronize()
+        wall_distance_info = {"ms": (time.time() - t_wd) * 1e3, "wall_points": int(pts.shape[0]),
+                              "what": "pcfd_wall_distance: exact search, every local node against every viscous wall node of every rank (set-up, once per mesh; wall clock incl. the upload of the points)"}
         tv = np.full(c.field_size(capi.F_TVAR), 1.341946)      # nu~ of the free stream (spalart.tcc:79)
         c.set_field(capi.F_TVAR, tv)
     c.set_field(capi.F_Q, q)
@@ -801,6 +809,8 @@ def implicit_bench(args, rank, world, local_rank, peak, torch, dist, stream, kin
            "state_finite_after_run": finite, "clip_fallbacks": r.clip_fallbacks(),
            "kernels_ms_rank0": {k: v[0] / max(v[1], 1) for k, v in tab.items()},
            "kernel": "k_sgs_tile (cp.async.bulk + mbarrier streamed tiles, PDL-chained levels)" if "k_sgs_tile" in tab else "k_sgs_level"}
+    if turb:
+        out["wall_distance"] = wall_distance_info
     if kind == "euler":
         # CRS::GMRES (10 directions, block-diagonal LU right preconditioner) on the freshly assembled system
         try:
