@@ -39,6 +39,7 @@ static inline double2 make_double2(double a, double b) { double2 r; r.x = a; r.y
 #define __launch_bounds__(...)
 template <class T> static inline T __ldg(const T* p) { return *p; }
 using std::isnan;
+using std::isfinite;
 #define __noinline__
 static inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, sizeof d); return d; }
 static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }   // explicit, exact on both sides
@@ -775,3 +776,109 @@ extern "C" void emu_wall_distance(int nn, const double* xyz, int npts, const dou
     assert np.array_equal(out, g["wallDistance"][:nn])
     lib.emu_wall_distance(nn, _p(xyz), 0, _p(np.zeros(3)), _p(out))
     assert np.isinf(out).all()
+
+
+# ------------------------------------------------------------------------------------------------ Spalart-Allmaras
+SA_DRIVER = r"""
+extern "C" {
+// TurbulenceModel::Compute as pcfd_turb_compute runs it (perfect gas): the kernels in the library's order; the scalar
+// Gauss-Seidel sweeps are walked row by row here (for any numbering the level schedule of the library equals that order)
+void emu_turb_sa(const emu_mesh* m, double gamma, double Re, double Pr, double PrT, double tref, double mach, int nsgs,
+                 const double* q, const double* qgrad, const double* s, const double* dist, const double* dt,
+                 const int* ia, const int* ja, const int* iau, const int* posLR, const int* posRL, const int* bpos,
+                 const int* tbnodes, int ntb, const int* wnodes, int nw, double* tvar, double* tgrad, double* b, double* A,
+                 double* x, double* mut, double* slots, double* bslots) {
+  DevMesh d = dev(m);
+  eq::ViscParams vp{gamma, Re, Pr, PrT, tref, mach};
+  TurbGas g;
+  g.Re = Re / mach; g.gstride = NTERMS * 3; g.goff = 3; g.pe = g.pb = g.pn = 0;
+  const int nn = m->nnode + m->gnode, nb = m->nbedge + m->ngedge;
+  for (int k = 0; k < ia[m->nnode]; k++) A[k] = 0.0;
+  for (int k = 0; k < nn; k++) x[k] = 0.0;
+  FOR_THREADS(ntb) k_turb_bcs(d, tbnodes, ntb, tvar);
+  FOR_THREADS(m->nnode) k_turb_gradient(d, tvar, s, tgrad);
+  FOR_THREADS(m->nedge) k_turb_edges<false>(d, vp, g, q, tvar, tgrad, posLR, posRL, slots, A);
+  FOR_THREADS(nb) k_turb_bedges<false>(d, vp, g, q, tvar, tgrad, bpos, bslots, A);
+  FOR_THREADS(m->nnode) k_turb_node<false>(d, vp, g, q, qgrad, tvar, dist, dt, slots, bslots, iau, posLR, posRL, b, A);
+  FOR_THREADS(nw) k_turb_wall(wnodes, nw, ia, iau, b, x, A);
+  FOR_THREADS(m->nnode) k_turb_invdiag(m->nnode, iau, A, b);
+  for (int sweep = 0; sweep < nsgs; sweep++)
+    for (int dir = 0; dir < 2; dir++)
+      for (int kk = 0; kk < m->nnode; kk++) {
+        const int row = dir ? m->nnode - 1 - kk : kk;
+        double rhs = b[row];
+        for (int k = ia[row] + 1; k < ia[row + 1]; k++) { const double vout = A[k] * x[ja[k]]; rhs -= vout; }
+        x[row] = A[ia[row]] * rhs;
+      }
+  FOR_THREADS(m->nnode) k_turb_update(m->nnode, x, tvar);
+  FOR_THREADS(nn) k_turb_mut<false>(nn, vp, g, q, tvar, mut);
+}
+}
+"""
+
+
+def test_spalart_allmaras_kernels_on_host_vs_reference_dump(tmp_path):
+    """The Spalart-Allmaras kernels of pcfd_kernels.cu (k_turb_*: BCs, unweighted LSQ gradient, convective / diffusive edge
+    terms, node assembly with the source term, wall rows, eddy viscosity), executed from their source text on the host in
+    the library's order, against the reference's own TurbulenceModel::Compute (tests/golden/box6_sa_implicit.npz).  With
+    glibc's exp / pow on both sides tgrad, b, A, x and nu~ are bit-exact, mu_t to the last bit (on the GPU: 1e-12,
+    tests/test_gpu_viscous.py)."""
+    from tests.oracle_lib import load_golden
+    internal = open(os.path.join(CSRC, "pcfd_internal.cuh")).read()
+    kernels = open(os.path.join(CSRC, "pcfd_kernels.cu")).read()
+    parts = [PRELUDE]
+    for n in ("struct DevMesh", "is_ghost", "load_avec", "lsq_weights"):
+        parts.append(extract(internal, n))
+    for n in ("load_q5", "load_q10"):
+        parts.append(extract(kernels, n))
+    i0 = kernels.index("namespace sa {")
+    parts.append(kernels[i0: kernels.index("}  // namespace sa", i0) + len("}  // namespace sa")] + "\n")
+    for n in ("k_turb_bcs", "k_turb_gradient", "struct TurbGas", "k_turb_edges", "k_turb_bedges", "k_turb_node", "k_turb_wall",
+              "k_turb_invdiag", "k_turb_update", "k_turb_mut"):
+        parts.append(extract(kernels, n))
+    parts.append(DRIVER[: DRIVER.index("void emu_gradient")] + "}\n")
+    parts.append(SA_DRIVER)
+    cpp = tmp_path / "emul_sa.cpp"
+    cpp.write_text("".join(parts))
+    so = tmp_path / "libemul_sa.so"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-I", CSRC,
+                           "-I", os.path.join(ROOT, "include"), "-o", str(so), str(cpp)])
+    lib = C.CDLL(str(so))
+    g, meta = load_golden("box6_sa_implicit")
+    mesh = {k: g[k] for k in ("edges_n", "edges_a", "bedges_n", "bedges_a", "bedges_bctype", "xyz", "vol")}
+    for k in ("nnode", "gnode", "nbnode", "nedge", "nbedge", "ngedge"):
+        mesh[k] = int(meta[k])
+    m, keep = build_mesh(mesh)
+    nnode, nedge, nb = mesh["nnode"], mesh["nedge"], mesh["nbedge"] + mesh["ngedge"]
+    ia, ja, iau = (np.ascontiguousarray(g[k], dtype=np.int32) for k in ("ia", "ja", "iau"))
+
+    def pos(row, col):
+        return ia[row] + int(np.nonzero(ja[ia[row]: ia[row + 1]] == col)[0][0])
+    en, ben = keep["en"], keep["ben"]
+    posLR = np.array([pos(l, r) for l, r in en], dtype=np.int32)
+    posRL = np.array([pos(r, l) for l, r in en], dtype=np.int32)
+    bpos = np.full(nb, -1, dtype=np.int32)
+    bct = g["bedges_bctype"][:nb]
+    tbnodes = np.unique(ben[bct != 0, 0]).astype(np.int32)
+    wnodes = np.unique(ben[bct == 4, 0]).astype(np.int32)
+    tvar = g["turb_tvar0"].copy()
+    nn = nnode + mesh["gnode"]
+    tgrad, b, A, x, mut = np.zeros(nn * 3), np.zeros(nnode), np.zeros(ja.size), np.zeros(nn), np.zeros(nn)
+    slots, bslots = np.zeros(nedge * 3), np.zeros(nb * 4)
+    lib.emu_turb_sa(C.byref(m), C.c_double(meta["gamma"]), C.c_double(meta["Re"]), C.c_double(meta["Pr"]), C.c_double(meta["PrT"]),
+                    C.c_double(meta["ref_temperature"]), C.c_double(meta["velocity"]), int(meta["nSgs"]),
+                    _p(np.ascontiguousarray(g["turb_q"])), _p(np.ascontiguousarray(g["turb_qgrad"])),
+                    _p(np.ascontiguousarray(g["lsq_s"])), _p(np.ascontiguousarray(g["wallDistance"])),
+                    _p(np.ascontiguousarray(g["turb_dt"])), _p(ia), _p(ja), _p(iau), _p(posLR), _p(posRL), _p(bpos),
+                    _p(tbnodes), int(tbnodes.size), _p(wnodes), int(wnodes.size), _p(tvar), _p(tgrad), _p(b), _p(A), _p(x),
+                    _p(mut), _p(slots), _p(bslots))
+    for name, arr in (("tgrad", tgrad), ("b", b), ("A", A), ("x", x)):
+        ref = g["turb_" + name]
+        assert np.array_equal(arr[: ref.size], ref), f"turb {name}: max diff {np.abs(arr[: ref.size] - ref).max():.3e}"
+    # the library's Sutherland law forms T^1.5 as T * sqrt(T) (eq::pow15), the reference calls pow(T, 1.5): the last bit
+    # of the molecular viscosity may differ, and with it the last bit of mu_t
+    ref = g["turb_mut"]
+    print("mu_t entries that differ in the last bit:", int((mut[: ref.size] != ref).sum()), "of", ref.size)
+    assert np.all(np.abs(mut[: ref.size] - ref) <= 1.0e-14 * np.abs(ref))      # fv1 = chi^3 / (chi^3 + cv1^3) amplifies it ~4x
+    assert np.array_equal(tvar, g["turb_tvar1"])
+    assert np.abs(g["turb_x"]).max() > 0
