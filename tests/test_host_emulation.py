@@ -306,6 +306,30 @@ static fr::Params<5> params(const pcfd_fr_params* h, double chi, double cfl, int
   for (int i = 0; i < 21; i++) p.qinf[i] = h->qinf[i];
   return p;
 }
+// HLLCFlux as the residual kernels call it (the composition of hllc_side_thermo / hllc_roe_c2 / hllc_assemble), and the same
+// flux put together the way kfr_jac_edges does for a perturbed left state: the right state's and -- for a velocity
+// perturbation -- every thermodynamic piece taken from the UNPERTURBED evaluation
+void emu_fr_flux(const pcfd_fr_params* h, const double* QL, const double* QR, const double* av, double vdotn, double beta,
+                 double* flux) {
+  fr::Params<5> p = params(h, 0.0, 1.0, 0, 2, 2);
+  fr::numerical_flux<5>(p, QL, QR, av, vdotn, beta, flux);
+}
+void emu_fr_flux_shared(const pcfd_fr_params* h, const double* QL0, const double* QR0, int column, double hstep, const double* av,
+                        double beta, double* direct, double* shared) {
+  fr::Params<5> p = params(h, 0.0, 1.0, 0, 2, 2);
+  double QL[11], QR[11], QP[11];
+  for (int k = 0; k < 11; k++) { QL[k] = QL0[k]; QR[k] = QR0[k]; QP[k] = QL0[k]; }
+  QP[column] += hstep;
+  fr::aux_pr(p, QP);
+  fr::numerical_flux<5>(p, QP, QR, av, 0.0, beta, direct);
+  double c2L, hrL, c2R, hrR, c2Lp, hrLp;
+  fr::hllc_side_thermo(p, QL, c2L, hrL);
+  fr::hllc_side_thermo(p, QR, c2R, hrR);
+  fr::hllc_side_thermo(p, QP, c2Lp, hrLp);
+  const bool thermo = column < 5 || column == 8;      // rho_i or T: new one-state and Roe pieces; u, v, w: the old ones
+  const double roe = thermo ? fr::hllc_roe_c2(p, QP, QR) : fr::hllc_roe_c2(p, QL, QR);
+  fr::hllc_assemble(p, QP, QR, av, 0.0, beta, thermo ? c2Lp : c2L, thermo ? hrLp : hrL, c2R, hrR, roe, shared);
+}
 void emu_fr_gradient(const emu_mesh* m, int gg, const double* q, const double* sw, double* qgrad) {
   DevMesh d = dev(m);
   for (blockIdx.x = 0; blockIdx.x < (unsigned)m->nnode; blockIdx.x++) {
@@ -882,3 +906,32 @@ def test_spalart_allmaras_kernels_on_host_vs_reference_dump(tmp_path):
     assert np.all(np.abs(mut[: ref.size] - ref) <= 1.0e-14 * np.abs(ref))      # fv1 = chi^3 / (chi^3 + cv1^3) amplifies it ~4x
     assert np.array_equal(tvar, g["turb_tvar1"])
     assert np.abs(g["turb_x"]).max() > 0
+
+
+def test_fr_hllc_pieces_on_host_vs_oracle(emu_fr, oracle):
+    """fr::numerical_flux -- since round 2 the composition of hllc_side_thermo / hllc_roe_c2 / hllc_assemble -- against the
+    oracle's HLLC (bit-exact) on every interior edge of the reacting fixture, and the flux of a perturbed left state put
+    together from SHARED pieces the way kfr_jac_edges does (the right state's pieces, and for a velocity perturbation all
+    of them, taken from the unperturbed evaluation) against the direct evaluation: identical bits for all nine columns."""
+    from tests.oracle_lib import FrOracle
+    g, meta, mesh, fp = fr_fixture("box4_fr_implicit")
+    o = FrOracle(oracle, g, meta)
+    q = g["q0"].reshape(-1, 21)
+    en = g["edges_n"].reshape(-1, 2)
+    ea = np.ascontiguousarray(g["edges_a"].reshape(-1, 4))
+    oracle.orc_fr_hllc_flux.restype = None
+    nchk = 0
+    for e in range(0, en.shape[0], 3):
+        QL, QR = np.ascontiguousarray(q[en[e, 0]]), np.ascontiguousarray(q[en[e, 1]])
+        av = np.ascontiguousarray(ea[e])
+        beta = 0.5 * (g["beta"][en[e, 0]] + g["beta"][en[e, 1]])
+        f, fo = np.zeros(9), np.zeros(9)
+        emu_fr.emu_fr_flux(C.byref(fp), _p(QL), _p(QR), _p(av), C.c_double(0.0), C.c_double(beta), _p(f))
+        oracle.orc_fr_hllc_flux(C.byref(o.p), _p(QL), _p(QR), _p(av), C.c_double(0.0), C.c_double(beta), _p(fo))
+        assert np.array_equal(f, fo), f"edge {e}: {f - fo}"
+        for col in range(9):
+            d, s = np.zeros(9), np.zeros(9)
+            emu_fr.emu_fr_flux_shared(C.byref(fp), _p(QL), _p(QR), col, C.c_double(1.0e-8), _p(av), C.c_double(beta), _p(d), _p(s))
+            assert np.array_equal(d, s), f"edge {e}, column {col}: {d - s}"
+        nchk += 1
+    assert nchk > 50
