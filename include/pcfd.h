@@ -171,8 +171,9 @@ int pcfd_sgs(pcfd_ctx* ctx, int nsgs, double* ddq);
 /* CRS::GMRES (crs.tcc:176-415): restarted GMRES (restarts x nsearch directions) with right preconditioning on the
    block-CRS system of the context: A = field PCFD_F_A as ASSEMBLED (before pcfd_prepare_sgs factors its diagonal in
    place; an error otherwise), b = PCFD_F_B, x = PCFD_F_X (initial guess in, solution out).  precond_type as
-   CRS::Preconditioner (:555-590): 0 none, 1 diagonal, 2 block diagonal (LU), 4 SGS (six sweeps on a copy of the matrix
-   per application -- the copy costs another matrix of device memory); 3 (local ILU0) is rejected.
+   CRS::Preconditioner (:555-590): 0 none, 1 diagonal, 2 block diagonal (LU), 3 local ILU0 (BuildILU0Local /
+   ILU0BackSub, crsmatrix.tcc:276-507: pivot-free, ghost columns left out, factored level by level on a copy), 4 SGS
+   (six sweeps on a copy of the matrix per application); the copy of 3 and 4 costs another matrix of device memory.
    dq_norm (may be NULL) receives the reference's return value |g[idir]|.  On connected contexts the vector that
    needs a halo before every product travels through pcfd_comm and the dot products are summed across ranks.  The
    reference's flow solver keeps this solver behind a comment (solutionSpace.tcc:734-750); move.tcc:714 calls it. (ABI v7) */

@@ -1485,6 +1485,120 @@ static void gm_sgs(int nnode, int neqn, int nsgs, const int* ia, const int* ja, 
   }
 }
 
+/* CRSMatrix::GetIndex (crsmatrix.tcc): position of block (row, col), -1 when the pattern has none */
+static int gm_block_index(const int* ia, const int* ja, int row, int col)
+{
+  int indx;
+  for(indx = ia[row]; indx < ia[row+1]; indx++) if(ja[indx] == col) return indx;
+  return -1;
+}
+
+/* CRSMatrix::BuildILU0Local (crsmatrix.tcc:276-428) on a copy N of A: scalar row by scalar row and without pivoting the
+   column below the pivot is scaled (inside the diagonal block and in every block (s, r), s > r), then for every local
+   block (r, col) of the pivot's block row -- the diagonal block first, as stored -- three outer-product updates: of the
+   diagonal block (r, r) (the reference subtracts it there, :365-381), of the rows below the pivot in (r, col), of the
+   columns right of the pivot in the mirror block (col, r).  Ghost columns are skipped and their blocks blanked at the end.
+   The reference scans all of ja for the blocks below the pivot (:336-346); the mirror blocks of the row are the same set. */
+void orc_ilu0_build(int nnode, int neqn, const int* ia, const int* ja, const int* iau, double* N)
+{
+  int i, j, k, l, n2 = neqn*neqn, n = nnode*neqn, nblocks = ia[nnode];
+  double temp[ORC_MAX_NEQN*ORC_MAX_NEQN];
+  for(i = 0; i < n; i++){
+    int blockrow = i/neqn, localrow = i%neqn, localcol = localrow, localn = localrow;
+    double* diag = &N[(size_t)iau[blockrow]*n2];
+    double pivot = diag[localrow*neqn + localcol];
+    pivot = 1.0/pivot;
+    for(j = localrow+1; j < neqn; j++) diag[j*neqn + localcol] *= pivot;
+    for(j = ia[blockrow+1]; j < nblocks; j++){
+      if(ja[j] == blockrow){
+	double* block = &N[(size_t)j*n2];
+	for(k = 0; k < neqn; k++) block[k*neqn + localcol] *= pivot;
+      }
+    }
+    for(j = ia[blockrow]; j < ia[blockrow+1]; j++){
+      int blockcol = ja[j], m;
+      double *block2, *block3, *block4;
+      if(blockcol >= nnode) continue;
+      block2 = &N[(size_t)j*n2];
+      m = gm_block_index(ia, ja, blockcol, blockrow);
+      block3 = m >= 0 ? &N[(size_t)m*n2] : NULL;   /* the reference dereferences it below either way: symmetric pattern */
+      if(block3 != NULL){
+	for(k = 0; k < neqn; k++)
+	  for(l = 0; l < neqn; l++) temp[k*neqn + l] = block2[localn*neqn + l]*block3[k*neqn + localn];
+	block4 = &N[(size_t)iau[blockrow]*n2];
+	for(k = 0; k < neqn; k++)
+	  for(l = 0; l < neqn; l++) block4[k*neqn + l] -= temp[k*neqn + l];
+      }
+      for(k = localn+1; k < neqn; k++)
+	for(l = 0; l < neqn; l++) temp[k*neqn + l] = block2[localn*neqn + l]*diag[k*neqn + localn];
+      block4 = block2;
+      for(k = localn+1; k < neqn; k++)
+	for(l = 0; l < neqn; l++) block4[k*neqn + l] -= temp[k*neqn + l];
+      for(k = 0; k < neqn; k++)
+	for(l = localn+1; l < neqn; l++) temp[k*neqn + l] = block2[localn*neqn + l]*block3[k*neqn + localn];
+      block4 = block3;
+      for(k = 0; k < neqn; k++)
+	for(l = localn+1; l < neqn; l++) block4[k*neqn + l] -= temp[k*neqn + l];
+    }
+  }
+  for(i = 0; i < nblocks; i++)
+    if(ja[i] >= nnode) memset(&N[(size_t)i*n2], 0, sizeof(double)*n2);
+}
+
+/* CRSMatrix::ILU0BackSub (crsmatrix.tcc:430-507): x blanked (ghost rows too); sweep down x_i = b_i - sum_{col<i} N x_col
+   (the strictly lower part of the diagonal block multiplies the still blank x_i, :452-458); sweep up with the strictly
+   upper part of the diagonal block applied to b_i (:484-490) and a division by the block's diagonal entries */
+void orc_ilu0_backsub(int nnode, int gnode, int neqn, const int* ia, const int* ja, const int* iau, const double* N,
+		      double* x, const double* b)
+{
+  int i, j, k, l, n2 = neqn*neqn;
+  double temp[ORC_MAX_NEQN], temp2[ORC_MAX_NEQN];
+  memset(x, 0, sizeof(double)*(size_t)neqn*(nnode+gnode));
+  for(i = 0; i < nnode; i++){
+    for(k = 0; k < neqn; k++) temp[k] = 0.0;
+    for(j = ia[i]; j < ia[i+1]; j++){
+      int col = ja[j];
+      if(col < i){
+	const double* a1 = &N[(size_t)j*n2];
+	const double* v1 = &x[(size_t)col*neqn];
+	for(k = 0; k < neqn; k++){
+	  temp2[k] = a1[k*neqn + 0]*v1[0];
+	  for(l = 1; l < neqn; l++) temp2[k] += a1[k*neqn + l]*v1[l];
+	}
+	for(k = 0; k < neqn; k++) temp[k] += temp2[k];
+      }
+      else if(col == i){
+	for(k = 0; k < neqn; k++)
+	  for(l = 0; l < k; l++) temp[k] += N[(size_t)j*n2 + k*neqn + l]*x[i*neqn + l];
+      }
+    }
+    for(k = 0; k < neqn; k++) x[i*neqn + k] = b[i*neqn + k] - temp[k];
+  }
+  for(i = nnode-1; i >= 0; i--){
+    for(k = 0; k < neqn; k++) temp[k] = 0.0;
+    for(j = ia[i]; j < ia[i+1]; j++){
+      int col = ja[j];
+      if(col > i){
+	const double* a1 = &N[(size_t)j*n2];
+	const double* v1 = &x[(size_t)col*neqn];
+	for(k = 0; k < neqn; k++){
+	  temp2[k] = a1[k*neqn + 0]*v1[0];
+	  for(l = 1; l < neqn; l++) temp2[k] += a1[k*neqn + l]*v1[l];
+	}
+	for(k = 0; k < neqn; k++) temp[k] += temp2[k];
+      }
+      else if(col == i){
+	for(k = neqn-1; k >= 0; k--)
+	  for(l = neqn-1; l > k; l--) temp[k] += N[(size_t)j*n2 + k*neqn + l]*b[i*neqn + l];
+      }
+    }
+    for(k = 0; k < neqn; k++){
+      int diag = iau[i];
+      x[i*neqn + k] = (x[i*neqn + k] - temp[k])/N[(size_t)diag*n2 + k*neqn + k];
+    }
+  }
+}
+
 double orc_gmres(int nnode, int gnode, int neqn, int restarts, int nSearchDir, int precondType, const int* ia,
 		 const int* ja, const int* iau, const double* A, const double* b, double* x)
 {
@@ -1514,6 +1628,12 @@ double orc_gmres(int nnode, int gnode, int neqn, int restarts, int nSearchDir, i
     memcpy(N, A, sizeof(double)*nblocks*n2);
     for(i = 0; i < nnode; i++) lu(&N[(size_t)iau[i]*n2], &pv[i*neqn], neqn);
   }
+  if(precondType == 3){   /* BuildILU0Local (crs.tcc:571-575) */
+    size_t nblocks = (size_t)ia[nnode];
+    N = (double*)malloc(sizeof(double)*nblocks*n2);
+    memcpy(N, A, sizeof(double)*nblocks*n2);
+    orc_ilu0_build(nnode, neqn, ia, ja, iau, N);
+  }
   for(irestart = 0; irestart < restarts; irestart++){
     double* v0 = vdat;
     gm_matvec(nnode, gnode, neqn, ia, ja, A, x, v0);
@@ -1530,6 +1650,7 @@ double orc_gmres(int nnode, int gnode, int neqn, int restarts, int nSearchDir, i
       double* vk = vdat + (size_t)idir*vstride;
       Hoffset[idir] = hpos;
       if(precondType == 4) gm_sgs(nnode, neqn, 6, ia, ja, iau, N, pv, vk, vtemp);
+      else if(precondType == 3) orc_ilu0_backsub(nnode, gnode, neqn, ia, ja, iau, N, vtemp, vk);
       else gm_precond_solve(precondType, nnode, neqn, N, pv, vtemp, vk);
       for(i = 0; i < (int)vstride; i++) uk[i] = 0.0;
       gm_matvec(nnode, gnode, neqn, ia, ja, A, vtemp, uk);
@@ -1578,6 +1699,7 @@ double orc_gmres(int nnode, int gnode, int neqn, int restarts, int nSearchDir, i
       for(ii = 0; ii < nloc; ii++) uk[ii] += (vj[ii]*g[jj]);
     }
     if(precondType == 4) gm_sgs(nnode, neqn, 6, ia, ja, iau, N, pv, uk, vtemp);
+    else if(precondType == 3) orc_ilu0_backsub(nnode, gnode, neqn, ia, ja, iau, N, vtemp, uk);
     else gm_precond_solve(precondType, nnode, neqn, N, pv, vtemp, uk);
     for(i = 0; i < nloc; i++) x[i] += vtemp[i];
   }

@@ -262,8 +262,14 @@ double orc_fr_turb_sa(const orc_case* c, const orc_fr_params* p, int nsgs, const
 		      const double* dist, const double* dt, const int* ia, const int* ja, const int* iau,
 		      double* tvar, double* tgrad, double* b, double* A, double* x, double* mut);
 
-/* CRS::GMRES (crs.tcc:176-415) on one rank: restarts x nSearchDir, right preconditioner type 0 / 1 / 2 (none, diagonal,
-   block diagonal LU; crs.tcc:555-641); any block size neqn <= 32.  A: assembled matrix before PrepareSGS; x: initial guess
+/* the local ILU0 preconditioner of CRS::GMRES: CRSMatrix::BuildILU0Local (crsmatrix.tcc:276-428) in place on a copy N of
+   the assembled matrix, and CRSMatrix::ILU0BackSub (crsmatrix.tcc:430-507), N x = b with x blanked first */
+void orc_ilu0_build(int nnode, int neqn, const int* ia, const int* ja, const int* iau, double* N);
+void orc_ilu0_backsub(int nnode, int gnode, int neqn, const int* ia, const int* ja, const int* iau, const double* N,
+		      double* x, const double* b);
+
+/* CRS::GMRES (crs.tcc:176-415) on one rank: restarts x nSearchDir, right preconditioner type 0 / 1 / 2 / 3 / 4 (none,
+   diagonal, block diagonal LU, local ILU0, SGS; crs.tcc:555-641); any block size neqn <= 32.  A: assembled matrix before PrepareSGS; x: initial guess
    in, solution out, (nnode+gnode)*neqn; returns the reference's dqNorm. */
 double orc_gmres(int nnode, int gnode, int neqn, int restarts, int nSearchDir, int precondType, const int* ia,
 		 const int* ja, const int* iau, const double* A, const double* b, double* x);

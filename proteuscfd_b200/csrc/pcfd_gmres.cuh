@@ -3,8 +3,9 @@
 // Restarted GMRES with right preconditioning on the block-CRS system of the context: A (PCFD_F_A, as assembled, NOT yet
 // factored by pcfd_prepare_sgs), b (PCFD_F_B), x (PCFD_F_X: initial guess in, solution out).  Preconditioner /
 // PrecondBackSolve (crs.tcc:555-641) types 0 (none), 1 (diagonal of the diagonal blocks), 2 (block diagonal, LU with the
-// permutation vector of matrix.h:110-190).  The reference's flow solver keeps this path behind a comment
-// (solutionSpace.tcc:734-750); its mesh-movement and design solvers call it (move.tcc:714).
+// permutation vector of matrix.h:110-190), 3 (local ILU0, crsmatrix.tcc:276-507), 4 (SGS on a copy of the matrix).  The
+// reference's flow solver keeps this path behind a comment (solutionSpace.tcc:734-750); its mesh-movement and design
+// solvers call it (move.tcc:714).
 //
 // What runs where: the block-CRS matrix-vector product, the preconditioner solve and every vector update are kernels
 // with the reference's arithmetic order per entry (bit-identical); dot products and norms are fixed-tree reductions
@@ -96,6 +97,126 @@ __global__ void __launch_bounds__(128) k_gm_precond_solve(int nnode, int type, c
     bb[i] = (xx[i] - sum) / a[p[i] * N + i];
   }
   for (int i = 0; i < N; i++) x[(size_t)nd * N + i] = bb[i];
+}
+
+// ---- preconditioner type 3: the local ILU0 (crs.tcc:571-575, 627-630)
+//
+// CRSMatrix::BuildILU0Local (crsmatrix.tcc:276-428) walks the scalar rows in order; everything the N scalar rows of block
+// row r touch is the block row r itself and its mirror blocks (col, r), so two block rows conflict only when they are
+// neighbours, and the forward levels of the SGS schedule (no two neighbours in a level, lower-numbered neighbours in
+// earlier levels) reproduce the sequential result: one launch per level, one thread per block row of the level, the
+// reference's statement order inside it.  The reference finds the blocks below the pivot by scanning all of ja
+// (:336-346, quadratic); on the symmetric pattern they are the mirror blocks of the row's upper neighbours.
+__device__ __forceinline__ int ilu0_find(const int* __restrict__ ia, const int* __restrict__ ja, int row, int col) {
+  for (int indx = ia[row]; indx < ia[row + 1]; indx++)
+    if (ja[indx] == col) return indx;
+  return -1;
+}
+
+template <int N>
+__global__ void __launch_bounds__(64) k_ilu0_build(const int* __restrict__ rows, int nr, int nnode, const int* __restrict__ ia,
+                                                   const int* __restrict__ ja, const int* __restrict__ iau, double* M) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nr) return;
+  const int r = rows[s];
+  double* diag = M + (size_t)iau[r] * N * N;
+  double temp[N * N];
+  for (int c = 0; c < N; c++) {
+    const double pivot = 1.0 / diag[c * N + c];   // no pivoting (:322-328)
+    for (int j = c + 1; j < N; j++) diag[j * N + c] *= pivot;
+    for (int j = ia[r]; j < ia[r + 1]; j++) {     // blocks (col, r) below the pivot: col > r, local rows only
+      const int col = ja[j];
+      if (col <= r || col >= nnode) continue;
+      const int m = ilu0_find(ia, ja, col, r);
+      if (m < 0) continue;
+      double* block = M + (size_t)m * N * N;
+      for (int k = 0; k < N; k++) block[k * N + c] *= pivot;
+    }
+    for (int j = ia[r]; j < ia[r + 1]; j++) {     // the pivot's block row as stored: diagonal block first
+      const int col = ja[j];
+      if (col >= nnode) continue;                 // ghost columns stay out of the local factorisation (:359-363)
+      double* block2 = M + (size_t)j * N * N;
+      const int m = ilu0_find(ia, ja, col, r);
+      if (m < 0) continue;                        // (the reference dereferences NULL here: symmetric pattern assumed)
+      double* block3 = M + (size_t)m * N * N;
+      for (int k = 0; k < N; k++)
+        for (int l = 0; l < N; l++) temp[k * N + l] = block2[c * N + l] * block3[k * N + c];
+      for (int k = 0; k < N; k++)                 // subtracted from the diagonal block of THIS row (:376-381)
+        for (int l = 0; l < N; l++) diag[k * N + l] -= temp[k * N + l];
+      for (int k = c + 1; k < N; k++)
+        for (int l = 0; l < N; l++) temp[k * N + l] = block2[c * N + l] * diag[k * N + c];
+      for (int k = c + 1; k < N; k++)
+        for (int l = 0; l < N; l++) block2[k * N + l] -= temp[k * N + l];
+      for (int k = 0; k < N; k++)
+        for (int l = c + 1; l < N; l++) temp[k * N + l] = block2[c * N + l] * block3[k * N + c];
+      for (int k = 0; k < N; k++)
+        for (int l = c + 1; l < N; l++) block3[k * N + l] -= temp[k * N + l];
+    }
+  }
+}
+
+// blocks of ghost columns blanked once the factorisation is through (:418-424)
+template <int N>
+__global__ void k_ilu0_blank_ghost(int nblocks, int nnode, const int* __restrict__ ja, double* M) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long blk = t / (N * N);
+  if (blk >= nblocks) return;
+  if (ja[blk] >= nnode) M[t] = 0.0;
+}
+
+// CRSMatrix::ILU0BackSub (crsmatrix.tcc:430-507), sweep down: one thread per (row of the level, component).  x has been
+// blanked; the strictly lower part of the diagonal block multiplies the row's own, still blank, entries (:452-458) --
+// the products are kept (a zero times whatever the factor holds) so that a NaN / Inf factor propagates as it does there.
+template <int N>
+__global__ void __launch_bounds__(128) k_ilu0_fwd(const int* __restrict__ rows, int nr, const int* __restrict__ ia,
+                                                   const int* __restrict__ ja, const double* __restrict__ M,
+                                                   const double* __restrict__ b, double* x) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = t / N;
+  if (s >= nr) return;
+  const int k = t - s * N;
+  const int i = rows[s];
+  double temp = 0.0;
+  for (int j = ia[i]; j < ia[i + 1]; j++) {
+    const int col = ja[j];
+    const double* a1 = M + (size_t)j * N * N + k * N;
+    if (col < i) {
+      const double* v1 = x + (size_t)col * N;
+      double temp2 = a1[0] * v1[0];
+      for (int l = 1; l < N; l++) temp2 += a1[l] * v1[l];
+      temp += temp2;
+    } else if (col == i) {
+      for (int l = 0; l < k; l++) temp += a1[l] * 0.0;
+    }
+  }
+  x[(size_t)i * N + k] = b[(size_t)i * N + k] - temp;
+}
+
+// sweep up: the strictly upper part of the diagonal block is applied to b (:484-490), then the division by the block's
+// own diagonal entry (:493-496).  Ghost columns count as above the row: their blocks and their x rows are zero.
+template <int N>
+__global__ void __launch_bounds__(128) k_ilu0_bwd(const int* __restrict__ rows, int nr, const int* __restrict__ ia,
+                                                   const int* __restrict__ ja, const int* __restrict__ iau,
+                                                   const double* __restrict__ M, const double* __restrict__ b, double* x) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = t / N;
+  if (s >= nr) return;
+  const int k = t - s * N;
+  const int i = rows[s];
+  double temp = 0.0;
+  for (int j = ia[i]; j < ia[i + 1]; j++) {
+    const int col = ja[j];
+    const double* a1 = M + (size_t)j * N * N + k * N;
+    if (col > i) {
+      const double* v1 = x + (size_t)col * N;
+      double temp2 = a1[0] * v1[0];
+      for (int l = 1; l < N; l++) temp2 += a1[l] * v1[l];
+      temp += temp2;
+    } else if (col == i) {
+      for (int l = N - 1; l > k; l--) temp += a1[l] * b[(size_t)i * N + l];
+    }
+  }
+  x[(size_t)i * N + k] = (x[(size_t)i * N + k] - temp) / M[(size_t)iau[i] * N * N + k * N + k];
 }
 
 // vector updates of crs.tcc:259-395, one entry per thread, the reference's expression per entry
@@ -193,7 +314,7 @@ int gmres_impl(pcfd_ctx* c, int restarts, int nSearchDir, int precondType, doubl
   double* const A = c->f[PCFD_F_A];
   double* const b = c->f[PCFD_F_B];
   int* const pvA = c->pv;
-  if (precondType == 4) {
+  if (precondType == 3 || precondType == 4) {
     // Preconditioner type 4 (crs.tcc:577-581): CopyMatrixStructure + PrepareSGS -- a copy of the whole matrix with its
     // diagonal blocks factored; every application is CRS::SGS(6, N, vtemp, rhs) (:629-632), the previous preconditioned
     // vector being the initial guess.  The sweeps are the context's own (pcfd_sgs) with its matrix / permutation /
@@ -208,10 +329,24 @@ int gmres_impl(pcfd_ctx* c, int restarts, int nSearchDir, int precondType, doubl
       c->gm_ncap = nA;
     }
     CK(cudaMemcpyAsync(c->gm_n, A, nA * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-    constexpr int RPW = 32 / N;
-    PROF("k_lu_diag");
-    k_lu_diag_lanes<N><<<nblk((long long)((nnode + RPW - 1) / RPW) * 32, 128), 128, 0, c->stream>>>(nnode, c->iau, c->gm_n, c->gm_npv);
-    LAUNCH_CHECK();
+    if (precondType == 4) {
+      constexpr int RPW = 32 / N;
+      PROF("k_lu_diag");
+      k_lu_diag_lanes<N><<<nblk((long long)((nnode + RPW - 1) / RPW) * 32, 128), 128, 0, c->stream>>>(nnode, c->iau, c->gm_n, c->gm_npv);
+      LAUNCH_CHECK();
+    } else {
+      // Preconditioner type 3 (crs.tcc:571-575): BuildILU0Local on the copy, level by level
+      for (size_t l = 0; l + 1 < c->lev_f.size(); l++) {
+        const int nr = c->lev_f[l + 1] - c->lev_f[l];
+        if (nr <= 0) continue;
+        PROF("k_ilu0_build");
+        k_ilu0_build<N><<<nblk(nr, 64), 64, 0, c->stream>>>(c->rows_f + c->lev_f[l], nr, nnode, c->ia, c->ja, c->iau, c->gm_n);
+        LAUNCH_CHECK();
+      }
+      PROF("k_ilu0_blank_ghost");
+      k_ilu0_blank_ghost<N><<<nblk((long long)c->nblocks * N * N, 256), 256, 0, c->stream>>>(c->nblocks, nnode, c->ja, c->gm_n);
+      LAUNCH_CHECK();
+    }
   }
   if (precondType == 1 || precondType == 2) {
     PROF("k_gm_precond_build");
@@ -232,6 +367,24 @@ int gmres_impl(pcfd_ctx* c, int restarts, int nSearchDir, int precondType, doubl
     }
     if (precondType == 0) {
       CK(cudaMemcpyAsync(out, rhs, (size_t)nloc * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+      return 0;
+    }
+    if (precondType == 3) {   // ILU0BackSub: x blanked with its ghost rows, one sweep down, one up
+      CK(cudaMemsetAsync(out, 0, vstride * sizeof(double), c->stream));
+      for (size_t l = 0; l + 1 < c->lev_f.size(); l++) {
+        const int nr = c->lev_f[l + 1] - c->lev_f[l];
+        if (nr <= 0) continue;
+        PROF("k_ilu0_fwd");
+        k_ilu0_fwd<N><<<nblk((long long)nr * N, 128), 128, 0, c->stream>>>(c->rows_f + c->lev_f[l], nr, c->ia, c->ja, c->gm_n, rhs, out);
+        LAUNCH_CHECK();
+      }
+      for (size_t l = 0; l + 1 < c->lev_b.size(); l++) {
+        const int nr = c->lev_b[l + 1] - c->lev_b[l];
+        if (nr <= 0) continue;
+        PROF("k_ilu0_bwd");
+        k_ilu0_bwd<N><<<nblk((long long)nr * N, 128), 128, 0, c->stream>>>(c->rows_b + c->lev_b[l], nr, c->ia, c->ja, c->iau, c->gm_n, rhs, out);
+        LAUNCH_CHECK();
+      }
       return 0;
     }
     PROF("k_gm_precond_solve");
@@ -330,9 +483,8 @@ int gmres_impl(pcfd_ctx* c, int restarts, int nSearchDir, int precondType, doubl
 extern "C" int pcfd_gmres(pcfd_ctx* c, int restarts, int nsearch, int precond_type, double* dq_norm) {
   if (!c) return 1;
   if (restarts < 1 || nsearch < 1 || nsearch > 200) return fail(c, "pcfd_gmres: restarts >= 1, 1 <= search directions <= 200");
-  if (precond_type < 0 || precond_type > 4 || precond_type == 3)
-    return fail(c, "pcfd_gmres: preconditioner 0 (none), 1 (diagonal), 2 (block diagonal) or 4 (SGS); the local ILU0 (3) of "
-                   "crs.tcc:571-575 is not built");
+  if (precond_type < 0 || precond_type > 4)
+    return fail(c, "pcfd_gmres: preconditioner 0 (none), 1 (diagonal), 2 (block diagonal), 3 (local ILU0) or 4 (SGS)");
   CK(cudaSetDevice(c->device));
   if (!c->f[PCFD_F_A]) return fail(c, "pcfd_gmres: no matrix (pcfd_jacobian or pcfd_set_field(PCFD_F_A) first)");
   if (c->ludiag) return fail(c, "pcfd_gmres: the diagonal blocks have been factored in place (pcfd_prepare_sgs); GMRES needs the assembled matrix");

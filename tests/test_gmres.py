@@ -111,7 +111,7 @@ def test_gpu_gmres_variants_and_errors():
     ctx.gmres(1, 6, 2)
     assert np.abs(ctx.get_field(capi.F_X) - ref).max() <= 1e-11 * np.abs(ref).max()
     with pytest.raises(capi.PcfdError):
-        ctx.gmres(1, 5, 3)              # ILU0 preconditioner: not built
+        ctx.gmres(1, 5, 5)              # no such preconditioner (crs.tcc:582-585 warns and carries on with garbage)
     ctx.prepare_sgs()
     with pytest.raises(capi.PcfdError):
         ctx.gmres(1, 5, 2)              # diagonal already factored in place

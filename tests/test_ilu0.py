@@ -1,0 +1,296 @@
+"""The local ILU0 right preconditioner of CRS::GMRES (precondType 3: CRSMatrix::BuildILU0Local / ILU0BackSub,
+ucs/crsmatrix.tcc:276-507, selected at ucs/crs.tcc:571-575, 627-630).
+
+CPU, three layers:
+  1. the C restatement (oracle/pcfd_oracle.c: orc_ilu0_build / orc_ilu0_backsub inside orc_gmres) against the solutions the
+     REFERENCE's own GMRES produced with this preconditioner (tests/golden/box6_gmres_ilu0: 5x5 blocks, 6 directions,
+     2 restarts; box4_fr_gmres_ilu0: 9x9 blocks, frozen chemistry -- with the source Jacobian in the diagonal blocks the
+     reference's pivot-free factorisation returns NaN): bit-exact, x and the returned norm;
+  2. host emulation of the device kernels from their source text (k_ilu0_build / k_ilu0_blank_ghost / k_ilu0_fwd /
+     k_ilu0_bwd of csrc/pcfd_gmres.cuh compiled with g++ -ffp-contract=off, the threads of a level run in REVERSED order
+     to show that a level's block rows do not touch each other's blocks) against the oracle's factor and solve, bit-exact,
+     with the level schedule rebuilt here the way pcfd_create builds it (build_levels, pcfd_kernels.cu);
+  3. the two-rank reference run (box8_2rank_gmres_ilu0_r*of2): the whole GMRES replayed on both ranks in lockstep with
+     the emulated kernels, numpy halos and rank-ordered dot products, against each rank's reference solution.
+The B200 run of the same kernels through pcfd_gmres is tests/test_zz_gpu_ilu0.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.oracle_lib import _d, _i, load_golden, load_oracle
+from tests.test_gmres import run_oracle
+from tests.test_host_emulation import CSRC, extract
+
+CASES = [("box6_gmres_ilu0", 5), ("box4_fr_gmres_ilu0", 9)]
+
+PRELUDE = r"""
+#include <cmath>
+#include <cstddef>
+#define __device__
+#define __global__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+struct idx3 { unsigned x, y, z; };
+static idx3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDim = {1, 1, 1};
+"""
+
+DRIVER = r"""
+extern "C" {
+// one emulated launch: the threads of the grid in reversed order
+#define FOR_THREADS_REV(n) for (long long t_ = (long long)(n) - 1; t_ >= 0 && ((blockIdx.x = (unsigned)t_), true); t_--)
+void emu_ilu0_build(int N, const int* rows, int nr, int nnode, const int* ia, const int* ja, const int* iau, double* M) {
+  FOR_THREADS_REV(nr) { if (N == 5) k_ilu0_build<5>(rows, nr, nnode, ia, ja, iau, M); else k_ilu0_build<9>(rows, nr, nnode, ia, ja, iau, M); }
+}
+void emu_ilu0_blank_ghost(int N, int nblocks, int nnode, const int* ja, double* M) {
+  FOR_THREADS_REV((long long)nblocks * N * N) { if (N == 5) k_ilu0_blank_ghost<5>(nblocks, nnode, ja, M); else k_ilu0_blank_ghost<9>(nblocks, nnode, ja, M); }
+}
+void emu_ilu0_fwd(int N, const int* rows, int nr, const int* ia, const int* ja, const double* M, const double* b, double* x) {
+  FOR_THREADS_REV(nr * N) { if (N == 5) k_ilu0_fwd<5>(rows, nr, ia, ja, M, b, x); else k_ilu0_fwd<9>(rows, nr, ia, ja, M, b, x); }
+}
+void emu_ilu0_bwd(int N, const int* rows, int nr, const int* ia, const int* ja, const int* iau, const double* M, const double* b,
+                  double* x) {
+  FOR_THREADS_REV(nr * N) { if (N == 5) k_ilu0_bwd<5>(rows, nr, ia, ja, iau, M, b, x); else k_ilu0_bwd<9>(rows, nr, ia, ja, iau, M, b, x); }
+}
+}
+"""
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    work = tmp_path_factory.mktemp("ilu0_emul")
+    src = open(os.path.join(CSRC, "pcfd_gmres.cuh")).read()
+    parts = [PRELUDE]
+    for name in ("ilu0_find", "k_ilu0_build", "k_ilu0_blank_ghost", "k_ilu0_fwd", "k_ilu0_bwd"):
+        parts.append(extract(src, name))
+    parts.append(DRIVER)
+    cpp = os.path.join(work, "ilu0_emu.cpp")
+    with open(cpp, "w") as f:
+        f.write("\n".join(parts))
+    so = os.path.join(work, "ilu0_emu.so")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, cpp], check=True)
+    return C.CDLL(so)
+
+
+def build_levels(n, ia, ja, forward):
+    """pcfd_kernels.cu build_levels: level = 1 + max level of the lower- (forward) / higher-numbered (backward) local
+    neighbours; rows of a level in sweep order"""
+    lev = np.zeros(n, dtype=np.int64)
+    order = range(n) if forward else range(n - 1, -1, -1)
+    for i in order:
+        l = 0
+        for k in range(ia[i] + 1, ia[i + 1]):
+            j = ja[k]
+            if j >= n:
+                continue
+            if (j < i) if forward else (j > i):
+                l = max(l, lev[j] + 1)
+        lev[i] = l
+    rows, off = [], [0]
+    for l in range(int(lev.max()) + 1):
+        rows += [i for i in order if lev[i] == l]
+        off.append(len(rows))
+    return np.array(rows, dtype=np.int32), off
+
+
+class EmuIlu0:
+    """the launch sequence of gmres_impl for precondType 3 on the emulated kernels"""
+
+    def __init__(self, emu, g, meta, neqn):
+        self.emu, self.N = emu, neqn
+        self.nnode, self.gnode = int(meta["nnode"]), int(meta["gnode"])
+        self.ia, self.ja, self.iau = (np.ascontiguousarray(g[k], dtype=np.int32) for k in ("ia", "ja", "iau"))
+        self.rows_f, self.lev_f = build_levels(self.nnode, self.ia, self.ja, True)
+        self.rows_b, self.lev_b = build_levels(self.nnode, self.ia, self.ja, False)
+        self.M = None
+
+    def build(self, A):
+        self.M = np.array(A, dtype=np.float64, copy=True)
+        for l in range(len(self.lev_f) - 1):
+            rows = np.ascontiguousarray(self.rows_f[self.lev_f[l]:self.lev_f[l + 1]])
+            self.emu.emu_ilu0_build(self.N, _i(rows), rows.size, self.nnode, _i(self.ia), _i(self.ja), _i(self.iau), _d(self.M))
+        self.emu.emu_ilu0_blank_ghost(self.N, int(self.ia[self.nnode]), self.nnode, _i(self.ja), _d(self.M))
+        return self.M
+
+    def solve(self, b):
+        x = np.zeros((self.nnode + self.gnode) * self.N)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        for l in range(len(self.lev_f) - 1):
+            rows = np.ascontiguousarray(self.rows_f[self.lev_f[l]:self.lev_f[l + 1]])
+            self.emu.emu_ilu0_fwd(self.N, _i(rows), rows.size, _i(self.ia), _i(self.ja), _d(self.M), _d(b), _d(x))
+        for l in range(len(self.lev_b) - 1):
+            rows = np.ascontiguousarray(self.rows_b[self.lev_b[l]:self.lev_b[l + 1]])
+            self.emu.emu_ilu0_bwd(self.N, _i(rows), rows.size, _i(self.ia), _i(self.ja), _i(self.iau), _d(self.M), _d(b), _d(x))
+        return x
+
+
+@pytest.mark.parametrize("name,neqn", CASES)
+def test_oracle_ilu0_gmres_equals_the_reference(name, neqn):
+    g, meta = load_golden(name)
+    assert int(g["gmres_cfg"][0]) == 3
+    x, dq = run_oracle(load_oracle(), g, meta, neqn)
+    assert np.array_equal(x, g["gmres_x"]) and dq == g["gmres_dq"][0]
+    assert np.isfinite(x).all() and np.abs(x).max() > 0
+
+
+def oracle_factor_and_solve(lib, g, meta, neqn, A, rhs):
+    nnode, gnode = int(meta["nnode"]), int(meta["gnode"])
+    N = np.array(A, dtype=np.float64, copy=True)
+    lib.orc_ilu0_build(nnode, neqn, _i(g["ia"]), _i(g["ja"]), _i(g["iau"]), _d(N))
+    x = np.full((nnode + gnode) * neqn, 7.0)      # ILU0BackSub blanks it
+    lib.orc_ilu0_backsub(nnode, gnode, neqn, _i(g["ia"]), _i(g["ja"]), _i(g["iau"]), _d(N), _d(x), _d(np.ascontiguousarray(rhs)))
+    return N, x
+
+
+@pytest.mark.parametrize("name,neqn", CASES + [("box8_2rank_gmres_ilu0_r0of2", 5), ("box8_2rank_gmres_ilu0_r1of2", 5)])
+def test_emulated_ilu0_kernels_equal_the_oracle(emu, name, neqn):
+    """factor (every block, ghost columns blanked) and one application, bit for bit; the partition fixtures carry ghost
+    columns, which the factorisation must skip"""
+    g, meta = load_golden(name)
+    lib = load_oracle()
+    rhs = g["b"][: int(meta["nnode"]) * neqn]
+    Nref, xref = oracle_factor_and_solve(lib, g, meta, neqn, g["A"], rhs)
+    e = EmuIlu0(emu, g, meta, neqn)
+    assert len(e.lev_f) > 3 and len(e.lev_b) > 3
+    M = e.build(g["A"])
+    assert np.array_equal(M, Nref)
+    assert not np.array_equal(M, g["A"])
+    x = e.solve(rhs)
+    assert np.array_equal(x, xref)
+    if "2rank" in name:
+        ghost = g["ja"] >= int(meta["nnode"])
+        assert ghost.any() and not M.reshape(-1, neqn * neqn)[ghost].any()
+
+
+def test_ilu0_is_the_exact_lu_of_a_block_diagonal_system(emu):
+    """with the off-diagonal blocks removed the factorisation is a pivot-free LU per block; the reference's back
+    substitution then applies L^-1 only through the blank x (crsmatrix.tcc:452-458) and the upper part to b (:484-490):
+    x_k = (b_k - sum_{l>k} U_kl b_l) / U_kk.  Pins the quirk on both sides."""
+    g, meta = load_golden("box6_gmres_ilu0")
+    nnode = int(meta["nnode"])
+    A = g["A"].reshape(-1, 5, 5).copy()
+    offd = np.ones(A.shape[0], dtype=bool)
+    offd[g["iau"][:nnode]] = False
+    A[offd] = 0.0
+    rhs = g["b"][: nnode * 5]
+    Nref, xref = oracle_factor_and_solve(load_oracle(), g, meta, 5, A.reshape(-1), rhs)
+    e = EmuIlu0(emu, g, meta, 5)
+    M = e.build(A.reshape(-1)).reshape(-1, 5, 5)
+    assert np.array_equal(M.reshape(-1), Nref)
+    x = e.solve(rhs)
+    assert np.array_equal(x, xref)
+    D = M[g["iau"][:nnode]]
+    B = rhs.reshape(-1, 5)
+    want = np.empty_like(B)
+    for k in range(5):
+        want[:, k] = (B[:, k] - sum(D[:, k, l] * B[:, l] for l in range(4, k, -1))) / D[:, k, k]
+    assert np.allclose(x[: nnode * 5].reshape(-1, 5), want, rtol=1e-13, atol=0)
+
+
+def test_two_rank_ilu0_gmres_replay_vs_reference(emu):
+    """CRS::GMRES with precondType 3 on the two-rank reference fixture, both ranks in lockstep: emulated ILU0 kernels,
+    the oracle-order matrix-vector product, numpy halos (PObj maps of the fixture) where the reference exchanges
+    (crs.tcc:249, :300, :399), dot products summed per rank and then in rank order.  Each rank's solution, ghost rows
+    included, to 1e-12 of its scale (MPI_Allreduce adds the two partial sums in the same order: usually bit-equal)."""
+    from proteuscfd_b200.parallel import build_local_group_maps
+    N = 5
+    parts = [load_golden(f"box8_2rank_gmres_ilu0_r{r}of2") for r in (0, 1)]
+    pobjs = build_local_group_maps([(g["gNodeOwner"], g["gNodeLocalId"]) for g, _ in parts])
+    es = [EmuIlu0(emu, g, m, N) for g, m in parts]
+    for e, (g, _) in zip(es, parts):
+        e.build(g["A"])
+    nn = [int(m["nnode"]) for _, m in parts]
+    tot = [int(m["nnode"]) + int(m["gnode"]) for _, m in parts]
+
+    def halo(vs):
+        packed = [pobjs[p].pack_numpy(vs[p], N) for p in (0, 1)]
+        for r in (0, 1):
+            pobjs[r].unpack_numpy(vs[r], N, nn[r], [packed[p][r] for p in (0, 1)])
+
+    def matvec(r, v):
+        g = parts[r][0]
+        A = g["A"].reshape(-1, N, N)
+        out = np.zeros(tot[r] * N)
+        V = v.reshape(-1, N)
+        for i in range(nn[r]):
+            acc = np.zeros(N)
+            for k in range(g["ia"][i], g["ia"][i + 1]):
+                a, w = A[k], V[g["ja"][k]]
+                t = a[:, 0] * w[0]
+                for c in range(1, N):
+                    t = t + a[:, c] * w[c]
+                acc = acc + t
+            out[i * N:(i + 1) * N] = acc
+        return out
+
+    def dot(us, vs):
+        tot_ = 0.0
+        for r in (0, 1):
+            s = 0.0
+            a, b = us[r][: nn[r] * N], vs[r][: nn[r] * N]
+            for i in range(a.size):
+                s += a[i] * b[i]
+            tot_ += s
+        return tot_
+
+    pt, nd, nrest = [int(v) for v in parts[0][0]["gmres_cfg"]]
+    assert pt == 3
+    x = [np.zeros(tot[r] * N) for r in (0, 1)]
+    b = [parts[r][0]["b"] for r in (0, 1)]
+    halo(x)
+    for _ in range(nrest):
+        v = [[matvec(r, x[r]) for r in (0, 1)]]
+        for r in (0, 1):
+            v[0][r][: nn[r] * N] = b[r][: nn[r] * N] - v[0][r][: nn[r] * N]
+        beta = np.sqrt(dot(v[0], v[0]))
+        for r in (0, 1):
+            v[0][r][: nn[r] * N] /= beta
+        gvec = np.zeros(nd + 2)
+        gvec[0] = beta
+        H, Q = {}, []
+        for idir in range(nd):
+            vt = [es[r].solve(v[idir][r][: nn[r] * N]) for r in (0, 1)]
+            halo(vt)
+            uk = [matvec(r, vt[r]) for r in (0, 1)]
+            for j in range(idir + 1):
+                h = dot(uk, v[j])
+                H[(j, idir)] = h
+                for r in (0, 1):
+                    uk[r][: nn[r] * N] -= h * v[j][r][: nn[r] * N]
+            hn = np.sqrt(dot(uk, uk))
+            H[(idir + 1, idir)] = hn
+            vn = [np.zeros(tot[r] * N) for r in (0, 1)]
+            for r in (0, 1):
+                vn[r][: nn[r] * N] = uk[r][: nn[r] * N] / hn
+            v.append(vn)
+            for jj in range(idir):
+                cs, sn = Q[jj]
+                t1, t2 = H[(jj, idir)], H[(jj + 1, idir)]
+                H[(jj, idir)] = cs * t1 + sn * t2
+                H[(jj + 1, idir)] = -sn * t1 + cs * t2
+            a1, a2 = H[(idir, idir)], H[(idir + 1, idir)]
+            alpha = np.sqrt(a1 * a1 + a2 * a2)
+            cs, sn = a1 / alpha, a2 / alpha
+            Q.append((cs, sn))
+            H[(idir, idir)], H[(idir + 1, idir)] = alpha, 0.0
+            t1, t2 = gvec[idir], gvec[idir + 1]
+            gvec[idir], gvec[idir + 1] = cs * t1 + sn * t2, -sn * t1 + cs * t2
+        for jj in range(nd - 1, -1, -1):
+            t1 = 0.0
+            for ii in range(jj + 1, nd):
+                t1 += H[(jj, ii)] * gvec[ii]
+            gvec[jj] = (gvec[jj] - t1) / H[(jj, jj)]
+        z = [np.zeros(nn[r] * N) for r in (0, 1)]
+        for jj in range(nd):
+            for r in (0, 1):
+                z[r] += v[jj][r][: nn[r] * N] * gvec[jj]
+        for r in (0, 1):
+            x[r][: nn[r] * N] += es[r].solve(z[r])[: nn[r] * N]
+        halo(x)
+    dq = abs(gvec[nd])
+    for r in (0, 1):
+        ref = parts[r][0]["gmres_x"]
+        assert np.abs(x[r] - ref).max() <= 1e-12 * np.abs(ref).max(), (r, np.abs(x[r] - ref).max() / np.abs(ref).max())
+        assert np.isclose(dq, parts[r][0]["gmres_dq"][0], rtol=1e-9)

@@ -311,6 +311,15 @@ CASES = {
                                            nsgs=3, cfl=5.0, gmres=(4, 2, 1), extra=FR_EXTRA.format(temp=3000, pres=101325, rxn=1)),
     "box4_fr_gmres": lambda: make_case("box4_fr_gmres", mesh=kuhn_box(4, jitter=0.15), eqnset="compressibleEulerFR",
                                        nsgs=3, cfl=5.0, gmres=(1, 6, 1), extra=FR_EXTRA.format(temp=3000, pres=101325, rxn=1)),
+    # GMRES with the local ILU0 right preconditioner (precondType 3: BuildILU0Local / ILU0BackSub, crsmatrix.tcc:276-507):
+    # both block sizes, and two reference ranks (ghost columns skipped by the factorisation and blanked afterwards).  The 9x9
+    # case freezes the chemistry: with the source Jacobian in the diagonal blocks the reference's pivot-free factorisation
+    # divides by zero and its GMRES returns NaN, which pins nothing.
+    "box6_gmres_ilu0": lambda: make_case("box6_gmres_ilu0", mesh=kuhn_box(6, jitter=0.15), nsgs=3, cfl=5.0, gmres=(3, 6, 2)),
+    "box4_fr_gmres_ilu0": lambda: make_case("box4_fr_gmres_ilu0", mesh=kuhn_box(4, jitter=0.15), eqnset="compressibleEulerFR",
+                                            nsgs=3, cfl=5.0, gmres=(3, 5, 1), extra=FR_EXTRA.format(temp=3000, pres=101325, rxn=0)),
+    "box8_2rank_gmres_ilu0": lambda: make_case("box8_2rank_gmres_ilu0", mesh=kuhn_box(8, jitter=0.15), np_ranks=2,
+                                               part=slab_part(kuhn_box(8, jitter=0.15)[0], 2), nsgs=3, cfl=5.0, gmres=(3, 6, 2)),
     # Forces::Compute / ComputeSurfaceAreas (forces.tcc): pressure and viscous forces, moments, cp / y+ / cf per
     # half-edge, lift / drag / moment coefficients of two composite bodies (the no-slip floor; three far-field faces)
     "box6_ns_forces": lambda: make_case("box6_ns_forces", mesh=kuhn_box(6, jitter=0.15),
