@@ -189,15 +189,15 @@ def test_ilu0_is_the_exact_lu_of_a_block_diagonal_system(emu):
     assert np.allclose(x[: nnode * 5].reshape(-1, 5), want, rtol=1e-13, atol=0)
 
 
-def test_two_rank_ilu0_gmres_replay_vs_reference(emu):
-    """CRS::GMRES with precondType 3 on the two-rank reference fixture, both ranks in lockstep: emulated ILU0 kernels,
-    the oracle-order matrix-vector product, numpy halos (PObj maps of the fixture) where the reference exchanges
-    (crs.tcc:249, :300, :399), dot products summed per rank and then in rank order.  Each rank's solution, ghost rows
-    included, to 1e-12 of its scale (MPI_Allreduce adds the two partial sums in the same order: usually bit-equal)."""
+def replay_gmres(emu, names, N, pairwise=False):
+    """CRS::GMRES with precondType 3 replayed on one or more reference ranks in lockstep: emulated ILU0 kernels, the
+    oracle-order matrix-vector product, numpy halos (PObj maps of the fixtures) where the reference exchanges
+    (crs.tcc:249, :300, :399), dot products summed per rank -- sequentially as the reference does, or pairwise (np.dot)
+    to see what the summation order alone moves -- and then in rank order.  Returns each rank's x and |g[idir]|."""
     from proteuscfd_b200.parallel import build_local_group_maps
-    N = 5
-    parts = [load_golden(f"box8_2rank_gmres_ilu0_r{r}of2") for r in (0, 1)]
-    pobjs = build_local_group_maps([(g["gNodeOwner"], g["gNodeLocalId"]) for g, _ in parts])
+    parts = [load_golden(n) for n in names]
+    R = range(len(parts))
+    pobjs = build_local_group_maps([(g["gNodeOwner"], g["gNodeLocalId"]) for g, _ in parts]) if len(parts) > 1 else None
     es = [EmuIlu0(emu, g, m, N) for g, m in parts]
     for e, (g, _) in zip(es, parts):
         e.build(g["A"])
@@ -205,9 +205,11 @@ def test_two_rank_ilu0_gmres_replay_vs_reference(emu):
     tot = [int(m["nnode"]) + int(m["gnode"]) for _, m in parts]
 
     def halo(vs):
-        packed = [pobjs[p].pack_numpy(vs[p], N) for p in (0, 1)]
-        for r in (0, 1):
-            pobjs[r].unpack_numpy(vs[r], N, nn[r], [packed[p][r] for p in (0, 1)])
+        if pobjs is None:
+            return
+        packed = [pobjs[p].pack_numpy(vs[p], N) for p in R]
+        for r in R:
+            pobjs[r].unpack_numpy(vs[r], N, nn[r], [packed[p][r] for p in R])
 
     def matvec(r, v):
         g = parts[r][0]
@@ -227,42 +229,45 @@ def test_two_rank_ilu0_gmres_replay_vs_reference(emu):
 
     def dot(us, vs):
         tot_ = 0.0
-        for r in (0, 1):
-            s = 0.0
+        for r in R:
             a, b = us[r][: nn[r] * N], vs[r][: nn[r] * N]
-            for i in range(a.size):
-                s += a[i] * b[i]
+            if pairwise:
+                s = float(np.dot(a, b))
+            else:
+                s = 0.0
+                for i in range(a.size):
+                    s += a[i] * b[i]
             tot_ += s
         return tot_
 
     pt, nd, nrest = [int(v) for v in parts[0][0]["gmres_cfg"]]
     assert pt == 3
-    x = [np.zeros(tot[r] * N) for r in (0, 1)]
-    b = [parts[r][0]["b"] for r in (0, 1)]
+    x = [np.zeros(tot[r] * N) for r in R]
+    b = [parts[r][0]["b"] for r in R]
     halo(x)
     for _ in range(nrest):
-        v = [[matvec(r, x[r]) for r in (0, 1)]]
-        for r in (0, 1):
+        v = [[matvec(r, x[r]) for r in R]]
+        for r in R:
             v[0][r][: nn[r] * N] = b[r][: nn[r] * N] - v[0][r][: nn[r] * N]
         beta = np.sqrt(dot(v[0], v[0]))
-        for r in (0, 1):
+        for r in R:
             v[0][r][: nn[r] * N] /= beta
         gvec = np.zeros(nd + 2)
         gvec[0] = beta
         H, Q = {}, []
         for idir in range(nd):
-            vt = [es[r].solve(v[idir][r][: nn[r] * N]) for r in (0, 1)]
+            vt = [es[r].solve(v[idir][r][: nn[r] * N]) for r in R]
             halo(vt)
-            uk = [matvec(r, vt[r]) for r in (0, 1)]
+            uk = [matvec(r, vt[r]) for r in R]
             for j in range(idir + 1):
                 h = dot(uk, v[j])
                 H[(j, idir)] = h
-                for r in (0, 1):
+                for r in R:
                     uk[r][: nn[r] * N] -= h * v[j][r][: nn[r] * N]
             hn = np.sqrt(dot(uk, uk))
             H[(idir + 1, idir)] = hn
-            vn = [np.zeros(tot[r] * N) for r in (0, 1)]
-            for r in (0, 1):
+            vn = [np.zeros(tot[r] * N) for r in R]
+            for r in R:
                 vn[r][: nn[r] * N] = uk[r][: nn[r] * N] / hn
             v.append(vn)
             for jj in range(idir):
@@ -282,15 +287,38 @@ def test_two_rank_ilu0_gmres_replay_vs_reference(emu):
             for ii in range(jj + 1, nd):
                 t1 += H[(jj, ii)] * gvec[ii]
             gvec[jj] = (gvec[jj] - t1) / H[(jj, jj)]
-        z = [np.zeros(nn[r] * N) for r in (0, 1)]
+        z = [np.zeros(nn[r] * N) for r in R]
         for jj in range(nd):
-            for r in (0, 1):
+            for r in R:
                 z[r] += v[jj][r][: nn[r] * N] * gvec[jj]
-        for r in (0, 1):
+        for r in R:
             x[r][: nn[r] * N] += es[r].solve(z[r])[: nn[r] * N]
         halo(x)
-    dq = abs(gvec[nd])
+    return x, abs(gvec[nd]), [H[(i, i)] for i in range(nd)], parts
+
+
+def test_two_rank_ilu0_gmres_replay_vs_reference(emu):
+    """the two-rank reference run: each rank's solution, ghost rows included, to 1e-12 of its scale (MPI_Allreduce adds
+    the two partial sums in the same order: usually bit-equal)"""
+    x, dq, _, parts = replay_gmres(emu, [f"box8_2rank_gmres_ilu0_r{r}of2" for r in (0, 1)], 5)
     for r in (0, 1):
         ref = parts[r][0]["gmres_x"]
         assert np.abs(x[r] - ref).max() <= 1e-12 * np.abs(ref).max(), (r, np.abs(x[r] - ref).max() / np.abs(ref).max())
         assert np.isclose(dq, parts[r][0]["gmres_dq"][0], rtol=1e-9)
+
+
+def test_what_the_summation_order_of_a_dot_product_moves(emu):
+    """Why the B200 bar of the 9x9 case is 1e-7 and not 1e-12 (tests/test_zz_gpu_ilu0.py; first B200 run: 5x5 inside
+    1e-12, 9x9 at 4.2e-9).  The replay with the reference's sequential dot products lands on the reference's x bit for bit
+    (both block sizes), so everything but the sums is pinned.  With pairwise sums and nothing else changed the 5x5
+    solution moves by 1e-13, the 9x9 one by 4e-9: the pivot-free ILU0 leaves the reacting system so badly scaled that the
+    Hessenberg diagonal of A N^-1 spans more than six decades, and the back substitution amplifies the 1e-16 of a sum by
+    that ratio.  The device's fixed-tree sums are a third order, as far from the reference's as np.dot's."""
+    for name, N, lo, hi, decades in (("box6_gmres_ilu0", 5, 0.0, 1e-12, 0.0), ("box4_fr_gmres_ilu0", 9, 1e-11, 1e-7, 6.0)):
+        x, dq, hd, parts = replay_gmres(emu, [name], N)
+        ref = parts[0][0]["gmres_x"]
+        assert np.array_equal(x[0], ref) and dq == parts[0][0]["gmres_dq"][0]
+        xp, _, _, _ = replay_gmres(emu, [name], N, pairwise=True)
+        moved = np.abs(xp[0] - ref).max() / np.abs(ref).max()
+        assert lo <= moved <= hi, (name, moved)
+        assert np.log10(max(hd) / min(hd)) >= decades, (name, hd)
