@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PCFD_ABI_VERSION 8
+#define PCFD_ABI_VERSION 9
 
 /* eqnset ids follow eqnset_defines.h / create_functions.h:17-45 */
 enum { PCFD_EQNSET_COMPRESSIBLE_EULER_FR = 0, PCFD_EQNSET_COMPRESSIBLE_NS_FR = 1, PCFD_EQNSET_COMPRESSIBLE_EULER = 2,
@@ -178,6 +178,17 @@ int pcfd_sgs(pcfd_ctx* ctx, int nsgs, double* ddq);
    needs a halo before every product travels through pcfd_comm and the dot products are summed across ranks.  The
    reference's flow solver keeps this solver behind a comment (solutionSpace.tcc:734-750); move.tcc:714 calls it. (ABI v7) */
 int pcfd_gmres(pcfd_ctx* ctx, int restarts, int nsearch, int precond_type, double* dq_norm);
+
+/* CRSMatrix::CRSTranspose (crsmatrix.tcc:568-599) on PCFD_F_A as ASSEMBLED (an error after pcfd_prepare_sgs): the
+   adjoint path's transposed Jacobian (Compute_dRdQ_Transpose, jacobian.tcc:121-127).  Every block is transposed and the
+   mirror blocks (i, j) <-> (j, i) of local node pairs change places; blocks of ghost columns are transposed where they
+   are.  On a partition they must then be replaced by the owning rank's block of the mirrored cut edge
+   (PObj::TransposeCommCRS, parallel.tcc:54-338): pcfd_crs_ghost_blocks moves them between the device and a host buffer
+   of ngedge * neqn^2 doubles (set = 0: device -> host, 1: host -> device), block e being A(bedges_n[2(nbedge+e)],
+   bedges_n[2(nbedge+e)+1]) -- the order of the parallel half-edges of pcfd_mesh_desc -- and the host routes them with the
+   transport it owns (MPI in ucs.x; proteuscfd_b200/parallel.py: crs_transpose).  (ABI v9) */
+int pcfd_crs_transpose(pcfd_ctx* ctx);
+int pcfd_crs_ghost_blocks(pcfd_ctx* ctx, int set, double* host);
 
 /* Forces (ucs/forces.tcc; called once per iteration at solutionSpace.tcc:884 and :924).  (ABI v8)
    pcfd_forces_configure takes the composite bodies the .bc file declares ("body #k = [factags]", composite.tcc:78-170;

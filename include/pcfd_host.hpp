@@ -37,6 +37,64 @@ inline void DefaultErrorHandler(const char* where, const char* message) {
   std::abort();
 }
 
+#ifndef PCFD_HOST_NO_MPI
+// The exchange of PObj::TransposeCommCRS (parallel.tcc:54-338) on packed ghost-column blocks: block e belongs to the
+// parallel half-edge ghost_edges[2e] (local node) -> ghost_edges[2e+1] (ghost id >= nnode) and is replaced by the block
+// the ghost's owner holds for the mirrored edge.  A request is the pair (owner's row = gNodeLocalId of my ghost, my
+// row) in LOCAL ids; the owner resolves it through its own ghost table.  Counts by MPI_Alltoall, pairs and blocks point
+// to point, like the reference.  Plain arrays only, so that it can be exercised without a device
+// (oracle/harness/transpose_route_test.cpp, tests/test_crs_transpose.py).
+inline bool RouteTransposedGhostBlocks(int nnode, int ngedge, const int* ghost_edges, const int* gNodeOwner,
+                                       const int* gNodeLocalId, int n2, double* blocks) {
+  int np = 1;
+  MPI_Comm_size(MPI_COMM_WORLD, &np);
+  std::vector<int> recvc(np, 0), sendc(np, 0), roff(np + 1, 0), soff(np + 1, 0), owner((size_t)(ngedge > 0 ? ngedge : 1));
+  for (int e = 0; e < ngedge; e++) {
+    owner[e] = gNodeOwner[ghost_edges[2 * e + 1] - nnode];
+    recvc[owner[e]]++;
+  }
+  MPI_Alltoall(recvc.data(), 1, MPI_INT, sendc.data(), 1, MPI_INT, MPI_COMM_WORLD);
+  for (int p = 0; p < np; p++) { roff[p + 1] = roff[p] + recvc[p]; soff[p + 1] = soff[p] + sendc[p]; }
+  const size_t nr = (size_t)(roff[np] > 0 ? roff[np] : 1), ns = (size_t)(soff[np] > 0 ? soff[np] : 1);
+  std::vector<int> ask(2 * nr), slot(nr), fill(roff.begin(), roff.end() - 1), asked(2 * ns);
+  for (int e = 0; e < ngedge; e++) {      // what I ask of each owner, in half-edge order, and the slot the answer fills
+    const int k = fill[owner[e]]++;
+    ask[2 * k] = gNodeLocalId[ghost_edges[2 * e + 1] - nnode];
+    ask[2 * k + 1] = ghost_edges[2 * e];
+    slot[k] = e;
+  }
+  std::vector<MPI_Request> rq((size_t)np), sq((size_t)np);
+  for (int p = 0; p < np; p++) if (sendc[p]) MPI_Irecv(&asked[2 * soff[p]], 2 * sendc[p], MPI_INT, p, 0, MPI_COMM_WORLD, &rq[p]);
+  for (int p = 0; p < np; p++) if (recvc[p]) MPI_Isend(&ask[2 * roff[p]], 2 * recvc[p], MPI_INT, p, 0, MPI_COMM_WORLD, &sq[p]);
+  for (int p = 0; p < np; p++) {
+    if (sendc[p]) MPI_Wait(&rq[p], MPI_STATUS_IGNORE);
+    if (recvc[p]) MPI_Wait(&sq[p], MPI_STATUS_IGNORE);
+  }
+  // serve: (my row j, asking rank p, p's local node i) -> my half-edge whose ghost p owns under the local id i
+  bool ok = true;
+  std::vector<double> out(ns * n2, 0.0), in(nr * n2);
+  for (int p = 0; p < np; p++)
+    for (int k = soff[p]; k < soff[p + 1]; k++) {
+      int found = -1;
+      for (int e = 0; e < ngedge && found < 0; e++) {
+        const int g = ghost_edges[2 * e + 1] - nnode;
+        if (ghost_edges[2 * e] == asked[2 * k] && gNodeOwner[g] == p && gNodeLocalId[g] == asked[2 * k + 1]) found = e;
+      }
+      if (found < 0) { ok = false; continue; }      // keep the exchange going: every rank must reach its waits
+      std::memcpy(&out[(size_t)k * n2], &blocks[(size_t)found * n2], sizeof(double) * n2);
+    }
+  for (int p = 0; p < np; p++) if (recvc[p]) MPI_Irecv(&in[(size_t)roff[p] * n2], recvc[p] * n2, MPI_DOUBLE, p, 1, MPI_COMM_WORLD, &rq[p]);
+  for (int p = 0; p < np; p++) if (sendc[p]) MPI_Isend(&out[(size_t)soff[p] * n2], sendc[p] * n2, MPI_DOUBLE, p, 1, MPI_COMM_WORLD, &sq[p]);
+  for (int p = 0; p < np; p++) {
+    if (recvc[p]) MPI_Wait(&rq[p], MPI_STATUS_IGNORE);
+    if (sendc[p]) MPI_Wait(&sq[p], MPI_STATUS_IGNORE);
+  }
+  for (int k = 0; k < roff[np]; k++) std::memcpy(&blocks[(size_t)slot[k] * n2], &in[(size_t)k * n2], sizeof(double) * n2);
+  return ok;
+}
+#endif
+
+#ifndef PCFD_HOST_ROUTING_ONLY   // (the device-free routing test includes the header without the reference's types)
 template <class Space>
 class DropIn {
  public:
@@ -292,7 +350,7 @@ class DropIn {
     return ss;
   }
   // CRS::GMRES(restarts, nSearchDir, precondType, ...) (crs.tcc:176-415) on the matrix of ComputeJacobians (not yet
-  // factored by PrepareSGS), b and x of the context; precondType 0 none, 1 diagonal, 2 block diagonal
+  // factored by PrepareSGS), b and x of the context; precondType 0 none, 1 diagonal, 2 block diagonal, 3 local ILU0, 4 SGS
   double GMRES(int restarts, int nSearchDir, int precondType) {
     double dq = 0.0;
     Check(pcfd_gmres(ctx_, restarts, nSearchDir, precondType, &dq), "CRS::GMRES");
@@ -337,6 +395,27 @@ class DropIn {
     MPI_Allgather(mine.data(), (int)bs, MPI_BYTE, all.data(), (int)bs, MPI_BYTE, MPI_COMM_WORLD);
     Check(pcfd_comm_connect(ctx_, all.data()), "pcfd_comm_connect");
     MPI_Barrier(MPI_COMM_WORLD);       // nobody posts before everybody is connected
+  }
+  // CRSMatrix::CRSTranspose (crsmatrix.tcc:568-599) of the device-resident Jacobian, for Compute_dRdQ_Transpose
+  // (jacobian.tcc:121-127).  The local part is three kernels; across ranks the blocks of the ghost columns are replaced by
+  // the owner's block of the mirrored cut edge as PObj::TransposeCommCRS does (parallel.tcc:54-338), with requests in LOCAL
+  // ids (RouteTransposedGhostBlocks above).  Once per adjoint solve, so the blocks go through the host.
+  void CRSTranspose() {
+    Check(pcfd_crs_transpose(ctx_), "CRSMatrix::CRSTranspose");
+    int np = 1;
+    MPI_Comm_size(MPI_COMM_WORLD, &np);
+    if (np == 1 || ngedge_ == 0) return;
+    const int n2 = neqn_ * neqn_;
+    std::vector<double> blocks((size_t)ngedge_ * n2);
+    std::vector<int> ge(2 * (size_t)ngedge_);
+    for (int e = 0; e < ngedge_; e++) {
+      ge[2 * e] = s_->m->bedges[nbedge_ + e].n[0];
+      ge[2 * e + 1] = s_->m->bedges[nbedge_ + e].n[1];
+    }
+    Check(pcfd_crs_ghost_blocks(ctx_, 0, blocks.data()), "pcfd_crs_ghost_blocks (get)");
+    if (!RouteTransposedGhostBlocks(nnode_, ngedge_, ge.data(), s_->m->gNodeOwner, s_->m->gNodeLocalId, n2, blocks.data()))
+      onError_("CRSTranspose", "a requested cut edge has no mirror on its owner");
+    Check(pcfd_crs_ghost_blocks(ctx_, 1, blocks.data()), "pcfd_crs_ghost_blocks (set)");
   }
   // PObj::UpdateGeneralVectors(v, n) for a device-resident field (PCFD_F_Q, _QGRAD, _LIMITER, _X, _LSQ_S, _LSQ_SW, ...)
   void UpdateGeneralVectors(int field) { Check(pcfd_comm_update(ctx_, field), "UpdateGeneralVectors"); }
@@ -439,6 +518,7 @@ class DropIn {
   bool forces_ready_ = false;
   int nnode_, gnode_, nbnode_, nedge_, nbedge_, ngedge_, neqn_, nvars_, nterms_;
 };
+#endif  // PCFD_HOST_ROUTING_ONLY
 
 }  // namespace pcfd
 

@@ -543,6 +543,13 @@ int main(int argc, char* argv[])
       Dump("ja", A->ja, (size_t)A->nblocks);
       Dump("iau", A->iau, (size_t)nnode);
       Dump("A", A->M, (size_t)A->nblocks*neqn*neqn);
+      if(getenv("PCFD_TRANSPOSE")){
+	// CRSMatrix::CRSTranspose on the device-resident matrix (ghost-column blocks through the host's MPI), and back
+	gpu.CRSTranspose();
+	gpu.PullMatrix();
+	Dump("A_T", A->M, (size_t)A->nblocks*neqn*neqn);
+	gpu.CRSTranspose();
+      }
       gpu.PrepareSGS();
       gpu.PullMatrix();
       Dump("A_lu", A->M, (size_t)A->nblocks*neqn*neqn);
@@ -625,6 +632,17 @@ int main(int argc, char* argv[])
 	Dump("gmres_dq", &dq, 1);
 	Dump("gmres_cfg", cfg, 3);
 	delete [] xg;
+      }
+      if(getenv("PCFD_TRANSPOSE")){
+	// CRSMatrix::CRSTranspose (crsmatrix.tcc:568-599, with PObj::TransposeCommCRS across ranks) on the assembled matrix;
+	// the matrix is put back afterwards so that every later dump is what it is without this block
+	size_t nA = (size_t)A->nblocks*neqn*neqn;
+	Real* keep = new Real[nA];
+	memcpy(keep, A->M, sizeof(Real)*nA);
+	A->CRSTranspose();
+	Dump("A_T", A->M, nA);
+	memcpy(A->M, keep, sizeof(Real)*nA);
+	delete [] keep;
       }
       A->PrepareSGS();
       Dump("A_lu", A->M, (size_t)A->nblocks*neqn*neqn);

@@ -27,6 +27,8 @@ namespace {
 
 int g_rank = 0, g_np = 1;
 bool g_init = false;
+bool g_finalizing = false;          // inside MPI_Finalize: a peer that is through its barrier may hang up
+std::vector<char> g_closed;         // peers that have hung up during finalisation
 std::vector<int> g_fd;            // g_fd[peer]
 std::vector<pid_t> g_children;    // rank 0 only
 
@@ -102,7 +104,7 @@ bool Progress(bool block)
   std::vector<pollfd> pfds;
   std::vector<int> peers;
   for(int p = 0; p < g_np; p++){
-    if(p == g_rank) continue;
+    if(p == g_rank || (!g_closed.empty() && g_closed[p])) continue;
     pollfd pf; pf.fd = g_fd[p]; pf.events = POLLIN; pf.revents = 0;
     if(!g_out[p].empty()) pf.events |= POLLOUT;
     pfds.push_back(pf); peers.push_back(p);
@@ -137,6 +139,9 @@ bool Progress(bool block)
 	}
 	if(r == 0){
 	  if(pfds[k].revents & POLLHUP){
+	    // a peer leaves MPI_Finalize as soon as ITS barrier is complete, possibly while this rank still polls for
+	    // the others: everything it owed has been read above
+	    if(g_finalizing){ g_closed[p] = 1; break; }
 	    fprintf(stderr, "mpi_shim[rank %d]: peer %d hung up\n", g_rank, p);
 	    _exit(99);
 	  }
@@ -271,6 +276,8 @@ int MPI_Finalize(void)
 {
   if(!g_init) return MPI_SUCCESS;
   if(g_np > 1){
+    g_finalizing = true;
+    g_closed.assign(g_np, 0);
     MPI_Barrier(MPI_COMM_WORLD);
     FlushAll();
   }

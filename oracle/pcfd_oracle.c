@@ -1485,6 +1485,37 @@ static void gm_sgs(int nnode, int neqn, int nsgs, const int* ia, const int* ja, 
   }
 }
 
+/* CRSMatrix::CRSTranspose (crsmatrix.tcc:568-599) without its parallel sync: every block transposed in place
+   (Transpose, matrix.h), then the mirror blocks of local node pairs swapped -- once per pair (i < j), ghost columns left
+   for PObj::TransposeCommCRS */
+void orc_crs_transpose_local(int nnode, int neqn, const int* ia, const int* ja, double* A)
+{
+  int i, j, k, l, indx, n2 = neqn*neqn, nblocks = ia[nnode];
+  double temp[ORC_MAX_NEQN*ORC_MAX_NEQN];
+  for(i = 0; i < nblocks; i++){
+    double* blk = &A[(size_t)i*n2];
+    for(k = 0; k < neqn; k++)
+      for(l = k+1; l < neqn; l++){
+	double t = blk[k*neqn + l];
+	blk[k*neqn + l] = blk[l*neqn + k];
+	blk[l*neqn + k] = t;
+      }
+  }
+  for(i = 0; i < nnode; i++){
+    for(indx = ia[i]+1; indx < ia[i+1]; indx++){
+      j = ja[indx];
+      if((i < j) && j < nnode){
+	int m = -1, q;
+	for(q = ia[j]; q < ia[j+1]; q++) if(ja[q] == i){ m = q; break; }
+	if(m < 0) continue;
+	memcpy(temp, &A[(size_t)indx*n2], sizeof(double)*n2);
+	memcpy(&A[(size_t)indx*n2], &A[(size_t)m*n2], sizeof(double)*n2);
+	memcpy(&A[(size_t)m*n2], temp, sizeof(double)*n2);
+      }
+    }
+  }
+}
+
 /* CRSMatrix::GetIndex (crsmatrix.tcc): position of block (row, col), -1 when the pattern has none */
 static int gm_block_index(const int* ia, const int* ja, int row, int col)
 {

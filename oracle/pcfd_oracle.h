@@ -262,6 +262,10 @@ double orc_fr_turb_sa(const orc_case* c, const orc_fr_params* p, int nsgs, const
 		      const double* dist, const double* dt, const int* ia, const int* ja, const int* iau,
 		      double* tvar, double* tgrad, double* b, double* A, double* x, double* mut);
 
+/* CRSMatrix::CRSTranspose (crsmatrix.tcc:568-599) up to its parallel sync (PObj::TransposeCommCRS replaces the ghost-column
+   blocks afterwards; tests/test_crs_transpose.py routes them) */
+void orc_crs_transpose_local(int nnode, int neqn, const int* ia, const int* ja, double* A);
+
 /* the local ILU0 preconditioner of CRS::GMRES: CRSMatrix::BuildILU0Local (crsmatrix.tcc:276-428) in place on a copy N of
    the assembled matrix, and CRSMatrix::ILU0BackSub (crsmatrix.tcc:430-507), N x = b with x blanked first */
 void orc_ilu0_build(int nnode, int neqn, const int* ia, const int* ja, const int* iau, double* N);

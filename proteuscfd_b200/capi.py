@@ -44,7 +44,7 @@ SYMBOLS = [
     "pcfd_comm_blob_size", "pcfd_comm_export", "pcfd_comm_connect", "pcfd_comm_disconnect", "pcfd_comm_connected",
     "pcfd_comm_post", "pcfd_comm_wait", "pcfd_comm_update", "pcfd_comm_allgather", "pcfd_comm_debug_flags", "pcfd_gmres",
     "pcfd_forces_configure", "pcfd_forces_areas", "pcfd_forces_compute", "pcfd_forces_get", "pcfd_zeroed_updates",
-    "pcfd_wall_distance",
+    "pcfd_wall_distance", "pcfd_crs_transpose", "pcfd_crs_ghost_blocks",
 ]
 
 
@@ -230,6 +230,8 @@ def load_library(path=LIB_PATH):
     lib.pcfd_turb_phase.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.pcfd_gmres.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp]
     lib.pcfd_wall_distance.argtypes = [C.c_void_p, _dp, C.c_int]
+    lib.pcfd_crs_transpose.argtypes = [C.c_void_p]
+    lib.pcfd_crs_ghost_blocks.argtypes = [C.c_void_p, C.c_int, _dp]
     lib.pcfd_zeroed_updates.argtypes = [C.c_void_p]
     lib.pcfd_zeroed_updates.restype = C.c_longlong
     lib.pcfd_forces_configure.argtypes = [C.c_void_p, C.POINTER(ForcesDesc)]
@@ -540,6 +542,25 @@ class Context:
         d = C.c_double()
         self._ck(self.lib.pcfd_gmres(self.h, int(restarts), int(nsearch), int(precond_type), C.byref(d)))
         return d.value
+
+    def crs_transpose(self):
+        """CRSMatrix::CRSTranspose on the assembled A: the local part (blocks transposed, mirror blocks of local node pairs
+        swapped, ghost-column blocks transposed in place); on a partition follow with parallel.crs_transpose_ghosts"""
+        self._ck(self.lib.pcfd_crs_transpose(self.h))
+
+    def get_ghost_blocks(self):
+        """the blocks of the ghost columns, [ngedge, neqn, neqn], in the order of the parallel half-edges"""
+        neqn = self.neqn
+        out = np.zeros((max(self.ngedge, 1), neqn, neqn))
+        self._ck(self.lib.pcfd_crs_ghost_blocks(self.h, 0, out.ctypes.data_as(_dp)))
+        return out[: self.ngedge]
+
+    def set_ghost_blocks(self, blocks):
+        neqn = self.neqn
+        b = np.ascontiguousarray(blocks, dtype=np.float64)
+        if b.size != self.ngedge * neqn * neqn:
+            raise ValueError("set_ghost_blocks: ngedge * neqn^2 doubles expected")
+        self._ck(self.lib.pcfd_crs_ghost_blocks(self.h, 1, b.ctypes.data_as(_dp)))
 
     def wall_distance(self, points):
         """ComputeWallDistOct: field F_WALLDIST = distance of every local node to the nearest of `points` [n, 3] (the viscous

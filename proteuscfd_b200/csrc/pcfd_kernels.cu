@@ -3869,6 +3869,8 @@ int pcfd_implicit_iterate(pcfd_ctx* c, int refresh_jac, int nsgs, double* sumsq,
 
 }  // extern "C"
 
+#include "pcfd_crsmatrix.cuh"
+
 int pcfd_internal_create(const pcfd_mesh_desc* mesh, const pcfd_params* params, int device, int neqn, int nvars,
                          int nterms, pcfd_ctx** out) {
   return create_impl(mesh, params, device, neqn, nvars, nterms, out);

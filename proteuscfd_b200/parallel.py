@@ -336,6 +336,66 @@ class CommExchange:
         self.ctx.comm_disconnect()
 
 
+class TransposeMaps:
+    """PObj::TransposeCommCRS (ucs/parallel.tcc:54-338) as maps: after CRSMatrix::CRSTranspose has transposed every
+    block and swapped the local mirror blocks, the block of every ghost column (local row i, ghost g) is replaced by the
+    block the owner of g holds for the mirrored cut edge -- its row j = gNodeLocalId[g], its ghost column of (this rank,
+    i) -- which the owner has already transposed in place.  The reference sends (row, column) pairs as global ids and the
+    owner maps them back (:227-287); here a request is the pair (j, i) of LOCAL ids, which the owner resolves through
+    its own ghost table.  ghost_edges: the parallel half-edges bedges_n[nbedge .. nbedge+ngedge) as (local node, ghost)
+    pairs -- the order pcfd_crs_ghost_blocks packs the blocks in."""
+
+    def __init__(self, rank, nranks, nnode, ghost_edges, g_node_owner, g_node_local_id):
+        self.rank, self.np = int(rank), int(nranks)
+        ge = np.asarray(ghost_edges, dtype=np.int64).reshape(-1, 2)
+        owner = np.asarray(g_node_owner, dtype=np.int64)
+        lid = np.asarray(g_node_local_id, dtype=np.int64)
+        gi = ge[:, 1] - nnode
+        if ge.size and (gi.min() < 0 or ge[:, 0].max() >= nnode):
+            raise ValueError("TransposeMaps: a parallel half-edge joins a local node and a ghost")
+        eo = owner[gi]
+        self.requests = [np.stack([lid[gi[eo == p]], ge[eo == p, 0]], axis=1).astype(np.int32) for p in range(self.np)]
+        self.slots = [np.nonzero(eo == p)[0] for p in range(self.np)]
+        # what a peer may ask for: (my row, peer, the peer's local id of my ghost column) -> my half-edge slot
+        self.lookup = {(int(ge[e, 0]), int(eo[e]), int(lid[gi[e]])): e for e in range(ge.shape[0])}
+
+    def serve(self, peer, pairs, blocks):
+        """blocks this rank owes `peer` for its request pairs (j = row here, i = the peer's local node)"""
+        idx = [self.lookup[(int(j), int(peer), int(i))] for j, i in np.asarray(pairs).reshape(-1, 2)]
+        return blocks[idx]
+
+    def place(self, blocks, from_peer):
+        out = np.array(blocks, copy=True)
+        for p in range(self.np):
+            if self.slots[p].size:
+                out[self.slots[p]] = from_peer[p]
+        return out
+
+
+def transpose_ghost_blocks_local(maps, blocks):
+    """all ranks in this process: blocks[r] = rank r's ghost-column blocks [ngedge_r, n, n] after the local transpose;
+    returns what TransposeCommCRS leaves in them"""
+    n = len(maps)
+    return [maps[r].place(blocks[r], [maps[p].serve(r, maps[r].requests[p], blocks[p]) if p != r else None
+                                      for p in range(n)]) for r in range(n)]
+
+
+def crs_transpose(ctx, mesh, group):
+    """CRSMatrix::CRSTranspose of the context's assembled matrix on a partition (one rank per process or thread):
+    local part on the device (pcfd_crs_transpose), ghost-column blocks routed through `group.allgather` of host
+    buffers -- once per adjoint solve, off the iteration's path.  mesh: the dict the context was created from."""
+    rank, nranks = group.rank, group.nranks
+    nnode, nb, ng = int(mesh["nnode"]), int(mesh["nbedge"]), int(mesh["ngedge"])
+    ge = np.asarray(mesh["bedges_n"]).reshape(-1, 2)[nb: nb + ng]
+    maps = TransposeMaps(rank, nranks, nnode, ge, mesh["gNodeOwner"], mesh["gNodeLocalId"])
+    ctx.crs_transpose()
+    blocks = ctx.get_ghost_blocks()
+    asked = group.allgather(maps.requests)                       # asked[r][p]: what r requests of p
+    served = group.allgather([maps.serve(r, asked[r][rank], blocks) if r != rank else None for r in range(nranks)])
+    ctx.set_ghost_blocks(maps.place(blocks, [served[p][rank] if p != rank else None for p in range(nranks)]))
+    return maps
+
+
 class DistributedHotPath:
     """SolutionSpace::NewtonIterate (ucs/solutionSpace.tcc:640-904) across ranks: the phase calls of one context
     with the reference's halo exchanges and reductions in the reference's places."""

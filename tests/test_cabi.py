@@ -31,7 +31,7 @@ def test_header_symbols_all_exported(lib):
     assert sorted(capi.SYMBOLS) == syms, "capi.SYMBOLS out of sync with include/pcfd.h"
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in pcfd.h but not exported"
-    assert lib.pcfd_abi_version() == 8
+    assert lib.pcfd_abi_version() == 9
 
 
 def test_no_cpu_fallback(lib):

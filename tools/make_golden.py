@@ -131,7 +131,7 @@ def collect(outdir, rank):
     return d
 
 
-def make_case(name, mesh=None, h5=None, bc=BOX_BC, np_ranks=1, part=None, unsteady=False, gmres=None, forces=False, **kw):
+def make_case(name, mesh=None, h5=None, bc=BOX_BC, np_ranks=1, part=None, unsteady=False, gmres=None, forces=False, transpose=False, **kw):
     opts = dict(eqnset="compressibleEuler", sorder=2, limiter=2, nsgs=0, mach=0.5, cfl=0.5,
                 fx=1.0, fy=0.0, fz=0.0, jactype=0, refvisc=1.0, vnn=0, turb=0, extra="")
     opts.update(kw)
@@ -158,6 +158,8 @@ def make_case(name, mesh=None, h5=None, bc=BOX_BC, np_ranks=1, part=None, unstea
             henv["PCFD_UNSTEADY"] = "1"
         if forces:                 # Forces::Compute on the bodies the .bc file declares
             henv["PCFD_FORCES"] = "1"
+        if transpose:              # CRSMatrix::CRSTranspose on the assembled matrix -> A_T
+            henv["PCFD_TRANSPOSE"] = "1"
         if gmres is not None:      # (precondType, search directions, restarts): also run CRS::GMRES on the assembled system
             henv.update(PCFD_GMRES=str(gmres[0]), PCFD_GMRES_NDIR=str(gmres[1]), PCFD_GMRES_RESTARTS=str(gmres[2]))
         run([os.path.join(REFBIN, "ref_harness"), os.path.join(work, name), os.path.join(work, "out"), "dump"], work, henv)
@@ -203,6 +205,11 @@ def slab_part(xyz, ranks, axis=2):
     """Partition id per node: equal slabs along one axis."""
     x = np.clip(xyz[:, axis], 0.0, 1.0 - 1e-12)
     return (x * ranks).astype(np.int64)
+
+
+def quadrant_part(xyz):
+    """Partition id per node: four columns cut at x = 0.5 and y = 0.5 (every part touches the other three)."""
+    return 2 * (xyz[:, 0] > 0.5).astype(np.int64) + (xyz[:, 1] > 0.5).astype(np.int64)
 
 
 def colored_box(n, **kw):
@@ -320,6 +327,16 @@ CASES = {
                                             nsgs=3, cfl=5.0, gmres=(3, 5, 1), extra=FR_EXTRA.format(temp=3000, pres=101325, rxn=0)),
     "box8_2rank_gmres_ilu0": lambda: make_case("box8_2rank_gmres_ilu0", mesh=kuhn_box(8, jitter=0.15), np_ranks=2,
                                                part=slab_part(kuhn_box(8, jitter=0.15)[0], 2), nsgs=3, cfl=5.0, gmres=(3, 6, 2)),
+    # CRSMatrix::CRSTranspose (crsmatrix.tcc:568-599) of the assembled Jacobian: blocks transposed in place, local mirror
+    # blocks swapped, ghost-column blocks replaced by the owner's through PObj::TransposeCommCRS (parallel.tcc:54-338) --
+    # one rank for both block sizes, two slabs, four quadrant columns (every rank has three neighbours)
+    "box5_transpose": lambda: make_case("box5_transpose", mesh=kuhn_box(5, jitter=0.15), nsgs=1, cfl=5.0, transpose=True),
+    "box4_fr_transpose": lambda: make_case("box4_fr_transpose", mesh=kuhn_box(4, jitter=0.15), eqnset="compressibleEulerFR",
+                                           nsgs=1, cfl=5.0, transpose=True, extra=FR_EXTRA.format(temp=3000, pres=101325, rxn=1)),
+    "box6_2rank_transpose": lambda: make_case("box6_2rank_transpose", mesh=kuhn_box(6, jitter=0.15), np_ranks=2,
+                                              part=slab_part(kuhn_box(6, jitter=0.15)[0], 2), nsgs=1, cfl=5.0, transpose=True),
+    "box6_4rank_transpose": lambda: make_case("box6_4rank_transpose", mesh=kuhn_box(6, jitter=0.15), np_ranks=4,
+                                              part=quadrant_part(kuhn_box(6, jitter=0.15)[0]), nsgs=1, cfl=5.0, transpose=True),
     # Forces::Compute / ComputeSurfaceAreas (forces.tcc): pressure and viscous forces, moments, cp / y+ / cf per
     # half-edge, lift / drag / moment coefficients of two composite bodies (the no-slip floor; three far-field faces)
     "box6_ns_forces": lambda: make_case("box6_ns_forces", mesh=kuhn_box(6, jitter=0.15),
