@@ -184,6 +184,21 @@ static void DumpMesh(SolutionSpace<Real>* space)
   }
   Dump("bedges_bctype", bt.data(), bt.size());
   Dump("xyz", m->xyz, 3*(size_t)(nnode+gnode));
+  if(getenv("PCFD_DUMP_ELEMENTS")){
+    // element list in the reference's internal winding (etypes.h: TRI 0 .. HEX 5): type, factag, 8 node slots (-1 padded)
+    std::vector<Int> et, ef, enodes;
+    for(size_t k = 0; k < m->elementList.size(); k++){
+      Element<Real>& el = *m->elementList[k];
+      Int* nodes = NULL;
+      Int nn = el.GetNodes(&nodes);
+      et.push_back(el.GetType());
+      ef.push_back(el.GetFactag());
+      for(Int j = 0; j < 8; j++) enodes.push_back(j < nn ? nodes[j] : -1);
+    }
+    Dump("elem_type", et.data(), et.size());
+    Dump("elem_factag", ef.data(), ef.size());
+    Dump("elem_nodes", enodes.data(), enodes.size());
+  }
   Dump("vol", m->vol, (size_t)nnode);
   Dump("ipsp", m->ipsp, (size_t)nnode+1);
   Dump("psp", m->psp, (size_t)m->ipsp[nnode]);

@@ -185,3 +185,110 @@ def kuhn_slab(n, k_lo, k_hi, nz_total, jitter=0.0, seed=1234):
             tris.append(f)
             tags.append(np.full(len(f), tag, dtype=np.int32))
     return xyz, tets.astype(np.int32), np.concatenate(tris).astype(np.int32), np.concatenate(tags), gid
+
+
+def mixed_box(n, kind="mixed", jitter=0.0, seed=4321):
+    """A unit box of n^3 cells with general elements, in UGRID winding (hex / prism: bottom face counter-clockwise seen
+    from the top face, then the top face; UGRID pyramids: see `_PYR_UGRID`; boundary faces with the right-hand normal
+    INTO the domain).  kind: "hex", "prism" (every cell cut into two prisms along the vertical 0-2 diagonal plane),
+    "pyramid" (six pyramids per cell around an extra centre node), "mixed" (columns i < n/2: prisms; the other columns:
+    hexes below n/2, pyramid-split cells above, and in the top layer the pyramid under the lid cut into two tets -- all
+    four element types, triangular and quadrilateral boundary faces, conforming).
+    Returns xyz, {"tet", "pyramid", "prism", "hex"} -> node arrays, tris, tri_tags, quads, quad_tags (tags as kuhn_box)."""
+    np1 = n + 1
+    g = np.arange(np1, dtype=np.float64) / n
+    kk, jj, ii = np.meshgrid(g, g, g, indexing="ij")
+    xyz = np.stack([ii.ravel(), jj.ravel(), kk.ravel()], axis=1)
+    if jitter > 0.0:
+        rng = np.random.default_rng(seed)
+        d = rng.uniform(-jitter / n, jitter / n, size=xyz.shape)
+        interior = np.all((xyz > 1e-12) & (xyz < 1 - 1e-12), axis=1)
+        xyz[interior] += d[interior]
+
+    def nid(a, b, c):
+        return a + np1 * (b + np1 * c)
+
+    extra = []          # cell-centre nodes of the pyramid-split cells
+    el = {"tet": [], "pyramid": [], "prism": [], "hex": []}
+    tris, ttags, quads, qtags = [], [], [], []
+
+    def bface(nodes, tag):   # nodes: right-hand normal into the domain
+        (quads if len(nodes) == 4 else tris).append(nodes)
+        (qtags if len(nodes) == 4 else ttags).append(tag)
+
+    for c in range(n):
+        for b in range(n):
+            for a in range(n):
+                v = [nid(a, b, c), nid(a + 1, b, c), nid(a + 1, b + 1, c), nid(a, b + 1, c),
+                     nid(a, b, c + 1), nid(a + 1, b, c + 1), nid(a + 1, b + 1, c + 1), nid(a, b + 1, c + 1)]
+                # the six faces of the cell, right-hand normal towards the cell centre, and the tag if on the box
+                faces = [((v[0], v[3], v[7], v[4]), 1 if a == 0 else 0), ((v[1], v[5], v[6], v[2]), 2 if a == n - 1 else 0),
+                         ((v[0], v[4], v[5], v[1]), 3 if b == 0 else 0), ((v[3], v[2], v[6], v[7]), 4 if b == n - 1 else 0),
+                         ((v[0], v[1], v[2], v[3]), 5 if c == 0 else 0), ((v[4], v[7], v[6], v[5]), 6 if c == n - 1 else 0)]
+                what = kind
+                if kind == "mixed":
+                    what = "prism" if a < n // 2 else ("hex" if c < n // 2 else "pyramid")
+                if what == "hex":
+                    el["hex"].append(v)
+                    for f, t in faces:
+                        if t:
+                            bface(f, t)
+                elif what == "prism":
+                    el["prism"].append([v[0], v[1], v[2], v[4], v[5], v[6]])
+                    el["prism"].append([v[0], v[2], v[3], v[4], v[6], v[7]])
+                    for f, t in faces[:4]:
+                        if t:
+                            bface(f, t)
+                    if c == 0:
+                        bface((v[0], v[1], v[2]), 5)
+                        bface((v[0], v[2], v[3]), 5)
+                    if c == n - 1:
+                        bface((v[4], v[6], v[5]), 6)
+                        bface((v[4], v[7], v[6]), 6)
+                else:
+                    ctr = np1 ** 3 + len(extra)
+                    extra.append(xyz[v].mean(axis=0))
+                    for f, t in faces:
+                        lid = kind == "mixed" and t == 6
+                        if lid:      # the pyramid under the lid as two tets; the lid face as two triangles
+                            el["tet"].append([f[0], f[1], f[2], ctr])
+                            el["tet"].append([f[0], f[2], f[3], ctr])
+                            bface((f[0], f[1], f[2]), t)
+                            bface((f[0], f[2], f[3]), t)
+                        else:
+                            el["pyramid"].append([f[0], f[1], f[2], f[3], ctr])
+                            if t:
+                                bface(f, t)
+    if extra:
+        xyz = np.concatenate([xyz, np.array(extra)])
+    width = {"tet": 4, "pyramid": 5, "prism": 6, "hex": 8}
+    el = {k: np.array(v, dtype=np.int32).reshape(-1, width[k]) for k, v in el.items()}
+    return (xyz, el, np.array(tris, dtype=np.int32).reshape(-1, 3), np.array(ttags, dtype=np.int32),
+            np.array(quads, dtype=np.int32).reshape(-1, 4), np.array(qtags, dtype=np.int32))
+
+
+# UGRID file order of a pyramid with base (b0, b1, b2, b3) (right-hand normal towards the apex) and apex p: the
+# reference's reader maps file slot translation[k] to its own slot k (ReadUGRID_Ascii, ucs/mesh.tcc:6751-6758:
+# {0, 3, 4, 1, 2}), so that its own winding is base 0-3, apex 4
+_PYR_UGRID = [0, 3, 4, 1, 2]
+
+
+def write_ugrid_general(path, xyz, el, tris, tri_tags, quads, quad_tags):
+    """AFLR3 ASCII .ugrid with all element types (pyramids: internal (b0..b3, apex) -> file order)."""
+    pyr = el["pyramid"]
+    if len(pyr):
+        filed = np.empty_like(pyr)
+        filed[:, _PYR_UGRID] = pyr
+        pyr = filed
+    with open(path, "w") as f:
+        f.write(f"{len(xyz)} {len(tris)} {len(quads)} {len(el['tet'])} {len(pyr)} {len(el['prism'])} {len(el['hex'])}\n")
+        np.savetxt(f, xyz, fmt="%.17g")
+        for arr in (tris, quads):
+            if len(arr):
+                np.savetxt(f, arr + 1, fmt="%d")
+        for arr in (tri_tags, quad_tags):
+            if len(arr):
+                np.savetxt(f, arr, fmt="%d")
+        for arr in (el["tet"], pyr, el["prism"], el["hex"]):
+            if len(arr):
+                np.savetxt(f, arr + 1, fmt="%d")

@@ -116,3 +116,150 @@ def closure_defect(mesh):
     np.add.at(s, en[:, 1], -v)
     np.add.at(s, bn[:, 0], ba[:, :3] * ba[:, 3:4])
     return np.abs(s).max()
+
+
+# ---- general elements (Mesh::CalcAreasVolumes, ucs/mesh.tcc:1653-2218).  The reference's element conventions as data:
+# element type ids (etypes.h), local edges with their preferred orientation, the two faces of every edge (the first one to
+# the left of the oriented edge seen from inside), and the nodes of every face, all in the reference's own winding.
+TRI, QUAD, TET, PYRAMID, PRISM, HEX = range(6)
+_NV = {TRI: 3, QUAD: 4, TET: 4, PYRAMID: 5, PRISM: 6, HEX: 8}
+_EDGES = {
+    TET: [(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)],
+    PYRAMID: [(0, 1), (0, 3), (0, 4), (1, 2), (1, 4), (2, 3), (2, 4), (3, 4)],
+    PRISM: [(0, 1), (0, 2), (0, 3), (1, 2), (1, 4), (2, 5), (3, 4), (3, 5), (4, 5)],
+    HEX: [(0, 1), (0, 3), (0, 4), (1, 2), (1, 5), (2, 3), (2, 6), (3, 7), (4, 5), (4, 7), (5, 6), (6, 7)],
+}
+_EDGE_FACES = {
+    TET: [(0, 1), (2, 0), (1, 2), (0, 3), (3, 1), (2, 3)],
+    PYRAMID: [(0, 1), (2, 0), (1, 2), (0, 3), (3, 1), (0, 4), (4, 3), (2, 4)],
+    PRISM: [(0, 1), (2, 0), (1, 2), (0, 3), (3, 1), (2, 3), (1, 4), (4, 2), (3, 4)],
+    HEX: [(0, 1), (2, 0), (1, 2), (0, 3), (3, 1), (0, 4), (4, 3), (2, 4), (1, 5), (5, 2), (3, 5), (4, 5)],
+}
+_FACES = {
+    TET: [(0, 1, 2), (0, 3, 1), (0, 2, 3), (1, 3, 2)],
+    PYRAMID: [(0, 1, 2, 3), (0, 4, 1), (0, 3, 4), (1, 4, 2), (2, 4, 3)],
+    PRISM: [(0, 1, 2), (0, 3, 4, 1), (0, 2, 5, 3), (1, 4, 5, 2), (3, 5, 4)],
+    HEX: [(0, 1, 2, 3), (0, 4, 5, 1), (0, 3, 7, 4), (1, 5, 6, 2), (2, 6, 7, 3), (4, 7, 6, 5)],
+}
+# the two neighbours of every node inside a boundary face (mesh.tcc:2127-2131)
+_FACE_NEIGHBOURS = {TRI: [(1, 2), (2, 0), (0, 1)], QUAD: [(1, 3), (2, 0), (3, 1), (0, 2)]}
+
+
+def _tri_area(p1, p2, p3):
+    return 0.5 * torch.linalg.cross(p2 - p1, p3 - p1)
+
+
+def _tet_vol(p1, p2, p3, p4):
+    return (torch.linalg.cross(p2 - p1, p3 - p1) * (p4 - p1)).sum(dim=1) / 6.0
+
+
+def median_dual_general(xyz, elem_type, elem_nodes, elem_factag, device="cpu"):
+    """Median-dual metrics of a mesh of tets, pyramids, prisms and hexes with triangular / quadrilateral boundary faces,
+    elements in the reference's winding (elem_nodes [nelem, 8], -1 padded; elem_type as etypes.h).  Per volume element and
+    local edge the dual face is two triangles (element centroid, face centroid, edge midpoint), signed by whether the
+    mesh edge n0 < n1 runs along the element's preferred edge orientation, and four tets for the two nodes' volumes
+    (mesh.tcc:1812-1945); per boundary face and node one half-edge of two triangles (:2142-2187).  Centroids are node
+    averages (geometry.h:217-249).  Same result layout as median_dual; edges sorted by (n0, n1), half-edges by face."""
+    dev = torch.device(device)
+    X = torch.as_tensor(np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3), device=dev)
+    et = np.asarray(elem_type).astype(np.int64)
+    en = np.asarray(elem_nodes).astype(np.int64).reshape(-1, 8)
+    ef = np.asarray(elem_factag).astype(np.int64)
+    nn = X.shape[0]
+    keys, avecs, vol = [], [], torch.zeros(nn, dtype=torch.float64, device=dev)
+    for t in (TET, PYRAMID, PRISM, HEX):
+        E = torch.as_tensor(en[et == t][:, :_NV[t]], device=dev)
+        if E.shape[0] == 0:
+            continue
+        P = X[E]                                    # [ne, nv, 3]
+        ctr = P.mean(dim=1)
+        fc = [P[:, list(f)].mean(dim=1) for f in _FACES[t]]
+        for (la, lb), (f1, f2) in zip(_EDGES[t], _EDGE_FACES[t]):
+            a, b = E[:, la], E[:, lb]
+            fwd = a < b                              # the mesh edge (n0 < n1) runs la -> lb
+            o = torch.where(fwd, 1.0, -1.0).to(torch.float64)
+            n0, n1 = torch.where(fwd, a, b), torch.where(fwd, b, a)
+            X0, X1 = X[n0], X[n1]
+            mid = (X0 + X1) / 2.0
+            area = (_tri_area(ctr, fc[f2], mid) + _tri_area(mid, fc[f1], ctr)) * o[:, None]
+            keys.append(n0 * nn + n1)
+            avecs.append(area)
+            vol.index_add_(0, n0, o * (_tet_vol(X0, ctr, fc[f2], mid) + _tet_vol(X0, fc[f1], ctr, mid)))
+            vol.index_add_(0, n1, o * (_tet_vol(X1, ctr, fc[f1], mid) + _tet_vol(X1, fc[f2], ctr, mid)))
+    keys = torch.cat(keys)
+    avecs = torch.cat(avecs)
+    order = torch.argsort(keys, stable=True)
+    keys, avecs = keys[order], avecs[order]
+    uniq, counts = torch.unique_consecutive(keys, return_counts=True)
+    ne = uniq.shape[0]
+    seg = torch.repeat_interleave(torch.arange(ne, device=dev), counts)
+    avec = torch.zeros((ne, 3), dtype=torch.float64, device=dev)
+    avec.index_add_(0, seg, avecs)
+    e0, e1 = uniq // nn, uniq % nn
+    area = torch.linalg.norm(avec, dim=1)
+    edges_a = torch.cat([avec / area[:, None], area[:, None]], dim=1)
+
+    bl, ba, bt = [], [], []
+    for t in (TRI, QUAD):
+        sel = et == t
+        F = torch.as_tensor(en[sel][:, :_NV[t]], device=dev)
+        if F.shape[0] == 0:
+            continue
+        P = X[F]
+        ctr = P.mean(dim=1)
+        tag = torch.as_tensor(ef[sel], device=dev)
+        for k, (a1, a2) in enumerate(_FACE_NEIGHBOURS[t]):
+            p = P[:, k]
+            v = _tri_area(ctr, p, (p + P[:, a1]) / 2.0) + _tri_area((p + P[:, a2]) / 2.0, p, ctr)
+            bl.append(F[:, k])
+            ba.append(v)
+            bt.append(tag)
+    left = torch.cat(bl)
+    bvec = torch.cat(ba)
+    btag = torch.cat(bt)
+    barea = torch.linalg.norm(bvec, dim=1)
+    bedges_a = torch.cat([bvec / barea[:, None], barea[:, None]], dim=1)
+    nbe = left.shape[0]
+    bedges_n = torch.stack([left, nn + torch.arange(nbe, device=dev)], dim=1)
+
+    a = torch.cat([e0, e1])
+    b = torch.cat([e1, e0])
+    o = torch.argsort(a * nn + b)
+    psp = b[o]
+    ipsp = torch.zeros(nn + 1, dtype=torch.int64, device=dev)
+    ipsp[1:] = torch.cumsum(torch.bincount(a, minlength=nn), 0)
+
+    def npi(v):
+        return v.to(torch.int32).cpu().numpy()
+
+    return dict(
+        nnode=nn, gnode=0, nbnode=nbe, nedge=ne, nbedge=nbe, ngedge=0,
+        edges_n=np.ascontiguousarray(npi(torch.stack([e0, e1], dim=1)).reshape(-1)),
+        edges_a=np.ascontiguousarray(edges_a.cpu().numpy().reshape(-1)),
+        bedges_n=np.ascontiguousarray(npi(bedges_n).reshape(-1)),
+        bedges_a=np.ascontiguousarray(bedges_a.cpu().numpy().reshape(-1)),
+        bedges_factag=npi(btag), xyz=np.ascontiguousarray(X.cpu().numpy().reshape(-1)),
+        vol=vol.cpu().numpy(), ipsp=npi(ipsp), psp=npi(psp))
+
+
+def ugrid_to_reference_winding(el, tris, tri_tags, quads, quad_tags):
+    """element list (type, 8 node slots, factag) in the reference's winding from UGRID-wound arrays, in the order the
+    reference's reader stores them (ReadUGRID_Ascii, mesh.tcc:6740-6935: boundary faces reversed, pyramids through
+    {0,3,4,1,2} -- boxmesh.mixed_box already hands pyramids over as (base, apex) --, the rest unchanged)"""
+    types, nodes, tags = [], [], []
+
+    def put(t, arr, tg=None):
+        arr = np.asarray(arr, dtype=np.int64).reshape(-1, _NV[t])
+        pad = -np.ones((arr.shape[0], 8), dtype=np.int64)
+        pad[:, :_NV[t]] = arr
+        nodes.append(pad)
+        types.append(np.full(arr.shape[0], t, dtype=np.int64))
+        tags.append(np.asarray(tg, dtype=np.int64) if tg is not None else np.zeros(arr.shape[0], dtype=np.int64))
+
+    put(TRI, np.asarray(tris).reshape(-1, 3)[:, ::-1], tri_tags)
+    put(QUAD, np.asarray(quads).reshape(-1, 4)[:, ::-1], quad_tags)
+    put(TET, el["tet"])
+    put(PYRAMID, el["pyramid"])
+    put(PRISM, el["prism"])
+    put(HEX, el["hex"])
+    return np.concatenate(types), np.concatenate(nodes), np.concatenate(tags)

@@ -1,0 +1,65 @@
+"""Median-dual metrics for general elements (proteuscfd_b200/dualmesh.py: median_dual_general -- tets, pyramids, prisms,
+hexes, triangular and quadrilateral boundary faces) against the metrics the REFERENCE computed (Mesh::CalcAreasVolumes,
+ucs/mesh.tcc:1653-2218) for boxes of hexes, of prisms, of pyramids, for a box with all four volume element types
+(tests/golden/elem_*.npz: boxmesh.mixed_box written as .ugrid, read and partitioned by the reference) and for the
+reference's own unit-test mesh (cube_LowFi: unitTest/meshResources, prisms + tets through its HDF5 reader).  The fixtures carry
+the reference's element list in its own winding (elem_type / elem_nodes / elem_factag).  Set-up plumbing (SURVEY.md 8f row
+2), off the hot path; sums of the same face pieces in another order, hence 1e-12, not bit equality."""
+import numpy as np
+import pytest
+
+from proteuscfd_b200.boxmesh import mixed_box
+from proteuscfd_b200.dualmesh import closure_defect, median_dual_general, ugrid_to_reference_winding
+from tests.oracle_lib import load_golden
+
+CASES = ["elem_hex", "elem_prism", "elem_pyramid", "elem_mixed", "cube_LowFi"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_general_median_dual_matches_reference_metrics(name):
+    g, meta = load_golden(name)
+    nn, nb = int(meta["nnode"]), int(meta["nbedge"])
+    m = median_dual_general(g["xyz"].reshape(-1, 3)[:nn], g["elem_type"], g["elem_nodes"], g["elem_factag"])
+    assert m["nnode"] == nn and m["nedge"] == int(meta["nedge"]) and m["nbedge"] == nb
+    assert (g["vol"] > 0).all()
+    assert np.allclose(m["vol"], g["vol"], rtol=1e-12, atol=0)
+    en, ea = m["edges_n"].reshape(-1, 2), m["edges_a"].reshape(-1, 4)
+    rn, ra = g["edges_n"].reshape(-1, 2), g["edges_a"].reshape(-1, 4)
+    assert (rn[:, 0] < rn[:, 1]).all()
+    ours = {(int(a), int(b)): v for (a, b), v in zip(en, ea)}
+    assert len(ours) == len(en) == len(rn)
+    for (a, b), v in zip(rn, ra):
+        w = ours[(int(a), int(b))]
+        assert abs(w[3] - v[3]) <= 1e-12 * v[3]
+        assert np.abs(w[:3] - v[:3]).max() <= 1e-11
+    ip, ps = g["ipsp"], g["psp"]
+    for n in range(nn):
+        assert sorted(ps[ip[n]:ip[n + 1]]) == list(m["psp"][m["ipsp"][n]:m["ipsp"][n + 1]])
+
+    # boundary half-edges: one per (boundary face, node); per (node, surface tag) the area vectors add up the same
+    def by_node_tag(bn, ba, tag):
+        acc = {}
+        for (l, _), a, t in zip(bn.reshape(-1, 2), ba.reshape(-1, 4), tag):
+            acc.setdefault((int(l), int(t)), np.zeros(3))
+            acc[(int(l), int(t))] += a[:3] * a[3]
+        return acc
+    A = by_node_tag(m["bedges_n"], m["bedges_a"], m["bedges_factag"])
+    B = by_node_tag(g["bedges_n"][: 2 * nb], g["bedges_a"][: 4 * nb], g["bedges_factag"][:nb])
+    assert A.keys() == B.keys()
+    for k in A:
+        assert np.abs(A[k] - B[k]).max() <= 1e-13
+    assert closure_defect(m) < 1e-15
+
+
+@pytest.mark.parametrize("kind", ["hex", "prism", "pyramid", "mixed"])
+def test_generator_winding_is_the_references(kind):
+    """what the reference's UGRID reader made of the generator's file is what ugrid_to_reference_winding says: same
+    elements, same winding (the reference keeps file order within a type)"""
+    g, meta = load_golden(f"elem_{kind}")
+    xyz, el, tris, tt, quads, qt = mixed_box(4, kind, jitter=0.12)
+    et, en, ef = ugrid_to_reference_winding(el, tris, tt, quads, qt)
+    ref = sorted(zip(g["elem_type"].tolist(), map(tuple, g["elem_nodes"].reshape(-1, 8).tolist()), g["elem_factag"].tolist()))
+    ours = sorted(zip(et.tolist(), map(tuple, en.tolist()), np.where(et <= 1, ef, 0).tolist()))
+    ref = [(t, n, f if t <= 1 else 0) for t, n, f in ref]
+    assert ours == ref
+    assert np.allclose(xyz, g["xyz"].reshape(-1, 3)[: len(xyz)], rtol=0, atol=1e-15)

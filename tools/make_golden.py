@@ -22,7 +22,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from proteuscfd_b200.boxmesh import kuhn_box, renumber, write_ugrid  # noqa: E402
+from proteuscfd_b200.boxmesh import kuhn_box, mixed_box, renumber, write_ugrid, write_ugrid_general  # noqa: E402
 from proteuscfd_b200.ordering import greedy_color_order  # noqa: E402
 
 REFBIN = os.path.join(ROOT, "oracle", "_ref")
@@ -67,7 +67,7 @@ massFractions = [0.20, 0.02, 0.01, 0.75, 0.02]
 reactionsOn = {rxn}
 """
 
-INT_ARRAYS = {"forces_body_lists", "species_fit_counts", "rxn_flags", "rxn_species", "chem_dims", "edges_n", "bedges_n", "bedges_factag", "bedges_bctype", "ipsp", "psp", "gNodeOwner",
+INT_ARRAYS = {"elem_type", "elem_factag", "elem_nodes", "forces_body_lists", "species_fit_counts", "rxn_flags", "rxn_species", "chem_dims", "edges_n", "bedges_n", "bedges_factag", "bedges_bctype", "ipsp", "psp", "gNodeOwner",
               "gNodeLocalId", "commCountsSend", "commCountsRecv", "commOffsetsRecv", "nodePackingList",
               "ia", "ja", "iau", "pv"}
 
@@ -131,7 +131,7 @@ def collect(outdir, rank):
     return d
 
 
-def make_case(name, mesh=None, h5=None, bc=BOX_BC, np_ranks=1, part=None, unsteady=False, gmres=None, forces=False, transpose=False, **kw):
+def make_case(name, mesh=None, h5=None, bc=BOX_BC, np_ranks=1, part=None, unsteady=False, gmres=None, forces=False, transpose=False, elements=False, ugrid=None, **kw):
     opts = dict(eqnset="compressibleEuler", sorder=2, limiter=2, nsgs=0, mach=0.5, cfl=0.5,
                 fx=1.0, fy=0.0, fz=0.0, jactype=0, refvisc=1.0, vnn=0, turb=0, extra="")
     opts.update(kw)
@@ -146,8 +146,11 @@ def make_case(name, mesh=None, h5=None, bc=BOX_BC, np_ranks=1, part=None, unstea
         if h5 is not None:
             shutil.copy(h5, os.path.join(work, f"{name}.0.h5"))
         else:
-            xyz, tets, tris, tags = mesh
-            write_ugrid(os.path.join(work, f"{name}.ugrid"), xyz, tets, tris, tags)
+            if ugrid is not None:      # a general-element mesh: the caller writes the .ugrid
+                ugrid(os.path.join(work, f"{name}.ugrid"))
+            else:
+                xyz, tets, tris, tags = mesh
+                write_ugrid(os.path.join(work, f"{name}.ugrid"), xyz, tets, tris, tags)
             env = {}
             if np_ranks > 1:
                 np.savetxt(os.path.join(work, "part.txt"), part, fmt="%d")
@@ -158,6 +161,8 @@ def make_case(name, mesh=None, h5=None, bc=BOX_BC, np_ranks=1, part=None, unstea
             henv["PCFD_UNSTEADY"] = "1"
         if forces:                 # Forces::Compute on the bodies the .bc file declares
             henv["PCFD_FORCES"] = "1"
+        if elements:               # the element list in the reference's internal winding
+            henv["PCFD_DUMP_ELEMENTS"] = "1"
         if transpose:              # CRSMatrix::CRSTranspose on the assembled matrix -> A_T
             henv["PCFD_TRANSPOSE"] = "1"
         if gmres is not None:      # (precondType, search directions, restarts): also run CRS::GMRES on the assembled system
@@ -327,6 +332,12 @@ CASES = {
                                             nsgs=3, cfl=5.0, gmres=(3, 5, 1), extra=FR_EXTRA.format(temp=3000, pres=101325, rxn=0)),
     "box8_2rank_gmres_ilu0": lambda: make_case("box8_2rank_gmres_ilu0", mesh=kuhn_box(8, jitter=0.15), np_ranks=2,
                                                part=slab_part(kuhn_box(8, jitter=0.15)[0], 2), nsgs=3, cfl=5.0, gmres=(3, 6, 2)),
+    # general elements: the reference's median-dual metrics (Mesh::CalcAreasVolumes, mesh.tcc:1653-2218) and its element list
+    # in its own winding for boxes of hexes, of prisms, of pyramids, and one with all four volume element types and both
+    # boundary face types (boxmesh.mixed_box)
+    **{f"elem_{kind}": (lambda kind=kind: make_case(
+        f"elem_{kind}", ugrid=lambda path: write_ugrid_general(path, *mixed_box(4, kind, jitter=0.12)), elements=True))
+       for kind in ("hex", "prism", "pyramid", "mixed")},
     # CRSMatrix::CRSTranspose (crsmatrix.tcc:568-599) of the assembled Jacobian: blocks transposed in place, local mirror
     # blocks swapped, ghost-column blocks replaced by the owner's through PObj::TransposeCommCRS (parallel.tcc:54-338) --
     # one rank for both block sizes, two slabs, four quadrant columns (every rank has three neighbours)
@@ -352,7 +363,7 @@ CASES = {
     # the reference's own unit-test fixture (unitTest/gradientTest.h:20-232): prism cube, 216 nodes
     "cube_LowFi": lambda: make_case(
         "cube_LowFi", h5=os.path.join(REFERENCE, "unitTest/meshResources/cubeStructuredSeries/cube_LowFi.0.h5"),
-        bc="".join(f"surface #{i} = farField\n" for i in range(1, 27)), nsgs=2, cfl=5.0),
+        bc="".join(f"surface #{i} = farField\n" for i in range(1, 27)), nsgs=2, cfl=5.0, elements=True),
 }
 
 
