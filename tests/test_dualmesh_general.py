@@ -2,7 +2,7 @@
 hexes, triangular and quadrilateral boundary faces) against the metrics the REFERENCE computed (Mesh::CalcAreasVolumes,
 ucs/mesh.tcc:1653-2218) for boxes of hexes, of prisms, of pyramids, for a box with all four volume element types
 (tests/golden/elem_*.npz: boxmesh.mixed_box written as .ugrid, read and partitioned by the reference) and for the
-reference's own unit-test mesh (cube_LowFi: unitTest/meshResources, prisms + tets through its HDF5 reader).  The fixtures carry
+reference's own unit-test mesh (cube_LowFi: unitTest/meshResources, prisms with triangular and quadrilateral faces through its HDF5 reader).  The fixtures carry
 the reference's element list in its own winding (elem_type / elem_nodes / elem_factag).  Set-up plumbing (SURVEY.md 8f row
 2), off the hot path; sums of the same face pieces in another order, hence 1e-12, not bit equality."""
 import numpy as np

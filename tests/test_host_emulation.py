@@ -935,3 +935,22 @@ def test_fr_hllc_pieces_on_host_vs_oracle(emu_fr, oracle):
             assert np.array_equal(d, s), f"edge {e}, column {col}: {d - s}"
         nchk += 1
     assert nchk > 50
+
+
+@pytest.mark.parametrize("name", ["elem_mixed", "elem_pyramid"])
+def test_gradient_kernel_on_general_elements_vs_reference(emu, name):
+    """k_gradient on meshes of hexes / prisms / pyramids / tets with quadrilateral boundary faces (node valences from 6 to
+    beyond 14), against the REFERENCE's own qgrad of that fixture, bit for bit: the edge-based kernels see the element
+    types only through the edge and half-edge lists (B200: tests/test_zzz_gpu_general_elements.py)"""
+    from tests.oracle_lib import load_golden
+    g, meta = load_golden(name)
+    mesh = {k: g[k] for k in ("edges_n", "edges_a", "bedges_n", "bedges_a", "bedges_bctype", "xyz", "vol")}
+    for k in ("nnode", "gnode", "nbnode", "nedge", "nbedge", "ngedge"):
+        mesh[k] = int(meta[k])
+    m, keep = build_mesh(mesh)
+    q0 = np.ascontiguousarray(g["q0"])
+    sw = np.ascontiguousarray(g["lsq_sw"])
+    out = np.zeros_like(g["qgrad"])
+    emu.emu_gradient(C.byref(m), 0, _p(q0), _p(sw), _p(out))
+    assert np.abs(g["qgrad"]).max() > 0
+    assert np.array_equal(out, g["qgrad"]), f"max diff {np.abs(out - g['qgrad']).max():.3e}"

@@ -23,11 +23,14 @@ NS_FFV = NS_ORACLE_ONLY
 JAC_ORACLE_ONLY = ["box6_implicit_central"]
 # oracle only so far: Green-Gauss gradients (gradientType = 1, gradient.tcc:170-248)
 GG_ORACLE_ONLY = ["box8_explicit_gg"]
-ALL = INVISCID + NS + NS_ORACLE_ONLY + JAC_ORACLE_ONLY + GG_ORACLE_ONLY
+# general elements (hexes, prisms, pyramids, tets, quadrilateral boundary faces: boxmesh.mixed_box through the reference's
+# UGRID reader); the hot path is edge-based and sees them only through the edge / half-edge lists
+GENERAL = ["elem_mixed", "elem_pyramid"]
+ALL = INVISCID + NS + NS_ORACLE_ONLY + JAC_ORACLE_ONLY + GG_ORACLE_ONLY + GENERAL
 INVISCID_IMPLICIT = ["box6_implicit_sgs", "box6c_implicit_sgs", "ramp15_implicit", "cube_LowFi", "box6_unsteady_bdf2"]
 IMPLICIT = INVISCID_IMPLICIT + NS + NS_ORACLE_ONLY + JAC_ORACLE_ONLY
 EXPLICIT = ["box8_explicit_venkat", "box8_explicit_barth", "box8_explicit_venkatmod"]      # also run on the GPU (test_gpu_parity)
-EXPLICIT_ORACLE = EXPLICIT + GG_ORACLE_ONLY
+EXPLICIT_ORACLE = EXPLICIT + GG_ORACLE_ONLY + GENERAL
 
 
 def exact(a, b, what):
