@@ -184,6 +184,14 @@ static void DumpMesh(SolutionSpace<Real>* space)
   }
   Dump("bedges_bctype", bt.data(), bt.size());
   Dump("xyz", m->xyz, 3*(size_t)(nnode+gnode));
+  if(getenv("PCFD_RCM")){
+    // Mesh::ReorderMeshCuthillMcKee (mesh.tcc:2412-2494) on the built neighbour lists: only the permutation is taken
+    // (ordering[new] = old), the mesh itself stays as it is; PCFD_RCM=2: reversed
+    std::vector<Int> keep(m->ordering, m->ordering + nnode);
+    m->ReorderMeshCuthillMcKee(atoi(getenv("PCFD_RCM")) == 2 ? 1 : 0);
+    Dump("rcm_ordering", m->ordering, (size_t)nnode);
+    for(Int k = 0; k < nnode; k++) m->ordering[k] = keep[k];
+  }
   if(getenv("PCFD_DUMP_ELEMENTS")){
     // element list in the reference's internal winding (etypes.h: TRI 0 .. HEX 5): type, factag, 8 node slots (-1 padded)
     std::vector<Int> et, ef, enodes;

@@ -67,7 +67,7 @@ massFractions = [0.20, 0.02, 0.01, 0.75, 0.02]
 reactionsOn = {rxn}
 """
 
-INT_ARRAYS = {"elem_type", "elem_factag", "elem_nodes", "forces_body_lists", "species_fit_counts", "rxn_flags", "rxn_species", "chem_dims", "edges_n", "bedges_n", "bedges_factag", "bedges_bctype", "ipsp", "psp", "gNodeOwner",
+INT_ARRAYS = {"rcm_ordering", "elem_type", "elem_factag", "elem_nodes", "forces_body_lists", "species_fit_counts", "rxn_flags", "rxn_species", "chem_dims", "edges_n", "bedges_n", "bedges_factag", "bedges_bctype", "ipsp", "psp", "gNodeOwner",
               "gNodeLocalId", "commCountsSend", "commCountsRecv", "commOffsetsRecv", "nodePackingList",
               "ia", "ja", "iau", "pv"}
 
@@ -131,7 +131,7 @@ def collect(outdir, rank):
     return d
 
 
-def make_case(name, mesh=None, h5=None, bc=BOX_BC, np_ranks=1, part=None, unsteady=False, gmres=None, forces=False, transpose=False, elements=False, ugrid=None, **kw):
+def make_case(name, mesh=None, h5=None, bc=BOX_BC, np_ranks=1, part=None, unsteady=False, gmres=None, forces=False, transpose=False, elements=False, ugrid=None, rcm=0, **kw):
     opts = dict(eqnset="compressibleEuler", sorder=2, limiter=2, nsgs=0, mach=0.5, cfl=0.5,
                 fx=1.0, fy=0.0, fz=0.0, jactype=0, refvisc=1.0, vnn=0, turb=0, extra="")
     opts.update(kw)
@@ -161,6 +161,8 @@ def make_case(name, mesh=None, h5=None, bc=BOX_BC, np_ranks=1, part=None, unstea
             henv["PCFD_UNSTEADY"] = "1"
         if forces:                 # Forces::Compute on the bodies the .bc file declares
             henv["PCFD_FORCES"] = "1"
+        if rcm:                    # Mesh::ReorderMeshCuthillMcKee's permutation (1: Cuthill-McKee, 2: reversed)
+            henv["PCFD_RCM"] = str(rcm)
         if elements:               # the element list in the reference's internal winding
             henv["PCFD_DUMP_ELEMENTS"] = "1"
         if transpose:              # CRSMatrix::CRSTranspose on the assembled matrix -> A_T
@@ -338,6 +340,12 @@ CASES = {
     **{f"elem_{kind}": (lambda kind=kind: make_case(
         f"elem_{kind}", ugrid=lambda path: write_ugrid_general(path, *mixed_box(4, kind, jitter=0.12)), elements=True))
        for kind in ("hex", "prism", "pyramid", "mixed")},
+    # Mesh::ReorderMeshCuthillMcKee (mesh.tcc:2412-2494): the permutation only (rcm_ordering), plain and reversed, on a Kuhn
+    # box, on the pyramid box (valences 8 .. 26: fronts beyond std::sort's insertion-sort threshold) and on a partition
+    "rcm_box6": lambda: make_case("rcm_box6", mesh=kuhn_box(6, jitter=0.15), rcm=2),
+    "rcm_pyramid": lambda: make_case("rcm_pyramid", ugrid=lambda path: write_ugrid_general(path, *mixed_box(5, "pyramid", jitter=0.1)), rcm=1),
+    "rcm_2rank": lambda: make_case("rcm_2rank", mesh=kuhn_box(6, jitter=0.15), np_ranks=2,
+                                   part=slab_part(kuhn_box(6, jitter=0.15)[0], 2), rcm=2),
     # CRSMatrix::CRSTranspose (crsmatrix.tcc:568-599) of the assembled Jacobian: blocks transposed in place, local mirror
     # blocks swapped, ghost-column blocks replaced by the owner's through PObj::TransposeCommCRS (parallel.tcc:54-338) --
     # one rank for both block sizes, two slabs, four quadrant columns (every rank has three neighbours)
