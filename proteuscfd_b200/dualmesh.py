@@ -153,13 +153,15 @@ def _tet_vol(p1, p2, p3, p4):
     return (torch.linalg.cross(p2 - p1, p3 - p1) * (p4 - p1)).sum(dim=1) / 6.0
 
 
-def median_dual_general(xyz, elem_type, elem_nodes, elem_factag, device="cpu"):
+def median_dual_general(xyz, elem_type, elem_nodes, elem_factag, device="cpu", reference_order=False):
     """Median-dual metrics of a mesh of tets, pyramids, prisms and hexes with triangular / quadrilateral boundary faces,
     elements in the reference's winding (elem_nodes [nelem, 8], -1 padded; elem_type as etypes.h).  Per volume element and
     local edge the dual face is two triangles (element centroid, face centroid, edge midpoint), signed by whether the
     mesh edge n0 < n1 runs along the element's preferred edge orientation, and four tets for the two nodes' volumes
     (mesh.tcc:1812-1945); per boundary face and node one half-edge of two triangles (:2142-2187).  Centroids are node
-    averages (geometry.h:217-249).  Same result layout as median_dual; edges sorted by (n0, n1), half-edges by face."""
+    averages (geometry.h:217-249).  Same result layout as median_dual; edges sorted by (n0, n1), half-edges by face --
+    or, with reference_order, everything arranged as build_maps (the reference's BuildPsp / BuildEdges) orders it, which
+    makes the dict a pcfd_mesh_desc whose results equal ucs.x's on the same element list."""
     dev = torch.device(device)
     X = torch.as_tensor(np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3), device=dev)
     et = np.asarray(elem_type).astype(np.int64)
@@ -199,7 +201,7 @@ def median_dual_general(xyz, elem_type, elem_nodes, elem_factag, device="cpu"):
     area = torch.linalg.norm(avec, dim=1)
     edges_a = torch.cat([avec / area[:, None], area[:, None]], dim=1)
 
-    bl, ba, bt = [], [], []
+    bl, ba, bt, bk = [], [], [], []
     for t in (TRI, QUAD):
         sel = et == t
         F = torch.as_tensor(en[sel][:, :_NV[t]], device=dev)
@@ -208,15 +210,20 @@ def median_dual_general(xyz, elem_type, elem_nodes, elem_factag, device="cpu"):
         P = X[F]
         ctr = P.mean(dim=1)
         tag = torch.as_tensor(ef[sel], device=dev)
+        eid = torch.as_tensor(np.nonzero(sel)[0], device=dev)
         for k, (a1, a2) in enumerate(_FACE_NEIGHBOURS[t]):
             p = P[:, k]
             v = _tri_area(ctr, p, (p + P[:, a1]) / 2.0) + _tri_area((p + P[:, a2]) / 2.0, p, ctr)
             bl.append(F[:, k])
             ba.append(v)
             bt.append(tag)
+            bk.append(eid * 4 + k)
     left = torch.cat(bl)
     bvec = torch.cat(ba)
     btag = torch.cat(bt)
+    if reference_order:      # surface elements in list order, their nodes in element order (BuildEdges, mesh.tcc:1103-1123)
+        o = torch.argsort(torch.cat(bk))
+        left, bvec, btag = left[o], bvec[o], btag[o]
     barea = torch.linalg.norm(bvec, dim=1)
     bedges_a = torch.cat([bvec / barea[:, None], barea[:, None]], dim=1)
     nbe = left.shape[0]
@@ -232,7 +239,7 @@ def median_dual_general(xyz, elem_type, elem_nodes, elem_factag, device="cpu"):
     def npi(v):
         return v.to(torch.int32).cpu().numpy()
 
-    return dict(
+    out = dict(
         nnode=nn, gnode=0, nbnode=nbe, nedge=ne, nbedge=nbe, ngedge=0,
         edges_n=np.ascontiguousarray(npi(torch.stack([e0, e1], dim=1)).reshape(-1)),
         edges_a=np.ascontiguousarray(edges_a.cpu().numpy().reshape(-1)),
@@ -240,6 +247,16 @@ def median_dual_general(xyz, elem_type, elem_nodes, elem_factag, device="cpu"):
         bedges_a=np.ascontiguousarray(bedges_a.cpu().numpy().reshape(-1)),
         bedges_factag=npi(btag), xyz=np.ascontiguousarray(X.cpu().numpy().reshape(-1)),
         vol=vol.cpu().numpy(), ipsp=npi(ipsp), psp=npi(psp))
+    if reference_order:
+        maps = build_maps(nn, 0, et, en, ef)
+        assert maps["nedge"] == ne and maps["nbedge"] == nbe
+        want = maps["edges_n"].reshape(-1, 2).astype(np.int64)
+        pos = np.searchsorted(uniq.cpu().numpy(), want[:, 0] * nn + want[:, 1])      # uniq: ascending edge keys
+        out["edges_n"] = maps["edges_n"]
+        out["edges_a"] = np.ascontiguousarray(out["edges_a"].reshape(-1, 4)[pos].reshape(-1))
+        assert np.array_equal(out["bedges_n"], maps["bedges_n"]) and np.array_equal(out["bedges_factag"], maps["bedges_factag"])
+        out["ipsp"], out["psp"] = maps["ipsp"], maps["psp"]
+    return out
 
 
 def ugrid_to_reference_winding(el, tris, tri_tags, quads, quad_tags):
@@ -263,3 +280,79 @@ def ugrid_to_reference_winding(el, tris, tri_tags, quads, quad_tags):
     put(PRISM, el["prism"])
     put(HEX, el["hex"])
     return np.concatenate(types), np.concatenate(nodes), np.concatenate(tags)
+
+
+# nodes connected to each node of an element, in the order Mesh::BuildPsp walks them (mesh.tcc:541-548)
+_NODE_NEIGHBOURS = {
+    TRI: [(1, 2), (2, 0), (0, 1)],
+    QUAD: [(1, 3), (2, 0), (3, 1), (0, 2)],
+    TET: [(1, 2, 3), (2, 0, 3), (0, 1, 3), (0, 1, 2)],
+    PYRAMID: [(1, 3, 4), (2, 0, 4), (3, 1, 4), (0, 2, 4), (0, 1, 2, 3)],
+    PRISM: [(1, 2, 3), (2, 0, 4), (0, 1, 5), (4, 5, 0), (5, 3, 1), (3, 4, 2)],
+    HEX: [(1, 3, 4), (2, 0, 5), (3, 1, 6), (0, 2, 7), (5, 7, 0), (6, 4, 1), (7, 5, 2), (4, 6, 3)],
+}
+
+
+def build_maps(nnode, gnode, elem_type, elem_nodes, elem_factag):
+    """The reference's connectivity maps IN THE REFERENCE'S ORDER (Mesh::BuildElsp / BuildPsp / BuildEdges,
+    ucs/mesh.tcc:397-515, 517-713, 1056-1167) from the element list in its winding and order: `psp` of a node lists its
+    neighbours by first occurrence while walking the node's elements in list order and each element's connected nodes in
+    table order (surface elements included); interior edges are (i, psp entry > i) in that order; one boundary half-edge
+    per (surface element, local node) with its own phantom node, then one per (local node, ghost neighbour).  With these
+    arrays the hot path's sums run in the reference's order, i.e. results on a mesh built here equal ucs.x's on the same
+    element list bit for bit.  Vectorised numpy (sorts + first-occurrence unique), set-up."""
+    et = np.asarray(elem_type).astype(np.int64)
+    en = np.asarray(elem_nodes).astype(np.int64).reshape(-1, 8)
+    ef = np.asarray(elem_factag).astype(np.int64)
+    ntot = nnode + gnode
+    owner, cand, eidx, lidx = [], [], [], []
+    for t, table in _NODE_NEIGHBOURS.items():
+        sel = np.nonzero(et == t)[0]
+        if sel.size == 0:
+            continue
+        E = en[sel]
+        for k, nbrs in enumerate(table):
+            for pos, l in enumerate(nbrs):
+                owner.append(E[:, k])
+                cand.append(E[:, l])
+                eidx.append(sel)
+                lidx.append(np.full(sel.size, pos))
+    owner, cand, eidx, lidx = (np.concatenate(a) for a in (owner, cand, eidx, lidx))
+    # walk order: node, then its elements in list order (BuildElsp), then the table order inside the element
+    order = np.lexsort((lidx, eidx, owner))
+    owner, cand = owner[order], cand[order]
+    # EliminateRepeats (mesh.tcc:1341-1375): first occurrences, order kept
+    key = owner * ntot + cand
+    _, first = np.unique(key, return_index=True)
+    first.sort()
+    owner, cand = owner[first], cand[first]
+    ipsp = np.zeros(ntot + 1, dtype=np.int64)
+    np.add.at(ipsp, owner + 1, 1)
+    ipsp = np.cumsum(ipsp)
+    psp = cand
+    loc = owner < nnode
+    interior = loc & (cand < nnode) & (cand > owner)
+    edges_n = np.stack([owner[interior], cand[interior]], axis=1)
+    # boundary half-edges: surface elements in list order, their nodes in element order, interior (local) nodes only
+    surf = np.nonzero(et <= QUAD)[0]
+    bn, bf, be = [], [], []
+    for t in (TRI, QUAD):
+        sel = surf[et[surf] == t]
+        for k in range(_NV[t]):
+            bn.append(en[sel, k])
+            bf.append(ef[sel])
+            be.append(sel * 4 + k)
+    bn, bf, be = (np.concatenate(a) if a else np.zeros(0, np.int64) for a in (bn, bf, be))
+    o = np.argsort(be, kind="stable")
+    bn, bf, be = bn[o], bf[o], be[o]
+    keep = bn < nnode
+    bn, bf, be = bn[keep], bf[keep], be[keep]
+    nbedge = bn.size
+    ghost = loc & (cand >= nnode)
+    bedges_n = np.concatenate([np.stack([bn, ntot + np.arange(nbedge)], axis=1), np.stack([owner[ghost], cand[ghost]], axis=1)])
+    return dict(ipsp=ipsp.astype(np.int32), psp=psp.astype(np.int32), edges_n=edges_n.astype(np.int32).reshape(-1),
+                bedges_n=bedges_n.astype(np.int32).reshape(-1),
+                bedges_factag=np.concatenate([bf, np.zeros(int(ghost.sum()), np.int64)]).astype(np.int32),
+                bedges_elem=np.concatenate([be // 4, -np.ones(int(ghost.sum()), np.int64)]).astype(np.int32),
+                bedges_local=(be % 4).astype(np.int32), nedge=int(interior.sum()), nbedge=int(nbedge), nbnode=int(nbedge),
+                ngedge=int(ghost.sum()))

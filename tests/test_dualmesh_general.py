@@ -63,3 +63,62 @@ def test_generator_winding_is_the_references(kind):
     ref = [(t, n, f if t <= 1 else 0) for t, n, f in ref]
     assert ours == ref
     assert np.allclose(xyz, g["xyz"].reshape(-1, 3)[: len(xyz)], rtol=0, atol=1e-15)
+
+
+MAPS = ["elem_hex", "elem_prism", "elem_pyramid", "elem_mixed", "rcm_2rank_r0of2", "rcm_2rank_r1of2"]
+
+
+@pytest.mark.parametrize("name", MAPS)
+def test_connectivity_maps_in_the_references_order(name):
+    """build_maps == Mesh::BuildPsp / BuildEdges on the reference's element list: neighbour lists, interior edges, boundary
+    and ghost half-edges, phantom nodes and surface tags, entry for entry -- also on both ranks of a partition (ghost nodes,
+    surface elements with ghost corners).  (cube_LowFi is left out: a pre-partitioned HDF5 mesh brings its own maps.)"""
+    from proteuscfd_b200.dualmesh import build_maps
+    g, meta = load_golden(name)
+    nn, gn, nb = int(meta["nnode"]), int(meta["gnode"]), int(meta["nbedge"])
+    m = build_maps(nn, gn, g["elem_type"], g["elem_nodes"], g["elem_factag"])
+    assert (m["nedge"], m["nbedge"], m["ngedge"]) == (int(meta["nedge"]), nb, int(meta["ngedge"]))
+    assert np.array_equal(m["ipsp"][: nn + 1], g["ipsp"])
+    assert np.array_equal(m["psp"][: g["psp"].size], g["psp"])
+    assert np.array_equal(m["edges_n"], g["edges_n"])
+    assert np.array_equal(m["bedges_n"], g["bedges_n"])
+    assert np.array_equal(m["bedges_factag"][:nb], g["bedges_factag"][:nb])
+
+
+@pytest.mark.parametrize("name", ["elem_mixed", "elem_pyramid", "elem_hex"])
+def test_reference_ordered_mesh_description(name):
+    """median_dual_general(reference_order=True) is the reference's mesh description position by position: index arrays
+    equal, metrics at 1e-12 -- a pcfd_mesh_desc built here from an element list feeds the hot path the reference's sums in
+    the reference's order"""
+    g, meta = load_golden(name)
+    nn, nb = int(meta["nnode"]), int(meta["nbedge"])
+    m = median_dual_general(g["xyz"].reshape(-1, 3)[:nn], g["elem_type"], g["elem_nodes"], g["elem_factag"], reference_order=True)
+    for k in ("edges_n", "bedges_n", "ipsp", "psp"):
+        assert np.array_equal(m[k], g[k][: m[k].size]), k
+    assert np.array_equal(m["bedges_factag"], g["bedges_factag"][:nb])
+    ea, ra = m["edges_a"].reshape(-1, 4), g["edges_a"].reshape(-1, 4)
+    assert np.abs(ea - ra).max() <= 1e-12
+    ba, rb = m["bedges_a"].reshape(-1, 4), g["bedges_a"].reshape(-1, 4)[:nb]
+    assert np.abs(ba - rb).max() <= 1e-12
+    assert np.allclose(m["vol"], g["vol"], rtol=1e-12, atol=0)
+
+
+def test_hot_path_on_a_mesh_built_here_reproduces_the_reference(oracle):
+    """element list -> build_maps + median_dual_general -> the C oracle's gradient / limiter / residual, against the
+    REFERENCE's own arrays for that mesh: same order of every sum, metrics within 1e-15, hence results within 1e-11 of
+    their scale (not bit equality: the dual-face pieces are added in another order)"""
+    from tests.oracle_lib import Oracle
+    g, meta = load_golden("elem_mixed")
+    nn, nb = int(meta["nnode"]), int(meta["nbedge"])
+    m = median_dual_general(g["xyz"].reshape(-1, 3)[:nn], g["elem_type"], g["elem_nodes"], g["elem_factag"], reference_order=True)
+    g2 = dict(g)
+    for k in ("edges_n", "edges_a", "bedges_n", "bedges_a", "vol", "ipsp", "psp"):
+        g2[k] = m[k]
+    tag2type = {int(t): int(b) for t, b in zip(g["bedges_factag"][:nb], g["bedges_bctype"][:nb])}
+    g2["bedges_bctype"] = np.array([tag2type[int(t)] for t in m["bedges_factag"]], dtype=np.int32)
+    assert np.array_equal(g2["bedges_bctype"], g["bedges_bctype"][:nb])
+    o = Oracle(oracle, g2, meta)
+    _, sw = o.lsq()
+    qgrad = o.gradient(g["q0"].copy(), sw)
+    assert np.abs(qgrad - g["qgrad"]).max() <= 1e-11 * np.abs(g["qgrad"]).max()
+    assert np.abs(sw - g["lsq_sw"]).max() <= 1e-11 * np.abs(g["lsq_sw"]).max()

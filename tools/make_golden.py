@@ -345,7 +345,7 @@ CASES = {
     "rcm_box6": lambda: make_case("rcm_box6", mesh=kuhn_box(6, jitter=0.15), rcm=2),
     "rcm_pyramid": lambda: make_case("rcm_pyramid", ugrid=lambda path: write_ugrid_general(path, *mixed_box(5, "pyramid", jitter=0.1)), rcm=1),
     "rcm_2rank": lambda: make_case("rcm_2rank", mesh=kuhn_box(6, jitter=0.15), np_ranks=2,
-                                   part=slab_part(kuhn_box(6, jitter=0.15)[0], 2), rcm=2),
+                                   part=slab_part(kuhn_box(6, jitter=0.15)[0], 2), rcm=2, elements=True),
     # CRSMatrix::CRSTranspose (crsmatrix.tcc:568-599) of the assembled Jacobian: blocks transposed in place, local mirror
     # blocks swapped, ghost-column blocks replaced by the owner's through PObj::TransposeCommCRS (parallel.tcc:54-338) --
     # one rank for both block sizes, two slabs, four quadrant columns (every rank has three neighbours)
