@@ -292,3 +292,32 @@ def write_ugrid_general(path, xyz, el, tris, tri_tags, quads, quad_tags):
         for arr in (el["tet"], pyr, el["prism"], el["hex"]):
             if len(arr):
                 np.savetxt(f, arr + 1, fmt="%d")
+
+
+def read_ugrid(path):
+    """AFLR3 ASCII .ugrid (the mesh file ucs.x's decomposer reads, Mesh::ReadUGRID_Ascii, ucs/mesh.tcc:6740-6935) ->
+    xyz, {"tet", "pyramid", "prism", "hex"} (pyramids as (base 0-3, apex): the file's slots 0,3,4,1,2), tris, tri_tags,
+    quads, quad_tags, all 0-based, file winding otherwise."""
+    with open(path) as f:
+        tok = f.read().split()
+    nn, ntri, nquad, ntet, npyr, npri, nhex = (int(v) for v in tok[:7])
+    pos = 7
+
+    def take(count, width, dtype):
+        nonlocal pos
+        a = np.array(tok[pos: pos + count * width], dtype=dtype).reshape(count, width)
+        pos += count * width
+        return a
+
+    xyz = take(nn, 3, np.float64)
+    tris = take(ntri, 3, np.int64) - 1
+    quads = take(nquad, 4, np.int64) - 1
+    tri_tags = take(ntri, 1, np.int64).reshape(-1)
+    quad_tags = take(nquad, 1, np.int64).reshape(-1)
+    tets = take(ntet, 4, np.int64) - 1
+    pyr = take(npyr, 5, np.int64) - 1
+    prisms = take(npri, 6, np.int64) - 1
+    hexes = take(nhex, 8, np.int64) - 1
+    el = {"tet": tets.astype(np.int32), "pyramid": pyr[:, _PYR_UGRID].astype(np.int32), "prism": prisms.astype(np.int32),
+          "hex": hexes.astype(np.int32)}
+    return xyz, el, tris.astype(np.int32), tri_tags.astype(np.int32), quads.astype(np.int32), quad_tags.astype(np.int32)

@@ -356,3 +356,14 @@ def build_maps(nnode, gnode, elem_type, elem_nodes, elem_factag):
                 bedges_elem=np.concatenate([be // 4, -np.ones(int(ghost.sum()), np.int64)]).astype(np.int32),
                 bedges_local=(be % 4).astype(np.int32), nedge=int(interior.sum()), nbedge=int(nbedge), nbnode=int(nbedge),
                 ngedge=int(ghost.sum()))
+
+
+def mesh_from_ugrid(path, device="cpu"):
+    """.ugrid file -> the mesh description ucs.x builds for it on one partition (element list in the reference's winding
+    and order, BuildPsp / BuildEdges order, median-dual metrics): what pcfd_mesh_desc takes, plus the element list."""
+    from .boxmesh import read_ugrid
+    xyz, el, tris, tri_tags, quads, quad_tags = read_ugrid(path)
+    et, en, ef = ugrid_to_reference_winding(el, tris, tri_tags, quads, quad_tags)
+    m = median_dual_general(xyz, et, en, ef, device=device, reference_order=True)
+    m.update(elem_type=et.astype(np.int32), elem_nodes=en.astype(np.int32), elem_factag=ef.astype(np.int32))
+    return m

@@ -122,3 +122,31 @@ def test_hot_path_on_a_mesh_built_here_reproduces_the_reference(oracle):
     qgrad = o.gradient(g["q0"].copy(), sw)
     assert np.abs(qgrad - g["qgrad"]).max() <= 1e-11 * np.abs(g["qgrad"]).max()
     assert np.abs(sw - g["lsq_sw"]).max() <= 1e-11 * np.abs(g["lsq_sw"]).max()
+
+
+@pytest.mark.parametrize("kind", ["mixed", "pyramid"])
+def test_mesh_file_to_mesh_description(tmp_path, kind):
+    """.ugrid -> mesh_from_ugrid: from the FILE alone the reference's mesh description, position by position (the same
+    file went through the reference's reader and decomposer for the fixture)"""
+    from proteuscfd_b200.boxmesh import read_ugrid, write_ugrid_general
+    from proteuscfd_b200.dualmesh import mesh_from_ugrid
+    g, meta = load_golden(f"elem_{kind}")
+    nn, nb = int(meta["nnode"]), int(meta["nbedge"])
+    path = str(tmp_path / "m.ugrid")
+    gen = mixed_box(4, kind, jitter=0.12)
+    write_ugrid_general(path, *gen)
+    back = read_ugrid(path)
+    assert np.array_equal(back[0], gen[0])
+    for k in gen[1]:
+        assert np.array_equal(back[1][k], gen[1][k]), k
+    for a, b in zip(back[2:], gen[2:]):
+        assert np.array_equal(a, b)
+    m = mesh_from_ugrid(path)
+    assert np.array_equal(m["elem_type"], g["elem_type"]) and np.array_equal(m["elem_nodes"].reshape(-1), g["elem_nodes"])
+    for k in ("edges_n", "bedges_n", "ipsp", "psp"):
+        assert np.array_equal(m[k], g[k][: m[k].size]), k
+    assert np.array_equal(m["bedges_factag"], g["bedges_factag"][:nb])
+    assert np.abs(m["edges_a"] - g["edges_a"]).max() <= 1e-12
+    assert np.abs(m["bedges_a"] - g["bedges_a"][: 4 * nb]).max() <= 1e-12
+    assert np.allclose(m["vol"], g["vol"], rtol=1e-12, atol=0)
+    assert np.array_equal(m["xyz"], g["xyz"][: 3 * nn])
