@@ -358,12 +358,24 @@ def build_maps(nnode, gnode, elem_type, elem_nodes, elem_factag):
                 ngedge=int(ghost.sum()))
 
 
-def mesh_from_ugrid(path, device="cpu"):
+def mesh_from_ugrid(path, device="cpu", reorder=False):
     """.ugrid file -> the mesh description ucs.x builds for it on one partition (element list in the reference's winding
-    and order, BuildPsp / BuildEdges order, median-dual metrics): what pcfd_mesh_desc takes, plus the element list."""
+    and order, BuildPsp / BuildEdges order, median-dual metrics): what pcfd_mesh_desc takes, plus the element list.
+    reorder: the solver's default start-up (reorderMesh = 1, solutionSpace.tcc:61-74) -- reverse Cuthill-McKee on the
+    first maps, then Mesh::ReorderC2nMap (mesh.tcc:224-262), which reads the permutation as NEW id of each OLD node
+    (nodes[i] = ordering[nodes[i]], xyz[ordering[i]] = xyz[i]), then maps and metrics on the renumbered mesh."""
     from .boxmesh import read_ugrid
+    from .ordering import cuthill_mckee
     xyz, el, tris, tri_tags, quads, quad_tags = read_ugrid(path)
     et, en, ef = ugrid_to_reference_winding(el, tris, tri_tags, quads, quad_tags)
+    if reorder:
+        nn = xyz.shape[0]
+        first = build_maps(nn, 0, et, en, ef)
+        ordering = cuthill_mckee(nn, first["ipsp"], first["psp"], reverse=True).astype(np.int64)
+        en = np.where(en >= 0, ordering[np.clip(en, 0, None)], -1)
+        moved = np.empty_like(xyz)
+        moved[ordering] = xyz
+        xyz = moved
     m = median_dual_general(xyz, et, en, ef, device=device, reference_order=True)
     m.update(elem_type=et.astype(np.int32), elem_nodes=en.astype(np.int32), elem_factag=ef.astype(np.int32))
     return m

@@ -150,3 +150,26 @@ def test_mesh_file_to_mesh_description(tmp_path, kind):
     assert np.abs(m["bedges_a"] - g["bedges_a"][: 4 * nb]).max() <= 1e-12
     assert np.allclose(m["vol"], g["vol"], rtol=1e-12, atol=0)
     assert np.array_equal(m["xyz"], g["xyz"][: 3 * nn])
+
+
+def test_mesh_file_to_reordered_mesh_description(tmp_path):
+    """the solver's DEFAULT start-up (reorderMesh = 1): .ugrid -> reverse Cuthill-McKee -> ReorderC2nMap -> maps and
+    metrics, against the reference run with reordering on (elem_mixed_rcm): the renumbered element list, coordinates and
+    every index array equal, metrics at 1e-12"""
+    from proteuscfd_b200.boxmesh import write_ugrid_general
+    from proteuscfd_b200.dualmesh import mesh_from_ugrid
+    g, meta = load_golden("elem_mixed_rcm")
+    plain, _ = load_golden("elem_mixed")
+    assert not np.array_equal(g["elem_nodes"], plain["elem_nodes"])          # the reference did renumber
+    nn, nb = int(meta["nnode"]), int(meta["nbedge"])
+    path = str(tmp_path / "m.ugrid")
+    write_ugrid_general(path, *mixed_box(4, "mixed", jitter=0.12))
+    m = mesh_from_ugrid(path, reorder=True)
+    assert np.array_equal(m["elem_nodes"].reshape(-1), g["elem_nodes"])
+    assert np.array_equal(m["xyz"], g["xyz"][: 3 * nn])
+    for k in ("edges_n", "bedges_n", "ipsp", "psp"):
+        assert np.array_equal(m[k], g[k][: m[k].size]), k
+    assert np.array_equal(m["bedges_factag"], g["bedges_factag"][:nb])
+    assert np.abs(m["edges_a"] - g["edges_a"]).max() <= 1e-12
+    assert np.abs(m["bedges_a"] - g["bedges_a"][: 4 * nb]).max() <= 1e-12
+    assert np.allclose(m["vol"], g["vol"], rtol=1e-12, atol=0)

@@ -44,7 +44,7 @@ fluxType = roeFlux
 spatialOrder = {sorder}
 limiter = {limiter}
 numberSGS = {nsgs}
-reorderMesh = 0
+reorderMesh = {reorder}
 refPressure = 101325
 velocity = {mach}
 CFL = {cfl}
@@ -133,7 +133,7 @@ def collect(outdir, rank):
 
 def make_case(name, mesh=None, h5=None, bc=BOX_BC, np_ranks=1, part=None, unsteady=False, gmres=None, forces=False, transpose=False, elements=False, ugrid=None, rcm=0, **kw):
     opts = dict(eqnset="compressibleEuler", sorder=2, limiter=2, nsgs=0, mach=0.5, cfl=0.5,
-                fx=1.0, fy=0.0, fz=0.0, jactype=0, refvisc=1.0, vnn=0, turb=0, extra="")
+                fx=1.0, fy=0.0, fz=0.0, jactype=0, refvisc=1.0, vnn=0, turb=0, reorder=0, extra="")
     opts.update(kw)
     work = tempfile.mkdtemp(prefix="pcfd_golden_")
     try:
@@ -346,6 +346,10 @@ CASES = {
     "rcm_pyramid": lambda: make_case("rcm_pyramid", ugrid=lambda path: write_ugrid_general(path, *mixed_box(5, "pyramid", jitter=0.1)), rcm=1),
     "rcm_2rank": lambda: make_case("rcm_2rank", mesh=kuhn_box(6, jitter=0.15), np_ranks=2,
                                    part=slab_part(kuhn_box(6, jitter=0.15)[0], 2), rcm=2, elements=True),
+    # the solver's default start-up (reorderMesh = 1, solutionSpace.tcc:61-74): reverse Cuthill-McKee, ReorderC2nMap (which
+    # takes ordering[] as new-of-old), maps and metrics rebuilt on the renumbered mesh
+    "elem_mixed_rcm": lambda: make_case(
+        "elem_mixed_rcm", ugrid=lambda path: write_ugrid_general(path, *mixed_box(4, "mixed", jitter=0.12)), elements=True, reorder=1),
     # CRSMatrix::CRSTranspose (crsmatrix.tcc:568-599) of the assembled Jacobian: blocks transposed in place, local mirror
     # blocks swapped, ghost-column blocks replaced by the owner's through PObj::TransposeCommCRS (parallel.tcc:54-338) --
     # one rank for both block sizes, two slabs, four quadrant columns (every rank has three neighbours)
