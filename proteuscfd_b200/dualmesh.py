@@ -153,7 +153,7 @@ def _tet_vol(p1, p2, p3, p4):
     return (torch.linalg.cross(p2 - p1, p3 - p1) * (p4 - p1)).sum(dim=1) / 6.0
 
 
-def median_dual_general(xyz, elem_type, elem_nodes, elem_factag, device="cpu", reference_order=False):
+def median_dual_general(xyz, elem_type, elem_nodes, elem_factag, device="cpu", reference_order=False, nnode=None):
     """Median-dual metrics of a mesh of tets, pyramids, prisms and hexes with triangular / quadrilateral boundary faces,
     elements in the reference's winding (elem_nodes [nelem, 8], -1 padded; elem_type as etypes.h).  Per volume element and
     local edge the dual face is two triangles (element centroid, face centroid, edge midpoint), signed by whether the
@@ -161,7 +161,13 @@ def median_dual_general(xyz, elem_type, elem_nodes, elem_factag, device="cpu", r
     (mesh.tcc:1812-1945); per boundary face and node one half-edge of two triangles (:2142-2187).  Centroids are node
     averages (geometry.h:217-249).  Same result layout as median_dual; edges sorted by (n0, n1), half-edges by face --
     or, with reference_order, everything arranged as build_maps (the reference's BuildPsp / BuildEdges) orders it, which
-    makes the dict a pcfd_mesh_desc whose results equal ucs.x's on the same element list."""
+    makes the dict a pcfd_mesh_desc whose results equal ucs.x's on the same element list.
+    nnode (with reference_order): a partition -- the first nnode nodes are local, the rest ghosts; elements are the rank's
+    local + split elements (partition.udecomp_elements).  Edges between two local nodes stay edges, (local, ghost) edges
+    become the ghost half-edges behind the boundary ones (whole dual face: every element around a cut edge is on the rank,
+    mesh.tcc:1948-2120), volumes and boundary half-edges are the local nodes' only."""
+    if nnode is not None and not reference_order:
+        raise ValueError("median_dual_general: a partition (nnode) is laid out in the reference's order only")
     dev = torch.device(device)
     X = torch.as_tensor(np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3), device=dev)
     et = np.asarray(elem_type).astype(np.int64)
@@ -224,6 +230,9 @@ def median_dual_general(xyz, elem_type, elem_nodes, elem_factag, device="cpu", r
     if reference_order:      # surface elements in list order, their nodes in element order (BuildEdges, mesh.tcc:1103-1123)
         o = torch.argsort(torch.cat(bk))
         left, bvec, btag = left[o], bvec[o], btag[o]
+        if nnode is not None:
+            keep = left < nnode
+            left, bvec, btag = left[keep], bvec[keep], btag[keep]
     barea = torch.linalg.norm(bvec, dim=1)
     bedges_a = torch.cat([bvec / barea[:, None], barea[:, None]], dim=1)
     nbe = left.shape[0]
@@ -248,14 +257,26 @@ def median_dual_general(xyz, elem_type, elem_nodes, elem_factag, device="cpu", r
         bedges_factag=npi(btag), xyz=np.ascontiguousarray(X.cpu().numpy().reshape(-1)),
         vol=vol.cpu().numpy(), ipsp=npi(ipsp), psp=npi(psp))
     if reference_order:
-        maps = build_maps(nn, 0, et, en, ef)
-        assert maps["nedge"] == ne and maps["nbedge"] == nbe
-        want = maps["edges_n"].reshape(-1, 2).astype(np.int64)
-        pos = np.searchsorted(uniq.cpu().numpy(), want[:, 0] * nn + want[:, 1])      # uniq: ascending edge keys
-        out["edges_n"] = maps["edges_n"]
-        out["edges_a"] = np.ascontiguousarray(out["edges_a"].reshape(-1, 4)[pos].reshape(-1))
-        assert np.array_equal(out["bedges_n"], maps["bedges_n"]) and np.array_equal(out["bedges_factag"], maps["bedges_factag"])
-        out["ipsp"], out["psp"] = maps["ipsp"], maps["psp"]
+        nloc = nn if nnode is None else int(nnode)
+        maps = build_maps(nloc, nn - nloc, et, en, ef)
+        assert maps["nbedge"] == nbe and (nnode is not None or maps["nedge"] == ne)
+        keys_sorted = uniq.cpu().numpy()                                               # ascending edge keys n0 * nn + n1
+        all_a = out["edges_a"].reshape(-1, 4)
+
+        def rows(pairs):
+            pairs = pairs.reshape(-1, 2).astype(np.int64)
+            pos = np.searchsorted(keys_sorted, pairs[:, 0] * nn + pairs[:, 1])
+            assert np.array_equal(keys_sorted[pos], pairs[:, 0] * nn + pairs[:, 1])
+            return all_a[pos]
+
+        ghost_n = maps["bedges_n"].reshape(-1, 2)[nbe:]
+        assert np.array_equal(out["bedges_n"], maps["bedges_n"][: 2 * nbe])
+        assert np.array_equal(out["bedges_factag"], maps["bedges_factag"][:nbe])
+        out.update(nnode=nloc, gnode=nn - nloc, nedge=maps["nedge"], ngedge=maps["ngedge"], edges_n=maps["edges_n"],
+                   edges_a=np.ascontiguousarray(rows(maps["edges_n"]).reshape(-1)), bedges_n=maps["bedges_n"],
+                   bedges_a=np.ascontiguousarray(np.concatenate([out["bedges_a"].reshape(-1, 4), rows(ghost_n)]).reshape(-1)),
+                   bedges_factag=maps["bedges_factag"], vol=out["vol"][:nloc], ipsp=maps["ipsp"][: nloc + 1],
+                   psp=maps["psp"][: int(maps["ipsp"][nloc])])
     return out
 
 

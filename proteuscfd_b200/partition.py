@@ -1,4 +1,4 @@
-"""Node partitions of a tetrahedral mesh in the layout `udecomp` writes (ucs/decomp.cpp:20-635) -- the input format of
+"""Node partitions of a mesh in the layout `udecomp` writes (ucs/decomp.cpp:20-635) -- the input format of
 the multi-rank hot path.
 
 `udecomp_partition` restates the part of udecomp that fixes the numbering a rank sees:
@@ -131,4 +131,44 @@ def udecomp_partition(xyz, tets, tris, tags, part, nranks, bc_lut=None, device="
             lut = np.asarray(bc_lut, dtype=np.int32)
             mesh["bedges_bctype"] = np.concatenate([lut[factag], np.zeros(len(gh_n), dtype=np.int32)]).astype(np.int32)
         out.append(mesh)
+    return out
+
+
+def udecomp_elements(elem_type, elem_nodes, elem_factag, part, nranks):
+    """Per rank the element list udecomp writes (ucs/decomp.cpp:155-210, 414-490) and the solver reads back: the elements
+    wholly inside the rank in global list order, then the elements split across ranks that touch it, in global list
+    order; nodes in the rank's numbering -- owned nodes in global order, ghosts behind them in first-occurrence order over
+    the split elements, regrouped by owner (:215-268).  Any element types (8 node slots, -1 padded).
+    Returns per rank: dict(elem_type, elem_nodes, elem_factag, owned, ghosts, gNodeOwner, gNodeLocalId)."""
+    et = np.asarray(elem_type).astype(np.int64)
+    en = np.asarray(elem_nodes).astype(np.int64).reshape(-1, 8)
+    ef = np.asarray(elem_factag).astype(np.int64)
+    part = np.asarray(part).astype(np.int64)
+    valid = en >= 0
+    dom = np.where(valid, part[np.clip(en, 0, None)], -1)
+    first = dom[:, 0]
+    whole = ((dom == first[:, None]) | ~valid).all(axis=1)
+    owned_of = [np.nonzero(part == r)[0] for r in range(nranks)]
+    out = []
+    for r in range(nranks):
+        local = np.nonzero(whole & (first == r))[0]
+        split = np.nonzero(~whole & (dom == r).any(axis=1))[0]
+        nodes = en[split][valid[split]]
+        nodes = nodes[part[nodes] != r]
+        _, fi = np.unique(nodes, return_index=True)
+        ghosts = nodes[np.sort(fi)]
+        ghosts = ghosts[np.argsort(part[ghosts], kind="stable")]
+        owned = owned_of[r]
+        new = np.full(part.size, -1, dtype=np.int64)
+        new[owned] = np.arange(owned.size)
+        new[ghosts] = owned.size + np.arange(ghosts.size)
+        sel = np.concatenate([local, split])
+        loc_nodes = np.where(valid[sel], new[np.clip(en[sel], 0, None)], -1)
+        g_owner = part[ghosts].astype(np.int32)
+        g_local = np.zeros(ghosts.size, dtype=np.int32)
+        for o in np.unique(g_owner):
+            s = g_owner == o
+            g_local[s] = np.searchsorted(owned_of[o], ghosts[s])
+        out.append(dict(elem_type=et[sel].astype(np.int32), elem_nodes=loc_nodes.astype(np.int32), elem_factag=ef[sel].astype(np.int32),
+                        owned=owned, ghosts=ghosts, gNodeOwner=g_owner, gNodeLocalId=g_local))
     return out

@@ -173,3 +173,61 @@ def test_mesh_file_to_reordered_mesh_description(tmp_path):
     assert np.abs(m["edges_a"] - g["edges_a"]).max() <= 1e-12
     assert np.abs(m["bedges_a"] - g["bedges_a"][: 4 * nb]).max() <= 1e-12
     assert np.allclose(m["vol"], g["vol"], rtol=1e-12, atol=0)
+
+
+def test_partitioned_mesh_description_from_the_global_element_list():
+    """global element list + node partition -> per rank what udecomp writes and the solver builds from it
+    (partition.udecomp_elements: local then split elements, owned nodes then ghosts grouped by owner; build_maps; metrics
+    with the cut edges as ghost half-edges), against both ranks of a reference run (rcm_2rank_r*of2): element lists, ghost
+    tables, coordinates and every index array entry for entry, metrics at 1e-12"""
+    import sys
+    from proteuscfd_b200.boxmesh import kuhn_box
+    from proteuscfd_b200.partition import udecomp_elements
+    xyz, tets, tris, tags = kuhn_box(6, jitter=0.15)
+    part = (np.clip(xyz[:, 2], 0.0, 1.0 - 1e-12) * 2).astype(np.int64)          # tools/make_golden.py: slab_part
+    none = {"pyramid": np.zeros((0, 5), int), "prism": np.zeros((0, 6), int), "hex": np.zeros((0, 8), int)}
+    et, en, ef = ugrid_to_reference_winding(dict(none, tet=tets), tris, tags, np.zeros((0, 4), int), np.zeros(0, int))
+    ranks = udecomp_elements(et, en, ef, part, 2)
+    for r in (0, 1):
+        g, meta = load_golden(f"rcm_2rank_r{r}of2")
+        R = ranks[r]
+        assert np.array_equal(R["elem_type"], g["elem_type"]) and np.array_equal(R["elem_nodes"].reshape(-1), g["elem_nodes"])
+        assert np.array_equal(R["gNodeOwner"], g["gNodeOwner"]) and np.array_equal(R["gNodeLocalId"], g["gNodeLocalId"])
+        gid = np.concatenate([R["owned"], R["ghosts"]])
+        m = median_dual_general(xyz[gid], R["elem_type"], R["elem_nodes"], R["elem_factag"], reference_order=True,
+                                nnode=R["owned"].size)
+        assert (m["nnode"], m["gnode"], m["nedge"], m["nbedge"], m["ngedge"]) == tuple(
+            int(meta[k]) for k in ("nnode", "gnode", "nedge", "nbedge", "ngedge"))
+        for k in ("edges_n", "bedges_n", "ipsp", "psp", "xyz"):
+            assert np.array_equal(m[k], g[k]), (r, k)
+        nb = m["nbedge"]
+        assert np.array_equal(m["bedges_factag"][:nb], g["bedges_factag"][:nb])
+        assert np.abs(m["edges_a"] - g["edges_a"]).max() <= 1e-12
+        assert np.abs(m["bedges_a"] - g["bedges_a"]).max() <= 1e-12
+        assert np.allclose(m["vol"], g["vol"], rtol=1e-12, atol=0)
+
+
+def test_partitioned_general_element_mesh_from_the_mesh_file(tmp_path):
+    """the same for the all-types box cut into two y-slabs through prisms, hexes, pyramids and tets, starting from the
+    .ugrid FILE (elem_mixed_2rank_r*of2)"""
+    from proteuscfd_b200.boxmesh import read_ugrid, write_ugrid_general
+    from proteuscfd_b200.partition import udecomp_elements
+    path = str(tmp_path / "m.ugrid")
+    write_ugrid_general(path, *mixed_box(4, "mixed", jitter=0.12))
+    xyz, el, tris, tt, quads, qt = read_ugrid(path)
+    et, en, ef = ugrid_to_reference_winding(el, tris, tt, quads, qt)
+    part = (np.clip(xyz[:, 1], 0.0, 1.0 - 1e-12) * 2).astype(np.int64)
+    ranks = udecomp_elements(et, en, ef, part, 2)
+    for r in (0, 1):
+        g, meta = load_golden(f"elem_mixed_2rank_r{r}of2")
+        R = ranks[r]
+        assert np.array_equal(R["elem_type"], g["elem_type"]) and np.array_equal(R["elem_nodes"].reshape(-1), g["elem_nodes"])
+        assert np.array_equal(R["gNodeOwner"], g["gNodeOwner"]) and np.array_equal(R["gNodeLocalId"], g["gNodeLocalId"])
+        gid = np.concatenate([R["owned"], R["ghosts"]])
+        m = median_dual_general(xyz[gid], R["elem_type"], R["elem_nodes"], R["elem_factag"], reference_order=True,
+                                nnode=R["owned"].size)
+        for k in ("edges_n", "bedges_n", "ipsp", "psp", "xyz"):
+            assert np.array_equal(m[k], g[k]), (r, k)
+        assert np.abs(m["edges_a"] - g["edges_a"]).max() <= 1e-12
+        assert np.abs(m["bedges_a"] - g["bedges_a"]).max() <= 1e-12
+        assert np.allclose(m["vol"], g["vol"], rtol=1e-12, atol=0)

@@ -350,6 +350,10 @@ CASES = {
     # takes ordering[] as new-of-old), maps and metrics rebuilt on the renumbered mesh
     "elem_mixed_rcm": lambda: make_case(
         "elem_mixed_rcm", ugrid=lambda path: write_ugrid_general(path, *mixed_box(4, "mixed", jitter=0.12)), elements=True, reorder=1),
+    # the all-types box cut into two y-slabs (through prisms, hexes, pyramids and tets): what udecomp writes per rank
+    "elem_mixed_2rank": lambda: make_case(
+        "elem_mixed_2rank", ugrid=lambda path: write_ugrid_general(path, *mixed_box(4, "mixed", jitter=0.12)), elements=True,
+        np_ranks=2, part=slab_part(mixed_box(4, "mixed", jitter=0.12)[0], 2, axis=1)),
     # CRSMatrix::CRSTranspose (crsmatrix.tcc:568-599) of the assembled Jacobian: blocks transposed in place, local mirror
     # blocks swapped, ghost-column blocks replaced by the owner's through PObj::TransposeCommCRS (parallel.tcc:54-338) --
     # one rank for both block sizes, two slabs, four quadrant columns (every rank has three neighbours)
