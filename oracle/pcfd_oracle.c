@@ -1186,6 +1186,7 @@ void orc_jacobian(const orc_case* c, double* q, const double* beta, const double
     const double* QR = &q[r*NVARS];
     double QPL[NVARS], QPR[NVARS], fluxS[NEQN], fluxL[NEQN], fluxR[NEQN], tempL[25], tempR[25];
     double *pR, *pL;
+    if(c->field_jac_type == 2) break;      /* Kernel_NumJac_Complex :370-433: pcfd_oracle_cs.c, below */
     if(c->field_jac_type == 1){
       /* Kernel_NumJac_Centered :306-366 */
       double fluxLd[NEQN], fluxRd[NEQN];
@@ -1224,6 +1225,9 @@ void orc_jacobian(const orc_case* c, double* q, const double* beta, const double
     for(k = 0; k < 25; k++) pR[k] += tempR[k];
     for(k = 0; k < 25; k++) pL[k] += tempL[k];
   }
+
+  if(c->field_jac_type == 2)
+    orc_jac_edges_complex(c->nedge, c->edges_n, c->edges_a, q, NVARS, gamma, ia, ja, A);
 
   /* Bkernel_NumJac :459-544 */
   for(e = 0; e < nb; e++){

@@ -262,6 +262,10 @@ double orc_fr_turb_sa(const orc_case* c, const orc_fr_params* p, int nsgs, const
 		      const double* dist, const double* dt, const int* ia, const int* ja, const int* iau,
 		      double* tvar, double* tgrad, double* b, double* A, double* x, double* mut);
 
+/* Kernel_NumJac_Complex (jacobian.tcc:370-433) over the interior edges, added into A (pcfd_oracle_cs.c) */
+void orc_jac_edges_complex(int nedge, const int* edges_n, const double* edges_a, const double* q, int nvars, double gamma_r,
+			   const int* ia, const int* ja, double* A);
+
 /* CRSMatrix::CRSTranspose (crsmatrix.tcc:568-599) up to its parallel sync (PObj::TransposeCommCRS replaces the ghost-column
    blocks afterwards; tests/test_crs_transpose.py routes them) */
 void orc_crs_transpose_local(int nnode, int neqn, const int* ia, const int* ja, double* A);

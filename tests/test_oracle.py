@@ -20,7 +20,9 @@ NS = ["box6_ns_implicit", "box6_ns_adiabatic", "box6_sa_implicit"]      # also t
 NS_ORACLE_ONLY = ["box6_ns_ffv"]
 NS_FFV = NS_ORACLE_ONLY
 # oracle only so far: central-difference flux Jacobians (jacobianFieldType = jacobianBoundaryType = 1)
-JAC_ORACLE_ONLY = ["box6_implicit_central"]
+JAC_ORACLE_ONLY = ["box6_implicit_central",
+                   # complex-step field Jacobians (jacobianFieldType = 2, jacobian.tcc:370-433; oracle/pcfd_oracle_cs.c)
+                   "box6_implicit_complex"]
 # oracle only so far: Green-Gauss gradients (gradientType = 1, gradient.tcc:170-248)
 GG_ORACLE_ONLY = ["box8_explicit_gg"]
 # general elements (hexes, prisms, pyramids, tets, quadrilateral boundary faces: boxmesh.mixed_box through the reference's

@@ -50,7 +50,7 @@ velocity = {mach}
 CFL = {cfl}
 flowDirection = [{fx}, {fy}, {fz}]
 jacobianFieldType = {jactype}
-jacobianBoundaryType = {jactype}
+jacobianBoundaryType = {jactype_b}
 refViscosity = {refvisc}
 enableVNN = {vnn}
 turbulenceModel = {turb}
@@ -135,6 +135,7 @@ def make_case(name, mesh=None, h5=None, bc=BOX_BC, np_ranks=1, part=None, unstea
     opts = dict(eqnset="compressibleEuler", sorder=2, limiter=2, nsgs=0, mach=0.5, cfl=0.5,
                 fx=1.0, fy=0.0, fz=0.0, jactype=0, refvisc=1.0, vnn=0, turb=0, reorder=0, extra="")
     opts.update(kw)
+    opts.setdefault("jactype_b", opts["jactype"])
     work = tempfile.mkdtemp(prefix="pcfd_golden_")
     try:
         if opts["eqnset"].endswith("FR"):
@@ -354,6 +355,10 @@ CASES = {
     "elem_mixed_2rank": lambda: make_case(
         "elem_mixed_2rank", ugrid=lambda path: write_ugrid_general(path, *mixed_box(4, "mixed", jitter=0.12)), elements=True,
         np_ranks=2, part=slab_part(mixed_box(4, "mixed", jitter=0.12)[0], 2, axis=1)),
+    # complex-step field Jacobians (jacobianFieldType = 2: Kernel_NumJac_Complex, jacobian.tcc:370-433) with the one-sided
+    # boundary Jacobian
+    "box6_implicit_complex": lambda: make_case("box6_implicit_complex", mesh=kuhn_box(6, jitter=0.15), nsgs=3, cfl=5.0,
+                                               jactype=2, jactype_b=0),
     # CRSMatrix::CRSTranspose (crsmatrix.tcc:568-599) of the assembled Jacobian: blocks transposed in place, local mirror
     # blocks swapped, ghost-column blocks replaced by the owner's through PObj::TransposeCommCRS (parallel.tcc:54-338) --
     # one rank for both block sizes, two slabs, four quadrant columns (every rank has three neighbours)
