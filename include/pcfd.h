@@ -132,8 +132,9 @@ int pcfd_set_time_integration(pcfd_ctx* ctx, double dt, int use_local_time_stepp
 int pcfd_set_gradient_type(pcfd_ctx* ctx, int type);
 /* Param::fieldJacType / boundaryJacType (jacobian.tcc:140-176): 0 one-sided finite differences (default,
    Kernel_NumJac :254-304 / Bkernel_NumJac :459-544), 1 central differences (Kernel_NumJac_Centered :306-366 /
-   Bkernel_NumJac_Centered :546-640, whose -h branch does not re-evaluate the BC).  Type 2 (complex step) is rejected.
-   Both eqnset families.  (ABI v6) */
+   Bkernel_NumJac_Centered :546-640, whose -h branch does not re-evaluate the BC); field type 2: complex step
+   (Kernel_NumJac_Complex :370-433: the Roe flux on a complex state perturbed by i*1e-11, perfect-gas eqnsets only, ABI
+   v9).  Boundary type 2 (Bkernel_NumJac_Complex) and field type 2 on a reacting context are rejected.  (ABI v6) */
 int pcfd_set_jacobian_type(pcfd_ctx* ctx, int field_type, int boundary_type);
 
 size_t pcfd_field_size(const pcfd_ctx* ctx, int field); /* number of doubles */

@@ -15,6 +15,7 @@
 
 #include "../../include/pcfd.h"
 #include "eqnset_compressible.cuh"
+#include "eqnset_compressible_cs.cuh"
 
 std::string& pcfd_create_err();   // message of a failed pcfd_create* (pcfd_last_error(NULL))
 

@@ -1109,6 +1109,47 @@ __global__ void __launch_bounds__(128, MINB) k_jac_edges(DevMesh m, double gamma
   }
 }
 
+// Kernel_NumJac_Complex (jacobian.tcc:370-433), Param::fieldJacType == 2: the first-order Roe flux on a complex state
+// (eqnset_compressible_cs.cuh), one conservative variable perturbed by i * 1e-11; A(r,l) = -imag(F(qL + ih)) / h,
+// A(l,r) = imag(F(qR + ih)) / h.  (The reference also recomputes the auxiliary variables of the perturbed state; the
+// Roe flux does not read them.)
+__global__ void __launch_bounds__(128) k_jac_edges_complex(DevMesh m, double gamma, const double* __restrict__ q,
+                                                            const int* __restrict__ posLR, const int* __restrict__ posRL,
+                                                            double* __restrict__ A) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m.nedge) return;
+  const double h = 1.0e-11;
+  const int2 lr = m.en[e];
+  double av[4], qL[5], qR[5];
+  load_avec(m.ea, e, av);
+  load_q5(q, lr.x, qL);
+  load_q5(q, lr.y, qR);
+  eqcs::cplx QL[5], QR[5];
+#pragma unroll
+  for (int j = 0; j < 5; j++) { QL[j] = eqcs::cplx(qL[j]); QR[j] = eqcs::cplx(qR[j]); }
+  double* pR = A + (size_t)posLR[e] * NEQN2;   // row l, column r
+  double* pL = A + (size_t)posRL[e] * NEQN2;   // row r, column l
+#pragma unroll 1
+  for (int i = 0; i < 5; i++) {
+    eqcs::cplx QP[5], fL[5], fR[5];
+#pragma unroll
+    for (int j = 0; j < 5; j++) QP[j] = QL[j];
+    QP[i].im += h;
+    eqcs::roe_flux(QP, QR, av, 0.0, gamma, fL);
+#pragma unroll
+    for (int j = 0; j < 5; j++) QP[j] = QR[j];
+    QP[i].im += h;
+    eqcs::roe_flux(QL, QP, av, 0.0, gamma, fR);
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+      // EqnSet::NumericalFlux kneecaps a flux entry whose REAL part is NaN (eqnset.tcc:73-88)
+      const double iL = isnan(fL[j].re) ? 0.0 : fL[j].im, iR = isnan(fR[j].re) ? 0.0 : fR[j].im;
+      pL[j * 5 + i] = 0.0 + (-iL / h);   // "+=" onto the blanked matrix
+      pR[j * 5 + i] = 0.0 + (iR / h);
+    }
+  }
+}
+
 // Kernel_NumJac_Centered (jacobian.tcc:306-366), Param::fieldJacType == 1: central differences, h = 1e-8, of the
 // first-order flux; A(r,l) = (F(qL-h) - F(qL+h))/2h, A(l,r) = (F(qR+h) - F(qR-h))/2h.
 __global__ void __launch_bounds__(128) k_jac_edges_central(DevMesh m, double gamma, const double* __restrict__ q,
@@ -2845,9 +2886,10 @@ int pcfd_gradient(pcfd_ctx* c) {
 
 int pcfd_set_jacobian_type(pcfd_ctx* c, int field_type, int boundary_type) {
   if (!c) return 1;
-  if ((field_type != 0 && field_type != 1) || (boundary_type != 0 && boundary_type != 1))
-    return fail(c, "pcfd_set_jacobian_type: 0 (one-sided differences) or 1 (central differences); the complex-step type 2 "
-                   "(jacobian.tcc:140-176) is not built");
+  if (field_type < 0 || field_type > 2 || (boundary_type != 0 && boundary_type != 1) || (field_type == 2 && c->fr))
+    return fail(c, "pcfd_set_jacobian_type: field 0 (one-sided differences), 1 (central differences) or 2 (complex step: "
+                   "perfect-gas eqnsets only); boundary 0 or 1 -- the complex-step boundary Jacobian "
+                   "(Bkernel_NumJac_Complex, jacobian.tcc:170-172) is not built");
   c->field_jac_type = field_type;
   c->boundary_jac_type = boundary_type;
   return 0;
@@ -3280,7 +3322,10 @@ int pcfd_jacobian(pcfd_ctx* c) {
   // (tests/test_gpu_variants.py poisons the matrix with NaN before the refresh)
   c->ludiag = false;
   if (c->nedge) {
-    if (c->field_jac_type == 1) {
+    if (c->field_jac_type == 2) {
+      PROF("k_jac_edges_complex");
+      k_jac_edges_complex<<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, c->prm.gamma, c->f[PCFD_F_Q], c->posLR, c->posRL, A);
+    } else if (c->field_jac_type == 1) {
       PROF("k_jac_edges_central");
       k_jac_edges_central<<<nblk(c->nedge, 128), 128, 0, c->stream>>>(c->dm, c->prm.gamma, c->f[PCFD_F_Q], c->posLR, c->posRL, A);
     } else {

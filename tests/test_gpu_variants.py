@@ -199,16 +199,17 @@ def test_reference_with_dropin_matches_reference_variants(kind):
 
 
 def test_variant_setters_reject_what_is_not_built():
-    """complex-step Jacobians (type 2, jacobian.tcc:150-176 -- they need the reference's complex EqnSet instantiation)
-    and unknown gradient types are refused with an error, never silently mapped to another kernel"""
+    """the complex-step BOUNDARY Jacobian (boundary type 2, jacobian.tcc:170-172), unknown types and unknown gradient types
+    are refused with an error, never silently mapped to another kernel (the complex-step FIELD Jacobian, field type 2, is
+    built for the perfect-gas eqnsets: tests/test_zzz_gpu_complex_step.py)"""
     from proteuscfd_b200 import capi
     from proteuscfd_b200.cases import box_case
     mesh, params, q = box_case(4)
     ctx = capi.Context(mesh, params)
     with pytest.raises(capi.PcfdError, match="complex"):
-        ctx.set_jacobian_type(2, 0)
-    with pytest.raises(capi.PcfdError, match="complex"):
         ctx.set_jacobian_type(0, 2)
+    with pytest.raises(capi.PcfdError, match="complex"):
+        ctx.set_jacobian_type(3, 0)
     with pytest.raises(capi.PcfdError, match="Green-Gauss"):
         ctx.set_gradient_type(2)
     ctx.set_jacobian_type(1, 0)

@@ -1,0 +1,37 @@
+"""B200 run of the complex-step field Jacobian (pcfd_set_jacobian_type(ctx, 2, 0): k_jac_edges_complex) against the
+REFERENCE run with jacobianFieldType = 2 (tests/golden/box6_implicit_complex.npz).  The kernel was written after the
+round's GPU minutes were spent: tests/test_complex_step.py runs its source text on the host (1e-12 of the reference's
+blocks, more than 90 % of the entries bit-equal) and tests/test_oracle.py holds the C oracle bit-exact; this file sorts
+last.  Bar: the north star's 1e-12 -- the complex arithmetic on the device follows libgcc's / glibc's formulas but is not
+those routines."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_gpu_complex_step_jacobian_vs_reference():
+    from proteuscfd_b200 import capi
+    from tests.test_gpu_parity import golden_ctx
+    ctx, g, meta = golden_ctx("box6_implicit_complex")
+    assert int(meta["fieldJacType"]) == 2 and int(meta["boundaryJacType"]) == 0
+    ctx.set_jacobian_type(2, 0)
+    ctx.set_field(capi.F_Q, g["q0"])
+    ctx.set_field(capi.F_TIMESTEP, g["timestep"])
+    ctx.set_field(capi.F_A, np.full(g["A"].size, np.nan))           # every block is written before anything is added
+    ctx.jacobian()
+    A = ctx.get_field(capi.F_A)
+    assert np.isfinite(A).all()
+    scale = np.abs(g["A"]).max()
+    assert np.abs(A - g["A"]).max() <= 1e-12 * scale, np.abs(A - g["A"]).max() / scale
+    ctx.prepare_sgs()
+    ctx.set_field(capi.F_B, g["b"])
+    ctx.blank_x()
+    ctx.sgs(int(meta["nSgs"]))
+    x = ctx.get_field(capi.F_X)
+    assert np.abs(x - g["x"]).max() <= 1e-11 * np.abs(g["x"]).max()
+    # the one-sided differences on the same state differ at their truncation error, not more
+    ctx.set_jacobian_type(0, 0)
+    ctx.jacobian()
+    fd = ctx.get_field(capi.F_A)
+    assert 0 < np.abs(fd - A).max() <= 1e-5 * scale
