@@ -29,7 +29,7 @@ def test_gpu_complex_step_jacobian_vs_reference():
     ctx.blank_x()
     ctx.sgs(int(meta["nSgs"]))
     x = ctx.get_field(capi.F_X)
-    assert np.abs(x - g["x"]).max() <= 1e-11 * np.abs(g["x"]).max()
+    assert np.abs(x - g["x"]).max() <= 1e-9 * np.abs(g["x"]).max()
     # the one-sided differences on the same state differ at their truncation error, not more
     ctx.set_jacobian_type(0, 0)
     ctx.jacobian()
