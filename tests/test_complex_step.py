@@ -141,3 +141,33 @@ def test_complex_step_is_the_derivative_the_differences_approximate(emu):
         emu.emu_flux_pair(_p(QL), _p(Qm), _p(n), gam, _p(fm), _p(tmp))
         cd = (fp - fm) / (2 * h)
         assert np.abs(im / 1e-11 - cd).max() <= 1e-6 * max(np.abs(cd).max(), 1e-3)
+
+
+@pytest.mark.parametrize("kind", [None, "dirichlet"])
+def test_complex_step_kernel_vs_oracle_on_other_states(emu, oracle, kind):
+    """the same kernel against the C oracle (field type 2) on the seeded boxes of tests/test_host_emulation.py -- other
+    states and BC sets than the reference fixture: off-diagonal blocks within 1e-12 of their scale"""
+    from tests.oracle_lib import oracle_for
+    from tests.test_host_emulation import case
+    mesh, params, q = case(kind)
+    o = oracle_for(oracle, mesh, params)
+    o.c.field_jac_type, o.c.boundary_jac_type = 2, 0
+    ia, ja, iau = o.crs_init()
+    qo = q.copy()
+    dt, _ = o.timestep(qo, np.zeros(1))
+    A = o.jacobian(qo, np.zeros(1), dt, ia, ja, iau).reshape(-1, 25)
+    m, keep = build_mesh(mesh)
+    nedge = int(mesh["nedge"])
+    posLR = np.arange(nedge, dtype=np.int32)
+    posRL = (nedge + np.arange(nedge)).astype(np.int32)
+    E = np.full((2 * nedge, 25), np.nan)
+    qe = q.copy()      # (the oracle's boundary pass hard-sets the Dirichlet nodes of qo AFTER its field pass)
+    emu.emu_jac_edges_complex(C.byref(m), C.c_double(params["gamma"]), _p(qe), _p(posLR), _p(posRL), _p(E))
+    assert np.isfinite(E).all()
+    en = keep["en"]
+
+    def pos(row, col):
+        return ia[row] + np.nonzero(ja[ia[row]:ia[row + 1]] == col)[0][0]
+    ref = np.array([A[pos(l, r)] for l, r in en] + [A[pos(r, l)] for l, r in en])
+    scale = np.abs(ref).max()
+    assert np.abs(E - ref).max() <= 1e-12 * scale, np.abs(E - ref).max() / scale
