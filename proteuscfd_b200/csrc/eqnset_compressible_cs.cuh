@@ -51,7 +51,11 @@ __device__ __forceinline__ cplx fabs(cplx a) { return (a.re < 0.0) ? -a : a; }  
 // imaginary part y / r / 2; an exactly real number keeps an exactly zero imaginary part
 __device__ __forceinline__ cplx sqrt(cplx a) {
   if (a.im == 0.0) return cplx(::sqrt(a.re), a.im);
-  const double r = ::sqrt(0.5 * (::hypot(a.re, a.im) + a.re));
+  // |z|: for |y| < 2^-27 |x| the correctly rounded modulus IS |x| (1 + y^2 / 2x^2 < 1 + 2^-55); keeps the complex-step
+  // regime independent of the device library's hypot, which is allowed an ulp
+  const double ar = ::fabs(a.re), ai = ::fabs(a.im);
+  const double mod = (ai < ar * 7.450580596923828e-09) ? ar : ::hypot(a.re, a.im);
+  const double r = ::sqrt(0.5 * (mod + a.re));
   return cplx(r, 0.5 * (a.im / r));
 }
 __device__ __forceinline__ double fabs(double a) { return ::fabs(a); }

@@ -1,9 +1,9 @@
 """B200 run of the complex-step field Jacobian (pcfd_set_jacobian_type(ctx, 2, 0): k_jac_edges_complex) against the
 REFERENCE run with jacobianFieldType = 2 (tests/golden/box6_implicit_complex.npz).  The kernel was written after the
-round's GPU minutes were spent: tests/test_complex_step.py runs its source text on the host (1e-12 of the reference's
-blocks, more than 90 % of the entries bit-equal) and tests/test_oracle.py holds the C oracle bit-exact; this file sorts
-last.  Bar: the north star's 1e-12 -- the complex arithmetic on the device follows libgcc's / glibc's formulas but is not
-those routines."""
+round's GPU minutes were spent: tests/test_complex_step.py runs its source text on the host (the reference's blocks bit
+for bit) and tests/test_oracle.py holds the C oracle bit-exact; this file sorts last.  Bar: the north star's 1e-12 -- the
+complex arithmetic on the device follows libgcc's / glibc's formulas but is not those routines (nvcc's code generation
+has not been seen on this kernel yet)."""
 import numpy as np
 import pytest
 
